@@ -1,0 +1,116 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (numpy path) in this container.
+
+    python tools/gen_golden.py [section ...]          # sections: kirchhoff undulator materials reflect screen
+
+The reference lives at /root/reference (read-only) and needs two import stubs (tools/ref_stubs: colorama,
+matplotlib) because those packages are not installed here.  Nothing in tests/, smoke()
+or bench.py reads /root/reference; they replay the committed .npz files.
+"""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, '/root/reference')
+sys.path.insert(0, os.path.join(HERE, 'ref_stubs'))
+
+import numpy as np  # noqa: E402
+
+import xrt.backends.raycing as raycing  # noqa: E402
+import xrt.backends.raycing.sources as rs  # noqa: E402
+import xrt.backends.raycing.oes as roe  # noqa: E402
+import xrt.backends.raycing.materials as rm  # noqa: E402
+import xrt.backends.raycing.screens as rsc  # noqa: E402
+import xrt.backends.raycing.apertures as ra  # noqa: E402
+import xrt.backends.raycing.waves as rw  # noqa: E402
+from xrt.backends.raycing import physconsts as rpc  # noqa: E402
+
+raycing._VERBOSITY_ = 0
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+os.makedirs(GOLD, exist_ok=True)
+
+
+def save(name, **kw):
+    path = os.path.join(GOLD, name + '.npz')
+    np.savez_compressed(path, **kw)
+    print('wrote', path, os.path.getsize(path), 'bytes')
+
+
+BEAM_FIELDS = ('x', 'y', 'z', 'a', 'b', 'c', 'path', 'E', 'Jss', 'Jpp', 'Jsp', 'state', 'Es', 'Ep',
+               'theta', 's', 'phi', 'r')
+
+
+def beam_dict(beam, prefix):
+    d = {}
+    for f in BEAM_FIELDS:
+        if hasattr(beam, f):
+            v = getattr(beam, f)
+            if isinstance(v, np.ndarray):
+                d[prefix + f] = v
+    return d
+
+
+# ------------------------------------------------------------------------------------------------ constants
+def gen_constants():
+    names = ['PI', 'PI2', 'SIE0', 'C', 'M0', 'SIM0', 'M0C2', 'HPLANCK', 'EV2ERG', 'EMC', 'FINE_STR', 'E2W',
+             'E2WC', 'R0', 'AVOGADRO', 'CHeVcm', 'CH', 'CHBAR', 'K2B']
+    save('constants', **{n: np.float64(getattr(rpc, n)) for n in names},
+         zEps=np.float64(raycing.zEps), dt=np.float64(raycing.dt),
+         maxIteration=np.int64(raycing.maxIteration), maxHalfSizeOfOE=np.float64(raycing.maxHalfSizeOfOE),
+         maxDepthOfOE=np.float64(raycing.maxDepthOfOE))
+
+
+# ------------------------------------------------------------------------------------------------ kirchhoff
+def _kirchhoff_case(seed, N, M, E0, dist, halfIn, halfOut, tilt):
+    rng = np.random.RandomState(seed)
+    oeLocal = rs.Beam(N, withAmplitudes=True)
+    oeLocal.x[:] = rng.uniform(-halfIn, halfIn, N)
+    oeLocal.z[:] = rng.uniform(-halfIn, halfIn, N)
+    oeLocal.y[:] = rng.normal(0, 1e-3, N) if tilt else 0.
+    oeLocal.state[:] = 1
+    oeLocal.state[rng.rand(N) < 0.07] = 2  # some samples are not good and must be skipped
+    oeLocal.E[:] = E0 * (1 + 1e-4 * rng.uniform(-1, 1, N))
+    oeLocal.Es[:] = rng.normal(size=N) + 1j * rng.normal(size=N)
+    oeLocal.Ep[:] = 0.3 * (rng.normal(size=N) + 1j * rng.normal(size=N))
+    a = rng.normal(0, 1e-4, N)
+    c = rng.normal(0, 1e-4, N)
+    oeLocal.a[:] = a
+    oeLocal.c[:] = c
+    oeLocal.b[:] = np.sqrt(1 - a**2 - c**2)
+    good = oeLocal.state == 1
+    if tilt:
+        nvec = rng.normal(size=(3, N)) * 0.05 + np.array([[0.], [1.], [0.]])
+        nvec /= np.linalg.norm(nvec, axis=0)
+        n = [nvec[0][good], nvec[1][good], nvec[2][good]]
+        nfull = nvec
+        nl = (oeLocal.a * nvec[0] + oeLocal.b * nvec[1] + oeLocal.c * nvec[2])
+    else:
+        n = [0, 1, 0]  # aperture branch of waves.diffract (waves.py:687-690)
+        nfull = np.array([[0.], [1.], [0.]]) * np.ones((3, N))
+        nl = oeLocal.a * n[0] + oeLocal.b * n[1] + oeLocal.c * n[2]
+
+    wave = rs.Beam(M, withAmplitudes=True)
+    wave.xDiffr = rng.uniform(-halfOut, halfOut, M)
+    wave.zDiffr = rng.uniform(-halfOut, halfOut, M)
+    wave.yDiffr = dist + rng.uniform(-1, 1, M) * (1. if tilt else 0.)
+    res = rw._diffraction_integral_conv(oeLocal, n, nl, wave, good)
+    return dict(x=oeLocal.x, y=oeLocal.y, z=oeLocal.z, E=oeLocal.E, Es=oeLocal.Es, Ep=oeLocal.Ep,
+                state=oeLocal.state, n=nfull, nl=nl,
+                xDiffr=wave.xDiffr, yDiffr=wave.yDiffr, zDiffr=wave.zDiffr,
+                out_Es=res[0], out_Ep=res[1], out_aE=res[2], out_bE=res[3], out_cE=res[4])
+
+
+def gen_kirchhoff():
+    # hard X-rays over 10 m: phases ~ 4.6e11 rad (ulp 6e-5 rad) -- the case that needs bit-exact r and k*r
+    save('kirchhoff_9keV_10m', **_kirchhoff_case(11, 700, 96, 9000., 1e4, 0.05, 0.5, False))
+    # soft X-rays over 1 m with per-sample normals (OE branch, waves.py:675-686)
+    save('kirchhoff_280eV_1m', **_kirchhoff_case(12, 500, 64, 280., 1e3, 2.0, 1.0, True))
+
+
+SECTIONS = {'constants': gen_constants, 'kirchhoff': gen_kirchhoff}
+
+if __name__ == '__main__':
+    todo = sys.argv[1:] or list(SECTIONS)
+    for s in todo:
+        SECTIONS[s]()

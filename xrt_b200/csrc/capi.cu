@@ -1,0 +1,224 @@
+// C ABI of libxrt_b200.so (declarations: include/xrt_b200.h).
+#include <stdarg.h>
+
+#include <mutex>
+#include <string>
+
+#include "../../include/xrt_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace xrtb {
+
+static thread_local char g_err[1024] = "";
+static int g_sms = 0;
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int num_sms() {
+  if (g_sms == 0) {
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess)
+      g_sms = prop.multiProcessorCount;
+    else
+      g_sms = 148;
+  }
+  return g_sms;
+}
+
+// ---------------------------------------------------------------- fp64 ceilings
+template <int MODE>
+__global__ void __launch_bounds__(256) fp64_probe_kernel(int iters, double* sink) {
+  double a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+  const double m = 1.0000000001, c = 1e-12;
+  double d0[4], d1[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) d0[i] = d1[i] = 0.0;
+  const double fa = 1.0 + 1e-12 * threadIdx.x, fb = 1.0 - 1e-12 * threadIdx.x;
+  for (int it = 0; it < iters; ++it) {
+    if (MODE == 0 || MODE == 2) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = fma(a[i], m, c);
+    }
+    if (MODE == 1 || MODE == 2) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(d0[i]), "+d"(d1[i])
+                     : "d"(fa), "d"(fb));
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s += d0[i] + d1[i];
+  if (s == 123.456) sink[0] = s;
+}
+
+static int fp64_probe(int mode, int iters, double* tflops, double* ms_out) {
+  XRTB_REQUIRE(mode >= 0 && mode <= 2, "fp64_probe: mode must be 0, 1 or 2");
+  double* sink = nullptr;
+  XRTB_CUDA_CHECK(cudaMalloc(&sink, 8));
+  const int ctas = num_sms() * 8;
+  cudaEvent_t e0, e1;
+  XRTB_CUDA_CHECK(cudaEventCreate(&e0));
+  XRTB_CUDA_CHECK(cudaEventCreate(&e1));
+  auto run = [&](int n) {
+    if (mode == 0) fp64_probe_kernel<0><<<ctas, 256>>>(n, sink);
+    if (mode == 1) fp64_probe_kernel<1><<<ctas, 256>>>(n, sink);
+    if (mode == 2) fp64_probe_kernel<2><<<ctas, 256>>>(n, sink);
+  };
+  run(iters / 8 + 1);
+  XRTB_CUDA_CHECK(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    XRTB_CUDA_CHECK(cudaEventRecord(e0));
+    run(iters);
+    XRTB_CUDA_CHECK(cudaEventRecord(e1));
+    XRTB_CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0;
+    XRTB_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  XRTB_CUDA_CHECK(cudaGetLastError());
+  double threads = (double)ctas * 256;
+  double flop = 0;
+  if (mode == 0 || mode == 2) flop += threads * 8.0 * 2.0 * iters;
+  if (mode == 1 || mode == 2) flop += (threads / 32.0) * 4.0 * (8 * 8 * 4 * 2.0) * iters;
+  *tflops = flop / (best * 1e-3) * 1e-12;
+  if (ms_out) *ms_out = best;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  return 0;
+}
+
+// ---------------------------------------------------------------- host staging helper
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  int alloc(size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    XRTB_CUDA_CHECK(cudaMalloc(&p, bytes));
+    return 0;
+  }
+  int upload(const void* h, size_t bytes, cudaStream_t st) {
+    if (alloc(bytes)) return 1;
+    if (bytes) XRTB_CUDA_CHECK(cudaMemcpyAsync(p, h, bytes, cudaMemcpyHostToDevice, st));
+    return 0;
+  }
+  template <typename T>
+  T* as() {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+}  // namespace xrtb
+
+using namespace xrtb;
+
+extern "C" {
+
+int xrt_b200_version(void) { return 100; }
+
+int xrt_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int xrt_b200_init(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    set_last_error("xrt_b200_init: no CUDA device available (%s); this library has no CPU fallback",
+                   e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    cudaGetLastError();
+    return 1;
+  }
+  XRTB_REQUIRE(device >= 0 && device < n, "xrt_b200_init: device %d out of range [0, %d)", device, n);
+  XRTB_CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  XRTB_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  XRTB_REQUIRE(prop.major >= 10, "xrt_b200_init: device %d is sm_%d%d; this build targets sm_100a (B200)", device,
+               prop.major, prop.minor);
+  g_sms = prop.multiProcessorCount;
+  return 0;
+}
+
+int xrt_b200_sm_count(void) { return num_sms(); }
+
+const char* xrt_b200_last_error(void) { return g_err; }
+
+int xrt_b200_sync(void* stream) {
+  XRTB_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+int xrt_b200_fp64_probe(int mode, int iters, double* tflops, double* ms) {
+  return fp64_probe(mode, iters, tflops, ms);
+}
+
+// ------------------------------------------------------------------ Kirchhoff
+static int k_R(int flags) {
+  int R = (flags >> 4) & 7;
+  return R == 0 ? 2 : R;
+}
+
+size_t xrt_kirchhoff_workspace_bytes(size_t M, size_t N, int flags) {
+  return kirchhoff_workspace_bytes(M, N, k_R(flags));
+}
+
+int xrt_kirchhoff_f64(size_t M, size_t N, const double* xM, const double* yM, const double* zM, const double* nl,
+                      const double* Es, const double* Ep, const double* k, const double* pos, int pos_stride,
+                      const double* nrm, int nrm_stride, double* S, double* P, double* A, double* B, double* C,
+                      int flags, void* workspace, void* stream) {
+  XRTB_REQUIRE(pos_stride >= 3 && nrm_stride >= 3, "kirchhoff: pos/nrm strides must be >= 3");
+  XRTB_REQUIRE(workspace != nullptr, "kirchhoff: workspace is NULL");
+  return kirchhoff_device(M, N, xM, yM, zM, nl, Es, Ep, k, pos, pos_stride, nrm, nrm_stride, S, P, A, B, C, flags,
+                          workspace, (cudaStream_t)stream);
+}
+
+int xrt_kirchhoff_f64_host(size_t M, size_t N, const double* xM, const double* yM, const double* zM,
+                           const double* nl, const double* Es, const double* Ep, const double* k, const double* pos,
+                           int pos_stride, const double* nrm, int nrm_stride, double* S, double* P, double* A,
+                           double* B, double* C, int flags) {
+  XRTB_REQUIRE(pos_stride >= 3 && nrm_stride >= 3, "kirchhoff: pos/nrm strides must be >= 3");
+  if (M == 0) return 0;
+  cudaStream_t st = 0;
+  DevBuf dx, dy, dz, dnl, des, dep, dk, dpos, dnrm, dout, dws;
+  if (dx.upload(xM, M * 8, st) || dy.upload(yM, M * 8, st) || dz.upload(zM, M * 8, st) ||
+      dnl.upload(nl, N * 8, st) || des.upload(Es, N * 16, st) || dep.upload(Ep, N * 16, st) ||
+      dk.upload(k, N * 8, st) || dpos.upload(pos, N * 8 * pos_stride, st) ||
+      dnrm.upload(nrm, N * 8 * nrm_stride, st))
+    return 1;
+  if (dout.alloc(5 * M * 16)) return 1;
+  if (dws.alloc(xrt_kirchhoff_workspace_bytes(M, N, flags))) return 1;
+  double* o = dout.as<double>();
+  int rc = kirchhoff_device(M, N, dx.as<double>(), dy.as<double>(), dz.as<double>(), dnl.as<double>(),
+                            des.as<double>(), dep.as<double>(), dk.as<double>(), dpos.as<double>(), pos_stride,
+                            dnrm.as<double>(), nrm_stride, o, o + 2 * M, o + 4 * M, o + 6 * M, o + 8 * M, flags,
+                            dws.p, st);
+  if (rc) return rc;
+  double* outs[5] = {S, P, A, B, C};
+  for (int c = 0; c < 5; ++c)
+    XRTB_CUDA_CHECK(cudaMemcpyAsync(outs[c], o + 2 * M * c, M * 16, cudaMemcpyDeviceToHost, st));
+  XRTB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // extern "C"

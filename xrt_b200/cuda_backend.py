@@ -1,0 +1,148 @@
+# -*- coding: utf-8 -*-
+"""`XRT_CUDA` -- drop-in for xrt's accelerator shim `XRT_CL`.
+
+Mirrors the object surface the reference's call sites use (xrt/backends/raycing/myopencl.py:86-97 ctor,
+:155-412 `set_cl`, :414-583 `run_parallel`): same constructor arguments, same `run_parallel` keyword
+signature and argument convention (scalars, sliced RO, non-sliced RO, sliced RW, non-sliced RW; RW arrays are
+written back into the caller's arrays *and* returned), same attributes (`cl_precisionF/C`, `cl_ctx`,
+`lastTargetOpenCL`, `cl_is_blocking`).  Kernels are looked up by the reference's kernel names:
+
+    'integrate_kirchhoff'  cl/diffract.cl:80     called from waves.py:892
+    'undulator'            cl/undulator.cl:54    called from sources/synchr.py:2174
+    'get_amplitude'        cl/materials.cl:715   called from tests/raycing/test_materials.py:624
+
+Differences, on purpose: fp64 only (`precisionOpenCL` 'auto'/'float64'); there is no silent `_disable_cl`
+fallback to numpy -- a missing library or GPU raises; multi-device slicing (`run_parallel_max`,
+myopencl.py:455-583) is replaced by one process per GPU (see xrt_b200/parallel.py).
+"""
+import numpy as np
+
+from . import _lib
+
+isOpenCL = False  # there is no OpenCL here; kept so `mcl.isOpenCL or mcl.isZMQ` style tests read the same
+isZMQ = False
+isCUDA = True
+ALL_CL_DEVICES = {'None': None, 'auto': 'auto', 'GPU': 'GPU', 'CUDA': 'CUDA'}
+
+_KIRCHHOFF_CONVENTIONS = {'numpy': 0, 'opencl': 1}
+
+
+class XRT_CUDA(object):
+    def __init__(self, filename=None, targetOpenCL='auto', precisionOpenCL='auto', kernelsource=None):
+        self.kernelsource = kernelsource  # accepted for signature parity; CUDA kernels are precompiled
+        self.cl_filename = filename
+        self.lastTargetOpenCL = None
+        self.lastPrecisionOpenCL = None
+        self.lastOpenCLError = None
+        self.cl_is_blocking = True
+        self.cl_queue = []
+        self.cl_ctx = []
+        self.cl_program = []
+        self.cl_mf = None
+        self.cl_precisionF = None
+        self.cl_precisionC = None
+        self.useZMQ = False
+        #: sign/scale convention of 'integrate_kirchhoff': 'numpy' follows waves._diffraction_integral_conv
+        #: (waves.py:844-850), 'opencl' follows cl/diffract.cl:137-149.  They differ by constant phase factors
+        #: that cancel in waves.diffract (last paragraph).
+        self.kirchhoffConvention = 'numpy'
+        self.kirchhoffRelaxed = False
+        self.set_cl(targetOpenCL, precisionOpenCL)
+
+    # ------------------------------------------------------------------ configuration
+    def set_cl(self, targetOpenCL='auto', precisionOpenCL='auto', strict=True):
+        if (targetOpenCL == self.lastTargetOpenCL) and (precisionOpenCL == self.lastPrecisionOpenCL):
+            return
+        if targetOpenCL is None:
+            self.lastTargetOpenCL = None
+            self.cl_ctx = []
+            return
+        device = None
+        if isinstance(targetOpenCL, str):
+            t = targetOpenCL.strip()
+            if t.upper() in ('AUTO', 'GPU', 'CUDA', 'ALL'):
+                device = None
+            elif t.upper().startswith('CUDA:'):
+                device = int(t.split(':', 1)[1].split(',')[0])
+            else:
+                raise ValueError("XRT_CUDA: unsupported targetOpenCL {0!r}; use 'auto', 'GPU', 'CUDA' or "
+                                 "'CUDA:<index>' (there is no CPU or OpenCL path)".format(targetOpenCL))
+        elif isinstance(targetOpenCL, (tuple, list)) and len(targetOpenCL) == 2 and \
+                all(isinstance(v, (int, np.integer)) for v in targetOpenCL):
+            device = int(targetOpenCL[1])  # (iPlatform, iDevice) of the reference -> CUDA device index
+        elif isinstance(targetOpenCL, (int, np.integer)):
+            device = int(targetOpenCL)
+        else:
+            raise ValueError("XRT_CUDA: unsupported targetOpenCL {0!r}".format(targetOpenCL))
+        if precisionOpenCL not in ('auto', 'float64'):
+            raise ValueError("XRT_CUDA computes in float64 only (got precisionOpenCL={0!r})".format(
+                precisionOpenCL))
+        self.device = _lib.init(device)  # raises without a GPU: no CPU fallback
+        self.lastTargetOpenCL = targetOpenCL
+        self.lastPrecisionOpenCL = precisionOpenCL
+        self.cl_precisionF = np.float64
+        self.cl_precisionC = np.complex128
+        self.cl_ctx = ['cuda:{0}'.format(self.device)]  # truthiness is what callers test (synchr.py:2043)
+        self.cl_queue = [None]
+        self.cl_program = [None]
+
+    # ------------------------------------------------------------------ dispatch
+    def run_parallel(self, kernelName='', scalarArgs=None, slicedROArgs=None, nonSlicedROArgs=None,
+                     slicedRWArgs=None, nonSlicedRWArgs=None, dimension=0, complexity=0, signal=None):
+        if self.lastTargetOpenCL is None:
+            raise _lib.XrtB200Error('XRT_CUDA is disabled (targetOpenCL=None)')
+        try:
+            fn = getattr(self, '_k_' + kernelName)
+        except AttributeError:
+            raise NotImplementedError(
+                "XRT_CUDA has no kernel named {0!r}; hot-path kernels: {1}".format(
+                    kernelName, sorted(n[3:] for n in dir(self) if n.startswith('_k_'))))
+        return fn(scalarArgs or [], slicedROArgs or [], nonSlicedROArgs or [], slicedRWArgs or [],
+                  nonSlicedRWArgs or [], int(dimension))
+
+    run_parallel_max = run_parallel
+
+    # ------------------------------------------------------------------ kernels
+    def _k_integrate_kirchhoff(self, scalarArgs, slicedRO, nonSlicedRO, slicedRW, nonSlicedRW, dimension):
+        """Argument layout of waves._diffraction_integral_CL (waves.py:864-894)."""
+        lib = _lib.load()
+        N = int(scalarArgs[0])
+        xM, yM, zM = (_lib.as_f64(a) for a in slicedRO)
+        M = dimension if dimension else len(xM)
+        nl, Es, Ep, k, pos, nrm = nonSlicedRO
+        nl = _lib.as_f64(nl)
+        Es = _lib.as_c128(Es)
+        Ep = _lib.as_c128(Ep)
+        k = _lib.as_f64(k)
+        pos, pstride = _as_vec_buffer(pos, N)
+        nrm, nstride = _as_vec_buffer(nrm, N)
+        if not (len(nl) == len(Es) == len(Ep) == len(k) == N):
+            raise ValueError('integrate_kirchhoff: non-sliced inputs must all have length fullnrays')
+        outs = []
+        for a in slicedRW:
+            if not (isinstance(a, np.ndarray) and a.dtype == np.complex128 and a.flags['C_CONTIGUOUS'] and
+                    len(a) == M):
+                raise ValueError('integrate_kirchhoff: slicedRWArgs must be 5 contiguous complex128[dimension]')
+            outs.append(a)
+        flags = (1 if self.kirchhoffRelaxed else 0) | (_KIRCHHOFF_CONVENTIONS[self.kirchhoffConvention] << 1)
+        rc = lib.xrt_kirchhoff_f64_host(
+            M, N, _lib.hptr(xM), _lib.hptr(yM), _lib.hptr(zM), _lib.hptr(nl), _lib.hptr(Es), _lib.hptr(Ep),
+            _lib.hptr(k), _lib.hptr(pos), pstride, _lib.hptr(nrm), nstride,
+            *[_lib.hptr(a) for a in outs], flags)
+        _lib.check(rc, 'xrt_kirchhoff_f64_host')
+        return tuple(outs)
+
+
+def _as_vec_buffer(a, N):
+    """The reference passes float3 buffers as np.array([x, y, z, 0], order='F') of shape (4, N), i.e. N
+    records of 4 doubles (waves.py:874-881).  Accept that, or a C-ordered (N, 3|4) array."""
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 2 and a.shape[1] == N and a.shape[0] in (3, 4) and a.flags['F_CONTIGUOUS']:
+        return a, a.shape[0]
+    if a.ndim == 2 and a.shape[0] == N and a.shape[1] in (3, 4):
+        a = np.ascontiguousarray(a)
+        return a, a.shape[1]
+    if a.ndim == 2 and a.shape[1] == N and a.shape[0] in (3, 4):
+        a = np.asfortranarray(a)
+        return a, a.shape[0]
+    raise ValueError('expected a (4, N) Fortran-ordered or (N, 3|4) C-ordered float64 array')

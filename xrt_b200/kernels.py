@@ -1,0 +1,55 @@
+# -*- coding: utf-8 -*-
+"""Device-resident entry points: torch CUDA tensors in, torch CUDA tensors out; every call goes through the
+C ABI (include/xrt_b200.h) with raw `data_ptr()` addresses on torch's current stream.  torch is used for
+device memory, streams and torch.distributed only."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+F64 = torch.float64
+C128 = torch.complex128
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t, dtype, n=None, name='tensor'):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise ValueError('{0}: expected a contiguous CUDA tensor of dtype {1}'.format(name, dtype))
+    if n is not None and t.numel() != n:
+        raise ValueError('{0}: expected {1} elements, got {2}'.format(name, n, t.numel()))
+    return t.data_ptr()
+
+
+def fp64_probe(mode=0, iters=4096):
+    """Measured fp64 ceiling of this GPU in TFLOP/s (0: DFMA, 1: DMMA m8n8k4, 2: both interleaved)."""
+    lib = _lib.load()
+    _lib.init()
+    tf = ctypes.c_double()
+    ms = ctypes.c_double()
+    _lib.check(lib.xrt_b200_fp64_probe(mode, iters, ctypes.byref(tf), ctypes.byref(ms)), 'fp64_probe')
+    return tf.value, ms.value
+
+
+def kirchhoff(xM, yM, zM, nl, Es, Ep, k, pos, nrm, out=None, convention='numpy', relaxed=False, R=0,
+              workspace=None):
+    """a17 on device tensors.  pos, nrm: (N, 3|4) float64 row-major.  Returns (S, P, A, B, C) complex128[M]."""
+    lib = _lib.load()
+    M, N = xM.numel(), nl.numel()
+    flags = (1 if relaxed else 0) | ((1 if convention == 'opencl' else 0) << 1) | (int(R) << 4)
+    need = lib.xrt_kirchhoff_workspace_bytes(M, N, flags)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(max(need, 16), dtype=torch.uint8, device=xM.device)
+    if out is None:
+        out = torch.empty((5, M), dtype=C128, device=xM.device)
+    ps, ns = pos.shape[1], nrm.shape[1]
+    rc = lib.xrt_kirchhoff_f64(
+        M, N, _chk(xM, F64, M, 'xM'), _chk(yM, F64, M, 'yM'), _chk(zM, F64, M, 'zM'), _chk(nl, F64, N, 'nl'),
+        _chk(Es, C128, N, 'Es'), _chk(Ep, C128, N, 'Ep'), _chk(k, F64, N, 'k'), _chk(pos, F64, N * ps, 'pos'), ps,
+        _chk(nrm, F64, N * ns, 'nrm'), ns, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+        out[3].data_ptr(), out[4].data_ptr(), flags, workspace.data_ptr(), _stream())
+    _lib.check(rc, 'xrt_kirchhoff_f64')
+    return out
