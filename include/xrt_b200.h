@@ -55,6 +55,31 @@ int xrt_kirchhoff_f64_host(size_t M, size_t N, const double* xM, const double* y
                            int pos_stride, const double* nrm, int nrm_stride, double* S, double* P, double* A,
                            double* B, double* C, int flags);
 
+/* ------------------------------------------------------------------ a4: undulator far-field integral
+ * Replaces kernel `undulator` (cl/undulator.cl:54-121) launched at sources/synchr.py:2174 with the argument
+ * list of Undulator._build_I_map_CL (synchr.py:2134-2155): scalars (alpha ignored), Kx, Ky, jend; per-sample
+ * gamma, wu, w, ww1, ddphi (theta), ddpsi (psi); node tables tg, ag, sintg, costg, sintgph, costgph[jend];
+ * outputs Is, Ip: c128[n] = the return value of Undulator._sp_sum (synchr.py:1929-2033, numpy convention).
+ * flags: bits4-6 = register blocking R in {1,2,4} (0 = default 2). */
+int xrt_undulator_f64(size_t n, int jend, double alpha, double Kx, double Ky, const double* gamma, const double* wu,
+                      const double* w, const double* ww1, const double* ddphi, const double* ddpsi, const double* tg,
+                      const double* ag, const double* sintg, const double* costg, const double* sintgph,
+                      const double* costgph, double* Is, double* Ip, int flags, void* stream);
+int xrt_undulator_f64_host(size_t n, int jend, double alpha, double Kx, double Ky, const double* gamma,
+                           const double* wu, const double* w, const double* ww1, const double* ddphi,
+                           const double* ddpsi, const double* tg, const double* ag, const double* sintg,
+                           const double* costg, const double* sintgph, const double* costgph, double* Is,
+                           double* Ip, int flags);
+/* a3+a4 fused: Undulator._build_I_map_conv (synchr.py:2048-2108) for device-resident sampling.
+ * Inputs w (eV), theta, psi [n]; gamma [n] or NULL (then gamma0 is used for every sample).
+ * amp_const = FINE_STR * eI / SIE0; bw_mode = 1 for distE == 'BW' (bwFact = 0.001) else bwFact = 1/w.
+ * Outputs I f64[n], Es c128[n], Ep c128[n] exactly as the tuple returned at synchr.py:2106-2108. */
+int xrt_undulator_imap_f64(size_t n, int jend, double Kx, double Ky, double L0, double Np, double gamma0,
+                           double amp_const, double dstep, int bw_mode, const double* gamma, const double* w,
+                           const double* theta, const double* psi, const double* tg, const double* ag,
+                           const double* sintg, const double* costg, const double* sintgph, const double* costgph,
+                           double* I, double* Es, double* Ep, int flags, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -108,7 +108,55 @@ def gen_kirchhoff():
     save('kirchhoff_280eV_1m', **_kirchhoff_case(12, 500, 64, 280., 1e3, 2.0, 1.0, True))
 
 
-SECTIONS = {'constants': gen_constants, 'kirchhoff': gen_kirchhoff}
+
+# ------------------------------------------------------------------------------------------------ undulator
+def _undulator_source(**kw):
+    """tests/speed/2_synchrotronSources_speed.py:136-155 base parameters (BASELINE.json configs[1])."""
+    bl = raycing.BeamLine()
+    kwargs = dict(eE=3., eI=0.5, period=30., n=40, K=1.45, eSigmaX=48.65, eSigmaZ=6.197, eEpsilonX=0.263,
+                  eEpsilonZ=0.008, xPrimeMax=0.1, zPrimeMax=0.1, xPrimeMaxAutoReduce=False,
+                  zPrimeMaxAutoReduce=False, targetOpenCL=None)
+    kwargs.update(kw)
+    return rs.Undulator(bl, **kwargs)
+
+
+def _undulator_dump(name, src, nsamp, seed, eEspread_seed=None):
+    src.reset() if src.needReset else None
+    rng = np.random.RandomState(seed)
+    w = rng.uniform(src.E_min, src.E_max, nsamp)
+    th = rng.uniform(src.Theta_min, src.Theta_max, nsamp)
+    ps = rng.uniform(src.Psi_min, src.Psi_max, nsamp)
+    gamma0 = src.gamma
+    if src.eEspread > 0:
+        np.random.seed(eEspread_seed)
+        gam = gamma0 + gamma0 * src.eEspread * np.random.normal(size=nsamp)  # synchr.py:2053-2059
+        np.random.seed(eEspread_seed)
+    else:
+        gam = gamma0 * np.ones(nsamp)
+    I, Es, Ep = src.build_I_map(w, th, ps)
+    assert src.gamma == gamma0 or src.eEspread > 0
+    save(name, L0=src.L0, Np=src.Np, Kx=src.Kx, Ky=src.Ky, eI=src.eI, gamma0=gamma0, phase=src.phase,
+         quadm=src.quadm, gIntervals=src.gIntervals, eEspread=src.eEspread,
+         tg=src.tg, ag=src.ag, sintg=src.sintg, costg=src.costg, sintgph=src.sintgph, costgph=src.costgph,
+         dstep=src.dstep, E_min=src.E_min, E_max=src.E_max, Theta_min=src.Theta_min, Theta_max=src.Theta_max,
+         Psi_min=src.Psi_min, Psi_max=src.Psi_max, E1=src.E1, dx=src.dx, dz=src.dz, dxprime=src.dxprime,
+         dzprime=src.dzprime, w=w, theta=th, psi=ps, gamma=gam, I=I, Es=Es, Ep=Ep)
+
+
+def gen_undulator():
+    # planar undulator of config 2, first harmonic +-0.5 %, grid found by the reference's convergence search
+    probe = _undulator_source(eMin=1000., eMax=1001., gNodes=16)
+    E1 = probe.E1
+    src = _undulator_source(eMin=E1*0.995, eMax=E1*1.005)
+    _undulator_dump('undulator_planar_h1', src, 1500, 21)
+    print('converged quadm', src.quadm, 'gIntervals', src.gIntervals, 'E1', E1)
+    # helical-ish undulator (Kx != 0, 90 deg phase), fixed grid, wide band incl. 3rd harmonic, energy spread
+    src = _undulator_source(K=0, Kx=0.9, Ky=1.2, phaseDeg=90, eMin=E1*0.5, eMax=E1*3.5, gNodes=40, gIntervals=3,
+                            eEspread=8e-4)
+    _undulator_dump('undulator_helical_spread', src, 900, 22, eEspread_seed=5)
+
+
+SECTIONS = {'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)

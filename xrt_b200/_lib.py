@@ -30,6 +30,9 @@ PROTOTYPES = {
     'xrt_kirchhoff_f64': (c_int, [c_sz, c_sz] + [c_dp] * 8 + [c_int, c_dp, c_int] + [c_dp] * 5 +
                           [c_int, c_dp, c_dp]),
     'xrt_kirchhoff_f64_host': (c_int, [c_sz, c_sz] + [c_dp] * 8 + [c_int, c_dp, c_int] + [c_dp] * 5 + [c_int]),
+    'xrt_undulator_f64': (c_int, [c_sz, c_int, c_dbl, c_dbl, c_dbl] + [c_dp] * 14 + [c_int, c_dp]),
+    'xrt_undulator_f64_host': (c_int, [c_sz, c_int, c_dbl, c_dbl, c_dbl] + [c_dp] * 14 + [c_int]),
+    'xrt_undulator_imap_f64': (c_int, [c_sz, c_int] + [c_dbl] * 7 + [c_int] + [c_dp] * 13 + [c_int, c_dp]),
 }
 
 

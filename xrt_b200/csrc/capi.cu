@@ -221,4 +221,53 @@ int xrt_kirchhoff_f64_host(size_t M, size_t N, const double* xM, const double* y
   return 0;
 }
 
+// ------------------------------------------------------------------ undulator
+int xrt_undulator_f64(size_t n, int jend, double alpha, double Kx, double Ky, const double* gamma, const double* wu,
+                      const double* w, const double* ww1, const double* ddphi, const double* ddpsi, const double* tg,
+                      const double* ag, const double* sintg, const double* costg, const double* sintgph,
+                      const double* costgph, double* Is, double* Ip, int flags, void* stream) {
+  (void)alpha;  // taper / near-field scalar of the sibling kernels; unused by `undulator` (undulator.cl:54)
+  return undulator_raw_device(n, jend, Kx, Ky, gamma, wu, w, ww1, ddphi, ddpsi, tg, ag, sintg, costg, sintgph,
+                              costgph, Is, Ip, (flags >> 4) & 7, (cudaStream_t)stream);
+}
+
+int xrt_undulator_f64_host(size_t n, int jend, double alpha, double Kx, double Ky, const double* gamma,
+                           const double* wu, const double* w, const double* ww1, const double* ddphi,
+                           const double* ddpsi, const double* tg, const double* ag, const double* sintg,
+                           const double* costg, const double* sintgph, const double* costgph, double* Is,
+                           double* Ip, int flags) {
+  (void)alpha;
+  if (n == 0) return 0;
+  XRTB_REQUIRE(jend > 0, "undulator: the integration grid is empty");
+  cudaStream_t st = 0;
+  DevBuf samp[6], tab[6], out;
+  const double* hs[6] = {gamma, wu, w, ww1, ddphi, ddpsi};
+  const double* ht[6] = {tg, ag, sintg, costg, sintgph, costgph};
+  for (int i = 0; i < 6; ++i) {
+    if (samp[i].upload(hs[i], n * 8, st)) return 1;
+    if (tab[i].upload(ht[i], (size_t)jend * 8, st)) return 1;
+  }
+  if (out.alloc(2 * n * 16)) return 1;
+  double* o = out.as<double>();
+  int rc = undulator_raw_device(n, jend, Kx, Ky, samp[0].as<double>(), samp[1].as<double>(), samp[2].as<double>(),
+                                samp[3].as<double>(), samp[4].as<double>(), samp[5].as<double>(), tab[0].as<double>(),
+                                tab[1].as<double>(), tab[2].as<double>(), tab[3].as<double>(), tab[4].as<double>(),
+                                tab[5].as<double>(), o, o + 2 * n, (flags >> 4) & 7, st);
+  if (rc) return rc;
+  XRTB_CUDA_CHECK(cudaMemcpyAsync(Is, o, n * 16, cudaMemcpyDeviceToHost, st));
+  XRTB_CUDA_CHECK(cudaMemcpyAsync(Ip, o + 2 * n, n * 16, cudaMemcpyDeviceToHost, st));
+  XRTB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int xrt_undulator_imap_f64(size_t n, int jend, double Kx, double Ky, double L0, double Np, double gamma0,
+                           double amp_const, double dstep, int bw_mode, const double* gamma, const double* w,
+                           const double* theta, const double* psi, const double* tg, const double* ag,
+                           const double* sintg, const double* costg, const double* sintgph, const double* costgph,
+                           double* I, double* Es, double* Ep, int flags, void* stream) {
+  return undulator_imap_device(n, jend, Kx, Ky, L0, Np, gamma0, amp_const, dstep, bw_mode, gamma, w, theta, psi, tg,
+                               ag, sintg, costg, sintgph, costgph, I, Es, Ep, (flags >> 4) & 7,
+                               (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -13,4 +13,16 @@ int kirchhoff_device(size_t M, size_t N, const double* xM, const double* yM, con
                      const double* nrm, int nrm_stride, double* S, double* P, double* A, double* B, double* C,
                      int flags, void* ws, cudaStream_t st);
 
+// undulator.cu
+int undulator_raw_device(size_t n, int jend, double Kx, double Ky, const double* gamma, const double* wu,
+                         const double* w, const double* ww1, const double* ddphi, const double* ddpsi,
+                         const double* tg, const double* ag, const double* sintg, const double* costg,
+                         const double* sintgph, const double* costgph, double* Is, double* Ip, int R,
+                         cudaStream_t st);
+int undulator_imap_device(size_t n, int jend, double Kx, double Ky, double L0, double Np, double gamma0,
+                          double amp_const, double dstep, int bw_mode, const double* gamma, const double* w,
+                          const double* theta, const double* psi, const double* tg, const double* ag,
+                          const double* sintg, const double* costg, const double* sintgph, const double* costgph,
+                          double* I, double* Es, double* Ep, int R, cudaStream_t st);
+
 }  // namespace xrtb

@@ -133,6 +133,31 @@ class XRT_CUDA(object):
         return tuple(outs)
 
 
+    def _k_undulator(self, scalarArgs, slicedRO, nonSlicedRO, slicedRW, nonSlicedRW, dimension):
+        """Argument layout of Undulator._build_I_map_CL (sources/synchr.py:2134-2155):
+        scalars [alpha, Kx, Ky, jend]; sliced RO [gamma, wu, w, ww1, ddtheta, ddpsi];
+        non-sliced RO [tg, ag, sintg, costg, sintgph, costgph]; sliced RW [Is, Ip]."""
+        lib = _lib.load()
+        alpha, Kx, Ky, jend = scalarArgs[:4]
+        samp = [_lib.as_f64(a) for a in slicedRO]
+        n = dimension if dimension else len(samp[0])
+        tabs = [_lib.as_f64(a) for a in nonSlicedRO]
+        if any(len(a) != n for a in samp) or len(samp) != 6:
+            raise ValueError('undulator: expected 6 sliced inputs of length dimension')
+        if any(len(a) != int(jend) for a in tabs) or len(tabs) != 6:
+            raise ValueError('undulator: expected 6 node tables of length jend')
+        Is, Ip = slicedRW
+        for a in (Is, Ip):
+            if not (isinstance(a, np.ndarray) and a.dtype == np.complex128 and a.flags['C_CONTIGUOUS'] and
+                    len(a) == n):
+                raise ValueError('undulator: slicedRWArgs must be 2 contiguous complex128[dimension]')
+        rc = lib.xrt_undulator_f64_host(
+            n, int(jend), float(alpha), float(Kx), float(Ky), *[_lib.hptr(a) for a in samp],
+            *[_lib.hptr(a) for a in tabs], _lib.hptr(Is), _lib.hptr(Ip), 0)
+        _lib.check(rc, 'xrt_undulator_f64_host')
+        return Is, Ip
+
+
 def _as_vec_buffer(a, N):
     """The reference passes float3 buffers as np.array([x, y, z, 0], order='F') of shape (4, N), i.e. N
     records of 4 doubles (waves.py:874-881).  Accept that, or a C-ordered (N, 3|4) array."""

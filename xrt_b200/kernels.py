@@ -53,3 +53,35 @@ def kirchhoff(xM, yM, zM, nl, Es, Ep, k, pos, nrm, out=None, convention='numpy',
         out[3].data_ptr(), out[4].data_ptr(), flags, workspace.data_ptr(), _stream())
     _lib.check(rc, 'xrt_kirchhoff_f64')
     return out
+
+
+def undulator_raw(Kx, Ky, gamma, wu, w, ww1, ddphi, ddpsi, tables, R=0):
+    """a4 on device tensors, the reference kernel interface: returns (Is, Ip) = Undulator._sp_sum."""
+    lib = _lib.load()
+    n = w.numel()
+    jend = tables[0].numel()
+    out = torch.empty((2, n), dtype=C128, device=w.device)
+    rc = lib.xrt_undulator_f64(
+        n, jend, 0.0, float(Kx), float(Ky), *[_chk(t, F64, n) for t in (gamma, wu, w, ww1, ddphi, ddpsi)],
+        *[_chk(t, F64, jend) for t in tables], out[0].data_ptr(), out[1].data_ptr(), int(R) << 4, _stream())
+    _lib.check(rc, 'xrt_undulator_f64')
+    return out[0], out[1]
+
+
+def undulator_imap(Kx, Ky, L0, Np, gamma0, amp_const, dstep, bw_mode, w, theta, psi, tables, gamma=None, R=0,
+                   out=None):
+    """a3+a4 fused on device tensors: returns (I, Es, Ep) of Undulator._build_I_map_conv."""
+    lib = _lib.load()
+    n = w.numel()
+    jend = tables[0].numel()
+    if out is None:
+        out = (torch.empty(n, dtype=F64, device=w.device), torch.empty(n, dtype=C128, device=w.device),
+               torch.empty(n, dtype=C128, device=w.device))
+    I, Es, Ep = out
+    rc = lib.xrt_undulator_imap_f64(
+        n, jend, float(Kx), float(Ky), float(L0), float(Np), float(gamma0), float(amp_const), float(dstep),
+        int(bw_mode), _chk(gamma, F64, n) if gamma is not None else None, _chk(w, F64, n), _chk(theta, F64, n),
+        _chk(psi, F64, n), *[_chk(t, F64, jend) for t in tables], _chk(I, F64, n), _chk(Es, C128, n),
+        _chk(Ep, C128, n), int(R) << 4, _stream())
+    _lib.check(rc, 'xrt_undulator_imap_f64')
+    return I, Es, Ep
