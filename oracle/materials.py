@@ -1,0 +1,201 @@
+"""Oracle: mirror Fresnel amplitude and thick-Bragg crystal amplitude (TEST INFRASTRUCTURE ONLY).
+
+Restates
+  * Element.get_f1f2 / get_f0            xrt/backends/raycing/materials/element.py:252-263, :203-207
+  * Material.get_refractive_index        materials/material.py:348-378
+  * Material.get_amplitude               materials/material.py:415-493 (kinds 'mirror', 'thin mirror')
+  * Crystal.get_amplitude (thick Bragg)  materials/crystal.py:492-645 (branch :568-597)
+  * Crystal.get_F_chi                    materials/crystal.py:297-306
+  * CrystalFcc/CrystalDiamond.get_structure_factor   materials/crystals_basic.py:22-31, :76-80
+  * Crystal.get_Bragg_angle              materials/crystal.py:1105-1120
+The element tables come from xrt_b200/data/elements.npz (a verbatim subset of the reference's data files,
+see tools/extract_tables.py)."""
+import os
+
+import numpy as np
+
+from .physconsts import PI, PI2, CH, CHBAR, R0, AVOGADRO
+
+_DATA = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'xrt_b200', 'data',
+                     'elements.npz')
+_tables = None
+
+
+def _load():
+    global _tables
+    if _tables is None:
+        with np.load(_DATA) as f:
+            _tables = {k: np.array(f[k]) for k in f.files}
+    return _tables
+
+
+class Element(object):
+    def __init__(self, name, table='Chantler'):
+        t = _load()
+        self.name = name
+        self.Z = int(t[name + '_Z'])
+        self.mass = float(t[name + '_mass'])
+        self.f0coeffs = [float(v) for v in t[name + '_f0']]
+        f2key = '_f2tot' if 'total' in table else '_f2'  # element.py:212
+        self.E, self.f1, self.f2 = t[name + '_E'], t[name + '_f1'], t[name + f2key]
+
+    def get_f0(self, qOver4pi=0):
+        return self.f0coeffs[5] + sum(a * np.exp(-b * qOver4pi**2)
+                                      for a, b in zip(self.f0coeffs[:5], self.f0coeffs[6:]))
+
+    def get_f1f2(self, E):
+        if np.any(E < self.E[0]) or np.any(E > self.E[-1]):
+            raise ValueError('E is out of the data table range')
+        f1 = np.interp(E, self.E, self.f1)
+        f2 = np.interp(E, self.E, self.f2)
+        return f1 + 1j*f2
+
+
+class Material(object):
+    def __init__(self, elements, quantities=None, kind='mirror', rho=0, t=None, table='Chantler total'):
+        if isinstance(elements, str):
+            elements = elements,
+        self.elements = [Element(e, table) for e in elements]
+        self.quantities = [1. for e in self.elements] if quantities is None else list(quantities)
+        self.kind = kind
+        self.rho = rho
+        self.t = t
+        self.mass = 0.
+        for elem, xi in zip(self.elements, self.quantities):
+            self.mass += xi * elem.mass
+
+    def get_refractive_index(self, E):
+        xf = np.zeros_like(E) * 0j
+        for elem, xi in zip(self.elements, self.quantities):
+            xf += (elem.Z + elem.get_f1f2(E)) * xi
+        return 1 - 1e-24 * AVOGADRO * R0 / PI2 * (CH/E)**2 * self.rho * xf / self.mass
+
+    def get_amplitude(self, E, beamInDotNormal, fromVacuum=True):
+        n = self.get_refractive_index(E)
+        if fromVacuum:
+            n1 = 1.
+            n2 = n
+        else:
+            n1 = n
+            n2 = 1.
+        cosAlpha = abs(beamInDotNormal)
+        sinAlpha2 = 1 - beamInDotNormal**2
+        if isinstance(sinAlpha2, np.ndarray):
+            sinAlpha2[sinAlpha2 < 0] = 0
+        n1cosAlpha = n1 * cosAlpha
+        cosBeta = np.sqrt(1 - (n1/n2)**2*sinAlpha2)
+        n2cosBeta = n2 * cosBeta
+        rs = (n1cosAlpha - n2cosBeta) / (n1cosAlpha + n2cosBeta)
+        rp = (n2*cosAlpha - n1*cosBeta) / (n2*cosAlpha + n1*cosBeta)
+        if self.kind == 'thin mirror':
+            p2 = np.exp(2j * E / CHBAR * n2cosBeta * self.t * 1e7)
+            rs *= (1 - p2) / (1 - rs**2*p2)
+            rp *= (1 - p2) / (1 - rp**2*p2)
+        return (rs, rp, abs(n.imag) * E / CHBAR * 2e8, n.real * E / CHBAR * 1e8)
+
+
+class CrystalDiamond(object):
+    """Single-element fcc/diamond crystal, thick Bragg reflection (geom 'Bragg reflected', t=None)."""
+    kind = 'crystal'
+
+    def __init__(self, hkl, d, element='Si', factDW=1., structure='diamond', table='Chantler total'):
+        self.hkl = tuple(int(i) for i in hkl)
+        self.d = d
+        self.sqrthkl2 = (sum(i**2 for i in self.hkl))**0.5
+        self.V = (d * self.sqrthkl2)**3
+        self.chiToF = -R0 / PI / self.V
+        self.factDW = factDW
+        self.structure = structure
+        self.elements = [Element(element, table)]
+
+    def get_structure_factor(self, E, sinThetaOverLambda=0):
+        anomalousPart = self.elements[0].get_f1f2(E)
+        F0 = 4 * (self.elements[0].Z+anomalousPart) * self.factDW
+        residue = sum(i % 2 for i in self.hkl)
+        if residue == 0 or residue == 3:
+            f0 = self.elements[0].get_f0(sinThetaOverLambda)
+            Fhkl = 4 * (f0+anomalousPart) * self.factDW
+        else:
+            Fhkl = 0.
+        if self.structure == 'fcc':
+            return F0, Fhkl, Fhkl
+        diamondToFcc = 1 + np.exp(0.5j * PI * sum(self.hkl))
+        return F0 * 2, Fhkl * diamondToFcc, Fhkl * diamondToFcc.conjugate()
+
+    def get_F_chi(self, E, sinThetaOverLambda):
+        F0, Fhkl, Fhkl_ = self.get_structure_factor(E, sinThetaOverLambda)
+        waveLength = CH / E
+        lambdaSquare = waveLength**2
+        chiToFlambdaSquare = self.chiToF * lambdaSquare
+        chi0 = F0.conjugate() * chiToFlambdaSquare
+        chih = Fhkl.conjugate() * chiToFlambdaSquare
+        chih_ = Fhkl_.conjugate() * chiToFlambdaSquare
+        return F0, Fhkl, Fhkl_, chi0, chih, chih_
+
+    def get_Bragg_angle(self, E, order=1):
+        a = order * CH / (2*self.d*E)
+        a = np.array(a)
+        a[a > 1] = 1 - 1e-16
+        a[a < -1] = -1 + 1e-16
+        return np.arcsin(a)
+
+    def get_dtheta_symmetric_Bragg(self, E):
+        F0, Fhkl, Fhkl_ = self.get_structure_factor(E, 0.5 / self.d)
+        waveLength = CH / E
+        lambdaSquare = waveLength ** 2
+        chiToFlambdaSquare = self.chiToF * lambdaSquare
+        chi0 = F0 * chiToFlambdaSquare
+        thetaB = self.get_Bragg_angle(E)
+        return (chi0 / np.sin(2*thetaB)).real
+
+    def get_dtheta(self, E, alpha=None):
+        """materials/crystal.py:1141-1173 (Bragg geometry)."""
+        if alpha is None:
+            alpha = 0
+        thetaB = self.get_Bragg_angle(E)
+        pm = -1
+        gamma0 = np.sin(thetaB + alpha)
+        gammah = pm * np.sin(thetaB - alpha)
+        symm_dt = self.get_dtheta_symmetric_Bragg(E)
+        osqg0 = np.sqrt(1. - gamma0**2)
+        dtheta0 = (pm*gamma0 - pm*np.sqrt(gamma0**2 + pm*(gamma0 - gammah) * osqg0 * symm_dt)) / osqg0
+        return -dtheta0
+
+    def get_amplitude(self, E, beamInDotNormal, beamOutDotNormal=None, beamInDotHNormal=None):
+        def for_one_polarization(polFactor):
+            delta = np.sqrt((alpha**2 + polFactor**2 * chih * chih_ / b))
+            with np.errstate(divide='ignore', invalid='ignore'):
+                ra = chih * polFactor / (alpha+delta)
+            ad = alpha - delta
+            ad[ad == 0] = 1e-100
+            rb = chih * polFactor / ad
+            indB = np.where(np.isnan(ra))
+            ra[indB] = rb[indB]
+            indB = np.where(abs(rb) < abs(ra))
+            ra[indB] = rb[indB]
+            return ra / np.sqrt(abs(b))
+
+        waveLength = CH / E
+        k = PI2 / waveLength
+        k0s = -beamInDotNormal * k
+        if beamOutDotNormal is None:
+            beamOutDotNormal = -beamInDotNormal
+        kHs = -beamOutDotNormal * k
+        if beamInDotHNormal is None:
+            beamInDotHNormal = beamInDotNormal
+        crystd = self.d
+        HH = PI2 / crystd
+        k0H = abs(beamInDotHNormal) * HH * k
+        k02 = k**2
+        H2 = HH**2
+        kHs0 = kHs == 0
+        kHs[kHs0] = 1
+        b = k0s / kHs
+        b[kHs0] = -1
+        F0, Fhkl, Fhkl_, chi0, chih, chih_ = self.get_F_chi(E, 0.5/crystd)
+        thetaB = self.get_Bragg_angle(E)
+        alpha = (H2/2 - k0H) / k02 + chi0/2 * (1/b - 1)
+        curveS = for_one_polarization(1.)
+        polFactor = np.cos(2. * thetaB)
+        curveP = for_one_polarization(polFactor)
+        return curveS, curveP

@@ -1,0 +1,533 @@
+"""Oracle: OE.reflect / DCM.double_reflect (TEST INFRASTRUCTURE ONLY, see oracle/__init__.py).
+
+Numpy restatement, in the reference's operation order, of
+  * OE.reflect                       xrt/backends/raycing/oes/reflect.py:17-163
+  * OE._reflect_local                oes/reflect.py:551-1139 (branches toWhere == 0: no material, 'mirror',
+                                     'thin mirror', 'crystal' thick Bragg without mosaicity/TT)
+  * OE._grating_deflection           oes/reflect.py:451-469, _get_asymmetric_reflection_grating :568-612
+  * OE._bracketing / _set_t          oes/base.py:1231-1295
+  * OE.find_intersection, find_dz    oes/base.py:801-885
+  * OE._use_my_method / _use_Brent_method   oes/base.py:933-1048
+  * OE.rays_good ('rect')            oes/base.py:1094-1163
+  * surfaces: OE flat (base.py:675-742), ToroidMirror (oes/__init__.py:398-411),
+              EllipticalMirrorParam (oes/parametric.py:213-246)
+  * DCM.double_reflect               oes/dcm.py:247-354 (+ local_n2 :234-238)
+"""
+import numpy as np
+
+from . import beam as ob
+from .physconsts import CH, CHBAR
+
+zEps = 1e-12
+dt = 1e-5
+maxIteration = 100
+maxHalfSizeOfOE = 1000.
+maxDepthOfOE = 100.
+
+
+class OESpec(object):
+    """Plain parameter bag (what the product passes to the CUDA kernel as OEParams)."""
+
+    def __init__(self, **kw):
+        self.azimuth = (0., 1.)  # (sinAzimuth, cosAzimuth)
+        self.center = [0., 0., 0.]
+        self.pitch = 0.
+        self.roll = 0.  # roll + positionRoll
+        self.yaw = 0.
+        self.rotationSequence = 'RzRyRx'
+        self.extraPitch = self.extraRoll = self.extraYaw = 0.
+        self.extraRotationSequence = 'RzRyRx'
+        self.dx = 0
+        self.surface = 'flat'
+        self.surfParams = {}
+        self.surfPhysX = [-maxHalfSizeOfOE, maxHalfSizeOfOE]
+        self.surfPhysY = [-maxHalfSizeOfOE, maxHalfSizeOfOE]
+        self.surfOptX = None
+        self.surfOptY = None
+        self.overEdge = 'yMax'
+        self.lostNum = -1
+        self.material = None
+        self.alpha = None
+        self.isParametric = False
+        self.__dict__.update(kw)
+
+    # ------------------------------------------------------------------ surfaces
+    def local_z(self, x, y):
+        if self.surface == 'flat':
+            return np.zeros_like(y)
+        if self.surface == 'toroid':
+            R, r = self.surfParams['R'], self.surfParams['r']
+            rx = 1 - (np.asarray(x)/r)**2
+            rx[rx < 0] = 0.
+            return y**2/2.0/R + r*(1 - rx**0.5)
+        raise ValueError(self.surface)
+
+    def local_n(self, x, y):
+        if self.surface == 'flat':
+            a = 0.
+            b = 0.
+            c = 1.
+            if self.alpha:
+                cosalpha, sinalpha = np.cos(self.alpha), np.sin(self.alpha)
+                bAlpha, cAlpha = ob.rotate_x(b, c, cosalpha, -sinalpha)
+                return [a, bAlpha, cAlpha, a, b, c]
+            return [a, b, c]
+        if self.surface == 'toroid':
+            R, r = self.surfParams['R'], self.surfParams['r']
+            rx = 1 - (np.asarray(x)/r)**2
+            with np.errstate(divide='ignore', invalid='ignore'):
+                ax = np.where(rx < 0, 0, rx**(-0.5))
+            a = -x / r * ax
+            b = -y / R
+            c = 1.
+            norm = (a**2 + b**2 + 1)**0.5
+            return [a/norm, b/norm, c/norm]
+        if self.surface == 'ellipse_param':
+            p = self.surfParams
+            s, phi = x, y
+            A2s2 = np.array(p['ellipseA']**2 - s**2)
+            A2s2[A2s2 <= 0] = 1e22
+            nr = -p['ellipseB'] / p['ellipseA'] * s / np.sqrt(A2s2)
+            norm = np.sqrt(nr**2 + 1)
+            b = nr / norm
+            if p['isCylindrical']:
+                a = np.zeros_like(phi)
+                c = 1. / norm
+            else:
+                a = -np.sin(phi) / norm
+                c = -np.cos(phi) / norm
+            bNew, cNew = ob.rotate_x(b, c, p['cosGamma'], -p['sinGamma'])
+            return [a, bNew, cNew]
+        raise ValueError(self.surface)
+
+    def xyz_to_param(self, x, y, z):
+        p = self.surfParams
+        yNew, zNew = ob.rotate_x(y - p['y0'], z - p['z0'], p['cosGamma'], p['sinGamma'])
+        return yNew, np.arctan2(x, zNew), np.sqrt(x**2 + zNew**2)
+
+    def param_to_xyz(self, s, phi, r):
+        p = self.surfParams
+        x = r * np.sin(phi)
+        y = s
+        z = r * np.cos(phi)
+        yNew, zNew = ob.rotate_x(y, z, p['cosGamma'], -p['sinGamma'])
+        return x, yNew + p['y0'], zNew + p['z0']
+
+    def local_r(self, s, phi):
+        p = self.surfParams
+        r = p['ellipseB'] * np.sqrt(abs(1 - s**2 / p['ellipseA']**2))
+        if p['isCylindrical']:
+            r /= abs(np.cos(phi))
+        return np.where(abs(phi) > np.pi/2, r, np.ones_like(phi)*1e20)
+
+
+# ---------------------------------------------------------------------- intersection machinery
+def find_dz(oe, local_f, t, x0, y0, z0, a, b, c, invertNormal):
+    x = x0 + a*t
+    y = y0 + b*t
+    z = z0 + c*t
+    if oe.isParametric:
+        if local_f is None:
+            local_f = oe.local_r
+        diffSign = -1
+    else:
+        if local_f is None:
+            local_f = oe.local_z
+        diffSign = 1
+    if oe.isParametric:
+        x, y, z = oe.xyz_to_param(x, y, z)
+    surf = local_f(x, y)
+    ind = np.isnan(surf)
+    if ind.sum() > 0:
+        surf[ind] = 0
+    dz = (z - surf) * diffSign * invertNormal
+    return dz, x, y, z
+
+
+def _use_my_method(oe, local_f, t1, t2, x, y, z, a, b, c, invertNormal, dz1, dz2, tMin, tMax, x2, y2, z2, ind):
+    numit = 2
+    while (ind.sum() > 0) and (numit < maxIteration):
+        t = t1[ind]
+        dz = dz1[ind]
+        t1[ind] = t2[ind]
+        dz1[ind] = dz2[ind]
+        t2[ind] = t - (t1[ind]-t) * dz / (dz1[ind]-dz)
+        swap = t2[ind] < tMin
+        t2[np.where(ind)[0][swap]] = tMin
+        swap = t2[ind] > tMax
+        t2[np.where(ind)[0][swap]] = tMax
+        dz2[ind], x2[ind], y2[ind], z2[ind] = find_dz(
+            oe, local_f, t2[ind], x[ind], y[ind], z[ind], a[ind], b[ind], c[ind], invertNormal)
+        swap = np.sign(dz2[ind]) == np.sign(dz1[ind])
+        t1[np.where(ind)[0][swap]] = t[swap]
+        dz1[np.where(ind)[0][swap]] = dz[swap]
+        ind = ind & (abs(dz2) > zEps)
+        numit += 1
+    return t2, x2, y2, z2, numit
+
+
+def _use_Brent_method(oe, local_f, t1, t2, x, y, z, a, b, c, invertNormal, dz1, dz2, tMin, tMax, x2, y2, z2, ind):
+    swap = abs(dz1[ind]) < abs(dz2[ind])
+    if swap.sum() > 0:
+        t1[np.where(ind)[0][swap]], t2[np.where(ind)[0][swap]] =\
+            t2[np.where(ind)[0][swap]], t1[np.where(ind)[0][swap]]
+        dz1[np.where(ind)[0][swap]], dz2[np.where(ind)[0][swap]] =\
+            dz2[np.where(ind)[0][swap]], dz1[np.where(ind)[0][swap]]
+    t3 = np.copy(t1)
+    dz3 = np.copy(dz1)
+    t4 = np.zeros_like(t1)
+    mflag = np.ones_like(t1, dtype='bool')
+    numit = 2
+    ind = ind & (abs(dz2) > zEps)
+    while (ind.sum() > 0) and (numit < maxIteration):
+        xa, xb, xc, xd = t1[ind], t2[ind], t3[ind], t4[ind]
+        fa, fb, fc = dz1[ind], dz2[ind], dz3[ind]
+        mf = mflag[ind]
+        xs = np.empty_like(xa)
+        inq = (fa != fc) & (fb != fc)
+        if inq.sum() > 0:
+            xai = xa[inq]
+            xbi = xb[inq]
+            xci = xc[inq]
+            fai = fa[inq]
+            fbi = fb[inq]
+            fci = fc[inq]
+            xs[inq] = \
+                xai * fbi * fci / (fai-fbi) / (fai-fci) + \
+                fai * xbi * fci / (fbi-fai) / (fbi-fci) + \
+                fai * fbi * xci / (fci-fai) / (fci-fbi)
+        inx = ~inq
+        if inx.sum() > 0:
+            xai = xa[inx]
+            xbi = xb[inx]
+            fai = fa[inx]
+            fbi = fb[inx]
+            xs[inx] = xbi - fbi * (xbi-xai) / (fbi-fai)
+        cond1 = ((xs < (3*xa + xb) / 4.) & (xs < xb) | (xs > (3*xa + xb) / 4.) & (xs > xb))
+        cond2 = mf & (abs(xs - xb) >= (abs(xb - xc) / 2.))
+        cond3 = (~mf) & (abs(xs - xb) >= (abs(xc - xd) / 2.))
+        cond4 = mf & (abs(xb - xc) < zEps)
+        cond5 = (~mf) & (abs(xc - xd) < zEps)
+        conds = cond1 | cond2 | cond3 | cond4 | cond5
+        xs[conds] = (xa[conds] + xb[conds]) / 2.
+        mf = conds
+        fs, x2[ind], y2[ind], z2[ind] = find_dz(
+            oe, local_f, xs, x[ind], y[ind], z[ind], a[ind], b[ind], c[ind], invertNormal)
+        xd[:] = xc[:]
+        xc[:] = xb[:]
+        fc[:] = fb[:]
+        fafsNeg = ((fa < 0) & (fs > 0)) | ((fa > 0) & (fs < 0))
+        xb[fafsNeg] = xs[fafsNeg]
+        fb[fafsNeg] = fs[fafsNeg]
+        fafsPos = ~fafsNeg
+        xa[fafsPos] = xs[fafsPos]
+        fa[fafsPos] = fs[fafsPos]
+        swap = abs(fa) < abs(fb)
+        xa[swap], xb[swap] = xb[swap], xa[swap]
+        fa[swap], fb[swap] = fb[swap], fa[swap]
+        t1[ind], t2[ind], t3[ind], t4[ind] = xa, xb, xc, xd
+        dz1[ind], dz2[ind], dz3[ind] = fa, fb, fc
+        mflag[ind] = mf
+        ind = ind & (abs(dz2) > zEps)
+        numit += 1
+    return t2, x2, y2, z2, numit
+
+
+def find_intersection(oe, local_f, t1, t2, x, y, z, a, b, c, invertNormal, info=None):
+    dz1, x1, y1, z1 = find_dz(oe, local_f, t1, x, y, z, a, b, c, invertNormal)
+    dz2, x2, y2, z2 = find_dz(oe, local_f, t2, x, y, z, a, b, c, invertNormal)
+    tMin = t1.min()
+    tMax = t2.max()
+    ind1 = dz1 <= 0
+    ind2 = dz2 >= 0
+    dz2[ind1 | ind2] = 0
+    t2[ind1] = t1[ind1]
+    x2[ind1] = x1[ind1]
+    y2[ind1] = y1[ind1]
+    z2[ind1] = z1[ind1]
+    ind = ~(ind1 | ind2)
+    useBrent = abs(dz2).max() > abs(dz1).max()*20
+    if info is not None:
+        info.update(tMin=tMin, tMax=tMax, useBrent=bool(useBrent), maxdz1=abs(dz1).max(), maxdz2=abs(dz2).max())
+    method = _use_Brent_method if useBrent else _use_my_method
+    t2, x2, y2, z2, numit = method(oe, local_f, t1, t2, x, y, z, a, b, c, invertNormal, dz1, dz2, tMin, tMax,
+                                   x2, y2, z2, ind)
+    if info is not None:
+        info['numit'] = numit
+    return t2, x2, y2, z2, ind1
+
+
+def _set_t(xyz, abc, surfPhys=None, defSize=maxHalfSizeOfOE):
+    if surfPhys is None:
+        limMin = -defSize
+        limMax = defSize
+    else:
+        limMin = surfPhys[0] if surfPhys[0] > -np.inf else -defSize
+        limMax = surfPhys[1] if surfPhys[1] < np.inf else defSize
+    if abc[0] > 0:
+        tMin = (limMin-xyz)/abc - dt
+        tMax = (limMax-xyz)/abc + dt
+    else:
+        tMin = (limMax-xyz)/abc - dt
+        tMax = (limMin-xyz)/abc + dt
+    return tMin, tMax
+
+
+def _bracketing(oe, x, y, z, a, b, c, surfPhysX, surfPhysY, mainPart, info=None):
+    try:
+        maxa = np.max(abs(a[mainPart]))
+        maxb = np.max(abs(b[mainPart]))
+        maxc = np.max(abs(c[mainPart]))
+    except ValueError:
+        maxa, maxb, maxc = 0, 1, 0
+    maxMax = max(maxa, maxb, maxc)
+    if maxMax == maxa:
+        tMin, tMax = _set_t(x, a, surfPhysX)
+        axis = 0
+    elif maxMax == maxb:
+        tMin, tMax = _set_t(y, b, surfPhysY)
+        axis = 1
+    else:
+        tMin, tMax = _set_t(z, c, defSize=maxDepthOfOE)
+        axis = 2
+    if info is not None:
+        info.update(axis=axis, maxa=maxa, maxb=maxb, maxc=maxc)
+    tMin[tMin < -1e6*zEps] = -1e6*zEps
+    return tMin, tMax
+
+
+def rays_good(oe, x, y, surfPhysX, surfPhysY, surfOptX, surfOptY):
+    locState = np.ones(x.size, dtype=np.int32)
+    if surfOptX is not None:
+        locState[((surfPhysX[0] <= x) & (x < surfOptX[0])) | ((surfOptX[1] <= x) & (x < surfPhysX[1]))] = 2
+    if surfOptY is not None:
+        locState[((surfPhysY[0] <= y) & (y < surfOptY[0])) | ((surfOptY[1] <= y) & (y < surfPhysY[1]))] = 2
+    ovE = str(oe.overEdge).lower()
+    outside = (x < surfPhysX[0]) | (x > surfPhysX[1]) | (y < surfPhysY[0]) | (y > surfPhysY[1])
+    over = np.zeros_like(outside)
+    if 'xmin' in ovE:
+        over |= x < surfPhysX[0]
+    if 'xmax' in ovE:
+        over |= x > surfPhysX[1]
+    if 'ymin' in ovE:
+        over |= y < surfPhysY[0]
+    if 'ymax' in ovE:
+        over |= y > surfPhysY[1]
+    locState[outside] = oe.lostNum
+    locState[over] = 3
+    return locState
+
+
+def _grating_deflection(goodN, lb, g, oeNormal, beamInDotNormal, order=1, sig=None):
+    beamInDotG = lb.a[goodN]*g[0] + lb.b[goodN]*g[1] + lb.c[goodN]*g[2]
+    G2 = g[0]**2 + g[1]**2 + g[2]**2
+    locOrder = order
+    orderLambda = locOrder * CH / lb.E[goodN] * 1e-7
+    u = beamInDotNormal**2 - 2*beamInDotG*orderLambda - G2*orderLambda**2
+    gs = np.sign(beamInDotNormal) if sig is None else sig
+    dn = beamInDotNormal + gs*np.sqrt(abs(u))
+    a_out = lb.a[goodN] - oeNormal[-3]*dn + g[0]*orderLambda
+    b_out = lb.b[goodN] - oeNormal[-2]*dn + g[1]*orderLambda
+    c_out = lb.c[goodN] - oeNormal[-1]*dn + g[2]*orderLambda
+    norm = (a_out**2 + b_out**2 + c_out**2)**0.5
+    return a_out/norm, b_out/norm, c_out/norm
+
+
+def reflect_local(oe, good, lb, vlb, pitch, roll, yaw, dx=None, dy=None, dz=None, local_n=None, material=None,
+                  is2ndXtal=False, surfPhysX=None, surfPhysY=None, surfOptX=None, surfOptY=None, info=None):
+    if local_n is None:
+        local_n = oe.local_n
+    if surfPhysX is None:
+        surfPhysX, surfPhysY, surfOptX, surfOptY = oe.surfPhysX, oe.surfPhysY, oe.surfOptX, oe.surfOptY
+    extraAnglesSign = 1.
+    if is2ndXtal:
+        ob.rotate_beam(lb, good, roll=-np.pi)
+        extraAnglesSign = -1.
+    ob.rotate_beam(lb, good, rotationSequence=oe.rotationSequence, pitch=-pitch, roll=-roll, yaw=-yaw)
+    if oe.extraPitch or oe.extraRoll or oe.extraYaw:
+        ob.rotate_beam(lb, good, rotationSequence=oe.extraRotationSequence,
+                       pitch=-extraAnglesSign*oe.extraPitch, roll=-oe.extraRoll, yaw=-extraAnglesSign*oe.extraYaw)
+    if dx:
+        lb.x[good] -= dx
+    if dy:
+        lb.y[good] -= dy
+    if dz:
+        lb.z[good] -= dz
+    invertNormal = 1
+    mainPartForBracketing = lb.state[good] == 1
+    tMin = np.zeros_like(lb.x)
+    tMax = np.zeros_like(lb.x)
+    tMin[good], tMax[good] = _bracketing(
+        oe, lb.x[good], lb.y[good], lb.z[good], lb.a[good], lb.b[good], lb.c[good], surfPhysX, surfPhysY,
+        mainPartForBracketing, info)
+    res_find = find_intersection(oe, None, tMin[good], tMax[good], lb.x[good], lb.y[good], lb.z[good],
+                                 lb.a[good], lb.b[good], lb.c[good], invertNormal, info)
+    tMax[good], lb.x[good], lb.y[good], lb.z[good] = res_find[:4]
+    _lost = res_find[4]
+    if oe.isParametric:
+        tX, tY, tZ = oe.param_to_xyz(lb.x[good], lb.y[good], lb.z[good])
+    else:
+        tX, tY, tZ = lb.x[good], lb.y[good], lb.z[good]
+    lb.state[good] = rays_good(oe, tX, tY, surfPhysX, surfPhysY, surfOptX, surfOptY)
+    lb.state[np.where(good)[0][_lost]] = oe.lostNum
+    goodN = (lb.state == 1)
+    goodNsum = goodN.sum()
+    if goodNsum > 0:
+        lb.path[goodN] += tMax[goodN]
+        matSur = material
+        isCrystal = material is not None and material.kind == 'crystal'
+        oeNormal = list(local_n(lb.x[goodN], lb.y[goodN]))
+        isAsymmetric = len(oeNormal) == 6
+        oeNormal = np.asarray(oeNormal, order='F')
+        beamInDotNormal = lb.a[goodN]*oeNormal[0] + lb.b[goodN]*oeNormal[1] + lb.c[goodN]*oeNormal[2]
+        lb.theta = np.zeros_like(lb.x)
+        beamInDotNormal[beamInDotNormal < -1] = -1
+        beamInDotNormal[beamInDotNormal > 1] = 1
+        lb.theta[goodN] = np.arccos(beamInDotNormal) - np.pi/2
+        if isAsymmetric:
+            beamInDotSurfaceNormal = lb.a[goodN]*oeNormal[-3] + lb.b[goodN]*oeNormal[-2] + lb.c[goodN]*oeNormal[-1]
+        else:
+            beamInDotSurfaceNormal = beamInDotNormal
+        if isCrystal:
+            # _get_asymmetric_reflection_grating (reflect.py:568-612)
+            normalDotSurfNormal = oeNormal[0]*oeNormal[-3] + oeNormal[1]*oeNormal[-2] + oeNormal[2]*oeNormal[-1]
+            bdn = beamInDotNormal.sum() / len(beamInDotNormal)
+            sgbdn = 1 if bdn < 0 else -1
+            wH = 0
+            crystd = matSur.d
+            wHd = (1 + wH) / (crystd * 1e-7)
+            gNormalCryst = np.asarray((
+                (oeNormal[0]-normalDotSurfNormal*oeNormal[-3]) * wHd,
+                (oeNormal[1]-normalDotSurfNormal*oeNormal[-2]) * wHd,
+                (oeNormal[2]-normalDotSurfNormal*oeNormal[-1]) * wHd), order='F') * sgbdn
+            a_out, b_out, c_out = _grating_deflection(goodN, lb, gNormalCryst, oeNormal, beamInDotSurfaceNormal,
+                                                      1, -1)
+        else:
+            a_out = lb.a[goodN] - oeNormal[0]*2*beamInDotNormal
+            b_out = lb.b[goodN] - oeNormal[1]*2*beamInDotNormal
+            c_out = lb.c[goodN] - oeNormal[2]*2*beamInDotNormal
+        lb.a[goodN] = a_out
+        lb.b[goodN] = b_out
+        lb.c[goodN] = c_out
+        rollAngle = roll + np.arctan2(oeNormal[-3], oeNormal[-1])
+        localJ = ob.rotate_coherency_matrix(lb, goodN, -rollAngle)
+        if hasattr(lb, 'Es'):
+            cosY, sinY = np.cos(rollAngle), np.sin(rollAngle)
+            lb.Es[goodN], lb.Ep[goodN] = ob.rotate_y(lb.Es[goodN], lb.Ep[goodN], cosY, -sinY)
+        if material is not None:
+            if isCrystal:
+                beamOutDotSurfaceNormal = a_out*oeNormal[-3] + b_out*oeNormal[-2] + c_out*oeNormal[-1]
+                refl = matSur.get_amplitude(lb.E[goodN], beamInDotSurfaceNormal, beamOutDotSurfaceNormal,
+                                            beamInDotNormal)
+            else:
+                refl = matSur.get_amplitude(lb.E[goodN], beamInDotNormal, True)
+        else:
+            refl = 1., 1.
+        ras, rap = refl[0], refl[1]
+        if isinstance(ras, np.ndarray):
+            ras[np.isnan(ras)] = 0.
+            rap[np.isnan(rap)] = 0.
+        lb.Jss[goodN] = (localJ[0] * ras * np.conjugate(ras)).real
+        lb.Jpp[goodN] = (localJ[1] * rap * np.conjugate(rap)).real
+        lb.Jsp[goodN] = localJ[2] * ras * np.conjugate(rap)
+        if hasattr(lb, 'Es'):
+            lb.Es[goodN] *= ras
+            lb.Ep[goodN] *= rap
+            mPh = np.exp(1e7j * lb.E[goodN]/CHBAR * tMax[goodN])
+            lb.Es[goodN] *= mPh
+            lb.Ep[goodN] *= mPh
+    if oe.isParametric:
+        lb.s = np.copy(lb.x)
+        lb.phi = np.copy(lb.y)
+        lb.r = np.copy(lb.z)
+        lb.x[good], lb.y[good], lb.z[good] = oe.param_to_xyz(lb.x[good], lb.y[good], lb.z[good])
+    if goodNsum > 0:
+        vlb.Jss[goodN], vlb.Jpp[goodN], vlb.Jsp[goodN] = ob.rotate_coherency_matrix(lb, goodN, rollAngle)
+        if hasattr(lb, 'Es'):
+            vlb.Es[goodN], vlb.Ep[goodN] = ob.rotate_y(lb.Es[goodN], lb.Ep[goodN], cosY, sinY)
+    if vlb is not lb:
+        ob.copy_beam(vlb, lb, good, includeState=True, includeJspEsp=False)
+    if dx:
+        vlb.x[good] += dx
+    if dy:
+        vlb.y[good] += dy
+    if dz:
+        vlb.z[good] += dz
+    if oe.extraPitch or oe.extraRoll or oe.extraYaw:
+        ob.rotate_beam(vlb, good, rotationSequence='-'+oe.extraRotationSequence,
+                       pitch=extraAnglesSign*oe.extraPitch, roll=oe.extraRoll, yaw=extraAnglesSign*oe.extraYaw)
+    ob.rotate_beam(vlb, good, rotationSequence='-'+oe.rotationSequence, pitch=pitch, roll=roll, yaw=yaw)
+    if is2ndXtal:
+        ob.rotate_beam(vlb, good, roll=np.pi)
+    if info is not None:
+        info['footprint'] = np.hstack((
+            np.min(np.vstack((vlb.x[good], vlb.y[good], vlb.z[good])), axis=1),
+            np.max(np.vstack((vlb.x[good], vlb.y[good], vlb.z[good])), axis=1))).reshape(2, 3)
+
+
+def reflect(oe, beam, needLocal=True, createdByDiffract=False, info=None):
+    """OE.reflect (reflect.py:104-135). Returns gb, lb."""
+    gb = ob.Beam(copyFrom=beam)
+    lb = ob.Beam(copyFrom=beam) if needLocal else gb
+    good = beam.state > 0
+    if good.sum() == 0:
+        return gb, lb
+    ob.global_to_virgin_local(oe.azimuth, beam, lb, oe.center, good)
+    reflect_local(oe, good, lb, gb, oe.pitch, oe.roll, oe.yaw, oe.dx, material=oe.material, info=info)
+    if createdByDiffract:
+        goodAfter = gb.state == 1
+    else:
+        goodAfter = (gb.state == 1) | (gb.state == 2)
+    if goodAfter.sum() > 0:
+        ob.virgin_local_to_global(oe.azimuth, gb, oe.center, goodAfter)
+    notGood = ~goodAfter
+    if notGood.sum() > 0:
+        ob.copy_beam(gb, beam, notGood)
+    return gb, lb
+
+
+def double_reflect(dcm, beam, needLocal=True, info1=None, info2=None):
+    """DCM.double_reflect (dcm.py:273-354). `dcm` is an OESpec with the extra DCM fields:
+    bragg, cryst1roll, cryst2roll, cryst2pitch, cryst2finePitch, cryst2perpTransl, cryst2longTransl, material2,
+    surfPhysX2, surfPhysY2, surfOptX2, surfOptY2.  Returns gb2, lo1, lo2."""
+    gb = ob.Beam(copyFrom=beam)
+    lo1 = ob.Beam(copyFrom=beam) if needLocal else gb
+    good1 = beam.state > 0
+    if good1.sum() == 0:
+        return gb, lo1, lo1
+    ob.global_to_virgin_local(dcm.azimuth, beam, lo1, dcm.center, good1)
+    reflect_local(dcm, good1, lo1, gb, dcm.pitch + dcm.bragg, dcm.roll + dcm.cryst1roll, dcm.yaw, dcm.dx,
+                  local_n=dcm.local_n, material=dcm.material, info=info1)
+    goodAfter1 = (gb.state == 1) | (gb.state == 2)
+    notGood = ~goodAfter1
+    if notGood.sum() > 0:
+        ob.copy_beam(gb, beam, notGood)
+    gb2 = ob.Beam(copyFrom=gb)
+    lo2 = ob.Beam(copyFrom=gb2) if needLocal else gb2
+    good2 = goodAfter1
+    if needLocal and (~good2).sum() > 0:
+        lo2.state[~good2] = 0
+        lo2.x[~good2] = 0.
+        lo2.y[~good2] = 0.
+        lo2.z[~good2] = 0.
+    if good2.sum() == 0:
+        return gb2, lo1, lo2
+
+    def local_n2(x, y):
+        res = dcm.local_n(x, y)
+        if dcm.alpha:
+            res[1] *= -1
+        return res
+
+    reflect_local(dcm, good2, lo2, gb2,
+                  -dcm.pitch - dcm.bragg + dcm.cryst2pitch + dcm.cryst2finePitch,
+                  dcm.roll + dcm.cryst2roll, -dcm.yaw, -dcm.dx, dcm.cryst2longTransl, -dcm.cryst2perpTransl,
+                  local_n=local_n2, material=dcm.material2, is2ndXtal=True,
+                  surfPhysX=dcm.surfPhysX2, surfPhysY=dcm.surfPhysY2, surfOptX=dcm.surfOptX2,
+                  surfOptY=dcm.surfOptY2, info=info2)
+    goodAfter2 = (gb2.state == 1) | (gb2.state == 2)
+    ob.virgin_local_to_global(dcm.azimuth, gb2, dcm.center, goodAfter2)
+    notGood = ~goodAfter2
+    if notGood.sum() > 0:
+        ob.copy_beam(gb2, beam, notGood)
+    return gb2, lo1, lo2

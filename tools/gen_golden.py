@@ -155,8 +155,84 @@ def gen_undulator():
                             eEspread=8e-4)
     _undulator_dump('undulator_helical_spread', src, 900, 22, eEspread_seed=5)
 
+# ------------------------------------------------------------------------------------------------ reflect
+def _source_beam(bl, nrays, seed, withAmplitudes=True, dx=0.1, dz=0.05, dxprime=1e-4, dzprime=5e-5,
+                 energies=(8990, 9010), polarization='h', kill=0.03):
+    np.random.seed(seed)
+    src = rs.GeometricSource(bl, 'src', nrays=nrays, dx=dx, dz=dz, dxprime=dxprime, dzprime=dzprime,
+                             distE='flat', energies=energies, polarization=polarization)
+    beam = src.shine(withAmplitudes=withAmplitudes)
+    rng = np.random.RandomState(seed + 1000)
+    dead = rng.rand(nrays) < kill
+    beam.state[dead] = -7  # rays absorbed upstream must pass through untouched
+    if withAmplitudes:
+        # GeometricSource gives real unit amplitudes: make them generic complex so that every term is exercised
+        ph = np.exp(1j * rng.uniform(0, 2*np.pi, nrays))
+        beam.Es *= ph
+        beam.Ep = beam.Ep * ph + 0.2 * np.abs(beam.Es) * np.exp(1j * rng.uniform(0, 2*np.pi, nrays))
+        beam.Jss[:] = np.abs(beam.Es)**2
+        beam.Jpp[:] = np.abs(beam.Ep)**2
+        beam.Jsp[:] = beam.Es * np.conj(beam.Ep)
+    return beam
 
-SECTIONS = {'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+
+def _oe_params(oe):
+    d = dict(center=np.array(oe.center, dtype=float), sinAzimuth=oe.bl.sinAzimuth, cosAzimuth=oe.bl.cosAzimuth,
+             pitch=float(oe.pitch), roll=float(oe.roll), positionRoll=float(oe.positionRoll), yaw=float(oe.yaw),
+             extraPitch=float(oe.extraPitch), extraRoll=float(oe.extraRoll), extraYaw=float(oe.extraYaw),
+             rotationSequence=np.array(oe.rotationSequence), lostNum=np.int64(oe.lostNum),
+             surfPhysX=np.array(oe.surfPhysX, dtype=float), surfPhysY=np.array(oe.surfPhysY, dtype=float),
+             overEdge=np.array(str(getattr(oe, 'overEdge', 'yMax'))), dx=float(oe.dx))
+    if oe.surfOptX is not None:
+        d['surfOptX'] = np.array(oe.surfOptX, dtype=float)
+    if oe.surfOptY is not None:
+        d['surfOptY'] = np.array(oe.surfOptY, dtype=float)
+    return d
+
+
+def _capture_reflect(oe, beam):
+    """Run oe.reflect and also record the beam-wide scalars the numpy code derives on the way."""
+    gb, lb = oe.reflect(beam)
+    d = {}
+    d.update(beam_dict(beam, 'in_'))
+    d.update(beam_dict(gb, 'gb_'))
+    d.update(beam_dict(lb, 'lb_'))
+    d['footprint'] = np.array(oe.footprint[-1])
+    return d
+
+
+def gen_reflect():
+    # (1) config 1: flat Au mirror at 4 mrad, small footprint limits so that rays are lost/over/out as well
+    bl = raycing.BeamLine(azimuth=0.3)  # non-zero azimuth exercises the Rz part of the frame change
+    beam = _source_beam(bl, 3000, 31)
+    Au = rm.Material('Au', rho=19.3)
+    p = 1e4
+    ctr = (p*np.sin(0.3), p*np.cos(0.3), 0)
+    oe = roe.OE(bl, 'M1', center=ctr, pitch=4e-3, roll=2e-3, yaw=-1e-3, material=Au,
+                limPhysX=[-0.25, 0.3], limPhysY=[-60, 50], limOptX=[-0.2, 0.25], limOptY=[-45, 40])
+    d = _capture_reflect(oe, beam)
+    d.update(_oe_params(oe))
+    save('reflect_flat_Au', rho=19.3, **d)
+
+    # (2) toroid Au mirror (config 2 geometry), beamline along y, p-polarised part present
+    bl = raycing.BeamLine()
+    beam = _source_beam(bl, 3000, 32, dx=0.5, dz=0.3, dxprime=2e-4, dzprime=1e-4, energies=(6000, 12000))
+    oe = roe.ToroidMirror(bl, 'TM', center=(0, 25000, 0), pitch=3e-3, R=8e6, r=75., material=Au,
+                          limPhysX=[-4, 4], limPhysY=[-500, 400])
+    d = _capture_reflect(oe, beam)
+    d.update(_oe_params(oe))
+    save('reflect_toroid_Au', rho=19.3, R=float(oe.R), r=float(oe.r), **d)
+
+    # (3) strongly curved toroid without material and without amplitudes: drives the Brent branch
+    beam = _source_beam(bl, 2000, 33, withAmplitudes=False, dx=1.0, dz=0.5, dxprime=1e-3, dzprime=1e-3)
+    oe = roe.ToroidMirror(bl, 'TM2', center=(0, 3000, 0), pitch=0.15, R=4000., r=8., positionRoll=np.pi/2,
+                          limPhysX=[-7, 7], limPhysY=[-200, 200])
+    d = _capture_reflect(oe, beam)
+    d.update(_oe_params(oe))
+    save('reflect_toroid_bare', R=float(oe.R), r=float(oe.r), **d)
+
+
+SECTIONS = {'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)
