@@ -32,6 +32,8 @@ int xrt_b200_device_count(void);
 int xrt_b200_sm_count(void);
 const char* xrt_b200_last_error(void);
 int xrt_b200_sync(void* stream);
+/* sizeof() of the ABI structs below (0: xrt_beam, 1: xrt_oe_params, 2: xrt_material_params), for binding checks */
+size_t xrt_b200_sizeof(int which);
 /* Measured fp64 ceilings used as roofline denominators (bench.py). mode 0: dependent-free DFMA stream,
  * mode 1: DMMA m8n8k4, mode 2: both interleaved. Writes TFLOP/s (2 flop per FMA). */
 int xrt_b200_fp64_probe(int mode, int iters, double* tflops, double* ms);
@@ -79,6 +81,81 @@ int xrt_undulator_imap_f64(size_t n, int jend, double Kx, double Ky, double L0, 
                            const double* theta, const double* psi, const double* tg, const double* ag,
                            const double* sintg, const double* costg, const double* sintgph, const double* costgph,
                            double* I, double* Es, double* Ep, int flags, void* stream);
+
+/* ------------------------------------------------------------------ a1, a6-a15: ray kernels on the Beam SoA
+ * The Beam container of the reference (sources/beams.py:96-186) is a struct of equal-length arrays; here it
+ * is a struct of DEVICE pointers.  Es/Ep may be NULL (beam without amplitudes); theta, s, phi, r are outputs
+ * of reflect() for the local beam only and may be NULL. */
+typedef struct xrt_beam {
+  double *x, *y, *z, *a, *b, *c, *path, *E, *Jss, *Jpp;
+  double *Jsp; /* complex128, interleaved */
+  double *Es, *Ep; /* complex128 or NULL */
+  int32_t* state;
+  double *theta, *s, *phi, *r; /* optional outputs (lb) */
+} xrt_beam;
+
+#define XRT_MAX_ROT 8
+#define XRT_MAX_ELEM 4
+
+/* Geometry of one optical surface = what OE.reflect / DCM.double_reflect read from `self`
+ * (oes/reflect.py:104-135, :551-640; oes/dcm.py:273-335; oes/base.py:1094-1163, :1231-1295). */
+typedef struct xrt_oe_params {
+  double center[3];
+  double sinAz, cosAz;    /* BeamLine azimuth (beamline.py:241-250); skipped when from_global == 0 */
+  int from_global;        /* 1: input is global (reflect, 1st crystal); 0: input is virgin local (2nd crystal) */
+  int to_global;          /* 1: gb leaves in global coordinates; 0: gb stays virgin local (1st crystal of a DCM) */
+  int n_rot_in;           /* elementary rotations global->local in application order (_rotate.py:23-57) */
+  int rot_in_axis[XRT_MAX_ROT]; /* 0 = Rx(pitch), 1 = Ry(roll), 2 = Rz(yaw) */
+  double rot_in_cos[XRT_MAX_ROT], rot_in_sin[XRT_MAX_ROT];
+  int n_rot_out;
+  int rot_out_axis[XRT_MAX_ROT];
+  double rot_out_cos[XRT_MAX_ROT], rot_out_sin[XRT_MAX_ROT];
+  double shift[3];        /* dx, dy, dz (reflect.py:630-635) */
+  double roll;            /* roll used for the polarisation frame, reflect.py:948 */
+  int surface;            /* 0 flat, 1 toroid (R, r), 2 elliptical cylinder/ellipsoid, parametric */
+  double sp[8];           /* surface parameters, cl_plist order of the reference classes */
+  int asymmetric;         /* local_n returns (n_B, n_s): crystal with alpha != 0 */
+  double nB[3];           /* n_B for a flat asymmetric crystal (base.py:736-739; dcm.py:234-238) */
+  double physX[2], physY[2], optX[2], optY[2];
+  int has_optX, has_optY;
+  int over_mask;          /* bit0 xmin, bit1 xmax, bit2 ymin, bit3 ymax (overEdge, base.py:1127-1136) */
+  int lostNum;
+  double brk_lim[3][2];   /* _set_t limits per axis after the +-inf -> defSize replacement (base.py:1233-1239) */
+  int created_by_diffract; /* goodAfter = (state == 1) only (reflect.py:125-128) */
+  int zero_dead_local;    /* DCM 2nd crystal: lo2 of rays that never reached it is zeroed (dcm.py:305-310) */
+  int good_mode;          /* which rays are traced: 0: state > 0 (reflect.py:110); 1: state in (1, 2) (dcm.py:303) */
+} xrt_oe_params;
+
+/* Material = what get_amplitude reads (materials/material.py:348-493, materials/crystal.py:492-645). */
+typedef struct xrt_material_params {
+  int kind;               /* 0 none, 1 mirror, 2 thin mirror, 3 crystal (thick Bragg, fcc/diamond, one element) */
+  int nelem;
+  double Z[XRT_MAX_ELEM], quantity[XRT_MAX_ELEM];
+  int tab_off[XRT_MAX_ELEM], tab_len[XRT_MAX_ELEM]; /* slices of the E/f1/f2 tables */
+  double rho, mass, t;
+  double d, chiToF, factDW;
+  double f0c[11];
+  double d2f_re, d2f_im;  /* diamondToFcc = 1 + exp(i pi/2 (h+k+l)); (1, 0) for fcc */
+  double f0scale;         /* 2 for diamond (F0 * 2), 1 for fcc */
+  int hkl_allowed;        /* h,k,l all even or all odd */
+} xrt_material_params;
+
+/* Beam-wide scalars numpy takes over the whole beam. 64 slots of 8 bytes, device
+ * memory.  Written by the pre-pass, read by the main pass; all-reduced (min/max) across ranks in between
+ * when rays are sharded. Layout documented in xrt_b200/csrc/reflect.cu. */
+#define XRT_REDUCTION_SLOTS 64
+
+/* OE.reflect / one _reflect_local pass.  tables: [E | f1 | f2] each `table_len` doubles (float32 data promoted).
+ * phase bit0: pre-pass (reductions), bit1: main pass.  lb may be NULL (needLocal=False).
+ * index_offset: global index of ray 0 of this shard (first-good-ray bookkeeping of _set_t, base.py:1241).
+ * fallback: beam whose values non-intersected rays receive in gb (reflect.py:131-134; the ORIGINAL beam for the
+ * 2nd crystal of a DCM, dcm.py:343-345); NULL = `in`.
+ * f0c[0] of the material holds f0(sin(theta)/lambda = 0.5/d) evaluated on the host (element.py:203-207). */
+int xrt_reflect_f64(size_t n, const xrt_oe_params* oe, const xrt_material_params* mat, const double* tables,
+                    size_t table_len, const xrt_beam* in, const xrt_beam* fallback, const xrt_beam* gb,
+                    const xrt_beam* lb, uint64_t* reductions, int phase, uint64_t index_offset, void* stream);
+/* decode one reduction slot to double (host helper; slots are order-preserving integer encodings) */
+double xrt_reduction_decode(uint64_t slot);
 
 #ifdef __cplusplus
 }

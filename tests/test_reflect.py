@@ -1,0 +1,138 @@
+"""a6-a12: OE.reflect (flat / toroid, Au mirror or bare) -- oracle pinned bit-exact on the reference's outputs
+(CPU) and the fused CUDA kernel against golden + oracle (GPU)."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from helpers import (oracle_spec, oracle_beam, product_beamline, product_oe_kwargs, device_beam, compare_beams,
+                     BEAM_FIELDS)
+from oracle import reflect as orf, materials as om
+
+CASES = [('reflect_flat_Au', 'flat'), ('reflect_toroid_Au', 'toroid'), ('reflect_toroid_bare', 'toroid')]
+OUT_FIELDS = BEAM_FIELDS + ('theta',)
+
+
+def _oracle_run(name, surface):
+    g = golden(name)
+    mat = om.Material('Au', rho=float(g['rho'])) if 'rho' in g.files else None
+    kw = {}
+    if surface == 'toroid':
+        kw['surfParams'] = dict(R=float(g['R']), r=float(g['r']))
+    sp = oracle_spec(g, surface, mat, **kw)
+    info = {}
+    gb, lb = orf.reflect(sp, oracle_beam(g, 'in_'), info=info)
+    return g, gb, lb, info
+
+
+@pytest.mark.parametrize('name,surface', CASES)
+def test_oracle_matches_reference_bit_exact(name, surface):
+    g, gb, lb, info = _oracle_run(name, surface)
+    for pre, b in (('gb_', gb), ('lb_', lb)):
+        for f in OUT_FIELDS:
+            if pre + f in g.files:
+                assert np.array_equal(getattr(b, f), g[pre + f]), pre + f
+    assert np.array_equal(info['footprint'], g['footprint'])
+    # the goldens exercise every state class
+    st = g['gb_state']
+    assert (st == 1).sum() > 50 and (st < 0).sum() > 10
+
+
+def _product_oe(g, surface):
+    from xrt_b200 import oes, materials
+    bl = product_beamline(g)
+    kw = product_oe_kwargs(g)
+    if 'rho' in g.files:
+        kw['material'] = materials.Material('Au', rho=float(g['rho']))
+    if surface == 'toroid':
+        oe = oes.ToroidMirror(bl, 'oe', R=float(g['R']), r=float(g['r']), **kw)
+    else:
+        oe = oes.OE(bl, 'oe', **kw)
+    oe.lostNum = int(g['lostNum'])
+    return oe
+
+
+# Tolerances: the kernel evaluates the reference's operation sequence without FMA contraction,
+# so geometry is expected bit-identical up to libm-vs-CUDA differences of transcendental functions (<= 2 ulp in
+# normals / angles): positions 1e-12 relative to the 1e4 mm scale, directions and amplitudes 1e-12.
+RTOL = 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name,surface', CASES)
+def test_cuda_reflect_vs_reference_golden(name, surface, cuda_device):
+    g = golden(name)
+    oe = _product_oe(g, surface)
+    beam = device_beam(oracle_beam(g, 'in_'))
+    gb, lb = oe.reflect(beam, withFootprint=True)
+    bad = []
+    for pre, b in (('gb_', gb), ('lb_', lb)):
+        ref = {f: g[pre + f] for f in OUT_FIELDS if pre + f in g.files}
+        bad += compare_beams(b.to_numpy(), ref, OUT_FIELDS, RTOL, pre)
+    assert not bad, bad
+    np.testing.assert_allclose(oe.footprint[0], g['footprint'], rtol=1e-12, atol=1e-12)
+    # intersection parameter: |dt| <= 2e-12 mm
+    good = g['lb_state'] == 1
+    assert np.abs(lb.to_numpy()['path'][good] - g['lb_path'][good]).max() <= 2e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name,surface', CASES[:2])
+def test_cuda_reflect_need_local_false(name, surface, cuda_device):
+    g = golden(name)
+    oe = _product_oe(g, surface)
+    gb, lb = oe.reflect(device_beam(oracle_beam(g, 'in_')), needLocal=False)
+    assert lb is gb
+    ref = {f: g['gb_' + f] for f in BEAM_FIELDS if 'gb_' + f in g.files}
+    assert not compare_beams(gb.to_numpy(), ref, BEAM_FIELDS, RTOL)
+
+
+@pytest.mark.gpu
+def test_cuda_reflect_all_dead_and_empty(cuda_device):
+    g = golden('reflect_flat_Au')
+    oe = _product_oe(g, 'flat')
+    b = oracle_beam(g, 'in_')
+    b.state[:] = -3
+    gb, lb = oe.reflect(device_beam(b))
+    out = gb.to_numpy()
+    for f in BEAM_FIELDS:
+        assert np.array_equal(out[f], getattr(b, f)), f
+    # zero-length beam
+    from xrt_b200.beams import Beam
+    e = Beam(0, withAmplitudes=True)
+    gb, lb = oe.reflect(e)
+    assert len(gb) == 0 and len(lb) == 0
+
+
+@pytest.mark.gpu
+def test_cuda_reflect_energy_outside_table_raises(cuda_device):
+    g = golden('reflect_flat_Au')
+    oe = _product_oe(g, 'flat')
+    b = oracle_beam(g, 'in_')
+    b.E[:] = 1e6  # above the Chantler table (4.3e5 eV): Element.get_f1f2 raises ValueError (element.py:254)
+    with pytest.raises(ValueError):
+        oe.reflect(device_beam(b))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('surface', ['flat', 'toroid'])
+def test_cuda_reflect_vs_oracle_large_seeded(surface, cuda_device):
+    """2e5 seeded rays (oracle finishes in seconds), ragged length, same comparison against the oracle."""
+    from xrt_b200 import synthetic
+    g = golden('reflect_toroid_Au' if surface == 'toroid' else 'reflect_flat_Au')
+    n = 200003
+    arrays = synthetic.geometric_beam(41, n, dx=0.3, dz=0.2, dxprime=1.5e-4, dzprime=8e-5,
+                                      energies=(7000., 11000.), azimuth=np.arctan2(float(g['sinAzimuth']),
+                                                                                   float(g['cosAzimuth'])))
+    ob_beam = oracle_beam({'in_' + k: v for k, v in arrays.items()}, 'in_') if False else None
+    from oracle import beam as obm
+    b = obm.Beam.__new__(obm.Beam)
+    for k, v in arrays.items():
+        setattr(b, k, v.copy())
+    mat = om.Material('Au', rho=float(g['rho']))
+    kw = {'surfParams': dict(R=float(g['R']), r=float(g['r']))} if surface == 'toroid' else {}
+    gbo, lbo = orf.reflect(oracle_spec(g, surface, mat, **kw), b)
+    oe = _product_oe(g, surface)
+    gb, lb = oe.reflect(device_beam(arrays))
+    bad = compare_beams(gb.to_numpy(), gbo, BEAM_FIELDS, RTOL, 'gb_') + \
+        compare_beams(lb.to_numpy(), lbo, OUT_FIELDS, RTOL, 'lb_')
+    assert not bad, bad

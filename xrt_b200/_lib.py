@@ -25,6 +25,7 @@ PROTOTYPES = {
     'xrt_b200_sm_count': (c_int, []),
     'xrt_b200_last_error': (ctypes.c_char_p, []),
     'xrt_b200_sync': (c_int, [c_dp]),
+    'xrt_b200_sizeof': (c_sz, [c_int]),
     'xrt_b200_fp64_probe': (c_int, [c_int, c_int, ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)]),
     'xrt_kirchhoff_workspace_bytes': (c_sz, [c_sz, c_sz, c_int]),
     'xrt_kirchhoff_f64': (c_int, [c_sz, c_sz] + [c_dp] * 8 + [c_int, c_dp, c_int] + [c_dp] * 5 +
@@ -32,6 +33,9 @@ PROTOTYPES = {
     'xrt_kirchhoff_f64_host': (c_int, [c_sz, c_sz] + [c_dp] * 8 + [c_int, c_dp, c_int] + [c_dp] * 5 + [c_int]),
     'xrt_undulator_f64': (c_int, [c_sz, c_int, c_dbl, c_dbl, c_dbl] + [c_dp] * 14 + [c_int, c_dp]),
     'xrt_undulator_f64_host': (c_int, [c_sz, c_int, c_dbl, c_dbl, c_dbl] + [c_dp] * 14 + [c_int]),
+    'xrt_reflect_f64': (c_int, [c_sz, c_dp, c_dp, c_dp, c_sz, c_dp, c_dp, c_dp, c_dp, c_dp, c_int,
+                                ctypes.c_uint64, c_dp]),
+    'xrt_reduction_decode': (c_dbl, [ctypes.c_uint64]),
     'xrt_undulator_imap_f64': (c_int, [c_sz, c_int] + [c_dbl] * 7 + [c_int] + [c_dp] * 13 + [c_int, c_dp]),
 }
 

@@ -1,0 +1,145 @@
+# -*- coding: utf-8 -*-
+"""Device-resident `Beam`: the SoA ray container of xrt (xrt/backends/raycing/sources/beams.py:96-186) with
+every array living in HBM as a torch CUDA tensor.
+
+Same attribute names (x y z a b c path E Jss Jpp Jsp state [Es Ep] [theta s phi r] ...), same constructor
+keywords (`nrays`, `copyFrom`, `withAmplitudes`), same bookkeeping scalars (`accepted`, `seeded`, ...), so
+that `run_process()` scripts and the plotting layer read it the same way; `to_numpy()` /
+`Beam.from_numpy()` cross the host boundary explicitly (100 B/ray, 132 B/ray with amplitudes).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+F64 = torch.float64
+C128 = torch.complex128
+I32 = torch.int32
+
+REAL_FIELDS = ('x', 'y', 'z', 'a', 'b', 'c', 'path', 'E', 'Jss', 'Jpp')
+COMPLEX_FIELDS = ('Jsp', 'Es', 'Ep')
+OPTIONAL_REAL = ('theta', 's', 'phi', 'r')
+SCALARS = ('accepted', 'acceptedE', 'seeded', 'seededI', 'sourceWeight', 'parentId', 'sourceSIGMAx',
+           'sourceSIGMAz', 'filamentDX', 'filamentDZ', 'filamentDtheta', 'filamentDpsi', 'filamentDgamma',
+           'area', 'createdByDiffract')
+
+
+class xrt_beam(ctypes.Structure):
+    """struct xrt_beam of include/xrt_b200.h"""
+    _fields_ = [(n, ctypes.c_void_p) for n in
+                ('x', 'y', 'z', 'a', 'b', 'c', 'path', 'E', 'Jss', 'Jpp', 'Jsp', 'Es', 'Ep', 'state',
+                 'theta', 's', 'phi', 'r')]
+
+
+def _device(device=None):
+    if device is None:
+        return torch.device('cuda', torch.cuda.current_device())
+    return torch.device(device)
+
+
+class Beam(object):
+    def __init__(self, nrays=0, copyFrom=None, withAmplitudes=False, device=None, uninitialized=False):
+        if copyFrom is not None:
+            for k, v in copyFrom.__dict__.items():
+                setattr(self, k, v.clone() if isinstance(v, torch.Tensor) else v)
+            return
+        dev = _device(device)
+        n = int(nrays)
+        new = torch.empty if uninitialized else torch.zeros
+        for f in REAL_FIELDS:
+            setattr(self, f, new(n, dtype=F64, device=dev))
+        self.Jsp = new(n, dtype=C128, device=dev)
+        self.state = new(n, dtype=I32, device=dev)
+        if withAmplitudes:
+            self.Es = new(n, dtype=C128, device=dev)
+            self.Ep = new(n, dtype=C128, device=dev)
+        if not uninitialized:
+            # defaults of the reference constructor (beams.py:165-182)
+            self.b.fill_(1.)
+            self.E.fill_(9000.)
+            self.Jss.fill_(1.)
+        self.parentId = None
+
+    # ------------------------------------------------------------------ structure
+    def __len__(self):
+        return self.x.numel()
+
+    @property
+    def nrays(self):
+        return self.x.numel()
+
+    @property
+    def device(self):
+        return self.x.device
+
+    def has_amplitudes(self):
+        return hasattr(self, 'Es')
+
+    def like(self, withLocal=False):
+        """Uninitialised beam of the same shape (output buffer of a kernel)."""
+        b = Beam(len(self), withAmplitudes=self.has_amplitudes(), device=self.device, uninitialized=True)
+        for k in SCALARS:
+            if hasattr(self, k):
+                setattr(b, k, getattr(self, k))
+        return b
+
+    def tensors(self):
+        return {k: v for k, v in self.__dict__.items() if isinstance(v, torch.Tensor)}
+
+    def bytes_per_ray(self):
+        return sum(v.element_size() for v in self.tensors().values())
+
+    def c_struct(self):
+        s = xrt_beam()
+        for name, _ in xrt_beam._fields_:
+            t = getattr(self, name, None)
+            if isinstance(t, torch.Tensor):
+                if not (t.is_cuda and t.is_contiguous() and t.numel() == len(self)):
+                    raise ValueError('Beam.{0} must be a contiguous CUDA tensor of the beam length'.format(name))
+                setattr(s, name, t.data_ptr())
+            else:
+                setattr(s, name, None)
+        return s
+
+    # ------------------------------------------------------------------ host boundary
+    @classmethod
+    def from_numpy(cls, arrays, device=None, pinned=False):
+        """arrays: mapping name -> ndarray (or an object with those attributes, e.g. a reference Beam)."""
+        if not isinstance(arrays, dict):
+            arrays = {k: v for k, v in arrays.__dict__.items()}
+        dev = _device(device)
+        b = cls.__new__(cls)
+        for k, v in arrays.items():
+            if isinstance(v, np.ndarray) and v.ndim == 1:
+                if k == 'state':
+                    v = np.ascontiguousarray(v, dtype=np.int32)
+                elif k in COMPLEX_FIELDS:
+                    v = np.ascontiguousarray(v, dtype=np.complex128)
+                else:
+                    v = np.ascontiguousarray(v, dtype=np.float64)
+                t = torch.from_numpy(v)
+                setattr(b, k, t.to(dev, non_blocking=pinned))
+            elif k in SCALARS:
+                setattr(b, k, v)
+        if not hasattr(b, 'parentId'):
+            b.parentId = None
+        return b
+
+    def to_numpy(self):
+        out = {}
+        for k, v in self.__dict__.items():
+            out[k] = v.cpu().numpy() if isinstance(v, torch.Tensor) else v
+        return out
+
+    def __array__(self):  # pragma: no cover - convenience for interactive use
+        raise TypeError('Beam is a container; use beam.to_numpy()')
+
+    def filter_by_index(self, index):
+        for k, v in list(self.__dict__.items()):
+            if isinstance(v, torch.Tensor):
+                setattr(self, k, v[index].contiguous())
+
+    def concatenate(self, other):
+        for k, v in list(self.__dict__.items()):
+            if isinstance(v, torch.Tensor):
+                setattr(self, k, torch.cat((v, getattr(other, k))))

@@ -162,6 +162,10 @@ int xrt_b200_init(int device) {
 
 int xrt_b200_sm_count(void) { return num_sms(); }
 
+size_t xrt_b200_sizeof(int which) {
+  return which == 0 ? sizeof(xrt_beam) : which == 1 ? sizeof(xrt_oe_params) : which == 2 ? sizeof(xrt_material_params) : 0;
+}
+
 const char* xrt_b200_last_error(void) { return g_err; }
 
 int xrt_b200_sync(void* stream) {
@@ -269,5 +273,15 @@ int xrt_undulator_imap_f64(size_t n, int jend, double Kx, double Ky, double L0, 
                                ag, sintg, costg, sintgph, costgph, I, Es, Ep, (flags >> 4) & 7,
                                (cudaStream_t)stream);
 }
+
+// ------------------------------------------------------------------ reflect
+int xrt_reflect_f64(size_t n, const xrt_oe_params* oe, const xrt_material_params* mat, const double* tables,
+                    size_t table_len, const xrt_beam* in, const xrt_beam* fallback, const xrt_beam* gb,
+                    const xrt_beam* lb, uint64_t* reductions, int phase, uint64_t index_offset, void* stream) {
+  return reflect_device(n, oe, mat, tables, table_len, in, fallback, gb, lb,
+                        reinterpret_cast<unsigned long long*>(reductions), phase, index_offset, (cudaStream_t)stream);
+}
+
+double xrt_reduction_decode(uint64_t slot) { return reduction_decode(slot); }
 
 }  // extern "C"

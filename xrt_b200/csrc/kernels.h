@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 
+#include "../../include/xrt_b200.h"
+
 namespace xrtb {
 
 // kirchhoff.cu
@@ -24,5 +26,12 @@ int undulator_imap_device(size_t n, int jend, double Kx, double Ky, double L0, d
                           const double* theta, const double* psi, const double* tg, const double* ag,
                           const double* sintg, const double* costg, const double* sintgph, const double* costgph,
                           double* I, double* Es, double* Ep, int R, cudaStream_t st);
+
+// reflect.cu (compiled with -fmad=false)
+int reflect_device(size_t n, const xrt_oe_params* oe, const xrt_material_params* mat, const double* tables,
+                   size_t table_len, const xrt_beam* in, const xrt_beam* fallback, const xrt_beam* gb,
+                   const xrt_beam* lb, unsigned long long* red, int phase, unsigned long long index_offset,
+                   cudaStream_t st);
+double reduction_decode(unsigned long long slot);
 
 }  // namespace xrtb

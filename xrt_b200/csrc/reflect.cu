@@ -1,0 +1,1034 @@
+// Fused ray-surface kernels for sm_100a: OE.reflect / DCM.double_reflect in one pass over the Beam SoA.
+//
+// Replaces the numpy pipeline OE.reflect -> _reflect_local (xrt/backends/raycing/oes/reflect.py:17-163,
+// :551-1139) with everything it calls: global_to_virgin_local / virgin_local_to_global
+// (beamline.py:230-287), rotate_beam (_rotate.py:23-57), _bracketing/_set_t (oes/base.py:1231-1295),
+// find_intersection / find_dz / _use_my_method / _use_Brent_method (oes/base.py:801-1048, the semantics of
+// the dead OpenCL kernel `find_intersection`, cl/OE.cl:313), rays_good (base.py:1094-1163), the surface
+// classes (flat base.py:675-742, ToroidMirror oes/__init__.py:398-411, EllipticalMirrorParam
+// oes/parametric.py:213-246), the direction / polarisation block (reflect.py:788-1064, :451-469, :568-612),
+// rotate_coherency_matrix (sources/beams.py:448-479) and the amplitudes Material.get_amplitude
+// (materials/material.py:348-493) / Crystal.get_amplitude thick Bragg (materials/crystal.py:492-645).
+// Oracle: oracle/reflect.py, oracle/materials.py (bit-exact against the reference's outputs).
+//
+// HBM-bound: one thread per ray, every Beam array is read once and written once with unit stride (SoA);
+// 132 B in + 132 B (gb) + 140 B (lb) per ray with amplitudes.  A pre-pass (52 B/ray) produces the beam-wide
+// scalars the numpy code derives with whole-array min/max (dominant direction component, global t bracket,
+// secant-vs-Brent choice, first good ray) for all six (axis, sign) variants at once, so that the main pass
+// needs no host round trip and ray shards on several GPUs can all-reduce 64 slots in between.
+//
+// THIS FILE IS COMPILED WITH -fmad=false: numpy rounds every multiply and add separately, and the
+// intersection iterates and grazing-incidence Fresnel terms amplify 1-ulp differences (cancellation ~1e6),
+// so FMA contraction would break parity.  fma() is used explicitly only where it cannot matter.
+#include "../../include/xrt_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace xrtb {
+
+// ---------------------------------------------------------------- reduction slots (uint64, order-preserving)
+enum {
+  RS_MAXA = 0,  // max |a|, |b|, |c| over rays with state == 1 (base.py:1257-1263)
+  RS_MAXB = 1,
+  RS_MAXC = 2,
+  RS_FIRST = 3,  // min over good rays of (global index << 3 | a>0 | b>0 << 1 | c>0 << 2)  (base.py:1241 `abc[0] > 0`)
+  RS_VAR = 4,    // 6 variants (axis * 2 + neg) x {min t1, max t2, max |dz1|, max |dz2| masked} (base.py:861-871)
+  RS_FOOT = 28,  // footprint min x,y,z / max x,y,z of the virgin-local output (reflect.py:1133-1136)
+  RS_NGOOD = 34, // number of rays with state > 0 on entry (plain integer count)
+  RS_NGOODN = 35 // number of rays with state == 1 after the surface (plain integer count)
+};
+constexpr double kZEps = 1e-12;      // raycing.zEps   (raycing/__init__.py:86)
+constexpr double kDt = 1e-5;         // raycing.dt     (:89)
+constexpr int kMaxIteration = 100;   // raycing.maxIteration (:92)
+constexpr double kPi = 3.141592653589793;
+
+__host__ __device__ inline unsigned long long enc(double d) {
+  unsigned long long u;
+  memcpy(&u, &d, 8);
+  return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+__host__ __device__ inline double dec(unsigned long long u) {
+  u = (u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u;
+  double d;
+  memcpy(&d, &u, 8);
+  return d;
+}
+
+struct Ray {
+  double x, y, z, a, b, c;
+};
+
+__device__ __forceinline__ void rot_axis(int axis, double cA, double sA, double& x, double& y, double& z) {
+  // rotate_x / rotate_y / rotate_z of _rotate.py:5-20
+  if (axis == 0) {
+    const double y1 = cA * y - sA * z, z1 = sA * y + cA * z;
+    y = y1;
+    z = z1;
+  } else if (axis == 1) {
+    const double x1 = cA * x + sA * z, z1 = -sA * x + cA * z;
+    x = x1;
+    z = z1;
+  } else {
+    const double x1 = cA * x - sA * y, y1 = sA * x + cA * y;
+    x = x1;
+    y = y1;
+  }
+}
+
+__device__ __forceinline__ void to_local(const xrt_oe_params& p, Ray& r) {
+  if (p.from_global) {
+    r.x -= p.center[0];
+    r.y -= p.center[1];
+    r.z -= p.center[2];
+    if (p.sinAz != 0.0) {
+      rot_axis(2, p.cosAz, p.sinAz, r.x, r.y, r.z);
+      rot_axis(2, p.cosAz, p.sinAz, r.a, r.b, r.c);
+    }
+  }
+  for (int i = 0; i < p.n_rot_in; ++i) {
+    rot_axis(p.rot_in_axis[i], p.rot_in_cos[i], p.rot_in_sin[i], r.x, r.y, r.z);
+    rot_axis(p.rot_in_axis[i], p.rot_in_cos[i], p.rot_in_sin[i], r.a, r.b, r.c);
+  }
+  if (p.shift[0] != 0.0) r.x -= p.shift[0];
+  if (p.shift[1] != 0.0) r.y -= p.shift[1];
+  if (p.shift[2] != 0.0) r.z -= p.shift[2];
+}
+
+__device__ __forceinline__ void to_virgin(const xrt_oe_params& p, Ray& r) {
+  if (p.shift[0] != 0.0) r.x += p.shift[0];
+  if (p.shift[1] != 0.0) r.y += p.shift[1];
+  if (p.shift[2] != 0.0) r.z += p.shift[2];
+  for (int i = 0; i < p.n_rot_out; ++i) {
+    rot_axis(p.rot_out_axis[i], p.rot_out_cos[i], p.rot_out_sin[i], r.x, r.y, r.z);
+    rot_axis(p.rot_out_axis[i], p.rot_out_cos[i], p.rot_out_sin[i], r.a, r.b, r.c);
+  }
+}
+
+__device__ __forceinline__ void virgin_to_global(const xrt_oe_params& p, Ray& r) {
+  if (p.sinAz != 0.0) {
+    rot_axis(2, p.cosAz, -p.sinAz, r.a, r.b, r.c);
+    rot_axis(2, p.cosAz, -p.sinAz, r.x, r.y, r.z);
+  }
+  r.x += p.center[0];
+  r.y += p.center[1];
+  r.z += p.center[2];
+}
+
+// ---------------------------------------------------------------- surfaces
+// x**(-0.5) as glibc pow returns it (< 1 ulp): 1/sqrt with one residual correction
+__device__ __forceinline__ double pow_m05(double x) {
+  const double y0 = 1.0 / sqrt(x);
+  const double e = fma(-x * y0, y0, 1.0);
+  return fma(0.5 * y0, e, y0);
+}
+
+template <int SURF>
+__device__ __forceinline__ double local_surface(const xrt_oe_params& p, double x, double y) {
+  if (SURF == 0) return 0.0;
+  if (SURF == 1) {
+    // ToroidMirror.local_z (oes/__init__.py:398-401)
+    const double R = p.sp[0], r = p.sp[1];
+    const double q = x / r;
+    double rx = 1.0 - q * q;
+    if (rx < 0.0) rx = 0.0;
+    return y * y / 2.0 / R + r * (1.0 - sqrt(rx));
+  }
+  // EllipticalMirrorParam.local_r (parametric.py:228-234): x = s, y = phi
+  const double A = p.sp[0], B = p.sp[1];
+  double rr = B * sqrt(fabs(1.0 - x * x / (A * A)));
+  if (p.sp[6] != 0.0) rr /= fabs(cos(y));
+  return (fabs(y) > kPi / 2) ? rr : 1e20;
+}
+
+template <int SURF>
+__device__ __forceinline__ void xyz_to_param(const xrt_oe_params& p, double& x, double& y, double& z) {
+  if (SURF != 2) return;
+  // parametric.py:213-216: rotate_x(y - y0, z - z0, cosGamma, sinGamma); s, phi, r
+  const double yy = y - p.sp[2], zz = z - p.sp[3];
+  const double cg = p.sp[4], sg = p.sp[5];
+  const double yN = cg * yy - sg * zz, zN = sg * yy + cg * zz;
+  const double xx = x;
+  x = yN;
+  y = atan2(xx, zN);
+  z = sqrt(xx * xx + zN * zN);
+}
+
+template <int SURF>
+__device__ __forceinline__ void param_to_xyz(const xrt_oe_params& p, double& x, double& y, double& z) {
+  if (SURF != 2) return;
+  // parametric.py:218-224
+  const double s = x, phi = y, r = z;
+  const double xx = r * sin(phi), yy = s, zz = r * cos(phi);
+  const double cg = p.sp[4], sg = -p.sp[5];
+  const double yN = cg * yy - sg * zz, zN = sg * yy + cg * zz;
+  x = xx;
+  y = yN + p.sp[2];
+  z = zN + p.sp[3];
+}
+
+// find_dz (base.py:801-846), derivOrder = 0, invertNormal = 1
+template <int SURF>
+__device__ __forceinline__ double find_dz(const xrt_oe_params& p, double t, const Ray& r, double& x, double& y,
+                                          double& z) {
+  x = r.x + r.a * t;
+  y = r.y + r.b * t;
+  z = r.z + r.c * t;
+  xyz_to_param<SURF>(p, x, y, z);
+  double surf = local_surface<SURF>(p, x, y);
+  if (isnan(surf)) surf = 0.0;
+  const double d = z - surf;
+  return (SURF == 2) ? -d : d;
+}
+
+// normal(s): n[0..2] = n_B (or the only normal), n[3..5] = surface normal
+template <int SURF>
+__device__ __forceinline__ void local_normal(const xrt_oe_params& p, double x, double y, double* n) {
+  if (SURF == 0) {
+    n[3] = 0.0;
+    n[4] = 0.0;
+    n[5] = 1.0;
+    if (p.asymmetric) {
+      n[0] = p.nB[0];
+      n[1] = p.nB[1];
+      n[2] = p.nB[2];
+    } else {
+      n[0] = 0.0;
+      n[1] = 0.0;
+      n[2] = 1.0;
+    }
+    return;
+  }
+  if (SURF == 1) {
+    // ToroidMirror.local_n (oes/__init__.py:403-411)
+    const double R = p.sp[0], r = p.sp[1];
+    const double q = x / r;
+    const double rx = 1.0 - q * q;
+    const double ax = (rx < 0.0) ? 0.0 : pow_m05(rx);
+    const double a = -x / r * ax;
+    const double b = -y / R;
+    const double norm = sqrt(a * a + b * b + 1.0);
+    n[0] = n[3] = a / norm;
+    n[1] = n[4] = b / norm;
+    n[2] = n[5] = 1.0 / norm;
+    return;
+  }
+  // EllipticalMirrorParam.local_n (parametric.py:236-249): x = s, y = phi
+  const double A = p.sp[0], B = p.sp[1];
+  double A2s2 = A * A - x * x;
+  if (A2s2 <= 0.0) A2s2 = 1e22;
+  const double nr = -B / A * x / sqrt(A2s2);
+  const double norm = sqrt(nr * nr + 1.0);
+  const double b = nr / norm;
+  double a, c;
+  if (p.sp[6] != 0.0) {
+    a = 0.0;
+    c = 1.0 / norm;
+  } else {
+    a = -sin(y) / norm;
+    c = -cos(y) / norm;
+  }
+  const double cg = p.sp[4], sg = -(-p.sp[5]);  // rotate_x(b, c, cosGamma, -sinGamma): -sinangle*z = +sinGamma*z
+  n[0] = n[3] = a;
+  n[1] = n[4] = cg * b - (-p.sp[5]) * c;
+  n[2] = n[5] = (-p.sp[5]) * b + cg * c;
+  (void)sg;
+}
+
+// _set_t (base.py:1231-1245) followed by the tMin clamp of _bracketing (:1275)
+__device__ __forceinline__ void bracket(const xrt_oe_params& p, int axis, int neg, const Ray& r, double& t1,
+                                        double& t2) {
+  const double xyz = axis == 0 ? r.x : (axis == 1 ? r.y : r.z);
+  const double abc = axis == 0 ? r.a : (axis == 1 ? r.b : r.c);
+  const double lo = p.brk_lim[axis][0], hi = p.brk_lim[axis][1];
+  if (!neg) {
+    t1 = (lo - xyz) / abc - kDt;
+    t2 = (hi - xyz) / abc + kDt;
+  } else {
+    t1 = (hi - xyz) / abc - kDt;
+    t2 = (lo - xyz) / abc + kDt;
+  }
+  if (t1 < -1e6 * kZEps) t1 = -1e6 * kZEps;
+}
+
+__device__ __forceinline__ Ray load_ray(const xrt_beam& b, size_t i) {
+  Ray r;
+  r.x = b.x[i];
+  r.y = b.y[i];
+  r.z = b.z[i];
+  r.a = b.a[i];
+  r.b = b.b[i];
+  r.c = b.c[i];
+  return r;
+}
+
+// ---------------------------------------------------------------- pre-pass: beam-wide scalars
+__global__ void reduction_init_kernel(unsigned long long* red) {
+  const int i = threadIdx.x;
+  if (i >= XRT_REDUCTION_SLOTS) return;
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  unsigned long long v = enc(-inf);  // max slots
+  if (i == RS_FIRST) v = ~0ull;
+  if (i >= RS_VAR && i < RS_VAR + 24 && ((i - RS_VAR) & 3) == 0) v = enc(inf);  // min t1
+  if (i >= RS_FOOT && i < RS_FOOT + 3) v = enc(inf);
+  if (i == RS_NGOOD || i == RS_NGOODN || i > RS_NGOODN) v = 0ull;
+  red[i] = v;
+}
+
+template <int SURF>
+__global__ void __launch_bounds__(256) reflect_prepass_kernel(size_t n, xrt_oe_params p, xrt_beam in,
+                                                              unsigned long long* red, unsigned long long index_offset) {
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  double mx[3] = {-inf, -inf, -inf};
+  double v[24];
+#pragma unroll
+  for (int k = 0; k < 24; ++k) v[k] = ((k & 3) == 0) ? inf : -inf;
+  unsigned long long first = ~0ull;
+  unsigned long long ngood = 0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int st = in.state[i];
+    if (!(p.good_mode ? (st == 1 || st == 2) : (st > 0))) continue;
+    ++ngood;
+    Ray r = load_ray(in, i);
+    to_local(p, r);
+    if (st == 1) {
+      mx[0] = fmax(mx[0], fabs(r.a));
+      mx[1] = fmax(mx[1], fabs(r.b));
+      mx[2] = fmax(mx[2], fabs(r.c));
+    }
+    const unsigned long long key = ((index_offset + i) << 3) | (r.a > 0.0 ? 1ull : 0ull) | (r.b > 0.0 ? 2ull : 0ull) |
+                                   (r.c > 0.0 ? 4ull : 0ull);
+    first = key < first ? key : first;
+#pragma unroll
+    for (int var = 0; var < 6; ++var) {
+      double t1, t2, x, y, z;
+      bracket(p, var >> 1, var & 1, r, t1, t2);
+      const double dz1 = find_dz<SURF>(p, t1, r, x, y, z);
+      double dz2 = find_dz<SURF>(p, t2, r, x, y, z);
+      if (dz1 <= 0.0 || dz2 >= 0.0) dz2 = 0.0;  // base.py:865 dz2[ind1 | ind2] = 0
+      // numpy's min/max propagate NaN; keep that by letting NaN win
+      v[var * 4 + 0] = (t1 < v[var * 4 + 0] || isnan(t1)) ? t1 : v[var * 4 + 0];
+      v[var * 4 + 1] = (t2 > v[var * 4 + 1] || isnan(t2)) ? t2 : v[var * 4 + 1];
+      v[var * 4 + 2] = (fabs(dz1) > v[var * 4 + 2] || isnan(dz1)) ? fabs(dz1) : v[var * 4 + 2];
+      v[var * 4 + 3] = (fabs(dz2) > v[var * 4 + 3] || isnan(dz2)) ? fabs(dz2) : v[var * 4 + 3];
+    }
+  }
+  // block reduction through shared memory, then one atomic per slot per block
+  __shared__ unsigned long long sh[8][29];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long e[29];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) e[k] = enc(mx[k]);
+  e[3] = first;
+#pragma unroll
+  for (int k = 0; k < 24; ++k) e[4 + k] = enc(v[k]);
+  e[28] = ngood;
+#pragma unroll
+  for (int k = 0; k < 29; ++k) {
+    unsigned long long x = e[k];
+    const bool is_min = (k == 3) || (k >= 4 && k < 28 && ((k - 4) & 3) == 0);
+    const bool is_sum = (k == 28);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      unsigned long long yv = __shfl_xor_sync(0xffffffffu, x, o);
+      x = is_sum ? x + yv : (is_min ? (yv < x ? yv : x) : (yv > x ? yv : x));
+    }
+    if (lane == 0) sh[warp][k] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < 29) {
+    const int k = threadIdx.x;
+    const bool is_min = (k == 3) || (k >= 4 && k < 28 && ((k - 4) & 3) == 0);
+    const bool is_sum = (k == 28);
+    unsigned long long x = sh[0][k];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      unsigned long long yv = sh[w][k];
+      x = is_sum ? x + yv : (is_min ? (yv < x ? yv : x) : (yv > x ? yv : x));
+    }
+    const int slot = (k == 28) ? RS_NGOOD : k;
+    if (is_sum)
+      atomicAdd(&red[slot], x);
+    else if (is_min)
+      atomicMin(&red[slot], x);
+    else
+      atomicMax(&red[slot], x);
+  }
+}
+
+// ---------------------------------------------------------------- numpy-faithful complex arithmetic
+__device__ __forceinline__ cplx cmul_np(cplx a, cplx b) {  // CDOUBLE_multiply
+  return cplx{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
+}
+__device__ __forceinline__ cplx csquare_np(cplx a) {  // CDOUBLE_square
+  return cplx{a.re * a.re - a.im * a.im, a.re * a.im + a.im * a.re};
+}
+__device__ __forceinline__ cplx cexp_i(double phi) {  // exp(0 + i phi)
+  double s, c;
+  sincos_big(phi, s, c);
+  return cplx{c, s};
+}
+
+// np.interp for one point (numpy/core/src/multiarray/compiled_base.c: binary search, slope form)
+__device__ __forceinline__ double interp1(const double* __restrict__ xp, const double* __restrict__ fp, int len,
+                                          double x) {
+  if (x <= xp[0]) return (x == xp[0]) ? fp[0] : fp[0];
+  if (x >= xp[len - 1]) return fp[len - 1];
+  int lo = 0, hi = len - 1;  // xp[lo] <= x < xp[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (x >= xp[mid])
+      lo = mid;
+    else
+      hi = mid;
+  }
+  if (xp[lo] == x) return fp[lo];
+  const double slope = (fp[lo + 1] - fp[lo]) / (xp[lo + 1] - xp[lo]);
+  double res = slope * (x - xp[lo]) + fp[lo];
+  if (isnan(res)) {
+    res = slope * (x - xp[lo + 1]) + fp[lo + 1];
+    if (isnan(res) && fp[lo] == fp[lo + 1]) res = fp[lo];
+  }
+  return res;
+}
+
+struct Tables {
+  const double *E, *f1, *f2;
+};
+
+// Element.get_f1f2 (element.py:252-263); the out-of-range ValueError becomes NaN + an error flag
+__device__ __forceinline__ cplx f1f2(const Tables& t, int off, int len, double E, int* oor) {
+  if (E < t.E[off] || E > t.E[off + len - 1]) {
+    *oor = 1;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    return cplx{nan, nan};
+  }
+  return cplx{interp1(t.E + off, t.f1 + off, len, E), interp1(t.E + off, t.f2 + off, len, E)};
+}
+
+// Material.get_refractive_index (material.py:372-378)
+__device__ __forceinline__ cplx refractive_index(const xrt_material_params& m, const Tables& t, double E, int* oor) {
+  cplx xf = cplx{0.0, 0.0};
+  for (int i = 0; i < m.nelem; ++i) {
+    const cplx f = f1f2(t, m.tab_off[i], m.tab_len[i], E, oor);
+    const cplx zf = cplx{m.Z[i] + f.re, f.im};            // elem.Z + (f1 + i f2)
+    const cplx term = cmul_np(zf, cplx{m.quantity[i], 0.0});  // * xi
+    xf = cadd(xf, term);
+  }
+  const double c0 = 1e-24 * 6.02214199e23 * 2.817940285e-5 / 6.283185307179586476925286766559;
+  const double CH = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8;
+  const double w = CH / E;
+  const double fac = c0 * (w * w) * m.rho;
+  const cplx num = cmul_np(cplx{fac, 0.0}, xf);
+  const cplx q = cdiv(num, cplx{m.mass, 0.0});
+  return cplx{1.0 - q.re, 0.0 - q.im};
+}
+
+// Material.get_amplitude, fromVacuum=True, kinds 'mirror' / 'thin mirror' (material.py:455-493)
+__device__ __forceinline__ void mirror_amplitude(const xrt_material_params& m, const Tables& t, double E,
+                                                 double bdn, cplx& rs, cplx& rp, int* oor) {
+  const cplx n2 = refractive_index(m, t, E, oor);
+  const double cosAlpha = fabs(bdn);
+  double sinAlpha2 = 1.0 - bdn * bdn;
+  if (sinAlpha2 < 0.0) sinAlpha2 = 0.0;
+  const double n1cosAlpha = 1.0 * cosAlpha;
+  const cplx n1n2 = cdiv(cplx{1.0, 0.0}, n2);
+  const cplx sq = cmul_np(csquare_np(n1n2), cplx{sinAlpha2, 0.0});
+  const cplx cosBeta = csqrt_(cplx{1.0 - sq.re, 0.0 - sq.im});
+  const cplx n2cosBeta = cmul_np(n2, cosBeta);
+  rs = cdiv(cplx{n1cosAlpha - n2cosBeta.re, 0.0 - n2cosBeta.im},
+            cplx{n1cosAlpha + n2cosBeta.re, 0.0 + n2cosBeta.im});
+  const cplx n2ca = cmul_np(n2, cplx{cosAlpha, 0.0});
+  const cplx n1cb = cmul_np(cplx{1.0, 0.0}, cosBeta);
+  rp = cdiv(csub(n2ca, n1cb), cadd(n2ca, n1cb));
+  if (m.kind == 2) {
+    // thin mirror: p2 = exp(2j * E / CHBAR * n2cosBeta * t * 1e7) (material.py:479-482)
+    const double CHBAR = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8 / 6.283185307179586476925286766559;
+    cplx z = cmul_np(cplx{0.0, 2.0}, cplx{E, 0.0});
+    z = cdiv(z, cplx{CHBAR, 0.0});
+    z = cmul_np(z, n2cosBeta);
+    z = cmul_np(z, cplx{m.t, 0.0});
+    z = cmul_np(z, cplx{1e7, 0.0});
+    const double ex = exp(z.re);
+    double s, c;
+    sincos(z.im, &s, &c);
+    const cplx p2 = cplx{ex * c, ex * s};
+    const cplx one_m_p2 = cplx{1.0 - p2.re, 0.0 - p2.im};
+    cplx den = cmul_np(csquare_np(rs), p2);
+    rs = cmul_np(rs, cdiv(one_m_p2, cplx{1.0 - den.re, 0.0 - den.im}));
+    den = cmul_np(csquare_np(rp), p2);
+    rp = cmul_np(rp, cdiv(one_m_p2, cplx{1.0 - den.re, 0.0 - den.im}));
+  }
+}
+
+// Crystal.get_amplitude, thick Bragg, one-element fcc/diamond structure (crystal.py:568-645)
+__device__ __forceinline__ cplx bragg_one_pol(double polFactor, cplx alpha, cplx chih, cplx chih_, double b) {
+  // delta = sqrt(alpha**2 + polFactor**2 * chih * chih_ / b)
+  cplx t = cmul_np(cplx{polFactor * polFactor, 0.0}, chih);
+  t = cmul_np(t, chih_);
+  t = cdiv(t, cplx{b, 0.0});
+  const cplx delta = csqrt_(cadd(csquare_np(alpha), t));
+  const cplx num = cmul_np(chih, cplx{polFactor, 0.0});
+  cplx ra = cdiv(num, cadd(alpha, delta));
+  cplx ad = csub(alpha, delta);
+  if (ad.re == 0.0 && ad.im == 0.0) ad = cplx{1e-100, 0.0};
+  const cplx rb = cdiv(num, ad);
+  if (isnan(ra.re) || isnan(ra.im)) ra = rb;
+  if (cabs(rb) < cabs(ra)) ra = rb;
+  return cdiv(ra, cplx{sqrt(fabs(b)), 0.0});
+}
+
+__device__ __forceinline__ void crystal_amplitude(const xrt_material_params& m, const Tables& t, double E,
+                                                  double bInDotN, double bOutDotN, double bInDotH, cplx& rs, cplx& rp,
+                                                  int* oor) {
+  const double CH = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8;
+  const double PI2 = 6.283185307179586476925286766559;
+  const double waveLength = CH / E;
+  const double k = PI2 / waveLength;
+  const double k0s = -bInDotN * k;
+  double kHs = -bOutDotN * k;
+  const double HH = PI2 / m.d;
+  const double k0H = fabs(bInDotH) * HH * k;
+  const double k02 = k * k;
+  const double H2 = HH * HH;
+  const bool kHs0 = (kHs == 0.0);
+  if (kHs0) kHs = 1.0;
+  double b = k0s / kHs;
+  if (kHs0) b = -1.0;
+  // structure factors (crystals_basic.py:22-31, :76-80)
+  const cplx anom = f1f2(t, m.tab_off[0], m.tab_len[0], E, oor);
+  cplx F0 = cmul_np(cmul_np(cplx{4.0, 0.0}, cplx{m.Z[0] + anom.re, anom.im}), cplx{m.factDW, 0.0});
+  cplx Fhkl = cplx{0.0, 0.0}, Fhkl_ = cplx{0.0, 0.0};
+  if (m.hkl_allowed) {
+    const double q = 0.5 / m.d;
+    // f0 = c + sum(a_i exp(-b_i q^2)) depends on the crystal only: evaluated by the host (element.py:203-207)
+    (void)q;
+    const double f0 = m.f0c[0];
+    Fhkl = cmul_np(cmul_np(cplx{4.0, 0.0}, cplx{f0 + anom.re, anom.im}), cplx{m.factDW, 0.0});
+    Fhkl_ = Fhkl;
+  }
+  if (m.f0scale != 1.0) {
+    F0 = cmul_np(F0, cplx{2.0, 0.0});
+    Fhkl = cmul_np(Fhkl, cplx{m.d2f_re, m.d2f_im});
+    Fhkl_ = cmul_np(Fhkl_, cplx{m.d2f_re, -m.d2f_im});
+  }
+  // get_F_chi (crystal.py:297-306)
+  const double c2f = m.chiToF * (waveLength * waveLength);
+  const cplx chi0 = cmul_np(cconj(F0), cplx{c2f, 0.0});
+  const cplx chih = cmul_np(cconj(Fhkl), cplx{c2f, 0.0});
+  const cplx chih_ = cmul_np(cconj(Fhkl_), cplx{c2f, 0.0});
+  // thetaB (crystal.py:1105-1120)
+  double sa = 1.0 * CH / (2.0 * m.d * E);
+  if (sa > 1.0) sa = 1.0 - 1e-16;
+  if (sa < -1.0) sa = -1.0 + 1e-16;
+  const double thetaB = asin(sa);
+  // alpha = (H2/2 - k0H) / k02 + chi0/2 * (1/b - 1)
+  const double a1 = (H2 / 2.0 - k0H) / k02;
+  const cplx half_chi0 = cdiv(chi0, cplx{2.0, 0.0});
+  const cplx a2 = cmul_np(half_chi0, cplx{1.0 / b - 1.0, 0.0});
+  const cplx alpha = cplx{a1 + a2.re, 0.0 + a2.im};
+  rs = bragg_one_pol(1.0, alpha, chih, chih_, b);
+  rp = bragg_one_pol(cos(2.0 * thetaB), alpha, chih, chih_, b);
+}
+
+// ---------------------------------------------------------------- main pass
+struct Decision {
+  int axis, neg, brent;
+  double tMin, tMax;
+};
+
+__device__ __forceinline__ Decision decide(const unsigned long long* red) {
+  Decision d;
+  double maxa = dec(red[RS_MAXA]), maxb = dec(red[RS_MAXB]), maxc = dec(red[RS_MAXC]);
+  if (maxa < 0.0 && maxb < 0.0 && maxc < 0.0) {  // no ray with state == 1: (0, 1, 0) (base.py:1261-1262)
+    maxa = 0.0;
+    maxb = 1.0;
+    maxc = 0.0;
+  }
+  const double maxMax = fmax(maxa, fmax(maxb, maxc));
+  d.axis = (maxMax == maxa) ? 0 : ((maxMax == maxb) ? 1 : 2);
+  const unsigned long long key = red[RS_FIRST];
+  const int positive = (int)((key >> d.axis) & 1ull);
+  d.neg = positive ? 0 : 1;
+  const int var = d.axis * 2 + d.neg;
+  d.tMin = dec(red[RS_VAR + var * 4 + 0]);
+  d.tMax = dec(red[RS_VAR + var * 4 + 1]);
+  const double mdz1 = dec(red[RS_VAR + var * 4 + 2]);
+  const double mdz2 = dec(red[RS_VAR + var * 4 + 3]);
+  d.brent = (mdz2 > mdz1 * 20.0) ? 1 : 0;  // base.py:871
+  return d;
+}
+
+__device__ __forceinline__ int sgn(double v) { return (v > 0.0) - (v < 0.0); }
+
+template <int SURF>
+__device__ __forceinline__ void solve_secant(const xrt_oe_params& p, const Ray& r, const Decision& d, double& t1,
+                                             double& t2, double& dz1, double& dz2, double& x2, double& y2,
+                                             double& z2) {
+  // _use_my_method (base.py:933-959)
+  int numit = 2;
+  while (fabs(dz2) > kZEps && numit < kMaxIteration) {
+    const double t = t1, dz = dz1;
+    t1 = t2;
+    dz1 = dz2;
+    t2 = t - (t1 - t) * dz / (dz1 - dz);
+    if (t2 < d.tMin) t2 = d.tMin;
+    if (t2 > d.tMax) t2 = d.tMax;
+    dz2 = find_dz<SURF>(p, t2, r, x2, y2, z2);
+    if (sgn(dz2) == sgn(dz1)) {
+      t1 = t;
+      dz1 = dz;
+    }
+    ++numit;
+  }
+}
+
+template <int SURF>
+__device__ __forceinline__ void solve_brent(const xrt_oe_params& p, const Ray& r, double& t1, double& t2,
+                                            double& dz1, double& dz2, double& x2, double& y2, double& z2) {
+  // _use_Brent_method (base.py:961-1048)
+  if (fabs(dz1) < fabs(dz2)) {
+    double tt = t1;
+    t1 = t2;
+    t2 = tt;
+    tt = dz1;
+    dz1 = dz2;
+    dz2 = tt;
+  }
+  double t3 = t1, dz3 = dz1, t4 = 0.0;
+  bool mflag = true;
+  int numit = 2;
+  while (fabs(dz2) > kZEps && numit < kMaxIteration) {
+    double xa = t1, xb = t2, xc = t3, xd = t4, fa = dz1, fb = dz2, fc = dz3, xs;
+    if (fa != fc && fb != fc) {
+      xs = xa * fb * fc / (fa - fb) / (fa - fc) + fa * xb * fc / (fb - fa) / (fb - fc) +
+           fa * fb * xc / (fc - fa) / (fc - fb);
+    } else {
+      xs = xb - fb * (xb - xa) / (fb - fa);
+    }
+    const double q = (3.0 * xa + xb) / 4.0;
+    const bool cond1 = ((xs < q) && (xs < xb)) || ((xs > q) && (xs > xb));
+    const bool cond2 = mflag && (fabs(xs - xb) >= (fabs(xb - xc) / 2.0));
+    const bool cond3 = (!mflag) && (fabs(xs - xb) >= (fabs(xc - xd) / 2.0));
+    const bool cond4 = mflag && (fabs(xb - xc) < kZEps);
+    const bool cond5 = (!mflag) && (fabs(xc - xd) < kZEps);
+    const bool conds = cond1 || cond2 || cond3 || cond4 || cond5;
+    if (conds) xs = (xa + xb) / 2.0;
+    mflag = conds;
+    const double fs = find_dz<SURF>(p, xs, r, x2, y2, z2);
+    xd = xc;
+    xc = xb;
+    fc = fb;
+    const bool neg = ((fa < 0.0) && (fs > 0.0)) || ((fa > 0.0) && (fs < 0.0));
+    if (neg) {
+      xb = xs;
+      fb = fs;
+    } else {
+      xa = xs;
+      fa = fs;
+    }
+    if (fabs(fa) < fabs(fb)) {
+      double tt = xa;
+      xa = xb;
+      xb = tt;
+      tt = fa;
+      fa = fb;
+      fb = tt;
+    }
+    t1 = xa;
+    t2 = xb;
+    t3 = xc;
+    t4 = xd;
+    dz1 = fa;
+    dz2 = fb;
+    dz3 = fc;
+    ++numit;
+  }
+}
+
+__device__ __forceinline__ cplx ld_c(const double* p, size_t i) {
+  const double2 v = reinterpret_cast<const double2*>(p)[i];
+  return cplx{v.x, v.y};
+}
+__device__ __forceinline__ void st_c(double* p, size_t i, cplx v) {
+  reinterpret_cast<double2*>(p)[i] = make_double2(v.re, v.im);
+}
+
+__device__ __forceinline__ void copy_ray(const xrt_beam& dst, const xrt_beam& src, size_t i, int state,
+                                         bool withState) {
+  dst.x[i] = src.x[i];
+  dst.y[i] = src.y[i];
+  dst.z[i] = src.z[i];
+  dst.a[i] = src.a[i];
+  dst.b[i] = src.b[i];
+  dst.c[i] = src.c[i];
+  dst.path[i] = src.path[i];
+  dst.E[i] = src.E[i];
+  dst.Jss[i] = src.Jss[i];
+  dst.Jpp[i] = src.Jpp[i];
+  st_c(dst.Jsp, i, ld_c(src.Jsp, i));
+  if (dst.Es && src.Es) {
+    st_c(dst.Es, i, ld_c(src.Es, i));
+    st_c(dst.Ep, i, ld_c(src.Ep, i));
+  }
+  if (withState) dst.state[i] = state;
+}
+
+template <int SURF, int MAT>
+__global__ void __launch_bounds__(256) reflect_main_kernel(size_t n, xrt_oe_params p, xrt_material_params m,
+                                                           Tables tab, xrt_beam in, xrt_beam fb, xrt_beam gb,
+                                                           xrt_beam lb, unsigned long long* red) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  double fmin3[3] = {inf, inf, inf}, fmax3[3] = {-inf, -inf, -inf};
+  unsigned long long ngoodN = 0;
+  int oor = 0;
+  const bool hasLb = lb.x != nullptr;
+
+  if (i < n) {
+    const int st0 = in.state[i];
+    if (!(p.good_mode ? (st0 == 1 || st0 == 2) : (st0 > 0))) {
+      // rays that are not alive pass through untouched (gb = lb = copy of the input, reflect.py:104-109)
+      copy_ray(gb, in, i, st0, true);
+      if (hasLb) {
+        copy_ray(lb, in, i, st0, true);
+        if (p.zero_dead_local) {  // dcm.py:305-310
+          lb.state[i] = 0;
+          lb.x[i] = 0.0;
+          lb.y[i] = 0.0;
+          lb.z[i] = 0.0;
+        }
+        if (lb.theta) lb.theta[i] = 0.0;
+        if (lb.s) {
+          lb.s[i] = lb.x[i];
+          lb.phi[i] = lb.y[i];
+          lb.r[i] = lb.z[i];
+        }
+      }
+    } else {
+      const Decision d = decide(red);
+      Ray r = load_ray(in, i);
+      const double E = in.E[i];
+      double path = in.path[i];
+      double Jss = in.Jss[i], Jpp = in.Jpp[i];
+      cplx Jsp = ld_c(in.Jsp, i);
+      const bool amp = in.Es != nullptr;
+      cplx Es = cplx{0, 0}, Ep = cplx{0, 0};
+      if (amp) {
+        Es = ld_c(in.Es, i);
+        Ep = ld_c(in.Ep, i);
+      }
+      to_local(p, r);
+      // bracketing + intersection (base.py:848-885)
+      double t1, t2, x1, y1, z1, x2, y2, z2;
+      bracket(p, d.axis, d.neg, r, t1, t2);
+      double dz1 = find_dz<SURF>(p, t1, r, x1, y1, z1);
+      double dz2 = find_dz<SURF>(p, t2, r, x2, y2, z2);
+      const bool ind1 = dz1 <= 0.0;  // lost: solution t1
+      const bool ind2 = dz2 >= 0.0;  // over: solution t2
+      if (ind1 || ind2) dz2 = 0.0;
+      if (ind1) {
+        t2 = t1;
+        x2 = x1;
+        y2 = y1;
+        z2 = z1;
+      }
+      if (!(ind1 || ind2)) {
+        if (d.brent)
+          solve_brent<SURF>(p, r, t1, t2, dz1, dz2, x2, y2, z2);
+        else
+          solve_secant<SURF>(p, r, d, t1, t2, dz1, dz2, x2, y2, z2);
+      }
+      const double tMax = t2;
+      // lb.x,y,z = intersection point (parametric: s, phi, r)
+      double lx = x2, ly = y2, lz = z2;
+      double cx = lx, cy = ly, cz = lz;  // Cartesian copy for rays_good
+      param_to_xyz<SURF>(p, cx, cy, cz);
+      // rays_good, shape 'rect' (base.py:1115-1139)
+      int st = 1;
+      if (p.has_optX && (((p.physX[0] <= cx) && (cx < p.optX[0])) || ((p.optX[1] <= cx) && (cx < p.physX[1])))) st = 2;
+      if (p.has_optY && (((p.physY[0] <= cy) && (cy < p.optY[0])) || ((p.optY[1] <= cy) && (cy < p.physY[1])))) st = 2;
+      const bool outside = (cx < p.physX[0]) || (cx > p.physX[1]) || (cy < p.physY[0]) || (cy > p.physY[1]);
+      bool over = false;
+      if (p.over_mask & 1) over = over || (cx < p.physX[0]);
+      if (p.over_mask & 2) over = over || (cx > p.physX[1]);
+      if (p.over_mask & 4) over = over || (cy < p.physY[0]);
+      if (p.over_mask & 8) over = over || (cy > p.physY[1]);
+      if (outside) st = p.lostNum;
+      if (over) st = 3;
+      if (ind1) st = p.lostNum;  // reflect.py:706-707
+
+      double la = r.a, lbb = r.b, lc = r.c;
+      double theta = 0.0;
+      double gJss = Jss, gJpp = Jpp;
+      cplx gJsp = Jsp, gEs = Es, gEp = Ep;
+      if (st == 1) {
+        ++ngoodN;
+        path += tMax;
+        double nrm[6];
+        local_normal<SURF>(p, lx, ly, nrm);
+        double bdn = la * nrm[0] + lbb * nrm[1] + lc * nrm[2];
+        if (bdn < -1.0) bdn = -1.0;
+        if (bdn > 1.0) bdn = 1.0;
+        theta = acos(bdn) - kPi / 2;
+        const double bds = p.asymmetric ? (la * nrm[3] + lbb * nrm[4] + lc * nrm[5]) : bdn;
+        double ao, bo, co;
+        if (MAT == 3) {
+          // crystal as a grating (reflect.py:568-612, :451-469); sgbdn is taken per ray here -- all good rays
+          // hit the same side of the crystal in the supported geometries (documented in DESIGN.md)
+          const double ndsn = nrm[0] * nrm[3] + nrm[1] * nrm[4] + nrm[2] * nrm[5];
+          const double sgbdn = (bdn < 0.0) ? 1.0 : -1.0;
+          const double wHd = (1.0 + 0.0) / (m.d * 1e-7);
+          const double g0 = (nrm[0] - ndsn * nrm[3]) * wHd * sgbdn;
+          const double g1 = (nrm[1] - ndsn * nrm[4]) * wHd * sgbdn;
+          const double g2 = (nrm[2] - ndsn * nrm[5]) * wHd * sgbdn;
+          const double CH = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8;
+          const double bdg = la * g0 + lbb * g1 + lc * g2;
+          const double G2 = g0 * g0 + g1 * g1 + g2 * g2;
+          const double ol = 1.0 * CH / E * 1e-7;
+          const double u = bds * bds - 2.0 * bdg * ol - G2 * (ol * ol);
+          const double dn = bds + (-1.0) * sqrt(fabs(u));
+          ao = la - nrm[3] * dn + g0 * ol;
+          bo = lbb - nrm[4] * dn + g1 * ol;
+          co = lc - nrm[5] * dn + g2 * ol;
+          const double nn = sqrt(ao * ao + bo * bo + co * co);
+          ao = ao / nn;
+          bo = bo / nn;
+          co = co / nn;
+        } else {
+          ao = la - nrm[0] * 2.0 * bdn;
+          bo = lbb - nrm[1] * 2.0 * bdn;
+          co = lc - nrm[2] * 2.0 * bdn;
+        }
+        la = ao;
+        lbb = bo;
+        lc = co;
+        // polarisation frame (reflect.py:948-953; beams.py:448-479)
+        const double rollAngle = p.roll + atan2(nrm[3], nrm[5]);
+        double cY, sY;
+        {
+          const double c = cos(-rollAngle), s = sin(-rollAngle);
+          const double c2 = c * c, s2 = s * s, cs = c * s;
+          const double J0 = Jss * c2 + Jpp * s2 + 2.0 * Jsp.re * cs;
+          const double J1 = Jss * s2 + Jpp * c2 - 2.0 * Jsp.re * cs;
+          const double J2r = (Jpp - Jss) * cs + Jsp.re * (c2 - s2);
+          Jss = J0;
+          Jpp = J1;
+          Jsp = cplx{J2r + (Jsp.im * 0.0), 0.0 + Jsp.im};
+        }
+        cY = cos(rollAngle);
+        sY = sin(rollAngle);
+        if (amp) {
+          // rotate_y(Es, Ep, cosY, -sinY): (c*x + s*z, -s*x + c*z) with s = -sinY
+          const double s = -sY;
+          const cplx e1 = cplx{cY * Es.re + s * Ep.re, cY * Es.im + s * Ep.im};
+          const cplx e2 = cplx{-s * Es.re + cY * Ep.re, -s * Es.im + cY * Ep.im};
+          Es = e1;
+          Ep = e2;
+        }
+        // amplitudes
+        cplx ras = cplx{1.0, 0.0}, rap = cplx{1.0, 0.0};
+        if (MAT == 1 || MAT == 2) mirror_amplitude(m, tab, E, bdn, ras, rap, &oor);
+        if (MAT == 3) {
+          const double bos = ao * nrm[3] + bo * nrm[4] + co * nrm[5];
+          crystal_amplitude(m, tab, E, bds, bos, bdn, ras, rap, &oor);
+        }
+        if (MAT != 0) {
+          if (isnan(ras.re) || isnan(ras.im)) ras = cplx{0.0, 0.0};
+          if (isnan(rap.re) || isnan(rap.im)) rap = cplx{0.0, 0.0};
+          // reflect.py:1038-1040
+          const cplx js = cmul_np(cmul_np(cplx{Jss, 0.0}, ras), cconj(ras));
+          const cplx jp = cmul_np(cmul_np(cplx{Jpp, 0.0}, rap), cconj(rap));
+          Jsp = cmul_np(cmul_np(Jsp, ras), cconj(rap));
+          Jss = js.re;
+          Jpp = jp.re;
+        } else {
+          // refl = 1., 1.: J * 1. * conj(1.) with Python floats leaves the values unchanged
+        }
+        if (amp) {
+          if (MAT != 0) {
+            Es = cmul_np(Es, ras);
+            Ep = cmul_np(Ep, rap);
+          }
+          // mPh = exp(1e7j * E/CHBAR * tMax) (reflect.py:1061-1064): im = ((1e7*E) * (1/CHBAR)) * tMax
+          const double CHBAR = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8 / 6.283185307179586476925286766559;
+          const double phi = ((1e7 * E) * (1.0 / CHBAR)) * tMax;
+          const cplx mPh = cexp_i(phi);
+          Es = cmul_np(Es, mPh);
+          Ep = cmul_np(Ep, mPh);
+        }
+        // rotate the coherency matrix back for the virgin-local/global beam (reflect.py:1106-1110)
+        {
+          const double c = cY, s = sY;
+          const double c2 = c * c, s2 = s * s, cs = c * s;
+          gJss = Jss * c2 + Jpp * s2 + 2.0 * Jsp.re * cs;
+          gJpp = Jss * s2 + Jpp * c2 - 2.0 * Jsp.re * cs;
+          const double J2r = (Jpp - Jss) * cs + Jsp.re * (c2 - s2);
+          gJsp = cplx{J2r + (Jsp.im * 0.0), 0.0 + Jsp.im};
+        }
+        if (amp) {
+          gEs = cplx{cY * Es.re + sY * Ep.re, cY * Es.im + sY * Ep.im};
+          gEp = cplx{-sY * Es.re + cY * Ep.re, -sY * Es.im + cY * Ep.im};
+        }
+      }
+      // local beam
+      if (hasLb) {
+        if (lb.s) {
+          lb.s[i] = lx;
+          lb.phi[i] = ly;
+          lb.r[i] = lz;
+        }
+        lb.x[i] = cx;
+        lb.y[i] = cy;
+        lb.z[i] = cz;
+        lb.a[i] = la;
+        lb.b[i] = lbb;
+        lb.c[i] = lc;
+        lb.path[i] = path;
+        lb.E[i] = E;
+        lb.Jss[i] = Jss;
+        lb.Jpp[i] = Jpp;
+        st_c(lb.Jsp, i, Jsp);
+        if (amp && lb.Es) {
+          st_c(lb.Es, i, Es);
+          st_c(lb.Ep, i, Ep);
+        }
+        lb.state[i] = st;
+        if (lb.theta) lb.theta[i] = theta;
+      }
+      // virgin-local beam -> global (reflect.py:1112-1136, :125-135)
+      Ray v{cx, cy, cz, la, lbb, lc};
+      to_virgin(p, v);
+      fmin3[0] = v.x;
+      fmin3[1] = v.y;
+      fmin3[2] = v.z;
+      fmax3[0] = v.x;
+      fmax3[1] = v.y;
+      fmax3[2] = v.z;
+      const bool goodAfter = p.created_by_diffract ? (st == 1) : (st == 1 || st == 2);
+      if (goodAfter) {
+        if (p.to_global) virgin_to_global(p, v);
+        gb.x[i] = v.x;
+        gb.y[i] = v.y;
+        gb.z[i] = v.z;
+        gb.a[i] = v.a;
+        gb.b[i] = v.b;
+        gb.c[i] = v.c;
+        gb.path[i] = path;
+        gb.E[i] = E;
+        gb.Jss[i] = gJss;
+        gb.Jpp[i] = gJpp;
+        st_c(gb.Jsp, i, gJsp);
+        if (amp && gb.Es) {
+          st_c(gb.Es, i, gEs);
+          st_c(gb.Ep, i, gEp);
+        }
+        gb.state[i] = st;
+      } else {
+        // not intersected rays remain unchanged except their state (reflect.py:131-134)
+        copy_ray(gb, fb, i, st, true);
+      }
+    }
+  }
+
+  // block-level footprint / counters
+  __shared__ unsigned long long sh[8][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long e[8];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    e[k] = enc(fmin3[k]);
+    e[3 + k] = enc(fmax3[k]);
+  }
+  e[6] = ngoodN;
+  e[7] = (unsigned long long)oor;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    unsigned long long x = e[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long y = __shfl_xor_sync(0xffffffffu, x, o);
+      x = (k >= 6) ? x + y : (k < 3 ? (y < x ? y : x) : (y > x ? y : x));
+    }
+    if (lane == 0) sh[warp][k] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    const int k = threadIdx.x;
+    unsigned long long x = sh[0][k];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      const unsigned long long y = sh[w][k];
+      x = (k >= 6) ? x + y : (k < 3 ? (y < x ? y : x) : (y > x ? y : x));
+    }
+    if (k < 3) {
+      if (x != enc(inf)) atomicMin(&red[RS_FOOT + k], x);
+    } else if (k < 6) {
+      if (x != enc(-inf)) atomicMax(&red[RS_FOOT + k], x);
+    } else if (k == 6) {
+      if (x) atomicAdd(&red[RS_NGOODN], x);
+    } else {
+      if (x) atomicAdd(&red[RS_NGOODN + 1], x);  // count of rays whose energy left the f1/f2 tables
+    }
+  }
+}
+
+// ---------------------------------------------------------------- launchers
+template <int SURF>
+static int launch_main_mat(int mat, unsigned grid, cudaStream_t st, size_t n, const xrt_oe_params& p,
+                           const xrt_material_params& m, const Tables& t, const xrt_beam& in, const xrt_beam& fb,
+                           const xrt_beam& gb, const xrt_beam& lb, unsigned long long* red) {
+  switch (mat) {
+    case 0: reflect_main_kernel<SURF, 0><<<grid, 256, 0, st>>>(n, p, m, t, in, fb, gb, lb, red); break;
+    case 1: reflect_main_kernel<SURF, 1><<<grid, 256, 0, st>>>(n, p, m, t, in, fb, gb, lb, red); break;
+    case 2: reflect_main_kernel<SURF, 2><<<grid, 256, 0, st>>>(n, p, m, t, in, fb, gb, lb, red); break;
+    case 3: reflect_main_kernel<SURF, 3><<<grid, 256, 0, st>>>(n, p, m, t, in, fb, gb, lb, red); break;
+    default: set_last_error("reflect: unknown material kind %d", mat); return 2;
+  }
+  XRTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int reflect_device(size_t n, const xrt_oe_params* oe, const xrt_material_params* mat, const double* tables,
+                   size_t table_len, const xrt_beam* in, const xrt_beam* fallback, const xrt_beam* gb,
+                   const xrt_beam* lb, unsigned long long* red, int phase, unsigned long long index_offset,
+                   cudaStream_t st) {
+  XRTB_REQUIRE(oe && in && gb && red, "reflect: NULL argument");
+  XRTB_REQUIRE(oe->surface >= 0 && oe->surface <= 2, "reflect: unknown surface kind %d", oe->surface);
+  XRTB_REQUIRE(oe->n_rot_in >= 0 && oe->n_rot_in <= XRT_MAX_ROT && oe->n_rot_out >= 0 && oe->n_rot_out <= XRT_MAX_ROT,
+               "reflect: too many elementary rotations");
+  xrt_material_params m;
+  memset(&m, 0, sizeof(m));
+  if (mat) m = *mat;
+  XRTB_REQUIRE(m.kind >= 0 && m.kind <= 3, "reflect: unknown material kind %d", m.kind);
+  XRTB_REQUIRE(m.kind == 0 || (tables != nullptr && table_len > 0), "reflect: material needs f1/f2 tables");
+  XRTB_REQUIRE(m.nelem >= 0 && m.nelem <= XRT_MAX_ELEM, "reflect: at most %d elements per material", XRT_MAX_ELEM);
+  Tables t{tables, tables ? tables + table_len : nullptr, tables ? tables + 2 * table_len : nullptr};
+  xrt_beam lbv;
+  memset(&lbv, 0, sizeof(lbv));
+  if (lb) lbv = *lb;
+  const xrt_beam fbv = fallback ? *fallback : *in;
+  if (phase & 1) {
+    reduction_init_kernel<<<1, XRT_REDUCTION_SLOTS, 0, st>>>(red);
+    if (n > 0) {
+      unsigned grid = (unsigned)num_sms() * 8;
+      const size_t need = (n + 255) / 256;
+      if (need < grid) grid = (unsigned)need;
+      if (oe->surface == 0) reflect_prepass_kernel<0><<<grid, 256, 0, st>>>(n, *oe, *in, red, index_offset);
+      if (oe->surface == 1) reflect_prepass_kernel<1><<<grid, 256, 0, st>>>(n, *oe, *in, red, index_offset);
+      if (oe->surface == 2) reflect_prepass_kernel<2><<<grid, 256, 0, st>>>(n, *oe, *in, red, index_offset);
+    }
+    XRTB_CUDA_CHECK(cudaGetLastError());
+  }
+  if ((phase & 2) && n > 0) {
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    int rc = 0;
+    if (oe->surface == 0) rc = launch_main_mat<0>(m.kind, grid, st, n, *oe, m, t, *in, fbv, *gb, lbv, red);
+    if (oe->surface == 1) rc = launch_main_mat<1>(m.kind, grid, st, n, *oe, m, t, *in, fbv, *gb, lbv, red);
+    if (oe->surface == 2) rc = launch_main_mat<2>(m.kind, grid, st, n, *oe, m, t, *in, fbv, *gb, lbv, red);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+double reduction_decode(unsigned long long slot) { return dec(slot); }
+
+}  // namespace xrtb

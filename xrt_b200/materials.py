@@ -1,0 +1,253 @@
+# -*- coding: utf-8 -*-
+"""Materials of the hot path: mirror coatings (Fresnel amplitude) and perfect fcc/diamond crystals (thick
+Bragg amplitude).  Host side = parameters + tables; the per-ray arithmetic runs in the CUDA kernels
+(xrt_b200/csrc/reflect.cu) inside OE.reflect, or stand-alone through `get_amplitude`.
+
+Mirrors the constructors of xrt's Material (xrt/backends/raycing/materials/material.py:26) and
+CrystalFcc / CrystalDiamond / CrystalSi (materials/crystals_basic.py:8-115): same keywords, same defaults
+(table 'Chantler total'), same derived quantities (mass, d, V, chiToF).  Scattering-factor tables:
+xrt_b200/data/elements.npz (see tools/extract_tables.py).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from .physconsts import PI, R0, CH
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data', 'elements.npz')
+_cache = None
+
+XRT_MAX_ELEM = 4
+
+
+class xrt_material_params(ctypes.Structure):
+    """struct xrt_material_params of include/xrt_b200.h"""
+    _fields_ = [('kind', ctypes.c_int), ('nelem', ctypes.c_int),
+                ('Z', ctypes.c_double * XRT_MAX_ELEM), ('quantity', ctypes.c_double * XRT_MAX_ELEM),
+                ('tab_off', ctypes.c_int * XRT_MAX_ELEM), ('tab_len', ctypes.c_int * XRT_MAX_ELEM),
+                ('rho', ctypes.c_double), ('mass', ctypes.c_double), ('t', ctypes.c_double),
+                ('d', ctypes.c_double), ('chiToF', ctypes.c_double), ('factDW', ctypes.c_double),
+                ('f0c', ctypes.c_double * 11), ('d2f_re', ctypes.c_double), ('d2f_im', ctypes.c_double),
+                ('f0scale', ctypes.c_double), ('hkl_allowed', ctypes.c_int)]
+
+
+def _tables():
+    global _cache
+    if _cache is None:
+        with np.load(_DATA) as f:
+            _cache = {k: np.array(f[k]) for k in f.files}
+    return _cache
+
+
+class Element(object):
+    """f0, f1, f2 of one chemical element (materials/element.py:92-263)."""
+
+    def __init__(self, elem=None, table='Chantler'):
+        t = _tables()
+        if elem + '_Z' not in t:
+            raise ValueError('element {0!r} is not in xrt_b200/data/elements.npz; add it to '
+                             'tools/extract_tables.py'.format(elem))
+        if not table.startswith('Chantler'):
+            raise ValueError("only the 'Chantler' / 'Chantler total' tables are packaged")
+        self.name = elem
+        self.table = table
+        self.Z = int(t[elem + '_Z'])
+        self.mass = float(t[elem + '_mass'])
+        self.f0coeffs = [float(v) for v in t[elem + '_f0']]
+        f2key = '_f2tot' if 'total' in table else '_f2'  # element.py:212
+        # float32 in the data files; np.interp promotes to float64 (element.py:261-262)
+        self.E = t[elem + '_E'].astype(np.float64)
+        self.f1 = t[elem + '_f1'].astype(np.float64)
+        self.f2 = t[elem + f2key].astype(np.float64)
+
+    def get_f0(self, qOver4pi=0):
+        return self.f0coeffs[5] + sum(a * np.exp(-b * qOver4pi**2)
+                                      for a, b in zip(self.f0coeffs[:5], self.f0coeffs[6:]))
+
+
+class Material(object):
+    """Mirror coating / bulk material; kinds 'mirror' and 'thin mirror' are on the hot path."""
+
+    def __init__(self, elements=None, quantities=None, kind='auto', rho=0, t=None, table='Chantler total',
+                 name=''):
+        if isinstance(elements, str):
+            elements = elements,
+        self.table = table
+        self.elements = [Element(e, table) for e in elements]
+        if quantities is None:
+            self.quantities = [1. for e in self.elements]
+        elif not isinstance(quantities, (list, tuple)):
+            self.quantities = [quantities]
+        else:
+            self.quantities = list(quantities)
+        if len(self.elements) > XRT_MAX_ELEM:
+            raise ValueError('at most {0} elements per material'.format(XRT_MAX_ELEM))
+        self.kind = kind
+        self.rho = rho
+        self.t = t
+        self.name = name or ''.join(e.name for e in self.elements)
+        self.mass = 0.
+        for elem, xi in zip(self.elements, self.quantities):  # material.py:262-275
+            self.mass += xi * elem.mass
+        self._dev_tables = {}
+
+    # ------------------------------------------------------------------ device plumbing
+    def _kind_code(self):
+        kind = 'mirror' if self.kind == 'auto' else self.kind  # material.py:450-451
+        if kind == 'mirror':
+            return 1
+        if kind == 'thin mirror':
+            if self.t is None:
+                raise ValueError('Give the thin mirror a thickness!')
+            return 2
+        raise NotImplementedError("material kind {0!r} is outside the hot path (SURVEY.md section 8f)".format(kind))
+
+    def host_tables(self):
+        """Concatenated [E | f1 | f2] tables of all elements and their slices."""
+        offs, lens, E, f1, f2 = [], [], [], [], []
+        pos = 0
+        for e in self.elements:
+            offs.append(pos)
+            lens.append(len(e.E))
+            pos += len(e.E)
+            E.append(e.E)
+            f1.append(e.f1)
+            f2.append(e.f2)
+        tab = np.concatenate([np.concatenate(E), np.concatenate(f1), np.concatenate(f2)])
+        return tab, pos, offs, lens
+
+    def device_tables(self, device):
+        import torch
+        key = str(device)
+        if key not in self._dev_tables:
+            tab, n, offs, lens = self.host_tables()
+            self._dev_tables[key] = (torch.from_numpy(tab).to(device), n, offs, lens)
+        return self._dev_tables[key]
+
+    def c_struct(self, offs, lens):
+        m = xrt_material_params()
+        m.kind = self._kind_code()
+        m.nelem = len(self.elements)
+        for i, (e, xi) in enumerate(zip(self.elements, self.quantities)):
+            m.Z[i] = float(e.Z)
+            m.quantity[i] = float(xi)
+            m.tab_off[i] = offs[i]
+            m.tab_len[i] = lens[i]
+        m.rho = float(self.rho)
+        m.mass = float(self.mass)
+        m.t = float(self.t) if self.t is not None else 0.
+        return m
+
+    # ------------------------------------------------------------------ stand-alone amplitude (a12)
+    def get_amplitude(self, E, beamInDotNormal, fromVacuum=True):
+        """(rs, rp) on host arrays through the CUDA kernel (material.py:415-493, kinds mirror / thin mirror).
+        The absorption outputs mu and n.real*k of the reference tuple are not on the hot path."""
+        if not fromVacuum:
+            raise NotImplementedError('fromVacuum=False (refraction) is outside the hot path')
+        from . import kernels
+        return kernels.material_amplitude_host(self, E, beamInDotNormal)
+
+
+class CrystalFcc(Material):
+    """Perfect one-element fcc crystal, thick Bragg case (materials/crystals_basic.py:8-31 with the
+    Crystal constructor crystal.py:39-181)."""
+    structure = 'fcc'
+
+    def __init__(self, hkl=(1, 1, 1), d=0, V=None, elements='Si', quantities=None, rho=0, t=None, factDW=1.,
+                 geom='Bragg reflected', table='Chantler total', name='', **kwargs):
+        super().__init__(elements, quantities, kind='crystal', rho=rho, t=t, table=table, name=name)
+        if len(self.elements) != 1:
+            raise NotImplementedError('multi-atom structure factors are outside the hot path')
+        if t is not None or not geom.startswith('Bragg') or geom.endswith('transmitted'):
+            raise NotImplementedError('only the thick Bragg reflected case is on the hot path '
+                                      '(crystal.py:570-597); thin/Laue/transmitted: SURVEY.md section 8f')
+        self.hkl = tuple(int(i) for i in hkl)
+        self.sqrthkl2 = (sum(i**2 for i in self.hkl))**0.5
+        self.d = d
+        self.V = V if V is not None else (d * self.sqrthkl2)**3  # crystal.py:172-176
+        self.chiToF = -R0 / PI / self.V  # minus! (crystal.py:179)
+        self.geom = geom
+        self.factDW = factDW
+
+    def _kind_code(self):
+        return 3
+
+    def get_Bragg_angle(self, E, order=1):
+        a = np.array(order * CH / (2*self.d*E))
+        a[a > 1] = 1 - 1e-16
+        a[a < -1] = -1 + 1e-16
+        return np.arcsin(a)
+
+    def _diamond_to_fcc(self):
+        return 1. + 0j
+
+    def c_struct(self, offs, lens):
+        m = super().c_struct(offs, lens)
+        m.d = float(self.d)
+        m.chiToF = float(self.chiToF)
+        m.factDW = float(self.factDW)
+        residue = sum(i % 2 for i in self.hkl)
+        m.hkl_allowed = 1 if residue in (0, 3) else 0
+        f0 = self.elements[0].get_f0(0.5 / self.d)  # crystal.py:630 get_F_chi(E, 0.5/crystd)
+        m.f0c[0] = float(f0)
+        d2f = self._diamond_to_fcc()
+        m.d2f_re, m.d2f_im = float(d2f.real), float(d2f.imag)
+        m.f0scale = 2. if self.structure == 'diamond' else 1.
+        return m
+
+    def get_amplitude(self, E, beamInDotNormal, beamOutDotNormal=None, beamInDotHNormal=None):
+        from . import kernels
+        return kernels.crystal_amplitude_host(self, E, beamInDotNormal, beamOutDotNormal, beamInDotHNormal)
+
+
+class CrystalDiamond(CrystalFcc):
+    """materials/crystals_basic.py:34-80"""
+    structure = 'diamond'
+
+    def __init__(self, *args, **kwargs):
+        a = kwargs.pop('a', None)
+        if a is not None:
+            hkl = kwargs.get('hkl', args[0] if args else (1, 1, 1))
+            kwargs['d'] = a / (sum(i**2 for i in hkl))**0.5
+        super().__init__(*args, **kwargs)
+        self.a = a if a is not None else self.d * self.sqrthkl2
+
+    def _diamond_to_fcc(self):
+        return 1 + np.exp(0.5j * PI * sum(self.hkl))  # crystals_basic.py:77
+
+
+class CrystalSi(CrystalDiamond):
+    """Silicon with the thermal expansion of Swenson (materials/crystals_basic.py:83-142)."""
+
+    def __init__(self, *args, **kwargs):
+        self.a0 = 5.430710
+        self.dl_l0 = self.dl_l(273.15 + 19.9)
+        self.tK = kwargs.pop('tK', 297.15)
+        hkl = kwargs.get('hkl', args[0] if args else (1, 1, 1))
+        kwargs['hkl'] = hkl
+        kwargs.pop('a', None)
+        kwargs['d'] = self.get_a() / (sum(i**2 for i in hkl))**0.5
+        kwargs['elements'] = 'Si'
+        kwargs.setdefault('name', 'Si')
+        super().__init__(*args[1:] if args else (), **kwargs)
+
+    def dl_l(self, t=None):
+        if t is None:
+            t = self.tK
+        if t >= 0.0 and t < 30.0:
+            return -2.154537e-004
+        elif t >= 30.0 and t < 130.0:
+            return -2.303956e-014 * t**4 + 7.834799e-011 * t**3 - \
+                1.724143e-008 * t**2 + 8.396104e-007 * t - 2.276144e-004
+        elif t >= 130.0 and t < 293.0:
+            return -1.223001e-011 * t**3 + 1.532991e-008 * t**2 - \
+                3.263667e-006 * t - 5.217231e-005
+        elif t >= 293.0 and t <= 1000.0:
+            return -1.161022e-012 * t**3 + 3.311476e-009 * t**2 + \
+                1.124129e-006 * t - 5.844535e-004
+        else:
+            return 1.0e+100
+
+    def get_a(self):
+        return self.a0 * (self.dl_l()-self.dl_l0+1)

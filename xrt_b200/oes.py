@@ -1,0 +1,398 @@
+# -*- coding: utf-8 -*-
+"""Optical elements of the hot path with xrt's public signatures:
+
+    OE(bl, name, center, pitch, roll, yaw, positionRoll, ..., material, alpha, limPhysX, limOptX, limPhysY,
+       limOptY, ...)                                   xrt/backends/raycing/oes/base.py:92-104
+    OE.reflect(beam, needLocal=True, ...) -> (beamGlobal, beamLocal)         oes/reflect.py:18-19
+    ToroidMirror(..., R, r)                                                   oes/__init__.py:320-411
+    EllipticalMirrorParam(..., p, q, isCylindrical)                           oes/parametric.py:9-249
+    DCM(..., bragg, cryst1roll, cryst2roll, cryst2pitch, cryst2finePitch, cryst2perpTransl,
+        cryst2longTransl, limPhysX2, limPhysY2, limOptX2, limOptY2, material2)          oes/dcm.py:12-354
+    DCM.double_reflect(beam, needLocal=True) -> (beamGlobal, beamLocal1, beamLocal2)    oes/dcm.py:248-250
+
+The host side only marshals geometry into `xrt_oe_params` (include/xrt_b200.h); all per-ray work is one fused
+CUDA kernel per surface (xrt_b200/csrc/reflect.cu) on device-resident Beams.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .beams import Beam
+from .materials import xrt_material_params
+
+XRT_MAX_ROT = 8
+maxHalfSizeOfOE = 1000.  # raycing/__init__.py:93-94
+maxDepthOfOE = 100.
+REDUCTION_SLOTS = 64
+RS_FOOT, RS_NGOOD, RS_NGOODN, RS_OOR = 28, 34, 35, 36
+
+
+class xrt_oe_params(ctypes.Structure):
+    """struct xrt_oe_params of include/xrt_b200.h"""
+    _fields_ = [('center', ctypes.c_double * 3), ('sinAz', ctypes.c_double), ('cosAz', ctypes.c_double),
+                ('from_global', ctypes.c_int), ('to_global', ctypes.c_int),
+                ('n_rot_in', ctypes.c_int), ('rot_in_axis', ctypes.c_int * XRT_MAX_ROT),
+                ('rot_in_cos', ctypes.c_double * XRT_MAX_ROT), ('rot_in_sin', ctypes.c_double * XRT_MAX_ROT),
+                ('n_rot_out', ctypes.c_int), ('rot_out_axis', ctypes.c_int * XRT_MAX_ROT),
+                ('rot_out_cos', ctypes.c_double * XRT_MAX_ROT), ('rot_out_sin', ctypes.c_double * XRT_MAX_ROT),
+                ('shift', ctypes.c_double * 3), ('roll', ctypes.c_double),
+                ('surface', ctypes.c_int), ('sp', ctypes.c_double * 8),
+                ('asymmetric', ctypes.c_int), ('nB', ctypes.c_double * 3),
+                ('physX', ctypes.c_double * 2), ('physY', ctypes.c_double * 2),
+                ('optX', ctypes.c_double * 2), ('optY', ctypes.c_double * 2),
+                ('has_optX', ctypes.c_int), ('has_optY', ctypes.c_int),
+                ('over_mask', ctypes.c_int), ('lostNum', ctypes.c_int),
+                ('brk_lim', (ctypes.c_double * 2) * 3),
+                ('created_by_diffract', ctypes.c_int), ('zero_dead_local', ctypes.c_int),
+                ('good_mode', ctypes.c_int)]
+
+
+_AXIS = {'x': 0, 'y': 1, 'z': 2}
+
+
+def _rotation_list(rotationSequence, pitch, roll, yaw):
+    """Elementary rotations of raycing.rotate_beam (_rotate.py:23-57) in application order, zero angles
+    skipped, cos/sin taken with numpy exactly as the reference does."""
+    angles = {'z': yaw, 'y': roll, 'x': pitch}
+    if rotationSequence[0] == '-':
+        seq = rotationSequence[6] + rotationSequence[4] + rotationSequence[2]
+    else:
+        seq = rotationSequence[1] + rotationSequence[3] + rotationSequence[5]
+    out = []
+    for s in seq:
+        angle = angles[s]
+        if angle != 0:
+            out.append((_AXIS[s], float(np.cos(angle)), float(np.sin(angle))))
+    return out
+
+
+def _fill_rot(params, which, rots):
+    if len(rots) > XRT_MAX_ROT:
+        raise ValueError('too many elementary rotations')
+    setattr(params, 'n_rot_' + which, len(rots))
+    for i, (ax, c, s) in enumerate(rots):
+        getattr(params, 'rot_{0}_axis'.format(which))[i] = ax
+        getattr(params, 'rot_{0}_cos'.format(which))[i] = c
+        getattr(params, 'rot_{0}_sin'.format(which))[i] = s
+
+
+class OE(object):
+    """Flat optical element (mirror or crystal)."""
+    surfaceKind = 0
+    isParametric = False
+
+    def __init__(self, bl=None, name='', center=[0, 0, 0], pitch=0, roll=0, yaw=0, positionRoll=0,
+                 rotationSequence='RzRyRx', extraPitch=0, extraRoll=0, extraYaw=0,
+                 extraRotationSequence='RzRyRx', alarmLevel=None, surface=None, material=None, alpha=None,
+                 limPhysX=None, limOptX=None, limPhysY=None, limOptY=None, isParametric=False, shape='rect',
+                 targetOpenCL='CUDA', precisionOpenCL='float64', **kwargs):
+        self.bl = bl
+        self.name = name
+        if bl is not None:
+            if self not in bl.oes:  # ordinal numbering -> lostNum (base.py:268-272)
+                bl.oes.append(self)
+            self.ordinalNum = len(bl.oes)
+            self.lostNum = -self.ordinalNum
+        else:
+            self.ordinalNum = 1
+            self.lostNum = -1
+        self.center = list(center)
+        self.pitch = pitch
+        self.roll = roll
+        self.yaw = yaw
+        self.positionRoll = positionRoll
+        self.rotationSequence = rotationSequence
+        self.extraPitch, self.extraRoll, self.extraYaw = extraPitch, extraRoll, extraYaw
+        self.extraRotationSequence = extraRotationSequence
+        self.alarmLevel = alarmLevel
+        self.material = material
+        self.alpha = alpha
+        self.shape = shape
+        if not shape.startswith('re'):
+            raise NotImplementedError("only shape='rect' is on the hot path")
+        self.overEdge = kwargs.pop('overEdge', 'yMax')
+        default = [-maxHalfSizeOfOE, maxHalfSizeOfOE]
+        self.limPhysX = list(limPhysX) if limPhysX is not None else list(default)  # base.py:465-476
+        self.limPhysY = list(limPhysY) if limPhysY is not None else list(default)
+        self.limOptX = limOptX
+        self.limOptY = limOptY
+        self.dx = 0
+        self.footprint = []
+        self.targetOpenCL = targetOpenCL
+        self.precisionOpenCL = precisionOpenCL
+        if targetOpenCL is None:
+            raise _lib.XrtB200Error('xrt_b200 elements always run on the GPU (targetOpenCL=None has no numpy '
+                                    'path to fall back to)')
+        self._red = {}
+
+    # ------------------------------------------------------------------ geometry -> C struct
+    def _surface_params(self):
+        return []
+
+    def _limits(self, second=False):
+        sfx = '2' if second else ''
+        return (getattr(self, 'limPhysX' + sfx), getattr(self, 'limPhysY' + sfx),
+                getattr(self, 'limOptX' + sfx), getattr(self, 'limOptY' + sfx))
+
+    def _local_nB(self, second=False):
+        # OE.local_n with alpha (base.py:736-739): rotate_x(b=0, c=1, cosalpha, -sinalpha); DCM.local_n2 flips y
+        cosalpha, sinalpha = np.cos(self.alpha), np.sin(self.alpha)
+        b, c = 0., 1.
+        bAlpha, cAlpha = cosalpha*b - (-sinalpha)*c, (-sinalpha)*b + cosalpha*c
+        if second:
+            bAlpha *= -1
+        return 0., bAlpha, cAlpha
+
+    def _make_params(self, pitch, roll, yaw, dx=0, dy=0, dz=0, is2ndXtal=False, from_global=True,
+                     to_global=True, createdByDiffract=False):
+        p = xrt_oe_params()
+        for i in range(3):
+            p.center[i] = float(self.center[i])
+        p.sinAz = float(self.bl.sinAzimuth) if self.bl is not None else 0.
+        p.cosAz = float(self.bl.cosAzimuth) if self.bl is not None else 1.
+        p.from_global = int(from_global)
+        p.to_global = int(to_global)
+        extraSign = -1. if is2ndXtal else 1.
+        hasExtra = bool(self.extraPitch or self.extraRoll or self.extraYaw)
+        rin = []
+        if is2ndXtal:  # reflect.py:619-621
+            rin += _rotation_list('RzRyRx', 0, -np.pi, 0)
+        rin += _rotation_list(self.rotationSequence, -pitch, -roll, -yaw)
+        if hasExtra:
+            rin += _rotation_list(self.extraRotationSequence, -extraSign*self.extraPitch, -self.extraRoll,
+                                  -extraSign*self.extraYaw)
+        rout = []
+        if hasExtra:
+            rout += _rotation_list('-'+self.extraRotationSequence, extraSign*self.extraPitch, self.extraRoll,
+                                   extraSign*self.extraYaw)
+        rout += _rotation_list('-'+self.rotationSequence, pitch, roll, yaw)
+        if is2ndXtal:
+            rout += _rotation_list('RzRyRx', 0, np.pi, 0)
+        _fill_rot(p, 'in', rin)
+        _fill_rot(p, 'out', rout)
+        p.shift[0], p.shift[1], p.shift[2] = float(dx or 0), float(dy or 0), float(dz or 0)
+        p.roll = float(roll)
+        p.surface = self.surfaceKind
+        for i, v in enumerate(self._surface_params()):
+            p.sp[i] = float(v)
+        p.asymmetric = 1 if self.alpha else 0
+        if self.alpha:
+            nB = self._local_nB(is2ndXtal)
+            for i in range(3):
+                p.nB[i] = nB[i]
+        physX, physY, optX, optY = self._limits(is2ndXtal)
+        p.physX[0], p.physX[1] = float(physX[0]), float(physX[1])
+        p.physY[0], p.physY[1] = float(physY[0]), float(physY[1])
+        p.has_optX = int(optX is not None)
+        p.has_optY = int(optY is not None)
+        if optX is not None:
+            p.optX[0], p.optX[1] = float(optX[0]), float(optX[1])
+        if optY is not None:
+            p.optY[0], p.optY[1] = float(optY[0]), float(optY[1])
+        ovE = str(self.overEdge).lower()
+        p.over_mask = (1 if 'xmin' in ovE else 0) | (2 if 'xmax' in ovE else 0) | \
+            (4 if 'ymin' in ovE else 0) | (8 if 'ymax' in ovE else 0)
+        p.lostNum = int(self.lostNum)
+        # _set_t limits (base.py:1233-1239)
+        for ax, lim, dflt in ((0, physX, maxHalfSizeOfOE), (1, physY, maxHalfSizeOfOE), (2, None, maxDepthOfOE)):
+            if lim is None:
+                lo, hi = -dflt, dflt
+            else:
+                lo = lim[0] if lim[0] > -np.inf else -dflt
+                hi = lim[1] if lim[1] < np.inf else dflt
+            p.brk_lim[ax][0], p.brk_lim[ax][1] = float(lo), float(hi)
+        p.created_by_diffract = int(createdByDiffract)
+        return p
+
+    # ------------------------------------------------------------------ kernel launch
+    def _launch(self, params, material, beam, gb, lb, fallback=None, index_offset=0, allreduce=None):
+        lib = _lib.load()
+        dev = beam.device
+        key = str(dev)
+        if key not in self._red:
+            self._red[key] = torch.zeros(REDUCTION_SLOTS, dtype=torch.int64, device=dev)
+        red = self._red[key]
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if material is not None:
+            tab, tlen, offs, lens = material.device_tables(dev)
+            mat = material.c_struct(offs, lens)
+            mat_ref, tab_ptr = ctypes.byref(mat), tab.data_ptr()
+        else:
+            mat_ref, tab_ptr, tlen = None, None, 0
+        cin, cgb = beam.c_struct(), gb.c_struct()
+        clb = lb.c_struct() if lb is not None else None
+        cfb = fallback.c_struct() if fallback is not None else None
+        args = (len(beam), ctypes.byref(params), mat_ref, tab_ptr, tlen, ctypes.byref(cin),
+                ctypes.byref(cfb) if cfb is not None else None, ctypes.byref(cgb),
+                ctypes.byref(clb) if clb is not None else None, red.data_ptr())
+        if allreduce is None:
+            _lib.check(lib.xrt_reflect_f64(*args, 3, index_offset, stream), 'xrt_reflect_f64')
+        else:
+            _lib.check(lib.xrt_reflect_f64(*args, 1, index_offset, stream), 'xrt_reflect_f64 (pre-pass)')
+            allreduce(red)  # min/max/sum of the beam-wide scalars over ray shards (xrt_b200/parallel.py)
+            _lib.check(lib.xrt_reflect_f64(*args, 2, index_offset, stream), 'xrt_reflect_f64 (main pass)')
+        return red
+
+    def _check_tables(self, red):
+        """Element.get_f1f2 raises ValueError when an energy is outside the table (element.py:254-260)."""
+        if int(red[RS_OOR].item()) > 0:
+            raise ValueError('E is out of the f1/f2 data table range')
+
+    def _footprint_from(self, red):
+        lib = _lib.load()
+        vals = [lib.xrt_reduction_decode(ctypes.c_uint64(int(v) & 0xFFFFFFFFFFFFFFFF)) for v in
+                red[RS_FOOT:RS_FOOT + 6].tolist()]
+        return np.array(vals).reshape(2, 3)
+
+    def _new_local(self, beam):
+        lb = beam.like()
+        lb.theta = torch.empty(len(beam), dtype=torch.float64, device=beam.device)
+        if self.isParametric:
+            for f in ('s', 'phi', 'r'):
+                setattr(lb, f, torch.empty(len(beam), dtype=torch.float64, device=beam.device))
+        return lb
+
+    def reflect(self, beam=None, needLocal=True, noIntersectionSearch=False, returnLocalAbsorbed=None,
+                checkTables=True, index_offset=0, allreduce=None, withFootprint=False):
+        """Returns (beamGlobal, beamLocal) like OE.reflect (oes/reflect.py:17-163)."""
+        if noIntersectionSearch:
+            raise NotImplementedError('noIntersectionSearch=True (wave mode) is not on this path yet')
+        pitch = self.pitch + (self.bragg if hasattr(self, 'bragg') else 0)
+        params = self._make_params(pitch, self.roll + self.positionRoll, self.yaw, self.dx,
+                                   createdByDiffract=bool(getattr(beam, 'createdByDiffract', False)))
+        gb = beam.like()
+        lb = self._new_local(beam) if needLocal else None
+        red = self._launch(params, self.material, beam, gb, lb, index_offset=index_offset, allreduce=allreduce)
+        if checkTables and self.material is not None:
+            self._check_tables(red)
+        if withFootprint:
+            self.footprint = [self._footprint_from(red)]
+        gb.parentId = lb_parent = getattr(self, 'uuid', self.name)
+        if lb is not None:
+            lb.parentId = lb_parent
+        return gb, (lb if needLocal else gb)
+
+
+class ToroidMirror(OE):
+    """z = y^2/2R + r (1 - sqrt(1 - x^2/r^2))  (oes/__init__.py:320-411)"""
+    surfaceKind = 1
+
+    def __init__(self, *args, **kwargs):
+        R = kwargs.pop('R', 5.0e6)
+        r = kwargs.pop('r', 50.)
+        OE.__init__(self, *args, **kwargs)
+        self.R = 1e100 if R in (0, None) else R
+        self.r = 1e100 if r in (0, None) else r
+        if isinstance(self.R, (list, tuple)) or isinstance(self.r, (list, tuple)):
+            raise NotImplementedError('give R and r as numbers (Coddington (p, q) tuples are resolved by xrt)')
+
+    def _surface_params(self):
+        return [self.R, self.r]
+
+
+class EllipticalMirrorParam(OE):
+    """Elliptical cylinder / ellipsoid in the parametric (s, phi, r) representation
+    (oes/parametric.py:9-249).  The ellipse parameters follow _reset_pq (:104-150) for the default p-arm
+    along the global y axis."""
+    surfaceKind = 2
+    isParametric = True
+
+    def __init__(self, *args, **kwargs):
+        self.p = kwargs.pop('p', 1000)
+        self.q = kwargs.pop('q', 1000)
+        self.isCylindrical = kwargs.pop('isCylindrical', False)
+        if kwargs.pop('isClosed', False):
+            raise NotImplementedError('isClosed=True is outside the hot path')
+        for k in ('f1', 'f2', 'pAxis'):
+            if kwargs.pop(k, None) is not None:
+                raise NotImplementedError('{0} is resolved by xrt; give p and q'.format(k))
+        OE.__init__(self, *args, **kwargs)
+        self._reset_pq()
+
+    def _reset_pq(self):
+        # the mirror normal in global coordinates (parametric.py:84-96, :113-117)
+        n = np.array([0., 0., 1.])
+        for ax, c, s in _rotation_list('-'+self.rotationSequence, self.pitch, self.roll+self.positionRoll,
+                                       self.yaw):
+            i, j = {0: (1, 2), 1: (0, 2), 2: (0, 1)}[ax]
+            if ax == 1:
+                n[i], n[j] = c*n[i] + s*n[j], -s*n[i] + c*n[j]
+            else:
+                n[i], n[j] = c*n[i] - s*n[j], s*n[i] + c*n[j]
+        a0 = self.bl.sinAzimuth if self.bl is not None else 0.
+        b0 = self.bl.cosAzimuth if self.bl is not None else 1.
+        if a0 != 0:
+            n[0], n[1] = b0*n[0] - (-a0)*n[1], (-a0)*n[0] + b0*n[1]
+        axis = [0, 1, 0]
+        norm = sum([a**2 for a in axis])**0.5
+        sintheta = sum([a*nn for a, nn in zip(axis, n)]) / norm
+        absPitch = abs(np.arcsin(sintheta))
+        gamma = np.arctan2((self.p - self.q) * np.sin(absPitch), (self.p + self.q) * np.cos(absPitch))
+        self.cosGamma = np.cos(gamma)
+        self.sinGamma = np.sin(gamma)
+        self.y0 = (self.q - self.p)/2. * np.cos(absPitch)
+        self.z0 = (self.q + self.p)/2. * np.sin(absPitch)
+        self.ellipseA = (self.q + self.p)/2.
+        self.ellipseB = np.sqrt(self.q * self.p) * np.sin(absPitch)
+
+    def _surface_params(self):
+        return [self.ellipseA, self.ellipseB, self.y0, self.z0, self.cosGamma, self.sinGamma,
+                1. if self.isCylindrical else 0.]
+
+
+class DCM(OE):
+    """Double-crystal monochromator: two flat crystals (oes/dcm.py:12-354)."""
+
+    def __init__(self, *args, **kwargs):
+        self.bragg = kwargs.pop('bragg', 0)
+        self.cryst1roll = kwargs.pop('cryst1roll', 0)
+        self.cryst2roll = kwargs.pop('cryst2roll', 0)
+        self.cryst2pitch = kwargs.pop('cryst2pitch', 0)
+        self.cryst2finePitch = kwargs.pop('cryst2finePitch', 0)
+        self.cryst2perpTransl = kwargs.pop('cryst2perpTransl', 0)
+        self.cryst2longTransl = kwargs.pop('cryst2longTransl', 0)
+        self.limPhysX2 = kwargs.pop('limPhysX2', [-maxHalfSizeOfOE, maxHalfSizeOfOE])
+        self.limPhysY2 = kwargs.pop('limPhysY2', [-maxHalfSizeOfOE, maxHalfSizeOfOE])
+        self.limOptX2 = kwargs.pop('limOptX2', None)
+        self.limOptY2 = kwargs.pop('limOptY2', None)
+        self.material2 = kwargs.pop('material2', None)
+        fixedOffset = kwargs.pop('fixedOffset', None)
+        OE.__init__(self, *args, **kwargs)
+        if self.material2 is None:
+            self.material2 = self.material
+        if isinstance(self.bragg, str):
+            raise NotImplementedError("bragg='auto'/energy strings are resolved by xrt's auto_align; give radians")
+        self.fixedOffset = fixedOffset
+        if fixedOffset not in [0, None]:
+            self.cryst2perpTransl = fixedOffset/2./np.cos(self.bragg)  # dcm.py:240-245
+
+    def reflect(self, *a, **k):
+        raise AttributeError('use DCM.double_reflect')
+
+    def double_reflect(self, beam=None, needLocal=True, fromVacuum1=True, fromVacuum2=True,
+                       returnLocalAbsorbed=None, checkTables=True, index_offset=0, allreduce=None):
+        """Returns (beamGlobal, beamLocal1, beamLocal2) like DCM.double_reflect (oes/dcm.py:247-354)."""
+        p1 = self._make_params(self.pitch + self.bragg, self.roll + self.positionRoll + self.cryst1roll,
+                               self.yaw, self.dx, to_global=False)
+        gb = beam.like()
+        lo1 = self._new_local(beam) if needLocal else None
+        red = self._launch(p1, self.material, beam, gb, lo1, index_offset=index_offset, allreduce=allreduce)
+        if checkTables and self.material is not None:
+            self._check_tables(red)
+        p2 = self._make_params(-self.pitch - self.bragg + self.cryst2pitch + self.cryst2finePitch,
+                               self.roll + self.cryst2roll + self.positionRoll, -self.yaw,
+                               -self.dx, self.cryst2longTransl, -self.cryst2perpTransl, is2ndXtal=True,
+                               from_global=False, to_global=True)
+        p2.good_mode = 1
+        p2.zero_dead_local = 1
+        gb2 = beam.like()
+        lo2 = self._new_local(beam) if needLocal else None
+        red = self._launch(p2, self.material2, gb, gb2, lo2, fallback=beam, index_offset=index_offset,
+                           allreduce=allreduce)
+        if checkTables and self.material2 is not None:
+            self._check_tables(red)
+        if not needLocal:
+            lo1 = lo2 = gb2
+        return gb2, lo1, lo2
