@@ -32,7 +32,7 @@ int xrt_b200_device_count(void);
 int xrt_b200_sm_count(void);
 const char* xrt_b200_last_error(void);
 int xrt_b200_sync(void* stream);
-/* sizeof() of the ABI structs below (0: xrt_beam, 1: xrt_oe_params, 2: xrt_material_params), for binding checks */
+/* sizeof() of the ABI structs below (0: xrt_beam, 1: xrt_oe_params, 2: xrt_material_params, 3: xrt_plane_params), for binding checks */
 size_t xrt_b200_sizeof(int which);
 /* Measured fp64 ceilings used as roofline denominators (bench.py). mode 0: dependent-free DFMA stream,
  * mode 1: DMMA m8n8k4, mode 2: both interleaved. Writes TFLOP/s (2 flop per FMA). */
@@ -156,6 +156,42 @@ int xrt_reflect_f64(size_t n, const xrt_oe_params* oe, const xrt_material_params
                     const xrt_beam* lb, uint64_t* reductions, int phase, uint64_t index_offset, void* stream);
 /* decode one reduction slot to double (host helper; slots are order-preserving integer encodings) */
 double xrt_reduction_decode(uint64_t slot);
+
+/* ------------------------------------------------------------------ a15: plane elements
+ * Screen.expose (screens.py:225-302) and RectangularAperture.propagate (apertures.py:333-413). */
+typedef struct xrt_plane_params {
+  double center[3];
+  double ex[3], ey[3], ez[3]; /* local axes in the global system (raycing.xyz_from_xz, beamline.py:290-318) */
+  double sinAz, cosAz;        /* used instead of the axes when basis_mode == 0 (beamline.py:241-250) */
+  int basis_mode;             /* 1: explicit axes (screens; apertures, whose xyz is always a list), 0: azimuth */
+  int lostNum;
+  int only_positive_path;     /* Screen.expose(onlyPositivePath=...) */
+  int has_compressX, has_compressZ;
+  double compressX, compressZ;
+  int n_blades;               /* aperture blades: kind 0 left (x < d lost), 1 right, 2 bottom, 3 top */
+  int blade_kind[4];
+  double blade_pos[4];
+  int is_beam_stop;
+} xrt_plane_params;
+
+/* out = Screen.expose(in): every ray is transported to the screen plane, local coordinates. Footprint min/max
+ * of the good rays lands in reduction slots 28..33, their count in slot 34. */
+int xrt_expose_f64(size_t n, const xrt_plane_params* p, const xrt_beam* in, const xrt_beam* out,
+                   uint64_t* reductions, void* stream);
+/* out = RectangularAperture.propagate(in): alive rays are transported to the aperture plane; rays hitting a
+ * blade get state = lostNum in `out` AND in `in` (the reference marks the incoming beam, apertures.py:364). */
+int xrt_propagate_rect_f64(size_t n, const xrt_plane_params* p, const xrt_beam* in, const xrt_beam* out,
+                           uint64_t* reductions, void* stream);
+
+/* ------------------------------------------------------------------ a12 / a13: stand-alone amplitudes
+ * Replaces kernel `get_amplitude` (cl/materials.cl:715-748; called from tests/raycing/test_materials.py:624) and
+ * the numpy methods Material.get_amplitude (material.py:415-493) / Crystal.get_amplitude (crystal.py:492-645).
+ * HOST pointers. mirror kinds: bIn = beamInDotNormal, bOut = bH = NULL. crystal: bIn = beamInDotNormal
+ * (surface), bOut = beamOutDotNormal or NULL (= -bIn), bH = beamInDotHNormal or NULL (= bIn).
+ * Returns 3 when an energy lies outside the f1/f2 table (the reference raises ValueError, element.py:254). */
+int xrt_get_amplitude_f64_host(size_t n, const xrt_material_params* mat, const double* tables, size_t table_len,
+                               const double* E, const double* bIn, const double* bOut, const double* bH, double* rs,
+                               double* rp);
 
 #ifdef __cplusplus
 }

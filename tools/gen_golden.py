@@ -231,8 +231,119 @@ def gen_reflect():
     d.update(_oe_params(oe))
     save('reflect_toroid_bare', R=float(oe.R), r=float(oe.r), **d)
 
+# ------------------------------------------------------------------------------------------------ planes
+def gen_planes():
+    bl = raycing.BeamLine(azimuth=-0.2)
+    beam = _source_beam(bl, 2500, 51, dx=0.4, dz=0.3, dxprime=3e-4, dzprime=2e-4)
+    beam.state[::17] = 2
+    beam.state[5::29] = 3
+    beam.b[7] = 0.  # a ray parallel to the screen: path = inf -> lost
+    beam.c[7] = np.sqrt(1 - beam.a[7]**2)
+    d = 7000.
+    scr = rsc.Screen(bl, 'scr', center=(d*np.sin(-0.2) + 0.3, d*np.cos(-0.2), 1.5), compressX=0.7)
+    blo = scr.expose(beam)
+    out = dict(center=np.array(scr.center, dtype=float), ex=np.array(scr.x, dtype=float),
+               ey=np.array(scr.y, dtype=float), ez=np.array(scr.z, dtype=float), lostNum=np.int64(scr.lostNum),
+               compressX=0.7, footprint=np.array(scr.footprint[-1]), sinAzimuth=bl.sinAzimuth,
+               cosAzimuth=bl.cosAzimuth)
+    out.update(beam_dict(beam, 'in_'))
+    out.update(beam_dict(blo, 'out_'))
+    save('expose_screen', **out)
+    # tilted screen given by explicit x and z, only positive paths
+    scr2 = rsc.Screen(bl, 'scr2', center=(0., -300., 0.), x=(1., 0., 0.2), z=(-0.2, 0., 1.))
+    blo = scr2.expose(beam, onlyPositivePath=True)
+    out = dict(center=np.array(scr2.center, dtype=float), ex=np.array(scr2.x, dtype=float),
+               ey=np.array(scr2.y, dtype=float), ez=np.array(scr2.z, dtype=float), lostNum=np.int64(scr2.lostNum))
+    out.update(beam_dict(beam, 'in_'))
+    out.update(beam_dict(blo, 'out_'))
+    save('expose_screen_tilted', **out)
 
-SECTIONS = {'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+    beam = _source_beam(bl, 2500, 52, dx=0.4, dz=0.3, dxprime=3e-4, dzprime=2e-4)
+    slit = ra.RectangularAperture(bl, 'slit', center=(4000*np.sin(-0.2), 4000*np.cos(-0.2), 0),
+                                  kind=('left', 'right', 'bottom', 'top'), opening=[-0.9, 1.1, -0.6, 0.5])
+    beam_in = rs.Beam(copyFrom=beam)
+    lo = slit.propagate(beam)
+    out = dict(center=np.array(slit.center, dtype=float), ex=np.array(slit.xyz[0], dtype=float),
+               ey=np.array(slit.xyz[1], dtype=float), ez=np.array(slit.xyz[2], dtype=float),
+               lostNum=np.int64(slit.lostNum), kinds=np.array(list(slit.blades.keys())),
+               opening=np.array(list(slit.blades.values()), dtype=float),
+               spotLimits=np.array(slit.spotLimits, dtype=float), in_state_after=beam.state)
+    out.update(beam_dict(beam_in, 'in_'))
+    out.update(beam_dict(lo, 'out_'))
+    save('propagate_slit', **out)
+
+# ------------------------------------------------------------------------------------------------ DCM + amplitudes
+def _dcm_params(dcm):
+    d = _oe_params(dcm)
+    for k in ('bragg', 'cryst1roll', 'cryst2roll', 'cryst2pitch', 'cryst2finePitch', 'cryst2perpTransl',
+              'cryst2longTransl'):
+        d[k] = float(getattr(dcm, k))
+    d['surfPhysX2'] = np.array(dcm.surfPhysX2, dtype=float)
+    d['surfPhysY2'] = np.array(dcm.surfPhysY2, dtype=float)
+    d['alpha'] = float(dcm.alpha) if dcm.alpha else 0.
+    return d
+
+
+def gen_dcm():
+    bl = raycing.BeamLine()
+    si = rm.CrystalSi(hkl=(1, 1, 1))
+    E0 = 9000.
+    for name, alpha in (('dcm_si111', None), ('dcm_si111_asym', np.radians(5.))):
+        beam = _source_beam(bl, 3000, 61, dx=0.2, dz=0.02, dxprime=5e-5, dzprime=2e-5, energies=(8995, 9005))
+        theta = si.get_Bragg_angle(E0) - si.get_dtheta(E0, alpha)
+        dcm = roe.DCM(bl, 'dcm', center=(0, 2e4, 0), bragg=float(theta), material=si, material2=si, alpha=alpha,
+                      cryst2perpTransl=10., cryst2finePitch=2e-6, cryst1roll=1e-4,
+                      limPhysX=[-50, 50], limPhysY=[-100, 100], limPhysX2=[-50, 50], limPhysY2=[-100, 200])
+        gb, lo1, lo2 = dcm.double_reflect(beam)
+        d = _dcm_params(dcm)
+        d.update(beam_dict(beam, 'in_'))
+        d.update(beam_dict(gb, 'gb_'))
+        d.update(beam_dict(lo1, 'lo1_'))
+        d.update(beam_dict(lo2, 'lo2_'))
+        save(name, d=si.d, tK=si.tK, E0=E0, **d)
+        print(name, 'theta', theta, {int(s): int((gb.state == s).sum()) for s in np.unique(gb.state)})
+
+
+def gen_amplitudes():
+    # a12: Au / Pt / SiO2-like mirrors on an (E, angle) grid incl. the critical-angle region
+    rng = np.random.RandomState(71)
+    n = 4000
+    E = rng.uniform(2000, 30000, n)
+    th = rng.uniform(5e-4, 2e-2, n)
+    bdn = -np.sin(th)
+    out = dict(E=E, beamInDotNormal=bdn)
+    for name, mat in (('Au', rm.Material('Au', rho=19.3)), ('Pt', rm.Material('Pt', rho=21.45)),
+                      ('SiO2', rm.Material(('Si', 'O'), quantities=(1, 2), rho=2.2)),
+                      ('AuThin', rm.Material('Au', rho=19.3, kind='thin mirror', t=2e-5))):
+        res = mat.get_amplitude(E, bdn.copy())
+        out[name + '_rs'], out[name + '_rp'] = res[0], res[1]
+    save('amplitude_mirrors', **out)
+    # a13: Si(111), Si(333) thick-Bragg rocking curves, symmetric and asymmetric (test_materials.py:239-352 recipe)
+    out = {}
+    for hkl in ((1, 1, 1), (3, 3, 3)):
+        si = rm.CrystalSi(hkl=hkl)
+        for alpha in (0., np.radians(5.), np.radians(-5.)):
+            E = np.ones(600) * 10000.
+            E[300:] = rng.uniform(9000, 11000, 300)
+            thetaB = si.get_Bragg_angle(E)
+            dth = np.linspace(-40, 80, 600) * 1e-6
+            theta = thetaB + dth
+            g0 = np.sin(theta + alpha)
+            gh = -np.sin(theta - alpha)
+            hns0 = np.sin(theta)
+            cs, cp = si.get_amplitude(E, g0.copy(), gh.copy(), hns0.copy())
+            key = 'Si%d%d%d_a%+d' % (hkl + (int(round(np.degrees(alpha))),))
+            out[key + '_E'] = E
+            out[key + '_g0'] = g0
+            out[key + '_gh'] = gh
+            out[key + '_hns0'] = hns0
+            out[key + '_rs'] = cs
+            out[key + '_rp'] = cp
+            out[key + '_d'] = si.d
+    save('amplitude_crystals', **out)
+
+
+SECTIONS = {'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)

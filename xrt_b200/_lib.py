@@ -36,6 +36,9 @@ PROTOTYPES = {
     'xrt_reflect_f64': (c_int, [c_sz, c_dp, c_dp, c_dp, c_sz, c_dp, c_dp, c_dp, c_dp, c_dp, c_int,
                                 ctypes.c_uint64, c_dp]),
     'xrt_reduction_decode': (c_dbl, [ctypes.c_uint64]),
+    'xrt_expose_f64': (c_int, [c_sz, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    'xrt_propagate_rect_f64': (c_int, [c_sz, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    'xrt_get_amplitude_f64_host': (c_int, [c_sz, c_dp, c_dp, c_sz] + [c_dp] * 6),
     'xrt_undulator_imap_f64': (c_int, [c_sz, c_int] + [c_dbl] * 7 + [c_int] + [c_dp] * 13 + [c_int, c_dp]),
 }
 

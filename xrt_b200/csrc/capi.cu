@@ -163,7 +163,7 @@ int xrt_b200_init(int device) {
 int xrt_b200_sm_count(void) { return num_sms(); }
 
 size_t xrt_b200_sizeof(int which) {
-  return which == 0 ? sizeof(xrt_beam) : which == 1 ? sizeof(xrt_oe_params) : which == 2 ? sizeof(xrt_material_params) : 0;
+  return which == 0 ? sizeof(xrt_beam) : which == 1 ? sizeof(xrt_oe_params) : which == 2 ? sizeof(xrt_material_params) : which == 3 ? sizeof(xrt_plane_params) : 0;
 }
 
 const char* xrt_b200_last_error(void) { return g_err; }
@@ -283,5 +283,46 @@ int xrt_reflect_f64(size_t n, const xrt_oe_params* oe, const xrt_material_params
 }
 
 double xrt_reduction_decode(uint64_t slot) { return reduction_decode(slot); }
+
+// ------------------------------------------------------------------ plane elements
+int xrt_expose_f64(size_t n, const xrt_plane_params* p, const xrt_beam* in, const xrt_beam* out,
+                   uint64_t* reductions, void* stream) {
+  return expose_device(n, p, in, out, reinterpret_cast<unsigned long long*>(reductions), (cudaStream_t)stream);
+}
+
+int xrt_propagate_rect_f64(size_t n, const xrt_plane_params* p, const xrt_beam* in, const xrt_beam* out,
+                           uint64_t* reductions, void* stream) {
+  return propagate_rect_device(n, p, in, out, reinterpret_cast<unsigned long long*>(reductions),
+                               (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ stand-alone amplitudes
+int xrt_get_amplitude_f64_host(size_t n, const xrt_material_params* mat, const double* tables, size_t table_len,
+                               const double* E, const double* bIn, const double* bOut, const double* bH, double* rs,
+                               double* rp) {
+  if (n == 0) return 0;
+  cudaStream_t st = 0;
+  DevBuf dt, dE, dIn, dOut, dH, dout, dcnt;
+  if (dt.upload(tables, 3 * table_len * 8, st) || dE.upload(E, n * 8, st) || dIn.upload(bIn, n * 8, st)) return 1;
+  if (bOut && dOut.upload(bOut, n * 8, st)) return 1;
+  if (bH && dH.upload(bH, n * 8, st)) return 1;
+  if (dout.alloc(2 * n * 16) || dcnt.alloc(8)) return 1;
+  XRTB_CUDA_CHECK(cudaMemsetAsync(dcnt.p, 0, 8, st));
+  double* o = dout.as<double>();
+  int rc = amplitude_device(n, mat, dt.as<double>(), table_len, dE.as<double>(), dIn.as<double>(),
+                            bOut ? dOut.as<double>() : nullptr, bH ? dH.as<double>() : nullptr, o, o + 2 * n,
+                            dcnt.as<unsigned long long>(), st);
+  if (rc) return rc;
+  unsigned long long cnt = 0;
+  XRTB_CUDA_CHECK(cudaMemcpyAsync(rs, o, n * 16, cudaMemcpyDeviceToHost, st));
+  XRTB_CUDA_CHECK(cudaMemcpyAsync(rp, o + 2 * n, n * 16, cudaMemcpyDeviceToHost, st));
+  XRTB_CUDA_CHECK(cudaMemcpyAsync(&cnt, dcnt.p, 8, cudaMemcpyDeviceToHost, st));
+  XRTB_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (cnt) {
+    set_last_error("get_amplitude: %llu energies are out of the f1/f2 data table range", cnt);
+    return 3;
+  }
+  return 0;
+}
 
 }  // extern "C"

@@ -33,5 +33,14 @@ int reflect_device(size_t n, const xrt_oe_params* oe, const xrt_material_params*
                    const xrt_beam* lb, unsigned long long* red, int phase, unsigned long long index_offset,
                    cudaStream_t st);
 double reduction_decode(unsigned long long slot);
+int amplitude_device(size_t n, const xrt_material_params* mat, const double* tables, size_t table_len,
+                     const double* E, const double* bIn, const double* bOut, const double* bH, double* rs, double* rp,
+                     unsigned long long* oor_count, cudaStream_t st);
+
+// rays.cu (compiled with -fmad=false)
+int expose_device(size_t n, const xrt_plane_params* p, const xrt_beam* in, const xrt_beam* out,
+                  unsigned long long* red, cudaStream_t st);
+int propagate_rect_device(size_t n, const xrt_plane_params* p, const xrt_beam* in, const xrt_beam* out,
+                          unsigned long long* red, cudaStream_t st);
 
 }  // namespace xrtb

@@ -1,0 +1,259 @@
+// Plane elements of the ray path for sm_100a: Screen.expose and RectangularAperture.propagate.
+//
+// Replaces Screen.expose (xrt/backends/raycing/screens.py:225-302) and RectangularAperture.propagate
+// (xrt/backends/raycing/apertures.py:333-413) with their frame changes (beamline.py:230-264).
+// Oracle: oracle/planes.py.  HBM-bound elementwise kernels: 132 B read + 132 B written per ray (with
+// amplitudes), one thread per ray, unit-stride SoA access.
+//
+// Compiled with -fmad=false (numpy rounding order, see reflect.cu); fma() appears only where numpy itself
+// fuses (its SIMD complex multiply).
+#include "../../include/xrt_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace xrtb {
+
+enum { RS_FOOT = 28, RS_NGOOD = 34 };
+
+__host__ __device__ inline unsigned long long enc2(double d) {
+  unsigned long long u;
+  memcpy(&u, &d, 8);
+  return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+
+__device__ __forceinline__ cplx cmul_np2(cplx a, cplx b) {  // numpy SIMD complex multiply (see reflect.cu)
+  const double ii = a.im * b.im, ir = a.im * b.re;
+  return cplx{fma(a.re, b.re, -ii), fma(a.re, b.im, ir)};
+}
+__device__ __forceinline__ cplx ldc(const double* p, size_t i) {
+  const double2 v = reinterpret_cast<const double2*>(p)[i];
+  return cplx{v.x, v.y};
+}
+__device__ __forceinline__ void stc(double* p, size_t i, cplx v) {
+  reinterpret_cast<double2*>(p)[i] = make_double2(v.re, v.im);
+}
+
+__global__ void plane_reduction_init_kernel(unsigned long long* red) {
+  const int i = threadIdx.x;
+  if (i >= XRT_REDUCTION_SLOTS) return;
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  unsigned long long v = 0ull;
+  if (i >= RS_FOOT && i < RS_FOOT + 3) v = enc2(inf);
+  if (i >= RS_FOOT + 3 && i < RS_FOOT + 6) v = enc2(-inf);
+  red[i] = v;
+}
+
+__device__ __forceinline__ void block_minmax(double* mn, double* mx, unsigned long long cnt,
+                                             unsigned long long* red) {
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  __shared__ unsigned long long sh[8][7];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long e[7];
+  for (int k = 0; k < 3; ++k) {
+    e[k] = enc2(mn[k]);
+    e[3 + k] = enc2(mx[k]);
+  }
+  e[6] = cnt;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    unsigned long long x = e[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long y = __shfl_xor_sync(0xffffffffu, x, o);
+      x = (k == 6) ? x + y : (k < 3 ? (y < x ? y : x) : (y > x ? y : x));
+    }
+    if (lane == 0) sh[warp][k] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < 7) {
+    const int k = threadIdx.x;
+    unsigned long long x = sh[0][k];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      const unsigned long long y = sh[w][k];
+      x = (k == 6) ? x + y : (k < 3 ? (y < x ? y : x) : (y > x ? y : x));
+    }
+    if (k < 3) {
+      if (x != enc2(inf)) atomicMin(&red[RS_FOOT + k], x);
+    } else if (k < 6) {
+      if (x != enc2(-inf)) atomicMax(&red[RS_FOOT + k], x);
+    } else if (x) {
+      atomicAdd(&red[RS_NGOOD], x);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- Screen.expose
+__global__ void __launch_bounds__(256) expose_kernel(size_t n, xrt_plane_params p, xrt_beam in, xrt_beam out,
+                                                     unsigned long long* red) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  double mn[3] = {inf, inf, inf}, mx[3] = {-inf, -inf, -inf};
+  unsigned long long cnt = 0;
+  if (i < n) {
+    // global_to_virgin_local with an explicit basis (beamline.py:251-264): every ray, whatever its state
+    const double x0 = in.x[i] - p.center[0], y0 = in.y[i] - p.center[1], z0 = in.z[i] - p.center[2];
+    const double a0 = in.a[i], b0 = in.b[i], c0 = in.c[i];
+    double x = p.ex[0] * x0 + p.ex[1] * y0 + p.ex[2] * z0;
+    const double y = p.ey[0] * x0 + p.ey[1] * y0 + p.ey[2] * z0;
+    double z = p.ez[0] * x0 + p.ez[1] * y0 + p.ez[2] * z0;
+    const double a = p.ex[0] * a0 + p.ex[1] * b0 + p.ex[2] * c0;
+    const double b = p.ey[0] * a0 + p.ey[1] * b0 + p.ey[2] * c0;
+    const double c = p.ez[0] * a0 + p.ez[1] * b0 + p.ez[2] * c0;
+    double path = -y / b;
+    int st = in.state[i];
+    bool bad = isnan(path) || isinf(path);
+    if (p.only_positive_path) bad = bad || (path < 0.0);
+    if (bad) {
+      path = 0.0;
+      st = p.lostNum;
+    }
+    const double E = in.E[i];
+    x = x + a * path;
+    z = z + c * path;
+    if (st == 1 || st == 2) {  // footprint (screens.py:262-268), before compression
+      mn[0] = mx[0] = x;
+      mn[1] = mx[1] = 0.0;
+      mn[2] = mx[2] = z;
+      cnt = 1;
+    }
+    if (p.has_compressX) x *= p.compressX;
+    if (p.has_compressZ) z *= p.compressZ;
+    out.x[i] = x;
+    out.y[i] = 0.0;
+    out.z[i] = z;
+    out.a[i] = a;
+    out.b[i] = b;
+    out.c[i] = c;
+    out.path[i] = in.path[i] + path;
+    out.E[i] = E;
+    out.Jss[i] = in.Jss[i];
+    out.Jpp[i] = in.Jpp[i];
+    stc(out.Jsp, i, ldc(in.Jsp, i));
+    out.state[i] = st;
+    if (in.Es && out.Es) {
+      // propPhase = exp(1e7j * (E/CHBAR) * path) (screens.py:257-260)
+      const double CHBAR = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8 / 6.283185307179586476925286766559;
+      const double phi = (1e7 * (E / CHBAR)) * path;
+      double s, cs;
+      sincos_big(phi, s, cs);
+      const cplx ph = cplx{cs, s};
+      stc(out.Es, i, cmul_np2(ldc(in.Es, i), ph));
+      stc(out.Ep, i, cmul_np2(ldc(in.Ep, i), ph));
+    }
+  }
+  block_minmax(mn, mx, cnt, red);
+}
+
+// ---------------------------------------------------------------- RectangularAperture.propagate
+__global__ void __launch_bounds__(256) propagate_rect_kernel(size_t n, xrt_plane_params p, xrt_beam in, xrt_beam out,
+                                                             unsigned long long* red) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  double mn[3] = {inf, inf, inf}, mx[3] = {-inf, -inf, -inf};
+  unsigned long long cnt = 0;
+  if (i < n) {
+    int st = in.state[i];
+    double x = in.x[i], y = in.y[i], z = in.z[i], a = in.a[i], b = in.b[i], c = in.c[i];
+    double path = in.path[i];
+    const double E = in.E[i];
+    cplx Es = cplx{0, 0}, Ep = cplx{0, 0};
+    const bool amp = in.Es && out.Es;
+    if (amp) {
+      Es = ldc(in.Es, i);
+      Ep = ldc(in.Ep, i);
+    }
+    if (st > 0) {
+      // global_to_virgin_local (beamline.py:239-264): the aperture's `xyz` is always an explicit basis
+      // (apertures.py:343 with :277-283); the azimuth form is kept for completeness
+      x -= p.center[0];
+      y -= p.center[1];
+      z -= p.center[2];
+      if (p.basis_mode) {
+        const double x0 = x, y0 = y, z0 = z, a0 = a, b0 = b, c0 = c;
+        x = p.ex[0] * x0 + p.ex[1] * y0 + p.ex[2] * z0;
+        y = p.ey[0] * x0 + p.ey[1] * y0 + p.ey[2] * z0;
+        z = p.ez[0] * x0 + p.ez[1] * y0 + p.ez[2] * z0;
+        a = p.ex[0] * a0 + p.ex[1] * b0 + p.ex[2] * c0;
+        b = p.ey[0] * a0 + p.ey[1] * b0 + p.ey[2] * c0;
+        c = p.ez[0] * a0 + p.ez[1] * b0 + p.ez[2] * c0;
+      } else if (p.sinAz != 0.0) {
+        const double x1 = p.cosAz * x - p.sinAz * y, y1 = p.sinAz * x + p.cosAz * y;
+        x = x1;
+        y = y1;
+        const double a1 = p.cosAz * a - p.sinAz * b, b1 = p.sinAz * a + p.cosAz * b;
+        a = a1;
+        b = b1;
+      }
+      const double dpath = -y / b;
+      x += a * dpath;
+      z += c * dpath;
+      path += dpath;
+      bool badI = false;
+      for (int k = 0; k < p.n_blades; ++k) {  // apertures.py:352-361
+        const double d = p.blade_pos[k];
+        const int kind = p.blade_kind[k];
+        if (kind == 0) badI = badI || (x < d);
+        if (kind == 1) badI = badI || (x > d);
+        if (kind == 2) badI = badI || (z < d);
+        if (kind == 3) badI = badI || (z > d);
+      }
+      if (p.is_beam_stop) badI = !badI;
+      if (badI) st = p.lostNum;
+      y = 0.0;
+      if (amp) {
+        const double CHBAR = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8 / 6.283185307179586476925286766559;
+        const double phi = (1e7 * (E / CHBAR)) * dpath;
+        double s, cs;
+        sincos_big(phi, s, cs);
+        const cplx ph = cplx{cs, s};
+        Es = cmul_np2(Es, ph);
+        Ep = cmul_np2(Ep, ph);
+      }
+      if (st > 0) {  // spotLimits (apertures.py:377-383)
+        mn[0] = mx[0] = x;
+        mn[1] = mx[1] = 0.0;
+        mn[2] = mx[2] = z;
+        cnt = 1;
+      }
+      in.state[i] = st;  // beam.state[badIndices] = self.lostNum: the INPUT beam is marked too (apertures.py:364)
+    }
+    out.x[i] = x;
+    out.y[i] = y;
+    out.z[i] = z;
+    out.a[i] = a;
+    out.b[i] = b;
+    out.c[i] = c;
+    out.path[i] = path;
+    out.E[i] = E;
+    out.Jss[i] = in.Jss[i];
+    out.Jpp[i] = in.Jpp[i];
+    stc(out.Jsp, i, ldc(in.Jsp, i));
+    out.state[i] = st;
+    if (amp) {
+      stc(out.Es, i, Es);
+      stc(out.Ep, i, Ep);
+    }
+  }
+  block_minmax(mn, mx, cnt, red);
+}
+
+int expose_device(size_t n, const xrt_plane_params* p, const xrt_beam* in, const xrt_beam* out,
+                  unsigned long long* red, cudaStream_t st) {
+  XRTB_REQUIRE(p && in && out && red, "expose: NULL argument");
+  plane_reduction_init_kernel<<<1, XRT_REDUCTION_SLOTS, 0, st>>>(red);
+  if (n > 0) expose_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, *p, *in, *out, red);
+  XRTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int propagate_rect_device(size_t n, const xrt_plane_params* p, const xrt_beam* in, const xrt_beam* out,
+                          unsigned long long* red, cudaStream_t st) {
+  XRTB_REQUIRE(p && in && out && red, "propagate: NULL argument");
+  XRTB_REQUIRE(p->n_blades >= 0 && p->n_blades <= 4, "propagate: a rectangular aperture has at most 4 blades");
+  plane_reduction_init_kernel<<<1, XRT_REDUCTION_SLOTS, 0, st>>>(red);
+  if (n > 0) propagate_rect_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, *p, *in, *out, red);
+  XRTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace xrtb

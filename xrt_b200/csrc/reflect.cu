@@ -356,12 +356,15 @@ __global__ void __launch_bounds__(256) reflect_prepass_kernel(size_t n, xrt_oe_p
 }
 
 // ---------------------------------------------------------------- numpy-faithful complex arithmetic
-__device__ __forceinline__ cplx cmul_np(cplx a, cplx b) {  // CDOUBLE_multiply
-  return cplx{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
+// numpy >= 1.25 evaluates complex multiply/square with its SIMD kernel on every x86 CPU that has FMA3
+// (numpy/_core/src/umath/loops_arithm_fp.dispatch.c.src, simd_cmul: ab = a_im * b_rev rounded, then
+// fmaddsub(a_re, b, ab)), i.e. re = fma(ar, br, -RN(ai*bi)), im = fma(ar, bi, RN(ai*br)).  The grazing-incidence
+// Fresnel chain amplifies 1-ulp differences by ~1e4, so the same fusion pattern is reproduced here.
+__device__ __forceinline__ cplx cmul_np(cplx a, cplx b) {
+  const double ii = a.im * b.im, ir = a.im * b.re;
+  return cplx{fma(a.re, b.re, -ii), fma(a.re, b.im, ir)};
 }
-__device__ __forceinline__ cplx csquare_np(cplx a) {  // CDOUBLE_square
-  return cplx{a.re * a.re - a.im * a.im, a.re * a.im + a.im * a.re};
-}
+__device__ __forceinline__ cplx csquare_np(cplx a) { return cmul_np(a, a); }
 __device__ __forceinline__ cplx cexp_i(double phi) {  // exp(0 + i phi)
   double s, c;
   sincos_big(phi, s, c);
@@ -1026,6 +1029,43 @@ int reflect_device(size_t n, const xrt_oe_params* oe, const xrt_material_params*
     if (oe->surface == 2) rc = launch_main_mat<2>(m.kind, grid, st, n, *oe, m, t, *in, fbv, *gb, lbv, red);
     if (rc) return rc;
   }
+  return 0;
+}
+
+// ---------------------------------------------------------------- stand-alone amplitudes (a12, a13)
+__global__ void __launch_bounds__(256) amplitude_kernel(size_t n, xrt_material_params m, Tables tab,
+                                                        const double* __restrict__ E, const double* __restrict__ bIn,
+                                                        const double* __restrict__ bOut, const double* __restrict__ bH,
+                                                        double2* __restrict__ rs, double2* __restrict__ rp,
+                                                        unsigned long long* oor_count) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int oor = 0;
+  cplx s, p;
+  if (m.kind == 3) {
+    const double in = bIn[i];
+    const double out = bOut ? bOut[i] : -in;   // crystal.py:618-619
+    const double h = bH ? bH[i] : in;          // crystal.py:621-622
+    crystal_amplitude(m, tab, E[i], in, out, h, s, p, &oor);
+  } else {
+    mirror_amplitude(m, tab, E[i], bIn[i], s, p, &oor);
+  }
+  rs[i] = make_double2(s.re, s.im);
+  rp[i] = make_double2(p.re, p.im);
+  if (oor) atomicAdd(oor_count, 1ull);
+}
+
+int amplitude_device(size_t n, const xrt_material_params* mat, const double* tables, size_t table_len,
+                     const double* E, const double* bIn, const double* bOut, const double* bH, double* rs, double* rp,
+                     unsigned long long* oor_count, cudaStream_t st) {
+  XRTB_REQUIRE(mat && tables && table_len > 0, "get_amplitude: material and tables are required");
+  XRTB_REQUIRE(mat->kind >= 1 && mat->kind <= 3, "get_amplitude: unsupported material kind %d", mat->kind);
+  if (n == 0) return 0;
+  Tables t{tables, tables + table_len, tables + 2 * table_len};
+  amplitude_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, *mat, t, E, bIn, bOut, bH,
+                                                               reinterpret_cast<double2*>(rs),
+                                                               reinterpret_cast<double2*>(rp), oor_count);
+  XRTB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 

@@ -85,3 +85,35 @@ def undulator_imap(Kx, Ky, L0, Np, gamma0, amp_const, dstep, bw_mode, w, theta, 
         _chk(Ep, C128, n), int(R) << 4, _stream())
     _lib.check(rc, 'xrt_undulator_imap_f64')
     return I, Es, Ep
+
+
+def _amplitude_host(material, E, bIn, bOut=None, bH=None):
+    import numpy as np
+    lib = _lib.load()
+    _lib.init()
+    E = _lib.as_f64(np.atleast_1d(E))
+    n = len(E)
+    arrs = [E] + [None if a is None else _lib.as_f64(np.broadcast_to(np.atleast_1d(a), E.shape))
+                  for a in (bIn, bOut, bH)]
+    tab, tlen, offs, lens = material.host_tables()
+    tab = _lib.as_f64(tab)
+    mat = material.c_struct(offs, lens)
+    rs = np.empty(n, dtype=np.complex128)
+    rp = np.empty(n, dtype=np.complex128)
+    rc = lib.xrt_get_amplitude_f64_host(n, ctypes.byref(mat), _lib.hptr(tab), tlen,
+                                        *[None if a is None else _lib.hptr(a) for a in arrs],
+                                        _lib.hptr(rs), _lib.hptr(rp))
+    if rc == 3:
+        raise ValueError(lib.xrt_b200_last_error().decode())
+    _lib.check(rc, 'xrt_get_amplitude_f64_host')
+    return rs, rp
+
+
+def material_amplitude_host(material, E, beamInDotNormal):
+    """a12: (rs, rp) of Material.get_amplitude for host arrays."""
+    return _amplitude_host(material, E, beamInDotNormal)
+
+
+def crystal_amplitude_host(crystal, E, beamInDotNormal, beamOutDotNormal=None, beamInDotHNormal=None):
+    """a13: (curveS, curveP) of Crystal.get_amplitude (thick Bragg) for host arrays."""
+    return _amplitude_host(crystal, E, beamInDotNormal, beamOutDotNormal, beamInDotHNormal)
