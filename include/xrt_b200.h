@@ -32,7 +32,7 @@ int xrt_b200_device_count(void);
 int xrt_b200_sm_count(void);
 const char* xrt_b200_last_error(void);
 int xrt_b200_sync(void* stream);
-/* sizeof() of the ABI structs below (0: xrt_beam, 1: xrt_oe_params, 2: xrt_material_params, 3: xrt_plane_params), for binding checks */
+/* sizeof() of the ABI structs below (0: xrt_beam, 1: xrt_oe_params, 2: xrt_material_params, 3: xrt_plane_params, 4: xrt_source_params), for binding checks */
 size_t xrt_b200_sizeof(int which);
 /* Measured fp64 ceilings used as roofline denominators (bench.py). mode 0: dependent-free DFMA stream,
  * mode 1: DMMA m8n8k4, mode 2: both interleaved. Writes TFLOP/s (2 flop per FMA). */
@@ -192,6 +192,33 @@ int xrt_propagate_rect_f64(size_t n, const xrt_plane_params* p, const xrt_beam* 
 int xrt_get_amplitude_f64_host(size_t n, const xrt_material_params* mat, const double* tables, size_t table_len,
                                const double* E, const double* bIn, const double* bOut, const double* bH, double* rs,
                                double* rp);
+
+/* ------------------------------------------------------------------ a5: IntegratedSource.shine building blocks
+ * (sources/sybase.py:1469-1812).  The host keeps the while-loop and the flux bookkeeping; the per-ray work is
+ *   xrt_source_sample_f64  -> (E, theta, psi) uniform in `window` = {Emin, Emax, Thetamin, Thetamax, Psimin,
+ *                             Psimax} (:1583-1617), four standard-normal deviates per ray and a uniform for
+ *                             the rejection test (:1637), counter-based Philox4x32-10 keyed by
+ *                             (seed, index_offset + i) so ray shards draw disjoint sub-streams;
+ *   xrt_undulator_imap_f64 -> Intensity, mJs, mJp (:1619);
+ *   xrt_source_fill_f64    -> the Beam (:1651-1721, :1769-1801), optionally gathering accepted samples. */
+typedef struct xrt_source_params {
+  double center[3];
+  double sinAz, cosAz;
+  int to_global;
+  int uniform;            /* uniformRayDensity */
+  double dx, dz, dxprime, dzprime; /* electron beam sizes [mm], divergences [rad] */
+  double L0, Np;          /* undulator period [mm], number of periods (photon source size, synchr.py:2200-2204) */
+  int has_pitch, has_yaw;
+  double cosPitch, sinPitch, cosYaw, sinYaw;
+} xrt_source_params;
+
+int xrt_source_sample_f64(size_t n, uint64_t seed, uint64_t index_offset, const double* window, double* E,
+                          double* theta, double* psi, double* n1, double* n2, double* n3, double* n4, double* u,
+                          void* stream);
+int xrt_source_fill_f64(size_t n, const xrt_source_params* p, const int64_t* idx, const double* rE,
+                        const double* rTheta, const double* rPsi, const double* mJs, const double* mJp,
+                        const double* n1, const double* n2, const double* n3, const double* n4, const xrt_beam* out,
+                        size_t out_offset, void* stream);
 
 #ifdef __cplusplus
 }

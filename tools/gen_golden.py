@@ -342,8 +342,30 @@ def gen_amplitudes():
             out[key + '_d'] = si.d
     save('amplitude_crystals', **out)
 
+# ------------------------------------------------------------------------------------------------ shine
+def gen_shine():
+    probe = _undulator_source(eMin=1000., eMax=1001., gNodes=16)
+    E1 = probe.E1
+    for name, uniform, nrays, seed in (('shine_uniform', True, 2500, 81), ('shine_rejection', False, 1200, 82)):
+        src = _undulator_source(eMin=E1*0.995, eMax=E1*1.005, gNodes=32, gIntervals=2, nrays=nrays,
+                                uniformRayDensity=uniform, center=(0.5, -2., 0.1), pitch=1e-5, yaw=-2e-5)
+        src.bl.azimuth = 0.05
+        np.random.seed(seed)
+        beam = src.shine()
+        d = dict(L0=src.L0, Np=src.Np, Kx=src.Kx, Ky=src.Ky, eI=src.eI, gamma=src.gamma, phase=src.phase,
+                 quadm=src.quadm, gIntervals=src.gIntervals, E_min=src.E_min, E_max=src.E_max,
+                 Theta_min=src.Theta_min, Theta_max=src.Theta_max, Psi_min=src.Psi_min, Psi_max=src.Psi_max,
+                 dx=src.dx, dz=src.dz, dxprime=src.dxprime, dzprime=src.dzprime, center=np.array(src.center, dtype=float),
+                 sinAzimuth=src.bl.sinAzimuth, cosAzimuth=src.bl.cosAzimuth, pitch=src.pitch, yaw=src.yaw,
+                 seed=seed, nrays=nrays, uniform=uniform, Imax=src.Imax, xzE=src.xzE, fluxConst=src.fluxConst,
+                 accepted=beam.accepted, acceptedE=beam.acceptedE, seeded=beam.seeded, seededI=beam.seededI,
+                 sourceWeight=beam.sourceWeight)
+        d.update(beam_dict(beam, 'out_'))
+        save(name, **d)
+        print(name, 'seeded', beam.seeded, 'rays', len(beam.x))
 
-SECTIONS = {'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+
+SECTIONS = {'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)

@@ -163,7 +163,7 @@ int xrt_b200_init(int device) {
 int xrt_b200_sm_count(void) { return num_sms(); }
 
 size_t xrt_b200_sizeof(int which) {
-  return which == 0 ? sizeof(xrt_beam) : which == 1 ? sizeof(xrt_oe_params) : which == 2 ? sizeof(xrt_material_params) : which == 3 ? sizeof(xrt_plane_params) : 0;
+  return which == 0 ? sizeof(xrt_beam) : which == 1 ? sizeof(xrt_oe_params) : which == 2 ? sizeof(xrt_material_params) : which == 3 ? sizeof(xrt_plane_params) : which == 4 ? sizeof(xrt_source_params) : 0;
 }
 
 const char* xrt_b200_last_error(void) { return g_err; }
@@ -323,6 +323,22 @@ int xrt_get_amplitude_f64_host(size_t n, const xrt_material_params* mat, const d
     return 3;
   }
   return 0;
+}
+
+// ------------------------------------------------------------------ source
+int xrt_source_sample_f64(size_t n, uint64_t seed, uint64_t index_offset, const double* window, double* E,
+                          double* theta, double* psi, double* n1, double* n2, double* n3, double* n4, double* u,
+                          void* stream) {
+  return source_sample_device(n, seed, index_offset, window, E, theta, psi, n1, n2, n3, n4, u,
+                              (cudaStream_t)stream);
+}
+
+int xrt_source_fill_f64(size_t n, const xrt_source_params* p, const int64_t* idx, const double* rE,
+                        const double* rTheta, const double* rPsi, const double* mJs, const double* mJp,
+                        const double* n1, const double* n2, const double* n3, const double* n4, const xrt_beam* out,
+                        size_t out_offset, void* stream) {
+  return source_fill_device(n, p, reinterpret_cast<const long long*>(idx), rE, rTheta, rPsi, mJs, mJp, n1, n2, n3,
+                            n4, out, out_offset, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,226 @@
+// Source-side kernels for sm_100a: Monte-Carlo sampling and Beam assembly of IntegratedSource.shine.
+//
+// Replaces the per-ray numpy body of IntegratedSource.shine (xrt/backends/raycing/sources/sybase.py:1580-1801):
+//   * sample_kernel : uniform (E, theta, psi) in the source window (:1583-1617) and the four normal deviates
+//                     used for source size / divergence smearing (:1669-1697) -- counter-based Philox4x32-10,
+//                     one independent counter range per ray, so rank r of N just offsets the counter;
+//   * fill_kernel   : Beam assembly from (E, theta, psi, I, mJs, mJp): positions ~ N(0, SIGMA(E))
+//                     (Undulator.get_SIGMA, sources/synchr.py:2200-2249, eEspread = 0), directions, coherency
+//                     matrix / amplitudes for uniformRayDensity or rejection-normalised rays (:1699-1721),
+//                     normalisation (:1769-1772), pitch/yaw (:1785-1786), virgin_local_to_global (:1800).
+// The field integral itself is undulator.cu.  Oracle: oracle/shine.py (same deviates fed to both).
+// Compiled with -fmad=false (numpy rounding order).
+#include "../../include/xrt_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace xrtb {
+
+// ---------------------------------------------------------------- Philox4x32-10 (Salmon et al., SC'11)
+struct Philox {
+  uint32_t c[4];
+  uint32_t k[2];
+};
+__device__ __forceinline__ void philox_round(uint32_t* c, const uint32_t* k) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  const uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+  const uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0;
+  c[0] = n0;
+  c[1] = n1;
+  c[2] = n2;
+  c[3] = n3;
+}
+__device__ __forceinline__ void philox4x32_10(uint64_t counter, uint32_t stream, uint64_t seed, uint32_t* out) {
+  uint32_t c[4] = {(uint32_t)counter, (uint32_t)(counter >> 32), stream, 0u};
+  uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k);
+    k[0] += 0x9E3779B9u;
+    k[1] += 0xBB67AE85u;
+  }
+  out[0] = c[0];
+  out[1] = c[1];
+  out[2] = c[2];
+  out[3] = c[3];
+}
+// 53-bit uniform in [0, 1) from two 32-bit words (the construction of numpy's random_sample)
+__device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
+  return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
+}
+
+// out: E, theta, psi uniform in their windows; n1..n4 standard normal; u uniform (rejection test)
+__global__ void __launch_bounds__(256) sample_kernel(size_t n, uint64_t seed, uint64_t index_offset, double Emin,
+                                                     double Emax, double Tmin, double Tmax, double Pmin, double Pmax,
+                                                     double* __restrict__ E, double* __restrict__ theta,
+                                                     double* __restrict__ psi, double* __restrict__ n1,
+                                                     double* __restrict__ n2, double* __restrict__ n3,
+                                                     double* __restrict__ n4, double* __restrict__ u) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t ctr = index_offset + i;
+  uint32_t w[4];
+  philox4x32_10(ctr, 0u, seed, w);
+  const double r0 = u53(w[0], w[1]), r1 = u53(w[2], w[3]);
+  philox4x32_10(ctr, 1u, seed, w);
+  const double r2 = u53(w[0], w[1]), r3 = u53(w[2], w[3]);
+  E[i] = r0 * (Emax - Emin) + Emin;      // sybase.py:1585-1586
+  theta[i] = r1 * (Tmax - Tmin) + Tmin;  // :1613-1615
+  psi[i] = r2 * (Pmax - Pmin) + Pmin;    // :1616-1617
+  if (u) u[i] = r3;
+  if (n1) {
+    // Box-Muller on (0, 1] uniforms
+    philox4x32_10(ctr, 2u, seed, w);
+    const double a0 = 1.0 - u53(w[0], w[1]), a1 = u53(w[2], w[3]);
+    philox4x32_10(ctr, 3u, seed, w);
+    const double b0 = 1.0 - u53(w[0], w[1]), b1 = u53(w[2], w[3]);
+    const double ra = sqrt(-2.0 * log(a0)), rb = sqrt(-2.0 * log(b0));
+    double s, c;
+    sincospi(2.0 * a1, &s, &c);
+    n1[i] = ra * c;
+    n2[i] = ra * s;
+    sincospi(2.0 * b1, &s, &c);
+    n3[i] = rb * c;
+    n4[i] = rb * s;
+  }
+}
+
+__device__ __forceinline__ cplx cmul_np3(cplx a, cplx b) {  // numpy SIMD complex multiply (see reflect.cu)
+  const double ii = a.im * b.im, ir = a.im * b.re;
+  return cplx{fma(a.re, b.re, -ii), fma(a.re, b.im, ir)};
+}
+
+// Beam assembly. idx: optional gather index (accepted samples of the rejection pass), else identity.
+__global__ void __launch_bounds__(256) fill_kernel(size_t n, xrt_source_params p, const long long* __restrict__ idx,
+                                                   const double* __restrict__ rE, const double* __restrict__ rTheta,
+                                                   const double* __restrict__ rPsi, const double2* __restrict__ mJs,
+                                                   const double2* __restrict__ mJp, const double* __restrict__ n1,
+                                                   const double* __restrict__ n2, const double* __restrict__ n3,
+                                                   const double* __restrict__ n4, xrt_beam out, size_t out_offset) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t j = idx ? (size_t)idx[i] : i;  // sample index
+  const size_t o = out_offset + i;            // ray index in the output beam
+  const double E = rE[j];
+  // get_SIGMA (synchr.py:2240-2249) with get_sigma_r2 = get_sigma_r02 (eEspread = 0): 2*CHeVcm/E*10*L0*Np/PI2**2
+  const double CHeVcm = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12;
+  const double PI2 = 6.283185307179586476925286766559;
+  const double sr2 = 2.0 * CHeVcm / E * 10.0 * p.L0 * p.Np / (PI2 * PI2);
+  const double SX = sqrt(p.dx * p.dx + sr2), SZ = sqrt(p.dz * p.dz + sr2);
+  double x = 0.0 + SX * n1[j];  // np.random.normal(0, SIGMA, n) = loc + scale * gauss
+  double y = 0.0;
+  double z = 0.0 + SZ * n2[j];
+  double a = rTheta[j], b = 1.0, c = rPsi[j];
+  if (p.dxprime > 0.0) a += 0.0 + p.dxprime * n3[j];
+  if (p.dzprime > 0.0) c += 0.0 + p.dzprime * n4[j];
+  const double2 s2 = mJs[j], p2 = mJp[j];
+  const cplx js = cplx{s2.x, s2.y}, jp = cplx{p2.x, p2.y};
+  const double mJs2 = cmul_np3(js, cconj(js)).re;
+  const double mJp2 = cmul_np3(jp, cconj(jp)).re;
+  cplx Jsp = cmul_np3(js, cconj(jp));
+  double Jss, Jpp;
+  cplx Es, Ep;
+  if (p.uniform) {
+    // sSP = 1. (sybase.py:1702-1707); x / 1. is exact
+    Jss = mJs2;
+    Jpp = mJp2;
+    Es = js;
+    Ep = jp;
+  } else {
+    const double sSP = mJs2 + mJp2;
+    if (sSP != 0.0) {
+      Jsp = cdiv(Jsp, cplx{sSP, 0.0});
+      Jss = mJs2 / sSP;
+      Jpp = mJp2 / sSP;
+    } else {
+      Jsp = cplx{0.0, 0.0};
+      Jss = 0.0;
+      Jpp = 0.0;
+    }
+    Es = cdiv(js, cplx{sqrt(mJs2), 0.0});  // mJs / mJs2**0.5 (sybase.py:1719-1720)
+    Ep = cdiv(jp, cplx{sqrt(mJp2), 0.0});
+  }
+  // normalise (sybase.py:1769-1772)
+  const double norm = sqrt(a * a + b * b + c * c);
+  a /= norm;
+  b /= norm;
+  c /= norm;
+  // pitch / yaw of the source (sybase.py:1785-1786): rotate_beam default sequence z then x
+  if (p.has_yaw) {
+    const double x1 = p.cosYaw * x - p.sinYaw * y, y1 = p.sinYaw * x + p.cosYaw * y;
+    x = x1;
+    y = y1;
+    const double a1 = p.cosYaw * a - p.sinYaw * b, b1 = p.sinYaw * a + p.cosYaw * b;
+    a = a1;
+    b = b1;
+  }
+  if (p.has_pitch) {
+    const double y1 = p.cosPitch * y - p.sinPitch * z, z1 = p.sinPitch * y + p.cosPitch * z;
+    y = y1;
+    z = z1;
+    const double b1 = p.cosPitch * b - p.sinPitch * c, c1 = p.sinPitch * b + p.cosPitch * c;
+    b = b1;
+    c = c1;
+  }
+  if (p.to_global) {  // virgin_local_to_global (beamline.py:267-287)
+    if (p.sinAz != 0.0) {
+      const double a1 = p.cosAz * a - (-p.sinAz) * b, b1 = (-p.sinAz) * a + p.cosAz * b;
+      a = a1;
+      b = b1;
+      const double x1 = p.cosAz * x - (-p.sinAz) * y, y1 = (-p.sinAz) * x + p.cosAz * y;
+      x = x1;
+      y = y1;
+    }
+    x += p.center[0];
+    y += p.center[1];
+    z += p.center[2];
+  }
+  out.x[o] = x;
+  out.y[o] = y;
+  out.z[o] = z;
+  out.a[o] = a;
+  out.b[o] = b;
+  out.c[o] = c;
+  out.path[o] = 0.0;
+  out.E[o] = E;
+  out.Jss[o] = Jss;
+  out.Jpp[o] = Jpp;
+  reinterpret_cast<double2*>(out.Jsp)[o] = make_double2(Jsp.re, Jsp.im);
+  if (out.Es) {
+    reinterpret_cast<double2*>(out.Es)[o] = make_double2(Es.re, Es.im);
+    reinterpret_cast<double2*>(out.Ep)[o] = make_double2(Ep.re, Ep.im);
+  }
+  out.state[o] = 1;
+}
+
+int source_sample_device(size_t n, uint64_t seed, uint64_t index_offset, const double* window, double* E,
+                         double* theta, double* psi, double* n1, double* n2, double* n3, double* n4, double* u,
+                         cudaStream_t st) {
+  if (n == 0) return 0;
+  XRTB_REQUIRE(window && E && theta && psi, "source_sample: NULL argument");
+  XRTB_REQUIRE((n1 == nullptr) == (n2 == nullptr) && (n1 == nullptr) == (n3 == nullptr) &&
+                   (n1 == nullptr) == (n4 == nullptr),
+               "source_sample: give all four normal-deviate arrays or none");
+  sample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, seed, index_offset, window[0], window[1], window[2],
+                                                            window[3], window[4], window[5], E, theta, psi, n1, n2,
+                                                            n3, n4, u);
+  XRTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int source_fill_device(size_t n, const xrt_source_params* p, const long long* idx, const double* rE,
+                       const double* rTheta, const double* rPsi, const double* mJs, const double* mJp,
+                       const double* n1, const double* n2, const double* n3, const double* n4, const xrt_beam* out,
+                       size_t out_offset, cudaStream_t st) {
+  if (n == 0) return 0;
+  XRTB_REQUIRE(p && rE && rTheta && rPsi && mJs && mJp && n1 && n2 && n3 && n4 && out, "source_fill: NULL argument");
+  fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, *p, idx, rE, rTheta, rPsi,
+                                                          reinterpret_cast<const double2*>(mJs),
+                                                          reinterpret_cast<const double2*>(mJp), n1, n2, n3, n4, *out,
+                                                          out_offset);
+  XRTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace xrtb

@@ -1,0 +1,408 @@
+# -*- coding: utf-8 -*-
+"""`Undulator` with xrt's constructor and `shine()` / `build_I_map()` signatures, computing on the GPU.
+
+Mirrors xrt/backends/raycing/sources/sybase.py (SourceBase :29-547, IntegratedSource :933-1812) and
+sources/synchr.py (Undulator :1349-2260) for the far-field planar/helical undulator without taper:
+same keywords and units (eE GeV, eI A, eSigma um, eEpsilon nm rad, xPrimeMax mrad, period mm), same derived
+quantities (gamma, dx/dz/dxprime/dzprime, Theta/Psi/E windows, Clenshaw-Curtis grid), same flux bookkeeping
+on the returned Beam (accepted, acceptedE, seeded, seededI, sourceWeight).  Out of scope:
+taper, near field (R0), filamentBeam, custom field, wave=... sampling.
+
+Per-ray work: xrt_b200/csrc/undulator.cu (field integral), source.cu (sampling, Beam assembly).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib, kernels
+from .beams import Beam
+from .cuda_backend import XRT_CUDA
+from .physconsts import PI, PI2, EV2ERG, M0, C, E2WC, FINE_STR, SIE0, K2B
+
+F64 = torch.float64
+C128 = torch.complex128
+
+
+class xrt_source_params(ctypes.Structure):
+    """struct xrt_source_params of include/xrt_b200.h"""
+    _fields_ = [('center', ctypes.c_double * 3), ('sinAz', ctypes.c_double), ('cosAz', ctypes.c_double),
+                ('to_global', ctypes.c_int), ('uniform', ctypes.c_int),
+                ('dx', ctypes.c_double), ('dz', ctypes.c_double), ('dxprime', ctypes.c_double),
+                ('dzprime', ctypes.c_double), ('L0', ctypes.c_double), ('Np', ctypes.c_double),
+                ('has_pitch', ctypes.c_int), ('has_yaw', ctypes.c_int),
+                ('cosPitch', ctypes.c_double), ('sinPitch', ctypes.c_double),
+                ('cosYaw', ctypes.c_double), ('sinYaw', ctypes.c_double)]
+
+
+def clenshaw_curtis(n):
+    """Nodes and weights on [-1, 1] (IntegratedSource._clenshaw_curtis, sybase.py:1106-1139, after quadpy)."""
+    points = -np.cos((np.pi * np.arange(n)) / (n - 1))
+    if n == 2:
+        return points, np.array([1.0, 1.0])
+    n -= 1
+    N = np.arange(1, n, 2)
+    length = len(N)
+    m = n - length
+    v0 = np.concatenate([2.0 / N / (N - 2), np.array([1.0 / N[-1]]), np.zeros(m)])
+    v2 = -v0[:-1] - v0[:0:-1]
+    g0 = -np.ones(n)
+    g0[length] += n
+    g0[m] += n
+    g = g0 / (n ** 2 - 1 + (n % 2))
+    w = np.fft.ihfft(v2 + g).real
+    if n % 2 == 1:
+        weights = np.concatenate([w, w[::-1]])
+    else:
+        weights = np.concatenate([w, w[len(w)-2::-1]])
+    return points, weights
+
+
+class Undulator(object):
+    def __init__(self, bl=None, name='und', center=(0, 0, 0), nrays=100000, eE=6.0, eI=0.1, eEspread=0.,
+                 eSigmaX=None, eSigmaZ=None, eEpsilonX=1., eEpsilonZ=0.01, betaX=9., betaZ=2., eMin=9000,
+                 eMax=9100, distE='eV', xPrimeMax=0.01, zPrimeMax=0.01, uniformRayDensity=False,
+                 filamentBeam=False, pitch=0, yaw=0, period=50, n=50, K=1, Kx=0, Ky=0, phaseDeg=0, gp=1e-6,
+                 gIntervals=2, gNodes=None, xPrimeMaxAutoReduce=True, zPrimeMaxAutoReduce=True,
+                 targetOpenCL='CUDA', precisionOpenCL='float64', R0=None, taper=None, seed=1234, **kwargs):
+        if R0 is not None or taper is not None or filamentBeam:
+            raise NotImplementedError('near field, taper and filamentBeam are outside the hot path '
+                                      '(SURVEY.md section 8f3)')
+        if targetOpenCL is None:
+            raise _lib.XrtB200Error('xrt_b200.Undulator always computes on the GPU (no numpy path)')
+        self.bl = bl
+        self.name = name
+        if bl is not None and self not in bl.sources:
+            bl.sources.append(self)
+        self.center = list(center)
+        self.nrays = int(nrays)
+        self.pitch, self.yaw = pitch, yaw
+        self.distE = distE
+        self.uniformRayDensity = uniformRayDensity
+        self.eE = float(eE)
+        self.gamma = self.eE * 1e9 * EV2ERG / (M0 * C**2)  # sybase.py:155
+        self.gamma2 = self.gamma**2
+        self.eEspread = eEspread
+        self.eI = float(eI)
+        # emittance [nm rad] -> [mm rad]; sizes [um] -> [mm]; beta [m] -> [mm] (sybase.py:218-347)
+        epsX = eEpsilonX * 1e-6 if eEpsilonX is not None else None
+        epsZ = eEpsilonZ * 1e-6 if eEpsilonZ is not None else None
+
+        def size(sigma, eps, beta):
+            if sigma is not None:
+                d = sigma * 1e-3
+            elif eps is not None and beta is not None:
+                d = np.sqrt(eps * beta * 1e3)
+            else:
+                d = 0
+            dprime = (eps / d if d > 0 else 0) if eps is not None else 0
+            return d, dprime
+        self.dx, self.dxprime = size(eSigmaX, epsX, betaX)
+        self.dz, self.dzprime = size(eSigmaZ, epsZ, betaZ)
+        self.eMin, self.eMax = float(eMin), float(eMax)
+        self.L0 = float(period)
+        self.Np = float(n)
+        self.phase = np.radians(phaseDeg)
+        if Kx == 0 and Ky == 0:  # synchr.py:1414-1431
+            self.Kx, self.Ky = 0., float(K)
+        else:
+            self.Kx, self.Ky = float(Kx), float(Ky)
+        self.B0x, self.B0y = K2B * self.Kx / self.L0, K2B * self.Ky / self.L0
+        self._xPrimeMax = self._prime(xPrimeMax)
+        self._zPrimeMax = self._prime(zPrimeMax)
+        if xPrimeMaxAutoReduce:  # sybase.py:372-386
+            K0 = self.Ky if abs(self.Ky) > 0 else 2.
+            self._xPrimeMax = [np.sign(v) * min(abs(v), K0 / self.gamma) for v in self._xPrimeMax]
+        if zPrimeMaxAutoReduce:
+            K0 = self.Kx if abs(self.Kx) > 0 else 2.
+            self._zPrimeMax = [np.sign(v) * min(abs(v), K0 / self.gamma) for v in self._zPrimeMax]
+        self.gp = gp
+        self.gIntervals = int(gIntervals)
+        self.quadm = int(gNodes) if gNodes is not None else None
+        self.maxIntegrationNodes = int(6e5)
+        self.seed = int(seed)
+        self._draws = 0
+        self.ucl = XRT_CUDA('undulator.cl', targetOpenCL, precisionOpenCL)
+        self.cl_ctx = self.ucl.cl_ctx
+        self.cl_precisionF, self.cl_precisionC = self.ucl.cl_precisionF, self.ucl.cl_precisionC
+        self.report_E1()
+        self.needReset = True
+
+    @staticmethod
+    def _prime(v):
+        if isinstance(v, (tuple, list)):
+            return [min(v) * 1e-3, max(v) * 1e-3]
+        return [-abs(v) * 1e-3, abs(v) * 1e-3]
+
+    def report_E1(self):  # synchr.py:1661-1677
+        wu = PI / self.L0 / self.gamma2 * (2*self.gamma2 - 1. - 0.5*self.Kx**2 - 0.5*self.Ky**2) / E2WC
+        self.E1 = 2*wu*self.gamma2 / (1 + 0.5*self.Kx**2 + 0.5*self.Ky**2)
+
+    # ------------------------------------------------------------------ reset / integration grid
+    def reset(self):
+        self.needReset = False
+        # limits corrected for divergence (sybase.py:479-515)
+        self.Theta_min = float(self._xPrimeMax[0] - self.dxprime)
+        self.Theta_max = float(self._xPrimeMax[1] + self.dxprime)
+        self.Psi_min = float(self._zPrimeMax[0] - self.dzprime)
+        self.Psi_max = float(self._zPrimeMax[1] + self.dzprime)
+        self.E_min = float(min(self.eMin, self.eMax))
+        self.E_max = float(max(self.eMin, self.eMax))
+        if self.quadm is None:
+            self._find_convergence_mixed()
+        self._build_integration_grid()
+        self.Imax = 0.
+        self.xzE = (self.E_max - self.E_min) * (self.Theta_max - self.Theta_min) * (self.Psi_max - self.Psi_min)
+        self.fluxConst = self.Imax * self.xzE
+
+    def _build_integration_grid(self):
+        """Undulator._build_integration_grid (synchr.py:1787-1801)."""
+        self.tg_n, self.ag_n = clenshaw_curtis(self.quadm)
+        dstep = 2 * PI / float(self.gIntervals)
+        dI = np.arange(-PI + 0.5 * dstep, PI, dstep)
+        self.tg = (dI[:, None]+0.5*dstep*self.tg_n).ravel()
+        self.ag = (dI[:, None]*0+self.ag_n).ravel()
+        self.sintg = np.sin(self.tg)
+        self.costg = np.cos(self.tg)
+        self.sintgph = np.sin(self.tg + self.phase)
+        self.costgph = np.cos(self.tg + self.phase)
+        self.dstep = dstep
+        self._dev_tables = None
+
+    def _tables(self, device):
+        if self._dev_tables is None or self._dev_tables[0].device != device:
+            self._dev_tables = [torch.from_numpy(np.ascontiguousarray(a)).to(device) for a in
+                                (self.tg, self.ag, self.sintg, self.costg, self.sintgph, self.costgph)]
+        return self._dev_tables
+
+    def _get_mad(self):
+        """IntegratedSource._get_mad (sybase.py:1245-1285) at (E_max, Theta_max, Psi_max)."""
+        tmp_quadm = self.quadm
+        k = self.quadm - 2
+        pltout, dIout = [], []
+        Iold = None
+        for m in range(5):
+            k += 1
+            self.quadm = k
+            self._build_integration_grid()
+            Inew = self._convergence_value()
+            if m > 0:
+                pltout.append(Inew)
+                dIout.append(np.abs(Inew-Iold)/Inew)
+            Iold = Inew
+        med = np.median(np.abs(np.array(pltout)))
+        mad = np.median(np.abs(np.abs(np.array(pltout)) - med))
+        self.quadm = tmp_quadm
+        return mad, np.median(dIout)
+
+    def _convergence_value(self):
+        """build_I_map with convergenceSearchFlag (synchr.py:2101-2103): |sqrt(|Is|^2+|Ip|^2) * dstep/2| for the
+        single corner sample, eEspread = 0; evaluated by the same CUDA kernel."""
+        w = np.array([self.E_max, self.E_max])  # two identical samples: the kernel path is the array path
+        th = np.array([self.Theta_max, self.Theta_max])
+        ps = np.array([self.Psi_max, self.Psi_max])
+        gamma = self.gamma * np.ones(2)
+        wu, ww1 = self._wu_ww1(gamma, w, th, ps)
+        Is, Ip = self._integral_host(gamma, wu, w, ww1, th, ps)
+        field = np.abs(Is[0])**2 + np.abs(Ip[0])**2
+        return np.abs(np.sqrt(field) * 0.5 * self.dstep)
+
+    def _find_convergence_mixed(self):
+        """IntegratedSource._find_convergence_mixed (sybase.py:1190-1243)."""
+        m = 3
+        while m < 10000:
+            m += 1
+            self.quadm = int(2**m)
+            mad, dimad = self._get_mad()
+            if (dimad < self.gp) or (mad < self.gp):
+                break
+            if self.quadm > self.maxIntegrationNodes:
+                break
+        ph2start = int(2**(m-1))
+        ph2end = self.quadm
+        jmax = int(np.log2((ph2end-ph2start) / (4*5)))
+        for j in range(jmax):
+            self.quadm = int(0.5*(ph2end+ph2start))
+            mad, dimad = self._get_mad()
+            if (dimad < self.gp) or (mad < self.gp):
+                ph2end = self.quadm
+            else:
+                ph2start = self.quadm
+        self.quadm = ph2end
+
+    # ------------------------------------------------------------------ build_I_map (host arrays, reference API)
+    def _wu_ww1(self, gamma, w, ddtheta, ddpsi):
+        gamma2 = gamma**2
+        wu = PI / self.L0 / gamma2 * (2*gamma2 - 1 - 0.5*self.Kx**2 - 0.5*self.Ky**2) / E2WC
+        ww1 = w * ((1. + 0.5 * self.Kx**2 + 0.5 * self.Ky**2) +
+                   gamma2 * (ddtheta * ddtheta + ddpsi * ddpsi)) / (2. * gamma2 * wu)
+        return wu, ww1
+
+    def _integral_host(self, gamma, wu, w, ww1, ddtheta, ddpsi):
+        """The dispatch of Undulator._build_I_map_CL (synchr.py:2134-2174) through XRT_CUDA.run_parallel."""
+        F = self.cl_precisionF
+        NRAYS = len(w)
+        scalarArgs = [F(0.), F(self.Kx), F(self.Ky), np.int32(len(self.tg))]
+        slicedROArgs = [F(gamma), F(wu), F(w), F(ww1), F(ddtheta), F(ddpsi)]
+        nonSlicedROArgs = [F(self.tg), F(self.ag), F(self.sintg), F(self.costg), F(self.sintgph), F(self.costgph)]
+        slicedRWArgs = [np.zeros(NRAYS, dtype=self.cl_precisionC), np.zeros(NRAYS, dtype=self.cl_precisionC)]
+        return self.ucl.run_parallel('undulator', scalarArgs, slicedROArgs, nonSlicedROArgs, slicedRWArgs,
+                                     dimension=NRAYS)
+
+    def build_I_map(self, w, ddtheta, ddpsi, harmonic=None, dg=None):
+        """(I, Es, Ep) on host arrays like Undulator.build_I_map (synchr.py:2035-2193)."""
+        if self.needReset:
+            self.reset()
+        w = np.atleast_1d(np.asarray(w, dtype=float))
+        ddtheta = np.asarray(ddtheta, dtype=float) * np.ones_like(w)
+        ddpsi = np.asarray(ddpsi, dtype=float) * np.ones_like(w)
+        NRAYS = len(w)
+        gamma = self.gamma
+        if self.eEspread > 0:
+            if dg is not None:
+                gamma = gamma + dg
+            else:
+                gamma = gamma + gamma * self.eEspread * np.random.normal(size=NRAYS)
+        gamma = gamma * np.ones(NRAYS)
+        wu, ww1 = self._wu_ww1(gamma, w, ddtheta, ddpsi)
+        ab = 1. / PI2 / wu * np.sin(PI * self.Np * ww1) / np.sin(PI * ww1)
+        Is_local, Ip_local = self._integral_host(gamma, wu, w, ww1, ddtheta, ddpsi)
+        bwFact = 0.001 if self.distE == 'BW' else 1./w
+        Amp2Flux = FINE_STR * bwFact * self.eI / SIE0
+        if harmonic is not None:
+            Is_local[ww1 > harmonic+0.5] = 0
+            Ip_local[ww1 > harmonic+0.5] = 0
+            Is_local[ww1 < harmonic-0.5] = 0
+            Ip_local[ww1 < harmonic-0.5] = 0
+        integralField = np.abs(Is_local)**2 + np.abs(Ip_local)**2
+        return (Amp2Flux * ab**2 * 0.25 * self.dstep**2 * integralField,
+                np.sqrt(Amp2Flux) * Is_local * ab * 0.5 * self.dstep,
+                np.sqrt(Amp2Flux) * Ip_local * ab * 0.5 * self.dstep)
+
+    # ------------------------------------------------------------------ device-resident building blocks
+    def build_I_map_device(self, w, theta, psi, gamma=None, out=None):
+        """(I, Es, Ep) as CUDA tensors from CUDA tensors (fused _build_I_map_conv)."""
+        if self.needReset:
+            self.reset()
+        return kernels.undulator_imap(self.Kx, self.Ky, self.L0, self.Np, self.gamma,
+                                      FINE_STR * self.eI / SIE0, self.dstep, 1 if self.distE == 'BW' else 0,
+                                      w, theta, psi, self._tables(w.device), gamma=gamma, out=out)
+
+    def _source_params(self, toGlobal):
+        p = xrt_source_params()
+        for i in range(3):
+            p.center[i] = float(self.center[i])
+        p.sinAz = float(self.bl.sinAzimuth) if self.bl is not None else 0.
+        p.cosAz = float(self.bl.cosAzimuth) if self.bl is not None else 1.
+        p.to_global = int(bool(toGlobal))
+        p.uniform = int(bool(self.uniformRayDensity))
+        p.dx, p.dz, p.dxprime, p.dzprime = float(self.dx), float(self.dz), float(self.dxprime), float(self.dzprime)
+        p.L0, p.Np = self.L0, self.Np
+        if self.pitch:
+            p.has_pitch, p.cosPitch, p.sinPitch = 1, float(np.cos(self.pitch)), float(np.sin(self.pitch))
+        if self.yaw:
+            p.has_yaw, p.cosYaw, p.sinYaw = 1, float(np.cos(self.yaw)), float(np.sin(self.yaw))
+        return p
+
+    def draw_samples(self, n, device=None, index_offset=0, withNormals=True, withU=True):
+        """Philox-sampled (E, theta, psi), four standard normal deviates and a uniform per ray (CUDA tensors)."""
+        if self.needReset:
+            self.reset()
+        lib = _lib.load()
+        dev = torch.device('cuda', torch.cuda.current_device()) if device is None else device
+        names = ['E', 'theta', 'psi'] + (['n1', 'n2', 'n3', 'n4'] if withNormals else []) + (['u'] if withU else [])
+        buf = torch.empty((len(names), n), dtype=F64, device=dev)
+        s = {k: buf[i] for i, k in enumerate(names)}
+        window = (ctypes.c_double * 6)(self.E_min, self.E_max, self.Theta_min, self.Theta_max, self.Psi_min,
+                                       self.Psi_max)
+        ptr = lambda k: s[k].data_ptr() if k in s else None  # noqa: E731
+        # every call advances the counter space so that successive passes never reuse deviates
+        offset = int(index_offset) + self._draws
+        self._draws += 1 << 40
+        rc = lib.xrt_source_sample_f64(n, self.seed, offset, window, ptr('E'), ptr('theta'), ptr('psi'), ptr('n1'),
+                                       ptr('n2'), ptr('n3'), ptr('n4'), ptr('u'),
+                                       ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, 'xrt_source_sample_f64')
+        return s
+
+    def fill_beam(self, samples, mJs, mJp, out, idx=None, out_offset=0, n=None, toGlobal=True):
+        lib = _lib.load()
+        if self.eEspread > 0:
+            raise NotImplementedError('source size with energy spread (Tanaka-Kitamura Qa) is not on the device '
+                                      'path yet; build_I_map supports eEspread')
+        p = self._source_params(toGlobal)
+        n = (len(idx) if idx is not None else samples['E'].numel()) if n is None else n
+        cout = out.c_struct()
+        rc = lib.xrt_source_fill_f64(
+            n, ctypes.byref(p), idx.data_ptr() if idx is not None else None, samples['E'].data_ptr(),
+            samples['theta'].data_ptr(), samples['psi'].data_ptr(), mJs.data_ptr(), mJp.data_ptr(),
+            samples['n1'].data_ptr(), samples['n2'].data_ptr(), samples['n3'].data_ptr(), samples['n4'].data_ptr(),
+            ctypes.byref(cout), out_offset, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, 'xrt_source_fill_f64')
+
+    # ------------------------------------------------------------------ shine
+    def shine(self, toGlobal=True, withAmplitudes=True, fixedEnergy=False, wave=None, accuBeam=None,
+              samples=None, index_offset=0, allreduce_max=None, bookkeeping=True):
+        """Returns the source Beam (device resident) like IntegratedSource.shine (sybase.py:1469-1812).
+
+        *samples* (optional): dict of CUDA tensors E, theta, psi, n1..n4[, u] to use instead of drawing them
+        (parity tests feed the deviates the numpy oracle used).  *allreduce_max*: callable applied to the
+        per-pass max intensity when rays are sharded over ranks (Imax is beam-wide, sybase.py:1627-1631)."""
+        if wave is not None or fixedEnergy or accuBeam is not None:
+            raise NotImplementedError('wave/fixedEnergy/accuBeam sampling is outside the hot path (SURVEY 8f3)')
+        if self.needReset:
+            self.reset()
+        if self.uniformRayDensity:
+            withAmplitudes = True
+        mcRays = self.nrays
+        dev = torch.device('cuda', torch.cuda.current_device())
+        bo = Beam(mcRays, withAmplitudes=withAmplitudes, device=dev, uninitialized=True)
+        length = 0
+        seeded = 0
+        seededI = 0.
+        sumE = None
+        sourceWeight = 0.
+        given = samples is not None
+        while True:
+            s = samples if given else self.draw_samples(mcRays, dev, index_offset=index_offset)
+            n = s['E'].numel()
+            seeded += n
+            I, mJs, mJp = self.build_I_map_device(s['E'], s['theta'], s['psi'])
+            if self.uniformRayDensity:
+                seededI += n * self.xzE
+                sourceWeight = self.xzE
+                if bookkeeping:
+                    tmp_max = I.max()
+                    if allreduce_max is not None:
+                        tmp_max = allreduce_max(tmp_max)
+                    self.Imax = max(self.Imax, float(tmp_max))
+                    self.fluxConst = self.Imax * self.xzE
+                self.fill_beam(s, mJs, mJp, bo, toGlobal=toGlobal)
+                length = n
+                break
+            # rejection sampling (sybase.py:1625-1641)
+            tmp_max = I.max()
+            if allreduce_max is not None:
+                tmp_max = allreduce_max(tmp_max)
+            seededI += float(I.sum()) * self.xzE
+            sourceWeight = seededI / seeded
+            if float(tmp_max) > self.Imax:
+                self.Imax = float(tmp_max)
+                self.fluxConst = self.Imax * self.xzE
+            idx = torch.nonzero(self.Imax * s['u'] < I).flatten()
+            npassed = min(int(idx.numel()), mcRays - length)
+            if npassed > 0:
+                self.fill_beam(s, mJs, mJp, bo, idx=idx, out_offset=length, n=npassed, toGlobal=toGlobal)
+                length += npassed
+            if length >= mcRays or given:
+                break
+        if length < mcRays:
+            bo.filter_by_index(slice(0, length))
+        if bookkeeping:
+            bo.accepted = length * self.fluxConst
+            bo.acceptedE = float(bo.E.sum()) * self.fluxConst * SIE0
+        bo.seeded = seeded
+        bo.seededI = seededI
+        bo.sourceWeight = sourceWeight / self.nrays
+        bo.parentId = getattr(self, 'uuid', self.name)
+        return bo
