@@ -1,0 +1,45 @@
+"""Method-level drop-in: xrt-shaped host objects (duck-typed with xrt's attribute names, filled from the golden
+files the reference produced) go through xrt_b200.bridge and come back as host beams equal to the reference's."""
+import types
+
+import numpy as np
+import pytest
+
+from conftest import golden
+from helpers import oracle_beam, compare_beams, BEAM_FIELDS
+
+
+class ToroidMirror(object):  # class name is what the adapter dispatches on, like isinstance in xrt
+    pass
+
+
+def _fake_xrt_oe(g):
+    class Elem(object):
+        name = 'Au'
+    mat = types.SimpleNamespace(elements=[Elem()], quantities=[1.], kind='mirror', rho=float(g['rho']), t=None,
+                                table='Chantler total')
+    oe = ToroidMirror()
+    bl = types.SimpleNamespace(sinAzimuth=float(g['sinAzimuth']), cosAzimuth=float(g['cosAzimuth']), oes=[])
+    oe.__dict__.update(dict(
+        bl=bl, name='TM', center=list(g['center']), pitch=float(g['pitch']), roll=float(g['roll']),
+        positionRoll=float(g['positionRoll']), yaw=float(g['yaw']), rotationSequence=str(g['rotationSequence']),
+        extraPitch=float(g['extraPitch']), extraRoll=float(g['extraRoll']), extraYaw=float(g['extraYaw']),
+        extraRotationSequence='RzRyRx', alpha=None, surfPhysX=list(g['surfPhysX']), surfPhysY=list(g['surfPhysY']),
+        surfOptX=None, surfOptY=None, overEdge=str(g['overEdge']), shape='rect', material=mat,
+        lostNum=int(g['lostNum']), dx=0, R=float(g['R']), r=float(g['r']), footprint=[]))
+    return oe
+
+
+@pytest.mark.gpu
+def test_bridge_reflect_host_objects(cuda_device):
+    from xrt_b200 import bridge
+    g = golden('reflect_toroid_Au')
+    oe = _fake_xrt_oe(g)
+    gb, lb = bridge.reflect(oe, oracle_beam(g, 'in_'))
+    assert isinstance(gb.x, np.ndarray)
+    bad = compare_beams(gb.__dict__, {f: g['gb_' + f] for f in BEAM_FIELDS}, BEAM_FIELDS, 1e-12, 'gb_')
+    bad += compare_beams(lb.__dict__, {f: g['lb_' + f] for f in BEAM_FIELDS + ('theta',)},
+                         BEAM_FIELDS + ('theta',), 1e-12, 'lb_')
+    assert not bad, bad
+    np.testing.assert_allclose(oe.footprint[0], g['footprint'], rtol=1e-12, atol=1e-12)
+    assert oe.bl.oes == []  # the adapter leaves the user's beamline numbering alone

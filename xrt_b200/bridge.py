@@ -1,0 +1,118 @@
+# -*- coding: utf-8 -*-
+"""Adapters that let *xrt's own objects* (duck-typed: anything with xrt's attribute names) run on the CUDA
+kernels: the method-level binding sketched in INTEGRATION.md section 2.
+
+    bridge.reflect(xrt_oe, xrt_beam, needLocal=True)          -> (gb, lb)      OE.reflect, oes/reflect.py:18
+    bridge.double_reflect(xrt_dcm, xrt_beam, needLocal=True)  -> (gb, lo1, lo2)  DCM.double_reflect, dcm.py:248
+    bridge.expose(xrt_screen, xrt_beam)                       -> blo           Screen.expose, screens.py:226
+
+Inputs and outputs are host objects with numpy attribute arrays (what xrt's flow, `get_output()` and plots
+consume), so every call pays one H2D and one D2H of the Beam; pipelines that stay on the GPU use the classes of
+xrt_b200.oes / planes / sources directly."""
+import numpy as np
+
+from . import materials as _mat, oes as _oes, planes as _planes
+from .beams import Beam
+
+
+class HostBeam(object):
+    """Attribute bag with numpy arrays, like xrt's Beam."""
+
+    def __init__(self, d):
+        self.__dict__.update(d)
+
+
+def _device_beam(b):
+    d = {k: v for k, v in b.__dict__.items() if isinstance(v, np.ndarray) and v.ndim == 1 and
+         k in ('x', 'y', 'z', 'a', 'b', 'c', 'path', 'E', 'Jss', 'Jpp', 'Jsp', 'state', 'Es', 'Ep')}
+    out = Beam.from_numpy(d)
+    if getattr(b, 'createdByDiffract', False):
+        out.createdByDiffract = True
+    return out
+
+
+def convert_material(m):
+    """xrt Material / CrystalFcc / CrystalDiamond / CrystalSi instance -> xrt_b200 material."""
+    if m is None:
+        return None
+    names = [e.name for e in m.elements]
+    table = getattr(m, 'table', 'Chantler total')
+    if getattr(m, 'kind', None) == 'crystal':
+        cls = type(m).__name__
+        kw = dict(hkl=tuple(m.hkl), d=m.d, V=getattr(m, 'V', None), elements=names[0], factDW=m.factDW,
+                  geom=m.geom, table=table, t=m.t)
+        if 'Fcc' in cls:
+            return _mat.CrystalFcc(**kw)
+        if any('Diamond' in c.__name__ for c in type(m).__mro__):
+            return _mat.CrystalDiamond(**kw)
+        raise NotImplementedError('crystal class {0} is outside the hot path'.format(cls))
+    return _mat.Material(names, list(m.quantities), kind=m.kind, rho=m.rho, t=m.t, table=table)
+
+
+def _oe_kwargs(oe):
+    kw = dict(center=list(oe.center), pitch=float(oe.pitch), roll=float(oe.roll),
+              positionRoll=float(oe.positionRoll), yaw=float(oe.yaw), rotationSequence=oe.rotationSequence,
+              extraPitch=float(oe.extraPitch), extraRoll=float(oe.extraRoll), extraYaw=float(oe.extraYaw),
+              extraRotationSequence=oe.extraRotationSequence, alpha=getattr(oe, 'alpha', None),
+              limPhysX=list(oe.surfPhysX), limPhysY=list(oe.surfPhysY),
+              limOptX=None if oe.surfOptX is None else list(oe.surfOptX),
+              limOptY=None if oe.surfOptY is None else list(oe.surfOptY),
+              overEdge=getattr(oe, 'overEdge', 'yMax'), shape=oe.shape, material=convert_material(oe.material))
+    return kw
+
+
+def convert_oe(oe):
+    """xrt OE / ToroidMirror / EllipticalMirrorParam / DCM instance -> the xrt_b200 element."""
+    cls = [c.__name__ for c in type(oe).__mro__]
+    kw = _oe_kwargs(oe)
+    if 'DCM' in cls:
+        for k in ('bragg', 'cryst1roll', 'cryst2roll', 'cryst2pitch', 'cryst2finePitch', 'cryst2perpTransl',
+                  'cryst2longTransl'):
+            kw[k] = float(getattr(oe, k))
+        kw.update(limPhysX2=list(oe.surfPhysX2), limPhysY2=list(oe.surfPhysY2),
+                  limOptX2=None if oe.surfOptX2 is None else list(oe.surfOptX2),
+                  limOptY2=None if oe.surfOptY2 is None else list(oe.surfOptY2),
+                  material2=convert_material(oe.material2))
+        out = _oes.DCM(oe.bl, oe.name, **kw)
+    elif 'ToroidMirror' in cls:
+        out = _oes.ToroidMirror(oe.bl, oe.name, R=float(oe.R), r=float(oe.r), **kw)
+    elif 'EllipticalMirrorParam' in cls:
+        out = _oes.EllipticalMirrorParam(oe.bl, oe.name, p=oe.p, q=oe.q, isCylindrical=oe.isCylindrical, **kw)
+        for k in ('ellipseA', 'ellipseB', 'y0', 'z0', 'cosGamma', 'sinGamma'):
+            setattr(out, k, float(getattr(oe, k)))  # take xrt's own ellipse parameters verbatim
+    elif type(oe).__name__ == 'OE' or 'OE' in cls:
+        out = _oes.OE(oe.bl, oe.name, **kw)
+    else:
+        raise NotImplementedError('{0} is outside the hot path'.format(type(oe).__name__))
+    if oe.bl is not None and out in getattr(oe.bl, 'oes', []):
+        oe.bl.oes.remove(out)  # the adapter must not renumber the user's beamline
+    out.lostNum = oe.lostNum
+    out.dx = getattr(oe, 'dx', 0)
+    return out
+
+
+def reflect(oe, beam, needLocal=True):
+    dev = convert_oe(oe)
+    gb, lb = dev.reflect(_device_beam(beam), needLocal=needLocal, withFootprint=True)
+    oe.footprint = dev.footprint
+    hgb = HostBeam(gb.to_numpy())
+    return hgb, (HostBeam(lb.to_numpy()) if needLocal else hgb)
+
+
+def double_reflect(dcm, beam, needLocal=True):
+    dev = convert_oe(dcm)
+    gb, lo1, lo2 = dev.double_reflect(_device_beam(beam), needLocal=needLocal)
+    hgb = HostBeam(gb.to_numpy())
+    if not needLocal:
+        return hgb, hgb, hgb
+    return hgb, HostBeam(lo1.to_numpy()), HostBeam(lo2.to_numpy())
+
+
+def expose(screen, beam, onlyPositivePath=False):
+    scr = _planes.Screen(None, screen.name, center=list(screen.center), compressX=screen.compressX,
+                         compressZ=screen.compressZ)
+    scr.x, scr.y, scr.z = list(screen.x), list(screen.y), list(screen.z)
+    scr.lostNum = screen.lostNum
+    blo = scr.expose(_device_beam(beam), onlyPositivePath=onlyPositivePath, withFootprint=True)
+    screen.footprint = scr.footprint
+    return HostBeam(blo.to_numpy())
