@@ -146,7 +146,9 @@ typedef struct xrt_material_params {
 #define XRT_REDUCTION_SLOTS 64
 
 /* OE.reflect / one _reflect_local pass.  tables: [E | f1 | f2] each `table_len` doubles (float32 data promoted).
- * phase bit0: pre-pass (reductions), bit1: main pass.  lb may be NULL (needLocal=False).
+ * phase bit0: pre-pass A (dominant direction, first good ray), bit2: pre-pass B (global bracket, solver
+ * switch), bit1: main pass; 7 = everything.  Ray shards all-reduce the slots after A and after B.
+ * lb may be NULL (needLocal=False).
  * index_offset: global index of ray 0 of this shard (first-good-ray bookkeeping of _set_t, base.py:1241).
  * fallback: beam whose values non-intersected rays receive in gb (reflect.py:131-134; the ORIGINAL beam for the
  * 2nd crystal of a DCM, dcm.py:343-345); NULL = `in`.

@@ -11,11 +11,12 @@
 // (materials/material.py:348-493) / Crystal.get_amplitude thick Bragg (materials/crystal.py:492-645).
 // Oracle: oracle/reflect.py, oracle/materials.py (bit-exact against the reference's outputs).
 //
-// HBM-bound: one thread per ray, every Beam array is read once and written once with unit stride (SoA);
-// 132 B in + 132 B (gb) + 140 B (lb) per ray with amplitudes.  A pre-pass (52 B/ray) produces the beam-wide
-// scalars the numpy code derives with whole-array min/max (dominant direction component, global t bracket,
-// secant-vs-Brent choice, first good ray) for all six (axis, sign) variants at once, so that the main pass
-// needs no host round trip and ray shards on several GPUs can all-reduce 64 slots in between.
+// One thread per ray, every Beam array is read once and written once with unit stride (SoA): 132 B in +
+// 132 B (gb) + 140 B (lb) per ray with amplitudes.  Two small pre-passes produce the beam-wide scalars the
+// numpy code derives with whole-array min/max: phase A (28 B/ray) the dominant direction component and the
+// first good ray, phase B (52 B/ray) the global t bracket and the secant-vs-Brent switch for the (axis, sign)
+// variant phase A selected.  They live in 64 device-resident slots, so the main pass needs no host round trip
+// and ray shards on several GPUs all-reduce the slots in between.
 //
 // THIS FILE IS COMPILED WITH -fmad=false: numpy rounds every multiply and add separately, and the
 // intersection iterates and grazing-incidence Fresnel terms amplify 1-ulp differences (cancellation ~1e6),
@@ -274,23 +275,26 @@ __global__ void reduction_init_kernel(unsigned long long* red) {
   red[i] = v;
 }
 
-template <int SURF>
-__global__ void __launch_bounds__(256) reflect_prepass_kernel(size_t n, xrt_oe_params p, xrt_beam in,
-                                                              unsigned long long* red, unsigned long long index_offset) {
+// Phase A: dominant direction component and first good ray (28 B/ray: state, a, b, c)
+__global__ void __launch_bounds__(256) reflect_prepass_dir_kernel(size_t n, xrt_oe_params p, xrt_beam in,
+                                                                  unsigned long long* red,
+                                                                  unsigned long long index_offset) {
   const double inf = __longlong_as_double(0x7ff0000000000000ll);
   double mx[3] = {-inf, -inf, -inf};
-  double v[24];
-#pragma unroll
-  for (int k = 0; k < 24; ++k) v[k] = ((k & 3) == 0) ? inf : -inf;
-  unsigned long long first = ~0ull;
-  unsigned long long ngood = 0;
+  unsigned long long first = ~0ull, ngood = 0;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const int st = in.state[i];
     if (!(p.good_mode ? (st == 1 || st == 2) : (st > 0))) continue;
     ++ngood;
-    Ray r = load_ray(in, i);
-    to_local(p, r);
+    Ray r;
+    r.x = r.y = r.z = 0.0;  // directions transform independently of positions
+    r.a = in.a[i];
+    r.b = in.b[i];
+    r.c = in.c[i];
+    // positions are not needed here: only the rotations act on (a, b, c)
+    if (p.from_global && p.sinAz != 0.0) rot_axis(2, p.cosAz, p.sinAz, r.a, r.b, r.c);
+    for (int k = 0; k < p.n_rot_in; ++k) rot_axis(p.rot_in_axis[k], p.rot_in_cos[k], p.rot_in_sin[k], r.a, r.b, r.c);
     if (st == 1) {
       mx[0] = fmax(mx[0], fabs(r.a));
       mx[1] = fmax(mx[1], fabs(r.b));
@@ -299,56 +303,99 @@ __global__ void __launch_bounds__(256) reflect_prepass_kernel(size_t n, xrt_oe_p
     const unsigned long long key = ((index_offset + i) << 3) | (r.a > 0.0 ? 1ull : 0ull) | (r.b > 0.0 ? 2ull : 0ull) |
                                    (r.c > 0.0 ? 4ull : 0ull);
     first = key < first ? key : first;
-#pragma unroll
-    for (int var = 0; var < 6; ++var) {
-      double t1, t2, x, y, z;
-      bracket(p, var >> 1, var & 1, r, t1, t2);
-      const double dz1 = find_dz<SURF>(p, t1, r, x, y, z);
-      double dz2 = find_dz<SURF>(p, t2, r, x, y, z);
-      if (dz1 <= 0.0 || dz2 >= 0.0) dz2 = 0.0;  // base.py:865 dz2[ind1 | ind2] = 0
-      // numpy's min/max propagate NaN; keep that by letting NaN win
-      v[var * 4 + 0] = (t1 < v[var * 4 + 0] || isnan(t1)) ? t1 : v[var * 4 + 0];
-      v[var * 4 + 1] = (t2 > v[var * 4 + 1] || isnan(t2)) ? t2 : v[var * 4 + 1];
-      v[var * 4 + 2] = (fabs(dz1) > v[var * 4 + 2] || isnan(dz1)) ? fabs(dz1) : v[var * 4 + 2];
-      v[var * 4 + 3] = (fabs(dz2) > v[var * 4 + 3] || isnan(dz2)) ? fabs(dz2) : v[var * 4 + 3];
-    }
   }
-  // block reduction through shared memory, then one atomic per slot per block
-  __shared__ unsigned long long sh[8][29];
+  __shared__ unsigned long long sh[8][5];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned long long e[29];
+  unsigned long long e[5] = {enc(mx[0]), enc(mx[1]), enc(mx[2]), first, ngood};
 #pragma unroll
-  for (int k = 0; k < 3; ++k) e[k] = enc(mx[k]);
-  e[3] = first;
-#pragma unroll
-  for (int k = 0; k < 24; ++k) e[4 + k] = enc(v[k]);
-  e[28] = ngood;
-#pragma unroll
-  for (int k = 0; k < 29; ++k) {
+  for (int k = 0; k < 5; ++k) {
     unsigned long long x = e[k];
-    const bool is_min = (k == 3) || (k >= 4 && k < 28 && ((k - 4) & 3) == 0);
-    const bool is_sum = (k == 28);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      unsigned long long yv = __shfl_xor_sync(0xffffffffu, x, o);
-      x = is_sum ? x + yv : (is_min ? (yv < x ? yv : x) : (yv > x ? yv : x));
+      const unsigned long long y = __shfl_xor_sync(0xffffffffu, x, o);
+      x = (k == 4) ? x + y : (k == 3 ? (y < x ? y : x) : (y > x ? y : x));
     }
     if (lane == 0) sh[warp][k] = x;
   }
   __syncthreads();
-  if (threadIdx.x < 29) {
+  if (threadIdx.x < 5) {
     const int k = threadIdx.x;
-    const bool is_min = (k == 3) || (k >= 4 && k < 28 && ((k - 4) & 3) == 0);
-    const bool is_sum = (k == 28);
     unsigned long long x = sh[0][k];
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
-      unsigned long long yv = sh[w][k];
-      x = is_sum ? x + yv : (is_min ? (yv < x ? yv : x) : (yv > x ? yv : x));
+      const unsigned long long y = sh[w][k];
+      x = (k == 4) ? x + y : (k == 3 ? (y < x ? y : x) : (y > x ? y : x));
     }
-    const int slot = (k == 28) ? RS_NGOOD : k;
-    if (is_sum)
-      atomicAdd(&red[slot], x);
-    else if (is_min)
+    if (k == 4) {
+      if (x) atomicAdd(&red[RS_NGOOD], x);
+    } else if (k == 3) {
+      atomicMin(&red[RS_FIRST], x);
+    } else {
+      atomicMax(&red[k], x);
+    }
+  }
+}
+
+__device__ __forceinline__ void decide_variant(const unsigned long long* red, int& axis, int& neg) {
+  double maxa = dec(red[RS_MAXA]), maxb = dec(red[RS_MAXB]), maxc = dec(red[RS_MAXC]);
+  if (maxa < 0.0 && maxb < 0.0 && maxc < 0.0) {  // no ray with state == 1: (0, 1, 0) (base.py:1261-1262)
+    maxa = 0.0;
+    maxb = 1.0;
+    maxc = 0.0;
+  }
+  const double maxMax = fmax(maxa, fmax(maxb, maxc));
+  axis = (maxMax == maxa) ? 0 : ((maxMax == maxb) ? 1 : 2);
+  const unsigned long long key = red[RS_FIRST];
+  neg = (int)((key >> axis) & 1ull) ? 0 : 1;
+}
+
+// Phase B: global t bracket and the secant-vs-Brent switch for the (axis, sign) variant phase A selected
+// (52 B/ray: state, x, y, z, a, b, c)
+template <int SURF>
+__global__ void __launch_bounds__(256) reflect_prepass_kernel(size_t n, xrt_oe_params p, xrt_beam in,
+                                                              unsigned long long* red) {
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  int axis, neg;
+  decide_variant(red, axis, neg);
+  double v[4] = {inf, -inf, -inf, -inf};
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int st = in.state[i];
+    if (!(p.good_mode ? (st == 1 || st == 2) : (st > 0))) continue;
+    Ray r = load_ray(in, i);
+    to_local(p, r);
+    double t1, t2, x, y, z;
+    bracket(p, axis, neg, r, t1, t2);
+    const double dz1 = find_dz<SURF>(p, t1, r, x, y, z);
+    double dz2 = find_dz<SURF>(p, t2, r, x, y, z);
+    if (dz1 <= 0.0 || dz2 >= 0.0) dz2 = 0.0;  // base.py:865 dz2[ind1 | ind2] = 0
+    // numpy's min/max propagate NaN; keep that by letting NaN win
+    v[0] = (t1 < v[0] || isnan(t1)) ? t1 : v[0];
+    v[1] = (t2 > v[1] || isnan(t2)) ? t2 : v[1];
+    v[2] = (fabs(dz1) > v[2] || isnan(dz1)) ? fabs(dz1) : v[2];
+    v[3] = (fabs(dz2) > v[3] || isnan(dz2)) ? fabs(dz2) : v[3];
+  }
+  __shared__ unsigned long long sh[8][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    unsigned long long x = enc(v[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long y = __shfl_xor_sync(0xffffffffu, x, o);
+      x = (k == 0) ? (y < x ? y : x) : (y > x ? y : x);
+    }
+    if (lane == 0) sh[warp][k] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    const int k = threadIdx.x;
+    unsigned long long x = sh[0][k];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      const unsigned long long y = sh[w][k];
+      x = (k == 0) ? (y < x ? y : x) : (y > x ? y : x);
+    }
+    const int slot = RS_VAR + (axis * 2 + neg) * 4 + k;
+    if (k == 0)
       atomicMin(&red[slot], x);
     else
       atomicMax(&red[slot], x);
@@ -541,17 +588,7 @@ struct Decision {
 
 __device__ __forceinline__ Decision decide(const unsigned long long* red) {
   Decision d;
-  double maxa = dec(red[RS_MAXA]), maxb = dec(red[RS_MAXB]), maxc = dec(red[RS_MAXC]);
-  if (maxa < 0.0 && maxb < 0.0 && maxc < 0.0) {  // no ray with state == 1: (0, 1, 0) (base.py:1261-1262)
-    maxa = 0.0;
-    maxb = 1.0;
-    maxc = 0.0;
-  }
-  const double maxMax = fmax(maxa, fmax(maxb, maxc));
-  d.axis = (maxMax == maxa) ? 0 : ((maxMax == maxb) ? 1 : 2);
-  const unsigned long long key = red[RS_FIRST];
-  const int positive = (int)((key >> d.axis) & 1ull);
-  d.neg = positive ? 0 : 1;
+  decide_variant(red, d.axis, d.neg);
   const int var = d.axis * 2 + d.neg;
   d.tMin = dec(red[RS_VAR + var * 4 + 0]);
   d.tMax = dec(red[RS_VAR + var * 4 + 1]);
@@ -676,8 +713,11 @@ __device__ __forceinline__ void copy_ray(const xrt_beam& dst, const xrt_beam& sr
   if (withState) dst.state[i] = state;
 }
 
+#ifndef XRTB_REFLECT_MINBLOCKS
+#define XRTB_REFLECT_MINBLOCKS 3
+#endif
 template <int SURF, int MAT>
-__global__ void __launch_bounds__(256) reflect_main_kernel(size_t n, xrt_oe_params p, xrt_material_params m,
+__global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kernel(size_t n, xrt_oe_params p, xrt_material_params m,
                                                            Tables tab, xrt_beam in, xrt_beam fb, xrt_beam gb,
                                                            xrt_beam lb, unsigned long long* red) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -808,8 +848,9 @@ __global__ void __launch_bounds__(256) reflect_main_kernel(size_t n, xrt_oe_para
         // polarisation frame (reflect.py:948-953; beams.py:448-479)
         const double rollAngle = p.roll + atan2(nrm[3], nrm[5]);
         double cY, sY;
+        sincos(rollAngle, &sY, &cY);  // cos(-x) == cos(x) and sin(-x) == -sin(x) exactly (numpy and CUDA alike)
         {
-          const double c = cos(-rollAngle), s = sin(-rollAngle);
+          const double c = cY, s = -sY;
           const double c2 = c * c, s2 = s * s, cs = c * s;
           const double J0 = Jss * c2 + Jpp * s2 + 2.0 * Jsp.re * cs;
           const double J1 = Jss * s2 + Jpp * c2 - 2.0 * Jsp.re * cs;
@@ -818,8 +859,6 @@ __global__ void __launch_bounds__(256) reflect_main_kernel(size_t n, xrt_oe_para
           Jpp = J1;
           Jsp = cplx{J2r + (Jsp.im * 0.0), 0.0 + Jsp.im};
         }
-        cY = cos(rollAngle);
-        sY = sin(rollAngle);
         if (amp) {
           // rotate_y(Es, Ep, cosY, -sinY): (c*x + s*z, -s*x + c*z) with s = -sinY
           const double s = -sY;
@@ -1009,16 +1048,20 @@ int reflect_device(size_t n, const xrt_oe_params* oe, const xrt_material_params*
   memset(&lbv, 0, sizeof(lbv));
   if (lb) lbv = *lb;
   const xrt_beam fbv = fallback ? *fallback : *in;
-  if (phase & 1) {
+  unsigned pgrid = (unsigned)num_sms() * 8;
+  {
+    const size_t need = (n + 255) / 256;
+    if (need < pgrid) pgrid = (unsigned)(need ? need : 1);
+  }
+  if (phase & 1) {  // phase A: dominant direction component, first good ray
     reduction_init_kernel<<<1, XRT_REDUCTION_SLOTS, 0, st>>>(red);
-    if (n > 0) {
-      unsigned grid = (unsigned)num_sms() * 8;
-      const size_t need = (n + 255) / 256;
-      if (need < grid) grid = (unsigned)need;
-      if (oe->surface == 0) reflect_prepass_kernel<0><<<grid, 256, 0, st>>>(n, *oe, *in, red, index_offset);
-      if (oe->surface == 1) reflect_prepass_kernel<1><<<grid, 256, 0, st>>>(n, *oe, *in, red, index_offset);
-      if (oe->surface == 2) reflect_prepass_kernel<2><<<grid, 256, 0, st>>>(n, *oe, *in, red, index_offset);
-    }
+    if (n > 0) reflect_prepass_dir_kernel<<<pgrid, 256, 0, st>>>(n, *oe, *in, red, index_offset);
+    XRTB_CUDA_CHECK(cudaGetLastError());
+  }
+  if ((phase & 4) && n > 0) {  // phase B: global bracket + solver switch of the selected variant
+    if (oe->surface == 0) reflect_prepass_kernel<0><<<pgrid, 256, 0, st>>>(n, *oe, *in, red);
+    if (oe->surface == 1) reflect_prepass_kernel<1><<<pgrid, 256, 0, st>>>(n, *oe, *in, red);
+    if (oe->surface == 2) reflect_prepass_kernel<2><<<pgrid, 256, 0, st>>>(n, *oe, *in, red);
     XRTB_CUDA_CHECK(cudaGetLastError());
   }
   if ((phase & 2) && n > 0) {

@@ -228,10 +228,13 @@ class OE(object):
                 ctypes.byref(cfb) if cfb is not None else None, ctypes.byref(cgb),
                 ctypes.byref(clb) if clb is not None else None, red.data_ptr())
         if allreduce is None:
-            _lib.check(lib.xrt_reflect_f64(*args, 3, index_offset, stream), 'xrt_reflect_f64')
+            _lib.check(lib.xrt_reflect_f64(*args, 7, index_offset, stream), 'xrt_reflect_f64')
         else:
-            _lib.check(lib.xrt_reflect_f64(*args, 1, index_offset, stream), 'xrt_reflect_f64 (pre-pass)')
-            allreduce(red)  # min/max/sum of the beam-wide scalars over ray shards (xrt_b200/parallel.py)
+            # min/max/sum of the beam-wide scalars over ray shards after each pre-pass (xrt_b200/parallel.py)
+            _lib.check(lib.xrt_reflect_f64(*args, 1, index_offset, stream), 'xrt_reflect_f64 (pre-pass A)')
+            allreduce(red)
+            _lib.check(lib.xrt_reflect_f64(*args, 4, index_offset, stream), 'xrt_reflect_f64 (pre-pass B)')
+            allreduce(red, False)  # counters were summed above
             _lib.check(lib.xrt_reflect_f64(*args, 2, index_offset, stream), 'xrt_reflect_f64 (main pass)')
         return red
 

@@ -46,13 +46,14 @@ def decode(s):
     return out.view(np.float64)
 
 
-def combine_slots(stacked):
-    """stacked: (world, 64) int64 tensor of slot buffers -> (64,) combined buffer."""
+def combine_slots(stacked, sums=True, own=None):
+    """stacked: (world, 64) int64 tensor of slot buffers -> (64,) combined buffer.  With sums=False the
+    counter slots keep this rank's values `own` (they were already summed by an earlier all-reduce)."""
     kinds = torch.from_numpy(slot_kinds()).to(stacked.device)
     s = stacked ^ _SIGN  # unsigned order -> signed order
     mx = s.max(dim=0).values ^ _SIGN
     mn = s.min(dim=0).values ^ _SIGN
-    sm = stacked.sum(dim=0)
+    sm = stacked.sum(dim=0) if sums or own is None else own
     return torch.where(kinds == 0, mx, torch.where(kinds == 1, mn, sm))
 
 
@@ -68,13 +69,13 @@ class Comm(object):
         stop = n if self.rank == self.world - 1 else start + per
         return start, stop
 
-    def allreduce_reductions(self, red):
+    def allreduce_reductions(self, red, sums=True):
         """In-place all-reduce of a reduction-slot buffer (int64[64]) over all ranks."""
         if self.world == 1:
             return red
         gathered = torch.empty(self.world * SLOTS, dtype=torch.int64, device=red.device)
         dist.all_gather_into_tensor(gathered, red)
-        red.copy_(combine_slots(gathered.view(self.world, SLOTS)))
+        red.copy_(combine_slots(gathered.view(self.world, SLOTS), sums, red.clone()))
         return red
 
     def allreduce_max(self, t):
