@@ -192,6 +192,8 @@ def run_ours(args):
     stage_names = ('sample', 'undulator', 'fill', 'reflect', 'expose')
     stage_events = []
     host_out = None
+    e2e_count = [0]
+    copy_stream = torch.cuda.Stream()
 
     def step(e2e=False, record=None):
         marks = [ev() for _ in range(6)] if record is not None else None
@@ -220,12 +222,21 @@ def run_ours(args):
         if args.gather == 'beam' and world > 1:
             blo = comm.allgather_beam(blo)
         if e2e:
-            for k, t in blo.tensors().items():
-                host_out[k].copy_(t[:host_out[k].numel()], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            # D2H of the result on a copy stream: the copy of step k overlaps the kernels of step k+1; two pinned
+            # host buffers alternate so a consumer owns one result while the next one lands
+            buf = host_out[e2e_count[0] % len(host_out)]
+            e2e_count[0] += 1
+            done = torch.cuda.Event()
+            done.record()
+            copy_stream.wait_event(done)
+            with torch.cuda.stream(copy_stream):
+                for k, t in blo.tensors().items():
+                    buf[k].copy_(t[:buf[k].numel()], non_blocking=True)
+                    t.record_stream(copy_stream)
         return blo
 
     def barrier():
+        copy_stream.synchronize()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -263,11 +274,12 @@ def run_ours(args):
     blo = step()
     bytes_per_ray = blo.bytes_per_ray()
     n_host = len(blo)
-    host_out = {k: torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for k, t in blo.tensors().items()}
+    host_out = [{k: torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for k, t in blo.tensors().items()}
+                for _ in range(2)]
     del blo
     for _ in range(max(1, args.warmup - 1)):
         step(e2e=True)
-    ms_e2e = timed(lambda: step(e2e=True), args.steps) / args.steps
+    ms_e2e = timed(lambda: step(e2e=True), args.steps) / args.steps  # barrier() drains the copy stream
     if rank == 0:
         sampler.stop_flag.set()
     e2e_value = world * nrays / (ms_e2e * 1e-3) / 1e6
@@ -315,11 +327,12 @@ def run_ours(args):
         kms = timed(kstep, ksteps) / ksteps
         pairs = float(N) * M / (kms * 1e-3)
         ktf = FLOP_PER_PAIR * pairs / 1e12
-        kir = {'workload': 'config4: %d samples -> %d receiving points, fp64, strict numpy rounding' % (N, M),
-               'ms': kms, 'pairs_per_s': pairs, 'value': ktf * 1e3, 'unit': 'GFLOP/s (57 flop/pair)',
-               'roofline': {'bound': 'fp64', 'achieved': ktf, 'peak': dfma_tflops, 'unit': 'TFLOP/s',
-                            'frac': ktf / dfma_tflops, 'traffic': None,
-                            'issue_slot_frac': 68 * 2 * pairs / 1e12 / dfma_tflops,
+        kir = {'workload': 'config4: %d samples -> %d receiving points (sharded over %d GPU(s)), fp64, strict '
+                           'numpy rounding' % (N, M, world),
+               'ms': kms, 'pairs_per_s': pairs, 'value': ktf * 1e3, 'unit': 'GFLOP/s (57 flop/pair), all GPUs',
+               'roofline': {'bound': 'fp64', 'achieved': ktf / world, 'peak': dfma_tflops, 'unit': 'TFLOP/s per GPU',
+                            'frac': ktf / world / dfma_tflops, 'traffic': None,
+                            'issue_slot_frac': 68 * 2 * pairs / world / 1e12 / dfma_tflops,
                             'note': '68 DFMA-pipe instructions per pair in SASS; frac counts the 57 algorithmic '
                                     'flops, issue_slot_frac the issued ones'}}
 
@@ -332,7 +345,7 @@ def run_ours(args):
                            'parallelism': 'rays sharded over %d GPU(s), gather=%s' % (world, args.gather)},
                 'e2e': {'value': e2e_value, 'unit': 'Mrays/s', 'h2d_bytes_per_step': h2d,
                         'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e},
-                'gpu_launches': args.steps * (8 + (0 if world == 1 else 0)),
+                'gpu_launches': args.steps * 9,  # sample, undulator, fill, 2 slot inits, pre-pass A/B, reflect, expose
                 'clocks': sampler.summary(),
                 'roofline': roofline, 'stages': hbm, 'kirchhoff': kir,
                 'cpu_baseline': cpu_baseline() if world == 1 and not args.no_cpu_baseline else None}

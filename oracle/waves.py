@@ -1,0 +1,147 @@
+"""Oracle: wave-mode bookkeeping around the Kirchhoff sum (TEST INFRASTRUCTURE ONLY, see oracle/__init__.py).
+
+Restates, for a RectangularAperture as diffracting element and a flat Screen as receiving element,
+  * Screen.prepare_wave              xrt/backends/raycing/screens.py:304-365
+  * waves.prepare_wave               xrt/backends/raycing/waves.py:505-584
+  * waves.diffract                   waves.py:606-831 (ConvexHull area :649-670, accumulation :707-717,
+                                     direction de-phasing :719-737, flux normalisation :739-749, frames :756-790)
+in numpy, in the reference's operation order."""
+import numpy as np
+from scipy.spatial import ConvexHull
+
+from . import beam as ob, kirchhoff as ok, planes as op
+
+
+class Plane(object):
+    def __init__(self, center, sinAz, cosAz):
+        self.center = list(center)
+        self.sinAzimuth, self.cosAzimuth = sinAz, cosAz
+        self.x, self.y, self.z = op.xyz_from_xz(sinAz, cosAz)
+
+    def local_to_global(self, x=0, y=0, z=0):
+        xglo = self.center[0] + x*self.x[0] + y*self.y[0] + z*self.z[0]
+        yglo = self.center[1] + x*self.x[1] + y*self.y[1] + z*self.z[1]
+        zglo = self.center[2] + x*self.x[2] + y*self.y[2] + z*self.z[2]
+        return xglo, yglo, zglo
+
+
+def prepare_wave(fromOE, wave, xglo, yglo, zglo):
+    nrays = len(wave.x)
+    wave.Es = np.zeros(nrays, dtype=complex)
+    wave.Ep = np.zeros(nrays, dtype=complex)
+    for k in ('EsAcc', 'EpAcc', 'aEacc', 'bEacc', 'cEacc'):
+        setattr(wave, k, np.zeros_like(wave.Es))
+    wave.Jss[:] = 0
+    wave.Jpp[:] = 0
+    wave.Jsp[:] = 0
+    x, y, z = np.array(xglo), np.array(yglo), np.array(zglo)
+    x -= fromOE.center[0]
+    y -= fromOE.center[1]
+    z -= fromOE.center[2]
+    a0, b0 = fromOE.sinAzimuth, fromOE.cosAzimuth
+    x[:], y[:] = ob.rotate_z(x, y, b0, a0)
+    wave.xDiffr = x
+    wave.yDiffr = y
+    wave.zDiffr = z
+    wave.rDiffr = (wave.xDiffr**2 + wave.yDiffr**2 + wave.zDiffr**2)**0.5
+    wave.a[:] = wave.xDiffr / wave.rDiffr
+    wave.b[:] = wave.yDiffr / wave.rDiffr
+    wave.c[:] = wave.zDiffr / wave.rDiffr
+    wave.path[:] = 0.
+    wave.fromOE = fromOE
+    wave.beamReflRays = np.int64(0)
+    wave.beamReflSumJ = 0.
+    wave.beamReflSumJnl = 0.
+    wave.diffract_repeats = np.int64(0)
+    return wave
+
+
+def screen_prepare_wave(screen, prevOE, dim1, dim2, dy=0):
+    d1s, d2s = np.meshgrid(dim1, dim2)
+    d1s = d1s.flatten()
+    d2s = d2s.flatten()
+    dS = (dim1[1] - dim1[0]) * (dim2[1] - dim2[0])
+    nrays = len(d1s)
+    xglo, yglo, zglo = screen.local_to_global(x=d1s, z=d2s)
+    wave = ob.Beam(nrays, withAmplitudes=True)
+    wave.state[:] = 1
+    wave.x[:] = d1s
+    wave.y[:] = np.zeros_like(d1s) + dy
+    wave.z[:] = d2s
+    wave.dS = dS
+    wave.toOE = screen
+    wave.area = (np.ones_like(d1s) * dS).sum()
+    return prepare_wave(prevOE, wave, xglo, yglo+dy, zglo)
+
+
+def diffract(oeLocal, wave):
+    oe = wave.fromOE
+    good = oeLocal.state == 1
+    goodlen = good.sum()
+    if getattr(oeLocal, 'area', None) is None or oeLocal.area <= 0:
+        impactPoints = np.vstack((oeLocal.x[good], oeLocal.z[good])).T
+        hull = ConvexHull(impactPoints)
+        outerPts = impactPoints[hull.vertices, :]
+        lines = np.hstack([outerPts, np.roll(outerPts, -1, axis=0)])
+        oeLocal.area = 0.5 * abs(sum(x1*y2-x2*y1 for x1, y1, x2, y2 in lines))
+    n = [0, 1, 0]
+    nl = oeLocal.a*n[0] + oeLocal.b*n[1] + oeLocal.c*n[2]
+    wave.diffract_repeats += 1
+    wave.beamReflRays += goodlen
+    wave.beamReflSumJ += (oeLocal.Jss[good] + oeLocal.Jpp[good]).sum()
+    wave.beamReflSumJnl += abs(((oeLocal.Jss[good] + oeLocal.Jpp[good]) * nl[good]).sum())
+    Es, Ep, aE, bE, cE = ok.diffraction_integral(
+        oeLocal.x[good], oeLocal.y[good], oeLocal.z[good], n, nl[good], oeLocal.Es[good], oeLocal.Ep[good],
+        oeLocal.E[good], wave.xDiffr, wave.yDiffr, wave.zDiffr)
+    wave.EsAcc += Es
+    wave.EpAcc += Ep
+    wave.aEacc += aE
+    wave.bEacc += bE
+    wave.cEacc += cE
+    wave.E[:] = oeLocal.E[0]
+    wave.Es[:] = wave.EsAcc
+    wave.Ep[:] = wave.EpAcc
+    wave.Jss[:] = (wave.Es * np.conj(wave.Es)).real
+    wave.Jpp[:] = (wave.Ep * np.conj(wave.Ep)).real
+    wave.Jsp[:] = wave.Es * np.conj(wave.Ep)
+    toReal = np.exp(-1j * np.angle(wave.bEacc))
+    wave.a[:] = (wave.aEacc * toReal).real
+    wave.b[:] = (wave.bEacc * toReal).real
+    wave.c[:] = (wave.cEacc * toReal).real
+    norm = (wave.a**2 + wave.b**2 + wave.c**2)**0.5
+    norm[norm == 0] = 1.
+    wave.a /= norm
+    wave.b /= norm
+    wave.c /= norm
+    norm = wave.dS * oeLocal.area * wave.beamReflSumJ
+    de = wave.beamReflRays * wave.beamReflSumJnl * wave.diffract_repeats
+    if de > 0:
+        norm /= de
+    else:
+        norm = 0
+    wave.Jss *= norm
+    wave.Jpp *= norm
+    wave.Jsp *= norm
+    wave.Es *= norm**0.5
+    wave.Ep *= norm**0.5
+    glo = ob.Beam(copyFrom=wave)
+    glo.x[:] = wave.xDiffr
+    glo.y[:] = wave.yDiffr
+    glo.z[:] = wave.zDiffr
+    x, y, z = glo.x, glo.y, glo.z  # aperture local_to_global (apertures.py:446-458)
+    xglo = oe.center[0] + x*oe.x[0] + y*oe.y[0] + z*oe.z[0]
+    yglo = oe.center[1] + x*oe.x[1] + y*oe.y[1] + z*oe.z[1]
+    zglo = oe.center[2] + x*oe.x[2] + y*oe.y[2] + z*oe.z[2]
+    glo.x, glo.y, glo.z = xglo, yglo, zglo
+    a, b, c = glo.a, glo.b, glo.c
+    aglo = a*oe.x[0] + b*oe.y[0] + c*oe.z[0]
+    bglo = a*oe.x[1] + b*oe.y[1] + c*oe.z[1]
+    cglo = a*oe.x[2] + b*oe.y[2] + c*oe.z[2]
+    glo.a, glo.b, glo.c = aglo, bglo, cglo
+    toOE = wave.toOE
+    wave.a[:], wave.b[:], wave.c[:] = glo.a, glo.b, glo.c
+    wave.Jss[:], wave.Jpp[:], wave.Jsp[:] = glo.Jss, glo.Jpp, glo.Jsp
+    wave.Es[:], wave.Ep[:] = glo.Es, glo.Ep
+    a0, b0 = toOE.sinAzimuth, toOE.cosAzimuth
+    wave.a[:], wave.b[:] = ob.rotate_z(wave.a, wave.b, b0, a0)
+    return glo

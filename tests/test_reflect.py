@@ -8,8 +8,11 @@ from helpers import (oracle_spec, oracle_beam, product_beamline, product_oe_kwar
                      BEAM_FIELDS)
 from oracle import reflect as orf, materials as om
 
-CASES = [('reflect_flat_Au', 'flat'), ('reflect_toroid_Au', 'toroid'), ('reflect_toroid_bare', 'toroid')]
-OUT_FIELDS = BEAM_FIELDS + ('theta',)
+CASES = [('reflect_flat_Au', 'flat'), ('reflect_toroid_Au', 'toroid'), ('reflect_toroid_bare', 'toroid'),
+         ('reflect_ellipse_vfm', 'ellipse_param'), ('reflect_ellipse_hfm', 'ellipse_param'),
+         ('reflect_ellipsoid', 'ellipse_param')]
+OUT_FIELDS = BEAM_FIELDS + ('theta', 's', 'phi', 'r')
+ELLIPSE_KEYS = ('ellipseA', 'ellipseB', 'y0', 'z0', 'cosGamma', 'sinGamma')
 
 
 def _oracle_run(name, surface):
@@ -18,6 +21,9 @@ def _oracle_run(name, surface):
     kw = {}
     if surface == 'toroid':
         kw['surfParams'] = dict(R=float(g['R']), r=float(g['r']))
+    if surface == 'ellipse_param':
+        kw['isParametric'] = True
+        kw['surfParams'] = dict(isCylindrical=bool(g['isCylindrical']), **{k: float(g[k]) for k in ELLIPSE_KEYS})
     sp = oracle_spec(g, surface, mat, **kw)
     info = {}
     gb, lb = orf.reflect(sp, oracle_beam(g, 'in_'), info=info)
@@ -45,6 +51,13 @@ def _product_oe(g, surface):
         kw['material'] = materials.Material('Au', rho=float(g['rho']))
     if surface == 'toroid':
         oe = oes.ToroidMirror(bl, 'oe', R=float(g['R']), r=float(g['r']), **kw)
+    elif surface == 'ellipse_param':
+        oe = oes.EllipticalMirrorParam(bl, 'oe', p=float(g['p']), q=float(g['q']),
+                                       isCylindrical=bool(g['isCylindrical']), **kw)
+        # the host mirror derives the ellipse from p, q, pitch like EllipticalMirrorParam._reset_pq
+        for k in ELLIPSE_KEYS:
+            assert abs(getattr(oe, k) - float(g[k])) <= 1e-13 * max(1., abs(float(g[k]))), k
+            setattr(oe, k, float(g[k]))
     else:
         oe = oes.OE(bl, 'oe', **kw)
     oe.lostNum = int(g['lostNum'])

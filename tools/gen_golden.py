@@ -364,8 +364,71 @@ def gen_shine():
         save(name, **d)
         print(name, 'seeded', beam.seeded, 'rays', len(beam.x))
 
+# ------------------------------------------------------------------------------------------------ KB mirrors
+def gen_kb():
+    bl = raycing.BeamLine()
+    Au = rm.Material('Au', rho=19.3)
+    for name, kw in (('reflect_ellipse_vfm', dict(pitch=4e-3, p=30000., q=2000., isCylindrical=True)),
+                     ('reflect_ellipse_hfm', dict(pitch=4e-3, p=30500., q=1500., isCylindrical=True,
+                                                  positionRoll=np.pi/2)),
+                     ('reflect_ellipsoid', dict(pitch=5e-3, p=20000., q=5000., isCylindrical=False))):
+        beam = _source_beam(bl, 2500, 91, dx=0.05, dz=0.03, dxprime=8e-6, dzprime=6e-6, energies=(8000, 10000))
+        oe = roe.EllipticalMirrorParam(bl, 'kb', center=(0, kw['p'], 0), material=Au,
+                                       limPhysX=[-3, 3], limPhysY=[-90, 80], **kw)
+        d = _capture_reflect(oe, beam)
+        d.update(_oe_params(oe))
+        for k in ('ellipseA', 'ellipseB', 'y0', 'z0', 'cosGamma', 'sinGamma', 'p', 'q'):
+            d[k] = float(getattr(oe, k))
+        d['isCylindrical'] = bool(oe.isCylindrical)
+        st = d['gb_state']
+        print(name, {int(x): int((st == x).sum()) for x in np.unique(st)})
+        save(name, rho=19.3, **d)
 
-SECTIONS = {'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+# ------------------------------------------------------------------------------------------------ wave mode
+def gen_diffract():
+    bl = raycing.BeamLine(azimuth=0.1)
+    d1, d2 = 1e4, 2e4
+    sa, ca = np.sin(0.1), np.cos(0.1)
+    slit = ra.RectangularAperture(bl, 'slit', center=(d1*sa, d1*ca, 0), kind=('left', 'right', 'bottom', 'top'),
+                                  opening=[-0.05, 0.05, -0.04, 0.04])
+    scr = rsc.Screen(bl, 'scr', center=(d2*sa, d2*ca, 0))
+    N = 3000
+    rng = np.random.RandomState(101)
+    oeLocal = rs.Beam(N, withAmplitudes=True)
+    oeLocal.x[:] = rng.uniform(-0.05, 0.05, N)
+    oeLocal.z[:] = rng.uniform(-0.04, 0.04, N)
+    oeLocal.y[:] = 0.
+    r = np.sqrt(oeLocal.x**2 + d1**2 + oeLocal.z**2)
+    oeLocal.a[:], oeLocal.b[:], oeLocal.c[:] = oeLocal.x / r, d1 / r, oeLocal.z / r
+    oeLocal.E[:] = 9000.
+    k = oeLocal.E / rpc.CHBAR * 1e7
+    oeLocal.Es[:] = np.exp(1j * k * r) / r * 1e4
+    oeLocal.Ep[:] = 0.05 * np.exp(1j * (k * r + 0.3)) / r * 1e4
+    oeLocal.Jss[:] = np.abs(oeLocal.Es)**2
+    oeLocal.Jpp[:] = np.abs(oeLocal.Ep)**2
+    oeLocal.Jsp[:] = oeLocal.Es * np.conj(oeLocal.Ep)
+    oeLocal.state[:] = 1
+    oeLocal.state[rng.rand(N) < 0.03] = 2
+    xm = np.linspace(-0.4, 0.4, 48)
+    zm = np.linspace(-0.3, 0.3, 40)
+    wave = scr.prepare_wave(slit, xm, zm)
+    pre = dict(xDiffr=wave.xDiffr.copy(), yDiffr=wave.yDiffr.copy(), zDiffr=wave.zDiffr.copy(),
+               rDiffr=wave.rDiffr.copy(), wa=wave.a.copy(), wb=wave.b.copy(), wc=wave.c.copy(), dS=wave.dS,
+               warea=wave.area)
+    glo = rw.diffract(oeLocal, wave)
+    d = dict(azimuth=0.1, slit_center=np.array(slit.center, dtype=float), scr_center=np.array(scr.center, dtype=float),
+             opening=np.array([-0.05, 0.05, -0.04, 0.04]), xmesh=xm, zmesh=zm, area=oeLocal.area, **pre)
+    d.update(beam_dict(oeLocal, 'in_'))
+    d.update(beam_dict(wave, 'wave_'))
+    d.update(beam_dict(glo, 'glo_'))
+    for k2 in ('EsAcc', 'EpAcc', 'aEacc', 'bEacc', 'cEacc'):
+        d['wave_' + k2] = getattr(wave, k2)
+    d['beamReflSumJ'] = wave.beamReflSumJ
+    d['beamReflSumJnl'] = wave.beamReflSumJnl
+    save('diffract_slit_screen', **d)
+
+
+SECTIONS = {'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)
