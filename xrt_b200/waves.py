@@ -167,7 +167,9 @@ def diffract(oeLocal, wave, targetOpenCL='CUDA', precisionOpenCL='float64'):
     wave.beamReflSumJnl += abs(float((Jtot * nl).sum()))
 
     E = sel(oeLocal.E)
-    k = E / CHBAR * 1e7  # waves.py:842
+    # waves.py:842.  torch divides a tensor by a Python scalar as a multiplication by its reciprocal, which is
+    # one ulp off numpy's true division often enough to move k*r by 6e-5 rad: divide by a tensor instead
+    k = torch.div(E, torch.full_like(E, CHBAR)) * 1e7
     pos = torch.stack((x, y, z, torch.zeros_like(x)), dim=1).contiguous()
     nrm = torch.tensor(nvec + (0.,), dtype=F64, device=x.device).repeat(goodlen, 1).contiguous()
     out = kernels.kirchhoff(wave.xDiffr.contiguous(), wave.yDiffr.contiguous(), wave.zDiffr.contiguous(), nl, sel(oeLocal.Es),
