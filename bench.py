@@ -322,7 +322,7 @@ def run_ours(args):
 
         def kstep():
             kernels.kirchhoff(d['xM'], d['yM'], d['zM'], d['nl'], d['Es'], d['Ep'], d['k'], d['pos'], d['nrm'],
-                              out=out, R=args.kirchhoff_r)
+                              out=out, R=args.kirchhoff_r, uniform_normal=True)  # slit: n = (0, 1, 0)
         kstep()
         ksteps = max(1, min(args.steps, 2))
         kms = timed(kstep, ksteps) / ksteps

@@ -46,6 +46,7 @@ int xrt_b200_fp64_probe(int mode, int iters, double* tflops, double* ms);
  * flags: bit0 = relaxed arithmetic (allow FMA contraction of |d|^2; default is numpy rounding order)
  *        bit1 = OpenCL sign/scale convention (default numpy convention, waves.py:844-850)
  *        bits4-6 = register blocking R in {1,2,4} (0 = default 2)
+ *        bit9 = all N normals are equal (aperture, flat OE): n.d = n.p - n.q with n.p hoisted per output
  * `workspace` must hold xrt_kirchhoff_workspace_bytes(M, N, flags) bytes of device memory. */
 size_t xrt_kirchhoff_workspace_bytes(size_t M, size_t N, int flags);
 int xrt_kirchhoff_f64(size_t M, size_t N, const double* xM, const double* yM, const double* zM, const double* nl,

@@ -26,9 +26,9 @@ namespace xrtb {
 
 struct __align__(16) KInput {
   double qx, qy, qz, nl;
-  double nx, ny, nz, k;
+  double nx2, ny2, nz2, k;  // 2 n (the kernel works with 0.5/r, see sqrt_hrsqrt), k
   double es_re, es_im, ep_re, ep_im;
-  double w_re, w_im, k2, pad;
+  double w_re, w_im, k2x, nq2;  // Es + Ep, 2 k, 2 n.q (uniform-normal fast path)
 };
 static_assert(sizeof(KInput) == 128, "KInput must be 128 bytes");
 
@@ -43,9 +43,10 @@ __global__ void kirchhoff_pack_kernel(size_t N, const double* __restrict__ nl, c
   r.qx = pos[j * pos_stride + 0];
   r.qy = pos[j * pos_stride + 1];
   r.qz = pos[j * pos_stride + 2];
-  r.nx = nrm[j * nrm_stride + 0];
-  r.ny = nrm[j * nrm_stride + 1];
-  r.nz = nrm[j * nrm_stride + 2];
+  const double nx = nrm[j * nrm_stride + 0], ny = nrm[j * nrm_stride + 1], nz = nrm[j * nrm_stride + 2];
+  r.nx2 = 2.0 * nx;
+  r.ny2 = 2.0 * ny;
+  r.nz2 = 2.0 * nz;
   r.nl = nl[j];
   double kj = k[j];
   r.k = kj;
@@ -56,17 +57,19 @@ __global__ void kirchhoff_pack_kernel(size_t N, const double* __restrict__ nl, c
   r.ep_im = ep.y;
   r.w_re = es.x + ep.x;  // numpy forms (Es + Ep) first as well (waves.py:847)
   r.w_im = es.y + ep.y;
-  r.k2 = kj * kj;
-  r.pad = 0.0;
+  r.k2x = 2.0 * kj;
+  r.nq2 = 2.0 * (nx * r.qx + ny * r.qy + nz * r.qz);
   out[j] = r;
 }
 
 // ---------------------------------------------------------------- main kernel
-template <int R, int THREADS, int TILE, bool STRICT>
+// UNIFORM_N: every sample has the same normal n (aperture, flat OE): n.d = n.p_i - n.q_j with n.p_i hoisted out
+// of the loop (exactly d_y for the aperture normal (0, 1, 0)).
+template <int R, int THREADS, int TILE, bool STRICT, bool UNIFORM_N>
 __global__ void __launch_bounds__(THREADS)
     kirchhoff_kernel(size_t M, size_t N, const double* __restrict__ xM, const double* __restrict__ yM,
                      const double* __restrict__ zM, const KInput* __restrict__ in, size_t n_per_split,
-                     double2* __restrict__ part) {
+                     double2* __restrict__ part, double un_x, double un_y, double un_z) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   KInput* tile = reinterpret_cast<KInput*>(smem_raw);                       // [2][TILE]
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + 2 * TILE * sizeof(KInput));  // [2]
@@ -79,7 +82,7 @@ __global__ void __launch_bounds__(THREADS)
   const size_t nloc = (j1 > j0) ? (j1 - j0) : 0;
   const int ntiles = (int)((nloc + TILE - 1) / TILE);
 
-  double px[R], py[R], pz[R];
+  double px[R], py[R], pz[R], np2[R];
   double acc[R][10];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -88,6 +91,7 @@ __global__ void __launch_bounds__(THREADS)
     px[r] = xM[ii];
     py[r] = yM[ii];
     pz[r] = zM[ii];
+    np2[r] = 2.0 * (un_x * px[r] + un_y * py[r] + un_z * pz[r]);
 #pragma unroll
     for (int c = 0; c < 10; ++c) acc[r][c] = 0.0;
   }
@@ -139,12 +143,12 @@ __global__ void __launch_bounds__(THREADS)
         } else {
           r2 = fma(dz, dz, fma(dy, dy, dx * dx));
         }
-        double rr, inv;
-        sqrt_rsqrt(r2, rr, inv);
-        const double dn = fma(dz, a1.z, fma(dy, a1.y, dx * a1.x));
-        const double tcos = fma(dn, inv, a0.w);  // n.d/r + nl
+        double rr, hinv;  // hinv = 0.5 / r
+        sqrt_hrsqrt(r2, rr, hinv);
+        const double dn2 = UNIFORM_N ? (np2[r] - a3.w) : fma(dz, a1.z, fma(dy, a1.y, dx * a1.x));  // 2 n.d
+        const double tcos = fma(dn2, hinv, a0.w);  // n.d/r + nl
         const double phase = STRICT ? __dmul_rn(a1.w, rr) : a1.w * rr;
-        const double kip = a1.w * inv;
+        const double kip = a3.z * hinv;  // k / r
         const double cr = kip * tcos;
         double sn, cs;
         sincos_big(phase, sn, cs);
@@ -160,7 +164,7 @@ __global__ void __launch_bounds__(THREADS)
         acc[r][3] = fma(gre, a2.w, acc[r][3]);
         acc[r][3] = fma(gim, a2.z, acc[r][3]);
         // h = (k^2 / r) * g * (Es + Ep)
-        const double kk = a3.z * inv;
+        const double kk = kip * a1.w;  // k^2 / r
         const double wre = fma(gre, a3.x, -gim * a3.y);
         const double wim = fma(gre, a3.y, gim * a3.x);
         const double hre = kk * wre;
@@ -226,20 +230,26 @@ __global__ void kirchhoff_finalize_kernel(size_t M, int nsplit, const double2* _
 }
 
 // ---------------------------------------------------------------- host-side launcher
-template <int R, int THREADS, int TILE>
-static int launch_main(bool strict, dim3 grid, size_t smem, cudaStream_t st, size_t M, size_t N, const double* xM,
-                       const double* yM, const double* zM, const KInput* in, size_t nps, double2* part) {
-  if (strict) {
-    XRTB_CUDA_CHECK(cudaFuncSetAttribute(kirchhoff_kernel<R, THREADS, TILE, true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kirchhoff_kernel<R, THREADS, TILE, true><<<grid, THREADS, smem, st>>>(M, N, xM, yM, zM, in, nps, part);
-  } else {
-    XRTB_CUDA_CHECK(cudaFuncSetAttribute(kirchhoff_kernel<R, THREADS, TILE, false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kirchhoff_kernel<R, THREADS, TILE, false><<<grid, THREADS, smem, st>>>(M, N, xM, yM, zM, in, nps, part);
-  }
+template <int R, int THREADS, int TILE, bool STRICT, bool UNI>
+static int launch_one(dim3 grid, size_t smem, cudaStream_t st, size_t M, size_t N, const double* xM, const double* yM,
+                      const double* zM, const KInput* in, size_t nps, double2* part, const double* un) {
+  XRTB_CUDA_CHECK(cudaFuncSetAttribute(kirchhoff_kernel<R, THREADS, TILE, STRICT, UNI>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kirchhoff_kernel<R, THREADS, TILE, STRICT, UNI><<<grid, THREADS, smem, st>>>(M, N, xM, yM, zM, in, nps, part, un[0],
+                                                                              un[1], un[2]);
   XRTB_CUDA_CHECK(cudaGetLastError());
   return 0;
+}
+
+template <int R, int THREADS, int TILE>
+static int launch_main(bool strict, bool uni, dim3 grid, size_t smem, cudaStream_t st, size_t M, size_t N,
+                       const double* xM, const double* yM, const double* zM, const KInput* in, size_t nps,
+                       double2* part, const double* un) {
+  if (strict)
+    return uni ? launch_one<R, THREADS, TILE, true, true>(grid, smem, st, M, N, xM, yM, zM, in, nps, part, un)
+               : launch_one<R, THREADS, TILE, true, false>(grid, smem, st, M, N, xM, yM, zM, in, nps, part, un);
+  return uni ? launch_one<R, THREADS, TILE, false, true>(grid, smem, st, M, N, xM, yM, zM, in, nps, part, un)
+             : launch_one<R, THREADS, TILE, false, false>(grid, smem, st, M, N, xM, yM, zM, in, nps, part, un);
 }
 
 constexpr int K_THREADS = 128;
@@ -274,6 +284,7 @@ int kirchhoff_device(size_t M, size_t N, const double* xM, const double* yM, con
   if (M == 0) return 0;
   const bool strict = !(flags & 1);
   const int convention = (flags >> 1) & 1;
+  const bool uni = (flags >> 9) & 1;  // caller guarantees that all N normals are equal
   int R = (flags >> 4) & 7;
   if (R == 0) R = 2;
   XRTB_REQUIRE(R == 1 || R == 2 || R == 4, "kirchhoff: register blocking R must be 1, 2 or 4 (got %d)", R);
@@ -293,12 +304,17 @@ int kirchhoff_device(size_t M, size_t N, const double* xM, const double* yM, con
   if (nps == 0) nps = K_TILE;
   const size_t smem = 2 * K_TILE * sizeof(KInput) + 2 * sizeof(uint64_t);
   int rc = 0;
+  double un[3] = {0.0, 0.0, 0.0};
+  if (uni && N > 0) {  // the common normal = the first sample's (3 doubles, device -> host)
+    XRTB_CUDA_CHECK(cudaMemcpyAsync(un, nrm, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    XRTB_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
   if (R == 1)
-    rc = launch_main<1, K_THREADS, K_TILE>(strict, grid, smem, st, M, N, xM, yM, zM, packed, nps, part);
+    rc = launch_main<1, K_THREADS, K_TILE>(strict, uni, grid, smem, st, M, N, xM, yM, zM, packed, nps, part, un);
   else if (R == 2)
-    rc = launch_main<2, K_THREADS, K_TILE>(strict, grid, smem, st, M, N, xM, yM, zM, packed, nps, part);
+    rc = launch_main<2, K_THREADS, K_TILE>(strict, uni, grid, smem, st, M, N, xM, yM, zM, packed, nps, part, un);
   else
-    rc = launch_main<4, K_THREADS, K_TILE>(strict, grid, smem, st, M, N, xM, yM, zM, packed, nps, part);
+    rc = launch_main<4, K_THREADS, K_TILE>(strict, uni, grid, smem, st, M, N, xM, yM, zM, packed, nps, part, un);
   if (rc) return rc;
   kirchhoff_finalize_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(
       M, nsplit, part, convention, reinterpret_cast<double2*>(S), reinterpret_cast<double2*>(P),

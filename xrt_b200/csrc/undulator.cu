@@ -54,36 +54,40 @@ __device__ __forceinline__ USample make_sample(double Kx, double Ky, double gamm
   return s;
 }
 
+// PLANAR (Kx == 0): beta_y, beta'_y and every product with them are exact zeros in the reference's arithmetic
+// (adding/subtracting +-0 is exact), so dropping those operations leaves every result bit-identical.
+template <bool PLANAR>
 __device__ __forceinline__ void node_step(const USample& s, const double4 n0, const double4 n1, double& bs_re,
                                           double& bs_im, double& bp_re, double& bp_im) {
   // phase (synchr.py:1997-2002), reassociated: every term is O(1..100) rad, error ~1e-14 rad
   double ucos = s.ww1 * n0.x;
   ucos = fma(s.b1, n1.x, ucos);
-  ucos = fma(s.b2, n1.y, ucos);
+  if (!PLANAR) ucos = fma(s.b2, n1.y, ucos);
   ucos = fma(s.a3, n1.z, ucos);
   double sn, cs;
   sincos_big(ucos, sn, cs);
   // velocity (synchr.py:2006-2008), reference rounding order
   const double bx = __dmul_rn(s.kyr, n0.z);
-  const double by = __dmul_rn(s.kxrn, n0.w);
-  const double t4 = __dadd_rn(__dadd_rn(s.revg2, __dmul_rn(bx, bx)), __dmul_rn(by, by));
+  const double by = PLANAR ? 0.0 : __dmul_rn(s.kxrn, n0.w);
+  double t4 = __dadd_rn(s.revg2, __dmul_rn(bx, bx));
+  if (!PLANAR) t4 = __dadd_rn(t4, __dmul_rn(by, by));
   const double bz = __dadd_rn(1.0, -0.5 * t4);
   // acceleration (synchr.py:2010-2016)
   const double bpz = __dmul_rn(s.hrevg, n1.z);
   // 1/(1 - n.beta) (synchr.py:2018), reference rounding order
   double den = __dadd_rn(1.0, -__dmul_rn(s.dirx, bx));
-  den = __dadd_rn(den, -__dmul_rn(s.diry, by));
+  if (!PLANAR) den = __dadd_rn(den, -__dmul_rn(s.diry, by));
   den = __dadd_rn(den, -__dmul_rn(s.dirz, bz));
   const double rk = rcp_fast(den);
   const double wgt = n0.y * (rk * rk);  // ag * rkrel**2 (synchr.py:2019)
   const double ere = cs * wgt, eim = sn * wgt;
   const double bnx = s.dirx - bx;
-  const double bny = s.diry - by;
+  const double bny = PLANAR ? s.diry : s.diry - by;
   const double bnz = s.dirz - bz;  // exact (Sterbenz)
-  const double ddbp = fma(s.dirz, bpz, fma(s.diry, n1.y, s.dirx * n1.x));
+  const double ddbp = PLANAR ? fma(s.dirz, bpz, s.dirx * n1.x) : fma(s.dirz, bpz, fma(s.diry, n1.y, s.dirx * n1.x));
   const double ddmb = fma(s.dirz, bnz, fma(s.diry, bny, s.dirx * bnx));
   const double ts = fma(bnx, ddbp, -(n1.x * ddmb));
-  const double tp = fma(bny, ddbp, -(n1.y * ddmb));
+  const double tp = PLANAR ? bny * ddbp : fma(bny, ddbp, -(n1.y * ddmb));
   bs_re = fma(ere, ts, bs_re);
   bs_im = fma(eim, ts, bs_im);
   bp_re = fma(ere, tp, bp_re);
@@ -122,7 +126,7 @@ struct UParams {
   int bw_mode;  // 1: distE == 'BW'
 };
 
-template <int R, int MODE>
+template <int R, int MODE, bool PLANAR>
 __global__ void __launch_bounds__(U_THREADS)
     undulator_kernel(size_t n, UParams p, UTables tab, const double* __restrict__ gamma, const double* __restrict__ wu,
                      const double* __restrict__ w, const double* __restrict__ ww1, const double* __restrict__ phi,
@@ -170,7 +174,7 @@ __global__ void __launch_bounds__(U_THREADS)
       const double4 n0 = q[0];
       const double4 n1 = q[1];
 #pragma unroll
-      for (int r = 0; r < R; ++r) node_step(s[r], n0, n1, acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+      for (int r = 0; r < R; ++r) node_step<PLANAR>(s[r], n0, n1, acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
     }
   }
 
@@ -212,8 +216,14 @@ static int launch(int mode, int R, size_t n, const UParams& p, const UTables& t,
   const unsigned grid = (unsigned)((n + per - 1) / per);
   double2* is2 = reinterpret_cast<double2*>(Is);
   double2* ip2 = reinterpret_cast<double2*>(Ip);
-#define XRTB_U_LAUNCH(RR, MM) \
-  undulator_kernel<RR, MM><<<grid, U_THREADS, 0, st>>>(n, p, t, gamma, wu, w, ww1, phi, psi, is2, ip2, I)
+  const bool planar = (p.Kx == 0.0);
+#define XRTB_U_LAUNCH(RR, MM)                                                                                      \
+  do {                                                                                                             \
+    if (planar)                                                                                                    \
+      undulator_kernel<RR, MM, true><<<grid, U_THREADS, 0, st>>>(n, p, t, gamma, wu, w, ww1, phi, psi, is2, ip2, I); \
+    else                                                                                                           \
+      undulator_kernel<RR, MM, false><<<grid, U_THREADS, 0, st>>>(n, p, t, gamma, wu, w, ww1, phi, psi, is2, ip2, I); \
+  } while (0)
   if (mode == 0) {
     if (R == 1) XRTB_U_LAUNCH(1, 0);
     else if (R == 2) XRTB_U_LAUNCH(2, 0);

@@ -125,6 +125,9 @@ class XRT_CUDA(object):
                 raise ValueError('integrate_kirchhoff: slicedRWArgs must be 5 contiguous complex128[dimension]')
             outs.append(a)
         flags = (1 if self.kirchhoffRelaxed else 0) | (_KIRCHHOFF_CONVENTIONS[self.kirchhoffConvention] << 1)
+        nview = nrm[:3, :] if nrm.shape[1] == N and nrm.shape[0] in (3, 4) and nrm.flags['F_CONTIGUOUS'] else nrm[:, :3].T
+        if N > 0 and np.all(nview == nview[:, :1]):
+            flags |= 1 << 9  # all normals equal (aperture / flat OE): the kernel hoists n.p out of the pair loop
         rc = lib.xrt_kirchhoff_f64_host(
             M, N, _lib.hptr(xM), _lib.hptr(yM), _lib.hptr(zM), _lib.hptr(nl), _lib.hptr(Es), _lib.hptr(Ep),
             _lib.hptr(k), _lib.hptr(pos), pstride, _lib.hptr(nrm), nstride,

@@ -35,11 +35,12 @@ def fp64_probe(mode=0, iters=4096):
 
 
 def kirchhoff(xM, yM, zM, nl, Es, Ep, k, pos, nrm, out=None, convention='numpy', relaxed=False, R=0,
-              workspace=None):
+              workspace=None, uniform_normal=False):
     """a17 on device tensors.  pos, nrm: (N, 3|4) float64 row-major.  Returns (S, P, A, B, C) complex128[M]."""
     lib = _lib.load()
     M, N = xM.numel(), nl.numel()
-    flags = (1 if relaxed else 0) | ((1 if convention == 'opencl' else 0) << 1) | (int(R) << 4)
+    flags = (1 if relaxed else 0) | ((1 if convention == 'opencl' else 0) << 1) | (int(R) << 4) | \
+        ((1 if uniform_normal else 0) << 9)
     need = lib.xrt_kirchhoff_workspace_bytes(M, N, flags)
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty(max(need, 16), dtype=torch.uint8, device=xM.device)

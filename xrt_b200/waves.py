@@ -173,7 +173,7 @@ def diffract(oeLocal, wave, targetOpenCL='CUDA', precisionOpenCL='float64'):
     pos = torch.stack((x, y, z, torch.zeros_like(x)), dim=1).contiguous()
     nrm = torch.tensor(nvec + (0.,), dtype=F64, device=x.device).repeat(goodlen, 1).contiguous()
     out = kernels.kirchhoff(wave.xDiffr.contiguous(), wave.yDiffr.contiguous(), wave.zDiffr.contiguous(), nl, sel(oeLocal.Es),
-                            sel(oeLocal.Ep), k, pos, nrm, convention='numpy')
+                            sel(oeLocal.Ep), k, pos, nrm, convention='numpy', uniform_normal=True)
     Es, Ep, aE, bE, cE = out[0], out[1], out[2], out[3], out[4]
 
     wave.EsAcc += Es
