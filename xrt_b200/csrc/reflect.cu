@@ -412,25 +412,28 @@ __device__ __forceinline__ cplx cmul_np(cplx a, cplx b) {
   return cplx{fma(a.re, b.re, -ii), fma(a.re, b.im, ir)};
 }
 __device__ __forceinline__ cplx csquare_np(cplx a) { return cmul_np(a, a); }
+// complex / real: numpy casts the real to (b, 0) and runs Smith's algorithm, where rat = 0/b = 0 and
+// scl = 1/(b + 0*0): the quotient is (a.re*scl, a.im*scl) -- one division instead of two, same bits
+__device__ __forceinline__ cplx cdiv_re(cplx a, double b) {
+  const double scl = 1.0 / b;
+  return cplx{a.re * scl, a.im * scl};
+}
 __device__ __forceinline__ cplx cexp_i(double phi) {  // exp(0 + i phi)
   double s, c;
   sincos_big(phi, s, c);
   return cplx{c, s};
 }
 
-// np.interp for one point (numpy/core/src/multiarray/compiled_base.c: binary search, slope form)
-__device__ __forceinline__ double interp1(const double* __restrict__ xp, const double* __restrict__ fp, int len,
-                                          double x) {
-  if (x <= xp[0]) return (x == xp[0]) ? fp[0] : fp[0];
-  if (x >= xp[len - 1]) return fp[len - 1];
-  int lo = 0, hi = len - 1;  // xp[lo] <= x < xp[hi]
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (x >= xp[mid])
-      lo = mid;
-    else
-      hi = mid;
-  }
+// np.interp (numpy/core/src/multiarray/compiled_base.c): binary search, slope form -- see f1f2() below
+struct Tables {
+  const double *E, *f1, *f2;
+};
+
+// slope form of np.interp at a located interval [lo, lo + 1]
+__device__ __forceinline__ double interp_at(const double* __restrict__ xp, const double* __restrict__ fp, int len,
+                                            int lo, double x) {
+  if (lo < 0) return fp[0];
+  if (lo >= len - 1) return fp[len - 1];
   if (xp[lo] == x) return fp[lo];
   const double slope = (fp[lo + 1] - fp[lo]) / (xp[lo + 1] - xp[lo]);
   double res = slope * (x - xp[lo]) + fp[lo];
@@ -441,18 +444,30 @@ __device__ __forceinline__ double interp1(const double* __restrict__ xp, const d
   return res;
 }
 
-struct Tables {
-  const double *E, *f1, *f2;
-};
-
-// Element.get_f1f2 (element.py:252-263); the out-of-range ValueError becomes NaN + an error flag
+// Element.get_f1f2 (element.py:252-263): f1 and f2 share the energy grid, so one binary search serves both
+// np.interp calls; the out-of-range ValueError becomes NaN + an error flag
 __device__ __forceinline__ cplx f1f2(const Tables& t, int off, int len, double E, int* oor) {
-  if (E < t.E[off] || E > t.E[off + len - 1]) {
+  const double* __restrict__ xp = t.E + off;
+  if (E < xp[0] || E > xp[len - 1]) {
     *oor = 1;
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
     return cplx{nan, nan};
   }
-  return cplx{interp1(t.E + off, t.f1 + off, len, E), interp1(t.E + off, t.f2 + off, len, E)};
+  int lo;
+  if (E >= xp[len - 1]) {
+    lo = len - 1;
+  } else {
+    lo = 0;
+    int hi = len - 1;  // xp[lo] <= E < xp[hi]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (E >= xp[mid])
+        lo = mid;
+      else
+        hi = mid;
+    }
+  }
+  return cplx{interp_at(xp, t.f1 + off, len, lo, E), interp_at(xp, t.f2 + off, len, lo, E)};
 }
 
 // Material.get_refractive_index (material.py:372-378)
@@ -469,7 +484,7 @@ __device__ __forceinline__ cplx refractive_index(const xrt_material_params& m, c
   const double w = CH / E;
   const double fac = c0 * (w * w) * m.rho;
   const cplx num = cmul_np(cplx{fac, 0.0}, xf);
-  const cplx q = cdiv(num, cplx{m.mass, 0.0});
+  const cplx q = cdiv_re(num, m.mass);
   return cplx{1.0 - q.re, 0.0 - q.im};
 }
 
@@ -494,7 +509,7 @@ __device__ __forceinline__ void mirror_amplitude(const xrt_material_params& m, c
     // thin mirror: p2 = exp(2j * E / CHBAR * n2cosBeta * t * 1e7) (material.py:479-482)
     const double CHBAR = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8 / 6.283185307179586476925286766559;
     cplx z = cmul_np(cplx{0.0, 2.0}, cplx{E, 0.0});
-    z = cdiv(z, cplx{CHBAR, 0.0});
+    z = cdiv_re(z, CHBAR);
     z = cmul_np(z, n2cosBeta);
     z = cmul_np(z, cplx{m.t, 0.0});
     z = cmul_np(z, cplx{1e7, 0.0});
@@ -515,7 +530,7 @@ __device__ __forceinline__ cplx bragg_one_pol(double polFactor, cplx alpha, cplx
   // delta = sqrt(alpha**2 + polFactor**2 * chih * chih_ / b)
   cplx t = cmul_np(cplx{polFactor * polFactor, 0.0}, chih);
   t = cmul_np(t, chih_);
-  t = cdiv(t, cplx{b, 0.0});
+  t = cdiv_re(t, b);
   const cplx delta = csqrt_(cadd(csquare_np(alpha), t));
   const cplx num = cmul_np(chih, cplx{polFactor, 0.0});
   cplx ra = cdiv(num, cadd(alpha, delta));
@@ -524,7 +539,7 @@ __device__ __forceinline__ cplx bragg_one_pol(double polFactor, cplx alpha, cplx
   const cplx rb = cdiv(num, ad);
   if (isnan(ra.re) || isnan(ra.im)) ra = rb;
   if (cabs(rb) < cabs(ra)) ra = rb;
-  return cdiv(ra, cplx{sqrt(fabs(b)), 0.0});
+  return cdiv_re(ra, sqrt(fabs(b)));
 }
 
 __device__ __forceinline__ void crystal_amplitude(const xrt_material_params& m, const Tables& t, double E,
@@ -573,7 +588,7 @@ __device__ __forceinline__ void crystal_amplitude(const xrt_material_params& m, 
   const double thetaB = asin(sa);
   // alpha = (H2/2 - k0H) / k02 + chi0/2 * (1/b - 1)
   const double a1 = (H2 / 2.0 - k0H) / k02;
-  const cplx half_chi0 = cdiv(chi0, cplx{2.0, 0.0});
+  const cplx half_chi0 = cdiv_re(chi0, 2.0);
   const cplx a2 = cmul_np(half_chi0, cplx{1.0 / b - 1.0, 0.0});
   const cplx alpha = cplx{a1 + a2.re, 0.0 + a2.im};
   rs = bragg_one_pol(1.0, alpha, chih, chih_, b);
