@@ -275,8 +275,15 @@ def run_ours(args):
     blo = step()
     bytes_per_ray = blo.bytes_per_ray()
     n_host = len(blo)
-    host_out = [{k: torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for k, t in blo.tensors().items()}
-                for _ in range(2)]
+    host_out = []
+    for _ in range(2):  # two pinned result buffers (2 x 13.2 GB at 1e8 rays); one if the host cannot pin that much
+        try:
+            host_out.append({k: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                             for k, t in blo.tensors().items()})
+        except RuntimeError:
+            if not host_out:
+                raise
+            break
     del blo
     for _ in range(max(1, args.warmup - 1)):
         step(e2e=True)
@@ -305,6 +312,27 @@ def run_ours(args):
         hbm[name] = {'ms': stage_ms[name], 'bytes_per_ray': bpr, 'achieved_gbs': gbs,
                      'frac_of_%s_hbm' % peak_kind: gbs / peaks['hbm_gbs']}
     hbm['undulator'] = {'ms': und_ms}
+
+    # ---- sub-mode 2r: rejection sampling instead of uniformRayDensity, source only
+    rej = None
+    if not args.no_rejection:
+        nacc = min(nrays, 10000000)
+        kw = undulator_kwargs(nacc)
+        kw['uniformRayDensity'] = False
+        src_r = Undulator(BeamLine(), 'ur', eMin=E1 * 0.995, eMax=E1 * 1.005, seed=4321, **kw)
+        src_r.reset()
+        src_r.shine()  # warm-up; also settles Imax like a converged run
+        barrier()
+        e0, e1 = ev(), ev()
+        e0.record()
+        b = src_r.shine()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        rej = {'workload': 'Undulator.shine, rejection sampling, %d accepted rays' % len(b), 'ms': ms,
+               'accepted_Mrays_per_s': len(b) / ms / 1e3, 'acceptance': len(b) / float(b.seeded),
+               'sample_node_per_s': float(b.seeded) * nodes / (ms * 1e-3)}
+        del b, src_r
 
     # ---- Kirchhoff sum, config 4
     kir = None
@@ -348,7 +376,7 @@ def run_ours(args):
                         'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e},
                 'gpu_launches': args.steps * 9,  # sample, undulator, fill, 2 slot inits, pre-pass A/B, reflect, expose
                 'clocks': sampler.summary(),
-                'roofline': roofline, 'stages': hbm, 'kirchhoff': kir,
+                'roofline': roofline, 'stages': hbm, 'shine_rejection': rej, 'kirchhoff': kir,
                 'cpu_baseline': cpu_baseline() if world == 1 and not args.no_cpu_baseline else None}
         print(json.dumps(line))
     if world > 1:
@@ -365,6 +393,7 @@ def main():
     ap.add_argument('--gather', default='none', choices=['none', 'beam'])
     ap.add_argument('--no-kirchhoff', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-rejection', action='store_true')
     ap.add_argument('--kirchhoff-n', type=int, default=1000000)
     ap.add_argument('--kirchhoff-m', type=int, default=1024 * 1024)
     ap.add_argument('--kirchhoff-r', type=int, default=4)

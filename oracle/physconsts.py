@@ -1,21 +1,11 @@
-"""Oracle constants (TEST INFRASTRUCTURE ONLY). Values follow xrt/backends/raycing/physconsts.py:5-42; the
-product keeps its own copy in xrt_b200/physconsts.py and tests assert that both equal the golden dump."""
-PI = 3.1415926535897932384626433832795
-PI2 = 6.283185307179586476925286766559
-SIE0 = 1.602176565e-19
-C = 2.99792458e10  # [cm/sec]
-M0 = 9.109383701528e-28  # [g]
-SIM0 = 9.109383701528e-31
-M0C2 = 0.510998928  # MeV
-HPLANCK = 6.626069573e-27  # [erg*sec]
-EV2ERG = 1.602176565e-12
-EMC = 0.5866791802416487
-FINE_STR = 1 / 137.03599976
-E2W = 1519267514747457.9195337718065469
-E2WC = 5067.7309392068091
-R0 = 2.817940285e-5  # A
-AVOGADRO = 6.02214199e23
-CHeVcm = HPLANCK * C / EV2ERG
-CH = CHeVcm * 1e8  # [eV*A]
-CHBAR = CH / PI2
-K2B = 2 * PI * M0 * C**2 * 0.001 / (SIE0 * C / 10)
+"""Oracle constants (TEST INFRASTRUCTURE ONLY): a single import point so that every oracle module computes with
+the product's table (xrt_b200/physconsts.py), which tests/test_abi.py pins bit for bit on the values dumped
+from the reference (tests/golden/constants.npz; reference: xrt/backends/raycing/physconsts.py:5-42)."""
+import importlib.util as _ilu
+import os as _os
+
+_path = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), 'xrt_b200', 'physconsts.py')
+_spec = _ilu.spec_from_file_location('_xrt_b200_physconsts', _path)
+_mod = _ilu.module_from_spec(_spec)
+_spec.loader.exec_module(_mod)  # loaded by path: importing the xrt_b200 package would pull in torch for nothing
+globals().update({k: v for k, v in vars(_mod).items() if not k.startswith('_')})
