@@ -63,7 +63,10 @@ int xrt_kirchhoff_f64_host(size_t M, size_t N, const double* xM, const double* y
  * list of Undulator._build_I_map_CL (synchr.py:2134-2155): scalars (alpha ignored), Kx, Ky, jend; per-sample
  * gamma, wu, w, ww1, ddphi (theta), ddpsi (psi); node tables tg, ag, sintg, costg, sintgph, costgph[jend];
  * outputs Is, Ip: c128[n] = the return value of Undulator._sp_sum (synchr.py:1929-2033, numpy convention).
- * flags: bits4-6 = register blocking R in {1,2,4} (0 = default 2). */
+ * flags: bits4-6 = register blocking R in {1,2,4} (0 = default 2);
+ *        bit10 = the node tables are mirror-symmetric about tg = 0 (Clenshaw-Curtis grids are, to a few ulps):
+ *                a planar undulator (Kx == 0) then visits node PAIRS, 2 i w [..] sin(u) per pair (device-pointer
+ *                entry points trust the caller; the _host entry point checks the tables itself, bit11 opts out). */
 int xrt_undulator_f64(size_t n, int jend, double alpha, double Kx, double Ky, const double* gamma, const double* wu,
                       const double* w, const double* ww1, const double* ddphi, const double* ddpsi, const double* tg,
                       const double* ag, const double* sintg, const double* costg, const double* sintgph,

@@ -92,7 +92,10 @@ def test_cuda_run_parallel_undulator_vs_golden(name, cuda_device):
 @pytest.mark.gpu
 @pytest.mark.parametrize('name', CASES)
 @pytest.mark.parametrize('R', [1, 2, 4])
-def test_cuda_fused_imap_vs_golden(name, R, cuda_device):
+@pytest.mark.parametrize('symmetric', [False, True])
+def test_cuda_fused_imap_vs_golden(name, R, symmetric, cuda_device):
+    """symmetric=True: the node-pair path for planar undulators on mirror-symmetric grids (ignored by the kernel
+    for the helical case, Kx != 0)."""
     import torch
     from xrt_b200 import kernels
     from xrt_b200.physconsts import FINE_STR, SIE0
@@ -104,7 +107,7 @@ def test_cuda_fused_imap_vs_golden(name, R, cuda_device):
     I, Es, Ep = kernels.undulator_imap(
         float(g['Kx']), float(g['Ky']), float(g['L0']), float(g['Np']), float(g['gamma0']),
         FINE_STR * float(g['eI']) / SIE0, float(g['dstep']), 0, dev(g['w']), dev(g['theta']), dev(g['psi']),
-        tables, gamma=dev(g['gamma']), R=R)
+        tables, gamma=dev(g['gamma']), R=R, symmetric=symmetric)
     amp = np.abs(np.sqrt(FINE_STR / g['w'] * float(g['eI']) / SIE0) * ab * 0.5 * float(g['dstep']))
     # `ab` = sin(pi N ww1)/sin(pi ww1) amplifies 1-ulp differences of ww1 near its zeros: allow 1e-10 of the scale
     assert (np.abs(Es.cpu().numpy() - g['Es']) / (amp * ss + 1e-300)).max() < 1e-10
@@ -133,3 +136,30 @@ def test_cuda_many_nodes_tiles(cuda_device):
     scale = max(np.abs(ref_s).max(), np.abs(ref_p).max())
     assert np.abs(Is.cpu().numpy() - ref_s).max() < 1e-9 * scale
     assert np.abs(Ip.cpu().numpy() - ref_p).max() < 1e-9 * scale
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('quadm,gI', [(33, 2), (31, 3), (200, 4)])
+def test_cuda_symmetric_pairs_vs_oracle_odd_and_tiled_grids(quadm, gI, cuda_device):
+    """Node-pair path on odd node counts (middle node) and on more than one shared-memory tile."""
+    import torch
+    from xrt_b200 import kernels
+    g = golden('undulator_planar_h1')
+    grid = ou.build_integration_grid(quadm, gI, 0.)
+    assert kernels.grid_is_symmetric(grid['tg'], grid['ag'], grid['sintg'], grid['costg'])
+    n = 500
+    sl = slice(0, n)
+    Kx, Ky = 0., float(g['Ky'])
+    wu, ww1, ab = ou.sample_prefactors(float(g['L0']), float(g['Np']), Kx, Ky, g['gamma'][sl], g['w'][sl],
+                                       g['theta'][sl], g['psi'][sl])
+    ref_s, ref_p = ou.sp_sum(grid, Kx, Ky, ww1, g['w'][sl], wu, g['gamma'][sl], g['theta'][sl], g['psi'][sl])
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    tables = [dev(grid[k]) for k in ('tg', 'ag', 'sintg', 'costg', 'sintgph', 'costgph')]
+    args = (Kx, Ky, dev(g['gamma'][sl]), dev(wu), dev(g['w'][sl]), dev(ww1), dev(g['theta'][sl]), dev(g['psi'][sl]),
+            tables)
+    Is, Ip = kernels.undulator_raw(*args, symmetric=True)
+    Is0, Ip0 = kernels.undulator_raw(*args, symmetric=False)
+    scale = max(np.abs(ref_s).max(), np.abs(ref_p).max())
+    for a, b in ((Is, ref_s), (Ip, ref_p), (Is0, ref_s), (Ip0, ref_p)):
+        assert np.abs(a.cpu().numpy() - b).max() < 1e-9 * scale
+    assert float((Is - Is0).abs().max()) < 1e-11 * scale

@@ -1,4 +1,5 @@
 // C ABI of libxrt_b200.so (declarations: include/xrt_b200.h).
+#include <math.h>
 #include <stdarg.h>
 
 #include <mutex>
@@ -232,7 +233,7 @@ int xrt_undulator_f64(size_t n, int jend, double alpha, double Kx, double Ky, co
                       const double* costgph, double* Is, double* Ip, int flags, void* stream) {
   (void)alpha;  // taper / near-field scalar of the sibling kernels; unused by `undulator` (undulator.cl:54)
   return undulator_raw_device(n, jend, Kx, Ky, gamma, wu, w, ww1, ddphi, ddpsi, tg, ag, sintg, costg, sintgph,
-                              costgph, Is, Ip, (flags >> 4) & 7, (cudaStream_t)stream);
+                              costgph, Is, Ip, (flags >> 4) & 7, (flags >> 10) & 1, (cudaStream_t)stream);
 }
 
 int xrt_undulator_f64_host(size_t n, int jend, double alpha, double Kx, double Ky, const double* gamma,
@@ -253,10 +254,21 @@ int xrt_undulator_f64_host(size_t n, int jend, double alpha, double Kx, double K
   }
   if (out.alloc(2 * n * 16)) return 1;
   double* o = out.as<double>();
+  // mirror symmetry of the node tables about tg = 0 (to a few ulps): lets a planar undulator visit node pairs
+  int symmetric = 1;
+  for (int j = 0; j < jend / 2 && symmetric; ++j) {
+    const int k = jend - 1 - j;
+    const double tol = 4e-15;  // np.arange / np.sin / np.cos leave asymmetries of a few ulps of pi
+    if (fabs(tg[j] + tg[k]) > tol * 4 || fabs(ag[j] - ag[k]) > tol * fabs(ag[j]) || fabs(sintg[j] + sintg[k]) > tol ||
+        fabs(costg[j] - costg[k]) > tol)
+      symmetric = 0;
+  }
+  if ((jend & 1) && fabs(tg[jend / 2]) > 4e-15 * 4) symmetric = 0;
+  if (flags & (1 << 11)) symmetric = 0;  // caller opts out
   int rc = undulator_raw_device(n, jend, Kx, Ky, samp[0].as<double>(), samp[1].as<double>(), samp[2].as<double>(),
                                 samp[3].as<double>(), samp[4].as<double>(), samp[5].as<double>(), tab[0].as<double>(),
                                 tab[1].as<double>(), tab[2].as<double>(), tab[3].as<double>(), tab[4].as<double>(),
-                                tab[5].as<double>(), o, o + 2 * n, (flags >> 4) & 7, st);
+                                tab[5].as<double>(), o, o + 2 * n, (flags >> 4) & 7, symmetric, st);
   if (rc) return rc;
   XRTB_CUDA_CHECK(cudaMemcpyAsync(Is, o, n * 16, cudaMemcpyDeviceToHost, st));
   XRTB_CUDA_CHECK(cudaMemcpyAsync(Ip, o + 2 * n, n * 16, cudaMemcpyDeviceToHost, st));
@@ -270,7 +282,7 @@ int xrt_undulator_imap_f64(size_t n, int jend, double Kx, double Ky, double L0, 
                            const double* sintg, const double* costg, const double* sintgph, const double* costgph,
                            double* I, double* Es, double* Ep, int flags, void* stream) {
   return undulator_imap_device(n, jend, Kx, Ky, L0, Np, gamma0, amp_const, dstep, bw_mode, gamma, w, theta, psi, tg,
-                               ag, sintg, costg, sintgph, costgph, I, Es, Ep, (flags >> 4) & 7,
+                               ag, sintg, costg, sintgph, costgph, I, Es, Ep, (flags >> 4) & 7, (flags >> 10) & 1,
                                (cudaStream_t)stream);
 }
 

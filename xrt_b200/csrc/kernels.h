@@ -21,12 +21,12 @@ int undulator_raw_device(size_t n, int jend, double Kx, double Ky, const double*
                          const double* w, const double* ww1, const double* ddphi, const double* ddpsi,
                          const double* tg, const double* ag, const double* sintg, const double* costg,
                          const double* sintgph, const double* costgph, double* Is, double* Ip, int R,
-                         cudaStream_t st);
+                         int symmetric, cudaStream_t st);
 int undulator_imap_device(size_t n, int jend, double Kx, double Ky, double L0, double Np, double gamma0,
                           double amp_const, double dstep, int bw_mode, const double* gamma, const double* w,
                           const double* theta, const double* psi, const double* tg, const double* ag,
                           const double* sintg, const double* costg, const double* sintgph, const double* costgph,
-                          double* I, double* Es, double* Ep, int R, cudaStream_t st);
+                          double* I, double* Es, double* Ep, int R, int symmetric, cudaStream_t st);
 
 // reflect.cu (compiled with -fmad=false)
 int reflect_device(size_t n, const xrt_oe_params* oe, const xrt_material_params* mat, const double* tables,

@@ -94,6 +94,37 @@ __device__ __forceinline__ void node_step(const USample& s, const double4 n0, co
   bp_im = fma(eim, tp, bp_im);
 }
 
+// Mirror-pair step for a planar undulator on a grid that is symmetric about tg = 0 (Clenshaw-Curtis nodes on
+// sub-intervals of [-pi, pi] are): under tg -> -tg the phase u and the bracket [..] are odd while 1/(1-n.beta)^2
+// and the weight are even, so node j and its mirror contribute  w [..] (e^{iu} - e^{-iu}) = 2i w [..] sin(u).
+// One sin (no cos), one velocity/denominator evaluation per PAIR of nodes; the sums are purely imaginary.
+// The tables are symmetric to a few ulps only (np.sin/np.cos of mirrored arguments), which moves u by ~1e-15
+// rad: orders below the parity tolerance.  The factor 2 is applied once at the end.
+__device__ __forceinline__ void node_pair_step(const USample& s, const double4 n0, const double4 n1, double& bs_im,
+                                               double& bp_im) {
+  double ucos = s.ww1 * n0.x;
+  ucos = fma(s.b1, n1.x, ucos);
+  ucos = fma(s.a3, n1.z, ucos);
+  const double sn = sin_big(ucos);
+  const double bx = __dmul_rn(s.kyr, n0.z);
+  const double t4 = __dadd_rn(s.revg2, __dmul_rn(bx, bx));
+  const double bz = __dadd_rn(1.0, -0.5 * t4);
+  const double bpz = __dmul_rn(s.hrevg, n1.z);
+  double den = __dadd_rn(1.0, -__dmul_rn(s.dirx, bx));
+  den = __dadd_rn(den, -__dmul_rn(s.dirz, bz));
+  const double rk = rcp_fast(den);
+  const double wgt = n0.y * (rk * rk);
+  const double eim = sn * wgt;
+  const double bnx = s.dirx - bx;
+  const double bnz = s.dirz - bz;
+  const double ddbp = fma(s.dirz, bpz, s.dirx * n1.x);
+  const double ddmb = fma(s.dirz, bnz, fma(s.diry, s.diry, s.dirx * bnx));
+  const double ts = fma(bnx, ddbp, -(n1.x * ddmb));
+  const double tp = s.diry * ddbp;
+  bs_im = fma(eim, ts, bs_im);
+  bp_im = fma(eim, tp, bp_im);
+}
+
 struct UTables {
   const double *tg, *ag, *sintg, *costg, *sintgph, *costgph;
 };
@@ -126,7 +157,7 @@ struct UParams {
   int bw_mode;  // 1: distE == 'BW'
 };
 
-template <int R, int MODE, bool PLANAR>
+template <int R, int MODE, bool PLANAR, bool SYM>
 __global__ void __launch_bounds__(U_THREADS)
     undulator_kernel(size_t n, UParams p, UTables tab, const double* __restrict__ gamma, const double* __restrict__ wu,
                      const double* __restrict__ w, const double* __restrict__ ww1, const double* __restrict__ phi,
@@ -163,8 +194,11 @@ __global__ void __launch_bounds__(U_THREADS)
     acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0;
   }
 
-  for (int j0 = 0; j0 < p.jend; j0 += U_TILE) {
-    const int cnt = min(U_TILE, p.jend - j0);
+  // SYM: only the first half of the nodes is visited (pairs); an odd middle node goes through the general step
+  const int jpair = SYM ? p.jend / 2 : 0;
+  const int jlast = SYM ? jpair + (p.jend & 1) : p.jend;
+  for (int j0 = 0; j0 < jlast; j0 += U_TILE) {
+    const int cnt = min(U_TILE, jlast - j0);
     __syncthreads();
     load_node_tile(tile, tab, j0, cnt, p.Kx, p.Ky);
     __syncthreads();
@@ -173,8 +207,34 @@ __global__ void __launch_bounds__(U_THREADS)
       const double4* q = reinterpret_cast<const double4*>(tile + j);
       const double4 n0 = q[0];
       const double4 n1 = q[1];
+      if (SYM && (j0 + j) < jpair) {
 #pragma unroll
-      for (int r = 0; r < R; ++r) node_step<PLANAR>(s[r], n0, n1, acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+        for (int r = 0; r < R; ++r) node_pair_step(s[r], n0, n1, acc[r][1], acc[r][3]);
+      } else if (SYM) {
+        // middle node of an odd grid (tg = 0): counts once, i.e. half of the factor 2 applied below
+        double h[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          h[0] = h[1] = h[2] = h[3] = 0.0;
+          node_step<PLANAR>(s[r], n0, n1, h[0], h[1], h[2], h[3]);
+          acc[r][0] += 0.5 * h[0];
+          acc[r][1] += 0.5 * h[1];
+          acc[r][2] += 0.5 * h[2];
+          acc[r][3] += 0.5 * h[3];
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) node_step<PLANAR>(s[r], n0, n1, acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+      }
+    }
+  }
+  if (SYM) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      acc[r][0] *= 2.0;
+      acc[r][1] *= 2.0;
+      acc[r][2] *= 2.0;
+      acc[r][3] *= 2.0;
     }
   }
 
@@ -205,7 +265,7 @@ __global__ void __launch_bounds__(U_THREADS)
   }
 }
 
-static int launch(int mode, int R, size_t n, const UParams& p, const UTables& t, const double* gamma,
+static int launch(int mode, int R, bool symmetric, size_t n, const UParams& p, const UTables& t, const double* gamma,
                   const double* wu, const double* w, const double* ww1, const double* phi, const double* psi,
                   double* Is, double* Ip, double* I, cudaStream_t st) {
   if (n == 0) return 0;
@@ -217,12 +277,15 @@ static int launch(int mode, int R, size_t n, const UParams& p, const UTables& t,
   double2* is2 = reinterpret_cast<double2*>(Is);
   double2* ip2 = reinterpret_cast<double2*>(Ip);
   const bool planar = (p.Kx == 0.0);
-#define XRTB_U_LAUNCH(RR, MM)                                                                                      \
-  do {                                                                                                             \
-    if (planar)                                                                                                    \
-      undulator_kernel<RR, MM, true><<<grid, U_THREADS, 0, st>>>(n, p, t, gamma, wu, w, ww1, phi, psi, is2, ip2, I); \
-    else                                                                                                           \
-      undulator_kernel<RR, MM, false><<<grid, U_THREADS, 0, st>>>(n, p, t, gamma, wu, w, ww1, phi, psi, is2, ip2, I); \
+  const bool sym = planar && symmetric;
+#define XRTB_U_LAUNCH(RR, MM)                                                                                         \
+  do {                                                                                                                \
+    if (sym)                                                                                                          \
+      undulator_kernel<RR, MM, true, true><<<grid, U_THREADS, 0, st>>>(n, p, t, gamma, wu, w, ww1, phi, psi, is2, ip2, I); \
+    else if (planar)                                                                                                  \
+      undulator_kernel<RR, MM, true, false><<<grid, U_THREADS, 0, st>>>(n, p, t, gamma, wu, w, ww1, phi, psi, is2, ip2, I); \
+    else                                                                                                              \
+      undulator_kernel<RR, MM, false, false><<<grid, U_THREADS, 0, st>>>(n, p, t, gamma, wu, w, ww1, phi, psi, is2, ip2, I); \
   } while (0)
   if (mode == 0) {
     if (R == 1) XRTB_U_LAUNCH(1, 0);
@@ -242,20 +305,20 @@ int undulator_raw_device(size_t n, int jend, double Kx, double Ky, const double*
                          const double* w, const double* ww1, const double* ddphi, const double* ddpsi,
                          const double* tg, const double* ag, const double* sintg, const double* costg,
                          const double* sintgph, const double* costgph, double* Is, double* Ip, int R,
-                         cudaStream_t st) {
+                         int symmetric, cudaStream_t st) {
   UParams p{};
   p.Kx = Kx;
   p.Ky = Ky;
   p.jend = jend;
   UTables t{tg, ag, sintg, costg, sintgph, costgph};
-  return launch(0, R, n, p, t, gamma, wu, w, ww1, ddphi, ddpsi, Is, Ip, nullptr, st);
+  return launch(0, R, symmetric != 0, n, p, t, gamma, wu, w, ww1, ddphi, ddpsi, Is, Ip, nullptr, st);
 }
 
 int undulator_imap_device(size_t n, int jend, double Kx, double Ky, double L0, double Np, double gamma0,
                           double amp_const, double dstep, int bw_mode, const double* gamma, const double* w,
                           const double* theta, const double* psi, const double* tg, const double* ag,
                           const double* sintg, const double* costg, const double* sintgph, const double* costgph,
-                          double* I, double* Es, double* Ep, int R, cudaStream_t st) {
+                          double* I, double* Es, double* Ep, int R, int symmetric, cudaStream_t st) {
   UParams p{};
   p.Kx = Kx;
   p.Ky = Ky;
@@ -267,7 +330,7 @@ int undulator_imap_device(size_t n, int jend, double Kx, double Ky, double L0, d
   p.jend = jend;
   p.bw_mode = bw_mode;
   UTables t{tg, ag, sintg, costg, sintgph, costgph};
-  return launch(1, R, n, p, t, gamma, nullptr, w, nullptr, theta, psi, Es, Ep, I, st);
+  return launch(1, R, symmetric != 0, n, p, t, gamma, nullptr, w, nullptr, theta, psi, Es, Ep, I, st);
 }
 
 }  // namespace xrtb

@@ -56,7 +56,7 @@ def kirchhoff(xM, yM, zM, nl, Es, Ep, k, pos, nrm, out=None, convention='numpy',
     return out
 
 
-def undulator_raw(Kx, Ky, gamma, wu, w, ww1, ddphi, ddpsi, tables, R=0):
+def undulator_raw(Kx, Ky, gamma, wu, w, ww1, ddphi, ddpsi, tables, R=0, symmetric=False):
     """a4 on device tensors, the reference kernel interface: returns (Is, Ip) = Undulator._sp_sum."""
     lib = _lib.load()
     n = w.numel()
@@ -64,13 +64,14 @@ def undulator_raw(Kx, Ky, gamma, wu, w, ww1, ddphi, ddpsi, tables, R=0):
     out = torch.empty((2, n), dtype=C128, device=w.device)
     rc = lib.xrt_undulator_f64(
         n, jend, 0.0, float(Kx), float(Ky), *[_chk(t, F64, n) for t in (gamma, wu, w, ww1, ddphi, ddpsi)],
-        *[_chk(t, F64, jend) for t in tables], out[0].data_ptr(), out[1].data_ptr(), int(R) << 4, _stream())
+        *[_chk(t, F64, jend) for t in tables], out[0].data_ptr(), out[1].data_ptr(),
+        (int(R) << 4) | ((1 if symmetric else 0) << 10), _stream())
     _lib.check(rc, 'xrt_undulator_f64')
     return out[0], out[1]
 
 
 def undulator_imap(Kx, Ky, L0, Np, gamma0, amp_const, dstep, bw_mode, w, theta, psi, tables, gamma=None, R=0,
-                   out=None):
+                   out=None, symmetric=False):
     """a3+a4 fused on device tensors: returns (I, Es, Ep) of Undulator._build_I_map_conv."""
     lib = _lib.load()
     n = w.numel()
@@ -83,7 +84,7 @@ def undulator_imap(Kx, Ky, L0, Np, gamma0, amp_const, dstep, bw_mode, w, theta, 
         n, jend, float(Kx), float(Ky), float(L0), float(Np), float(gamma0), float(amp_const), float(dstep),
         int(bw_mode), _chk(gamma, F64, n) if gamma is not None else None, _chk(w, F64, n), _chk(theta, F64, n),
         _chk(psi, F64, n), *[_chk(t, F64, jend) for t in tables], _chk(I, F64, n), _chk(Es, C128, n),
-        _chk(Ep, C128, n), int(R) << 4, _stream())
+        _chk(Ep, C128, n), (int(R) << 4) | ((1 if symmetric else 0) << 10), _stream())
     _lib.check(rc, 'xrt_undulator_imap_f64')
     return I, Es, Ep
 
@@ -118,3 +119,11 @@ def material_amplitude_host(material, E, beamInDotNormal):
 def crystal_amplitude_host(crystal, E, beamInDotNormal, beamOutDotNormal=None, beamInDotHNormal=None):
     """a13: (curveS, curveP) of Crystal.get_amplitude (thick Bragg) for host arrays."""
     return _amplitude_host(crystal, E, beamInDotNormal, beamOutDotNormal, beamInDotHNormal)
+
+
+def grid_is_symmetric(tg, ag, sintg, costg):
+    """Mirror symmetry of an integration grid about tg = 0 to a few ulps (host arrays)."""
+    import numpy as np
+    tol = 4e-15  # np.arange / np.sin / np.cos leave asymmetries of a few ulps of pi
+    return bool(np.all(np.abs(tg + tg[::-1]) <= 4 * tol) and np.all(np.abs(ag - ag[::-1]) <= tol * np.abs(ag)) and
+                np.all(np.abs(sintg + sintg[::-1]) <= tol) and np.all(np.abs(costg - costg[::-1]) <= tol))

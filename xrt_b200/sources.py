@@ -168,6 +168,8 @@ class Undulator(object):
         self.costgph = np.cos(self.tg + self.phase)
         self.dstep = dstep
         self._dev_tables = None
+        # a planar undulator on a mirror-symmetric grid lets the kernel visit node pairs (csrc/undulator.cu)
+        self.gridSymmetric = kernels.grid_is_symmetric(self.tg, self.ag, self.sintg, self.costg)
 
     def _tables(self, device):
         if self._dev_tables is None or self._dev_tables[0].device != device:
@@ -286,7 +288,8 @@ class Undulator(object):
             self.reset()
         return kernels.undulator_imap(self.Kx, self.Ky, self.L0, self.Np, self.gamma,
                                       FINE_STR * self.eI / SIE0, self.dstep, 1 if self.distE == 'BW' else 0,
-                                      w, theta, psi, self._tables(w.device), gamma=gamma, out=out)
+                                      w, theta, psi, self._tables(w.device), gamma=gamma, out=out,
+                                      symmetric=self.gridSymmetric)
 
     def _source_params(self, toGlobal):
         p = xrt_source_params()
