@@ -295,23 +295,52 @@ def run_ours(args):
     d2h = n_host * bytes_per_ray
     host_out = None
 
-    # ---- roofline of the dominant kernel (undulator field integral, FP64-pipe bound)
+    # ---- per-kernel times of reflect() (pre-pass A, pre-pass B, main) in a few extra untimed steps
+    mirror.profileEvents = []
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    refl_ms = [float(np.mean([e[i].elapsed_time(e[i + 1]) for e in mirror.profileEvents])) for i in range(3)]
+    mirror.profileEvents = None
+
+    # ---- rooflines.  Denominators: HBM from MEASURED_PEAKS.json; FP64 has no entry there, so a DFMA stream is
+    # measured in this run (xrt_b200_fp64_probe).
     peaks, peak_kind = measured_peaks()
     dfma_tflops, _ = kernels.fp64_probe(0, 8192)
     und_ms = stage_ms['undulator']
     und_tflops = FLOP_PER_SAMPLE_NODE * nrays * nodes / (und_ms * 1e-3) / 1e12
-    roofline = {'kernel': 'undulator_kernel<2,1> (Undulator.build_I_map)', 'bound': 'fp64',
-                'achieved': und_tflops, 'peak': dfma_tflops, 'unit': 'TFLOP/s', 'frac': und_tflops / dfma_tflops,
-                'traffic': None,
-                'peak_source': 'DFMA stream measured by xrt_b200_fp64_probe in this run (MEASURED_PEAKS.json has '
-                               'no fp64 entry); 63 algorithmic flop per (sample, node)',
-                'share_of_step': und_ms / ms_step}
+    pair_path = bool(src.gridSymmetric and src.Kx == 0)
+    und_instr = 24.5 if pair_path else 57.0  # DFMA-pipe instructions per (sample, node) in SASS
+    roofline_und = {'kernel': 'undulator_kernel<2,1,planar,%s> (Undulator.build_I_map)' % ('pairs' if pair_path else 'nodes'),
+                    'bound': 'fp64', 'achieved': und_tflops, 'peak': dfma_tflops, 'unit': 'TFLOP/s',
+                    'frac': und_tflops / dfma_tflops, 'traffic': None,
+                    'issue_slot_frac': 2 * und_instr * nrays * nodes / (und_ms * 1e-3) / 1e12 / dfma_tflops,
+                    'note': 'achieved counts the 63 flop per (sample, node) of the reference algorithm (SURVEY 8d); '
+                            'the kernel evaluates mirror PAIRS of nodes for a planar undulator on a symmetric grid '
+                            '(49 DFMA-pipe instructions per pair), so issue_slot_frac is the pipe utilisation',
+                    'ms': und_ms, 'share_of_step': und_ms / ms_step}
+    main_ms = refl_ms[2]
+    main_bytes = 132 + 132 + 140
+    main_gbs = main_bytes * nrays / (main_ms * 1e-3) / 1e9
+    roofline_main = {'kernel': 'reflect_main_kernel<toroid, mirror> (OE.reflect)', 'bound': 'hbm',
+                     'achieved': main_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': main_gbs / peaks['hbm_gbs'],
+                     'traffic': None, 'peak_source': '%s HBM copy bandwidth (MEASURED_PEAKS.json)' % peak_kind,
+                     'note': '%d algorithmic bytes per ray (132 in, 132 gb, 140 lb); currently limited by the issue rate '
+                             'of the IEEE div/sqrt chains numpy parity requires (~3600 instructions per ray), not by HBM'
+                             % main_bytes,
+                     'ms': main_ms, 'share_of_step': main_ms / ms_step}
+    # the dominant kernel of the step goes first
+    roofline = roofline_main if main_ms >= und_ms else roofline_und
+    roofline_other = roofline_und if main_ms >= und_ms else roofline_main
     hbm = {}
-    for name, bpr in (('reflect', 52 + 132 + 132 + 140), ('expose', 264), ('fill', 96 + 132), ('sample', 64)):
-        gbs = bpr * nrays / (stage_ms[name] * 1e-3) / 1e9
-        hbm[name] = {'ms': stage_ms[name], 'bytes_per_ray': bpr, 'achieved_gbs': gbs,
+    for name, bpr, ms in (('reflect_prepass_dir', 28, refl_ms[0]), ('reflect_prepass_bracket', 52, refl_ms[1]),
+                          ('reflect_main', main_bytes, refl_ms[2]), ('expose', 264, stage_ms['expose']),
+                          ('fill', 96 + 132, stage_ms['fill']), ('sample', 64, stage_ms['sample'])):
+        gbs = bpr * nrays / (ms * 1e-3) / 1e9
+        hbm[name] = {'ms': ms, 'bytes_per_ray': bpr, 'achieved_gbs': gbs,
                      'frac_of_%s_hbm' % peak_kind: gbs / peaks['hbm_gbs']}
     hbm['undulator'] = {'ms': und_ms}
+    hbm['reflect_total_in_step'] = {'ms': stage_ms['reflect']}
 
     # ---- sub-mode 2r: rejection sampling instead of uniformRayDensity, source only
     rej = None
@@ -361,9 +390,9 @@ def run_ours(args):
                'ms': kms, 'pairs_per_s': pairs, 'value': ktf * 1e3, 'unit': 'GFLOP/s (57 flop/pair), all GPUs',
                'roofline': {'bound': 'fp64', 'achieved': ktf / world, 'peak': dfma_tflops, 'unit': 'TFLOP/s per GPU',
                             'frac': ktf / world / dfma_tflops, 'traffic': None,
-                            'issue_slot_frac': 68 * 2 * pairs / world / 1e12 / dfma_tflops,
-                            'note': '68 DFMA-pipe instructions per pair in SASS; frac counts the 57 algorithmic '
-                                    'flops, issue_slot_frac the issued ones'}}
+                            'issue_slot_frac': 65 * 2 * pairs / world / 1e12 / dfma_tflops,
+                            'note': '65 DFMA-pipe instructions per pair in SASS (uniform-normal variant); frac counts '
+                                    'the 57 algorithmic flops, issue_slot_frac the issued ones'}}
 
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': 'Mrays/s', 'n_gpus': world, 'steps': args.steps,
@@ -376,7 +405,7 @@ def run_ours(args):
                         'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e},
                 'gpu_launches': args.steps * 9,  # sample, undulator, fill, 2 slot inits, pre-pass A/B, reflect, expose
                 'clocks': sampler.summary(),
-                'roofline': roofline, 'stages': hbm, 'shine_rejection': rej, 'kirchhoff': kir,
+                'roofline': roofline, 'roofline_second_kernel': roofline_other, 'stages': hbm, 'shine_rejection': rej, 'kirchhoff': kir,
                 'cpu_baseline': cpu_baseline() if world == 1 and not args.no_cpu_baseline else None}
         print(json.dumps(line))
     if world > 1:

@@ -227,7 +227,15 @@ class OE(object):
         args = (len(beam), ctypes.byref(params), mat_ref, tab_ptr, tlen, ctypes.byref(cin),
                 ctypes.byref(cfb) if cfb is not None else None, ctypes.byref(cgb),
                 ctypes.byref(clb) if clb is not None else None, red.data_ptr())
-        if allreduce is None:
+        if allreduce is None and getattr(self, 'profileEvents', None) is not None:
+            # per-kernel timing for bench.py: the three phases as separate calls with CUDA events in between
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            evs[0].record()
+            for i, ph in enumerate((1, 4, 2)):
+                _lib.check(lib.xrt_reflect_f64(*args, ph, index_offset, stream), 'xrt_reflect_f64')
+                evs[i + 1].record()
+            self.profileEvents.append(evs)
+        elif allreduce is None:
             _lib.check(lib.xrt_reflect_f64(*args, 7, index_offset, stream), 'xrt_reflect_f64')
         else:
             # min/max/sum of the beam-wide scalars over ray shards after each pre-pass (xrt_b200/parallel.py)
