@@ -83,6 +83,20 @@ class ClockSampler(threading.Thread):
                 'reasons': reasons, 'samples': len(self.samples)}
 
 
+def measured_traffic(kernel_prefix, nrays):
+    """dram bytes per launch of a ray kernel, from the committed ncu --set full capture (bytes/ray x rays)."""
+    path = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        for k, v in t['bytes_per_ray'].items():
+            if k.startswith(kernel_prefix):
+                return v * nrays
+    except Exception:
+        pass
+    return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -313,7 +327,7 @@ def run_ours(args):
     und_instr = 24.5 if pair_path else 57.0  # DFMA-pipe instructions per (sample, node) in SASS
     roofline_und = {'kernel': 'undulator_kernel<2,1,planar,%s> (Undulator.build_I_map)' % ('pairs' if pair_path else 'nodes'),
                     'bound': 'fp64', 'achieved': und_tflops, 'peak': dfma_tflops, 'unit': 'TFLOP/s',
-                    'frac': und_tflops / dfma_tflops, 'traffic': None,
+                    'frac': und_tflops / dfma_tflops, 'traffic': measured_traffic('undulator_kernel', nrays),
                     'issue_slot_frac': 2 * und_instr * nrays * nodes / (und_ms * 1e-3) / 1e12 / dfma_tflops,
                     'note': 'achieved counts the 63 flop per (sample, node) of the reference algorithm (SURVEY 8d); '
                             'the kernel evaluates mirror PAIRS of nodes for a planar undulator on a symmetric grid '
@@ -324,7 +338,8 @@ def run_ours(args):
     main_gbs = main_bytes * nrays / (main_ms * 1e-3) / 1e9
     roofline_main = {'kernel': 'reflect_main_kernel<toroid, mirror> (OE.reflect)', 'bound': 'hbm',
                      'achieved': main_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': main_gbs / peaks['hbm_gbs'],
-                     'traffic': None, 'peak_source': '%s HBM copy bandwidth (MEASURED_PEAKS.json)' % peak_kind,
+                     'traffic': measured_traffic('reflect_main_kernel', nrays),
+                     'peak_source': '%s HBM copy bandwidth (MEASURED_PEAKS.json)' % peak_kind,
                      'note': '%d algorithmic bytes per ray (132 in, 132 gb, 140 lb); currently limited by the issue rate '
                              'of the IEEE div/sqrt chains numpy parity requires (~3600 instructions per ray), not by HBM'
                              % main_bytes,
