@@ -97,6 +97,17 @@ def measured_traffic(kernel_prefix, nrays):
     return None
 
 
+def _finite(o):
+    """NaN/inf -> None so that the line is strict JSON."""
+    if isinstance(o, dict):
+        return {k: _finite(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [_finite(v) for v in o]
+    if isinstance(o, float) and not np.isfinite(o):
+        return None
+    return o
+
+
 def measured_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -189,6 +200,12 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device: xrt_b200 has no CPU path')
     torch.cuda.set_device(local_rank)
+    try:  # run next to the GPU: pinned result buffers then come from the NUMA node the GPU hangs on
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+    except Exception:
+        pass
     _lib.init(local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
@@ -314,7 +331,8 @@ def run_ours(args):
     for _ in range(3):
         step()
     torch.cuda.synchronize()
-    refl_ms = [float(np.mean([e[i].elapsed_time(e[i + 1]) for e in mirror.profileEvents])) for i in range(3)]
+    refl_ms = [float(np.mean([e[a].elapsed_time(e[b]) for e in mirror.profileEvents]))
+               for a, b in ((0, 1), (4, 2), (5, 3))]
     mirror.profileEvents = None
 
     # ---- rooflines.  Denominators: HBM from MEASURED_PEAKS.json; FP64 has no entry there, so a DFMA stream is
@@ -422,7 +440,7 @@ def run_ours(args):
                 'clocks': sampler.summary(),
                 'roofline': roofline, 'roofline_second_kernel': roofline_other, 'stages': hbm, 'shine_rejection': rej, 'kirchhoff': kir,
                 'cpu_baseline': cpu_baseline() if world == 1 and not args.no_cpu_baseline else None}
-        print(json.dumps(line))
+        print(json.dumps(_finite(line)))
     if world > 1:
         dist.destroy_process_group()
 

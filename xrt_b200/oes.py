@@ -227,23 +227,36 @@ class OE(object):
         args = (len(beam), ctypes.byref(params), mat_ref, tab_ptr, tlen, ctypes.byref(cin),
                 ctypes.byref(cfb) if cfb is not None else None, ctypes.byref(cgb),
                 ctypes.byref(clb) if clb is not None else None, red.data_ptr())
-        if allreduce is None and getattr(self, 'profileEvents', None) is not None:
-            # per-kernel timing for bench.py: the three phases as separate calls with CUDA events in between
-            evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-            evs[0].record()
-            for i, ph in enumerate((1, 4, 2)):
-                _lib.check(lib.xrt_reflect_f64(*args, ph, index_offset, stream), 'xrt_reflect_f64')
-                evs[i + 1].record()
-            self.profileEvents.append(evs)
-        elif allreduce is None:
+        profile = getattr(self, 'profileEvents', None)
+        if allreduce is None and profile is None:
             _lib.check(lib.xrt_reflect_f64(*args, 7, index_offset, stream), 'xrt_reflect_f64')
         else:
-            # min/max/sum of the beam-wide scalars over ray shards after each pre-pass (xrt_b200/parallel.py)
+            # the three phases as separate calls: ray shards all-reduce the beam-wide scalars (min/max/sum over
+            # the 64 slots, xrt_b200/parallel.py) after each pre-pass; bench.py takes per-kernel CUDA events
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if profile is not None else None
+            if evs:
+                evs[0].record()
             _lib.check(lib.xrt_reflect_f64(*args, 1, index_offset, stream), 'xrt_reflect_f64 (pre-pass A)')
-            allreduce(red)
+            if evs:
+                evs[1].record()
+            if allreduce is not None:
+                allreduce(red)
+            if evs:
+                evs.append(torch.cuda.Event(enable_timing=True))
+                evs[4].record()
             _lib.check(lib.xrt_reflect_f64(*args, 4, index_offset, stream), 'xrt_reflect_f64 (pre-pass B)')
-            allreduce(red, False)  # counters were summed above
+            if evs:
+                evs[2].record()
+            if allreduce is not None:
+                allreduce(red, False)  # counters were summed above
+            if evs:
+                evs.append(torch.cuda.Event(enable_timing=True))
+                evs[5].record()
             _lib.check(lib.xrt_reflect_f64(*args, 2, index_offset, stream), 'xrt_reflect_f64 (main pass)')
+            if evs:
+                evs[3].record()
+                # kernel intervals: A = 0->1, B = 4->2, main = 5->3 (the all-reduces sit in between)
+                profile.append(evs)
         return red
 
     def _check_tables(self, red):
