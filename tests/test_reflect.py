@@ -9,6 +9,7 @@ from helpers import (oracle_spec, oracle_beam, product_beamline, product_oe_kwar
 from oracle import reflect as orf, materials as om
 
 CASES = [('reflect_flat_Au', 'flat'), ('reflect_toroid_Au', 'toroid'), ('reflect_toroid_bare', 'toroid'),
+         ('reflect_toroid_brent', 'toroid'),  # drives _use_Brent_method (base.py:871, :961-1048)
          ('reflect_ellipse_vfm', 'ellipse_param'), ('reflect_ellipse_hfm', 'ellipse_param'),
          ('reflect_ellipsoid', 'ellipse_param')]
 OUT_FIELDS = BEAM_FIELDS + ('theta', 's', 'phi', 'r')
@@ -17,7 +18,7 @@ ELLIPSE_KEYS = ('ellipseA', 'ellipseB', 'y0', 'z0', 'cosGamma', 'sinGamma')
 
 def _oracle_run(name, surface):
     g = golden(name)
-    mat = om.Material('Au', rho=float(g['rho'])) if 'rho' in g.files else None
+    mat = om.Material('Pt' if 'brent' in name else 'Au', rho=float(g['rho'])) if 'rho' in g.files else None
     kw = {}
     if surface == 'toroid':
         kw['surfParams'] = dict(R=float(g['R']), r=float(g['r']))
@@ -38,6 +39,7 @@ def test_oracle_matches_reference_bit_exact(name, surface):
             if pre + f in g.files:
                 assert np.array_equal(getattr(b, f), g[pre + f]), pre + f
     assert np.array_equal(info['footprint'], g['footprint'])
+    assert info['useBrent'] == ('brent' in name)
     # the goldens exercise every state class
     st = g['gb_state']
     assert (st == 1).sum() > 50 and (st < 0).sum() > 10
@@ -48,7 +50,7 @@ def _product_oe(g, surface):
     bl = product_beamline(g)
     kw = product_oe_kwargs(g)
     if 'rho' in g.files:
-        kw['material'] = materials.Material('Au', rho=float(g['rho']))
+        kw['material'] = materials.Material('Pt' if float(g['rho']) > 20 else 'Au', rho=float(g['rho']))
     if surface == 'toroid':
         oe = oes.ToroidMirror(bl, 'oe', R=float(g['R']), r=float(g['r']), **kw)
     elif surface == 'ellipse_param':

@@ -153,3 +153,23 @@ def test_cuda_shine_end_to_end_statistics(cuda_device):
     assert abs(out['E'].mean() - ref.E.mean()) < 0.2 * ref.E.std()
     assert np.allclose(out['Jss'] + out['Jpp'], 1, atol=1e-12)
     assert abs(src.Imax - float(g['Imax'])) < 0.05 * float(g['Imax'])
+
+
+@pytest.mark.gpu
+def test_cuda_convergence_search_finds_reference_grid(cuda_device):
+    """gNodes=None: IntegratedSource._find_convergence_mixed (sybase.py:1190-1243) run on the CUDA kernel ends at
+    the same number of nodes as the reference's numpy search (32 per interval for the config-2 undulator)."""
+    from xrt_b200.sources import Undulator
+    from xrt_b200.beamline import BeamLine
+    g = golden('undulator_planar_h1')
+    src = Undulator(BeamLine(), 'u', nrays=1000, eE=3., eI=0.5, period=30., n=40, K=1.45, eSigmaX=48.65,
+                    eSigmaZ=6.197, eEpsilonX=0.263, eEpsilonZ=0.008, xPrimeMax=0.1, zPrimeMax=0.1,
+                    xPrimeMaxAutoReduce=False, zPrimeMaxAutoReduce=False, eMin=float(g['E_min']),
+                    eMax=float(g['E_max']))
+    src.reset()
+    assert src.quadm == int(g['quadm']) and src.gIntervals == int(g['gIntervals'])
+    assert np.array_equal(src.tg, g['tg']) and np.array_equal(src.ag, g['ag'])
+    assert abs(src.E1 - float(g['E1'])) <= 1e-12 * float(g['E1'])
+    # and build_I_map on host arrays through run_parallel('undulator') reproduces the reference's flux map
+    I, Es, Ep = src.build_I_map(g['w'], g['theta'], g['psi'])
+    assert np.abs(I - g['I']).max() <= 1e-9 * g['I'].max()

@@ -427,8 +427,33 @@ def gen_diffract():
     d['beamReflSumJnl'] = wave.beamReflSumJnl
     save('diffract_slit_screen', **d)
 
+# ------------------------------------------------------------------------------------------------ Brent branch
+def gen_brent():
+    """A source sitting 0.06 mm above a strongly pitched toroid: |dz| at the near bracket end is tiny and at the
+    far end large, which flips find_intersection to _use_Brent_method (base.py:871)."""
+    import io
+    import contextlib
+    bl = raycing.BeamLine()
+    p = 0.15
+    lo = np.array([0., -30., 30.**2 / 2. / 2000. + 0.06])
+    cy = -(np.cos(p) * lo[1] - np.sin(p) * lo[2])
+    cz = -(np.sin(p) * lo[1] + np.cos(p) * lo[2])
+    beam = _source_beam(bl, 2000, 111, dx=0.3, dz=0.004, dxprime=2e-3, dzprime=1e-3, energies=(8000, 9000))
+    oe = roe.ToroidMirror(bl, 'TMB', center=(0, cy, cz), pitch=p, R=2000., r=15., material=rm.Material('Pt', rho=21.45),
+                          limPhysX=[-5, 5], limPhysY=[-100, 100])
+    raycing._VERBOSITY_ = 20
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        d = _capture_reflect(oe, beam)
+    raycing._VERBOSITY_ = 0
+    print(buf.getvalue().strip().splitlines()[-1])
+    d.update(_oe_params(oe))
+    st = d['gb_state']
+    print('brent', {int(x): int((st == x).sum()) for x in np.unique(st)})
+    save('reflect_toroid_brent', rho=21.45, R=float(oe.R), r=float(oe.r), **d)
 
-SECTIONS = {'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+
+SECTIONS = {'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)
