@@ -226,22 +226,32 @@ def run_ours(args):
     e2e_count = [0]
     copy_stream = torch.cuda.Stream()
 
-    def step(e2e=False, record=None):
+    def step(e2e=False, record=None, fused=not args.unfused_source):
         marks = [ev() for _ in range(6)] if record is not None else None
         off = rank * nrays
-        if marks:
-            marks[0].record()
-        s = src.draw_samples(nrays, index_offset=off)
-        if marks:
-            marks[1].record()
-        I, mJs, mJp = src.build_I_map_device(s['E'], s['theta'], s['psi'])
-        if marks:
-            marks[2].record()
         from xrt_b200.beams import Beam
         beam = Beam(nrays, withAmplitudes=True, uninitialized=True)
-        src.fill_beam(s, mJs, mJp, beam)
-        if marks:
-            marks[3].record()
+        if fused:
+            # Undulator.shine(): one fused kernel (sample + field integral + Beam assembly)
+            if marks:
+                marks[0].record()
+                marks[1].record()
+            src.shine_uniform_fused(beam, index_offset=off)
+            if marks:
+                marks[2].record()
+                marks[3].record()
+        else:
+            if marks:
+                marks[0].record()
+            s = src.draw_samples(nrays, index_offset=off)
+            if marks:
+                marks[1].record()
+            I, mJs, mJp = src.build_I_map_device(s['E'], s['theta'], s['psi'])
+            if marks:
+                marks[2].record()
+            src.fill_beam(s, mJs, mJp, beam)
+            if marks:
+                marks[3].record()
         gb, lb = mirror.reflect(beam, needLocal=True, checkTables=False, index_offset=off,
                                 allreduce=comm.allreduce_reductions if world > 1 else None)
         if marks:
@@ -343,9 +353,11 @@ def run_ours(args):
     und_tflops = FLOP_PER_SAMPLE_NODE * nrays * nodes / (und_ms * 1e-3) / 1e12
     pair_path = bool(src.gridSymmetric and src.Kx == 0)
     und_instr = 24.5 if pair_path else 57.0  # DFMA-pipe instructions per (sample, node) in SASS
-    roofline_und = {'kernel': 'undulator_kernel<2,1,planar,%s> (Undulator.build_I_map)' % ('pairs' if pair_path else 'nodes'),
+    roofline_und = {'kernel': ('undulator_kernel<2,1,planar,%s> (Undulator.build_I_map)' if args.unfused_source else
+                               'shine_uniform_kernel<2,planar,%s> (Undulator.shine: sample + field integral + Beam '
+                               'assembly)') % ('pairs' if pair_path else 'nodes'),
                     'bound': 'fp64', 'achieved': und_tflops, 'peak': dfma_tflops, 'unit': 'TFLOP/s',
-                    'frac': und_tflops / dfma_tflops, 'traffic': measured_traffic('undulator_kernel', nrays),
+                    'frac': und_tflops / dfma_tflops, 'traffic': measured_traffic('undulator_kernel' if args.unfused_source else 'shine_uniform_kernel', nrays),
                     'issue_slot_frac': 2 * und_instr * nrays * nodes / (und_ms * 1e-3) / 1e12 / dfma_tflops,
                     'note': 'achieved counts the 63 flop per (sample, node) of the reference algorithm (SURVEY 8d); '
                             'the kernel evaluates mirror PAIRS of nodes for a planar undulator on a symmetric grid '
@@ -366,13 +378,15 @@ def run_ours(args):
     roofline = roofline_main if main_ms >= und_ms else roofline_und
     roofline_other = roofline_und if main_ms >= und_ms else roofline_main
     hbm = {}
-    for name, bpr, ms in (('reflect_prepass_dir', 28, refl_ms[0]), ('reflect_prepass_bracket', 52, refl_ms[1]),
-                          ('reflect_main', main_bytes, refl_ms[2]), ('expose', 264, stage_ms['expose']),
-                          ('fill', 96 + 132, stage_ms['fill']), ('sample', 64, stage_ms['sample'])):
+    stage_list = [('reflect_prepass_dir', 28, refl_ms[0]), ('reflect_prepass_bracket', 52, refl_ms[1]),
+                  ('reflect_main', main_bytes, refl_ms[2]), ('expose', 264, stage_ms['expose'])]
+    if args.unfused_source:
+        stage_list += [('fill', 96 + 132, stage_ms['fill']), ('sample', 64, stage_ms['sample'])]
+    for name, bpr, ms in stage_list:
         gbs = bpr * nrays / (ms * 1e-3) / 1e9
         hbm[name] = {'ms': ms, 'bytes_per_ray': bpr, 'achieved_gbs': gbs,
                      'frac_of_%s_hbm' % peak_kind: gbs / peaks['hbm_gbs']}
-    hbm['undulator'] = {'ms': und_ms}
+    hbm['undulator' if args.unfused_source else 'shine_fused (sample + undulator + fill)'] = {'ms': und_ms}
     hbm['reflect_total_in_step'] = {'ms': stage_ms['reflect']}
 
     # ---- sub-mode 2r: rejection sampling instead of uniformRayDensity, source only
@@ -436,7 +450,8 @@ def run_ours(args):
                            'parallelism': 'rays sharded over %d GPU(s), gather=%s' % (world, args.gather)},
                 'e2e': {'value': e2e_value, 'unit': 'Mrays/s', 'h2d_bytes_per_step': h2d,
                         'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e},
-                'gpu_launches': args.steps * 9,  # sample, undulator, fill, 2 slot inits, pre-pass A/B, reflect, expose
+                'gpu_launches': args.steps * (9 if args.unfused_source else 7),  # source (1 fused or 3), 2 slot inits,
+                # pre-pass A/B, reflect main, expose
                 'clocks': sampler.summary(),
                 'roofline': roofline, 'roofline_second_kernel': roofline_other, 'stages': hbm, 'shine_rejection': rej, 'kirchhoff': kir,
                 'cpu_baseline': cpu_baseline() if world == 1 and not args.no_cpu_baseline else None}
@@ -456,6 +471,8 @@ def main():
     ap.add_argument('--no-kirchhoff', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-rejection', action='store_true')
+    ap.add_argument('--unfused-source', action='store_true',
+                    help='time Undulator.shine as three kernels (sample, field integral, fill) instead of the fused one')
     ap.add_argument('--kirchhoff-n', type=int, default=1000000)
     ap.add_argument('--kirchhoff-m', type=int, default=1024 * 1024)
     ap.add_argument('--kirchhoff-r', type=int, default=4)

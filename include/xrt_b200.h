@@ -128,6 +128,8 @@ typedef struct xrt_oe_params {
   int created_by_diffract; /* goodAfter = (state == 1) only (reflect.py:125-128) */
   int zero_dead_local;    /* DCM 2nd crystal: lo2 of rays that never reached it is zeroed (dcm.py:305-310) */
   int good_mode;          /* which rays are traced: 0: state > 0 (reflect.py:110); 1: state in (1, 2) (dcm.py:303) */
+  int want_footprint;     /* 1: reduce the footprint min/max and the good-ray / out-of-table counters into the
+                             slots (reflect.py:1133-1136); 0 skips those block reductions (device pipelines) */
 } xrt_oe_params;
 
 /* Material = what get_amplitude reads (materials/material.py:348-493, materials/crystal.py:492-645). */
@@ -225,6 +227,16 @@ int xrt_source_fill_f64(size_t n, const xrt_source_params* p, const int64_t* idx
                         const double* rTheta, const double* rPsi, const double* mJs, const double* mJp,
                         const double* n1, const double* n2, const double* n3, const double* n4, const xrt_beam* out,
                         size_t out_offset, void* stream);
+
+/* Fused uniformRayDensity source: xrt_source_sample_f64 + xrt_undulator_imap_f64 + xrt_source_fill_f64 in one
+ * kernel (same Philox counters, same device functions => the same Beam bit for bit; samples and (I, mJs, mJp)
+ * stay in registers).  *imax_slot (device, 8 bytes, zero-initialised by the caller) receives the bit pattern of
+ * max I over the rays (non-negative doubles order like unsigned integers; all-reduce MAX across ranks). */
+int xrt_shine_uniform_f64(size_t n, uint64_t seed, uint64_t index_offset, const double* window, int jend, double Kx,
+                          double Ky, double L0, double Np, double gamma0, double amp_const, double dstep, int bw_mode,
+                          int symmetric, const double* tg, const double* ag, const double* sintg, const double* costg,
+                          const double* sintgph, const double* costgph, const xrt_source_params* p,
+                          const xrt_beam* out, uint64_t* imax_slot, void* stream);
 
 #ifdef __cplusplus
 }

@@ -173,3 +173,25 @@ def test_cuda_convergence_search_finds_reference_grid(cuda_device):
     # and build_I_map on host arrays through run_parallel('undulator') reproduces the reference's flux map
     I, Es, Ep = src.build_I_map(g['w'], g['theta'], g['psi'])
     assert np.abs(I - g['I']).max() <= 1e-9 * g['I'].max()
+
+
+@pytest.mark.gpu
+def test_cuda_fused_uniform_source_equals_three_kernels(cuda_device):
+    """The fused source kernel (sample + integral + Beam assembly) gives the same Beam, bit for bit, as the three
+    separate kernels that are parity-tested against the oracle (same Philox counters, same device functions)."""
+    import torch
+    g = golden('shine_uniform')
+    n = 300007
+    a = _product_source(g, n)
+    b = _product_source(g, n)
+    beam_f = a.shine(fused=True)
+    beam_u = b.shine(fused=False)
+    for k, v in beam_u.tensors().items():
+        w = getattr(beam_f, k)
+        if v.is_complex():
+            assert bool((torch.view_as_real(v) == torch.view_as_real(w)).all()), k
+        else:
+            assert bool((v == w).all()), k
+    assert a.Imax == b.Imax and a.Imax > 0
+    for k in ('accepted', 'acceptedE', 'seeded', 'seededI', 'sourceWeight'):
+        assert getattr(beam_f, k) == getattr(beam_u, k), k

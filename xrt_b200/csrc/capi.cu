@@ -353,4 +353,14 @@ int xrt_source_fill_f64(size_t n, const xrt_source_params* p, const int64_t* idx
                             n4, out, out_offset, (cudaStream_t)stream);
 }
 
+int xrt_shine_uniform_f64(size_t n, uint64_t seed, uint64_t index_offset, const double* window, int jend, double Kx,
+                          double Ky, double L0, double Np, double gamma0, double amp_const, double dstep, int bw_mode,
+                          int symmetric, const double* tg, const double* ag, const double* sintg, const double* costg,
+                          const double* sintgph, const double* costgph, const xrt_source_params* p,
+                          const xrt_beam* out, uint64_t* imax_slot, void* stream) {
+  return shine_uniform_device(n, seed, index_offset, window, jend, Kx, Ky, L0, Np, gamma0, amp_const, dstep, bw_mode,
+                              symmetric, tg, ag, sintg, costg, sintgph, costgph, p, out,
+                              reinterpret_cast<unsigned long long*>(imax_slot), (cudaStream_t)stream);
+}
+
 }  // extern "C"

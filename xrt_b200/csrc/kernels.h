@@ -53,4 +53,10 @@ int source_fill_device(size_t n, const xrt_source_params* p, const long long* id
                        const double* n1, const double* n2, const double* n3, const double* n4, const xrt_beam* out,
                        size_t out_offset, cudaStream_t st);
 
+int shine_uniform_device(size_t n, uint64_t seed, uint64_t index_offset, const double* window, int jend, double Kx,
+                         double Ky, double L0, double Np, double gamma0, double amp_const, double dstep, int bw_mode,
+                         int symmetric, const double* tg, const double* ag, const double* sintg, const double* costg,
+                         const double* sintgph, const double* costgph, const xrt_source_params* sp,
+                         const xrt_beam* out, unsigned long long* imax_slot, cudaStream_t st);
+
 }  // namespace xrtb

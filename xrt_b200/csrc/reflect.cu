@@ -741,6 +741,9 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
   unsigned long long ngoodN = 0;
   int oor = 0;
   const bool hasLb = lb.x != nullptr;
+  __shared__ Decision sdec;  // the beam-wide decision is decoded once per block
+  if (threadIdx.x == 0) sdec = decide(red);
+  __syncthreads();
 
   if (i < n) {
     const int st0 = in.state[i];
@@ -763,7 +766,7 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
         }
       }
     } else {
-      const Decision d = decide(red);
+      const Decision d = sdec;
       Ray r = load_ray(in, i);
       const double E = in.E[i];
       double path = in.path[i];
@@ -987,7 +990,8 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
     }
   }
 
-  // block-level footprint / counters
+  // block-level footprint / counters (skipped when nobody asked for them)
+  if (!p.want_footprint) return;
   __shared__ unsigned long long sh[8][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned long long e[8];

@@ -13,6 +13,7 @@
 #include "../../include/xrt_b200.h"
 #include "common.cuh"
 #include "kernels.h"
+#include "undulator_core.cuh"
 
 namespace xrtb {
 
@@ -50,7 +51,41 @@ __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
   return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
 }
 
-// out: E, theta, psi uniform in their windows; n1..n4 standard normal; u uniform (rejection test)
+struct Draw {
+  double E, theta, psi, u, n1, n2, n3, n4;
+};
+// E, theta, psi uniform in their windows (sybase.py:1583-1617), u uniform (rejection test, :1637), n1..n4
+// standard normal (Box-Muller on (0, 1] uniforms); four Philox blocks per ray
+__device__ __forceinline__ Draw draw_ray(uint64_t ctr, uint64_t seed, double Emin, double Emax, double Tmin,
+                                         double Tmax, double Pmin, double Pmax, bool normals) {
+  Draw d;
+  uint32_t w[4];
+  philox4x32_10(ctr, 0u, seed, w);
+  const double r0 = u53(w[0], w[1]), r1 = u53(w[2], w[3]);
+  philox4x32_10(ctr, 1u, seed, w);
+  const double r2 = u53(w[0], w[1]), r3 = u53(w[2], w[3]);
+  d.E = r0 * (Emax - Emin) + Emin;
+  d.theta = r1 * (Tmax - Tmin) + Tmin;
+  d.psi = r2 * (Pmax - Pmin) + Pmin;
+  d.u = r3;
+  d.n1 = d.n2 = d.n3 = d.n4 = 0.0;
+  if (normals) {
+    philox4x32_10(ctr, 2u, seed, w);
+    const double a0 = 1.0 - u53(w[0], w[1]), a1 = u53(w[2], w[3]);
+    philox4x32_10(ctr, 3u, seed, w);
+    const double b0 = 1.0 - u53(w[0], w[1]), b1 = u53(w[2], w[3]);
+    const double ra = sqrt(-2.0 * log(a0)), rb = sqrt(-2.0 * log(b0));
+    double sn, cs;
+    sincospi(2.0 * a1, &sn, &cs);
+    d.n1 = ra * cs;
+    d.n2 = ra * sn;
+    sincospi(2.0 * b1, &sn, &cs);
+    d.n3 = rb * cs;
+    d.n4 = rb * sn;
+  }
+  return d;
+}
+
 __global__ void __launch_bounds__(256) sample_kernel(size_t n, uint64_t seed, uint64_t index_offset, double Emin,
                                                      double Emax, double Tmin, double Tmax, double Pmin, double Pmax,
                                                      double* __restrict__ E, double* __restrict__ theta,
@@ -59,30 +94,16 @@ __global__ void __launch_bounds__(256) sample_kernel(size_t n, uint64_t seed, ui
                                                      double* __restrict__ n4, double* __restrict__ u) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint64_t ctr = index_offset + i;
-  uint32_t w[4];
-  philox4x32_10(ctr, 0u, seed, w);
-  const double r0 = u53(w[0], w[1]), r1 = u53(w[2], w[3]);
-  philox4x32_10(ctr, 1u, seed, w);
-  const double r2 = u53(w[0], w[1]), r3 = u53(w[2], w[3]);
-  E[i] = r0 * (Emax - Emin) + Emin;      // sybase.py:1585-1586
-  theta[i] = r1 * (Tmax - Tmin) + Tmin;  // :1613-1615
-  psi[i] = r2 * (Pmax - Pmin) + Pmin;    // :1616-1617
-  if (u) u[i] = r3;
+  const Draw d = draw_ray(index_offset + i, seed, Emin, Emax, Tmin, Tmax, Pmin, Pmax, n1 != nullptr);
+  E[i] = d.E;
+  theta[i] = d.theta;
+  psi[i] = d.psi;
+  if (u) u[i] = d.u;
   if (n1) {
-    // Box-Muller on (0, 1] uniforms
-    philox4x32_10(ctr, 2u, seed, w);
-    const double a0 = 1.0 - u53(w[0], w[1]), a1 = u53(w[2], w[3]);
-    philox4x32_10(ctr, 3u, seed, w);
-    const double b0 = 1.0 - u53(w[0], w[1]), b1 = u53(w[2], w[3]);
-    const double ra = sqrt(-2.0 * log(a0)), rb = sqrt(-2.0 * log(b0));
-    double s, c;
-    sincospi(2.0 * a1, &s, &c);
-    n1[i] = ra * c;
-    n2[i] = ra * s;
-    sincospi(2.0 * b1, &s, &c);
-    n3[i] = rb * c;
-    n4[i] = rb * s;
+    n1[i] = d.n1;
+    n2[i] = d.n2;
+    n3[i] = d.n3;
+    n4[i] = d.n4;
   }
 }
 
@@ -91,31 +112,21 @@ __device__ __forceinline__ cplx cmul_np3(cplx a, cplx b) {  // numpy SIMD comple
   return cplx{fma(a.re, b.re, -ii), fma(a.re, b.im, ir)};
 }
 
-// Beam assembly. idx: optional gather index (accepted samples of the rejection pass), else identity.
-__global__ void __launch_bounds__(256) fill_kernel(size_t n, xrt_source_params p, const long long* __restrict__ idx,
-                                                   const double* __restrict__ rE, const double* __restrict__ rTheta,
-                                                   const double* __restrict__ rPsi, const double2* __restrict__ mJs,
-                                                   const double2* __restrict__ mJp, const double* __restrict__ n1,
-                                                   const double* __restrict__ n2, const double* __restrict__ n3,
-                                                   const double* __restrict__ n4, xrt_beam out, size_t out_offset) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const size_t j = idx ? (size_t)idx[i] : i;  // sample index
-  const size_t o = out_offset + i;            // ray index in the output beam
-  const double E = rE[j];
+// Beam assembly of one ray (sybase.py:1651-1721, :1769-1801) into slot `o` of the output beam
+__device__ __forceinline__ void fill_ray(const xrt_source_params& p, double E, double rTheta, double rPsi, cplx js,
+                                         cplx jp, double g1, double g2, double g3, double g4, const xrt_beam& out,
+                                         size_t o) {
   // get_SIGMA (synchr.py:2240-2249) with get_sigma_r2 = get_sigma_r02 (eEspread = 0): 2*CHeVcm/E*10*L0*Np/PI2**2
   const double CHeVcm = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12;
   const double PI2 = 6.283185307179586476925286766559;
   const double sr2 = 2.0 * CHeVcm / E * 10.0 * p.L0 * p.Np / (PI2 * PI2);
   const double SX = sqrt(p.dx * p.dx + sr2), SZ = sqrt(p.dz * p.dz + sr2);
-  double x = 0.0 + SX * n1[j];  // np.random.normal(0, SIGMA, n) = loc + scale * gauss
+  double x = 0.0 + SX * g1;  // np.random.normal(0, SIGMA, n) = loc + scale * gauss
   double y = 0.0;
-  double z = 0.0 + SZ * n2[j];
-  double a = rTheta[j], b = 1.0, c = rPsi[j];
-  if (p.dxprime > 0.0) a += 0.0 + p.dxprime * n3[j];
-  if (p.dzprime > 0.0) c += 0.0 + p.dzprime * n4[j];
-  const double2 s2 = mJs[j], p2 = mJp[j];
-  const cplx js = cplx{s2.x, s2.y}, jp = cplx{p2.x, p2.y};
+  double z = 0.0 + SZ * g2;
+  double a = rTheta, b = 1.0, c = rPsi;
+  if (p.dxprime > 0.0) a += 0.0 + p.dxprime * g3;
+  if (p.dzprime > 0.0) c += 0.0 + p.dzprime * g4;
   const double mJs2 = cmul_np3(js, cconj(js)).re;
   const double mJp2 = cmul_np3(jp, cconj(jp)).re;
   cplx Jsp = cmul_np3(js, cconj(jp));
@@ -194,6 +205,66 @@ __global__ void __launch_bounds__(256) fill_kernel(size_t n, xrt_source_params p
   out.state[o] = 1;
 }
 
+// Beam assembly from sample arrays. idx: optional gather index (accepted samples of the rejection pass)
+__global__ void __launch_bounds__(256) fill_kernel(size_t n, xrt_source_params p, const long long* __restrict__ idx,
+                                                   const double* __restrict__ rE, const double* __restrict__ rTheta,
+                                                   const double* __restrict__ rPsi, const double2* __restrict__ mJs,
+                                                   const double2* __restrict__ mJp, const double* __restrict__ n1,
+                                                   const double* __restrict__ n2, const double* __restrict__ n3,
+                                                   const double* __restrict__ n4, xrt_beam out, size_t out_offset) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t j = idx ? (size_t)idx[i] : i;  // sample index
+  const double2 s2 = mJs[j], p2 = mJp[j];
+  fill_ray(p, rE[j], rTheta[j], rPsi[j], cplx{s2.x, s2.y}, cplx{p2.x, p2.y}, n1[j], n2[j], n3[j], n4[j], out,
+           out_offset + i);
+}
+
+// ---------------------------------------------------------------- fused source for uniformRayDensity
+// sample -> field integral -> Beam in one kernel: the (E, theta, psi) samples, the four deviates and
+// (I, mJs, mJp) never travel through HBM (saves 64 + 64 + 40 + 40 B/ray and two launches); the Philox /
+// Box-Muller integer work and the 132 B/ray of stores hide under the FP64-bound node loop.  Same device
+// functions as the three separate kernels, so the beams are bit-identical (tests/test_shine.py).
+template <int R, bool PLANAR, bool SYM>
+__global__ void __launch_bounds__(U_THREADS)
+    shine_uniform_kernel(size_t n, uint64_t seed, uint64_t index_offset, double Emin, double Emax, double Tmin,
+                         double Tmax, double Pmin, double Pmax, UParams up, UTables tab, xrt_source_params sp,
+                         xrt_beam out, unsigned long long* imax_slot) {
+  __shared__ UNode tile[U_TILE];
+  const size_t base = (size_t)blockIdx.x * (U_THREADS * R);
+  Draw d[R];
+  USample s[R];
+  double acc[R][4];
+  double abv[R], fin[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const size_t i = base + (size_t)r * U_THREADS + threadIdx.x;
+    d[r] = draw_ray(index_offset + i, seed, Emin, Emax, Tmin, Tmax, Pmin, Pmax, true);
+    double wui, ww1i;
+    sample_prefactors(up, up.gamma0, d[r].E, d[r].theta, d[r].psi, wui, ww1i, abv[r]);
+    s[r] = make_sample(up.Kx, up.Ky, up.gamma0, wui, d[r].E, ww1i, d[r].theta, d[r].psi);
+    fin[r] = wui * (1.0 / up.gamma0);
+    acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0;
+  }
+  node_loop<R, PLANAR, SYM>(up, tab, tile, s, acc);
+  double imax = 0.0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const size_t i = base + (size_t)r * U_THREADS + threadIdx.x;
+    if (i >= n) continue;
+    const double f = fin[r];
+    double I;
+    double2 es, ep;
+    imap_outputs(up, d[r].E, abv[r], f * acc[r][0], f * acc[r][1], f * acc[r][2], f * acc[r][3], I, es, ep);
+    imax = fmax(imax, I);
+    fill_ray(sp, d[r].E, d[r].theta, d[r].psi, cplx{es.x, es.y}, cplx{ep.x, ep.y}, d[r].n1, d[r].n2, d[r].n3,
+             d[r].n4, out, i);
+  }
+  // beam-wide max intensity (Imax bookkeeping, sybase.py:1627-1631): non-negative doubles order like integers
+  imax = warp_reduce(imax, OpMax());
+  if ((threadIdx.x & 31) == 0 && imax > 0.0) atomicMax(imax_slot, (unsigned long long)__double_as_longlong(imax));
+}
+
 int source_sample_device(size_t n, uint64_t seed, uint64_t index_offset, const double* window, double* E,
                          double* theta, double* psi, double* n1, double* n2, double* n3, double* n4, double* u,
                          cudaStream_t st) {
@@ -219,6 +290,43 @@ int source_fill_device(size_t n, const xrt_source_params* p, const long long* id
                                                           reinterpret_cast<const double2*>(mJs),
                                                           reinterpret_cast<const double2*>(mJp), n1, n2, n3, n4, *out,
                                                           out_offset);
+  XRTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int shine_uniform_device(size_t n, uint64_t seed, uint64_t index_offset, const double* window, int jend, double Kx,
+                         double Ky, double L0, double Np, double gamma0, double amp_const, double dstep, int bw_mode,
+                         int symmetric, const double* tg, const double* ag, const double* sintg, const double* costg,
+                         const double* sintgph, const double* costgph, const xrt_source_params* sp,
+                         const xrt_beam* out, unsigned long long* imax_slot, cudaStream_t st) {
+  if (n == 0) return 0;
+  XRTB_REQUIRE(window && sp && out && imax_slot, "shine_uniform: NULL argument");
+  XRTB_REQUIRE(jend > 0, "shine_uniform: the integration grid is empty");
+  XRTB_REQUIRE(sp->uniform, "shine_uniform: the fused kernel is for uniformRayDensity sources");
+  UParams p{};
+  p.Kx = Kx;
+  p.Ky = Ky;
+  p.L0 = L0;
+  p.Np = Np;
+  p.gamma0 = gamma0;
+  p.amp_const = amp_const;
+  p.dstep = dstep;
+  p.jend = jend;
+  p.bw_mode = bw_mode;
+  UTables t{tg, ag, sintg, costg, sintgph, costgph};
+  constexpr int R = 2;
+  const unsigned grid = (unsigned)((n + U_THREADS * R - 1) / (U_THREADS * R));
+  const bool planar = (Kx == 0.0);
+#define XRTB_S_LAUNCH(PL, SY)                                                                                    \
+  shine_uniform_kernel<R, PL, SY><<<grid, U_THREADS, 0, st>>>(n, seed, index_offset, window[0], window[1], window[2], \
+                                                             window[3], window[4], window[5], p, t, *sp, *out, imax_slot)
+  if (planar && symmetric)
+    XRTB_S_LAUNCH(true, true);
+  else if (planar)
+    XRTB_S_LAUNCH(true, false);
+  else
+    XRTB_S_LAUNCH(false, false);
+#undef XRTB_S_LAUNCH
   XRTB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

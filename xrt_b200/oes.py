@@ -46,7 +46,7 @@ class xrt_oe_params(ctypes.Structure):
                 ('over_mask', ctypes.c_int), ('lostNum', ctypes.c_int),
                 ('brk_lim', (ctypes.c_double * 2) * 3),
                 ('created_by_diffract', ctypes.c_int), ('zero_dead_local', ctypes.c_int),
-                ('good_mode', ctypes.c_int)]
+                ('good_mode', ctypes.c_int), ('want_footprint', ctypes.c_int)]
 
 
 _AXIS = {'x': 0, 'y': 1, 'z': 2}
@@ -204,6 +204,7 @@ class OE(object):
                 hi = lim[1] if lim[1] < np.inf else dflt
             p.brk_lim[ax][0], p.brk_lim[ax][1] = float(lo), float(hi)
         p.created_by_diffract = int(createdByDiffract)
+        p.want_footprint = 1
         return p
 
     # ------------------------------------------------------------------ kernel launch
@@ -286,6 +287,8 @@ class OE(object):
         pitch = self.pitch + (self.bragg if hasattr(self, 'bragg') else 0)
         params = self._make_params(pitch, self.roll + self.positionRoll, self.yaw, self.dx,
                                    createdByDiffract=bool(getattr(beam, 'createdByDiffract', False)))
+        # the footprint / counter reductions are only paid for when somebody reads them
+        params.want_footprint = int(bool(withFootprint or (checkTables and self.material is not None)))
         gb = beam.like()
         lb = self._new_local(beam) if needLocal else None
         red = self._launch(params, self.material, beam, gb, lb, index_offset=index_offset, allreduce=allreduce)

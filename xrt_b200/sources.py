@@ -343,9 +343,34 @@ class Undulator(object):
             ctypes.byref(cout), out_offset, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
         _lib.check(rc, 'xrt_source_fill_f64')
 
+    def shine_uniform_fused(self, out, index_offset=0, toGlobal=True):
+        """uniformRayDensity source in ONE kernel (sample + field integral + Beam assembly fused; bit-identical to
+        draw_samples -> build_I_map_device -> fill_beam).  Returns the device slot holding max(I) of this call."""
+        lib = _lib.load()
+        if self.needReset:
+            self.reset()
+        if self.eEspread > 0:
+            raise NotImplementedError('the fused source kernel covers eEspread = 0')
+        dev = out.device
+        slot = torch.zeros(1, dtype=torch.int64, device=dev)
+        tabs = self._tables(dev)
+        p = self._source_params(toGlobal)
+        cout = out.c_struct()
+        window = (ctypes.c_double * 6)(self.E_min, self.E_max, self.Theta_min, self.Theta_max, self.Psi_min,
+                                       self.Psi_max)
+        offset = int(index_offset) + self._draws
+        self._draws += 1 << 40
+        rc = lib.xrt_shine_uniform_f64(
+            len(out), self.seed, offset, window, len(self.tg), self.Kx, self.Ky, self.L0, self.Np, self.gamma,
+            FINE_STR * self.eI / SIE0, self.dstep, 1 if self.distE == 'BW' else 0, int(self.gridSymmetric),
+            *[t.data_ptr() for t in tabs], ctypes.byref(p), ctypes.byref(cout), slot.data_ptr(),
+            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, 'xrt_shine_uniform_f64')
+        return slot
+
     # ------------------------------------------------------------------ shine
     def shine(self, toGlobal=True, withAmplitudes=True, fixedEnergy=False, wave=None, accuBeam=None,
-              samples=None, index_offset=0, allreduce_max=None, bookkeeping=True):
+              samples=None, index_offset=0, allreduce_max=None, bookkeeping=True, fused=True):
         """Returns the source Beam (device resident) like IntegratedSource.shine (sybase.py:1469-1812).
 
         *samples* (optional): dict of CUDA tensors E, theta, psi, n1..n4[, u] to use instead of drawing them
@@ -366,6 +391,24 @@ class Undulator(object):
         sumE = None
         sourceWeight = 0.
         given = samples is not None
+        if self.uniformRayDensity and not given and self.eEspread == 0 and fused:
+            # one fused kernel: samples and (I, mJs, mJp) never leave the registers
+            slot = self.shine_uniform_fused(bo, index_offset=index_offset, toGlobal=toGlobal)
+            seeded = mcRays
+            seededI = mcRays * self.xzE
+            if bookkeeping:
+                tmp_max = slot.view(torch.float64)
+                if allreduce_max is not None:
+                    tmp_max = allreduce_max(tmp_max)
+                self.Imax = max(self.Imax, float(tmp_max))
+                self.fluxConst = self.Imax * self.xzE
+                bo.accepted = mcRays * self.fluxConst
+                bo.acceptedE = float(bo.E.sum()) * self.fluxConst * SIE0
+            bo.seeded = seeded
+            bo.seededI = seededI
+            bo.sourceWeight = self.xzE / self.nrays
+            bo.parentId = getattr(self, 'uuid', self.name)
+            return bo
         while True:
             s = samples if given else self.draw_samples(mcRays, dev, index_offset=index_offset)
             n = s['E'].numel()
