@@ -218,11 +218,14 @@ typedef struct xrt_source_params {
   double L0, Np;          /* undulator period [mm], number of periods (photon source size, synchr.py:2200-2204) */
   int has_pitch, has_yaw;
   double cosPitch, sinPitch, cosYaw, sinYaw;
+  double eEspread, E1;    /* relative electron energy spread and first-harmonic energy: photon source size with the
+                             Tanaka-Kitamura Qa factor (synchr.py:2210-2223, sybase.py:664-674); 0 = no spread */
+  double gamma0;          /* Lorentz factor; per-ray gamma = gamma0 + gamma0*eEspread*n5 (synchr.py:2053-2059) */
 } xrt_source_params;
 
 int xrt_source_sample_f64(size_t n, uint64_t seed, uint64_t index_offset, const double* window, double* E,
                           double* theta, double* psi, double* n1, double* n2, double* n3, double* n4, double* u,
-                          void* stream);
+                          double* n5, void* stream);
 int xrt_source_fill_f64(size_t n, const xrt_source_params* p, const int64_t* idx, const double* rE,
                         const double* rTheta, const double* rPsi, const double* mJs, const double* mJp,
                         const double* n1, const double* n2, const double* n3, const double* n4, const xrt_beam* out,

@@ -7,7 +7,7 @@ that the CUDA path can be fed the same numbers."""
 import numpy as np
 
 from . import beam as ob, undulator as ou
-from .physconsts import PI2, CHeVcm, SIE0
+from .physconsts import PI2, CHeVcm, SIE0, PI
 
 
 class UndulatorSpec(object):
@@ -23,12 +23,29 @@ class UndulatorSpec(object):
         self.fluxConst = self.Imax * self.xzE
         self.grid = ou.build_integration_grid(self.quadm, self.gIntervals, self.phase)
 
-    def build_I_map(self, w, th, ps):
-        return ou.build_I_map(self.grid, self.L0, self.Np, self.Kx, self.Ky, self.eI, self.gamma * np.ones(len(w)),
+    def build_I_map(self, w, th, ps, record=None):
+        gamma = self.gamma
+        if getattr(self, 'eEspread', 0) > 0:  # synchr.py:2053-2059
+            g5 = np.random.normal(size=len(w))
+            gamma = gamma + gamma * self.eEspread * g5
+            if record is not None:
+                record['g5'] = g5
+        return ou.build_I_map(self.grid, self.L0, self.Np, self.Kx, self.Ky, self.eI, gamma * np.ones(len(w)),
                               w, th, ps, self.distE)
 
-    def get_SIGMA(self, E):  # synchr.py:2200-2249, eEspread = 0
+    def get_SIGMA(self, E):  # synchr.py:2200-2249 (onlyOddHarmonics=False as shine passes it), sybase.py:664-674
         sigma_r2 = 2 * CHeVcm/E*10 * self.L0*self.Np / PI2**2
+        if getattr(self, 'eEspread', 0) > 0:
+            from scipy import special
+            harmonic = np.floor_divide(E, self.E1)
+            eEspread_norm = PI2 * harmonic * self.Np * self.eEspread
+            x = eEspread_norm/4.
+            ret = np.ones_like(x, dtype=float)
+            xarr = np.array(x)
+            y = 2**0.5 * xarr[xarr > 1e-6]
+            y2 = y**2
+            ret[x > 1e-6] = y2 / (np.exp(-y2) + PI**0.5*y*special.erf(y) - 1)
+            sigma_r2 = sigma_r2 * ret**(2/3.)
         return (self.dx**2 + sigma_r2)**0.5, (self.dz**2 + sigma_r2)**0.5
 
 
@@ -49,7 +66,8 @@ def shine(src, nrays, toGlobal=True, withAmplitudes=True, record=None):
         rTheta = rndg * (src.Theta_max - src.Theta_min) + src.Theta_min
         rndg = np.random.rand(mcRays)
         rPsi = rndg * (src.Psi_max - src.Psi_min) + src.Psi_min
-        Intensity, mJs, mJp = src.build_I_map(rE, rTheta, rPsi)
+        extra = {}
+        Intensity, mJs, mJp = src.build_I_map(rE, rTheta, rPsi, extra)
         if src.uniformRayDensity:
             seededI += mcRays * src.xzE
             sourceWeight = src.xzE
@@ -90,7 +108,7 @@ def shine(src, nrays, toGlobal=True, withAmplitudes=True, record=None):
             g4 = np.random.standard_normal(npassed)
             bot.c[:] += 0. + src.dzprime * g4
         passes.append(dict(E=rE, theta=rTheta, psi=rPsi, u=u, I_pass=I_pass, g1=g1, g2=g2, g3=g3, g4=g4,
-                           Imax=src.Imax))
+                           Imax=src.Imax, **extra))
         mJs = mJs[I_pass]
         mJp = mJp[I_pass]
         mJs2 = (mJs * np.conj(mJs)).real

@@ -8,7 +8,7 @@ from conftest import golden
 from helpers import compare_beams, BEAM_FIELDS
 from oracle import shine as osh
 
-CASES = ['shine_uniform', 'shine_rejection']
+CASES = ['shine_uniform', 'shine_rejection', 'shine_uniform_spread']
 SPEC_KEYS = ('L0', 'Np', 'Kx', 'Ky', 'eI', 'gamma', 'phase', 'E_min', 'E_max', 'Theta_min', 'Theta_max', 'Psi_min',
              'Psi_max', 'dx', 'dz', 'dxprime', 'dzprime', 'pitch', 'yaw')
 
@@ -17,7 +17,8 @@ def _spec(g):
     kw = {k: float(g[k]) for k in SPEC_KEYS}
     return osh.UndulatorSpec(quadm=int(g['quadm']), gIntervals=int(g['gIntervals']), center=list(g['center']),
                              azimuth=(float(g['sinAzimuth']), float(g['cosAzimuth'])),
-                             uniformRayDensity=bool(g['uniform']), **kw)
+                             uniformRayDensity=bool(g['uniform']), eEspread=float(g['eEspread']), E1=float(g['E1']),
+                             **kw)
 
 
 @pytest.mark.parametrize('name', CASES)
@@ -42,7 +43,8 @@ def _product_source(g, nrays):
                     eSigmaX=48.65, eSigmaZ=6.197, eEpsilonX=0.263, eEpsilonZ=0.008, xPrimeMax=0.1, zPrimeMax=0.1,
                     xPrimeMaxAutoReduce=False, zPrimeMaxAutoReduce=False, eMin=float(g['E_min']),
                     eMax=float(g['E_max']), gNodes=int(g['quadm']), gIntervals=int(g['gIntervals']),
-                    uniformRayDensity=bool(g['uniform']), pitch=float(g['pitch']), yaw=float(g['yaw']))
+                    uniformRayDensity=bool(g['uniform']), pitch=float(g['pitch']), yaw=float(g['yaw']),
+                    eEspread=float(g['eEspread']))
     return src
 
 
@@ -85,6 +87,8 @@ def test_cuda_shine_with_reference_deviates(name, cuda_device):
             full[key] = arr
         s = dict(E=dev(p['E']), theta=dev(p['theta']), psi=dev(p['psi']),
                  u=dev(p['u'] if p['u'] is not None else np.zeros(n)), **{k: dev(v) for k, v in full.items()})
+        if 'g5' in p:
+            s['n5'] = dev(p['g5'])
         b = src.shine(samples=s)
         if not bool(g['uniform']):
             # the accepted set must be the reference's (same running Imax, same uniforms)
@@ -176,11 +180,12 @@ def test_cuda_convergence_search_finds_reference_grid(cuda_device):
 
 
 @pytest.mark.gpu
-def test_cuda_fused_uniform_source_equals_three_kernels(cuda_device):
+@pytest.mark.parametrize('case', ['shine_uniform', 'shine_uniform_spread'])
+def test_cuda_fused_uniform_source_equals_three_kernels(case, cuda_device):
     """The fused source kernel (sample + integral + Beam assembly) gives the same Beam, bit for bit, as the three
     separate kernels that are parity-tested against the oracle (same Philox counters, same device functions)."""
     import torch
-    g = golden('shine_uniform')
+    g = golden(case)
     n = 300007
     a = _product_source(g, n)
     b = _product_source(g, n)

@@ -346,8 +346,9 @@ def gen_amplitudes():
 def gen_shine():
     probe = _undulator_source(eMin=1000., eMax=1001., gNodes=16)
     E1 = probe.E1
-    for name, uniform, nrays, seed in (('shine_uniform', True, 2500, 81), ('shine_rejection', False, 1200, 82)):
-        src = _undulator_source(eMin=E1*0.995, eMax=E1*1.005, gNodes=32, gIntervals=2, nrays=nrays,
+    for name, uniform, nrays, seed, spread in (('shine_uniform', True, 2500, 81, 0.), ('shine_rejection', False, 1200, 82, 0.),
+                                               ('shine_uniform_spread', True, 2000, 83, 1e-3)):
+        src = _undulator_source(eMin=E1*0.995, eMax=E1*1.005, gNodes=32, gIntervals=2, nrays=nrays, eEspread=spread,
                                 uniformRayDensity=uniform, center=(0.5, -2., 0.1), pitch=1e-5, yaw=-2e-5)
         src.bl.azimuth = 0.05
         np.random.seed(seed)
@@ -357,7 +358,7 @@ def gen_shine():
                  Theta_min=src.Theta_min, Theta_max=src.Theta_max, Psi_min=src.Psi_min, Psi_max=src.Psi_max,
                  dx=src.dx, dz=src.dz, dxprime=src.dxprime, dzprime=src.dzprime, center=np.array(src.center, dtype=float),
                  sinAzimuth=src.bl.sinAzimuth, cosAzimuth=src.bl.cosAzimuth, pitch=src.pitch, yaw=src.yaw,
-                 seed=seed, nrays=nrays, uniform=uniform, Imax=src.Imax, xzE=src.xzE, fluxConst=src.fluxConst,
+                 seed=seed, nrays=nrays, uniform=uniform, eEspread=spread, E1=src.E1, Imax=src.Imax, xzE=src.xzE, fluxConst=src.fluxConst,
                  accepted=beam.accepted, acceptedE=beam.acceptedE, seeded=beam.seeded, seededI=beam.seededI,
                  sourceWeight=beam.sourceWeight)
         d.update(beam_dict(beam, 'out_'))

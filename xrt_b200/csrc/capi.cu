@@ -340,8 +340,8 @@ int xrt_get_amplitude_f64_host(size_t n, const xrt_material_params* mat, const d
 // ------------------------------------------------------------------ source
 int xrt_source_sample_f64(size_t n, uint64_t seed, uint64_t index_offset, const double* window, double* E,
                           double* theta, double* psi, double* n1, double* n2, double* n3, double* n4, double* u,
-                          void* stream) {
-  return source_sample_device(n, seed, index_offset, window, E, theta, psi, n1, n2, n3, n4, u,
+                          double* n5, void* stream) {
+  return source_sample_device(n, seed, index_offset, window, E, theta, psi, n1, n2, n3, n4, u, n5,
                               (cudaStream_t)stream);
 }
 

@@ -47,7 +47,7 @@ int propagate_rect_device(size_t n, const xrt_plane_params* p, const xrt_beam* i
 // source.cu (compiled with -fmad=false)
 int source_sample_device(size_t n, uint64_t seed, uint64_t index_offset, const double* window, double* E,
                          double* theta, double* psi, double* n1, double* n2, double* n3, double* n4, double* u,
-                         cudaStream_t st);
+                         double* n5, cudaStream_t st);
 int source_fill_device(size_t n, const xrt_source_params* p, const long long* idx, const double* rE,
                        const double* rTheta, const double* rPsi, const double* mJs, const double* mJp,
                        const double* n1, const double* n2, const double* n3, const double* n4, const xrt_beam* out,

@@ -52,12 +52,12 @@ __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
 }
 
 struct Draw {
-  double E, theta, psi, u, n1, n2, n3, n4;
+  double E, theta, psi, u, n1, n2, n3, n4, n5;
 };
 // E, theta, psi uniform in their windows (sybase.py:1583-1617), u uniform (rejection test, :1637), n1..n4
 // standard normal (Box-Muller on (0, 1] uniforms); four Philox blocks per ray
 __device__ __forceinline__ Draw draw_ray(uint64_t ctr, uint64_t seed, double Emin, double Emax, double Tmin,
-                                         double Tmax, double Pmin, double Pmax, bool normals) {
+                                         double Tmax, double Pmin, double Pmax, bool normals, bool spread) {
   Draw d;
   uint32_t w[4];
   philox4x32_10(ctr, 0u, seed, w);
@@ -83,6 +83,14 @@ __device__ __forceinline__ Draw draw_ray(uint64_t ctr, uint64_t seed, double Emi
     d.n3 = rb * cs;
     d.n4 = rb * sn;
   }
+  d.n5 = 0.0;
+  if (spread) {  // electron energy deviate (one more Philox block)
+    philox4x32_10(ctr, 4u, seed, w);
+    const double c0 = 1.0 - u53(w[0], w[1]), c1 = u53(w[2], w[3]);
+    double sn, cs;
+    sincospi(2.0 * c1, &sn, &cs);
+    d.n5 = sqrt(-2.0 * log(c0)) * cs;
+  }
   return d;
 }
 
@@ -91,10 +99,12 @@ __global__ void __launch_bounds__(256) sample_kernel(size_t n, uint64_t seed, ui
                                                      double* __restrict__ E, double* __restrict__ theta,
                                                      double* __restrict__ psi, double* __restrict__ n1,
                                                      double* __restrict__ n2, double* __restrict__ n3,
-                                                     double* __restrict__ n4, double* __restrict__ u) {
+                                                     double* __restrict__ n4, double* __restrict__ u,
+                                                     double* __restrict__ n5) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const Draw d = draw_ray(index_offset + i, seed, Emin, Emax, Tmin, Tmax, Pmin, Pmax, n1 != nullptr);
+  const Draw d = draw_ray(index_offset + i, seed, Emin, Emax, Tmin, Tmax, Pmin, Pmax, n1 != nullptr, n5 != nullptr);
+  if (n5) n5[i] = d.n5;
   E[i] = d.E;
   theta[i] = d.theta;
   psi[i] = d.psi;
@@ -119,7 +129,21 @@ __device__ __forceinline__ void fill_ray(const xrt_source_params& p, double E, d
   // get_SIGMA (synchr.py:2240-2249) with get_sigma_r2 = get_sigma_r02 (eEspread = 0): 2*CHeVcm/E*10*L0*Np/PI2**2
   const double CHeVcm = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12;
   const double PI2 = 6.283185307179586476925286766559;
-  const double sr2 = 2.0 * CHeVcm / E * 10.0 * p.L0 * p.Np / (PI2 * PI2);
+  double sr2 = 2.0 * CHeVcm / E * 10.0 * p.L0 * p.Np / (PI2 * PI2);
+  if (p.eEspread > 0.0) {
+    // get_sigma_r2 with energy spread (synchr.py:2210-2223, onlyOddHarmonics=False as shine passes it) and
+    // tanaka_kitamura_Qa2 (sybase.py:664-674)
+    const double harmonic = floor(E / p.E1);  // np.floor_divide for positive operands
+    const double enorm = PI2 * harmonic * p.Np * p.eEspread;
+    const double xq = enorm / 4.0;
+    double Qa2 = 1.0;
+    if (xq > 1e-6) {
+      const double yq = 1.4142135623730951 * xq;
+      const double y2 = yq * yq;
+      Qa2 = y2 / (exp(-y2) + 1.7724538509055159 * yq * erf(yq) - 1.0);
+    }
+    sr2 = sr2 * pow(Qa2, 2.0 / 3.0);
+  }
   const double SX = sqrt(p.dx * p.dx + sr2), SZ = sqrt(p.dz * p.dz + sr2);
   double x = 0.0 + SX * g1;  // np.random.normal(0, SIGMA, n) = loc + scale * gauss
   double y = 0.0;
@@ -239,11 +263,13 @@ __global__ void __launch_bounds__(U_THREADS)
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const size_t i = base + (size_t)r * U_THREADS + threadIdx.x;
-    d[r] = draw_ray(index_offset + i, seed, Emin, Emax, Tmin, Tmax, Pmin, Pmax, true);
+    d[r] = draw_ray(index_offset + i, seed, Emin, Emax, Tmin, Tmax, Pmin, Pmax, true, sp.eEspread > 0.0);
+    // gamma += gamma * eEspread * normal (synchr.py:2053-2059)
+    const double g = (sp.eEspread > 0.0) ? up.gamma0 + up.gamma0 * sp.eEspread * d[r].n5 : up.gamma0;
     double wui, ww1i;
-    sample_prefactors(up, up.gamma0, d[r].E, d[r].theta, d[r].psi, wui, ww1i, abv[r]);
-    s[r] = make_sample(up.Kx, up.Ky, up.gamma0, wui, d[r].E, ww1i, d[r].theta, d[r].psi);
-    fin[r] = wui * (1.0 / up.gamma0);
+    sample_prefactors(up, g, d[r].E, d[r].theta, d[r].psi, wui, ww1i, abv[r]);
+    s[r] = make_sample(up.Kx, up.Ky, g, wui, d[r].E, ww1i, d[r].theta, d[r].psi);
+    fin[r] = wui * (1.0 / g);
     acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0;
   }
   node_loop<R, PLANAR, SYM>(up, tab, tile, s, acc);
@@ -267,7 +293,7 @@ __global__ void __launch_bounds__(U_THREADS)
 
 int source_sample_device(size_t n, uint64_t seed, uint64_t index_offset, const double* window, double* E,
                          double* theta, double* psi, double* n1, double* n2, double* n3, double* n4, double* u,
-                         cudaStream_t st) {
+                         double* n5, cudaStream_t st) {
   if (n == 0) return 0;
   XRTB_REQUIRE(window && E && theta && psi, "source_sample: NULL argument");
   XRTB_REQUIRE((n1 == nullptr) == (n2 == nullptr) && (n1 == nullptr) == (n3 == nullptr) &&
@@ -275,7 +301,7 @@ int source_sample_device(size_t n, uint64_t seed, uint64_t index_offset, const d
                "source_sample: give all four normal-deviate arrays or none");
   sample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, seed, index_offset, window[0], window[1], window[2],
                                                             window[3], window[4], window[5], E, theta, psi, n1, n2,
-                                                            n3, n4, u);
+                                                            n3, n4, u, n5);
   XRTB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

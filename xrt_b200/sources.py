@@ -32,7 +32,8 @@ class xrt_source_params(ctypes.Structure):
                 ('dzprime', ctypes.c_double), ('L0', ctypes.c_double), ('Np', ctypes.c_double),
                 ('has_pitch', ctypes.c_int), ('has_yaw', ctypes.c_int),
                 ('cosPitch', ctypes.c_double), ('sinPitch', ctypes.c_double),
-                ('cosYaw', ctypes.c_double), ('sinYaw', ctypes.c_double)]
+                ('cosYaw', ctypes.c_double), ('sinYaw', ctypes.c_double),
+                ('eEspread', ctypes.c_double), ('E1', ctypes.c_double), ('gamma0', ctypes.c_double)]
 
 
 def clenshaw_curtis(n):
@@ -305,6 +306,7 @@ class Undulator(object):
             p.has_pitch, p.cosPitch, p.sinPitch = 1, float(np.cos(self.pitch)), float(np.sin(self.pitch))
         if self.yaw:
             p.has_yaw, p.cosYaw, p.sinYaw = 1, float(np.cos(self.yaw)), float(np.sin(self.yaw))
+        p.eEspread, p.E1, p.gamma0 = float(self.eEspread), float(self.E1), float(self.gamma)
         return p
 
     def draw_samples(self, n, device=None, index_offset=0, withNormals=True, withU=True):
@@ -313,7 +315,8 @@ class Undulator(object):
             self.reset()
         lib = _lib.load()
         dev = torch.device('cuda', torch.cuda.current_device()) if device is None else device
-        names = ['E', 'theta', 'psi'] + (['n1', 'n2', 'n3', 'n4'] if withNormals else []) + (['u'] if withU else [])
+        names = ['E', 'theta', 'psi'] + (['n1', 'n2', 'n3', 'n4'] if withNormals else []) + (['u'] if withU else []) \
+            + (['n5'] if self.eEspread > 0 else [])
         buf = torch.empty((len(names), n), dtype=F64, device=dev)
         s = {k: buf[i] for i, k in enumerate(names)}
         window = (ctypes.c_double * 6)(self.E_min, self.E_max, self.Theta_min, self.Theta_max, self.Psi_min,
@@ -323,16 +326,13 @@ class Undulator(object):
         offset = int(index_offset) + self._draws
         self._draws += 1 << 40
         rc = lib.xrt_source_sample_f64(n, self.seed, offset, window, ptr('E'), ptr('theta'), ptr('psi'), ptr('n1'),
-                                       ptr('n2'), ptr('n3'), ptr('n4'), ptr('u'),
+                                       ptr('n2'), ptr('n3'), ptr('n4'), ptr('u'), ptr('n5'),
                                        ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
         _lib.check(rc, 'xrt_source_sample_f64')
         return s
 
     def fill_beam(self, samples, mJs, mJp, out, idx=None, out_offset=0, n=None, toGlobal=True):
         lib = _lib.load()
-        if self.eEspread > 0:
-            raise NotImplementedError('source size with energy spread (Tanaka-Kitamura Qa) is not on the device '
-                                      'path yet; build_I_map supports eEspread')
         p = self._source_params(toGlobal)
         n = (len(idx) if idx is not None else samples['E'].numel()) if n is None else n
         cout = out.c_struct()
@@ -349,8 +349,6 @@ class Undulator(object):
         lib = _lib.load()
         if self.needReset:
             self.reset()
-        if self.eEspread > 0:
-            raise NotImplementedError('the fused source kernel covers eEspread = 0')
         dev = out.device
         slot = torch.zeros(1, dtype=torch.int64, device=dev)
         tabs = self._tables(dev)
@@ -391,7 +389,7 @@ class Undulator(object):
         sumE = None
         sourceWeight = 0.
         given = samples is not None
-        if self.uniformRayDensity and not given and self.eEspread == 0 and fused:
+        if self.uniformRayDensity and not given and fused:
             # one fused kernel: samples and (I, mJs, mJp) never leave the registers
             slot = self.shine_uniform_fused(bo, index_offset=index_offset, toGlobal=toGlobal)
             seeded = mcRays
@@ -413,7 +411,10 @@ class Undulator(object):
             s = samples if given else self.draw_samples(mcRays, dev, index_offset=index_offset)
             n = s['E'].numel()
             seeded += n
-            I, mJs, mJp = self.build_I_map_device(s['E'], s['theta'], s['psi'])
+            gam = None
+            if self.eEspread > 0:  # gamma += gamma * eEspread * normal (synchr.py:2053-2059)
+                gam = self.gamma + (self.gamma * self.eEspread) * s['n5']
+            I, mJs, mJp = self.build_I_map_device(s['E'], s['theta'], s['psi'], gamma=gam)
             if self.uniformRayDensity:
                 seededI += n * self.xzE
                 sourceWeight = self.xzE
