@@ -241,6 +241,12 @@ int xrt_shine_uniform_f64(size_t n, uint64_t seed, uint64_t index_offset, const 
                           const double* sintgph, const double* costgph, const xrt_source_params* p,
                           const xrt_beam* out, uint64_t* imax_slot, void* stream);
 
+/* Surface normals of an OE at local Cartesian points (x, y, z): OE.local_n, preceded by xyz_to_param for
+ * parametric surfaces, as waves.diffract (waves.py:675-686) and OE.local_to_global (oes/base.py:1213-1217) call
+ * it. Device pointers; nx, ny, nz receive the surface normal. */
+int xrt_oe_normals_f64(size_t n, const xrt_oe_params* oe, const double* x, const double* y, const double* z,
+                       double* nx, double* ny, double* nz, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -145,3 +145,133 @@ def diffract(oeLocal, wave):
     a0, b0 = toOE.sinAzimuth, toOE.cosAzimuth
     wave.a[:], wave.b[:] = ob.rotate_z(wave.a, wave.b, b0, a0)
     return glo
+
+
+# ---------------------------------------------------------------------------------------------- OE as the
+# diffracting element (waves.py:675-686, :719-724, :756-767; OE.local_to_global oes/base.py:1165-1229)
+def prepare_wave_from_oe(oe, wave, xglo, yglo, zglo):
+    """waves.prepare_wave for fromOE with a rotationSequence (waves.py:547-572). `oe` is an oracle OESpec."""
+    wave = prepare_wave(Plane(oe.center, oe.azimuth[0], oe.azimuth[1]), wave, xglo, yglo, zglo)
+    x, y, z = wave.xDiffr, wave.yDiffr, wave.zDiffr
+    hold = ob.Beam(len(x))
+    hold.x, hold.y, hold.z = x, y, z
+    ob.rotate_beam(hold, rotationSequence=oe.rotationSequence, pitch=-oe.pitch, roll=-oe.roll, yaw=-oe.yaw)
+    if oe.extraPitch or oe.extraRoll or oe.extraYaw:
+        ob.rotate_beam(hold, rotationSequence=oe.extraRotationSequence, pitch=-oe.extraPitch, roll=-oe.extraRoll,
+                       yaw=-oe.extraYaw)
+    wave.xDiffr, wave.yDiffr, wave.zDiffr = hold.x, hold.y, hold.z
+    wave.rDiffr = (wave.xDiffr**2 + wave.yDiffr**2 + wave.zDiffr**2)**0.5
+    wave.a[:] = wave.xDiffr / wave.rDiffr
+    wave.b[:] = wave.yDiffr / wave.rDiffr
+    wave.c[:] = wave.zDiffr / wave.rDiffr
+    wave.fromOE = oe
+    return wave
+
+
+def screen_prepare_wave_from_oe(screen, oe, dim1, dim2):
+    d1s, d2s = np.meshgrid(dim1, dim2)
+    d1s = d1s.flatten()
+    d2s = d2s.flatten()
+    dS = (dim1[1] - dim1[0]) * (dim2[1] - dim2[0])
+    xglo, yglo, zglo = screen.local_to_global(x=d1s, z=d2s)
+    wave = ob.Beam(len(d1s), withAmplitudes=True)
+    wave.state[:] = 1
+    wave.x[:] = d1s
+    wave.y[:] = np.zeros_like(d1s)
+    wave.z[:] = d2s
+    wave.dS = dS
+    wave.toOE = screen
+    wave.area = (np.ones_like(d1s) * dS).sum()
+    return prepare_wave_from_oe(oe, wave, xglo, yglo, zglo)
+
+
+def oe_local_to_global(oe, lb):
+    """OE.local_to_global (oes/base.py:1165-1229) for a plain OE (no second crystal)."""
+    if oe.dx:
+        lb.x += oe.dx
+    if oe.extraPitch or oe.extraRoll or oe.extraYaw:
+        ob.rotate_beam(lb, rotationSequence='-'+oe.extraRotationSequence, pitch=oe.extraPitch, roll=oe.extraRoll,
+                       yaw=oe.extraYaw)
+    ob.rotate_beam(lb, rotationSequence='-'+oe.rotationSequence, pitch=oe.pitch, roll=oe.roll, yaw=oe.yaw)
+    if oe.isParametric:
+        s, phi, r = oe.xyz_to_param(lb.x, lb.y, lb.z)
+        oeNormal = list(oe.local_n(s, phi))
+    else:
+        oeNormal = list(oe.local_n(lb.x, lb.y))
+    roll = oe.roll + np.arctan2(oeNormal[-3], oeNormal[-1])
+    lb.Jss[:], lb.Jpp[:], lb.Jsp[:] = ob.rotate_coherency_matrix(lb, slice(None), roll)
+    if hasattr(lb, 'Es'):
+        cosY, sinY = np.cos(roll), np.sin(roll)
+        lb.Es[:], lb.Ep[:] = ob.rotate_y(lb.Es, lb.Ep, cosY, sinY)
+    ob.virgin_local_to_global(oe.azimuth, lb, oe.center)
+
+
+def diffract_from_oe(oeLocal, wave):
+    """waves.diffract with an OE as wave.fromOE and a Screen as wave.toOE. All rays of oeLocal must be good (the
+    reference's numpy integral broadcasts the un-masked normals against the masked samples, waves.py:840)."""
+    oe = wave.fromOE
+    good = oeLocal.state == 1
+    goodlen = good.sum()
+    if getattr(oeLocal, 'area', None) is None or oeLocal.area <= 0:
+        impactPoints = np.vstack((oeLocal.x[good], oeLocal.y[good])).T
+        hull = ConvexHull(impactPoints)
+        outerPts = impactPoints[hull.vertices, :]
+        lines = np.hstack([outerPts, np.roll(outerPts, -1, axis=0)])
+        oeLocal.area = 0.5 * abs(sum(x1*y2-x2*y1 for x1, y1, x2, y2 in lines))
+    if oe.isParametric:
+        s, phi, r = oe.xyz_to_param(oeLocal.x, oeLocal.y, oeLocal.z)
+        n = oe.local_n(s, phi)
+    else:
+        n = oe.local_n(oeLocal.x, oeLocal.y)[-3:]
+    nl = (oeLocal.a*np.asarray([n[-3]]) + oeLocal.b*np.asarray([n[-2]]) + oeLocal.c*np.asarray([n[-1]])).flatten()
+    wave.diffract_repeats += 1
+    wave.beamReflRays += goodlen
+    wave.beamReflSumJ += (oeLocal.Jss[good] + oeLocal.Jpp[good]).sum()
+    wave.beamReflSumJnl += abs(((oeLocal.Jss[good] + oeLocal.Jpp[good]) * nl[good]).sum())
+    nn = [np.asarray(n[i]) * np.ones(len(oeLocal.x)) for i in range(3)]
+    Es, Ep, aE, bE, cE = ok.diffraction_integral(
+        oeLocal.x[good], oeLocal.y[good], oeLocal.z[good], [nn[0][good], nn[1][good], nn[2][good]], nl[good],
+        oeLocal.Es[good], oeLocal.Ep[good], oeLocal.E[good], wave.xDiffr, wave.yDiffr, wave.zDiffr)
+    wave.EsAcc += Es
+    wave.EpAcc += Ep
+    wave.aEacc += aE
+    wave.bEacc += bE
+    wave.cEacc += cE
+    wave.E[:] = oeLocal.E[0]
+    wave.Es[:] = wave.EsAcc
+    wave.Ep[:] = wave.EpAcc
+    wave.Jss[:] = (wave.Es * np.conj(wave.Es)).real
+    wave.Jpp[:] = (wave.Ep * np.conj(wave.Ep)).real
+    wave.Jsp[:] = wave.Es * np.conj(wave.Ep)
+    toRealComp = wave.cEacc if abs(wave.cEacc[0]) > abs(wave.bEacc[0]) else wave.bEacc
+    toReal = np.exp(-1j * np.angle(toRealComp))
+    wave.a[:] = (wave.aEacc * toReal).real
+    wave.b[:] = (wave.bEacc * toReal).real
+    wave.c[:] = (wave.cEacc * toReal).real
+    norm = (wave.a**2 + wave.b**2 + wave.c**2)**0.5
+    norm[norm == 0] = 1.
+    wave.a /= norm
+    wave.b /= norm
+    wave.c /= norm
+    norm = wave.dS * oeLocal.area * wave.beamReflSumJ
+    de = wave.beamReflRays * wave.beamReflSumJnl * wave.diffract_repeats
+    norm = norm / de if de > 0 else 0
+    wave.Jss *= norm
+    wave.Jpp *= norm
+    wave.Jsp *= norm
+    wave.Es *= norm**0.5
+    wave.Ep *= norm**0.5
+    glo = ob.Beam(copyFrom=wave)
+    glo.x[:] = wave.xDiffr
+    glo.y[:] = wave.yDiffr
+    glo.z[:] = wave.zDiffr
+    oe_local_to_global(oe, glo)
+    # waves.py:776-784: the coherency rotation back to global acts on the local Es, Ep variables of diffract()
+    # only (dead code for the outputs); then the wave takes the global beam and is turned by the azimuth
+    toOE = wave.toOE
+    wave.a[:], wave.b[:], wave.c[:] = glo.a, glo.b, glo.c
+    wave.Jss[:], wave.Jpp[:], wave.Jsp[:] = glo.Jss, glo.Jpp, glo.Jsp
+    wave.Es[:], wave.Ep[:] = glo.Es, glo.Ep
+    a0, b0 = toOE.sinAzimuth, toOE.cosAzimuth
+    wave.a[:], wave.b[:] = ob.rotate_z(wave.a, wave.b, b0, a0)
+    return glo

@@ -63,3 +63,58 @@ def test_cuda_prepare_wave_and_diffract_vs_golden(cuda_device):
     bad += compare_beams(glo.to_numpy(), {f: g['glo_' + f] for f in GLO_FIELDS}, GLO_FIELDS, 1e-11, 'glo_')
     assert not bad, bad
     assert abs(wave.beamReflSumJ - float(g['beamReflSumJ'])) <= 1e-12 * float(g['beamReflSumJ'])
+
+
+def _kb_oracle(g):
+    from helpers import oracle_spec
+    from oracle import materials as om
+    return oracle_spec(g, 'ellipse_param', om.Material('Au', rho=19.3), isParametric=True,
+                       surfParams=dict(isCylindrical=True, **{k: float(g[k]) for k in
+                                       ('ellipseA', 'ellipseB', 'y0', 'z0', 'cosGamma', 'sinGamma')}))
+
+
+def test_oracle_diffract_from_kb_mirror_bit_exact():
+    """Config 5, last step: the rays traced onto an elliptical KB mirror are the diffracting samples."""
+    g = golden('diffract_kb_screen')
+    kb = _kb_oracle(g)
+    scr = ow.Plane(list(g['scr_center']), float(g['sinAzimuth']), float(g['cosAzimuth']))
+    wave = ow.screen_prepare_wave_from_oe(scr, kb, g['xmesh'], g['zmesh'])
+    for k in ('xDiffr', 'yDiffr', 'zDiffr'):
+        assert np.array_equal(getattr(wave, k), g[k]), k
+    lb = oracle_beam(g, 'in_')
+    glo = ow.diffract_from_oe(lb, wave)
+    assert lb.area == float(g['area'])
+    for f in WAVE_FIELDS:
+        assert np.array_equal(getattr(wave, f), g['wave_' + f]), 'wave_' + f
+    for f in ('EsAcc', 'EpAcc', 'aEacc', 'bEacc', 'cEacc'):
+        assert np.array_equal(getattr(wave, f), g['wave_' + f]), f
+    for f in GLO_FIELDS:
+        assert np.array_equal(getattr(glo, f), g['glo_' + f]), 'glo_' + f
+
+
+@pytest.mark.gpu
+def test_cuda_diffract_from_kb_mirror_vs_golden(cuda_device):
+    from xrt_b200 import waves, oes, materials
+    from xrt_b200.planes import Screen
+    from helpers import product_beamline, product_oe_kwargs
+    g = golden('diffract_kb_screen')
+    bl = product_beamline(g)
+    kb = oes.EllipticalMirrorParam(bl, 'kb', p=float(g['p']), q=float(g['q']), isCylindrical=True,
+                                   material=materials.Material('Au', rho=19.3), **product_oe_kwargs(g))
+    for k in ('ellipseA', 'ellipseB', 'y0', 'z0', 'cosGamma', 'sinGamma'):
+        assert abs(getattr(kb, k) - float(g[k])) <= 1e-13 * max(1., abs(float(g[k]))), k
+        setattr(kb, k, float(g[k]))
+    scr = Screen(bl, 'scr', center=list(g['scr_center']))
+    wave = waves.screen_prepare_wave(scr, kb, g['xmesh'], g['zmesh'])
+    for k in ('xDiffr', 'yDiffr', 'zDiffr'):
+        np.testing.assert_allclose(getattr(wave, k).cpu().numpy(), g[k], rtol=1e-13, atol=1e-11)
+    lb = device_beam(oracle_beam(g, 'in_'))
+    glo = waves.diffract(lb, wave)
+    assert abs(lb.area - float(g['area'])) <= 1e-12 * float(g['area'])
+    w = wave.to_numpy()
+    for f in ('EsAcc', 'EpAcc', 'aEacc', 'bEacc', 'cEacc'):
+        ref = g['wave_' + f]
+        assert np.abs(w[f] - ref).max() <= 1e-11 * np.abs(ref).max(), f
+    bad = compare_beams(w, {f: g['wave_' + f] for f in WAVE_FIELDS}, WAVE_FIELDS, 1e-10, 'wave_')
+    bad += compare_beams(glo.to_numpy(), {f: g['glo_' + f] for f in GLO_FIELDS}, GLO_FIELDS, 1e-10, 'glo_')
+    assert not bad, bad

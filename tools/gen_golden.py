@@ -453,8 +453,38 @@ def gen_brent():
     print('brent', {int(x): int((st == x).sum()) for x in np.unique(st)})
     save('reflect_toroid_brent', rho=21.45, R=float(oe.R), r=float(oe.r), **d)
 
+# ------------------------------------------------------------------------------------------------ wave from an OE
+def gen_diffract_oe():
+    """Rays traced to a KB mirror (elliptical cylinder, parametric) are the diffracting samples; the field is
+    propagated to a screen in the focus with rw.diffract (config 5, last step)."""
+    bl = raycing.BeamLine()
+    Au = rm.Material('Au', rho=19.3)
+    pitch, p_, q_ = 4e-3, 30000., 2000.
+    beam = _source_beam(bl, 3000, 121, dx=0.02, dz=0.01, dxprime=5e-6, dzprime=4e-6, energies=(8999.9, 9000.1),
+                        kill=0.)
+    kb = roe.EllipticalMirrorParam(bl, 'kb', center=(0, p_, 0), pitch=pitch, p=p_, q=q_, isCylindrical=True,
+                                   material=Au, limPhysX=[-5, 5], limPhysY=[-200, 200])
+    gb, lb = kb.reflect(beam)
+    assert (lb.state == 1).all()
+    scr = rsc.Screen(bl, 'scr', center=(0, p_ + q_*np.cos(2*pitch), q_*np.sin(2*pitch)))
+    xm = np.linspace(-0.08, 0.08, 40)
+    zm = np.linspace(-0.004, 0.004, 36)
+    wave = scr.prepare_wave(kb, xm, zm)
+    pre = dict(xDiffr=wave.xDiffr.copy(), yDiffr=wave.yDiffr.copy(), zDiffr=wave.zDiffr.copy(), dS=wave.dS)
+    glo = rw.diffract(lb, wave)
+    d = dict(scr_center=np.array(scr.center, dtype=float), xmesh=xm, zmesh=zm, area=lb.area, **pre)
+    d.update(_oe_params(kb))
+    for k in ('ellipseA', 'ellipseB', 'y0', 'z0', 'cosGamma', 'sinGamma', 'p', 'q'):
+        d[k] = float(getattr(kb, k))
+    d.update(beam_dict(lb, 'in_'))
+    d.update(beam_dict(wave, 'wave_'))
+    d.update(beam_dict(glo, 'glo_'))
+    for k2 in ('EsAcc', 'EpAcc', 'aEacc', 'bEacc', 'cEacc'):
+        d['wave_' + k2] = getattr(wave, k2)
+    save('diffract_kb_screen', **d)
 
-SECTIONS = {'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+
+SECTIONS = {'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)

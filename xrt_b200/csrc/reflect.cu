@@ -1131,6 +1131,38 @@ int amplitude_device(size_t n, const xrt_material_params* mat, const double* tab
   return 0;
 }
 
+// ---------------------------------------------------------------- surface normals at given local points
+// OE.local_n (with xyz_to_param for parametric surfaces) as waves.diffract and OE.local_to_global use it
+// (waves.py:675-686, oes/base.py:1213-1217): out = the surface normal n[-3:].
+template <int SURF>
+__global__ void __launch_bounds__(256) normals_kernel(size_t n, xrt_oe_params p, const double* __restrict__ x,
+                                                      const double* __restrict__ y, const double* __restrict__ z,
+                                                      double* __restrict__ nx, double* __restrict__ ny,
+                                                      double* __restrict__ nz) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double px = x[i], py = y[i], pz = z[i];
+  xyz_to_param<SURF>(p, px, py, pz);
+  double nrm[6];
+  local_normal<SURF>(p, px, py, nrm);
+  nx[i] = nrm[3];
+  ny[i] = nrm[4];
+  nz[i] = nrm[5];
+}
+
+int normals_device(size_t n, const xrt_oe_params* oe, const double* x, const double* y, const double* z, double* nx,
+                   double* ny, double* nz, cudaStream_t st) {
+  XRTB_REQUIRE(oe && x && y && z && nx && ny && nz, "oe_normals: NULL argument");
+  XRTB_REQUIRE(oe->surface >= 0 && oe->surface <= 2, "oe_normals: unknown surface kind %d", oe->surface);
+  if (n == 0) return 0;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  if (oe->surface == 0) normals_kernel<0><<<grid, 256, 0, st>>>(n, *oe, x, y, z, nx, ny, nz);
+  if (oe->surface == 1) normals_kernel<1><<<grid, 256, 0, st>>>(n, *oe, x, y, z, nx, ny, nz);
+  if (oe->surface == 2) normals_kernel<2><<<grid, 256, 0, st>>>(n, *oe, x, y, z, nx, ny, nz);
+  XRTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 double reduction_decode(unsigned long long slot) { return dec(slot); }
 
 }  // namespace xrtb

@@ -271,6 +271,59 @@ class OE(object):
                 red[RS_FOOT:RS_FOOT + 6].tolist()]
         return np.array(vals).reshape(2, 3)
 
+    def local_n_device(self, x, y, z):
+        """Surface normal (nx, ny, nz) at local Cartesian points given as CUDA tensors: OE.local_n after
+        xyz_to_param for parametric surfaces (waves.py:675-686)."""
+        lib = _lib.load()
+        n = x.numel()
+        out = torch.empty((3, n), dtype=torch.float64, device=x.device)
+        params = self._make_params(self.pitch, self.roll + self.positionRoll, self.yaw, self.dx)
+        rc = lib.xrt_oe_normals_f64(n, ctypes.byref(params), x.contiguous().data_ptr(), y.contiguous().data_ptr(),
+                                    z.contiguous().data_ptr(), out[0].data_ptr(), out[1].data_ptr(),
+                                    out[2].data_ptr(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, 'xrt_oe_normals_f64')
+        return out[0], out[1], out[2]
+
+    def local_to_global(self, lb):
+        """OE.local_to_global (oes/base.py:1165-1229) for a device Beam, in place: back-rotation, coherency matrix
+        and amplitudes turned by roll + atan2(n_x, n_z), then virgin local -> global."""
+        if self.dx:
+            lb.x = lb.x + self.dx
+        rots = []
+        if self.extraPitch or self.extraRoll or self.extraYaw:
+            rots += _rotation_list('-'+self.extraRotationSequence, self.extraPitch, self.extraRoll, self.extraYaw)
+        rots += _rotation_list('-'+self.rotationSequence, self.pitch, self.roll + self.positionRoll, self.yaw)
+        for ax, c, s in rots:
+            if ax == 0:
+                lb.y, lb.z = c*lb.y - s*lb.z, s*lb.y + c*lb.z
+                lb.b, lb.c = c*lb.b - s*lb.c, s*lb.b + c*lb.c
+            elif ax == 1:
+                lb.x, lb.z = c*lb.x + s*lb.z, -s*lb.x + c*lb.z
+                lb.a, lb.c = c*lb.a + s*lb.c, -s*lb.a + c*lb.c
+            else:
+                lb.x, lb.y = c*lb.x - s*lb.y, s*lb.x + c*lb.y
+                lb.a, lb.b = c*lb.a - s*lb.b, s*lb.a + c*lb.b
+        nx, ny, nz = self.local_n_device(lb.x, lb.y, lb.z)
+        roll = (self.roll + self.positionRoll) + torch.atan2(nx, nz)
+        c, s = torch.cos(roll), torch.sin(roll)
+        c2, s2, cs = c**2, s**2, c * s
+        Jss, Jpp, Jsp = lb.Jss, lb.Jpp, lb.Jsp
+        JssN = Jss*c2 + Jpp*s2 + 2*Jsp.real*cs
+        JppN = Jss*s2 + Jpp*c2 - 2*Jsp.real*cs
+        JspN = torch.complex((Jpp-Jss)*cs + Jsp.real*(c2-s2), Jsp.imag.clone())
+        lb.Jss, lb.Jpp, lb.Jsp = JssN, JppN, JspN
+        if hasattr(lb, 'Es'):
+            Es, Ep = lb.Es, lb.Ep
+            lb.Es, lb.Ep = c*Es + s*Ep, -s*Es + c*Ep
+        a0 = self.bl.sinAzimuth if self.bl is not None else 0.
+        b0 = self.bl.cosAzimuth if self.bl is not None else 1.
+        if a0 != 0:
+            lb.a, lb.b = b0*lb.a - (-a0)*lb.b, (-a0)*lb.a + b0*lb.b
+            lb.x, lb.y = b0*lb.x - (-a0)*lb.y, (-a0)*lb.x + b0*lb.y
+        lb.x = lb.x + self.center[0]
+        lb.y = lb.y + self.center[1]
+        lb.z = lb.z + self.center[2]
+
     def _new_local(self, beam):
         lb = beam.like()
         lb.theta = torch.empty(len(beam), dtype=torch.float64, device=beam.device)

@@ -11,8 +11,9 @@ is expressed with elementwise torch operations on the same device -- one roundin
 numpy statements it follows.  The footprint area uses scipy's ConvexHull on the host exactly like the reference
 (waves.py:649-670) when the local beam does not carry an `area` yet.
 
-Supported on this path: diffracting element = RectangularAperture (or any plane with normal (0, 1, 0)) or a
-flat OE; receiving element = Screen.  OE.prepare_wave / propagate_wave (oes/reflect.py:266-449) are the next row.
+Supported on this path: diffracting element = RectangularAperture or an OE of the hot path (flat, toroid,
+elliptical parametric: the traced local beam is the set of samples); receiving element = Screen.
+OE.prepare_wave / propagate_wave (oes/reflect.py:266-449, samples drawn on the OE surface) are the next row.
 """
 import numpy as np
 import torch
@@ -154,12 +155,18 @@ def diffract(oeLocal, wave, targetOpenCL='CUDA', precisionOpenCL='float64'):
     x, y, z = sel(oeLocal.x), sel(oeLocal.y), sel(oeLocal.z)
     a, b, c = sel(oeLocal.a), sel(oeLocal.b), sel(oeLocal.c)
     if isOE:
-        if getattr(oe, 'surfaceKind', 0) != 0 or getattr(oe, 'alpha', None):
-            raise NotImplementedError('diffract from curved / asymmetric OEs is the next row (SURVEY.md 8f)')
-        nvec = (0., 0., 1.)
+        if getattr(oe, 'alpha', None):
+            raise NotImplementedError('diffract from asymmetric crystals is the next row (SURVEY.md 8f)')
+        if goodlen != len(oeLocal):
+            # the reference's numpy integral broadcasts the un-masked normals against the masked samples
+            # (waves.py:840): it only works when every ray of oeLocal is good -- same contract here
+            raise ValueError('diffract from an OE needs a local beam whose rays are all good; filter it first')
+        nX, nY, nZ = oe.local_n_device(oeLocal.x, oeLocal.y, oeLocal.z)  # waves.py:675-686
+        nl = a*nX + b*nY + c*nZ
+        nvec = None
     else:
         nvec = (0., 1., 0.)
-    nl = a*nvec[0] + b*nvec[1] + c*nvec[2]
+        nl = a*nvec[0] + b*nvec[1] + c*nvec[2]
     Jtot = sel(oeLocal.Jss) + sel(oeLocal.Jpp)
     wave.diffract_repeats += 1
     wave.beamReflRays += goodlen
@@ -171,9 +178,13 @@ def diffract(oeLocal, wave, targetOpenCL='CUDA', precisionOpenCL='float64'):
     # one ulp off numpy's true division often enough to move k*r by 6e-5 rad: divide by a tensor instead
     k = torch.div(E, torch.full_like(E, CHBAR)) * 1e7
     pos = torch.stack((x, y, z, torch.zeros_like(x)), dim=1).contiguous()
-    nrm = torch.tensor(nvec + (0.,), dtype=F64, device=x.device).repeat(goodlen, 1).contiguous()
-    out = kernels.kirchhoff(wave.xDiffr.contiguous(), wave.yDiffr.contiguous(), wave.zDiffr.contiguous(), nl, sel(oeLocal.Es),
-                            sel(oeLocal.Ep), k, pos, nrm, convention='numpy', uniform_normal=True)
+    if nvec is not None:
+        nrm = torch.tensor(nvec + (0.,), dtype=F64, device=x.device).repeat(goodlen, 1).contiguous()
+    else:
+        nrm = torch.stack((nX, nY, nZ, torch.zeros_like(nX)), dim=1).contiguous()
+    out = kernels.kirchhoff(wave.xDiffr.contiguous(), wave.yDiffr.contiguous(), wave.zDiffr.contiguous(), nl,
+                            sel(oeLocal.Es), sel(oeLocal.Ep), k, pos, nrm, convention='numpy',
+                            uniform_normal=nvec is not None)
     Es, Ep, aE, bE, cE = out[0], out[1], out[2], out[3], out[4]
 
     wave.EsAcc += Es
@@ -217,8 +228,8 @@ def diffract(oeLocal, wave, targetOpenCL='CUDA', precisionOpenCL='float64'):
     glo.parentId = getattr(oe, 'uuid', getattr(oe, 'name', None))
     glo.x, glo.y, glo.z = wave.xDiffr.clone(), wave.yDiffr.clone(), wave.zDiffr.clone()
     if isOE:
-        raise NotImplementedError('OE.local_to_global of the diffracted beam is the next row')
-    if hasattr(oe, 'local_to_global'):  # aperture: apertures.py:446-458
+        oe.local_to_global(glo)  # oes/base.py:1165-1229
+    elif hasattr(oe, 'local_to_global'):  # aperture: apertures.py:446-458
         gx = oe.center[0] + glo.x*oe.x[0] + glo.y*oe.y[0] + glo.z*oe.z[0]
         gy = oe.center[1] + glo.x*oe.x[1] + glo.y*oe.y[1] + glo.z*oe.z[1]
         gz = oe.center[2] + glo.x*oe.x[2] + glo.y*oe.y[2] + glo.z*oe.z[2]
