@@ -336,6 +336,33 @@ def run_ours(args):
     d2h = n_host * bytes_per_ray
     host_out = None
 
+    # ---- end to end the way xrt's runner consumes a repeat: only the screen image (get_output + do_hist2d,
+    # xrt/multipro.py:119-171) leaves the GPU -- device histogram, 256 x 256 doubles D2H per step
+    from xrt_b200 import histogram
+    blo = step()
+    gd = blo.state == 1
+    xl = [float(blo.x[gd].min()), float(blo.x[gd].max())]
+    zl = [float(blo.z[gd].min()), float(blo.z[gd].max())]
+    del blo, gd
+    img = torch.zeros((256, 256), dtype=torch.float64, device='cuda')
+    host_img = torch.empty((256, 256), dtype=torch.float64, pin_memory=True)
+
+    def step_hist():
+        b = step()
+        img.zero_()
+        histogram.hist2d(b, xl, zl, bins=(256, 256), out=img)
+        if world > 1:
+            dist.all_reduce(img)
+        host_img.copy_(img, non_blocking=True)
+
+    step_hist()
+    ms_hist = timed(step_hist, args.steps) / args.steps
+    e2e_hist = {'value': world * nrays / (ms_hist * 1e-3) / 1e6, 'unit': 'Mrays/s', 'ms_per_step': ms_hist,
+                'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 256 * 256 * 8,
+                'note': 'same step + device 2-D histogram of the screen beam (xrt_b200.histogram.hist2d == '
+                        'np.histogram2d of do_hist2d); the 256 x 256 image is what crosses PCIe, as in xrt where '
+                        'histograms, not rays, are accumulated over repeats (xrt/runner.py:526-530)'}
+
     # ---- per-kernel times of reflect() (pre-pass A, pre-pass B, main) in a few extra untimed steps
     mirror.profileEvents = []
     for _ in range(3):
@@ -450,6 +477,7 @@ def run_ours(args):
                            'parallelism': 'rays sharded over %d GPU(s), gather=%s' % (world, args.gather)},
                 'e2e': {'value': e2e_value, 'unit': 'Mrays/s', 'h2d_bytes_per_step': h2d,
                         'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e},
+                'e2e_histogram': e2e_hist,
                 'gpu_launches': args.steps * (9 if args.unfused_source else 7),  # source (1 fused or 3), 2 slot inits,
                 # pre-pass A/B, reflect main, expose
                 'clocks': sampler.summary(),

@@ -247,6 +247,16 @@ int xrt_shine_uniform_f64(size_t n, uint64_t seed, uint64_t index_offset, const 
 int xrt_oe_normals_f64(size_t n, const xrt_oe_params* oe, const double* x, const double* y, const double* z,
                        double* nx, double* ny, double* nz, void* stream);
 
+/* ------------------------------------------------------------------ f1 (next row): device histogram
+ * np.histogram2d(y, x, bins=[ny, nx], range=[[ey0, eyN], [ex0, exN]], weights=w1 (+ w2)) as do_hist2d
+ * (xrt/multipro.py:119-171) accumulates it, over the rays whose state passes `state_mask` (bit0 state == 1 good,
+ * bit1 == 2 out, bit2 == 3 over, bit3 < 0 dead; raycing.get_output's rayFlag).  ex[nx+1], ey[ny+1]: bin edges
+ * (np.linspace on the host).  out[ny * nx] is ACCUMULATED into (zero it first), so repeats / ray shards add up;
+ * w1/w2/state may be NULL (weight 1, no filter).  Device pointers. */
+int xrt_hist2d_f64(size_t n, const double* x, const double* y, const double* w1, const double* w2,
+                   const int32_t* state, int state_mask, const double* ex, int nx, const double* ey, int ny,
+                   double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

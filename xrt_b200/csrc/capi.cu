@@ -368,4 +368,10 @@ int xrt_oe_normals_f64(size_t n, const xrt_oe_params* oe, const double* x, const
   return normals_device(n, oe, x, y, z, nx, ny, nz, (cudaStream_t)stream);
 }
 
+int xrt_hist2d_f64(size_t n, const double* x, const double* y, const double* w1, const double* w2,
+                   const int32_t* state, int state_mask, const double* ex, int nx, const double* ey, int ny,
+                   double* out, void* stream) {
+  return hist2d_device(n, x, y, w1, w2, state, state_mask, ex, nx, ey, ny, out, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -256,4 +256,61 @@ int propagate_rect_device(size_t n, const xrt_plane_params* p, const xrt_beam* i
   return 0;
 }
 
+// ---------------------------------------------------------------- f1: weighted 2-D histogram on the device
+// np.histogram2d(y, x, bins=[ny, nx], range=..., weights=w) as xrt's do_hist2d calls it (xrt/multipro.py:119-171)
+// on the rays raycing.get_output selects (state filter) with intensity = Jss + Jpp.  Bin edges come from the host
+// (np.linspace, so they are numpy's edges bit for bit); a ray lands in bin b with e[b] <= v < e[b+1], the last
+// edge inclusive (np.histogramdd: searchsorted(side='right') and the on_edge fix-up).
+__device__ __forceinline__ int find_bin(const double* __restrict__ e, int nb, double v, double inv_w) {
+  if (!(v >= e[0]) || !(v <= e[nb])) return -1;  // outliers and NaN
+  int g = (int)((v - e[0]) * inv_w);
+  g = g < 0 ? 0 : (g > nb - 1 ? nb - 1 : g);
+  while (g > 0 && v < e[g]) --g;
+  while (g < nb - 1 && v >= e[g + 1]) ++g;
+  return g;
+}
+
+__global__ void __launch_bounds__(256) hist2d_kernel(size_t n, const double* __restrict__ x,
+                                                     const double* __restrict__ y, const double* __restrict__ w1,
+                                                     const double* __restrict__ w2, const int* __restrict__ state,
+                                                     int state_mask, const double* __restrict__ ex, int nx,
+                                                     const double* __restrict__ ey, int ny, double* __restrict__ out) {
+  extern __shared__ double sedges[];  // ex[nx + 1] | ey[ny + 1]
+  double* sx = sedges;
+  double* sy = sedges + nx + 1;
+  for (int i = threadIdx.x; i <= nx; i += blockDim.x) sx[i] = ex[i];
+  for (int i = threadIdx.x; i <= ny; i += blockDim.x) sy[i] = ey[i];
+  __syncthreads();
+  const double inv_wx = nx / (sx[nx] - sx[0]), inv_wy = ny / (sy[ny] - sy[0]);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (state) {
+      const int st = state[i];
+      const int bit = st == 1 ? 1 : (st == 2 ? 2 : (st == 3 ? 4 : (st < 0 ? 8 : 16)));
+      if (!(bit & state_mask)) continue;
+    }
+    const int bx = find_bin(sx, nx, x[i], inv_wx);
+    if (bx < 0) continue;
+    const int by = find_bin(sy, ny, y[i], inv_wy);
+    if (by < 0) continue;
+    double w = w1 ? w1[i] : 1.0;
+    if (w2) w = w + w2[i];
+    atomicAdd(&out[(size_t)by * nx + bx], w);
+  }
+}
+
+int hist2d_device(size_t n, const double* x, const double* y, const double* w1, const double* w2, const int* state,
+                  int state_mask, const double* ex, int nx, const double* ey, int ny, double* out, cudaStream_t st) {
+  XRTB_REQUIRE(x && y && ex && ey && out, "hist2d: NULL argument");
+  XRTB_REQUIRE(nx > 0 && ny > 0 && nx + ny + 2 <= 12000, "hist2d: 1 <= bins and nx + ny <= 11998");
+  if (n == 0) return 0;
+  unsigned grid = (unsigned)num_sms() * 8;
+  const size_t need = (n + 255) / 256;
+  if (need < grid) grid = (unsigned)need;
+  const size_t smem = (size_t)(nx + ny + 2) * sizeof(double);
+  hist2d_kernel<<<grid, 256, smem, st>>>(n, x, y, w1, w2, state, state_mask, ex, nx, ey, ny, out);
+  XRTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace xrtb
