@@ -130,6 +130,8 @@ typedef struct xrt_oe_params {
   int good_mode;          /* which rays are traced: 0: state > 0 (reflect.py:110); 1: state in (1, 2) (dcm.py:303) */
   int want_footprint;     /* 1: reduce the footprint min/max and the good-ray / out-of-table counters into the
                              slots (reflect.py:1133-1136); 0 skips those block reductions (device pipelines) */
+  int no_intersection;    /* noIntersectionSearch (reflect.py:676-681): the rays already sit on the surface (wave
+                             samples): t = 0, the point is taken as it is (xyz_to_param for parametric OEs) */
 } xrt_oe_params;
 
 /* Material = what get_amplitude reads (materials/material.py:348-493, materials/crystal.py:492-645). */
@@ -244,6 +246,10 @@ int xrt_shine_uniform_f64(size_t n, uint64_t seed, uint64_t index_offset, const 
 /* Surface normals of an OE at local Cartesian points (x, y, z): OE.local_n, preceded by xyz_to_param for
  * parametric surfaces, as waves.diffract (waves.py:675-686) and OE.local_to_global (oes/base.py:1213-1217) call
  * it. Device pointers; nx, ny, nz receive the surface normal. */
+/* Surface height at local (x, y): z = OE.local_z(x, y), or for parametric surfaces the chain
+ * xyz_to_param(x, y, 0) -> local_r(s, phi) -> param_to_xyz(...)[2] of OE.prepare_wave (oes/reflect.py:335-340). */
+int xrt_oe_surface_f64(size_t n, const xrt_oe_params* oe, const double* x, const double* y, double* z, void* stream);
+
 int xrt_oe_normals_f64(size_t n, const xrt_oe_params* oe, const double* x, const double* y, const double* z,
                        double* nx, double* ny, double* nz, void* stream);
 

@@ -7,11 +7,18 @@ import numpy as np
 FIELDS = ('x', 'y', 'z', 'a', 'b', 'c', 'path', 'E', 'Jss', 'Jpp', 'Jsp', 'state', 'Es', 'Ep')
 
 
+COPIED = ('x', 'y', 'z', 'sourceSIGMAx', 'sourceSIGMAz', 'filamentDX', 'filamentDZ', 'filamentDtheta', 'filamentDpsi',
+          'filamentDgamma', 'state', 'a', 'b', 'c', 'path', 'E', 'Jss', 'Jpp', 'Jsp', 'elevationD', 'elevationX',
+          'elevationY', 'elevationZ', 's', 'phi', 'r', 'theta', 'order', 'accepted', 'acceptedE', 'seeded', 'seededI',
+          'Es', 'Ep', 'nRefl', 'sourceWeight')
+
+
 class Beam(object):
     def __init__(self, nrays=0, copyFrom=None, withAmplitudes=False):
-        if copyFrom is not None:
-            for k, v in copyFrom.__dict__.items():
-                setattr(self, k, np.copy(v) if isinstance(v, np.ndarray) else v)
+        if copyFrom is not None:  # only the listed attributes travel (beams.py:96-117): no area, toOE, ...
+            for k in COPIED:
+                if hasattr(copyFrom, k):
+                    setattr(self, k, np.copy(getattr(copyFrom, k)))
             return
         self.x = np.zeros(nrays)
         self.y = np.zeros(nrays)
@@ -36,6 +43,11 @@ class Beam(object):
             if key.startswith(prefix):
                 setattr(b, key[len(prefix):], np.array(g[key]))
         return b
+
+    def filter_by_index(self, indarr):
+        for k, v in list(self.__dict__.items()):
+            if isinstance(v, np.ndarray):
+                setattr(self, k, v[indarr])
 
 
 def rotate_x(y, z, cosangle, sinangle):

@@ -51,6 +51,9 @@ class OESpec(object):
         self.isParametric = False
         self.__dict__.update(kw)
 
+    sinAzimuth = property(lambda self: self.azimuth[0])
+    cosAzimuth = property(lambda self: self.azimuth[1])
+
     # ------------------------------------------------------------------ surfaces
     def local_z(self, x, y):
         if self.surface == 'flat':
@@ -334,7 +337,8 @@ def _grating_deflection(goodN, lb, g, oeNormal, beamInDotNormal, order=1, sig=No
 
 
 def reflect_local(oe, good, lb, vlb, pitch, roll, yaw, dx=None, dy=None, dz=None, local_n=None, material=None,
-                  is2ndXtal=False, surfPhysX=None, surfPhysY=None, surfOptX=None, surfOptY=None, info=None):
+                  is2ndXtal=False, surfPhysX=None, surfPhysY=None, surfOptX=None, surfOptY=None, info=None,
+                  noIntersectionSearch=False):
     if local_n is None:
         local_n = oe.local_n
     if surfPhysX is None:
@@ -360,10 +364,16 @@ def reflect_local(oe, good, lb, vlb, pitch, roll, yaw, dx=None, dy=None, dz=None
     tMin[good], tMax[good] = _bracketing(
         oe, lb.x[good], lb.y[good], lb.z[good], lb.a[good], lb.b[good], lb.c[good], surfPhysX, surfPhysY,
         mainPartForBracketing, info)
-    res_find = find_intersection(oe, None, tMin[good], tMax[good], lb.x[good], lb.y[good], lb.z[good],
-                                 lb.a[good], lb.b[good], lb.c[good], invertNormal, info)
-    tMax[good], lb.x[good], lb.y[good], lb.z[good] = res_find[:4]
-    _lost = res_find[4]
+    if noIntersectionSearch:  # reflect.py:676-681
+        tMax[good] = 0.
+        if oe.isParametric:
+            lb.x[good], lb.y[good], lb.z[good] = oe.xyz_to_param(lb.x[good], lb.y[good], lb.z[good])
+        _lost = np.zeros(int(good.sum()), dtype=bool)
+    else:
+        res_find = find_intersection(oe, None, tMin[good], tMax[good], lb.x[good], lb.y[good], lb.z[good],
+                                     lb.a[good], lb.b[good], lb.c[good], invertNormal, info)
+        tMax[good], lb.x[good], lb.y[good], lb.z[good] = res_find[:4]
+        _lost = res_find[4]
     if oe.isParametric:
         tX, tY, tZ = oe.param_to_xyz(lb.x[good], lb.y[good], lb.z[good])
     else:
@@ -465,7 +475,7 @@ def reflect_local(oe, good, lb, vlb, pitch, roll, yaw, dx=None, dy=None, dz=None
             np.max(np.vstack((vlb.x[good], vlb.y[good], vlb.z[good])), axis=1))).reshape(2, 3)
 
 
-def reflect(oe, beam, needLocal=True, createdByDiffract=False, info=None):
+def reflect(oe, beam, needLocal=True, createdByDiffract=False, info=None, noIntersectionSearch=False):
     """OE.reflect (reflect.py:104-135). Returns gb, lb."""
     gb = ob.Beam(copyFrom=beam)
     lb = ob.Beam(copyFrom=beam) if needLocal else gb
@@ -473,7 +483,8 @@ def reflect(oe, beam, needLocal=True, createdByDiffract=False, info=None):
     if good.sum() == 0:
         return gb, lb
     ob.global_to_virgin_local(oe.azimuth, beam, lb, oe.center, good)
-    reflect_local(oe, good, lb, gb, oe.pitch, oe.roll, oe.yaw, oe.dx, material=oe.material, info=info)
+    reflect_local(oe, good, lb, gb, oe.pitch, oe.roll, oe.yaw, oe.dx, material=oe.material, info=info,
+                  noIntersectionSearch=noIntersectionSearch)
     if createdByDiffract:
         goodAfter = gb.state == 1
     else:

@@ -275,3 +275,105 @@ def diffract_from_oe(oeLocal, wave):
     a0, b0 = toOE.sinAzimuth, toOE.cosAzimuth
     wave.a[:], wave.b[:] = ob.rotate_z(wave.a, wave.b, b0, a0)
     return glo
+
+
+# ---------------------------------------------------------------------------------------------- OE as the
+# receiving element: OE.prepare_wave (oes/reflect.py:266-403) and the toOE frames of diffract (waves.py:786-824)
+def oe_surface_z(oe, x, y):
+    """z of the surface at local (x, y) as OE.prepare_wave takes it (reflect.py:335-340)."""
+    if oe.isParametric:
+        s, phi, r = oe.xyz_to_param(x, y, 0)
+        r = oe.local_r(s, phi)
+        return oe.param_to_xyz(s, phi, r)[2]
+    return oe.local_z(x, y)
+
+
+def oe_surface_centre_global(oe):
+    """Middle point of the physical limits on the surface, global (reflect.py:344-361)."""
+    cx = (oe.surfPhysX[1] + oe.surfPhysX[0])*0.5
+    cy = (oe.surfPhysY[1] + oe.surfPhysY[0])*0.5
+    lbc = ob.Beam(1)
+    lbc.x[:] = cx
+    lbc.y[:] = cy
+    lbc.z[:] = oe_surface_z(oe, lbc.x.copy(), lbc.y.copy())
+    oe_local_to_global(oe, lbc)
+    return [lbc.x[0], lbc.y[0], lbc.z[0]]
+
+
+def oe_prepare_wave(oe, prevOE, x, y, area='auto'):
+    """OE.prepare_wave for sample positions (x, y) already drawn / meshed by the caller (reflect.py:302-333 is
+    plain numpy on limPhys*).  `oe`, and `prevOE` when it is an OE, are OESpec; an aperture prevOE is a Plane."""
+    from . import reflect as orf
+    nsamples = len(x)
+    if area == 'auto':
+        area = (oe.surfPhysX[1] - oe.surfPhysX[0]) * (oe.surfPhysY[1] - oe.surfPhysY[0])
+    lb = ob.Beam(nsamples, withAmplitudes=True)
+    lb.state[:] = 1
+    lb.x[:] = x
+    lb.y[:] = y
+    lb.z[:] = oe_surface_z(oe, x, y)
+    oe_local_to_global(oe, lb)
+    prevIsOE = hasattr(prevOE, 'rotationSequence')
+    prevCenter = oe_surface_centre_global(prevOE) if prevIsOE else prevOE.center
+    lb.a[:] = lb.x - prevCenter[0]
+    lb.b[:] = lb.y - prevCenter[1]
+    lb.c[:] = lb.z - prevCenter[2]
+    norm = (lb.a**2 + lb.b**2 + lb.c**2)**0.5
+    lb.a /= norm
+    lb.b /= norm
+    lb.c /= norm
+    lb.x[:] = prevCenter[0]
+    lb.y[:] = prevCenter[1]
+    lb.z[:] = prevCenter[2]
+    lbn = ob.Beam(1)
+    lbn.b[:] = 0.
+    lbn.c[:] = 1.
+    oe_local_to_global(oe, lbn)
+    a = lbn.x - prevCenter[0]
+    b = lbn.y - prevCenter[1]
+    c = lbn.z - prevCenter[2]
+    norm = (a**2 + b**2 + c**2)**0.5
+    areaNormalFact = abs(float(((a*lbn.a[0] + b*lbn.b[0] + c*lbn.c[0]) / norm)[0]))
+    waveGlobal, waveLocal = orf.reflect(oe, lb)
+    good = (waveLocal.state == 1) | (waveLocal.state == 2)
+    waveGlobal.filter_by_index(good)
+    waveLocal.filter_by_index(good)
+    area *= good.sum() / float(len(good))
+    waveLocal.area = area
+    waveLocal.areaNormal = area * areaNormalFact
+    waveLocal.dS = area / float(len(good))
+    waveLocal.toOE = oe
+    if prevIsOE:
+        return prepare_wave_from_oe(prevOE, waveLocal, waveGlobal.x, waveGlobal.y, waveGlobal.z)
+    return prepare_wave(prevOE, waveLocal, waveGlobal.x, waveGlobal.y, waveGlobal.z)
+
+
+def to_oe_frames(wave, glo):
+    """The part of diffract() that turns directions, coherency matrix and amplitudes into the local frame of a
+    receiving OE and applies the obliquity factor (waves.py:786-824); call after diffract / diffract_from_oe."""
+    toOE = wave.toOE
+    if toOE.isParametric:
+        s, phi, r = toOE.xyz_to_param(wave.x, wave.y, wave.z)
+        oeNormal = list(toOE.local_n(s, phi))
+    else:
+        oeNormal = list(toOE.local_n(wave.x, wave.y))
+    rollAngle = toOE.roll + np.arctan2(oeNormal[-3], oeNormal[-1])
+    wave.Jss[:], wave.Jpp[:], wave.Jsp[:] = ob.rotate_coherency_matrix(wave, slice(None), -rollAngle)
+    cosY, sinY = np.cos(rollAngle), np.sin(rollAngle)
+    wave.Es[:], wave.Ep[:] = ob.rotate_y(wave.Es, wave.Ep, cosY, -sinY)
+    hold = ob.Beam(len(wave.x))
+    hold.x, hold.y, hold.z = wave.a, wave.b, wave.c
+    ob.rotate_beam(hold, rotationSequence=toOE.rotationSequence, pitch=-toOE.pitch, roll=-toOE.roll, yaw=-toOE.yaw)
+    if toOE.extraPitch or toOE.extraRoll or toOE.extraYaw:
+        ob.rotate_beam(hold, rotationSequence=toOE.extraRotationSequence, pitch=-toOE.extraPitch,
+                       roll=-toOE.extraRoll, yaw=-toOE.extraYaw)
+    wave.a, wave.b, wave.c = hold.x, hold.y, hold.z
+    norm = -wave.a*oeNormal[-3] - wave.b*oeNormal[-2] - wave.c*oeNormal[-1]
+    norm = np.abs(norm)
+    for b in (wave, glo):
+        b.Jss *= norm
+        b.Jpp *= norm
+        b.Jsp *= norm
+        b.Es *= norm**0.5
+        b.Ep *= norm**0.5
+    return glo

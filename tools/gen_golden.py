@@ -483,8 +483,99 @@ def gen_diffract_oe():
         d['wave_' + k2] = getattr(wave, k2)
     save('diffract_kb_screen', **d)
 
+# ------------------------------------------------------------------------------------------------ wave onto an OE
+def _slit_field(N, seed, d1, hx, hz, E0=9000.):
+    rng = np.random.RandomState(seed)
+    oeLocal = rs.Beam(N, withAmplitudes=True)
+    oeLocal.x[:] = rng.uniform(-hx, hx, N)
+    oeLocal.z[:] = rng.uniform(-hz, hz, N)
+    oeLocal.y[:] = 0.
+    r = np.sqrt(oeLocal.x**2 + d1**2 + oeLocal.z**2)
+    oeLocal.a[:], oeLocal.b[:], oeLocal.c[:] = oeLocal.x / r, d1 / r, oeLocal.z / r
+    oeLocal.E[:] = E0
+    k = oeLocal.E / rpc.CHBAR * 1e7
+    oeLocal.Es[:] = np.exp(1j * k * r) / r * 1e4
+    oeLocal.Ep[:] = 0.05 * np.exp(1j * (k * r + 0.3)) / r * 1e4
+    oeLocal.Jss[:] = np.abs(oeLocal.Es)**2
+    oeLocal.Jpp[:] = np.abs(oeLocal.Ep)**2
+    oeLocal.Jsp[:] = oeLocal.Es * np.conj(oeLocal.Ep)
+    oeLocal.state[:] = 1
+    return oeLocal
 
-SECTIONS = {'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+
+def _wave_onto_oe(name, mirror, slit, oeLocal, nrays, scr, xm, zm, seed, extra):
+    """The body of OE.propagate_wave (oes/reflect.py:405-449) without the auto-alignment: prepare_wave on the
+    mirror, diffract slit -> mirror, reflect(noIntersectionSearch=True), then mirror -> screen."""
+    np.random.seed(seed)
+    xy = None
+    if isinstance(nrays, int):
+        st = np.random.get_state()
+        xy = np.random.rand(nrays, 2)
+        np.random.set_state(st)
+    waveOnMirror = mirror.prepare_wave(slit, nrays, rw=rw)
+    d = dict(extra)
+    if xy is not None:
+        d['xy'] = xy
+    d.update(beam_dict(oeLocal, 'in_'))
+    d.update({k: v.copy() for k, v in beam_dict(waveOnMirror, 'pw_').items()})
+    for k in ('xDiffr', 'yDiffr', 'zDiffr', 'rDiffr'):
+        d['pw_' + k] = getattr(waveOnMirror, k).copy()
+    d['pw_area'], d['pw_areaNormal'], d['pw_dS'] = waveOnMirror.area, waveOnMirror.areaNormal, waveOnMirror.dS
+    beamToMirror = rw.diffract(oeLocal, waveOnMirror)
+    d['slit_area'] = oeLocal.area
+    d.update(beam_dict(waveOnMirror, 'wave_'))
+    d.update(beam_dict(beamToMirror, 'glo_'))
+    for k2 in ('EsAcc', 'EpAcc', 'aEacc', 'bEacc', 'cEacc'):
+        d['wave_' + k2] = getattr(waveOnMirror, k2)
+    mglo, mloc = mirror.reflect(beamToMirror, noIntersectionSearch=True)
+    d.update(beam_dict(mglo, 'mglo_'))
+    d.update(beam_dict(mloc, 'mloc_'))
+    print(name, 'states on mirror', {int(x): int((mloc.state == x).sum()) for x in np.unique(mloc.state)})
+    wave2 = scr.prepare_wave(mirror, xm, zm)
+    glo2 = rw.diffract(mloc, wave2)
+    d['mirror_area'] = mloc.area
+    d.update(beam_dict(wave2, 'wave2_'))
+    d.update(beam_dict(glo2, 'glo2_'))
+    for k2 in ('EsAcc', 'EpAcc', 'aEacc', 'bEacc', 'cEacc'):
+        d['wave2_' + k2] = getattr(wave2, k2)
+    d.update(_oe_params(mirror))
+    save(name, **d)
+
+
+def gen_wave_oe():
+    bl = raycing.BeamLine()
+    Au = rm.Material('Au', rho=19.3)
+    d1 = 1e4
+    slit = ra.RectangularAperture(bl, 'slit', center=(0, d1, 0), kind=('left', 'right', 'bottom', 'top'),
+                                  opening=[-0.05, 0.05, -0.04, 0.04])
+    oeLocal = _slit_field(1500, 131, d1, 0.05, 0.04)
+    # (1) toroid, random samples
+    pitch = 4e-3
+    tm = roe.ToroidMirror(bl, 'tm', center=(0, d1 + 3000., 0), pitch=pitch, R=1.2e6, r=80., material=Au,
+                          limPhysX=[-0.4, 0.4], limPhysY=[-60, 60])
+    scr = rsc.Screen(bl, 'scr', center=(0, d1 + 3000. + 2000.*np.cos(2*pitch), 2000.*np.sin(2*pitch)))
+    xm = np.linspace(-0.3, 0.3, 24)
+    zm = np.linspace(-0.3, 0.3, 20)
+    _wave_onto_oe('wave_slit_toroid_screen', tm, slit, oeLocal, 1200, scr, xm, zm, 5,
+                  dict(slit_center=np.array(slit.center, dtype=float), opening=np.array([-0.05, 0.05, -0.04, 0.04]),
+                       scr_center=np.array(scr.center, dtype=float), xmesh=xm, zmesh=zm, R=float(tm.R), r=float(tm.r),
+                       rho=19.3))
+    # (2) elliptical cylinder (parametric), mesh samples, rolled to deflect horizontally
+    oeLocal = _slit_field(1500, 132, d1, 0.05, 0.04)
+    p_, q_ = d1 + 3000., 1500.
+    kb = roe.EllipticalMirrorParam(bl, 'kb', center=(0, p_, 0), pitch=pitch, p=p_, q=q_, isCylindrical=True,
+                                   material=Au, limPhysX=[-0.3, 0.3], limPhysY=[-50, 50])
+    scr2 = rsc.Screen(bl, 'scr2', center=(0, p_ + q_*np.cos(2*pitch), q_*np.sin(2*pitch)))
+    xm = np.linspace(-0.3, 0.3, 20)
+    zm = np.linspace(-0.01, 0.01, 24)
+    extra = dict(slit_center=np.array(slit.center, dtype=float), opening=np.array([-0.05, 0.05, -0.04, 0.04]),
+                 scr_center=np.array(scr2.center, dtype=float), xmesh=xm, zmesh=zm, rho=19.3, mesh=np.array([24, 40]))
+    for k in ('ellipseA', 'ellipseB', 'y0', 'z0', 'cosGamma', 'sinGamma', 'p', 'q'):
+        extra[k] = float(getattr(kb, k))
+    _wave_onto_oe('wave_slit_kb_screen', kb, slit, oeLocal, (24, 40), scr2, xm, zm, 6, extra)
+
+
+SECTIONS = {'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)

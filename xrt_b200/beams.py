@@ -20,8 +20,12 @@ REAL_FIELDS = ('x', 'y', 'z', 'a', 'b', 'c', 'path', 'E', 'Jss', 'Jpp')
 COMPLEX_FIELDS = ('Jsp', 'Es', 'Ep')
 OPTIONAL_REAL = ('theta', 's', 'phi', 'r')
 SCALARS = ('accepted', 'acceptedE', 'seeded', 'seededI', 'sourceWeight', 'parentId', 'sourceSIGMAx',
-           'sourceSIGMAz', 'filamentDX', 'filamentDZ', 'filamentDtheta', 'filamentDpsi', 'filamentDgamma',
-           'area', 'createdByDiffract')
+           'sourceSIGMAz', 'filamentDX', 'filamentDZ', 'filamentDtheta', 'filamentDpsi', 'filamentDgamma')
+# Beam(copyFrom=...) copies exactly the reference's listOfAttrs (sources/beams.py:96-105)
+COPIED = ('x', 'y', 'z', 'sourceSIGMAx', 'sourceSIGMAz', 'filamentDX', 'filamentDZ', 'filamentDtheta', 'filamentDpsi',
+          'filamentDgamma', 'state', 'a', 'b', 'c', 'path', 'E', 'Jss', 'Jpp', 'Jsp', 'elevationD', 'elevationX',
+          'elevationY', 'elevationZ', 's', 'phi', 'r', 'theta', 'order', 'accepted', 'acceptedE', 'seeded', 'seededI',
+          'Es', 'Ep', 'nRefl', 'sourceWeight')
 
 
 class xrt_beam(ctypes.Structure):
@@ -39,9 +43,12 @@ def _device(device=None):
 
 class Beam(object):
     def __init__(self, nrays=0, copyFrom=None, withAmplitudes=False, device=None, uninitialized=False):
-        if copyFrom is not None:
-            for k, v in copyFrom.__dict__.items():
-                setattr(self, k, v.clone() if isinstance(v, torch.Tensor) else v)
+        if copyFrom is not None:  # only the reference's listOfAttrs travel (beams.py:96-117): no area, toOE, ...
+            for k in COPIED:
+                if hasattr(copyFrom, k):
+                    v = getattr(copyFrom, k)
+                    setattr(self, k, v.clone() if isinstance(v, torch.Tensor) else v)
+            self.parentId = getattr(copyFrom, 'parentId', None)
             return
         dev = _device(device)
         n = int(nrays)
@@ -119,7 +126,7 @@ class Beam(object):
                     v = np.ascontiguousarray(v, dtype=np.float64)
                 t = torch.from_numpy(v)
                 setattr(b, k, t.to(dev, non_blocking=pinned))
-            elif k in SCALARS:
+            elif k in SCALARS or k in ('area', 'createdByDiffract', 'dS', 'areaNormal'):
                 setattr(b, k, v)
         if not hasattr(b, 'parentId'):
             b.parentId = None

@@ -363,6 +363,11 @@ int xrt_shine_uniform_f64(size_t n, uint64_t seed, uint64_t index_offset, const 
                               reinterpret_cast<unsigned long long*>(imax_slot), (cudaStream_t)stream);
 }
 
+int xrt_oe_surface_f64(size_t n, const xrt_oe_params* oe, const double* x, const double* y, double* z,
+                       void* stream) {
+  return surface_device(n, oe, x, y, z, (cudaStream_t)stream);
+}
+
 int xrt_oe_normals_f64(size_t n, const xrt_oe_params* oe, const double* x, const double* y, const double* z,
                        double* nx, double* ny, double* nz, void* stream) {
   return normals_device(n, oe, x, y, z, nx, ny, nz, (cudaStream_t)stream);

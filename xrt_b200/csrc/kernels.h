@@ -34,6 +34,7 @@ int reflect_device(size_t n, const xrt_oe_params* oe, const xrt_material_params*
                    const xrt_beam* lb, unsigned long long* red, int phase, unsigned long long index_offset,
                    cudaStream_t st);
 double reduction_decode(unsigned long long slot);
+int surface_device(size_t n, const xrt_oe_params* oe, const double* x, const double* y, double* z, cudaStream_t st);
 int normals_device(size_t n, const xrt_oe_params* oe, const double* x, const double* y, const double* z, double* nx,
                    double* ny, double* nz, cudaStream_t st);
 int amplitude_device(size_t n, const xrt_material_params* mat, const double* tables, size_t table_len,

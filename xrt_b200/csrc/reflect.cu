@@ -779,25 +779,35 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
         Ep = ld_c(in.Ep, i);
       }
       to_local(p, r);
-      // bracketing + intersection (base.py:848-885)
       double t1, t2, x1, y1, z1, x2, y2, z2;
-      bracket(p, d.axis, d.neg, r, t1, t2);
-      double dz1 = find_dz<SURF>(p, t1, r, x1, y1, z1);
-      double dz2 = find_dz<SURF>(p, t2, r, x2, y2, z2);
-      const bool ind1 = dz1 <= 0.0;  // lost: solution t1
-      const bool ind2 = dz2 >= 0.0;  // over: solution t2
-      if (ind1 || ind2) dz2 = 0.0;
-      if (ind1) {
-        t2 = t1;
-        x2 = x1;
-        y2 = y1;
-        z2 = z1;
-      }
-      if (!(ind1 || ind2)) {
-        if (d.brent)
-          solve_brent<SURF>(p, r, t1, t2, dz1, dz2, x2, y2, z2);
-        else
-          solve_secant<SURF>(p, r, d, t1, t2, dz1, dz2, x2, y2, z2);
+      bool ind1 = false;
+      if (p.no_intersection) {
+        // noIntersectionSearch (reflect.py:676-681): tMax = 0, the point stays where it is
+        t2 = 0.0;
+        x2 = r.x;
+        y2 = r.y;
+        z2 = r.z;
+        xyz_to_param<SURF>(p, x2, y2, z2);
+      } else {
+        // bracketing + intersection (base.py:848-885)
+        bracket(p, d.axis, d.neg, r, t1, t2);
+        double dz1 = find_dz<SURF>(p, t1, r, x1, y1, z1);
+        double dz2 = find_dz<SURF>(p, t2, r, x2, y2, z2);
+        ind1 = dz1 <= 0.0;             // lost: solution t1
+        const bool ind2 = dz2 >= 0.0;  // over: solution t2
+        if (ind1 || ind2) dz2 = 0.0;
+        if (ind1) {
+          t2 = t1;
+          x2 = x1;
+          y2 = y1;
+          z2 = z1;
+        }
+        if (!(ind1 || ind2)) {
+          if (d.brent)
+            solve_brent<SURF>(p, r, t1, t2, dz1, dz2, x2, y2, z2);
+          else
+            solve_secant<SURF>(p, r, d, t1, t2, dz1, dz2, x2, y2, z2);
+        }
       }
       const double tMax = t2;
       // lb.x,y,z = intersection point (parametric: s, phi, r)
@@ -1148,6 +1158,35 @@ __global__ void __launch_bounds__(256) normals_kernel(size_t n, xrt_oe_params p,
   nx[i] = nrm[3];
   ny[i] = nrm[4];
   nz[i] = nrm[5];
+}
+
+// OE.prepare_wave's surface height at mesh / random (x, y) samples (oes/reflect.py:335-340)
+template <int SURF>
+__global__ void __launch_bounds__(256) surface_kernel(size_t n, xrt_oe_params p, const double* __restrict__ x,
+                                                      const double* __restrict__ y, double* __restrict__ z) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double px = x[i], py = y[i], pz = 0.0;
+  if (SURF == 2) {
+    xyz_to_param<SURF>(p, px, py, pz);
+    pz = local_surface<SURF>(p, px, py);
+    param_to_xyz<SURF>(p, px, py, pz);
+  } else {
+    pz = local_surface<SURF>(p, px, py);
+  }
+  z[i] = pz;
+}
+
+int surface_device(size_t n, const xrt_oe_params* oe, const double* x, const double* y, double* z, cudaStream_t st) {
+  XRTB_REQUIRE(oe && x && y && z, "oe_surface: NULL argument");
+  XRTB_REQUIRE(oe->surface >= 0 && oe->surface <= 2, "oe_surface: unknown surface kind %d", oe->surface);
+  if (n == 0) return 0;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  if (oe->surface == 0) surface_kernel<0><<<grid, 256, 0, st>>>(n, *oe, x, y, z);
+  if (oe->surface == 1) surface_kernel<1><<<grid, 256, 0, st>>>(n, *oe, x, y, z);
+  if (oe->surface == 2) surface_kernel<2><<<grid, 256, 0, st>>>(n, *oe, x, y, z);
+  XRTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
 }
 
 int normals_device(size_t n, const xrt_oe_params* oe, const double* x, const double* y, const double* z, double* nx,

@@ -46,7 +46,8 @@ class xrt_oe_params(ctypes.Structure):
                 ('over_mask', ctypes.c_int), ('lostNum', ctypes.c_int),
                 ('brk_lim', (ctypes.c_double * 2) * 3),
                 ('created_by_diffract', ctypes.c_int), ('zero_dead_local', ctypes.c_int),
-                ('good_mode', ctypes.c_int), ('want_footprint', ctypes.c_int)]
+                ('good_mode', ctypes.c_int), ('want_footprint', ctypes.c_int),
+                ('no_intersection', ctypes.c_int)]
 
 
 _AXIS = {'x': 0, 'y': 1, 'z': 2}
@@ -284,6 +285,17 @@ class OE(object):
         _lib.check(rc, 'xrt_oe_normals_f64')
         return out[0], out[1], out[2]
 
+    def local_z_device(self, x, y):
+        """Surface height at local (x, y) CUDA tensors, as OE.prepare_wave takes it (oes/reflect.py:335-340)."""
+        lib = _lib.load()
+        n = x.numel()
+        out = torch.empty(n, dtype=torch.float64, device=x.device)
+        params = self._make_params(self.pitch, self.roll + self.positionRoll, self.yaw, self.dx)
+        rc = lib.xrt_oe_surface_f64(n, ctypes.byref(params), x.contiguous().data_ptr(), y.contiguous().data_ptr(),
+                                    out.data_ptr(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, 'xrt_oe_surface_f64')
+        return out
+
     def local_to_global(self, lb):
         """OE.local_to_global (oes/base.py:1165-1229) for a device Beam, in place: back-rotation, coherency matrix
         and amplitudes turned by roll + atan2(n_x, n_z), then virgin local -> global."""
@@ -335,11 +347,10 @@ class OE(object):
     def reflect(self, beam=None, needLocal=True, noIntersectionSearch=False, returnLocalAbsorbed=None,
                 checkTables=True, index_offset=0, allreduce=None, withFootprint=False):
         """Returns (beamGlobal, beamLocal) like OE.reflect (oes/reflect.py:17-163)."""
-        if noIntersectionSearch:
-            raise NotImplementedError('noIntersectionSearch=True (wave mode) is not on this path yet')
         pitch = self.pitch + (self.bragg if hasattr(self, 'bragg') else 0)
         params = self._make_params(pitch, self.roll + self.positionRoll, self.yaw, self.dx,
                                    createdByDiffract=bool(getattr(beam, 'createdByDiffract', False)))
+        params.no_intersection = int(bool(noIntersectionSearch))  # reflect.py:676-681
         # the footprint / counter reductions are only paid for when somebody reads them
         params.want_footprint = int(bool(withFootprint or (checkTables and self.material is not None)))
         gb = beam.like()
@@ -353,6 +364,126 @@ class OE(object):
         if lb is not None:
             lb.parentId = lb_parent
         return gb, (lb if needLocal else gb)
+
+
+    # ------------------------------------------------------------------ wave mode (oes/reflect.py:266-449)
+    def _surface_centre_global(self):
+        """The middle point of limPhysX x limPhysY on the surface, in global coordinates (reflect.py:344-361)."""
+        cx = (self.limPhysX[1] + self.limPhysX[0])*0.5
+        cy = (self.limPhysY[1] + self.limPhysY[0])*0.5
+        dev = torch.device('cuda', torch.cuda.current_device())
+        lbc = Beam(1, device=dev)
+        lbc.x.fill_(cx)
+        lbc.y.fill_(cy)
+        lbc.z = self.local_z_device(lbc.x, lbc.y)
+        self.local_to_global(lbc)
+        return [float(lbc.x[0]), float(lbc.y[0]), float(lbc.z[0])]
+
+    def prepare_wave(self, prevOE, nrays, shape='auto', area='auto', rw=None, xy=None, device=None):
+        """OE.prepare_wave (oes/reflect.py:266-403): samples on this surface as receiving points for
+        waves.diffract.  *nrays*: int (random samples; *xy* optionally supplies the (nrays, 2) uniform deviates
+        the reference draws with np.random.rand), (nx, ny) mesh sizes, or (xarray, yarray)."""
+        if rw is None:
+            from . import waves as rw
+        dev = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+        if isinstance(nrays, (int, float)):
+            nsamples = int(nrays)
+            if xy is None:
+                xy = np.random.rand(nsamples, 2)
+            if shape == 'auto':
+                shape = self.shape
+            if not shape.startswith('re'):
+                raise NotImplementedError("only shape='rect' is on the hot path")
+            dX = self.limPhysX[1] - self.limPhysX[0]
+            dY = self.limPhysY[1] - self.limPhysY[0]
+            x = xy[:, 0] * dX + self.limPhysX[0]
+            y = xy[:, 1] * dY + self.limPhysY[0]
+            if area == 'auto':
+                area = dX * dY
+        elif isinstance(nrays, (list, tuple)):
+            if isinstance(nrays[0], (int, float)):
+                xx = np.linspace(*self.limPhysX, nrays[0])
+                yy = np.linspace(*self.limPhysY, nrays[1])
+            elif isinstance(nrays[0], np.ndarray) and isinstance(nrays[1], np.ndarray):
+                xx, yy = nrays
+            else:
+                raise ValueError('wrong type of `nrays`!')
+            X, Y = np.meshgrid(xx, yy)
+            x = X.ravel()
+            y = Y.ravel()
+            nsamples = len(x)
+            if area == 'auto':
+                dX = self.limPhysX[1] - self.limPhysX[0]
+                dY = self.limPhysY[1] - self.limPhysY[0]
+                area = dX * dY
+        else:
+            raise ValueError('wrong type of `nrays`!')
+        lb = Beam(nsamples, withAmplitudes=True, device=dev)
+        lb.state.fill_(1)
+        lb.parentId = getattr(prevOE, 'uuid', getattr(prevOE, 'name', None))
+        lb.x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(dev)
+        lb.y = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float64)).to(dev)
+        lb.z = self.local_z_device(lb.x, lb.y)
+        self.local_to_global(lb)
+        if hasattr(prevOE, 'rotationSequence'):  # OE: the middle of its surface, not its centre
+            prevCenter = prevOE._surface_centre_global()
+        else:
+            prevCenter = [float(v) for v in prevOE.center]
+        lb.a = lb.x - prevCenter[0]
+        lb.b = lb.y - prevCenter[1]
+        lb.c = lb.z - prevCenter[2]
+        norm = (lb.a**2 + lb.b**2 + lb.c**2)**0.5
+        lb.a = lb.a / norm
+        lb.b = lb.b / norm
+        lb.c = lb.c / norm
+        lb.x = torch.full_like(lb.a, prevCenter[0])
+        lb.y = torch.full_like(lb.a, prevCenter[1])
+        lb.z = torch.full_like(lb.a, prevCenter[2])
+        # the unit z vector of this OE seen from prevCenter (reflect.py:376-385)
+        lbn = Beam(1, device=dev)
+        lbn.b.fill_(0.)
+        lbn.c.fill_(1.)
+        self.local_to_global(lbn)
+        nh = lbn.to_numpy()
+        a = nh['x'] - prevCenter[0]
+        b = nh['y'] - prevCenter[1]
+        c = nh['z'] - prevCenter[2]
+        norm = (a**2 + b**2 + c**2)**0.5
+        areaNormalFact = abs(float(((a*nh['a'][0] + b*nh['b'][0] + c*nh['c'][0]) / norm)[0]))
+
+        waveGlobal, waveLocal = self.reflect(lb)
+        good = (waveLocal.state == 1) | (waveLocal.state == 2)
+        ngood = int(good.sum())
+        waveGlobal.filter_by_index(good)
+        waveLocal.filter_by_index(good)
+        area *= ngood / float(nsamples)
+        waveLocal.area = area
+        waveLocal.areaNormal = area * areaNormalFact
+        waveLocal.dS = area / float(nsamples)
+        waveLocal.toOE = self
+        waveLocal.parentId = getattr(self, 'uuid', self.name)
+        rw.prepare_wave(prevOE, waveLocal, waveGlobal.x, waveGlobal.y, waveGlobal.z)
+        return waveLocal
+
+    def propagate_wave(self, wave=None, beam=None, nrays='auto', prevOE=None, xy=None):
+        """OE.propagate_wave (oes/reflect.py:405-449): Kirchhoff-propagates *wave* (the local beam on the
+        previous element) onto this surface and reflects it.  Returns (beamGlobal, beamLocal).  The previous
+        element is looked up through bl.oesDict like in xrt, or given as *prevOE*; auto-alignment is xrt's
+        host-side business and is not repeated here."""
+        from . import waves as rw
+        waveSize = len(wave) if nrays == 'auto' else int(nrays)
+        if prevOE is None:
+            prevOE = getattr(wave, 'toOE', None) or self.bl.oesDict[wave.parentId][0]
+        waveOnSelf = self.prepare_wave(prevOE, waveSize, rw=rw, xy=xy, device=wave.device)
+        if hasattr(prevOE, 'shine'):
+            beamToSelf = prevOE.shine(wave=waveOnSelf)
+            nIS = False
+        else:
+            beamToSelf = rw.diffract(wave, waveOnSelf)
+            nIS = True
+        retGlo, retLoc = self.reflect(beamToSelf, noIntersectionSearch=nIS)
+        retLoc.parentId = getattr(self, 'uuid', self.name)
+        return retGlo, retLoc
 
 
 class ToroidMirror(OE):

@@ -12,8 +12,8 @@ numpy statements it follows.  The footprint area uses scipy's ConvexHull on the 
 (waves.py:649-670) when the local beam does not carry an `area` yet.
 
 Supported on this path: diffracting element = RectangularAperture or an OE of the hot path (flat, toroid,
-elliptical parametric: the traced local beam is the set of samples); receiving element = Screen.
-OE.prepare_wave / propagate_wave (oes/reflect.py:266-449, samples drawn on the OE surface) are the next row.
+elliptical parametric: the traced local beam is the set of samples); receiving element = Screen or such an OE
+(OE.prepare_wave / propagate_wave, oes/reflect.py:266-449, live in xrt_b200/oes.py).
 """
 import numpy as np
 import torch
@@ -246,7 +246,39 @@ def diffract(oeLocal, wave, targetOpenCL='CUDA', precisionOpenCL='float64'):
         wave.Es, wave.Ep = glo.Es.clone(), glo.Ep.clone()
         a0, b0 = toOE.bl.sinAzimuth, toOE.bl.cosAzimuth
         wave.a, wave.b = _rotate_z(wave.a, wave.b, b0, a0)
-        if hasattr(toOE, 'rotationSequence'):
-            raise NotImplementedError('diffract onto an OE is the next row (SURVEY.md 8f)')
+        if hasattr(toOE, 'rotationSequence'):  # receiving surface is an OE (waves.py:786-824)
+            from .oes import _rotation_list
+            nX, nY, nZ = toOE.local_n_device(wave.x, wave.y, wave.z)
+            rollAngle = (toOE.roll + toOE.positionRoll) + torch.atan2(nX, nZ)
+            c, s = torch.cos(-rollAngle), torch.sin(-rollAngle)  # rotate_coherency_matrix(wave, ., -rollAngle)
+            c2, s2, cs = c**2, s**2, c * s
+            Jss, Jpp, Jsp = wave.Jss, wave.Jpp, wave.Jsp
+            JssN = Jss*c2 + Jpp*s2 + 2*Jsp.real*cs
+            JppN = Jss*s2 + Jpp*c2 - 2*Jsp.real*cs
+            JspN = torch.complex((Jpp-Jss)*cs + Jsp.real*(c2-s2), Jsp.imag.clone())
+            wave.Jss, wave.Jpp, wave.Jsp = JssN, JppN, JspN
+            cosY, sinY = torch.cos(rollAngle), torch.sin(rollAngle)
+            Es, Ep = wave.Es, wave.Ep  # rotate_y(Es, Ep, cosY, -sinY)
+            wave.Es, wave.Ep = cosY*Es + (-sinY)*Ep, -(-sinY)*Es + cosY*Ep
+            rots = _rotation_list(toOE.rotationSequence, -toOE.pitch, -toOE.roll-toOE.positionRoll, -toOE.yaw)
+            if toOE.extraPitch or toOE.extraRoll or toOE.extraYaw:
+                rots += _rotation_list(toOE.extraRotationSequence, -toOE.extraPitch, -toOE.extraRoll,
+                                       -toOE.extraYaw)
+            wa, wb, wc = wave.a, wave.b, wave.c
+            for ax, cA, sA in rots:
+                if ax == 0:
+                    wb, wc = cA*wb - sA*wc, sA*wb + cA*wc
+                elif ax == 1:
+                    wa, wc = cA*wa + sA*wc, -sA*wa + cA*wc
+                else:
+                    wa, wb = cA*wa - sA*wb, sA*wa + cA*wb
+            wave.a, wave.b, wave.c = wa, wb, wc
+            norm = torch.abs(-wave.a*nX - wave.b*nY - wave.c*nZ)
+            for b in (wave, glo):
+                b.Jss = b.Jss * norm
+                b.Jpp = b.Jpp * norm
+                b.Jsp = b.Jsp * norm
+                b.Es = b.Es * norm**0.5
+                b.Ep = b.Ep * norm**0.5
     glo.createdByDiffract = True
     return glo
