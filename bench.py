@@ -343,25 +343,34 @@ def run_ours(args):
     gd = blo.state == 1
     xl = [float(blo.x[gd].min()), float(blo.x[gd].max())]
     zl = [float(blo.z[gd].min()), float(blo.z[gd].max())]
+    blo_E_min, blo_E_max = blo.E[gd].min(), blo.E[gd].max()
     del blo, gd
-    img = torch.zeros((256, 256), dtype=torch.float64, device='cuda')
-    host_img = torch.empty((256, 256), dtype=torch.float64, pin_memory=True)
+    el = [float(blo_E_min), float(blo_E_max)]
+    ph = histogram.PlotHistograms(histogram.Axis('x', xl, 256), histogram.Axis('z', zl, 256),
+                                  histogram.Axis('E', el, 256), fluxKind='total', rayFlag=(1,))
+    hbytes = sum(t.numel() * t.element_size() for t in (ph._h2, ph._hx, ph._hy, ph._hc, ph._counters))
+    host_img = torch.empty(hbytes // 8, dtype=torch.float64, pin_memory=True)
 
     def step_hist():
         b = step()
-        img.zero_()
-        histogram.hist2d(b, xl, zl, bins=(256, 256), out=img)
+        for t in (ph._h2, ph._hx, ph._hy, ph._hc, ph._counters):
+            t.zero_()
+        ph.accumulate(b)
         if world > 1:
-            dist.all_reduce(img)
-        host_img.copy_(img, non_blocking=True)
+            ph.allreduce()
+        o = 0
+        for t in (ph._h2, ph._hx, ph._hy, ph._hc):
+            host_img[o:o + t.numel()].copy_(t.reshape(-1), non_blocking=True)
+            o += t.numel()
 
     step_hist()
     ms_hist = timed(step_hist, args.steps) / args.steps
     e2e_hist = {'value': world * nrays / (ms_hist * 1e-3) / 1e6, 'unit': 'Mrays/s', 'ms_per_step': ms_hist,
-                'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 256 * 256 * 8,
-                'note': 'same step + device 2-D histogram of the screen beam (xrt_b200.histogram.hist2d == '
-                        'np.histogram2d of do_hist2d); the 256 x 256 image is what crosses PCIe, as in xrt where '
-                        'histograms, not rays, are accumulated over repeats (xrt/runner.py:526-530)'}
+                'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': hbytes,
+                'note': 'same step + one XYCPlot on the device (xrt_b200.histogram.PlotHistograms: 256 x 256 image and '
+                        'the x, z, E 1-D histograms, each with flux + RGB channels == get_output + do_hist1d/2d); '
+                        'only the histograms cross PCIe, as in xrt where histograms, not rays, are accumulated over '
+                        'repeats (xrt/runner.py:526-530, xrt/multipro.py:296-340)'}
 
     # ---- per-kernel times of reflect() (pre-pass A, pre-pass B, main) in a few extra untimed steps
     mirror.profileEvents = []

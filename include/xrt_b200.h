@@ -263,6 +263,36 @@ int xrt_hist2d_f64(size_t n, const double* x, const double* y, const double* w1,
                    const int32_t* state, int state_mask, const double* ex, int nx, const double* ey, int ny,
                    double* out, void* stream);
 
+/* One XYCPlot's worth of histograms in a single pass over the beam (xrt/multipro.py:296-330 `run`: get_output ->
+ * cData01 -> HSV -> RGB -> do_hist1d x 3 + do_hist2d): per selected ray the flux weight (fluxKind) and its three
+ * RGB weights (hue = the colour-axis value mapped to [0, 1], saturation = colorSaturation, value = flux;
+ * matplotlib.colors.hsv_to_rgb's sextant formula) are accumulated into
+ *   hist2d[ny][nx][4], histx[nx][4], histy[ny][4], histc[nc][4]       (channel 0 = flux, 1..3 = R, G, B)
+ * with np.histogram / np.histogram2d bin semantics (edges from np.linspace on the host, last edge inclusive).
+ * All output arrays are ACCUMULATED into; any of them may be NULL.  counters[6] += {selected, alive, good, out,
+ * over, dead} (raycing.get_output's locAlive, locGood, ...).  Device pointers. */
+typedef struct xrt_plot_params {
+  const double *x, *y, *c;       /* axis data: beam attributes (x, z, E, ...); c NULL: no colour axis (R=G=B=flux) */
+  double xfactor, yfactor, cfactor; /* XYCAxis.factor (get_output multiplies the data by it) */
+  const double *ex, *ey, *ec;    /* bin edges, nx+1 / ny+1 / nc+1 */
+  int nx, ny, nc;
+  const double *Jss, *Jpp, *Jsp; /* Jsp: interleaved (re, im) */
+  const double *E;
+  const int32_t* state;
+  int state_mask;                /* rayFlag (raycing/__init__.py:203-218): bit0 state == 1, bit1 == 2, bit2 == 3,
+                                    bit4 any other state > 0 (rayFlag 4 = alive sets bits 0, 1, 2, 4), bit3 every
+                                    state < 0; exact negative flags go into dead_flags */
+  int n_dead_flags;
+  int dead_flags[4];             /* rayFlag < 0: rays with exactly this state */
+  int flux_kind;                 /* 0 total, 1 's', 2 'p', 3 '+/-45', 4 'left-right', 5 'power' (__init__.py:267-296) */
+  double srcWt;                  /* nrays * beam.sourceWeight, or 1 */
+  double climits[2], colorFactor, colorSaturation;
+  double *hist2d, *histx, *histy, *histc;
+  unsigned long long* counters;
+} xrt_plot_params;
+
+int xrt_plot_hist_f64(size_t n, const xrt_plot_params* plot, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

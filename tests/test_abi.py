@@ -33,6 +33,12 @@ def test_struct_layouts_match_ctypes_mirrors():
     assert lib.xrt_b200_sizeof(0) == ctypes.sizeof(xrt_beam)
     assert lib.xrt_b200_sizeof(1) == ctypes.sizeof(xrt_oe_params)
     assert lib.xrt_b200_sizeof(2) == ctypes.sizeof(xrt_material_params)
+    from xrt_b200.planes import xrt_plane_params
+    from xrt_b200.sources import xrt_source_params
+    from xrt_b200.histogram import xrt_plot_params
+    assert lib.xrt_b200_sizeof(3) == ctypes.sizeof(xrt_plane_params)
+    assert lib.xrt_b200_sizeof(4) == ctypes.sizeof(xrt_source_params)
+    assert lib.xrt_b200_sizeof(5) == ctypes.sizeof(xrt_plot_params)
 
 
 def test_no_cpu_fallback_without_gpu():

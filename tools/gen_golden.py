@@ -574,8 +574,49 @@ def gen_wave_oe():
         extra[k] = float(getattr(kb, k))
     _wave_onto_oe('wave_slit_kb_screen', kb, slit, oeLocal, (24, 40), scr2, xm, zm, 6, extra)
 
+# ------------------------------------------------------------------------------------------------ plot histograms
+def gen_hist():
+    """raycing.get_output (the reference's) on a traced screen beam for several flux kinds / ray flags; the
+    histogram calls of multipro (np.histogram, np.histogram2d) are applied to its outputs by oracle/histogram.py
+    (multipro itself needs matplotlib, absent here)."""
+    import types
+    sys.path.insert(0, ROOT)
+    from oracle import histogram as oh
+    bl = raycing.BeamLine()
+    beam = _source_beam(bl, 8000, 141, dx=0.5, dz=0.2, dxprime=2e-4, dzprime=1e-4, energies=(8900, 9100),
+                        polarization=None)
+    oe = roe.ToroidMirror(bl, 'TM', center=(0, 1e4, 0), pitch=4e-3, R=1e6, r=100., material=rm.Material('Au', rho=19.3),
+                          limPhysX=[-1.5, 1.5], limPhysY=[-150, 150], limOptX=[-1.2, 1.2], limOptY=[-120, 120])
+    gb, lb = oe.reflect(beam)
+    scr = rsc.Screen(bl, 'scr', center=(0, 2e4, 1e4*np.tan(8e-3)))
+    blo = scr.expose(gb)
+    blo.sourceWeight = 1.7e-3
+    d = dict(beam_dict(blo, 'b_'), sourceWeight=blo.sourceWeight)
+    xl, zl, el = [-4., 4.], [-1.5, 1.5], [8900., 9100.]
+    d.update(xlimits=np.array(xl), ylimits=np.array(zl), climits=np.array(el), bins=np.array([64, 48, 32]),
+             xfactor=1., yfactor=1e3, cfactor=1.)
+    cases = [('total', (1,)), ('s', (1, 2)), ('p', (1, 3)), ('+/-45', (1, 2, 3)), ('left-right', (1,)),
+             ('power', (1, 2, 3, -1))]
+    for n, (fk, flags) in enumerate(cases):
+        plot = types.SimpleNamespace(
+            beam='b', showAbsorbed=False, beamState=None, rayFlag=flags, beamC=None, fluxKind=fk,
+            xaxis=types.SimpleNamespace(data=raycing.get_x, factor=1.),
+            yaxis=types.SimpleNamespace(data=raycing.get_z, factor=1e3),
+            caxis=types.SimpleNamespace(data=raycing.get_energy, factor=1., useCategory=False))
+        sel = raycing.get_output(plot, {'b': blo})
+        for k, v in zip(('x', 'y', 'intensity', 'flux', 'cData'), sel[:5]):
+            d['c%d_%s' % (n, k)] = v
+        d['c%d_counts' % n] = np.array([int(v) for v in sel[5:11]])
+        h = oh.plot_histograms(None, oh.Axis('x', xl, 64), oh.Axis('z', [zl[0]*1e3, zl[1]*1e3], 48, 1e3),
+                               oh.Axis('E', el, 32), fk, flags, selected=sel)
+        for k, v in h.items():
+            d['c%d_%s' % (n, k)] = v
+    d['fluxKinds'] = np.array([c[0] for c in cases])
+    d['rayFlags'] = np.array([','.join(str(f) for f in c[1]) for c in cases])
+    save('plot_histograms', **d)
 
-SECTIONS = {'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+
+SECTIONS = {'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)

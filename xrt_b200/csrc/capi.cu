@@ -164,7 +164,7 @@ int xrt_b200_init(int device) {
 int xrt_b200_sm_count(void) { return num_sms(); }
 
 size_t xrt_b200_sizeof(int which) {
-  return which == 0 ? sizeof(xrt_beam) : which == 1 ? sizeof(xrt_oe_params) : which == 2 ? sizeof(xrt_material_params) : which == 3 ? sizeof(xrt_plane_params) : which == 4 ? sizeof(xrt_source_params) : 0;
+  return which == 0 ? sizeof(xrt_beam) : which == 1 ? sizeof(xrt_oe_params) : which == 2 ? sizeof(xrt_material_params) : which == 3 ? sizeof(xrt_plane_params) : which == 4 ? sizeof(xrt_source_params) : which == 5 ? sizeof(xrt_plot_params) : 0;
 }
 
 const char* xrt_b200_last_error(void) { return g_err; }
@@ -371,6 +371,10 @@ int xrt_oe_surface_f64(size_t n, const xrt_oe_params* oe, const double* x, const
 int xrt_oe_normals_f64(size_t n, const xrt_oe_params* oe, const double* x, const double* y, const double* z,
                        double* nx, double* ny, double* nz, void* stream) {
   return normals_device(n, oe, x, y, z, nx, ny, nz, (cudaStream_t)stream);
+}
+
+int xrt_plot_hist_f64(size_t n, const xrt_plot_params* plot, void* stream) {
+  return plot_hist_device(n, plot, (cudaStream_t)stream);
 }
 
 int xrt_hist2d_f64(size_t n, const double* x, const double* y, const double* w1, const double* w2,

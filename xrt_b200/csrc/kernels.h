@@ -56,6 +56,7 @@ int source_fill_device(size_t n, const xrt_source_params* p, const long long* id
                        const double* n1, const double* n2, const double* n3, const double* n4, const xrt_beam* out,
                        size_t out_offset, cudaStream_t st);
 
+int plot_hist_device(size_t n, const xrt_plot_params* p, cudaStream_t st);
 int hist2d_device(size_t n, const double* x, const double* y, const double* w1, const double* w2, const int* state,
                   int state_mask, const double* ex, int nx, const double* ey, int ny, double* out, cudaStream_t st);
 int shine_uniform_device(size_t n, uint64_t seed, uint64_t index_offset, const double* window, int jend, double Kx,

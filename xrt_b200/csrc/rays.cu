@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(256) hist2d_kernel(size_t n, const double* __r
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     if (state) {
       const int st = state[i];
-      const int bit = st == 1 ? 1 : (st == 2 ? 2 : (st == 3 ? 4 : (st < 0 ? 8 : 16)));
+      const int bit = st == 1 ? 1 : (st == 2 ? 2 : (st == 3 ? 4 : (st < 0 ? 8 : (st > 0 ? 16 : 32))));
       if (!(bit & state_mask)) continue;
     }
     const int bx = find_bin(sx, nx, x[i], inv_wx);
@@ -302,13 +302,132 @@ __global__ void __launch_bounds__(256) hist2d_kernel(size_t n, const double* __r
 int hist2d_device(size_t n, const double* x, const double* y, const double* w1, const double* w2, const int* state,
                   int state_mask, const double* ex, int nx, const double* ey, int ny, double* out, cudaStream_t st) {
   XRTB_REQUIRE(x && y && ex && ey && out, "hist2d: NULL argument");
-  XRTB_REQUIRE(nx > 0 && ny > 0 && nx + ny + 2 <= 12000, "hist2d: 1 <= bins and nx + ny <= 11998");
+  XRTB_REQUIRE(nx > 0 && ny > 0 && nx + ny + 2 <= 6000, "hist2d: 1 <= bins and nx + ny <= 5998");
   if (n == 0) return 0;
   unsigned grid = (unsigned)num_sms() * 8;
   const size_t need = (n + 255) / 256;
   if (need < grid) grid = (unsigned)need;
   const size_t smem = (size_t)(nx + ny + 2) * sizeof(double);
   hist2d_kernel<<<grid, 256, smem, st>>>(n, x, y, w1, w2, state, state_mask, ex, nx, ey, ny, out);
+  XRTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------- f1: one XYCPlot in one pass
+// flux by fluxKind (raycing/__init__.py:267-296), hue -> RGB (matplotlib.colors.hsv_to_rgb), 1-D histograms of
+// the x, y and colour axes and the 2-D image, each with 4 channels (flux, R, G, B); xrt/multipro.py:296-340.
+__device__ __forceinline__ void hsv_to_rgb(double h, double s, double v, double& r, double& g, double& b) {
+  if (s == 0.0) {
+    r = g = b = v;
+    return;
+  }
+  const double h6 = h * 6.0;
+  const int i = (int)h6;
+  const double f = h6 - (double)i;
+  const double p = v * (1.0 - s);
+  const double q = v * (1.0 - s * f);
+  const double t = v * (1.0 - s * (1.0 - f));
+  switch (i % 6) {
+    case 0: r = v; g = t; b = p; break;
+    case 1: r = q; g = v; b = p; break;
+    case 2: r = p; g = v; b = t; break;
+    case 3: r = p; g = q; b = v; break;
+    case 4: r = t; g = p; b = v; break;
+    default: r = v; g = p; b = q; break;
+  }
+}
+
+__device__ __forceinline__ void add4(double* __restrict__ h, size_t bin, const double* w) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) atomicAdd(&h[bin * 4 + k], w[k]);
+}
+
+__global__ void __launch_bounds__(256) plot_hist_kernel(size_t n, xrt_plot_params p) {
+  extern __shared__ double sedges[];  // ex[nx + 1] | ey[ny + 1] | ec[nc + 1]
+  double* sx = sedges;
+  double* sy = sx + p.nx + 1;
+  double* sc = sy + p.ny + 1;
+  for (int i = threadIdx.x; i <= p.nx; i += blockDim.x) sx[i] = p.ex[i];
+  for (int i = threadIdx.x; i <= p.ny; i += blockDim.x) sy[i] = p.ey[i];
+  if (p.c && p.ec)
+    for (int i = threadIdx.x; i <= p.nc; i += blockDim.x) sc[i] = p.ec[i];
+  __shared__ unsigned long long scnt[6];
+  if (threadIdx.x < 6) scnt[threadIdx.x] = 0;
+  __syncthreads();
+  const double inv_wx = p.nx / (sx[p.nx] - sx[0]), inv_wy = p.ny / (sy[p.ny] - sy[0]);
+  const double inv_wc = (p.c && p.ec) ? p.nc / (sc[p.nc] - sc[0]) : 0.0;
+  const double SIE0 = 1.602176565e-19;
+  unsigned cnt[6] = {0, 0, 0, 0, 0, 0};
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int st = p.state ? p.state[i] : 1;
+    const int bit = st == 1 ? 1 : (st == 2 ? 2 : (st == 3 ? 4 : (st < 0 ? 8 : (st > 0 ? 16 : 32))));
+    cnt[1] += st > 0;
+    bool sel = (bit & p.state_mask) != 0;
+    for (int k = 0; k < p.n_dead_flags; ++k) sel = sel || (st == p.dead_flags[k]);
+    if (!sel) continue;
+    cnt[0] += 1;
+    cnt[2] += st == 1;
+    cnt[3] += st == 2;
+    cnt[4] += st == 3;
+    cnt[5] += st < 0;
+    double flux;
+    switch (p.flux_kind) {
+      case 1: flux = p.Jss[i] * p.srcWt; break;
+      case 2: flux = p.Jpp[i] * p.srcWt; break;
+      case 3: flux = 2.0 * p.Jsp[2 * i] * p.srcWt; break;
+      case 4: flux = 2.0 * p.Jsp[2 * i + 1] * p.srcWt; break;
+      case 5: flux = (p.Jss[i] + p.Jpp[i]) * p.E[i] * SIE0 * p.srcWt; break;
+      default: flux = (p.Jss[i] + p.Jpp[i]) * p.srcWt; break;
+    }
+    double w[4];
+    w[0] = flux;
+    double cv = 0.0;
+    if (p.c) {
+      cv = p.c[i] * p.cfactor;
+      double c01 = (cv - p.climits[0]) * p.colorFactor / (p.climits[1] - p.climits[0]);
+      if (c01 < 0.0) c01 = 0.0;
+      if (c01 > 1.0) c01 = 1.0;
+      hsv_to_rgb(c01, p.colorSaturation, flux, w[1], w[2], w[3]);
+    } else {
+      w[1] = w[2] = w[3] = flux;
+    }
+    const int bx = find_bin(sx, p.nx, p.x[i] * p.xfactor, inv_wx);
+    const int by = find_bin(sy, p.ny, p.y[i] * p.yfactor, inv_wy);
+    if (bx >= 0 && p.histx) add4(p.histx, (size_t)bx, w);
+    if (by >= 0 && p.histy) add4(p.histy, (size_t)by, w);
+    if (bx >= 0 && by >= 0 && p.hist2d) add4(p.hist2d, (size_t)by * p.nx + bx, w);
+    if (p.c && p.ec && p.histc) {
+      const int bc = find_bin(sc, p.nc, cv, inv_wc);
+      if (bc >= 0) add4(p.histc, (size_t)bc, w);
+    }
+  }
+  if (p.counters) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      unsigned v = cnt[k];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0 && v) atomicAdd(&scnt[k], (unsigned long long)v);
+    }
+    __syncthreads();
+    if (threadIdx.x < 6 && scnt[threadIdx.x]) atomicAdd(&p.counters[threadIdx.x], scnt[threadIdx.x]);
+  }
+}
+
+int plot_hist_device(size_t n, const xrt_plot_params* p, cudaStream_t st) {
+  XRTB_REQUIRE(p && p->x && p->y && p->ex && p->ey, "plot_hist: NULL axis data or edges");
+  XRTB_REQUIRE(p->nx > 0 && p->ny > 0 && p->nc >= 0 && p->nx + p->ny + p->nc + 3 <= 6000,
+               "plot_hist: 1 <= bins and nx + ny + nc <= 5997");
+  XRTB_REQUIRE(p->flux_kind >= 0 && p->flux_kind <= 5, "plot_hist: unknown flux kind %d", p->flux_kind);
+  XRTB_REQUIRE(p->n_dead_flags >= 0 && p->n_dead_flags <= 4, "plot_hist: at most 4 negative ray flags");
+  XRTB_REQUIRE(p->Jss && p->Jpp && (p->flux_kind < 3 || p->flux_kind == 5 || p->Jsp) && (p->flux_kind != 5 || p->E),
+               "plot_hist: the beam arrays the flux kind needs are missing");
+  if (n == 0) return 0;
+  unsigned grid = (unsigned)num_sms() * 8;
+  const size_t need = (n + 255) / 256;
+  if (need < grid) grid = (unsigned)need;
+  const size_t smem = (size_t)(p->nx + p->ny + p->nc + 3) * sizeof(double);
+  plot_hist_kernel<<<grid, 256, smem, st>>>(n, *p);
   XRTB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
