@@ -342,20 +342,29 @@ __device__ __forceinline__ void add4(double* __restrict__ h, size_t bin, const d
   for (int k = 0; k < 4; ++k) atomicAdd(&h[bin * 4 + k], w[k]);
 }
 
-__global__ void __launch_bounds__(256) plot_hist_kernel(size_t n, xrt_plot_params p) {
-  extern __shared__ double sedges[];  // ex[nx + 1] | ey[ny + 1] | ec[nc + 1]
+// PRIV: the three 1-D histograms (a few hundred hot bins hit by every ray) are privatised per block in shared
+// memory and flushed once at the end; the 2-D image goes to global memory with RED.ADD.F64.
+template <bool PRIV>
+__global__ void __launch_bounds__(1024) plot_hist_kernel(size_t n, xrt_plot_params p) {
+  extern __shared__ double sedges[];  // ex[nx + 1] | ey[ny + 1] | ec[nc + 1] | PRIV: hx[nx*4] | hy[ny*4] | hc[nc*4]
   double* sx = sedges;
   double* sy = sx + p.nx + 1;
   double* sc = sy + p.ny + 1;
+  double* hx = sc + p.nc + 1;
+  double* hy = hx + 4 * p.nx;
+  double* hc = hy + 4 * p.ny;
+  const bool hasC = p.c && p.ec && p.nc > 0;
   for (int i = threadIdx.x; i <= p.nx; i += blockDim.x) sx[i] = p.ex[i];
   for (int i = threadIdx.x; i <= p.ny; i += blockDim.x) sy[i] = p.ey[i];
-  if (p.c && p.ec)
+  if (hasC)
     for (int i = threadIdx.x; i <= p.nc; i += blockDim.x) sc[i] = p.ec[i];
+  if (PRIV)
+    for (int i = threadIdx.x; i < 4 * (p.nx + p.ny + p.nc); i += blockDim.x) hx[i] = 0.0;
   __shared__ unsigned long long scnt[6];
   if (threadIdx.x < 6) scnt[threadIdx.x] = 0;
   __syncthreads();
   const double inv_wx = p.nx / (sx[p.nx] - sx[0]), inv_wy = p.ny / (sy[p.ny] - sy[0]);
-  const double inv_wc = (p.c && p.ec) ? p.nc / (sc[p.nc] - sc[0]) : 0.0;
+  const double inv_wc = hasC ? p.nc / (sc[p.nc] - sc[0]) : 0.0;
   const double SIE0 = 1.602176565e-19;
   unsigned cnt[6] = {0, 0, 0, 0, 0, 0};
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -394,12 +403,12 @@ __global__ void __launch_bounds__(256) plot_hist_kernel(size_t n, xrt_plot_param
     }
     const int bx = find_bin(sx, p.nx, p.x[i] * p.xfactor, inv_wx);
     const int by = find_bin(sy, p.ny, p.y[i] * p.yfactor, inv_wy);
-    if (bx >= 0 && p.histx) add4(p.histx, (size_t)bx, w);
-    if (by >= 0 && p.histy) add4(p.histy, (size_t)by, w);
+    if (bx >= 0 && p.histx) add4(PRIV ? hx : p.histx, (size_t)bx, w);
+    if (by >= 0 && p.histy) add4(PRIV ? hy : p.histy, (size_t)by, w);
     if (bx >= 0 && by >= 0 && p.hist2d) add4(p.hist2d, (size_t)by * p.nx + bx, w);
-    if (p.c && p.ec && p.histc) {
+    if (hasC && p.histc) {
       const int bc = find_bin(sc, p.nc, cv, inv_wc);
-      if (bc >= 0) add4(p.histc, (size_t)bc, w);
+      if (bc >= 0) add4(PRIV ? hc : p.histc, (size_t)bc, w);
     }
   }
   if (p.counters) {
@@ -409,8 +418,16 @@ __global__ void __launch_bounds__(256) plot_hist_kernel(size_t n, xrt_plot_param
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       if ((threadIdx.x & 31) == 0 && v) atomicAdd(&scnt[k], (unsigned long long)v);
     }
-    __syncthreads();
-    if (threadIdx.x < 6 && scnt[threadIdx.x]) atomicAdd(&p.counters[threadIdx.x], scnt[threadIdx.x]);
+  }
+  __syncthreads();
+  if (p.counters && threadIdx.x < 6 && scnt[threadIdx.x]) atomicAdd(&p.counters[threadIdx.x], scnt[threadIdx.x]);
+  if (PRIV) {
+    for (int i = threadIdx.x; i < 4 * p.nx; i += blockDim.x)
+      if (p.histx && hx[i] != 0.0) atomicAdd(&p.histx[i], hx[i]);
+    for (int i = threadIdx.x; i < 4 * p.ny; i += blockDim.x)
+      if (p.histy && hy[i] != 0.0) atomicAdd(&p.histy[i], hy[i]);
+    for (int i = threadIdx.x; i < 4 * p.nc; i += blockDim.x)
+      if (p.histc && hasC && hc[i] != 0.0) atomicAdd(&p.histc[i], hc[i]);
   }
 }
 
@@ -426,8 +443,25 @@ int plot_hist_device(size_t n, const xrt_plot_params* p, cudaStream_t st) {
   unsigned grid = (unsigned)num_sms() * 8;
   const size_t need = (n + 255) / 256;
   if (need < grid) grid = (unsigned)need;
-  const size_t smem = (size_t)(p->nx + p->ny + p->nc + 3) * sizeof(double);
-  plot_hist_kernel<<<grid, 256, smem, st>>>(n, *p);
+  const size_t nb = (size_t)p->nx + p->ny + p->nc;
+  const size_t smem_priv = (nb + 3 + 4 * nb) * sizeof(double);
+  if (smem_priv <= 46 * 1024) {
+    plot_hist_kernel<true><<<grid, 256, smem_priv, st>>>(n, *p);
+  } else if (smem_priv <= 200 * 1024) {
+    // many bins: one 1024-thread block per SM with the opt-in shared-memory carve-out
+    static bool attr_set = false;
+    if (!attr_set) {
+      XRTB_CUDA_CHECK(cudaFuncSetAttribute(plot_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           200 * 1024));
+      attr_set = true;
+    }
+    unsigned g1 = (unsigned)num_sms();
+    const size_t need1 = (n + 1023) / 1024;
+    if (need1 < g1) g1 = (unsigned)need1;
+    plot_hist_kernel<true><<<g1, 1024, smem_priv, st>>>(n, *p);
+  } else {
+    plot_hist_kernel<false><<<grid, 256, (nb + 3) * sizeof(double), st>>>(n, *p);
+  }
   XRTB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
