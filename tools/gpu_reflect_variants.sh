@@ -1,12 +1,12 @@
 #!/bin/bash
 # GPU-side experiment: occupancy of reflect_main_kernel (register cap via __launch_bounds__ min blocks)
 mkdir -p gpurun_out
-for MB in 2 3 4; do
+for MB in ${MBS:-3 4}; do
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -fmad=false -DXRTB_REFLECT_MINBLOCKS=$MB \
      -Xptxas -v -I include -c -o build/obj/reflect.o xrt_b200/csrc/reflect.cu 2>&1 | grep -A2 "reflect_main_kernelILi1ELi1E" | grep -E "registers|spill" | head -2
   nvcc -gencode arch=compute_100a,code=sm_100a -shared -o xrt_b200/libxrt_b200.so build/obj/*.o
   echo "MINBLOCKS=$MB"
-  python bench.py --steps 3 --warmup 2 --nrays 50000000 --no-kirchhoff --no-cpu-baseline 2>&1 | python -c "
+  python bench.py --steps 3 --warmup 3 --nrays 100000000 --no-kirchhoff --no-cpu-baseline --no-rejection 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):

@@ -123,20 +123,37 @@ __device__ __forceinline__ double pow_m05(double x) {
   return fma(0.5 * y0, e, y0);
 }
 
+// the surface's loop-invariant divisors with their reciprocals refined once per thread (common.cuh, Divisor)
+struct SurfDiv {
+  Divisor d0, d1;  // toroid: r, R; ellipse: A*A
+};
+
 template <int SURF>
-__device__ __forceinline__ double local_surface(const xrt_oe_params& p, double x, double y) {
+__device__ __forceinline__ SurfDiv make_surf_div(const xrt_oe_params& p) {
+  SurfDiv sd;
+  sd.d0 = sd.d1 = Divisor{1.0, 1.0};
+  if (SURF == 1) {
+    sd.d0 = make_divisor(p.sp[1]);
+    sd.d1 = make_divisor(p.sp[0]);
+  }
+  if (SURF == 2) sd.d0 = make_divisor(p.sp[0] * p.sp[0]);
+  return sd;
+}
+
+template <int SURF>
+__device__ __forceinline__ double local_surface(const xrt_oe_params& p, const SurfDiv& sd, double x, double y) {
   if (SURF == 0) return 0.0;
   if (SURF == 1) {
     // ToroidMirror.local_z (oes/__init__.py:398-401)
-    const double R = p.sp[0], r = p.sp[1];
-    const double q = x / r;
+    const double r = p.sp[1];
+    const double q = div_by(x, sd.d0);  // x / r
     double rx = 1.0 - q * q;
     if (rx < 0.0) rx = 0.0;
-    return y * y / 2.0 / R + r * (1.0 - sqrt(rx));
+    return div_by(y * y / 2.0, sd.d1) + r * (1.0 - sqrt(rx));  // y**2 / 2.0 / R
   }
   // EllipticalMirrorParam.local_r (parametric.py:228-234): x = s, y = phi
-  const double A = p.sp[0], B = p.sp[1];
-  double rr = B * sqrt(fabs(1.0 - x * x / (A * A)));
+  const double B = p.sp[1];
+  double rr = B * sqrt(fabs(1.0 - div_by(x * x, sd.d0)));  // s**2 / A**2
   if (p.sp[6] != 0.0) rr /= fabs(cos(y));
   return (fabs(y) > kPi / 2) ? rr : 1e20;
 }
@@ -169,13 +186,13 @@ __device__ __forceinline__ void param_to_xyz(const xrt_oe_params& p, double& x, 
 
 // find_dz (base.py:801-846), derivOrder = 0, invertNormal = 1
 template <int SURF>
-__device__ __forceinline__ double find_dz(const xrt_oe_params& p, double t, const Ray& r, double& x, double& y,
-                                          double& z) {
+__device__ __forceinline__ double find_dz(const xrt_oe_params& p, const SurfDiv& sd, double t, const Ray& r,
+                                          double& x, double& y, double& z) {
   x = r.x + r.a * t;
   y = r.y + r.b * t;
   z = r.z + r.c * t;
   xyz_to_param<SURF>(p, x, y, z);
-  double surf = local_surface<SURF>(p, x, y);
+  double surf = local_surface<SURF>(p, sd, x, y);
   if (isnan(surf)) surf = 0.0;
   const double d = z - surf;
   return (SURF == 2) ? -d : d;
@@ -183,7 +200,8 @@ __device__ __forceinline__ double find_dz(const xrt_oe_params& p, double t, cons
 
 // normal(s): n[0..2] = n_B (or the only normal), n[3..5] = surface normal
 template <int SURF>
-__device__ __forceinline__ void local_normal(const xrt_oe_params& p, double x, double y, double* n) {
+__device__ __forceinline__ void local_normal(const xrt_oe_params& p, const SurfDiv& sd, double x, double y,
+                                             double* n) {
   if (SURF == 0) {
     n[3] = 0.0;
     n[4] = 0.0;
@@ -201,12 +219,11 @@ __device__ __forceinline__ void local_normal(const xrt_oe_params& p, double x, d
   }
   if (SURF == 1) {
     // ToroidMirror.local_n (oes/__init__.py:403-411)
-    const double R = p.sp[0], r = p.sp[1];
-    const double q = x / r;
+    const double q = div_by(x, sd.d0);  // x / r
     const double rx = 1.0 - q * q;
     const double ax = (rx < 0.0) ? 0.0 : pow_m05(rx);
-    const double a = -x / r * ax;
-    const double b = -y / R;
+    const double a = div_by(-x, sd.d0) * ax;
+    const double b = div_by(-y, sd.d1);  // -y / R
     const double norm = sqrt(a * a + b * b + 1.0);
     n[0] = n[3] = a / norm;
     n[1] = n[4] = b / norm;
@@ -357,6 +374,7 @@ __global__ void __launch_bounds__(256) reflect_prepass_kernel(size_t n, xrt_oe_p
   int axis, neg;
   decide_variant(red, axis, neg);
   double v[4] = {inf, -inf, -inf, -inf};
+  const SurfDiv sd = make_surf_div<SURF>(p);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const int st = in.state[i];
@@ -365,8 +383,8 @@ __global__ void __launch_bounds__(256) reflect_prepass_kernel(size_t n, xrt_oe_p
     to_local(p, r);
     double t1, t2, x, y, z;
     bracket(p, axis, neg, r, t1, t2);
-    const double dz1 = find_dz<SURF>(p, t1, r, x, y, z);
-    double dz2 = find_dz<SURF>(p, t2, r, x, y, z);
+    const double dz1 = find_dz<SURF>(p, sd, t1, r, x, y, z);
+    double dz2 = find_dz<SURF>(p, sd, t2, r, x, y, z);
     if (dz1 <= 0.0 || dz2 >= 0.0) dz2 = 0.0;  // base.py:865 dz2[ind1 | ind2] = 0
     // numpy's min/max propagate NaN; keep that by letting NaN win
     v[0] = (t1 < v[0] || isnan(t1)) ? t1 : v[0];
@@ -616,7 +634,8 @@ __device__ __forceinline__ Decision decide(const unsigned long long* red) {
 __device__ __forceinline__ int sgn(double v) { return (v > 0.0) - (v < 0.0); }
 
 template <int SURF>
-__device__ __forceinline__ void solve_secant(const xrt_oe_params& p, const Ray& r, const Decision& d, double& t1,
+__device__ __forceinline__ void solve_secant(const xrt_oe_params& p, const SurfDiv& sd, const Ray& r,
+                                             const Decision& d, double& t1,
                                              double& t2, double& dz1, double& dz2, double& x2, double& y2,
                                              double& z2) {
   // _use_my_method (base.py:933-959)
@@ -628,7 +647,7 @@ __device__ __forceinline__ void solve_secant(const xrt_oe_params& p, const Ray& 
     t2 = t - (t1 - t) * dz / (dz1 - dz);
     if (t2 < d.tMin) t2 = d.tMin;
     if (t2 > d.tMax) t2 = d.tMax;
-    dz2 = find_dz<SURF>(p, t2, r, x2, y2, z2);
+    dz2 = find_dz<SURF>(p, sd, t2, r, x2, y2, z2);
     if (sgn(dz2) == sgn(dz1)) {
       t1 = t;
       dz1 = dz;
@@ -638,7 +657,8 @@ __device__ __forceinline__ void solve_secant(const xrt_oe_params& p, const Ray& 
 }
 
 template <int SURF>
-__device__ __forceinline__ void solve_brent(const xrt_oe_params& p, const Ray& r, double& t1, double& t2,
+__device__ __forceinline__ void solve_brent(const xrt_oe_params& p, const SurfDiv& sd, const Ray& r, double& t1,
+                                            double& t2,
                                             double& dz1, double& dz2, double& x2, double& y2, double& z2) {
   // _use_Brent_method (base.py:961-1048)
   if (fabs(dz1) < fabs(dz2)) {
@@ -669,7 +689,7 @@ __device__ __forceinline__ void solve_brent(const xrt_oe_params& p, const Ray& r
     const bool conds = cond1 || cond2 || cond3 || cond4 || cond5;
     if (conds) xs = (xa + xb) / 2.0;
     mflag = conds;
-    const double fs = find_dz<SURF>(p, xs, r, x2, y2, z2);
+    const double fs = find_dz<SURF>(p, sd, xs, r, x2, y2, z2);
     xd = xc;
     xc = xb;
     fc = fb;
@@ -729,7 +749,7 @@ __device__ __forceinline__ void copy_ray(const xrt_beam& dst, const xrt_beam& sr
 }
 
 #ifndef XRTB_REFLECT_MINBLOCKS
-#define XRTB_REFLECT_MINBLOCKS 3
+#define XRTB_REFLECT_MINBLOCKS 4
 #endif
 template <int SURF, int MAT>
 __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kernel(size_t n, xrt_oe_params p, xrt_material_params m,
@@ -768,17 +788,9 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
     } else {
       const Decision d = sdec;
       Ray r = load_ray(in, i);
-      const double E = in.E[i];
-      double path = in.path[i];
-      double Jss = in.Jss[i], Jpp = in.Jpp[i];
-      cplx Jsp = ld_c(in.Jsp, i);
       const bool amp = in.Es != nullptr;
-      cplx Es = cplx{0, 0}, Ep = cplx{0, 0};
-      if (amp) {
-        Es = ld_c(in.Es, i);
-        Ep = ld_c(in.Ep, i);
-      }
       to_local(p, r);
+      const SurfDiv sd = make_surf_div<SURF>(p);
       double t1, t2, x1, y1, z1, x2, y2, z2;
       bool ind1 = false;
       if (p.no_intersection) {
@@ -791,8 +803,8 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
       } else {
         // bracketing + intersection (base.py:848-885)
         bracket(p, d.axis, d.neg, r, t1, t2);
-        double dz1 = find_dz<SURF>(p, t1, r, x1, y1, z1);
-        double dz2 = find_dz<SURF>(p, t2, r, x2, y2, z2);
+        double dz1 = find_dz<SURF>(p, sd, t1, r, x1, y1, z1);
+        double dz2 = find_dz<SURF>(p, sd, t2, r, x2, y2, z2);
         ind1 = dz1 <= 0.0;             // lost: solution t1
         const bool ind2 = dz2 >= 0.0;  // over: solution t2
         if (ind1 || ind2) dz2 = 0.0;
@@ -804,14 +816,16 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
         }
         if (!(ind1 || ind2)) {
           if (d.brent)
-            solve_brent<SURF>(p, r, t1, t2, dz1, dz2, x2, y2, z2);
+            solve_brent<SURF>(p, sd, r, t1, t2, dz1, dz2, x2, y2, z2);
           else
-            solve_secant<SURF>(p, r, d, t1, t2, dz1, dz2, x2, y2, z2);
+            solve_secant<SURF>(p, sd, r, d, t1, t2, dz1, dz2, x2, y2, z2);
         }
       }
       const double tMax = t2;
+      // Stores are issued as soon as a value is final (geometry first, fields last): outputs never alias inputs
+      // (include/xrt_b200.h), and the short live ranges keep the 35 output values out of local memory.
       // lb.x,y,z = intersection point (parametric: s, phi, r)
-      double lx = x2, ly = y2, lz = z2;
+      const double lx = x2, ly = y2, lz = z2;
       double cx = lx, cy = ly, cz = lz;  // Cartesian copy for rays_good
       param_to_xyz<SURF>(p, cx, cy, cz);
       // rays_good, shape 'rect' (base.py:1115-1139)
@@ -827,21 +841,30 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
       if (outside) st = p.lostNum;
       if (over) st = 3;
       if (ind1) st = p.lostNum;  // reflect.py:706-707
+      if (hasLb) {
+        if (lb.s) {
+          lb.s[i] = lx;
+          lb.phi[i] = ly;
+          lb.r[i] = lz;
+        }
+        lb.x[i] = cx;
+        lb.y[i] = cy;
+        lb.z[i] = cz;
+        lb.state[i] = st;
+      }
 
       double la = r.a, lbb = r.b, lc = r.c;
       double theta = 0.0;
-      double gJss = Jss, gJpp = Jpp;
-      cplx gJsp = Jsp, gEs = Es, gEp = Ep;
+      double bdn = 0.0, bds = 0.0, bos = 0.0, cY = 1.0, sY = 0.0;
       if (st == 1) {
         ++ngoodN;
-        path += tMax;
         double nrm[6];
-        local_normal<SURF>(p, lx, ly, nrm);
-        double bdn = la * nrm[0] + lbb * nrm[1] + lc * nrm[2];
+        local_normal<SURF>(p, sd, lx, ly, nrm);
+        bdn = la * nrm[0] + lbb * nrm[1] + lc * nrm[2];
         if (bdn < -1.0) bdn = -1.0;
         if (bdn > 1.0) bdn = 1.0;
         theta = acos(bdn) - kPi / 2;
-        const double bds = p.asymmetric ? (la * nrm[3] + lbb * nrm[4] + lc * nrm[5]) : bdn;
+        bds = p.asymmetric ? (la * nrm[3] + lbb * nrm[4] + lc * nrm[5]) : bdn;
         double ao, bo, co;
         if (MAT == 3) {
           // crystal as a grating (reflect.py:568-612, :451-469); sgbdn is taken per ray here -- all good rays
@@ -855,7 +878,7 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
           const double CH = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8;
           const double bdg = la * g0 + lbb * g1 + lc * g2;
           const double G2 = g0 * g0 + g1 * g1 + g2 * g2;
-          const double ol = 1.0 * CH / E * 1e-7;
+          const double ol = 1.0 * CH / in.E[i] * 1e-7;
           const double u = bds * bds - 2.0 * bdg * ol - G2 * (ol * ol);
           const double dn = bds + (-1.0) * sqrt(fabs(u));
           ao = la - nrm[3] * dn + g0 * ol;
@@ -865,6 +888,7 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
           ao = ao / nn;
           bo = bo / nn;
           co = co / nn;
+          bos = ao * nrm[3] + bo * nrm[4] + co * nrm[5];
         } else {
           ao = la - nrm[0] * 2.0 * bdn;
           bo = lbb - nrm[1] * 2.0 * bdn;
@@ -875,8 +899,51 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
         lc = co;
         // polarisation frame (reflect.py:948-953; beams.py:448-479)
         const double rollAngle = p.roll + atan2(nrm[3], nrm[5]);
-        double cY, sY;
         sincos(rollAngle, &sY, &cY);  // cos(-x) == cos(x) and sin(-x) == -sin(x) exactly (numpy and CUDA alike)
+      }
+      if (hasLb) {
+        lb.a[i] = la;
+        lb.b[i] = lbb;
+        lb.c[i] = lc;
+        if (lb.theta) lb.theta[i] = theta;
+      }
+      // virgin-local beam -> global (reflect.py:1112-1136, :125-135)
+      const bool goodAfter = p.created_by_diffract ? (st == 1) : (st == 1 || st == 2);
+      {
+        Ray v{cx, cy, cz, la, lbb, lc};
+        to_virgin(p, v);
+        fmin3[0] = v.x;
+        fmin3[1] = v.y;
+        fmin3[2] = v.z;
+        fmax3[0] = v.x;
+        fmax3[1] = v.y;
+        fmax3[2] = v.z;
+        if (goodAfter) {
+          if (p.to_global) virgin_to_global(p, v);
+          gb.x[i] = v.x;
+          gb.y[i] = v.y;
+          gb.z[i] = v.z;
+          gb.a[i] = v.a;
+          gb.b[i] = v.b;
+          gb.c[i] = v.c;
+          gb.state[i] = st;
+        }
+      }
+
+      // the field part of the ray is only fetched now: 12 doubles less to keep alive across the solver
+      const double E = in.E[i];
+      double path = in.path[i];
+      double Jss = in.Jss[i], Jpp = in.Jpp[i];
+      cplx Jsp = ld_c(in.Jsp, i);
+      cplx Es = cplx{0, 0}, Ep = cplx{0, 0};
+      if (amp) {
+        Es = ld_c(in.Es, i);
+        Ep = ld_c(in.Ep, i);
+      }
+      double gJss = Jss, gJpp = Jpp;
+      cplx gJsp = Jsp, gEs = Es, gEp = Ep;
+      if (st == 1) {
+        path += tMax;
         {
           const double c = cY, s = -sY;
           const double c2 = c * c, s2 = s * s, cs = c * s;
@@ -898,10 +965,7 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
         // amplitudes
         cplx ras = cplx{1.0, 0.0}, rap = cplx{1.0, 0.0};
         if (MAT == 1 || MAT == 2) mirror_amplitude(m, tab, E, bdn, ras, rap, &oor);
-        if (MAT == 3) {
-          const double bos = ao * nrm[3] + bo * nrm[4] + co * nrm[5];
-          crystal_amplitude(m, tab, E, bds, bos, bdn, ras, rap, &oor);
-        }
+        if (MAT == 3) crystal_amplitude(m, tab, E, bds, bos, bdn, ras, rap, &oor);
         if (MAT != 0) {
           if (isnan(ras.re) || isnan(ras.im)) ras = cplx{0.0, 0.0};
           if (isnan(rap.re) || isnan(rap.im)) rap = cplx{0.0, 0.0};
@@ -940,19 +1004,7 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
           gEp = cplx{-sY * Es.re + cY * Ep.re, -sY * Es.im + cY * Ep.im};
         }
       }
-      // local beam
       if (hasLb) {
-        if (lb.s) {
-          lb.s[i] = lx;
-          lb.phi[i] = ly;
-          lb.r[i] = lz;
-        }
-        lb.x[i] = cx;
-        lb.y[i] = cy;
-        lb.z[i] = cz;
-        lb.a[i] = la;
-        lb.b[i] = lbb;
-        lb.c[i] = lc;
         lb.path[i] = path;
         lb.E[i] = E;
         lb.Jss[i] = Jss;
@@ -962,27 +1014,8 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
           st_c(lb.Es, i, Es);
           st_c(lb.Ep, i, Ep);
         }
-        lb.state[i] = st;
-        if (lb.theta) lb.theta[i] = theta;
       }
-      // virgin-local beam -> global (reflect.py:1112-1136, :125-135)
-      Ray v{cx, cy, cz, la, lbb, lc};
-      to_virgin(p, v);
-      fmin3[0] = v.x;
-      fmin3[1] = v.y;
-      fmin3[2] = v.z;
-      fmax3[0] = v.x;
-      fmax3[1] = v.y;
-      fmax3[2] = v.z;
-      const bool goodAfter = p.created_by_diffract ? (st == 1) : (st == 1 || st == 2);
       if (goodAfter) {
-        if (p.to_global) virgin_to_global(p, v);
-        gb.x[i] = v.x;
-        gb.y[i] = v.y;
-        gb.z[i] = v.z;
-        gb.a[i] = v.a;
-        gb.b[i] = v.b;
-        gb.c[i] = v.c;
         gb.path[i] = path;
         gb.E[i] = E;
         gb.Jss[i] = gJss;
@@ -992,7 +1025,6 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
           st_c(gb.Es, i, gEs);
           st_c(gb.Ep, i, gEp);
         }
-        gb.state[i] = st;
       } else {
         // not intersected rays remain unchanged except their state (reflect.py:131-134)
         copy_ray(gb, fb, i, st, true);
@@ -1154,7 +1186,7 @@ __global__ void __launch_bounds__(256) normals_kernel(size_t n, xrt_oe_params p,
   double px = x[i], py = y[i], pz = z[i];
   xyz_to_param<SURF>(p, px, py, pz);
   double nrm[6];
-  local_normal<SURF>(p, px, py, nrm);
+  local_normal<SURF>(p, make_surf_div<SURF>(p), px, py, nrm);
   nx[i] = nrm[3];
   ny[i] = nrm[4];
   nz[i] = nrm[5];
@@ -1169,10 +1201,10 @@ __global__ void __launch_bounds__(256) surface_kernel(size_t n, xrt_oe_params p,
   double px = x[i], py = y[i], pz = 0.0;
   if (SURF == 2) {
     xyz_to_param<SURF>(p, px, py, pz);
-    pz = local_surface<SURF>(p, px, py);
+    pz = local_surface<SURF>(p, make_surf_div<SURF>(p), px, py);
     param_to_xyz<SURF>(p, px, py, pz);
   } else {
-    pz = local_surface<SURF>(p, px, py);
+    pz = local_surface<SURF>(p, make_surf_div<SURF>(p), px, py);
   }
   z[i] = pz;
 }
