@@ -135,8 +135,10 @@ typedef struct xrt_oe_params {
 } xrt_oe_params;
 
 /* Material = what get_amplitude reads (materials/material.py:348-493, materials/crystal.py:492-645). */
+struct xrt_multilayer_params;
 typedef struct xrt_material_params {
-  int kind;               /* 0 none, 1 mirror, 2 thin mirror, 3 crystal (thick Bragg, fcc/diamond, one element) */
+  int kind;               /* 0 none, 1 mirror, 2 thin mirror, 3 crystal (thick Bragg, fcc/diamond, one element),
+                             4 multilayer (reflected; `multilayer` points to the stack) */
   int nelem;
   double Z[XRT_MAX_ELEM], quantity[XRT_MAX_ELEM];
   int tab_off[XRT_MAX_ELEM], tab_len[XRT_MAX_ELEM]; /* slices of the E/f1/f2 tables */
@@ -146,7 +148,22 @@ typedef struct xrt_material_params {
   double d2f_re, d2f_im;  /* diamondToFcc = 1 + exp(i pi/2 (h+k+l)); (1, 0) for fcc */
   double f0scale;         /* 2 for diamond (F0 * 2), 1 for fcc */
   int hkl_allowed;        /* h,k,l all even or all odd */
+  const struct xrt_multilayer_params* multilayer; /* kind 4: HOST pointer to the layer stack, else NULL */
 } xrt_material_params;
+
+/* Multilayer (materials/multilayer.py:14-515), geom 'reflected': top layer / bottom layer / substrate materials
+ * (their element tables are slices of the same `tables` array the call receives), nPairs periods with the
+ * per-period thicknesses dti[nPairs], dbi[nPairs] in Angstrom (set_dti / set_dbi: constant or depth graded),
+ * interdiffusion rms.  dti/dbi live where the call's arrays live (device for xrt_reflect_f64, host for the
+ * *_host entry points, which stage them). */
+typedef struct xrt_multilayer_params {
+  xrt_material_params tLayer, bLayer, substrate;  /* kind 1; only the refractive index is used */
+  int nPairs;
+  int uniform;            /* 1: every period has dti[0], dbi[0] -- the two phase factors are taken once per ray */
+  double idThickness;     /* interdiffusion / roughness rms, Angstrom */
+  double d;               /* tThickness + bThickness: the period (grating deflection, Bragg angle) */
+  const double *dti, *dbi;
+} xrt_multilayer_params;
 
 /* Beam-wide scalars numpy takes over the whole beam. 64 slots of 8 bytes, device
  * memory.  Written by the pre-pass, read by the main pass; all-reduced (min/max) across ranks in between
@@ -252,6 +269,21 @@ int xrt_oe_surface_f64(size_t n, const xrt_oe_params* oe, const double* x, const
 
 int xrt_oe_normals_f64(size_t n, const xrt_oe_params* oe, const double* x, const double* y, const double* z,
                        double* nx, double* ny, double* nz, void* stream);
+
+/* ------------------------------------------------------------------ f2: multilayer recursion
+ * Kernel `get_amplitude_graded_multilayer` of the reference (cl/materials.cl:568-622, called from
+ * Multilayer.get_amplitude, materials/multilayer.py:471-484, through XRT_CL.run_parallel): the Parratt recursion
+ * from the substrate up, per ray, given the interface Fresnel amplitudes rbs, rtb, rvt (s and p), the layer wave
+ * vectors Qt, Qb (all complex128, n each, interleaved re/im) and the thicknesses dti, dbi [npairs].  Follows the
+ * reference's numpy statements (:432-460: p1 = exp(0.5j Q d), p2 = p1**2, r = (r_ij + r_j p2)/(1 + r_ij r_j p2)).
+ * Out: ri_s, ri_p.  Device pointers; the *_host variant stages host arrays. */
+int xrt_multilayer_f64(size_t n, int npairs, const double* rbs_s, const double* rbs_p, const double* rtb_s,
+                       const double* rtb_p, const double* rvt_s, const double* rvt_p, const double* Qt,
+                       const double* Qb, const double* dti, const double* dbi, double* ri_s, double* ri_p,
+                       void* stream);
+int xrt_multilayer_f64_host(size_t n, int npairs, const double* rbs_s, const double* rbs_p, const double* rtb_s,
+                            const double* rtb_p, const double* rvt_s, const double* rvt_p, const double* Qt,
+                            const double* Qb, const double* dti, const double* dbi, double* ri_s, double* ri_p);
 
 /* ------------------------------------------------------------------ f1 (next row): device histogram
  * np.histogram2d(y, x, bins=[ny, nx], range=[[ey0, eyN], [ex0, exN]], weights=w1 (+ w2)) as do_hist2d

@@ -199,3 +199,90 @@ class CrystalDiamond(object):
         polFactor = np.cos(2. * thetaB)
         curveP = for_one_polarization(polFactor)
         return curveS, curveP
+
+
+class Multilayer(object):
+    """Multilayer.get_amplitude, geom 'reflected', numpy branch (materials/multilayer.py:254-508; thickness laws
+    set_dti / set_dbi :187-215).  tLayer, bLayer, substrate: oracle Material."""
+    kind = 'multilayer'
+    geom = 'reflected'
+
+    def __init__(self, tLayer, tThickness, bLayer, bThickness, nPairs, substrate, tThicknessLow=0., bThicknessLow=0.,
+                 idThickness=0., power=2.):
+        self.tLayer, self.bLayer, self.substrate = tLayer, bLayer, substrate
+        self.nPairs = int(nPairs)
+        self.power = power
+        self.tThicknessHigh, self.tThicknessLow = float(tThickness), float(tThicknessLow)
+        self.bThicknessHigh, self.bThicknessLow = float(bThickness), float(bThicknessLow)
+        self.idThickness = idThickness
+        self.d = float(self.tThicknessHigh + self.bThicknessHigh)
+        self.dti = self._graded(self.tThicknessHigh, self.tThicknessLow)
+        self.dbi = self._graded(self.bThicknessHigh, self.bThicknessLow)
+
+    def _graded(self, high, low):
+        if low:
+            layers = np.arange(1, self.nPairs+1)
+            qRoot = (high/low)**(1./self.power)
+            qB = (self.nPairs-qRoot) / (qRoot-1.)
+            qA = high * (qB+1)**self.power
+            return qA * (qB+layers)**(-self.power)
+        return np.ones(self.nPairs) * float(high)
+
+    def fresnel_terms(self, E, beamInDotNormal):
+        """The interface amplitudes and layer wave vectors the reference hands to its accelerator kernel
+        (multilayer.py:364-409, :471-477)."""
+        k = E / CHBAR
+        nt = self.tLayer.get_refractive_index(E).conjugate()
+        nb = self.bLayer.get_refractive_index(E).conjugate()
+        ns = self.substrate.get_refractive_index(E).conjugate()
+        Q = 2 * k * abs(beamInDotNormal)
+        Q2 = Q**2
+        k28 = 8 * k**2
+        Qt = (Q2 + (nt-1)*k28)**0.5
+        Qb = (Q2 + (nb-1)*k28)**0.5
+        Qs = (Q2 + (ns-1)*k28)**0.5
+        id2 = self.idThickness**2
+        roughvt = np.exp(-0.5 * Q * Qt * id2)
+        rvt_s = np.complex128((Q-Qt) / (Q+Qt) * roughvt)
+        rvt_p = np.complex128((Q*nt - Qt/nt) / (Q*nt + Qt/nt) * roughvt)
+        roughtb = np.exp(-0.5 * Qt * Qb * id2)
+        rtb_s = np.complex128((Qt-Qb) / (Qt+Qb) * roughtb)
+        rtb_p = np.complex128((Qt/nt*nb - Qb/nb*nt) / (Qt/nt*nb + Qb/nb*nt) * roughtb)
+        rmsbs = id2
+        roughbs = np.exp(-0.5 * Qb * Qs * rmsbs)
+        rbs_s = np.complex128((Qb-Qs) / (Qb+Qs) * roughbs)
+        rbs_p = np.complex128((Qb/nb*ns - Qs/ns*nb) / (Qb/nb*ns + Qs/ns*nb) * roughbs)
+        return dict(rbs_s=rbs_s, rbs_p=rbs_p, rtb_s=rtb_s, rtb_p=rtb_p, rvt_s=rvt_s, rvt_p=rvt_p, Qt=Qt, Qb=Qb, nt=nt)
+
+    def recursion(self, f):
+        rj_s, rj_p = f['rbs_s'], f['rbs_p']
+        rbt_s, rbt_p = -f['rtb_s'], -f['rtb_p']
+        ri_s = np.zeros_like(rj_s)
+        ri_p = np.zeros_like(rj_p)
+        for i in reversed(range(2*self.nPairs)):
+            if i % 2 == 0:
+                if i == 0:
+                    rij_s, rij_p = f['rvt_s'], f['rvt_p']
+                else:
+                    rij_s, rij_p = rbt_s, rbt_p
+                iQT = f['Qt'] * self.dti[i//2]
+            else:
+                rij_s, rij_p = f['rtb_s'], f['rtb_p']
+                iQT = f['Qb'] * self.dbi[i//2]
+            p1i = np.complex128(np.exp(0.5j*iQT))
+            p2i = p1i**2
+            rj2i_s = rj_s * p2i
+            rj2i_p = rj_p * p2i
+            ri_s = (rij_s + rj2i_s) / (1 + rij_s*rj2i_s)
+            ri_p = (rij_p + rj2i_p) / (1 + rij_p*rj2i_p)
+            rj_s, rj_p = ri_s, ri_p
+        return ri_s, ri_p
+
+    def get_amplitude(self, E, beamInDotNormal, x=None, y=None):
+        f = self.fresnel_terms(E, beamInDotNormal)
+        ri_s, ri_p = self.recursion(f)
+        nt = f['nt']
+        nn = nt[0] if isinstance(nt, np.ndarray) else nt
+        if (nn - 1) > 0:
+            return ri_s.conjugate(), ri_p.conjugate()
+        return ri_s, ri_p

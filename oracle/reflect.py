@@ -398,7 +398,8 @@ def reflect_local(oe, good, lb, vlb, pitch, roll, yaw, dx=None, dy=None, dz=None
             beamInDotSurfaceNormal = lb.a[goodN]*oeNormal[-3] + lb.b[goodN]*oeNormal[-2] + lb.c[goodN]*oeNormal[-1]
         else:
             beamInDotSurfaceNormal = beamInDotNormal
-        if isCrystal:
+        isMultilayer = material is not None and material.kind == 'multilayer'
+        if isCrystal or isMultilayer:
             # _get_asymmetric_reflection_grating (reflect.py:568-612)
             normalDotSurfNormal = oeNormal[0]*oeNormal[-3] + oeNormal[1]*oeNormal[-2] + oeNormal[2]*oeNormal[-1]
             bdn = beamInDotNormal.sum() / len(beamInDotNormal)
@@ -429,6 +430,8 @@ def reflect_local(oe, good, lb, vlb, pitch, roll, yaw, dx=None, dy=None, dz=None
                 beamOutDotSurfaceNormal = a_out*oeNormal[-3] + b_out*oeNormal[-2] + c_out*oeNormal[-1]
                 refl = matSur.get_amplitude(lb.E[goodN], beamInDotSurfaceNormal, beamOutDotSurfaceNormal,
                                             beamInDotNormal)
+            elif isMultilayer:  # reflect.py:999-1003
+                refl = matSur.get_amplitude(lb.E[goodN], beamInDotSurfaceNormal, lb.x[goodN], lb.y[goodN])
             else:
                 refl = matSur.get_amplitude(lb.E[goodN], beamInDotNormal, True)
         else:

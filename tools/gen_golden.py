@@ -615,8 +615,45 @@ def gen_hist():
     d['rayFlags'] = np.array([','.join(str(f) for f in c[1]) for c in cases])
     save('plot_histograms', **d)
 
+# ------------------------------------------------------------------------------------------------ multilayers
+def gen_multilayer():
+    W, Si, Mo, C = (rm.Material('W', rho=19.3), rm.Material('Si', rho=2.33), rm.Material('Mo', rho=10.28),
+                    rm.Material('C', rho=2.26))
+    stacks = {
+        'wsi': dict(tLayer=W, tThickness=12., bLayer=Si, bThickness=22., nPairs=60, substrate=Si, idThickness=2.),
+        'moc_graded': dict(tLayer=Mo, tThickness=25., bLayer=C, bThickness=35., nPairs=40, substrate=Si,
+                           tThicknessLow=15., bThicknessLow=20., idThickness=3., power=2.),
+    }
+    d = {}
+    rng = np.random.RandomState(151)
+    for name, kw in stacks.items():
+        ml = rm.Multilayer(**kw)
+        E0 = 9000.
+        thB = float(ml.get_Bragg_angle(E0) - ml.get_dtheta(E0))
+        n = 3000
+        theta = np.linspace(0.3*thB, 2.2*thB, n)
+        E = E0 + rng.uniform(-30, 30, n)
+        bdn = -np.sin(theta)
+        rs, rp = ml.get_amplitude(E, bdn)
+        d.update({name + '_E': E, name + '_bdn': bdn, name + '_rs': rs, name + '_rp': rp, name + '_dti': ml.dti,
+                  name + '_dbi': ml.dbi, name + '_thB': thB, name + '_d': ml.d})
+        print(name, 'peak |rs|^2', (abs(rs)**2).max(), 'thetaB', thB)
+    save('multilayer_amplitudes', **d)
+    # a flat multilayer mirror in a beam line
+    bl = raycing.BeamLine()
+    ml = rm.Multilayer(**stacks['wsi'])
+    thB = float(ml.get_Bragg_angle(9000.) - ml.get_dtheta(9000.))
+    beam = _source_beam(bl, 4000, 152, dx=0.2, dz=0.05, dxprime=1e-4, dzprime=2e-4, energies=(8950, 9050))
+    oe = roe.OE(bl, 'mlm', center=(0, 1e4, 0), pitch=thB, material=ml, limPhysX=[-5, 5], limPhysY=[-80, 80])
+    dd = _capture_reflect(oe, beam)
+    dd.update(_oe_params(oe))
+    st = dd['gb_state']
+    print('multilayer mirror', {int(x): int((st == x).sum()) for x in np.unique(st)},
+          'mean R', float((dd['gb_Jss'] + dd['gb_Jpp'])[st == 1].mean() / (dd['in_Jss'] + dd['in_Jpp'])[st == 1].mean()))
+    save('reflect_multilayer_flat', thB=thB, **dd)
 
-SECTIONS = {'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+
+SECTIONS = {'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)

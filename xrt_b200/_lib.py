@@ -45,6 +45,8 @@ PROTOTYPES = {
                               [c_int, c_int] + [c_dp] * 6 + [c_dp, c_dp, c_dp, c_dp]),
     'xrt_oe_surface_f64': (c_int, [c_sz, c_dp] + [c_dp] * 3 + [c_dp]),
     'xrt_oe_normals_f64': (c_int, [c_sz, c_dp] + [c_dp] * 6 + [c_dp]),
+    'xrt_multilayer_f64': (c_int, [c_sz, c_int] + [c_dp] * 12 + [c_dp]),
+    'xrt_multilayer_f64_host': (c_int, [c_sz, c_int] + [c_dp] * 12),
     'xrt_plot_hist_f64': (c_int, [c_sz, c_dp, c_dp]),
     'xrt_hist2d_f64': (c_int, [c_sz, c_dp, c_dp, c_dp, c_dp, c_dp, c_int, c_dp, c_int, c_dp, c_int, c_dp, c_dp]),
     'xrt_undulator_imap_f64': (c_int, [c_sz, c_int] + [c_dbl] * 7 + [c_int] + [c_dp] * 13 + [c_int, c_dp]),

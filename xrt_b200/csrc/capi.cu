@@ -164,7 +164,7 @@ int xrt_b200_init(int device) {
 int xrt_b200_sm_count(void) { return num_sms(); }
 
 size_t xrt_b200_sizeof(int which) {
-  return which == 0 ? sizeof(xrt_beam) : which == 1 ? sizeof(xrt_oe_params) : which == 2 ? sizeof(xrt_material_params) : which == 3 ? sizeof(xrt_plane_params) : which == 4 ? sizeof(xrt_source_params) : which == 5 ? sizeof(xrt_plot_params) : 0;
+  return which == 0 ? sizeof(xrt_beam) : which == 1 ? sizeof(xrt_oe_params) : which == 2 ? sizeof(xrt_material_params) : which == 3 ? sizeof(xrt_plane_params) : which == 4 ? sizeof(xrt_source_params) : which == 5 ? sizeof(xrt_plot_params) : which == 6 ? sizeof(xrt_multilayer_params) : 0;
 }
 
 const char* xrt_b200_last_error(void) { return g_err; }
@@ -321,6 +321,20 @@ int xrt_get_amplitude_f64_host(size_t n, const xrt_material_params* mat, const d
   if (dout.alloc(2 * n * 16) || dcnt.alloc(8)) return 1;
   XRTB_CUDA_CHECK(cudaMemsetAsync(dcnt.p, 0, 8, st));
   double* o = dout.as<double>();
+  // a multilayer's thickness arrays are host arrays at this entry point: stage them and patch the pointers
+  xrt_material_params mcopy = *mat;
+  xrt_multilayer_params mlcopy;
+  DevBuf ddti, ddbi;
+  if (mat->kind == 4 && mat->multilayer) {
+    mlcopy = *mat->multilayer;
+    XRTB_REQUIRE(mlcopy.nPairs >= 0 && mlcopy.dti && mlcopy.dbi, "get_amplitude: multilayer thickness arrays missing");
+    if (ddti.upload(mlcopy.dti, (size_t)mlcopy.nPairs * 8, st) || ddbi.upload(mlcopy.dbi, (size_t)mlcopy.nPairs * 8, st))
+      return 1;
+    mlcopy.dti = ddti.as<double>();
+    mlcopy.dbi = ddbi.as<double>();
+    mcopy.multilayer = &mlcopy;
+  }
+  mat = &mcopy;
   int rc = amplitude_device(n, mat, dt.as<double>(), table_len, dE.as<double>(), dIn.as<double>(),
                             bOut ? dOut.as<double>() : nullptr, bH ? dH.as<double>() : nullptr, o, o + 2 * n,
                             dcnt.as<unsigned long long>(), st);
@@ -334,6 +348,47 @@ int xrt_get_amplitude_f64_host(size_t n, const xrt_material_params* mat, const d
     set_last_error("get_amplitude: %llu energies are out of the f1/f2 data table range", cnt);
     return 3;
   }
+  return 0;
+}
+
+// ------------------------------------------------------------------ f2: multilayer recursion
+static int all_equal(const double* v, int n) {
+  for (int i = 1; i < n; ++i)
+    if (v[i] != v[0]) return 0;
+  return 1;
+}
+
+int xrt_multilayer_f64(size_t n, int npairs, const double* rbs_s, const double* rbs_p, const double* rtb_s,
+                       const double* rtb_p, const double* rvt_s, const double* rvt_p, const double* Qt,
+                       const double* Qb, const double* dti, const double* dbi, double* ri_s, double* ri_p,
+                       void* stream) {
+  return multilayer_device(n, npairs, 0, rbs_s, rbs_p, rtb_s, rtb_p, rvt_s, rvt_p, Qt, Qb, dti, dbi, ri_s, ri_p,
+                           (cudaStream_t)stream);
+}
+
+int xrt_multilayer_f64_host(size_t n, int npairs, const double* rbs_s, const double* rbs_p, const double* rtb_s,
+                            const double* rtb_p, const double* rvt_s, const double* rvt_p, const double* Qt,
+                            const double* Qb, const double* dti, const double* dbi, double* ri_s, double* ri_p) {
+  if (n == 0) return 0;
+  XRTB_REQUIRE(npairs >= 0 && dti && dbi, "multilayer: nPairs >= 0 and the thickness arrays are required");
+  cudaStream_t st = 0;
+  const double* in[8] = {rbs_s, rbs_p, rtb_s, rtb_p, rvt_s, rvt_p, Qt, Qb};
+  DevBuf d[8], ddti, ddbi, dout;
+  for (int k = 0; k < 8; ++k) {
+    XRTB_REQUIRE(in[k] != nullptr, "multilayer: NULL argument");
+    if (d[k].upload(in[k], n * 16, st)) return 1;
+  }
+  if (ddti.upload(dti, (size_t)npairs * 8, st) || ddbi.upload(dbi, (size_t)npairs * 8, st)) return 1;
+  if (dout.alloc(2 * n * 16)) return 1;
+  double* o = dout.as<double>();
+  const int uniform = all_equal(dti, npairs) && all_equal(dbi, npairs);
+  int rc = multilayer_device(n, npairs, uniform, d[0].as<double>(), d[1].as<double>(), d[2].as<double>(),
+                             d[3].as<double>(), d[4].as<double>(), d[5].as<double>(), d[6].as<double>(),
+                             d[7].as<double>(), ddti.as<double>(), ddbi.as<double>(), o, o + 2 * n, st);
+  if (rc) return rc;
+  XRTB_CUDA_CHECK(cudaMemcpyAsync(ri_s, o, n * 16, cudaMemcpyDeviceToHost, st));
+  XRTB_CUDA_CHECK(cudaMemcpyAsync(ri_p, o + 2 * n, n * 16, cudaMemcpyDeviceToHost, st));
+  XRTB_CUDA_CHECK(cudaStreamSynchronize(st));
   return 0;
 }
 

@@ -37,6 +37,10 @@ double reduction_decode(unsigned long long slot);
 int surface_device(size_t n, const xrt_oe_params* oe, const double* x, const double* y, double* z, cudaStream_t st);
 int normals_device(size_t n, const xrt_oe_params* oe, const double* x, const double* y, const double* z, double* nx,
                    double* ny, double* nz, cudaStream_t st);
+int multilayer_device(size_t n, int npairs, int uniform, const double* rbs_s, const double* rbs_p,
+                      const double* rtb_s, const double* rtb_p, const double* rvt_s, const double* rvt_p,
+                      const double* Qt, const double* Qb, const double* dti, const double* dbi, double* ri_s,
+                      double* ri_p, cudaStream_t st);
 int amplitude_device(size_t n, const xrt_material_params* mat, const double* tables, size_t table_len,
                      const double* E, const double* bIn, const double* bOut, const double* bH, double* rs, double* rp,
                      unsigned long long* oor_count, cudaStream_t st);

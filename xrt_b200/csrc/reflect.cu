@@ -613,6 +613,149 @@ __device__ __forceinline__ void crystal_amplitude(const xrt_material_params& m, 
   rp = bragg_one_pol(cos(2.0 * thetaB), alpha, chih, chih_, b);
 }
 
+// ---------------------------------------------------------------- f2: multilayer (materials/multilayer.py)
+// np.exp on complex128 = glibc cexp: exp(re) * (cos(im), sin(im)), with sin(im) = im, cos(im) = 1 below DBL_MIN
+__device__ __forceinline__ cplx cexp_np(cplx z) {
+  double sn = z.im, cs = 1.0;
+  if (fabs(z.im) > 2.2250738585072014e-308) sincos(z.im, &sn, &cs);
+  const double e = exp(z.re);
+  return cplx{e * cs, e * sn};
+}
+
+// one step of the Parratt recursion (multilayer.py:453-456): (rij + rj*p2) / (1 + rij*(rj*p2))
+__device__ __forceinline__ cplx parratt_step(cplx rij, cplx rj, cplx p2) {
+  const cplx rj2 = cmul_np(rj, p2);
+  const cplx den = cmul_np(rij, rj2);
+  return cdiv(cadd(rij, rj2), cplx{1.0 + den.re, 0.0 + den.im});
+}
+
+// p2i = exp(0.5j * (Q * d))**2 (multilayer.py:440-450)
+__device__ __forceinline__ cplx layer_phase(cplx Q, double d) {
+  const cplx iQT = cmul_np(Q, cplx{d, 0.0});
+  const cplx p1 = cexp_np(cmul_np(cplx{0.0, 0.5}, iQT));
+  return csquare_np(p1);
+}
+
+// the loop `for i in reversed(range(2*nPairs))` of Multilayer.get_amplitude, geom 'reflected' (multilayer.py:432-460)
+// == kernel get_amplitude_graded_multilayer (cl/materials.cl:568-622)
+__device__ __forceinline__ void multilayer_recursion(int npairs, int uniform, cplx rbs_s, cplx rbs_p, cplx rtb_s,
+                                                     cplx rtb_p, cplx rvt_s, cplx rvt_p, cplx Qt, cplx Qb,
+                                                     const double* __restrict__ dti,
+                                                     const double* __restrict__ dbi, cplx& ri_s, cplx& ri_p) {
+  cplx rj_s = rbs_s, rj_p = rbs_p;
+  const cplx rbt_s = cplx{-rtb_s.re, -rtb_s.im}, rbt_p = cplx{-rtb_p.re, -rtb_p.im};
+  cplx p2t = cplx{1.0, 0.0}, p2b = cplx{1.0, 0.0};
+  if (uniform && npairs > 0) {
+    p2t = layer_phase(Qt, dti[0]);
+    p2b = layer_phase(Qb, dbi[0]);
+  }
+  for (int i = 2 * npairs - 1; i >= 0; --i) {
+    cplx rij_s, rij_p, p2;
+    if (i & 1) {
+      rij_s = rtb_s;
+      rij_p = rtb_p;
+      p2 = uniform ? p2b : layer_phase(Qb, dbi[i >> 1]);
+    } else {
+      rij_s = (i == 0) ? rvt_s : rbt_s;
+      rij_p = (i == 0) ? rvt_p : rbt_p;
+      p2 = uniform ? p2t : layer_phase(Qt, dti[i >> 1]);
+    }
+    rj_s = parratt_step(rij_s, rj_s, p2);
+    rj_p = parratt_step(rij_p, rj_p, p2);
+  }
+  ri_s = rj_s;
+  ri_p = rj_p;
+  if (npairs <= 0) ri_s = ri_p = cplx{0.0, 0.0};  // ri = zeros_like(rj) when the loop does not run
+}
+
+// (Qi/ni*nj - Qj/nj*ni) / (Qi/ni*nj + Qj/nj*ni) (multilayer.py:391-392, :404-405)
+__device__ __forceinline__ cplx fresnel_p(cplx Qi, cplx ni, cplx Qj, cplx nj) {
+  const cplx a = cmul_np(cdiv(Qi, ni), nj);
+  const cplx b = cmul_np(cdiv(Qj, nj), ni);
+  return cdiv(csub(a, b), cadd(a, b));
+}
+
+// Multilayer.get_amplitude, geom 'reflected', all three materials present (multilayer.py:364-508)
+__device__ __forceinline__ void multilayer_amplitude(const xrt_multilayer_params& ml, const Tables& tab, double E,
+                                                     double bdn, cplx& rs, cplx& rp, int* oor) {
+  const double CHBAR = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8 / 6.283185307179586476925286766559;
+  const double k = E / CHBAR;
+  const cplx nt = cconj(refractive_index(ml.tLayer, tab, E, oor));
+  const cplx nb = cconj(refractive_index(ml.bLayer, tab, E, oor));
+  const cplx ns = cconj(refractive_index(ml.substrate, tab, E, oor));
+  const double Q = 2.0 * k * fabs(bdn);
+  const double Q2 = Q * Q;
+  const double k28 = 8.0 * (k * k);
+  cplx z = cmul_np(cplx{nt.re - 1.0, nt.im}, cplx{k28, 0.0});
+  const cplx Qt = csqrt_(cplx{Q2 + z.re, 0.0 + z.im});
+  z = cmul_np(cplx{nb.re - 1.0, nb.im}, cplx{k28, 0.0});
+  const cplx Qb = csqrt_(cplx{Q2 + z.re, 0.0 + z.im});
+  z = cmul_np(cplx{ns.re - 1.0, ns.im}, cplx{k28, 0.0});
+  const cplx Qs = csqrt_(cplx{Q2 + z.re, 0.0 + z.im});
+  const cplx id2 = cplx{ml.idThickness * ml.idThickness, 0.0};
+  const cplx Qc = cplx{Q, 0.0};
+  // vacuum - top
+  const cplx roughvt = cexp_np(cmul_np(cmul_np(cplx{-0.5 * Q, 0.0}, Qt), id2));
+  const cplx rvt_s = cmul_np(cdiv(cplx{Q - Qt.re, 0.0 - Qt.im}, cplx{Q + Qt.re, 0.0 + Qt.im}), roughvt);
+  cplx a = cmul_np(Qc, nt), b = cdiv(Qt, nt);
+  const cplx rvt_p = cmul_np(cdiv(csub(a, b), cadd(a, b)), roughvt);
+  // top - bottom
+  const cplx roughtb = cexp_np(cmul_np(cmul_np(cmul_np(cplx{-0.5, 0.0}, Qt), Qb), id2));
+  const cplx rtb_s = cmul_np(cdiv(csub(Qt, Qb), cadd(Qt, Qb)), roughtb);
+  const cplx rtb_p = cmul_np(fresnel_p(Qt, nt, Qb, nb), roughtb);
+  // bottom - substrate (rmsbs = id2 because the top layer exists, multilayer.py:402)
+  const cplx roughbs = cexp_np(cmul_np(cmul_np(cmul_np(cplx{-0.5, 0.0}, Qb), Qs), id2));
+  const cplx rbs_s = cmul_np(cdiv(csub(Qb, Qs), cadd(Qb, Qs)), roughbs);
+  const cplx rbs_p = cmul_np(fresnel_p(Qb, nb, Qs, ns), roughbs);
+  multilayer_recursion(ml.nPairs, ml.uniform, rbs_s, rbs_p, rtb_s, rtb_p, rvt_s, rvt_p, Qt, Qb, ml.dti, ml.dbi, rs,
+                       rp);
+  // multilayer.py:501-505: tabulation artefacts with n.real > 1 flip the sign convention.  The reference tests
+  // the FIRST ray's nt (complex comparison = lexicographic); here per ray (identical for x-ray energies)
+  const double nr = nt.re - 1.0;
+  if (nr > 0.0 || (nr == 0.0 && nt.im > 0.0)) {
+    rs = cconj(rs);
+    rp = cconj(rp);
+  }
+}
+
+__global__ void __launch_bounds__(256) multilayer_kernel(size_t n, int npairs, int uniform,
+                                                         const double2* __restrict__ rbs_s,
+                                                         const double2* __restrict__ rbs_p,
+                                                         const double2* __restrict__ rtb_s,
+                                                         const double2* __restrict__ rtb_p,
+                                                         const double2* __restrict__ rvt_s,
+                                                         const double2* __restrict__ rvt_p,
+                                                         const double2* __restrict__ Qt,
+                                                         const double2* __restrict__ Qb,
+                                                         const double* __restrict__ dti,
+                                                         const double* __restrict__ dbi, double2* __restrict__ ri_s,
+                                                         double2* __restrict__ ri_p) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  auto ld = [](const double2* p, size_t k) { return cplx{p[k].x, p[k].y}; };
+  cplx s, q;
+  multilayer_recursion(npairs, uniform, ld(rbs_s, i), ld(rbs_p, i), ld(rtb_s, i), ld(rtb_p, i), ld(rvt_s, i),
+                       ld(rvt_p, i), ld(Qt, i), ld(Qb, i), dti, dbi, s, q);
+  ri_s[i] = make_double2(s.re, s.im);
+  ri_p[i] = make_double2(q.re, q.im);
+}
+
+int multilayer_device(size_t n, int npairs, int uniform, const double* rbs_s, const double* rbs_p,
+                      const double* rtb_s, const double* rtb_p, const double* rvt_s, const double* rvt_p,
+                      const double* Qt, const double* Qb, const double* dti, const double* dbi, double* ri_s,
+                      double* ri_p, cudaStream_t st) {
+  XRTB_REQUIRE(rbs_s && rbs_p && rtb_s && rtb_p && rvt_s && rvt_p && Qt && Qb && dti && dbi && ri_s && ri_p,
+               "multilayer: NULL argument");
+  XRTB_REQUIRE(npairs >= 0, "multilayer: nPairs must be >= 0");
+  if (n == 0) return 0;
+  auto c = [](const double* p) { return reinterpret_cast<const double2*>(p); };
+  multilayer_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+      n, npairs, uniform, c(rbs_s), c(rbs_p), c(rtb_s), c(rtb_p), c(rvt_s), c(rvt_p), c(Qt), c(Qb), dti, dbi,
+      reinterpret_cast<double2*>(ri_s), reinterpret_cast<double2*>(ri_p));
+  XRTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 // ---------------------------------------------------------------- main pass
 struct Decision {
   int axis, neg, brent;
@@ -753,8 +896,9 @@ __device__ __forceinline__ void copy_ray(const xrt_beam& dst, const xrt_beam& sr
 #endif
 template <int SURF, int MAT>
 __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kernel(size_t n, xrt_oe_params p, xrt_material_params m,
-                                                           Tables tab, xrt_beam in, xrt_beam fb, xrt_beam gb,
-                                                           xrt_beam lb, unsigned long long* red) {
+                                                           xrt_multilayer_params ml, Tables tab, xrt_beam in,
+                                                           xrt_beam fb, xrt_beam gb, xrt_beam lb,
+                                                           unsigned long long* red) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const double inf = __longlong_as_double(0x7ff0000000000000ll);
   double fmin3[3] = {inf, inf, inf}, fmax3[3] = {-inf, -inf, -inf};
@@ -866,12 +1010,12 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
         theta = acos(bdn) - kPi / 2;
         bds = p.asymmetric ? (la * nrm[3] + lbb * nrm[4] + lc * nrm[5]) : bdn;
         double ao, bo, co;
-        if (MAT == 3) {
-          // crystal as a grating (reflect.py:568-612, :451-469); sgbdn is taken per ray here -- all good rays
-          // hit the same side of the crystal in the supported geometries (documented in DESIGN.md)
+        if (MAT == 3 || MAT == 4) {
+          // crystal / multilayer as a grating (reflect.py:568-612, :451-469); sgbdn is taken per ray here -- all
+          // good rays hit the same side of the crystal in the supported geometries (documented in DESIGN.md)
           const double ndsn = nrm[0] * nrm[3] + nrm[1] * nrm[4] + nrm[2] * nrm[5];
           const double sgbdn = (bdn < 0.0) ? 1.0 : -1.0;
-          const double wHd = (1.0 + 0.0) / (m.d * 1e-7);
+          const double wHd = (1.0 + 0.0) / ((MAT == 4 ? ml.d : m.d) * 1e-7);
           const double g0 = (nrm[0] - ndsn * nrm[3]) * wHd * sgbdn;
           const double g1 = (nrm[1] - ndsn * nrm[4]) * wHd * sgbdn;
           const double g2 = (nrm[2] - ndsn * nrm[5]) * wHd * sgbdn;
@@ -966,6 +1110,7 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
         cplx ras = cplx{1.0, 0.0}, rap = cplx{1.0, 0.0};
         if (MAT == 1 || MAT == 2) mirror_amplitude(m, tab, E, bdn, ras, rap, &oor);
         if (MAT == 3) crystal_amplitude(m, tab, E, bds, bos, bdn, ras, rap, &oor);
+        if (MAT == 4) multilayer_amplitude(ml, tab, E, bds, ras, rap, &oor);  // reflect.py:999-1003
         if (MAT != 0) {
           if (isnan(ras.re) || isnan(ras.im)) ras = cplx{0.0, 0.0};
           if (isnan(rap.re) || isnan(rap.im)) rap = cplx{0.0, 0.0};
@@ -1077,16 +1222,31 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
 // ---------------------------------------------------------------- launchers
 template <int SURF>
 static int launch_main_mat(int mat, unsigned grid, cudaStream_t st, size_t n, const xrt_oe_params& p,
-                           const xrt_material_params& m, const Tables& t, const xrt_beam& in, const xrt_beam& fb,
-                           const xrt_beam& gb, const xrt_beam& lb, unsigned long long* red) {
+                           const xrt_material_params& m, const xrt_multilayer_params& ml, const Tables& t,
+                           const xrt_beam& in, const xrt_beam& fb, const xrt_beam& gb, const xrt_beam& lb,
+                           unsigned long long* red) {
   switch (mat) {
-    case 0: reflect_main_kernel<SURF, 0><<<grid, 256, 0, st>>>(n, p, m, t, in, fb, gb, lb, red); break;
-    case 1: reflect_main_kernel<SURF, 1><<<grid, 256, 0, st>>>(n, p, m, t, in, fb, gb, lb, red); break;
-    case 2: reflect_main_kernel<SURF, 2><<<grid, 256, 0, st>>>(n, p, m, t, in, fb, gb, lb, red); break;
-    case 3: reflect_main_kernel<SURF, 3><<<grid, 256, 0, st>>>(n, p, m, t, in, fb, gb, lb, red); break;
+    case 0: reflect_main_kernel<SURF, 0><<<grid, 256, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
+    case 1: reflect_main_kernel<SURF, 1><<<grid, 256, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
+    case 2: reflect_main_kernel<SURF, 2><<<grid, 256, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
+    case 3: reflect_main_kernel<SURF, 3><<<grid, 256, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
+    case 4: reflect_main_kernel<SURF, 4><<<grid, 256, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
     default: set_last_error("reflect: unknown material kind %d", mat); return 2;
   }
   XRTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+static int check_multilayer(const xrt_material_params& m, xrt_multilayer_params& ml) {
+  memset(&ml, 0, sizeof(ml));
+  if (m.kind != 4) return 0;
+  XRTB_REQUIRE(m.multilayer != nullptr, "multilayer: material kind 4 needs the layer stack");
+  ml = *m.multilayer;
+  XRTB_REQUIRE(ml.nPairs >= 0 && ml.dti && ml.dbi, "multilayer: nPairs >= 0 and the thickness arrays are required");
+  XRTB_REQUIRE(ml.tLayer.nelem > 0 && ml.bLayer.nelem > 0 && ml.substrate.nelem > 0,
+               "multilayer: top layer, bottom layer and substrate materials are all required");
+  XRTB_REQUIRE(ml.tLayer.nelem <= XRT_MAX_ELEM && ml.bLayer.nelem <= XRT_MAX_ELEM && ml.substrate.nelem <= XRT_MAX_ELEM,
+               "multilayer: at most %d elements per material", XRT_MAX_ELEM);
   return 0;
 }
 
@@ -1101,7 +1261,9 @@ int reflect_device(size_t n, const xrt_oe_params* oe, const xrt_material_params*
   xrt_material_params m;
   memset(&m, 0, sizeof(m));
   if (mat) m = *mat;
-  XRTB_REQUIRE(m.kind >= 0 && m.kind <= 3, "reflect: unknown material kind %d", m.kind);
+  XRTB_REQUIRE(m.kind >= 0 && m.kind <= 4, "reflect: unknown material kind %d", m.kind);
+  xrt_multilayer_params ml;
+  if (int rc = check_multilayer(m, ml)) return rc;
   XRTB_REQUIRE(m.kind == 0 || (tables != nullptr && table_len > 0), "reflect: material needs f1/f2 tables");
   XRTB_REQUIRE(m.nelem >= 0 && m.nelem <= XRT_MAX_ELEM, "reflect: at most %d elements per material", XRT_MAX_ELEM);
   Tables t{tables, tables ? tables + table_len : nullptr, tables ? tables + 2 * table_len : nullptr};
@@ -1128,16 +1290,17 @@ int reflect_device(size_t n, const xrt_oe_params* oe, const xrt_material_params*
   if ((phase & 2) && n > 0) {
     const unsigned grid = (unsigned)((n + 255) / 256);
     int rc = 0;
-    if (oe->surface == 0) rc = launch_main_mat<0>(m.kind, grid, st, n, *oe, m, t, *in, fbv, *gb, lbv, red);
-    if (oe->surface == 1) rc = launch_main_mat<1>(m.kind, grid, st, n, *oe, m, t, *in, fbv, *gb, lbv, red);
-    if (oe->surface == 2) rc = launch_main_mat<2>(m.kind, grid, st, n, *oe, m, t, *in, fbv, *gb, lbv, red);
+    if (oe->surface == 0) rc = launch_main_mat<0>(m.kind, grid, st, n, *oe, m, ml, t, *in, fbv, *gb, lbv, red);
+    if (oe->surface == 1) rc = launch_main_mat<1>(m.kind, grid, st, n, *oe, m, ml, t, *in, fbv, *gb, lbv, red);
+    if (oe->surface == 2) rc = launch_main_mat<2>(m.kind, grid, st, n, *oe, m, ml, t, *in, fbv, *gb, lbv, red);
     if (rc) return rc;
   }
   return 0;
 }
 
 // ---------------------------------------------------------------- stand-alone amplitudes (a12, a13)
-__global__ void __launch_bounds__(256) amplitude_kernel(size_t n, xrt_material_params m, Tables tab,
+__global__ void __launch_bounds__(256) amplitude_kernel(size_t n, xrt_material_params m, xrt_multilayer_params ml,
+                                                        Tables tab,
                                                         const double* __restrict__ E, const double* __restrict__ bIn,
                                                         const double* __restrict__ bOut, const double* __restrict__ bH,
                                                         double2* __restrict__ rs, double2* __restrict__ rp,
@@ -1151,6 +1314,8 @@ __global__ void __launch_bounds__(256) amplitude_kernel(size_t n, xrt_material_p
     const double out = bOut ? bOut[i] : -in;   // crystal.py:618-619
     const double h = bH ? bH[i] : in;          // crystal.py:621-622
     crystal_amplitude(m, tab, E[i], in, out, h, s, p, &oor);
+  } else if (m.kind == 4) {
+    multilayer_amplitude(ml, tab, E[i], bIn[i], s, p, &oor);
   } else {
     mirror_amplitude(m, tab, E[i], bIn[i], s, p, &oor);
   }
@@ -1163,10 +1328,12 @@ int amplitude_device(size_t n, const xrt_material_params* mat, const double* tab
                      const double* E, const double* bIn, const double* bOut, const double* bH, double* rs, double* rp,
                      unsigned long long* oor_count, cudaStream_t st) {
   XRTB_REQUIRE(mat && tables && table_len > 0, "get_amplitude: material and tables are required");
-  XRTB_REQUIRE(mat->kind >= 1 && mat->kind <= 3, "get_amplitude: unsupported material kind %d", mat->kind);
+  XRTB_REQUIRE(mat->kind >= 1 && mat->kind <= 4, "get_amplitude: unsupported material kind %d", mat->kind);
+  xrt_multilayer_params ml;
+  if (int rc = check_multilayer(*mat, ml)) return rc;
   if (n == 0) return 0;
   Tables t{tables, tables + table_len, tables + 2 * table_len};
-  amplitude_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, *mat, t, E, bIn, bOut, bH,
+  amplitude_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, *mat, ml, t, E, bIn, bOut, bH,
                                                                reinterpret_cast<double2*>(rs),
                                                                reinterpret_cast<double2*>(rp), oor_count);
   XRTB_CUDA_CHECK(cudaGetLastError());

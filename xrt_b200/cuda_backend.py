@@ -161,6 +161,32 @@ class XRT_CUDA(object):
         return Is, Ip
 
 
+    def _k_get_amplitude_graded_multilayer(self, scalarArgs, slicedRO, nonSlicedRO, slicedRW, nonSlicedRW,
+                                           dimension):
+        """Argument layout of Multilayer.get_amplitude's accelerator call (materials/multilayer.py:471-484):
+        scalars [nPairs]; sliced RO [rbs_s, rbs_p, rtb_s, rtb_p, rvt_s, rvt_p, Qt, Qb] complex; non-sliced RO
+        [dti, dbi]; sliced RW [ri_s, ri_p]."""
+        lib = _lib.load()
+        npairs = int(scalarArgs[0])
+        ins = [_lib.as_c128(a) for a in slicedRO]
+        n = dimension if dimension else len(ins[0])
+        if len(ins) != 8 or any(len(a) != n for a in ins):
+            raise ValueError('get_amplitude_graded_multilayer: expected 8 sliced complex inputs of length dimension')
+        dti, dbi = (_lib.as_f64(a) for a in nonSlicedRO)
+        if len(dti) < npairs or len(dbi) < npairs:
+            raise ValueError('get_amplitude_graded_multilayer: dti and dbi must hold nPairs thicknesses')
+        ri_s, ri_p = slicedRW
+        for a in (ri_s, ri_p):
+            if not (isinstance(a, np.ndarray) and a.dtype == np.complex128 and a.flags['C_CONTIGUOUS'] and
+                    len(a) == n):
+                raise ValueError('get_amplitude_graded_multilayer: slicedRWArgs must be 2 contiguous '
+                                 'complex128[dimension]')
+        rc = lib.xrt_multilayer_f64_host(n, npairs, *[_lib.hptr(a) for a in ins], _lib.hptr(dti), _lib.hptr(dbi),
+                                         _lib.hptr(ri_s), _lib.hptr(ri_p))
+        _lib.check(rc, 'xrt_multilayer_f64_host')
+        return ri_s, ri_p
+
+
 def _as_vec_buffer(a, N):
     """The reference passes float3 buffers as np.array([x, y, z, 0], order='F') of shape (4, N), i.e. N
     records of 4 doubles (waves.py:874-881).  Accept that, or a C-ordered (N, 3|4) array."""

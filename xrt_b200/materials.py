@@ -13,7 +13,7 @@ import os
 
 import numpy as np
 
-from .physconsts import PI, R0, CH
+from .physconsts import PI, R0, CH, AVOGADRO, PI2
 
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data', 'elements.npz')
 _cache = None
@@ -29,7 +29,14 @@ class xrt_material_params(ctypes.Structure):
                 ('rho', ctypes.c_double), ('mass', ctypes.c_double), ('t', ctypes.c_double),
                 ('d', ctypes.c_double), ('chiToF', ctypes.c_double), ('factDW', ctypes.c_double),
                 ('f0c', ctypes.c_double * 11), ('d2f_re', ctypes.c_double), ('d2f_im', ctypes.c_double),
-                ('f0scale', ctypes.c_double), ('hkl_allowed', ctypes.c_int)]
+                ('f0scale', ctypes.c_double), ('hkl_allowed', ctypes.c_int), ('multilayer', ctypes.c_void_p)]
+
+
+class xrt_multilayer_params(ctypes.Structure):
+    """struct xrt_multilayer_params of include/xrt_b200.h"""
+    _fields_ = [('tLayer', xrt_material_params), ('bLayer', xrt_material_params), ('substrate', xrt_material_params),
+                ('nPairs', ctypes.c_int), ('uniform', ctypes.c_int), ('idThickness', ctypes.c_double),
+                ('d', ctypes.c_double), ('dti', ctypes.c_void_p), ('dbi', ctypes.c_void_p)]
 
 
 def _tables():
@@ -138,6 +145,19 @@ class Material(object):
         m.mass = float(self.mass)
         m.t = float(self.t) if self.t is not None else 0.
         return m
+
+    def get_refractive_index(self, E):
+        """Host (numpy) refractive index, material.py:348-378 -- used by alignment helpers only (get_dtheta of
+        multilayers); the per-ray evaluation lives in the CUDA kernels."""
+        E = np.asarray(E, dtype=float)
+        xf = np.zeros_like(E) * 0j
+        for elem, xi in zip(self.elements, self.quantities):
+            if np.any(E < elem.E[0]) or np.any(E > elem.E[-1]):
+                raise ValueError('E is out of the f1/f2 data table range')
+            f1 = np.interp(E, elem.E, elem.f1)
+            f2 = np.interp(E, elem.E, elem.f2)
+            xf += (elem.Z + f1 + 1j*f2) * xi
+        return 1 - 1e-24 * AVOGADRO * R0 / PI2 * (CH/E)**2 * self.rho * xf / self.mass
 
     # ------------------------------------------------------------------ stand-alone amplitude (a12)
     def get_amplitude(self, E, beamInDotNormal, fromVacuum=True):
@@ -251,3 +271,115 @@ class CrystalSi(CrystalDiamond):
 
     def get_a(self):
         return self.a0 * (self.dl_l()-self.dl_l0+1)
+
+
+class Multilayer(object):
+    """Periodic or depth-graded multilayer on a substrate, geom 'reflected' (materials/multilayer.py:14-515): same
+    constructor keywords, the same thickness laws (set_dti / set_dbi, :187-215).  The Parratt recursion over the
+    2 x nPairs interfaces runs per ray in the CUDA kernels (csrc/reflect.cu: multilayer_amplitude inside
+    OE.reflect, multilayer_kernel for the reference's run_parallel('get_amplitude_graded_multilayer') call)."""
+
+    def __init__(self, tLayer=None, tThickness=0., bLayer=None, bThickness=0., nPairs=0, substrate=None,
+                 tThicknessLow=0., bThicknessLow=0., idThickness=0., power=2., substRoughness=0.,
+                 substThickness=np.inf, name='', geom='reflected', **kwargs):
+        if tLayer is None or bLayer is None or substrate is None:
+            raise NotImplementedError('top layer, bottom layer and substrate are all required on this path')
+        if geom and 'tran' in geom:
+            raise NotImplementedError("geom='transmitted' multilayers are the next row (SURVEY.md 8f)")
+        self.tLayer, self.bLayer, self.substrate = tLayer, bLayer, substrate
+        self.nPairs = int(nPairs)
+        self.power = power
+        self.tThicknessHigh, self.tThicknessLow = float(tThickness), float(tThicknessLow)
+        self.bThicknessHigh, self.bThicknessLow = float(bThickness), float(bThicknessLow)
+        self.kind = 'multilayer'
+        self.geom = geom or 'reflected'
+        self.idThickness = idThickness
+        self.substRoughness = float(substRoughness)
+        self.substThickness = substThickness
+        self.name = name
+        self.dti = self._graded(self.tThicknessHigh, self.tThicknessLow)
+        self.dbi = self._graded(self.bThicknessHigh, self.bThicknessLow)
+        self._dev = {}
+        self._keep = None
+
+    tThickness = property(lambda self: self.tThicknessHigh)
+    bThickness = property(lambda self: self.bThicknessHigh)
+    d = property(lambda self: float(self.tThicknessHigh + self.bThicknessHigh))
+
+    def _graded(self, high, low):
+        """set_dti / set_dbi (multilayer.py:187-215)"""
+        if low:
+            layers = np.arange(1, self.nPairs+1)
+            qRoot = (high/low)**(1./self.power)
+            qB = (self.nPairs-qRoot) / (qRoot-1.)
+            qA = high * (qB+1)**self.power
+            return qA * (qB+layers)**(-self.power)
+        return np.ones(self.nPairs) * float(high)
+
+    # ------------------------------------------------------------------ alignment helpers (host, multilayer.py:217-252)
+    def get_sin_Bragg_angle(self, E, order=1):
+        a = np.array(order * CH / (2*self.d*E))
+        a[a > 1] = 1 - 1e-16
+        a[a < -1] = -1 + 1e-16
+        return a
+
+    def get_Bragg_angle(self, E, order=1):
+        return np.arcsin(self.get_sin_Bragg_angle(E, order))
+
+    def get_dtheta(self, E, order=1):
+        nt = self.tLayer.get_refractive_index(E).real
+        nb = self.bLayer.get_refractive_index(E).real
+        d_ = abs((nt-1) * self.tThicknessHigh + (nb-1) * self.bThicknessHigh) / self.d
+        return self.get_Bragg_angle(E, order) - np.arcsin(((order * CH / E)**2 + self.d**2 * 8*d_)**0.5 / (2*self.d))
+
+    # ------------------------------------------------------------------ device plumbing
+    def host_tables(self):
+        parts = [m.host_tables() for m in (self.tLayer, self.bLayer, self.substrate)]
+        E, f1, f2, offs, lens, pos = [], [], [], [], [], 0
+        for tab, n, o, ln in parts:
+            E.append(tab[:n])
+            f1.append(tab[n:2*n])
+            f2.append(tab[2*n:])
+            offs.append([pos + v for v in o])
+            lens.append(list(ln))
+            pos += n
+        tab = np.concatenate([np.concatenate(E), np.concatenate(f1), np.concatenate(f2)])
+        dti = np.ascontiguousarray(self.dti, dtype=np.float64)
+        dbi = np.ascontiguousarray(self.dbi, dtype=np.float64)
+        return tab, pos, (offs, dti, dbi, dti.ctypes.data, dbi.ctypes.data), lens
+
+    def device_tables(self, device):
+        import torch
+        key = str(device)
+        if key not in self._dev:
+            tab, n, (offs, dti, dbi, _, _), lens = self.host_tables()
+            ddti, ddbi = torch.from_numpy(dti).to(device), torch.from_numpy(dbi).to(device)
+            self._dev[key] = (torch.from_numpy(tab).to(device), n,
+                              (offs, ddti, ddbi, ddti.data_ptr(), ddbi.data_ptr()), lens)
+        return self._dev[key]
+
+    def c_struct(self, offs, lens):
+        offs, dti, dbi, pdti, pdbi = offs
+        ml = xrt_multilayer_params()
+        for name, mat, o, ln in zip(('tLayer', 'bLayer', 'substrate'), (self.tLayer, self.bLayer, self.substrate),
+                                    offs, lens):
+            sub = Material.c_struct(mat, o, ln) if not hasattr(mat, 'hkl') else None
+            if sub is None:
+                raise NotImplementedError('crystal layers in a multilayer')
+            sub.kind = 1
+            setattr(ml, name, sub)
+        ml.nPairs = self.nPairs
+        ml.uniform = int(self.nPairs > 0 and bool(np.all(self.dti == self.dti[0]) and np.all(self.dbi == self.dbi[0])))
+        ml.idThickness = float(self.idThickness)
+        ml.d = self.d
+        ml.dti, ml.dbi = pdti, pdbi
+        m = xrt_material_params()
+        m.kind = 4
+        m.multilayer = ctypes.addressof(ml)
+        self._keep = (ml, dti, dbi)  # the stack and its arrays must outlive the call
+        return m
+
+    def get_amplitude(self, E, beamInDotNormal, x=None, y=None, ucl=None):
+        """(ri_s, ri_p) on host arrays (multilayer.py:254-508, geom 'reflected')."""
+        from . import kernels
+        return kernels.material_amplitude_host(self, E, beamInDotNormal)
