@@ -137,7 +137,7 @@ typedef struct xrt_oe_params {
 /* Material = what get_amplitude reads (materials/material.py:348-493, materials/crystal.py:492-645). */
 struct xrt_multilayer_params;
 typedef struct xrt_material_params {
-  int kind;               /* 0 none, 1 mirror, 2 thin mirror, 3 crystal (thick Bragg, fcc/diamond, one element),
+  int kind;               /* 0 none, 1 mirror, 2 thin mirror, 3 crystal (fcc/diamond, one element; thick Bragg or thickness t with geom),
                              4 multilayer (reflected; `multilayer` points to the stack) */
   int nelem;
   double Z[XRT_MAX_ELEM], quantity[XRT_MAX_ELEM];
@@ -148,6 +148,8 @@ typedef struct xrt_material_params {
   double d2f_re, d2f_im;  /* diamondToFcc = 1 + exp(i pi/2 (h+k+l)); (1, 0) for fcc */
   double f0scale;         /* 2 for diamond (F0 * 2), 1 for fcc */
   int hkl_allowed;        /* h,k,l all even or all odd */
+  int geom;               /* crystal: bit0 Laue (else Bragg), bit1 transmitted (else reflected); with t > 0 (mm) the
+                             finite-thickness amplitudes of crystal.py:598-616, t == 0: thick Bragg */
   const struct xrt_multilayer_params* multilayer; /* kind 4: HOST pointer to the layer stack, else NULL */
 } xrt_material_params;
 

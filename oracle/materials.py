@@ -95,10 +95,14 @@ class Material(object):
 
 
 class CrystalDiamond(object):
-    """Single-element fcc/diamond crystal, thick Bragg reflection (geom 'Bragg reflected', t=None)."""
+    """Single-element fcc/diamond crystal: thick Bragg reflection (t=None) or thickness t (mm) with geom
+    Bragg / Laue, reflected / transmitted (crystal.py:566-616)."""
     kind = 'crystal'
 
-    def __init__(self, hkl, d, element='Si', factDW=1., structure='diamond', table='Chantler total'):
+    def __init__(self, hkl, d, element='Si', factDW=1., structure='diamond', table='Chantler total', t=None,
+                 geom='Bragg reflected'):
+        self.t = t
+        self.geom = geom
         self.hkl = tuple(int(i) for i in hkl)
         self.d = d
         self.sqrthkl2 = (sum(i**2 for i in self.hkl))**0.5
@@ -164,16 +168,36 @@ class CrystalDiamond(object):
     def get_amplitude(self, E, beamInDotNormal, beamOutDotNormal=None, beamInDotHNormal=None):
         def for_one_polarization(polFactor):
             delta = np.sqrt((alpha**2 + polFactor**2 * chih * chih_ / b))
-            with np.errstate(divide='ignore', invalid='ignore'):
-                ra = chih * polFactor / (alpha+delta)
-            ad = alpha - delta
-            ad[ad == 0] = 1e-100
-            rb = chih * polFactor / ad
-            indB = np.where(np.isnan(ra))
-            ra[indB] = rb[indB]
-            indB = np.where(abs(rb) < abs(ra))
-            ra[indB] = rb[indB]
-            return ra / np.sqrt(abs(b))
+            if self.t is None:  # thick Bragg
+                with np.errstate(divide='ignore', invalid='ignore'):
+                    ra = chih * polFactor / (alpha+delta)
+                ad = alpha - delta
+                ad[ad == 0] = 1e-100
+                rb = chih * polFactor / ad
+                indB = np.where(np.isnan(ra))
+                ra[indB] = rb[indB]
+                indB = np.where(abs(rb) < abs(ra))
+                ra[indB] = rb[indB]
+                return ra / np.sqrt(abs(b))
+            # finite thickness, crystal.py:598-616
+            t = self.t * 1e7
+            l = t * delta * k02 / 2. / kHs  # noqa: E741
+            with np.errstate(over='ignore'):
+                if self.geom.startswith('Bragg'):
+                    if self.geom.endswith('transmitted'):
+                        ra = 1 / (np.cos(l) - 1j * alpha * np.sin(l) / delta) * \
+                            np.exp(1j * k02 * t * (chi0 - alpha*b) / 2 / k0s)
+                    else:
+                        ra = chih * polFactor / (alpha + 1j*delta / np.tan(l))
+                else:  # Laue
+                    if self.geom.endswith('transmitted'):
+                        ra = (np.cos(l) + 1j * alpha * np.sin(l) / delta) * \
+                            np.exp(1j * k02 * t * (chi0 - alpha*b) / 2 / k0s)
+                    else:
+                        ra = chih * polFactor * np.sin(l) / delta * np.exp(1j * k02 * t * (chi0 - alpha*b) / 2 / k0s)
+            if not self.geom.endswith('transmitted'):
+                ra /= np.sqrt(abs(b))
+            return ra
 
         waveLength = CH / E
         k = PI2 / waveLength

@@ -399,7 +399,8 @@ def reflect_local(oe, good, lb, vlb, pitch, roll, yaw, dx=None, dy=None, dz=None
         else:
             beamInDotSurfaceNormal = beamInDotNormal
         isMultilayer = material is not None and material.kind == 'multilayer'
-        if isCrystal or isMultilayer:
+        transmitted = isCrystal and matSur.geom.endswith('transmitted')  # toWhere = 2 (reflect.py:756, :862-878)
+        if (isCrystal or isMultilayer) and not transmitted:
             # _get_asymmetric_reflection_grating (reflect.py:568-612)
             normalDotSurfNormal = oeNormal[0]*oeNormal[-3] + oeNormal[1]*oeNormal[-2] + oeNormal[2]*oeNormal[-1]
             bdn = beamInDotNormal.sum() / len(beamInDotNormal)
@@ -411,15 +412,17 @@ def reflect_local(oe, good, lb, vlb, pitch, roll, yaw, dx=None, dy=None, dz=None
                 (oeNormal[0]-normalDotSurfNormal*oeNormal[-3]) * wHd,
                 (oeNormal[1]-normalDotSurfNormal*oeNormal[-2]) * wHd,
                 (oeNormal[2]-normalDotSurfNormal*oeNormal[-1]) * wHd), order='F') * sgbdn
+            sg = 1 if matSur.geom.startswith('Laue') else -1  # reflect.py:608
             a_out, b_out, c_out = _grating_deflection(goodN, lb, gNormalCryst, oeNormal, beamInDotSurfaceNormal,
-                                                      1, -1)
+                                                      1, sg)
         else:
             a_out = lb.a[goodN] - oeNormal[0]*2*beamInDotNormal
             b_out = lb.b[goodN] - oeNormal[1]*2*beamInDotNormal
             c_out = lb.c[goodN] - oeNormal[2]*2*beamInDotNormal
-        lb.a[goodN] = a_out
-        lb.b[goodN] = b_out
-        lb.c[goodN] = c_out
+        if not transmitted:  # toWhere = 2: the ray passes straight
+            lb.a[goodN] = a_out
+            lb.b[goodN] = b_out
+            lb.c[goodN] = c_out
         rollAngle = roll + np.arctan2(oeNormal[-3], oeNormal[-1])
         localJ = ob.rotate_coherency_matrix(lb, goodN, -rollAngle)
         if hasattr(lb, 'Es'):

@@ -652,8 +652,54 @@ def gen_multilayer():
           'mean R', float((dd['gb_Jss'] + dd['gb_Jpp'])[st == 1].mean() / (dd['in_Jss'] + dd['in_Jpp'])[st == 1].mean()))
     save('reflect_multilayer_flat', thB=thB, **dd)
 
+# ------------------------------------------------------------------------------------------------ thin crystals
+THIN = {'bragg_thin': ('Bragg reflected', 0.005, 0.), 'bragg_t': ('Bragg transmitted', 0.05, 0.),
+        'laue_r': ('Laue reflected', 0.1, np.pi/2), 'laue_t': ('Laue transmitted', 0.1, np.pi/2)}
 
-SECTIONS = {'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+
+def gen_thin_crystals():
+    rng = np.random.RandomState(161)
+    out = {}
+    for key, (geom, t, alpha) in THIN.items():
+        si = rm.CrystalSi(hkl=(1, 1, 1), geom=geom, t=t)
+        E = np.ones(600) * 10000.
+        E[300:] = rng.uniform(9500, 10500, 300)
+        thetaB = si.get_Bragg_angle(E)
+        dth = np.linspace(-60, 90, 600) * 1e-6
+        theta = thetaB + dth
+        a = alpha + (np.radians(3.) if 'laue' in key else 0.)
+        # the sign convention of _reflect_local: the beam goes INTO the surface (beamInDotNormal < 0)
+        g0 = -np.sin(theta + a)
+        gh = np.sin(theta - a)
+        hns0 = -np.sin(theta)
+        cs, cp = si.get_amplitude(E, g0.copy(), gh.copy(), hns0.copy())
+        for k, v in (('E', E), ('g0', g0), ('gh', gh), ('hns0', hns0), ('rs', cs), ('rp', cp)):
+            out[key + '_' + k] = v
+        out[key + '_d'] = si.d
+        print(key, 'max |rs|^2', float((abs(cs)**2).max()), 'nan', int(np.isnan(cs).sum()))
+    save('amplitude_crystals_thin', **out)
+    bl = raycing.BeamLine()
+    E0 = 9000.
+    for key, (geom, t, alpha) in THIN.items():
+        si = rm.CrystalSi(hkl=(1, 1, 1), geom=geom, t=t)
+        beam = _source_beam(bl, 1500, 162, dx=0.2, dz=0.02, dxprime=5e-5, dzprime=2e-5, energies=(8998, 9002))
+        thetaB = float(si.get_Bragg_angle(E0))
+        if 'laue' in key:
+            pitch, al = np.pi/2 - thetaB, alpha
+        else:
+            pitch, al = thetaB - float(si.get_dtheta(E0)), None
+        oe = roe.OE(bl, 'xtal', center=(0, 2e4, 0), pitch=pitch, material=si, alpha=al,
+                    limPhysX=[-20, 20], limPhysY=[-20, 20])
+        dd = _capture_reflect(oe, beam)
+        dd.update(_oe_params(oe))
+        st = dd['gb_state']
+        good = st == 1
+        print(key, {int(x): int((st == x).sum()) for x in np.unique(st)}, 'mean T/R',
+              float((dd['gb_Jss'] + dd['gb_Jpp'])[good].mean() / (dd['in_Jss'] + dd['in_Jpp'])[good].mean()))
+        save('reflect_crystal_' + key, d=si.d, tK=si.tK, t=t, geom=np.array(geom), alpha=0. if al is None else al, **dd)
+
+
+SECTIONS = {'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)

@@ -543,14 +543,83 @@ __device__ __forceinline__ void mirror_amplitude(const xrt_material_params& m, c
   }
 }
 
-// Crystal.get_amplitude, thick Bragg, one-element fcc/diamond structure (crystal.py:568-645)
-__device__ __forceinline__ cplx bragg_one_pol(double polFactor, cplx alpha, cplx chih, cplx chih_, double b) {
+// np.exp / np.sin / np.cos / np.tan on complex128 = glibc cexp / csin / ccos / ctan (finite arguments of
+// moderate size; the overflow-scaling branches of glibc for |im| > 709 (355 for ctan) are not reproduced)
+__device__ __forceinline__ cplx cexp_np(cplx z) {
+  double sn = z.im, cs = 1.0;
+  if (fabs(z.im) > 2.2250738585072014e-308) sincos(z.im, &sn, &cs);
+  const double e = exp(z.re);
+  return cplx{e * cs, e * sn};
+}
+__device__ __forceinline__ cplx csin_np(cplx z) {
+  double sn = z.re, cs = 1.0;
+  if (fabs(z.re) > 2.2250738585072014e-308) sincos(z.re, &sn, &cs);
+  return cplx{cosh(z.im) * sn, sinh(z.im) * cs};
+}
+__device__ __forceinline__ cplx ccos_np(cplx z) {  // ccosh(i z), i z = (-im, re)
+  const double x = -z.im, y = z.re;
+  double sn = y, cs = 1.0;
+  if (fabs(y) > 2.2250738585072014e-308) sincos(y, &sn, &cs);
+  return cplx{cosh(x) * cs, sinh(x) * sn};
+}
+__device__ __forceinline__ cplx ctan_np(cplx z) {
+  double sn = z.re, cs = 1.0;
+  if (fabs(z.re) > 2.2250738585072014e-308) sincos(z.re, &sn, &cs);
+  double sh = z.im, ch = 1.0;
+  if (fabs(z.im) > 2.2250738585072014e-308) {
+    sh = sinh(z.im);
+    ch = cosh(z.im);
+  }
+  double den = cs * cs;
+  if (fabs(sh) > fabs(cs) * 2.220446049250313e-16) den = cs * cs + sh * sh;
+  return cplx{sn * cs / den, sh * ch / den};
+}
+
+// Crystal.get_amplitude, one-element fcc/diamond structure (crystal.py:566-616): thick Bragg, and for a crystal
+// of thickness t (mm) the Bragg / Laue, reflected / transmitted amplitudes of Belyakov & Dmitrienko.
+// geom bit0 = Laue, bit1 = transmitted
+__device__ __forceinline__ cplx bragg_one_pol(double polFactor, cplx alpha, cplx chih, cplx chih_, double b,
+                                              double tmm, int geom, cplx chi0, double k02, double kHs, double k0s) {
   // delta = sqrt(alpha**2 + polFactor**2 * chih * chih_ / b)
   cplx t = cmul_np(cplx{polFactor * polFactor, 0.0}, chih);
   t = cmul_np(t, chih_);
   t = cdiv_re(t, b);
   const cplx delta = csqrt_(cadd(csquare_np(alpha), t));
   const cplx num = cmul_np(chih, cplx{polFactor, 0.0});
+  if (tmm > 0.0) {
+    const double tA = tmm * 1e7;
+    // l = t * delta * k02 / 2. / kHs
+    cplx l = cmul_np(cmul_np(cplx{tA, 0.0}, delta), cplx{k02, 0.0});
+    l = cdiv_re(cdiv_re(l, 2.0), kHs);
+    cplx ra;
+    // exp(1j * k02 * t * (chi0 - alpha*b) / 2 / k0s)
+    cplx ph = cplx{0.0, 0.0};
+    if (geom != 0) {
+      const cplx w = csub(chi0, cmul_np(alpha, cplx{b, 0.0}));
+      cplx e = cmul_np(cmul_np(cmul_np(cplx{0.0, 1.0}, cplx{k02, 0.0}), cplx{tA, 0.0}), w);
+      e = cdiv_re(cdiv_re(e, 2.0), k0s);
+      ph = cexp_np(e);
+    }
+    const cplx ia = cmul_np(cplx{0.0, 1.0}, alpha);
+    if (!(geom & 1)) {  // Bragg
+      if (geom & 2) {
+        const cplx q = cdiv(cmul_np(ia, csin_np(l)), delta);
+        ra = cmul_np(cdiv(cplx{1.0, 0.0}, csub(ccos_np(l), q)), ph);
+      } else {
+        const cplx q = cdiv(cmul_np(cplx{0.0, 1.0}, delta), ctan_np(l));
+        ra = cdiv(num, cadd(alpha, q));
+      }
+    } else {  // Laue
+      if (geom & 2) {
+        const cplx q = cdiv(cmul_np(ia, csin_np(l)), delta);
+        ra = cmul_np(cadd(ccos_np(l), q), ph);
+      } else {
+        ra = cmul_np(cdiv(cmul_np(num, csin_np(l)), delta), ph);
+      }
+    }
+    if (!(geom & 2)) ra = cdiv_re(ra, sqrt(fabs(b)));
+    return ra;
+  }
   cplx ra = cdiv(num, cadd(alpha, delta));
   cplx ad = csub(alpha, delta);
   if (ad.re == 0.0 && ad.im == 0.0) ad = cplx{1e-100, 0.0};
@@ -609,19 +678,11 @@ __device__ __forceinline__ void crystal_amplitude(const xrt_material_params& m, 
   const cplx half_chi0 = cdiv_re(chi0, 2.0);
   const cplx a2 = cmul_np(half_chi0, cplx{1.0 / b - 1.0, 0.0});
   const cplx alpha = cplx{a1 + a2.re, 0.0 + a2.im};
-  rs = bragg_one_pol(1.0, alpha, chih, chih_, b);
-  rp = bragg_one_pol(cos(2.0 * thetaB), alpha, chih, chih_, b);
+  rs = bragg_one_pol(1.0, alpha, chih, chih_, b, m.t, m.geom, chi0, k02, kHs, k0s);
+  rp = bragg_one_pol(cos(2.0 * thetaB), alpha, chih, chih_, b, m.t, m.geom, chi0, k02, kHs, k0s);
 }
 
 // ---------------------------------------------------------------- f2: multilayer (materials/multilayer.py)
-// np.exp on complex128 = glibc cexp: exp(re) * (cos(im), sin(im)), with sin(im) = im, cos(im) = 1 below DBL_MIN
-__device__ __forceinline__ cplx cexp_np(cplx z) {
-  double sn = z.im, cs = 1.0;
-  if (fabs(z.im) > 2.2250738585072014e-308) sincos(z.im, &sn, &cs);
-  const double e = exp(z.re);
-  return cplx{e * cs, e * sn};
-}
-
 // one step of the Parratt recursion (multilayer.py:453-456): (rij + rj*p2) / (1 + rij*(rj*p2))
 __device__ __forceinline__ cplx parratt_step(cplx rij, cplx rj, cplx p2) {
   const cplx rj2 = cmul_np(rj, p2);
@@ -1010,7 +1071,8 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
         theta = acos(bdn) - kPi / 2;
         bds = p.asymmetric ? (la * nrm[3] + lbb * nrm[4] + lc * nrm[5]) : bdn;
         double ao, bo, co;
-        if (MAT == 3 || MAT == 4) {
+        const bool transmitted = (MAT == 3) && (m.geom & 2);  // toWhere = 2 (reflect.py:756, :862-878)
+        if ((MAT == 3 || MAT == 4) && !transmitted) {
           // crystal / multilayer as a grating (reflect.py:568-612, :451-469); sgbdn is taken per ray here -- all
           // good rays hit the same side of the crystal in the supported geometries (documented in DESIGN.md)
           const double ndsn = nrm[0] * nrm[3] + nrm[1] * nrm[4] + nrm[2] * nrm[5];
@@ -1024,7 +1086,8 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
           const double G2 = g0 * g0 + g1 * g1 + g2 * g2;
           const double ol = 1.0 * CH / in.E[i] * 1e-7;
           const double u = bds * bds - 2.0 * bdg * ol - G2 * (ol * ol);
-          const double dn = bds + (-1.0) * sqrt(fabs(u));
+          const double sg = (MAT == 3 && (m.geom & 1)) ? 1.0 : -1.0;  // reflect.py:608: +1 for Laue
+          const double dn = bds + sg * sqrt(fabs(u));
           ao = la - nrm[3] * dn + g0 * ol;
           bo = lbb - nrm[4] * dn + g1 * ol;
           co = lc - nrm[5] * dn + g2 * ol;
@@ -1037,10 +1100,13 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
           ao = la - nrm[0] * 2.0 * bdn;
           bo = lbb - nrm[1] * 2.0 * bdn;
           co = lc - nrm[2] * 2.0 * bdn;
+          if (MAT == 3) bos = ao * nrm[3] + bo * nrm[4] + co * nrm[5];
         }
-        la = ao;
-        lbb = bo;
-        lc = co;
+        if (!transmitted) {  // 'transmitted': the ray passes straight, (ao, bo, co) only feeds the amplitude
+          la = ao;
+          lbb = bo;
+          lc = co;
+        }
         // polarisation frame (reflect.py:948-953; beams.py:448-479)
         const double rollAngle = p.roll + atan2(nrm[3], nrm[5]);
         sincos(rollAngle, &sY, &cY);  // cos(-x) == cos(x) and sin(-x) == -sin(x) exactly (numpy and CUDA alike)

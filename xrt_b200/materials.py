@@ -29,7 +29,8 @@ class xrt_material_params(ctypes.Structure):
                 ('rho', ctypes.c_double), ('mass', ctypes.c_double), ('t', ctypes.c_double),
                 ('d', ctypes.c_double), ('chiToF', ctypes.c_double), ('factDW', ctypes.c_double),
                 ('f0c', ctypes.c_double * 11), ('d2f_re', ctypes.c_double), ('d2f_im', ctypes.c_double),
-                ('f0scale', ctypes.c_double), ('hkl_allowed', ctypes.c_int), ('multilayer', ctypes.c_void_p)]
+                ('f0scale', ctypes.c_double), ('hkl_allowed', ctypes.c_int), ('geom', ctypes.c_int),
+                ('multilayer', ctypes.c_void_p)]
 
 
 class xrt_multilayer_params(ctypes.Structure):
@@ -170,8 +171,8 @@ class Material(object):
 
 
 class CrystalFcc(Material):
-    """Perfect one-element fcc crystal, thick Bragg case (materials/crystals_basic.py:8-31 with the
-    Crystal constructor crystal.py:39-181)."""
+    """Perfect one-element fcc crystal (materials/crystals_basic.py:8-31 with the Crystal constructor
+    crystal.py:39-181): thick Bragg case, or thickness *t* (mm) in Bragg / Laue geometry, reflected / transmitted."""
     structure = 'fcc'
 
     def __init__(self, hkl=(1, 1, 1), d=0, V=None, elements='Si', quantities=None, rho=0, t=None, factDW=1.,
@@ -179,9 +180,10 @@ class CrystalFcc(Material):
         super().__init__(elements, quantities, kind='crystal', rho=rho, t=t, table=table, name=name)
         if len(self.elements) != 1:
             raise NotImplementedError('multi-atom structure factors are outside the hot path')
-        if t is not None or not geom.startswith('Bragg') or geom.endswith('transmitted'):
-            raise NotImplementedError('only the thick Bragg reflected case is on the hot path '
-                                      '(crystal.py:570-597); thin/Laue/transmitted: SURVEY.md section 8f')
+        if not (geom.startswith('Bragg') or geom.startswith('Laue')) or geom.endswith('Fresnel'):
+            raise NotImplementedError('geom {0!r}: Bragg / Laue, reflected / transmitted are on this path'.format(geom))
+        if t is None and geom != 'Bragg reflected':
+            raise ValueError('Laue and transmitted geometries need a crystal thickness t')
         self.hkl = tuple(int(i) for i in hkl)
         self.sqrthkl2 = (sum(i**2 for i in self.hkl))**0.5
         self.d = d
@@ -209,6 +211,7 @@ class CrystalFcc(Material):
         m.factDW = float(self.factDW)
         residue = sum(i % 2 for i in self.hkl)
         m.hkl_allowed = 1 if residue in (0, 3) else 0
+        m.geom = (1 if self.geom.startswith('Laue') else 0) | (2 if self.geom.endswith('transmitted') else 0)
         f0 = self.elements[0].get_f0(0.5 / self.d)  # crystal.py:630 get_F_chi(E, 0.5/crystd)
         m.f0c[0] = float(f0)
         d2f = self._diamond_to_fcc()
