@@ -86,6 +86,30 @@ int xrt_undulator_imap_f64(size_t n, int jend, double Kx, double Ky, double L0, 
                            const double* sintg, const double* costg, const double* sintgph, const double* costgph,
                            double* I, double* Es, double* Ep, int flags, void* stream);
 
+/* f3: tapered and near-field undulators.  Replace kernels `undulator_taper` (cl/undulator.cl:123-202) and
+ * `undulator_nf` (cl/undulator.cl:204-298), launched at sources/synchr.py:2174 with the scalar list
+ * [taper | R0*pi*2/L0, Kx, Ky, jend, Np] (synchr.py:2134-2146) and the sliced / non-sliced arrays of `undulator`.
+ * variant 1: taper, scalar0 = Undulator._taperVal; variant 2: near field, scalar0 = R0*pi*2/L0.  nmax = Np periods,
+ * summed explicitly.  Outputs Is, Ip c128[n] = Undulator._sp_sum(..., R0) (synchr.py:1929-2033, numpy convention). */
+int xrt_undulator_ext_f64(int variant, size_t n, int jend, int nmax, double scalar0, double Kx, double Ky,
+                          const double* gamma, const double* wu, const double* w, const double* ww1,
+                          const double* ddphi, const double* ddpsi, const double* tg, const double* ag,
+                          const double* sintg, const double* costg, const double* sintgph, const double* costgph,
+                          double* Is, double* Ip, void* stream);
+int xrt_undulator_ext_f64_host(int variant, size_t n, int jend, int nmax, double scalar0, double Kx, double Ky,
+                               const double* gamma, const double* wu, const double* w, const double* ww1,
+                               const double* ddphi, const double* ddpsi, const double* tg, const double* ag,
+                               const double* sintg, const double* costg, const double* sintgph,
+                               const double* costgph, double* Is, double* Ip);
+/* ... and fused with Undulator._build_I_map_conv (synchr.py:2048-2108; ab = 1/(2 pi wu), :2067-2068) for
+ * device-resident sampling: same arguments as xrt_undulator_imap_f64 plus variant, nmax = Np and scalar0. */
+int xrt_undulator_ext_imap_f64(int variant, size_t n, int jend, int nmax, double scalar0, double Kx, double Ky,
+                               double L0, double gamma0, double amp_const, double dstep, int bw_mode,
+                               const double* gamma, const double* w, const double* theta, const double* psi,
+                               const double* tg, const double* ag, const double* sintg, const double* costg,
+                               const double* sintgph, const double* costgph, double* I, double* Es, double* Ep,
+                               void* stream);
+
 /* ------------------------------------------------------------------ a1, a6-a15: ray kernels on the Beam SoA
  * The Beam container of the reference (sources/beams.py:96-186) is a struct of equal-length arrays; here it
  * is a struct of DEVICE pointers.  Es/Ep may be NULL (beam without amplitudes); theta, s, phi, r are outputs

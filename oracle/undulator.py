@@ -3,7 +3,8 @@
 Restates, in numpy and in the reference's operation order:
   * IntegratedSource._clenshaw_curtis        xrt/backends/raycing/sources/sybase.py:1106-1139
   * Undulator._build_integration_grid        xrt/backends/raycing/sources/synchr.py:1787-1801
-  * Undulator._sp_sum (far field, no taper)  synchr.py:1929-2033 (the `else` branch :1997-2003 + :2005-2031)
+  * Undulator._sp_sum                        synchr.py:1929-2033: far field (the `else` branch :1997-2003),
+                                             taper (:1958-1971) and near field R0 (:1972-1996) + :2005-2031
   * Undulator._build_I_map_conv              synchr.py:2048-2108
 """
 import numpy as np
@@ -48,42 +49,96 @@ def build_integration_grid(quadm, gIntervals, phase):
                 costgph=np.cos(tg + phase), dstep=dstep)
 
 
-def sp_sum(grid, Kx, Ky, ww1S, wS, wuS, gS, ddphiS, ddpsiS):
+def sp_sum(grid, Kx, Ky, ww1S, wS, wuS, gS, ddphiS, ddpsiS, R0=None, taperVal=None, Np=1, with_scale=False):
+    """R0: (3, n) array in units of L0/2pi (synchr.py:2072-2077) or None; taperVal: Undulator._taperVal or
+    None; Np: number of periods (the explicit period loop runs only with R0 or taper, synchr.py:1947).
+    with_scale (test helper, not in the reference): also return sum_j |term_j| for Bs and Bp, the honest
+    scale of an oscillatory quadrature."""
     sintg, costg, sintgph, costgph, tg, ag = (grid[k] for k in
                                               ('sintg', 'costg', 'sintgph', 'costgph', 'tg', 'ag'))
+    taperC = 1
+    alphaS = 0
     sin2x = 2.*sintg*costg
     sin2xph = 2.*sintgph*costgph
     revgamma = 1. / gS
     revgamma2 = revgamma**2
+    betam = 1. - (1. + 0.5*Kx**2 + 0.5*Ky**2)*0.5*revgamma2
     wwuS = wS/wuS
     Bsr = np.complex128(0)
     Bpr = np.complex128(0)
+    Ssr = 0.
+    Spr = 0.
     dirx = ddphiS
     diry = ddpsiS
     dirz = 1. - 0.5*(ddphiS**2 + ddpsiS**2)
-    taperC = 1
-    alphaS = 0
-    for i in range(len(tg)):
-        ucos = ww1S*tg[i] + wwuS*revgamma *\
-            (-Ky*ddphiS*sintg[i] + Kx*ddpsiS*sintgph[i] +
-             0.125*revgamma*(Ky**2 * sin2x[i] + Kx**2 * sin2xph[i]))
-        eucos = np.exp(1j*ucos)
-        betax = taperC*Ky*revgamma*costg[i]
-        betay = -Kx*revgamma*costgph[i]
-        betaz = 1. - 0.5*(revgamma2 + betax*betax + betay*betay)
-        betaPx = -Ky*(alphaS*costg[i] + taperC*sintg[i])
-        betaPy = Kx*sintgph[i]
-        betaPz = 0.5*revgamma *\
-            (Ky**2 * taperC*(alphaS*costg[i]**2 + taperC*sin2x[i]) + Kx**2 * sin2xph[i])
-        rkrel = 1./(1. - dirx*betax - diry*betay - dirz*betaz)
-        eucos *= ag[i] * rkrel**2
-        bnx = dirx - betax
-        bny = diry - betay
-        bnz = dirz - betaz
-        dirDotBetaP = dirx*betaPx + diry*betaPy + dirz*betaPz
-        dirDotDmB = dirx*bnx + diry*bny + dirz*bnz
-        Bsr += eucos*(bnx*dirDotBetaP - betaPx*dirDotDmB)
-        Bpr += eucos*(bny*dirDotBetaP - betaPy*dirDotDmB)
+    Nmx = int(Np) if (R0 is not None or taperVal is not None) else 1
+    if R0 is not None:
+        sinr0z = np.sin(R0[-1])
+        cosr0z = np.cos(R0[-1])
+    for Nperiod in range(Nmx):
+        for i in range(len(tg)):
+            if taperVal is not None:
+                zloc = -(Nmx-1)*np.pi + Nperiod*PI2 + tg[i]
+                alphaS = taperVal/E2WC
+                taperC = 1. - alphaS*zloc/wuS
+                ucos = ww1S*zloc +\
+                    wwuS*revgamma *\
+                    (-Ky*dirx*(sintg[i] + alphaS/wuS *
+                               (1 - costg[i] -
+                                zloc*sintg[i])) +
+                     Kx*diry*sintg[i] + 0.125*revgamma *
+                     (Kx**2 * sin2xph[i] + Ky**2 * (sin2x[i] -
+                      2*alphaS/wuS*(zloc**2 + costg[i]**2 +
+                                    zloc*sin2x[i]))))
+                eucos = np.exp(1j*ucos)
+            elif R0 is not None:
+                zterm = 0.5*(Ky**2*sin2x[i] + Kx**2*sin2xph[i])*revgamma
+                zloc = -(Nmx-1)*np.pi + Nperiod*PI2 + tg[i]
+                rloc = np.array([Ky*sintg[i]*revgamma,
+                                 Kx*sintgph[i]*revgamma,
+                                 betam*zloc-0.25*zterm*revgamma])
+                dr = R0 - rloc
+                dist = np.linalg.norm(dr, axis=0)
+                drs = 0.5*(dr[0, :]**2+dr[1, :]**2) / dr[2, :]
+                sinzloc = np.sin(wwuS * zloc*(1.-betam))
+                coszloc = np.cos(wwuS * zloc*(1.-betam))
+                sindrs = np.sin(wwuS * (drs + 0.25*zterm*revgamma))
+                cosdrs = np.cos(wwuS * (drs + 0.25*zterm*revgamma))
+                eucosx = (-sinr0z*sinzloc*cosdrs - sinr0z*coszloc*sindrs -
+                          cosr0z*sinzloc*sindrs + cosr0z*coszloc*cosdrs)
+                eucosy = (-sinr0z*sinzloc*sindrs + sinr0z*coszloc*cosdrs +
+                          cosr0z*sinzloc*cosdrs + cosr0z*coszloc*sindrs)
+                eucos = eucosx + 1j*eucosy
+                direction = dr/dist
+                dirx = direction[0, :]
+                diry = direction[1, :]
+                dirz = direction[2, :]
+            else:
+                ucos = ww1S*tg[i] + wwuS*revgamma *\
+                    (-Ky*ddphiS*sintg[i] + Kx*ddpsiS*sintgph[i] +
+                     0.125*revgamma*(Ky**2 * sin2x[i] + Kx**2 * sin2xph[i]))
+                eucos = np.exp(1j*ucos)
+            betax = taperC*Ky*revgamma*costg[i]
+            betay = -Kx*revgamma*costgph[i]
+            betaz = 1. - 0.5*(revgamma2 + betax*betax + betay*betay)
+            betaPx = -Ky*(alphaS*costg[i] + taperC*sintg[i])
+            betaPy = Kx*sintgph[i]
+            betaPz = 0.5*revgamma *\
+                (Ky**2 * taperC*(alphaS*costg[i]**2 + taperC*sin2x[i]) + Kx**2 * sin2xph[i])
+            rkrel = 1./(1. - dirx*betax - diry*betay - dirz*betaz)
+            eucos *= ag[i] * rkrel**2
+            bnx = dirx - betax
+            bny = diry - betay
+            bnz = dirz - betaz
+            dirDotBetaP = dirx*betaPx + diry*betaPy + dirz*betaPz
+            dirDotDmB = dirx*bnx + diry*bny + dirz*bnz
+            Bsr += eucos*(bnx*dirDotBetaP - betaPx*dirDotDmB)
+            Bpr += eucos*(bny*dirDotBetaP - betaPy*dirDotDmB)
+            if with_scale:
+                Ssr = Ssr + np.abs(eucos)*(np.abs(bnx*dirDotBetaP) + np.abs(betaPx*dirDotDmB))
+                Spr = Spr + np.abs(eucos)*(np.abs(bny*dirDotBetaP) + np.abs(betaPy*dirDotDmB))
+    if with_scale:
+        return wuS*revgamma*Bsr, wuS*revgamma*Bpr, wuS*revgamma*Ssr, wuS*revgamma*Spr
     return wuS*revgamma*Bsr, wuS*revgamma*Bpr
 
 
@@ -96,13 +151,21 @@ def sample_prefactors(L0, Np, Kx, Ky, gamma, w, ddtheta, ddpsi):
     return wu, ww1, ab
 
 
-def build_I_map(grid, L0, Np, Kx, Ky, eI, gamma, w, ddtheta, ddpsi, distE='eV'):
+def build_I_map(grid, L0, Np, Kx, Ky, eI, gamma, w, ddtheta, ddpsi, distE='eV', R0=None, taperVal=None):
     """Returns (I, Es, Ep) of synchr.py:2104-2108 for per-sample gamma (array) -- the energy-spread draw
-    (synchr.py:2053-2059) is the caller's business."""
+    (synchr.py:2053-2059) is the caller's business.  R0 [mm] / taperVal switch to the explicit period sum with
+    ab = 1/(2 pi wu) (synchr.py:2067-2079)."""
     NRAYS = len(w)
     gamma = gamma * np.ones(NRAYS)
     wu, ww1, ab = sample_prefactors(L0, Np, Kx, Ky, gamma, w, ddtheta, ddpsi)
-    Is_local, Ip_local = sp_sum(grid, Kx, Ky, ww1, w, wu, gamma, ddtheta, ddpsi)
+    if (taperVal is not None) or (R0 is not None):
+        ab = 1. / PI2 / wu
+    if R0:
+        R0v = np.array((np.tan(ddtheta), np.tan(ddpsi), np.ones_like(ddpsi)))
+        R0v *= R0*np.pi*2/L0
+    else:
+        R0v = None
+    Is_local, Ip_local = sp_sum(grid, Kx, Ky, ww1, w, wu, gamma, ddtheta, ddpsi, R0v, taperVal, Np)
     bwFact = 0.001 if distE == 'BW' else 1./w
     Amp2Flux = FINE_STR * bwFact * eI / SIE0
     integralField = np.abs(Is_local)**2 + np.abs(Ip_local)**2

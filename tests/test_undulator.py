@@ -163,3 +163,120 @@ def test_cuda_symmetric_pairs_vs_oracle_odd_and_tiled_grids(quadm, gI, cuda_devi
     for a, b in ((Is, ref_s), (Ip, ref_p), (Is0, ref_s), (Ip0, ref_p)):
         assert np.abs(a.cpu().numpy() - b).max() < 1e-9 * scale
     assert float((Is - Is0).abs().max()) < 1e-11 * scale
+
+
+# ------------------------------------------------------------------ f3: tapered and near-field undulators
+EXT_CASES = ['undulator_taper', 'undulator_taper_elliptical', 'undulator_nf', 'undulator_nf_elliptical']
+
+
+def _ext_args(g):
+    taper = None if np.isnan(g['taperVal']) else float(g['taperVal'])
+    R0 = None if np.isnan(g['R0']) else float(g['R0'])
+    return taper, R0
+
+
+@pytest.mark.parametrize('name', EXT_CASES)
+def test_oracle_ext_matches_reference_bit_exact(name):
+    g = golden(name)
+    grid = _grid(g)
+    for k in ('tg', 'ag', 'sintg', 'costg', 'sintgph', 'costgph'):
+        assert np.array_equal(grid[k], g[k]), k
+    taper, R0 = _ext_args(g)
+    assert (taper is None) != (R0 is None)
+    I, Es, Ep = ou.build_I_map(grid, float(g['L0']), int(g['Np']), float(g['Kx']), float(g['Ky']),
+                               float(g['eI']), g['gamma'], g['w'], g['theta'], g['psi'], R0=R0, taperVal=taper)
+    assert np.array_equal(I, g['I'])
+    assert np.array_equal(Es, g['Es'])
+    assert np.array_equal(Ep, g['Ep'])
+
+
+def _ext_reference_sums(g, grid):
+    taper, R0 = _ext_args(g)
+    L0, Np, Kx, Ky = float(g['L0']), int(g['Np']), float(g['Kx']), float(g['Ky'])
+    wu, ww1, _ = ou.sample_prefactors(L0, Np, Kx, Ky, g['gamma'], g['w'], g['theta'], g['psi'])
+    R0v = None
+    scalar0 = taper
+    if R0 is not None:
+        R0v = np.array((np.tan(g['theta']), np.tan(g['psi']), np.ones_like(g['psi'])))
+        R0v *= R0*np.pi*2/L0
+        scalar0 = R0*np.pi*2/L0
+    ref_s, ref_p, ss, sp = ou.sp_sum(grid, Kx, Ky, ww1, g['w'], wu, g['gamma'], g['theta'], g['psi'], R0v, taper, Np,
+                                     with_scale=True)
+    return wu, ww1, scalar0, ref_s, ref_p, ss, sp
+
+
+# Tolerance: the kernel evaluates the reference's expressions in the reference's rounding order (-fmad=false,
+# IEEE sqrt and division); what remains are <= 2 ulp differences of sin/cos.  In the near field the phase
+# k*(drs + ...) is ~1e3..1e4 rad, one ulp of which is ~1e-12 rad: assert 1e-11 * sum|terms|.
+EXT_TOL = 1e-11
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', EXT_CASES)
+def test_cuda_run_parallel_undulator_ext_vs_oracle(name, cuda_device):
+    """XRT_CUDA.run_parallel('undulator_taper' | 'undulator_nf', ...) with the argument list of
+    Undulator._build_I_map_CL (synchr.py:2134-2176)."""
+    from xrt_b200.cuda_backend import XRT_CUDA
+    g = golden(name)
+    grid = _grid(g)
+    wu, ww1, scalar0, ref_s, ref_p, ss, sp = _ext_reference_sums(g, grid)
+    taper, R0 = _ext_args(g)
+    ucl = XRT_CUDA('undulator.cl', targetOpenCL='CUDA:0')
+    n = len(g['w'])
+    Is = np.zeros(n, dtype=np.complex128)
+    Ip = np.zeros(n, dtype=np.complex128)
+    ret = ucl.run_parallel(
+        'undulator_taper' if taper is not None else 'undulator_nf',
+        [np.float64(scalar0), np.float64(g['Kx']), np.float64(g['Ky']), np.int32(len(grid['tg'])),
+         np.int32(g['Np'])],
+        [g['gamma'], wu, g['w'], ww1, g['theta'], g['psi']],
+        [grid[k] for k in ('tg', 'ag', 'sintg', 'costg', 'sintgph', 'costgph')], [Is, Ip], dimension=n)
+    assert ret[0] is Is and ret[1] is Ip
+    assert (np.abs(Is - ref_s) / ss).max() < EXT_TOL
+    assert (np.abs(Ip - ref_p) / (sp + ss)).max() < EXT_TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', EXT_CASES)
+def test_cuda_undulator_ext_build_I_map_vs_golden(name, cuda_device):
+    """Undulator(taper=... | R0=...).build_I_map (host arrays) and build_I_map_device (fused) against the
+    reference's own (I, Es, Ep)."""
+    import torch
+    from xrt_b200.sources import Undulator
+    from oracle.physconsts import FINE_STR, SIE0
+    g = golden(name)
+    grid = _grid(g)
+    wu, ww1, scalar0, ref_s, ref_p, ss, sp = _ext_reference_sums(g, grid)
+    taper, R0 = _ext_args(g)
+    src = Undulator(eE=3., eI=float(g['eI']), period=float(g['L0']), n=int(g['Np']), K=0, Kx=float(g['Kx']),
+                    Ky=float(g['Ky']), phaseDeg=float(np.degrees(g['phase'])), eMin=float(g['E_min']),
+                    eMax=float(g['E_max']), gNodes=int(g['quadm']), gIntervals=int(g['gIntervals']),
+                    taper=taper, R0=R0, eEspread=float(g['eEspread']), xPrimeMaxAutoReduce=False,
+                    zPrimeMaxAutoReduce=False)
+    assert src.gamma == float(g['gamma0'])
+    dg = g['gamma'] - float(g['gamma0'])
+    I, Es, Ep = src.build_I_map(g['w'], g['theta'], g['psi'], dg=dg if src.eEspread > 0 else None)
+    amp = np.abs(np.sqrt(FINE_STR / g['w'] * float(g['eI']) / SIE0) / (2 * np.pi) / wu * 0.5 * float(g['dstep']))
+    assert (np.abs(Es - g['Es']) / (amp * ss)).max() < EXT_TOL
+    assert (np.abs(Ep - g['Ep']) / (amp * (ss + sp))).max() < EXT_TOL
+    assert (np.abs(I - g['I']) / (amp**2 * (ss + sp)**2)).max() < EXT_TOL
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    Id, Esd, Epd = src.build_I_map_device(dev(g['w']), dev(g['theta']), dev(g['psi']), gamma=dev(g['gamma']))
+    assert (np.abs(Esd.cpu().numpy() - g['Es']) / (amp * ss)).max() < EXT_TOL
+    assert (np.abs(Epd.cpu().numpy() - g['Ep']) / (amp * (ss + sp))).max() < EXT_TOL
+    assert (np.abs(Id.cpu().numpy() - g['I']) / (amp**2 * (ss + sp)**2)).max() < EXT_TOL
+
+
+@pytest.mark.gpu
+def test_cuda_undulator_taper_shine(cuda_device):
+    """shine() of a tapered undulator runs the unfused device path (sample -> undulator_ext -> fill) and its
+    flux map equals build_I_map_device on the same samples."""
+    import torch
+    from xrt_b200.sources import Undulator
+    src = Undulator(eE=3., eI=0.5, period=30., n=20, K=1.45, eMin=1400., eMax=1500., gNodes=16, gIntervals=2,
+                    taper=(0.4, 10.), uniformRayDensity=True, nrays=5000, xPrimeMax=0.1, zPrimeMax=0.1)
+    beam = src.shine()
+    assert len(beam) == 5000
+    J = (beam.Jss + beam.Jpp).cpu().numpy()
+    assert np.all(np.isfinite(J)) and J.max() > 0
+    assert int((beam.state == 1).sum()) == 5000

@@ -140,7 +140,9 @@ def _undulator_dump(name, src, nsamp, seed, eEspread_seed=None):
          tg=src.tg, ag=src.ag, sintg=src.sintg, costg=src.costg, sintgph=src.sintgph, costgph=src.costgph,
          dstep=src.dstep, E_min=src.E_min, E_max=src.E_max, Theta_min=src.Theta_min, Theta_max=src.Theta_max,
          Psi_min=src.Psi_min, Psi_max=src.Psi_max, E1=src.E1, dx=src.dx, dz=src.dz, dxprime=src.dxprime,
-         dzprime=src.dzprime, w=w, theta=th, psi=ps, gamma=gam, I=I, Es=Es, Ep=Ep)
+         dzprime=src.dzprime, w=w, theta=th, psi=ps, gamma=gam, I=I, Es=Es, Ep=Ep,
+         taperVal=np.float64(np.nan if src._taperVal is None else src._taperVal),
+         R0=np.float64(np.nan if src.R0 is None else src.R0))
 
 
 def gen_undulator():
@@ -154,6 +156,26 @@ def gen_undulator():
     src = _undulator_source(K=0, Kx=0.9, Ky=1.2, phaseDeg=90, eMin=E1*0.5, eMax=E1*3.5, gNodes=40, gIntervals=3,
                             eEspread=8e-4)
     _undulator_dump('undulator_helical_spread', src, 900, 22, eEspread_seed=5)
+
+
+def gen_undulator_ext():
+    """f3: tapered and near-field undulators (explicit sum over the periods, synchr.py:1947-1996)."""
+    probe = _undulator_source(eMin=1000., eMax=1001., gNodes=16)
+    E1 = probe.E1
+    # planar, linear gap taper 0.5 mm over the device at a 10 mm gap
+    src = _undulator_source(eMin=E1*0.97, eMax=E1*1.03, gNodes=24, gIntervals=2, taper=(0.5, 10.))
+    _undulator_dump('undulator_taper', src, 240, 23)
+    # elliptical with taper (exercises the Kx terms of the taper branch), 3rd harmonic in the band
+    src = _undulator_source(K=0, Kx=0.7, Ky=1.1, phaseDeg=90, n=12, eMin=E1*0.8, eMax=E1*3.6, gNodes=20,
+                            gIntervals=3, taper=(-0.3, 12.))
+    _undulator_dump('undulator_taper_elliptical', src, 240, 24)
+    # near field: screen 25 m from a planar device; xPrimeMax wide enough for the finite-distance terms to matter
+    src = _undulator_source(eMin=E1*0.97, eMax=E1*1.03, gNodes=24, gIntervals=2, R0=25000.)
+    _undulator_dump('undulator_nf', src, 240, 25)
+    # near field, elliptical, short distance (5 m), energy spread
+    src = _undulator_source(K=0, Kx=0.7, Ky=1.1, phaseDeg=90, n=12, eMin=E1*0.8, eMax=E1*3.6, gNodes=20,
+                            gIntervals=3, R0=5000., eEspread=8e-4)
+    _undulator_dump('undulator_nf_elliptical', src, 240, 26, eEspread_seed=6)
 
 # ------------------------------------------------------------------------------------------------ reflect
 def _source_beam(bl, nrays, seed, withAmplitudes=True, dx=0.1, dz=0.05, dxprime=1e-4, dzprime=5e-5,
@@ -699,7 +721,7 @@ def gen_thin_crystals():
         save('reflect_crystal_' + key, d=si.d, tK=si.tK, t=t, geom=np.array(geom), alpha=0. if al is None else al, **dd)
 
 
-SECTIONS = {'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+SECTIONS = {'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)

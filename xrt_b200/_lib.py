@@ -49,6 +49,10 @@ PROTOTYPES = {
     'xrt_multilayer_f64_host': (c_int, [c_sz, c_int] + [c_dp] * 12),
     'xrt_plot_hist_f64': (c_int, [c_sz, c_dp, c_dp]),
     'xrt_hist2d_f64': (c_int, [c_sz, c_dp, c_dp, c_dp, c_dp, c_dp, c_int, c_dp, c_int, c_dp, c_int, c_dp, c_dp]),
+    'xrt_undulator_ext_f64': (c_int, [c_int, c_sz, c_int, c_int, c_dbl, c_dbl, c_dbl] + [c_dp] * 14 + [c_dp]),
+    'xrt_undulator_ext_f64_host': (c_int, [c_int, c_sz, c_int, c_int, c_dbl, c_dbl, c_dbl] + [c_dp] * 14),
+    'xrt_undulator_ext_imap_f64': (c_int, [c_int, c_sz, c_int, c_int] + [c_dbl] * 7 + [c_int] + [c_dp] * 13 +
+                                   [c_dp]),
     'xrt_undulator_imap_f64': (c_int, [c_sz, c_int] + [c_dbl] * 7 + [c_int] + [c_dp] * 13 + [c_int, c_dp]),
 }
 

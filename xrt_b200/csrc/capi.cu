@@ -286,6 +286,56 @@ int xrt_undulator_imap_f64(size_t n, int jend, double Kx, double Ky, double L0, 
                                (cudaStream_t)stream);
 }
 
+int xrt_undulator_ext_f64(int variant, size_t n, int jend, int nmax, double scalar0, double Kx, double Ky,
+                          const double* gamma, const double* wu, const double* w, const double* ww1,
+                          const double* ddphi, const double* ddpsi, const double* tg, const double* ag,
+                          const double* sintg, const double* costg, const double* sintgph, const double* costgph,
+                          double* Is, double* Ip, void* stream) {
+  return undulator_ext_device(variant, 0, n, jend, nmax, scalar0, Kx, Ky, 0.0, 0.0, 0.0, 0.0, 0, gamma, wu, w, ww1,
+                              ddphi, ddpsi, tg, ag, sintg, costg, sintgph, costgph, Is, Ip, nullptr,
+                              (cudaStream_t)stream);
+}
+
+int xrt_undulator_ext_f64_host(int variant, size_t n, int jend, int nmax, double scalar0, double Kx, double Ky,
+                               const double* gamma, const double* wu, const double* w, const double* ww1,
+                               const double* ddphi, const double* ddpsi, const double* tg, const double* ag,
+                               const double* sintg, const double* costg, const double* sintgph,
+                               const double* costgph, double* Is, double* Ip) {
+  if (n == 0) return 0;
+  XRTB_REQUIRE(jend > 0, "undulator_ext: the integration grid is empty");
+  cudaStream_t st = 0;
+  DevBuf samp[6], tab[6], out;
+  const double* hs[6] = {gamma, wu, w, ww1, ddphi, ddpsi};
+  const double* ht[6] = {tg, ag, sintg, costg, sintgph, costgph};
+  for (int i = 0; i < 6; ++i) {
+    if (samp[i].upload(hs[i], n * 8, st)) return 1;
+    if (tab[i].upload(ht[i], (size_t)jend * 8, st)) return 1;
+  }
+  if (out.alloc(2 * n * 16)) return 1;
+  double* o = out.as<double>();
+  int rc = undulator_ext_device(variant, 0, n, jend, nmax, scalar0, Kx, Ky, 0.0, 0.0, 0.0, 0.0, 0,
+                                samp[0].as<double>(), samp[1].as<double>(), samp[2].as<double>(),
+                                samp[3].as<double>(), samp[4].as<double>(), samp[5].as<double>(), tab[0].as<double>(),
+                                tab[1].as<double>(), tab[2].as<double>(), tab[3].as<double>(), tab[4].as<double>(),
+                                tab[5].as<double>(), o, o + 2 * n, nullptr, st);
+  if (rc) return rc;
+  XRTB_CUDA_CHECK(cudaMemcpyAsync(Is, o, n * 16, cudaMemcpyDeviceToHost, st));
+  XRTB_CUDA_CHECK(cudaMemcpyAsync(Ip, o + 2 * n, n * 16, cudaMemcpyDeviceToHost, st));
+  XRTB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int xrt_undulator_ext_imap_f64(int variant, size_t n, int jend, int nmax, double scalar0, double Kx, double Ky,
+                               double L0, double gamma0, double amp_const, double dstep, int bw_mode,
+                               const double* gamma, const double* w, const double* theta, const double* psi,
+                               const double* tg, const double* ag, const double* sintg, const double* costg,
+                               const double* sintgph, const double* costgph, double* I, double* Es, double* Ep,
+                               void* stream) {
+  return undulator_ext_device(variant, 1, n, jend, nmax, scalar0, Kx, Ky, L0, gamma0, amp_const, dstep, bw_mode,
+                              gamma, nullptr, w, nullptr, theta, psi, tg, ag, sintg, costg, sintgph, costgph, Es, Ep,
+                              I, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------ reflect
 int xrt_reflect_f64(size_t n, const xrt_oe_params* oe, const xrt_material_params* mat, const double* tables,
                     size_t table_len, const xrt_beam* in, const xrt_beam* fallback, const xrt_beam* gb,

@@ -27,6 +27,14 @@ int undulator_imap_device(size_t n, int jend, double Kx, double Ky, double L0, d
                           const double* theta, const double* psi, const double* tg, const double* ag,
                           const double* sintg, const double* costg, const double* sintgph, const double* costgph,
                           double* I, double* Es, double* Ep, int R, int symmetric, cudaStream_t st);
+// undulator_ext.cu: variant 1 = taper (scalar0 = _taperVal), 2 = near field (scalar0 = R0*2pi/L0);
+// mode 0 = raw (Is, Ip) of _sp_sum, 1 = fused _build_I_map_conv (I, Es, Ep)
+int undulator_ext_device(int variant, int mode, size_t n, int jend, int nmax, double scalar0, double Kx, double Ky,
+                         double L0, double gamma0, double amp_const, double dstep, int bw_mode, const double* gamma,
+                         const double* wu, const double* w, const double* ww1, const double* ddphi,
+                         const double* ddpsi, const double* tg, const double* ag, const double* sintg,
+                         const double* costg, const double* sintgph, const double* costgph, double* Is, double* Ip,
+                         double* I, cudaStream_t st);
 
 // reflect.cu (compiled with -fmad=false)
 int reflect_device(size_t n, const xrt_oe_params* oe, const xrt_material_params* mat, const double* tables,

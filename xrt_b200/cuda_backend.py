@@ -161,6 +161,39 @@ class XRT_CUDA(object):
         return Is, Ip
 
 
+    def _undulator_ext(self, variant, name, scalarArgs, slicedRO, nonSlicedRO, slicedRW, dimension):
+        """Argument layout of Undulator._build_I_map_CL for the tapered / near-field kernels
+        (sources/synchr.py:2134-2176): scalars [taper | R0*2pi/L0, Kx, Ky, jend, Np]; arrays as `undulator`."""
+        lib = _lib.load()
+        if len(scalarArgs) < 5:
+            raise ValueError(name + ': expected 5 scalars [taper or R0*2pi/L0, Kx, Ky, jend, Np]')
+        scalar0, Kx, Ky, jend, nmax = scalarArgs[:5]
+        samp = [_lib.as_f64(a) for a in slicedRO]
+        n = dimension if dimension else len(samp[0])
+        tabs = [_lib.as_f64(a) for a in nonSlicedRO]
+        if any(len(a) != n for a in samp) or len(samp) != 6:
+            raise ValueError(name + ': expected 6 sliced inputs of length dimension')
+        if any(len(a) != int(jend) for a in tabs) or len(tabs) != 6:
+            raise ValueError(name + ': expected 6 node tables of length jend')
+        Is, Ip = slicedRW
+        for a in (Is, Ip):
+            if not (isinstance(a, np.ndarray) and a.dtype == np.complex128 and a.flags['C_CONTIGUOUS'] and
+                    len(a) == n):
+                raise ValueError(name + ': slicedRWArgs must be 2 contiguous complex128[dimension]')
+        rc = lib.xrt_undulator_ext_f64_host(
+            variant, n, int(jend), int(nmax), float(scalar0), float(Kx), float(Ky), *[_lib.hptr(a) for a in samp],
+            *[_lib.hptr(a) for a in tabs], _lib.hptr(Is), _lib.hptr(Ip))
+        _lib.check(rc, 'xrt_undulator_ext_f64_host')
+        return Is, Ip
+
+    def _k_undulator_taper(self, scalarArgs, slicedRO, nonSlicedRO, slicedRW, nonSlicedRW, dimension):
+        """kernel `undulator_taper` (cl/undulator.cl:123-202), numpy-path numerics (synchr.py:1958-1971)."""
+        return self._undulator_ext(1, 'undulator_taper', scalarArgs, slicedRO, nonSlicedRO, slicedRW, dimension)
+
+    def _k_undulator_nf(self, scalarArgs, slicedRO, nonSlicedRO, slicedRW, nonSlicedRW, dimension):
+        """kernel `undulator_nf` (cl/undulator.cl:204-298), numpy-path numerics (synchr.py:1972-1996)."""
+        return self._undulator_ext(2, 'undulator_nf', scalarArgs, slicedRO, nonSlicedRO, slicedRW, dimension)
+
     def _k_get_amplitude_graded_multilayer(self, scalarArgs, slicedRO, nonSlicedRO, slicedRW, nonSlicedRW,
                                            dimension):
         """Argument layout of Multilayer.get_amplitude's accelerator call (materials/multilayer.py:471-484):

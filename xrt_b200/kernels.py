@@ -89,6 +89,26 @@ def undulator_imap(Kx, Ky, L0, Np, gamma0, amp_const, dstep, bw_mode, w, theta, 
     return I, Es, Ep
 
 
+def undulator_ext_imap(variant, scalar0, Kx, Ky, L0, Np, gamma0, amp_const, dstep, bw_mode, w, theta, psi, tables,
+                       gamma=None, out=None):
+    """f3 on device tensors: (I, Es, Ep) of Undulator._build_I_map_conv for a tapered (variant 1, scalar0 =
+    _taperVal) or near-field (variant 2, scalar0 = R0*pi*2/L0) undulator; Np periods summed explicitly."""
+    lib = _lib.load()
+    n = w.numel()
+    jend = tables[0].numel()
+    if out is None:
+        out = (torch.empty(n, dtype=F64, device=w.device), torch.empty(n, dtype=C128, device=w.device),
+               torch.empty(n, dtype=C128, device=w.device))
+    I, Es, Ep = out
+    rc = lib.xrt_undulator_ext_imap_f64(
+        int(variant), n, jend, int(Np), float(scalar0), float(Kx), float(Ky), float(L0), float(gamma0),
+        float(amp_const), float(dstep), int(bw_mode), _chk(gamma, F64, n) if gamma is not None else None,
+        _chk(w, F64, n), _chk(theta, F64, n), _chk(psi, F64, n), *[_chk(t, F64, jend) for t in tables],
+        _chk(I, F64, n), _chk(Es, C128, n), _chk(Ep, C128, n), _stream())
+    _lib.check(rc, 'xrt_undulator_ext_imap_f64')
+    return I, Es, Ep
+
+
 def _amplitude_host(material, E, bIn, bOut=None, bH=None):
     import numpy as np
     lib = _lib.load()

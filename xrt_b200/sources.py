@@ -2,11 +2,11 @@
 """`Undulator` with xrt's constructor and `shine()` / `build_I_map()` signatures, computing on the GPU.
 
 Mirrors xrt/backends/raycing/sources/sybase.py (SourceBase :29-547, IntegratedSource :933-1812) and
-sources/synchr.py (Undulator :1349-2260) for the far-field planar/helical undulator without taper:
-same keywords and units (eE GeV, eI A, eSigma um, eEpsilon nm rad, xPrimeMax mrad, period mm), same derived
+sources/synchr.py (Undulator :1349-2260) for planar/helical undulators in the far field, with a linear gap
+taper (`taper=(dgap, gap)`) or in the near field (`R0`): same keywords and units (eE GeV, eI A, eSigma um, eEpsilon nm rad, xPrimeMax mrad, period mm), same derived
 quantities (gamma, dx/dz/dxprime/dzprime, Theta/Psi/E windows, Clenshaw-Curtis grid), same flux bookkeeping
 on the returned Beam (accepted, acceptedE, seeded, seededI, sourceWeight).  Out of scope:
-taper, near field (R0), filamentBeam, custom field, wave=... sampling.
+filamentBeam, custom field, wave=... sampling.
 
 Per-ray work: xrt_b200/csrc/undulator.cu (field integral), source.cu (sampling, Beam assembly).
 """
@@ -66,9 +66,8 @@ class Undulator(object):
                  filamentBeam=False, pitch=0, yaw=0, period=50, n=50, K=1, Kx=0, Ky=0, phaseDeg=0, gp=1e-6,
                  gIntervals=2, gNodes=None, xPrimeMaxAutoReduce=True, zPrimeMaxAutoReduce=True,
                  targetOpenCL='CUDA', precisionOpenCL='float64', R0=None, taper=None, seed=1234, **kwargs):
-        if R0 is not None or taper is not None or filamentBeam:
-            raise NotImplementedError('near field, taper and filamentBeam are outside the hot path '
-                                      '(SURVEY.md section 8f3)')
+        if filamentBeam:
+            raise NotImplementedError('filamentBeam is outside the hot path (SURVEY.md section 8f3)')
         if targetOpenCL is None:
             raise _lib.XrtB200Error('xrt_b200.Undulator always computes on the GPU (no numpy path)')
         self.bl = bl
@@ -103,6 +102,10 @@ class Undulator(object):
         self.eMin, self.eMax = float(eMin), float(eMax)
         self.L0 = float(period)
         self.Np = float(n)
+        self.R0 = R0  # near field: distance to the screen [mm] (sybase.py:84-149)
+        self._set_taper(taper)
+        if self.R0 is not None:  # required for convergence (synchr.py:1433-1435)
+            xPrimeMaxAutoReduce = zPrimeMaxAutoReduce = True
         self.phase = np.radians(phaseDeg)
         if Kx == 0 and Ky == 0:  # synchr.py:1414-1431
             self.Kx, self.Ky = 0., float(K)
@@ -128,6 +131,36 @@ class Undulator(object):
         self.cl_precisionF, self.cl_precisionC = self.ucl.cl_precisionF, self.ucl.cl_precisionC
         self.report_E1()
         self.needReset = True
+
+    def _set_taper(self, taper):
+        """Undulator.taper setter (synchr.py:1566-1594): a number is dB/dx/B-like `_taperVal` itself, a pair is
+        (dgap, gap) [mm] -> _taperVal = dgap / Np / L0 / gap."""
+        if taper is None:
+            self._taperVal = None
+            self.taper = None
+        elif np.ndim(taper) == 0:
+            self._taperVal = float(taper)
+            self.taper = self._taperVal
+        else:
+            t = np.asarray(taper, dtype=float).ravel()
+            if len(t) == 1:
+                dgap, gap = 0., t[0]
+            elif len(t) == 2:
+                dgap, gap = t
+            else:
+                raise ValueError('Cannot set taper from {0}'.format(taper))
+            self.taper = (dgap, gap)
+            self.gap = gap
+            self._taperVal = None if dgap == 0 else dgap / self.Np / self.L0 / gap
+
+    @property
+    def _ext_variant(self):
+        """(variant, scalar0) of the explicit-period kernels, the dispatch of synchr.py:2136-2170; None: far field."""
+        if self._taperVal is not None:
+            return 1, self._taperVal
+        if self.R0 is not None:
+            return 2, self.R0*np.pi*2/self.L0
+        return None
 
     @staticmethod
     def _prime(v):
@@ -245,11 +278,24 @@ class Undulator(object):
         """The dispatch of Undulator._build_I_map_CL (synchr.py:2134-2174) through XRT_CUDA.run_parallel."""
         F = self.cl_precisionF
         NRAYS = len(w)
-        scalarArgs = [F(0.), F(self.Kx), F(self.Ky), np.int32(len(self.tg))]
+        scalarArgs = [F(0.)]
+        if self.R0 is not None:
+            scalarArgs = [F(self.R0*np.pi*2/self.L0)]
+        elif self._taperVal:
+            scalarArgs = [F(self._taperVal)]
+        scalarArgs.extend([F(self.Kx), F(self.Ky), np.int32(len(self.tg))])
+        if (self._taperVal is not None) or (self.R0 is not None):
+            scalarArgs.extend([np.int32(self.Np)])
         slicedROArgs = [F(gamma), F(wu), F(w), F(ww1), F(ddtheta), F(ddpsi)]
         nonSlicedROArgs = [F(self.tg), F(self.ag), F(self.sintg), F(self.costg), F(self.sintgph), F(self.costgph)]
         slicedRWArgs = [np.zeros(NRAYS, dtype=self.cl_precisionC), np.zeros(NRAYS, dtype=self.cl_precisionC)]
-        return self.ucl.run_parallel('undulator', scalarArgs, slicedROArgs, nonSlicedROArgs, slicedRWArgs,
+        if self._taperVal is not None:
+            clKernel = 'undulator_taper'
+        elif self.R0 is not None:
+            clKernel = 'undulator_nf'
+        else:
+            clKernel = 'undulator'
+        return self.ucl.run_parallel(clKernel, scalarArgs, slicedROArgs, nonSlicedROArgs, slicedRWArgs,
                                      dimension=NRAYS)
 
     def build_I_map(self, w, ddtheta, ddpsi, harmonic=None, dg=None):
@@ -268,7 +314,10 @@ class Undulator(object):
                 gamma = gamma + gamma * self.eEspread * np.random.normal(size=NRAYS)
         gamma = gamma * np.ones(NRAYS)
         wu, ww1 = self._wu_ww1(gamma, w, ddtheta, ddpsi)
-        ab = 1. / PI2 / wu * np.sin(PI * self.Np * ww1) / np.sin(PI * ww1)
+        if (self._taperVal is not None) or (self.R0 is not None):  # synchr.py:2129-2132
+            ab = 1. / PI2 / wu
+        else:
+            ab = 1. / PI2 / wu * np.sin(PI * self.Np * ww1) / np.sin(PI * ww1)
         Is_local, Ip_local = self._integral_host(gamma, wu, w, ww1, ddtheta, ddpsi)
         bwFact = 0.001 if self.distE == 'BW' else 1./w
         Amp2Flux = FINE_STR * bwFact * self.eI / SIE0
@@ -287,6 +336,12 @@ class Undulator(object):
         """(I, Es, Ep) as CUDA tensors from CUDA tensors (fused _build_I_map_conv)."""
         if self.needReset:
             self.reset()
+        ext = self._ext_variant
+        if ext is not None:
+            return kernels.undulator_ext_imap(ext[0], ext[1], self.Kx, self.Ky, self.L0, self.Np, self.gamma,
+                                              FINE_STR * self.eI / SIE0, self.dstep,
+                                              1 if self.distE == 'BW' else 0, w, theta, psi,
+                                              self._tables(w.device), gamma=gamma, out=out)
         return kernels.undulator_imap(self.Kx, self.Ky, self.L0, self.Np, self.gamma,
                                       FINE_STR * self.eI / SIE0, self.dstep, 1 if self.distE == 'BW' else 0,
                                       w, theta, psi, self._tables(w.device), gamma=gamma, out=out,
@@ -389,7 +444,7 @@ class Undulator(object):
         sumE = None
         sourceWeight = 0.
         given = samples is not None
-        if self.uniformRayDensity and not given and fused:
+        if self.uniformRayDensity and not given and fused and self._ext_variant is None:
             # one fused kernel: samples and (I, mJs, mJp) never leave the registers
             slot = self.shine_uniform_fused(bo, index_offset=index_offset, toGlobal=toGlobal)
             seeded = mcRays
