@@ -32,7 +32,8 @@ int xrt_b200_device_count(void);
 int xrt_b200_sm_count(void);
 const char* xrt_b200_last_error(void);
 int xrt_b200_sync(void* stream);
-/* sizeof() of the ABI structs below (0: xrt_beam, 1: xrt_oe_params, 2: xrt_material_params, 3: xrt_plane_params, 4: xrt_source_params), for binding checks */
+/* sizeof() of the ABI structs below (0: xrt_beam, 1: xrt_oe_params, 2: xrt_material_params, 3: xrt_plane_params, 4: xrt_source_params,
+ * 5: xrt_plot_params, 6: xrt_multilayer_params, 7: xrt_bm_params), for binding checks */
 size_t xrt_b200_sizeof(int which);
 /* Measured fp64 ceilings used as roofline denominators (bench.py). mode 0: dependent-free DFMA stream,
  * mode 1: DMMA m8n8k4, mode 2: both interleaved. Writes TFLOP/s (2 flop per FMA). */
@@ -156,6 +157,14 @@ typedef struct xrt_oe_params {
                              slots (reflect.py:1133-1136); 0 skips those block reductions (device pipelines) */
   int no_intersection;    /* noIntersectionSearch (reflect.py:676-681): the rays already sit on the surface (wave
                              samples): t = 0, the point is taken as it is (xyz_to_param for parametric OEs) */
+  /* f4: grating (material kind 'grating', toWhere = 3, reflect.py:840-861 + _grating_deflection :451-469).
+   * OE.local_g (base.py:688-717): 0 no grating; 1 / 2: groove density rho0 * sum_i (i+1) c_i coord^i along x / y
+   * (gratingDensity = ['x'|'y', rho0, c0, c1, ...]); 3: constant (0, g_rho0, 0) */
+  int grating;
+  int g_ncoef;
+  double g_rho0, g_coef[8];
+  double g_order;         /* diffraction order (a single int in the reference's OE.order) */
+  double g_amp;           /* >= 0: amplitude sqrt(efficiency) of that order (material.py:391-413); < 0: none */
 } xrt_oe_params;
 
 /* Material = what get_amplitude reads (materials/material.py:348-493, materials/crystal.py:492-645). */
@@ -275,6 +284,36 @@ int xrt_source_fill_f64(size_t n, const xrt_source_params* p, const int64_t* idx
                         const double* rTheta, const double* rPsi, const double* mJs, const double* mJp,
                         const double* n1, const double* n2, const double* n3, const double* n4, const xrt_beam* out,
                         size_t out_offset, void* stream);
+
+/* ------------------------------------------------------------------ f3: bending magnet / wiggler
+ * BendingMagnet / Wiggler (sources/synchr.py:69-609).  The reference computes these on the CPU only ("a GPU is not
+ * required and is not implemented", synchr.py:70-73); here they are device kernels so that the beam is born in HBM. */
+typedef struct xrt_bm_params {
+  double gamma0;          /* electron Lorentz factor (sybase.py:155) */
+  double B;               /* field [T] (synchr.py:88-103) */
+  double ro;              /* bending radius [m] */
+  double K, L0, Np, X0;   /* wiggler: deflection parameter, period [mm], periods, trajectory amplitude [mm]; a bending
+                             magnet has Np = 0.5 (synchr.py:96) */
+  double eI;              /* ring current [A] */
+  int isMPW;              /* 1: wiggler branches (synchr.py:204-206, :432-448) */
+  int bw_mode;            /* 1: distE == 'BW' */
+} xrt_bm_params;
+/* (I, Es, Ep) = BendingMagnet.build_I_map(w, theta, psi) (synchr.py:185-226); gamma[n] or NULL (then gamma0). */
+int xrt_bm_imap_f64(size_t n, const xrt_bm_params* bm, const double* gamma, const double* w, const double* theta,
+                    const double* psi, double* I, double* Es, double* Ep, void* stream);
+int xrt_bm_imap_f64_host(size_t n, const xrt_bm_params* bm, const double* gamma, const double* w,
+                         const double* theta, const double* psi, double* I, double* Es, double* Ep);
+/* Beam assembly of BendingMagnet.shine (synchr.py:370-480, :492-505) from samples (idx: optional gather of the
+ * accepted ones), (mJs, mJp) of xrt_bm_imap_f64, five standard normal deviates per sample (horizontal divergence,
+ * 1/gamma opening, vertical divergence, horizontal size, vertical size) and, for a wiggler, the period index. */
+int xrt_bm_fill_f64(size_t n, const struct xrt_source_params* p, const xrt_bm_params* bm, const long long* idx,
+                    const double* rE, const double* rTheta, const double* rPsi, const double* mJs, const double* mJp,
+                    const double* g1, const double* g2, const double* g3, const double* g4, const double* g5,
+                    const double* kint, const xrt_beam* out, size_t out_offset, void* stream);
+/* uniformRayDensity shine in one kernel (Philox sampling -> build_I_map -> Beam); imax_slot as xrt_shine_uniform_f64 */
+int xrt_bm_shine_uniform_f64(size_t n, uint64_t seed, uint64_t index_offset, const double* window,
+                             const struct xrt_source_params* sp, const xrt_bm_params* bm, const xrt_beam* out,
+                             uint64_t* imax_slot, void* stream);
 
 /* Fused uniformRayDensity source: xrt_source_sample_f64 + xrt_undulator_imap_f64 + xrt_source_fill_f64 in one
  * kernel (same Philox counters, same device functions => the same Beam bit for bit; samples and (I, mJs, mJp)

@@ -51,8 +51,19 @@ class Element(object):
         return f1 + 1j*f2
 
 
+class EmptyMaterial(object):
+    """materials/__init__.py:101-113: a 'grating' material without reflectivity (no get_amplitude)."""
+
+    def __init__(self, kind='grating'):
+        self.kind = kind
+        self.geom = ''
+        self.efficiency = None
+
+
 class Material(object):
-    def __init__(self, elements, quantities=None, kind='mirror', rho=0, t=None, table='Chantler total'):
+    def __init__(self, elements, quantities=None, kind='mirror', rho=0, t=None, table='Chantler total',
+                 efficiency=None):
+        self.efficiency = efficiency  # material.py:78-93, constant [(order, value), ...] only
         if isinstance(elements, str):
             elements = elements,
         self.elements = [Element(e, table) for e in elements]
@@ -69,6 +80,15 @@ class Material(object):
         for elem, xi in zip(self.elements, self.quantities):
             xf += (elem.Z + elem.get_f1f2(E)) * xi
         return 1 - 1e-24 * AVOGADRO * R0 / PI2 * (CH/E)**2 * self.rho * xf / self.mass
+
+    def get_grating_efficiency(self, beam, good):
+        """material.py:391-413 without an efficiency file."""
+        resI = np.zeros(good.sum())
+        order = beam.order[good]
+        for eff in self.efficiency:
+            resI[order == eff[0]] = eff[1]
+        resA = resI**0.5
+        return resA, resA, 0
 
     def get_amplitude(self, E, beamInDotNormal, fromVacuum=True):
         n = self.get_refractive_index(E)

@@ -49,6 +49,8 @@ class OESpec(object):
         self.material = None
         self.alpha = None
         self.isParametric = False
+        self.gratingDensity = None  # ['x'|'y', rho0, c0, c1, ...] (base.py:213-230)
+        self.order = 1
         self.__dict__.update(kw)
 
     sinAzimuth = property(lambda self: self.azimuth[0])
@@ -64,6 +66,21 @@ class OESpec(object):
             rx[rx < 0] = 0.
             return y**2/2.0/R + r*(1 - rx**0.5)
         raise ValueError(self.surface)
+
+    def local_g(self, x, y, rho=-100.):
+        """OE.local_g (base.py:688-717)."""
+        rhoList = self.gratingDensity
+        if rhoList is not None:
+            coord = x if rhoList[0] == 'x' else y
+            poly = 0.
+            for ic, coeff in enumerate(rhoList[2:]):
+                poly += (ic+1) * coeff * coord**ic
+            N = rhoList[1] * poly
+            if rhoList[0] == 'x':
+                return N, np.zeros_like(N), np.zeros_like(N)
+            elif rhoList[0] == 'y':
+                return np.zeros_like(N), N, np.zeros_like(N)
+        return 0, rho, 0
 
     def local_n(self, x, y):
         if self.surface == 'flat':
@@ -325,6 +342,8 @@ def _grating_deflection(goodN, lb, g, oeNormal, beamInDotNormal, order=1, sig=No
     beamInDotG = lb.a[goodN]*g[0] + lb.b[goodN]*g[1] + lb.c[goodN]*g[2]
     G2 = g[0]**2 + g[1]**2 + g[2]**2
     locOrder = order
+    lb.order = np.zeros(len(lb.a))  # reflect.py:458-459
+    lb.order[goodN] = locOrder
     orderLambda = locOrder * CH / lb.E[goodN] * 1e-7
     u = beamInDotNormal**2 - 2*beamInDotG*orderLambda - G2*orderLambda**2
     gs = np.sign(beamInDotNormal) if sig is None else sig
@@ -400,7 +419,17 @@ def reflect_local(oe, good, lb, vlb, pitch, roll, yaw, dx=None, dy=None, dz=None
             beamInDotSurfaceNormal = beamInDotNormal
         isMultilayer = material is not None and material.kind == 'multilayer'
         transmitted = isCrystal and matSur.geom.endswith('transmitted')  # toWhere = 2 (reflect.py:756, :862-878)
-        if (isCrystal or isMultilayer) and not transmitted:
+        isGrating = material is not None and material.kind == 'grating'  # toWhere = 3 (reflect.py:743-744)
+        if isGrating:
+            # reflect.py:840-861
+            if oe.isParametric:
+                tXN, tYN = oe.param_to_xyz(lb.x[goodN], lb.y[goodN], lb.z[goodN])[0:2]
+            else:
+                tXN, tYN = lb.x[goodN], lb.y[goodN]
+            gNormal = np.asarray(oe.local_g(tXN, tYN), order='F')
+            a_out, b_out, c_out = _grating_deflection(goodN, lb, gNormal, oeNormal, beamInDotSurfaceNormal,
+                                                      oe.order, -1)
+        elif (isCrystal or isMultilayer) and not transmitted:
             # _get_asymmetric_reflection_grating (reflect.py:568-612)
             normalDotSurfNormal = oeNormal[0]*oeNormal[-3] + oeNormal[1]*oeNormal[-2] + oeNormal[2]*oeNormal[-1]
             bdn = beamInDotNormal.sum() / len(beamInDotNormal)
@@ -435,6 +464,10 @@ def reflect_local(oe, good, lb, vlb, pitch, roll, yaw, dx=None, dy=None, dz=None
                                             beamInDotNormal)
             elif isMultilayer:  # reflect.py:999-1003
                 refl = matSur.get_amplitude(lb.E[goodN], beamInDotSurfaceNormal, lb.x[goodN], lb.y[goodN])
+            elif not hasattr(matSur, 'get_amplitude'):  # EmptyMaterial: findReflectivity stays False (:940-942)
+                refl = 1., 1.
+            elif isGrating and matSur.efficiency is not None:  # reflect.py:1005-1011
+                refl = matSur.get_grating_efficiency(lb, goodN)
             else:
                 refl = matSur.get_amplitude(lb.E[goodN], beamInDotNormal, True)
         else:

@@ -721,7 +721,90 @@ def gen_thin_crystals():
         save('reflect_crystal_' + key, d=si.d, tK=si.tK, t=t, geom=np.array(geom), alpha=0. if al is None else al, **dd)
 
 
-SECTIONS = {'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+def gen_gratings():
+    """f4: gratings (toWhere = 3, reflect.py:840-861)."""
+    bl = raycing.BeamLine()
+    # (1) plane VLS grating, Au coated, order -1, soft X-rays at 2 deg grazing, density along y
+    beam = _source_beam(bl, 2500, 51, dx=0.3, dz=0.1, dxprime=2e-4, dzprime=1e-4, energies=(395., 405.))
+    Au = rm.Material('Au', rho=19.3, kind='grating')
+    gd = ['y', 1200., 1., 2e-4, -3e-7, 1.5e-9]
+    oe = roe.OE(bl, 'PG', center=(0, 20000, 0), pitch=np.radians(2.), material=Au, gratingDensity=gd, order=-1,
+                limPhysX=[-8, 8], limPhysY=[-40, 35])
+    d = _capture_reflect(oe, beam)
+    d.update(_oe_params(oe))
+    save('reflect_grating_vls', rho=19.3, gratingDensity=np.array(gd[1:], dtype=float), gratingAxis=np.array('y'),
+         order=np.int64(-1), **d)
+    # (2) toroidal grating without coating (EmptyMaterial), grooves along x (sagittal), order +2, 'auto' kind
+    beam = _source_beam(bl, 2500, 52, dx=0.3, dz=0.1, dxprime=2e-4, dzprime=1e-4, energies=(900., 1000.))
+    gd = ['x', 600., 1., -1e-3]
+    oe = roe.ToroidMirror(bl, 'TG', center=(0, 15000, 0), pitch=np.radians(1.5), R=5e5, r=400.,
+                          gratingDensity=gd, order=2, limPhysX=[-6, 6], limPhysY=[-60, 60])
+    d = _capture_reflect(oe, beam)
+    d.update(_oe_params(oe))
+    save('reflect_grating_toroid', R=float(oe.R), r=float(oe.r), gratingDensity=np.array(gd[1:], dtype=float),
+         gratingAxis=np.array('x'), order=np.int64(2), **d)
+    # (3) constant line density through the default local_g (0, -100, 0) with tabulated efficiencies
+    beam = _source_beam(bl, 2000, 53, dx=0.3, dz=0.1, dxprime=2e-4, dzprime=1e-4, energies=(395., 405.))
+    mat = rm.Material('Au', rho=19.3, kind='grating', efficiency=[(1, 0.3), (2, 0.05)])
+    oe = roe.OE(bl, 'PG2', center=(0, 20000, 0), pitch=np.radians(2.), material=mat, order=1,
+                limPhysX=[-8, 8], limPhysY=[-40, 35])
+    d = _capture_reflect(oe, beam)
+    d.update(_oe_params(oe))
+    save('reflect_grating_efficiency', rho=19.3, order=np.int64(1), eff_orders=np.array([1, 2]),
+         eff_values=np.array([0.3, 0.05]), **d)
+
+
+def _bm_source(kind, **kw):
+    bl = raycing.BeamLine()
+    kwargs = dict(eE=3., eI=0.5, eSigmaX=48.65, eSigmaZ=6.197, eEpsilonX=0.263, eEpsilonZ=0.008,
+                  eMin=2000., eMax=22000., xPrimeMax=0.5, zPrimeMax=0.2)
+    if kind == 'bm':
+        kwargs.update(B0=1.7)
+    else:
+        kwargs.update(K=12., period=80., n=10)
+    kwargs.update(kw)
+    return (rs.BendingMagnet if kind == 'bm' else rs.Wiggler)(bl, **kwargs)
+
+
+def _bm_params(src):
+    return dict(gamma=src.gamma, B=src.B, ro=src.ro, Np=float(src.Np), isMPW=src.isMPW,
+                K=float(getattr(src, 'K', 0.)), L0=float(getattr(src, 'L0', 0.)), X0=float(getattr(src, 'X0', 0.)),
+                eI=src.eI, eEspread=src.eEspread, E_min=src.E_min, E_max=src.E_max, Theta_min=src.Theta_min,
+                Theta_max=src.Theta_max, Psi_min=src.Psi_min, Psi_max=src.Psi_max, dx=src.dx, dz=src.dz,
+                dxprime=src.dxprime, dzprime=src.dzprime, distE=np.array(src.distE))
+
+
+def gen_bm():
+    """f3: BendingMagnet / Wiggler (sources/synchr.py:69-609): build_I_map on seeded samples and seeded shine."""
+    for kind in ('bm', 'wiggler'):
+        src = _bm_source(kind)
+        src.reset()
+        rng = np.random.RandomState(61)
+        n = 3000
+        w = rng.uniform(src.E_min, src.E_max, n)
+        th = rng.uniform(src.Theta_min, src.Theta_max, n)
+        ps = rng.uniform(src.Psi_min, src.Psi_max, n)
+        w[:40] = np.geomspace(5., 3e5, 40)  # eta from ~1e-4 to the underflow of K_nu
+        I, Es, Ep = src.build_I_map(w, th, ps)
+        save('%s_imap' % kind, w=w, theta=th, psi=ps, I=I, Es=Es, Ep=Ep, **_bm_params(src))
+        for mode, uniform, nrays, seed, spread in (('uniform', True, 2500, 62, 0.), ('rejection', False, 1200, 63, 1e-3)):
+            src = _bm_source(kind, nrays=nrays, uniformRayDensity=uniform, eEspread=spread,
+                             center=(0.5, -2., 0.1), pitch=1e-5, yaw=-2e-5, eMin=5000., eMax=9000.)
+            src.bl.azimuth = 0.05
+            np.random.seed(seed)
+            beam = src.shine()
+            d = _bm_params(src)
+            d.update(center=np.array(src.center, dtype=float), sinAzimuth=src.bl.sinAzimuth,
+                     cosAzimuth=src.bl.cosAzimuth, pitch=src.pitch, yaw=src.yaw, seed=seed, nrays=nrays,
+                     uniform=uniform, Imax=src.Imax, xzE=src.xzE, fluxConst=src.fluxConst, accepted=beam.accepted,
+                     acceptedE=beam.acceptedE, seeded=beam.seeded, seededI=beam.seededI,
+                     sourceWeight=beam.sourceWeight)
+            d.update(beam_dict(beam, 'out_'))
+            save('%s_shine_%s' % (kind, mode), **d)
+            print(kind, mode, 'seeded', beam.seeded, 'rays', len(beam.x))
+
+
+SECTIONS = {'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)

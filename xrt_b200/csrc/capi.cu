@@ -164,7 +164,7 @@ int xrt_b200_init(int device) {
 int xrt_b200_sm_count(void) { return num_sms(); }
 
 size_t xrt_b200_sizeof(int which) {
-  return which == 0 ? sizeof(xrt_beam) : which == 1 ? sizeof(xrt_oe_params) : which == 2 ? sizeof(xrt_material_params) : which == 3 ? sizeof(xrt_plane_params) : which == 4 ? sizeof(xrt_source_params) : which == 5 ? sizeof(xrt_plot_params) : which == 6 ? sizeof(xrt_multilayer_params) : 0;
+  return which == 0 ? sizeof(xrt_beam) : which == 1 ? sizeof(xrt_oe_params) : which == 2 ? sizeof(xrt_material_params) : which == 3 ? sizeof(xrt_plane_params) : which == 4 ? sizeof(xrt_source_params) : which == 5 ? sizeof(xrt_plot_params) : which == 6 ? sizeof(xrt_multilayer_params) : which == 7 ? sizeof(xrt_bm_params) : 0;
 }
 
 const char* xrt_b200_last_error(void) { return g_err; }
@@ -466,6 +466,47 @@ int xrt_shine_uniform_f64(size_t n, uint64_t seed, uint64_t index_offset, const 
   return shine_uniform_device(n, seed, index_offset, window, jend, Kx, Ky, L0, Np, gamma0, amp_const, dstep, bw_mode,
                               symmetric, tg, ag, sintg, costg, sintgph, costgph, p, out,
                               reinterpret_cast<unsigned long long*>(imax_slot), (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ bending magnet / wiggler
+int xrt_bm_imap_f64(size_t n, const xrt_bm_params* bm, const double* gamma, const double* w, const double* theta,
+                    const double* psi, double* I, double* Es, double* Ep, void* stream) {
+  return bm_imap_device(n, bm, gamma, w, theta, psi, I, Es, Ep, (cudaStream_t)stream);
+}
+
+int xrt_bm_imap_f64_host(size_t n, const xrt_bm_params* bm, const double* gamma, const double* w,
+                         const double* theta, const double* psi, double* I, double* Es, double* Ep) {
+  if (n == 0) return 0;
+  XRTB_REQUIRE(bm && w && theta && psi && I && Es && Ep, "bm_imap: NULL argument");
+  cudaStream_t st = 0;
+  DevBuf dg, dw, dt, dp, out;
+  if (gamma && dg.upload(gamma, n * 8, st)) return 1;
+  if (dw.upload(w, n * 8, st) || dt.upload(theta, n * 8, st) || dp.upload(psi, n * 8, st)) return 1;
+  if (out.alloc(n * 40)) return 1;
+  double* o = out.as<double>();
+  int rc = bm_imap_device(n, bm, gamma ? dg.as<double>() : nullptr, dw.as<double>(), dt.as<double>(),
+                          dp.as<double>(), o, o + n, o + 3 * n, st);
+  if (rc) return rc;
+  XRTB_CUDA_CHECK(cudaMemcpyAsync(I, o, n * 8, cudaMemcpyDeviceToHost, st));
+  XRTB_CUDA_CHECK(cudaMemcpyAsync(Es, o + n, n * 16, cudaMemcpyDeviceToHost, st));
+  XRTB_CUDA_CHECK(cudaMemcpyAsync(Ep, o + 3 * n, n * 16, cudaMemcpyDeviceToHost, st));
+  XRTB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int xrt_bm_fill_f64(size_t n, const xrt_source_params* p, const xrt_bm_params* bm, const long long* idx,
+                    const double* rE, const double* rTheta, const double* rPsi, const double* mJs, const double* mJp,
+                    const double* g1, const double* g2, const double* g3, const double* g4, const double* g5,
+                    const double* kint, const xrt_beam* out, size_t out_offset, void* stream) {
+  return bm_fill_device(n, p, bm, idx, rE, rTheta, rPsi, mJs, mJp, g1, g2, g3, g4, g5, kint, out, out_offset,
+                        (cudaStream_t)stream);
+}
+
+int xrt_bm_shine_uniform_f64(size_t n, uint64_t seed, uint64_t index_offset, const double* window,
+                             const xrt_source_params* sp, const xrt_bm_params* bm, const xrt_beam* out,
+                             uint64_t* imax_slot, void* stream) {
+  return bm_shine_uniform_device(n, seed, index_offset, window, sp, bm, out,
+                                 reinterpret_cast<unsigned long long*>(imax_slot), (cudaStream_t)stream);
 }
 
 int xrt_oe_surface_f64(size_t n, const xrt_oe_params* oe, const double* x, const double* y, double* z,

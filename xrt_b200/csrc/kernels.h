@@ -68,6 +68,16 @@ int source_fill_device(size_t n, const xrt_source_params* p, const long long* id
                        const double* n1, const double* n2, const double* n3, const double* n4, const xrt_beam* out,
                        size_t out_offset, cudaStream_t st);
 
+int bm_imap_device(size_t n, const xrt_bm_params* bm, const double* gamma, const double* w, const double* theta,
+                   const double* psi, double* I, double* Es, double* Ep, cudaStream_t st);
+int bm_fill_device(size_t n, const xrt_source_params* p, const xrt_bm_params* bm, const long long* idx,
+                   const double* rE, const double* rTheta, const double* rPsi, const double* mJs, const double* mJp,
+                   const double* g1, const double* g2, const double* g3, const double* g4, const double* g5,
+                   const double* kint, const xrt_beam* out, size_t out_offset, cudaStream_t st);
+int bm_shine_uniform_device(size_t n, uint64_t seed, uint64_t index_offset, const double* window,
+                            const xrt_source_params* sp, const xrt_bm_params* bm, const xrt_beam* out,
+                            unsigned long long* imax_slot, cudaStream_t st);
+
 int plot_hist_device(size_t n, const xrt_plot_params* p, cudaStream_t st);
 int hist2d_device(size_t n, const double* x, const double* y, const double* w1, const double* w2, const int* state,
                   int state_mask, const double* ex, int nx, const double* ey, int ny, double* out, cudaStream_t st);

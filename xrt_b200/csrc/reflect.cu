@@ -1096,6 +1096,36 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
           bo = bo / nn;
           co = co / nn;
           bos = ao * nrm[3] + bo * nrm[4] + co * nrm[5];
+        } else if (p.grating) {
+          // toWhere = 3 (reflect.py:840-861): g = OE.local_g(x, y) (base.py:688-717), then _grating_deflection
+          // (reflect.py:451-469) with the surface normal, beamInDotSurfaceNormal, the order and sig = -1
+          double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+          if (p.grating == 3) {
+            g1 = p.g_rho0;
+          } else {
+            const double coord = (p.grating == 1) ? cx : cy;
+            double poly = 0.0;
+            for (int ic = 0; ic < p.g_ncoef; ++ic) {
+              // (ic+1) * coeff * coord**ic: numpy takes x**0 = 1, x**1 = x, x**2 = x*x and pow() beyond
+              const double pw = ic == 0 ? 1.0 : ic == 1 ? coord : ic == 2 ? coord * coord : pow(coord, (double)ic);
+              poly += ((double)(ic + 1) * p.g_coef[ic]) * pw;
+            }
+            const double N = p.g_rho0 * poly;
+            if (p.grating == 1) g0 = N; else g1 = N;
+          }
+          const double CH = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8;
+          const double bdg = la * g0 + lbb * g1 + lc * g2;
+          const double G2 = g0 * g0 + g1 * g1 + g2 * g2;
+          const double ol = p.g_order * CH / in.E[i] * 1e-7;
+          const double u = bds * bds - 2.0 * bdg * ol - G2 * (ol * ol);
+          const double dn = bds + (-1.0) * sqrt(fabs(u));
+          ao = la - nrm[3] * dn + g0 * ol;
+          bo = lbb - nrm[4] * dn + g1 * ol;
+          co = lc - nrm[5] * dn + g2 * ol;
+          const double nn = sqrt(ao * ao + bo * bo + co * co);
+          ao = ao / nn;
+          bo = bo / nn;
+          co = co / nn;
         } else {
           ao = la - nrm[0] * 2.0 * bdn;
           bo = lbb - nrm[1] * 2.0 * bdn;
@@ -1186,6 +1216,13 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
           Jsp = cmul_np(cmul_np(Jsp, ras), cconj(rap));
           Jss = js.re;
           Jpp = jp.re;
+        } else if (p.grating && p.g_amp >= 0.0) {
+          // grating efficiency (material.py:391-413): ras = rap = resI**0.5, a real array
+          ras = cplx{p.g_amp, 0.0};
+          rap = ras;
+          Jss = (Jss * p.g_amp) * p.g_amp;
+          Jpp = (Jpp * p.g_amp) * p.g_amp;
+          Jsp = cplx{(Jsp.re * p.g_amp) * p.g_amp, (Jsp.im * p.g_amp) * p.g_amp};
         } else {
           // refl = 1., 1.: J * 1. * conj(1.) with Python floats leaves the values unchanged
         }
@@ -1193,6 +1230,9 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
           if (MAT != 0) {
             Es = cmul_np(Es, ras);
             Ep = cmul_np(Ep, rap);
+          } else if (p.grating && p.g_amp >= 0.0) {
+            Es = cplx{Es.re * p.g_amp, Es.im * p.g_amp};
+            Ep = cplx{Ep.re * p.g_amp, Ep.im * p.g_amp};
           }
           // mPh = exp(1e7j * E/CHBAR * tMax) (reflect.py:1061-1064): im = ((1e7*E) * (1/CHBAR)) * tMax
           const double CHBAR = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8 / 6.283185307179586476925286766559;

@@ -291,6 +291,309 @@ __global__ void __launch_bounds__(U_THREADS)
   if ((threadIdx.x & 31) == 0 && imax > 0.0) atomicMax(imax_slot, (unsigned long long)__double_as_longlong(imax));
 }
 
+// ---------------------------------------------------------------- f3: bending magnet / wiggler
+// Replaces the per-ray numpy body of BendingMagnet.build_I_map (sources/synchr.py:185-226, Wiggler = the isMPW
+// branch) and of BendingMagnet.shine (synchr.py:321-480).  Oracle: oracle/synchrotron.py.
+
+// K_{1/3}(x) and K_{2/3}(x) for x > 0 (scipy.special.kv in the reference, synchr.py:215-217): the pair
+// (K_mu, K_{mu+1}) with mu = -1/3 (K_{-1/3} = K_{1/3}) by Temme's series for x <= 2 and Steed's continued
+// fraction CF2 above (the construction of Numerical Recipes' bessik); relative accuracy ~2e-14 near x = 2
+// (where AMOS, behind scipy, is at 4e-14 itself) and ~1e-15 elsewhere (checked against 40-digit values).
+__device__ __forceinline__ void bessel_k13_k23(double x, double& k13, double& k23) {
+  if (!(x > 0.0)) {  // kv(nu, 0) = inf, kv(nu, nan) = nan
+    k13 = k23 = (x == 0.0) ? __longlong_as_double(0x7ff0000000000000ll) : __longlong_as_double(0x7ff8000000000000ll);
+    return;
+  }
+  if (x > 800.0) {  // exp(-x) underflows (kv returns 0 beyond ~745)
+    k13 = k23 = 0.0;
+    return;
+  }
+  const double xmu = -0.33333333333333333333, xmu2 = xmu * xmu;
+  const double gampl = 0.738488111621648312935754375165, gammi = 1.11984652172218568497905093727;
+  const double gam1 = -0.572037615150806058064944843158, gam2 = 0.929167316671916998957402656217;
+  const double xi = 1.0 / x, xi2 = 2.0 * xi;
+  if (x <= 2.0) {
+    const double x2 = 0.5 * x;
+    const double fact = 1.20919957615614523372938550509;  // pi mu / sin(pi mu)
+    double d = -log(x2);
+    double e = xmu * d;
+    const double fact2 = (fabs(e) < 1e-150) ? 1.0 : sinh(e) / e;
+    double ff = fact * (gam1 * cosh(e) + gam2 * fact2 * d);
+    double sum = ff;
+    e = exp(e);
+    double p = 0.5 * e / gampl, q = 0.5 / (e * gammi), c = 1.0, sum1 = p;
+    d = x2 * x2;
+    for (int i = 1; i <= 80; ++i) {
+      const double di = (double)i;
+      ff = (di * ff + p + q) / (di * di - xmu2);
+      c *= d / di;
+      p /= (di - xmu);
+      q /= (di + xmu);
+      const double del = c * ff;
+      sum += del;
+      sum1 += c * (p - di * ff);
+      if (fabs(del) < fabs(sum) * 1e-17) break;
+    }
+    k13 = sum;
+    k23 = sum1 * xi2;
+  } else {
+    double b = 2.0 * (1.0 + x), d = 1.0 / b, h = d, delh = d;
+    double q1 = 0.0, q2 = 1.0;
+    const double a1 = 0.25 - xmu2;
+    double q = a1, c = a1, a = -a1;
+    double s = 1.0 + q * delh;
+    for (int i = 2; i <= 400; ++i) {
+      a -= 2.0 * (double)(i - 1);
+      c = -a * c / (double)i;
+      const double qnew = (q1 - b * q2) / a;
+      q1 = q2;
+      q2 = qnew;
+      q += c * qnew;
+      b += 2.0;
+      d = 1.0 / (b + a * d);
+      delh = (b * d - 1.0) * delh;
+      h += delh;
+      const double dels = q * delh;
+      s += dels;
+      if (fabs(dels / s) < 1e-17) break;
+    }
+    h = a1 * h;
+    k13 = sqrt(3.1415926535897932384626433832795 / (2.0 * x)) * exp(-x) / s;
+    k23 = k13 * (xmu + x + 0.5 - h) * xi;
+  }
+}
+
+__device__ __forceinline__ bool finite_d(double v) { return fabs(v) <= 1.7976931348623157e308; }
+
+// One sample of BendingMagnet.build_I_map.  ampS is purely imaginary and ampP purely real in the reference's
+// complex arithmetic (-0.5j * ..., then 1j * ...): js = (0, s), jp = (p, 0).  Complex-by-real division in numpy
+// multiplies by the reciprocal (Smith's algorithm with a zero imaginary divisor), reproduced here.
+__device__ __forceinline__ void bm_sample(const xrt_bm_params& p, double gamma, double dde, double ddtheta,
+                                          double ddpsi, double& I, cplx& js, cplx& jp) {
+  const double SIE0 = 1.602176565e-19, SIM0 = 9.109383701528e-31, E2W = 1519267514747457.9195337718065469;
+  const double PI_ = 3.1415926535897932384626433832795, SQ3 = 1.7320508075688772935274463415059;
+  const double FINE_STR = 1 / 137.03599976;
+  const double gamma2 = gamma * gamma;
+  double w_cr = 1.5 * gamma2 * p.B * SIE0 / SIM0;
+  if (p.isMPW) {
+    const double thetaArg = ddtheta * gamma / p.K;
+    double cl = 1.0 - thetaArg * thetaArg;
+    if (cl < 0.0) cl = 0.0;
+    w_cr *= sqrt(cl);
+  }
+  if (!finite_d(w_cr)) w_cr = 0.0;
+  const double gammapsi = gamma * ddpsi;
+  const double g2p1 = gammapsi * gammapsi + 1.0;
+  const double eta = 0.5 * dde * E2W / w_cr * pow(g2p1, 1.5);
+  const double c0 = (-0.5 * SQ3) / PI_;  // imaginary part of -0.5j * SQ3 / PI
+  const double sp = (c0 * gamma * dde * E2W) * (1.0 / w_cr) * g2p1;  // Im(ampSP)
+  double k13, k23;
+  bessel_k13_k23(eta, k13, k23);
+  double aS = sp * k23;                                       // Im(ampS)
+  double aP = (-(gammapsi * sp)) * k13 * (1.0 / sqrt(g2p1));  // Re(ampP)
+  if (!finite_d(aS)) aS = 0.0;
+  if (!finite_d(aP)) aP = 0.0;
+  const double bwFact = p.bw_mode ? 0.001 : 1.0 / dde;
+  const double Amp2Flux = FINE_STR * bwFact * p.eI / SIE0 * 2.0 * p.Np;
+  const double mS = fabs(aS), mP = fabs(aP);
+  I = Amp2Flux * (mS * mS + mP * mP);
+  const double sq = sqrt(Amp2Flux);
+  js = cplx{0.0, sq * aS};
+  jp = cplx{sq * aP, 0.0};
+}
+
+__global__ void __launch_bounds__(256) bm_imap_kernel(size_t n, xrt_bm_params p, const double* __restrict__ gamma,
+                                                      const double* __restrict__ w, const double* __restrict__ theta,
+                                                      const double* __restrict__ psi, double* __restrict__ Iout,
+                                                      double2* __restrict__ Es, double2* __restrict__ Ep) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double I;
+  cplx js, jp;
+  bm_sample(p, gamma ? gamma[i] : p.gamma0, w[i], theta[i], psi[i], I, js, jp);
+  Iout[i] = I;
+  Es[i] = make_double2(js.re, js.im);
+  Ep[i] = make_double2(jp.re, jp.im);
+}
+
+// Beam assembly of BendingMagnet.shine (synchr.py:370-480) for one accepted sample.  g1..g5: standard normal
+// deviates (horizontal divergence, 1/gamma opening [bending magnet only], vertical divergence, horizontal size,
+// vertical size); kint: the period index np.random.randint(-Np, Np) of a wiggler.
+__device__ __forceinline__ void bm_fill_ray(const xrt_source_params& p, const xrt_bm_params& bm, double E,
+                                            double Theta0, double Psi0, cplx js, cplx jp, double g1, double g2,
+                                            double g3, double g4, double g5, double kint, const xrt_beam& out,
+                                            size_t o) {
+  const double PI_ = 3.1415926535897932384626433832795, PI2 = 6.283185307179586476925286766559;
+  double dtheta = 0.0, dpsi = 0.0;
+  if (p.dxprime > 0.0) dtheta = 0.0 + p.dxprime * g1;
+  if (!bm.isMPW) dtheta += 0.0 + 1.0 / bm.gamma0 * g2;
+  if (p.dzprime > 0.0) dpsi = 0.0 + p.dzprime * g3;
+  double a = tan(Theta0 + dtheta), b = 1.0, c = tan(Psi0 + dpsi);
+  const double intensS = cmul_np3(js, cconj(js)).re;
+  const double intensP = cmul_np3(jp, cconj(jp)).re;
+  const double sSP = p.uniform ? 1.0 : intensS + intensP;
+  double x, y, z = 0.0;
+  cplx Jsp{0.0, 0.0};
+  if (bm.isMPW) {
+    const double CHeVcm = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12;
+    const double sigma_r2 = 2.0 * (CHeVcm / E * 10.0 * bm.L0 * bm.Np) / (PI2 * PI2);
+    const double SX = sqrt(p.dx * p.dx + sigma_r2), SZ = sqrt(p.dz * p.dz + sigma_r2);
+    double thetaArg = Theta0 * bm.gamma0 / bm.K;
+    if (thetaArg < -1.0) thetaArg = -1.0;
+    if (thetaArg > 1.0) thetaArg = 1.0;
+    y = ((acos(thetaArg) / PI_) + kint - 0.5) * 0.5 * bm.L0;
+    x = bm.X0 * sin(PI2 * y / bm.L0) + (0.0 + SX * g4);
+    z = 0.0 + SZ * g5;
+  } else {
+    if (p.dz > 0.0) z = 0.0 + p.dz * g5;
+    const double R1 = (p.dx > 0.0) ? bm.ro * 1e3 + p.dx * g4 : bm.ro * 1e3;
+    x = -R1 * cos(Theta0) + bm.ro * 1000.0;
+    y = R1 * sin(Theta0);
+    if (sSP != 0.0) {
+      const cplx jj = cmul_np3(js, cconj(jp));
+      const double scl = 1.0 / sSP;  // complex / real in numpy: multiply by the reciprocal
+      Jsp = cplx{jj.re * scl, jj.im * scl};
+    }
+  }
+  double Jss = 0.0, Jpp = 0.0;
+  if (sSP != 0.0) {
+    Jss = intensS / sSP;
+    Jpp = intensP / sSP;
+  }
+  const double norm = sqrt(a * a + 1.0 + c * c);
+  a /= norm;
+  b /= norm;
+  c /= norm;
+  if (p.has_yaw) {
+    const double x1 = p.cosYaw * x - p.sinYaw * y, y1 = p.sinYaw * x + p.cosYaw * y;
+    x = x1;
+    y = y1;
+    const double a1 = p.cosYaw * a - p.sinYaw * b, b1 = p.sinYaw * a + p.cosYaw * b;
+    a = a1;
+    b = b1;
+  }
+  if (p.has_pitch) {
+    const double y1 = p.cosPitch * y - p.sinPitch * z, z1 = p.sinPitch * y + p.cosPitch * z;
+    y = y1;
+    z = z1;
+    const double b1 = p.cosPitch * b - p.sinPitch * c, c1 = p.sinPitch * b + p.cosPitch * c;
+    b = b1;
+    c = c1;
+  }
+  if (p.to_global) {
+    if (p.sinAz != 0.0) {
+      const double a1 = p.cosAz * a - (-p.sinAz) * b, b1 = (-p.sinAz) * a + p.cosAz * b;
+      a = a1;
+      b = b1;
+      const double x1 = p.cosAz * x - (-p.sinAz) * y, y1 = (-p.sinAz) * x + p.cosAz * y;
+      x = x1;
+      y = y1;
+    }
+    x += p.center[0];
+    y += p.center[1];
+    z += p.center[2];
+  }
+  out.x[o] = x;
+  out.y[o] = y;
+  out.z[o] = z;
+  out.a[o] = a;
+  out.b[o] = b;
+  out.c[o] = c;
+  out.path[o] = 0.0;
+  out.E[o] = E;
+  out.Jss[o] = Jss;
+  out.Jpp[o] = Jpp;
+  reinterpret_cast<double2*>(out.Jsp)[o] = make_double2(Jsp.re, Jsp.im);
+  if (out.Es) {
+    reinterpret_cast<double2*>(out.Es)[o] = make_double2(js.re, js.im);
+    reinterpret_cast<double2*>(out.Ep)[o] = make_double2(jp.re, jp.im);
+  }
+  out.state[o] = 1;
+}
+
+__global__ void __launch_bounds__(256)
+    bm_fill_kernel(size_t n, xrt_source_params p, xrt_bm_params bm, const long long* __restrict__ idx,
+                   const double* __restrict__ rE, const double* __restrict__ rTheta, const double* __restrict__ rPsi,
+                   const double2* __restrict__ mJs, const double2* __restrict__ mJp, const double* __restrict__ g1,
+                   const double* __restrict__ g2, const double* __restrict__ g3, const double* __restrict__ g4,
+                   const double* __restrict__ g5, const double* __restrict__ kint, xrt_beam out, size_t out_offset) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t j = idx ? (size_t)idx[i] : i;
+  const double2 s2 = mJs[j], p2 = mJp[j];
+  bm_fill_ray(p, bm, rE[j], rTheta[j], rPsi[j], cplx{s2.x, s2.y}, cplx{p2.x, p2.y}, g1[j], g2[j], g3[j], g4[j],
+              g5[j], kint ? kint[j] : 0.0, out, out_offset + i);
+}
+
+// uniformRayDensity in one kernel: Philox sampling -> build_I_map -> Beam (no sample arrays in HBM)
+__global__ void __launch_bounds__(256)
+    bm_shine_uniform_kernel(size_t n, uint64_t seed, uint64_t index_offset, double Emin, double Emax, double Tmin,
+                            double Tmax, double Pmin, double Pmax, xrt_source_params sp, xrt_bm_params bm,
+                            xrt_beam out, unsigned long long* imax_slot) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double imax = 0.0;
+  if (i < n) {
+    const Draw d = draw_ray(index_offset + i, seed, Emin, Emax, Tmin, Tmax, Pmin, Pmax, true, false);
+    // a second counter range (stream ids 5, 6) feeds the fifth normal deviate and the wiggler's period index
+    uint32_t w[4];
+    philox4x32_10(index_offset + i, 5u, seed, w);
+    const double e0 = 1.0 - u53(w[0], w[1]), e1 = u53(w[2], w[3]);
+    double sn, cs;
+    sincospi(2.0 * e1, &sn, &cs);
+    const double re = sqrt(-2.0 * log(e0));
+    const double g5 = re * cs, g6 = re * sn;
+    philox4x32_10(index_offset + i, 6u, seed, w);
+    const double kint = floor(u53(w[0], w[1]) * (2.0 * floor(bm.Np))) - floor(bm.Np);
+    const double gamma = (sp.eEspread > 0.0) ? bm.gamma0 + (0.0 + bm.gamma0 * sp.eEspread * g6) : bm.gamma0;
+    double I;
+    cplx js, jp;
+    bm_sample(bm, gamma, d.E, d.theta, d.psi, I, js, jp);
+    imax = I;
+    bm_fill_ray(sp, bm, d.E, d.theta, d.psi, js, jp, d.n1, d.n2, d.n3, d.n4, g5, kint, out, i);
+  }
+  imax = warp_reduce(imax, OpMax());
+  if ((threadIdx.x & 31) == 0 && imax > 0.0) atomicMax(imax_slot, (unsigned long long)__double_as_longlong(imax));
+}
+
+int bm_imap_device(size_t n, const xrt_bm_params* bm, const double* gamma, const double* w, const double* theta,
+                   const double* psi, double* I, double* Es, double* Ep, cudaStream_t st) {
+  if (n == 0) return 0;
+  XRTB_REQUIRE(bm && w && theta && psi && I && Es && Ep, "bm_imap: NULL argument");
+  bm_imap_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, *bm, gamma, w, theta, psi, I,
+                                                             reinterpret_cast<double2*>(Es),
+                                                             reinterpret_cast<double2*>(Ep));
+  XRTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int bm_fill_device(size_t n, const xrt_source_params* p, const xrt_bm_params* bm, const long long* idx,
+                   const double* rE, const double* rTheta, const double* rPsi, const double* mJs, const double* mJp,
+                   const double* g1, const double* g2, const double* g3, const double* g4, const double* g5,
+                   const double* kint, const xrt_beam* out, size_t out_offset, cudaStream_t st) {
+  if (n == 0) return 0;
+  XRTB_REQUIRE(p && bm && rE && rTheta && rPsi && mJs && mJp && g1 && g2 && g3 && g4 && g5 && out,
+               "bm_fill: NULL argument");
+  XRTB_REQUIRE(!bm->isMPW || kint, "bm_fill: a wiggler needs the period indices");
+  bm_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+      n, *p, *bm, idx, rE, rTheta, rPsi, reinterpret_cast<const double2*>(mJs), reinterpret_cast<const double2*>(mJp),
+      g1, g2, g3, g4, g5, kint, *out, out_offset);
+  XRTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int bm_shine_uniform_device(size_t n, uint64_t seed, uint64_t index_offset, const double* window,
+                            const xrt_source_params* sp, const xrt_bm_params* bm, const xrt_beam* out,
+                            unsigned long long* imax_slot, cudaStream_t st) {
+  if (n == 0) return 0;
+  XRTB_REQUIRE(window && sp && bm && out && imax_slot, "bm_shine_uniform: NULL argument");
+  XRTB_REQUIRE(sp->uniform, "bm_shine_uniform: the fused kernel is for uniformRayDensity sources");
+  bm_shine_uniform_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, seed, index_offset, window[0], window[1],
+                                                                      window[2], window[3], window[4], window[5], *sp,
+                                                                      *bm, *out, imax_slot);
+  XRTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 int source_sample_device(size_t n, uint64_t seed, uint64_t index_offset, const double* window, double* E,
                          double* theta, double* psi, double* n1, double* n2, double* n3, double* n4, double* u,
                          double* n5, cudaStream_t st) {

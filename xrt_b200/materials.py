@@ -74,11 +74,23 @@ class Element(object):
                                       for a, b in zip(self.f0coeffs[:5], self.f0coeffs[6:]))
 
 
+class EmptyMaterial(object):
+    """materials/__init__.py:101-113: a material whose only property is its kind (a grating without a coating):
+    no get_amplitude, i.e. reflectivity 1."""
+
+    def __init__(self, kind='grating'):
+        self.kind = kind
+        self.geom = ''
+        self.name = ''
+        self.efficiency = None
+
+
 class Material(object):
-    """Mirror coating / bulk material; kinds 'mirror' and 'thin mirror' are on the hot path."""
+    """Mirror coating / bulk material; kinds 'mirror', 'thin mirror' and 'grating' are on the hot path."""
 
     def __init__(self, elements=None, quantities=None, kind='auto', rho=0, t=None, table='Chantler total',
-                 name=''):
+                 efficiency=None, name=''):
+        self.efficiency = efficiency  # [(order, value), ...] for kind 'grating' (material.py:78-93)
         if isinstance(elements, str):
             elements = elements,
         self.table = table
@@ -103,7 +115,7 @@ class Material(object):
     # ------------------------------------------------------------------ device plumbing
     def _kind_code(self):
         kind = 'mirror' if self.kind == 'auto' else self.kind  # material.py:450-451
-        if kind == 'mirror':
+        if kind in ('mirror', 'grating'):  # a grating reflects like a mirror (material.py:475)
             return 1
         if kind == 'thin mirror':
             if self.t is None:

@@ -47,7 +47,9 @@ class xrt_oe_params(ctypes.Structure):
                 ('brk_lim', (ctypes.c_double * 2) * 3),
                 ('created_by_diffract', ctypes.c_int), ('zero_dead_local', ctypes.c_int),
                 ('good_mode', ctypes.c_int), ('want_footprint', ctypes.c_int),
-                ('no_intersection', ctypes.c_int)]
+                ('no_intersection', ctypes.c_int),
+                ('grating', ctypes.c_int), ('g_ncoef', ctypes.c_int), ('g_rho0', ctypes.c_double),
+                ('g_coef', ctypes.c_double * 8), ('g_order', ctypes.c_double), ('g_amp', ctypes.c_double)]
 
 
 _AXIS = {'x': 0, 'y': 1, 'z': 2}
@@ -114,6 +116,13 @@ class OE(object):
         if not shape.startswith('re'):
             raise NotImplementedError("only shape='rect' is on the hot path")
         self.overEdge = kwargs.pop('overEdge', 'yMax')
+        # gratings (base.py:213-230, :491-508): gratingDensity = ['x'|'y', rho0 (1/mm), c0, c1, ...], order: int
+        self.gratingDensity = kwargs.pop('gratingDensity', None)
+        order = kwargs.pop('order', None)
+        self.order = 1 if order is None else order
+        if self.gratingDensity is not None and self.material is None:
+            from .materials import EmptyMaterial
+            self.material = EmptyMaterial()
         default = [-maxHalfSizeOfOE, maxHalfSizeOfOE]
         self.limPhysX = list(limPhysX) if limPhysX is not None else list(default)  # base.py:465-476
         self.limPhysY = list(limPhysY) if limPhysY is not None else list(default)
@@ -206,7 +215,42 @@ class OE(object):
             p.brk_lim[ax][0], p.brk_lim[ax][1] = float(lo), float(hi)
         p.created_by_diffract = int(createdByDiffract)
         p.want_footprint = 1
+        self._fill_grating(p, self.material2 if (is2ndXtal and hasattr(self, 'material2')) else self.material)
         return p
+
+    def _fill_grating(self, p, material):
+        """toWhere = 3 (reflect.py:743-744): the material's kind decides; 'auto' becomes 'grating' when the OE has a
+        gratingDensity (base.py:1089-1093).  OE.local_g (base.py:688-717) is marshalled as polynomial coefficients."""
+        p.g_amp = -1.
+        kind = getattr(material, 'kind', None)
+        if kind == 'auto' and self.gratingDensity is not None:
+            kind = 'grating'
+        if kind != 'grating':
+            return
+        if not isinstance(self.order, (int, np.integer)):
+            raise NotImplementedError('a sequence of diffraction orders (random choice per ray) is outside the '
+                                      'hot path; give OE.order as one int')
+        p.g_order = float(self.order)
+        rhoList = self.gratingDensity
+        if rhoList is not None:
+            coefs = list(rhoList[2:])
+            if len(coefs) > 8:
+                raise ValueError('gratingDensity: at most 8 polynomial coefficients')
+            p.grating = 1 if rhoList[0] == 'x' else 2
+            p.g_rho0 = float(rhoList[1])
+            p.g_ncoef = len(coefs)
+            for i, c in enumerate(coefs):
+                p.g_coef[i] = float(c)
+        else:
+            p.grating = 3
+            p.g_rho0 = -100.  # default local_g: (0, rho=-100., 0) (base.py:688, :717)
+        eff = getattr(material, 'efficiency', None)
+        if eff is not None:  # Material.get_grating_efficiency (material.py:391-413), constant efficiencies
+            resI = 0.
+            for o, v in eff:
+                if o == self.order:
+                    resI = v
+            p.g_amp = float(resI)**0.5
 
     # ------------------------------------------------------------------ kernel launch
     def _launch(self, params, material, beam, gb, lb, fallback=None, index_offset=0, allreduce=None):
@@ -217,6 +261,8 @@ class OE(object):
             self._red[key] = torch.zeros(REDUCTION_SLOTS, dtype=torch.int64, device=dev)
         red = self._red[key]
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if params.grating and (params.g_amp >= 0 or not hasattr(material, 'device_tables')):
+            material = None  # EmptyMaterial or a tabulated efficiency: no Fresnel amplitude (reflect.py:1005-1011)
         if material is not None:
             tab, tlen, offs, lens = material.device_tables(dev)
             mat = material.c_struct(offs, lens)

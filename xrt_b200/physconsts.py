@@ -9,6 +9,7 @@ import math as _math
 PI = _math.pi                      # 3.141592653589793
 PI2 = 2.0 * _math.pi               # 6.283185307179586
 SQRT2PI = PI2 ** 0.5
+SQ3 = 1.7320508075688772935274463415059
 
 # CGS / SI mixture inherited from xrt (lengths in cm here, mm / Angstrom at the call sites)
 C = 2.99792458e10                  # speed of light [cm/s]

@@ -508,3 +508,301 @@ class Undulator(object):
         bo.sourceWeight = sourceWeight / self.nrays
         bo.parentId = getattr(self, 'uuid', self.name)
         return bo
+
+
+class xrt_bm_params(ctypes.Structure):
+    """struct xrt_bm_params of include/xrt_b200.h"""
+    _fields_ = [('gamma0', ctypes.c_double), ('B', ctypes.c_double), ('ro', ctypes.c_double),
+                ('K', ctypes.c_double), ('L0', ctypes.c_double), ('Np', ctypes.c_double), ('X0', ctypes.c_double),
+                ('eI', ctypes.c_double), ('isMPW', ctypes.c_int), ('bw_mode', ctypes.c_int)]
+
+
+class BendingMagnet(object):
+    """Bending magnet with xrt's constructor, `build_I_map()` and `shine()` (sources/synchr.py:69-509; SourceBase
+    sources/sybase.py:29-547), computing on the GPU: xrt_b200/csrc/source.cu (`bm_imap_kernel`, `bm_fill_kernel`,
+    `bm_shine_uniform_kernel`).  Out of scope: filamentBeam, fixedEnergy, accuBeam."""
+    isMPW = False
+
+    def __init__(self, bl=None, name='BM', center=(0, 0, 0), nrays=100000, eE=6.0, eI=0.1, eEspread=0.,
+                 eSigmaX=None, eSigmaZ=None, eEpsilonX=1., eEpsilonZ=0.01, betaX=9., betaZ=2., eMin=5000.,
+                 eMax=15000., distE='eV', xPrimeMax=0.5, zPrimeMax=0.5, uniformRayDensity=False,
+                 filamentBeam=False, pitch=0, yaw=0, B0=1., rho=None, targetOpenCL='CUDA',
+                 precisionOpenCL='float64', seed=1234, **kwargs):
+        if filamentBeam:
+            raise NotImplementedError('filamentBeam is outside the hot path (SURVEY.md section 8f3)')
+        if targetOpenCL is None:
+            raise _lib.XrtB200Error('xrt_b200 sources always compute on the GPU (no numpy path)')
+        self.bl = bl
+        self.name = name
+        if bl is not None and self not in bl.sources:
+            bl.sources.append(self)
+        self.center = list(center)
+        self.nrays = int(nrays)
+        self.pitch, self.yaw = pitch, yaw
+        self.distE = distE
+        self.uniformRayDensity = uniformRayDensity
+        self.eE = float(eE)
+        self.gamma = self.eE * 1e9 * EV2ERG / (M0 * C**2)  # sybase.py:155
+        self.gamma2 = self.gamma**2
+        self.eEspread = eEspread
+        self.eI = float(eI)
+        epsX = eEpsilonX * 1e-6 if eEpsilonX is not None else None
+        epsZ = eEpsilonZ * 1e-6 if eEpsilonZ is not None else None
+
+        def size(sigma, eps, beta):  # sybase.py:218-347
+            if sigma is not None:
+                d = sigma * 1e-3
+            elif eps is not None and beta is not None:
+                d = np.sqrt(eps * beta * 1e3)
+            else:
+                d = 0
+            dprime = (eps / d if d > 0 else 0) if eps is not None else 0
+            return d, dprime
+        self.dx, self.dxprime = size(eSigmaX, epsX, betaX)
+        self.dz, self.dzprime = size(eSigmaZ, epsZ, betaZ)
+        self.eMin, self.eMax = float(eMin), float(eMax)
+        self._xPrimeMax = Undulator._prime(xPrimeMax)
+        self._zPrimeMax = Undulator._prime(zPrimeMax)
+        E0 = SIE0 * C / 10
+        if self.isMPW:  # synchr.py:88-94
+            self.B = K2B * self.K / self.L0
+            self.ro = M0 * C**2 * self.gamma / self.B / E0 / 1e6
+            self.X0 = 0.5 * self.K * self.L0 / self.gamma / PI
+            lim = self.K / self.gamma  # _xPrimeMaxAutoReduce (sybase.py:369-387), K0 = _Ky
+            self._xPrimeMax = [np.sign(v) * min(abs(v), lim) for v in self._xPrimeMax]
+        else:  # synchr.py:95-104
+            self.Np = 0.5
+            self.K = self.L0 = self.X0 = 0.
+            self.B = B0
+            self.ro = rho
+            if self.ro:
+                if not self.B:
+                    self.B = M0 * C**2 * self.gamma / self.ro / E0 / 1e6
+            elif self.B:
+                self.ro = M0 * C**2 * self.gamma / self.B / E0 / 1e6
+        self.seed = int(seed)
+        self._draws = 0
+        _lib.init(None)
+        self.needReset = True
+
+    def reset(self):  # sybase.py:479-547
+        self.needReset = False
+        self.Theta_min = float(self._xPrimeMax[0] - self.dxprime)
+        self.Theta_max = float(self._xPrimeMax[1] + self.dxprime)
+        self.Psi_min = float(self._zPrimeMax[0] - self.dzprime)
+        self.Psi_max = float(self._zPrimeMax[1] + self.dzprime)
+        self.E_min = float(min(self.eMin, self.eMax))
+        self.E_max = float(max(self.eMin, self.eMax))
+        self.Imax = 0.
+        self.xzE = (self.E_max - self.E_min) * (self.Theta_max - self.Theta_min) * (self.Psi_max - self.Psi_min)
+        self.fluxConst = self.Imax * self.xzE
+
+    # ------------------------------------------------------------------ C structs
+    def _bm_params(self):
+        p = xrt_bm_params()
+        p.gamma0, p.B, p.ro = float(self.gamma), float(self.B), float(self.ro)
+        p.K, p.L0, p.Np, p.X0 = float(self.K), float(self.L0), float(self.Np), float(self.X0)
+        p.eI = self.eI
+        p.isMPW = int(self.isMPW)
+        p.bw_mode = 1 if self.distE == 'BW' else 0
+        return p
+
+    _source_params = Undulator._source_params  # placement, sizes, pitch / yaw, azimuth: the same struct
+
+    @property
+    def E1(self):  # only read by the shared struct filler
+        return 0.
+
+    # ------------------------------------------------------------------ build_I_map
+    def build_I_map(self, dde, ddtheta, ddpsi, harmonic=None, dg=None):
+        """(I, Es, Ep) on host arrays like BendingMagnet.build_I_map (synchr.py:185-226).  *dg*: optional
+        per-sample gamma offsets instead of the energy-spread draw."""
+        if self.needReset:
+            self.reset()
+        lib = _lib.load()
+        dde = np.ascontiguousarray(np.atleast_1d(dde), dtype=np.float64)
+        n = len(dde)
+        th = np.ascontiguousarray(np.asarray(ddtheta, dtype=np.float64) * np.ones(n))
+        ps = np.ascontiguousarray(np.asarray(ddpsi, dtype=np.float64) * np.ones(n))
+        gam = None
+        if self.eEspread > 0 and n > 1:
+            if dg is None:
+                dg = np.random.normal(0, self.gamma*self.eEspread, dde.shape)
+            gam = np.ascontiguousarray(self.gamma + dg)
+        I = np.empty(n)
+        Es = np.empty(n, dtype=np.complex128)
+        Ep = np.empty(n, dtype=np.complex128)
+        bm = self._bm_params()
+        rc = lib.xrt_bm_imap_f64_host(n, ctypes.byref(bm), _lib.hptr(gam) if gam is not None else None,
+                                      _lib.hptr(dde), _lib.hptr(th), _lib.hptr(ps), _lib.hptr(I), _lib.hptr(Es),
+                                      _lib.hptr(Ep))
+        _lib.check(rc, 'xrt_bm_imap_f64_host')
+        return I, Es, Ep
+
+    def build_I_map_device(self, w, theta, psi, gamma=None):
+        lib = _lib.load()
+        n = w.numel()
+        I = torch.empty(n, dtype=F64, device=w.device)
+        Es = torch.empty(n, dtype=C128, device=w.device)
+        Ep = torch.empty(n, dtype=C128, device=w.device)
+        bm = self._bm_params()
+        rc = lib.xrt_bm_imap_f64(n, ctypes.byref(bm), gamma.data_ptr() if gamma is not None else None,
+                                 w.data_ptr(), theta.data_ptr(), psi.data_ptr(), I.data_ptr(), Es.data_ptr(),
+                                 Ep.data_ptr(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, 'xrt_bm_imap_f64')
+        return I, Es, Ep
+
+    # ------------------------------------------------------------------ sampling
+    def draw_samples(self, n, device=None, index_offset=0):
+        """Philox-sampled (E, theta, psi), the rejection uniform u, five standard normal deviates g1..g5, the
+        energy-spread deviate g6 and the wiggler's period index k per sample (CUDA tensors)."""
+        if self.needReset:
+            self.reset()
+        lib = _lib.load()
+        dev = torch.device('cuda', torch.cuda.current_device()) if device is None else device
+        names = ['E', 'theta', 'psi', 'g1', 'g2', 'g3', 'g4', 'u', 'g6', 'E2', 't2', 'p2', 'g5', 'h2', 'h3', 'h4',
+                 'u2']
+        buf = torch.empty((len(names), n), dtype=F64, device=dev)
+        s = {k: buf[i] for i, k in enumerate(names)}
+        window = (ctypes.c_double * 6)(self.E_min, self.E_max, self.Theta_min, self.Theta_max, self.Psi_min,
+                                       self.Psi_max)
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        offset = int(index_offset) + self._draws
+        self._draws += 1 << 40
+        rc = lib.xrt_source_sample_f64(n, self.seed, offset, window, s['E'].data_ptr(), s['theta'].data_ptr(),
+                                       s['psi'].data_ptr(), s['g1'].data_ptr(), s['g2'].data_ptr(),
+                                       s['g3'].data_ptr(), s['g4'].data_ptr(), s['u'].data_ptr(), s['g6'].data_ptr(),
+                                       stream)
+        _lib.check(rc, 'xrt_source_sample_f64')
+        # a second, disjoint counter range for the remaining deviates
+        rc = lib.xrt_source_sample_f64(n, self.seed, offset + (1 << 39), window, s['E2'].data_ptr(),
+                                       s['t2'].data_ptr(), s['p2'].data_ptr(), s['g5'].data_ptr(),
+                                       s['h2'].data_ptr(), s['h3'].data_ptr(), s['h4'].data_ptr(),
+                                       s['u2'].data_ptr(), None, stream)
+        _lib.check(rc, 'xrt_source_sample_f64')
+        if self.isMPW:
+            s['k'] = torch.floor(s['u2'] * (2 * int(self.Np))) - int(self.Np)
+        return s
+
+    def fill_beam(self, s, mJs, mJp, out, idx=None, out_offset=0, n=None, toGlobal=True):
+        lib = _lib.load()
+        p = self._source_params(toGlobal)
+        bm = self._bm_params()
+        n = (len(idx) if idx is not None else s['E'].numel()) if n is None else n
+        cout = out.c_struct()
+        zeros = None
+
+        def ptr(k):
+            nonlocal zeros
+            if k in s and s[k] is not None:
+                return s[k].data_ptr()
+            if zeros is None:
+                zeros = torch.zeros_like(s['E'])
+            return zeros.data_ptr()
+        rc = lib.xrt_bm_fill_f64(
+            n, ctypes.byref(p), ctypes.byref(bm), idx.data_ptr() if idx is not None else None, s['E'].data_ptr(),
+            s['theta'].data_ptr(), s['psi'].data_ptr(), mJs.data_ptr(), mJp.data_ptr(), ptr('g1'), ptr('g2'),
+            ptr('g3'), ptr('g4'), ptr('g5'), s['k'].data_ptr() if self.isMPW else None, ctypes.byref(cout),
+            out_offset, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, 'xrt_bm_fill_f64')
+
+    # ------------------------------------------------------------------ shine
+    def shine(self, toGlobal=True, withAmplitudes=True, fixedEnergy=False, accuBeam=None, samples=None,
+              index_offset=0, allreduce_max=None, fused=True):
+        """Returns the source Beam (device resident) like BendingMagnet.shine (synchr.py:229-509).
+
+        *samples* (optional): list of dicts (one per Monte-Carlo pass) of CUDA tensors E, theta, psi, u, g1..g5
+        [, g6, k] to use instead of drawing them -- parity tests feed the deviates the numpy oracle drew; the
+        accepted-ray deviates g1..g5, k are indexed like the samples (scattered by the test)."""
+        if fixedEnergy or accuBeam is not None:
+            raise NotImplementedError('fixedEnergy / accuBeam are outside the hot path (SURVEY 8f3)')
+        if self.needReset:
+            self.reset()
+        lib = _lib.load()
+        if self.uniformRayDensity:
+            withAmplitudes = True
+        mcRays = int(self.nrays * 1.2) if not self.uniformRayDensity else self.nrays
+        dev = torch.device('cuda', torch.cuda.current_device())
+        given = samples is not None
+        nalloc = self.nrays if self.uniformRayDensity else self.nrays + mcRays
+        bo = Beam(nalloc, withAmplitudes=withAmplitudes, device=dev, uninitialized=True)
+        if self.uniformRayDensity and not given and fused:
+            slot = torch.zeros(1, dtype=torch.int64, device=dev)
+            p = self._source_params(toGlobal)
+            bm = self._bm_params()
+            cout = bo.c_struct()
+            window = (ctypes.c_double * 6)(self.E_min, self.E_max, self.Theta_min, self.Theta_max, self.Psi_min,
+                                           self.Psi_max)
+            offset = int(index_offset) + self._draws
+            self._draws += 1 << 40
+            rc = lib.xrt_bm_shine_uniform_f64(len(bo), self.seed, offset, window, ctypes.byref(p), ctypes.byref(bm),
+                                              ctypes.byref(cout), slot.data_ptr(),
+                                              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+            _lib.check(rc, 'xrt_bm_shine_uniform_f64')
+            tmp_max = slot.view(torch.float64)
+            if allreduce_max is not None:
+                tmp_max = allreduce_max(tmp_max)
+            self.Imax = max(self.Imax, float(tmp_max))
+            self.fluxConst = self.Imax * self.xzE
+            seeded, seededI, sourceWeight, length = mcRays, self.nrays * self.xzE, self.xzE, mcRays
+        else:
+            length = 0
+            seeded = 0
+            seededI = 0.
+            ipass = 0
+            while True:
+                s = samples[ipass] if given else self.draw_samples(mcRays, dev, index_offset=index_offset)
+                ipass += 1
+                n = s['E'].numel()
+                seeded += n
+                gam = None
+                if self.eEspread > 0:  # gamma += normal(0, gamma*eEspread) (synchr.py:192-197)
+                    gam = self.gamma + (self.gamma * self.eEspread) * s['g6']
+                I, mJs, mJp = self.build_I_map_device(s['E'], s['theta'], s['psi'], gamma=gam)
+                if self.uniformRayDensity:
+                    seededI += self.nrays * self.xzE
+                    sourceWeight = self.xzE
+                else:
+                    seededI += float(I.sum()) * self.xzE
+                    sourceWeight = seededI / seeded
+                tmp_max = I.max()
+                if allreduce_max is not None:
+                    tmp_max = allreduce_max(tmp_max)
+                if float(tmp_max) > self.Imax:
+                    self.Imax = float(tmp_max)
+                    self.fluxConst = self.Imax * self.xzE
+                if self.uniformRayDensity:
+                    self.fill_beam(s, mJs, mJp, bo, toGlobal=toGlobal)
+                    length = n
+                    break
+                idx = torch.nonzero(self.Imax * s['u'] < I).flatten()
+                npassed = int(idx.numel())
+                if npassed > 0:
+                    self.fill_beam(s, mJs, mJp, bo, idx=idx, out_offset=length, n=npassed, toGlobal=toGlobal)
+                    length += npassed
+                if length >= self.nrays or (given and ipass >= len(samples)):
+                    break
+        Esum = float(bo.E[:length].sum())  # the reference sums before cutting to nrays (synchr.py:482-490)
+        if length != nalloc or length > self.nrays:
+            bo.filter_by_index(slice(0, min(length, self.nrays)))
+        if length >= self.nrays:
+            bo.accepted = length * self.fluxConst
+            bo.acceptedE = Esum * self.fluxConst * SIE0
+            bo.seeded = seeded
+            bo.seededI = seededI
+            bo.sourceWeight = sourceWeight / self.nrays
+        bo.parentId = getattr(self, 'uuid', self.name)
+        return bo
+
+
+class Wiggler(BendingMagnet):
+    """Multipole wiggler (sources/synchr.py:511-609): BendingMagnet with B from K and the period, the critical
+    energy modulated along the horizontal angle and the source points spread over the 2 Np poles."""
+    isMPW = True
+
+    def __init__(self, *args, **kwargs):
+        self.K = float(kwargs.pop('K', 8.446))
+        self.L0 = float(kwargs.pop('period', 50))
+        self.Np = kwargs.pop('n', 40)
+        kwargs.setdefault('name', 'wiggler')
+        super(Wiggler, self).__init__(*args, **kwargs)
