@@ -141,7 +141,8 @@ typedef struct xrt_oe_params {
   double rot_out_cos[XRT_MAX_ROT], rot_out_sin[XRT_MAX_ROT];
   double shift[3];        /* dx, dy, dz (reflect.py:630-635) */
   double roll;            /* roll used for the polarisation frame, reflect.py:948 */
-  int surface;            /* 0 flat, 1 toroid (R, r), 2 elliptical cylinder/ellipsoid, parametric */
+  int surface;            /* 0 flat, 1 toroid (R, r), 2 elliptical cylinder/ellipsoid, parametric,
+                             3 paraboloid / parabolic cylinder lens surface (focus, zmax, has_zmax, isCylinder) */
   double sp[8];           /* surface parameters, cl_plist order of the reference classes */
   int asymmetric;         /* local_n returns (n_B, n_s): crystal with alpha != 0 */
   double nB[3];           /* n_B for a flat asymmetric crystal (base.py:736-739; dcm.py:234-238) */
@@ -157,6 +158,10 @@ typedef struct xrt_oe_params {
                              slots (reflect.py:1133-1136); 0 skips those block reductions (device pipelines) */
   int no_intersection;    /* noIntersectionSearch (reflect.py:676-681): the rays already sit on the surface (wave
                              samples): t = 0, the point is taken as it is (xyz_to_param for parametric OEs) */
+  /* f4: refraction (materials of kind 'plate' / 'lens', toWhere = 1, reflect.py:894-919; oes/refractive.py) */
+  int from_vacuum;        /* 1: the ray enters the material (invertNormal = 1); 0: it leaves it (invertNormal = -1,
+                             attenuation and phase inside the material, reflect.py:638-641, :1048-1059) */
+  int dead_state_lost;    /* Plate (dcm.py:311-312, :331-332): rays that are not good after a surface get lostNum */
   /* f4: grating (material kind 'grating', toWhere = 3, reflect.py:840-861 + _grating_deflection :451-469).
    * OE.local_g (base.py:688-717): 0 no grating; 1 / 2: groove density rho0 * sum_i (i+1) c_i coord^i along x / y
    * (gratingDensity = ['x'|'y', rho0, c0, c1, ...]); 3: constant (0, g_rho0, 0) */
@@ -171,7 +176,8 @@ typedef struct xrt_oe_params {
 struct xrt_multilayer_params;
 typedef struct xrt_material_params {
   int kind;               /* 0 none, 1 mirror, 2 thin mirror, 3 crystal (fcc/diamond, one element; thick Bragg or thickness t with geom),
-                             4 multilayer (reflected; `multilayer` points to the stack) */
+                             4 multilayer (reflected; `multilayer` points to the stack),
+                             5 plate / lens (refraction + transmittivity, material.py:482-486) */
   int nelem;
   double Z[XRT_MAX_ELEM], quantity[XRT_MAX_ELEM];
   int tab_off[XRT_MAX_ELEM], tab_len[XRT_MAX_ELEM]; /* slices of the E/f1/f2 tables */

@@ -105,12 +105,19 @@ class Material(object):
         n1cosAlpha = n1 * cosAlpha
         cosBeta = np.sqrt(1 - (n1/n2)**2*sinAlpha2)
         n2cosBeta = n2 * cosBeta
-        rs = (n1cosAlpha - n2cosBeta) / (n1cosAlpha + n2cosBeta)
-        rp = (n2*cosAlpha - n1*cosBeta) / (n2*cosAlpha + n1*cosBeta)
-        if self.kind == 'thin mirror':
-            p2 = np.exp(2j * E / CHBAR * n2cosBeta * self.t * 1e7)
-            rs *= (1 - p2) / (1 - rs**2*p2)
-            rp *= (1 - p2) / (1 - rp**2*p2)
+        if self.kind in ('mirror', 'thin mirror', 'grating'):  # reflectivity
+            rs = (n1cosAlpha - n2cosBeta) / (n1cosAlpha + n2cosBeta)
+            rp = (n2*cosAlpha - n1*cosBeta) / (n2*cosAlpha + n1*cosBeta)
+            if self.kind == 'thin mirror':
+                p2 = np.exp(2j * E / CHBAR * n2cosBeta * self.t * 1e7)
+                rs *= (1 - p2) / (1 - rs**2*p2)
+                rp *= (1 - p2) / (1 - rp**2*p2)
+        elif self.kind in ('plate', 'lens'):  # transmittivity (material.py:482-486)
+            tf = np.sqrt((n2cosBeta * n1.conjugate()).real / cosAlpha) / abs(n1)
+            rs = 2 * n1cosAlpha / (n1cosAlpha + n2cosBeta) * tf
+            rp = 2 * n1cosAlpha / (n2*cosAlpha + n1*cosBeta) * tf
+        else:
+            raise ValueError('Unknown kind of material')
         return (rs, rp, abs(n.imag) * E / CHBAR * 2e8, n.real * E / CHBAR * 1e8)
 
 

@@ -65,6 +65,15 @@ class OESpec(object):
             rx = 1 - (np.asarray(x)/r)**2
             rx[rx < 0] = 0.
             return y**2/2.0/R + r*(1 - rx**0.5)
+        if self.surface == 'paraboloid':
+            # ParaboloidFlatLens.local_z1 (refractive.py:394-399); ParabolicCylinderFlatLens passes x = 0 (:613-614)
+            p = self.surfParams
+            if p.get('isCylinder'):
+                x = 0
+            z = (x**2 + y**2) / (4 * p['focus'])
+            if p['zmax'] is not None:
+                z[z > p['zmax']] = p['zmax']
+            return z
         raise ValueError(self.surface)
 
     def local_g(self, x, y, rho=-100.):
@@ -100,6 +109,22 @@ class OESpec(object):
             a = -x / r * ax
             b = -y / R
             c = 1.
+            norm = (a**2 + b**2 + 1)**0.5
+            return [a/norm, b/norm, c/norm]
+        if self.surface == 'paraboloid':
+            # ParaboloidFlatLens.local_n1 (refractive.py:405-419); cylinder: x = 0 (:616-617)
+            p = self.surfParams
+            if p.get('isCylinder'):
+                x = 0
+            a = -x / (2*p['focus'])
+            b = -y / (2*p['focus'])
+            if p['zmax'] is not None:
+                z = (x**2 + y**2) / (4*p['focus'])
+                if isinstance(a, np.ndarray):
+                    a[z > p['zmax']] = 0
+                if isinstance(b, np.ndarray):
+                    b[z > p['zmax']] = 0
+            c = np.ones_like(x)
             norm = (a**2 + b**2 + 1)**0.5
             return [a/norm, b/norm, c/norm]
         if self.surface == 'ellipse_param':
@@ -357,7 +382,7 @@ def _grating_deflection(goodN, lb, g, oeNormal, beamInDotNormal, order=1, sig=No
 
 def reflect_local(oe, good, lb, vlb, pitch, roll, yaw, dx=None, dy=None, dz=None, local_n=None, material=None,
                   is2ndXtal=False, surfPhysX=None, surfPhysY=None, surfOptX=None, surfOptY=None, info=None,
-                  noIntersectionSearch=False):
+                  noIntersectionSearch=False, fromVacuum=True):
     if local_n is None:
         local_n = oe.local_n
     if surfPhysX is None:
@@ -376,7 +401,7 @@ def reflect_local(oe, good, lb, vlb, pitch, roll, yaw, dx=None, dy=None, dz=None
         lb.y[good] -= dy
     if dz:
         lb.z[good] -= dz
-    invertNormal = 1
+    invertNormal = 1 if fromVacuum else -1  # reflect.py:638-641
     mainPartForBracketing = lb.state[good] == 1
     tMin = np.zeros_like(lb.x)
     tMax = np.zeros_like(lb.x)
@@ -420,7 +445,22 @@ def reflect_local(oe, good, lb, vlb, pitch, roll, yaw, dx=None, dy=None, dz=None
         isMultilayer = material is not None and material.kind == 'multilayer'
         transmitted = isCrystal and matSur.geom.endswith('transmitted')  # toWhere = 2 (reflect.py:756, :862-878)
         isGrating = material is not None and material.kind == 'grating'  # toWhere = 3 (reflect.py:743-744)
-        if isGrating:
+        isRefr = material is not None and material.kind in ('plate', 'lens')  # toWhere = 1 (reflect.py:732-733)
+        if isRefr:
+            # reflect.py:894-919
+            refractive_index = matSur.get_refractive_index(lb.E[goodN]).real
+            if fromVacuum:
+                n1overn2 = 1. / refractive_index
+            else:
+                n1overn2 = refractive_index
+            signN = np.sign(-beamInDotNormal)
+            n1overn2cosTheta1 = -n1overn2 * beamInDotNormal
+            cosTheta2 = signN * np.sqrt(1 - n1overn2**2 + n1overn2cosTheta1**2)
+            dn = (n1overn2cosTheta1 - cosTheta2)
+            a_out = lb.a[goodN] * n1overn2 + oeNormal[0]*dn
+            b_out = lb.b[goodN] * n1overn2 + oeNormal[1]*dn
+            c_out = lb.c[goodN] * n1overn2 + oeNormal[2]*dn
+        elif isGrating:
             # reflect.py:840-861
             if oe.isParametric:
                 tXN, tYN = oe.param_to_xyz(lb.x[goodN], lb.y[goodN], lb.z[goodN])[0:2]
@@ -469,7 +509,7 @@ def reflect_local(oe, good, lb, vlb, pitch, roll, yaw, dx=None, dy=None, dz=None
             elif isGrating and matSur.efficiency is not None:  # reflect.py:1005-1011
                 refl = matSur.get_grating_efficiency(lb, goodN)
             else:
-                refl = matSur.get_amplitude(lb.E[goodN], beamInDotNormal, True)
+                refl = matSur.get_amplitude(lb.E[goodN], beamInDotNormal, fromVacuum)
         else:
             refl = 1., 1.
         ras, rap = refl[0], refl[1]
@@ -482,6 +522,17 @@ def reflect_local(oe, good, lb, vlb, pitch, roll, yaw, dx=None, dy=None, dz=None
         if hasattr(lb, 'Es'):
             lb.Es[goodN] *= ras
             lb.Ep[goodN] *= rap
+        if (not fromVacuum) and material is not None and material.kind not in ('crystal', 'multilayer'):
+            # reflect.py:1048-1059: tMax in mm, refl[2] = mu0 in 1/cm, refl[3] = n.real * k in 1/cm
+            att = np.exp(-refl[2] * tMax[goodN] * 0.1)
+            lb.Jss[goodN] *= att
+            lb.Jpp[goodN] *= att
+            lb.Jsp[goodN] *= att
+            if hasattr(lb, 'Es'):
+                mPh = att**0.5 * np.exp(0.1j * refl[3] * tMax[goodN])
+                lb.Es[goodN] *= mPh
+                lb.Ep[goodN] *= mPh
+        elif hasattr(lb, 'Es'):
             mPh = np.exp(1e7j * lb.E[goodN]/CHBAR * tMax[goodN])
             lb.Es[goodN] *= mPh
             lb.Ep[goodN] *= mPh
@@ -536,7 +587,7 @@ def reflect(oe, beam, needLocal=True, createdByDiffract=False, info=None, noInte
     return gb, lb
 
 
-def double_reflect(dcm, beam, needLocal=True, info1=None, info2=None):
+def double_reflect(dcm, beam, needLocal=True, info1=None, info2=None, fromVacuum1=True, fromVacuum2=True):
     """DCM.double_reflect (dcm.py:273-354). `dcm` is an OESpec with the extra DCM fields:
     bragg, cryst1roll, cryst2roll, cryst2pitch, cryst2finePitch, cryst2perpTransl, cryst2longTransl, material2,
     surfPhysX2, surfPhysY2, surfOptX2, surfOptY2.  Returns gb2, lo1, lo2."""
@@ -547,7 +598,7 @@ def double_reflect(dcm, beam, needLocal=True, info1=None, info2=None):
         return gb, lo1, lo1
     ob.global_to_virgin_local(dcm.azimuth, beam, lo1, dcm.center, good1)
     reflect_local(dcm, good1, lo1, gb, dcm.pitch + dcm.bragg, dcm.roll + dcm.cryst1roll, dcm.yaw, dcm.dx,
-                  local_n=dcm.local_n, material=dcm.material, info=info1)
+                  local_n=dcm.local_n, material=dcm.material, info=info1, fromVacuum=fromVacuum1)
     goodAfter1 = (gb.state == 1) | (gb.state == 2)
     notGood = ~goodAfter1
     if notGood.sum() > 0:
@@ -560,6 +611,8 @@ def double_reflect(dcm, beam, needLocal=True, info1=None, info2=None):
         lo2.x[~good2] = 0.
         lo2.y[~good2] = 0.
         lo2.z[~good2] = 0.
+    if hasattr(dcm, 't'):  # is instance of Plate (dcm.py:311-312)
+        gb2.state[~good2] = dcm.lostNum
     if good2.sum() == 0:
         return gb2, lo1, lo2
 
@@ -574,10 +627,60 @@ def double_reflect(dcm, beam, needLocal=True, info1=None, info2=None):
                   dcm.roll + dcm.cryst2roll, -dcm.yaw, -dcm.dx, dcm.cryst2longTransl, -dcm.cryst2perpTransl,
                   local_n=local_n2, material=dcm.material2, is2ndXtal=True,
                   surfPhysX=dcm.surfPhysX2, surfPhysY=dcm.surfPhysY2, surfOptX=dcm.surfOptX2,
-                  surfOptY=dcm.surfOptY2, info=info2)
+                  surfOptY=dcm.surfOptY2, info=info2, fromVacuum=fromVacuum2)
     goodAfter2 = (gb2.state == 1) | (gb2.state == 2)
     ob.virgin_local_to_global(dcm.azimuth, gb2, dcm.center, goodAfter2)
     notGood = ~goodAfter2
+    if hasattr(dcm, 't'):  # dcm.py:331-332
+        gb2.state[notGood] = dcm.lostNum
     if notGood.sum() > 0:
         ob.copy_beam(gb2, beam, notGood)
     return gb2, lo1, lo2
+
+
+def double_refract(plate, beam, needLocal=True):
+    """Plate.double_refract (refractive.py:171-234).  `plate` is a DCM-like OESpec with t (cryst2perpTransl = -t,
+    cryst2pitch = wedgeAngle, limits 2 mirrored in x) and a material of kind 'plate' / 'lens'."""
+    return double_reflect(plate, beam, needLocal, fromVacuum1=True, fromVacuum2=False)
+
+
+def rotate_point(point, rotationSequence='RzRyRx', pitch=0, roll=0, yaw=0):
+    """raycing.rotate_point (_rotate.py:87-108)."""
+    angles = {'z': yaw, 'y': roll, 'x': pitch}
+    rotates = {'z': ob.rotate_z, 'y': ob.rotate_y, 'x': ob.rotate_x}
+    ind1 = {'z': 0, 'y': 0, 'x': 1}
+    ind2 = {'z': 1, 'y': 2, 'x': 2}
+    newp = [coord for coord in point]
+    if rotationSequence[0] == '-':
+        seq = rotationSequence[6] + rotationSequence[4] + rotationSequence[2]
+    else:
+        seq = rotationSequence[1] + rotationSequence[3] + rotationSequence[5]
+    for sq in seq:
+        angle, rotate = angles[sq], rotates[sq]
+        if angle != 0:
+            cA = np.cos(angle)
+            sA = np.sin(angle)
+            newp[ind1[sq]], newp[ind2[sq]] = rotate(newp[ind1[sq]], newp[ind2[sq]], cA, sA)
+    return newp
+
+
+def multiple_refract(lens, beam, needLocal=True):
+    """ParaboloidFlatLens.multiple_refract (refractive.py:457-549); lens.nCRL, lens.zmax, lens.isDouble."""
+    if lens.nCRL == 1:
+        return double_refract(lens, beam, needLocal)
+    tempCenter = [c for c in lens.center]
+    beamIn = beam
+    zmax = 5 if lens.zmax is None else lens.zmax
+    step = 2.*zmax + lens.t if lens.isDouble else zmax + lens.t
+    for ilens in range(lens.nCRL):
+        lglobal, tlocal1, tlocal2 = double_refract(lens, beamIn, needLocal)
+        if lens.zmax is not None:
+            toward = rotate_point([0, 0, 1], lens.rotationSequence, lens.pitch, lens.roll, lens.yaw)
+            lens.center[0] -= step * toward[0]
+            lens.center[1] -= step * toward[1]
+            lens.center[2] -= step * toward[2]
+        beamIn = lglobal
+        if ilens == 0:
+            llocal1, llocal2 = tlocal1, tlocal2
+    lens.center = tempCenter
+    return lglobal, llocal1, llocal2

@@ -804,7 +804,50 @@ def gen_bm():
             print(kind, mode, 'seeded', beam.seeded, 'rays', len(beam.x))
 
 
-SECTIONS = {'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+def _capture_refract(oe, beam, multiple=False):
+    gb, l1, l2 = oe.multiple_refract(beam) if multiple else oe.double_refract(beam)
+    d = {}
+    d.update(beam_dict(beam, 'in_'))
+    d.update(beam_dict(gb, 'gb_'))
+    d.update(beam_dict(l1, 'lo1_'))
+    d.update(beam_dict(l2, 'lo2_'))
+    d.update(_oe_params(oe))
+    d.update(t=float(oe.t), wedgeAngle=float(oe.wedgeAngle), surfPhysX2=np.array(oe.surfPhysX2, dtype=float),
+             surfPhysY2=np.array(oe.surfPhysY2, dtype=float), rho=float(oe.material.rho))
+    return d
+
+
+def gen_refractive():
+    """f4: plates and parabolic lenses (oes/refractive.py), refraction + transmittivity + absorption."""
+    bl = raycing.BeamLine(azimuth=0.1)
+    ctr = (1e4*np.sin(0.1), 1e4*np.cos(0.1), 0)
+    # (1) diamond window, 0.3 mm, tilted 50 deg with a 2 mrad wedge
+    beam = _source_beam(bl, 2500, 71, dx=0.4, dz=0.3, dxprime=2e-5, dzprime=2e-5, energies=(7000, 11000))
+    C = rm.Material('C', rho=3.52, kind='plate')
+    pl = roe.Plate(bl, 'W', center=ctr, pitch=np.radians(50.), t=0.3, wedgeAngle=2e-3, material=C,
+                   limPhysX=[-0.9, 1.1], limPhysY=[-1.2, 1.0])
+    save('refract_plate', **_capture_refract(pl, beam))
+    # (2) single Be lens, paraboloid, zmax reached by part of the beam
+    bl = raycing.BeamLine()
+    beam = _source_beam(bl, 2500, 72, dx=0.35, dz=0.35, dxprime=1e-5, dzprime=1e-5, energies=(8500, 9500))
+    Be = rm.Material('Be', rho=1.848, kind='lens')
+    ln = roe.ParaboloidFlatLens(bl, 'L1', center=(0, 10000, 0), pitch=np.pi/2, t=0.05, material=Be, focus=0.2,
+                                zmax=0.6, limPhysX=[-1, 1], limPhysY=[-1, 1])
+    save('refract_lens_single', focus=0.2, zmax=0.6, nCRL=np.int64(1), **_capture_refract(ln, beam))
+    # (3) CRL: 5 double paraboloid lenses through multiple_refract
+    beam = _source_beam(bl, 2500, 73, dx=0.2, dz=0.2, dxprime=1e-5, dzprime=1e-5, energies=(8500, 9500))
+    ln = roe.DoubleParaboloidLens(bl, 'CRL', center=(0, 10000, 0), pitch=np.pi/2, t=0.03, material=Be, focus=0.1,
+                                  zmax=0.5, nCRL=5, limPhysX=[-0.6, 0.6], limPhysY=[-0.6, 0.6])
+    save('refract_crl_double', focus=0.1, zmax=0.5, nCRL=np.int64(5), **_capture_refract(ln, beam, True))
+    # (4) 1-D focusing: 3 parabolic cylinder lenses
+    beam = _source_beam(bl, 2000, 74, dx=0.2, dz=0.2, dxprime=1e-5, dzprime=1e-5, energies=(8500, 9500))
+    ln = roe.ParabolicCylinderFlatLens(bl, 'CL', center=(0, 10000, 0), pitch=np.pi/2, t=0.04,
+                                       material=Be, focus=0.15, zmax=0.4, nCRL=3, limPhysX=[-0.5, 0.5],
+                                       limPhysY=[-0.5, 0.5])
+    save('refract_crl_cylinder', focus=0.15, zmax=0.4, nCRL=np.int64(3), **_capture_refract(ln, beam, True))
+
+
+SECTIONS = {'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)

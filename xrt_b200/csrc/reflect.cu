@@ -137,12 +137,24 @@ __device__ __forceinline__ SurfDiv make_surf_div(const xrt_oe_params& p) {
     sd.d1 = make_divisor(p.sp[0]);
   }
   if (SURF == 2) sd.d0 = make_divisor(p.sp[0] * p.sp[0]);
+  if (SURF == 3) {
+    sd.d0 = make_divisor(4.0 * p.sp[0]);  // 4 * focus
+    sd.d1 = make_divisor(2.0 * p.sp[0]);  // 2 * focus
+  }
   return sd;
 }
 
 template <int SURF>
 __device__ __forceinline__ double local_surface(const xrt_oe_params& p, const SurfDiv& sd, double x, double y) {
   if (SURF == 0) return 0.0;
+  if (SURF == 3) {
+    // ParaboloidFlatLens.local_z1 (oes/refractive.py:394-399); the parabolic cylinder passes x = 0 (:613-614).
+    // sp: focus, zmax, has_zmax, isCylinder
+    const double xx = (p.sp[3] != 0.0) ? 0.0 : x * x;
+    double z = div_by(xx + y * y, sd.d0);
+    if (p.sp[2] != 0.0 && z > p.sp[1]) z = p.sp[1];
+    return z;
+  }
   if (SURF == 1) {
     // ToroidMirror.local_z (oes/__init__.py:398-401)
     const double r = p.sp[1];
@@ -184,7 +196,7 @@ __device__ __forceinline__ void param_to_xyz(const xrt_oe_params& p, double& x, 
   z = zN + p.sp[3];
 }
 
-// find_dz (base.py:801-846), derivOrder = 0, invertNormal = 1
+// find_dz (base.py:801-846), derivOrder = 0; invertNormal = 1 from vacuum, -1 from inside a plate / lens
 template <int SURF>
 __device__ __forceinline__ double find_dz(const xrt_oe_params& p, const SurfDiv& sd, double t, const Ray& r,
                                           double& x, double& y, double& z) {
@@ -194,8 +206,9 @@ __device__ __forceinline__ double find_dz(const xrt_oe_params& p, const SurfDiv&
   xyz_to_param<SURF>(p, x, y, z);
   double surf = local_surface<SURF>(p, sd, x, y);
   if (isnan(surf)) surf = 0.0;
-  const double d = z - surf;
-  return (SURF == 2) ? -d : d;
+  double d = z - surf;
+  if (SURF == 2) d = -d;
+  return (p.from_vacuum == 0) ? -d : d;  // * invertNormal = -1 from inside the material (reflect.py:638-641)
 }
 
 // normal(s): n[0..2] = n_B (or the only normal), n[3..5] = surface normal
@@ -215,6 +228,24 @@ __device__ __forceinline__ void local_normal(const xrt_oe_params& p, const SurfD
       n[1] = 0.0;
       n[2] = 1.0;
     }
+    return;
+  }
+  if (SURF == 3) {
+    // ParaboloidFlatLens.local_n1 (oes/refractive.py:405-419); cylinder: x = 0 (:616-617)
+    double a = (p.sp[3] != 0.0) ? 0.0 : div_by(-x, sd.d1);  // -x / (2*focus)
+    double b = div_by(-y, sd.d1);
+    if (p.sp[2] != 0.0) {
+      const double xx = (p.sp[3] != 0.0) ? 0.0 : x * x;
+      const double z = div_by(xx + y * y, sd.d0);
+      if (z > p.sp[1]) {
+        if (p.sp[3] == 0.0) a = 0.0;  // the cylinder's a is a Python scalar 0 that the mask never touches
+        b = 0.0;
+      }
+    }
+    const double norm = sqrt(a * a + b * b + 1.0);
+    n[0] = n[3] = a / norm;
+    n[1] = n[4] = b / norm;
+    n[2] = n[5] = 1.0 / norm;
     return;
   }
   if (SURF == 1) {
@@ -540,6 +571,46 @@ __device__ __forceinline__ void mirror_amplitude(const xrt_material_params& m, c
     rs = cmul_np(rs, cdiv(one_m_p2, cplx{1.0 - den.re, 0.0 - den.im}));
     den = cmul_np(csquare_np(rp), p2);
     rp = cmul_np(rp, cdiv(one_m_p2, cplx{1.0 - den.re, 0.0 - den.im}));
+  }
+}
+
+// Material.get_amplitude, kinds 'plate' / 'lens' (transmittivity, material.py:455-493), from vacuum into the
+// material or back.  mu = abs(n.imag)*E/CHBAR*2e8 [1/cm], nk = n.real*E/CHBAR*1e8 [1/cm].
+__device__ __forceinline__ void plate_amplitude(const xrt_material_params& m, const Tables& t, double E, double bdn,
+                                                bool fromVacuum, cplx& rs, cplx& rp, double& mu, double& nk,
+                                                double& nreal, int* oor) {
+  const cplx n = refractive_index(m, t, E, oor);
+  const double CHBAR = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8 / 6.283185307179586476925286766559;
+  mu = fabs(n.im) * E / CHBAR * 2e8;
+  nk = n.re * E / CHBAR * 1e8;
+  nreal = n.re;
+  const double cosAlpha = fabs(bdn);
+  double sinAlpha2 = 1.0 - bdn * bdn;
+  if (sinAlpha2 < 0.0) sinAlpha2 = 0.0;
+  if (fromVacuum) {
+    // n1 = 1., n2 = n
+    const double n1cosAlpha = 1.0 * cosAlpha;
+    const cplx n1n2 = cdiv(cplx{1.0, 0.0}, n);
+    const cplx sq = cmul_np(csquare_np(n1n2), cplx{sinAlpha2, 0.0});
+    const cplx cosBeta = csqrt_(cplx{1.0 - sq.re, 0.0 - sq.im});
+    const cplx n2cosBeta = cmul_np(n, cosBeta);
+    const double tf = sqrt(n2cosBeta.re / cosAlpha) / 1.0;  // (n2cosBeta * 1.0.conjugate()).real / cosAlpha
+    const cplx two = cplx{2.0 * n1cosAlpha, 0.0};
+    rs = cmul_np(cdiv(two, cplx{n1cosAlpha + n2cosBeta.re, 0.0 + n2cosBeta.im}), cplx{tf, 0.0});
+    const cplx n2ca = cmul_np(n, cplx{cosAlpha, 0.0});
+    const cplx n1cb = cmul_np(cplx{1.0, 0.0}, cosBeta);
+    rp = cmul_np(cdiv(two, cadd(n2ca, n1cb)), cplx{tf, 0.0});
+  } else {
+    // n1 = n, n2 = 1.
+    const cplx n1cosAlpha = cmul_np(n, cplx{cosAlpha, 0.0});
+    const cplx sq = cmul_np(csquare_np(n), cplx{sinAlpha2, 0.0});  // (n / 1.)**2 * sinAlpha2
+    const cplx cosBeta = csqrt_(cplx{1.0 - sq.re, 0.0 - sq.im});
+    const cplx n2cosBeta = cosBeta;  // 1. * cosBeta
+    const double tf = sqrt(cmul_np(n2cosBeta, cconj(n)).re / cosAlpha) / hypot(n.re, n.im);
+    const cplx two = cplx{2.0 * n1cosAlpha.re, 2.0 * n1cosAlpha.im};
+    rs = cmul_np(cdiv(two, cadd(n1cosAlpha, n2cosBeta)), cplx{tf, 0.0});
+    const cplx n1cb = cmul_np(n, cosBeta);
+    rp = cmul_np(cdiv(two, cplx{1.0 * cosAlpha + n1cb.re, 0.0 + n1cb.im}), cplx{tf, 0.0});
   }
 }
 
@@ -974,7 +1045,7 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
     const int st0 = in.state[i];
     if (!(p.good_mode ? (st0 == 1 || st0 == 2) : (st0 > 0))) {
       // rays that are not alive pass through untouched (gb = lb = copy of the input, reflect.py:104-109)
-      copy_ray(gb, in, i, st0, true);
+      copy_ray(gb, in, i, p.dead_state_lost ? p.lostNum : st0, true);  // Plate: dcm.py:311-312
       if (hasLb) {
         copy_ray(lb, in, i, st0, true);
         if (p.zero_dead_local) {  // dcm.py:305-310
@@ -1061,6 +1132,8 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
       double la = r.a, lbb = r.b, lc = r.c;
       double theta = 0.0;
       double bdn = 0.0, bds = 0.0, bos = 0.0, cY = 1.0, sY = 0.0;
+      cplx ras5 = cplx{1.0, 0.0}, rap5 = cplx{1.0, 0.0};  // MAT 5: transmittivity, absorption, n.real * k
+      double mu0 = 0.0, nk0 = 0.0;
       if (st == 1) {
         ++ngoodN;
         double nrm[6];
@@ -1096,6 +1169,18 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
           bo = bo / nn;
           co = co / nn;
           bos = ao * nrm[3] + bo * nrm[4] + co * nrm[5];
+        } else if (MAT == 5) {
+          // toWhere = 1, refraction (reflect.py:894-919); the transmittivity is evaluated here once (same n)
+          double nre;
+          plate_amplitude(m, tab, in.E[i], bdn, p.from_vacuum != 0, ras5, rap5, mu0, nk0, nre, &oor);
+          const double n1overn2 = p.from_vacuum ? 1.0 / nre : nre;
+          const double signN = (-bdn > 0.0) ? 1.0 : ((-bdn < 0.0) ? -1.0 : 0.0);
+          const double n1c = -n1overn2 * bdn;
+          const double cosTheta2 = signN * sqrt(1.0 - n1overn2 * n1overn2 + n1c * n1c);
+          const double dn = n1c - cosTheta2;
+          ao = la * n1overn2 + nrm[0] * dn;
+          bo = lbb * n1overn2 + nrm[1] * dn;
+          co = lc * n1overn2 + nrm[2] * dn;
         } else if (p.grating) {
           // toWhere = 3 (reflect.py:840-861): g = OE.local_g(x, y) (base.py:688-717), then _grating_deflection
           // (reflect.py:451-469) with the surface normal, beamInDotSurfaceNormal, the order and sig = -1
@@ -1207,6 +1292,10 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
         if (MAT == 1 || MAT == 2) mirror_amplitude(m, tab, E, bdn, ras, rap, &oor);
         if (MAT == 3) crystal_amplitude(m, tab, E, bds, bos, bdn, ras, rap, &oor);
         if (MAT == 4) multilayer_amplitude(ml, tab, E, bds, ras, rap, &oor);  // reflect.py:999-1003
+        if (MAT == 5) {
+          ras = ras5;
+          rap = rap5;
+        }
         if (MAT != 0) {
           if (isnan(ras.re) || isnan(ras.im)) ras = cplx{0.0, 0.0};
           if (isnan(rap.re) || isnan(rap.im)) rap = cplx{0.0, 0.0};
@@ -1234,12 +1323,29 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
             Es = cplx{Es.re * p.g_amp, Es.im * p.g_amp};
             Ep = cplx{Ep.re * p.g_amp, Ep.im * p.g_amp};
           }
-          // mPh = exp(1e7j * E/CHBAR * tMax) (reflect.py:1061-1064): im = ((1e7*E) * (1/CHBAR)) * tMax
-          const double CHBAR = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8 / 6.283185307179586476925286766559;
-          const double phi = ((1e7 * E) * (1.0 / CHBAR)) * tMax;
-          const cplx mPh = cexp_i(phi);
-          Es = cmul_np(Es, mPh);
-          Ep = cmul_np(Ep, mPh);
+          if (MAT == 5 && !p.from_vacuum) {
+            // inside the material (reflect.py:1048-1059): att = exp(-mu0 * tMax * 0.1);
+            // mPh = att**0.5 * exp(0.1j * refl[3] * tMax)
+            const double att = exp(-mu0 * tMax * 0.1);
+            const double sa = sqrt(att);
+            const cplx ph = cexp_i((0.1 * nk0) * tMax);
+            const cplx mPh = cplx{sa * ph.re, sa * ph.im};
+            Es = cmul_np(Es, mPh);
+            Ep = cmul_np(Ep, mPh);
+          } else {
+            // mPh = exp(1e7j * E/CHBAR * tMax) (reflect.py:1061-1064): im = ((1e7*E) * (1/CHBAR)) * tMax
+            const double CHBAR = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8 / 6.283185307179586476925286766559;
+            const double phi = ((1e7 * E) * (1.0 / CHBAR)) * tMax;
+            const cplx mPh = cexp_i(phi);
+            Es = cmul_np(Es, mPh);
+            Ep = cmul_np(Ep, mPh);
+          }
+        }
+        if (MAT == 5 && !p.from_vacuum) {
+          const double att = exp(-mu0 * tMax * 0.1);
+          Jss *= att;
+          Jpp *= att;
+          Jsp = cplx{Jsp.re * att, Jsp.im * att};
         }
         // rotate the coherency matrix back for the virgin-local/global beam (reflect.py:1106-1110)
         {
@@ -1278,7 +1384,7 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
         }
       } else {
         // not intersected rays remain unchanged except their state (reflect.py:131-134)
-        copy_ray(gb, fb, i, st, true);
+        copy_ray(gb, fb, i, p.dead_state_lost ? p.lostNum : st, true);  // Plate: dcm.py:331-332
       }
     }
   }
@@ -1337,6 +1443,14 @@ static int launch_main_mat(int mat, unsigned grid, cudaStream_t st, size_t n, co
     case 2: reflect_main_kernel<SURF, 2><<<grid, 256, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
     case 3: reflect_main_kernel<SURF, 3><<<grid, 256, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
     case 4: reflect_main_kernel<SURF, 4><<<grid, 256, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
+    case 5:
+      if constexpr (SURF == 0) {
+        reflect_main_kernel<SURF, 5><<<grid, 256, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red);
+      } else {
+        set_last_error("reflect: refraction is built for flat and parabolic surfaces");
+        return 2;
+      }
+      break;
     default: set_last_error("reflect: unknown material kind %d", mat); return 2;
   }
   XRTB_CUDA_CHECK(cudaGetLastError());
@@ -1356,18 +1470,35 @@ static int check_multilayer(const xrt_material_params& m, xrt_multilayer_params&
   return 0;
 }
 
+// refractive elements: plates (flat) and parabolic lenses, bare or of kind 'plate' / 'lens'
+template <int SURF>
+static int launch_main_refr(int mat, unsigned grid, cudaStream_t st, size_t n, const xrt_oe_params& p,
+                            const xrt_material_params& m, const xrt_multilayer_params& ml, const Tables& t,
+                            const xrt_beam& in, const xrt_beam& fb, const xrt_beam& gb, const xrt_beam& lb,
+                            unsigned long long* red) {
+  switch (mat) {
+    case 0: reflect_main_kernel<SURF, 0><<<grid, 256, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
+    case 5: reflect_main_kernel<SURF, 5><<<grid, 256, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
+    default: set_last_error("reflect: a parabolic lens takes a material of kind 'lens' / 'plate' or none (got %d)", mat); return 2;
+  }
+  XRTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 int reflect_device(size_t n, const xrt_oe_params* oe, const xrt_material_params* mat, const double* tables,
                    size_t table_len, const xrt_beam* in, const xrt_beam* fallback, const xrt_beam* gb,
                    const xrt_beam* lb, unsigned long long* red, int phase, unsigned long long index_offset,
                    cudaStream_t st) {
   XRTB_REQUIRE(oe && in && gb && red, "reflect: NULL argument");
-  XRTB_REQUIRE(oe->surface >= 0 && oe->surface <= 2, "reflect: unknown surface kind %d", oe->surface);
+  XRTB_REQUIRE(oe->surface >= 0 && oe->surface <= 3, "reflect: unknown surface kind %d", oe->surface);
   XRTB_REQUIRE(oe->n_rot_in >= 0 && oe->n_rot_in <= XRT_MAX_ROT && oe->n_rot_out >= 0 && oe->n_rot_out <= XRT_MAX_ROT,
                "reflect: too many elementary rotations");
   xrt_material_params m;
   memset(&m, 0, sizeof(m));
   if (mat) m = *mat;
-  XRTB_REQUIRE(m.kind >= 0 && m.kind <= 4, "reflect: unknown material kind %d", m.kind);
+  XRTB_REQUIRE(m.kind >= 0 && m.kind <= 5, "reflect: unknown material kind %d", m.kind);
+  XRTB_REQUIRE(m.kind != 5 || oe->surface == 0 || oe->surface == 3,
+               "reflect: refraction (kind plate / lens) is built for flat and parabolic surfaces");
   xrt_multilayer_params ml;
   if (int rc = check_multilayer(m, ml)) return rc;
   XRTB_REQUIRE(m.kind == 0 || (tables != nullptr && table_len > 0), "reflect: material needs f1/f2 tables");
@@ -1391,6 +1522,7 @@ int reflect_device(size_t n, const xrt_oe_params* oe, const xrt_material_params*
     if (oe->surface == 0) reflect_prepass_kernel<0><<<pgrid, 256, 0, st>>>(n, *oe, *in, red);
     if (oe->surface == 1) reflect_prepass_kernel<1><<<pgrid, 256, 0, st>>>(n, *oe, *in, red);
     if (oe->surface == 2) reflect_prepass_kernel<2><<<pgrid, 256, 0, st>>>(n, *oe, *in, red);
+    if (oe->surface == 3) reflect_prepass_kernel<3><<<pgrid, 256, 0, st>>>(n, *oe, *in, red);
     XRTB_CUDA_CHECK(cudaGetLastError());
   }
   if ((phase & 2) && n > 0) {
@@ -1399,6 +1531,7 @@ int reflect_device(size_t n, const xrt_oe_params* oe, const xrt_material_params*
     if (oe->surface == 0) rc = launch_main_mat<0>(m.kind, grid, st, n, *oe, m, ml, t, *in, fbv, *gb, lbv, red);
     if (oe->surface == 1) rc = launch_main_mat<1>(m.kind, grid, st, n, *oe, m, ml, t, *in, fbv, *gb, lbv, red);
     if (oe->surface == 2) rc = launch_main_mat<2>(m.kind, grid, st, n, *oe, m, ml, t, *in, fbv, *gb, lbv, red);
+    if (oe->surface == 3) rc = launch_main_refr<3>(m.kind, grid, st, n, *oe, m, ml, t, *in, fbv, *gb, lbv, red);
     if (rc) return rc;
   }
   return 0;

@@ -121,6 +121,8 @@ class Material(object):
             if self.t is None:
                 raise ValueError('Give the thin mirror a thickness!')
             return 2
+        if kind in ('plate', 'lens'):  # transmittivity + refraction (material.py:482-486, reflect.py:894-919)
+            return 5
         raise NotImplementedError("material kind {0!r} is outside the hot path (SURVEY.md section 8f)".format(kind))
 
     def host_tables(self):

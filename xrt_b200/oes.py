@@ -47,7 +47,7 @@ class xrt_oe_params(ctypes.Structure):
                 ('brk_lim', (ctypes.c_double * 2) * 3),
                 ('created_by_diffract', ctypes.c_int), ('zero_dead_local', ctypes.c_int),
                 ('good_mode', ctypes.c_int), ('want_footprint', ctypes.c_int),
-                ('no_intersection', ctypes.c_int),
+                ('no_intersection', ctypes.c_int), ('from_vacuum', ctypes.c_int), ('dead_state_lost', ctypes.c_int),
                 ('grating', ctypes.c_int), ('g_ncoef', ctypes.c_int), ('g_rho0', ctypes.c_double),
                 ('g_coef', ctypes.c_double * 8), ('g_order', ctypes.c_double), ('g_amp', ctypes.c_double)]
 
@@ -215,6 +215,7 @@ class OE(object):
             p.brk_lim[ax][0], p.brk_lim[ax][1] = float(lo), float(hi)
         p.created_by_diffract = int(createdByDiffract)
         p.want_footprint = 1
+        p.from_vacuum = 1
         self._fill_grating(p, self.material2 if (is2ndXtal and hasattr(self, 'material2')) else self.material)
         return p
 
@@ -633,6 +634,7 @@ class DCM(OE):
         """Returns (beamGlobal, beamLocal1, beamLocal2) like DCM.double_reflect (oes/dcm.py:247-354)."""
         p1 = self._make_params(self.pitch + self.bragg, self.roll + self.positionRoll + self.cryst1roll,
                                self.yaw, self.dx, to_global=False)
+        p1.from_vacuum = int(bool(fromVacuum1))
         gb = beam.like()
         lo1 = self._new_local(beam) if needLocal else None
         red = self._launch(p1, self.material, beam, gb, lo1, index_offset=index_offset, allreduce=allreduce)
@@ -644,6 +646,8 @@ class DCM(OE):
                                from_global=False, to_global=True)
         p2.good_mode = 1
         p2.zero_dead_local = 1
+        p2.from_vacuum = int(bool(fromVacuum2))
+        p2.dead_state_lost = int(hasattr(self, 't'))  # is instance of Plate (dcm.py:311-312, :331-332)
         gb2 = beam.like()
         lo2 = self._new_local(beam) if needLocal else None
         red = self._launch(p2, self.material2, gb, gb2, lo2, fallback=beam, index_offset=index_offset,
@@ -653,3 +657,122 @@ class DCM(OE):
         if not needLocal:
             lo1 = lo2 = gb2
         return gb2, lo1, lo2
+
+
+class Plate(DCM):
+    """A body with two surfaces (oes/refractive.py:12-234): derived from DCM like the reference's, the second
+    'crystal' is the exit surface at cryst2perpTransl = -t, tilted by wedgeAngle."""
+
+    def __init__(self, *args, **kwargs):
+        self.t = kwargs.pop('t', 0)
+        self.wedgeAngle = kwargs.pop('wedgeAngle', 0)
+        kwargs.setdefault('overEdge', '')
+        DCM.__init__(self, *args, **kwargs)
+        self.cryst2perpTransl = -self.t
+        self.cryst2pitch = self.wedgeAngle
+        # refractive.py:39-48 mirrors the x limits only `if isinstance(self.limPhysX, (list, tuple))`; by then the
+        # property setter has wrapped them in raycing.Limits, so the reference ends up with limits 2 == limits 1
+        # (verified on its outputs: tests/golden/refract_*.npz carry surfPhysX2 == surfPhysX).
+        self.limPhysX2 = self.limPhysX
+        self.limPhysY2 = self.limPhysY
+        self.limOptX2 = self.limOptX
+        self.limOptY2 = self.limOptY
+        self.material2 = self.material
+
+    def double_reflect(self, *a, **k):
+        raise AttributeError('use Plate.double_refract')
+
+    def double_refract(self, beam=None, needLocal=True, returnLocalAbsorbed=None, **kw):
+        """Returns (beamGlobal, beamLocal1, beamLocal2) like Plate.double_refract (oes/refractive.py:171-234)."""
+        return DCM.double_reflect(self, beam=beam, needLocal=needLocal, fromVacuum1=True, fromVacuum2=False, **kw)
+
+
+class ParaboloidFlatLens(Plate):
+    """Refractive lens / CRL stack, z = (x^2 + y^2) / (4 focus) limited to zmax (oes/refractive.py:237-549).  As
+    in the reference, local_z2 resolves to local_z -> local_z1 (:401-403, :424-425): both interfaces carry the
+    parabolic profile."""
+    surfaceKind = 3
+    isCylinder = False
+    isDouble = False
+
+    def __init__(self, *args, **kwargs):
+        focus = kwargs.pop('focus', 1.)
+        self.zmax = kwargs.pop('zmax', None)
+        nCRL = kwargs.pop('nCRL', 1)
+        kwargs.setdefault('pitch', np.pi/2)
+        Plate.__init__(self, *args, **kwargs)
+        if isinstance(focus, (list, tuple)) or isinstance(nCRL, (list, tuple)):
+            raise NotImplementedError('give focus and nCRL as numbers (the (f, E) forms need the host refractive '
+                                      'index: use get_nCRL / get_focus)')
+        self.focus = focus
+        self.nCRL = max(int(round(nCRL)), 1)  # refractive.py:340-344
+
+    def _surface_params(self):
+        return [self.focus, self.zmax if self.zmax is not None else 0., 0. if self.zmax is None else 1.,
+                1. if self.isCylinder else 0.]
+
+    def get_nCRL(self, f, E):  # refractive.py:430-441
+        nFactor = 0.5 if self.isDouble else 1.
+        df = 1. - self.material.get_refractive_index(E).real
+        return self.focus / (f*df) * (2*nFactor)
+
+    def get_focus(self, f, E):  # refractive.py:443-455
+        nFactor = 0.5 if self.isDouble else 1.
+        df = 1. - self.material.get_refractive_index(E).real
+        return (f*df) * self.nCRL / (2*nFactor)
+
+    def multiple_refract(self, beam=None, needLocal=True, returnLocalAbsorbed=None, **kw):
+        """Sequentially applies double_refract to the nCRL lenslets, each shifted by zmax + t (2 zmax + t for the
+        double lenses) along the local [0, 0, -1] (oes/refractive.py:457-549).  Returns (beamGlobal of the last
+        lens, beamLocal1, beamLocal2 of the first one)."""
+        if self.nCRL == 1:
+            self.centerShift = np.zeros(3)
+            return self.double_refract(beam=beam, needLocal=needLocal, **kw)
+        tempCenter = [c for c in self.center]
+        beamIn = beam
+        zmax = 5 if self.zmax is None else self.zmax
+        step = 2.*zmax + self.t if self.isDouble else zmax + self.t
+        toward = [0, -step, 0]
+        for ilens in range(self.nCRL):
+            lglobal, tlocal1, tlocal2 = self.double_refract(beam=beamIn, needLocal=needLocal, **kw)
+            if self.zmax is not None:
+                toward = _rotate_point([0, 0, 1], self.rotationSequence, self.pitch, self.roll+self.positionRoll,
+                                       self.yaw)
+                self.center[0] -= step * toward[0]
+                self.center[1] -= step * toward[1]
+                self.center[2] -= step * toward[2]
+            beamIn = lglobal
+            if ilens == 0:
+                llocal1, llocal2 = tlocal1, tlocal2
+        self.centerShift = step * np.array(toward)
+        self.center = tempCenter
+        return lglobal, llocal1, llocal2
+
+
+class ParabolicCylinderFlatLens(ParaboloidFlatLens):
+    """oes/refractive.py:552-617: the profile depends on y only."""
+    isCylinder = True
+
+
+class DoubleParaboloidLens(ParaboloidFlatLens):
+    """oes/refractive.py:620-652 (stack step 2 zmax + t)."""
+    isDouble = True
+
+
+class DoubleParabolicCylinderLens(ParabolicCylinderFlatLens):
+    """oes/refractive.py:655-663."""
+    isDouble = True
+
+
+def _rotate_point(point, rotationSequence='RzRyRx', pitch=0, roll=0, yaw=0):
+    """raycing.rotate_point (_rotate.py:87-108)."""
+    newp = [coord for coord in point]
+    ind1 = {0: 1, 1: 0, 2: 0}
+    ind2 = {0: 2, 1: 2, 2: 1}
+    for ax, cA, sA in _rotation_list(rotationSequence, pitch, roll, yaw):
+        u, v = newp[ind1[ax]], newp[ind2[ax]]
+        if ax == 1:  # rotate_y
+            newp[ind1[ax]], newp[ind2[ax]] = cA*u + sA*v, -sA*u + cA*v
+        else:  # rotate_x, rotate_z
+            newp[ind1[ax]], newp[ind2[ax]] = cA*u - sA*v, sA*u + cA*v
+    return newp
