@@ -177,7 +177,9 @@ struct xrt_multilayer_params;
 typedef struct xrt_material_params {
   int kind;               /* 0 none, 1 mirror, 2 thin mirror, 3 crystal (fcc/diamond, one element; thick Bragg or thickness t with geom),
                              4 multilayer (reflected; `multilayer` points to the stack),
-                             5 plate / lens (refraction + transmittivity, material.py:482-486) */
+                             5 plate / lens (refraction + transmittivity, material.py:482-486),
+                             6 grating with a mirror coating, 7 grating without reflectivity or with tabulated
+                             efficiencies (xrt_oe_params.grating != 0 goes with 6 / 7 and only with them) */
   int nelem;
   double Z[XRT_MAX_ELEM], quantity[XRT_MAX_ELEM];
   int tab_off[XRT_MAX_ELEM], tab_len[XRT_MAX_ELEM]; /* slices of the E/f1/f2 tables */

@@ -197,7 +197,7 @@ __device__ __forceinline__ void param_to_xyz(const xrt_oe_params& p, double& x, 
 }
 
 // find_dz (base.py:801-846), derivOrder = 0; invertNormal = 1 from vacuum, -1 from inside a plate / lens
-template <int SURF>
+template <int SURF, bool REFR = true>
 __device__ __forceinline__ double find_dz(const xrt_oe_params& p, const SurfDiv& sd, double t, const Ray& r,
                                           double& x, double& y, double& z) {
   x = r.x + r.a * t;
@@ -208,7 +208,9 @@ __device__ __forceinline__ double find_dz(const xrt_oe_params& p, const SurfDiv&
   if (isnan(surf)) surf = 0.0;
   double d = z - surf;
   if (SURF == 2) d = -d;
-  return (p.from_vacuum == 0) ? -d : d;  // * invertNormal = -1 from inside the material (reflect.py:638-641)
+  // * invertNormal = -1 from inside the material (reflect.py:638-641); REFR = false (kernels of non-refractive
+  // materials) compiles the test away
+  return (REFR && p.from_vacuum == 0) ? -d : d;
 }
 
 // normal(s): n[0..2] = n_B (or the only normal), n[3..5] = surface normal
@@ -908,7 +910,7 @@ __device__ __forceinline__ Decision decide(const unsigned long long* red) {
 
 __device__ __forceinline__ int sgn(double v) { return (v > 0.0) - (v < 0.0); }
 
-template <int SURF>
+template <int SURF, bool REFR>
 __device__ __forceinline__ void solve_secant(const xrt_oe_params& p, const SurfDiv& sd, const Ray& r,
                                              const Decision& d, double& t1,
                                              double& t2, double& dz1, double& dz2, double& x2, double& y2,
@@ -922,7 +924,7 @@ __device__ __forceinline__ void solve_secant(const xrt_oe_params& p, const SurfD
     t2 = t - (t1 - t) * dz / (dz1 - dz);
     if (t2 < d.tMin) t2 = d.tMin;
     if (t2 > d.tMax) t2 = d.tMax;
-    dz2 = find_dz<SURF>(p, sd, t2, r, x2, y2, z2);
+    dz2 = find_dz<SURF, REFR>(p, sd, t2, r, x2, y2, z2);
     if (sgn(dz2) == sgn(dz1)) {
       t1 = t;
       dz1 = dz;
@@ -931,7 +933,7 @@ __device__ __forceinline__ void solve_secant(const xrt_oe_params& p, const SurfD
   }
 }
 
-template <int SURF>
+template <int SURF, bool REFR>
 __device__ __forceinline__ void solve_brent(const xrt_oe_params& p, const SurfDiv& sd, const Ray& r, double& t1,
                                             double& t2,
                                             double& dz1, double& dz2, double& x2, double& y2, double& z2) {
@@ -964,7 +966,7 @@ __device__ __forceinline__ void solve_brent(const xrt_oe_params& p, const SurfDi
     const bool conds = cond1 || cond2 || cond3 || cond4 || cond5;
     if (conds) xs = (xa + xb) / 2.0;
     mflag = conds;
-    const double fs = find_dz<SURF>(p, sd, xs, r, x2, y2, z2);
+    const double fs = find_dz<SURF, REFR>(p, sd, xs, r, x2, y2, z2);
     xd = xc;
     xc = xb;
     fc = fb;
@@ -1079,8 +1081,8 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
       } else {
         // bracketing + intersection (base.py:848-885)
         bracket(p, d.axis, d.neg, r, t1, t2);
-        double dz1 = find_dz<SURF>(p, sd, t1, r, x1, y1, z1);
-        double dz2 = find_dz<SURF>(p, sd, t2, r, x2, y2, z2);
+        double dz1 = find_dz<SURF, MAT == 5>(p, sd, t1, r, x1, y1, z1);
+        double dz2 = find_dz<SURF, MAT == 5>(p, sd, t2, r, x2, y2, z2);
         ind1 = dz1 <= 0.0;             // lost: solution t1
         const bool ind2 = dz2 >= 0.0;  // over: solution t2
         if (ind1 || ind2) dz2 = 0.0;
@@ -1092,9 +1094,9 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
         }
         if (!(ind1 || ind2)) {
           if (d.brent)
-            solve_brent<SURF>(p, sd, r, t1, t2, dz1, dz2, x2, y2, z2);
+            solve_brent<SURF, MAT == 5>(p, sd, r, t1, t2, dz1, dz2, x2, y2, z2);
           else
-            solve_secant<SURF>(p, sd, r, d, t1, t2, dz1, dz2, x2, y2, z2);
+            solve_secant<SURF, MAT == 5>(p, sd, r, d, t1, t2, dz1, dz2, x2, y2, z2);
         }
       }
       const double tMax = t2;
@@ -1181,7 +1183,7 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
           ao = la * n1overn2 + nrm[0] * dn;
           bo = lbb * n1overn2 + nrm[1] * dn;
           co = lc * n1overn2 + nrm[2] * dn;
-        } else if (p.grating) {
+        } else if (MAT == 6 || MAT == 7) {
           // toWhere = 3 (reflect.py:840-861): g = OE.local_g(x, y) (base.py:688-717), then _grating_deflection
           // (reflect.py:451-469) with the surface normal, beamInDotSurfaceNormal, the order and sig = -1
           double g0 = 0.0, g1 = 0.0, g2 = 0.0;
@@ -1289,14 +1291,14 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
         }
         // amplitudes
         cplx ras = cplx{1.0, 0.0}, rap = cplx{1.0, 0.0};
-        if (MAT == 1 || MAT == 2) mirror_amplitude(m, tab, E, bdn, ras, rap, &oor);
+        if (MAT == 1 || MAT == 2 || MAT == 6) mirror_amplitude(m, tab, E, bdn, ras, rap, &oor);
         if (MAT == 3) crystal_amplitude(m, tab, E, bds, bos, bdn, ras, rap, &oor);
         if (MAT == 4) multilayer_amplitude(ml, tab, E, bds, ras, rap, &oor);  // reflect.py:999-1003
         if (MAT == 5) {
           ras = ras5;
           rap = rap5;
         }
-        if (MAT != 0) {
+        if (MAT != 0 && MAT != 7) {
           if (isnan(ras.re) || isnan(ras.im)) ras = cplx{0.0, 0.0};
           if (isnan(rap.re) || isnan(rap.im)) rap = cplx{0.0, 0.0};
           // reflect.py:1038-1040
@@ -1305,7 +1307,7 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
           Jsp = cmul_np(cmul_np(Jsp, ras), cconj(rap));
           Jss = js.re;
           Jpp = jp.re;
-        } else if (p.grating && p.g_amp >= 0.0) {
+        } else if (MAT == 7 && p.g_amp >= 0.0) {
           // grating efficiency (material.py:391-413): ras = rap = resI**0.5, a real array
           ras = cplx{p.g_amp, 0.0};
           rap = ras;
@@ -1316,10 +1318,10 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
           // refl = 1., 1.: J * 1. * conj(1.) with Python floats leaves the values unchanged
         }
         if (amp) {
-          if (MAT != 0) {
+          if (MAT != 0 && MAT != 7) {
             Es = cmul_np(Es, ras);
             Ep = cmul_np(Ep, rap);
-          } else if (p.grating && p.g_amp >= 0.0) {
+          } else if (MAT == 7 && p.g_amp >= 0.0) {
             Es = cplx{Es.re * p.g_amp, Es.im * p.g_amp};
             Ep = cplx{Ep.re * p.g_amp, Ep.im * p.g_amp};
           }
@@ -1443,6 +1445,8 @@ static int launch_main_mat(int mat, unsigned grid, cudaStream_t st, size_t n, co
     case 2: reflect_main_kernel<SURF, 2><<<grid, 256, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
     case 3: reflect_main_kernel<SURF, 3><<<grid, 256, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
     case 4: reflect_main_kernel<SURF, 4><<<grid, 256, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
+    case 6: reflect_main_kernel<SURF, 6><<<grid, 256, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
+    case 7: reflect_main_kernel<SURF, 7><<<grid, 256, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
     case 5:
       if constexpr (SURF == 0) {
         reflect_main_kernel<SURF, 5><<<grid, 256, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red);
@@ -1496,12 +1500,15 @@ int reflect_device(size_t n, const xrt_oe_params* oe, const xrt_material_params*
   xrt_material_params m;
   memset(&m, 0, sizeof(m));
   if (mat) m = *mat;
-  XRTB_REQUIRE(m.kind >= 0 && m.kind <= 5, "reflect: unknown material kind %d", m.kind);
+  XRTB_REQUIRE(m.kind >= 0 && m.kind <= 7, "reflect: unknown material kind %d", m.kind);
+  XRTB_REQUIRE((m.kind == 6 || m.kind == 7) == (oe->grating != 0),
+               "reflect: material kinds 6 / 7 (grating) and xrt_oe_params.grating go together");
+  XRTB_REQUIRE(oe->surface != 3 || (m.kind == 0 || m.kind == 5), "reflect: a parabolic lens refracts or is bare");
   XRTB_REQUIRE(m.kind != 5 || oe->surface == 0 || oe->surface == 3,
                "reflect: refraction (kind plate / lens) is built for flat and parabolic surfaces");
   xrt_multilayer_params ml;
   if (int rc = check_multilayer(m, ml)) return rc;
-  XRTB_REQUIRE(m.kind == 0 || (tables != nullptr && table_len > 0), "reflect: material needs f1/f2 tables");
+  XRTB_REQUIRE(m.kind == 0 || m.kind == 7 || (tables != nullptr && table_len > 0), "reflect: material needs f1/f2 tables");
   XRTB_REQUIRE(m.nelem >= 0 && m.nelem <= XRT_MAX_ELEM, "reflect: at most %d elements per material", XRT_MAX_ELEM);
   Tables t{tables, tables ? tables + table_len : nullptr, tables ? tables + 2 * table_len : nullptr};
   xrt_beam lbv;

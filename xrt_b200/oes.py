@@ -263,10 +263,15 @@ class OE(object):
         red = self._red[key]
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         if params.grating and (params.g_amp >= 0 or not hasattr(material, 'device_tables')):
-            material = None  # EmptyMaterial or a tabulated efficiency: no Fresnel amplitude (reflect.py:1005-1011)
-        if material is not None:
+            # EmptyMaterial or a tabulated efficiency: no Fresnel amplitude (reflect.py:1005-1011): kind 7
+            mat = xrt_material_params()
+            mat.kind = 7
+            mat_ref, tab_ptr, tlen = ctypes.byref(mat), None, 0
+        elif material is not None:
             tab, tlen, offs, lens = material.device_tables(dev)
             mat = material.c_struct(offs, lens)
+            if params.grating:
+                mat.kind = 6  # coated grating: grating deflection + mirror amplitude
             mat_ref, tab_ptr = ctypes.byref(mat), tab.data_ptr()
         else:
             mat_ref, tab_ptr, tlen = None, None, 0
