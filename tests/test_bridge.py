@@ -43,3 +43,59 @@ def test_bridge_reflect_host_objects(cuda_device):
     assert not bad, bad
     np.testing.assert_allclose(oe.footprint[0], g['footprint'], rtol=1e-12, atol=1e-12)
     assert oe.bl.oes == []  # the adapter leaves the user's beamline numbering alone
+
+
+class Plate(object):
+    pass
+
+
+class DoubleParaboloidLens(Plate):
+    pass
+
+
+class OE(object):
+    pass
+
+
+def _fake_common(g, cls, mat, **extra):
+    oe = cls()
+    bl = types.SimpleNamespace(sinAzimuth=float(g['sinAzimuth']), cosAzimuth=float(g['cosAzimuth']), oes=[])
+    oe.__dict__.update(dict(
+        bl=bl, name='E', center=list(g['center']), pitch=float(g['pitch']), roll=float(g['roll']),
+        positionRoll=float(g['positionRoll']), yaw=float(g['yaw']), rotationSequence=str(g['rotationSequence']),
+        extraPitch=float(g['extraPitch']), extraRoll=float(g['extraRoll']), extraYaw=float(g['extraYaw']),
+        extraRotationSequence='RzRyRx', alpha=None, surfPhysX=list(g['surfPhysX']), surfPhysY=list(g['surfPhysY']),
+        surfOptX=None, surfOptY=None, overEdge=str(g['overEdge']), shape='rect', material=mat,
+        lostNum=int(g['lostNum']), dx=0, footprint=[]))
+    oe.__dict__.update(extra)
+    return oe
+
+
+def _fake_material(name, g, kind, **kw):
+    class Elem(object):
+        pass
+    e = Elem()
+    e.name = name
+    return types.SimpleNamespace(elements=[e], quantities=[1.], kind=kind, rho=float(g['rho']), t=None,
+                                 table='Chantler total', **kw)
+
+
+@pytest.mark.gpu
+def test_bridge_refract_and_grating_host_objects(cuda_device):
+    from xrt_b200 import bridge
+    g = golden('refract_crl_double')
+    lens = _fake_common(g, DoubleParaboloidLens, _fake_material('Be', g, 'lens'), t=float(g['t']), wedgeAngle=0.,
+                        focus=float(g['focus']), zmax=float(g['zmax']), nCRL=int(g['nCRL']))
+    gb, lo1, lo2 = bridge.multiple_refract(lens, oracle_beam(g, 'in_'))
+    bad = []
+    for pre, b in (('gb_', gb), ('lo1_', lo1), ('lo2_', lo2)):
+        bad += compare_beams(b.__dict__, {f: g[pre + f] for f in BEAM_FIELDS}, BEAM_FIELDS, 1e-12, pre)
+    assert not bad, bad
+    g = golden('reflect_grating_vls')
+    gd = [str(g['gratingAxis'])] + [float(v) for v in g['gratingDensity']]
+    oe = _fake_common(g, OE, _fake_material('Au', g, 'grating', efficiency=None), gratingDensity=gd,
+                      order=int(g['order']))
+    gb, lb = bridge.reflect(oe, oracle_beam(g, 'in_'))
+    bad = compare_beams(gb.__dict__, {f: g['gb_' + f] for f in BEAM_FIELDS}, BEAM_FIELDS, 1e-12, 'gb_')
+    bad += compare_beams(lb.__dict__, {f: g['lb_' + f] for f in BEAM_FIELDS}, BEAM_FIELDS, 1e-12, 'lb_')
+    assert not bad, bad

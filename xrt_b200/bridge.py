@@ -5,6 +5,8 @@ kernels: the method-level binding sketched in INTEGRATION.md section 2.
     bridge.reflect(xrt_oe, xrt_beam, needLocal=True)          -> (gb, lb)      OE.reflect, oes/reflect.py:18
     bridge.double_reflect(xrt_dcm, xrt_beam, needLocal=True)  -> (gb, lo1, lo2)  DCM.double_reflect, dcm.py:248
     bridge.expose(xrt_screen, xrt_beam)                       -> blo           Screen.expose, screens.py:226
+    bridge.double_refract(xrt_plate, xrt_beam)                -> (gb, lo1, lo2)  Plate.double_refract, refractive.py:171
+    bridge.multiple_refract(xrt_lens, xrt_beam)               -> (gb, lo1, lo2)  multiple_refract, refractive.py:457
 
 Inputs and outputs are host objects with numpy attribute arrays (what xrt's flow, `get_output()` and plots
 consume), so every call pays one H2D and one D2H of the Beam; pipelines that stay on the GPU use the classes of
@@ -35,6 +37,8 @@ def convert_material(m):
     """xrt Material / CrystalFcc / CrystalDiamond / CrystalSi instance -> xrt_b200 material."""
     if m is None:
         return None
+    if not hasattr(m, 'elements'):  # EmptyMaterial (materials/__init__.py:101-113)
+        return _mat.EmptyMaterial(kind=m.kind)
     names = [e.name for e in m.elements]
     table = getattr(m, 'table', 'Chantler total')
     if getattr(m, 'kind', None) == 'crystal':
@@ -46,7 +50,8 @@ def convert_material(m):
         if any('Diamond' in c.__name__ for c in type(m).__mro__):
             return _mat.CrystalDiamond(**kw)
         raise NotImplementedError('crystal class {0} is outside the hot path'.format(cls))
-    return _mat.Material(names, list(m.quantities), kind=m.kind, rho=m.rho, t=m.t, table=table)
+    return _mat.Material(names, list(m.quantities), kind=m.kind, rho=m.rho, t=m.t, table=table,
+                         efficiency=getattr(m, 'efficiency', None))
 
 
 def _oe_kwargs(oe):
@@ -58,6 +63,10 @@ def _oe_kwargs(oe):
               limOptX=None if oe.surfOptX is None else list(oe.surfOptX),
               limOptY=None if oe.surfOptY is None else list(oe.surfOptY),
               overEdge=getattr(oe, 'overEdge', 'yMax'), shape=oe.shape, material=convert_material(oe.material))
+    if getattr(oe, 'gratingDensity', None) is not None:
+        kw['gratingDensity'] = list(oe.gratingDensity)
+    if getattr(kw['material'], 'kind', None) in ('grating', 'auto') or 'gratingDensity' in kw:
+        kw['order'] = getattr(oe, 'order', 1)
     return kw
 
 
@@ -65,7 +74,17 @@ def convert_oe(oe):
     """xrt OE / ToroidMirror / EllipticalMirrorParam / DCM instance -> the xrt_b200 element."""
     cls = [c.__name__ for c in type(oe).__mro__]
     kw = _oe_kwargs(oe)
-    if 'DCM' in cls:
+    if 'Plate' in cls:  # Plate and the parabolic lenses (oes/refractive.py)
+        kw.update(t=float(oe.t), wedgeAngle=float(getattr(oe, 'wedgeAngle', 0)))
+        for name in ('DoubleParabolicCylinderLens', 'DoubleParaboloidLens', 'ParabolicCylinderFlatLens',
+                     'ParaboloidFlatLens'):
+            if name in cls:
+                out = getattr(_oes, name)(oe.bl, oe.name, focus=float(oe.focus), zmax=oe.zmax, nCRL=int(oe.nCRL),
+                                          **kw)
+                break
+        else:
+            out = _oes.Plate(oe.bl, oe.name, **kw)
+    elif 'DCM' in cls:
         for k in ('bragg', 'cryst1roll', 'cryst2roll', 'cryst2pitch', 'cryst2finePitch', 'cryst2perpTransl',
                   'cryst2longTransl'):
             kw[k] = float(getattr(oe, k))
@@ -116,3 +135,20 @@ def expose(screen, beam, onlyPositivePath=False):
     blo = scr.expose(_device_beam(beam), onlyPositivePath=onlyPositivePath, withFootprint=True)
     screen.footprint = scr.footprint
     return HostBeam(blo.to_numpy())
+
+
+def _three(gb, lo1, lo2, needLocal):
+    hgb = HostBeam(gb.to_numpy())
+    if not needLocal:
+        return hgb, hgb, hgb
+    return hgb, HostBeam(lo1.to_numpy()), HostBeam(lo2.to_numpy())
+
+
+def double_refract(plate, beam, needLocal=True):
+    dev = convert_oe(plate)
+    return _three(*dev.double_refract(_device_beam(beam), needLocal=needLocal), needLocal)
+
+
+def multiple_refract(lens, beam, needLocal=True):
+    dev = convert_oe(lens)
+    return _three(*dev.multiple_refract(_device_beam(beam), needLocal=needLocal), needLocal)
