@@ -39,6 +39,11 @@ size_t xrt_b200_sizeof(int which);
  * mode 1: DMMA m8n8k4, mode 2: both interleaved. Writes TFLOP/s (2 flop per FMA). */
 int xrt_b200_fp64_probe(int mode, int iters, double* tflops, double* ms);
 
+/* Known-answer access to the device math helpers the kernels are built from (host arrays; tests only):
+ * which 0 sincos_big -> (sin, cos); 1 sin_big; 2 rcp_fast; 3 sqrt_rsqrt -> (sqrt, 1/sqrt); 4 (K_1/3, K_2/3);
+ * 6 rcp_cubic; 7 sqrt_hrsqrt -> (sqrt, 0.5/sqrt). */
+int xrt_b200_math_probe_host(int which, size_t n, const double* x, double* y0, double* y1);
+
 /* ------------------------------------------------------------------ a17: Fresnel-Kirchhoff sum
  * Replaces kernel `integrate_kirchhoff` (cl/diffract.cl:80-151) launched at waves.py:892.
  *   M outputs (xM,yM,zM); N inputs: nl[N], Es[N] c128, Ep[N] c128, k[N], pos[N*pos_stride] (x,y,z,..),

@@ -27,6 +27,7 @@ PROTOTYPES = {
     'xrt_b200_sync': (c_int, [c_dp]),
     'xrt_b200_sizeof': (c_sz, [c_int]),
     'xrt_b200_fp64_probe': (c_int, [c_int, c_int, ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)]),
+    'xrt_b200_math_probe_host': (c_int, [c_int, c_sz, c_dp, c_dp, c_dp]),
     'xrt_kirchhoff_workspace_bytes': (c_sz, [c_sz, c_sz, c_int]),
     'xrt_kirchhoff_f64': (c_int, [c_sz, c_sz] + [c_dp] * 8 + [c_int, c_dp, c_int] + [c_dp] * 5 +
                           [c_int, c_dp, c_dp]),

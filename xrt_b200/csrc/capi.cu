@@ -103,6 +103,27 @@ static int fp64_probe(int mode, int iters, double* tflops, double* ms_out) {
   return 0;
 }
 
+// ---------------------------------------------------------------- device math helpers, exposed for known-answer tests
+__global__ void math_probe_kernel(int which, size_t n, const double* __restrict__ x, double* __restrict__ y0,
+                                  double* __restrict__ y1) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = x[i];
+  double a = 0.0, b = 0.0;
+  switch (which) {
+    case 0: sincos_big(v, a, b); break;
+    case 1: a = sin_big(v); break;
+    case 2: a = rcp_fast(v); break;
+    case 3: sqrt_rsqrt(v, a, b); break;
+    case 4: bessel_k13_k23(v, a, b); break;
+    case 6: a = rcp_cubic(v); break;
+    case 7: sqrt_hrsqrt(v, a, b); break;
+    default: break;
+  }
+  y0[i] = a;
+  y1[i] = b;
+}
+
 // ---------------------------------------------------------------- host staging helper
 struct DevBuf {
   void* p = nullptr;
@@ -222,6 +243,21 @@ int xrt_kirchhoff_f64_host(size_t M, size_t N, const double* xM, const double* y
   double* outs[5] = {S, P, A, B, C};
   for (int c = 0; c < 5; ++c)
     XRTB_CUDA_CHECK(cudaMemcpyAsync(outs[c], o + 2 * M * c, M * 16, cudaMemcpyDeviceToHost, st));
+  XRTB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int xrt_b200_math_probe_host(int which, size_t n, const double* x, double* y0, double* y1) {
+  if (n == 0) return 0;
+  XRTB_REQUIRE(which >= 0 && which <= 7 && x && y0 && y1, "math_probe: bad arguments");
+  cudaStream_t st = 0;
+  DevBuf dx, out;
+  if (dx.upload(x, n * 8, st) || out.alloc(2 * n * 8)) return 1;
+  double* o = out.as<double>();
+  math_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(which, n, dx.as<double>(), o, o + n);
+  XRTB_CUDA_CHECK(cudaGetLastError());
+  XRTB_CUDA_CHECK(cudaMemcpyAsync(y0, o, n * 8, cudaMemcpyDeviceToHost, st));
+  XRTB_CUDA_CHECK(cudaMemcpyAsync(y1, o + n, n * 8, cudaMemcpyDeviceToHost, st));
   XRTB_CUDA_CHECK(cudaStreamSynchronize(st));
   return 0;
 }

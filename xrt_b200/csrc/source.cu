@@ -295,74 +295,6 @@ __global__ void __launch_bounds__(U_THREADS)
 // Replaces the per-ray numpy body of BendingMagnet.build_I_map (sources/synchr.py:185-226, Wiggler = the isMPW
 // branch) and of BendingMagnet.shine (synchr.py:321-480).  Oracle: oracle/synchrotron.py.
 
-// K_{1/3}(x) and K_{2/3}(x) for x > 0 (scipy.special.kv in the reference, synchr.py:215-217): the pair
-// (K_mu, K_{mu+1}) with mu = -1/3 (K_{-1/3} = K_{1/3}) by Temme's series for x <= 2 and Steed's continued
-// fraction CF2 above (the construction of Numerical Recipes' bessik); relative accuracy ~2e-14 near x = 2
-// (where AMOS, behind scipy, is at 4e-14 itself) and ~1e-15 elsewhere (checked against 40-digit values).
-__device__ __forceinline__ void bessel_k13_k23(double x, double& k13, double& k23) {
-  if (!(x > 0.0)) {  // kv(nu, 0) = inf, kv(nu, nan) = nan
-    k13 = k23 = (x == 0.0) ? __longlong_as_double(0x7ff0000000000000ll) : __longlong_as_double(0x7ff8000000000000ll);
-    return;
-  }
-  if (x > 800.0) {  // exp(-x) underflows (kv returns 0 beyond ~745)
-    k13 = k23 = 0.0;
-    return;
-  }
-  const double xmu = -0.33333333333333333333, xmu2 = xmu * xmu;
-  const double gampl = 0.738488111621648312935754375165, gammi = 1.11984652172218568497905093727;
-  const double gam1 = -0.572037615150806058064944843158, gam2 = 0.929167316671916998957402656217;
-  const double xi = 1.0 / x, xi2 = 2.0 * xi;
-  if (x <= 2.0) {
-    const double x2 = 0.5 * x;
-    const double fact = 1.20919957615614523372938550509;  // pi mu / sin(pi mu)
-    double d = -log(x2);
-    double e = xmu * d;
-    const double fact2 = (fabs(e) < 1e-150) ? 1.0 : sinh(e) / e;
-    double ff = fact * (gam1 * cosh(e) + gam2 * fact2 * d);
-    double sum = ff;
-    e = exp(e);
-    double p = 0.5 * e / gampl, q = 0.5 / (e * gammi), c = 1.0, sum1 = p;
-    d = x2 * x2;
-    for (int i = 1; i <= 80; ++i) {
-      const double di = (double)i;
-      ff = (di * ff + p + q) / (di * di - xmu2);
-      c *= d / di;
-      p /= (di - xmu);
-      q /= (di + xmu);
-      const double del = c * ff;
-      sum += del;
-      sum1 += c * (p - di * ff);
-      if (fabs(del) < fabs(sum) * 1e-17) break;
-    }
-    k13 = sum;
-    k23 = sum1 * xi2;
-  } else {
-    double b = 2.0 * (1.0 + x), d = 1.0 / b, h = d, delh = d;
-    double q1 = 0.0, q2 = 1.0;
-    const double a1 = 0.25 - xmu2;
-    double q = a1, c = a1, a = -a1;
-    double s = 1.0 + q * delh;
-    for (int i = 2; i <= 400; ++i) {
-      a -= 2.0 * (double)(i - 1);
-      c = -a * c / (double)i;
-      const double qnew = (q1 - b * q2) / a;
-      q1 = q2;
-      q2 = qnew;
-      q += c * qnew;
-      b += 2.0;
-      d = 1.0 / (b + a * d);
-      delh = (b * d - 1.0) * delh;
-      h += delh;
-      const double dels = q * delh;
-      s += dels;
-      if (fabs(dels / s) < 1e-17) break;
-    }
-    h = a1 * h;
-    k13 = sqrt(3.1415926535897932384626433832795 / (2.0 * x)) * exp(-x) / s;
-    k23 = k13 * (xmu + x + 0.5 - h) * xi;
-  }
-}
-
 __device__ __forceinline__ bool finite_d(double v) { return fabs(v) <= 1.7976931348623157e308; }
 
 // One sample of BendingMagnet.build_I_map.  ampS is purely imaginary and ampP purely real in the reference's

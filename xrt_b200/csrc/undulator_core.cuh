@@ -65,7 +65,7 @@ __device__ __forceinline__ void node_step(const USample& s, const double4 n0, co
   double den = __dadd_rn(1.0, -__dmul_rn(s.dirx, bx));
   if (!PLANAR) den = __dadd_rn(den, -__dmul_rn(s.diry, by));
   den = __dadd_rn(den, -__dmul_rn(s.dirz, bz));
-  const double rk = rcp_fast(den);
+  const double rk = rcp_cubic(den);
   const double wgt = n0.y * (rk * rk);  // ag * rkrel**2 (synchr.py:2019)
   const double ere = cs * wgt, eim = sn * wgt;
   const double bnx = s.dirx - bx;
@@ -99,7 +99,7 @@ __device__ __forceinline__ void node_pair_step(const USample& s, const double4 n
   const double bpz = __dmul_rn(s.hrevg, n1.z);
   double den = __dadd_rn(1.0, -__dmul_rn(s.dirx, bx));
   den = __dadd_rn(den, -__dmul_rn(s.dirz, bz));
-  const double rk = rcp_fast(den);
+  const double rk = rcp_cubic(den);
   const double wgt = n0.y * (rk * rk);
   const double eim = sn * wgt;
   const double bnx = s.dirx - bx;
@@ -160,7 +160,9 @@ __device__ __forceinline__ void imap_outputs(const UParams& p, double w, double 
                                              double ip_re, double ip_im, double& I, double2& Es, double2& Ep) {
   const double bw = p.bw_mode ? 0.001 : 1.0 / w;
   const double amp2flux = p.amp_const * bw;  // FINE_STR * bwFact * eI / SIE0
-  const double as = hypot(is_re, is_im), ap = hypot(ip_re, ip_im);
+  // np.abs of a purely imaginary sum (the node-pair path of a planar undulator) is |im| exactly
+  const double as = (is_re == 0.0) ? fabs(is_im) : hypot(is_re, is_im);
+  const double ap = (ip_re == 0.0) ? fabs(ip_im) : hypot(ip_re, ip_im);
   const double field = as * as + ap * ap;
   I = amp2flux * (ab * ab) * 0.25 * (p.dstep * p.dstep) * field;
   const double sc = sqrt(amp2flux) * ab;
