@@ -925,7 +925,10 @@ __device__ __forceinline__ void solve_secant(const xrt_oe_params& p, const SurfD
     if (t2 < d.tMin) t2 = d.tMin;
     if (t2 > d.tMax) t2 = d.tMax;
     dz2 = find_dz<SURF, REFR>(p, sd, t2, r, x2, y2, z2);
-    if (sgn(dz2) == sgn(dz1)) {
+    // np.sign(dz2) == np.sign(dz1) (base.py:951): inside this loop dz1 is never 0 or NaN (it starts > 0 and only
+    // takes values of earlier dz2 with |dz2| > zEps), and when dz2 is 0 or NaN the loop ends right here with t1, dz1
+    // unused -- so the comparison of the sign bits decides every case that matters, on the integer pipe
+    if ((__double2hiint(dz2) ^ __double2hiint(dz1)) >= 0) {
       t1 = t;
       dz1 = dz;
     }
@@ -1143,7 +1146,7 @@ __global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kern
         bdn = la * nrm[0] + lbb * nrm[1] + lc * nrm[2];
         if (bdn < -1.0) bdn = -1.0;
         if (bdn > 1.0) bdn = 1.0;
-        theta = acos(bdn) - kPi / 2;
+        if (hasLb && lb.theta) theta = acos(bdn) - kPi / 2;  // only the local beam carries theta
         bds = p.asymmetric ? (la * nrm[3] + lbb * nrm[4] + lc * nrm[5]) : bdn;
         double ao, bo, co;
         const bool transmitted = (MAT == 3) && (m.geom & 2);  // toWhere = 2 (reflect.py:756, :862-878)
