@@ -446,6 +446,38 @@ def run_ours(args):
                'sample_node_per_s': float(b.seeded) * nodes / (ms * 1e-3)}
         del b, src_r
 
+    # ---- config 3: seeded GeometricSource -> DCM Si(111) -> Screen (crystal amplitude path), same ray count
+    dcm_rep = None
+    if not args.no_dcm:
+        from xrt_b200.sources import GeometricSource
+        from xrt_b200.oes import DCM
+        from xrt_b200.materials import CrystalSi
+        bl3 = BeamLine()
+        gs = GeometricSource(bl3, 'gs', nrays=nrays, dx=0.2, dz=0.02, dxprime=5e-5, dzprime=2e-5, distE='flat',
+                             energies=(8995., 9005.), polarization='h', seed=4242)
+        si = CrystalSi(hkl=(1, 1, 1))
+        E0 = np.array([9000.])
+        theta = float(si.get_Bragg_angle(E0)[0] - si.get_dtheta(E0)[0])
+        dcm = DCM(bl3, 'dcm', center=(0, 2e4, 0), bragg=theta, material=si, material2=si, cryst2perpTransl=10.,
+                  limPhysX=[-50, 50], limPhysY=[-100, 100], limPhysX2=[-50, 50], limPhysY2=[-100, 200])
+        scr3 = Screen(bl3, 'scr3', center=(0, 3e4, 2 * 10. * np.cos(theta)))
+        ar = comm.allreduce_reductions if world > 1 else None
+
+        def step3():
+            b = gs.shine(withAmplitudes=True, index_offset=rank * nrays)
+            gb, lo1, lo2 = dcm.double_reflect(b, needLocal=True, checkTables=False, index_offset=rank * nrays,
+                                              allreduce=ar)
+            return scr3.expose(gb)
+        out3 = step3()
+        good3 = float((out3.state == 1).sum()) / len(out3)
+        del out3
+        step3()
+        ms3 = timed(step3, max(1, min(args.steps, 3))) / max(1, min(args.steps, 3))
+        dcm_rep = {'workload': 'config3: GeometricSource -> DCM Si(111) (two crystals, thick Bragg amplitudes) -> '
+                               'Screen, %d rays per GPU' % nrays, 'ms_per_step': ms3,
+                   'value': world * nrays / (ms3 * 1e-3) / 1e6, 'unit': 'Mrays/s', 'good_fraction': good3}
+        del gs, dcm, scr3
+
     # ---- Kirchhoff sum, config 4
     kir = None
     if not args.no_kirchhoff:
@@ -490,7 +522,7 @@ def run_ours(args):
                 'gpu_launches': args.steps * (9 if args.unfused_source else 7),  # source (1 fused or 3), 2 slot inits,
                 # pre-pass A/B, reflect main, expose
                 'clocks': sampler.summary(),
-                'roofline': roofline, 'roofline_second_kernel': roofline_other, 'stages': hbm, 'shine_rejection': rej, 'kirchhoff': kir,
+                'roofline': roofline, 'roofline_second_kernel': roofline_other, 'stages': hbm, 'shine_rejection': rej, 'dcm': dcm_rep, 'kirchhoff': kir,
                 'cpu_baseline': cpu_baseline() if world == 1 and not args.no_cpu_baseline else None}
         print(json.dumps(_finite(line)))
     if world > 1:
@@ -508,6 +540,7 @@ def main():
     ap.add_argument('--no-kirchhoff', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-rejection', action='store_true')
+    ap.add_argument('--no-dcm', action='store_true', help='skip the config-3 (DCM) sub-report')
     ap.add_argument('--unfused-source', action='store_true',
                     help='time Undulator.shine as three kernels (sample, field integral, fill) instead of the fused one')
     ap.add_argument('--kirchhoff-n', type=int, default=1000000)

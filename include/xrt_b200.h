@@ -33,7 +33,7 @@ int xrt_b200_sm_count(void);
 const char* xrt_b200_last_error(void);
 int xrt_b200_sync(void* stream);
 /* sizeof() of the ABI structs below (0: xrt_beam, 1: xrt_oe_params, 2: xrt_material_params, 3: xrt_plane_params, 4: xrt_source_params,
- * 5: xrt_plot_params, 6: xrt_multilayer_params, 7: xrt_bm_params), for binding checks */
+ * 5: xrt_plot_params, 6: xrt_multilayer_params, 7: xrt_bm_params, 8: xrt_geom_params), for binding checks */
 size_t xrt_b200_sizeof(int which);
 /* Measured fp64 ceilings used as roofline denominators (bench.py). mode 0: dependent-free DFMA stream,
  * mode 1: DMMA m8n8k4, mode 2: both interleaved. Writes TFLOP/s (2 flop per FMA). */
@@ -297,6 +297,40 @@ int xrt_source_fill_f64(size_t n, const xrt_source_params* p, const int64_t* idx
                         const double* rTheta, const double* rPsi, const double* mJs, const double* mJp,
                         const double* n1, const double* n2, const double* n3, const double* n4, const xrt_beam* out,
                         size_t out_offset, void* stream);
+
+/* ------------------------------------------------------------------ GeometricSource
+ * GeometricSource.shine (sources/geoms.py:193-534): the input generator of BASELINE.json configs 1 and 3.  Per ray
+ * up to seven standard deviates (uniform [0, 1) or standard normal, depending on the distribution law): streams
+ * 0 polarisation (unpolarised Ep), 1 y, 2 x, 3 z, 4 x', 5 z', 6 E -- drawn from Philox4x32-10 at counter
+ * (seed, index_offset + i, stream) or read from `deviates[k]` when that pointer is non-NULL (parity tests feed
+ * the numbers the numpy oracle drew; for distE = 'lines' stream 6 then holds the line index). */
+#define XRT_GEOM_MAX_LINES 16
+typedef struct xrt_geom_params {
+  double center[3];
+  double sinAz, cosAz;
+  int to_global;
+  int n_rot;              /* rotate_beam(pitch, roll, yaw) with the default sequence: Rz(yaw), Ry(roll), Rx(pitch) */
+  int rot_axis[3];
+  double rot_cos[3], rot_sin[3];
+  int dist[5];            /* y, x, z, x', z': 0 None, 1 normal, 2 flat, 3 normal sampled uniformly (uniformRayDensity) */
+  double p0[5], p1[5];    /* normal: sigma; flat: (aMin, aMax); uniform-normal: (sigma, cutLim) (geoms.py:370-405) */
+  int annulus_xz, annulus_ac;   /* 1: (x, z) / (x', z') come from _set_annulus (geoms.py:409-418) */
+  double ann_xz[4], ann_ac[4];  /* rMin, rMax, phiMin, phiMax */
+  double sqrt_pi2;        /* PI2**0.5 as the host computes it */
+  int with_amp;
+  double Jss, Jpp, Jsp_re, Jsp_im, Es_re, Es_im, Ep_re, Ep_im;  /* make_polarization (geoms.py:64-175) */
+  int ep_random;          /* unpolarised: Ep = uniform * 2**-0.5 */
+  int distE;              /* 0 None, 1 normal (e0 mean, e1 sigma), 2 flat (e0, e1), 3 lines */
+  double e0, e1;
+  int n_lines, weighted;
+  double lines[XRT_GEOM_MAX_LINES], cdf[XRT_GEOM_MAX_LINES];
+} xrt_geom_params;
+/* flag: one uint64 of device memory (zeroed by the caller): counts rays with a^2 + c^2 > 1, which switches the
+ * normalisation of the direction for the WHOLE beam (geoms.py:503-511); ray shards all-reduce it between the two
+ * phases (phase bit0: sample, bit1: normalise + rotate + to global; 3 = both). */
+int xrt_geometric_source_f64(size_t n, const xrt_geom_params* p, uint64_t seed, uint64_t index_offset,
+                             const double* const* deviates, const xrt_beam* out, uint64_t* flag, int phase,
+                             void* stream);
 
 /* ------------------------------------------------------------------ f3: bending magnet / wiggler
  * BendingMagnet / Wiggler (sources/synchr.py:69-609).  The reference computes these on the CPU only ("a GPU is not

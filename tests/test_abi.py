@@ -39,8 +39,9 @@ def test_struct_layouts_match_ctypes_mirrors():
     assert lib.xrt_b200_sizeof(3) == ctypes.sizeof(xrt_plane_params)
     assert lib.xrt_b200_sizeof(4) == ctypes.sizeof(xrt_source_params)
     assert lib.xrt_b200_sizeof(5) == ctypes.sizeof(xrt_plot_params)
-    from xrt_b200.sources import xrt_bm_params
+    from xrt_b200.sources import xrt_bm_params, xrt_geom_params
     assert lib.xrt_b200_sizeof(7) == ctypes.sizeof(xrt_bm_params)
+    assert lib.xrt_b200_sizeof(8) == ctypes.sizeof(xrt_geom_params)
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -75,3 +75,14 @@ def test_cuda_amplitude_out_of_table_raises(cuda_device):
     from xrt_b200.materials import Material
     with pytest.raises(ValueError):
         Material('Au', rho=19.3).get_amplitude(np.array([1e6]), np.array([-0.004]))
+
+
+def test_host_alignment_helpers_match_oracle():
+    """Crystal.get_Bragg_angle / get_dtheta (crystal.py:1105-1173): host-side numpy helpers of the product."""
+    from xrt_b200 import materials
+    si = materials.CrystalSi(hkl=(1, 1, 1))
+    o = om.CrystalDiamond((1, 1, 1), si.d, 'Si')
+    E = np.array([9000., 7000., 12000.])
+    assert np.array_equal(si.get_Bragg_angle(E), o.get_Bragg_angle(E))
+    assert np.array_equal(si.get_dtheta(E), o.get_dtheta(E))
+    assert np.array_equal(si.get_dtheta(E, 0.05), o.get_dtheta(E, 0.05))

@@ -847,7 +847,48 @@ def gen_refractive():
     save('refract_crl_cylinder', focus=0.15, zmax=0.4, nCRL=np.int64(3), **_capture_refract(ln, beam, True))
 
 
-SECTIONS = {'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+def _geom_case(name, seed, withAmplitudes, azimuth=0., **kw):
+    bl = raycing.BeamLine(azimuth=azimuth)
+    np.random.seed(seed)
+    src = rs.GeometricSource(bl, 'gs', **kw)
+    beam = src.shine(withAmplitudes=withAmplitudes)
+    d = beam_dict(beam, 'out_')
+    d.update(seed=seed, withAmplitudes=withAmplitudes, sinAzimuth=bl.sinAzimuth, cosAzimuth=bl.cosAzimuth)
+    for k in ('sourceWeight', 'seeded', 'seededI', 'accepted', 'acceptedE'):
+        if hasattr(beam, k):
+            d[k] = getattr(beam, k)
+    save(name, **d)
+
+
+GEOM_CASES = {
+    # config 1 of BASELINE.json
+    'geom_config1': dict(seed=1234, withAmplitudes=True, kw=dict(
+        nrays=4000, dx=0.1, dz=0.05, dxprime=1e-4, dzprime=5e-5, distE='flat', energies=(8990, 9010),
+        polarization='h')),
+    # uniformRayDensity with cut limits, flat x, annular divergence, weighted lines, circular polarisation, canted
+    'geom_uniform_annulus': dict(seed=77, withAmplitudes=True, azimuth=0.2, kw=dict(
+        nrays=3000, center=(1., -2., 0.5), distx='flat', dx=(-0.3, 0.5), distz='normal', dz=(0.02, 0.07),
+        disty='flat', dy=2., distxprime='annulus', dxprime=(1e-4, 3e-4), distzprime='annulus', dzprime=(0.3, 2.5),
+        distE='lines', energies=(8000., 9000., 12000.), energyWeights=(0.2, 0.5, 0.3), polarization='r',
+        uniformRayDensity=True, pitch=1e-3, roll=0.3, yaw=-2e-3)),
+    # unpolarised, normal energy band, everything normal incl. y, absolute flux
+    'geom_unpolarized_flux': dict(seed=78, withAmplitudes=True, kw=dict(
+        nrays=3000, disty='normal', dy=5., distE='normal', energies=(9000., 3.), polarization=None,
+        totalFlux=1e12)),
+    # no amplitudes, custom coherency matrix, unweighted lines, point source in z
+    'geom_custom_pol': dict(seed=79, withAmplitudes=False, kw=dict(
+        nrays=3000, distz=None, dz=0, distE='lines', energies=(5000., 7000.), polarization=(0.7, 0.3, 0.1, -0.2),
+        dxprime=2e-3, dzprime=1.5e-3)),
+}
+
+
+def gen_geometric():
+    """GeometricSource.shine (sources/geoms.py:193-534): the input generator of BASELINE.json configs 1 and 3."""
+    for name, c in GEOM_CASES.items():
+        _geom_case(name, c['seed'], c['withAmplitudes'], c.get('azimuth', 0.), **c['kw'])
+
+
+SECTIONS = {'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)

@@ -3,7 +3,7 @@
 set -x
 mkdir -p gpurun_out
 NR=${NR:-50000000}
-COMMON="--no-cpu-baseline --no-rejection"
+COMMON="--no-cpu-baseline --no-rejection --no-dcm"
 # (1) every launch of two bench steps with its device time (cold-cache, serialised: compare SHARES)
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_rays.csv \
     python bench.py --steps 2 --warmup 1 --nrays $NR --no-kirchhoff $COMMON > gpurun_out/bench_under_ncu_rays.log 2>&1

@@ -8,7 +8,7 @@ for V in ${VARIANTS:-"4:" "4:-DXRTB_REFLECT_NO_PREFETCH" "5:" "3:"}; do
      -Xptxas -v -I include -c -o build/obj/reflect.o xrt_b200/csrc/reflect.cu 2>&1 | grep -A2 "reflect_main_kernelILi1ELi1E" | grep -E "registers|spill" | head -2
   nvcc -gencode arch=compute_100a,code=sm_100a -shared -o xrt_b200/libxrt_b200.so build/obj/*.o
   echo "VARIANT MINBLOCKS=$MB $EX"
-  python bench.py --steps 3 --warmup 3 --nrays 100000000 --no-kirchhoff --no-cpu-baseline --no-rejection 2>&1 | python -c "
+  python bench.py --steps 3 --warmup 3 --nrays 100000000 --no-kirchhoff --no-cpu-baseline --no-rejection --no-dcm 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):

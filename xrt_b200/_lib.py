@@ -54,6 +54,7 @@ PROTOTYPES = {
     'xrt_undulator_ext_f64_host': (c_int, [c_int, c_sz, c_int, c_int, c_dbl, c_dbl, c_dbl] + [c_dp] * 14),
     'xrt_undulator_ext_imap_f64': (c_int, [c_int, c_sz, c_int, c_int] + [c_dbl] * 7 + [c_int] + [c_dp] * 13 +
                                    [c_dp]),
+    'xrt_geometric_source_f64': (c_int, [c_sz, c_dp, ctypes.c_uint64, ctypes.c_uint64, c_dp, c_dp, c_dp, c_int, c_dp]),
     'xrt_bm_imap_f64': (c_int, [c_sz, c_dp] + [c_dp] * 7 + [c_dp]),
     'xrt_bm_imap_f64_host': (c_int, [c_sz, c_dp] + [c_dp] * 7),
     'xrt_bm_fill_f64': (c_int, [c_sz, c_dp, c_dp, c_dp] + [c_dp] * 11 + [c_dp, c_sz, c_dp]),

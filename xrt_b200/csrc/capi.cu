@@ -185,7 +185,7 @@ int xrt_b200_init(int device) {
 int xrt_b200_sm_count(void) { return num_sms(); }
 
 size_t xrt_b200_sizeof(int which) {
-  return which == 0 ? sizeof(xrt_beam) : which == 1 ? sizeof(xrt_oe_params) : which == 2 ? sizeof(xrt_material_params) : which == 3 ? sizeof(xrt_plane_params) : which == 4 ? sizeof(xrt_source_params) : which == 5 ? sizeof(xrt_plot_params) : which == 6 ? sizeof(xrt_multilayer_params) : which == 7 ? sizeof(xrt_bm_params) : 0;
+  return which == 0 ? sizeof(xrt_beam) : which == 1 ? sizeof(xrt_oe_params) : which == 2 ? sizeof(xrt_material_params) : which == 3 ? sizeof(xrt_plane_params) : which == 4 ? sizeof(xrt_source_params) : which == 5 ? sizeof(xrt_plot_params) : which == 6 ? sizeof(xrt_multilayer_params) : which == 7 ? sizeof(xrt_bm_params) : which == 8 ? sizeof(xrt_geom_params) : 0;
 }
 
 const char* xrt_b200_last_error(void) { return g_err; }
@@ -502,6 +502,13 @@ int xrt_shine_uniform_f64(size_t n, uint64_t seed, uint64_t index_offset, const 
   return shine_uniform_device(n, seed, index_offset, window, jend, Kx, Ky, L0, Np, gamma0, amp_const, dstep, bw_mode,
                               symmetric, tg, ag, sintg, costg, sintgph, costgph, p, out,
                               reinterpret_cast<unsigned long long*>(imax_slot), (cudaStream_t)stream);
+}
+
+int xrt_geometric_source_f64(size_t n, const xrt_geom_params* p, uint64_t seed, uint64_t index_offset,
+                             const double* const* deviates, const xrt_beam* out, uint64_t* flag, int phase,
+                             void* stream) {
+  return geometric_source_device(n, p, seed, index_offset, deviates, out,
+                                 reinterpret_cast<unsigned long long*>(flag), phase, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------ bending magnet / wiggler

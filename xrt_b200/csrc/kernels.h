@@ -78,6 +78,10 @@ int bm_shine_uniform_device(size_t n, uint64_t seed, uint64_t index_offset, cons
                             const xrt_source_params* sp, const xrt_bm_params* bm, const xrt_beam* out,
                             unsigned long long* imax_slot, cudaStream_t st);
 
+int geometric_source_device(size_t n, const xrt_geom_params* p, uint64_t seed, uint64_t index_offset,
+                            const double* const* deviates, const xrt_beam* out, unsigned long long* flag, int phase,
+                            cudaStream_t st);
+
 int plot_hist_device(size_t n, const xrt_plot_params* p, cudaStream_t st);
 int hist2d_device(size_t n, const double* x, const double* y, const double* w1, const double* w2, const int* state,
                   int state_mask, const double* ex, int nx, const double* ey, int ny, double* out, cudaStream_t st);

@@ -526,6 +526,210 @@ int bm_shine_uniform_device(size_t n, uint64_t seed, uint64_t index_offset, cons
   return 0;
 }
 
+// ---------------------------------------------------------------- GeometricSource (sources/geoms.py:193-534)
+struct GeomDev {
+  const double* d[7];
+};
+
+// one standard deviate of stream k for ray i: supplied by the caller or drawn from Philox (uniform, or normal by
+// Box-Muller on the (0, 1] / [0, 1) pair of the same block)
+__device__ __forceinline__ double geom_deviate(const GeomDev& dv, int k, bool normal, uint64_t ctr, uint64_t seed,
+                                               size_t i) {
+  if (dv.d[k]) return dv.d[k][i];
+  uint32_t w[4];
+  philox4x32_10(ctr, 16u + (uint32_t)k, seed, w);
+  const double u0 = u53(w[0], w[1]);
+  if (!normal) return u0;
+  double sn, cs;
+  sincospi(2.0 * u53(w[2], w[3]), &sn, &cs);
+  return sqrt(-2.0 * log(1.0 - u0)) * cs;
+}
+
+struct GeomAmp {
+  double Jss, Jpp;
+  cplx Jsp, Es, Ep;
+};
+
+// GeometricSource._apply_distribution (geoms.py:370-405) for one axis value
+__device__ __forceinline__ double geom_axis(const xrt_geom_params& p, int ax, const GeomDev& dv, uint64_t ctr,
+                                            uint64_t seed, size_t i, double cur, GeomAmp& A) {
+  const int kind = p.dist[ax];
+  if (kind == 0) return cur;
+  const int stream = ax + 1;
+  if (kind == 1) return 0.0 + p.p0[ax] * geom_deviate(dv, stream, true, ctr, seed, i);
+  if (kind == 2) return p.p0[ax] + (p.p1[ax] - p.p0[ax]) * geom_deviate(dv, stream, false, ctr, seed, i);
+  // uniformRayDensity: uniform in +-cutLim, Gaussian weight on the amplitudes (geoms.py:372-391)
+  const double sigma = p.p0[ax], cut = p.p1[ax];
+  const double v = -cut + (cut - (-cut)) * geom_deviate(dv, stream, false, ctr, seed, i);
+  double amp = exp(-(v * v) / (sigma * sigma) / 2.0) / p.sqrt_pi2 / sigma * 2.0 * cut;
+  A.Jss *= amp;
+  A.Jpp *= amp;
+  A.Jsp = cplx{A.Jsp.re * amp, A.Jsp.im * amp};
+  amp = sqrt(amp);
+  A.Es = cplx{A.Es.re * amp, A.Es.im * amp};
+  A.Ep = cplx{A.Ep.re * amp, A.Ep.im * amp};
+  return v;
+}
+
+// _set_annulus (geoms.py:409-418)
+__device__ __forceinline__ void geom_annulus(const double* an, int s1, int s2, const GeomDev& dv, uint64_t ctr,
+                                             uint64_t seed, size_t i, double& v1, double& v2) {
+  const double rMin = an[0], rMax = an[1], phiMin = an[2], phiMax = an[3];
+  double r = rMax;
+  if (rMax > rMin) {
+    const double A = 2.0 / (rMax * rMax - rMin * rMin);
+    const double u = 0.0 + (1.0 - 0.0) * geom_deviate(dv, s1, false, ctr, seed, i);
+    r = sqrt(2.0 * u / A + rMin * rMin);
+  }
+  const double phi = phiMin + (phiMax - phiMin) * geom_deviate(dv, s2, false, ctr, seed, i);
+  v1 = r * cos(phi);
+  v2 = r * sin(phi);
+}
+
+__global__ void __launch_bounds__(256) geom_sample_kernel(size_t n, xrt_geom_params p, uint64_t seed,
+                                                          uint64_t index_offset, GeomDev dv, xrt_beam out,
+                                                          unsigned long long* flag) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool over = false;
+  if (i < n) {
+    const uint64_t ctr = index_offset + i;
+    GeomAmp A;
+    A.Jss = p.Jss;
+    A.Jpp = p.Jpp;
+    A.Jsp = cplx{p.Jsp_re, p.Jsp_im};
+    A.Es = cplx{p.Es_re, p.Es_im};
+    A.Ep = cplx{p.Ep_re, p.Ep_im};
+    if (p.ep_random && p.with_amp) A.Ep = cplx{geom_deviate(dv, 0, false, ctr, seed, i) * 0.70710678118654757, 0.0};
+    // Beam() starts with x = y = z = a = c = 0, b = 1 (sources/beams.py:60-75)
+    double x = 0.0, y = 0.0, z = 0.0, a = 0.0, c = 0.0;
+    y = geom_axis(p, 0, dv, ctr, seed, i, y, A);
+    if (p.annulus_xz) {
+      geom_annulus(p.ann_xz, 2, 3, dv, ctr, seed, i, x, z);
+    } else {
+      x = geom_axis(p, 1, dv, ctr, seed, i, x, A);
+      z = geom_axis(p, 2, dv, ctr, seed, i, z, A);
+    }
+    if (p.annulus_ac) {
+      geom_annulus(p.ann_ac, 4, 5, dv, ctr, seed, i, a, c);
+    } else {
+      a = geom_axis(p, 3, dv, ctr, seed, i, a, A);
+      c = geom_axis(p, 4, dv, ctr, seed, i, c, A);
+    }
+    double E = 0.0;
+    if (p.distE == 1) {
+      E = p.e0 + p.e1 * geom_deviate(dv, 6, true, ctr, seed, i);
+    } else if (p.distE == 2) {
+      E = p.e0 + (p.e1 - p.e0) * geom_deviate(dv, 6, false, ctr, seed, i);
+    } else if (p.distE == 3) {
+      int k;
+      if (dv.d[6]) {
+        k = (int)dv.d[6][i];  // the caller supplies the line index
+      } else {
+        const double u = geom_deviate(dv, 6, false, ctr, seed, i);
+        if (p.weighted) {  // np.random.choice(p=...): cdf.searchsorted(u, side='right')
+          k = 0;
+          while (k < p.n_lines - 1 && p.cdf[k] <= u) ++k;
+        } else {
+          k = (int)(u * p.n_lines);
+        }
+      }
+      if (k < 0) k = 0;
+      if (k >= p.n_lines) k = p.n_lines - 1;
+      E = p.lines[k];
+    }
+    over = (a * a + c * c) > 1.0;
+    out.x[i] = x;
+    out.y[i] = y;
+    out.z[i] = z;
+    out.a[i] = a;
+    out.b[i] = 1.0;
+    out.c[i] = c;
+    out.path[i] = 0.0;
+    out.E[i] = E;
+    out.Jss[i] = A.Jss;
+    out.Jpp[i] = A.Jpp;
+    reinterpret_cast<double2*>(out.Jsp)[i] = make_double2(A.Jsp.re, A.Jsp.im);
+    if (out.Es) {
+      reinterpret_cast<double2*>(out.Es)[i] = make_double2(A.Es.re, A.Es.im);
+      reinterpret_cast<double2*>(out.Ep)[i] = make_double2(A.Ep.re, A.Ep.im);
+    }
+    out.state[i] = 1;
+  }
+  const unsigned ball = __ballot_sync(0xffffffffu, over);
+  if ((threadIdx.x & 31) == 0 && ball) atomicAdd(flag, (unsigned long long)__popc(ball));
+}
+
+// direction normalisation (geoms.py:503-511: one formula for the whole beam), rotate_beam, virgin_local_to_global
+__global__ void __launch_bounds__(256) geom_finish_kernel(size_t n, xrt_geom_params p, xrt_beam out,
+                                                          const unsigned long long* flag) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x = out.x[i], y = out.y[i], z = out.z[i], a = out.a[i], c = out.c[i], b;
+  const double ac = a * a + c * c;
+  if (*flag > 0) {
+    b = sqrt(ac + 1.0);
+    a /= b;
+    c /= b;
+    b = 1.0 / b;
+  } else {
+    b = sqrt(1.0 - ac);
+  }
+  for (int k = 0; k < p.n_rot; ++k) {
+    const double cA = p.rot_cos[k], sA = p.rot_sin[k];
+    if (p.rot_axis[k] == 2) {  // rotate_z(x, y)
+      const double x1 = cA * x - sA * y, y1 = sA * x + cA * y, a1 = cA * a - sA * b, b1 = sA * a + cA * b;
+      x = x1, y = y1, a = a1, b = b1;
+    } else if (p.rot_axis[k] == 1) {  // rotate_y(x, z)
+      const double x1 = cA * x + sA * z, z1 = -sA * x + cA * z, a1 = cA * a + sA * c, c1 = -sA * a + cA * c;
+      x = x1, z = z1, a = a1, c = c1;
+    } else {  // rotate_x(y, z)
+      const double y1 = cA * y - sA * z, z1 = sA * y + cA * z, b1 = cA * b - sA * c, c1 = sA * b + cA * c;
+      y = y1, z = z1, b = b1, c = c1;
+    }
+  }
+  if (p.to_global) {
+    if (p.sinAz != 0.0) {
+      const double a1 = p.cosAz * a - (-p.sinAz) * b, b1 = (-p.sinAz) * a + p.cosAz * b;
+      a = a1;
+      b = b1;
+      const double x1 = p.cosAz * x - (-p.sinAz) * y, y1 = (-p.sinAz) * x + p.cosAz * y;
+      x = x1;
+      y = y1;
+    }
+    x += p.center[0];
+    y += p.center[1];
+    z += p.center[2];
+  }
+  out.x[i] = x;
+  out.y[i] = y;
+  out.z[i] = z;
+  out.a[i] = a;
+  out.b[i] = b;
+  out.c[i] = c;
+}
+
+int geometric_source_device(size_t n, const xrt_geom_params* p, uint64_t seed, uint64_t index_offset,
+                            const double* const* deviates, const xrt_beam* out, unsigned long long* flag, int phase,
+                            cudaStream_t st) {
+  XRTB_REQUIRE(p && out && flag, "geometric_source: NULL argument");
+  XRTB_REQUIRE(p->n_lines >= 0 && p->n_lines <= XRT_GEOM_MAX_LINES, "geometric_source: at most %d energy lines",
+               XRT_GEOM_MAX_LINES);
+  XRTB_REQUIRE(p->distE != 3 || p->n_lines > 0, "geometric_source: distE = 'lines' needs at least one energy");
+  XRTB_REQUIRE(p->n_rot >= 0 && p->n_rot <= 3, "geometric_source: at most 3 elementary rotations");
+  GeomDev dv;
+  for (int k = 0; k < 7; ++k) dv.d[k] = deviates ? deviates[k] : nullptr;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  if (phase & 1) {  // (the caller zeroes `flag`)
+    if (n > 0) geom_sample_kernel<<<grid, 256, 0, st>>>(n, *p, seed, index_offset, dv, *out, flag);
+    XRTB_CUDA_CHECK(cudaGetLastError());
+  }
+  if ((phase & 2) && n > 0) {
+    geom_finish_kernel<<<grid, 256, 0, st>>>(n, *p, *out, flag);
+    XRTB_CUDA_CHECK(cudaGetLastError());
+  }
+  return 0;
+}
+
 int source_sample_device(size_t n, uint64_t seed, uint64_t index_offset, const double* window, double* E,
                          double* theta, double* psi, double* n1, double* n2, double* n3, double* n4, double* u,
                          double* n5, cudaStream_t st) {

@@ -218,6 +218,34 @@ class CrystalFcc(Material):
     def _diamond_to_fcc(self):
         return 1. + 0j
 
+    # alignment helpers on the host (numpy): per-element scalars a beamline script computes once, not per-ray work
+    def get_dtheta_symmetric_Bragg(self, E):
+        """crystal.py:1122-1139: chi0 / sin(2 thetaB), F0 from the tables (crystals_basic.py:22-31, :76-80)."""
+        E = np.asarray(E, dtype=float)
+        elem = self.elements[0]
+        if np.any(E < elem.E[0]) or np.any(E > elem.E[-1]):
+            raise ValueError('E is out of the f1/f2 data table range')
+        anomalous = np.interp(E, elem.E, elem.f1) + 1j*np.interp(E, elem.E, elem.f2)
+        F0 = 4 * (elem.Z + anomalous) * self.factDW
+        if self.structure == 'diamond':
+            F0 = F0 * 2
+        chi0 = F0 * (self.chiToF * (CH / E)**2)
+        return (chi0 / np.sin(2*self.get_Bragg_angle(E))).real
+
+    def get_dtheta(self, E, alpha=None):
+        """Crystal.get_dtheta (crystal.py:1141-1173), Bragg geometry: the refraction correction to the Bragg angle
+        a script subtracts when it sets `bragg` (what auto_align does, beamline.py:636-681)."""
+        if alpha is None:
+            alpha = 0
+        thetaB = self.get_Bragg_angle(E)
+        pm = -1
+        gamma0 = np.sin(thetaB + alpha)
+        gammah = pm * np.sin(thetaB - alpha)
+        symm_dt = self.get_dtheta_symmetric_Bragg(E)
+        osqg0 = np.sqrt(1. - gamma0**2)
+        dtheta0 = (pm*gamma0 - pm*np.sqrt(gamma0**2 + pm*(gamma0 - gammah) * osqg0 * symm_dt)) / osqg0
+        return -dtheta0
+
     def c_struct(self, offs, lens):
         m = super().c_struct(offs, lens)
         m.d = float(self.d)

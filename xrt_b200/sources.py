@@ -806,3 +806,260 @@ class Wiggler(BendingMagnet):
         self.Np = kwargs.pop('n', 40)
         kwargs.setdefault('name', 'wiggler')
         super(Wiggler, self).__init__(*args, **kwargs)
+
+
+XRT_GEOM_MAX_LINES = 16
+
+
+class xrt_geom_params(ctypes.Structure):
+    """struct xrt_geom_params of include/xrt_b200.h"""
+    _fields_ = [('center', ctypes.c_double * 3), ('sinAz', ctypes.c_double), ('cosAz', ctypes.c_double),
+                ('to_global', ctypes.c_int), ('n_rot', ctypes.c_int), ('rot_axis', ctypes.c_int * 3),
+                ('rot_cos', ctypes.c_double * 3), ('rot_sin', ctypes.c_double * 3),
+                ('dist', ctypes.c_int * 5), ('p0', ctypes.c_double * 5), ('p1', ctypes.c_double * 5),
+                ('annulus_xz', ctypes.c_int), ('annulus_ac', ctypes.c_int),
+                ('ann_xz', ctypes.c_double * 4), ('ann_ac', ctypes.c_double * 4), ('sqrt_pi2', ctypes.c_double),
+                ('with_amp', ctypes.c_int),
+                ('Jss', ctypes.c_double), ('Jpp', ctypes.c_double), ('Jsp_re', ctypes.c_double),
+                ('Jsp_im', ctypes.c_double), ('Es_re', ctypes.c_double), ('Es_im', ctypes.c_double),
+                ('Ep_re', ctypes.c_double), ('Ep_im', ctypes.c_double), ('ep_random', ctypes.c_int),
+                ('distE', ctypes.c_int), ('e0', ctypes.c_double), ('e1', ctypes.c_double),
+                ('n_lines', ctypes.c_int), ('weighted', ctypes.c_int),
+                ('lines', ctypes.c_double * XRT_GEOM_MAX_LINES), ('cdf', ctypes.c_double * XRT_GEOM_MAX_LINES)]
+
+
+def _auto_units_angle(angle, defaultFactor=1., aliases=None):
+    """raycing.auto_units_angle (_flow_utils.py:74-115)."""
+    if isinstance(angle, str):
+        text = angle.strip()
+        low = text.lower()
+        if aliases is not None:
+            for alias, value in aliases.items():
+                if low.startswith(alias):
+                    return value
+        for unit, cut, factor in (('mrad', 'm', 1e-3), ('urad', 'u', 1e-6), ('nrad', 'n', 1e-9), ('rad', 'r', 1.)):
+            if unit in angle:
+                return float(angle.split(cut)[0].strip()) * factor
+        if 'deg' in angle:
+            return np.radians(float(angle.split('d')[0].strip()))
+        return float(text) * defaultFactor
+    if angle is None or isinstance(angle, (list, tuple)):
+        return angle
+    return angle * defaultFactor
+
+
+class GeometricSource(object):
+    """Geometric source with xrt's constructor and `shine()` (sources/geoms.py:193-534): ray origin, divergence and
+    energy sampled with the given distribution laws ('normal', 'flat', 'annulus', None; distE 'normal', 'flat',
+    'lines', None), every polarisation xrt knows, uniformRayDensity, canted sources, totalFlux.  One CUDA kernel
+    draws the rays in HBM (Philox4x32-10 counters, so ray shards on several GPUs draw disjoint sub-streams), a second
+    one normalises and places them: xrt_b200/csrc/source.cu.  Out of scope: filamentBeam, accuBeam."""
+
+    def __init__(self, bl=None, name='', center=(0, 0, 0), nrays=100000, distx='normal', dx=0.32, disty=None, dy=0,
+                 distz='normal', dz=0.018, distxprime='normal', dxprime=1e-3, distzprime='normal', dzprime=1e-4,
+                 distE='lines', energies=(9000.,), energyWeights=None, polarization='horizontal',
+                 filamentBeam=False, uniformRayDensity=False, pitch=0, roll=0, yaw=0, totalFlux=None, seed=1234,
+                 targetOpenCL='CUDA', **kwargs):
+        if filamentBeam:
+            raise NotImplementedError('filamentBeam is outside the hot path (SURVEY.md section 8f3)')
+        if targetOpenCL is None:
+            raise _lib.XrtB200Error('xrt_b200 sources always compute on the GPU (no numpy path)')
+        self.bl = bl
+        self.name = name
+        if bl is not None and self not in bl.sources:
+            bl.sources.append(self)
+        self.center = list(center)
+        self.nrays = int(nrays)
+        self.distx, self.dx = distx, dx
+        self.disty, self.dy = disty, dy
+        self.distz, self.dz = distz, dz
+        self.distxprime, self.dxprime = distxprime, _auto_units_angle(dxprime)
+        self.distzprime, self.dzprime = distzprime, _auto_units_angle(dzprime)
+        self.distE, self.energies, self.energyWeights = distE, energies, energyWeights
+        self.polarization = polarization
+        self.uniformRayDensity = uniformRayDensity
+        self.pitch, self.roll, self.yaw = (_auto_units_angle(v) for v in (pitch, roll, yaw))
+        self.totalFlux = totalFlux
+        self.seed = int(seed)
+        self._draws = 0
+
+    # ------------------------------------------------------------------ marshalling
+    def _axis(self, p, k, dist, d):
+        """_apply_distribution (geoms.py:370-405) -> (kind, p0, p1) of axis k."""
+        if dist == 'normal':
+            if self.uniformRayDensity:
+                arr = np.atleast_1d(d)
+                sigma = arr[0]
+                cut = 5 * abs(sigma) if len(arr) < 2 else arr[-1]
+                p.dist[k], p.p0[k], p.p1[k] = 3, float(sigma), float(cut)
+            else:
+                sigma = d[0] if isinstance(d, (list, tuple)) else d
+                p.dist[k], p.p0[k] = 1, float(sigma)
+        elif dist == 'flat':
+            if isinstance(d, (list, tuple, np.ndarray)):
+                aMin, aMax = d[0], d[1]
+            else:
+                if d <= 0:
+                    return
+                aMin, aMax = -d*0.5, d*0.5
+            p.dist[k], p.p0[k], p.p1[k] = 2, float(aMin), float(aMax)
+
+    def _pair(self, p, k1, k2, d1, v1, d2, v2, which):
+        isAnnulus = False
+        if d1 == 'annulus' or d2 == 'annulus':  # geoms.py:467-477
+            isAnnulus = True
+            if isinstance(v1, (list, tuple, np.ndarray)):
+                rMin, rMax = v1
+            else:
+                isAnnulus = False
+            if isinstance(v2, (list, tuple, np.ndarray)):
+                phiMin, phiMax = v2
+            else:
+                phiMin, phiMax = 0, PI2
+        if isAnnulus:
+            setattr(p, 'annulus_' + which, 1)
+            arr = getattr(p, 'ann_' + which)
+            arr[0], arr[1], arr[2], arr[3] = float(rMin), float(rMax), float(phiMin), float(phiMax)
+        else:
+            self._axis(p, k1, d1, v1)
+            self._axis(p, k2, d2, v2)
+
+    def _polarization(self, p):
+        """make_polarization (geoms.py:64-175)."""
+        def fill(Jss, Jpp, Jsp, Es, Ep):
+            p.Jss, p.Jpp, p.Jsp_re, p.Jsp_im = float(Jss), float(Jpp), complex(Jsp).real, complex(Jsp).imag
+            p.Es_re, p.Es_im = complex(Es).real, complex(Es).imag
+            if isinstance(Ep, str):
+                p.ep_random = 1
+            else:
+                p.Ep_re, p.Ep_im = complex(Ep).real, complex(Ep).imag
+
+        def linear(angle):
+            Es, Ep = np.cos(angle), np.sin(angle)
+            fill(Es*Es, Ep*Ep, Es*Ep, Es, Ep)
+
+        def as_angle(value):
+            if isinstance(value, (bool, np.bool_)):
+                return None
+            angle = _auto_units_angle(value, defaultFactor=np.pi / 180., aliases={'h': 0., 'v': np.pi / 2.})
+            return angle if isinstance(angle, (int, float, np.integer, np.floating)) else None
+
+        pol = self.polarization
+        if pol is None:
+            fill(0.5, 0.5, 0, 2**(-0.5), 'random phase')
+        elif isinstance(pol, (tuple, list, np.ndarray)):
+            if len(pol) != 4:
+                raise ValueError('wrong coherency matrix: must be a 4-sequence!')
+            p.Jss, p.Jpp, p.Jsp_re, p.Jsp_im = float(pol[0]), float(pol[1]), float(pol[2]), float(pol[3])
+        elif isinstance(pol, str) and pol.lower().startswith('un'):
+            fill(0.5, 0.5, 0, 2**(-0.5), 'random phase')
+        elif isinstance(pol, str) and pol.lower().startswith('r'):
+            fill(0.5, 0.5, 0.5j, 2**(-0.5), -1j * 2**(-0.5))
+        elif isinstance(pol, str) and pol.lower().startswith('l'):
+            fill(0.5, 0.5, -0.5j, 2**(-0.5), 1j * 2**(-0.5))
+        else:
+            angle = as_angle(pol.lower() if isinstance(pol, str) else pol)
+            if angle is None:
+                raise ValueError('wrong polarization!')
+            linear(angle)
+
+    def _energy(self, p):
+        """make_energy (geoms.py:14-61)."""
+        if self.distE is None:
+            return
+        eArr = np.atleast_1d(self.energies).astype(float)
+        if self.distE == 'normal':
+            eMean = eArr[0]
+            eSigma = eArr[1] if len(eArr) == 2 else 0
+            p.distE, p.e0, p.e1 = 1, float(eMean), float(0 if abs(eSigma) > 0.1*abs(eMean) else abs(eSigma))
+        elif self.distE == 'flat':
+            eMin = eArr[0]
+            eMax = (eArr[1] or eArr[0]) if len(eArr) == 2 else eArr[0]
+            p.distE, p.e0, p.e1 = 2, float(eMin), float(eMax)
+        elif self.distE == 'lines':
+            w = np.atleast_1d(self.energyWeights).astype(float) if self.energyWeights is not None else None
+            if 0 in eArr:
+                eArr = eArr[eArr > 0]
+            if len(eArr) > XRT_GEOM_MAX_LINES:
+                raise ValueError('at most {0} energy lines'.format(XRT_GEOM_MAX_LINES))
+            p.distE, p.n_lines = 3, len(eArr)
+            for i, e in enumerate(eArr):
+                p.lines[i] = float(e)
+            if w is not None and len(w) == len(eArr):
+                p.weighted = 1
+                cdf = w.cumsum()
+                cdf /= cdf[-1]
+                for i, c in enumerate(cdf):
+                    p.cdf[i] = float(c)
+        else:
+            raise ValueError('unknown distE {0!r}'.format(self.distE))
+
+    def _params(self, toGlobal, withAmplitudes):
+        p = xrt_geom_params()
+        for i in range(3):
+            p.center[i] = float(self.center[i])
+        p.sinAz = float(self.bl.sinAzimuth) if self.bl is not None else 0.
+        p.cosAz = float(self.bl.cosAzimuth) if self.bl is not None else 1.
+        p.to_global = int(bool(toGlobal))
+        nrot = 0
+        for ax, angle in ((2, self.yaw), (1, self.roll), (0, self.pitch)):  # rotate_beam default 'RzRyRx'
+            if angle != 0:
+                p.rot_axis[nrot], p.rot_cos[nrot], p.rot_sin[nrot] = ax, float(np.cos(angle)), float(np.sin(angle))
+                nrot += 1
+        p.n_rot = nrot
+        p.sqrt_pi2 = PI2**0.5
+        p.with_amp = int(bool(withAmplitudes))
+        self._polarization(p)
+        self._axis(p, 0, self.disty, self.dy)
+        self._pair(p, 1, 2, self.distx, self.dx, self.distz, self.dz, 'xz')
+        self._pair(p, 3, 4, self.distxprime, self.dxprime, self.distzprime, self.dzprime, 'ac')
+        self._energy(p)
+        return p
+
+    # ------------------------------------------------------------------ shine
+    def shine(self, toGlobal=True, withAmplitudes=False, accuBeam=None, samples=None, index_offset=0,
+              allreduce_sum=None):
+        """Returns the source Beam (device resident) like GeometricSource.shine (geoms.py:420-534).
+
+        *samples* (optional): dict of CUDA tensors with the standard deviates to use instead of Philox draws, keys
+        'pol', 'y', 'x', 'z', 'a', 'c', 'E' (the numpy oracle's record).  *allreduce_sum*: callable applied to the
+        1-element tensors that are beam-wide (the a^2 + c^2 > 1 count, the intensity sum of totalFlux) when the
+        rays are sharded over ranks."""
+        if accuBeam is not None:
+            raise NotImplementedError('accuBeam is outside the hot path')
+        lib = _lib.load()
+        _lib.init(None)
+        if self.uniformRayDensity:
+            withAmplitudes = True
+        dev = torch.device('cuda', torch.cuda.current_device())
+        bo = Beam(self.nrays, withAmplitudes=withAmplitudes, device=dev, uninitialized=True)
+        p = self._params(toGlobal, withAmplitudes)
+        flag = torch.zeros(1, dtype=torch.int64, device=dev)
+        devs = (ctypes.c_void_p * 7)()
+        if samples is not None:
+            for k, key in enumerate(('pol', 'y', 'x', 'z', 'a', 'c', 'E')):
+                t = samples.get(key)
+                if t is not None:
+                    devs[k] = t.data_ptr()
+        cout = bo.c_struct()
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        offset = int(index_offset) + self._draws
+        self._draws += 1 << 40
+        args = (self.nrays, ctypes.byref(p), self.seed, offset, devs, ctypes.byref(cout), flag.data_ptr())
+        _lib.check(lib.xrt_geometric_source_f64(*args, 1, stream), 'xrt_geometric_source_f64 (sample)')
+        if allreduce_sum is not None:
+            allreduce_sum(flag)
+        if np.isscalar(self.totalFlux) and self.totalFlux > 0:  # make_flux_normalization (geoms.py:178-190)
+            isum = (bo.Jss + bo.Jpp).sum().reshape(1)
+            if allreduce_sum is not None:
+                allreduce_sum(isum)
+            intensitySum = float(isum)
+            if intensitySum > 0:
+                bo.sourceWeight = self.totalFlux / intensitySum
+                bo.seeded = self.nrays
+                bo.seededI = 1.
+                bo.accepted = 1.
+                bo.acceptedE = 1.
+        _lib.check(lib.xrt_geometric_source_f64(*args, 2, stream), 'xrt_geometric_source_f64 (finish)')
+        bo.parentId = getattr(self, 'uuid', self.name)
+        return bo
