@@ -6,6 +6,7 @@ Restates, in numpy and in the reference's operation order:
   * Undulator._sp_sum                        synchr.py:1929-2033: far field (the `else` branch :1997-2003),
                                              taper (:1958-1971) and near field R0 (:1972-1996) + :2005-2031
   * Undulator._build_I_map_conv              synchr.py:2048-2108
+  * SourceBase.intensities_on_mesh           sybase.py:740-928 (resultKind='Stokes')
 """
 import numpy as np
 
@@ -173,3 +174,79 @@ def build_I_map(grid, L0, Np, Kx, Ky, eI, gamma, w, ddtheta, ddpsi, distE='eV', 
     return (Amp2Flux * ab**2 * 0.25 * dstep**2 * integralField,
             np.sqrt(Amp2Flux) * ab * Is_local * 0.5 * dstep,
             np.sqrt(Amp2Flux) * ab * Ip_local * 0.5 * dstep)
+
+
+def intensities_on_mesh(grid, L0, Np, Kx, Ky, eI, gamma0, eEspread, dxprime, dzprime, energy, theta, psi,
+                        harmonic=None, eSpreadSigmas=3.5, eSpreadNSamples=36, mode='constant', distE='eV'):
+    """SourceBase.intensities_on_mesh (sybase.py:740-928), Stokes result, for the far-field undulator."""
+    tomesh = [energy, theta, psi]
+    if harmonic is not None:
+        tomesh.append(harmonic)
+        iharmonic = len(tomesh)-1
+    else:
+        iharmonic = None
+    if eEspread > 0:
+        spr = np.linspace(-eSpreadSigmas, eSpreadSigmas, eSpreadNSamples)
+        dgamma = gamma0 * spr * eEspread
+        wspr = np.exp(-0.5 * spr**2)
+        wspr /= wspr.sum()
+        tomesh.append(dgamma)
+        ispread = len(tomesh)-1
+    else:
+        ispread = None
+    mesh = np.meshgrid(*tomesh, indexing='ij')
+    xE, xTheta, xPsi = mesh[0].ravel(), mesh[1].ravel(), mesh[2].ravel()
+    sh = [len(energy), len(theta), len(psi)]
+    if iharmonic:
+        xH = mesh[iharmonic].ravel()
+        sh.append(len(harmonic))
+    else:
+        xH = None
+    gamma = gamma0
+    if ispread:
+        gamma = gamma + mesh[ispread].ravel()  # synchr.py:2053-2056
+        sh.append(len(dgamma))
+    NRAYS = len(xE)
+    gamma = gamma * np.ones(NRAYS)
+    wu, ww1, ab = sample_prefactors(L0, Np, Kx, Ky, gamma, xE, xTheta, xPsi)
+    Is_local, Ip_local = sp_sum(grid, Kx, Ky, ww1, xE, wu, gamma, xTheta, xPsi)
+    bwFact = 0.001 if distE == 'BW' else 1./xE
+    Amp2Flux = FINE_STR * bwFact * eI / SIE0
+    if xH is not None:  # synchr.py:2094-2098
+        Is_local[ww1 > xH+0.5] = 0
+        Ip_local[ww1 > xH+0.5] = 0
+        Is_local[ww1 < xH-0.5] = 0
+        Ip_local[ww1 < xH-0.5] = 0
+    dstep = grid['dstep']
+    Es = (np.sqrt(Amp2Flux) * ab * Is_local * 0.5 * dstep).reshape(sh)
+    Ep = (np.sqrt(Amp2Flux) * ab * Ip_local * 0.5 * dstep).reshape(sh)
+    Is = (Es*np.conj(Es)).real.astype(float)
+    Ip = (Ep*np.conj(Ep)).real.astype(float)
+    Isp = Es*np.conj(Ep).astype(complex)
+    if ispread:
+        if iharmonic:
+            ws = wspr[np.newaxis, np.newaxis, np.newaxis, np.newaxis, :]
+        else:
+            ws = wspr[np.newaxis, np.newaxis, np.newaxis, :]
+        Is = (Is * ws).sum(axis=ispread)
+        Ip = (Ip * ws).sum(axis=ispread)
+        Isp = (Isp * ws).sum(axis=ispread)
+    s0 = Is + Ip
+    s1 = Is - Ip
+    s2 = 2. * np.real(Isp)
+    s3 = -2. * np.imag(Isp)
+    ss = [s0, s1, s2, s3]
+    if (dxprime > 0 or dzprime > 0) and len(theta) > 1 and len(psi) > 1:
+        from scipy.ndimage import gaussian_filter
+        Sx = dxprime / (theta[1] - theta[0])
+        Sz = dzprime / (psi[1] - psi[0])
+        for ie, ee in enumerate(energy):
+            if harmonic is None:
+                for arr in ss:
+                    arr[ie, :, :] = gaussian_filter(arr[ie, :, :], [Sx, Sz], mode=mode)
+            else:
+                for ih, hh in enumerate(harmonic):
+                    for arr in ss:
+                        arr[ie, :, :, ih] = gaussian_filter(arr[ie, :, :, ih], [Sx, Sz], mode=mode)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        return [s0, np.where(s0, s1/s0, s0), np.where(s0, s2/s0, s0), np.where(s0, s3/s0, s0)]

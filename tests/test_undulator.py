@@ -280,3 +280,76 @@ def test_cuda_undulator_taper_shine(cuda_device):
     J = (beam.Jss + beam.Jpp).cpu().numpy()
     assert np.all(np.isfinite(J)) and J.max() > 0
     assert int((beam.state == 1).sum()) == 5000
+
+
+# ------------------------------------------------------------------ flux maps: intensities_on_mesh
+MESH_CASES = ['mesh_planar_harmonics', 'mesh_elliptical']
+
+
+def _mesh_kwargs(g):
+    kw = dict(eSpreadSigmas=float(g['eSpreadSigmas']), eSpreadNSamples=int(g['eSpreadNSamples']))
+    harm = list(g['harmonic']) if 'harmonic' in g.files else None
+    return harm, kw
+
+
+@pytest.mark.parametrize('name', MESH_CASES)
+def test_oracle_intensities_on_mesh_matches_reference_bit_exact(name):
+    g = golden(name)
+    grid = _grid(g)
+    harm, kw = _mesh_kwargs(g)
+    ss = ou.intensities_on_mesh(grid, float(g['L0']), float(g['Np']), float(g['Kx']), float(g['Ky']), float(g['eI']),
+                                float(g['gamma0']), float(g['eEspread']), float(g['dxprime']), float(g['dzprime']),
+                                g['energy'], g['theta'], g['psi'], harm, distE=str(g['distE']), **kw)
+    for i in range(4):
+        assert np.array_equal(ss[i], g['s%d' % i], equal_nan=True), i
+    assert g['s0'].max() > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', MESH_CASES)
+def test_cuda_intensities_on_mesh_vs_reference_golden(name, cuda_device):
+    """Undulator.intensities_on_mesh (sybase.py:740-928): Stokes parameters on an (E, theta, psi[, harmonic]) mesh,
+    averaged over the energy spread and convolved with the electron divergence like the reference."""
+    from xrt_b200.sources import Undulator
+    g = golden(name)
+    harm, kw = _mesh_kwargs(g)
+    zero_emittance = float(g['dxprime']) == 0
+    src = Undulator(eE=3., eI=float(g['eI']), period=float(g['L0']), n=int(g['Np']), K=0, Kx=float(g['Kx']),
+                    Ky=float(g['Ky']), phaseDeg=float(np.degrees(g['phase'])), eMin=float(g['energy'][0]),
+                    eMax=float(g['energy'][-1]), gNodes=int(g['quadm']), gIntervals=int(g['gIntervals']),
+                    eEspread=float(g['eEspread']), distE=str(g['distE']), xPrimeMaxAutoReduce=False,
+                    zPrimeMaxAutoReduce=False, eSigmaX=0. if zero_emittance else 48.65,
+                    eSigmaZ=0. if zero_emittance else 6.197, eEpsilonX=0. if zero_emittance else 0.263,
+                    eEpsilonZ=0. if zero_emittance else 0.008)
+    assert src.dxprime == float(g['dxprime']) and src.dzprime == float(g['dzprime'])
+    ss = src.intensities_on_mesh(g['energy'], g['theta'], g['psi'], harm, **kw)
+    s0 = g['s0']
+    # flux density: 1e-10 of the map's maximum (the harmonic window zeroes samples at ww1 = h +- 0.5 exactly as the
+    # reference does: ww1 is computed on the host in both); degrees of polarisation where there is light
+    assert np.abs(ss[0] - s0).max() <= 1e-10 * s0.max()
+    lit = s0 > 1e-6 * s0.max()
+    for i in (1, 2, 3):
+        assert np.abs(ss[i] - g['s%d' % i])[lit].max() <= 1e-8, i
+
+
+@pytest.mark.gpu
+def test_cuda_tuning_curve_follows_the_undulator_equation(cuda_device):
+    """Undulator.tuning_curves (synchr.py:1710-1750): the flux maximum of harmonic h sits just below
+    h * E1(K) = h * 2 gamma^2 hc / (L0 (1 + K^2 / 2)), for every K."""
+    from xrt_b200.sources import Undulator
+    src = Undulator(eE=3., eI=0.5, period=30., n=40, K=1.45, eMin=500., eMax=6000., gNodes=40, gIntervals=2,
+                    eSigmaX=0., eSigmaZ=0., eEpsilonX=0., eEpsilonZ=0., distE='BW', xPrimeMaxAutoReduce=False,
+                    zPrimeMaxAutoReduce=False)
+    theta = np.linspace(-1, 1, 9) * 1.5e-5
+    psi = np.linspace(-1, 1, 9) * 1.5e-5
+    Ks = [0.8, 1.45]
+    for K in Ks:
+        src.Ky = K
+        src.report_E1()
+        e1 = src.E1
+        energy = np.linspace(0.9 * e1, 1.03 * e1, 40)
+        tE, tF = src.tuning_curves(energy, theta, psi, [1], [K])
+        assert tE.shape == (1, 1) and tF[0, 0] > 0
+        assert 0.97 * e1 < tE[0, 0] * 1e3 <= 1.005 * e1
+    p = src.power_vs_K(np.linspace(500., 6000., 12), theta, psi, None, Ks)
+    assert p.shape == (2,) and p[1] > p[0] > 0  # more field, more power

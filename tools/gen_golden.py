@@ -888,7 +888,35 @@ def gen_geometric():
         _geom_case(name, c['seed'], c['withAmplitudes'], c.get('azimuth', 0.), **c['kw'])
 
 
-SECTIONS = {'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+def gen_mesh():
+    """SourceBase.intensities_on_mesh (sybase.py:740-928): the flux-map use of the undulator kernel."""
+    probe = _undulator_source(eMin=1000., eMax=1001., gNodes=16)
+    E1 = probe.E1
+    # (1) planar, harmonics 1 and 3 separated, energy spread (5 samples), emittance convolution
+    src = _undulator_source(eMin=E1*0.9, eMax=E1*3.2, gNodes=40, gIntervals=2, eEspread=8e-4, distE='BW')
+    energy = np.linspace(E1*0.9, E1*3.2, 14)
+    theta = np.linspace(-1, 1, 21) * 8e-5
+    psi = np.linspace(-1, 1, 15) * 6e-5
+    harm = [1, 3]
+    ss = src.intensities_on_mesh(energy, theta, psi, harm, eSpreadSigmas=3., eSpreadNSamples=5)
+    save('mesh_planar_harmonics', energy=energy, theta=theta, psi=psi, harmonic=np.array(harm), s0=ss[0], s1=ss[1],
+         s2=ss[2], s3=ss[3], L0=src.L0, Np=src.Np, Kx=src.Kx, Ky=src.Ky, eI=src.eI, gamma0=src.gamma,
+         phase=src.phase, quadm=src.quadm, gIntervals=src.gIntervals, eEspread=src.eEspread, dxprime=src.dxprime,
+         dzprime=src.dzprime, eSpreadSigmas=3., eSpreadNSamples=5, distE=np.array('BW'))
+    # (2) elliptical, zero emittance, no spread, no harmonic axis
+    src = _undulator_source(K=0, Kx=0.9, Ky=1.2, phaseDeg=90, eMin=E1*0.5, eMax=E1*1.5, gNodes=40, gIntervals=3,
+                            eEpsilonX=0., eEpsilonZ=0., eSigmaX=0., eSigmaZ=0.)
+    energy = np.linspace(E1*0.5, E1*1.5, 9)
+    theta = np.linspace(-1, 1, 17) * 1e-4
+    psi = np.linspace(-1, 1, 13) * 1e-4
+    ss = src.intensities_on_mesh(energy, theta, psi)
+    save('mesh_elliptical', energy=energy, theta=theta, psi=psi, s0=ss[0], s1=ss[1], s2=ss[2], s3=ss[3], L0=src.L0,
+         Np=src.Np, Kx=src.Kx, Ky=src.Ky, eI=src.eI, gamma0=src.gamma, phase=src.phase, quadm=src.quadm,
+         gIntervals=src.gIntervals, eEspread=src.eEspread, dxprime=src.dxprime, dzprime=src.dzprime,
+         eSpreadSigmas=3.5, eSpreadNSamples=36, distE=np.array('eV'))
+
+
+SECTIONS = {'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)

@@ -510,6 +510,121 @@ class Undulator(object):
         return bo
 
 
+def _intensities_on_mesh(self, energy, theta, psi, harmonic=None, eSpreadSigmas=3.5, eSpreadNSamples=36,
+                         mode='constant'):
+    """SourceBase.intensities_on_mesh (sources/sybase.py:740-928), resultKind='Stokes': [s0, s1/s0, s2/s0, s3/s0] in
+    the shape (energy, theta, psi[, harmonic]); the field of every mesh point comes from the CUDA kernels through
+    `build_I_map`, the incoherent averaging over energy spread and the angular convolution with the electron beam
+    divergence (scipy.ndimage.gaussian_filter, like the reference) run on the small result arrays on the host."""
+    if self.needReset:
+        self.reset()
+    energy, theta, psi = (np.asarray(a, dtype=float) for a in (energy, theta, psi))
+    tomesh = [energy, theta, psi]
+    iharmonic = None
+    if harmonic is not None:
+        tomesh.append(np.asarray(harmonic))
+        iharmonic = len(tomesh)-1
+    ispread = None
+    if self.eEspread > 0:
+        spr = np.linspace(-eSpreadSigmas, eSpreadSigmas, eSpreadNSamples)
+        dgamma = self.gamma * spr * self.eEspread
+        wspr = np.exp(-0.5 * spr**2)
+        wspr /= wspr.sum()
+        tomesh.append(dgamma)
+        ispread = len(tomesh)-1
+    mesh = np.meshgrid(*tomesh, indexing='ij')
+    xE, xTheta, xPsi = mesh[0].ravel(), mesh[1].ravel(), mesh[2].ravel()
+    sh = [len(energy), len(theta), len(psi)]
+    xH = xG = None
+    if iharmonic:
+        xH = mesh[iharmonic].ravel()
+        sh.append(len(harmonic))
+    if ispread:
+        xG = mesh[ispread].ravel()
+        sh.append(len(dgamma))
+    res = self.build_I_map(xE, xTheta, xPsi, xH, xG)
+    Es = res[1].reshape(sh)
+    Ep = res[2].reshape(sh)
+    Is = (Es*np.conj(Es)).real.astype(float)
+    Ip = (Ep*np.conj(Ep)).real.astype(float)
+    Isp = Es*np.conj(Ep).astype(complex)
+    if ispread:
+        ws = wspr[(np.newaxis,) * (len(sh) - 1) + (slice(None),)]
+        Is = (Is * ws).sum(axis=ispread)
+        Ip = (Ip * ws).sum(axis=ispread)
+        Isp = (Isp * ws).sum(axis=ispread)
+    self.Is, self.Ip, self.Isp = Is, Ip, Isp
+    s0 = Is + Ip
+    s1 = Is - Ip
+    s2 = 2. * np.real(Isp)
+    s3 = -2. * np.imag(Isp)
+    ss = [s0, s1, s2, s3]
+    if (self.dxprime > 0 or self.dzprime > 0) and len(theta) > 1 and len(psi) > 1:
+        from scipy.ndimage import gaussian_filter
+        Sx = self.dxprime / (theta[1] - theta[0])
+        Sz = self.dzprime / (psi[1] - psi[0])
+        for ie in range(len(energy)):
+            if harmonic is None:
+                for arr in ss:
+                    arr[ie, :, :] = gaussian_filter(arr[ie, :, :], [Sx, Sz], mode=mode)
+            else:
+                for ih in range(len(harmonic)):
+                    for arr in ss:
+                        arr[ie, :, :, ih] = gaussian_filter(arr[ie, :, :, ih], [Sx, Sz], mode=mode)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        return [s0, np.where(s0, s1/s0, s0), np.where(s0, s2/s0, s0), np.where(s0, s3/s0, s0)]
+
+
+def _tuning_curves(self, energy, theta, psi, harmonics, Ks):
+    """Undulator.tuning_curves (sources/synchr.py:1710-1750): maximum flux of the given harmonics at the given K
+    values through the aperture (theta, psi).  Returns (energy in keV, flux in ph/s/0.1%bw), rows = Ks, columns =
+    harmonics."""
+    try:
+        dtheta, dpsi = theta[1] - theta[0], psi[1] - psi[0]
+    except TypeError:
+        dtheta, dpsi = 1, 1
+    tunesE, tunesF = [], []
+    tmpKy = self.Ky
+    for K in Ks:
+        self.Ky = K
+        flux = None
+        for e in energy:
+            I0 = self.intensities_on_mesh([e], theta, psi, harmonics)[0]
+            iflux = I0.sum(axis=(1, 2)) * dtheta * dpsi
+            flux = iflux if flux is None else np.vstack((flux, iflux))
+        argm = np.argmax(flux, axis=0)
+        fluxm = np.max(flux, axis=0)
+        tunesE.append(np.asarray(energy)[argm] / 1000.)
+        tunesF.append(fluxm)
+    self.Ky = tmpKy
+    return np.array(tunesE).T, np.array(tunesF).T
+
+
+def _power_vs_K(self, energy, theta, psi, harmonics, Ks):
+    """Undulator.power_vs_K (sources/synchr.py:1752-1785): total power [W] through the aperture for each K."""
+    try:
+        dtheta, dpsi, dE = theta[1] - theta[0], psi[1] - psi[0], energy[1] - energy[0]
+    except TypeError:
+        dtheta, dpsi, dE = 1, 1, 1
+    tmpKy = self.Ky
+    powers = []
+    for K in Ks:
+        self.Ky = K
+        I0 = self.intensities_on_mesh(energy, theta, psi, harmonics)[0]
+        if self.distE == 'BW':
+            I0 = I0 * 1e3
+        else:
+            I0 = I0 * np.asarray(energy)[(slice(None),) + (np.newaxis,) * (I0.ndim - 1)]
+        powers.append(I0.sum() * dtheta * dpsi * dE * EV2ERG * 1e-7)
+    self.Ky = tmpKy
+    return np.array(powers)
+
+
+Undulator.intensities_on_mesh = _intensities_on_mesh
+Undulator.tuning_curves = _tuning_curves
+Undulator.power_vs_K = _power_vs_K
+
+
 class xrt_bm_params(ctypes.Structure):
     """struct xrt_bm_params of include/xrt_b200.h"""
     _fields_ = [('gamma0', ctypes.c_double), ('B', ctypes.c_double), ('ro', ctypes.c_double),
@@ -793,6 +908,9 @@ class BendingMagnet(object):
             bo.sourceWeight = sourceWeight / self.nrays
         bo.parentId = getattr(self, 'uuid', self.name)
         return bo
+
+
+BendingMagnet.intensities_on_mesh = _intensities_on_mesh
 
 
 class Wiggler(BendingMagnet):
