@@ -916,7 +916,33 @@ def gen_mesh():
          eSpreadSigmas=3.5, eSpreadNSamples=36, distE=np.array('eV'))
 
 
-SECTIONS = {'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+def gen_config1():
+    """BASELINE.json configs[0] exactly as SURVEY.md 8d states it: np.random.seed(1234); GeometricSource(1e5 rays)
+    -> flat Au mirror at 4 mrad -> Screen.  The fixture keeps every 50th ray of the three beams plus whole-beam sums
+    (the full beams are 3 x 13 MB); the oracle reproduces the complete beams from the same seed."""
+    np.random.seed(1234)
+    bl = raycing.BeamLine()
+    src = rs.GeometricSource(bl, 'src', nrays=100000, dx=0.1, dz=0.05, dxprime=1e-4, dzprime=5e-5, distE='flat',
+                             energies=(8990, 9010), polarization='h')
+    pitch = 4e-3
+    oe = roe.OE(bl, 'M1', center=(0, 1e4, 0), pitch=pitch, material=rm.Material('Au', rho=19.3),
+                limPhysX=[-20, 20], limPhysY=[-300, 300])
+    scr = rsc.Screen(bl, 'scr', center=(0, 2e4, 1e4*np.tan(2*pitch)))
+    beam = src.shine(withAmplitudes=True)
+    gb, lb = oe.reflect(beam)
+    blo = scr.expose(gb)
+    d = dict(stride=50, nrays=100000, seed=1234, pitch=pitch, lostNum=np.int64(oe.lostNum),
+             scr_lostNum=np.int64(scr.lostNum), footprint=np.array(oe.footprint[-1]))
+    for pre, b in (('src_', beam), ('gb_', gb), ('lb_', lb), ('scr_', blo)):
+        for f in BEAM_FIELDS:
+            if hasattr(b, f) and isinstance(getattr(b, f), np.ndarray):
+                v = getattr(b, f)
+                d[pre + f] = v[::50]
+                d[pre + f + '_sum'] = v.sum()
+    save('config1_chain', **d)
+
+
+SECTIONS = {'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)
