@@ -1031,8 +1031,11 @@ __device__ __forceinline__ void copy_ray(const xrt_beam& dst, const xrt_beam& sr
 #ifndef XRTB_REFLECT_MINBLOCKS
 #define XRTB_REFLECT_MINBLOCKS 4
 #endif
+#ifndef XRTB_REFLECT_THREADS
+#define XRTB_REFLECT_THREADS 256
+#endif
 template <int SURF, int MAT>
-__global__ void __launch_bounds__(256, XRTB_REFLECT_MINBLOCKS) reflect_main_kernel(size_t n, xrt_oe_params p, xrt_material_params m,
+__global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) reflect_main_kernel(size_t n, xrt_oe_params p, xrt_material_params m,
                                                            xrt_multilayer_params ml, Tables tab, xrt_beam in,
                                                            xrt_beam fb, xrt_beam gb, xrt_beam lb,
                                                            unsigned long long* red) {
@@ -1443,16 +1446,16 @@ static int launch_main_mat(int mat, unsigned grid, cudaStream_t st, size_t n, co
                            const xrt_beam& in, const xrt_beam& fb, const xrt_beam& gb, const xrt_beam& lb,
                            unsigned long long* red) {
   switch (mat) {
-    case 0: reflect_main_kernel<SURF, 0><<<grid, 256, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
-    case 1: reflect_main_kernel<SURF, 1><<<grid, 256, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
-    case 2: reflect_main_kernel<SURF, 2><<<grid, 256, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
-    case 3: reflect_main_kernel<SURF, 3><<<grid, 256, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
-    case 4: reflect_main_kernel<SURF, 4><<<grid, 256, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
-    case 6: reflect_main_kernel<SURF, 6><<<grid, 256, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
-    case 7: reflect_main_kernel<SURF, 7><<<grid, 256, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
+    case 0: reflect_main_kernel<SURF, 0><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
+    case 1: reflect_main_kernel<SURF, 1><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
+    case 2: reflect_main_kernel<SURF, 2><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
+    case 3: reflect_main_kernel<SURF, 3><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
+    case 4: reflect_main_kernel<SURF, 4><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
+    case 6: reflect_main_kernel<SURF, 6><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
+    case 7: reflect_main_kernel<SURF, 7><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
     case 5:
       if constexpr (SURF == 0) {
-        reflect_main_kernel<SURF, 5><<<grid, 256, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red);
+        reflect_main_kernel<SURF, 5><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red);
       } else {
         set_last_error("reflect: refraction is built for flat and parabolic surfaces");
         return 2;
@@ -1484,8 +1487,8 @@ static int launch_main_refr(int mat, unsigned grid, cudaStream_t st, size_t n, c
                             const xrt_beam& in, const xrt_beam& fb, const xrt_beam& gb, const xrt_beam& lb,
                             unsigned long long* red) {
   switch (mat) {
-    case 0: reflect_main_kernel<SURF, 0><<<grid, 256, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
-    case 5: reflect_main_kernel<SURF, 5><<<grid, 256, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
+    case 0: reflect_main_kernel<SURF, 0><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
+    case 5: reflect_main_kernel<SURF, 5><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
     default: set_last_error("reflect: a parabolic lens takes a material of kind 'lens' / 'plate' or none (got %d)", mat); return 2;
   }
   XRTB_CUDA_CHECK(cudaGetLastError());
@@ -1536,7 +1539,7 @@ int reflect_device(size_t n, const xrt_oe_params* oe, const xrt_material_params*
     XRTB_CUDA_CHECK(cudaGetLastError());
   }
   if ((phase & 2) && n > 0) {
-    const unsigned grid = (unsigned)((n + 255) / 256);
+    const unsigned grid = (unsigned)((n + XRTB_REFLECT_THREADS - 1) / XRTB_REFLECT_THREADS);
     int rc = 0;
     if (oe->surface == 0) rc = launch_main_mat<0>(m.kind, grid, st, n, *oe, m, ml, t, *in, fbv, *gb, lbv, red);
     if (oe->surface == 1) rc = launch_main_mat<1>(m.kind, grid, st, n, *oe, m, ml, t, *in, fbv, *gb, lbv, red);
