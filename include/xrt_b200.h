@@ -116,6 +116,21 @@ int xrt_undulator_ext_imap_f64(int variant, size_t n, int jend, int nmax, double
                                const double* sintgph, const double* costgph, double* I, double* Es, double* Ep,
                                void* stream);
 
+/* f3: radiation integral along the trajectory in a tabulated field.  Replaces kernel `custom_field`
+ * (cl/undulator.cl) launched at sources/synchr.py:1259 with scalars [jend, betam, R0], sliced [gamma, w, ddtheta,
+ * ddpsi], node tables [tg, ag, Bx, By, Bz, betax, betay, trajx, trajy, trajz] (synchr.py:1227-1257).  Outputs Is, Ip
+ * c128[n] = SourceFromField._sp_sum (synchr.py:888-973, not filamentBeam); R0 = 0: far field. */
+int xrt_custom_field_f64(size_t n, int jend, double betam, double R0, const double* gamma, const double* w,
+                         const double* ddtheta, const double* ddpsi, const double* tg, const double* ag,
+                         const double* Bx, const double* By, const double* Bz, const double* betax,
+                         const double* betay, const double* trajx, const double* trajy, const double* trajz,
+                         double* Is, double* Ip, void* stream);
+int xrt_custom_field_f64_host(size_t n, int jend, double betam, double R0, const double* gamma, const double* w,
+                              const double* ddtheta, const double* ddpsi, const double* tg, const double* ag,
+                              const double* Bx, const double* By, const double* Bz, const double* betax,
+                              const double* betay, const double* trajx, const double* trajy, const double* trajz,
+                              double* Is, double* Ip);
+
 /* ------------------------------------------------------------------ a1, a6-a15: ray kernels on the Beam SoA
  * The Beam container of the reference (sources/beams.py:96-186) is a struct of equal-length arrays; here it
  * is a struct of DEVICE pointers.  Es/Ep may be NULL (beam without amplitudes); theta, s, phi, r are outputs

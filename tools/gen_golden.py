@@ -942,7 +942,44 @@ def gen_config1():
     save('config1_chain', **d)
 
 
-SECTIONS = {'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+def _custom_field(ncol):
+    L0, Np = 30., 10
+    z = np.linspace(-0.5*L0*Np - 30, 0.5*L0*Np + 30, 2401)
+    env = 0.5*(np.tanh((z + 0.5*L0*Np)/8.) - np.tanh((z - 0.5*L0*Np)/8.))
+    By = 0.5*np.sin(2*np.pi*z/L0)*env
+    Bx = 0.2*np.cos(2*np.pi*z/L0)*env
+    cols = {2: (z, By), 3: (z, Bx, By), 4: (z, Bx, By, 0.01*env)}[ncol]
+    return np.vstack(cols).T
+
+
+def gen_field_source():
+    """f3: SourceFromField (sources/synchr.py:612-1347): tabulated field -> RK4 trajectory -> radiation integral."""
+    for name, ncol, R0, spread, seed in (('field_source_far', 4, None, 0., 91), ('field_source_near', 2, 20000., 8e-4, 92)):
+        bl = raycing.BeamLine()
+        field = _custom_field(ncol)
+        src = rs.SourceFromField(bl, eE=3., eI=0.5, eEpsilonX=0.263, eEpsilonZ=0.008, eSigmaX=48.65, eSigmaZ=6.197,
+                                 xPrimeMax=0.1, zPrimeMax=0.1, eMin=1380., eMax=1520., customField=field, gNodes=60,
+                                 gIntervals=12, R0=R0, eEspread=spread, targetOpenCL=None)
+        src.deviceLength = src._fwhm(field[:, 0], np.abs(field[:, 1:]).max(axis=1))  # what read_custom_field sets
+        src.reset() if src.needReset else None
+        rng = np.random.RandomState(seed)
+        n = 300
+        w = rng.uniform(src.E_min, src.E_max, n)
+        th = rng.uniform(src.Theta_min, src.Theta_max, n)
+        ps = rng.uniform(src.Psi_min, src.Psi_max, n)
+        gamma0 = src.gamma
+        dg = gamma0 * spread * rng.normal(size=n) if spread > 0 else None
+        I, Es, Ep = src.build_I_map(w, th, ps, None, dg)
+        save(name, field=field, gamma0=gamma0, eI=src.eI, quadm=src.quadm, gIntervals=src.gIntervals, tg=src.tg,
+             ag=src.ag, dstep=src.dstep, R0=np.float64(np.nan if R0 is None else R0), eEspread=spread,
+             deviceLength=src.deviceLength, E_min=src.E_min, E_max=src.E_max, Theta_min=src.Theta_min,
+             Theta_max=src.Theta_max, Psi_min=src.Psi_min, Psi_max=src.Psi_max, w=w, theta=th, psi=ps,
+             gamma=gamma0 + (dg if dg is not None else 0.) * np.ones(n), I=I, Es=Es, Ep=Ep,
+             beta_x=src.beta[0], beta_y=src.beta[1], traj_x=src.trajectory[0], traj_y=src.trajectory[1],
+             traj_z=src.trajectory[2])
+
+
+SECTIONS = {'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)

@@ -59,6 +59,8 @@ PROTOTYPES = {
     'xrt_bm_imap_f64_host': (c_int, [c_sz, c_dp] + [c_dp] * 7),
     'xrt_bm_fill_f64': (c_int, [c_sz, c_dp, c_dp, c_dp] + [c_dp] * 11 + [c_dp, c_sz, c_dp]),
     'xrt_bm_shine_uniform_f64': (c_int, [c_sz, ctypes.c_uint64, ctypes.c_uint64, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    'xrt_custom_field_f64': (c_int, [c_sz, c_int, c_dbl, c_dbl] + [c_dp] * 16 + [c_dp]),
+    'xrt_custom_field_f64_host': (c_int, [c_sz, c_int, c_dbl, c_dbl] + [c_dp] * 16),
     'xrt_undulator_imap_f64': (c_int, [c_sz, c_int] + [c_dbl] * 7 + [c_int] + [c_dp] * 13 + [c_int, c_dp]),
 }
 

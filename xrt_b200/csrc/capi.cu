@@ -372,6 +372,43 @@ int xrt_undulator_ext_imap_f64(int variant, size_t n, int jend, int nmax, double
                               I, (cudaStream_t)stream);
 }
 
+int xrt_custom_field_f64(size_t n, int jend, double betam, double R0, const double* gamma, const double* w,
+                         const double* ddtheta, const double* ddpsi, const double* tg, const double* ag,
+                         const double* Bx, const double* By, const double* Bz, const double* betax,
+                         const double* betay, const double* trajx, const double* trajy, const double* trajz,
+                         double* Is, double* Ip, void* stream) {
+  return custom_field_device(n, jend, betam, R0, gamma, w, ddtheta, ddpsi, tg, ag, Bx, By, Bz, betax, betay, trajx,
+                             trajy, trajz, Is, Ip, (cudaStream_t)stream);
+}
+
+int xrt_custom_field_f64_host(size_t n, int jend, double betam, double R0, const double* gamma, const double* w,
+                              const double* ddtheta, const double* ddpsi, const double* tg, const double* ag,
+                              const double* Bx, const double* By, const double* Bz, const double* betax,
+                              const double* betay, const double* trajx, const double* trajy, const double* trajz,
+                              double* Is, double* Ip) {
+  if (n == 0) return 0;
+  XRTB_REQUIRE(jend > 0, "custom_field: the integration grid is empty");
+  cudaStream_t st = 0;
+  DevBuf samp[4], tab[10], out;
+  const double* hs[4] = {gamma, w, ddtheta, ddpsi};
+  const double* ht[10] = {tg, ag, Bx, By, Bz, betax, betay, trajx, trajy, trajz};
+  for (int i = 0; i < 4; ++i)
+    if (samp[i].upload(hs[i], n * 8, st)) return 1;
+  for (int i = 0; i < 10; ++i)
+    if (tab[i].upload(ht[i], (size_t)jend * 8, st)) return 1;
+  if (out.alloc(2 * n * 16)) return 1;
+  double* o = out.as<double>();
+  int rc = custom_field_device(n, jend, betam, R0, samp[0].as<double>(), samp[1].as<double>(), samp[2].as<double>(),
+                               samp[3].as<double>(), tab[0].as<double>(), tab[1].as<double>(), tab[2].as<double>(),
+                               tab[3].as<double>(), tab[4].as<double>(), tab[5].as<double>(), tab[6].as<double>(),
+                               tab[7].as<double>(), tab[8].as<double>(), tab[9].as<double>(), o, o + 2 * n, st);
+  if (rc) return rc;
+  XRTB_CUDA_CHECK(cudaMemcpyAsync(Is, o, n * 16, cudaMemcpyDeviceToHost, st));
+  XRTB_CUDA_CHECK(cudaMemcpyAsync(Ip, o + 2 * n, n * 16, cudaMemcpyDeviceToHost, st));
+  XRTB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return 0;
+}
+
 // ------------------------------------------------------------------ reflect
 int xrt_reflect_f64(size_t n, const xrt_oe_params* oe, const xrt_material_params* mat, const double* tables,
                     size_t table_len, const xrt_beam* in, const xrt_beam* fallback, const xrt_beam* gb,

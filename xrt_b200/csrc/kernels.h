@@ -59,6 +59,12 @@ int expose_device(size_t n, const xrt_plane_params* p, const xrt_beam* in, const
 int propagate_rect_device(size_t n, const xrt_plane_params* p, const xrt_beam* in, const xrt_beam* out,
                           unsigned long long* red, cudaStream_t st);
 
+int custom_field_device(size_t n, int jend, double betam, double R0, const double* gamma, const double* w,
+                        const double* ddtheta, const double* ddpsi, const double* tg, const double* ag,
+                        const double* Bx, const double* By, const double* Bz, const double* betax,
+                        const double* betay, const double* trajx, const double* trajy, const double* trajz,
+                        double* Is, double* Ip, cudaStream_t st);
+
 // source.cu (compiled with -fmad=false)
 int source_sample_device(size_t n, uint64_t seed, uint64_t index_offset, const double* window, double* E,
                          double* theta, double* psi, double* n1, double* n2, double* n3, double* n4, double* u,

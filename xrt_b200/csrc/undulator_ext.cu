@@ -183,6 +183,151 @@ __global__ void __launch_bounds__(E_THREADS)
   }
 }
 
+// ---------------------------------------------------------------- custom field (SourceFromField)
+// Replaces kernel `custom_field` (cl/undulator.cl:1001-...) launched from
+// SourceFromField._build_I_map_custom_field_CL (sources/synchr.py:1227-1259) with scalars [jend, betam, R0], sliced
+// [gamma, w, ddtheta, ddpsi], node tables [tg, ag, Bx, By, Bz, betax, betay, trajx, trajy, trajz].  Numerics follow
+// the numpy path SourceFromField._sp_sum (synchr.py:888-973), not filamentBeam: far field, or near field for R0 > 0.
+// The phase wc * (tg - n_z z(tg)) is a ~1e7 cancellation (wc ~ 5e7 / mm against a path difference of ~1e-4 mm out of
+// ~1e3 mm), so everything is evaluated in the reference's rounding order (this file is compiled with -fmad=false).
+struct __align__(16) FNode {
+  double tg, ag, betax, betay;
+  double trajx, trajy, trajz, Bx;
+  double By, Bz, pad0, pad1;
+};
+constexpr int F_TILE = 128;
+
+struct FTables {
+  const double *tg, *ag, *Bx, *By, *Bz, *betax, *betay, *trajx, *trajy, *trajz;
+};
+
+template <bool NF>
+__global__ void __launch_bounds__(E_THREADS)
+    custom_field_kernel(size_t n, int jend, double betam, double R0, FTables tab, const double* __restrict__ gamma,
+                        const double* __restrict__ w_in, const double* __restrict__ phi_in,
+                        const double* __restrict__ psi_in, double2* __restrict__ Is, double2* __restrict__ Ip) {
+  __shared__ FNode tile[F_TILE];
+  const double EMC_ = 0.5866791802416487;
+  const double K0 = 1.602176565e-19 / 9.109383701528e-31 / 2.99792458e10 / 10.;  // SIE0 / SIM0 / C / 10.
+  const size_t i = (size_t)blockIdx.x * E_THREADS + threadIdx.x;
+  const size_t ii = i < n ? i : n - 1;
+  const double g = gamma[ii], wS = w_in[ii], ddphi = phi_in[ii], ddpsi = psi_in[ii];
+  const double emcg = K0 / g;
+  double dirx = ddphi, diry = ddpsi;
+  double dirz = sqrt(1.0 - ddphi * ddphi - ddpsi * ddpsi);  // synchr.py:899
+  const double revgamma2 = 1.0 / (g * g);
+  const double wc = wS * 5067.7309392068091 / betam;  // w * E2WC / betam
+  const double zf = 1.0 - 0.5 * revgamma2, zt = EMC_ * EMC_ * revgamma2;
+  double R0x = 0.0, R0y = 0.0, R0z = 0.0, sinr0z = 0.0, cosr0z = 1.0;
+  if (NF) {
+    R0x = tan(ddphi) * R0;
+    R0y = tan(ddpsi) * R0;
+    R0z = 1.0 * R0;
+    sincos_big(wc * R0z, sinr0z, cosr0z);
+  }
+  double bs_re = 0.0, bs_im = 0.0, bp_re = 0.0, bp_im = 0.0;
+  for (int j0 = 0; j0 < jend; j0 += F_TILE) {
+    const int cnt = min(F_TILE, jend - j0);
+    __syncthreads();
+    for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
+      const int q = j0 + j;
+      FNode nd;
+      nd.tg = tab.tg[q];
+      nd.ag = tab.ag[q];
+      nd.betax = tab.betax[q];
+      nd.betay = tab.betay[q];
+      nd.trajx = tab.trajx[q];
+      nd.trajy = tab.trajy[q];
+      nd.trajz = tab.trajz[q];
+      nd.Bx = tab.Bx[q];
+      nd.By = tab.By[q];
+      nd.Bz = tab.Bz[q];
+      nd.pad0 = nd.pad1 = 0.0;
+      tile[j] = nd;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int j = 0; j < cnt; ++j) {
+      const double4* q4 = reinterpret_cast<const double4*>(tile + j);
+      const double4 n0 = q4[0];  // tg ag betax betay
+      const double4 n1 = q4[1];  // trajx trajy trajz Bx
+      const double4 n2 = q4[2];  // By Bz
+      const double betax_ = emcg * n0.z, betay_ = emcg * n0.w;
+      const double trajx_ = emcg * n1.x, trajy_ = emcg * n1.y;
+      const double trajz_ = n0.x * zf + zt * n1.z;  // synchr.py:919-920
+      double ere, eim;
+      if (NF) {
+        const double drx = R0x - trajx_, dry = R0y - trajy_, drz = R0z - trajz_;
+        const double dist = sqrt((drx * drx + dry * dry) + drz * drz);
+        const double rdrz = 1.0 / drz;
+        const double drs = (drx * drx + dry * dry) * rdrz;
+        const double LRS = (0.5 * drs - (0.125 * (drs * drs)) * rdrz) + (0.0625 * (drs * drs * drs)) * (rdrz * rdrz);
+        double sinzloc, coszloc, sindrs, cosdrs;
+        sincos_big(wc * (n0.x - trajz_), sinzloc, coszloc);
+        sincos_big(wc * LRS, sindrs, cosdrs);
+        ere = (((-sinr0z) * sinzloc) * cosdrs - (sinr0z * coszloc) * sindrs - (cosr0z * sinzloc) * sindrs) +
+              (cosr0z * coszloc) * cosdrs;
+        eim = ((((-sinr0z) * sinzloc) * sindrs + (sinr0z * coszloc) * cosdrs) + (cosr0z * sinzloc) * cosdrs) +
+              (cosr0z * coszloc) * sindrs;
+        dirx = drx / dist;
+        diry = dry / dist;
+        dirz = drz / dist;
+      } else {
+        const double phz = wc * (n0.x - dirz * trajz_);
+        const double phxy = wc * (dirx * trajx_ + diry * trajy_);
+        double sinphz, cosphz, sinphxy, cosphxy;
+        sincos_big(phz, sinphz, cosphz);
+        sincos_big(phxy, sinphxy, cosphxy);
+        ere = sinphz * cosphxy - cosphz * sinphxy;
+        eim = cosphz * cosphxy + sinphz * sinphxy;
+      }
+      const double sm = (revgamma2 + betax_ * betax_) + betay_ * betay_;
+      const double betaz = ((1.0 - 0.5 * sm) - 0.125 * (sm * sm)) - 0.0625 * (sm * sm * sm);
+      const double betaPx = betay_ * n2.y - betaz * n2.x;
+      const double betaPy = (-betax_) * n2.y + betaz * n1.w;
+      const double betaPz = betax_ * n2.x - betay_ * n1.w;
+      const double rkrel = 1.0 / (((1.0 - dirx * betax_) - diry * betay_) - dirz * betaz);
+      const double wgt = n0.y * (rkrel * rkrel);
+      ere *= wgt;
+      eim *= wgt;
+      const double bnx = dirx - betax_, bny = diry - betay_, bnz = dirz - betaz;
+      const double ddbp = (dirx * betaPx + diry * betaPy) + dirz * betaPz;
+      const double ddmb = (dirx * bnx + diry * bny) + dirz * bnz;
+      const double ts = bnx * ddbp - betaPx * ddmb;
+      const double tp = bny * ddbp - betaPy * ddmb;
+      bs_re += ere * ts;
+      bs_im += eim * ts;
+      bp_re += ere * tp;
+      bp_im += eim * tp;
+    }
+  }
+  if (i >= n) return;
+  Is[i] = make_double2(bs_re * emcg, bs_im * emcg);
+  Ip[i] = make_double2(bp_re * emcg, bp_im * emcg);
+}
+
+int custom_field_device(size_t n, int jend, double betam, double R0, const double* gamma, const double* w,
+                        const double* ddtheta, const double* ddpsi, const double* tg, const double* ag,
+                        const double* Bx, const double* By, const double* Bz, const double* betax,
+                        const double* betay, const double* trajx, const double* trajy, const double* trajz,
+                        double* Is, double* Ip, cudaStream_t st) {
+  if (n == 0) return 0;
+  XRTB_REQUIRE(jend > 0, "custom_field: the integration grid is empty");
+  XRTB_REQUIRE(gamma && w && ddtheta && ddpsi && tg && ag && Bx && By && Bz && betax && betay && trajx && trajy &&
+                   trajz && Is && Ip,
+               "custom_field: NULL argument");
+  FTables t{tg, ag, Bx, By, Bz, betax, betay, trajx, trajy, trajz};
+  const unsigned grid = (unsigned)((n + E_THREADS - 1) / E_THREADS);
+  double2* is2 = reinterpret_cast<double2*>(Is);
+  double2* ip2 = reinterpret_cast<double2*>(Ip);
+  if (R0 != 0.0)  // `if self.R0:` (synchr.py:1319)
+    custom_field_kernel<true><<<grid, E_THREADS, 0, st>>>(n, jend, betam, R0, t, gamma, w, ddtheta, ddpsi, is2, ip2);
+  else
+    custom_field_kernel<false><<<grid, E_THREADS, 0, st>>>(n, jend, betam, R0, t, gamma, w, ddtheta, ddpsi, is2, ip2);
+  XRTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 int undulator_ext_device(int variant, int mode, size_t n, int jend, int nmax, double scalar0, double Kx, double Ky,
                          double L0, double gamma0, double amp_const, double dstep, int bw_mode, const double* gamma,
                          const double* wu, const double* w, const double* ww1, const double* ddphi,

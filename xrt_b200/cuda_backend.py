@@ -194,6 +194,30 @@ class XRT_CUDA(object):
         """kernel `undulator_nf` (cl/undulator.cl:204-298), numpy-path numerics (synchr.py:1972-1996)."""
         return self._undulator_ext(2, 'undulator_nf', scalarArgs, slicedRO, nonSlicedRO, slicedRW, dimension)
 
+    def _k_custom_field(self, scalarArgs, slicedRO, nonSlicedRO, slicedRW, nonSlicedRW, dimension):
+        """Argument layout of SourceFromField._build_I_map_custom_field_CL (sources/synchr.py:1227-1259): scalars
+        [jend, betam, R0]; sliced RO [gamma, w, ddtheta, ddpsi]; non-sliced RO [tg, ag, Bx, By, Bz, betax, betay,
+        trajx, trajy, trajz]; sliced RW [Is, Ip]."""
+        lib = _lib.load()
+        jend, betam, R0 = scalarArgs[:3]
+        samp = [_lib.as_f64(a) for a in slicedRO]
+        n = dimension if dimension else len(samp[0])
+        tabs = [_lib.as_f64(a) for a in nonSlicedRO]
+        if len(samp) != 4 or any(len(a) != n for a in samp):
+            raise ValueError('custom_field: expected 4 sliced inputs of length dimension')
+        if len(tabs) != 10 or any(len(a) != int(jend) for a in tabs):
+            raise ValueError('custom_field: expected 10 node tables of length jend')
+        Is, Ip = slicedRW
+        for a in (Is, Ip):
+            if not (isinstance(a, np.ndarray) and a.dtype == np.complex128 and a.flags['C_CONTIGUOUS'] and
+                    len(a) == n):
+                raise ValueError('custom_field: slicedRWArgs must be 2 contiguous complex128[dimension]')
+        rc = lib.xrt_custom_field_f64_host(n, int(jend), float(betam), float(R0) if R0 is not None else 0.,
+                                           *[_lib.hptr(a) for a in samp], *[_lib.hptr(a) for a in tabs],
+                                           _lib.hptr(Is), _lib.hptr(Ip))
+        _lib.check(rc, 'xrt_custom_field_f64_host')
+        return Is, Ip
+
     def _k_get_amplitude_graded_multilayer(self, scalarArgs, slicedRO, nonSlicedRO, slicedRW, nonSlicedRW,
                                            dimension):
         """Argument layout of Multilayer.get_amplitude's accelerator call (materials/multilayer.py:471-484):

@@ -18,7 +18,7 @@ import torch
 from . import _lib, kernels
 from .beams import Beam
 from .cuda_backend import XRT_CUDA
-from .physconsts import PI, PI2, EV2ERG, M0, C, E2WC, FINE_STR, SIE0, K2B
+from .physconsts import PI, PI2, EV2ERG, M0, C, E2WC, FINE_STR, SIE0, K2B, EMC
 
 F64 = torch.float64
 C128 = torch.complex128
@@ -1181,3 +1181,231 @@ class GeometricSource(object):
         _lib.check(lib.xrt_geometric_source_f64(*args, 2, stream), 'xrt_geometric_source_f64 (finish)')
         bo.parentId = getattr(self, 'uuid', self.name)
         return bo
+
+
+class SourceFromField(Undulator):
+    """Source based on a tabulated magnetic field (sources/synchr.py:612-1347): *customField* is an (N, 2 | 3 | 4)
+    array [z (mm), {B_hor,} B_ver {, B_long}] (T), a text-file name or (fileName, loadtxt-kwargs).  The electron
+    trajectory is integrated once on the host with the reference's RK4 scheme (it is sequential, O(field samples));
+    the radiation integral along it for every (E, theta, psi) sample runs on the GPU (`custom_field_kernel`,
+    xrt_b200/csrc/undulator_ext.cu).  Far field, or near field with *R0*.  Out of scope: filamentBeam, Excel input,
+    the periodic test field of customField=None."""
+
+    def __init__(self, *args, **kwargs):
+        customField = kwargs.pop('customField', None)
+        if customField is None:
+            raise NotImplementedError('give customField (the built-in periodic test field is not on the hot path)')
+        kwargs.setdefault('xPrimeMaxAutoReduce', False)
+        kwargs.setdefault('zPrimeMaxAutoReduce', False)
+        kwargs.setdefault('K', 1.)  # unused; the Undulator constructor wants some K
+        R0 = kwargs.pop('R0', None)
+        taper = kwargs.pop('taper', None)
+        if taper is not None:
+            raise ValueError('taper has no meaning for a tabulated field')
+        Undulator.__init__(self, *args, **kwargs)
+        self.R0 = R0
+        if isinstance(customField, (tuple, list)):
+            self.customFieldData = self.read_custom_field(customField[0], customField[1])
+        elif isinstance(customField, np.ndarray):
+            self.customFieldData = np.asarray(customField, dtype=float)
+            z = self.customFieldData[:, 0]
+            self.deviceLength = self._fwhm(z, np.abs(self.customFieldData[:, 1:]).max(axis=1))
+        else:
+            self.customFieldData = self.read_custom_field(customField, {})
+        self.spl_kw = {'kind': 'cubic', 'bounds_error': False, 'fill_value': 'extrapolate'}
+        self._traj = None
+        self.needReset = True
+
+    # ------------------------------------------------------------------ host: field, grid, trajectory
+    def read_custom_field(self, fname, kwargs={}):  # synchr.py:695-705 (text files)
+        if fname.endswith('.xls') or fname.endswith('.xlsx'):
+            raise NotImplementedError('Excel field tables: convert to text or pass a numpy array')
+        data = np.loadtxt(fname, **kwargs)
+        self.deviceLength = self._fwhm(data[:, 0], np.abs(data[:, 1:]).max(axis=1))
+        return data
+
+    @staticmethod
+    def _fwhm(z, a):  # synchr.py:707-710
+        dz = z[1] - z[0]
+        args = np.argwhere(a >= a.max()*0.5)
+        return z[np.max(args)] - z[np.min(args)] + dz
+
+    def report_E1(self):
+        self.E1 = 0.
+
+    def _magnetic_field(self, grid=None):  # synchr.py:727-765
+        from scipy.interpolate import interp1d
+        data = self.customFieldData
+        dataz = data[:, 0]
+        if grid is None:
+            lenmm = np.abs(dataz[-1] - dataz[0])
+            self.wtGrid = np.linspace(dataz[0], dataz[-1], int(lenmm*10))
+            self.BGrid = np.linspace(dataz[0], dataz[-1], 2*len(self.wtGrid)-1)
+            grid = self.BGrid
+        cols = {2: (None, 1, None), 3: (1, 2, None), 4: (1, 2, 3)}.get(data.shape[1])
+        if cols is None:
+            raise ValueError('Unknown field table structure')
+        out = []
+        for c in cols:
+            out.append(np.zeros_like(grid) if c is None else interp1d(dataz, data[:, c], **self.spl_kw)(grid))
+        return out[0], out[1], out[2]
+
+    def _build_integration_grid(self):  # synchr.py:988-1003
+        self.tg_n, self.ag_n = clenshaw_curtis(self.quadm)
+        dataz = self.customFieldData[:, 0]
+        dstep = (dataz[-1] - dataz[0]) / float(self.gIntervals)
+        dI = np.arange(0.5 * dstep + dataz[0], dataz[-1], dstep)
+        self.tg = (dI[:, None]+0.5*dstep*self.tg_n).ravel()
+        self.ag = (dI[:, None]*0+self.ag_n).ravel()
+        self.dstep = dstep
+        self._traj = None
+        self._dev_tables = None
+        self.gridSymmetric = False
+
+    def _build_trajectory(self, Bx, By, Bz):
+        """SourceFromField._build_trajectory_conv (synchr.py:1049-1147), not filamentBeam: RK4 for the transverse
+        velocity in units of e/(m c gamma), three passes (mean velocity, mean position, tabulation)."""
+        from scipy.interpolate import interp1d
+        wt = self.wtGrid
+
+        def f_beta(B, beta):
+            return np.array((beta[1]*B[2]-B[1], B[0] - beta[0]*B[2]))
+
+        def f_traj(beta):
+            return np.array((beta[0], beta[1], -0.5*(beta[0]**2 + beta[1]**2)))
+
+        def step(iB, h, beta, traj=None):
+            B0, B1, B2 = ([Bx[iB+k], By[iB+k], Bz[iB+k]] for k in range(3))
+            k1b = h * f_beta(B0, beta)
+            k2b = h * f_beta(B1, beta + 0.5*k1b)
+            k3b = h * f_beta(B1, beta + 0.5*k2b)
+            k4b = h * f_beta(B2, beta + k3b)
+            newb = beta + (k1b + 2*k2b + 2*k3b + k4b)/6.
+            if traj is None:
+                return newb
+            k1t = h * f_traj(beta)
+            k2t = h * f_traj(beta + 0.5*k1b)
+            k3t = h * f_traj(beta + 0.5*k2b)
+            k4t = h * f_traj(beta + k3b)
+            return newb, traj + (k1t + 2*k2t + 2*k3t + k4t)/6.
+
+        n = len(wt) - 1
+        beta_next = np.zeros(2)
+        beta0 = np.zeros(2)
+        for i in range(n):
+            h = wt[i+1] - wt[i]
+            beta_next = step(2*i, h, beta_next)
+            beta0 += h * beta_next
+        beta0 /= -(wt[-1] - wt[0])
+        beta_next = np.copy(beta0)
+        traj_next = np.zeros(3)
+        traj0 = np.zeros(3)
+        betam_int = 0
+        for i in range(n):
+            h = wt[i+1] - wt[i]
+            beta_next, traj_next = step(2*i, h, beta_next, traj_next)
+            traj0 += h * traj_next
+            betam_int += beta_next[0]**2 + beta_next[1]**2
+        traj0 /= -(wt[-1] - wt[0])
+        betam_int *= -0.5/n
+        beta_next = np.copy(beta0)
+        traj_next = np.copy(traj0)
+        rows = [[beta0[0], beta0[1], traj0[0], traj0[1], traj0[2]]]
+        for i in range(n):
+            h = wt[i+1] - wt[i]
+            beta_next, traj_next = step(2*i, h, beta_next, traj_next)
+            rows.append([beta_next[0], beta_next[1], traj_next[0], traj_next[1], traj_next[2]])
+        rows = np.array(rows)
+        betax, betay, trajx, trajy, trajz = (interp1d(wt, rows[:, k], **self.spl_kw)(self.tg) for k in range(5))
+        return betax, betay, betam_int, trajx, trajy, trajz
+
+    def _field_tables(self):
+        """(betam, [tg, ag, Bx, By, Bz, betax, betay, trajx, trajy, trajz]) on the integration grid."""
+        if self._traj is None:
+            Bx, By, Bz = self._magnetic_field()
+            betax, betay, betam, trajx, trajy, trajz = self._build_trajectory(Bx, By, Bz)
+            Bxt, Byt, Bzt = self._magnetic_field(self.tg)
+            self._traj = (betam, [np.ascontiguousarray(a, dtype=np.float64) for a in
+                                  (self.tg, self.ag, Bxt, Byt, Bzt, betax, betay, trajx, trajy, trajz)])
+            self._dev_tables = None
+        return self._traj
+
+    def _tables(self, device):
+        betam, tabs = self._field_tables()
+        if self._dev_tables is None or self._dev_tables[0].device != device:
+            self._dev_tables = [torch.from_numpy(a).to(device) for a in tabs]
+        return self._dev_tables
+
+    @property
+    def _ext_variant(self):
+        return 3, 0.  # never the fused far-field undulator kernel
+
+    def _source_params(self, toGlobal):
+        p = Undulator._source_params(self, toGlobal)
+        # get_sigma_r02 = 2 CHeVcm / E * 10 * deviceLength / PI2**2 (synchr.py:712-725): L0 * Np -> deviceLength
+        p.L0, p.Np = float(self.deviceLength), 1.
+        p.eEspread = 0.  # SourceFromField.get_SIGMA has no energy-spread term
+        return p
+
+    # ------------------------------------------------------------------ build_I_map
+    def _finish(self, xp, w, gamma, Is_local, Ip_local, betam):
+        """synchr.py:1264-1272 / :1335-1347 on numpy (xp = np) or torch (xp = torch) arrays."""
+        ab = 0.5 / np.pi / (1. - 0.5/gamma**2 + betam*EMC**2/gamma**2)
+        bwFact = 0.001 if self.distE == 'BW' else 1./w
+        Amp2Flux = FINE_STR * bwFact * self.eI / SIE0
+        integralField = xp.abs(Is_local)**2 + xp.abs(Ip_local)**2
+        sq = Amp2Flux**0.5
+        return (Amp2Flux * 0.25 * self.dstep**2 * ab**2 * integralField,
+                sq * Is_local * 0.5 * self.dstep * ab,
+                sq * Ip_local * 0.5 * self.dstep * ab)
+
+    def _integral_host(self, gamma, w, ddtheta, ddpsi):
+        F = self.cl_precisionF
+        betam, tabs = self._field_tables()
+        NRAYS = len(w)
+        scalarArgs = [np.int32(len(self.tg)), F(betam), F(self.R0 if self.R0 else 0.)]
+        slicedRWArgs = [np.zeros(NRAYS, dtype=self.cl_precisionC), np.zeros(NRAYS, dtype=self.cl_precisionC)]
+        return self.ucl.run_parallel('custom_field', scalarArgs, [F(gamma), F(w), F(ddtheta), F(ddpsi)], tabs,
+                                     slicedRWArgs, None, NRAYS)
+
+    def build_I_map(self, w, ddtheta, ddpsi, harmonic=None, dg=None):
+        """(I, Es, Ep) on host arrays like SourceFromField.build_I_map (synchr.py:975-986, :1157-1272)."""
+        if self.needReset:
+            self.reset()
+        w = np.atleast_1d(np.asarray(w, dtype=float))
+        ddtheta = np.asarray(ddtheta, dtype=float) * np.ones_like(w)
+        ddpsi = np.asarray(ddpsi, dtype=float) * np.ones_like(w)
+        NRAYS = len(w)
+        gamma = self.gamma
+        if self.eEspread > 0:
+            if dg is not None:
+                gamma = gamma + dg
+            else:
+                gamma = gamma + gamma * self.eEspread * np.random.normal(size=NRAYS)
+        gamma = gamma * np.ones(NRAYS)
+        Is_local, Ip_local = self._integral_host(gamma, w, ddtheta, ddpsi)
+        return self._finish(np, w, gamma, Is_local, Ip_local, self._field_tables()[0])
+
+    def _convergence_value(self):
+        w = np.array([self.E_max, self.E_max])
+        th = np.array([self.Theta_max, self.Theta_max])
+        ps = np.array([self.Psi_max, self.Psi_max])
+        Is, Ip = self._integral_host(self.gamma * np.ones(2), w, th, ps)
+        return np.abs(np.sqrt(np.abs(Is[0])**2 + np.abs(Ip[0])**2) * 0.5 * self.dstep)
+
+    def build_I_map_device(self, w, theta, psi, gamma=None, out=None):
+        if self.needReset:
+            self.reset()
+        lib = _lib.load()
+        n = w.numel()
+        tabs = self._tables(w.device)
+        betam = self._field_tables()[0]
+        if gamma is None:
+            gamma = torch.full_like(w, self.gamma)
+        raw = torch.empty((2, n), dtype=C128, device=w.device)
+        rc = lib.xrt_custom_field_f64(n, len(self.tg), float(betam), float(self.R0 if self.R0 else 0.),
+                                      gamma.data_ptr(), w.data_ptr(), theta.data_ptr(), psi.data_ptr(),
+                                      *[t.data_ptr() for t in tabs], raw[0].data_ptr(), raw[1].data_ptr(),
+                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, 'xrt_custom_field_f64')
+        return self._finish(torch, w, gamma, raw[0], raw[1], betam)
