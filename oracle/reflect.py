@@ -58,6 +58,8 @@ class OESpec(object):
 
     # ------------------------------------------------------------------ surfaces
     def local_z(self, x, y):
+        if self.surface == 'custom':  # a subclass surface (oracle/surfaces.py), like the reference's overrides
+            return self.surfParams['obj'].local_z(x, y)
         if self.surface == 'flat':
             return np.zeros_like(y)
         if self.surface == 'toroid':
@@ -92,6 +94,8 @@ class OESpec(object):
         return 0, rho, 0
 
     def local_n(self, x, y):
+        if self.surface == 'custom':
+            return self.surfParams['obj'].local_n(x, y)
         if self.surface == 'flat':
             a = 0.
             b = 0.

@@ -1,0 +1,140 @@
+# -*- coding: utf-8 -*-
+"""TEST INFRASTRUCTURE ONLY (see oracle/__init__.py): numpy restatements of the reference's curved optical elements
+whose surface the product compiles from spliced CUDA texts (xrt_b200/oes_spliced.py).  Each class gives
+local_z(x, y) and local_n(x, y) in the reference's operation order; oracle.reflect.OESpec(surface='custom',
+surfParams={'obj': <instance>}) plugs them into the common intersection / reflection machinery.
+
+Pinned bit for bit on the reference's own outputs (tests/golden/reflect_spliced_*.npz, tools/gen_golden.py
+section `spliced`)."""
+import numpy as np
+
+from . import beam as ob
+
+
+class BentFlatMirror(object):
+    """oes/__init__.py:240-304: meridionally bent parabolic cylinder with fixed ends."""
+
+    def __init__(self, R, limPhysY0):
+        self.R = R
+        self.limPhysY0 = limPhysY0
+
+    def local_z(self, x, y):  # :289-293
+        return (y**2 - self.limPhysY0**2) / 2.0 / self.R
+
+    def local_n(self, x, y):  # :295-304
+        a = 0.
+        b = -y / self.R
+        c = 1.
+        norm = (b**2 + 1)**0.5
+        return [a/norm, b/norm, c/norm]
+
+
+class ConicalMirror(object):
+    """oes/__init__.py:589-636."""
+
+    def __init__(self, L0, theta):
+        self.L0 = L0
+        self.tt = np.tan(theta)  # :610-615
+        self.t2t = np.tan(2*theta)
+        self.redfocus = np.cos(theta)**2 / (1./self.tt - 1./self.t2t)
+
+    def local_z(self, x, y):  # :623-627
+        sqroot = np.sqrt(0.25*self.t2t**2*(y - self.L0)**2 - self.redfocus*self.t2t*x**2)
+        z = -0.5*self.t2t*(y-self.L0) - np.sign(self.t2t)*sqroot
+        return z
+
+    def local_n(self, x, y):  # :629-636
+        sqroot = np.sign(self.t2t)*np.sqrt(0.25*self.t2t**2*(y - self.L0)**2 - self.redfocus*x*x*self.t2t)
+        a = -x*self.redfocus*self.t2t/sqroot
+        b = .5*self.t2t + 0.25*self.t2t**2*(y-self.L0)/sqroot
+        c = 1.
+        norm = (a**2 + b**2 + 1.)**0.5
+        return [a/norm, b/norm, c/norm]
+
+
+class JohannCylinder(object):
+    """oes/bragg.py:104-176: simply bent reflective crystal."""
+
+    def __init__(self, Rm, crossSection='circular', alpha=None):
+        self.Rm = Rm
+        self.crossSection = crossSection
+        self.alpha = alpha
+        if alpha:
+            self.cosalpha, self.sinalpha = np.cos(alpha), np.sin(alpha)
+
+    def local_z(self, x, y):  # :145-152
+        if self.crossSection.startswith('circ'):
+            sq = self.Rm**2 - y**2
+            return self.Rm - np.sqrt(sq)
+        else:
+            return y**2 / 2.0 / self.Rm
+
+    def local_n_cylinder(self, x, y, R, alpha):  # :154-171
+        a = np.zeros_like(x)
+        b = -y / R
+        if self.crossSection.startswith('circ'):
+            c = (R**2 - y**2)**0.5 / R
+        else:
+            norm = (b**2 + 1)**0.5
+            b /= norm
+            c = 1. / norm
+        if alpha:
+            bAlpha, cAlpha = ob.rotate_x(b, c, self.cosalpha, -self.sinalpha)
+            return [a, bAlpha, cAlpha, a, b, c]
+        else:
+            return [a, b, c]
+
+    def local_n(self, x, y):  # :173-176
+        return self.local_n_cylinder(x, y, self.Rm, self.alpha)
+
+
+class JohanssonCylinder(JohannCylinder):
+    """oes/bragg.py:179-197: ground-bent crystal, exact expressions."""
+
+    def local_n(self, x, y):
+        nSurf = self.local_n_cylinder(x, y, self.Rm, None)
+        a = np.zeros_like(x)
+        b = -y
+        c = (self.Rm**2 - y**2)**0.5 + self.Rm
+        if self.alpha:
+            b, c = ob.rotate_x(b, c, self.cosalpha, -self.sinalpha)
+        norm = np.sqrt(b**2 + c**2)
+        return [a/norm, b/norm, c/norm, nSurf[-3], nSurf[-2], nSurf[-1]]
+
+
+def _rotate_y(x, z, cosangle, sinangle):  # _rotate.py:11-14
+    return cosangle*x + sinangle*z, -sinangle*x + cosangle*z
+
+
+class JohannToroid(object):
+    """oes/bragg.py:200-269: 2D bent reflective crystal."""
+
+    def __init__(self, Rm, Rs=None, alpha=None):
+        self.Rm = Rm
+        self.Rs = Rs if Rs is not None else Rm
+        self.alpha = alpha
+        if alpha:
+            self.cosalpha, self.sinalpha = np.cos(alpha), np.sin(alpha)
+
+    def local_z(self, x, y):  # :238-243
+        z = self.Rm - self.Rs - (self.Rm**2 - y**2)**0.5
+        cosangle, sinangle = (z**2 - x**2)**0.5 / abs(z), -x/abs(z)
+        bla, z = _rotate_y(0, z, cosangle, sinangle)
+        return z + self.Rs
+
+    def local_n(self, x, y):  # :245-269
+        Rm, Rs, alpha = self.Rm, self.Rs, self.alpha
+        a = np.zeros_like(x)
+        b = -y / Rm
+        c = (Rm**2 - y**2)**0.5 / Rm
+        if alpha:
+            aAlpha = np.zeros_like(x)
+            bAlpha, cAlpha = ob.rotate_x(b, c, self.cosalpha, -self.sinalpha)
+        r = Rs - (Rm - (Rm**2 - y**2)**0.5)
+        cosangle, sinangle = (r**2 - x**2)**0.5 / r, -x/r
+        a, c = _rotate_y(a, c, cosangle, sinangle)
+        if alpha:
+            aAlpha, cAlpha = _rotate_y(aAlpha, cAlpha, cosangle, sinangle)
+            return [aAlpha, bAlpha, cAlpha, a, b, c]
+        else:
+            return [a, b, c]

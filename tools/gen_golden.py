@@ -979,7 +979,56 @@ def gen_field_source():
              traj_z=src.trajectory[2])
 
 
-SECTIONS = {'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+def gen_spliced():
+    """Curved elements the product compiles from spliced CUDA texts (xrt_b200/oes_spliced.py): BentFlatMirror,
+    ConicalMirror (oes/__init__.py:240-306, :589-636), JohannCylinder, JohanssonCylinder, JohannToroid
+    (oes/bragg.py:104-269), the bent crystals with and without asymmetry angle."""
+    bl = raycing.BeamLine(azimuth=0.1)
+    Au = rm.Material('Au', rho=19.3)
+    p = 2e4
+    ctr = (p*np.sin(0.1), p*np.cos(0.1), 0)
+    beam = _source_beam(bl, 2500, 201, dx=0.3, dz=0.1, dxprime=1.2e-4, dzprime=6e-5, energies=(7000, 11000))
+    oe = roe.BentFlatMirror(bl, 'VCM', center=ctr, pitch=3e-3, R=4.2e6, material=Au, limPhysX=[-2, 2.5],
+                            limPhysY=[-350, 300], limOptY=[-300, 280])
+    d = _capture_reflect(oe, beam)
+    d.update(_oe_params(oe))
+    save('reflect_spliced_bentflat', rho=19.3, R=float(oe.R), **d)
+
+    beam = _source_beam(bl, 2500, 202, dx=0.3, dz=0.1, dxprime=1.2e-4, dzprime=6e-5, energies=(7000, 11000))
+    oe = roe.ConicalMirror(bl, 'cone', center=ctr, pitch=4e-3, roll=1e-3, L0=1500., theta=4e-3, material=Au,
+                           limPhysX=[-2, 2.5], limPhysY=[-400, 380])
+    d = _capture_reflect(oe, beam)
+    d.update(_oe_params(oe))
+    save('reflect_spliced_conical', rho=19.3, L0=float(oe.L0), theta=float(oe.theta), **d)
+
+    bl = raycing.BeamLine()
+    si = rm.CrystalSi(hkl=(1, 1, 1))
+    E0 = 9000.
+    thetaB = float(si.get_Bragg_angle(E0))
+    pdist = 500.
+    Rm = pdist / np.sin(thetaB)  # the source sits on the Rowland circle (diameter Rm)
+    cases = (('johann_circ', roe.JohannCylinder, dict(Rm=Rm, crossSection='circular'), None),
+             ('johann_parab_alpha', roe.JohannCylinder, dict(Rm=Rm, crossSection='parabolic'), np.radians(4.)),
+             ('johansson', roe.JohanssonCylinder, dict(Rm=Rm), None),
+             ('johansson_alpha', roe.JohanssonCylinder, dict(Rm=Rm), np.radians(-3.)),
+             ('johann_toroid', roe.JohannToroid, dict(Rm=Rm, Rs=Rm*np.sin(thetaB)**2), None),
+             ('johann_toroid_alpha', roe.JohannToroid, dict(Rm=Rm, Rs=Rm*np.sin(thetaB)**2), np.radians(5.)))
+    for i, (name, cls, kw, alpha) in enumerate(cases):
+        beam = _source_beam(bl, 1500, 210 + i, dx=0.02, dz=0.02, dxprime=8e-3, dzprime=1.5e-2, energies=(8998, 9002))
+        pitch = thetaB - float(si.get_dtheta(E0, alpha)) + (alpha or 0.)
+        oe = cls(bl, name, center=(0, pdist, 0), pitch=pitch, material=si, alpha=alpha, limPhysX=[-4, 4],
+                 limPhysY=[-30, 30], **kw)
+        d = _capture_reflect(oe, beam)
+        d.update(_oe_params(oe))
+        st = d['gb_state']
+        good = st == 1
+        print(name, {int(x): int((st == x).sum()) for x in np.unique(st)}, 'mean R',
+              float((d['gb_Jss'] + d['gb_Jpp'])[good].mean() / (d['in_Jss'] + d['in_Jpp'])[good].mean()))
+        save('reflect_spliced_' + name, d=si.d, tK=si.tK, alpha=0. if alpha is None else alpha,
+             Rm=float(oe.Rm), Rs=float(getattr(oe, 'Rs', 0.)), **d)
+
+
+SECTIONS = {'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)

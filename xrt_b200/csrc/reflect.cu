@@ -25,6 +25,27 @@
 #include "common.cuh"
 #include "kernels.h"
 
+// ---------------------------------------------------------------- spliced surfaces (plug-in builds only)
+// The CUDA counterpart of the reference's MY_LOCAL_Z / MY_LOCAL_N / MY_XYZPARAM text splicing
+// (oes/base.py:548-569 into cl/OE.cl:60-66; the class attributes cl_plist, cl_local_z, cl_local_n of e.g.
+// oes/__init__.py:245-256): xrt_b200/custom.py writes the element's `cu_local_z`, `cu_local_n` (and, for a
+// parametric element, `cu_xyz_param`) function texts into a header and compiles THIS file once more with
+//   -DXRTB_USER_SURFACE='"<header>"' -DXRTB_PLUGIN [-DXRTB_USER_PARAMETRIC]
+// into a small shared object next to libxrt_b200.so.  The header defines, in namespace xrtb_user,
+//   __device__ double local_z(const double* cu_plist, double x, double y);            // or local_r(plist, s, phi)
+//   __device__ void   local_n(const double* cu_plist, double x, double y, double* n); // n[0..2], or n[0..5] = (n_B, n_s)
+//   __device__ void   xyz_to_param(const double* cu_plist, double& x, double& y, double& z);   // parametric only
+//   __device__ void   param_to_xyz(const double* cu_plist, double& s, double& phi, double& r); // parametric only
+// and the kernels below see it as surface kind 4 (z(x, y)) or 5 (parametric).  cu_plist = xrt_oe_params.sp.
+#ifdef XRTB_USER_SURFACE
+#include XRTB_USER_SURFACE
+#endif
+#ifdef XRTB_USER_PARAMETRIC
+#define XRTB_USER_KIND 5
+#else
+#define XRTB_USER_KIND 4
+#endif
+
 namespace xrtb {
 
 // ---------------------------------------------------------------- reduction slots (uint64, order-preserving)
@@ -147,6 +168,9 @@ __device__ __forceinline__ SurfDiv make_surf_div(const xrt_oe_params& p) {
 template <int SURF>
 __device__ __forceinline__ double local_surface(const xrt_oe_params& p, const SurfDiv& sd, double x, double y) {
   if (SURF == 0) return 0.0;
+#ifdef XRTB_USER_SURFACE
+  if (SURF == 4 || SURF == 5) return xrtb_user::local_z(p.sp, x, y);
+#endif
   if (SURF == 3) {
     // ParaboloidFlatLens.local_z1 (oes/refractive.py:394-399); the parabolic cylinder passes x = 0 (:613-614).
     // sp: focus, zmax, has_zmax, isCylinder
@@ -172,6 +196,12 @@ __device__ __forceinline__ double local_surface(const xrt_oe_params& p, const Su
 
 template <int SURF>
 __device__ __forceinline__ void xyz_to_param(const xrt_oe_params& p, double& x, double& y, double& z) {
+#ifdef XRTB_USER_PARAMETRIC
+  if (SURF == 5) {
+    xrtb_user::xyz_to_param(p.sp, x, y, z);
+    return;
+  }
+#endif
   if (SURF != 2) return;
   // parametric.py:213-216: rotate_x(y - y0, z - z0, cosGamma, sinGamma); s, phi, r
   const double yy = y - p.sp[2], zz = z - p.sp[3];
@@ -185,6 +215,12 @@ __device__ __forceinline__ void xyz_to_param(const xrt_oe_params& p, double& x, 
 
 template <int SURF>
 __device__ __forceinline__ void param_to_xyz(const xrt_oe_params& p, double& x, double& y, double& z) {
+#ifdef XRTB_USER_PARAMETRIC
+  if (SURF == 5) {
+    xrtb_user::param_to_xyz(p.sp, x, y, z);
+    return;
+  }
+#endif
   if (SURF != 2) return;
   // parametric.py:218-224
   const double s = x, phi = y, r = z;
@@ -207,7 +243,7 @@ __device__ __forceinline__ double find_dz(const xrt_oe_params& p, const SurfDiv&
   double surf = local_surface<SURF>(p, sd, x, y);
   if (isnan(surf)) surf = 0.0;
   double d = z - surf;
-  if (SURF == 2) d = -d;
+  if (SURF == 2 || SURF == 5) d = -d;  // parametric: local_f = local_r, diffSign = -1 (base.py:809-813, :840)
   // * invertNormal = -1 from inside the material (reflect.py:638-641); REFR = false (kernels of non-refractive
   // materials) compiles the test away
   return (REFR && p.from_vacuum == 0) ? -d : d;
@@ -217,6 +253,17 @@ __device__ __forceinline__ double find_dz(const xrt_oe_params& p, const SurfDiv&
 template <int SURF>
 __device__ __forceinline__ void local_normal(const xrt_oe_params& p, const SurfDiv& sd, double x, double y,
                                              double* n) {
+#ifdef XRTB_USER_SURFACE
+  if (SURF == 4 || SURF == 5) {
+    xrtb_user::local_n(p.sp, x, y, n);
+    if (!p.asymmetric) {  // one normal returned: oeNormal[-3:] is the same vector (reflect.py:783-787)
+      n[3] = n[0];
+      n[4] = n[1];
+      n[5] = n[2];
+    }
+    return;
+  }
+#endif
   if (SURF == 0) {
     n[3] = 0.0;
     n[4] = 0.0;
@@ -1454,7 +1501,7 @@ static int launch_main_mat(int mat, unsigned grid, cudaStream_t st, size_t n, co
     case 6: reflect_main_kernel<SURF, 6><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
     case 7: reflect_main_kernel<SURF, 7><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
     case 5:
-      if constexpr (SURF == 0) {
+      if constexpr (SURF == 0 || SURF == 4) {
         reflect_main_kernel<SURF, 5><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red);
       } else {
         set_last_error("reflect: refraction is built for flat and parabolic surfaces");
@@ -1500,7 +1547,15 @@ int reflect_device(size_t n, const xrt_oe_params* oe, const xrt_material_params*
                    const xrt_beam* lb, unsigned long long* red, int phase, unsigned long long index_offset,
                    cudaStream_t st) {
   XRTB_REQUIRE(oe && in && gb && red, "reflect: NULL argument");
+#ifdef XRTB_PLUGIN
+  XRTB_REQUIRE(oe->surface == XRTB_USER_KIND, "reflect (plug-in): this object serves surface kind %d only (got %d)",
+               XRTB_USER_KIND, oe->surface);
+#else
+  XRTB_REQUIRE(oe->surface != 4 && oe->surface != 5,
+               "reflect: surface kinds 4 / 5 (spliced cu_local_z / cu_local_n) live in plug-in objects built by "
+               "xrt_b200.custom, not in libxrt_b200.so");
   XRTB_REQUIRE(oe->surface >= 0 && oe->surface <= 3, "reflect: unknown surface kind %d", oe->surface);
+#endif
   XRTB_REQUIRE(oe->n_rot_in >= 0 && oe->n_rot_in <= XRT_MAX_ROT && oe->n_rot_out >= 0 && oe->n_rot_out <= XRT_MAX_ROT,
                "reflect: too many elementary rotations");
   xrt_material_params m;
@@ -1510,8 +1565,8 @@ int reflect_device(size_t n, const xrt_oe_params* oe, const xrt_material_params*
   XRTB_REQUIRE((m.kind == 6 || m.kind == 7) == (oe->grating != 0),
                "reflect: material kinds 6 / 7 (grating) and xrt_oe_params.grating go together");
   XRTB_REQUIRE(oe->surface != 3 || (m.kind == 0 || m.kind == 5), "reflect: a parabolic lens refracts or is bare");
-  XRTB_REQUIRE(m.kind != 5 || oe->surface == 0 || oe->surface == 3,
-               "reflect: refraction (kind plate / lens) is built for flat and parabolic surfaces");
+  XRTB_REQUIRE(m.kind != 5 || oe->surface == 0 || oe->surface == 3 || oe->surface == 4,
+               "reflect: refraction (kind plate / lens) is built for flat, parabolic and spliced z(x, y) surfaces");
   xrt_multilayer_params ml;
   if (int rc = check_multilayer(m, ml)) return rc;
   XRTB_REQUIRE(m.kind == 0 || m.kind == 7 || (tables != nullptr && table_len > 0), "reflect: material needs f1/f2 tables");
@@ -1532,19 +1587,27 @@ int reflect_device(size_t n, const xrt_oe_params* oe, const xrt_material_params*
     XRTB_CUDA_CHECK(cudaGetLastError());
   }
   if ((phase & 4) && n > 0) {  // phase B: global bracket + solver switch of the selected variant
+#ifdef XRTB_PLUGIN
+    reflect_prepass_kernel<XRTB_USER_KIND><<<pgrid, 256, 0, st>>>(n, *oe, *in, red);
+#else
     if (oe->surface == 0) reflect_prepass_kernel<0><<<pgrid, 256, 0, st>>>(n, *oe, *in, red);
     if (oe->surface == 1) reflect_prepass_kernel<1><<<pgrid, 256, 0, st>>>(n, *oe, *in, red);
     if (oe->surface == 2) reflect_prepass_kernel<2><<<pgrid, 256, 0, st>>>(n, *oe, *in, red);
     if (oe->surface == 3) reflect_prepass_kernel<3><<<pgrid, 256, 0, st>>>(n, *oe, *in, red);
+#endif
     XRTB_CUDA_CHECK(cudaGetLastError());
   }
   if ((phase & 2) && n > 0) {
     const unsigned grid = (unsigned)((n + XRTB_REFLECT_THREADS - 1) / XRTB_REFLECT_THREADS);
     int rc = 0;
+#ifdef XRTB_PLUGIN
+    rc = launch_main_mat<XRTB_USER_KIND>(m.kind, grid, st, n, *oe, m, ml, t, *in, fbv, *gb, lbv, red);
+#else
     if (oe->surface == 0) rc = launch_main_mat<0>(m.kind, grid, st, n, *oe, m, ml, t, *in, fbv, *gb, lbv, red);
     if (oe->surface == 1) rc = launch_main_mat<1>(m.kind, grid, st, n, *oe, m, ml, t, *in, fbv, *gb, lbv, red);
     if (oe->surface == 2) rc = launch_main_mat<2>(m.kind, grid, st, n, *oe, m, ml, t, *in, fbv, *gb, lbv, red);
     if (oe->surface == 3) rc = launch_main_refr<3>(m.kind, grid, st, n, *oe, m, ml, t, *in, fbv, *gb, lbv, red);
+#endif
     if (rc) return rc;
   }
   return 0;
@@ -1618,7 +1681,7 @@ __global__ void __launch_bounds__(256) surface_kernel(size_t n, xrt_oe_params p,
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double px = x[i], py = y[i], pz = 0.0;
-  if (SURF == 2) {
+  if (SURF == 2 || SURF == 5) {
     xyz_to_param<SURF>(p, px, py, pz);
     pz = local_surface<SURF>(p, make_surf_div<SURF>(p), px, py);
     param_to_xyz<SURF>(p, px, py, pz);
@@ -1630,12 +1693,18 @@ __global__ void __launch_bounds__(256) surface_kernel(size_t n, xrt_oe_params p,
 
 int surface_device(size_t n, const xrt_oe_params* oe, const double* x, const double* y, double* z, cudaStream_t st) {
   XRTB_REQUIRE(oe && x && y && z, "oe_surface: NULL argument");
+#ifdef XRTB_PLUGIN
+  XRTB_REQUIRE(oe->surface == XRTB_USER_KIND, "oe_surface (plug-in): surface kind %d expected", XRTB_USER_KIND);
+  if (n == 0) return 0;
+  surface_kernel<XRTB_USER_KIND><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, *oe, x, y, z);
+#else
   XRTB_REQUIRE(oe->surface >= 0 && oe->surface <= 2, "oe_surface: unknown surface kind %d", oe->surface);
   if (n == 0) return 0;
   const unsigned grid = (unsigned)((n + 255) / 256);
   if (oe->surface == 0) surface_kernel<0><<<grid, 256, 0, st>>>(n, *oe, x, y, z);
   if (oe->surface == 1) surface_kernel<1><<<grid, 256, 0, st>>>(n, *oe, x, y, z);
   if (oe->surface == 2) surface_kernel<2><<<grid, 256, 0, st>>>(n, *oe, x, y, z);
+#endif
   XRTB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1643,12 +1712,18 @@ int surface_device(size_t n, const xrt_oe_params* oe, const double* x, const dou
 int normals_device(size_t n, const xrt_oe_params* oe, const double* x, const double* y, const double* z, double* nx,
                    double* ny, double* nz, cudaStream_t st) {
   XRTB_REQUIRE(oe && x && y && z && nx && ny && nz, "oe_normals: NULL argument");
+#ifdef XRTB_PLUGIN
+  XRTB_REQUIRE(oe->surface == XRTB_USER_KIND, "oe_normals (plug-in): surface kind %d expected", XRTB_USER_KIND);
+  if (n == 0) return 0;
+  normals_kernel<XRTB_USER_KIND><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, *oe, x, y, z, nx, ny, nz);
+#else
   XRTB_REQUIRE(oe->surface >= 0 && oe->surface <= 2, "oe_normals: unknown surface kind %d", oe->surface);
   if (n == 0) return 0;
   const unsigned grid = (unsigned)((n + 255) / 256);
   if (oe->surface == 0) normals_kernel<0><<<grid, 256, 0, st>>>(n, *oe, x, y, z, nx, ny, nz);
   if (oe->surface == 1) normals_kernel<1><<<grid, 256, 0, st>>>(n, *oe, x, y, z, nx, ny, nz);
   if (oe->surface == 2) normals_kernel<2><<<grid, 256, 0, st>>>(n, *oe, x, y, z, nx, ny, nz);
+#endif
   XRTB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1656,3 +1731,28 @@ int normals_device(size_t n, const xrt_oe_params* oe, const double* x, const dou
 double reduction_decode(unsigned long long slot) { return dec(slot); }
 
 }  // namespace xrtb
+
+#ifdef XRTB_PLUGIN
+// C ABI of a spliced-surface plug-in object: the three entry points of include/xrt_b200.h that depend on the
+// surface, same argument lists (xrt_reflect_f64, xrt_oe_surface_f64, xrt_oe_normals_f64), plus the struct size the
+// object was compiled against.  Everything else in this translation unit has hidden visibility.
+#define XRTB_EXPORT extern "C" __attribute__((visibility("default")))
+XRTB_EXPORT int xrt_plugin_reflect_f64(size_t n, const xrt_oe_params* oe, const xrt_material_params* mat,
+                                       const double* tables, size_t table_len, const xrt_beam* in,
+                                       const xrt_beam* fallback, const xrt_beam* gb, const xrt_beam* lb,
+                                       uint64_t* reductions, int phase, uint64_t index_offset, void* stream) {
+  return xrtb::reflect_device(n, oe, mat, tables, table_len, in, fallback, gb, lb,
+                              reinterpret_cast<unsigned long long*>(reductions), phase, index_offset,
+                              (cudaStream_t)stream);
+}
+XRTB_EXPORT int xrt_plugin_oe_surface_f64(size_t n, const xrt_oe_params* oe, const double* x, const double* y,
+                                          double* z, void* stream) {
+  return xrtb::surface_device(n, oe, x, y, z, (cudaStream_t)stream);
+}
+XRTB_EXPORT int xrt_plugin_oe_normals_f64(size_t n, const xrt_oe_params* oe, const double* x, const double* y,
+                                          const double* z, double* nx, double* ny, double* nz, void* stream) {
+  return xrtb::normals_device(n, oe, x, y, z, nx, ny, nz, (cudaStream_t)stream);
+}
+XRTB_EXPORT size_t xrt_plugin_sizeof_oe_params(void) { return sizeof(xrt_oe_params); }
+XRTB_EXPORT int xrt_plugin_surface_kind(void) { return XRTB_USER_KIND; }
+#endif

@@ -82,9 +82,19 @@ def _fill_rot(params, which, rots):
 
 
 class OE(object):
-    """Flat optical element (mirror or crystal)."""
+    """Flat optical element (mirror or crystal).
+
+    A subclass with another surface either names a built-in kernel (`surfaceKind` 1..3) or carries the CUDA texts of
+    its surface -- `cu_plist`, `cu_local_z`, `cu_local_n` (+ `cu_xyz_param` for a parametric element), the
+    counterparts of the reference's `cl_plist`, `cl_local_z`, `cl_local_n`, `cl_xyz_param` (oes/base.py:548-569) --
+    which xrt_b200.custom compiles into the same fused kernels (surface kinds 4 / 5)."""
     surfaceKind = 0
     isParametric = False
+    cu_plist = ()
+    cu_local_z = None
+    cu_local_n = None
+    cu_xyz_param = None
+    cu_two_normals = None  # None: two normals (n_B, n_s) are returned iff alpha is set, like OE.local_n
 
     def __init__(self, bl=None, name='', center=[0, 0, 0], pitch=0, roll=0, yaw=0, positionRoll=0,
                  rotationSequence='RzRyRx', extraPitch=0, extraRoll=0, extraYaw=0,
@@ -139,7 +149,22 @@ class OE(object):
 
     # ------------------------------------------------------------------ geometry -> C struct
     def _surface_params(self):
-        return []
+        out = []
+        for name in self.cu_plist:  # cl_plist marshalling (base.py:897-899): up to 8 numbers, sequences flattened
+            v = getattr(self, name)
+            out.extend([float(u) for u in v] if isinstance(v, (list, tuple, np.ndarray)) else [float(v)])
+        if len(out) > 8:
+            raise ValueError('cu_plist: at most 8 numbers')
+        return out
+
+    def _plugin(self):
+        """The spliced-surface plug-in object of this element, or None for the built-in surfaces."""
+        if self.cu_local_z is None:
+            return None
+        if self.cu_local_n is None:
+            raise _lib.XrtB200Error('a spliced surface needs both cu_local_z and cu_local_n')
+        from . import custom
+        return custom.plugin_for(self.cu_local_z, self.cu_local_n, self.cu_xyz_param)
 
     def _limits(self, second=False):
         sfx = '2' if second else ''
@@ -185,10 +210,14 @@ class OE(object):
         p.shift[0], p.shift[1], p.shift[2] = float(dx or 0), float(dy or 0), float(dz or 0)
         p.roll = float(roll)
         p.surface = self.surfaceKind
+        if self.cu_local_z is not None:
+            p.surface = 5 if self.cu_xyz_param else 4
         for i, v in enumerate(self._surface_params()):
             p.sp[i] = float(v)
         p.asymmetric = 1 if self.alpha else 0
-        if self.alpha:
+        if self.cu_local_z is not None and self.cu_two_normals is not None:
+            p.asymmetric = int(bool(self.cu_two_normals))
+        if self.alpha and self.cu_local_z is None:
             nB = self._local_nB(is2ndXtal)
             for i in range(3):
                 p.nB[i] = nB[i]
@@ -282,15 +311,17 @@ class OE(object):
                 ctypes.byref(cfb) if cfb is not None else None, ctypes.byref(cgb),
                 ctypes.byref(clb) if clb is not None else None, red.data_ptr())
         profile = getattr(self, 'profileEvents', None)
+        plugin = self._plugin()
+        xrt_reflect_f64 = lib.xrt_reflect_f64 if plugin is None else plugin.reflect
         if allreduce is None and profile is None:
-            _lib.check(lib.xrt_reflect_f64(*args, 7, index_offset, stream), 'xrt_reflect_f64')
+            _lib.check(xrt_reflect_f64(*args, 7, index_offset, stream), 'xrt_reflect_f64')
         else:
             # the three phases as separate calls: ray shards all-reduce the beam-wide scalars (min/max/sum over
             # the 64 slots, xrt_b200/parallel.py) after each pre-pass; bench.py takes per-kernel CUDA events
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if profile is not None else None
             if evs:
                 evs[0].record()
-            _lib.check(lib.xrt_reflect_f64(*args, 1, index_offset, stream), 'xrt_reflect_f64 (pre-pass A)')
+            _lib.check(xrt_reflect_f64(*args, 1, index_offset, stream), 'xrt_reflect_f64 (pre-pass A)')
             if evs:
                 evs[1].record()
             if allreduce is not None:
@@ -298,7 +329,7 @@ class OE(object):
             if evs:
                 evs.append(torch.cuda.Event(enable_timing=True))
                 evs[4].record()
-            _lib.check(lib.xrt_reflect_f64(*args, 4, index_offset, stream), 'xrt_reflect_f64 (pre-pass B)')
+            _lib.check(xrt_reflect_f64(*args, 4, index_offset, stream), 'xrt_reflect_f64 (pre-pass B)')
             if evs:
                 evs[2].record()
             if allreduce is not None:
@@ -306,7 +337,7 @@ class OE(object):
             if evs:
                 evs.append(torch.cuda.Event(enable_timing=True))
                 evs[5].record()
-            _lib.check(lib.xrt_reflect_f64(*args, 2, index_offset, stream), 'xrt_reflect_f64 (main pass)')
+            _lib.check(xrt_reflect_f64(*args, 2, index_offset, stream), 'xrt_reflect_f64 (main pass)')
             if evs:
                 evs[3].record()
                 # kernel intervals: A = 0->1, B = 4->2, main = 5->3 (the all-reduces sit in between)
@@ -331,9 +362,11 @@ class OE(object):
         n = x.numel()
         out = torch.empty((3, n), dtype=torch.float64, device=x.device)
         params = self._make_params(self.pitch, self.roll + self.positionRoll, self.yaw, self.dx)
-        rc = lib.xrt_oe_normals_f64(n, ctypes.byref(params), x.contiguous().data_ptr(), y.contiguous().data_ptr(),
-                                    z.contiguous().data_ptr(), out[0].data_ptr(), out[1].data_ptr(),
-                                    out[2].data_ptr(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        plugin = self._plugin()
+        oe_normals = lib.xrt_oe_normals_f64 if plugin is None else plugin.oe_normals
+        rc = oe_normals(n, ctypes.byref(params), x.contiguous().data_ptr(), y.contiguous().data_ptr(),
+                        z.contiguous().data_ptr(), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                        ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
         _lib.check(rc, 'xrt_oe_normals_f64')
         return out[0], out[1], out[2]
 
@@ -343,8 +376,10 @@ class OE(object):
         n = x.numel()
         out = torch.empty(n, dtype=torch.float64, device=x.device)
         params = self._make_params(self.pitch, self.roll + self.positionRoll, self.yaw, self.dx)
-        rc = lib.xrt_oe_surface_f64(n, ctypes.byref(params), x.contiguous().data_ptr(), y.contiguous().data_ptr(),
-                                    out.data_ptr(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        plugin = self._plugin()
+        oe_surface = lib.xrt_oe_surface_f64 if plugin is None else plugin.oe_surface
+        rc = oe_surface(n, ctypes.byref(params), x.contiguous().data_ptr(), y.contiguous().data_ptr(),
+                        out.data_ptr(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
         _lib.check(rc, 'xrt_oe_surface_f64')
         return out
 
@@ -781,3 +816,15 @@ def _rotate_point(point, rotationSequence='RzRyRx', pitch=0, roll=0, yaw=0):
         else:  # rotate_x, rotate_z
             newp[ind1[ax]], newp[ind2[ax]] = cA*u - sA*v, sA*u + cA*v
     return newp
+
+
+_SPLICED = ('BentFlatMirror', 'SimpleVCM', 'ConicalMirror', 'JohannCylinder', 'JohanssonCylinder', 'JohannToroid')
+
+
+def __getattr__(name):
+    """The curved elements whose surfaces are spliced CUDA texts (xrt_b200/oes_spliced.py) carry xrt's names in this
+    namespace too (resolved lazily: that module derives its classes from OE above)."""
+    if name in _SPLICED:
+        from . import oes_spliced
+        return getattr(oes_spliced, name)
+    raise AttributeError(name)

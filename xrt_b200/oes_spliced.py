@@ -1,0 +1,225 @@
+# -*- coding: utf-8 -*-
+"""Curved optical elements of xrt whose surfaces are spliced CUDA texts (xrt_b200/custom.py), with xrt's class names
+and constructor arguments:
+
+    BentFlatMirror(..., R) = SimpleVCM                      oes/__init__.py:240-306
+    ConicalMirror(..., L0, theta)                           oes/__init__.py:589-636
+    JohannCylinder(..., Rm, crossSection)                   oes/bragg.py:104-176
+    JohanssonCylinder(..., Rm, crossSection)                oes/bragg.py:179-197
+    JohannToroid(..., Rm, Rs)                               oes/bragg.py:200-269
+
+The texts follow the reference's numpy expressions operation by operation (the plug-in is compiled with
+-fmad=false); scalars the reference forms from Python floats (`self.Rm**2`, `0.25*self.t2t**2`) are formed on the
+host by the same Python expressions and travel in `cu_plist`, so they carry the same roundings.  These classes double
+as the worked examples of writing `cu_local_z` / `cu_local_n` for an element of one's own."""
+import numpy as np
+
+from .oes import OE
+
+# rotate_x / rotate_y of _rotate.py:5-14, for the texts below
+_ROT = '''
+__device__ __forceinline__ void rot_x(double y, double z, double c, double s, double& yo, double& zo)
+{ yo = c * y - s * z; zo = s * y + c * z; }
+'''
+
+
+class BentFlatMirror(OE):
+    """z = (y^2 - limPhysY[0]^2) / 2R: a meridionally bent parabolic cylinder with fixed ends."""
+    cu_plist = ('R', '_y0sq')
+    cu_local_z = '''
+    __device__ double local_z(const double* cu_plist, double x, double y)
+    { return (y * y - cu_plist[1]) / 2.0 / cu_plist[0]; }'''
+    cu_local_n = '''
+    __device__ void local_n(const double* cu_plist, double x, double y, double* n)
+    {
+        const double b = -y / cu_plist[0];
+        const double norm = sqrt(b * b + 1.0);
+        n[0] = 0.0 / norm; n[1] = b / norm; n[2] = 1.0 / norm;
+    }'''
+
+    def __init__(self, *args, **kwargs):
+        R = kwargs.pop('R', 5.0e6)
+        OE.__init__(self, *args, **kwargs)
+        if isinstance(R, (list, tuple)):
+            raise NotImplementedError('give R as a number (Coddington (p, q) tuples are resolved by xrt)')
+        self.R = 1e100 if R is None else R
+
+    @property
+    def _y0sq(self):
+        return self.limPhysY[0]**2
+
+
+SimpleVCM = BentFlatMirror
+
+
+class ConicalMirror(OE):
+    """Conical mirror with its base parallel to the side of the cone."""
+    cu_plist = ('L0', 't2t', 'redfocus', '_c1', '_c2', '_sgn')
+    cu_local_z = '''
+    __device__ double local_z(const double* cu_plist, double x, double y)
+    {
+        const double L0 = cu_plist[0], t2t = cu_plist[1], c1 = cu_plist[3], c2 = cu_plist[4], sgn = cu_plist[5];
+        const double yl = y - L0;
+        const double sqroot = sqrt(c1 * (yl * yl) - c2 * (x * x));
+        return (-0.5 * t2t) * yl - sgn * sqroot;
+    }'''
+    cu_local_n = '''
+    __device__ void local_n(const double* cu_plist, double x, double y, double* n)
+    {
+        const double L0 = cu_plist[0], t2t = cu_plist[1], rf = cu_plist[2], c1 = cu_plist[3], sgn = cu_plist[5];
+        const double yl = y - L0;
+        const double sqroot = sgn * sqrt(c1 * (yl * yl) - ((rf * x) * x) * t2t);
+        const double a = ((-x) * rf) * t2t / sqroot;
+        const double b = 0.5 * t2t + c1 * yl / sqroot;
+        const double norm = sqrt(a * a + b * b + 1.0);
+        n[0] = a / norm; n[1] = b / norm; n[2] = 1.0 / norm;
+    }'''
+
+    def __init__(self, *args, **kwargs):
+        self.L0 = kwargs.pop('L0', 1000.)
+        theta = kwargs.pop('theta', np.pi/6.)
+        OE.__init__(self, *args, **kwargs)
+        self.theta = theta
+
+    @property
+    def theta(self):
+        return self._theta
+
+    @theta.setter
+    def theta(self, theta):  # oes/__init__.py:610-615
+        self._theta = theta
+        self.tt = np.tan(self._theta)
+        self.t2t = np.tan(2*self._theta)
+        self.redfocus = np.cos(self._theta)**2 / (1./self.tt - 1./self.t2t)
+
+    _c1 = property(lambda self: 0.25*self.t2t**2)
+    _c2 = property(lambda self: self.redfocus*self.t2t)
+    _sgn = property(lambda self: float(np.sign(self.t2t)))
+
+
+class JohannCylinder(OE):
+    """Simply bent reflective crystal; with alpha the normals (n_B, n_s) are both returned."""
+    cu_plist = ('crossSectionInt', 'Rm', '_Rm2', '_cosalpha', '_sinalpha')
+    cu_local_z = '''
+    __device__ double local_z(const double* cu_plist, double x, double y)
+    {
+        if (cu_plist[0] == 0.0) return cu_plist[1] - sqrt(cu_plist[2] - y * y);
+        return y * y / 2.0 / cu_plist[1];
+    }'''
+    _cu_cylinder = _ROT + '''
+    __device__ __forceinline__ void n_cylinder(const double* cu_plist, double y, double& b, double& c)
+    {
+        const double R = cu_plist[1];
+        b = -y / R;
+        if (cu_plist[0] == 0.0) {
+            c = sqrt(cu_plist[2] - y * y) / R;
+        } else {
+            const double norm = sqrt(b * b + 1.0);
+            b = b / norm;
+            c = 1.0 / norm;
+        }
+    }'''
+    cu_local_n = _cu_cylinder + '''
+    __device__ void local_n(const double* cu_plist, double x, double y, double* n)
+    {
+        double b, c;
+        n_cylinder(cu_plist, y, b, c);
+        n[0] = 0.0; n[1] = b; n[2] = c;
+        if (cu_plist[4] != 0.0 || cu_plist[3] != 1.0) {  // alpha: (n_B, n_s)
+            n[3] = 0.0; n[4] = b; n[5] = c;
+            rot_x(b, c, cu_plist[3], -cu_plist[4], n[1], n[2]);
+        }
+    }'''
+
+    def __init__(self, *args, **kwargs):
+        self.Rm = kwargs.pop('Rm', 1000.)
+        self.crossSection = kwargs.pop('crossSection', 'circular')
+        if not (self.crossSection.startswith('circ') or self.crossSection.startswith('parab')):
+            raise ValueError('unknown crossSection!')
+        self.crossSectionInt = 0 if self.crossSection.startswith('circ') else 1
+        OE.__init__(self, *args, **kwargs)
+
+    _Rm2 = property(lambda self: self.Rm**2)
+    _cosalpha = property(lambda self: float(np.cos(self.alpha)) if self.alpha else 1.)
+    _sinalpha = property(lambda self: float(np.sin(self.alpha)) if self.alpha else 0.)
+
+
+class JohanssonCylinder(JohannCylinder):
+    """Ground-bent (Johansson) crystal: atomic planes on 2 Rm, surface on Rm (exact expressions)."""
+    cu_two_normals = True
+    cu_local_n = JohannCylinder._cu_cylinder + '''
+    __device__ void local_n(const double* cu_plist, double x, double y, double* n)
+    {
+        double bs, cs;
+        n_cylinder(cu_plist, y, bs, cs);
+        double b = -y;
+        double c = sqrt(cu_plist[2] - y * y) + cu_plist[1];
+        if (cu_plist[4] != 0.0 || cu_plist[3] != 1.0) {
+            const double b0 = b, c0 = c;
+            rot_x(b0, c0, cu_plist[3], -cu_plist[4], b, c);
+        }
+        const double norm = sqrt(b * b + c * c);
+        n[0] = 0.0 / norm; n[1] = b / norm; n[2] = c / norm;
+        n[3] = 0.0; n[4] = bs; n[5] = cs;
+    }'''
+
+
+class JohannToroid(OE):
+    """2D bent reflective crystal with meridional and sagittal radii Rm, Rs."""
+    cu_plist = ('Rm', 'Rs', '_Rm2', '_RmRs', '_cosalpha', '_sinalpha')
+    cu_local_z = '''
+    __device__ double local_z(const double* cu_plist, double x, double y)
+    {
+        const double z = cu_plist[3] - sqrt(cu_plist[2] - y * y);
+        const double cosangle = sqrt(z * z - x * x) / fabs(z);
+        return cosangle * z + cu_plist[1];
+    }'''
+    cu_local_n = _ROT + '''
+    __device__ void local_n(const double* cu_plist, double x, double y, double* n)
+    {
+        const double Rm = cu_plist[0], Rs = cu_plist[1];
+        const double sq = sqrt(cu_plist[2] - y * y);
+        const double b = -y / Rm;
+        const double c = sq / Rm;
+        const double r = Rs - (Rm - sq);
+        const double cosangle = sqrt(r * r - x * x) / r, sinangle = -x / r;
+        if (cu_plist[5] != 0.0 || cu_plist[4] != 1.0) {
+            double bA, cA;
+            rot_x(b, c, cu_plist[4], -cu_plist[5], bA, cA);
+            n[0] = sinangle * cA; n[1] = bA; n[2] = cosangle * cA;
+            n[3] = sinangle * c;  n[4] = b;  n[5] = cosangle * c;
+        } else {
+            n[0] = sinangle * c; n[1] = b; n[2] = cosangle * c;
+        }
+    }'''
+
+    def __init__(self, *args, **kwargs):
+        self.Rm = kwargs.pop('Rm', 1000.)
+        self._Rs = kwargs.pop('Rs', None)
+        OE.__init__(self, *args, **kwargs)
+
+    @property
+    def Rs(self):
+        return self._Rs if self._Rs is not None else self.Rm
+
+    @Rs.setter
+    def Rs(self, Rs):
+        self._Rs = Rs
+
+    _Rm2 = property(lambda self: self.Rm**2)
+    _RmRs = property(lambda self: self.Rm - self.Rs)
+    _cosalpha = property(lambda self: float(np.cos(self.alpha)) if self.alpha else 1.)
+    _sinalpha = property(lambda self: float(np.sin(self.alpha)) if self.alpha else 0.)
+
+
+LIBRARY = (BentFlatMirror, ConicalMirror, JohannCylinder, JohanssonCylinder, JohannToroid)
+
+
+def prebuild(verbose=False):
+    """Compile the plug-in objects of the classes above (what __graft_entry__.build() does, so that a fresh GPU box
+    finds them next to libxrt_b200.so)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from . import custom
+    jobs = [(c.cu_local_z, c.cu_local_n, c.cu_xyz_param) for c in LIBRARY]
+    with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+        return list(ex.map(lambda j: custom.build_plugin(*j, verbose=verbose), jobs))
