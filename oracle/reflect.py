@@ -150,11 +150,15 @@ class OESpec(object):
         raise ValueError(self.surface)
 
     def xyz_to_param(self, x, y, z):
+        if self.surface == 'custom':
+            return self.surfParams['obj'].xyz_to_param(x, y, z)
         p = self.surfParams
         yNew, zNew = ob.rotate_x(y - p['y0'], z - p['z0'], p['cosGamma'], p['sinGamma'])
         return yNew, np.arctan2(x, zNew), np.sqrt(x**2 + zNew**2)
 
     def param_to_xyz(self, s, phi, r):
+        if self.surface == 'custom':
+            return self.surfParams['obj'].param_to_xyz(s, phi, r)
         p = self.surfParams
         x = r * np.sin(phi)
         y = s
@@ -163,6 +167,8 @@ class OESpec(object):
         return x, yNew + p['y0'], zNew + p['z0']
 
     def local_r(self, s, phi):
+        if self.surface == 'custom':
+            return self.surfParams['obj'].local_r(s, phi)
         p = self.surfParams
         r = p['ellipseB'] * np.sqrt(abs(1 - s**2 / p['ellipseA']**2))
         if p['isCylindrical']:

@@ -138,3 +138,45 @@ class JohannToroid(object):
             return [aAlpha, bAlpha, cAlpha, a, b, c]
         else:
             return [a, b, c]
+
+
+class ParabolicalMirrorParam(object):
+    """oes/parametric.py:252-476: paraboloid / parabolic cylinder in the parametric (s, phi, r) representation; the
+    scalars parabParam, y0, z0, cosGamma, sinGamma are those of _reset_pq (:405-430)."""
+
+    def __init__(self, parabParam, y0, z0, cosGamma, sinGamma, isCylindrical=False):
+        self.parabParam, self.y0, self.z0 = parabParam, y0, z0
+        self.cosGamma, self.sinGamma = cosGamma, sinGamma
+        self.isCylindrical = isCylindrical
+
+    def xyz_to_param(self, x, y, z):  # :441-444
+        yNew, zNew = ob.rotate_x(y - self.y0, z - self.z0, self.cosGamma, self.sinGamma)
+        return yNew, np.arctan2(x, zNew), np.sqrt(x**2 + zNew**2)
+
+    def param_to_xyz(self, s, phi, r):  # :446-451
+        x = r * np.sin(phi)
+        y = s
+        z = r * np.cos(phi)
+        yNew, zNew = ob.rotate_x(y, z, self.cosGamma, -self.sinGamma)
+        return x, yNew + self.y0, zNew + self.z0
+
+    def local_r(self, s, phi):  # :453-461 (isClosed = False)
+        r2 = self.parabParam*s + self.parabParam**2
+        r2[r2 < 0] = 0
+        r = 2 * r2**0.5
+        if self.isCylindrical:
+            r /= abs(np.cos(phi))
+        return np.where(abs(phi) > np.pi/2, r, np.ones_like(phi)*1e20)
+
+    def local_n(self, s, phi):  # :463-474
+        nr = self.parabParam / (self.parabParam*s + self.parabParam**2)**0.5
+        norm = np.sqrt(nr**2 + 1)
+        b = nr / norm
+        if self.isCylindrical:
+            a = np.zeros_like(phi)
+            c = 1. / norm
+        else:
+            a = -np.sin(phi) / norm
+            c = -np.cos(phi) / norm
+        bNew, cNew = ob.rotate_x(b, c, self.cosGamma, -self.sinGamma)
+        return [a, bNew, cNew]

@@ -1001,6 +1001,22 @@ def gen_spliced():
     d.update(_oe_params(oe))
     save('reflect_spliced_conical', rho=19.3, L0=float(oe.L0), theta=float(oe.theta), **d)
 
+    # parametric: collimating paraboloid (p given) and focusing parabolic cylinder (q given, rolled to the side)
+    bl = raycing.BeamLine()
+    for name, kw, okw in (('parab_p', dict(p=20000.), dict(pitch=4e-3)),
+                          ('parab_q_cyl', dict(q=8000., isCylindrical=True), dict(pitch=3e-3, positionRoll=np.pi/2))):
+        beam = _source_beam(bl, 2500, 205, dx=0.3, dz=0.1, dxprime=1.2e-4, dzprime=6e-5, energies=(7000, 11000))
+        oe = roe.ParabolicalMirrorParam(bl, name, center=(0, 20000., 0), material=Au, limPhysX=[-3, 2.5],
+                                        limPhysY=[-400, 380], **dict(kw, **okw))
+        d = _capture_reflect(oe, beam)
+        d.update(_oe_params(oe))
+        st = d['gb_state']
+        print(name, {int(x): int((st == x).sum()) for x in np.unique(st)})
+        save('reflect_spliced_' + name, rho=19.3, p=np.float64(np.nan if oe.p is None else oe.p),
+             q=np.float64(np.nan if oe.q is None else oe.q), isCylindrical=bool(oe.isCylindrical),
+             parabParam=float(oe.parabParam), y0=float(oe.y0), z0=float(oe.z0), cosGamma=float(oe.cosGamma),
+             sinGamma=float(oe.sinGamma), **d)
+
     bl = raycing.BeamLine()
     si = rm.CrystalSi(hkl=(1, 1, 1))
     E0 = 9000.

@@ -590,6 +590,25 @@ class ToroidMirror(OE):
         return [self.R, self.r]
 
 
+def _abs_pitch_to_axis(oe, axis=(0, 1, 0)):
+    """|angle| between the mirror surface and *axis* (global): the mirror normal (0, 0, 1) taken to global coordinates
+    as in EllipticalMirrorParam._reset_pq / ParabolicalMirrorParam._reset_pq (parametric.py:84-96, :113-117, :379-396)."""
+    n = np.array([0., 0., 1.])
+    for ax, c, s in _rotation_list('-'+oe.rotationSequence, oe.pitch, oe.roll+oe.positionRoll, oe.yaw):
+        i, j = {0: (1, 2), 1: (0, 2), 2: (0, 1)}[ax]
+        if ax == 1:
+            n[i], n[j] = c*n[i] + s*n[j], -s*n[i] + c*n[j]
+        else:
+            n[i], n[j] = c*n[i] - s*n[j], s*n[i] + c*n[j]
+    a0 = oe.bl.sinAzimuth if oe.bl is not None else 0.
+    b0 = oe.bl.cosAzimuth if oe.bl is not None else 1.
+    if a0 != 0:
+        n[0], n[1] = b0*n[0] - (-a0)*n[1], (-a0)*n[0] + b0*n[1]
+    norm = sum([a**2 for a in axis])**0.5
+    sintheta = sum([a*nn for a, nn in zip(axis, n)]) / norm
+    return abs(np.arcsin(sintheta))
+
+
 class EllipticalMirrorParam(OE):
     """Elliptical cylinder / ellipsoid in the parametric (s, phi, r) representation
     (oes/parametric.py:9-249).  The ellipse parameters follow _reset_pq (:104-150) for the default p-arm
@@ -610,23 +629,7 @@ class EllipticalMirrorParam(OE):
         self._reset_pq()
 
     def _reset_pq(self):
-        # the mirror normal in global coordinates (parametric.py:84-96, :113-117)
-        n = np.array([0., 0., 1.])
-        for ax, c, s in _rotation_list('-'+self.rotationSequence, self.pitch, self.roll+self.positionRoll,
-                                       self.yaw):
-            i, j = {0: (1, 2), 1: (0, 2), 2: (0, 1)}[ax]
-            if ax == 1:
-                n[i], n[j] = c*n[i] + s*n[j], -s*n[i] + c*n[j]
-            else:
-                n[i], n[j] = c*n[i] - s*n[j], s*n[i] + c*n[j]
-        a0 = self.bl.sinAzimuth if self.bl is not None else 0.
-        b0 = self.bl.cosAzimuth if self.bl is not None else 1.
-        if a0 != 0:
-            n[0], n[1] = b0*n[0] - (-a0)*n[1], (-a0)*n[0] + b0*n[1]
-        axis = [0, 1, 0]
-        norm = sum([a**2 for a in axis])**0.5
-        sintheta = sum([a*nn for a, nn in zip(axis, n)]) / norm
-        absPitch = abs(np.arcsin(sintheta))
+        absPitch = _abs_pitch_to_axis(self)
         gamma = np.arctan2((self.p - self.q) * np.sin(absPitch), (self.p + self.q) * np.cos(absPitch))
         self.cosGamma = np.cos(gamma)
         self.sinGamma = np.sin(gamma)
@@ -818,7 +821,8 @@ def _rotate_point(point, rotationSequence='RzRyRx', pitch=0, roll=0, yaw=0):
     return newp
 
 
-_SPLICED = ('BentFlatMirror', 'SimpleVCM', 'ConicalMirror', 'JohannCylinder', 'JohanssonCylinder', 'JohannToroid')
+_SPLICED = ('BentFlatMirror', 'SimpleVCM', 'ConicalMirror', 'JohannCylinder', 'JohanssonCylinder', 'JohannToroid',
+            'ParabolicalMirrorParam', 'ParabolicMirror')
 
 
 def __getattr__(name):

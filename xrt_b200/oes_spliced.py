@@ -7,6 +7,7 @@ and constructor arguments:
     JohannCylinder(..., Rm, crossSection)                   oes/bragg.py:104-176
     JohanssonCylinder(..., Rm, crossSection)                oes/bragg.py:179-197
     JohannToroid(..., Rm, Rs)                               oes/bragg.py:200-269
+    ParabolicalMirrorParam(..., p | q, isCylindrical)       oes/parametric.py:252-476  (parametric: s, phi, r)
 
 The texts follow the reference's numpy expressions operation by operation (the plug-in is compiled with
 -fmad=false); scalars the reference forms from Python floats (`self.Rm**2`, `0.25*self.t2t**2`) are formed on the
@@ -14,7 +15,7 @@ host by the same Python expressions and travel in `cu_plist`, so they carry the 
 as the worked examples of writing `cu_local_z` / `cu_local_n` for an element of one's own."""
 import numpy as np
 
-from .oes import OE
+from .oes import OE, _abs_pitch_to_axis
 
 # rotate_x / rotate_y of _rotate.py:5-14, for the texts below
 _ROT = '''
@@ -212,7 +213,87 @@ class JohannToroid(OE):
     _sinalpha = property(lambda self: float(np.sin(self.alpha)) if self.alpha else 0.)
 
 
-LIBRARY = (BentFlatMirror, ConicalMirror, JohannCylinder, JohanssonCylinder, JohannToroid)
+class ParabolicalMirrorParam(OE):
+    """Paraboloid / parabolic cylinder in the parametric (s, phi, r) representation: s along the paraboloid axis
+    from the focus, (phi, r) polar coordinates normal to it.  One of *p* (collimating) or *q* (focusing); the axis is
+    the global y axis (f1 / f2 / parabolaAxis are resolved by xrt)."""
+    isParametric = True
+    cu_plist = ('parabParam', '_pp2', 'y0', 'z0', 'cosGamma', 'sinGamma', '_isCyl')
+    cu_local_z = '''
+    __device__ double local_z(const double* cu_plist, double s, double phi)   // = local_r(s, phi)
+    {
+        double r2 = cu_plist[0] * s + cu_plist[1];
+        if (r2 < 0.0) r2 = 0.0;
+        double r = 2.0 * sqrt(r2);
+        if (cu_plist[6] != 0.0) r /= fabs(cos(phi));
+        return (fabs(phi) > 3.141592653589793 / 2) ? r : 1e20;
+    }'''
+    cu_local_n = _ROT + '''
+    __device__ void local_n(const double* cu_plist, double s, double phi, double* n)
+    {
+        const double nr = cu_plist[0] / sqrt(cu_plist[0] * s + cu_plist[1]);
+        const double norm = sqrt(nr * nr + 1.0);
+        const double b = nr / norm;
+        double a, c;
+        if (cu_plist[6] != 0.0) { a = 0.0; c = 1.0 / norm; }
+        else { a = -sin(phi) / norm; c = -cos(phi) / norm; }
+        n[0] = a;
+        rot_x(b, c, cu_plist[4], -cu_plist[5], n[1], n[2]);
+    }'''
+    cu_xyz_param = '''  // (rot_x comes with cu_local_n above: the texts share one header)
+    __device__ void xyz_to_param(const double* cu_plist, double& x, double& y, double& z)
+    {
+        double yN, zN;
+        rot_x(y - cu_plist[2], z - cu_plist[3], cu_plist[4], cu_plist[5], yN, zN);
+        const double xx = x;
+        x = yN; y = atan2(xx, zN); z = sqrt(xx * xx + zN * zN);
+    }
+    __device__ void param_to_xyz(const double* cu_plist, double& s, double& phi, double& r)
+    {
+        const double xx = r * sin(phi), yy = s, zz = r * cos(phi);
+        double yN, zN;
+        rot_x(yy, zz, cu_plist[4], -cu_plist[5], yN, zN);
+        s = xx; phi = yN + cu_plist[2]; r = zN + cu_plist[3];
+    }'''
+
+    def __init__(self, *args, **kwargs):
+        self.p = kwargs.pop('p', None)
+        self.q = kwargs.pop('q', None)
+        self.isCylindrical = kwargs.pop('isCylindrical', False)
+        if kwargs.pop('isClosed', False):
+            raise NotImplementedError('isClosed=True is outside the hot path')
+        for k in ('f1', 'f2', 'parabolaAxis'):
+            if kwargs.pop(k, None) is not None:
+                raise NotImplementedError('{0} is resolved by xrt; give p or q'.format(k))
+        if self.p is None and self.q is None:
+            self.p = 10000  # the reference's default (parametric.py:434)
+        if (self.p is None) == (self.q is None):
+            raise ValueError('One and only one of p (or f1) or q (or f2) must be None!')
+        OE.__init__(self, *args, **kwargs)
+        self._reset_pq()
+
+    def _reset_pq(self):  # parametric.py:405-430
+        absPitch = _abs_pitch_to_axis(self)
+        if self.p is None:
+            self.y0 = self.q * np.cos(absPitch)
+            self.z0 = self.q * np.sin(absPitch)
+            self.parabParam = -self.q * np.sin(absPitch)**2
+            gamma = absPitch
+        else:
+            self.y0 = -self.p * np.cos(absPitch)
+            self.z0 = self.p * np.sin(absPitch)
+            self.parabParam = self.p * np.sin(absPitch)**2
+            gamma = -absPitch
+        self.cosGamma = np.cos(gamma)
+        self.sinGamma = np.sin(gamma)
+
+    _pp2 = property(lambda self: self.parabParam**2)
+    _isCyl = property(lambda self: 1. if self.isCylindrical else 0.)
+
+
+ParabolicMirror = ParabolicalMirrorParam
+
+LIBRARY = (BentFlatMirror, ConicalMirror, JohannCylinder, JohanssonCylinder, JohannToroid, ParabolicalMirrorParam)
 
 
 def prebuild(verbose=False):
