@@ -50,6 +50,16 @@ class Beam(object):
                 setattr(self, k, v[indarr])
 
 
+def concatenate(self, beam):
+    """Beam.concatenate (beams.py:230-295): the geometric / coherency fields and the optional per-ray extras
+    (nRefl, s, phi, r, theta, order, Es, Ep) are stacked."""
+    for k in ('state', 'x', 'y', 'z', 'a', 'b', 'c', 'path', 'E', 'Jss', 'Jpp', 'Jsp'):
+        setattr(self, k, np.concatenate((getattr(self, k), getattr(beam, k))))
+    for k in ('nRefl', 's', 'phi', 'r', 'theta', 'order', 'Es', 'Ep'):
+        if hasattr(self, k) and hasattr(beam, k):
+            setattr(self, k, np.concatenate((getattr(self, k), getattr(beam, k))))
+
+
 def rotate_x(y, z, cosangle, sinangle):
     return cosangle*y - sinangle*z, sinangle*y + cosangle*z
 

@@ -21,6 +21,7 @@ from .physconsts import CH, CHBAR
 zEps = 1e-12
 dt = 1e-5
 maxIteration = 100
+ds = 0.  # raycing.ds (raycing/__init__.py:90): margin used in multiple reflections
 maxHalfSizeOfOE = 1000.
 maxDepthOfOE = 100.
 
@@ -177,29 +178,37 @@ class OESpec(object):
 
 
 # ---------------------------------------------------------------------- intersection machinery
-def find_dz(oe, local_f, t, x0, y0, z0, a, b, c, invertNormal):
+def find_dz(oe, local_f, t, x0, y0, z0, a, b, c, invertNormal, derivOrder=0):
     x = x0 + a*t
     y = y0 + b*t
     z = z0 + c*t
-    if oe.isParametric:
+    if derivOrder == 0:
+        if oe.isParametric:
+            if local_f is None:
+                local_f = oe.local_r
+            diffSign = -1
+        else:
+            if local_f is None:
+                local_f = oe.local_z
+            diffSign = 1
+    else:  # base.py:818-820
         if local_f is None:
-            local_f = oe.local_r
-        diffSign = -1
-    else:
-        if local_f is None:
-            local_f = oe.local_z
-        diffSign = 1
+            local_f = oe.local_n
     if oe.isParametric:
         x, y, z = oe.xyz_to_param(x, y, z)
     surf = local_f(x, y)
-    ind = np.isnan(surf)
-    if ind.sum() > 0:
-        surf[ind] = 0
-    dz = (z - surf) * diffSign * invertNormal
+    if derivOrder == 0:
+        ind = np.isnan(surf)
+        if ind.sum() > 0:
+            surf[ind] = 0
+        dz = (z - surf) * diffSign * invertNormal
+    else:  # base.py:842-845: the ray direction along the surface normal
+        dz = (a*surf[-3] + b*surf[-2] + c*surf[-1]) * invertNormal
     return dz, x, y, z
 
 
-def _use_my_method(oe, local_f, t1, t2, x, y, z, a, b, c, invertNormal, dz1, dz2, tMin, tMax, x2, y2, z2, ind):
+def _use_my_method(oe, local_f, t1, t2, x, y, z, a, b, c, invertNormal, dz1, dz2, tMin, tMax, x2, y2, z2, ind,
+                   derivOrder=0):
     numit = 2
     while (ind.sum() > 0) and (numit < maxIteration):
         t = t1[ind]
@@ -212,7 +221,7 @@ def _use_my_method(oe, local_f, t1, t2, x, y, z, a, b, c, invertNormal, dz1, dz2
         swap = t2[ind] > tMax
         t2[np.where(ind)[0][swap]] = tMax
         dz2[ind], x2[ind], y2[ind], z2[ind] = find_dz(
-            oe, local_f, t2[ind], x[ind], y[ind], z[ind], a[ind], b[ind], c[ind], invertNormal)
+            oe, local_f, t2[ind], x[ind], y[ind], z[ind], a[ind], b[ind], c[ind], invertNormal, derivOrder)
         swap = np.sign(dz2[ind]) == np.sign(dz1[ind])
         t1[np.where(ind)[0][swap]] = t[swap]
         dz1[np.where(ind)[0][swap]] = dz[swap]
@@ -221,7 +230,8 @@ def _use_my_method(oe, local_f, t1, t2, x, y, z, a, b, c, invertNormal, dz1, dz2
     return t2, x2, y2, z2, numit
 
 
-def _use_Brent_method(oe, local_f, t1, t2, x, y, z, a, b, c, invertNormal, dz1, dz2, tMin, tMax, x2, y2, z2, ind):
+def _use_Brent_method(oe, local_f, t1, t2, x, y, z, a, b, c, invertNormal, dz1, dz2, tMin, tMax, x2, y2, z2, ind,
+                      derivOrder=0):
     swap = abs(dz1[ind]) < abs(dz2[ind])
     if swap.sum() > 0:
         t1[np.where(ind)[0][swap]], t2[np.where(ind)[0][swap]] =\
@@ -267,7 +277,7 @@ def _use_Brent_method(oe, local_f, t1, t2, x, y, z, a, b, c, invertNormal, dz1, 
         xs[conds] = (xa[conds] + xb[conds]) / 2.
         mf = conds
         fs, x2[ind], y2[ind], z2[ind] = find_dz(
-            oe, local_f, xs, x[ind], y[ind], z[ind], a[ind], b[ind], c[ind], invertNormal)
+            oe, local_f, xs, x[ind], y[ind], z[ind], a[ind], b[ind], c[ind], invertNormal, derivOrder)
         xd[:] = xc[:]
         xc[:] = xb[:]
         fc[:] = fb[:]
@@ -288,9 +298,9 @@ def _use_Brent_method(oe, local_f, t1, t2, x, y, z, a, b, c, invertNormal, dz1, 
     return t2, x2, y2, z2, numit
 
 
-def find_intersection(oe, local_f, t1, t2, x, y, z, a, b, c, invertNormal, info=None):
-    dz1, x1, y1, z1 = find_dz(oe, local_f, t1, x, y, z, a, b, c, invertNormal)
-    dz2, x2, y2, z2 = find_dz(oe, local_f, t2, x, y, z, a, b, c, invertNormal)
+def find_intersection(oe, local_f, t1, t2, x, y, z, a, b, c, invertNormal, info=None, derivOrder=0):
+    dz1, x1, y1, z1 = find_dz(oe, local_f, t1, x, y, z, a, b, c, invertNormal, derivOrder)
+    dz2, x2, y2, z2 = find_dz(oe, local_f, t2, x, y, z, a, b, c, invertNormal, derivOrder)
     tMin = t1.min()
     tMax = t2.max()
     ind1 = dz1 <= 0
@@ -306,7 +316,7 @@ def find_intersection(oe, local_f, t1, t2, x, y, z, a, b, c, invertNormal, info=
         info.update(tMin=tMin, tMax=tMax, useBrent=bool(useBrent), maxdz1=abs(dz1).max(), maxdz2=abs(dz2).max())
     method = _use_Brent_method if useBrent else _use_my_method
     t2, x2, y2, z2, numit = method(oe, local_f, t1, t2, x, y, z, a, b, c, invertNormal, dz1, dz2, tMin, tMax,
-                                   x2, y2, z2, ind)
+                                   x2, y2, z2, ind, derivOrder)
     if info is not None:
         info['numit'] = numit
     return t2, x2, y2, z2, ind1
@@ -328,7 +338,8 @@ def _set_t(xyz, abc, surfPhys=None, defSize=maxHalfSizeOfOE):
     return tMin, tMax
 
 
-def _bracketing(oe, x, y, z, a, b, c, surfPhysX, surfPhysY, mainPart, info=None):
+def _bracketing(oe, x, y, z, a, b, c, surfPhysX, surfPhysY, mainPart, info=None, isMulti=False, local_n=None,
+                invertNormal=1):
     try:
         maxa = np.max(abs(a[mainPart]))
         maxb = np.max(abs(b[mainPart]))
@@ -348,6 +359,16 @@ def _bracketing(oe, x, y, z, a, b, c, surfPhysX, surfPhysY, mainPart, info=None)
     if info is not None:
         info.update(axis=axis, maxa=maxa, maxb=maxb, maxc=maxc)
     tMin[tMin < -1e6*zEps] = -1e6*zEps
+    if isMulti:  # base.py:1279-1289: leave the surface first -- the root of the direction along the normal
+        tMin[:] = 0
+        tMaxTmp = np.copy(tMax)
+        infoD = {} if info is not None else None
+        tMax, _, _, _, _ = find_intersection(oe, local_n, tMin, tMax, x, y, z, a, b, c, invertNormal, infoD,
+                                             derivOrder=1)
+        if info is not None:
+            info['deriv'] = infoD
+        tMin = tMax + ds
+        tMax = tMaxTmp
     return tMin, tMax
 
 
@@ -392,7 +413,7 @@ def _grating_deflection(goodN, lb, g, oeNormal, beamInDotNormal, order=1, sig=No
 
 def reflect_local(oe, good, lb, vlb, pitch, roll, yaw, dx=None, dy=None, dz=None, local_n=None, material=None,
                   is2ndXtal=False, surfPhysX=None, surfPhysY=None, surfOptX=None, surfOptY=None, info=None,
-                  noIntersectionSearch=False, fromVacuum=True):
+                  noIntersectionSearch=False, fromVacuum=True, isMulti=False):
     if local_n is None:
         local_n = oe.local_n
     if surfPhysX is None:
@@ -417,7 +438,7 @@ def reflect_local(oe, good, lb, vlb, pitch, roll, yaw, dx=None, dy=None, dz=None
     tMax = np.zeros_like(lb.x)
     tMin[good], tMax[good] = _bracketing(
         oe, lb.x[good], lb.y[good], lb.z[good], lb.a[good], lb.b[good], lb.c[good], surfPhysX, surfPhysY,
-        mainPartForBracketing, info)
+        mainPartForBracketing, info, isMulti=isMulti, local_n=local_n, invertNormal=invertNormal)
     if noIntersectionSearch:  # reflect.py:676-681
         tMax[good] = 0.
         if oe.isParametric:
@@ -595,6 +616,50 @@ def reflect(oe, beam, needLocal=True, createdByDiffract=False, info=None, noInte
     if notGood.sum() > 0:
         ob.copy_beam(gb, beam, notGood)
     return gb, lb
+
+
+def multiple_reflect(oe, beam, maxReflections=1000, infos=None):
+    """OE.multiple_reflect (reflect.py:165-264) without the elevation map.  gb and lb are ONE object there, so every
+    pass works in place on the virgin-local beam; lbN stacks the passes with Beam.concatenate (beams.py:230-295)."""
+    gb = ob.Beam(copyFrom=beam)
+    lb = gb
+    good = beam.state > 0
+    if good.sum() == 0:
+        return gb, lb
+    ob.global_to_virgin_local(oe.azimuth, beam, lb, oe.center, good)
+    iRefl = 0
+    isMulti = False
+    while iRefl < maxReflections:
+        tmpX, tmpY, tmpZ = np.copy(lb.x[good]), np.copy(lb.y[good]), np.copy(lb.z[good])
+        info = {} if infos is not None else None
+        reflect_local(oe, good, lb, gb, oe.pitch, oe.roll, oe.yaw, oe.dx, material=oe.material, info=info,
+                      isMulti=isMulti)
+        if infos is not None:
+            infos.append(info)
+        if iRefl == 0:
+            isMulti = True
+            lb.nRefl = np.zeros_like(lb.state)
+        ov = lb.state[good] == 3
+        lb.x[np.where(good)[0][ov]] = tmpX[ov]
+        lb.y[np.where(good)[0][ov]] = tmpY[ov]
+        lb.z[np.where(good)[0][ov]] = tmpZ[ov]
+        good = (lb.state == 1) | (lb.state == 2)
+        lb.nRefl[good] += 1
+        if iRefl == 0:
+            lbN = ob.Beam(copyFrom=lb)
+        else:
+            ob.concatenate(lbN, lb)
+        iRefl += 1
+        if good.sum() == 0:
+            break
+    goodAfter = gb.nRefl > 0
+    gb.state[goodAfter] = 1
+    if goodAfter.sum() > 0:
+        ob.virgin_local_to_global(oe.azimuth, gb, oe.center, goodAfter)
+    notGood = ~goodAfter
+    if notGood.sum() > 0:
+        ob.copy_beam(gb, beam, notGood)
+    return gb, lbN
 
 
 def double_reflect(dcm, beam, needLocal=True, info1=None, info2=None, fromVacuum1=True, fromVacuum2=True):

@@ -1044,7 +1044,31 @@ def gen_spliced():
              Rm=float(oe.Rm), Rs=float(getattr(oe, 'Rs', 0.)), **d)
 
 
-SECTIONS = {'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+def gen_multi():
+    """OE.multiple_reflect (oes/reflect.py:165-264): whispering-gallery passes along a strongly bent mirror -- the
+    meridional cylinder BentFlatMirror and a ToroidMirror -- up to 8 reflections, rays lost / over on the way."""
+    bl = raycing.BeamLine()
+    Au = rm.Material('Au', rho=19.3)
+    for name, cls, kw in (('bentflat', roe.BentFlatMirror, dict(R=2000.)),
+                          ('toroid', roe.ToroidMirror, dict(R=2000., r=60.))):
+        beam = _source_beam(bl, 600, 301, dx=0.05, dz=0.02, dxprime=1e-4, dzprime=5e-4, energies=(8000, 9000))
+        oe = cls(bl, 'wg', center=(0, 1000, 4.9 if name == 'bentflat' else 2.4), pitch=0.05, material=Au,
+                 limPhysX=[-5, 5], limPhysY=[-100, 100], **kw)
+        gb, lbN = oe.multiple_reflect(beam, maxReflections=8)
+        d = {}
+        d.update(beam_dict(beam, 'in_'))
+        d.update(beam_dict(gb, 'gb_'))
+        d.update(beam_dict(lbN, 'lbN_'))
+        d['gb_nRefl'] = gb.nRefl
+        d['lbN_nRefl'] = lbN.nRefl
+        d['footprints'] = np.array(oe.footprint)
+        d.update(_oe_params(oe))
+        print(name, 'passes', len(oe.footprint), 'nRefl', dict(zip(*np.unique(gb.nRefl, return_counts=True))),
+              'state', dict(zip(*np.unique(gb.state, return_counts=True))))
+        save('multi_reflect_' + name, rho=19.3, R=float(oe.R), r=float(getattr(oe, 'r', 0.)), **d)
+
+
+SECTIONS = {'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)
