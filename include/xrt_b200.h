@@ -190,6 +190,12 @@ typedef struct xrt_oe_params {
   double g_rho0, g_coef[8];
   double g_order;         /* diffraction order (a single int in the reference's OE.order) */
   double g_amp;           /* >= 0: amplitude sqrt(efficiency) of that order (material.py:391-413); < 0: none */
+  /* f4: OE.multiple_reflect (oes/reflect.py:165-264) */
+  int multi;              /* 1: one pass of multiple_reflect -- gb receives EVERY traced ray in virgin-local coordinates
+                             with its new state (gb and lb are one beam there), rays over the edge keep their entry
+                             point (:224-227), gb.theta is written when present; input is virgin local */
+  const double* multi_tmin; /* passes after the first: per-ray lower bracket end = the derivative-stage root
+                             (xrt_reflect_multi_deriv_f64; base.py:1279-1289); NULL: the usual _set_t bracket */
 } xrt_oe_params;
 
 /* Material = what get_amplitude reads (materials/material.py:348-493, materials/crystal.py:492-645). */
@@ -244,6 +250,15 @@ typedef struct xrt_multilayer_params {
 int xrt_reflect_f64(size_t n, const xrt_oe_params* oe, const xrt_material_params* mat, const double* tables,
                     size_t table_len, const xrt_beam* in, const xrt_beam* fallback, const xrt_beam* gb,
                     const xrt_beam* lb, uint64_t* reductions, int phase, uint64_t index_offset, void* stream);
+/* f4: derivative stage of OE.multiple_reflect -- `_bracketing(isMulti=True)` (oes/base.py:1279-1289) calls
+ * find_intersection(local_n, tMin = 0, tMax, ..., derivOrder = 1) (base.py:848-885 with find_dz :818-820, :842-845):
+ * the root of (ray direction . surface normal) along each ray, i.e. where the ray is farthest from the surface it has
+ * just left.  Run after pre-pass A of xrt_reflect_f64 (phase 1) on the same `reductions`:
+ *   phase 1: beam-wide scalars of that search (t2.max(), secant-vs-Brent switch) -> slots 40..43;
+ *   phase 2: per-ray roots -> tD[n] (rays that are not traced keep their tD untouched).
+ * Then xrt_reflect_f64 phases 4 | 2 with xrt_oe_params.multi_tmin = tD search the next intersection. */
+int xrt_reflect_multi_deriv_f64(size_t n, const xrt_oe_params* oe, const xrt_beam* in, uint64_t* reductions,
+                                double* tD, int phase, void* stream);
 /* decode one reduction slot to double (host helper; slots are order-preserving integer encodings) */
 double xrt_reduction_decode(uint64_t slot);
 

@@ -33,3 +33,51 @@ def test_oracle_multiple_reflect_bit_exact(name):
     assert len(lbN.x) == 8 * len(gb.x) == len(lbN.Es)
     assert np.array_equal(np.array([i['footprint'] for i in infos]), g['footprints'])
     assert gb.nRefl.max() == 8 and (gb.nRefl == 3).sum() > 20
+
+
+def _product_oe(name, g):
+    from xrt_b200 import oes, materials
+    kw = product_oe_kwargs(g)
+    kw['material'] = materials.Material('Au', rho=float(g['rho']))
+    if name == 'toroid':
+        oe = oes.ToroidMirror(product_beamline(g), name, R=float(g['R']), r=float(g['r']), **kw)
+    else:
+        oe = oes.BentFlatMirror(product_beamline(g), name, R=float(g['R']), **kw)  # a spliced surface (plug-in)
+    oe.lostNum = int(g['lostNum'])
+    return oe
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', CASES)
+def test_cuda_multiple_reflect_vs_reference_golden(name, cuda_device):
+    """Every pass, every ray: states and reflection counts identical, geometry / coherency / amplitudes to 1e-12 of the
+    group scales -- after 8 consecutive intersections, i.e. the solver iterates stay on the reference's (|dt| <= 2e-12
+    mm per pass would already show up as 1e-4 rad in exp(i k t))."""
+    g = golden('multi_reflect_' + name)
+    oe = _product_oe(name, g)
+    gb, lbN = oe.multiple_reflect(device_beam(oracle_beam(g, 'in_')), maxReflections=8)
+    assert len(lbN) == len(g['lbN_x']) and len(oe.footprint) == len(g['footprints'])
+    dgb, dlb = gb.to_numpy(), lbN.to_numpy()
+    assert np.array_equal(dgb['nRefl'], g['gb_nRefl']) and np.array_equal(dlb['nRefl'], g['lbN_nRefl'])
+    bad = compare_beams(dgb, {f: g['gb_' + f] for f in BEAM_FIELDS}, BEAM_FIELDS, 1e-12, 'gb_')
+    bad += compare_beams(dlb, {f: g['lbN_' + f] for f in BEAM_FIELDS + ('theta',)}, BEAM_FIELDS + ('theta',), 1e-12,
+                         'lbN_')
+    assert not bad, bad
+    np.testing.assert_allclose(np.array(oe.footprint), g['footprints'], rtol=1e-12, atol=1e-12)
+    assert np.abs(dlb['path'] - g['lbN_path']).max() <= 2e-12 * 8
+
+
+@pytest.mark.gpu
+def test_cuda_multiple_reflect_single_pass_equals_reflect(cuda_device):
+    """maxReflections = 1 is one reflect: the global beam of the good rays is OE.reflect's."""
+    g = golden('multi_reflect_toroid')
+    oe = _product_oe('toroid', g)
+    beam = device_beam(oracle_beam(g, 'in_'))
+    gb1, _ = oe.multiple_reflect(beam, maxReflections=1)
+    gb2, _ = oe.reflect(beam)
+    d1, d2 = gb1.to_numpy(), gb2.to_numpy()
+    good = d2['state'] == 1
+    assert good.sum() > 100 and np.array_equal(d1['state'] == 1, good)
+    for f in BEAM_FIELDS:
+        if f != 'state':
+            assert np.array_equal(d1[f][good], d2[f][good]), f

@@ -417,6 +417,12 @@ int xrt_reflect_f64(size_t n, const xrt_oe_params* oe, const xrt_material_params
                         reinterpret_cast<unsigned long long*>(reductions), phase, index_offset, (cudaStream_t)stream);
 }
 
+int xrt_reflect_multi_deriv_f64(size_t n, const xrt_oe_params* oe, const xrt_beam* in, uint64_t* reductions,
+                                double* tD, int phase, void* stream) {
+  return reflect_multi_deriv_device(n, oe, in, reinterpret_cast<unsigned long long*>(reductions), tD, phase,
+                                    (cudaStream_t)stream);
+}
+
 double xrt_reduction_decode(uint64_t slot) { return reduction_decode(slot); }
 
 // ------------------------------------------------------------------ plane elements

@@ -57,11 +57,13 @@ enum {
   RS_VAR = 4,    // 6 variants (axis * 2 + neg) x {min t1, max t2, max |dz1|, max |dz2| masked} (base.py:861-871)
   RS_FOOT = 28,  // footprint min x,y,z / max x,y,z of the virgin-local output (reflect.py:1133-1136)
   RS_NGOOD = 34, // number of rays with state > 0 on entry (plain integer count)
-  RS_NGOODN = 35 // number of rays with state == 1 after the surface (plain integer count)
+  RS_NGOODN = 35, // number of rays with state == 1 after the surface (plain integer count); 36: out-of-table count
+  RS_DERIV = 40   // multiple_reflect, derivative stage: {min t1, max t2, max |dz1|, max |dz2| masked} (base.py:861-871)
 };
 constexpr double kZEps = 1e-12;      // raycing.zEps   (raycing/__init__.py:86)
 constexpr double kDt = 1e-5;         // raycing.dt     (:89)
 constexpr int kMaxIteration = 100;   // raycing.maxIteration (:92)
+constexpr double kDs = 0.0;          // raycing.ds     (:90) margin used in multiple reflections
 constexpr double kPi = 3.141592653589793;
 
 __host__ __device__ inline unsigned long long enc(double d) {
@@ -232,14 +234,26 @@ __device__ __forceinline__ void param_to_xyz(const xrt_oe_params& p, double& x, 
   z = zN + p.sp[3];
 }
 
-// find_dz (base.py:801-846), derivOrder = 0; invertNormal = 1 from vacuum, -1 from inside a plate / lens
-template <int SURF, bool REFR = true>
+template <int SURF>
+__device__ __forceinline__ void local_normal(const xrt_oe_params& p, const SurfDiv& sd, double x, double y,
+                                             double* n);
+
+// find_dz (base.py:801-846); invertNormal = 1 from vacuum, -1 from inside a plate / lens.  DERIV = 0: the z (or r)
+// difference between the ray and the surface; DERIV = 1 (multiple_reflect, base.py:818-820, :842-845): the ray
+// direction along the surface normal at the point, whose root is where the ray is farthest from the surface
+template <int SURF, bool REFR = true, int DERIV = 0>
 __device__ __forceinline__ double find_dz(const xrt_oe_params& p, const SurfDiv& sd, double t, const Ray& r,
                                           double& x, double& y, double& z) {
   x = r.x + r.a * t;
   y = r.y + r.b * t;
   z = r.z + r.c * t;
   xyz_to_param<SURF>(p, x, y, z);
+  if (DERIV == 1) {
+    double n[6];
+    local_normal<SURF>(p, sd, x, y, n);
+    const double dn = r.a * n[3] + r.b * n[4] + r.c * n[5];
+    return (REFR && p.from_vacuum == 0) ? -dn : dn;
+  }
   double surf = local_surface<SURF>(p, sd, x, y);
   if (isnan(surf)) surf = 0.0;
   double d = z - surf;
@@ -368,7 +382,8 @@ __global__ void reduction_init_kernel(unsigned long long* red) {
   if (i == RS_FIRST) v = ~0ull;
   if (i >= RS_VAR && i < RS_VAR + 24 && ((i - RS_VAR) & 3) == 0) v = enc(inf);  // min t1
   if (i >= RS_FOOT && i < RS_FOOT + 3) v = enc(inf);
-  if (i == RS_NGOOD || i == RS_NGOODN || i > RS_NGOODN) v = 0ull;
+  if (i == RS_DERIV) v = enc(inf);
+  if (i == RS_NGOOD || i == RS_NGOODN || (i > RS_NGOODN && i < RS_DERIV) || i >= RS_DERIV + 4) v = 0ull;
   red[i] = v;
 }
 
@@ -485,6 +500,7 @@ __global__ void __launch_bounds__(256) reflect_prepass_kernel(size_t n, xrt_oe_p
     to_local(p, r);
     double t1, t2, x, y, z;
     bracket(p, axis, neg, r, t1, t2);
+    if (p.multi_tmin) t1 = p.multi_tmin[i] + kDs;  // base.py:1288: tMin = tMax(derivative root) + ds
     const double dz1 = find_dz<SURF>(p, sd, t1, r, x, y, z);
     double dz2 = find_dz<SURF>(p, sd, t2, r, x, y, z);
     if (dz1 <= 0.0 || dz2 >= 0.0) dz2 = 0.0;  // base.py:865 dz2[ind1 | ind2] = 0
@@ -979,7 +995,7 @@ __device__ __forceinline__ Decision decide(const unsigned long long* red) {
 
 __device__ __forceinline__ int sgn(double v) { return (v > 0.0) - (v < 0.0); }
 
-template <int SURF, bool REFR>
+template <int SURF, bool REFR, int DERIV = 0>
 __device__ __forceinline__ void solve_secant(const xrt_oe_params& p, const SurfDiv& sd, const Ray& r,
                                              const Decision& d, double& t1,
                                              double& t2, double& dz1, double& dz2, double& x2, double& y2,
@@ -993,7 +1009,7 @@ __device__ __forceinline__ void solve_secant(const xrt_oe_params& p, const SurfD
     t2 = t - (t1 - t) * dz / (dz1 - dz);
     if (t2 < d.tMin) t2 = d.tMin;
     if (t2 > d.tMax) t2 = d.tMax;
-    dz2 = find_dz<SURF, REFR>(p, sd, t2, r, x2, y2, z2);
+    dz2 = find_dz<SURF, REFR, DERIV>(p, sd, t2, r, x2, y2, z2);
     // np.sign(dz2) == np.sign(dz1) (base.py:951): inside this loop dz1 is never 0 or NaN (it starts > 0 and only
     // takes values of earlier dz2 with |dz2| > zEps), and when dz2 is 0 or NaN the loop ends right here with t1, dz1
     // unused -- so the comparison of the sign bits decides every case that matters, on the integer pipe
@@ -1005,7 +1021,7 @@ __device__ __forceinline__ void solve_secant(const xrt_oe_params& p, const SurfD
   }
 }
 
-template <int SURF, bool REFR>
+template <int SURF, bool REFR, int DERIV = 0>
 __device__ __forceinline__ void solve_brent(const xrt_oe_params& p, const SurfDiv& sd, const Ray& r, double& t1,
                                             double& t2,
                                             double& dz1, double& dz2, double& x2, double& y2, double& z2) {
@@ -1038,7 +1054,7 @@ __device__ __forceinline__ void solve_brent(const xrt_oe_params& p, const SurfDi
     const bool conds = cond1 || cond2 || cond3 || cond4 || cond5;
     if (conds) xs = (xa + xb) / 2.0;
     mflag = conds;
-    const double fs = find_dz<SURF, REFR>(p, sd, xs, r, x2, y2, z2);
+    const double fs = find_dz<SURF, REFR, DERIV>(p, sd, xs, r, x2, y2, z2);
     xd = xc;
     xc = xb;
     fc = fb;
@@ -1066,6 +1082,84 @@ __device__ __forceinline__ void solve_brent(const xrt_oe_params& p, const SurfDi
     dz2 = fb;
     dz3 = fc;
     ++numit;
+  }
+}
+
+// ---------------------------------------------------------------- multiple_reflect: derivative stage
+// _bracketing(isMulti=True) (base.py:1279-1289): before the next intersection is searched, the ray has to leave the
+// surface -- find_intersection(local_n, tMin = 0, tMax, derivOrder = 1) finds the root of (ray direction . surface
+// normal) along the ray.  Phase 1 reduces that search's beam-wide scalars (t2.max(), the secant-vs-Brent switch) into
+// the RS_DERIV slots, phase 2 solves per ray and stores the root, which the z stage then uses as its tMin.
+template <int SURF, int PHASE>
+__global__ void __launch_bounds__(256) multi_deriv_kernel(size_t n, xrt_oe_params p, xrt_beam in,
+                                                          unsigned long long* red, double* __restrict__ tD) {
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  int axis, neg;
+  decide_variant(red, axis, neg);
+  double v[4] = {inf, -inf, -inf, -inf};
+  Decision d;
+  if (PHASE == 2) {
+    d.axis = axis;
+    d.neg = neg;
+    d.tMin = dec(red[RS_DERIV + 0]);
+    d.tMax = dec(red[RS_DERIV + 1]);
+    d.brent = (dec(red[RS_DERIV + 3]) > dec(red[RS_DERIV + 2]) * 20.0) ? 1 : 0;
+  }
+  const SurfDiv sd = make_surf_div<SURF>(p);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int st = in.state[i];
+    if (!(p.good_mode ? (st == 1 || st == 2) : (st > 0))) continue;
+    Ray r = load_ray(in, i);
+    to_local(p, r);
+    double t1, t2, x, y, z;
+    bracket(p, axis, neg, r, t1, t2);
+    t1 = 0.0;  // tMin[:] = 0 (base.py:1280)
+    double dz1 = find_dz<SURF, true, 1>(p, sd, t1, r, x, y, z);
+    double dz2 = find_dz<SURF, true, 1>(p, sd, t2, r, x, y, z);
+    const bool ind1 = dz1 <= 0.0, ind2 = dz2 >= 0.0;
+    if (ind1 || ind2) dz2 = 0.0;
+    if (PHASE == 1) {
+      v[0] = (t1 < v[0] || isnan(t1)) ? t1 : v[0];
+      v[1] = (t2 > v[1] || isnan(t2)) ? t2 : v[1];
+      v[2] = (fabs(dz1) > v[2] || isnan(dz1)) ? fabs(dz1) : v[2];
+      v[3] = (fabs(dz2) > v[3] || isnan(dz2)) ? fabs(dz2) : v[3];
+    } else {
+      if (ind1) t2 = t1;
+      if (!(ind1 || ind2)) {
+        if (d.brent)
+          solve_brent<SURF, true, 1>(p, sd, r, t1, t2, dz1, dz2, x, y, z);
+        else
+          solve_secant<SURF, true, 1>(p, sd, r, d, t1, t2, dz1, dz2, x, y, z);
+      }
+      tD[i] = t2;
+    }
+  }
+  if (PHASE == 2) return;
+  __shared__ unsigned long long sh[8][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    unsigned long long x = enc(v[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long y = __shfl_xor_sync(0xffffffffu, x, o);
+      x = (k == 0) ? (y < x ? y : x) : (y > x ? y : x);
+    }
+    if (lane == 0) sh[warp][k] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    const int k = threadIdx.x;
+    unsigned long long x = sh[0][k];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      const unsigned long long y = sh[w][k];
+      x = (k == 0) ? (y < x ? y : x) : (y > x ? y : x);
+    }
+    if (k == 0)
+      atomicMin(&red[RS_DERIV + k], x);
+    else
+      atomicMax(&red[RS_DERIV + k], x);
   }
 }
 
@@ -1123,6 +1217,7 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
     if (!(p.good_mode ? (st0 == 1 || st0 == 2) : (st0 > 0))) {
       // rays that are not alive pass through untouched (gb = lb = copy of the input, reflect.py:104-109)
       copy_ray(gb, in, i, p.dead_state_lost ? p.lostNum : st0, true);  // Plate: dcm.py:311-312
+      if (p.multi && gb.theta) gb.theta[i] = 0.0;  // lb.theta = zeros_like(lb.x) in every pass (reflect.py:789)
       if (hasLb) {
         copy_ray(lb, in, i, st0, true);
         if (p.zero_dead_local) {  // dcm.py:305-310
@@ -1156,6 +1251,7 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
       } else {
         // bracketing + intersection (base.py:848-885)
         bracket(p, d.axis, d.neg, r, t1, t2);
+        if (p.multi_tmin) t1 = p.multi_tmin[i] + kDs;  // multiple_reflect, passes after the first (base.py:1288)
         double dz1 = find_dz<SURF, MAT == 5>(p, sd, t1, r, x1, y1, z1);
         double dz2 = find_dz<SURF, MAT == 5>(p, sd, t2, r, x2, y2, z2);
         ind1 = dz1 <= 0.0;             // lost: solution t1
@@ -1218,7 +1314,7 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
         bdn = la * nrm[0] + lbb * nrm[1] + lc * nrm[2];
         if (bdn < -1.0) bdn = -1.0;
         if (bdn > 1.0) bdn = 1.0;
-        if (hasLb && lb.theta) theta = acos(bdn) - kPi / 2;  // only the local beam carries theta
+        if ((hasLb && lb.theta) || (p.multi && gb.theta)) theta = acos(bdn) - kPi / 2;  // the local beam's theta
         bds = p.asymmetric ? (la * nrm[3] + lbb * nrm[4] + lc * nrm[5]) : bdn;
         double ao, bo, co;
         const bool transmitted = (MAT == 3) && (m.geom & 2);  // toWhere = 2 (reflect.py:756, :862-878)
@@ -1310,7 +1406,9 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
         if (lb.theta) lb.theta[i] = theta;
       }
       // virgin-local beam -> global (reflect.py:1112-1136, :125-135)
-      const bool goodAfter = p.created_by_diffract ? (st == 1) : (st == 1 || st == 2);
+      // multiple_reflect (reflect.py:205-232): gb and lb are one beam there, so EVERY traced ray leaves in virgin-local
+      // coordinates with its new state; rays that went over the edge get their entry point back (:224-227)
+      const bool goodAfter = p.multi ? true : (p.created_by_diffract ? (st == 1) : (st == 1 || st == 2));
       {
         Ray v{cx, cy, cz, la, lbb, lc};
         to_virgin(p, v);
@@ -1320,6 +1418,18 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
         fmax3[0] = v.x;
         fmax3[1] = v.y;
         fmax3[2] = v.z;
+        if (p.multi && st == 3) {  // tmpX, tmpY, tmpZ: the entry point in virgin-local coordinates (after the footprint)
+          double wx = in.x[i], wy = in.y[i], wz = in.z[i];
+          if (p.from_global) {
+            wx -= p.center[0];
+            wy -= p.center[1];
+            wz -= p.center[2];
+            if (p.sinAz != 0.0) rot_axis(2, p.cosAz, p.sinAz, wx, wy, wz);
+          }
+          v.x = wx;
+          v.y = wy;
+          v.z = wz;
+        }
         if (goodAfter) {
           if (p.to_global) virgin_to_global(p, v);
           gb.x[i] = v.x;
@@ -1329,6 +1439,7 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
           gb.b[i] = v.b;
           gb.c[i] = v.c;
           gb.state[i] = st;
+          if (p.multi && gb.theta) gb.theta[i] = theta;
         }
       }
 
@@ -1750,6 +1861,37 @@ int normals_device(size_t n, const xrt_oe_params* oe, const double* x, const dou
   return 0;
 }
 
+// multiple_reflect, derivative stage (see multi_deriv_kernel): phase 1 = beam-wide scalars, 2 = per-ray roots -> tD
+int reflect_multi_deriv_device(size_t n, const xrt_oe_params* oe, const xrt_beam* in, unsigned long long* red,
+                               double* tD, int phase, cudaStream_t st) {
+  XRTB_REQUIRE(oe && in && red && tD, "reflect_multi_deriv: NULL argument");
+  XRTB_REQUIRE(phase == 1 || phase == 2, "reflect_multi_deriv: phase is 1 (scalars) or 2 (roots)");
+  if (n == 0) return 0;
+  unsigned grid = (unsigned)num_sms() * 8;
+  const size_t need = (n + 255) / 256;
+  if (need < grid) grid = (unsigned)need;
+#define XRTB_LAUNCH_DERIV(S)                                                             \
+  do {                                                                                   \
+    if (phase == 1)                                                                      \
+      multi_deriv_kernel<S, 1><<<grid, 256, 0, st>>>(n, *oe, *in, red, tD);             \
+    else                                                                                 \
+      multi_deriv_kernel<S, 2><<<grid, 256, 0, st>>>(n, *oe, *in, red, tD);             \
+  } while (0)
+#ifdef XRTB_PLUGIN
+  XRTB_REQUIRE(oe->surface == XRTB_USER_KIND, "reflect_multi_deriv (plug-in): surface kind %d expected", XRTB_USER_KIND);
+  XRTB_LAUNCH_DERIV(XRTB_USER_KIND);
+#else
+  XRTB_REQUIRE(oe->surface >= 0 && oe->surface <= 2, "reflect_multi_deriv: surface kind %d has no multiple_reflect",
+               oe->surface);
+  if (oe->surface == 0) XRTB_LAUNCH_DERIV(0);
+  if (oe->surface == 1) XRTB_LAUNCH_DERIV(1);
+  if (oe->surface == 2) XRTB_LAUNCH_DERIV(2);
+#endif
+#undef XRTB_LAUNCH_DERIV
+  XRTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 double reduction_decode(unsigned long long slot) { return dec(slot); }
 
 }  // namespace xrtb
@@ -1774,6 +1916,11 @@ XRTB_EXPORT int xrt_plugin_oe_surface_f64(size_t n, const xrt_oe_params* oe, con
 XRTB_EXPORT int xrt_plugin_oe_normals_f64(size_t n, const xrt_oe_params* oe, const double* x, const double* y,
                                           const double* z, double* nx, double* ny, double* nz, void* stream) {
   return xrtb::normals_device(n, oe, x, y, z, nx, ny, nz, (cudaStream_t)stream);
+}
+XRTB_EXPORT int xrt_plugin_reflect_multi_deriv_f64(size_t n, const xrt_oe_params* oe, const xrt_beam* in,
+                                                   uint64_t* reductions, double* tD, int phase, void* stream) {
+  return xrtb::reflect_multi_deriv_device(n, oe, in, reinterpret_cast<unsigned long long*>(reductions), tD, phase,
+                                          (cudaStream_t)stream);
 }
 XRTB_EXPORT size_t xrt_plugin_sizeof_oe_params(void) { return sizeof(xrt_oe_params); }
 XRTB_EXPORT int xrt_plugin_surface_kind(void) { return XRTB_USER_KIND; }

@@ -49,7 +49,8 @@ class xrt_oe_params(ctypes.Structure):
                 ('good_mode', ctypes.c_int), ('want_footprint', ctypes.c_int),
                 ('no_intersection', ctypes.c_int), ('from_vacuum', ctypes.c_int), ('dead_state_lost', ctypes.c_int),
                 ('grating', ctypes.c_int), ('g_ncoef', ctypes.c_int), ('g_rho0', ctypes.c_double),
-                ('g_coef', ctypes.c_double * 8), ('g_order', ctypes.c_double), ('g_amp', ctypes.c_double)]
+                ('g_coef', ctypes.c_double * 8), ('g_order', ctypes.c_double), ('g_amp', ctypes.c_double),
+                ('multi', ctypes.c_int), ('multi_tmin', ctypes.c_void_p)]
 
 
 _AXIS = {'x': 0, 'y': 1, 'z': 2}
@@ -283,7 +284,7 @@ class OE(object):
             p.g_amp = float(resI)**0.5
 
     # ------------------------------------------------------------------ kernel launch
-    def _launch(self, params, material, beam, gb, lb, fallback=None, index_offset=0, allreduce=None):
+    def _launch(self, params, material, beam, gb, lb, fallback=None, index_offset=0, allreduce=None, phases=None):
         lib = _lib.load()
         dev = beam.device
         key = str(dev)
@@ -313,7 +314,10 @@ class OE(object):
         profile = getattr(self, 'profileEvents', None)
         plugin = self._plugin()
         xrt_reflect_f64 = lib.xrt_reflect_f64 if plugin is None else plugin.reflect
-        if allreduce is None and profile is None:
+        if phases is not None:  # multiple_reflect interleaves the derivative stage between the phases
+            for ph in phases:
+                _lib.check(xrt_reflect_f64(*args, ph, index_offset, stream), 'xrt_reflect_f64')
+        elif allreduce is None and profile is None:
             _lib.check(xrt_reflect_f64(*args, 7, index_offset, stream), 'xrt_reflect_f64')
         else:
             # the three phases as separate calls: ray shards all-reduce the beam-wide scalars (min/max/sum over
@@ -452,6 +456,89 @@ class OE(object):
             lb.parentId = lb_parent
         return gb, (lb if needLocal else gb)
 
+
+    def multiple_reflect(self, beam=None, maxReflections=1000, needElevationMap=False, returnLocalAbsorbed=None):
+        """OE.multiple_reflect (oes/reflect.py:165-264): like reflect, with up to *maxReflections* reflections on the
+        same surface.  Returns (beamGlobal, beamLocalN): beamGlobal carries *nRefl*; beamLocalN stacks the passes (all
+        footprints, virgin-local coordinates as in the reference, where gb and lb are one beam), *nRefl* and *theta*
+        included.  Every pass is the fused reflect kernel in its `multi` mode; passes after the first are preceded by
+        the derivative stage (xrt_reflect_multi_deriv_f64: the ray leaves the surface before the next intersection is
+        searched).  One host synchronisation per pass (the count of rays still alive ends the loop)."""
+        if needElevationMap:
+            raise NotImplementedError('needElevationMap is outside the hot path')
+        if self.material is not None and getattr(self.material, 'kind', 'mirror') not in ('auto', 'mirror', 'thin mirror'):
+            raise NotImplementedError('multiple_reflect is on the hot path for mirrors (and bare surfaces)')
+        lib = _lib.load()
+        plugin = self._plugin()
+        deriv = lib.xrt_reflect_multi_deriv_f64 if plugin is None else plugin.reflect_multi_deriv
+        self.footprint = []
+        n = len(beam)
+        dev = beam.device
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        nRefl = torch.zeros(n, dtype=torch.int32, device=dev)
+        tD = torch.empty(n, dtype=torch.float64, device=dev)
+        cur = beam
+        passes = []
+        if int((beam.state > 0).sum()) == 0:  # reflect.py:200-201
+            gb = Beam(copyFrom=beam)
+            return gb, gb
+        for iRefl in range(int(maxReflections)):
+            params = self._make_params(self.pitch, self.roll + self.positionRoll, self.yaw, self.dx,
+                                       from_global=(iRefl == 0), to_global=False)
+            params.multi = 1
+            params.good_mode = 0 if iRefl == 0 else 1  # state > 0, then state in (1, 2) (reflect.py:198, :228)
+            out = cur.like()
+            out.theta = torch.empty(n, dtype=torch.float64, device=dev)
+            if iRefl == 0:
+                red = self._launch(params, self.material, cur, out, None)
+            else:
+                # pre-pass A, derivative stage (scalars, roots), then pre-pass B + main pass from the roots
+                red = self._launch(params, self.material, cur, out, None, phases=(1,))
+                cin = cur.c_struct()
+                for ph in (1, 2):
+                    _lib.check(deriv(n, ctypes.byref(params), ctypes.byref(cin), red.data_ptr(), tD.data_ptr(), ph,
+                                     stream), 'xrt_reflect_multi_deriv_f64')
+                params.multi_tmin = tD.data_ptr()
+                red = self._launch(params, self.material, cur, out, None, phases=(6,))
+            self._check_tables(red)
+            self.footprint.append(self._footprint_from(red))
+            good = (out.state == 1) | (out.state == 2)
+            nRefl = nRefl + good.to(torch.int32)
+            out.nRefl = nRefl.clone()
+            ngood, ngoodN = torch.stack((good.sum(), (out.state == 1).sum())).tolist()
+            if ngoodN == 0 and passes:
+                out.theta = passes[-1].theta.clone()  # lb.theta is only renewed when a ray reflects (reflect.py:789)
+            passes.append(out)
+            cur = out
+            if ngood == 0:
+                break
+        lbN = passes[0]
+        for b in passes[1:]:
+            lbN.concatenate(b)
+        # in global coordinates (reflect.py:245-253)
+        gb = Beam(copyFrom=cur)
+        gb.nRefl = nRefl
+        goodAfter = nRefl > 0
+        gb.state = torch.where(goodAfter, torch.ones_like(gb.state), gb.state)
+        a0 = self.bl.sinAzimuth if self.bl is not None else 0.
+        b0 = self.bl.cosAzimuth if self.bl is not None else 1.
+        ga, gbb, gx, gy = gb.a, gb.b, gb.x, gb.y
+        if a0 != 0:  # rotate_z(., ., b0, -a0)
+            ga, gbb = b0*gb.a - (-a0)*gb.b, (-a0)*gb.a + b0*gb.b
+            gx, gy = b0*gb.x - (-a0)*gb.y, (-a0)*gb.x + b0*gb.y
+        gx = gx + self.center[0]
+        gy = gy + self.center[1]
+        gz = gb.z + self.center[2]
+        # not intersected rays remain unchanged except their state (copy_beam without the state, :251-253)
+        for f, v in (('x', gx), ('y', gy), ('z', gz), ('a', ga), ('b', gbb), ('c', gb.c)):
+            setattr(gb, f, torch.where(goodAfter, v, getattr(beam, f)))
+        for f in ('path', 'E', 'Jss', 'Jpp', 'Jsp', 'Es', 'Ep'):
+            if hasattr(gb, f):
+                setattr(gb, f, torch.where(goodAfter, getattr(gb, f), getattr(beam, f)))
+        if hasattr(gb, 'theta'):
+            del gb.theta
+        gb.parentId = lbN.parentId = getattr(self, 'uuid', self.name)
+        return gb, lbN
 
     # ------------------------------------------------------------------ wave mode (oes/reflect.py:266-449)
     def _surface_centre_global(self):
