@@ -155,3 +155,155 @@ def shine(src, nrays, toGlobal=True, withAmplitudes=True, record=None):
     if record is not None:
         record.extend(passes)
     return bor
+
+
+class Wave(object):
+    """The fields of a prepared wave that shine(wave=...) reads and writes (waves.prepare_wave, waves.py:505-584)."""
+
+    def __init__(self, xDiffr, yDiffr, zDiffr, area, areaNormal=None):
+        n = len(xDiffr)
+        self.xDiffr, self.yDiffr, self.zDiffr = np.array(xDiffr), np.array(yDiffr), np.array(zDiffr)
+        self.area = area
+        if areaNormal is not None:
+            self.areaNormal = areaNormal
+        b = ob.Beam(n, withAmplitudes=True)
+        self.__dict__.update({k: v for k, v in b.__dict__.items() if k not in self.__dict__})
+        self.rDiffr = (self.xDiffr**2 + self.yDiffr**2 + self.zDiffr**2)**0.5
+        self.a[:] = self.xDiffr / self.rDiffr
+        self.b[:] = self.yDiffr / self.rDiffr
+        self.c[:] = self.zDiffr / self.rDiffr
+        self.Jss[:] = 0
+        self.Jpp[:] = 0
+
+
+def shine_wave(src, wave, filamentBeam=False, toGlobal=True, record=None, R0=None):
+    """IntegratedSource.shine(wave=wave) with uniformRayDensity (sybase.py:1513-1812): the receiving points of *wave*
+    (in source-local coordinates xDiffr, yDiffr, zDiffr) are illuminated; *wave* gets E, directions, J, Es, Ep (with
+    the propagation phase), the returned beam sits at the source.  Consumes np.random in the reference's order and
+    records the deviates."""
+    from .physconsts import CHBAR
+    assert src.uniformRayDensity
+    mcRays = len(wave.a)
+    rec = {}
+    dgamma = None
+    if filamentBeam:  # :1541-1552
+        rec['uE'] = np.random.random_sample()
+        rsE = rec['uE'] * float(src.E_max - src.E_min) + src.E_min
+        rec['gX'], rec['gZ'] = np.random.standard_normal(), None
+        rX = src.dx * rec['gX']
+        rec['gZ'] = np.random.standard_normal()
+        rZ = src.dz * rec['gZ']
+        rec['gT'] = np.random.standard_normal()
+        dtheta = src.dxprime * rec['gT']
+        rec['gP'] = np.random.standard_normal()
+        dpsi = src.dzprime * rec['gP']
+        if getattr(src, 'eEspread', 0) > 0:
+            rec['gG'] = np.random.standard_normal()
+            dgamma = src.gamma * src.eEspread * rec['gG']
+    seeded = np.int64(0) + mcRays
+    if filamentBeam:
+        rE = rsE * np.ones(mcRays)
+    else:
+        rec['uE'] = np.random.rand(mcRays)
+        rE = rec['uE'] * float(src.E_max - src.E_min) + src.E_min
+    src.xzE = (src.E_max - src.E_min)  # :1589
+    if filamentBeam:
+        shiftX, shiftZ = rX, rZ
+    else:
+        rec['gX'] = np.random.standard_normal(mcRays) if src.dx > 0 else None
+        shiftX = 0. + src.dx * rec['gX'] if src.dx > 0 else 0
+        rec['gZ'] = np.random.standard_normal(mcRays) if src.dz > 0 else None
+        shiftZ = 0. + src.dz * rec['gZ'] if src.dz > 0 else 0
+    x = wave.xDiffr + shiftX
+    y = wave.yDiffr
+    z = wave.zDiffr + shiftZ
+    rDiffr = np.sqrt((x**2 + y**2 + z**2))
+    rTheta = x / rDiffr
+    rPsi = z / rDiffr
+    if filamentBeam:
+        rTheta += dtheta
+        rPsi += dpsi
+    else:
+        if src.dxprime > 0:
+            rec['gT'] = np.random.standard_normal(mcRays)
+            rTheta += 0. + src.dxprime * rec['gT']
+        if src.dzprime > 0:
+            rec['gP'] = np.random.standard_normal(mcRays)
+            rPsi += 0. + src.dzprime * rec['gP']
+    gamma = src.gamma
+    if getattr(src, 'eEspread', 0) > 0:  # synchr.py:2053-2059
+        if dgamma is not None:
+            gamma = gamma + dgamma
+        else:
+            sz = 1 if filamentBeam else mcRays
+            rec['g5'] = np.random.normal(size=sz)
+            gamma = gamma + gamma * src.eEspread * rec['g5']
+    rec['gamma'] = gamma * np.ones(mcRays)
+    Intensity, mJs, mJp = ou.build_I_map(src.grid, src.L0, src.Np, src.Kx, src.Ky, src.eI, gamma * np.ones(mcRays),
+                                         rE, rTheta, rPsi, src.distE)
+    seededI = 0. + mcRays * src.xzE
+    sourceWeight = src.xzE
+    tmp_max = np.max(Intensity)
+    if tmp_max > src.Imax:
+        src.Imax = tmp_max
+        src.fluxConst = src.Imax * src.xzE
+    bot = wave
+    bot.state[:] = 1
+    bot.E[:] = rE
+    if filamentBeam:
+        dxR, dzR = rX, rZ
+    else:
+        SX, SZ = src.get_SIGMA(bot.E)
+        rec['g1'] = np.random.standard_normal(mcRays)
+        dxR = 0. + SX * rec['g1']
+        rec['g2'] = np.random.standard_normal(mcRays)
+        dzR = 0. + SZ * rec['g2']
+    wave.rDiffr = np.sqrt(((wave.xDiffr - dxR)**2 + wave.yDiffr**2 + (wave.zDiffr - dzR)**2))
+    wave.path[:] = 0
+    wave.a[:] = (wave.xDiffr - dxR) / wave.rDiffr
+    wave.b[:] = wave.yDiffr / wave.rDiffr
+    wave.c[:] = (wave.zDiffr - dzR) / wave.rDiffr
+    area = wave.areaNormal if hasattr(wave, 'areaNormal') else wave.area
+    norm = area**0.5 / wave.rDiffr
+    mJs = mJs * norm
+    mJp = mJp * norm
+    mJs2 = (mJs * np.conj(mJs)).real
+    mJp2 = (mJp * np.conj(mJp)).real
+    sSP = 1.
+    bot.Jsp[:] = np.where(sSP, mJs * np.conj(mJp) / sSP, 0)
+    bot.Jss[:] = np.where(sSP, mJs2 / sSP, 0)
+    bot.Jpp[:] = np.where(sSP, mJp2 / sSP, 0)
+    bot.Es[:] = mJs
+    bot.Ep[:] = mJp
+    bo = bot
+    length = len(bo.a)
+    bo.accepted = length * src.fluxConst
+    bo.acceptedE = bo.E.sum() * src.fluxConst * SIE0
+    bo.seeded = seeded
+    bo.seededI = seededI
+    bo.sourceWeight = sourceWeight / len(wave.a)
+    if filamentBeam:
+        bo.filamentDtheta, bo.filamentDpsi, bo.filamentDX, bo.filamentDZ = dtheta, dpsi, rX, rZ
+        bo.filamentDgamma = dgamma
+    norm = (bo.a**2 + bo.b**2 + bo.c**2)**0.5
+    bo.a /= norm
+    bo.b /= norm
+    bo.c /= norm
+    if src.pitch or src.yaw:
+        ob.rotate_beam(bo, pitch=src.pitch, yaw=src.yaw)
+    bor = ob.Beam(copyFrom=bo)
+    for k in ('accepted', 'acceptedE', 'seeded', 'seededI', 'sourceWeight'):
+        setattr(bor, k, getattr(bo, k))
+    bor.x[:] = dxR
+    bor.y[:] = 0.
+    bor.z[:] = dzR
+    if R0 is None:
+        bor.path[:] = 0.
+        mPh = np.exp(1e7j * wave.E/CHBAR * wave.rDiffr)
+        wave.Es *= mPh
+        wave.Ep *= mPh
+    if toGlobal:
+        ob.virgin_local_to_global(src.azimuth, bor, src.center)
+    if record is not None:
+        record.update(rec)
+    return bor

@@ -1068,7 +1068,49 @@ def gen_multi():
         save('multi_reflect_' + name, rho=19.3, R=float(oe.R), r=float(getattr(oe, 'r', 0.)), **d)
 
 
-SECTIONS = {'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+def gen_shine_wave():
+    """IntegratedSource.shine(wave=...) (sources/sybase.py:1513-1527, :1588-1612, :1651-1703, :1786-1796): the source
+    illuminates the receiving points of a wave prepared by Screen.prepare_wave -- filament beam (one electron, with
+    energy spread) and the full emittance (per-sample shifts)."""
+    probe = _undulator_source(eMin=1000., eMax=1001., gNodes=16)
+    E1 = probe.E1
+    for name, filament, seed, spread in (('shine_wave_filament', True, 91, 8e-4), ('shine_wave_full', False, 92, 0.)):
+        src = _undulator_source(eMin=E1*0.999, eMax=E1*1.001, gNodes=32, gIntervals=2, nrays=1000, eEspread=spread,
+                                uniformRayDensity=True, filamentBeam=filament, center=(0.3, -1., 0.05))
+        src.bl.azimuth = 0.02
+        scr = rsc.Screen(src.bl, 'scr', center=(25000.*np.sin(0.02), 25000.*np.cos(0.02), 0.2))
+        xm = np.linspace(-2., 2., 31)
+        zm = np.linspace(-1.5, 1.5, 25)
+        wave = scr.prepare_wave(src, xm, zm)
+        d = dict(xDiffr=wave.xDiffr.copy(), yDiffr=wave.yDiffr.copy(), zDiffr=wave.zDiffr.copy(), area=wave.area,
+                 dS=wave.dS, wave_in_x=wave.x.copy(), wave_in_y=wave.y.copy(), wave_in_z=wave.z.copy())
+        # a filament source probes Imax with nrays random samples inside reset() (sybase.py:529-541): do that before
+        # seeding, so that the seeded stream starts at shine, and hand the probed Imax to the oracle
+        np.random.seed(seed + 1000)
+        if src.needReset:
+            src.reset()
+        d['Imax0'] = src.Imax
+        np.random.seed(seed)
+        bor = src.shine(wave=wave)
+        d.update(L0=src.L0, Np=src.Np, Kx=src.Kx, Ky=src.Ky, eI=src.eI, gamma=src.gamma, phase=src.phase,
+                 quadm=src.quadm, gIntervals=src.gIntervals, E_min=src.E_min, E_max=src.E_max,
+                 Theta_min=src.Theta_min, Theta_max=src.Theta_max, Psi_min=src.Psi_min, Psi_max=src.Psi_max,
+                 dx=src.dx, dz=src.dz, dxprime=src.dxprime, dzprime=src.dzprime,
+                 center=np.array(src.center, dtype=float), sinAzimuth=src.bl.sinAzimuth, cosAzimuth=src.bl.cosAzimuth,
+                 seed=seed, filament=filament, eEspread=spread, E1=src.E1, Imax=src.Imax, xzE=src.xzE,
+                 fluxConst=src.fluxConst, accepted=bor.accepted, acceptedE=bor.acceptedE, seeded=bor.seeded,
+                 seededI=bor.seededI, sourceWeight=bor.sourceWeight, xm=xm, zm=zm,
+                 screen_center=np.array(scr.center, dtype=float), rDiffr=wave.rDiffr)
+        if filament:
+            d.update(filamentDX=bor.filamentDX, filamentDZ=bor.filamentDZ, filamentDtheta=bor.filamentDtheta,
+                     filamentDpsi=bor.filamentDpsi, filamentDgamma=bor.filamentDgamma)
+        d.update(beam_dict(bor, 'bor_'))
+        d.update(beam_dict(wave, 'wave_'))
+        save(name, **d)
+        print(name, 'samples', len(wave.x), 'max |Es|', float(np.abs(wave.Es).max()))
+
+
+SECTIONS = {'shine_wave': gen_shine_wave, 'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)

@@ -65,8 +65,11 @@ __global__ void kirchhoff_pack_kernel(size_t N, const double* __restrict__ nl, c
 // ---------------------------------------------------------------- main kernel
 // UNIFORM_N: every sample has the same normal n (aperture, flat OE): n.d = n.p_i - n.q_j with n.p_i hoisted out
 // of the loop (exactly d_y for the aperture normal (0, 1, 0)).
+#ifndef XRTB_KIRCHHOFF_MINBLOCKS
+#define XRTB_KIRCHHOFF_MINBLOCKS 2
+#endif
 template <int R, int THREADS, int TILE, bool STRICT, bool UNIFORM_N>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, XRTB_KIRCHHOFF_MINBLOCKS)
     kirchhoff_kernel(size_t M, size_t N, const double* __restrict__ xM, const double* __restrict__ yM,
                      const double* __restrict__ zM, const KInput* __restrict__ in, size_t n_per_split,
                      double2* __restrict__ part, double un_x, double un_y, double un_z) {
@@ -252,7 +255,10 @@ static int launch_main(bool strict, bool uni, dim3 grid, size_t smem, cudaStream
              : launch_one<R, THREADS, TILE, false, false>(grid, smem, st, M, N, xM, yM, zM, in, nps, part, un);
 }
 
-constexpr int K_THREADS = 128;
+#ifndef XRTB_KIRCHHOFF_THREADS
+#define XRTB_KIRCHHOFF_THREADS 128
+#endif
+constexpr int K_THREADS = XRTB_KIRCHHOFF_THREADS;
 constexpr int K_TILE = 128;
 
 size_t kirchhoff_packed_bytes(size_t N) { return N * sizeof(KInput); }

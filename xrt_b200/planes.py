@@ -122,6 +122,16 @@ class Screen(_Plane):
         return blo
 
 
+def _screen_prepare_wave(self, prevOE, dim1, dim2, dy=0, rw=None, condition=None):
+    """Screen.prepare_wave (screens.py:304-365): a mesh of receiving points on the screen for waves.diffract or
+    source.shine(wave=...)."""
+    from . import waves
+    return waves.screen_prepare_wave(self, prevOE, dim1, dim2, dy=dy, condition=condition)
+
+
+Screen.prepare_wave = _screen_prepare_wave
+
+
 class RectangularAperture(_Plane):
     """Rectangular aperture / slit (apertures.py:52-413)."""
 
@@ -194,3 +204,12 @@ class RectangularAperture(_Plane):
                                    min(self.spotLimits[2], mm[0, 2]), max(self.spotLimits[3], mm[1, 2])]
         lo.parentId = getattr(self, 'uuid', self.name)
         return lo
+
+
+def _aperture_prepare_wave(self, prevOE, nrays, rw=None, xy=None):
+    """RectangularAperture.prepare_wave (apertures.py:467-499): random receiving points in the opening."""
+    from . import waves
+    return waves.aperture_prepare_wave(self, prevOE, nrays, xy=xy)
+
+
+RectangularAperture.prepare_wave = _aperture_prepare_wave

@@ -18,7 +18,7 @@ import torch
 from . import _lib, kernels
 from .beams import Beam
 from .cuda_backend import XRT_CUDA
-from .physconsts import PI, PI2, EV2ERG, M0, C, E2WC, FINE_STR, SIE0, K2B, EMC
+from .physconsts import PI, PI2, EV2ERG, M0, C, E2WC, FINE_STR, SIE0, K2B, EMC, CHBAR, CHeVcm
 
 F64 = torch.float64
 C128 = torch.complex128
@@ -66,10 +66,11 @@ class Undulator(object):
                  filamentBeam=False, pitch=0, yaw=0, period=50, n=50, K=1, Kx=0, Ky=0, phaseDeg=0, gp=1e-6,
                  gIntervals=2, gNodes=None, xPrimeMaxAutoReduce=True, zPrimeMaxAutoReduce=True,
                  targetOpenCL='CUDA', precisionOpenCL='float64', R0=None, taper=None, seed=1234, **kwargs):
-        if filamentBeam:
-            raise NotImplementedError('filamentBeam is outside the hot path (SURVEY.md section 8f3)')
         if targetOpenCL is None:
             raise _lib.XrtB200Error('xrt_b200.Undulator always computes on the GPU (no numpy path)')
+        # a filament beam (one electron per shine) is built for the wave-mode entry shine(wave=...); the ray-mode
+        # filament loop (nrepmax repeats, sybase.py:1742-1744) stays outside the hot path
+        self.filamentBeam = bool(filamentBeam)
         self.bl = bl
         self.name = name
         if bl is not None and self not in bl.sources:
@@ -186,8 +187,158 @@ class Undulator(object):
             self._find_convergence_mixed()
         self._build_integration_grid()
         self.Imax = 0.
+        if self.filamentBeam and not hasattr(self, 'dimExy'):
+            # sybase.py:529-541: Imax probed with nrays uniform samples (no energy spread), 20 % head room
+            dev = torch.device('cuda', torch.cuda.current_device())
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(self.seed * 7919 + 17)
+            u = torch.rand((4, self.nrays), dtype=torch.float64, device=dev, generator=gen)
+            DistI = self.build_I_map_device(u[0] * (self.E_max - self.E_min) + self.E_min,
+                                            u[1] * (self.Theta_max - self.Theta_min) + self.Theta_min,
+                                            u[2] * (self.Psi_max - self.Psi_min) + self.Psi_min)[0]
+            self.Imax = float(DistI.max()) * 1.2
+            self.nrepmax = np.floor(self.nrays / max(int((self.Imax * u[3] < DistI).sum()), 1))
         self.xzE = (self.E_max - self.E_min) * (self.Theta_max - self.Theta_min) * (self.Psi_max - self.Psi_min)
         self.fluxConst = self.Imax * self.xzE
+
+    def get_SIGMA_device(self, E):
+        """(SIGMAx, SIGMAz) per sample: get_SIGMA with onlyOddHarmonics=False as shine passes it (synchr.py:2200-2249,
+        sybase.py:664-674), CUDA tensors."""
+        sigma_r2 = 2 * CHeVcm/E*10 * self.L0*self.Np / PI2**2
+        if self.eEspread > 0:
+            harmonic = torch.floor(E / self.E1)
+            x = (PI2 * harmonic * self.Np * self.eEspread) / 4.
+            y = 2**0.5 * x
+            y2 = y**2
+            qa = y2 / (torch.exp(-y2) + np.pi**0.5 * y * torch.special.erf(y) - 1)
+            ret = torch.where(x > 1e-6, qa, torch.ones_like(x))
+            sigma_r2 = sigma_r2 * ret**(2/3.)
+        return (self.dx**2 + sigma_r2)**0.5, (self.dz**2 + sigma_r2)**0.5
+
+    def shine_wave(self, wave, toGlobal=True, samples=None):
+        """IntegratedSource.shine(wave=wave) (sybase.py:1513-1527, :1588-1612, :1651-1703, :1786-1796): the receiving
+        points of a prepared wave (Screen / aperture / OE .prepare_wave with this source as the previous element) are
+        illuminated; *wave* receives E, directions, coherency matrix and Es / Ep with the propagation phase, the
+        returned Beam sits at the source.  The field of every sample is the CUDA `build_I_map`; the O(M) rest is
+        device elementwise work.  *samples*: optional dict of deviates (parity tests feed the oracle's): filament
+        beam: scalars uE, gX, gZ, gT, gP[, gG]; full emittance: CUDA tensors uE, gX, gZ, gT, gP, g1, g2[, g5]."""
+        if not hasattr(wave, 'rDiffr'):
+            raise ValueError("If you want to use a `wave`, run a `prepare_wave` before shine!")
+        if self.needReset:
+            self.reset()
+        self.uniformRayDensity = True  # sybase.py:1523
+        n = len(wave)
+        dev = wave.device
+        s = samples
+        if s is None:
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(self.seed * 104729 + self._draws)
+            self._draws += 1
+            if self.filamentBeam:
+                u = torch.rand(1, dtype=torch.float64, device=dev, generator=gen)
+                g = torch.randn(5, dtype=torch.float64, device=dev, generator=gen).tolist()
+                s = dict(uE=float(u), gX=g[0], gZ=g[1], gT=g[2], gP=g[3], gG=g[4])
+            else:
+                g = torch.randn((7, n), dtype=torch.float64, device=dev, generator=gen)
+                s = dict(uE=torch.rand(n, dtype=torch.float64, device=dev, generator=gen), gX=g[0], gZ=g[1], gT=g[2],
+                         gP=g[3], g1=g[4], g2=g[5], g5=g[6])
+        dgamma = None
+        if self.filamentBeam:  # one electron: energy, position, direction [and energy deviation] (sybase.py:1541-1552)
+            rX, rZ = self.dx * s['gX'], self.dz * s['gZ']
+            dtheta, dpsi = self.dxprime * s['gT'], self.dzprime * s['gP']
+            if self.eEspread > 0:
+                dgamma = self.gamma * self.eEspread * s['gG']
+            rE = torch.full((n,), s['uE'] * float(self.E_max - self.E_min) + self.E_min, dtype=torch.float64,
+                            device=dev)
+            shiftX, shiftZ = rX, rZ
+        else:
+            rE = s['uE'] * float(self.E_max - self.E_min) + self.E_min
+            shiftX = 0. + self.dx * s['gX'] if self.dx > 0 else 0
+            shiftZ = 0. + self.dz * s['gZ'] if self.dz > 0 else 0
+        self.xzE = (self.E_max - self.E_min)  # sybase.py:1589
+        x = wave.xDiffr + shiftX
+        y = wave.yDiffr
+        z = wave.zDiffr + shiftZ
+        rDiffr = torch.sqrt(x**2 + y**2 + z**2)
+        rTheta = x / rDiffr
+        rPsi = z / rDiffr
+        if self.filamentBeam:
+            rTheta = rTheta + dtheta
+            rPsi = rPsi + dpsi
+        else:
+            if self.dxprime > 0:
+                rTheta = rTheta + (0. + self.dxprime * s['gT'])
+            if self.dzprime > 0:
+                rPsi = rPsi + (0. + self.dzprime * s['gP'])
+        gam = None
+        if self.eEspread > 0:  # synchr.py:2053-2059
+            if dgamma is not None:
+                gam = torch.full((n,), self.gamma + dgamma, dtype=torch.float64, device=dev)
+            else:
+                gam = self.gamma + (self.gamma * self.eEspread) * s['g5']
+        Intensity, mJs, mJp = self.build_I_map_device(rE.contiguous(), rTheta.contiguous(), rPsi.contiguous(),
+                                                      gamma=gam)
+        seeded = n
+        seededI = 0. + n * self.xzE
+        tmp_max = float(Intensity.max())
+        if tmp_max > self.Imax:
+            self.Imax = tmp_max
+            self.fluxConst = self.Imax * self.xzE
+        wave.state = torch.ones_like(wave.state)
+        wave.E = rE
+        if self.filamentBeam:
+            dxR, dzR = rX, rZ
+        else:
+            SX, SZ = self.get_SIGMA_device(rE)
+            wave.sourceSIGMAx, wave.sourceSIGMAz = SX, SZ
+            dxR = 0. + SX * s['g1']
+            dzR = 0. + SZ * s['g2']
+        wave.rDiffr = torch.sqrt((wave.xDiffr - dxR)**2 + wave.yDiffr**2 + (wave.zDiffr - dzR)**2)
+        wave.path = torch.zeros_like(wave.path)
+        a = (wave.xDiffr - dxR) / wave.rDiffr
+        b = wave.yDiffr / wave.rDiffr
+        c = (wave.zDiffr - dzR) / wave.rDiffr
+        area = wave.areaNormal if hasattr(wave, 'areaNormal') else wave.area
+        norm = area**0.5 / wave.rDiffr
+        mJs = mJs * norm
+        mJp = mJp * norm
+        wave.Jsp = mJs * torch.conj(mJp)
+        wave.Jss = (mJs * torch.conj(mJs)).real.contiguous()
+        wave.Jpp = (mJp * torch.conj(mJp)).real.contiguous()
+        wave.accepted = n * self.fluxConst
+        wave.acceptedE = float(rE.sum()) * self.fluxConst * SIE0
+        wave.seeded = seeded
+        wave.seededI = seededI
+        wave.sourceWeight = self.xzE / n
+        if self.filamentBeam:
+            wave.filamentDtheta, wave.filamentDpsi, wave.filamentDX, wave.filamentDZ = dtheta, dpsi, rX, rZ
+            wave.filamentDgamma = dgamma
+        norm = (a**2 + b**2 + c**2)**0.5
+        wave.a, wave.b, wave.c = a / norm, b / norm, c / norm
+        if self.pitch or self.yaw:
+            raise NotImplementedError('shine(wave=...) with a pitched / yawed source is outside the hot path')
+        wave.Es, wave.Ep = mJs, mJp
+        bor = Beam(copyFrom=wave)
+        for k in ('accepted', 'acceptedE', 'seeded', 'seededI', 'sourceWeight'):
+            setattr(bor, k, getattr(wave, k))
+        bor.x = torch.zeros_like(wave.x) + dxR
+        bor.y = torch.zeros_like(wave.y)
+        bor.z = torch.zeros_like(wave.z) + dzR
+        if self.R0 is None:  # sybase.py:1791-1796
+            mPh = torch.exp(1e7j * rE / CHBAR * wave.rDiffr)
+            wave.Es = wave.Es * mPh
+            wave.Ep = wave.Ep * mPh
+        bor.parentId = getattr(self, 'uuid', self.name)
+        if toGlobal:  # virgin_local_to_global (beamline.py:262-287)
+            a0 = self.bl.sinAzimuth if self.bl is not None else 0.
+            b0 = self.bl.cosAzimuth if self.bl is not None else 1.
+            if a0 != 0:
+                bor.a, bor.b = b0*bor.a - (-a0)*bor.b, (-a0)*bor.a + b0*bor.b
+                bor.x, bor.y = b0*bor.x - (-a0)*bor.y, (-a0)*bor.x + b0*bor.y
+            bor.x = bor.x + self.center[0]
+            bor.y = bor.y + self.center[1]
+            bor.z = bor.z + self.center[2]
+        return bor
 
     def _build_integration_grid(self):
         """Undulator._build_integration_grid (synchr.py:1787-1801)."""
@@ -429,8 +580,13 @@ class Undulator(object):
         *samples* (optional): dict of CUDA tensors E, theta, psi, n1..n4[, u] to use instead of drawing them
         (parity tests feed the deviates the numpy oracle used).  *allreduce_max*: callable applied to the
         per-pass max intensity when rays are sharded over ranks (Imax is beam-wide, sybase.py:1627-1631)."""
-        if wave is not None or fixedEnergy or accuBeam is not None:
-            raise NotImplementedError('wave/fixedEnergy/accuBeam sampling is outside the hot path (SURVEY 8f3)')
+        if fixedEnergy or accuBeam is not None:
+            raise NotImplementedError('fixedEnergy / accuBeam sampling is outside the hot path (SURVEY 8f3)')
+        if wave is not None:
+            return self.shine_wave(wave, toGlobal=toGlobal, samples=samples)
+        if self.filamentBeam:
+            raise NotImplementedError('a filament beam is built for shine(wave=...); its ray-mode repeats '
+                                      '(sybase.py:1742-1744) are outside the hot path')
         if self.needReset:
             self.reset()
         if self.uniformRayDensity:
