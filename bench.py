@@ -208,6 +208,9 @@ def run_ours(args):
         pass
     _lib.init(local_rank)
     if world > 1:
+        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
+            # NCCL writes its version banner to stdout, which carries exactly one JSON line here
+            os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     comm = parallel.Comm(world, rank)
 

@@ -99,3 +99,29 @@ def test_bridge_refract_and_grating_host_objects(cuda_device):
     bad = compare_beams(gb.__dict__, {f: g['gb_' + f] for f in BEAM_FIELDS}, BEAM_FIELDS, 1e-12, 'gb_')
     bad += compare_beams(lb.__dict__, {f: g['lb_' + f] for f in BEAM_FIELDS}, BEAM_FIELDS, 1e-12, 'lb_')
     assert not bad, bad
+
+
+class BentFlatMirror(OE):
+    pass
+
+
+class VCM(BentFlatMirror):  # a subclass with a surface of its own must not be silently taken for its base
+    pass
+
+
+@pytest.mark.gpu
+def test_bridge_spliced_element_and_multiple_reflect(cuda_device):
+    """An xrt-shaped BentFlatMirror goes through the spliced-surface plug-in: multiple_reflect (8 whispering-gallery
+    passes) equals the reference's beams; an unknown subclass is refused instead of being traced as something else."""
+    from xrt_b200 import bridge
+    g = golden('multi_reflect_bentflat')
+    oe = _fake_common(g, BentFlatMirror, _fake_material('Au', g, 'mirror'), R=float(g['R']),
+                      limPhysY=list(g['surfPhysY']))
+    gb, lbN = bridge.multiple_reflect(oe, oracle_beam(g, 'in_'), maxReflections=8)
+    bad = compare_beams(gb.__dict__, {f: g['gb_' + f] for f in BEAM_FIELDS}, BEAM_FIELDS, 1e-12, 'gb_')
+    bad += compare_beams(lbN.__dict__, {f: g['lbN_' + f] for f in BEAM_FIELDS}, BEAM_FIELDS, 1e-12, 'lbN_')
+    assert not bad, bad
+    assert np.array_equal(gb.nRefl, g['gb_nRefl']) and len(oe.footprint) == 8
+    other = _fake_common(g, VCM, _fake_material('Au', g, 'mirror'), R=float(g['R']), limPhysY=list(g['surfPhysY']))
+    with pytest.raises(NotImplementedError):
+        bridge.reflect(other, oracle_beam(g, 'in_'))

@@ -3,6 +3,7 @@
 kernels: the method-level binding sketched in INTEGRATION.md section 2.
 
     bridge.reflect(xrt_oe, xrt_beam, needLocal=True)          -> (gb, lb)      OE.reflect, oes/reflect.py:18
+    bridge.multiple_reflect(xrt_oe, xrt_beam, maxReflections) -> (gb, lbN)     OE.multiple_reflect, oes/reflect.py:165
     bridge.double_reflect(xrt_dcm, xrt_beam, needLocal=True)  -> (gb, lo1, lo2)  DCM.double_reflect, dcm.py:248
     bridge.expose(xrt_screen, xrt_beam)                       -> blo           Screen.expose, screens.py:226
     bridge.double_refract(xrt_plate, xrt_beam)                -> (gb, lo1, lo2)  Plate.double_refract, refractive.py:171
@@ -99,7 +100,24 @@ def convert_oe(oe):
         out = _oes.EllipticalMirrorParam(oe.bl, oe.name, p=oe.p, q=oe.q, isCylindrical=oe.isCylindrical, **kw)
         for k in ('ellipseA', 'ellipseB', 'y0', 'z0', 'cosGamma', 'sinGamma'):
             setattr(out, k, float(getattr(oe, k)))  # take xrt's own ellipse parameters verbatim
-    elif type(oe).__name__ == 'OE' or 'OE' in cls:
+    elif 'ParabolicalMirrorParam' in cls:
+        if getattr(oe, 'isClosed', False):
+            raise NotImplementedError('isClosed=True is outside the hot path')
+        pq = dict(p=oe.p) if oe.p is not None else dict(q=oe.q)
+        out = _oes.ParabolicalMirrorParam(oe.bl, oe.name, isCylindrical=oe.isCylindrical, **pq, **kw)
+        for k in ('parabParam', 'y0', 'z0', 'cosGamma', 'sinGamma'):
+            setattr(out, k, float(getattr(oe, k)))  # xrt's own parabola parameters verbatim
+    elif 'JohanssonCylinder' in cls or 'JohannCylinder' in cls:
+        out = getattr(_oes, 'JohanssonCylinder' if 'JohanssonCylinder' in cls else 'JohannCylinder')(
+            oe.bl, oe.name, Rm=float(oe.Rm), crossSection=oe.crossSection, **kw)
+    elif 'JohannToroid' in cls and not any(c in cls for c in ('JohanssonToroid', 'GeneralBraggToroid', 'DicedOE')):
+        out = _oes.JohannToroid(oe.bl, oe.name, Rm=float(oe.Rm), Rs=float(oe.Rs), **kw)
+    elif 'ConicalMirror' in cls:
+        out = _oes.ConicalMirror(oe.bl, oe.name, L0=float(oe.L0), theta=float(oe.theta), **kw)
+    elif 'BentFlatMirror' in cls and type(oe).__name__ in ('BentFlatMirror', 'SimpleVCM'):
+        out = _oes.BentFlatMirror(oe.bl, oe.name, R=float(oe.R), **kw)
+        out.limPhysY = list(oe.limPhysY)  # local_z reads limPhysY[0], not surfPhysY (oes/__init__.py:293)
+    elif type(oe).__name__ == 'OE':
         out = _oes.OE(oe.bl, oe.name, **kw)
     else:
         raise NotImplementedError('{0} is outside the hot path'.format(type(oe).__name__))
@@ -116,6 +134,13 @@ def reflect(oe, beam, needLocal=True):
     oe.footprint = dev.footprint
     hgb = HostBeam(gb.to_numpy())
     return hgb, (HostBeam(lb.to_numpy()) if needLocal else hgb)
+
+
+def multiple_reflect(oe, beam, maxReflections=1000):
+    dev = convert_oe(oe)
+    gb, lbN = dev.multiple_reflect(_device_beam(beam), maxReflections=maxReflections)
+    oe.footprint = dev.footprint
+    return HostBeam(gb.to_numpy()), HostBeam(lbN.to_numpy())
 
 
 def double_reflect(dcm, beam, needLocal=True):
