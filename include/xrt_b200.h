@@ -273,7 +273,8 @@ typedef struct xrt_plane_params {
   int only_positive_path;     /* Screen.expose(onlyPositivePath=...) */
   int has_compressX, has_compressZ;
   double compressX, compressZ;
-  int n_blades;               /* aperture blades: kind 0 left (x < d lost), 1 right, 2 bottom, 3 top */
+  int n_blades;               /* aperture blades: kind 0 left (x < d lost), 1 right, 2 bottom, 3 top;
+                                 kind 4: round opening of radius d (RoundAperture.propagate, apertures.py:769-825) */
   int blade_kind[4];
   double blade_pos[4];
   int is_beam_stop;

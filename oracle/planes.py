@@ -86,3 +86,28 @@ def propagate_rect(beam, center, xyz, blades, lostNum, isBeamStop=False, info=No
     if info is not None and goodN.sum() > 0:
         info['spotLimits'] = [lo.x[goodN].min(), lo.x[goodN].max(), lo.z[goodN].min(), lo.z[goodN].max()]
     return lo
+
+
+def propagate_round(beam, center, xyz, r, lostNum, isBeamStop=False):
+    """RoundAperture.propagate (apertures.py:769-825). `beam.state` is modified in place. Returns lo (with lo.r, the
+    radii of the good rays)."""
+    good = beam.state > 0
+    lo = ob.Beam(copyFrom=beam)
+    ob.global_to_virgin_local(xyz, beam, lo, center, good)
+    path = -lo.y[good] / lo.b[good]
+    lo.x[good] += lo.a[good] * path
+    lo.z[good] += lo.c[good] * path
+    lo.r = (lo.x[good]**2 + lo.z[good]**2)**0.5
+    lo.path[good] += path
+    badIndices = np.zeros(len(beam.x), dtype=bool)
+    badIndices[good] = lo.r > r
+    if isBeamStop:
+        badIndices[good] = np.invert(badIndices[good])
+    beam.state[badIndices] = lostNum
+    lo.state[good] = beam.state[good]
+    lo.y[good] = 0.
+    if hasattr(lo, 'Es'):
+        propPhase = np.exp(1e7j * (lo.E[good]/CHBAR) * path)
+        lo.Es[good] *= propPhase
+        lo.Ep[good] *= propPhase
+    return lo

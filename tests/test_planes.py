@@ -91,3 +91,51 @@ def test_cuda_propagate_vs_golden(cuda_device):
     assert not compare_beams(lo.to_numpy(), ref, BEAM_FIELDS, RTOL)
     assert np.array_equal(beam.state.cpu().numpy(), g['in_state_after'])  # the incoming beam is marked too
     np.testing.assert_allclose(slit.spotLimits, g['spotLimits'], rtol=1e-13, atol=1e-13)
+
+
+@pytest.mark.parametrize('name', ['propagate_round', 'propagate_round_stop'])
+def test_oracle_propagate_round_bit_exact(name):
+    """RoundAperture.propagate (apertures.py:769-825): a pipe and a round beam stop."""
+    g = golden(name)
+    b = oracle_beam(g, 'in_')
+    lo = op.propagate_round(b, list(g['center']), _basis(g), float(g['r']), int(g['lostNum']),
+                            isBeamStop=bool(g['isBeamStop']))
+    for f in BEAM_FIELDS:
+        assert np.array_equal(getattr(lo, f), g['out_' + f]), f
+    assert np.array_equal(b.state, g['in_state_after']) and np.array_equal(lo.r, g['lo_r'])
+    assert (lo.state == 1).sum() > 500 and (lo.state == int(g['lostNum'])).sum() > 500
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['propagate_round', 'propagate_round_stop'])
+def test_cuda_propagate_round_vs_golden(name, cuda_device):
+    from xrt_b200.planes import RoundAperture
+    g = golden(name)
+    ap = RoundAperture(None, 'pipe', center=list(g['center']), r=float(g['r']), isBeamStop=bool(g['isBeamStop']))
+    ap.x, ap.y, ap.z = list(g['ex']), list(g['ey']), list(g['ez'])
+    ap.lostNum = int(g['lostNum'])
+    beam = device_beam(oracle_beam(g, 'in_'))
+    lo = ap.propagate(beam)
+    assert not compare_beams(lo.to_numpy(), {f: g['out_' + f] for f in BEAM_FIELDS}, BEAM_FIELDS, RTOL)
+    assert np.array_equal(beam.state.cpu().numpy(), g['in_state_after'])  # the incoming beam is marked too
+
+
+@pytest.mark.gpu
+def test_cuda_round_prepare_wave_vs_golden(cuda_device):
+    """RoundAperture.prepare_wave (apertures.py:848-875) with the reference's uniform deviates."""
+    import types
+    from xrt_b200.planes import RoundAperture
+    g = golden('prepare_wave_round')
+    bl = types.SimpleNamespace(sinAzimuth=float(g['sinAzimuth']), cosAzimuth=float(g['cosAzimuth']))
+    ap = RoundAperture(None, 'pipe', center=list(g['center']), r=float(g['r']))
+    ap.x, ap.y, ap.z = list(g['ex']), list(g['ey']), list(g['ez'])
+    src = types.SimpleNamespace(center=list(g['src_center']), bl=bl, name='src')
+    wave = ap.prepare_wave(src, 700, xy=g['xy'])
+    d = wave.to_numpy()
+    for k in ('x', 'z'):
+        assert np.abs(d[k] - g[k]).max() <= 1e-15 * float(g['r']) * 4, k  # r cos(phi), r sin(phi): numpy on the host
+    for k in ('xDiffr', 'yDiffr', 'zDiffr', 'rDiffr'):
+        assert np.abs(d[k] - g[k]).max() <= 1e-12 * 4000., k
+    for k in ('a', 'b', 'c'):
+        assert np.abs(d[k] - g[k]).max() <= 1e-12, k
+    assert wave.area == float(g['area']) and wave.dS == float(g['dS'])

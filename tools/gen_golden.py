@@ -1110,7 +1110,37 @@ def gen_shine_wave():
         print(name, 'samples', len(wave.x), 'max |Es|', float(np.abs(wave.Es).max()))
 
 
-SECTIONS = {'shine_wave': gen_shine_wave, 'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+def gen_round():
+    """RoundAperture.propagate (apertures.py:769-825): a pipe and a round beam stop; RoundAperture.prepare_wave
+    (:848-875) with seeded samples in the disk."""
+    bl = raycing.BeamLine(azimuth=-0.2)
+    for name, stop in (('propagate_round', False), ('propagate_round_stop', True)):
+        beam = _source_beam(bl, 2500, 53, dx=0.4, dz=0.3, dxprime=3e-4, dzprime=2e-4)
+        ap = ra.RoundAperture(bl, 'pipe', center=(4000*np.sin(-0.2), 4000*np.cos(-0.2), 0.1), r=1.05)
+        ap.isBeamStop = stop
+        beam_in = rs.Beam(copyFrom=beam)
+        lo = ap.propagate(beam)
+        out = dict(center=np.array(ap.center, dtype=float), ex=np.array(ap.xyz[0], dtype=float),
+                   ey=np.array(ap.xyz[1], dtype=float), ez=np.array(ap.xyz[2], dtype=float),
+                   lostNum=np.int64(ap.lostNum), r=float(ap.r), isBeamStop=stop, in_state_after=beam.state, lo_r=lo.r)
+        out.update(beam_dict(beam_in, 'in_'))
+        out.update(beam_dict(lo, 'out_'))
+        st = lo.state
+        print(name, {int(x): int((st == x).sum()) for x in np.unique(st)})
+        save(name, **out)
+    src = rs.GeometricSource(bl, 'src', nrays=10)
+    np.random.seed(54)
+    xy = np.random.rand(700, 2)
+    np.random.seed(54)
+    wave = ap.prepare_wave(src, 700)
+    save('prepare_wave_round', xy=xy, r=float(ap.r), center=np.array(ap.center, dtype=float),
+         ex=np.array(ap.xyz[0], dtype=float), ey=np.array(ap.xyz[1], dtype=float), ez=np.array(ap.xyz[2], dtype=float),
+         sinAzimuth=bl.sinAzimuth, cosAzimuth=bl.cosAzimuth, src_center=np.array(src.center, dtype=float),
+         x=wave.x, z=wave.z, area=wave.area, dS=wave.dS, xDiffr=wave.xDiffr, yDiffr=wave.yDiffr, zDiffr=wave.zDiffr,
+         rDiffr=wave.rDiffr, a=wave.a, b=wave.b, c=wave.c)
+
+
+SECTIONS = {'round': gen_round, 'shine_wave': gen_shine_wave, 'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)

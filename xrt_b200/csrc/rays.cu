@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(256) propagate_rect_kernel(size_t n, xrt_plane
         if (kind == 1) badI = badI || (x > d);
         if (kind == 2) badI = badI || (z < d);
         if (kind == 3) badI = badI || (z > d);
+        if (kind == 4) badI = badI || (sqrt(x * x + z * z) > d);  // RoundAperture: lo.r > self.r (apertures.py:790-794)
       }
       if (p.is_beam_stop) badI = !badI;
       if (badI) st = p.lostNum;

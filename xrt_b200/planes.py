@@ -185,7 +185,8 @@ class RectangularAperture(_Plane):
         lib = _lib.load()
         p = self._base_params()
         kinds = {'l': 0, 'r': 1, 'b': 2, 't': 3}
-        items = [(kinds[k[0]], float(d)) for k, d in self.blades.items() if k[0] in kinds]
+        items = self._blade_items() if hasattr(self, '_blade_items') else \
+            [(kinds[k[0]], float(d)) for k, d in self.blades.items() if k[0] in kinds]
         p.n_blades = len(items)
         for i, (k, d) in enumerate(items):
             p.blade_kind[i] = k
@@ -204,6 +205,27 @@ class RectangularAperture(_Plane):
                                    min(self.spotLimits[2], mm[0, 2]), max(self.spotLimits[3], mm[1, 2])]
         lo.parentId = getattr(self, 'uuid', self.name)
         return lo
+
+
+class RoundAperture(RectangularAperture):
+    """Round aperture: a pipe or a flange (apertures.py:668-875).  The same kernel as the rectangular one with a single
+    'blade' of the round kind: rays with sqrt(x^2 + z^2) > r are lost (inverted for a beam stop)."""
+
+    def __init__(self, bl=None, name='', center=[0, 0, 0], r=1, x='auto', z='auto', alarmLevel=None, **kwargs):
+        RectangularAperture.__init__(self, bl, name, center, x=x, z=z, alarmLevel=alarmLevel, blades={},
+                                     isBeamStop=kwargs.get('isBeamStop', False))
+        self.r = r
+        self.limOptX = [-r, r]
+        self.limOptY = [-r, r]
+        self.shape = 'round'
+
+    def _blade_items(self):
+        return [(4, float(self.r))]
+
+    def prepare_wave(self, prevOE, nrays, rw=None, xy=None):
+        """RoundAperture.prepare_wave (apertures.py:848-875): random receiving points in the disk (uniform in area)."""
+        from . import waves
+        return waves.aperture_prepare_wave(self, prevOE, nrays, xy=xy, round_r=self.r)
 
 
 def _aperture_prepare_wave(self, prevOE, nrays, rw=None, xy=None):

@@ -101,16 +101,24 @@ def screen_prepare_wave(screen, prevOE, dim1, dim2, dy=0, condition=None, device
     return prepare_wave(prevOE, wave, t(xglo), t(yglo + dy), t(zglo))
 
 
-def aperture_prepare_wave(slit, prevOE, nrays, xy=None, device=None):
-    """RectangularAperture.prepare_wave (apertures.py:467-499). *xy*: optional (nrays, 2) uniform deviates
-    (the reference draws np.random.rand(nrays, 2)); drawn with numpy's global stream when omitted."""
+def aperture_prepare_wave(slit, prevOE, nrays, xy=None, device=None, round_r=None):
+    """RectangularAperture.prepare_wave (apertures.py:467-499) and, with *round_r*, RoundAperture.prepare_wave
+    (apertures.py:848-875). *xy*: optional (nrays, 2) uniform deviates (the reference draws np.random.rand(nrays, 2));
+    drawn with numpy's global stream when omitted."""
     nrays = int(nrays)
     if xy is None:
         xy = np.random.rand(nrays, 2)
-    dX = slit.limOptX[1] - slit.limOptX[0]
-    dZ = slit.limOptY[1] - slit.limOptY[0]
-    xl = xy[:, 0] * dX + slit.limOptX[0]
-    zl = xy[:, 1] * dZ + slit.limOptY[0]
+    if round_r is not None:
+        r = xy[:, 0]**0.5 * round_r
+        phi = xy[:, 1] * 2*np.pi
+        xl = r * np.cos(phi)
+        zl = r * np.sin(phi)
+        dX, dZ = np.pi * round_r**2, 1.  # wave.area = pi r^2
+    else:
+        dX = slit.limOptX[1] - slit.limOptX[0]
+        dZ = slit.limOptY[1] - slit.limOptY[0]
+        xl = xy[:, 0] * dX + slit.limOptX[0]
+        zl = xy[:, 1] * dZ + slit.limOptY[0]
     wave = Beam(nrays, withAmplitudes=True, device=device)
     wave.state.fill_(1)
     dev = wave.device
