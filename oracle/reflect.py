@@ -197,6 +197,9 @@ def find_dz(oe, local_f, t, x0, y0, z0, a, b, c, invertNormal, derivOrder=0):
     if oe.isParametric:
         x, y, z = oe.xyz_to_param(x, y, z)
     surf = local_f(x, y)
+    fe = getattr(oe, 'figureError', None)
+    if fe is not None and not oe.isParametric and derivOrder == 0:  # base.py:825-829
+        surf = surf + fe.local_z_distorted(x, y)
     if derivOrder == 0:
         ind = np.isnan(surf)
         if ind.sum() > 0:
@@ -462,6 +465,14 @@ def reflect_local(oe, good, lb, vlb, pitch, roll, yaw, dx=None, dy=None, dz=None
         matSur = material
         isCrystal = material is not None and material.kind == 'crystal'
         oeNormal = list(local_n(lb.x[goodN], lb.y[goodN]))
+        fe = getattr(oe, 'figureError', None)
+        if fe is not None:  # reflect.py:767-776: d_pitch, d_roll rotations of the surface normal
+            oeNormal = [np.asarray(v) * np.ones(int(goodNsum)) for v in oeNormal]
+            n_distorted = fe.local_n_distorted(lb.x[goodN], lb.y[goodN])
+            cosX, sinX = np.cos(n_distorted[0]), np.sin(n_distorted[0])
+            oeNormal[-2], oeNormal[-1] = ob.rotate_x(oeNormal[-2], oeNormal[-1], cosX, sinX)
+            cosY, sinY = np.cos(n_distorted[1]), np.sin(n_distorted[1])
+            oeNormal[-3], oeNormal[-1] = ob.rotate_y(oeNormal[-3], oeNormal[-1], cosY, sinY)
         isAsymmetric = len(oeNormal) == 6
         oeNormal = np.asarray(oeNormal, order='F')
         beamInDotNormal = lb.a[goodN]*oeNormal[0] + lb.b[goodN]*oeNormal[1] + lb.c[goodN]*oeNormal[2]

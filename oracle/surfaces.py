@@ -180,3 +180,22 @@ class ParabolicalMirrorParam(object):
             c = -np.cos(phi) / norm
         bNew, cNew = ob.rotate_x(b, c, self.cosGamma, -self.sinGamma)
         return [a, bNew, cNew]
+
+
+class FigureErrorSpline(object):
+    """FigureErrorBase.build_spline / local_z_distorted / local_n_distorted (figure_error.py:207-265): a height map in
+    nm on (y1d, x1d) -> scipy RectBivariateSpline (kx = ky = 3, the primitive the reference itself uses); heights in
+    mm, slopes as (d_pitch, d_roll)."""
+
+    def __init__(self, x1d, y1d, z_nm, xShift=0., yShift=0., splineOrder=3):
+        from scipy import interpolate
+        self.local_z_spline = interpolate.RectBivariateSpline(y1d, x1d, z_nm, kx=splineOrder, ky=splineOrder)
+        self.xShift, self.yShift = xShift, yShift
+
+    def local_z_distorted(self, x, y):
+        return self.local_z_spline.ev(y+self.yShift, x+self.xShift) * 1e-6
+
+    def local_n_distorted(self, x, y):
+        a = self.local_z_spline.ev(y+self.yShift, x+self.xShift, dx=0, dy=1) * 1e-6
+        b = self.local_z_spline.ev(y+self.yShift, x+self.xShift, dx=1, dy=0) * 1e-6
+        return [np.arctan(b), -np.arctan(a)]

@@ -1140,7 +1140,39 @@ def gen_round():
          rDiffr=wave.rDiffr, a=wave.a, b=wave.b, c=wave.c)
 
 
-SECTIONS = {'round': gen_round, 'shine_wave': gen_shine_wave, 'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+def gen_figure_error():
+    """OE.reflect with a figureError object (oes/base.py:681-686, :744-770; find_dz :825-829; reflect.py:767-776;
+    figure_error.py:207-265): a Gaussian bump on a toroid, waviness on a flat mirror.  The bicubic spline of the height
+    map (knots, coefficients) is stored as the reference's scipy RectBivariateSpline holds it."""
+    import xrt.backends.raycing.figure_error as rfe
+    bl = raycing.BeamLine(azimuth=0.1)
+    Au = rm.Material('Au', rho=19.3)
+    p = 2e4
+    ctr = (p*np.sin(0.1), p*np.cos(0.1), 0)
+    cases = (('toroid_bump', roe.ToroidMirror, dict(R=8e6, r=75.),
+              lambda lx, ly: rfe.GaussianBump(bumpHeight=40., cX=0.5, cY=-30., sigmaX=1.5, sigmaY=60., limPhysX=lx,
+                                              limPhysY=ly, gridStep=4.)),
+             ('flat_waviness', roe.OE, dict(),
+              lambda lx, ly: rfe.Waviness(amplitude=15., xWaveLength=3., yWaveLength=70., limPhysX=lx, limPhysY=ly,
+                                          gridStep=4.)))
+    for name, cls, kw, mkfe in cases:
+        beam = _source_beam(bl, 2500, 401, dx=0.3, dz=0.1, dxprime=1.2e-4, dzprime=6e-5, energies=(7000, 11000))
+        lx, ly = [-4, 4], [-350, 300]
+        fe = mkfe(lx, ly)
+        oe = cls(bl, name, center=ctr, pitch=3e-3, material=Au, limPhysX=lx, limPhysY=ly, figureError=fe, **kw)
+        d = _capture_reflect(oe, beam)
+        d.update(_oe_params(oe))
+        spl = fe.local_z_spline
+        ty, tx = spl.get_knots()
+        st = d['gb_state']
+        print(name, {int(x): int((st == x).sum()) for x in np.unique(st)}, 'knots', len(ty), len(tx), 'coeffs',
+              spl.get_coeffs().shape, 'rms nm', float(fe.get_rms()))
+        save('reflect_figerr_' + name, rho=19.3, R=float(getattr(oe, 'R', 0.)), r=float(getattr(oe, 'r', 0.)),
+             fe_ty=ty, fe_tx=tx, fe_c=spl.get_coeffs(), fe_xShift=fe.xShift, fe_yShift=fe.yShift,
+             fe_x1d=fe.x1d, fe_y1d=fe.y1d, fe_z=fe.generate_profile(), **d)
+
+
+SECTIONS = {'figure_error': gen_figure_error, 'round': gen_round, 'shine_wave': gen_shine_wave, 'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)

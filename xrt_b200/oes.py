@@ -696,6 +696,9 @@ def _abs_pitch_to_axis(oe, axis=(0, 1, 0)):
     return abs(np.arcsin(sintheta))
 
 
+SimpleVFM = ToroidMirror  # oes/__init__.py:414
+
+
 class EllipticalMirrorParam(OE):
     """Elliptical cylinder / ellipsoid in the parametric (s, phi, r) representation
     (oes/parametric.py:9-249).  The ellipse parameters follow _reset_pq (:104-150) for the default p-arm

@@ -28,6 +28,8 @@ def slot_kinds():
     kinds[28:31] = 1                  # footprint min
     kinds[31:34] = 0                  # footprint max
     kinds[34:] = 2                    # counters
+    kinds[40] = 1                     # multiple_reflect, derivative stage: min t1 ...
+    kinds[41:44] = 0                  # ... max t2, max |dz1|, max |dz2|
     return kinds
 
 
