@@ -194,6 +194,13 @@ typedef struct xrt_oe_params {
   int multi;              /* 1: one pass of multiple_reflect -- gb receives EVERY traced ray in virgin-local coordinates
                              with its new state (gb and lb are one beam there), rays over the edge keep their entry
                              point (:224-227), gb.theta is written when present; input is virgin local */
+  /* f4: figure error (OE(figureError=...), figure_error.py:207-265): height map in nm as the bicubic B-spline of scipy's
+   * RectBivariateSpline(y1d, x1d, z): knots fe_tu[fe_nu] along y, fe_tv[fe_nv] along x, coefficients
+   * fe_c[(fe_nu - 4) * (fe_nv - 4)] (device pointers), evaluated at (y + fe_ushift, x + fe_vshift).  NULL fe_c: none.
+   * Served by figure-error plug-in variants only (xrt_b200/custom.py); libxrt_b200.so refuses a non-NULL fe_c. */
+  const double *fe_tu, *fe_tv, *fe_c;
+  int fe_nu, fe_nv;
+  double fe_ushift, fe_vshift;
   const double* multi_tmin; /* passes after the first: per-ray lower bracket end = the derivative-stage root
                              (xrt_reflect_multi_deriv_f64; base.py:1279-1289); NULL: the usual _set_t bracket */
 } xrt_oe_params;

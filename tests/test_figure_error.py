@@ -30,3 +30,87 @@ def test_oracle_figure_error_bit_exact(name, surface):
             if pre + f in g.files:
                 assert np.array_equal(getattr(b, f), g[pre + f]), pre + f
     assert np.array_equal(info['footprint'], g['footprint'])
+
+
+def _product_oe(name, surface, g, fe):
+    from xrt_b200 import oes, materials
+    kw = product_oe_kwargs(g)
+    kw['material'] = materials.Material('Au', rho=float(g['rho']))
+    if surface == 'toroid':
+        oe = oes.ToroidMirror(product_beamline(g), name, R=float(g['R']), r=float(g['r']), figureError=fe, **kw)
+    else:
+        oe = oes.OE(product_beamline(g), name, figureError=fe, **kw)
+    oe.lostNum = int(g['lostNum'])
+    return oe
+
+
+def test_product_figure_error_profiles_and_splines_equal_reference():
+    """Host side (no GPU): the product's GaussianBump / Waviness generate the reference's height maps on the
+    reference's grids, and their splines have the reference's knots and coefficients bit for bit."""
+    from xrt_b200 import figure_error as pfe
+    g = golden('reflect_figerr_toroid_bump')
+    fe = pfe.GaussianBump(bumpHeight=40., cX=0.5, cY=-30., sigmaX=1.5, sigmaY=60., limPhysX=[-4, 4],
+                          limPhysY=[-350, 300], gridStep=4.)
+    assert np.array_equal(fe.x1d, g['fe_x1d']) and np.array_equal(fe.y1d, g['fe_y1d'])
+    assert np.array_equal(fe.generate_profile(), g['fe_z'])
+    assert np.array_equal(fe.local_z_spline.get_coeffs(), g['fe_c'])
+    g = golden('reflect_figerr_flat_waviness')
+    fe = pfe.Waviness(amplitude=15., xWaveLength=3., yWaveLength=70., limPhysX=[-4, 4], limPhysY=[-350, 300],
+                      gridStep=4.)
+    assert np.array_equal(fe.generate_profile(), g['fe_z'])
+    ty, tx = fe.local_z_spline.get_knots()
+    assert np.array_equal(ty, g['fe_ty']) and np.array_equal(tx, g['fe_tx'])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name,surface', CASES)
+def test_cuda_figure_error_vs_reference_golden(name, surface, cuda_device):
+    """The spline is evaluated on the device in FITPACK's operation order; what remains are the ulp-level differences of
+    the de Boor recurrences, which move the solver's stopping point like any transcendental (as for parametric
+    surfaces): |dt| <= 4e-12 mm, fields compared after removing exp(i k dt); everything else 1e-12."""
+    from xrt_b200 import figure_error as pfe
+    from xrt_b200.physconsts import CHBAR
+    g = golden('reflect_figerr_' + name)
+    fe = pfe.FigureErrorMap(g['fe_x1d'], g['fe_y1d'], g['fe_z'])
+    oe = _product_oe(name, surface, g, fe)
+    gb, lb = oe.reflect(device_beam(oracle_beam(g, 'in_')), withFootprint=True)
+    bad = []
+    good = g['lb_state'] == 1
+    for pre, b in (('gb_', gb), ('lb_', lb)):
+        ref = {f: g[pre + f] for f in OUT_FIELDS if pre + f in g.files}
+        dev = b.to_numpy()
+        dpath = dev['path'] - ref['path']
+        assert np.abs(dpath[good]).max() <= 4e-12
+        comp = np.exp(-1e7j * ref['E'] / CHBAR * dpath)
+        dev = dict(dev, Es=dev['Es'] * comp, Ep=dev['Ep'] * comp)
+        phase_ulp = np.spacing((1e7 * ref['E'] / CHBAR * ref['path']).max())
+        bad += compare_beams(dev, ref, ('Es', 'Ep'), 2 * phase_ulp, pre)
+        bad += compare_beams(dev, ref, [f for f in OUT_FIELDS if f not in ('Es', 'Ep')], 1e-12, pre)
+    assert not bad, bad
+    assert np.array_equal(gb.to_numpy()['state'], g['gb_state'])
+    np.testing.assert_allclose(oe.footprint[0], g['footprint'], rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_cuda_figure_error_changes_the_beam_and_library_refuses_it(cuda_device):
+    """Sanity: the bump really deflects rays (the slopes are ~1e-7 rad), and the plain library object refuses a
+    figure-error parameter block instead of ignoring it."""
+    import ctypes
+    from xrt_b200 import figure_error as pfe, _lib
+    g = golden('reflect_figerr_toroid_bump')
+    fe = pfe.FigureErrorMap(g['fe_x1d'], g['fe_y1d'], g['fe_z'])
+    beam = device_beam(oracle_beam(g, 'in_'))
+    with_fe = _product_oe('a', 'toroid', g, fe).reflect(beam)[0].to_numpy()
+    plain_oe = _product_oe('b', 'toroid', g, None)
+    plain = plain_oe.reflect(beam)[0].to_numpy()
+    good = (with_fe['state'] == 1) & (plain['state'] == 1)
+    d = np.abs(with_fe['c'][good] - plain['c'][good]).max()
+    assert 1e-9 < d < 1e-5, d
+    params = plain_oe._make_params(plain_oe.pitch, 0., 0.)
+    fe.fill_params(params, beam.device)
+    out = beam.like()
+    cin, cout = beam.c_struct(), out.c_struct()
+    red = plain_oe._red[str(beam.device)]
+    rc = _lib.load().xrt_reflect_f64(len(beam), ctypes.byref(params), None, None, 0, ctypes.byref(cin), None,
+                                     ctypes.byref(cout), None, red.data_ptr(), 7, 0, None)
+    assert rc != 0 and b'figure' in _lib.load().xrt_b200_last_error()

@@ -90,12 +90,14 @@ def test_plugin_objects_build_and_export_without_gpu():
     from xrt_b200 import custom, oes_spliced
     from xrt_b200.oes import xrt_oe_params
     paths = oes_spliced.prebuild()
-    assert len(set(paths)) == len({(c.cu_local_z, c.cu_local_n) for c in oes_spliced.LIBRARY})
-    assert sorted(custom.SurfacePlugin(p).kind for p in paths).count(5) == 1  # ParabolicalMirrorParam
+    assert len(set(paths)) == len({(c.cu_local_z, c.cu_local_n) for c in oes_spliced.LIBRARY}) + 2
+    plugs = [custom.SurfacePlugin(p) for p in paths]
+    assert sorted(q.kind for q in plugs).count(5) == 1  # ParabolicalMirrorParam
+    assert sorted((q.kind, q.figure_error) for q in plugs if q.figure_error) == [(0, True), (1, True)]
     for p in paths:
         assert os.path.dirname(p) == custom.PLUGIN_DIR and os.path.exists(p)
         plug = custom.SurfacePlugin(p)
-        assert plug.kind in (4, 5)
+        assert plug.kind in (0, 1, 4, 5)
         assert plug.lib.xrt_plugin_sizeof_oe_params() == ctypes.sizeof(xrt_oe_params)
 
 

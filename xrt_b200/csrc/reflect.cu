@@ -40,11 +40,17 @@
 #ifdef XRTB_USER_SURFACE
 #include XRTB_USER_SURFACE
 #endif
-#ifdef XRTB_USER_PARAMETRIC
+#if defined(XRTB_PLUGIN_KIND)
+#define XRTB_USER_KIND XRTB_PLUGIN_KIND  // a built-in surface compiled as a plug-in variant (figure error, below)
+#elif defined(XRTB_USER_PARAMETRIC)
 #define XRTB_USER_KIND 5
 #else
 #define XRTB_USER_KIND 4
 #endif
+// Figure errors (OE(figureError=...): oes/base.py:681-686, :744-770, find_dz :825-829, reflect.py:767-776,
+// figure_error.py:207-265) are a plug-in variant as well: -DXRTB_FIGURE_ERROR compiles the bicubic-spline height map
+// into find_dz and the normal of ONE surface kind (-DXRTB_PLUGIN_KIND=<0|1> or a spliced kind 4), so the kernels of
+// libxrt_b200.so keep their register budget.
 
 namespace xrtb {
 
@@ -145,6 +151,94 @@ __device__ __forceinline__ double pow_m05(double x) {
   const double e = fma(-x * y0, y0, 1.0);
   return fma(0.5 * y0, e, y0);
 }
+
+#ifdef XRTB_FIGURE_ERROR
+// ---------------------------------------------------------------- figure error: bicubic spline height map
+// scipy's RectBivariateSpline(y1d, x1d, z_nm, kx=3, ky=3).ev(y, x[, dx, dy]) as FITPACK evaluates it (fpbisp with
+// fpbspl; parder for the first derivatives): u = y + yShift runs along the first knot vector, v = x + xShift along
+// the second; c is (nu - 4) x (nv - 4).  Same operation order as FITPACK (this file is compiled with -fmad=false).
+__device__ __forceinline__ int fe_interval(const double* __restrict__ t, int n, int k, double& arg) {
+  // fpbisp: clamp to [t(k+1), t(n-k)], then t(l) <= arg < t(l+1) or l = n-k-1 (1-based); returns the 0-based l
+  const double tb = t[k], te = t[n - k - 1];
+  if (arg < tb) arg = tb;
+  if (arg > te) arg = te;
+  int lo = k, hi = n - k - 2;  // 0-based candidates
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (t[mid] <= arg) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+template <int K>
+__device__ __forceinline__ void fe_bspl(const double* __restrict__ t, double x, int L, double* h) {
+  // fpbspl: the K+1 non-zero B-splines of degree K at t[L] <= x < t[L+1] (de Boor - Cox)
+  double hh[K + 1];
+  h[0] = 1.0;
+#pragma unroll
+  for (int j = 1; j <= K; ++j) {
+#pragma unroll
+    for (int i = 0; i < j; ++i) hh[i] = h[i];
+    h[0] = 0.0;
+#pragma unroll
+    for (int i = 1; i <= j; ++i) {
+      const double tli = t[L + i], tlj = t[L + i - j];
+      const double f = hh[i - 1] / (tli - tlj);
+      h[i - 1] = h[i - 1] + f * (tli - x);
+      h[i] = f * (x - tlj);
+    }
+  }
+}
+// value (which = 0), d/du (1: first variable, y) or d/dv (2: second variable, x), in the map's units (nm, nm/mm)
+__device__ __noinline__ double fe_eval_at(const double* __restrict__ tu, const double* __restrict__ tv,
+                                          const double* __restrict__ c, int fe_nu, int fe_nv, double u, double v,
+                                          int which) {
+  const int nkv = fe_nv - 4;  // coefficients per row
+  double hu[4], hv[4];
+  double sp = 0.0;
+  if (which == 0) {
+    const int Lu = fe_interval(tu, fe_nu, 3, u), Lv = fe_interval(tv, fe_nv, 3, v);
+    fe_bspl<3>(tu, u, Lu, hu);
+    fe_bspl<3>(tv, v, Lv, hv);
+    for (int a = 0; a < 4; ++a)
+      for (int b = 0; b < 4; ++b) sp = sp + c[(size_t)(Lu - 3 + a) * nkv + (Lv - 3 + b)] * hu[a] * hv[b];
+  } else if (which == 1) {
+    // parder, nux = 1: d[i][j] = (c[i+1][j] - c[i][j]) * 3 / (tu[i+4] - tu[i+1]) on the knots tu[1 .. nu-2], degree 2
+    const double* __restrict__ tu1 = tu + 1;
+    const int Lu = fe_interval(tu1, fe_nu - 2, 2, u), Lv = fe_interval(tv, fe_nv, 3, v);
+    fe_bspl<2>(tu1, u, Lu, hu);
+    fe_bspl<3>(tv, v, Lv, hv);
+    for (int a = 0; a < 3; ++a) {
+      const int i = Lu - 2 + a;
+      const double fac = tu[i + 4] - tu[i + 1];
+      for (int b = 0; b < 4; ++b) {
+        const int j = Lv - 3 + b;
+        const double c0 = c[(size_t)i * nkv + j], c1 = c[(size_t)(i + 1) * nkv + j];
+        const double d = fac > 0.0 ? (c1 - c0) * 3.0 / fac : c0;
+        sp = sp + d * hu[a] * hv[b];
+      }
+    }
+  } else {
+    const double* __restrict__ tv1 = tv + 1;
+    const int Lu = fe_interval(tu, fe_nu, 3, u), Lv = fe_interval(tv1, fe_nv - 2, 2, v);
+    fe_bspl<3>(tu, u, Lu, hu);
+    fe_bspl<2>(tv1, v, Lv, hv);
+    for (int a = 0; a < 4; ++a) {
+      const int i = Lu - 3 + a;
+      for (int b = 0; b < 3; ++b) {
+        const int j = Lv - 2 + b;
+        const double fac = tv[j + 4] - tv[j + 1];
+        const double c0 = c[(size_t)i * nkv + j], c1 = c[(size_t)i * nkv + j + 1];
+        const double d = fac > 0.0 ? (c1 - c0) * 3.0 / fac : c0;
+        sp = sp + d * hu[a] * hv[b];
+      }
+    }
+  }
+  return sp;
+}
+__device__ __forceinline__ double fe_eval(const xrt_oe_params& p, double x, double y, int which) {
+  return fe_eval_at(p.fe_tu, p.fe_tv, p.fe_c, p.fe_nu, p.fe_nv, y + p.fe_ushift, x + p.fe_vshift, which);
+}
+#endif
 
 // the surface's loop-invariant divisors with their reciprocals refined once per thread (common.cuh, Divisor)
 struct SurfDiv {
@@ -255,6 +349,9 @@ __device__ __forceinline__ double find_dz(const xrt_oe_params& p, const SurfDiv&
     return (REFR && p.from_vacuum == 0) ? -dn : dn;
   }
   double surf = local_surface<SURF>(p, sd, x, y);
+#ifdef XRTB_FIGURE_ERROR
+  if (p.fe_c) surf = surf + fe_eval(p, x, y, 0) * 1e-6;  // surf += z_distorted, nm -> mm (base.py:825-829)
+#endif
   if (isnan(surf)) surf = 0.0;
   double d = z - surf;
   if (SURF == 2 || SURF == 5) d = -d;  // parametric: local_f = local_r, diffSign = -1 (base.py:809-813, :840)
@@ -1311,6 +1408,26 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
         ++ngoodN;
         double nrm[6];
         local_normal<SURF>(p, sd, lx, ly, nrm);
+#ifdef XRTB_FIGURE_ERROR
+        if (p.fe_c) {
+          // local_n_distorted -> (d_pitch, d_roll) = (atan(dz/dy), -atan(dz/dx)); the surface normal is turned by
+          // rotate_x, then rotate_y (reflect.py:767-776); with one normal it is also the normal of the planes
+          const double aa = fe_eval(p, lx, ly, 2) * 1e-6, bb = fe_eval(p, lx, ly, 1) * 1e-6;
+          double sX, cX, sYY, cYY;
+          sincos(atan(bb), &sX, &cX);
+          sincos(-atan(aa), &sYY, &cYY);
+          const double n4 = cX * nrm[4] - sX * nrm[5], n5 = sX * nrm[4] + cX * nrm[5];
+          nrm[4] = n4;
+          const double n3 = cYY * nrm[3] + sYY * n5;
+          nrm[5] = -sYY * nrm[3] + cYY * n5;
+          nrm[3] = n3;
+          if (!p.asymmetric) {
+            nrm[0] = nrm[3];
+            nrm[1] = nrm[4];
+            nrm[2] = nrm[5];
+          }
+        }
+#endif
         bdn = la * nrm[0] + lbb * nrm[1] + lc * nrm[2];
         if (bdn < -1.0) bdn = -1.0;
         if (bdn > 1.0) bdn = 1.0;
@@ -1691,6 +1808,13 @@ int reflect_device(size_t n, const xrt_oe_params* oe, const xrt_material_params*
 #endif
   XRTB_REQUIRE(oe->n_rot_in >= 0 && oe->n_rot_in <= XRT_MAX_ROT && oe->n_rot_out >= 0 && oe->n_rot_out <= XRT_MAX_ROT,
                "reflect: too many elementary rotations");
+#ifndef XRTB_FIGURE_ERROR
+  XRTB_REQUIRE(oe->fe_c == nullptr, "reflect: a figure error (fe_c) is served by the figure-error plug-in variant of the "
+                                    "surface kind (xrt_b200.custom), not by this object");
+#else
+  XRTB_REQUIRE(oe->fe_c == nullptr || (oe->fe_tu && oe->fe_tv && oe->fe_nu >= 8 && oe->fe_nv >= 8),
+               "reflect: figure error needs both knot vectors (>= 8 knots each) and the coefficients");
+#endif
   xrt_material_params m;
   memset(&m, 0, sizeof(m));
   if (mat) m = *mat;
@@ -1924,4 +2048,11 @@ XRTB_EXPORT int xrt_plugin_reflect_multi_deriv_f64(size_t n, const xrt_oe_params
 }
 XRTB_EXPORT size_t xrt_plugin_sizeof_oe_params(void) { return sizeof(xrt_oe_params); }
 XRTB_EXPORT int xrt_plugin_surface_kind(void) { return XRTB_USER_KIND; }
+XRTB_EXPORT int xrt_plugin_has_figure_error(void) {
+#ifdef XRTB_FIGURE_ERROR
+  return 1;
+#else
+  return 0;
+#endif
+}
 #endif

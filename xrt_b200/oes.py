@@ -50,7 +50,11 @@ class xrt_oe_params(ctypes.Structure):
                 ('no_intersection', ctypes.c_int), ('from_vacuum', ctypes.c_int), ('dead_state_lost', ctypes.c_int),
                 ('grating', ctypes.c_int), ('g_ncoef', ctypes.c_int), ('g_rho0', ctypes.c_double),
                 ('g_coef', ctypes.c_double * 8), ('g_order', ctypes.c_double), ('g_amp', ctypes.c_double),
-                ('multi', ctypes.c_int), ('multi_tmin', ctypes.c_void_p)]
+                ('multi', ctypes.c_int),
+                ('fe_tu', ctypes.c_void_p), ('fe_tv', ctypes.c_void_p), ('fe_c', ctypes.c_void_p),
+                ('fe_nu', ctypes.c_int), ('fe_nv', ctypes.c_int),
+                ('fe_ushift', ctypes.c_double), ('fe_vshift', ctypes.c_double),
+                ('multi_tmin', ctypes.c_void_p)]
 
 
 _AXIS = {'x': 0, 'y': 1, 'z': 2}
@@ -123,6 +127,7 @@ class OE(object):
         self.alarmLevel = alarmLevel
         self.material = material
         self.alpha = alpha
+        self.figureError = kwargs.pop('figureError', None)  # xrt_b200.figure_error object (base.py:160, :310)
         self.shape = shape
         if not shape.startswith('re'):
             raise NotImplementedError("only shape='rect' is on the hot path")
@@ -159,13 +164,21 @@ class OE(object):
         return out
 
     def _plugin(self):
-        """The spliced-surface plug-in object of this element, or None for the built-in surfaces."""
+        """The plug-in object that serves this element -- a spliced surface and / or the figure-error variant of its
+        kernels -- or None for the built-in surfaces without figure error."""
+        fe = self.figureError is not None
         if self.cu_local_z is None:
-            return None
+            if not fe:
+                return None
+            if self.surfaceKind not in (0, 1) or hasattr(self, 'bragg'):
+                raise NotImplementedError('figure errors are on the hot path for flat, toroidal and spliced z(x, y) '
+                                          'single-surface elements')
+            from . import custom
+            return custom.plugin_for(builtin_kind=self.surfaceKind, figure_error=True)
         if self.cu_local_n is None:
             raise _lib.XrtB200Error('a spliced surface needs both cu_local_z and cu_local_n')
         from . import custom
-        return custom.plugin_for(self.cu_local_z, self.cu_local_n, self.cu_xyz_param)
+        return custom.plugin_for(self.cu_local_z, self.cu_local_n, self.cu_xyz_param, figure_error=fe)
 
     def _limits(self, second=False):
         sfx = '2' if second else ''
@@ -247,6 +260,8 @@ class OE(object):
         p.want_footprint = 1
         p.from_vacuum = 1
         self._fill_grating(p, self.material2 if (is2ndXtal and hasattr(self, 'material2')) else self.material)
+        if self.figureError is not None:
+            self.figureError.fill_params(p, torch.device('cuda', torch.cuda.current_device()))
         return p
 
     def _fill_grating(self, p, material):
@@ -362,6 +377,8 @@ class OE(object):
     def local_n_device(self, x, y, z):
         """Surface normal (nx, ny, nz) at local Cartesian points given as CUDA tensors: OE.local_n after
         xyz_to_param for parametric surfaces (waves.py:675-686)."""
+        if self.figureError is not None:
+            raise NotImplementedError('wave-mode helpers with a figure error are outside the hot path')
         lib = _lib.load()
         n = x.numel()
         out = torch.empty((3, n), dtype=torch.float64, device=x.device)
@@ -466,6 +483,8 @@ class OE(object):
         searched).  One host synchronisation per pass (the count of rays still alive ends the loop)."""
         if needElevationMap:
             raise NotImplementedError('needElevationMap is outside the hot path')
+        if self.figureError is not None:
+            raise NotImplementedError('multiple_reflect with a figure error is outside the hot path')
         if self.material is not None and getattr(self.material, 'kind', 'mirror') not in ('auto', 'mirror', 'thin mirror'):
             raise NotImplementedError('multiple_reflect is on the hot path for mirrors (and bare surfaces)')
         lib = _lib.load()
