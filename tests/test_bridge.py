@@ -125,3 +125,21 @@ def test_bridge_spliced_element_and_multiple_reflect(cuda_device):
     other = _fake_common(g, VCM, _fake_material('Au', g, 'mirror'), R=float(g['R']), limPhysY=list(g['surfPhysY']))
     with pytest.raises(NotImplementedError):
         bridge.reflect(other, oracle_beam(g, 'in_'))
+
+
+@pytest.mark.gpu
+def test_bridge_figure_error_host_objects(cuda_device):
+    """An xrt-shaped toroid carrying an xrt-shaped FigureError (a scipy spline + shifts) is traced by the figure-error
+    plug-in variant: states equal the reference's, positions to 1e-12."""
+    from scipy import interpolate
+    from xrt_b200 import bridge
+    g = golden('reflect_figerr_toroid_bump')
+    oe = _fake_xrt_oe(g)
+    oe.figureError = types.SimpleNamespace(
+        local_z_spline=interpolate.RectBivariateSpline(g['fe_y1d'], g['fe_x1d'], g['fe_z'], kx=3, ky=3),
+        xShift=float(g['fe_xShift']), yShift=float(g['fe_yShift']), name='bump')
+    gb, lb = bridge.reflect(oe, oracle_beam(g, 'in_'))
+    assert np.array_equal(gb.state, g['gb_state'])
+    geo = ('x', 'y', 'z', 'a', 'b', 'c', 'Jss', 'Jpp', 'Jsp')
+    bad = compare_beams(gb.__dict__, {f: g['gb_' + f] for f in BEAM_FIELDS}, geo, 1e-12, 'gb_')
+    assert not bad, bad

@@ -64,6 +64,10 @@ def _oe_kwargs(oe):
               limOptX=None if oe.surfOptX is None else list(oe.surfOptX),
               limOptY=None if oe.surfOptY is None else list(oe.surfOptY),
               overEdge=getattr(oe, 'overEdge', 'yMax'), shape=oe.shape, material=convert_material(oe.material))
+    fe = getattr(oe, 'figureError', None)
+    if fe is not None and hasattr(fe, 'local_z_spline'):  # any of xrt's FigureError classes (figure_error.py:207-212)
+        from .figure_error import FigureErrorSpline
+        kw['figureError'] = FigureErrorSpline(fe.local_z_spline, fe.xShift, fe.yShift, getattr(fe, 'name', ''))
     if getattr(oe, 'gratingDensity', None) is not None:
         kw['gratingDensity'] = list(oe.gratingDensity)
     if getattr(kw['material'], 'kind', None) in ('grating', 'auto') or 'gratingDensity' in kw:

@@ -106,6 +106,19 @@ class FigureErrorMap(FigureErrorBase):
         return self._z + self._base_profile()
 
 
+class FigureErrorSpline(FigureErrorBase):
+    """A ready scipy RectBivariateSpline(y1d, x1d, z_nm, kx=3, ky=3) with its shifts -- what any of xrt's own
+    FigureError objects holds as `local_z_spline`, `xShift`, `yShift` (xrt_b200.bridge converts them this way)."""
+
+    def __init__(self, spline, xShift=0., yShift=0., name=''):
+        self.name = name
+        self.baseFE = None
+        self.splineOrder = 3
+        self.xShift, self.yShift = float(xShift), float(yShift)
+        self.local_z_spline = spline
+        self._dev = {}
+
+
 class GaussianBump(FigureErrorBase):
     def __init__(self, bumpHeight=10., cX=0., cY=0., sigmaX=10., sigmaY=10., **kwargs):
         self.bumpHeight, self.cX, self.cY, self.sigmaX, self.sigmaY = bumpHeight, cX, cY, sigmaX, sigmaY
