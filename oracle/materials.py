@@ -259,8 +259,9 @@ class Multilayer(object):
     geom = 'reflected'
 
     def __init__(self, tLayer, tThickness, bLayer, bThickness, nPairs, substrate, tThicknessLow=0., bThicknessLow=0.,
-                 idThickness=0., power=2.):
+                 idThickness=0., power=2., substRoughness=0.):
         self.tLayer, self.bLayer, self.substrate = tLayer, bLayer, substrate
+        self.substRoughness = substRoughness
         self.nPairs = int(nPairs)
         self.power = power
         self.tThicknessHigh, self.tThicknessLow = float(tThickness), float(tThicknessLow)
@@ -283,7 +284,7 @@ class Multilayer(object):
         """The interface amplitudes and layer wave vectors the reference hands to its accelerator kernel
         (multilayer.py:364-409, :471-477)."""
         k = E / CHBAR
-        nt = self.tLayer.get_refractive_index(E).conjugate()
+        nt = self.tLayer.get_refractive_index(E).conjugate() if self.tLayer else 1.  # multilayer.py:373
         nb = self.bLayer.get_refractive_index(E).conjugate()
         ns = self.substrate.get_refractive_index(E).conjugate()
         Q = 2 * k * abs(beamInDotNormal)
@@ -299,7 +300,7 @@ class Multilayer(object):
         roughtb = np.exp(-0.5 * Qt * Qb * id2)
         rtb_s = np.complex128((Qt-Qb) / (Qt+Qb) * roughtb)
         rtb_p = np.complex128((Qt/nt*nb - Qb/nb*nt) / (Qt/nt*nb + Qb/nb*nt) * roughtb)
-        rmsbs = id2
+        rmsbs = id2 if self.tLayer else self.substRoughness**2  # multilayer.py:401
         roughbs = np.exp(-0.5 * Qb * Qs * rmsbs)
         rbs_s = np.complex128((Qb-Qs) / (Qb+Qs) * roughbs)
         rbs_p = np.complex128((Qb/nb*ns - Qs/ns*nb) / (Qb/nb*ns + Qs/ns*nb) * roughbs)
@@ -337,3 +338,14 @@ class Multilayer(object):
         if (nn - 1) > 0:
             return ri_s.conjugate(), ri_p.conjugate()
         return ri_s, ri_p
+
+
+class Coated(Multilayer):
+    """Coated (materials/multilayer.py:528-584): a single reflective layer on a substrate = a Multilayer without top
+    layer (vacuum, zero thickness), nPairs = 1, idThickness = the surface roughness; kind 'mirror', so OE.reflect
+    treats it as a mirror (specular reflection; get_amplitude(E, beamInDotNormal, fromVacuum), reflect.py:1003-1025)."""
+    kind = 'mirror'
+
+    def __init__(self, coating, cThickness, substrate, surfaceRoughness=0., substRoughness=0.):
+        Multilayer.__init__(self, None, 0., coating, cThickness, 1, substrate, idThickness=surfaceRoughness,
+                            substRoughness=substRoughness)

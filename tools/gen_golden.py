@@ -1172,7 +1172,34 @@ def gen_figure_error():
              fe_x1d=fe.x1d, fe_y1d=fe.y1d, fe_z=fe.generate_profile(), **d)
 
 
-SECTIONS = {'figure_error': gen_figure_error, 'round': gen_round, 'shine_wave': gen_shine_wave, 'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+def gen_coated():
+    """Coated (materials/multilayer.py:528-584): one reflective layer on a substrate, with surface and substrate
+    roughness, kind 'mirror' -- amplitudes on a grid and a toroid mirror in a beam line."""
+    Pt, Si = rm.Material('Pt', rho=21.45), rm.Material('Si', rho=2.33)
+    kw = dict(coating=Pt, cThickness=350., surfaceRoughness=3., substrate=Si, substRoughness=5.)
+    cm = rm.Coated(**kw)
+    rng = np.random.RandomState(171)
+    n = 2500
+    theta = np.linspace(0.5e-3, 12e-3, n)
+    E = rng.uniform(6000, 12000, n)
+    bdn = -np.sin(theta)
+    rs, rp = cm.get_amplitude(E.copy(), bdn.copy(), True)
+    print('coated |rs|^2 range', float((abs(rs)**2).min()), float((abs(rs)**2).max()))
+    save('coated_amplitudes', E=E, bdn=bdn, rs=rs, rp=rp, **{k: v for k, v in kw.items() if isinstance(v, float)})
+    bl = raycing.BeamLine()
+    beam = _source_beam(bl, 3000, 172, dx=0.5, dz=0.3, dxprime=2e-4, dzprime=1e-4, energies=(6000, 12000))
+    oe = roe.ToroidMirror(bl, 'TM', center=(0, 25000, 0), pitch=3e-3, R=8e6, r=75., material=rm.Coated(**kw),
+                          limPhysX=[-4, 4], limPhysY=[-500, 400])
+    d = _capture_reflect(oe, beam)
+    d.update(_oe_params(oe))
+    st = d['gb_state']
+    print('coated toroid', {int(x): int((st == x).sum()) for x in np.unique(st)}, 'mean R',
+          float((d['gb_Jss'] + d['gb_Jpp'])[st == 1].mean() / (d['in_Jss'] + d['in_Jpp'])[st == 1].mean()))
+    save('reflect_coated_toroid', R=float(oe.R), r=float(oe.r),
+         **{k: v for k, v in kw.items() if isinstance(v, float)}, **d)
+
+
+SECTIONS = {'coated': gen_coated, 'figure_error': gen_figure_error, 'round': gen_round, 'shine_wave': gen_shine_wave, 'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)
