@@ -239,6 +239,11 @@ typedef struct xrt_multilayer_params {
   double idThickness;     /* interdiffusion / roughness rms, Angstrom */
   double d;               /* tThickness + bThickness: the period (grating deflection, Bragg angle) */
   const double *dti, *dbi;
+  /* Coated (materials/multilayer.py:528-584): tLayer.nelem == 0 means no top layer (vacuum, n = 1); the bottom-layer /
+   * substrate interface then takes substRoughness instead of idThickness (multilayer.py:401) */
+  double substRoughness;
+  int specular;           /* 1: kind 'mirror' -- specular reflection with this amplitude instead of the multilayer's
+                             grating-like deflection (reflect.py:1003-1025 vs :999-1002) */
 } xrt_multilayer_params;
 
 /* Beam-wide scalars numpy takes over the whole beam. 64 slots of 8 bytes, device

@@ -996,7 +996,8 @@ __device__ __forceinline__ void multilayer_amplitude(const xrt_multilayer_params
                                                      double bdn, cplx& rs, cplx& rp, int* oor) {
   const double CHBAR = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8 / 6.283185307179586476925286766559;
   const double k = E / CHBAR;
-  const cplx nt = cconj(refractive_index(ml.tLayer, tab, E, oor));
+  // no top layer (Coated): nt = 1. (multilayer.py:373)
+  const cplx nt = ml.tLayer.nelem > 0 ? cconj(refractive_index(ml.tLayer, tab, E, oor)) : cplx{1.0, 0.0};
   const cplx nb = cconj(refractive_index(ml.bLayer, tab, E, oor));
   const cplx ns = cconj(refractive_index(ml.substrate, tab, E, oor));
   const double Q = 2.0 * k * fabs(bdn);
@@ -1019,8 +1020,9 @@ __device__ __forceinline__ void multilayer_amplitude(const xrt_multilayer_params
   const cplx roughtb = cexp_np(cmul_np(cmul_np(cmul_np(cplx{-0.5, 0.0}, Qt), Qb), id2));
   const cplx rtb_s = cmul_np(cdiv(csub(Qt, Qb), cadd(Qt, Qb)), roughtb);
   const cplx rtb_p = cmul_np(fresnel_p(Qt, nt, Qb, nb), roughtb);
-  // bottom - substrate (rmsbs = id2 because the top layer exists, multilayer.py:402)
-  const cplx roughbs = cexp_np(cmul_np(cmul_np(cmul_np(cplx{-0.5, 0.0}, Qb), Qs), id2));
+  // bottom - substrate: rmsbs = id2 if the top layer exists, else substRoughness**2 (multilayer.py:401)
+  const cplx rmsbs = ml.tLayer.nelem > 0 ? id2 : cplx{ml.substRoughness * ml.substRoughness, 0.0};
+  const cplx roughbs = cexp_np(cmul_np(cmul_np(cmul_np(cplx{-0.5, 0.0}, Qb), Qs), rmsbs));
   const cplx rbs_s = cmul_np(cdiv(csub(Qb, Qs), cadd(Qb, Qs)), roughbs);
   const cplx rbs_p = cmul_np(fresnel_p(Qb, nb, Qs, ns), roughbs);
   multilayer_recursion(ml.nPairs, ml.uniform, rbs_s, rbs_p, rtb_s, rtb_p, rvt_s, rvt_p, Qt, Qb, ml.dti, ml.dbi, rs,
@@ -1435,7 +1437,7 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
         bds = p.asymmetric ? (la * nrm[3] + lbb * nrm[4] + lc * nrm[5]) : bdn;
         double ao, bo, co;
         const bool transmitted = (MAT == 3) && (m.geom & 2);  // toWhere = 2 (reflect.py:756, :862-878)
-        if ((MAT == 3 || MAT == 4) && !transmitted) {
+        if ((MAT == 3 || MAT == 4) && !transmitted && !(MAT == 4 && ml.specular)) {
           // crystal / multilayer as a grating (reflect.py:568-612, :451-469); sgbdn is taken per ray here -- all
           // good rays hit the same side of the crystal in the supported geometries (documented in DESIGN.md)
           const double ndsn = nrm[0] * nrm[3] + nrm[1] * nrm[4] + nrm[2] * nrm[5];
@@ -1770,8 +1772,8 @@ static int check_multilayer(const xrt_material_params& m, xrt_multilayer_params&
   XRTB_REQUIRE(m.multilayer != nullptr, "multilayer: material kind 4 needs the layer stack");
   ml = *m.multilayer;
   XRTB_REQUIRE(ml.nPairs >= 0 && ml.dti && ml.dbi, "multilayer: nPairs >= 0 and the thickness arrays are required");
-  XRTB_REQUIRE(ml.tLayer.nelem > 0 && ml.bLayer.nelem > 0 && ml.substrate.nelem > 0,
-               "multilayer: top layer, bottom layer and substrate materials are all required");
+  XRTB_REQUIRE(ml.tLayer.nelem >= 0 && ml.bLayer.nelem > 0 && ml.substrate.nelem > 0,
+               "multilayer: bottom layer and substrate materials are required (no top layer = a coated mirror)");
   XRTB_REQUIRE(ml.tLayer.nelem <= XRT_MAX_ELEM && ml.bLayer.nelem <= XRT_MAX_ELEM && ml.substrate.nelem <= XRT_MAX_ELEM,
                "multilayer: at most %d elements per material", XRT_MAX_ELEM);
   return 0;

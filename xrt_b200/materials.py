@@ -37,7 +37,8 @@ class xrt_multilayer_params(ctypes.Structure):
     """struct xrt_multilayer_params of include/xrt_b200.h"""
     _fields_ = [('tLayer', xrt_material_params), ('bLayer', xrt_material_params), ('substrate', xrt_material_params),
                 ('nPairs', ctypes.c_int), ('uniform', ctypes.c_int), ('idThickness', ctypes.c_double),
-                ('d', ctypes.c_double), ('dti', ctypes.c_void_p), ('dbi', ctypes.c_void_p)]
+                ('d', ctypes.c_double), ('dti', ctypes.c_void_p), ('dbi', ctypes.c_void_p),
+                ('substRoughness', ctypes.c_double), ('specular', ctypes.c_int)]
 
 
 def _tables():
@@ -327,8 +328,9 @@ class Multilayer(object):
     def __init__(self, tLayer=None, tThickness=0., bLayer=None, bThickness=0., nPairs=0, substrate=None,
                  tThicknessLow=0., bThicknessLow=0., idThickness=0., power=2., substRoughness=0.,
                  substThickness=np.inf, name='', geom='reflected', **kwargs):
-        if tLayer is None or bLayer is None or substrate is None:
-            raise NotImplementedError('top layer, bottom layer and substrate are all required on this path')
+        if bLayer is None or substrate is None or (tLayer is None and not isinstance(self, Coated)):
+            raise NotImplementedError('top layer, bottom layer and substrate are all required on this path '
+                                      '(a single layer on a substrate is `Coated`)')
         if geom and 'tran' in geom:
             raise NotImplementedError("geom='transmitted' multilayers are the next row (SURVEY.md 8f)")
         self.tLayer, self.bLayer, self.substrate = tLayer, bLayer, substrate
@@ -379,7 +381,8 @@ class Multilayer(object):
 
     # ------------------------------------------------------------------ device plumbing
     def host_tables(self):
-        parts = [m.host_tables() for m in (self.tLayer, self.bLayer, self.substrate)]
+        empty = (np.zeros(0), 0, [], [])  # no top layer (Coated)
+        parts = [m.host_tables() if m is not None else empty for m in (self.tLayer, self.bLayer, self.substrate)]
         E, f1, f2, offs, lens, pos = [], [], [], [], [], 0
         for tab, n, o, ln in parts:
             E.append(tab[:n])
@@ -408,6 +411,9 @@ class Multilayer(object):
         ml = xrt_multilayer_params()
         for name, mat, o, ln in zip(('tLayer', 'bLayer', 'substrate'), (self.tLayer, self.bLayer, self.substrate),
                                     offs, lens):
+            if mat is None:  # no top layer: nelem = 0
+                setattr(ml, name, xrt_material_params())
+                continue
             sub = Material.c_struct(mat, o, ln) if not hasattr(mat, 'hkl') else None
             if sub is None:
                 raise NotImplementedError('crystal layers in a multilayer')
@@ -418,6 +424,8 @@ class Multilayer(object):
         ml.idThickness = float(self.idThickness)
         ml.d = self.d
         ml.dti, ml.dbi = pdti, pdbi
+        ml.substRoughness = float(self.substRoughness)
+        ml.specular = int(self.kind == 'mirror')
         m = xrt_material_params()
         m.kind = 4
         m.multilayer = ctypes.addressof(ml)
@@ -428,3 +436,20 @@ class Multilayer(object):
         """(ri_s, ri_p) on host arrays (multilayer.py:254-508, geom 'reflected')."""
         from . import kernels
         return kernels.material_amplitude_host(self, E, beamInDotNormal)
+
+
+class Coated(Multilayer):
+    """A single reflective layer on a substrate (materials/multilayer.py:528-584): a Multilayer without top layer,
+    nPairs = 1, idThickness = the surface roughness, kind 'mirror' (specular reflection with the Parratt amplitude)."""
+
+    def __init__(self, *args, **kwargs):
+        coating = kwargs.pop('coating', None)
+        cThickness = kwargs.pop('cThickness', 0)
+        surfaceRoughness = kwargs.pop('surfaceRoughness', 0)
+        Multilayer.__init__(self, *args, bLayer=coating, bThickness=cThickness, idThickness=surfaceRoughness, nPairs=1,
+                            **kwargs)
+        self.kind = 'mirror'
+
+    coating = property(lambda self: self.bLayer)
+    cThickness = property(lambda self: self.bThickness)
+    surfaceRoughness = property(lambda self: self.idThickness)
