@@ -38,6 +38,17 @@ def convert_material(m):
     """xrt Material / CrystalFcc / CrystalDiamond / CrystalSi instance -> xrt_b200 material."""
     if m is None:
         return None
+    if hasattr(m, 'bLayer'):  # Multilayer / Coated (materials/multilayer.py:14-584)
+        if 'tran' in (getattr(m, 'geom', None) or 'reflected'):
+            raise NotImplementedError("geom='transmitted' multilayers are outside the hot path")
+        common = dict(substrate=convert_material(m.substrate), substRoughness=m.substRoughness)
+        if m.tLayer is None:
+            return _mat.Coated(coating=convert_material(m.bLayer), cThickness=m.bThickness,
+                               surfaceRoughness=m.idThickness, **common)
+        return _mat.Multilayer(tLayer=convert_material(m.tLayer), tThickness=m.tThickness,
+                               bLayer=convert_material(m.bLayer), bThickness=m.bThickness, nPairs=m.nPairs,
+                               tThicknessLow=m.tThicknessLow, bThicknessLow=m.bThicknessLow,
+                               idThickness=m.idThickness, power=m.power, **common)
     if not hasattr(m, 'elements'):  # EmptyMaterial (materials/__init__.py:101-113)
         return _mat.EmptyMaterial(kind=m.kind)
     names = [e.name for e in m.elements]
