@@ -199,3 +199,54 @@ class FigureErrorSpline(object):
         a = self.local_z_spline.ev(y+self.yShift, x+self.xShift, dx=0, dy=1) * 1e-6
         b = self.local_z_spline.ev(y+self.yShift, x+self.xShift, dx=1, dy=0) * 1e-6
         return [np.arctan(b), -np.arctan(a)]
+
+
+class LauePlate(object):
+    """oes/laue.py:11-24: a flat Laue plate -- the normal to the diffracting planes lies (nearly) in the surface."""
+
+    def __init__(self, alpha=None):
+        self.alpha = alpha
+        if alpha:
+            self.cosalpha, self.sinalpha = np.cos(alpha), np.sin(alpha)
+
+    def local_z(self, x, y):
+        return np.zeros_like(y)
+
+    def local_n(self, x, y):
+        a, b, c = 0, 0, 1
+        if self.alpha:
+            bB, cB = ob.rotate_x(b, c, -self.sinalpha, -self.cosalpha)
+        else:
+            bB, cB = c, -b
+        return [a, bB, cB, a, b, c]
+
+
+class BentLaueCylinder(object):
+    """oes/laue.py:26-175 (local_z :143-148, local_n_cylinder :150-169): cylindrically bent Laue crystal."""
+
+    def __init__(self, R, crossSection='parabolic', alpha=None):
+        self.R, self.crossSection, self.alpha = R, crossSection, alpha
+        if alpha:
+            self.cosalpha, self.sinalpha = np.cos(alpha), np.sin(alpha)
+
+    def local_z(self, x, y):
+        if self.crossSection.startswith('circ'):
+            return self.R - np.sqrt(self.R**2 - y**2)
+        else:
+            return y**2 / 2.0 / self.R
+
+    def local_n(self, x, y):
+        R = self.R
+        a = np.zeros_like(x)
+        b = -y / R
+        if self.crossSection.startswith('circ'):
+            c = (R**2 - y**2)**0.5 / R
+        else:
+            norm = (b**2 + 1)**0.5
+            b /= norm
+            c = 1. / norm
+        if self.alpha:
+            bB, cB = ob.rotate_x(b, c, -self.sinalpha, -self.cosalpha)
+        else:
+            bB, cB = c, -b
+        return [a, bB, cB, a, b, c]

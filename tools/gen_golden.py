@@ -1199,7 +1199,32 @@ def gen_coated():
          **{k: v for k, v in kw.items() if isinstance(v, float)}, **d)
 
 
-SECTIONS = {'coated': gen_coated, 'figure_error': gen_figure_error, 'round': gen_round, 'shine_wave': gen_shine_wave, 'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+def gen_laue():
+    """LauePlate and BentLaueCylinder (oes/laue.py:11-24, :26-175): Laue-geometry crystals with the planes' normal
+    (n_B) and the surface normal returned together; Si(111) 'Laue reflected', with and without asymmetry angle."""
+    bl = raycing.BeamLine()
+    E0 = 9000.
+    cases = (('laueplate', roe.LauePlate, dict(), None), ('laueplate_alpha', roe.LauePlate, dict(), np.radians(6.)),
+             ('bentlaue_parab', roe.BentLaueCylinder, dict(R=2.5e4, crossSection='parabolic'), None),
+             ('bentlaue_circ_alpha', roe.BentLaueCylinder, dict(R=2.5e4, crossSection='circular'), np.radians(-5.)))
+    for i, (name, cls, kw, alpha) in enumerate(cases):
+        si = rm.CrystalSi(hkl=(1, 1, 1), geom='Laue reflected', t=0.1)
+        beam = _source_beam(bl, 1500, 230 + i, dx=0.2, dz=0.02, dxprime=5e-5, dzprime=2e-5, energies=(8998, 9002))
+        thetaB = float(si.get_Bragg_angle(E0))
+        pitch = np.pi/2 - thetaB + (alpha or 0.)
+        oe = cls(bl, name, center=(0, 2e4, 0), pitch=pitch, material=si, alpha=alpha, limPhysX=[-20, 20],
+                 limPhysY=[-20, 20], **kw)
+        dd = _capture_reflect(oe, beam)
+        dd.update(_oe_params(oe))
+        st = dd['gb_state']
+        good = st == 1
+        print(name, {int(x): int((st == x).sum()) for x in np.unique(st)}, 'mean R',
+              float((dd['gb_Jss'] + dd['gb_Jpp'])[good].mean() / (dd['in_Jss'] + dd['in_Jpp'])[good].mean()))
+        save('reflect_laue_' + name, d=si.d, tK=si.tK, t=0.1, alpha=0. if alpha is None else alpha,
+             R=float(kw.get('R', 0.)), **dd)
+
+
+SECTIONS = {'laue': gen_laue, 'coated': gen_coated, 'figure_error': gen_figure_error, 'round': gen_round, 'shine_wave': gen_shine_wave, 'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)

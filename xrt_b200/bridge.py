@@ -127,6 +127,12 @@ def convert_oe(oe):
             oe.bl, oe.name, Rm=float(oe.Rm), crossSection=oe.crossSection, **kw)
     elif 'JohannToroid' in cls and not any(c in cls for c in ('JohanssonToroid', 'GeneralBraggToroid', 'DicedOE')):
         out = _oes.JohannToroid(oe.bl, oe.name, Rm=float(oe.Rm), Rs=float(oe.Rs), **kw)
+    elif type(oe).__name__ == 'LauePlate':
+        out = _oes.LauePlate(oe.bl, oe.name, **kw)
+    elif type(oe).__name__ == 'BentLaueCylinder':
+        if getattr(oe.material, 'volumetricDiffraction', False):
+            raise NotImplementedError('volumetric diffraction is outside the hot path')
+        out = _oes.BentLaueCylinder(oe.bl, oe.name, R=float(oe.R), crossSection=oe.crossSection, **kw)
     elif 'ConicalMirror' in cls:
         out = _oes.ConicalMirror(oe.bl, oe.name, L0=float(oe.L0), theta=float(oe.theta), **kw)
     elif 'BentFlatMirror' in cls and type(oe).__name__ in ('BentFlatMirror', 'SimpleVCM'):

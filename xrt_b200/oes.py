@@ -228,10 +228,10 @@ class OE(object):
             p.surface = 5 if self.cu_xyz_param else 4
         for i, v in enumerate(self._surface_params()):
             p.sp[i] = float(v)
-        p.asymmetric = 1 if self.alpha else 0
+        p.asymmetric = 1 if (self.alpha or getattr(self, 'alwaysTwoNormals', False)) else 0
         if self.cu_local_z is not None and self.cu_two_normals is not None:
             p.asymmetric = int(bool(self.cu_two_normals))
-        if self.alpha and self.cu_local_z is None:
+        if p.asymmetric and self.cu_local_z is None:
             nB = self._local_nB(is2ndXtal)
             for i in range(3):
                 p.nB[i] = nB[i]
@@ -931,7 +931,7 @@ def _rotate_point(point, rotationSequence='RzRyRx', pitch=0, roll=0, yaw=0):
 
 
 _SPLICED = ('BentFlatMirror', 'SimpleVCM', 'ConicalMirror', 'JohannCylinder', 'JohanssonCylinder', 'JohannToroid',
-            'ParabolicalMirrorParam', 'ParabolicMirror')
+            'ParabolicalMirrorParam', 'ParabolicMirror', 'LauePlate', 'BentLaueCylinder')
 
 
 def __getattr__(name):

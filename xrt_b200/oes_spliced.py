@@ -8,6 +8,8 @@ and constructor arguments:
     JohanssonCylinder(..., Rm, crossSection)                oes/bragg.py:179-197
     JohannToroid(..., Rm, Rs)                               oes/bragg.py:200-269
     ParabolicalMirrorParam(..., p | q, isCylindrical)       oes/parametric.py:252-476  (parametric: s, phi, r)
+    BentLaueCylinder(..., R, crossSection)                  oes/laue.py:26-175   (planes' normal + surface normal)
+    LauePlate(...)                                          oes/laue.py:11-24    (flat: the built-in kernel, no texts)
 
 The texts follow the reference's numpy expressions operation by operation (the plug-in is compiled with
 -fmad=false); scalars the reference forms from Python floats (`self.Rm**2`, `0.25*self.t2t**2`) are formed on the
@@ -293,7 +295,65 @@ class ParabolicalMirrorParam(OE):
 
 ParabolicMirror = ParabolicalMirrorParam
 
-LIBRARY = (BentFlatMirror, ConicalMirror, JohannCylinder, JohanssonCylinder, JohannToroid, ParabolicalMirrorParam)
+class LauePlate(OE):
+    """A flat Laue plate (the thickness is in its material): n_B = rotate_x(0, 1, -sin(alpha), -cos(alpha)) =
+    (0, cos(alpha), -sin(alpha)), or (0, 1, 0) without alpha; the surface normal is (0, 0, 1).  Flat, so this is the
+    built-in flat kernel with both normals given (no spliced texts)."""
+    alwaysTwoNormals = True
+
+    def _local_nB(self, second=False):
+        if self.alpha:
+            cosalpha, sinalpha = np.cos(self.alpha), np.sin(self.alpha)
+            b, c = 0, 1
+            return 0., (-sinalpha)*b - (-cosalpha)*c, (-cosalpha)*b + (-sinalpha)*c  # rotate_x(b, c, -sin, -cos)
+        return 0., 1., 0.
+
+
+class BentLaueCylinder(OE):
+    """Cylindrically bent crystal in Laue geometry (duMond): the surface of JohannCylinder, the planes' normal turned
+    by 90 degrees (+ alpha) from the surface normal.  The volumetric-diffraction model of the reference
+    (local_n_depth) is outside the hot path."""
+    cu_two_normals = True
+    cu_plist = ('crossSectionInt', 'R', '_R2', '_cosalpha', '_sinalpha', '_hasAlpha')
+    cu_local_z = '''
+    __device__ double local_z(const double* cu_plist, double x, double y)
+    {
+        if (cu_plist[0] == 0.0) return cu_plist[1] - sqrt(cu_plist[2] - y * y);
+        return y * y / 2.0 / cu_plist[1];
+    }'''
+    cu_local_n = _ROT + '''
+    __device__ void local_n(const double* cu_plist, double x, double y, double* n)
+    {
+        const double R = cu_plist[1];
+        double b = -y / R, c;
+        if (cu_plist[0] == 0.0) {
+            c = sqrt(cu_plist[2] - y * y) / R;
+        } else {
+            const double norm = sqrt(b * b + 1.0);
+            b = b / norm;
+            c = 1.0 / norm;
+        }
+        n[0] = 0.0; n[3] = 0.0; n[4] = b; n[5] = c;
+        if (cu_plist[5] != 0.0) rot_x(b, c, -cu_plist[4], -cu_plist[3], n[1], n[2]);  // rotate_x(b, c, -sin, -cos)
+        else { n[1] = c; n[2] = -b; }
+    }'''
+
+    def __init__(self, *args, **kwargs):
+        self.R = kwargs.pop('R', 1.0e4)
+        self.crossSection = kwargs.pop('crossSection', 'parabolic')
+        if not (self.crossSection.startswith('circ') or self.crossSection.startswith('parab')):
+            raise ValueError('unknown crossSection!')
+        self.crossSectionInt = 0 if self.crossSection.startswith('circ') else 1
+        OE.__init__(self, *args, **kwargs)
+
+    _R2 = property(lambda self: self.R**2)
+    _cosalpha = property(lambda self: float(np.cos(self.alpha)) if self.alpha else 1.)
+    _sinalpha = property(lambda self: float(np.sin(self.alpha)) if self.alpha else 0.)
+    _hasAlpha = property(lambda self: 1. if self.alpha else 0.)
+
+
+LIBRARY = (BentFlatMirror, ConicalMirror, JohannCylinder, JohanssonCylinder, JohannToroid, ParabolicalMirrorParam,
+           BentLaueCylinder)
 
 
 def prebuild(verbose=False):
