@@ -456,7 +456,11 @@ def reflect_local(oe, good, lb, vlb, pitch, roll, yaw, dx=None, dy=None, dz=None
         tX, tY, tZ = oe.param_to_xyz(lb.x[good], lb.y[good], lb.z[good])
     else:
         tX, tY, tZ = lb.x[good], lb.y[good], lb.z[good]
+    gNormalFZP = None
     lb.state[good] = rays_good(oe, tX, tY, surfPhysX, surfPhysY, surfOptX, surfOptY)
+    fzp = getattr(oe, 'fzp', None)
+    if fzp is not None:  # use_rays_good_gn (reflect.py:697-698; NormalFZP.rays_good_gn, gratings.py:120-137)
+        lb.state[good], gNormalFZP = fzp.rays_good_gn(lb.state[good], tX, tY, oe.lostNum)
     lb.state[np.where(good)[0][_lost]] = oe.lostNum
     goodN = (lb.state == 1)
     goodNsum = goodN.sum()
@@ -487,6 +491,7 @@ def reflect_local(oe, good, lb, vlb, pitch, roll, yaw, dx=None, dy=None, dz=None
         isMultilayer = material is not None and material.kind == 'multilayer'
         transmitted = isCrystal and matSur.geom.endswith('transmitted')  # toWhere = 2 (reflect.py:756, :862-878)
         isGrating = material is not None and material.kind == 'grating'  # toWhere = 3 (reflect.py:743-744)
+        isFZP = material is not None and material.kind == 'FZP'  # toWhere = 4 (reflect.py:745-746)
         isRefr = material is not None and material.kind in ('plate', 'lens')  # toWhere = 1 (reflect.py:732-733)
         if isRefr:
             # reflect.py:894-919
@@ -502,6 +507,10 @@ def reflect_local(oe, good, lb, vlb, pitch, roll, yaw, dx=None, dy=None, dz=None
             a_out = lb.a[goodN] * n1overn2 + oeNormal[0]*dn
             b_out = lb.b[goodN] * n1overn2 + oeNormal[1]*dn
             c_out = lb.c[goodN] * n1overn2 + oeNormal[2]*dn
+        elif isFZP:
+            # reflect.py:840-861 with the g vectors rays_good_gn returned (they belong to the rays it kept: state 1)
+            a_out, b_out, c_out = _grating_deflection(goodN, lb, np.asarray(gNormalFZP, order='F'), oeNormal,
+                                                      beamInDotSurfaceNormal, oe.order, 1)
         elif isGrating:
             # reflect.py:840-861
             if oe.isParametric:
@@ -546,7 +555,8 @@ def reflect_local(oe, good, lb, vlb, pitch, roll, yaw, dx=None, dy=None, dz=None
                                             beamInDotNormal)
             elif isMultilayer:  # reflect.py:999-1003
                 refl = matSur.get_amplitude(lb.E[goodN], beamInDotSurfaceNormal, lb.x[goodN], lb.y[goodN])
-            elif not hasattr(matSur, 'get_amplitude'):  # EmptyMaterial: findReflectivity stays False (:940-942)
+            elif not hasattr(matSur, 'get_amplitude') or isFZP:
+                # EmptyMaterial: findReflectivity stays False (:940-942); kind 'FZP': (1, 1, 0) (material.py:457-458)
                 refl = 1., 1.
             elif isGrating and matSur.efficiency is not None:  # reflect.py:1005-1011
                 refl = matSur.get_grating_efficiency(lb, goodN)

@@ -250,3 +250,29 @@ class BentLaueCylinder(object):
         else:
             bB, cB = c, -b
         return [a, bB, cB, a, b, c]
+
+
+class NormalFZP(object):
+    """NormalFZP (oes/gratings.py:10-137): zone radii rn (reset, :94-117) and rays_good_gn (:120-137): rays in opaque
+    zones are lost, the others get the local radial groove vector."""
+
+    def __init__(self, f, E, N, isCentralZoneBlack=True):
+        from scipy import interpolate
+        from .physconsts import CH
+        self.isCentralZoneBlack = isCentralZoneBlack
+        lambdaE = CH / E * 1e-7
+        self.zones = np.arange(N+1)
+        self.rn = np.sqrt(self.zones*f*lambdaE + 0.25*(self.zones*lambdaE)**2)
+        self.r_to_i = interpolate.interp1d(self.rn, self.zones, bounds_error=False, fill_value=0)
+        self.i_to_r = interpolate.interp1d(self.zones, self.rn, bounds_error=False, fill_value=0)
+
+    def rays_good_gn(self, locState, x, y, lostNum):
+        r = np.sqrt(x**2 + y**2)
+        i = (self.r_to_i(r)).astype(int)
+        good = ((i % 2 == int(self.isCentralZoneBlack)) & (r < self.rn[-1]) & (locState == 1))
+        locState[~good] = lostNum
+        gz = np.zeros_like(x[good])
+        rho = 1./(self.i_to_r(i[good]+1) - self.i_to_r(i[good]-1))
+        gx = -x[good] / r[good] * rho
+        gy = -y[good] / r[good] * rho
+        return locState, (gx, gy, gz)

@@ -1224,7 +1224,23 @@ def gen_laue():
              R=float(kw.get('R', 0.)), **dd)
 
 
-SECTIONS = {'laue': gen_laue, 'coated': gen_coated, 'figure_error': gen_figure_error, 'round': gen_round, 'shine_wave': gen_shine_wave, 'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+def gen_fzp():
+    """NormalFZP (oes/gratings.py:10-137) with a material of kind 'FZP' (toWhere = 4, reflect.py:840-861): opaque
+    zones absorb, transparent zones deflect by the local radial groove density; first and third order."""
+    bl = raycing.BeamLine()
+    for name, order, black in (('fzp_o1', 1, True), ('fzp_o3_white', 3, False)):
+        mat = rm.Material('Au', rho=19.3, kind='FZP')
+        beam = _source_beam(bl, 3000, 241, dx=0.02, dz=0.02, dxprime=2e-6, dzprime=2e-6, energies=(8990, 9010))
+        oe = roe.NormalFZP(bl, name, center=(0, 5000, 0), pitch=np.pi/2, material=mat, f=100., E=9000., N=220,
+                           isCentralZoneBlack=black, order=order)
+        d = _capture_reflect(oe, beam)
+        d.update(_oe_params(oe))
+        st = d['gb_state']
+        print(name, {int(x): int((st == x).sum()) for x in np.unique(st)}, 'rN', float(oe.rn[-1]))
+        save('reflect_' + name, f=float(oe.f), E0=float(oe.E), N=int(oe.N), black=black, order=order, rn=oe.rn, **d)
+
+
+SECTIONS = {'fzp': gen_fzp, 'laue': gen_laue, 'coated': gen_coated, 'figure_error': gen_figure_error, 'round': gen_round, 'shine_wave': gen_shine_wave, 'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)
