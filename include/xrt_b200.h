@@ -184,12 +184,17 @@ typedef struct xrt_oe_params {
   int dead_state_lost;    /* Plate (dcm.py:311-312, :331-332): rays that are not good after a surface get lostNum */
   /* f4: grating (material kind 'grating', toWhere = 3, reflect.py:840-861 + _grating_deflection :451-469).
    * OE.local_g (base.py:688-717): 0 no grating; 1 / 2: groove density rho0 * sum_i (i+1) c_i coord^i along x / y
-   * (gratingDensity = ['x'|'y', rho0, c0, c1, ...]); 3: constant (0, g_rho0, 0) */
+   * (gratingDensity = ['x'|'y', rho0, c0, c1, ...]); 3: constant (0, g_rho0, 0); 4: Fresnel zone plate (fzp_* below) */
   int grating;
   int g_ncoef;
   double g_rho0, g_coef[8];
   double g_order;         /* diffraction order (a single int in the reference's OE.order) */
   double g_amp;           /* >= 0: amplitude sqrt(efficiency) of that order (material.py:391-413); < 0: none */
+  /* f4: NormalFZP (oes/gratings.py:10-137; grating = 4, material kind 7): fzp_rn[fzp_n] zone radii r_0 = 0 .. r_N
+   * (device pointer), fzp_black = int(isCentralZoneBlack): rays whose zone index i has i % 2 != fzp_black are lost,
+   * the others are deflected by the local radial groove vector with giveSign = +1 (reflect.py:840-861) */
+  const double* fzp_rn;
+  int fzp_n, fzp_black;
   /* f4: OE.multiple_reflect (oes/reflect.py:165-264) */
   int multi;              /* 1: one pass of multiple_reflect -- gb receives EVERY traced ray in virgin-local coordinates
                              with its new state (gb and lb are one beam there), rays over the edge keep their entry

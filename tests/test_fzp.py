@@ -27,3 +27,24 @@ def test_oracle_fzp_bit_exact(name):
             if pre + f in g.files:
                 assert np.array_equal(getattr(b, f), g[pre + f]), pre + f
     assert (g['gb_state'] == 1).sum() > 1000 and (g['gb_state'] == int(g['lostNum'])).sum() > 1000
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', CASES)
+def test_cuda_fzp_vs_reference_golden(name, cuda_device):
+    from xrt_b200 import oes, materials
+    g = golden('reflect_' + name)
+    kw = product_oe_kwargs(g)
+    kw.pop('limPhysX'), kw.pop('limPhysY')
+    oe = oes.NormalFZP(product_beamline(g), name, material=materials.Material('Au', rho=19.3, kind='FZP'),
+                       f=float(g['f']), E=float(g['E0']), N=int(g['N']), isCentralZoneBlack=bool(g['black']),
+                       order=int(g['order']), **kw)
+    assert np.array_equal(oe.rn, g['rn']) and oe.limPhysX == list(g['surfPhysX'])
+    oe.lostNum = int(g['lostNum'])
+    gb, lb = oe.reflect(device_beam(oracle_beam(g, 'in_')))
+    assert np.array_equal(gb.to_numpy()['state'], g['gb_state'])  # zone membership is exact
+    bad = compare_beams(gb.to_numpy(), {f: g['gb_' + f] for f in OUT_FIELDS if 'gb_' + f in g.files}, OUT_FIELDS,
+                        1e-12, 'gb_')
+    bad += compare_beams(lb.to_numpy(), {f: g['lb_' + f] for f in OUT_FIELDS if 'lb_' + f in g.files}, OUT_FIELDS,
+                         1e-12, 'lb_')
+    assert not bad, bad

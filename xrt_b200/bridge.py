@@ -81,7 +81,8 @@ def _oe_kwargs(oe):
         kw['figureError'] = FigureErrorSpline(fe.local_z_spline, fe.xShift, fe.yShift, getattr(fe, 'name', ''))
     if getattr(oe, 'gratingDensity', None) is not None:
         kw['gratingDensity'] = list(oe.gratingDensity)
-    if getattr(kw['material'], 'kind', None) in ('grating', 'auto') or 'gratingDensity' in kw:
+    if (getattr(kw['material'], 'kind', None) in ('grating', 'auto') or 'gratingDensity' in kw) and \
+            type(oe).__name__ != 'NormalFZP':
         kw['order'] = getattr(oe, 'order', 1)
     return kw
 
@@ -127,6 +128,10 @@ def convert_oe(oe):
             oe.bl, oe.name, Rm=float(oe.Rm), crossSection=oe.crossSection, **kw)
     elif 'JohannToroid' in cls and not any(c in cls for c in ('JohanssonToroid', 'GeneralBraggToroid', 'DicedOE')):
         out = _oes.JohannToroid(oe.bl, oe.name, Rm=float(oe.Rm), Rs=float(oe.Rs), **kw)
+    elif type(oe).__name__ == 'NormalFZP':
+        kw.pop('limPhysX'), kw.pop('limPhysY')
+        out = _oes.NormalFZP(oe.bl, oe.name, f=oe.f, E=oe.E, N=oe.N, isCentralZoneBlack=oe.isCentralZoneBlack,
+                             order=getattr(oe, 'order', 1), **kw)
     elif type(oe).__name__ == 'LauePlate':
         out = _oes.LauePlate(oe.bl, oe.name, **kw)
     elif type(oe).__name__ == 'BentLaueCylinder':

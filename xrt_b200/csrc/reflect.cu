@@ -1388,6 +1388,35 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
       if (p.over_mask & 8) over = over || (cy > p.physY[1]);
       if (outside) st = p.lostNum;
       if (over) st = 3;
+      double fzp_gx = 0.0, fzp_gy = 0.0;
+      if ((MAT == 6 || MAT == 7) && p.grating == 4) {
+        // NormalFZP.rays_good_gn (oes/gratings.py:120-137): zone index from r through scipy's linear interp1d
+        // (rn -> zones, then astype(int)); rays in opaque zones, outside the last zone or not 'good' are lost; the
+        // others get g = -(x, y)/r * rho with rho = 1 / (i_to_r(i+1) - i_to_r(i-1)), i_to_r the linear interp1d
+        // zones -> rn evaluated AT the nodes: (rn[j] - rn[j-1]) + rn[j-1], and 0 outside [0, N]
+        const double* __restrict__ rn = p.fzp_rn;
+        const int nz = p.fzp_n;  // N + 1 radii
+        const double r = sqrt(cx * cx + cy * cy);
+        int lo = 0, hi = nz;  // searchsorted(rn, r, side='left')
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (rn[mid] < r) lo = mid + 1; else hi = mid;
+        }
+        int idx = lo < 1 ? 1 : (lo > nz - 1 ? nz - 1 : lo);
+        double zi_f = (1.0 / (rn[idx] - rn[idx - 1])) * (r - rn[idx - 1]) + (double)(idx - 1);
+        if (r > rn[nz - 1] || r < rn[0]) zi_f = 0.0;  // bounds_error=False, fill_value=0
+        const int zi = (int)zi_f;
+        const bool zgood = ((zi % 2) == p.fzp_black) && (r < rn[nz - 1]) && (st == 1);
+        if (!zgood) {
+          st = p.lostNum;
+        } else {
+          const double r_up = (rn[zi + 1] - rn[zi]) + rn[zi];  // zi + 1 <= N here
+          const double r_dn = zi - 1 < 0 ? 0.0 : (zi - 1 == 0 ? rn[0] : (rn[zi - 1] - rn[zi - 2]) + rn[zi - 2]);
+          const double rho = 1.0 / (r_up - r_dn);
+          fzp_gx = -cx / r * rho;
+          fzp_gy = -cy / r * rho;
+        }
+      }
       if (ind1) st = p.lostNum;  // reflect.py:706-707
       if (hasLb) {
         if (lb.s) {
@@ -1477,7 +1506,10 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
           // toWhere = 3 (reflect.py:840-861): g = OE.local_g(x, y) (base.py:688-717), then _grating_deflection
           // (reflect.py:451-469) with the surface normal, beamInDotSurfaceNormal, the order and sig = -1
           double g0 = 0.0, g1 = 0.0, g2 = 0.0;
-          if (p.grating == 3) {
+          if (p.grating == 4) {  // FZP: the radial groove vector found with the zone (toWhere = 4)
+            g0 = fzp_gx;
+            g1 = fzp_gy;
+          } else if (p.grating == 3) {
             g1 = p.g_rho0;
           } else {
             const double coord = (p.grating == 1) ? cx : cy;
@@ -1495,7 +1527,7 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
           const double G2 = g0 * g0 + g1 * g1 + g2 * g2;
           const double ol = p.g_order * CH / in.E[i] * 1e-7;
           const double u = bds * bds - 2.0 * bdg * ol - G2 * (ol * ol);
-          const double dn = bds + (-1.0) * sqrt(fabs(u));
+          const double dn = bds + (p.grating == 4 ? 1.0 : -1.0) * sqrt(fabs(u));  // giveSign (reflect.py:857)
           ao = la - nrm[3] * dn + g0 * ol;
           bo = lbb - nrm[4] * dn + g1 * ol;
           co = lc - nrm[5] * dn + g2 * ol;
@@ -1821,6 +1853,8 @@ int reflect_device(size_t n, const xrt_oe_params* oe, const xrt_material_params*
   memset(&m, 0, sizeof(m));
   if (mat) m = *mat;
   XRTB_REQUIRE(m.kind >= 0 && m.kind <= 7, "reflect: unknown material kind %d", m.kind);
+  XRTB_REQUIRE(oe->grating != 4 || (oe->fzp_rn != nullptr && oe->fzp_n >= 3 && m.kind == 7),
+               "reflect: a zone plate (grating = 4) needs its zone radii and goes with material kind 7");
   XRTB_REQUIRE((m.kind == 6 || m.kind == 7) == (oe->grating != 0),
                "reflect: material kinds 6 / 7 (grating) and xrt_oe_params.grating go together");
   XRTB_REQUIRE(oe->surface != 3 || (m.kind == 0 || m.kind == 5), "reflect: a parabolic lens refracts or is bare");

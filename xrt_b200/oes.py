@@ -50,6 +50,7 @@ class xrt_oe_params(ctypes.Structure):
                 ('no_intersection', ctypes.c_int), ('from_vacuum', ctypes.c_int), ('dead_state_lost', ctypes.c_int),
                 ('grating', ctypes.c_int), ('g_ncoef', ctypes.c_int), ('g_rho0', ctypes.c_double),
                 ('g_coef', ctypes.c_double * 8), ('g_order', ctypes.c_double), ('g_amp', ctypes.c_double),
+                ('fzp_rn', ctypes.c_void_p), ('fzp_n', ctypes.c_int), ('fzp_black', ctypes.c_int),
                 ('multi', ctypes.c_int),
                 ('fe_tu', ctypes.c_void_p), ('fe_tv', ctypes.c_void_p), ('fe_c', ctypes.c_void_p),
                 ('fe_nu', ctypes.c_int), ('fe_nv', ctypes.c_int),
@@ -271,6 +272,19 @@ class OE(object):
         kind = getattr(material, 'kind', None)
         if kind == 'auto' and self.gratingDensity is not None:
             kind = 'grating'
+        if hasattr(self, 'rn') and kind in ('FZP', 'auto'):  # NormalFZP: assign_auto_material_kind -> 'FZP'
+            if not isinstance(self.order, (int, np.integer)):
+                raise NotImplementedError('give OE.order as one int')
+            dev = torch.device('cuda', torch.cuda.current_device())
+            key = str(dev)
+            if getattr(self, '_rn_dev', (None,))[0] != key:
+                self._rn_dev = (key, torch.from_numpy(np.ascontiguousarray(self.rn, dtype=np.float64)).to(dev))
+            p.grating = 4
+            p.g_order = float(self.order)
+            p.fzp_rn = self._rn_dev[1].data_ptr()
+            p.fzp_n = len(self.rn)
+            p.fzp_black = int(bool(self.isCentralZoneBlack))
+            return
         if kind != 'grating':
             return
         if not isinstance(self.order, (int, np.integer)):
@@ -307,7 +321,8 @@ class OE(object):
             self._red[key] = torch.zeros(REDUCTION_SLOTS, dtype=torch.int64, device=dev)
         red = self._red[key]
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        if params.grating and (params.g_amp >= 0 or not hasattr(material, 'device_tables')):
+        if params.grating and (params.g_amp >= 0 or params.grating == 4 or not hasattr(material, 'device_tables')):
+            # ... or a zone plate: kind 'FZP' has amplitude (1, 1) (material.py:457-458)
             # EmptyMaterial or a tabulated efficiency: no Fresnel amplitude (reflect.py:1005-1011): kind 7
             mat = xrt_material_params()
             mat.kind = 7
@@ -716,6 +731,34 @@ def _abs_pitch_to_axis(oe, axis=(0, 1, 0)):
 
 
 SimpleVFM = ToroidMirror  # oes/__init__.py:414
+
+
+class NormalFZP(OE):
+    """Circular Fresnel zone plate in the local xy plane, optical axis along local z (oes/gratings.py:10-137): zones of
+    zero thickness with transmittivity 0 and 1.  Give the material kind='FZP' (or leave it 'auto').  The zone mask
+    and the radial groove vector are evaluated per ray inside the fused kernel from the zone radii *rn*."""
+
+    def __init__(self, *args, **kwargs):
+        self.f = kwargs.pop('f', 50)
+        self.E = kwargs.pop('E', 1000)
+        self.N = kwargs.pop('N', 1000)
+        self.isCentralZoneBlack = kwargs.pop('isCentralZoneBlack', True)
+        self.thinnestZone = kwargs.pop('thinnestZone', None)
+        self.reset()
+        kwargs['limPhysX'] = [-self.rn[-1], self.rn[-1]]
+        kwargs['limPhysY'] = [-self.rn[-1], self.rn[-1]]
+        OE.__init__(self, *args, **kwargs)
+        if self.material is None or getattr(self.material, 'kind', 'auto') not in ('FZP', 'auto'):
+            raise ValueError("NormalFZP needs a material of kind='FZP'")
+
+    def reset(self):  # gratings.py:94-117
+        from .physconsts import CH
+        lambdaE = CH / self.E * 1e-7
+        if self.thinnestZone is not None:
+            self.N = lambdaE * self.f / 4. / self.thinnestZone**2
+        self.zones = np.arange(self.N+1)
+        self.rn = np.sqrt(self.zones*self.f*lambdaE + 0.25*(self.zones*lambdaE)**2)
+        self._rn_dev = (None,)
 
 
 class EllipticalMirrorParam(OE):
