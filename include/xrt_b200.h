@@ -190,6 +190,10 @@ typedef struct xrt_oe_params {
   double g_rho0, g_coef[8];
   double g_order;         /* diffraction order (a single int in the reference's OE.order) */
   double g_amp;           /* >= 0: amplitude sqrt(efficiency) of that order (material.py:391-413); < 0: none */
+  /* OE shape 'round' (rays_good, base.py:1140-1156): an ellipse in limPhysX x limPhysY; shape_r = centerX, radiusX,
+   * centerY, radiusY; rays outside are lost (no 'out' / 'over' states) */
+  int shape_round;
+  double shape_r[4];
   /* f4: NormalFZP (oes/gratings.py:10-137; grating = 4, material kind 7): fzp_rn[fzp_n] zone radii r_0 = 0 .. r_N
    * (device pointer), fzp_black = int(isCentralZoneBlack): rays whose zone index i has i % 2 != fzp_black are lost,
    * the others are deflected by the local radial groove vector with giveSign = +1 (reflect.py:840-861) */

@@ -377,6 +377,18 @@ def _bracketing(oe, x, y, z, a, b, c, surfPhysX, surfPhysY, mainPart, info=None,
 
 def rays_good(oe, x, y, surfPhysX, surfPhysY, surfOptX, surfOptY):
     locState = np.ones(x.size, dtype=np.int32)
+    if str(getattr(oe, 'shape', 'rect')).startswith('ro'):  # base.py:1140-1156
+        centerX = (surfPhysX[0]+surfPhysX[1]) * 0.5
+        if np.isnan(centerX):
+            centerX = 0
+        radiusX = (surfPhysX[1]-surfPhysX[0]) * 0.5
+        centerY = (surfPhysY[0]+surfPhysY[1]) * 0.5
+        radiusY = (surfPhysY[1]-surfPhysY[0]) * 0.5
+        if np.isnan(centerY):
+            centerY = 0
+        if not np.isinf(radiusX):
+            locState[((x-centerX)/radiusX)**2 + ((y-centerY)/radiusY)**2 > 1] = oe.lostNum
+        return locState
     if surfOptX is not None:
         locState[((surfPhysX[0] <= x) & (x < surfOptX[0])) | ((surfOptX[1] <= x) & (x < surfPhysX[1]))] = 2
     if surfOptY is not None:

@@ -253,6 +253,17 @@ def gen_reflect():
     d.update(_oe_params(oe))
     save('reflect_toroid_bare', R=float(oe.R), r=float(oe.r), **d)
 
+    # (4) a round (elliptical) flat Au mirror: shape='round' (rays_good, base.py:1140-1156)
+    bl = raycing.BeamLine(azimuth=0.3)
+    beam = _source_beam(bl, 3000, 34)
+    oe = roe.OE(bl, 'Mr', center=ctr, pitch=4e-3, roll=2e-3, yaw=-1e-3, material=Au, shape='round',
+                limPhysX=[-0.25, 0.3], limPhysY=[-60, 50])
+    d = _capture_reflect(oe, beam)
+    d.update(_oe_params(oe))
+    st = d['gb_state']
+    print('round', {int(x): int((st == x).sum()) for x in np.unique(st)})
+    save('reflect_flat_round', rho=19.3, **d)
+
 # ------------------------------------------------------------------------------------------------ planes
 def gen_planes():
     bl = raycing.BeamLine(azimuth=-0.2)

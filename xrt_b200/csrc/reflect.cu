@@ -1378,16 +1378,23 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
       param_to_xyz<SURF>(p, cx, cy, cz);
       // rays_good, shape 'rect' (base.py:1115-1139)
       int st = 1;
-      if (p.has_optX && (((p.physX[0] <= cx) && (cx < p.optX[0])) || ((p.optX[1] <= cx) && (cx < p.physX[1])))) st = 2;
-      if (p.has_optY && (((p.physY[0] <= cy) && (cy < p.optY[0])) || ((p.optY[1] <= cy) && (cy < p.physY[1])))) st = 2;
-      const bool outside = (cx < p.physX[0]) || (cx > p.physX[1]) || (cy < p.physY[0]) || (cy > p.physY[1]);
-      bool over = false;
-      if (p.over_mask & 1) over = over || (cx < p.physX[0]);
-      if (p.over_mask & 2) over = over || (cx > p.physX[1]);
-      if (p.over_mask & 4) over = over || (cy < p.physY[0]);
-      if (p.over_mask & 8) over = over || (cy > p.physY[1]);
-      if (outside) st = p.lostNum;
-      if (over) st = 3;
+      if (p.shape_round) {
+        // shape 'round' (base.py:1140-1156): an ellipse inscribed in limPhysX x limPhysY; outside -> lost.
+        // sr: centerX, radiusX, centerY, radiusY formed by the host like the reference does
+        const double ex = (cx - p.shape_r[0]) / p.shape_r[1], ey = (cy - p.shape_r[2]) / p.shape_r[3];
+        if (ex * ex + ey * ey > 1.0) st = p.lostNum;
+      } else {
+        if (p.has_optX && (((p.physX[0] <= cx) && (cx < p.optX[0])) || ((p.optX[1] <= cx) && (cx < p.physX[1])))) st = 2;
+        if (p.has_optY && (((p.physY[0] <= cy) && (cy < p.optY[0])) || ((p.optY[1] <= cy) && (cy < p.physY[1])))) st = 2;
+        const bool outside = (cx < p.physX[0]) || (cx > p.physX[1]) || (cy < p.physY[0]) || (cy > p.physY[1]);
+        bool over = false;
+        if (p.over_mask & 1) over = over || (cx < p.physX[0]);
+        if (p.over_mask & 2) over = over || (cx > p.physX[1]);
+        if (p.over_mask & 4) over = over || (cy < p.physY[0]);
+        if (p.over_mask & 8) over = over || (cy > p.physY[1]);
+        if (outside) st = p.lostNum;
+        if (over) st = 3;
+      }
       double fzp_gx = 0.0, fzp_gy = 0.0;
       if ((MAT == 6 || MAT == 7) && p.grating == 4) {
         // NormalFZP.rays_good_gn (oes/gratings.py:120-137): zone index from r through scipy's linear interp1d

@@ -50,6 +50,7 @@ class xrt_oe_params(ctypes.Structure):
                 ('no_intersection', ctypes.c_int), ('from_vacuum', ctypes.c_int), ('dead_state_lost', ctypes.c_int),
                 ('grating', ctypes.c_int), ('g_ncoef', ctypes.c_int), ('g_rho0', ctypes.c_double),
                 ('g_coef', ctypes.c_double * 8), ('g_order', ctypes.c_double), ('g_amp', ctypes.c_double),
+                ('shape_round', ctypes.c_int), ('shape_r', ctypes.c_double * 4),
                 ('fzp_rn', ctypes.c_void_p), ('fzp_n', ctypes.c_int), ('fzp_black', ctypes.c_int),
                 ('multi', ctypes.c_int),
                 ('fe_tu', ctypes.c_void_p), ('fe_tv', ctypes.c_void_p), ('fe_c', ctypes.c_void_p),
@@ -130,8 +131,8 @@ class OE(object):
         self.alpha = alpha
         self.figureError = kwargs.pop('figureError', None)  # xrt_b200.figure_error object (base.py:160, :310)
         self.shape = shape
-        if not shape.startswith('re'):
-            raise NotImplementedError("only shape='rect' is on the hot path")
+        if not (isinstance(shape, str) and (shape.startswith('re') or shape.startswith('ro'))):
+            raise NotImplementedError("shapes 'rect' and 'round' are on the hot path (polygons are not)")
         self.overEdge = kwargs.pop('overEdge', 'yMax')
         # gratings (base.py:213-230, :491-508): gratingDensity = ['x'|'y', rho0 (1/mm), c0, c1, ...], order: int
         self.gratingDensity = kwargs.pop('gratingDensity', None)
@@ -249,6 +250,23 @@ class OE(object):
         p.over_mask = (1 if 'xmin' in ovE else 0) | (2 if 'xmax' in ovE else 0) | \
             (4 if 'ymin' in ovE else 0) | (8 if 'ymax' in ovE else 0)
         p.lostNum = int(self.lostNum)
+        if self.shape.startswith('ro'):  # base.py:1140-1156
+            if is2ndXtal:
+                raise NotImplementedError("shape='round' on a second crystal")
+            centerX = (physX[0]+physX[1]) * 0.5
+            centerX = 0 if np.isnan(centerX) else centerX
+            radiusX = (physX[1]-physX[0]) * 0.5
+            centerY = (physY[0]+physY[1]) * 0.5
+            centerY = 0 if np.isnan(centerY) else centerY
+            radiusY = (physY[1]-physY[0]) * 0.5
+            if not np.isinf(radiusX):
+                p.shape_round = 1
+                for i, v in enumerate((centerX, radiusX, centerY, radiusY)):
+                    p.shape_r[i] = float(v)
+            else:
+                p.shape_round = 1  # infinite ellipse: nothing is lost
+                for i, v in enumerate((0., 1e300, 0., 1e300)):
+                    p.shape_r[i] = v
         # _set_t limits (base.py:1233-1239)
         for ax, lim, dflt in ((0, physX, maxHalfSizeOfOE), (1, physY, maxHalfSizeOfOE), (2, None, maxDepthOfOE)):
             if lim is None:
