@@ -679,35 +679,44 @@ __device__ __forceinline__ double interp_at(const double* __restrict__ xp, const
 
 // Element.get_f1f2 (element.py:252-263): f1 and f2 share the energy grid, so one binary search serves both
 // np.interp calls; the out-of-range ValueError becomes NaN + an error flag
-__device__ __forceinline__ cplx f1f2(const Tables& t, int off, int len, double E, int* oor) {
+// the interval of np.interp's binary search: xp[lo] <= E < xp[lo + 1] (lo = len - 1 at the last point), -2: E is
+// outside the table.  Ten dependent loads for a 768-point table -- the kernel issues it before the intersection
+// search, whose FP64 work then hides that latency (XRTB_HOIST_TABLE_SEARCH)
+__device__ __forceinline__ int f1f2_locate(const Tables& t, int off, int len, double E) {
   const double* __restrict__ xp = t.E + off;
-  if (E < xp[0] || E > xp[len - 1]) {
+  if (E < xp[0] || E > xp[len - 1]) return -2;
+  if (E >= xp[len - 1]) return len - 1;
+  int lo = 0, hi = len - 1;  // xp[lo] <= E < xp[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (E >= xp[mid])
+      lo = mid;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ cplx f1f2_at(const Tables& t, int off, int len, int lo, double E, int* oor) {
+  if (lo == -2) {
     *oor = 1;
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
     return cplx{nan, nan};
   }
-  int lo;
-  if (E >= xp[len - 1]) {
-    lo = len - 1;
-  } else {
-    lo = 0;
-    int hi = len - 1;  // xp[lo] <= E < xp[hi]
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (E >= xp[mid])
-        lo = mid;
-      else
-        hi = mid;
-    }
-  }
+  const double* __restrict__ xp = t.E + off;
   return cplx{interp_at(xp, t.f1 + off, len, lo, E), interp_at(xp, t.f2 + off, len, lo, E)};
+}
+__device__ __forceinline__ cplx f1f2(const Tables& t, int off, int len, double E, int* oor) {
+  return f1f2_at(t, off, len, f1f2_locate(t, off, len, E), E, oor);
 }
 
 // Material.get_refractive_index (material.py:372-378)
-__device__ __forceinline__ cplx refractive_index(const xrt_material_params& m, const Tables& t, double E, int* oor) {
+// lo0 >= -2: the located interval of the FIRST element's table (f1f2_locate), found earlier by the caller
+__device__ __forceinline__ cplx refractive_index(const xrt_material_params& m, const Tables& t, double E, int* oor,
+                                                 int lo0 = -3) {
   cplx xf = cplx{0.0, 0.0};
   for (int i = 0; i < m.nelem; ++i) {
-    const cplx f = f1f2(t, m.tab_off[i], m.tab_len[i], E, oor);
+    const cplx f = (i == 0 && lo0 != -3) ? f1f2_at(t, m.tab_off[0], m.tab_len[0], lo0, E, oor)
+                                         : f1f2(t, m.tab_off[i], m.tab_len[i], E, oor);
     const cplx zf = cplx{m.Z[i] + f.re, f.im};            // elem.Z + (f1 + i f2)
     const cplx term = cmul_np(zf, cplx{m.quantity[i], 0.0});  // * xi
     xf = cadd(xf, term);
@@ -723,8 +732,8 @@ __device__ __forceinline__ cplx refractive_index(const xrt_material_params& m, c
 
 // Material.get_amplitude, fromVacuum=True, kinds 'mirror' / 'thin mirror' (material.py:455-493)
 __device__ __forceinline__ void mirror_amplitude(const xrt_material_params& m, const Tables& t, double E,
-                                                 double bdn, cplx& rs, cplx& rp, int* oor) {
-  const cplx n2 = refractive_index(m, t, E, oor);
+                                                 double bdn, cplx& rs, cplx& rp, int* oor, int lo0 = -3) {
+  const cplx n2 = refractive_index(m, t, E, oor, lo0);
   const double cosAlpha = fabs(bdn);
   double sinAlpha2 = 1.0 - bdn * bdn;
   if (sinAlpha2 < 0.0) sinAlpha2 = 0.0;
@@ -1336,6 +1345,12 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
       const Decision d = sdec;
       Ray r = load_ray(in, i);
       const bool amp = in.Es != nullptr;
+#ifdef XRTB_HOIST_TABLE_SEARCH
+      int lo0 = -3;
+      if (MAT == 1 || MAT == 2 || MAT == 6) lo0 = f1f2_locate(tab, m.tab_off[0], m.tab_len[0], in.E[i]);
+#else
+      const int lo0 = -3;
+#endif
       to_local(p, r);
       const SurfDiv sd = make_surf_div<SURF>(p);
       double t1, t2, x1, y1, z1, x2, y2, z2;
@@ -1635,7 +1650,7 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
         }
         // amplitudes
         cplx ras = cplx{1.0, 0.0}, rap = cplx{1.0, 0.0};
-        if (MAT == 1 || MAT == 2 || MAT == 6) mirror_amplitude(m, tab, E, bdn, ras, rap, &oor);
+        if (MAT == 1 || MAT == 2 || MAT == 6) mirror_amplitude(m, tab, E, bdn, ras, rap, &oor, lo0);
         if (MAT == 3) crystal_amplitude(m, tab, E, bds, bos, bdn, ras, rap, &oor);
         if (MAT == 4) multilayer_amplitude(ml, tab, E, bds, ras, rap, &oor);  // reflect.py:999-1003
         if (MAT == 5) {
