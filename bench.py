@@ -208,10 +208,19 @@ def run_ours(args):
         pass
     _lib.init(local_rank)
     if world > 1:
-        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
-            # NCCL writes its version banner to stdout, which carries exactly one JSON line here
-            os.environ['NCCL_DEBUG'] = 'WARN'
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        # NCCL writes its version banner (NCCL_DEBUG=VERSION / WARN) and any warnings to stdout, which carries exactly
+        # one JSON line here: communicator set-up runs with fd 1 pointing at stderr
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     comm = parallel.Comm(world, rank)
 
     nrays = args.nrays
