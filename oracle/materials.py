@@ -259,9 +259,11 @@ class Multilayer(object):
     geom = 'reflected'
 
     def __init__(self, tLayer, tThickness, bLayer, bThickness, nPairs, substrate, tThicknessLow=0., bThicknessLow=0.,
-                 idThickness=0., power=2., substRoughness=0.):
+                 idThickness=0., power=2., substRoughness=0., substThickness=np.inf, geom='reflected'):
         self.tLayer, self.bLayer, self.substrate = tLayer, bLayer, substrate
         self.substRoughness = substRoughness
+        self.substThickness = substThickness
+        self.geom = geom
         self.nPairs = int(nPairs)
         self.power = power
         self.tThicknessHigh, self.tThicknessLow = float(tThickness), float(tThicknessLow)
@@ -304,7 +306,56 @@ class Multilayer(object):
         roughbs = np.exp(-0.5 * Qb * Qs * rmsbs)
         rbs_s = np.complex128((Qb-Qs) / (Qb+Qs) * roughbs)
         rbs_p = np.complex128((Qb/nb*ns - Qs/ns*nb) / (Qb/nb*ns + Qs/ns*nb) * roughbs)
-        return dict(rbs_s=rbs_s, rbs_p=rbs_p, rtb_s=rtb_s, rtb_p=rtb_p, rvt_s=rvt_s, rvt_p=rvt_p, Qt=Qt, Qb=Qb, nt=nt)
+        out = dict(rbs_s=rbs_s, rbs_p=rbs_p, rtb_s=rtb_s, rtb_p=rtb_p, rvt_s=rvt_s, rvt_p=rvt_p, Qt=Qt, Qb=Qb, nt=nt)
+        if 'tran' in self.geom:  # multilayer.py:388-417
+            out.update(
+                tvt_s=np.complex128(2*Q / (Q+Qt) * roughvt),
+                tvt_p=np.complex128(2*Q*nt / (Q*nt + Qt/nt) * roughvt),
+                ttb_s=np.complex128(2*Qt / (Qt+Qb) * roughtb),
+                ttb_p=np.complex128(2*Qt/nt*nb / (Qt/nt*nb + Qb/nb*nt) * roughtb),
+                tbt_s=np.complex128(2*Qb / (Qt+Qb) * roughtb),
+                tbt_p=np.complex128(2*Qb/nb*nt / (Qt/nt*nb + Qb/nb*nt) * roughtb),
+                tbs_s=np.complex128(2*Qb / (Qb+Qs) * roughbs),
+                tbs_p=np.complex128(2*Qb/nb*ns / (Qb/nb*ns + Qs/ns*nb) * roughbs),
+                rsv_s=np.complex128((Qs-Q) / (Qs+Q) * roughbs),
+                rsv_p=np.complex128((Qs/ns - Q*ns) / (Qs/ns + Q*ns) * roughbs),
+                tsv_s=np.complex128(2*Qs / (Qs+Q) * roughbs),
+                tsv_p=np.complex128(2*Qs/ns / (Qs/ns + Q*ns) * roughbs), Qs=Qs)
+        return out
+
+    def recursion_tran(self, f):
+        """The loop of Multilayer.get_amplitude for geom 'transmitted' (multilayer.py:419-462) == kernel
+        get_amplitude_graded_multilayer_tran: the substrate is one more layer, then vacuum."""
+        rj_s, rj_p = f['rsv_s'], f['rsv_p']
+        tj_s, tj_p = f['tsv_s'], f['tsv_p']
+        rbt_s, rbt_p = -f['rtb_s'], -f['rtb_p']
+        ti_s = np.zeros_like(rj_s)
+        ti_p = np.zeros_like(rj_p)
+        for i in reversed(range(2*self.nPairs+1)):
+            if i % 2 == 0:
+                if i == 0:
+                    rij_s, rij_p, tij_s, tij_p = f['rvt_s'], f['rvt_p'], f['tvt_s'], f['tvt_p']
+                    iQT = f['Qt'] * self.dti[i//2]
+                elif i == 2*self.nPairs:
+                    rij_s, rij_p, tij_s, tij_p = f['rbs_s'], f['rbs_p'], f['tbs_s'], f['tbs_p']
+                    iQT = f['Qs'] * self.substThickness
+                else:
+                    rij_s, rij_p, tij_s, tij_p = rbt_s, rbt_p, f['tbt_s'], f['tbt_p']
+                    iQT = f['Qt'] * self.dti[i//2]
+            else:
+                rij_s, rij_p, tij_s, tij_p = f['rtb_s'], f['rtb_p'], f['ttb_s'], f['ttb_p']
+                iQT = f['Qb'] * self.dbi[i//2]
+            p1i = np.complex128(np.exp(0.5j*iQT))
+            p2i = p1i**2
+            rj2i_s = rj_s * p2i
+            rj2i_p = rj_p * p2i
+            ri_s = (rij_s + rj2i_s) / (1 + rij_s*rj2i_s)
+            ri_p = (rij_p + rj2i_p) / (1 + rij_p*rj2i_p)
+            ti_s = tij_s * tj_s * p1i / (1 + rij_s*rj2i_s)
+            ti_p = tij_p * tj_p * p1i / (1 + rij_p*rj2i_p)
+            tj_s, tj_p = ti_s, ti_p
+            rj_s, rj_p = ri_s, ri_p
+        return ti_s, ti_p
 
     def recursion(self, f):
         rj_s, rj_p = f['rbs_s'], f['rbs_p']
@@ -332,6 +383,8 @@ class Multilayer(object):
 
     def get_amplitude(self, E, beamInDotNormal, x=None, y=None):
         f = self.fresnel_terms(E, beamInDotNormal)
+        if 'tran' in self.geom:
+            return self.recursion_tran(f)
         ri_s, ri_p = self.recursion(f)
         nt = f['nt']
         nn = nt[0] if isinstance(nt, np.ndarray) else nt

@@ -501,7 +501,7 @@ def reflect_local(oe, good, lb, vlb, pitch, roll, yaw, dx=None, dy=None, dz=None
         else:
             beamInDotSurfaceNormal = beamInDotNormal
         isMultilayer = material is not None and material.kind == 'multilayer'
-        transmitted = isCrystal and matSur.geom.endswith('transmitted')  # toWhere = 2 (reflect.py:756, :862-878)
+        transmitted = (isCrystal or isMultilayer) and matSur.geom.endswith('transmitted')  # toWhere = 2 (reflect.py:749-757)
         isGrating = material is not None and material.kind == 'grating'  # toWhere = 3 (reflect.py:743-744)
         isFZP = material is not None and material.kind == 'FZP'  # toWhere = 4 (reflect.py:745-746)
         isRefr = material is not None and material.kind in ('plate', 'lens')  # toWhere = 1 (reflect.py:732-733)

@@ -1,0 +1,38 @@
+"""f2: transmitted multilayers -- Multilayer(geom='transmitted') (materials/multilayer.py:388-516; the reference's
+kernel get_amplitude_graded_multilayer_tran, cl/materials.cl) stand-alone and inside OE.reflect (toWhere = 2: the rays
+pass straight, reflect.py:749-757); cf. the reference's tests/raycing/test_multilayer_transmission.py.  Oracle bit-exact
+on the reference's outputs (CPU); CUDA against the same goldens (GPU)."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from helpers import (oracle_spec, oracle_beam, product_beamline, product_oe_kwargs, device_beam, compare_beams,
+                     BEAM_FIELDS)
+from oracle import materials as om, reflect as orf
+
+OUT_FIELDS = BEAM_FIELDS + ('theta',)
+KW = dict(tThickness=15., bThickness=25., nPairs=30, substThickness=100., idThickness=1.5, geom='transmitted')
+
+
+def _oracle_ml():
+    return om.Multilayer(om.Material('Cr', rho=7.18), KW['tThickness'], om.Material('C', rho=2.26), KW['bThickness'],
+                         KW['nPairs'], om.Material('C', rho=2.26), idThickness=KW['idThickness'],
+                         substThickness=KW['substThickness'], geom='transmitted')
+
+
+def test_oracle_multilayer_transmission_bit_exact():
+    g = golden('multilayer_tran_amplitudes')
+    ts, tp = _oracle_ml().get_amplitude(g['E'].copy(), g['bdn'].copy())
+    assert np.array_equal(ts, g['ts']) and np.array_equal(tp, g['tp'])
+    assert 0.01 < (np.abs(ts)**2).max() < 1.0
+
+
+def test_oracle_multilayer_transmission_reflect_bit_exact():
+    g = golden('reflect_multilayer_tran')
+    gb, lb = orf.reflect(oracle_spec(g, 'flat', _oracle_ml()), oracle_beam(g, 'in_'))
+    for pre, b in (('gb_', gb), ('lb_', lb)):
+        for f in OUT_FIELDS:
+            if pre + f in g.files:
+                assert np.array_equal(getattr(b, f), g[pre + f]), pre + f
+    good = g['gb_state'] == 1
+    assert np.array_equal(g['gb_a'][good], g['in_a'][good])  # the rays pass straight

@@ -1251,7 +1251,35 @@ def gen_fzp():
         save('reflect_' + name, f=float(oe.f), E0=float(oe.E), N=int(oe.N), black=black, order=order, rn=oe.rn, **d)
 
 
-SECTIONS = {'fzp': gen_fzp, 'laue': gen_laue, 'coated': gen_coated, 'figure_error': gen_figure_error, 'round': gen_round, 'shine_wave': gen_shine_wave, 'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+def gen_multilayer_tran():
+    """Multilayer(geom='transmitted') (materials/multilayer.py:388-516): transmitted amplitudes through the stack and
+    its (thin) substrate -- on a grid and for a free-standing multilayer in a beam line (toWhere = 2: the rays pass
+    straight, reflect.py:756, :862-878); cf. tests/raycing/test_multilayer_transmission.py."""
+    Cr, C = rm.Material('Cr', rho=7.18), rm.Material('C', rho=2.26)
+    kw = dict(tLayer=Cr, tThickness=15., bLayer=C, bThickness=25., nPairs=30, substrate=C, substThickness=100.,
+              idThickness=1.5, geom='transmitted')
+    ml = rm.Multilayer(**kw)
+    rng = np.random.RandomState(181)
+    n = 2500
+    theta = np.linspace(np.radians(25.), np.radians(55.), n)
+    E = rng.uniform(265., 275., n)
+    bdn = -np.sin(theta)
+    ts, tp = ml.get_amplitude(E.copy(), bdn.copy())
+    print('ML transmission |ts|^2 range', float((abs(ts)**2).min()), float((abs(ts)**2).max()))
+    save('multilayer_tran_amplitudes', E=E, bdn=bdn, ts=ts, tp=tp, dti=ml.dti, dbi=ml.dbi)
+    bl = raycing.BeamLine()
+    beam = _source_beam(bl, 2500, 182, dx=0.5, dz=0.01, dxprime=1e-4, dzprime=2e-2, energies=(268., 272.))
+    oe = roe.OE(bl, 'mlt', center=(0, 100., 0), pitch=np.radians(35.), material=rm.Multilayer(**kw),
+                limPhysX=[-5, 5], limPhysY=[-4, 4])
+    dd = _capture_reflect(oe, beam)
+    dd.update(_oe_params(oe))
+    st = dd['gb_state']
+    print('ML transmission plate', {int(x): int((st == x).sum()) for x in np.unique(st)}, 'mean T',
+          float((dd['gb_Jss'] + dd['gb_Jpp'])[st == 1].mean() / (dd['in_Jss'] + dd['in_Jpp'])[st == 1].mean()))
+    save('reflect_multilayer_tran', **dd)
+
+
+SECTIONS = {'multilayer_tran': gen_multilayer_tran, 'fzp': gen_fzp, 'laue': gen_laue, 'coated': gen_coated, 'figure_error': gen_figure_error, 'round': gen_round, 'shine_wave': gen_shine_wave, 'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)
