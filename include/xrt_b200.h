@@ -251,6 +251,9 @@ typedef struct xrt_multilayer_params {
   /* Coated (materials/multilayer.py:528-584): tLayer.nelem == 0 means no top layer (vacuum, n = 1); the bottom-layer /
    * substrate interface then takes substRoughness instead of idThickness (multilayer.py:401) */
   double substRoughness;
+  int transmitted;        /* 1: geom 'transmitted' (multilayer.py:388-516): the amplitude transmitted through the stack and
+                             its substrate of thickness substThickness (Angstrom); the rays pass straight */
+  double substThickness;
   int specular;           /* 1: kind 'mirror' -- specular reflection with this amplitude instead of the multilayer's
                              grating-like deflection (reflect.py:1003-1025 vs :999-1002) */
 } xrt_multilayer_params;

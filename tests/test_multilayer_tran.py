@@ -36,3 +36,32 @@ def test_oracle_multilayer_transmission_reflect_bit_exact():
                 assert np.array_equal(getattr(b, f), g[pre + f]), pre + f
     good = g['gb_state'] == 1
     assert np.array_equal(g['gb_a'][good], g['in_a'][good])  # the rays pass straight
+
+
+def _product_ml():
+    from xrt_b200 import materials
+    return materials.Multilayer(tLayer=materials.Material('Cr', rho=7.18), bLayer=materials.Material('C', rho=2.26),
+                                substrate=materials.Material('C', rho=2.26), **KW)
+
+
+@pytest.mark.gpu
+def test_cuda_multilayer_transmission_amplitude(cuda_device):
+    g = golden('multilayer_tran_amplitudes')
+    ts, tp = _product_ml().get_amplitude(g['E'], g['bdn'])
+    assert np.abs(ts - g['ts']).max() < 1e-12, np.abs(ts - g['ts']).max()  # |t| <= 0.27 here
+    assert np.abs(tp - g['tp']).max() < 1e-12, np.abs(tp - g['tp']).max()
+
+
+@pytest.mark.gpu
+def test_cuda_multilayer_transmission_reflect(cuda_device):
+    from xrt_b200 import oes
+    g = golden('reflect_multilayer_tran')
+    oe = oes.OE(product_beamline(g), 'mlt', material=_product_ml(), **product_oe_kwargs(g))
+    oe.lostNum = int(g['lostNum'])
+    gb, lb = oe.reflect(device_beam(oracle_beam(g, 'in_')))
+    bad = compare_beams(gb.to_numpy(), {f: g['gb_' + f] for f in OUT_FIELDS if 'gb_' + f in g.files}, OUT_FIELDS,
+                        1e-12, 'gb_')
+    bad += compare_beams(lb.to_numpy(), {f: g['lb_' + f] for f in OUT_FIELDS if 'lb_' + f in g.files}, OUT_FIELDS,
+                         1e-12, 'lb_')
+    assert not bad, bad
+    assert np.array_equal(gb.to_numpy()['state'], g['gb_state'])

@@ -993,6 +993,47 @@ __device__ __forceinline__ void multilayer_recursion(int npairs, int uniform, cp
   if (npairs <= 0) ri_s = ri_p = cplx{0.0, 0.0};  // ri = zeros_like(rj) when the loop does not run
 }
 
+// geom 'transmitted' (multilayer.py:419-462) == kernel get_amplitude_graded_multilayer_tran (cl/materials.cl): the
+// substrate is one more layer (thickness substThickness), then vacuum; r and t recurse together:
+//   ri = (rij + rj p2) / (1 + rij rj p2),  ti = tij tj p1 / (1 + rij rj p2)
+struct MLTran {
+  cplx rvt_s, rvt_p, tvt_s, tvt_p, rbs_s, rbs_p, tbs_s, tbs_p, rsv_s, rsv_p, tsv_s, tsv_p, rtb_s, rtb_p, ttb_s, ttb_p,
+      tbt_s, tbt_p, Qt, Qb, Qs;
+};
+__device__ __forceinline__ void multilayer_recursion_tran(int npairs, double substThickness, const MLTran& f,
+                                                          const double* __restrict__ dti,
+                                                          const double* __restrict__ dbi, cplx& ti_s, cplx& ti_p) {
+  cplx rj_s = f.rsv_s, rj_p = f.rsv_p, tj_s = f.tsv_s, tj_p = f.tsv_p;
+  const cplx rbt_s = cplx{-f.rtb_s.re, -f.rtb_s.im}, rbt_p = cplx{-f.rtb_p.re, -f.rtb_p.im};
+  ti_s = ti_p = cplx{0.0, 0.0};
+  for (int i = 2 * npairs; i >= 0; --i) {
+    cplx rij_s, rij_p, tij_s, tij_p, iQT;
+    if (i & 1) {
+      rij_s = f.rtb_s, rij_p = f.rtb_p, tij_s = f.ttb_s, tij_p = f.ttb_p;
+      iQT = cmul_np(f.Qb, cplx{dbi[i >> 1], 0.0});
+    } else if (i == 0) {
+      rij_s = f.rvt_s, rij_p = f.rvt_p, tij_s = f.tvt_s, tij_p = f.tvt_p;
+      iQT = cmul_np(f.Qt, cplx{dti[0], 0.0});
+    } else if (i == 2 * npairs) {
+      rij_s = f.rbs_s, rij_p = f.rbs_p, tij_s = f.tbs_s, tij_p = f.tbs_p;
+      iQT = cmul_np(f.Qs, cplx{substThickness, 0.0});
+    } else {
+      rij_s = rbt_s, rij_p = rbt_p, tij_s = f.tbt_s, tij_p = f.tbt_p;
+      iQT = cmul_np(f.Qt, cplx{dti[i >> 1], 0.0});
+    }
+    const cplx p1 = cexp_np(cmul_np(cplx{0.0, 0.5}, iQT));
+    const cplx p2 = csquare_np(p1);
+    const cplx rj2_s = cmul_np(rj_s, p2), rj2_p = cmul_np(rj_p, p2);
+    const cplx ds = cmul_np(rij_s, rj2_s), dp = cmul_np(rij_p, rj2_p);
+    const cplx den_s = cplx{1.0 + ds.re, 0.0 + ds.im}, den_p = cplx{1.0 + dp.re, 0.0 + dp.im};
+    const cplx ri_s = cdiv(cadd(rij_s, rj2_s), den_s), ri_p = cdiv(cadd(rij_p, rj2_p), den_p);
+    ti_s = cdiv(cmul_np(cmul_np(tij_s, tj_s), p1), den_s);
+    ti_p = cdiv(cmul_np(cmul_np(tij_p, tj_p), p1), den_p);
+    tj_s = ti_s, tj_p = ti_p;
+    rj_s = ri_s, rj_p = ri_p;
+  }
+}
+
 // (Qi/ni*nj - Qj/nj*ni) / (Qi/ni*nj + Qj/nj*ni) (multilayer.py:391-392, :404-405)
 __device__ __forceinline__ cplx fresnel_p(cplx Qi, cplx ni, cplx Qj, cplx nj) {
   const cplx a = cmul_np(cdiv(Qi, ni), nj);
@@ -1034,6 +1075,32 @@ __device__ __forceinline__ void multilayer_amplitude(const xrt_multilayer_params
   const cplx roughbs = cexp_np(cmul_np(cmul_np(cmul_np(cplx{-0.5, 0.0}, Qb), Qs), rmsbs));
   const cplx rbs_s = cmul_np(cdiv(csub(Qb, Qs), cadd(Qb, Qs)), roughbs);
   const cplx rbs_p = cmul_np(fresnel_p(Qb, nb, Qs, ns), roughbs);
+  if (ml.transmitted) {
+    // the transmission coefficients of every interface (multilayer.py:388-417); numpy: 2*Q / (Q+Qt) * roughvt etc.
+    MLTran f;
+    f.rvt_s = rvt_s, f.rvt_p = rvt_p, f.rbs_s = rbs_s, f.rbs_p = rbs_p, f.rtb_s = rtb_s, f.rtb_p = rtb_p;
+    f.Qt = Qt, f.Qb = Qb, f.Qs = Qs;
+    const cplx two = cplx{2.0, 0.0};
+    const cplx Q2c = cplx{2.0 * Q, 0.0};
+    f.tvt_s = cmul_np(cdiv(Q2c, cplx{Q + Qt.re, 0.0 + Qt.im}), roughvt);
+    f.tvt_p = cmul_np(cdiv(cmul_np(Q2c, nt), cadd(a, b)), roughvt);  // a = Q*nt, b = Qt/nt (above)
+    const cplx tn = cmul_np(cdiv(Qt, nt), nb), bn = cmul_np(cdiv(Qb, nb), nt);  // Qt/nt*nb, Qb/nb*nt
+    const cplx Qt2 = cmul_np(two, Qt), Qb2 = cmul_np(two, Qb), Qs2 = cmul_np(two, Qs);
+    f.ttb_s = cmul_np(cdiv(Qt2, cadd(Qt, Qb)), roughtb);
+    f.ttb_p = cmul_np(cdiv(cmul_np(cdiv(Qt2, nt), nb), cadd(tn, bn)), roughtb);
+    f.tbt_s = cmul_np(cdiv(Qb2, cadd(Qt, Qb)), roughtb);
+    f.tbt_p = cmul_np(cdiv(cmul_np(cdiv(Qb2, nb), nt), cadd(tn, bn)), roughtb);
+    const cplx bs = cmul_np(cdiv(Qb, nb), ns), sb = cmul_np(cdiv(Qs, ns), nb);  // Qb/nb*ns, Qs/ns*nb
+    f.tbs_s = cmul_np(cdiv(Qb2, cadd(Qb, Qs)), roughbs);
+    f.tbs_p = cmul_np(cdiv(cmul_np(cdiv(Qb2, nb), ns), cadd(bs, sb)), roughbs);
+    const cplx Qsn = cdiv(Qs, ns), Qns = cmul_np(Qc, ns);  // Qs/ns, Q*ns
+    f.rsv_s = cmul_np(cdiv(cplx{Qs.re - Q, Qs.im}, cplx{Qs.re + Q, Qs.im}), roughbs);
+    f.rsv_p = cmul_np(cdiv(csub(Qsn, Qns), cadd(Qsn, Qns)), roughbs);
+    f.tsv_s = cmul_np(cdiv(Qs2, cplx{Qs.re + Q, Qs.im}), roughbs);
+    f.tsv_p = cmul_np(cdiv(cdiv(Qs2, ns), cadd(Qsn, Qns)), roughbs);
+    multilayer_recursion_tran(ml.nPairs, ml.substThickness, f, ml.dti, ml.dbi, rs, rp);
+    return;
+  }
   multilayer_recursion(ml.nPairs, ml.uniform, rbs_s, rbs_p, rtb_s, rtb_p, rvt_s, rvt_p, Qt, Qb, ml.dti, ml.dbi, rs,
                        rp);
   // multilayer.py:501-505: tabulation artefacts with n.real > 1 flip the sign convention.  The reference tests
@@ -1487,7 +1554,7 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
         if ((hasLb && lb.theta) || (p.multi && gb.theta)) theta = acos(bdn) - kPi / 2;  // the local beam's theta
         bds = p.asymmetric ? (la * nrm[3] + lbb * nrm[4] + lc * nrm[5]) : bdn;
         double ao, bo, co;
-        const bool transmitted = (MAT == 3) && (m.geom & 2);  // toWhere = 2 (reflect.py:756, :862-878)
+        const bool transmitted = ((MAT == 3) && (m.geom & 2)) || (MAT == 4 && ml.transmitted);  // toWhere = 2 (reflect.py:749-757, :862-878)
         if ((MAT == 3 || MAT == 4) && !transmitted && !(MAT == 4 && ml.specular)) {
           // crystal / multilayer as a grating (reflect.py:568-612, :451-469); sgbdn is taken per ray here -- all
           // good rays hit the same side of the crystal in the supported geometries (documented in DESIGN.md)

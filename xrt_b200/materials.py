@@ -38,7 +38,8 @@ class xrt_multilayer_params(ctypes.Structure):
     _fields_ = [('tLayer', xrt_material_params), ('bLayer', xrt_material_params), ('substrate', xrt_material_params),
                 ('nPairs', ctypes.c_int), ('uniform', ctypes.c_int), ('idThickness', ctypes.c_double),
                 ('d', ctypes.c_double), ('dti', ctypes.c_void_p), ('dbi', ctypes.c_void_p),
-                ('substRoughness', ctypes.c_double), ('specular', ctypes.c_int)]
+                ('substRoughness', ctypes.c_double), ('transmitted', ctypes.c_int),
+                ('substThickness', ctypes.c_double), ('specular', ctypes.c_int)]
 
 
 def _tables():
@@ -331,8 +332,8 @@ class Multilayer(object):
         if bLayer is None or substrate is None or (tLayer is None and not isinstance(self, Coated)):
             raise NotImplementedError('top layer, bottom layer and substrate are all required on this path '
                                       '(a single layer on a substrate is `Coated`)')
-        if geom and 'tran' in geom:
-            raise NotImplementedError("geom='transmitted' multilayers are the next row (SURVEY.md 8f)")
+        if geom and 'tran' in geom and not np.isfinite(substThickness):
+            raise ValueError("geom='transmitted' needs a finite substThickness")
         self.tLayer, self.bLayer, self.substrate = tLayer, bLayer, substrate
         self.nPairs = int(nPairs)
         self.power = power
@@ -425,6 +426,8 @@ class Multilayer(object):
         ml.d = self.d
         ml.dti, ml.dbi = pdti, pdbi
         ml.substRoughness = float(self.substRoughness)
+        ml.transmitted = int('tran' in self.geom)
+        ml.substThickness = float(self.substThickness) if np.isfinite(self.substThickness) else 0.
         ml.specular = int(self.kind == 'mirror')
         m = xrt_material_params()
         m.kind = 4
