@@ -451,6 +451,16 @@ int xrt_multilayer_f64(size_t n, int npairs, const double* rbs_s, const double* 
 int xrt_multilayer_f64_host(size_t n, int npairs, const double* rbs_s, const double* rbs_p, const double* rtb_s,
                             const double* rtb_p, const double* rvt_s, const double* rvt_p, const double* Qt,
                             const double* Qb, const double* dti, const double* dbi, double* ri_s, double* ri_p);
+/* Kernel `get_amplitude_graded_multilayer_tran` (cl/materials.cl; Multilayer.get_amplitude with geom 'transmitted',
+ * materials/multilayer.py:485-503): r and t recurse together from the vacuum behind the substrate up through the
+ * substrate layer (thickness substThickness, Angstrom) and the stack (:419-462).  in23: table of the 23 sliced
+ * complex128[n] inputs in the reference's order -- rvt_s, rvt_p, tvt_s, tvt_p, rbs_s, rbs_p, tbs_s, tbs_p, rsv_s,
+ * rsv_p, tsv_s, tsv_p, rbt_s, rbt_p, tbt_s, tbt_p, rtb_s, rtb_p, ttb_s, ttb_p, Qt, Qb, Qs.  Out: ti_s, ti_p.
+ * Device pointers (the table itself is a host array of device pointers); the *_host variant stages host arrays. */
+int xrt_multilayer_tran_f64(size_t n, int npairs, double substThickness, const double* const* in23, const double* dti,
+                            const double* dbi, double* ti_s, double* ti_p, void* stream);
+int xrt_multilayer_tran_f64_host(size_t n, int npairs, double substThickness, const double* const* in23,
+                                 const double* dti, const double* dbi, double* ti_s, double* ti_p);
 
 /* ------------------------------------------------------------------ f1 (next row): device histogram
  * np.histogram2d(y, x, bins=[ny, nx], range=[[ey0, eyN], [ex0, exN]], weights=w1 (+ w2)) as do_hist2d

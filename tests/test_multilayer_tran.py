@@ -65,3 +65,26 @@ def test_cuda_multilayer_transmission_reflect(cuda_device):
                          1e-12, 'lb_')
     assert not bad, bad
     assert np.array_equal(gb.to_numpy()['state'], g['gb_state'])
+
+
+@pytest.mark.gpu
+def test_cuda_run_parallel_multilayer_tran_kernel(cuda_device):
+    """Kernel-dispatch level: XRT_CUDA.run_parallel('get_amplitude_graded_multilayer_tran', ...) with the argument
+    lists Multilayer.get_amplitude hands to its accelerator (multilayer.py:485-503), fed with the oracle's interface
+    amplitudes: the recursion alone reproduces the reference's (ts, tp)."""
+    from xrt_b200.cuda_backend import XRT_CUDA
+    g = golden('multilayer_tran_amplitudes')
+    ml = _oracle_ml()
+    f = ml.fresnel_terms(g['E'].copy(), g['bdn'].copy())
+    order = ['rvt', 'tvt', 'rbs', 'tbs', 'rsv', 'tsv', 'rbt', 'tbt', 'rtb', 'ttb']
+    f['rbt_s'], f['rbt_p'] = -f['rtb_s'], -f['rtb_p']
+    sliced = [np.ascontiguousarray(f[k + sfx]) for k in order for sfx in ('_s', '_p')] + \
+        [np.ascontiguousarray(f[k]) for k in ('Qt', 'Qb', 'Qs')]
+    n = len(g['E'])
+    ti_s, ti_p = np.zeros(n, dtype=complex), np.zeros(n, dtype=complex)
+    ucl = XRT_CUDA(targetOpenCL='CUDA', precisionOpenCL='float64')
+    out = ucl.run_parallel('get_amplitude_graded_multilayer_tran',
+                           [np.int32(ml.nPairs), np.float64(ml.substThickness)], sliced,
+                           [np.float64(ml.dti), np.float64(ml.dbi)], [ti_s, ti_p], None, n)
+    assert out[0] is ti_s and out[1] is ti_p
+    assert np.abs(ti_s - g['ts']).max() < 1e-13 and np.abs(ti_p - g['tp']).max() < 1e-13

@@ -49,6 +49,8 @@ PROTOTYPES = {
     'xrt_oe_normals_f64': (c_int, [c_sz, c_dp] + [c_dp] * 6 + [c_dp]),
     'xrt_multilayer_f64': (c_int, [c_sz, c_int] + [c_dp] * 12 + [c_dp]),
     'xrt_multilayer_f64_host': (c_int, [c_sz, c_int] + [c_dp] * 12),
+    'xrt_multilayer_tran_f64': (c_int, [c_sz, c_int, c_dbl, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    'xrt_multilayer_tran_f64_host': (c_int, [c_sz, c_int, c_dbl, c_dp, c_dp, c_dp, c_dp, c_dp]),
     'xrt_plot_hist_f64': (c_int, [c_sz, c_dp, c_dp]),
     'xrt_hist2d_f64': (c_int, [c_sz, c_dp, c_dp, c_dp, c_dp, c_dp, c_int, c_dp, c_int, c_dp, c_int, c_dp, c_dp]),
     'xrt_undulator_ext_f64': (c_int, [c_int, c_sz, c_int, c_int, c_dbl, c_dbl, c_dbl] + [c_dp] * 14 + [c_dp]),

@@ -521,6 +521,35 @@ int xrt_multilayer_f64_host(size_t n, int npairs, const double* rbs_s, const dou
   return 0;
 }
 
+int xrt_multilayer_tran_f64(size_t n, int npairs, double substThickness, const double* const* in23, const double* dti,
+                            const double* dbi, double* ti_s, double* ti_p, void* stream) {
+  return multilayer_tran_device(n, npairs, substThickness, in23, dti, dbi, ti_s, ti_p, (cudaStream_t)stream);
+}
+
+int xrt_multilayer_tran_f64_host(size_t n, int npairs, double substThickness, const double* const* in23,
+                                 const double* dti, const double* dbi, double* ti_s, double* ti_p) {
+  if (n == 0) return 0;
+  XRTB_REQUIRE(npairs >= 0 && in23 && dti && dbi, "multilayer_tran: nPairs >= 0, the inputs and the thickness arrays");
+  cudaStream_t st = 0;
+  DevBuf d[23], ddti, ddbi, dout;
+  const double* dev[23];
+  for (int k = 0; k < 23; ++k) {
+    XRTB_REQUIRE(in23[k] != nullptr, "multilayer_tran: input %d is NULL", k);
+    if (d[k].upload(in23[k], n * 16, st)) return 1;
+    dev[k] = d[k].as<double>();
+  }
+  if (ddti.upload(dti, (size_t)npairs * 8, st) || ddbi.upload(dbi, (size_t)npairs * 8, st)) return 1;
+  if (dout.alloc(2 * n * 16)) return 1;
+  double* o = dout.as<double>();
+  int rc = multilayer_tran_device(n, npairs, substThickness, dev, ddti.as<double>(), ddbi.as<double>(), o, o + 2 * n,
+                                  st);
+  if (rc) return rc;
+  XRTB_CUDA_CHECK(cudaMemcpyAsync(ti_s, o, n * 16, cudaMemcpyDeviceToHost, st));
+  XRTB_CUDA_CHECK(cudaMemcpyAsync(ti_p, o + 2 * n, n * 16, cudaMemcpyDeviceToHost, st));
+  XRTB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return 0;
+}
+
 // ------------------------------------------------------------------ source
 int xrt_source_sample_f64(size_t n, uint64_t seed, uint64_t index_offset, const double* window, double* E,
                           double* theta, double* psi, double* n1, double* n2, double* n3, double* n4, double* u,

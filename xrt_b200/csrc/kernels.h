@@ -51,6 +51,8 @@ int multilayer_device(size_t n, int npairs, int uniform, const double* rbs_s, co
                       const double* rtb_s, const double* rtb_p, const double* rvt_s, const double* rvt_p,
                       const double* Qt, const double* Qb, const double* dti, const double* dbi, double* ri_s,
                       double* ri_p, cudaStream_t st);
+int multilayer_tran_device(size_t n, int npairs, double substThickness, const double* const* in23, const double* dti,
+                           const double* dbi, double* ti_s, double* ti_p, cudaStream_t st);
 int amplitude_device(size_t n, const xrt_material_params* mat, const double* tables, size_t table_len,
                      const double* E, const double* bIn, const double* bOut, const double* bH, double* rs, double* rp,
                      unsigned long long* oor_count, cudaStream_t st);

@@ -1150,6 +1150,47 @@ int multilayer_device(size_t n, int npairs, int uniform, const double* rbs_s, co
   return 0;
 }
 
+// kernel get_amplitude_graded_multilayer_tran (cl/materials.cl; launched at multilayer.py:485-503): the 23 sliced
+// complex inputs in the reference's order -- rvt_s, rvt_p, tvt_s, tvt_p, rbs_s, rbs_p, tbs_s, tbs_p, rsv_s, rsv_p,
+// tsv_s, tsv_p, rbt_s, rbt_p, tbt_s, tbt_p, rtb_s, rtb_p, ttb_s, ttb_p, Qt, Qb, Qs -- as one table of device pointers
+struct MLTranPtrs {
+  const double2* a[23];
+};
+__global__ void __launch_bounds__(256) multilayer_tran_kernel(size_t n, int npairs, double substThickness,
+                                                              MLTranPtrs in, const double* __restrict__ dti,
+                                                              const double* __restrict__ dbi,
+                                                              double2* __restrict__ ti_s, double2* __restrict__ ti_p) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  auto ld = [&](int k) { return cplx{in.a[k][i].x, in.a[k][i].y}; };
+  MLTran f;
+  f.rvt_s = ld(0), f.rvt_p = ld(1), f.tvt_s = ld(2), f.tvt_p = ld(3), f.rbs_s = ld(4), f.rbs_p = ld(5);
+  f.tbs_s = ld(6), f.tbs_p = ld(7), f.rsv_s = ld(8), f.rsv_p = ld(9), f.tsv_s = ld(10), f.tsv_p = ld(11);
+  // 12, 13 = rbt (= -rtb, multilayer.py:394-395: the recursion forms it itself)
+  f.tbt_s = ld(14), f.tbt_p = ld(15), f.rtb_s = ld(16), f.rtb_p = ld(17), f.ttb_s = ld(18), f.ttb_p = ld(19);
+  f.Qt = ld(20), f.Qb = ld(21), f.Qs = ld(22);
+  cplx s, q;
+  multilayer_recursion_tran(npairs, substThickness, f, dti, dbi, s, q);
+  ti_s[i] = make_double2(s.re, s.im);
+  ti_p[i] = make_double2(q.re, q.im);
+}
+
+int multilayer_tran_device(size_t n, int npairs, double substThickness, const double* const* in23, const double* dti,
+                           const double* dbi, double* ti_s, double* ti_p, cudaStream_t st) {
+  XRTB_REQUIRE(in23 && dti && dbi && ti_s && ti_p && npairs >= 0, "multilayer_tran: NULL argument");
+  if (n == 0) return 0;
+  MLTranPtrs p;
+  for (int k = 0; k < 23; ++k) {
+    XRTB_REQUIRE(in23[k] != nullptr, "multilayer_tran: input %d is NULL", k);
+    p.a[k] = reinterpret_cast<const double2*>(in23[k]);
+  }
+  multilayer_tran_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, npairs, substThickness, p, dti, dbi,
+                                                                      reinterpret_cast<double2*>(ti_s),
+                                                                      reinterpret_cast<double2*>(ti_p));
+  XRTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 // ---------------------------------------------------------------- main pass
 struct Decision {
   int axis, neg, brent;

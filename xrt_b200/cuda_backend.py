@@ -10,6 +10,8 @@ written back into the caller's arrays *and* returned), same attributes (`cl_prec
     'integrate_kirchhoff'  cl/diffract.cl:80     called from waves.py:892
     'undulator'            cl/undulator.cl:54    called from sources/synchr.py:2174
     'get_amplitude'        cl/materials.cl:715   called from tests/raycing/test_materials.py:624
+    'get_amplitude_graded_multilayer[_tran]'  cl/materials.cl:568-840  called from materials/multilayer.py:471-503
+    'undulator_taper', 'undulator_nf', 'custom_field'  cl/undulator.cl:123-298  called from sources/synchr.py:2174
 
 Differences, on purpose: fp64 only (`precisionOpenCL` 'auto'/'float64'); there is no silent `_disable_cl`
 fallback to numpy -- a missing library or GPU raises; multi-device slicing (`run_parallel_max`,
@@ -242,6 +244,35 @@ class XRT_CUDA(object):
                                          _lib.hptr(ri_s), _lib.hptr(ri_p))
         _lib.check(rc, 'xrt_multilayer_f64_host')
         return ri_s, ri_p
+
+    def _k_get_amplitude_graded_multilayer_tran(self, scalarArgs, slicedRO, nonSlicedRO, slicedRW, nonSlicedRW,
+                                                dimension):
+        """Argument layout of Multilayer.get_amplitude's accelerator call for geom 'transmitted'
+        (materials/multilayer.py:485-503): scalars [nPairs, substThickness]; sliced RO: 23 complex arrays (rvt, tvt,
+        rbs, tbs, rsv, tsv, rbt, tbt, rtb, ttb for s and p, then Qt, Qb, Qs); non-sliced RO [dti, dbi]; sliced RW
+        [ti_s, ti_p]."""
+        import ctypes
+        lib = _lib.load()
+        npairs, substThickness = int(scalarArgs[0]), float(scalarArgs[1])
+        ins = [_lib.as_c128(a) for a in slicedRO]
+        n = dimension if dimension else len(ins[0])
+        if len(ins) != 23 or any(len(a) != n for a in ins):
+            raise ValueError('get_amplitude_graded_multilayer_tran: expected 23 sliced complex inputs of length '
+                             'dimension')
+        dti, dbi = (_lib.as_f64(a) for a in nonSlicedRO)
+        if len(dti) < npairs or len(dbi) < npairs:
+            raise ValueError('get_amplitude_graded_multilayer_tran: dti and dbi must hold nPairs thicknesses')
+        ti_s, ti_p = slicedRW
+        for a in (ti_s, ti_p):
+            if not (isinstance(a, np.ndarray) and a.dtype == np.complex128 and a.flags['C_CONTIGUOUS'] and
+                    len(a) == n):
+                raise ValueError('get_amplitude_graded_multilayer_tran: slicedRWArgs must be 2 contiguous '
+                                 'complex128[dimension]')
+        table = (ctypes.c_void_p * 23)(*[_lib.hptr(a) for a in ins])
+        rc = lib.xrt_multilayer_tran_f64_host(n, npairs, substThickness, ctypes.addressof(table), _lib.hptr(dti),
+                                              _lib.hptr(dbi), _lib.hptr(ti_s), _lib.hptr(ti_p))
+        _lib.check(rc, 'xrt_multilayer_tran_f64_host')
+        return ti_s, ti_p
 
 
 def _as_vec_buffer(a, N):
