@@ -310,6 +310,11 @@ int xrt_expose_f64(size_t n, const xrt_plane_params* p, const xrt_beam* in, cons
                    uint64_t* reductions, void* stream);
 /* out = RectangularAperture.propagate(in): alive rays are transported to the aperture plane; rays hitting a
  * blade get state = lostNum in `out` AND in `in` (the reference marks the incoming beam, apertures.py:364). */
+/* HemisphericScreen.expose (screens.py:422-545): rays meet the sphere of radius R around p->center; positions in the
+ * screen's local frame (p->ex, ey, ez), directions stay global, out->theta / out->phi receive the angular
+ * coordinates minus their offsets.  Uses center, ex / ey / ez, lostNum, only_positive_path of the plane parameters. */
+int xrt_expose_hemispheric_f64(size_t n, const xrt_plane_params* p, double R, double thetaOffset, double phiOffset,
+                               const xrt_beam* in, const xrt_beam* out, void* stream);
 int xrt_propagate_rect_f64(size_t n, const xrt_plane_params* p, const xrt_beam* in, const xrt_beam* out,
                            uint64_t* reductions, void* stream);
 

@@ -111,3 +111,33 @@ def propagate_round(beam, center, xyz, r, lostNum, isBeamStop=False):
         lo.Es[good] *= propPhase
         lo.Ep[good] *= propPhase
     return lo
+
+
+def expose_hemispheric(beam, center, xyz, R, lostNum, phiOffset=0, thetaOffset=0, onlyPositivePath=False):
+    """HemisphericScreen.expose (screens.py:501-545); xyz = (x, y, z) local axes in the global system."""
+    lx, ly, lz = xyz
+    blo = ob.Beam(copyFrom=beam)
+    sqb_2 = (beam.a * (beam.x-center[0]) + beam.b * (beam.y-center[1]) + beam.c * (beam.z-center[2]))
+    sqc = ((beam.x-center[0])**2 + (beam.y-center[1])**2 + (beam.z-center[2])**2 - R**2)
+    with np.errstate(invalid='ignore'):
+        path = -sqb_2 + (sqb_2**2 - sqc)**0.5
+    condBad = np.isnan(path) | np.isinf(path)
+    if onlyPositivePath:
+        condBad = condBad | (path < 0)
+    indBad = np.where(condBad)
+    path[indBad] = 0.
+    blo.state[indBad] = lostNum
+    blo.path += path
+    rx = beam.x + beam.a*path - center[0]
+    ry = beam.y + beam.b*path - center[1]
+    rz = beam.z + beam.c*path - center[2]
+    blo.z = rx*lz[0] + ry*lz[1] + rz*lz[2]
+    blo.y = rx*ly[0] + ry*ly[1] + rz*ly[2]
+    blo.x = rx*lx[0] + ry*lx[1] + rz*lx[2]
+    blo.theta = np.arcsin(blo.z / R) - thetaOffset
+    blo.phi = np.arctan2(blo.y, blo.x) - phiOffset
+    if hasattr(blo, 'Es'):
+        propPhase = np.exp(1e7j * (blo.E / CHBAR) * path)
+        blo.Es *= propPhase
+        blo.Ep *= propPhase
+    return blo

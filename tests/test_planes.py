@@ -139,3 +139,34 @@ def test_cuda_round_prepare_wave_vs_golden(cuda_device):
     for k in ('a', 'b', 'c'):
         assert np.abs(d[k] - g[k]).max() <= 1e-12, k
     assert wave.area == float(g['area']) and wave.dS == float(g['dS'])
+
+
+def test_oracle_expose_hemispheric_bit_exact():
+    """HemisphericScreen.expose (screens.py:501-545)."""
+    g = golden('expose_hemispheric')
+    with np.errstate(invalid='ignore'):
+        blo = op.expose_hemispheric(oracle_beam(g, 'in_'), list(g['center']), _basis(g), float(g['R']),
+                                    int(g['lostNum']), float(g['phiOffset']), float(g['thetaOffset']))
+    for f in BEAM_FIELDS + ('theta',):
+        assert np.array_equal(getattr(blo, f), g['out_' + f], equal_nan=True), f
+    assert np.array_equal(blo.phi, g['out_phi'], equal_nan=True)
+    assert (blo.state == int(g['lostNum'])).sum() > 100
+
+
+@pytest.mark.gpu
+def test_cuda_expose_hemispheric_vs_golden(cuda_device):
+    import types
+    from xrt_b200.planes import HemisphericScreen
+    g = golden('expose_hemispheric')
+    bl = types.SimpleNamespace(sinAzimuth=float(g['sinAzimuth']), cosAzimuth=float(g['cosAzimuth']), screens=[])
+    scr = HemisphericScreen(bl, 'hemi', center=list(g['center']), R=float(g['R']), phiOffset=float(g['phiOffset']),
+                            thetaOffset=float(g['thetaOffset']))
+    for k, v in (('x', 'ex'), ('y', 'ey'), ('z', 'ez')):  # the default orientation is the reference's
+        assert np.allclose(getattr(scr, k), g[v], rtol=0, atol=1e-15), k
+    scr.lostNum = int(g['lostNum'])
+    blo = scr.expose(device_beam(oracle_beam(g, 'in_'))).to_numpy()
+    ref = {f: g['out_' + f] for f in BEAM_FIELDS}
+    assert not compare_beams(blo, ref, BEAM_FIELDS, RTOL)
+    ok = g['out_state'] > 0
+    assert np.abs(blo['theta'][ok] - g['out_theta'][ok]).max() <= 1e-12
+    assert np.abs(blo['phi'][ok] - g['out_phi'][ok]).max() <= 1e-12

@@ -1279,7 +1279,28 @@ def gen_multilayer_tran():
     save('reflect_multilayer_tran', **dd)
 
 
-SECTIONS = {'multilayer_tran': gen_multilayer_tran, 'fzp': gen_fzp, 'laue': gen_laue, 'coated': gen_coated, 'figure_error': gen_figure_error, 'round': gen_round, 'shine_wave': gen_shine_wave, 'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+def gen_hemispheric():
+    """HemisphericScreen.expose (screens.py:422-545): a beam scattered into a wide cone, exposed on a sphere; some
+    rays start outside the sphere and fly away from it (no intersection: lost)."""
+    bl = raycing.BeamLine(azimuth=0.15)
+    beam = _source_beam(bl, 2500, 61, dx=0.4, dz=0.3, dxprime=0.3, dzprime=0.2)
+    far = np.random.RandomState(62).rand(2500) < 0.1
+    beam.x[far] += 5000.  # outside the sphere
+    scr = rsc.HemisphericScreen(bl, 'hemi', center=(30*np.sin(0.15), 30*np.cos(0.15), 0.5), R=400., phiOffset=-0.1,
+                                thetaOffset=0.05)
+    blo = scr.expose(beam)
+    st = blo.state
+    print('hemispheric', {int(x): int((st == x).sum()) for x in np.unique(st)})
+    out = dict(center=np.array(scr.center, dtype=float), ex=np.array(scr.x, dtype=float), ey=np.array(scr.y, dtype=float),
+               ez=np.array(scr.z, dtype=float), lostNum=np.int64(scr.lostNum), R=float(scr.R),
+               phiOffset=float(scr.phiOffset), thetaOffset=float(scr.thetaOffset), sinAzimuth=bl.sinAzimuth,
+               cosAzimuth=bl.cosAzimuth, out_phi=blo.phi)
+    out.update(beam_dict(beam, 'in_'))
+    out.update(beam_dict(blo, 'out_'))
+    save('expose_hemispheric', **out)
+
+
+SECTIONS = {'hemispheric': gen_hemispheric, 'multilayer_tran': gen_multilayer_tran, 'fzp': gen_fzp, 'laue': gen_laue, 'coated': gen_coated, 'figure_error': gen_figure_error, 'round': gen_round, 'shine_wave': gen_shine_wave, 'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)

@@ -40,6 +40,7 @@ PROTOTYPES = {
     'xrt_reduction_decode': (c_dbl, [ctypes.c_uint64]),
     'xrt_expose_f64': (c_int, [c_sz, c_dp, c_dp, c_dp, c_dp, c_dp]),
     'xrt_propagate_rect_f64': (c_int, [c_sz, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    'xrt_expose_hemispheric_f64': (c_int, [c_sz, c_dp, c_dbl, c_dbl, c_dbl, c_dp, c_dp, c_dp]),
     'xrt_get_amplitude_f64_host': (c_int, [c_sz, c_dp, c_dp, c_sz] + [c_dp] * 6),
     'xrt_source_sample_f64': (c_int, [c_sz, ctypes.c_uint64, ctypes.c_uint64] + [c_dp] * 10 + [c_dp]),
     'xrt_source_fill_f64': (c_int, [c_sz, c_dp, c_dp] + [c_dp] * 9 + [c_dp, c_sz, c_dp]),

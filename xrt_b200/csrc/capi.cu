@@ -431,6 +431,11 @@ int xrt_expose_f64(size_t n, const xrt_plane_params* p, const xrt_beam* in, cons
   return expose_device(n, p, in, out, reinterpret_cast<unsigned long long*>(reductions), (cudaStream_t)stream);
 }
 
+int xrt_expose_hemispheric_f64(size_t n, const xrt_plane_params* p, double R, double thetaOffset, double phiOffset,
+                               const xrt_beam* in, const xrt_beam* out, void* stream) {
+  return expose_hemispheric_device(n, p, R, thetaOffset, phiOffset, in, out, (cudaStream_t)stream);
+}
+
 int xrt_propagate_rect_f64(size_t n, const xrt_plane_params* p, const xrt_beam* in, const xrt_beam* out,
                            uint64_t* reductions, void* stream) {
   return propagate_rect_device(n, p, in, out, reinterpret_cast<unsigned long long*>(reductions),

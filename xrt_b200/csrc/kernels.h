@@ -60,6 +60,8 @@ int amplitude_device(size_t n, const xrt_material_params* mat, const double* tab
 // rays.cu (compiled with -fmad=false)
 int expose_device(size_t n, const xrt_plane_params* p, const xrt_beam* in, const xrt_beam* out,
                   unsigned long long* red, cudaStream_t st);
+int expose_hemispheric_device(size_t n, const xrt_plane_params* p, double R, double thetaOffset, double phiOffset,
+                              const xrt_beam* in, const xrt_beam* out, cudaStream_t st);
 int propagate_rect_device(size_t n, const xrt_plane_params* p, const xrt_beam* in, const xrt_beam* out,
                           unsigned long long* red, cudaStream_t st);
 

@@ -144,6 +144,68 @@ __global__ void __launch_bounds__(256) expose_kernel(size_t n, xrt_plane_params 
   block_minmax(mn, mx, cnt, red);
 }
 
+// ---------------------------------------------------------------- HemisphericScreen.expose (screens.py:501-545)
+// Intersection with the sphere of radius R around the centre, in global coordinates; positions go to the screen's
+// local frame, directions stay global (the reference copies them untouched); theta = asin(z/R) - thetaOffset,
+// phi = atan2(y, x) - phiOffset land in out.theta / out.phi.
+__global__ void __launch_bounds__(256) expose_hemi_kernel(size_t n, xrt_plane_params p, double R, double R2,
+                                                          double thetaOffset, double phiOffset, xrt_beam in,
+                                                          xrt_beam out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double bx = in.x[i], by = in.y[i], bz = in.z[i], a = in.a[i], b = in.b[i], c = in.c[i];
+  const double dx = bx - p.center[0], dy = by - p.center[1], dz = bz - p.center[2];
+  const double sqb_2 = a * dx + b * dy + c * dz;
+  const double sqc = dx * dx + dy * dy + dz * dz - R2;
+  double path = -sqb_2 + sqrt(sqb_2 * sqb_2 - sqc);
+  int st = in.state[i];
+  bool bad = isnan(path) || isinf(path);
+  if (p.only_positive_path) bad = bad || (path < 0.0);
+  if (bad) {
+    path = 0.0;
+    st = p.lostNum;
+  }
+  const double rx = bx + a * path - p.center[0], ry = by + b * path - p.center[1], rz = bz + c * path - p.center[2];
+  const double lz = rx * p.ez[0] + ry * p.ez[1] + rz * p.ez[2];
+  const double ly = rx * p.ey[0] + ry * p.ey[1] + rz * p.ey[2];
+  const double lx = rx * p.ex[0] + ry * p.ex[1] + rz * p.ex[2];
+  out.x[i] = lx;
+  out.y[i] = ly;
+  out.z[i] = lz;
+  out.a[i] = a;
+  out.b[i] = b;
+  out.c[i] = c;
+  out.path[i] = in.path[i] + path;
+  const double E = in.E[i];
+  out.E[i] = E;
+  out.Jss[i] = in.Jss[i];
+  out.Jpp[i] = in.Jpp[i];
+  stc(out.Jsp, i, ldc(in.Jsp, i));
+  out.state[i] = st;
+  if (out.theta) out.theta[i] = asin(lz / R) - thetaOffset;
+  if (out.phi) out.phi[i] = atan2(ly, lx) - phiOffset;
+  if (in.Es && out.Es) {
+    const double CHBAR = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8 / 6.283185307179586476925286766559;
+    const double phi = (1e7 * (E / CHBAR)) * path;
+    double s, cs;
+    sincos_big(phi, s, cs);
+    const cplx ph = cplx{cs, s};
+    stc(out.Es, i, cmul_np2(ldc(in.Es, i), ph));
+    stc(out.Ep, i, cmul_np2(ldc(in.Ep, i), ph));
+  }
+}
+
+int expose_hemispheric_device(size_t n, const xrt_plane_params* p, double R, double thetaOffset, double phiOffset,
+                              const xrt_beam* in, const xrt_beam* out, cudaStream_t st) {
+  XRTB_REQUIRE(p && in && out, "expose_hemispheric: NULL argument");
+  XRTB_REQUIRE(R > 0.0, "expose_hemispheric: the radius must be positive");
+  if (n > 0)
+    expose_hemi_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, *p, R, R * R, thetaOffset, phiOffset, *in,
+                                                                    *out);
+  XRTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 // ---------------------------------------------------------------- RectangularAperture.propagate
 __global__ void __launch_bounds__(256) propagate_rect_kernel(size_t n, xrt_plane_params p, xrt_beam in, xrt_beam out,
                                                              unsigned long long* red) {

@@ -122,6 +122,50 @@ class Screen(_Plane):
         return blo
 
 
+class HemisphericScreen(Screen):
+    """Hemispheric screen (screens.py:422-545): rays are exposed on the sphere of radius *R* around *center*; the
+    returned local beam carries *theta* and *phi* (minus their offsets).  Default orientation: local x along the beam
+    line, local z horizontal (screens.py:470-487)."""
+
+    def __init__(self, bl=None, name='', center=[0, 0, 0], R=1000., x='auto', z='auto', phiOffset=0, thetaOffset=0,
+                 **kwargs):
+        Screen.__init__(self, bl, name, center, **kwargs)
+        self.R = R
+        self.phiOffset = phiOffset
+        self.thetaOffset = thetaOffset
+        sinAz = bl.sinAzimuth if bl is not None else 0.
+        cosAz = bl.cosAzimuth if bl is not None else 1.
+        if isinstance(x, (list, tuple, np.ndarray)):
+            norm = sum([xc**2 for xc in x])**0.5
+            self.x = [xc/norm for xc in x]
+        else:
+            self.x = [sinAz, cosAz, 0.]
+        if isinstance(z, (list, tuple, np.ndarray)):
+            norm = sum([zc**2 for zc in z])**0.5
+            self.z = [zc/norm for zc in z]
+        else:
+            self.z = [cosAz, -sinAz, 0.]
+        self.y = list(np.cross(self.z, self.x))
+
+    def expose(self, beam=None, onlyPositivePath=False):
+        lib = _lib.load()
+        p = self._base_params()
+        p.only_positive_path = int(bool(onlyPositivePath))
+        blo = beam.like()
+        blo.theta = torch.empty(len(beam), dtype=torch.float64, device=beam.device)
+        blo.phi = torch.empty(len(beam), dtype=torch.float64, device=beam.device)
+        cin, cout = beam.c_struct(), blo.c_struct()
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(lib.xrt_expose_hemispheric_f64(len(beam), ctypes.byref(p), float(self.R), float(self.thetaOffset),
+                                                  float(self.phiOffset), ctypes.byref(cin), ctypes.byref(cout),
+                                                  stream), 'xrt_expose_hemispheric_f64')
+        blo.parentId = getattr(self, 'uuid', self.name)
+        return blo
+
+    def prepare_wave(self, *a, **k):
+        raise NotImplementedError('HemisphericScreen.prepare_wave is outside the hot path')
+
+
 def _screen_prepare_wave(self, prevOE, dim1, dim2, dy=0, rw=None, condition=None):
     """Screen.prepare_wave (screens.py:304-365): a mesh of receiving points on the screen for waves.diffract or
     source.shine(wave=...)."""
