@@ -143,3 +143,16 @@ def test_bridge_figure_error_host_objects(cuda_device):
     geo = ('x', 'y', 'z', 'a', 'b', 'c', 'Jss', 'Jpp', 'Jsp')
     bad = compare_beams(gb.__dict__, {f: g['gb_' + f] for f in BEAM_FIELDS}, geo, 1e-12, 'gb_')
     assert not bad, bad
+
+
+@pytest.mark.gpu
+def test_bridge_propagate_round_aperture_host_objects(cuda_device):
+    from xrt_b200 import bridge
+    g = golden('propagate_round')
+    ap = types.SimpleNamespace(name='pipe', center=list(g['center']), r=float(g['r']), shape='round',
+                               isBeamStop=False, xyz=[list(g['ex']), list(g['ey']), list(g['ez'])],
+                               lostNum=int(g['lostNum']))
+    beam = oracle_beam(g, 'in_')
+    lo = bridge.propagate(ap, beam)
+    assert not compare_beams(lo.__dict__, {f: g['out_' + f] for f in BEAM_FIELDS}, BEAM_FIELDS, 1e-12)
+    assert np.array_equal(beam.state, g['in_state_after'])

@@ -5,7 +5,8 @@ kernels: the method-level binding sketched in INTEGRATION.md section 2.
     bridge.reflect(xrt_oe, xrt_beam, needLocal=True)          -> (gb, lb)      OE.reflect, oes/reflect.py:18
     bridge.multiple_reflect(xrt_oe, xrt_beam, maxReflections) -> (gb, lbN)     OE.multiple_reflect, oes/reflect.py:165
     bridge.double_reflect(xrt_dcm, xrt_beam, needLocal=True)  -> (gb, lo1, lo2)  DCM.double_reflect, dcm.py:248
-    bridge.expose(xrt_screen, xrt_beam)                       -> blo           Screen.expose, screens.py:226
+    bridge.expose(xrt_screen, xrt_beam)                       -> blo           Screen / HemisphericScreen.expose
+    bridge.propagate(xrt_aperture, xrt_beam)                  -> lo            Rectangular / RoundAperture.propagate
     bridge.double_refract(xrt_plate, xrt_beam)                -> (gb, lo1, lo2)  Plate.double_refract, refractive.py:171
     bridge.multiple_refract(xrt_lens, xrt_beam)               -> (gb, lo1, lo2)  multiple_refract, refractive.py:457
 
@@ -178,7 +179,32 @@ def double_reflect(dcm, beam, needLocal=True):
     return hgb, HostBeam(lo1.to_numpy()), HostBeam(lo2.to_numpy())
 
 
+def propagate(aperture, beam):
+    """RectangularAperture.propagate / RoundAperture.propagate (apertures.py:333-413, :769-825): returns the local
+    beam; `beam.state` of the caller's host beam is marked like the reference marks it."""
+    if getattr(aperture, 'shape', '') == 'round' or hasattr(aperture, 'r'):
+        ap = _planes.RoundAperture(None, aperture.name, center=list(aperture.center), r=float(aperture.r),
+                                   isBeamStop=getattr(aperture, 'isBeamStop', False))
+    else:
+        ap = _planes.RectangularAperture(None, aperture.name, center=list(aperture.center),
+                                         blades=dict(aperture.blades),
+                                         isBeamStop=getattr(aperture, 'isBeamStop', False))
+    ap.x, ap.y, ap.z = [list(v) for v in aperture.xyz]
+    ap.lostNum = aperture.lostNum
+    dev = _device_beam(beam)
+    lo = ap.propagate(dev)
+    beam.state[:] = dev.state.cpu().numpy()
+    return HostBeam(lo.to_numpy())
+
+
 def expose(screen, beam, onlyPositivePath=False):
+    if hasattr(screen, 'thetaOffset'):  # HemisphericScreen (screens.py:422-545)
+        scr = _planes.HemisphericScreen(None, screen.name, center=list(screen.center), R=float(screen.R),
+                                        x=list(screen.x), z=list(screen.z), phiOffset=screen.phiOffset,
+                                        thetaOffset=screen.thetaOffset)
+        scr.y = list(screen.y)
+        scr.lostNum = screen.lostNum
+        return HostBeam(scr.expose(_device_beam(beam), onlyPositivePath=onlyPositivePath).to_numpy())
     scr = _planes.Screen(None, screen.name, center=list(screen.center), compressX=screen.compressX,
                          compressZ=screen.compressZ)
     scr.x, scr.y, scr.z = list(screen.x), list(screen.y), list(screen.z)
