@@ -460,10 +460,15 @@ def reflect_local(oe, good, lb, vlb, pitch, roll, yaw, dx=None, dy=None, dz=None
             lb.x[good], lb.y[good], lb.z[good] = oe.xyz_to_param(lb.x[good], lb.y[good], lb.z[good])
         _lost = np.zeros(int(good.sum()), dtype=bool)
     else:
-        res_find = find_intersection(oe, None, tMin[good], tMax[good], lb.x[good], lb.y[good], lb.z[good],
-                                     lb.a[good], lb.b[good], lb.c[good], invertNormal, info)
+        own = getattr(oe.surfParams.get('obj', None), 'find_intersection', None) if oe.surface == 'custom' else None
+        if own is not None:  # an element with its own intersection method (BlazedGrating, gratings.py:489-520)
+            res_find = own(tMin[good], tMax[good], lb.x[good], lb.y[good], lb.z[good], lb.a[good], lb.b[good],
+                           lb.c[good], invertNormal)
+        else:
+            res_find = find_intersection(oe, None, tMin[good], tMax[good], lb.x[good], lb.y[good], lb.z[good],
+                                         lb.a[good], lb.b[good], lb.c[good], invertNormal, info)
         tMax[good], lb.x[good], lb.y[good], lb.z[good] = res_find[:4]
-        _lost = res_find[4]
+        _lost = res_find[4] if len(res_find) > 4 else np.zeros(int(good.sum()), dtype=bool)
     if oe.isParametric:
         tX, tY, tZ = oe.param_to_xyz(lb.x[good], lb.y[good], lb.z[good])
     else:

@@ -276,3 +276,52 @@ class NormalFZP(object):
         gx = -x[good] / r[good] * rho
         gy = -y[good] / r[good] * rho
         return locState, (gx, gy, gz)
+
+
+class BlazedGrating(object):
+    """BlazedGrating with a constant line density (oes/gratings.py:316-535: reset :416-441, local_pre :459-473,
+    local_z :475-480, local_n :482-490, find_intersection :492-520)."""
+
+    def __init__(self, blaze, antiblaze, rho0):
+        self.blaze, self.antiblaze, self.rho0 = blaze, antiblaze, rho0
+        self.rho_1 = 1. / rho0
+        self.sinBlaze, self.cosBlaze, self.tanBlaze = np.sin(blaze), np.cos(blaze), np.tan(blaze)
+        self.sinAntiblaze, self.cosAntiblaze, self.tanAntiblaze = \
+            np.sin(antiblaze), np.cos(antiblaze), np.tan(antiblaze)
+
+    def local_pre(self, x, y):
+        y0 = (y // self.rho_1) * self.rho_1
+        y1 = y0 + self.rho_1
+        yL = y % self.rho_1
+        yC = (y1-y0) / (1 + self.tanAntiblaze/self.tanBlaze)
+        return 0, y0, y1, yC, yL
+
+    def local_z(self, x, y):
+        y0ind, y0, y1, yC, yL = self.local_pre(x, y)
+        return np.where(yL > yC, -(y1-y) * self.tanBlaze, -yL * self.tanAntiblaze)
+
+    def local_n(self, x, y):
+        y0ind, y0, y1, yC, yL = self.local_pre(x, y)
+        return [np.zeros_like(x), np.where(yL > yC, -self.sinBlaze, self.sinAntiblaze),
+                np.where(yL > yC, self.cosBlaze, self.cosAntiblaze)]
+
+    def find_intersection(self, t1, t2, x, y, z, a, b, c, invertNormal):
+        b_c = b / c
+        n = np.floor((y - b_c*z) / self.rho_1)
+        y0 = self.rho_1 * n
+        y1 = y0 + self.rho_1
+        if self.antiblaze == np.pi/2:
+            zabl = (y0-y) / b_c + z
+        else:
+            zabl = -self.tanAntiblaze * (y - b_c*z - y0) / (1 + self.tanAntiblaze*b_c)
+        if self.blaze == np.pi/2:
+            zbl = (y1-y) / b_c + z
+        else:
+            zbl = self.tanBlaze * (y - b_c*z - y1) / (1 - self.tanBlaze*b_c)
+        zabl[zabl > 0] = zbl[zabl > 0] - 1
+        zbl[zbl > 0] = zabl[zbl > 0] - 1
+        z2 = zbl
+        y2 = b_c * (z2 - z) + y
+        t2 = (y2 - y) / b
+        x2 = x + t2 * a
+        return t2, x2, y2, z2

@@ -1300,7 +1300,24 @@ def gen_hemispheric():
     save('expose_hemispheric', **out)
 
 
-SECTIONS = {'hemispheric': gen_hemispheric, 'multilayer_tran': gen_multilayer_tran, 'fzp': gen_fzp, 'laue': gen_laue, 'coated': gen_coated, 'figure_error': gen_figure_error, 'round': gen_round, 'shine_wave': gen_shine_wave, 'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+def gen_blazed():
+    """BlazedGrating (oes/gratings.py:316-535), constant line density: sawtooth surface with its own analytic
+    find_intersection (first facet hit, shadowing respected) and facet normals; material kind 'mirror'."""
+    bl = raycing.BeamLine()
+    Au = rm.Material('Au', rho=19.3, kind='mirror')
+    for name, kw in (('blazed', dict(blaze=np.radians(1.2), rho=300.)),
+                     ('blazed_anti', dict(blaze=np.radians(0.8), antiblaze=np.radians(30.), rho=600.))):
+        beam = _source_beam(bl, 2500, 251, dx=0.3, dz=0.02, dxprime=1e-4, dzprime=3e-5, energies=(395., 405.))
+        oe = roe.BlazedGrating(bl, name, center=(0, 15000., 0), pitch=np.radians(2.), material=Au, limPhysX=[-5, 5],
+                               limPhysY=[-40, 45], **kw)
+        d = _capture_reflect(oe, beam)
+        d.update(_oe_params(oe))
+        st = d['gb_state']
+        print(name, {int(x): int((st == x).sum()) for x in np.unique(st)})
+        save('reflect_' + name, rho=19.3, blaze=float(oe.blaze), antiblaze=float(oe.antiblaze), rho0=float(oe.rho0), **d)
+
+
+SECTIONS = {'blazed': gen_blazed, 'hemispheric': gen_hemispheric, 'multilayer_tran': gen_multilayer_tran, 'fzp': gen_fzp, 'laue': gen_laue, 'coated': gen_coated, 'figure_error': gen_figure_error, 'round': gen_round, 'shine_wave': gen_shine_wave, 'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)
