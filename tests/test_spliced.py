@@ -91,6 +91,7 @@ def test_plugin_objects_build_and_export_without_gpu():
     from xrt_b200.oes import xrt_oe_params
     paths = oes_spliced.prebuild()
     assert len(set(paths)) == len({(c.cu_local_z, c.cu_local_n) for c in oes_spliced.LIBRARY}) + 3
+    assert sum(custom.SurfacePlugin(p).own_intersection for p in paths) == 1  # BlazedGrating
     plugs = [custom.SurfacePlugin(p) for p in paths]
     assert sorted(q.kind for q in plugs).count(5) == 1  # ParabolicalMirrorParam
     assert sorted((q.kind, q.figure_error) for q in plugs if q.figure_error) == [(0, True), (1, True), (4, True)]

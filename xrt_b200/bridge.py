@@ -129,6 +129,12 @@ def convert_oe(oe):
             oe.bl, oe.name, Rm=float(oe.Rm), crossSection=oe.crossSection, **kw)
     elif 'JohannToroid' in cls and not any(c in cls for c in ('JohanssonToroid', 'GeneralBraggToroid', 'DicedOE')):
         out = _oes.JohannToroid(oe.bl, oe.name, Rm=float(oe.Rm), Rs=float(oe.Rs), **kw)
+    elif type(oe).__name__ == 'BlazedGrating':
+        if getattr(oe, 'gratingDensity', None) is not None:
+            raise NotImplementedError('a variable line density is outside the hot path')
+        kw.pop('gratingDensity', None), kw.pop('order', None)
+        out = _oes.BlazedGrating(oe.bl, oe.name, blaze=float(oe.blaze), antiblaze=float(oe.antiblaze),
+                                 rho=float(oe.rho0), **kw)
     elif type(oe).__name__ == 'NormalFZP':
         kw.pop('limPhysX'), kw.pop('limPhysY')
         out = _oes.NormalFZP(oe.bl, oe.name, f=oe.f, E=oe.E, N=oe.N, isCentralZoneBlack=oe.isCentralZoneBlack,

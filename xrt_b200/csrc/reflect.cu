@@ -36,6 +36,10 @@
 //   __device__ void   local_n(const double* cu_plist, double x, double y, double* n); // n[0..2], or n[0..5] = (n_B, n_s)
 //   __device__ void   xyz_to_param(const double* cu_plist, double& x, double& y, double& z);   // parametric only
 //   __device__ void   param_to_xyz(const double* cu_plist, double& s, double& phi, double& r); // parametric only
+// and, with -DXRTB_USER_INTERSECTION, an element's OWN intersection method instead of the bracketed root search
+// (the reference's BlazedGrating overrides OE.find_intersection this way, oes/gratings.py:492-520):
+//   __device__ void   find_intersection(const double* cu_plist, double x, double y, double z, double a, double b,
+//                                        double c, double& t2, double& x2, double& y2, double& z2);
 // and the kernels below see it as surface kind 4 (z(x, y)) or 5 (parametric).  cu_plist = xrt_oe_params.sp.
 #ifdef XRTB_USER_SURFACE
 #include XRTB_USER_SURFACE
@@ -1470,6 +1474,11 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
         y2 = r.y;
         z2 = r.z;
         xyz_to_param<SURF>(p, x2, y2, z2);
+#ifdef XRTB_USER_INTERSECTION
+      } else if (SURF == 4) {
+        // the element's own find_intersection: no bracket, no lost-by-bracket rays (4 values returned, reflect.py:686-690)
+        xrtb_user::find_intersection(p.sp, r.x, r.y, r.z, r.a, r.b, r.c, t2, x2, y2, z2);
+#endif
       } else {
         // bracketing + intersection (base.py:848-885)
         bracket(p, d.axis, d.neg, r, t1, t2);
@@ -2214,6 +2223,13 @@ XRTB_EXPORT int xrt_plugin_reflect_multi_deriv_f64(size_t n, const xrt_oe_params
 }
 XRTB_EXPORT size_t xrt_plugin_sizeof_oe_params(void) { return sizeof(xrt_oe_params); }
 XRTB_EXPORT int xrt_plugin_surface_kind(void) { return XRTB_USER_KIND; }
+XRTB_EXPORT int xrt_plugin_has_own_intersection(void) {
+#ifdef XRTB_USER_INTERSECTION
+  return 1;
+#else
+  return 0;
+#endif
+}
 XRTB_EXPORT int xrt_plugin_has_figure_error(void) {
 #ifdef XRTB_FIGURE_ERROR
   return 1;

@@ -101,6 +101,7 @@ class OE(object):
     cu_local_z = None
     cu_local_n = None
     cu_xyz_param = None
+    cu_find_intersection = None  # an element's own intersection method instead of the bracketed root search
     cu_two_normals = None  # None: two normals (n_B, n_s) are returned iff alpha is set, like OE.local_n
 
     def __init__(self, bl=None, name='', center=[0, 0, 0], pitch=0, roll=0, yaw=0, positionRoll=0,
@@ -180,7 +181,8 @@ class OE(object):
         if self.cu_local_n is None:
             raise _lib.XrtB200Error('a spliced surface needs both cu_local_z and cu_local_n')
         from . import custom
-        return custom.plugin_for(self.cu_local_z, self.cu_local_n, self.cu_xyz_param, figure_error=fe)
+        extra = (self.cu_xyz_param, self.cu_find_intersection) if self.cu_find_intersection else self.cu_xyz_param
+        return custom.plugin_for(self.cu_local_z, self.cu_local_n, extra, figure_error=fe)
 
     def _limits(self, second=False):
         sfx = '2' if second else ''
@@ -496,7 +498,10 @@ class OE(object):
         params.want_footprint = int(bool(withFootprint or (checkTables and self.material is not None)))
         gb = beam.like()
         lb = self._new_local(beam) if needLocal else None
-        red = self._launch(params, self.material, beam, gb, lb, index_offset=index_offset, allreduce=allreduce)
+        # an element with its own intersection method needs no bracket: pre-pass B is skipped
+        phases = (1, 2) if (self.cu_find_intersection and not noIntersectionSearch) else None
+        red = self._launch(params, self.material, beam, gb, lb, index_offset=index_offset, allreduce=allreduce,
+                           phases=phases)
         if checkTables and self.material is not None:
             self._check_tables(red)
         if withFootprint:
@@ -992,7 +997,7 @@ def _rotate_point(point, rotationSequence='RzRyRx', pitch=0, roll=0, yaw=0):
 
 
 _SPLICED = ('BentFlatMirror', 'SimpleVCM', 'ConicalMirror', 'JohannCylinder', 'JohanssonCylinder', 'JohannToroid',
-            'ParabolicalMirrorParam', 'ParabolicMirror', 'LauePlate', 'BentLaueCylinder')
+            'ParabolicalMirrorParam', 'ParabolicMirror', 'LauePlate', 'BentLaueCylinder', 'BlazedGrating')
 
 
 def __getattr__(name):

@@ -10,6 +10,7 @@ and constructor arguments:
     ParabolicalMirrorParam(..., p | q, isCylindrical)       oes/parametric.py:252-476  (parametric: s, phi, r)
     BentLaueCylinder(..., R, crossSection)                  oes/laue.py:26-175   (planes' normal + surface normal)
     LauePlate(...)                                          oes/laue.py:11-24    (flat: the built-in kernel, no texts)
+    BlazedGrating(..., blaze, antiblaze, rho)               oes/gratings.py:316-535  (own analytic find_intersection)
 
 The texts follow the reference's numpy expressions operation by operation (the plug-in is compiled with
 -fmad=false); scalars the reference forms from Python floats (`self.Rm**2`, `0.25*self.t2t**2`) are formed on the
@@ -352,8 +353,105 @@ class BentLaueCylinder(OE):
     _hasAlpha = property(lambda self: 1. if self.alpha else 0.)
 
 
+# numpy's float floor_divide / remainder (npy_divmod, numpy/core/src/npymath/npy_math_internal.h.src)
+_DIVMOD = '''
+__device__ __forceinline__ void np_divmod(double a, double b, double& floordiv, double& mod)
+{
+    mod = fmod(a, b);
+    double div = (a - mod) / b;
+    if (mod != 0.0) {
+        if ((b < 0.0) != (mod < 0.0)) { mod += b; div -= 1.0; }
+    } else {
+        mod = copysign(0.0, b);
+    }
+    if (div != 0.0) {
+        floordiv = floor(div);
+        if (div - floordiv > 0.5) floordiv += 1.0;
+    } else {
+        floordiv = copysign(0.0, a / b);
+    }
+}
+'''
+
+
+class BlazedGrating(OE):
+    """Grating of triangular profile given by the *blaze* and *antiblaze* angles, constant line density *rho* (1/mm).
+    Meant for wave propagation (the diffraction comes from the surface itself): the material is a mirror.  Like the
+    reference it carries its OWN intersection method -- the first facet a ray meets, so shadowing is respected --
+    instead of the bracketed root search (oes/gratings.py:492-520)."""
+    cu_plist = ('rho_1', 'tanBlaze', 'tanAntiblaze', 'sinBlaze', 'cosBlaze', 'sinAntiblaze', 'cosAntiblaze', '_den')
+    cu_local_z = _DIVMOD + '''
+    __device__ __forceinline__ bool on_blaze_side(const double* cu_plist, double y, double& y1, double& yL)
+    {
+        double fd;
+        np_divmod(y, cu_plist[0], fd, yL);          // y // rho_1, y % rho_1
+        const double y0 = fd * cu_plist[0];
+        y1 = y0 + cu_plist[0];
+        const double yC = (y1 - y0) / cu_plist[7];  // 1 + tanAntiblaze / tanBlaze
+        return yL > yC;
+    }
+    __device__ double local_z(const double* cu_plist, double x, double y)
+    {
+        double y1, yL;
+        return on_blaze_side(cu_plist, y, y1, yL) ? (-(y1 - y)) * cu_plist[1] : (-yL) * cu_plist[2];
+    }'''
+    cu_local_n = '''
+    __device__ void local_n(const double* cu_plist, double x, double y, double* n)
+    {
+        double y1, yL;
+        const bool bl = on_blaze_side(cu_plist, y, y1, yL);
+        n[0] = 0.0; n[1] = bl ? -cu_plist[3] : cu_plist[5]; n[2] = bl ? cu_plist[4] : cu_plist[6];
+    }'''
+    cu_find_intersection = '''
+    __device__ void find_intersection(const double* cu_plist, double x, double y, double z, double a, double b,
+                                      double c, double& t2, double& x2, double& y2, double& z2)
+    {
+        const double rho_1 = cu_plist[0], tB = cu_plist[1], tA = cu_plist[2];
+        const double b_c = b / c;
+        const double yz = y - b_c * z;
+        const double n = floor(yz / rho_1);
+        const double y0 = rho_1 * n, y1 = y0 + rho_1;
+        double zabl = (-tA) * (yz - y0) / (1.0 + tA * b_c);
+        double zbl = tB * (yz - y1) / (1.0 - tB * b_c);
+        if (zabl > 0.0) zabl = zbl - 1.0;
+        if (zbl > 0.0) zbl = zabl - 1.0;
+        z2 = zbl;
+        y2 = b_c * (z2 - z) + y;
+        t2 = (y2 - y) / b;
+        x2 = x + t2 * a;
+    }'''
+
+    def __init__(self, *args, **kwargs):
+        self.blaze = kwargs.pop('blaze')
+        self.antiblaze = kwargs.pop('antiblaze', np.pi*0.4999)
+        self.rho0 = kwargs.pop('rho', 1)
+        if kwargs.get('gratingDensity') is not None:
+            raise NotImplementedError('a variable line density (ticks search) is outside the hot path')
+        if self.blaze == np.pi/2 or self.antiblaze == np.pi/2:
+            raise NotImplementedError('vertical facets (angle == pi/2) are outside the hot path')
+        OE.__init__(self, *args, **kwargs)
+        self.reset()
+
+    def reset(self):  # gratings.py:416-441
+        self.rho_1 = 1. / self.rho0
+        self.sinBlaze, self.cosBlaze, self.tanBlaze = np.sin(self.blaze), np.cos(self.blaze), np.tan(self.blaze)
+        self.sinAntiblaze, self.cosAntiblaze, self.tanAntiblaze = \
+            np.sin(self.antiblaze), np.cos(self.antiblaze), np.tan(self.antiblaze)
+
+    _den = property(lambda self: 1 + self.tanAntiblaze/self.tanBlaze)
+
+    def get_grating_area_fraction(self):  # gratings.py:522-534
+        tanPitch = np.tan(abs(self.pitch))
+        y1 = self.rho_1 * self.tanBlaze / (self.tanBlaze + tanPitch)
+        z1 = -y1 * tanPitch
+        y2 = self.rho_1
+        z2 = 0
+        d = ((y2-y1)**2 + (z2-z1)**2)**0.5
+        return d * self.rho0
+
+
 LIBRARY = (BentFlatMirror, ConicalMirror, JohannCylinder, JohanssonCylinder, JohannToroid, ParabolicalMirrorParam,
-           BentLaueCylinder)
+           BentLaueCylinder, BlazedGrating)
 
 
 def prebuild(verbose=False):
@@ -361,7 +459,9 @@ def prebuild(verbose=False):
     finds them next to libxrt_b200.so)."""
     from concurrent.futures import ThreadPoolExecutor
     from . import custom
-    jobs = [dict(cu_local_z=c.cu_local_z, cu_local_n=c.cu_local_n, cu_xyz_param=c.cu_xyz_param) for c in LIBRARY]
+    jobs = [dict(cu_local_z=c.cu_local_z, cu_local_n=c.cu_local_n,
+                 cu_xyz_param=(c.cu_xyz_param, c.cu_find_intersection) if c.cu_find_intersection else c.cu_xyz_param)
+            for c in LIBRARY]
     # figure-error variants of the built-in flat and toroidal surfaces (xrt_b200/figure_error.py)
     jobs += [dict(builtin_kind=0, figure_error=True), dict(builtin_kind=1, figure_error=True),
              dict(cu_local_z=BentFlatMirror.cu_local_z, cu_local_n=BentFlatMirror.cu_local_n, figure_error=True)]
