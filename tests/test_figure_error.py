@@ -114,3 +114,22 @@ def test_cuda_figure_error_changes_the_beam_and_library_refuses_it(cuda_device):
     rc = _lib.load().xrt_reflect_f64(len(beam), ctypes.byref(params), None, None, 0, ctypes.byref(cin), None,
                                      ctypes.byref(cout), None, red.data_ptr(), 7, 0, None)
     assert rc != 0 and b'figure' in _lib.load().xrt_b200_last_error()
+
+
+@pytest.mark.parametrize('name,kw', [('height', dict(rms=2.5, rmsKind='height', corrLength=7., seed=12345)),
+                                     ('slope', dict(rms=0.8, rmsKind='slope', corrLength=12., seed=777)),
+                                     ('slope_dir', dict(rms=(0.5, 1.5), rmsKind='slope', corrLength=15., seed=4242))])
+def test_product_random_roughness_equals_reference(name, kw):
+    """Host side (no GPU): seeded RandomRoughness maps (RMS height, isotropic and directional RMS slope, one on top of a
+    Gaussian bump) and their spline coefficients equal the reference's."""
+    from xrt_b200 import figure_error as pfe
+    g = golden('figure_error_roughness')
+    lims = dict(limPhysX=[-4, 4], limPhysY=[-350, 300], gridStep=6.)
+    base = pfe.GaussianBump(bumpHeight=10., sigmaX=2., sigmaY=80., **lims) if name == 'slope' else None
+    fe = pfe.RandomRoughness(baseFE=base, **kw, **lims)
+    z = fe.generate_profile()
+    scale = np.abs(g[name + '_z']).max()
+    assert np.abs(z - g[name + '_z']).max() <= 1e-13 * scale
+    assert np.abs(fe.local_z_spline.get_coeffs() - g[name + '_c']).max() <= 1e-12 * scale
+    if name == 'height':
+        assert abs(fe.get_rms() - 2.5) < 1e-12

@@ -1317,7 +1317,24 @@ def gen_blazed():
         save('reflect_' + name, rho=19.3, blaze=float(oe.blaze), antiblaze=float(oe.antiblaze), rho0=float(oe.rho0), **d)
 
 
-SECTIONS = {'blazed': gen_blazed, 'hemispheric': gen_hemispheric, 'multilayer_tran': gen_multilayer_tran, 'fzp': gen_fzp, 'laue': gen_laue, 'coated': gen_coated, 'figure_error': gen_figure_error, 'round': gen_round, 'shine_wave': gen_shine_wave, 'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+def gen_roughness():
+    """RandomRoughness height maps (figure_error.py:463-622) for seeded generators: RMS height, isotropic RMS slope and
+    directional RMS slopes, one of them on top of a Gaussian bump (baseFE)."""
+    import xrt.backends.raycing.figure_error as rfe
+    lims = dict(limPhysX=[-4, 4], limPhysY=[-350, 300], gridStep=6.)
+    out = {}
+    for name, kw in (('height', dict(rms=2.5, rmsKind='height', corrLength=7., seed=12345)),
+                     ('slope', dict(rms=0.8, rmsKind='slope', corrLength=12., seed=777)),
+                     ('slope_dir', dict(rms=(0.5, 1.5), rmsKind='slope', corrLength=15., seed=4242))):
+        base = rfe.GaussianBump(bumpHeight=10., sigmaX=2., sigmaY=80., **lims) if name == 'slope' else None
+        fe = rfe.RandomRoughness(baseFE=base, **kw, **lims)
+        out[name + '_z'] = fe.generate_profile()
+        out[name + '_c'] = fe.local_z_spline.get_coeffs()
+        print(name, 'rms nm', float(fe.get_rms()), 'rms slopes', [float(v) for v in fe.get_rms_slope()])
+    save('figure_error_roughness', **out)
+
+
+SECTIONS = {'roughness': gen_roughness, 'blazed': gen_blazed, 'hemispheric': gen_hemispheric, 'multilayer_tran': gen_multilayer_tran, 'fzp': gen_fzp, 'laue': gen_laue, 'coated': gen_coated, 'figure_error': gen_figure_error, 'round': gen_round, 'shine_wave': gen_shine_wave, 'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)

@@ -4,6 +4,7 @@
 
     GaussianBump(bumpHeight, cX, cY, sigmaX, sigmaY, limPhysX=, limPhysY=, gridStep=, baseFE=)   figure_error.py:623-715
     Waviness(amplitude, xWaveLength, yWaveLength, ...)                                           figure_error.py:717-773
+    RandomRoughness(rms, rmsKind, corrLength, seed, ...)                                         figure_error.py:463-622
     FigureErrorMap(x1d, y1d, z_nm)      a given height map (what FigureErrorImported holds after reading its file)
 
 The height map (nm) is generated once on the host exactly like the reference (its grid rules included) and turned into
@@ -117,6 +118,58 @@ class FigureErrorSpline(FigureErrorBase):
         self.xShift, self.yShift = float(xShift), float(yShift)
         self.local_z_spline = spline
         self._dev = {}
+
+
+class RandomRoughness(FigureErrorBase):
+    """Stochastic roughness (figure_error.py:463-622): seeded white noise (numpy default_rng) low-passed with a Gaussian
+    spectral filter of the given correlation length, normalised to an RMS height [nm] (rmsKind='height') or RMS
+    slope [urad] (rmsKind='slope'; a (pitch, roll) pair gives directional slopes)."""
+
+    def __init__(self, rms=1., rmsKind='height', corrLength=5., seed=None, **kwargs):
+        self.rms, self.rmsKind, self.corrLength = rms, rmsKind, corrLength
+        self.seed = np.random.SeedSequence().entropy if seed is None else seed
+        kwargs['name'] = kwargs.get('name', 'random roughness')
+        FigureErrorBase.__init__(self, **kwargs)
+
+    def get_grids(self):
+        FigureErrorBase.get_grids(self)
+        self.dx = np.abs(self.limPhysX[-1] - self.limPhysX[0]) / self.nx  # figure_error.py:173-174
+        self.dy = np.abs(self.limPhysY[-1] - self.limPhysY[0]) / self.ny
+
+    def generate_profile(self):
+        rng = np.random.default_rng(self.seed)
+        self.get_grids()
+        base_z = self._base_profile()
+        directional = isinstance(self.rms, (tuple, list))
+        z = rng.normal(loc=0.0, scale=1.0, size=(self.ny, self.nx))
+        if self.corrLength is not None:  # Gaussian low-pass in the spatial-frequency domain
+            spectrum = np.fft.rfft2(z)
+            kx = 2 * np.pi * np.fft.rfftfreq(self.nx, d=self.dx)
+            ky = 2 * np.pi * np.fft.fftfreq(self.ny, d=self.dy)
+            KX, KY = np.meshgrid(kx, ky, indexing='xy')
+            corrY = self.corrLength
+            corrX = self.corrLength * self.rms[0] / self.rms[1] if directional else self.corrLength
+            z = np.fft.irfft2(spectrum * np.exp(-0.5*(KX**2*corrX**2 + KY**2*corrY**2)), s=(self.ny, self.nx))
+        z -= z.mean()
+        if self.rmsKind == 'height':
+            current = np.sqrt((z**2).mean())
+            if current > 0:
+                z *= (self.rms / current)
+        elif self.rmsKind == 'slope':
+            a2d, b2d = np.gradient(z*1e-6, self.y1d, self.x1d)
+            rms_pitch = np.sqrt((np.arctan(a2d)**2).mean())
+            rms_roll = np.sqrt((np.arctan(b2d)**2).mean())
+            if directional:
+                scale_y = self.rms[0] * 1e-6 / rms_pitch
+                scale_x = self.rms[1] * 1e-6 / rms_roll
+                spectrum = np.fft.rfft2(z)
+                spectrum *= np.sqrt((scale_x * KX)**2 + (scale_y * KY)**2) / np.sqrt(KX**2 + KY**2 + 1e-30)
+                z = np.fft.irfft2(spectrum, s=(self.ny, self.nx))
+            else:
+                z *= self.rms * 1e-6 / np.sqrt(0.5 * (rms_pitch**2 + rms_roll**2))
+        else:
+            raise ValueError("rmsKind is 'height' or 'slope'")
+        return z + base_z
 
 
 class GaussianBump(FigureErrorBase):
