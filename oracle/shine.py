@@ -176,7 +176,7 @@ class Wave(object):
         self.Jpp[:] = 0
 
 
-def shine_wave(src, wave, filamentBeam=False, toGlobal=True, record=None, R0=None):
+def shine_wave(src, wave, filamentBeam=False, toGlobal=True, record=None, R0=None, accuBeam=None):
     """IntegratedSource.shine(wave=wave) with uniformRayDensity (sybase.py:1513-1812): the receiving points of *wave*
     (in source-local coordinates xDiffr, yDiffr, zDiffr) are illuminated; *wave* gets E, directions, J, Es, Ep (with
     the propagation phase), the returned beam sits at the source.  Consumes np.random in the reference's order and
@@ -186,7 +186,14 @@ def shine_wave(src, wave, filamentBeam=False, toGlobal=True, record=None, R0=Non
     mcRays = len(wave.a)
     rec = {}
     dgamma = None
-    if filamentBeam:  # :1541-1552
+    seeded0, seededI0 = np.int64(0), 0.
+    if filamentBeam and accuBeam is not None:  # the same electron as in an earlier shine (:1553-1561)
+        rsE = accuBeam.E[0]
+        rX, rZ = accuBeam.filamentDX, accuBeam.filamentDZ
+        dtheta, dpsi = accuBeam.filamentDtheta, accuBeam.filamentDpsi
+        dgamma = accuBeam.filamentDgamma
+        seeded0, seededI0 = accuBeam.seeded, accuBeam.seededI
+    elif filamentBeam:  # :1541-1552
         rec['uE'] = np.random.random_sample()
         rsE = rec['uE'] * float(src.E_max - src.E_min) + src.E_min
         rec['gX'], rec['gZ'] = np.random.standard_normal(), None
@@ -200,7 +207,7 @@ def shine_wave(src, wave, filamentBeam=False, toGlobal=True, record=None, R0=Non
         if getattr(src, 'eEspread', 0) > 0:
             rec['gG'] = np.random.standard_normal()
             dgamma = src.gamma * src.eEspread * rec['gG']
-    seeded = np.int64(0) + mcRays
+    seeded = seeded0 + mcRays
     if filamentBeam:
         rE = rsE * np.ones(mcRays)
     else:
@@ -241,7 +248,7 @@ def shine_wave(src, wave, filamentBeam=False, toGlobal=True, record=None, R0=Non
     rec['gamma'] = gamma * np.ones(mcRays)
     Intensity, mJs, mJp = ou.build_I_map(src.grid, src.L0, src.Np, src.Kx, src.Ky, src.eI, gamma * np.ones(mcRays),
                                          rE, rTheta, rPsi, src.distE)
-    seededI = 0. + mcRays * src.xzE
+    seededI = seededI0 + mcRays * src.xzE
     sourceWeight = src.xzE
     tmp_max = np.max(Intensity)
     if tmp_max > src.Imax:

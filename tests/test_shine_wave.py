@@ -123,3 +123,44 @@ def test_cuda_shine_wave_own_draws(cuda_device):
     inten = (np.abs(d['Es'])**2 + np.abs(d['Ep'])**2).reshape(len(g['zm']), len(g['xm']))
     iz, ix = np.unravel_index(np.argmax(inten), inten.shape)
     assert abs(g['xm'][ix]) < 1.5 and abs(g['zm'][iz]) < 1.2 and np.isfinite(inten).all()
+
+
+def test_oracle_shine_wave_accubeam_bit_exact():
+    """shine(wave=wave2, accuBeam=bor): the same electron (energy, offsets, energy deviation) illuminates a second
+    wave; seeded / seededI accumulate (sybase.py:1553-1561)."""
+    g, src, wave, bor = _oracle_run('shine_wave_filament')
+    for k in ('filamentDX', 'filamentDZ', 'filamentDtheta', 'filamentDpsi', 'filamentDgamma'):
+        setattr(bor, k, getattr(wave, k))
+    wave2 = osh.Wave(g['w2_xDiffr'], g['w2_yDiffr'], g['w2_zDiffr'], float(g['w2_area']))
+    bor2 = osh.shine_wave(src, wave2, filamentBeam=True, accuBeam=bor)
+    for f in ('a', 'b', 'c', 'E', 'Jss', 'Jpp', 'Jsp', 'Es', 'Ep', 'path', 'state'):
+        assert np.array_equal(getattr(wave2, f), g['w2_' + f]), f
+    assert np.array_equal(wave2.rDiffr, g['w2_rDiffr'])
+    assert bor2.seeded == g['w2_seeded'] and bor2.seededI == g['w2_seededI']
+    assert np.array_equal(bor2.x, g['w2_bor_x']) and np.array_equal(bor2.a, g['w2_bor_a'])
+
+
+@pytest.mark.gpu
+def test_cuda_shine_wave_accubeam(cuda_device):
+    import torch
+    from xrt_b200.planes import Screen
+    from helpers import compare_beams
+    rec = {}
+    g, osrc, owave, obor = _oracle_run('shine_wave_filament', record=rec)
+    src, bl, E1 = _product_source(g)
+    src.Imax = float(g['Imax0'])
+    src.fluxConst = src.Imax * src.xzE
+    scr = Screen(bl, 'scr', center=list(g['screen_center']))
+    wave = scr.prepare_wave(src, g['xm'], g['zm'])
+    samples = {k: float(v) for k, v in rec.items() if k in ('uE', 'gX', 'gZ', 'gT', 'gP', 'gG')}
+    bor = src.shine(wave=wave, samples=samples)
+    wave2 = scr.prepare_wave(src, g['xm'][::2] + 0.3, g['zm'][::2] - 0.2)
+    bor2 = src.shine(wave=wave2, accuBeam=bor)
+    d = wave2.to_numpy()
+    ref = {f: g['w2_' + f] for f in BEAM_FIELDS}
+    geo = [f for f in BEAM_FIELDS if f not in ('Es', 'Ep', 'Jss', 'Jpp', 'Jsp', 'x', 'y', 'z')]
+    bad = compare_beams(d, ref, geo, 1e-12, 'w2_')
+    bad += compare_beams(d, ref, ('Es', 'Ep', 'Jss', 'Jpp', 'Jsp'), 1e-10, 'w2_')
+    assert not bad, bad
+    assert bor2.seeded == int(g['w2_seeded']) and abs(bor2.seededI - float(g['w2_seededI'])) <= 1e-12 * float(g['w2_seededI'])
+    assert np.abs(bor2.to_numpy()['x'] - g['w2_bor_x']).max() <= 1e-12

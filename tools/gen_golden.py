@@ -1109,10 +1109,19 @@ def gen_shine_wave():
                  dx=src.dx, dz=src.dz, dxprime=src.dxprime, dzprime=src.dzprime,
                  center=np.array(src.center, dtype=float), sinAzimuth=src.bl.sinAzimuth, cosAzimuth=src.bl.cosAzimuth,
                  seed=seed, filament=filament, eEspread=spread, E1=src.E1, Imax=src.Imax, xzE=src.xzE,
-                 fluxConst=src.fluxConst, accepted=bor.accepted, acceptedE=bor.acceptedE, seeded=bor.seeded,
-                 seededI=bor.seededI, sourceWeight=bor.sourceWeight, xm=xm, zm=zm,
+                 fluxConst=src.fluxConst, accepted=np.copy(bor.accepted), acceptedE=np.copy(bor.acceptedE),
+                 seeded=np.copy(bor.seeded),  # copies: a later shine(accuBeam=bor) adds to these 0-d arrays in place
+                 seededI=np.copy(bor.seededI), sourceWeight=np.copy(bor.sourceWeight), xm=xm, zm=zm,
                  screen_center=np.array(scr.center, dtype=float), rDiffr=wave.rDiffr)
         if filament:
+            # the same electron illuminates a second wave: shine(wave=wave2, accuBeam=bor) (sybase.py:1553-1561)
+            wave2 = scr.prepare_wave(src, xm[::2] + 0.3, zm[::2] - 0.2)
+            d.update(w2_xDiffr=wave2.xDiffr.copy(), w2_yDiffr=wave2.yDiffr.copy(), w2_zDiffr=wave2.zDiffr.copy(),
+                     w2_area=wave2.area)
+            bor2 = src.shine(wave=wave2, accuBeam=bor)
+            d.update(beam_dict(wave2, 'w2_'))
+            d.update(w2_rDiffr=wave2.rDiffr, w2_seeded=bor2.seeded, w2_seededI=bor2.seededI,
+                     w2_bor_x=bor2.x, w2_bor_a=bor2.a)
             d.update(filamentDX=bor.filamentDX, filamentDZ=bor.filamentDZ, filamentDtheta=bor.filamentDtheta,
                      filamentDpsi=bor.filamentDpsi, filamentDgamma=bor.filamentDgamma)
         d.update(beam_dict(bor, 'bor_'))

@@ -215,7 +215,7 @@ class Undulator(object):
             sigma_r2 = sigma_r2 * ret**(2/3.)
         return (self.dx**2 + sigma_r2)**0.5, (self.dz**2 + sigma_r2)**0.5
 
-    def shine_wave(self, wave, toGlobal=True, samples=None):
+    def shine_wave(self, wave, toGlobal=True, samples=None, accuBeam=None):
         """IntegratedSource.shine(wave=wave) (sybase.py:1513-1527, :1588-1612, :1651-1703, :1786-1796): the receiving
         points of a prepared wave (Screen / aperture / OE .prepare_wave with this source as the previous element) are
         illuminated; *wave* receives E, directions, coherency matrix and Es / Ep with the propagation phase, the
@@ -230,6 +230,13 @@ class Undulator(object):
         n = len(wave)
         dev = wave.device
         s = samples
+        seeded0, seededI0 = 0, 0.
+        if accuBeam is not None:  # the same electron as in an earlier shine (sybase.py:1553-1561)
+            if not self.filamentBeam:
+                raise NotImplementedError('accuBeam goes with filamentBeam=True')
+            E0 = float(accuBeam.E[0])
+            s = dict(uE=None, gX=None, gZ=None, gT=None, gP=None, gG=None)
+            seeded0, seededI0 = accuBeam.seeded, accuBeam.seededI
         if s is None:
             gen = torch.Generator(device=dev)
             gen.manual_seed(self.seed * 104729 + self._draws)
@@ -243,7 +250,13 @@ class Undulator(object):
                 s = dict(uE=torch.rand(n, dtype=torch.float64, device=dev, generator=gen), gX=g[0], gZ=g[1], gT=g[2],
                          gP=g[3], g1=g[4], g2=g[5], g5=g[6])
         dgamma = None
-        if self.filamentBeam:  # one electron: energy, position, direction [and energy deviation] (sybase.py:1541-1552)
+        if self.filamentBeam and accuBeam is not None:
+            rX, rZ = accuBeam.filamentDX, accuBeam.filamentDZ
+            dtheta, dpsi = accuBeam.filamentDtheta, accuBeam.filamentDpsi
+            dgamma = accuBeam.filamentDgamma
+            rE = torch.full((n,), E0, dtype=torch.float64, device=dev)
+            shiftX, shiftZ = rX, rZ
+        elif self.filamentBeam:  # one electron: energy, position, direction [and energy deviation] (sybase.py:1541-1552)
             rX, rZ = self.dx * s['gX'], self.dz * s['gZ']
             dtheta, dpsi = self.dxprime * s['gT'], self.dzprime * s['gP']
             if self.eEspread > 0:
@@ -278,8 +291,8 @@ class Undulator(object):
                 gam = self.gamma + (self.gamma * self.eEspread) * s['g5']
         Intensity, mJs, mJp = self.build_I_map_device(rE.contiguous(), rTheta.contiguous(), rPsi.contiguous(),
                                                       gamma=gam)
-        seeded = n
-        seededI = 0. + n * self.xzE
+        seeded = seeded0 + n
+        seededI = seededI0 + n * self.xzE
         tmp_max = float(Intensity.max())
         if tmp_max > self.Imax:
             self.Imax = tmp_max
@@ -580,10 +593,10 @@ class Undulator(object):
         *samples* (optional): dict of CUDA tensors E, theta, psi, n1..n4[, u] to use instead of drawing them
         (parity tests feed the deviates the numpy oracle used).  *allreduce_max*: callable applied to the
         per-pass max intensity when rays are sharded over ranks (Imax is beam-wide, sybase.py:1627-1631)."""
-        if fixedEnergy or accuBeam is not None:
-            raise NotImplementedError('fixedEnergy / accuBeam sampling is outside the hot path (SURVEY 8f3)')
+        if fixedEnergy or (accuBeam is not None and wave is None):
+            raise NotImplementedError('fixedEnergy / ray-mode accuBeam sampling is outside the hot path (SURVEY 8f3)')
         if wave is not None:
-            return self.shine_wave(wave, toGlobal=toGlobal, samples=samples)
+            return self.shine_wave(wave, toGlobal=toGlobal, samples=samples, accuBeam=accuBeam)
         if self.filamentBeam:
             raise NotImplementedError('a filament beam is built for shine(wave=...); its ray-mode repeats '
                                       '(sybase.py:1742-1744) are outside the hot path')
