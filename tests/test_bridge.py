@@ -156,3 +156,18 @@ def test_bridge_propagate_round_aperture_host_objects(cuda_device):
     lo = bridge.propagate(ap, beam)
     assert not compare_beams(lo.__dict__, {f: g['out_' + f] for f in BEAM_FIELDS}, BEAM_FIELDS, 1e-12)
     assert np.array_equal(beam.state, g['in_state_after'])
+
+
+@pytest.mark.skipif(not __import__('os').path.isdir('/root/reference'), reason='needs the reference tree')
+def test_bridge_converts_real_reference_objects():
+    """Build container only (no GPU): the unmodified reference's own element / material / figure-error objects go
+    through bridge.convert_oe -- 18 classes -- in a separate interpreter (tools/check_bridge_reference.py)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, 'tools', 'check_bridge_reference.py')],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True, timeout=600)
+    assert res.returncode == 0, res.stdout
+    lines = [ln for ln in res.stdout.splitlines() if ' -> ' in ln]
+    assert len(lines) == 18 and not any('FAILED' in ln for ln in res.stdout.splitlines()), res.stdout
