@@ -329,13 +329,16 @@ def run_ours(args):
     bytes_per_ray = blo.bytes_per_ray()
     n_host = len(blo)
     host_out = []
+    e2e_note = None
     for _ in range(2):  # two pinned result buffers (2 x 13.2 GB at 1e8 rays); one if the host cannot pin that much
         try:
             host_out.append({k: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
                              for k, t in blo.tensors().items()})
         except RuntimeError:
             if not host_out:
-                raise
+                # not even one pinned Beam: pageable host memory keeps the run alive (slower copies, said in the line)
+                host_out.append({k: torch.empty(t.shape, dtype=t.dtype) for k, t in blo.tensors().items()})
+                e2e_note = 'pinned allocation failed: pageable host buffers'
             break
     del blo
     for _ in range(max(1, args.warmup - 1)):
@@ -529,7 +532,8 @@ def run_ours(args):
                            'l2': 'inputs larger than L2 (>= 13 GB of Beam arrays per step)',
                            'parallelism': 'rays sharded over %d GPU(s), gather=%s' % (world, args.gather)},
                 'e2e': {'value': e2e_value, 'unit': 'Mrays/s', 'h2d_bytes_per_step': h2d,
-                        'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e},
+                        'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e,
+                        **({'note': e2e_note} if e2e_note else {})},
                 'e2e_histogram': e2e_hist,
                 'gpu_launches': args.steps * (9 if args.unfused_source else 7),  # source (1 fused or 3), 2 slot inits,
                 # pre-pass A/B, reflect main, expose
