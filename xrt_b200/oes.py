@@ -181,8 +181,8 @@ class OE(object):
         if self.cu_local_n is None:
             raise _lib.XrtB200Error('a spliced surface needs both cu_local_z and cu_local_n')
         from . import custom
-        extra = (self.cu_xyz_param, self.cu_find_intersection) if self.cu_find_intersection else self.cu_xyz_param
-        return custom.plugin_for(self.cu_local_z, self.cu_local_n, extra, figure_error=fe)
+        return custom.plugin_for(self.cu_local_z, self.cu_local_n, self.cu_xyz_param, figure_error=fe,
+                                 cu_find_intersection=self.cu_find_intersection)
 
     def _limits(self, second=False):
         sfx = '2' if second else ''

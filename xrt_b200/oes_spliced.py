@@ -459,9 +459,8 @@ def prebuild(verbose=False):
     finds them next to libxrt_b200.so)."""
     from concurrent.futures import ThreadPoolExecutor
     from . import custom
-    jobs = [dict(cu_local_z=c.cu_local_z, cu_local_n=c.cu_local_n,
-                 cu_xyz_param=(c.cu_xyz_param, c.cu_find_intersection) if c.cu_find_intersection else c.cu_xyz_param)
-            for c in LIBRARY]
+    jobs = [dict(cu_local_z=c.cu_local_z, cu_local_n=c.cu_local_n, cu_xyz_param=c.cu_xyz_param,
+                 cu_find_intersection=c.cu_find_intersection) for c in LIBRARY]
     # figure-error variants of the built-in flat and toroidal surfaces (xrt_b200/figure_error.py)
     jobs += [dict(builtin_kind=0, figure_error=True), dict(builtin_kind=1, figure_error=True),
              dict(cu_local_z=BentFlatMirror.cu_local_z, cu_local_n=BentFlatMirror.cu_local_n, figure_error=True)]
