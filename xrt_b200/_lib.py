@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libxrt_b200.so')
+# XRT_B200_LIB names another build of the same library (kernel-variant sweeps, tools/build_variant.sh)
+LIB_PATH = os.environ.get('XRT_B200_LIB') or os.path.join(_HERE, 'libxrt_b200.so')
 
 c_dp = ctypes.c_void_p  # device or host pointer passed as an integer address
 c_sz = ctypes.c_size_t

@@ -1220,23 +1220,25 @@ __device__ __forceinline__ void solve_secant(const xrt_oe_params& p, const SurfD
                                              const Decision& d, double& t1,
                                              double& t2, double& dz1, double& dz2, double& x2, double& y2,
                                              double& z2) {
-  // _use_my_method (base.py:933-959)
+  // _use_my_method (base.py:933-959).  The reference shifts (t1, dz1) <- (t2, dz2), takes the secant step from the old
+  // pair and, when the new dz2 has the sign of the shifted dz1, restores the old pair.  Written here without the shift:
+  // the new point always replaces (t2, dz2), and (t1, dz1) <- old (t2, dz2) only when the signs differ -- the same
+  // values in the same operations, with two predicated moves per iteration instead of eight.
   int numit = 2;
   while (fabs(dz2) > kZEps && numit < kMaxIteration) {
-    const double t = t1, dz = dz1;
-    t1 = t2;
-    dz1 = dz2;
-    t2 = t - (t1 - t) * dz / (dz1 - dz);
-    if (t2 < d.tMin) t2 = d.tMin;
-    if (t2 > d.tMax) t2 = d.tMax;
-    dz2 = find_dz<SURF, REFR, DERIV>(p, sd, t2, r, x2, y2, z2);
-    // np.sign(dz2) == np.sign(dz1) (base.py:951): inside this loop dz1 is never 0 or NaN (it starts > 0 and only
-    // takes values of earlier dz2 with |dz2| > zEps), and when dz2 is 0 or NaN the loop ends right here with t1, dz1
-    // unused -- so the comparison of the sign bits decides every case that matters, on the integer pipe
-    if ((__double2hiint(dz2) ^ __double2hiint(dz1)) >= 0) {
-      t1 = t;
-      dz1 = dz;
+    double t3 = t1 - (t2 - t1) * dz1 / (dz2 - dz1);
+    if (t3 < d.tMin) t3 = d.tMin;
+    if (t3 > d.tMax) t3 = d.tMax;
+    const double dz3 = find_dz<SURF, REFR, DERIV>(p, sd, t3, r, x2, y2, z2);
+    // np.sign(dz2) == np.sign(dz1) (base.py:951): inside this loop the shifted dz1 (= dz2 here) is never 0 or NaN
+    // (|dz2| > zEps), and when dz3 is 0 or NaN the loop ends right here with t1, dz1 unused -- so the comparison of
+    // the sign bits decides every case that matters, on the integer pipe
+    if ((__double2hiint(dz3) ^ __double2hiint(dz2)) < 0) {
+      t1 = t2;
+      dz1 = dz2;
     }
+    t2 = t3;
+    dz2 = dz3;
     ++numit;
   }
 }
@@ -1417,29 +1419,117 @@ __device__ __forceinline__ void copy_ray(const xrt_beam& dst, const xrt_beam& sr
 #ifndef XRTB_REFLECT_THREADS
 #define XRTB_REFLECT_THREADS 256
 #endif
+// r02 structure.  One thread per ray, every global access with unit stride.  The FIELD part of the tile (path, E, Jss,
+// Jpp, Jsp, Es, Ep: 80 B/ray) is fetched by bulk-async copies (cp.async.bulk, the TMA engine; completion on an mbarrier)
+// into shared memory while the threads load the geometry and run the root search, and is read from there when the
+// amplitudes are applied: no register holds a field across the solver (r01 spilled them -- ncu: 13 % of the long-
+// scoreboard stalls sat on the STL that waited for those loads and 50 % on the LDL -> STG reload chain of the final
+// stores, with 488 B/ray of DRAM traffic for 404 algorithmic), and the load latency hides behind the search.  Every
+// output is stored as soon as it is final.  A block-level class sort (dense warps for the rays that reach the surface)
+// was measured and rejected: profiles/r02_reflect_variants.json.
+struct FieldTile {
+  double path[XRTB_REFLECT_THREADS], E[XRTB_REFLECT_THREADS], Jss[XRTB_REFLECT_THREADS], Jpp[XRTB_REFLECT_THREADS];
+  double2 Jsp[XRTB_REFLECT_THREADS], Es[XRTB_REFLECT_THREADS], Ep[XRTB_REFLECT_THREADS];
+};
+
+// gb (or lb) of a ray that is passed through: geometry from `src` in global memory, fields from the staged tile when
+// `src` is the input beam itself
+__device__ __forceinline__ void copy_ray_staged(const xrt_beam& dst, const xrt_beam& src, bool srcIsInput,
+                                                const FieldTile& ft, int tid, bool amp, size_t i, int state) {
+  dst.x[i] = src.x[i];
+  dst.y[i] = src.y[i];
+  dst.z[i] = src.z[i];
+  dst.a[i] = src.a[i];
+  dst.b[i] = src.b[i];
+  dst.c[i] = src.c[i];
+  if (srcIsInput) {
+    dst.path[i] = ft.path[tid];
+    dst.E[i] = ft.E[tid];
+    dst.Jss[i] = ft.Jss[tid];
+    dst.Jpp[i] = ft.Jpp[tid];
+    reinterpret_cast<double2*>(dst.Jsp)[i] = ft.Jsp[tid];
+    if (dst.Es && amp) {
+      reinterpret_cast<double2*>(dst.Es)[i] = ft.Es[tid];
+      reinterpret_cast<double2*>(dst.Ep)[i] = ft.Ep[tid];
+    }
+  } else {
+    dst.path[i] = src.path[i];
+    dst.E[i] = src.E[i];
+    dst.Jss[i] = src.Jss[i];
+    dst.Jpp[i] = src.Jpp[i];
+    st_c(dst.Jsp, i, ld_c(src.Jsp, i));
+    if (dst.Es && src.Es) {
+      st_c(dst.Es, i, ld_c(src.Es, i));
+      st_c(dst.Ep, i, ld_c(src.Ep, i));
+    }
+  }
+  dst.state[i] = state;
+}
+
 template <int SURF, int MAT>
 __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) reflect_main_kernel(size_t n, xrt_oe_params p, xrt_material_params m,
                                                            xrt_multilayer_params ml, Tables tab, xrt_beam in,
                                                            xrt_beam fb, xrt_beam gb, xrt_beam lb,
-                                                           unsigned long long* red) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                                           unsigned long long* red, int bulk_ok) {
+  constexpr int BT = XRTB_REFLECT_THREADS;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const size_t base = (size_t)blockIdx.x * BT;
+  const size_t i = base + tid;
   const double inf = __longlong_as_double(0x7ff0000000000000ll);
   double fmin3[3] = {inf, inf, inf}, fmax3[3] = {-inf, -inf, -inf};
   unsigned long long ngoodN = 0;
   int oor = 0;
   const bool hasLb = lb.x != nullptr;
+  const bool amp = in.Es != nullptr;
+  const bool fbIsInput = fb.x == in.x;
   __shared__ Decision sdec;  // the beam-wide decision is decoded once per block
-  if (threadIdx.x == 0) sdec = decide(red);
+  __shared__ double srollc[2];  // cos, sin of the beam-wide roll (polarisation frame)
+  __shared__ __align__(16) FieldTile ft;
+  __shared__ __align__(8) uint64_t sbar;
+  // full tiles of 16-byte aligned arrays go through the bulk-copy engine; the last (ragged) tile and beams that are
+  // views at odd offsets are staged with plain loads (each thread only ever reads its own slot)
+  const bool bulk = bulk_ok && (base + BT <= n);
+  if (tid == 0) {
+    if (bulk) {
+      mbar_init(&sbar, 1);
+      mbar_fence_init();
+      mbar_expect_tx(&sbar, (uint32_t)(BT * (4 * 8 + (amp ? 3 : 1) * 16)));
+      bulk_g2s(ft.path, in.path + base, BT * 8, &sbar);
+      bulk_g2s(ft.E, in.E + base, BT * 8, &sbar);
+      bulk_g2s(ft.Jss, in.Jss + base, BT * 8, &sbar);
+      bulk_g2s(ft.Jpp, in.Jpp + base, BT * 8, &sbar);
+      bulk_g2s(ft.Jsp, in.Jsp + 2 * base, BT * 16, &sbar);
+      if (amp) {
+        bulk_g2s(ft.Es, in.Es + 2 * base, BT * 16, &sbar);
+        bulk_g2s(ft.Ep, in.Ep + 2 * base, BT * 16, &sbar);
+      }
+    }
+    sdec = decide(red);
+  }
+  if (tid == 32) sincos(p.roll, &srollc[1], &srollc[0]);
+  if (!bulk && i < n) {
+    ft.path[tid] = in.path[i];
+    ft.E[tid] = in.E[i];
+    ft.Jss[tid] = in.Jss[i];
+    ft.Jpp[tid] = in.Jpp[i];
+    ft.Jsp[tid] = reinterpret_cast<const double2*>(in.Jsp)[i];
+    if (amp) {
+      ft.Es[tid] = reinterpret_cast<const double2*>(in.Es)[i];
+      ft.Ep[tid] = reinterpret_cast<const double2*>(in.Ep)[i];
+    }
+  }
   __syncthreads();
 
   if (i < n) {
     const int st0 = in.state[i];
     if (!(p.good_mode ? (st0 == 1 || st0 == 2) : (st0 > 0))) {
       // rays that are not alive pass through untouched (gb = lb = copy of the input, reflect.py:104-109)
-      copy_ray(gb, in, i, p.dead_state_lost ? p.lostNum : st0, true);  // Plate: dcm.py:311-312
+      if (bulk) mbar_wait(&sbar, 0);
+      copy_ray_staged(gb, in, true, ft, tid, amp, i, p.dead_state_lost ? p.lostNum : st0);  // Plate: dcm.py:311-312
       if (p.multi && gb.theta) gb.theta[i] = 0.0;  // lb.theta = zeros_like(lb.x) in every pass (reflect.py:789)
       if (hasLb) {
-        copy_ray(lb, in, i, st0, true);
+        copy_ray_staged(lb, in, true, ft, tid, amp, i, st0);
         if (p.zero_dead_local) {  // dcm.py:305-310
           lb.state[i] = 0;
           lb.x[i] = 0.0;
@@ -1456,13 +1546,7 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
     } else {
       const Decision d = sdec;
       Ray r = load_ray(in, i);
-      const bool amp = in.Es != nullptr;
-#ifdef XRTB_HOIST_TABLE_SEARCH
-      int lo0 = -3;
-      if (MAT == 1 || MAT == 2 || MAT == 6) lo0 = f1f2_locate(tab, m.tab_off[0], m.tab_len[0], in.E[i]);
-#else
       const int lo0 = -3;
-#endif
       to_local(p, r);
       const SurfDiv sd = make_surf_div<SURF>(p);
       double t1, t2, x1, y1, z1, x2, y2, z2;
@@ -1501,6 +1585,7 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
             solve_secant<SURF, MAT == 5>(p, sd, r, d, t1, t2, dz1, dz2, x2, y2, z2);
         }
       }
+      if (bulk) mbar_wait(&sbar, 0);  // the field tile landed long ago
       const double tMax = t2;
       // Stores are issued as soon as a value is final (geometry first, fields last): outputs never alias inputs
       // (include/xrt_b200.h), and the short live ranges keep the 35 output values out of local memory.
@@ -1617,7 +1702,7 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
           const double CH = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8;
           const double bdg = la * g0 + lbb * g1 + lc * g2;
           const double G2 = g0 * g0 + g1 * g1 + g2 * g2;
-          const double ol = 1.0 * CH / in.E[i] * 1e-7;
+          const double ol = 1.0 * CH / ft.E[tid] * 1e-7;
           const double u = bds * bds - 2.0 * bdg * ol - G2 * (ol * ol);
           const double sg = (MAT == 3 && (m.geom & 1)) ? 1.0 : -1.0;  // reflect.py:608: +1 for Laue
           const double dn = bds + sg * sqrt(fabs(u));
@@ -1632,7 +1717,7 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
         } else if (MAT == 5) {
           // toWhere = 1, refraction (reflect.py:894-919); the transmittivity is evaluated here once (same n)
           double nre;
-          plate_amplitude(m, tab, in.E[i], bdn, p.from_vacuum != 0, ras5, rap5, mu0, nk0, nre, &oor);
+          plate_amplitude(m, tab, ft.E[tid], bdn, p.from_vacuum != 0, ras5, rap5, mu0, nk0, nre, &oor);
           const double n1overn2 = p.from_vacuum ? 1.0 / nre : nre;
           const double signN = (-bdn > 0.0) ? 1.0 : ((-bdn < 0.0) ? -1.0 : 0.0);
           const double n1c = -n1overn2 * bdn;
@@ -1664,7 +1749,7 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
           const double CH = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8;
           const double bdg = la * g0 + lbb * g1 + lc * g2;
           const double G2 = g0 * g0 + g1 * g1 + g2 * g2;
-          const double ol = p.g_order * CH / in.E[i] * 1e-7;
+          const double ol = p.g_order * CH / ft.E[tid] * 1e-7;
           const double u = bds * bds - 2.0 * bdg * ol - G2 * (ol * ol);
           const double dn = bds + (p.grating == 4 ? 1.0 : -1.0) * sqrt(fabs(u));  // giveSign (reflect.py:857)
           ao = la - nrm[3] * dn + g0 * ol;
@@ -1686,8 +1771,30 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
           lc = co;
         }
         // polarisation frame (reflect.py:948-953; beams.py:448-479)
+#ifndef XRTB_POLFRAME_ATAN2
+        // cos / sin of rollAngle = roll + atan2(n_x, n_z) by the addition theorem: (n_z, n_x) / hypot(n_x, n_z) IS
+        // (cos, sin) of atan2(n_x, n_z), and cos / sin of the beam-wide roll are taken once per block.  Differs from
+        // numpy's sincos(float(rollAngle)) by <= 4e-16 absolute (numpy rounds the angle itself to 2e-16) -- 1e-12 is
+        // the parity bar -- and replaces ~170 instructions (atan2 + sincos) by 12.
+        {
+          const double hx = nrm[3], hz = nrm[5];
+          const double h2 = hx * hx + hz * hz;
+          double cphi = 1.0, sphi = 0.0;  // atan2(0, 0) = 0
+          if (h2 > 0.0) {
+            double y0;
+            asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(h2));
+            const double e = fma(-h2 * y0, y0, 1.0);
+            const double inv = fma(y0, e * fma(0.375, e, 0.5), y0);
+            cphi = hz * inv;
+            sphi = hx * inv;
+          }
+          cY = fma(srollc[0], cphi, -(srollc[1] * sphi));
+          sY = fma(srollc[1], cphi, srollc[0] * sphi);
+        }
+#else
         const double rollAngle = p.roll + atan2(nrm[3], nrm[5]);
         sincos(rollAngle, &sY, &cY);  // cos(-x) == cos(x) and sin(-x) == -sin(x) exactly (numpy and CUDA alike)
+#endif
       }
       if (hasLb) {
         lb.a[i] = la;
@@ -1733,38 +1840,23 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
         }
       }
 
-      // the field part of the ray is only fetched now: 12 doubles less to keep alive across the solver
-      const double E = in.E[i];
-      double path = in.path[i];
-      double Jss = in.Jss[i], Jpp = in.Jpp[i];
-      cplx Jsp = ld_c(in.Jsp, i);
-      cplx Es = cplx{0, 0}, Ep = cplx{0, 0};
-      if (amp) {
-        Es = ld_c(in.Es, i);
-        Ep = ld_c(in.Ep, i);
+      // The field part of the ray comes from the staged tile, group by group, and every group is stored before the
+      // next one is touched: path / E, then the amplitudes (nothing but E and three cosines live), then the coherency
+      // matrix, then Es / Ep.  The arithmetic of each value is unchanged; only independent groups were reordered.
+      const double E = ft.E[tid];
+      {
+        double path = ft.path[tid];
+        if (st == 1) path += tMax;
+        if (hasLb) {
+          lb.path[i] = path;
+          lb.E[i] = E;
+        }
+        if (goodAfter) {
+          gb.path[i] = path;
+          gb.E[i] = E;
+        }
       }
-      double gJss = Jss, gJpp = Jpp;
-      cplx gJsp = Jsp, gEs = Es, gEp = Ep;
-      if (st == 1) {
-        path += tMax;
-        {
-          const double c = cY, s = -sY;
-          const double c2 = c * c, s2 = s * s, cs = c * s;
-          const double J0 = Jss * c2 + Jpp * s2 + 2.0 * Jsp.re * cs;
-          const double J1 = Jss * s2 + Jpp * c2 - 2.0 * Jsp.re * cs;
-          const double J2r = (Jpp - Jss) * cs + Jsp.re * (c2 - s2);
-          Jss = J0;
-          Jpp = J1;
-          Jsp = cplx{J2r + (Jsp.im * 0.0), 0.0 + Jsp.im};
-        }
-        if (amp) {
-          // rotate_y(Es, Ep, cosY, -sinY): (c*x + s*z, -s*x + c*z) with s = -sinY
-          const double s = -sY;
-          const cplx e1 = cplx{cY * Es.re + s * Ep.re, cY * Es.im + s * Ep.im};
-          const cplx e2 = cplx{-s * Es.re + cY * Ep.re, -s * Es.im + cY * Ep.im};
-          Es = e1;
-          Ep = e2;
-        }
+      if (st == 1) {  // (then goodAfter holds in every mode)
         // amplitudes
         cplx ras = cplx{1.0, 0.0}, rap = cplx{1.0, 0.0};
         if (MAT == 1 || MAT == 2 || MAT == 6) mirror_amplitude(m, tab, E, bdn, ras, rap, &oor, lo0);
@@ -1777,23 +1869,66 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
         if (MAT != 0 && MAT != 7) {
           if (isnan(ras.re) || isnan(ras.im)) ras = cplx{0.0, 0.0};
           if (isnan(rap.re) || isnan(rap.im)) rap = cplx{0.0, 0.0};
-          // reflect.py:1038-1040
-          const cplx js = cmul_np(cmul_np(cplx{Jss, 0.0}, ras), cconj(ras));
-          const cplx jp = cmul_np(cmul_np(cplx{Jpp, 0.0}, rap), cconj(rap));
-          Jsp = cmul_np(cmul_np(Jsp, ras), cconj(rap));
-          Jss = js.re;
-          Jpp = jp.re;
-        } else if (MAT == 7 && p.g_amp >= 0.0) {
-          // grating efficiency (material.py:391-413): ras = rap = resI**0.5, a real array
-          ras = cplx{p.g_amp, 0.0};
-          rap = ras;
-          Jss = (Jss * p.g_amp) * p.g_amp;
-          Jpp = (Jpp * p.g_amp) * p.g_amp;
-          Jsp = cplx{(Jsp.re * p.g_amp) * p.g_amp, (Jsp.im * p.g_amp) * p.g_amp};
-        } else {
-          // refl = 1., 1.: J * 1. * conj(1.) with Python floats leaves the values unchanged
+        }
+        double att = 1.0;
+        if (MAT == 5 && !p.from_vacuum) att = exp(-mu0 * tMax * 0.1);  // inside the material (reflect.py:1048-1059)
+        {
+          // coherency matrix into the local polarisation frame (reflect.py:948-953; beams.py:448-479)
+          double Jss = ft.Jss[tid], Jpp = ft.Jpp[tid];
+          cplx Jsp = cplx{ft.Jsp[tid].x, ft.Jsp[tid].y};
+          {
+            const double c = cY, s = -sY;
+            const double c2 = c * c, s2 = s * s, cs = c * s;
+            const double J0 = Jss * c2 + Jpp * s2 + 2.0 * Jsp.re * cs;
+            const double J1 = Jss * s2 + Jpp * c2 - 2.0 * Jsp.re * cs;
+            const double J2r = (Jpp - Jss) * cs + Jsp.re * (c2 - s2);
+            Jss = J0;
+            Jpp = J1;
+            Jsp = cplx{J2r + (Jsp.im * 0.0), 0.0 + Jsp.im};
+          }
+          if (MAT != 0 && MAT != 7) {
+            // reflect.py:1038-1040
+            const cplx js = cmul_np(cmul_np(cplx{Jss, 0.0}, ras), cconj(ras));
+            const cplx jp = cmul_np(cmul_np(cplx{Jpp, 0.0}, rap), cconj(rap));
+            Jsp = cmul_np(cmul_np(Jsp, ras), cconj(rap));
+            Jss = js.re;
+            Jpp = jp.re;
+          } else if (MAT == 7 && p.g_amp >= 0.0) {
+            // grating efficiency (material.py:391-413): ras = rap = resI**0.5, a real array
+            Jss = (Jss * p.g_amp) * p.g_amp;
+            Jpp = (Jpp * p.g_amp) * p.g_amp;
+            Jsp = cplx{(Jsp.re * p.g_amp) * p.g_amp, (Jsp.im * p.g_amp) * p.g_amp};
+          } else {
+            // refl = 1., 1.: J * 1. * conj(1.) with Python floats leaves the values unchanged
+          }
+          if (MAT == 5 && !p.from_vacuum) {
+            Jss *= att;
+            Jpp *= att;
+            Jsp = cplx{Jsp.re * att, Jsp.im * att};
+          }
+          if (hasLb) {
+            lb.Jss[i] = Jss;
+            lb.Jpp[i] = Jpp;
+            st_c(lb.Jsp, i, Jsp);
+          }
+          // ... and back for the virgin-local / global beam (reflect.py:1106-1110)
+          const double c = cY, s = sY;
+          const double c2 = c * c, s2 = s * s, cs = c * s;
+          gb.Jss[i] = Jss * c2 + Jpp * s2 + 2.0 * Jsp.re * cs;
+          gb.Jpp[i] = Jss * s2 + Jpp * c2 - 2.0 * Jsp.re * cs;
+          const double J2r = (Jpp - Jss) * cs + Jsp.re * (c2 - s2);
+          st_c(gb.Jsp, i, cplx{J2r + (Jsp.im * 0.0), 0.0 + Jsp.im});
         }
         if (amp) {
+          cplx Es = cplx{ft.Es[tid].x, ft.Es[tid].y}, Ep = cplx{ft.Ep[tid].x, ft.Ep[tid].y};
+          {
+            // rotate_y(Es, Ep, cosY, -sinY): (c*x + s*z, -s*x + c*z) with s = -sinY
+            const double s = -sY;
+            const cplx e1 = cplx{cY * Es.re + s * Ep.re, cY * Es.im + s * Ep.im};
+            const cplx e2 = cplx{-s * Es.re + cY * Ep.re, -s * Es.im + cY * Ep.im};
+            Es = e1;
+            Ep = e2;
+          }
           if (MAT != 0 && MAT != 7) {
             Es = cmul_np(Es, ras);
             Ep = cmul_np(Ep, rap);
@@ -1802,9 +1937,7 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
             Ep = cplx{Ep.re * p.g_amp, Ep.im * p.g_amp};
           }
           if (MAT == 5 && !p.from_vacuum) {
-            // inside the material (reflect.py:1048-1059): att = exp(-mu0 * tMax * 0.1);
             // mPh = att**0.5 * exp(0.1j * refl[3] * tMax)
-            const double att = exp(-mu0 * tMax * 0.1);
             const double sa = sqrt(att);
             const cplx ph = cexp_i((0.1 * nk0) * tMax);
             const cplx mPh = cplx{sa * ph.re, sa * ph.im};
@@ -1818,59 +1951,45 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
             Es = cmul_np(Es, mPh);
             Ep = cmul_np(Ep, mPh);
           }
-        }
-        if (MAT == 5 && !p.from_vacuum) {
-          const double att = exp(-mu0 * tMax * 0.1);
-          Jss *= att;
-          Jpp *= att;
-          Jsp = cplx{Jsp.re * att, Jsp.im * att};
-        }
-        // rotate the coherency matrix back for the virgin-local/global beam (reflect.py:1106-1110)
-        {
-          const double c = cY, s = sY;
-          const double c2 = c * c, s2 = s * s, cs = c * s;
-          gJss = Jss * c2 + Jpp * s2 + 2.0 * Jsp.re * cs;
-          gJpp = Jss * s2 + Jpp * c2 - 2.0 * Jsp.re * cs;
-          const double J2r = (Jpp - Jss) * cs + Jsp.re * (c2 - s2);
-          gJsp = cplx{J2r + (Jsp.im * 0.0), 0.0 + Jsp.im};
-        }
-        if (amp) {
-          gEs = cplx{cY * Es.re + sY * Ep.re, cY * Es.im + sY * Ep.im};
-          gEp = cplx{-sY * Es.re + cY * Ep.re, -sY * Es.im + cY * Ep.im};
-        }
-      }
-      if (hasLb) {
-        lb.path[i] = path;
-        lb.E[i] = E;
-        lb.Jss[i] = Jss;
-        lb.Jpp[i] = Jpp;
-        st_c(lb.Jsp, i, Jsp);
-        if (amp && lb.Es) {
-          st_c(lb.Es, i, Es);
-          st_c(lb.Ep, i, Ep);
-        }
-      }
-      if (goodAfter) {
-        gb.path[i] = path;
-        gb.E[i] = E;
-        gb.Jss[i] = gJss;
-        gb.Jpp[i] = gJpp;
-        st_c(gb.Jsp, i, gJsp);
-        if (amp && gb.Es) {
-          st_c(gb.Es, i, gEs);
-          st_c(gb.Ep, i, gEp);
+          if (hasLb && lb.Es) {
+            st_c(lb.Es, i, Es);
+            st_c(lb.Ep, i, Ep);
+          }
+          if (gb.Es) {
+            st_c(gb.Es, i, cplx{cY * Es.re + sY * Ep.re, cY * Es.im + sY * Ep.im});
+            st_c(gb.Ep, i, cplx{-sY * Es.re + cY * Ep.re, -sY * Es.im + cY * Ep.im});
+          }
         }
       } else {
-        // not intersected rays remain unchanged except their state (reflect.py:131-134)
-        copy_ray(gb, fb, i, p.dead_state_lost ? p.lostNum : st, true);  // Plate: dcm.py:331-332
+        // alive but not good after the surface: the fields stay as they were
+        if (hasLb) {
+          lb.Jss[i] = ft.Jss[tid];
+          lb.Jpp[i] = ft.Jpp[tid];
+          reinterpret_cast<double2*>(lb.Jsp)[i] = ft.Jsp[tid];
+          if (amp && lb.Es) {
+            reinterpret_cast<double2*>(lb.Es)[i] = ft.Es[tid];
+            reinterpret_cast<double2*>(lb.Ep)[i] = ft.Ep[tid];
+          }
+        }
+        if (goodAfter) {
+          gb.Jss[i] = ft.Jss[tid];
+          gb.Jpp[i] = ft.Jpp[tid];
+          reinterpret_cast<double2*>(gb.Jsp)[i] = ft.Jsp[tid];
+          if (amp && gb.Es) {
+            reinterpret_cast<double2*>(gb.Es)[i] = ft.Es[tid];
+            reinterpret_cast<double2*>(gb.Ep)[i] = ft.Ep[tid];
+          }
+        } else {
+          // not intersected rays remain unchanged except their state (reflect.py:131-134)
+          copy_ray_staged(gb, fb, fbIsInput, ft, tid, amp, i, p.dead_state_lost ? p.lostNum : st);  // Plate: dcm.py:331-332
+        }
       }
     }
   }
 
   // block-level footprint / counters (skipped when nobody asked for them)
   if (!p.want_footprint) return;
-  __shared__ unsigned long long sh[8][8];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ unsigned long long sh[BT / 32][8];
   unsigned long long e[8];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
@@ -1881,11 +2000,19 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
   e[7] = (unsigned long long)oor;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    unsigned long long x = e[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long y = __shfl_xor_sync(0xffffffffu, x, o);
-      x = (k >= 6) ? x + y : (k < 3 ? (y < x ? y : x) : (y > x ? y : x));
+    // warp reduction on REDUX (two 32-bit passes per 64-bit key) instead of five 64-bit shuffle rounds
+    const unsigned hi = (unsigned)(e[k] >> 32), lo = (unsigned)e[k];
+    unsigned long long x;
+    if (k >= 6) {
+      x = __reduce_add_sync(0xffffffffu, lo);  // per-thread counts are 0 / 1
+    } else if (k < 3) {
+      const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+      const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+      x = ((unsigned long long)mh << 32) | ml;
+    } else {
+      const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+      const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+      x = ((unsigned long long)mh << 32) | ml;
     }
     if (lane == 0) sh[warp][k] = x;
   }
@@ -1893,7 +2020,7 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
   if (threadIdx.x < 8) {
     const int k = threadIdx.x;
     unsigned long long x = sh[0][k];
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+    for (int w = 1; w < BT / 32; ++w) {
       const unsigned long long y = sh[w][k];
       x = (k >= 6) ? x + y : (k < 3 ? (y < x ? y : x) : (y > x ? y : x));
     }
@@ -1910,22 +2037,29 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
 }
 
 // ---------------------------------------------------------------- launchers
+// cp.async.bulk needs 16-byte aligned global addresses: true for whole torch / cudaMalloc allocations, not for a view
+// that starts at an odd element
+static int bulk_copy_ok(const xrt_beam& in) {
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  return al(in.path) && al(in.E) && al(in.Jss) && al(in.Jpp) && al(in.Jsp) && (in.Es == nullptr || (al(in.Es) && al(in.Ep)));
+}
 template <int SURF>
 static int launch_main_mat(int mat, unsigned grid, cudaStream_t st, size_t n, const xrt_oe_params& p,
                            const xrt_material_params& m, const xrt_multilayer_params& ml, const Tables& t,
                            const xrt_beam& in, const xrt_beam& fb, const xrt_beam& gb, const xrt_beam& lb,
                            unsigned long long* red) {
+  const int bulk_ok = bulk_copy_ok(in);
   switch (mat) {
-    case 0: reflect_main_kernel<SURF, 0><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
-    case 1: reflect_main_kernel<SURF, 1><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
-    case 2: reflect_main_kernel<SURF, 2><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
-    case 3: reflect_main_kernel<SURF, 3><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
-    case 4: reflect_main_kernel<SURF, 4><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
-    case 6: reflect_main_kernel<SURF, 6><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
-    case 7: reflect_main_kernel<SURF, 7><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
+    case 0: reflect_main_kernel<SURF, 0><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red, bulk_ok); break;
+    case 1: reflect_main_kernel<SURF, 1><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red, bulk_ok); break;
+    case 2: reflect_main_kernel<SURF, 2><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red, bulk_ok); break;
+    case 3: reflect_main_kernel<SURF, 3><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red, bulk_ok); break;
+    case 4: reflect_main_kernel<SURF, 4><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red, bulk_ok); break;
+    case 6: reflect_main_kernel<SURF, 6><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red, bulk_ok); break;
+    case 7: reflect_main_kernel<SURF, 7><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red, bulk_ok); break;
     case 5:
       if constexpr (SURF == 0 || SURF == 4) {
-        reflect_main_kernel<SURF, 5><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red);
+        reflect_main_kernel<SURF, 5><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red, bulk_ok);
       } else {
         set_last_error("reflect: refraction is built for flat and parabolic surfaces");
         return 2;
@@ -1956,9 +2090,10 @@ static int launch_main_refr(int mat, unsigned grid, cudaStream_t st, size_t n, c
                             const xrt_material_params& m, const xrt_multilayer_params& ml, const Tables& t,
                             const xrt_beam& in, const xrt_beam& fb, const xrt_beam& gb, const xrt_beam& lb,
                             unsigned long long* red) {
+  const int bulk_ok = bulk_copy_ok(in);
   switch (mat) {
-    case 0: reflect_main_kernel<SURF, 0><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
-    case 5: reflect_main_kernel<SURF, 5><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red); break;
+    case 0: reflect_main_kernel<SURF, 0><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red, bulk_ok); break;
+    case 5: reflect_main_kernel<SURF, 5><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red, bulk_ok); break;
     default: set_last_error("reflect: a parabolic lens takes a material of kind 'lens' / 'plate' or none (got %d)", mat); return 2;
   }
   XRTB_CUDA_CHECK(cudaGetLastError());
