@@ -308,6 +308,17 @@ typedef struct xrt_plane_params {
  * of the good rays lands in reduction slots 28..33, their count in slot 34. */
 int xrt_expose_f64(size_t n, const xrt_plane_params* p, const xrt_beam* in, const xrt_beam* out,
                    uint64_t* reductions, void* stream);
+/* out = Screen.expose(OE.reflect(in)[0]) in ONE main-pass kernel: xrt_reflect_f64 whose global beam goes through
+ * Screen.expose (screens.py:225-302) in registers instead of being written to `gb` and read back by xrt_expose_f64 --
+ * 264 B/ray less HBM traffic and one launch less for chains that only consume the screen (xrt's run_process functions
+ * that plot a screen behind a mirror, e.g. tests/speed/3_Softi_CXIw2D_speed.py:348-409).  Arguments as xrt_reflect_f64
+ * (no gb) + the screen's plane, its output beam and its reduction slots (footprint, good-ray count as xrt_expose_f64
+ * leaves them).  `out` equals the two-call result bit for bit.  Built for surfaces 0..2 with material kinds 0, 1, 3
+ * (returns 4 otherwise: call the two entry points). */
+int xrt_reflect_expose_f64(size_t n, const xrt_oe_params* oe, const xrt_material_params* mat, const double* tables,
+                           size_t table_len, const xrt_beam* in, const xrt_beam* fallback, const xrt_beam* lb,
+                           uint64_t* reductions, const xrt_plane_params* screen, const xrt_beam* out,
+                           uint64_t* screen_reductions, int phase, uint64_t index_offset, void* stream);
 /* out = RectangularAperture.propagate(in): alive rays are transported to the aperture plane; rays hitting a
  * blade get state = lostNum in `out` AND in `in` (the reference marks the incoming beam, apertures.py:364). */
 /* HemisphericScreen.expose (screens.py:422-545): rays meet the sphere of radius R around p->center; positions in the

@@ -68,6 +68,17 @@ def main():
         ts.append(e0.elapsed_time(e1))
         del s
     res['expose_ms'] = float(np.median(ts))
+    # fused reflect + expose (xrt_reflect_expose_f64): main kernel time with and without the local beam
+    for needLocal in (True, False):
+        mirror.profileEvents = []
+        for _ in range(args.reps + 2):
+            out = mirror.reflect(beam, needLocal=needLocal, checkTables=False, exposeOn=screen)
+            del out
+        torch.cuda.synchronize()
+        ev = mirror.profileEvents[2:]
+        res['fused_expose_' + ('lb' if needLocal else 'nolb')] = {
+            'main_ms': float(np.median([e[5].elapsed_time(e[3]) for e in ev]))}
+        mirror.profileEvents = None
     del gb, lb, beam
     if not args.no_dcm:
         bl3 = BeamLine()

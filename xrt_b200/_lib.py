@@ -37,6 +37,8 @@ PROTOTYPES = {
     'xrt_undulator_f64_host': (c_int, [c_sz, c_int, c_dbl, c_dbl, c_dbl] + [c_dp] * 14 + [c_int]),
     'xrt_reflect_f64': (c_int, [c_sz, c_dp, c_dp, c_dp, c_sz, c_dp, c_dp, c_dp, c_dp, c_dp, c_int,
                                 ctypes.c_uint64, c_dp]),
+    'xrt_reflect_expose_f64': (c_int, [c_sz, c_dp, c_dp, c_dp, c_sz, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_int,
+                                       ctypes.c_uint64, c_dp]),
     'xrt_reflect_multi_deriv_f64': (c_int, [c_sz, c_dp, c_dp, c_dp, c_dp, c_int, c_dp]),
     'xrt_reduction_decode': (c_dbl, [ctypes.c_uint64]),
     'xrt_expose_f64': (c_int, [c_sz, c_dp, c_dp, c_dp, c_dp, c_dp]),

@@ -417,6 +417,16 @@ int xrt_reflect_f64(size_t n, const xrt_oe_params* oe, const xrt_material_params
                         reinterpret_cast<unsigned long long*>(reductions), phase, index_offset, (cudaStream_t)stream);
 }
 
+int xrt_reflect_expose_f64(size_t n, const xrt_oe_params* oe, const xrt_material_params* mat, const double* tables,
+                           size_t table_len, const xrt_beam* in, const xrt_beam* fallback, const xrt_beam* lb,
+                           uint64_t* reductions, const xrt_plane_params* screen, const xrt_beam* out,
+                           uint64_t* screen_reductions, int phase, uint64_t index_offset, void* stream) {
+  return reflect_expose_device(n, oe, mat, tables, table_len, in, fallback, nullptr, lb,
+                               reinterpret_cast<unsigned long long*>(reductions), screen, out,
+                               reinterpret_cast<unsigned long long*>(screen_reductions), phase, index_offset,
+                               (cudaStream_t)stream);
+}
+
 int xrt_reflect_multi_deriv_f64(size_t n, const xrt_oe_params* oe, const xrt_beam* in, uint64_t* reductions,
                                 double* tD, int phase, void* stream) {
   return reflect_multi_deriv_device(n, oe, in, reinterpret_cast<unsigned long long*>(reductions), tD, phase,

@@ -41,6 +41,11 @@ int reflect_device(size_t n, const xrt_oe_params* oe, const xrt_material_params*
                    size_t table_len, const xrt_beam* in, const xrt_beam* fallback, const xrt_beam* gb,
                    const xrt_beam* lb, unsigned long long* red, int phase, unsigned long long index_offset,
                    cudaStream_t st);
+int reflect_expose_device(size_t n, const xrt_oe_params* oe, const xrt_material_params* mat, const double* tables,
+                          size_t table_len, const xrt_beam* in, const xrt_beam* fallback, const xrt_beam* gb,
+                          const xrt_beam* lb, unsigned long long* red, const xrt_plane_params* scr_plane,
+                          const xrt_beam* scr, unsigned long long* scr_red, int phase,
+                          unsigned long long index_offset, cudaStream_t st);
 int reflect_multi_deriv_device(size_t n, const xrt_oe_params* oe, const xrt_beam* in, unsigned long long* red,
                                double* tD, int phase, cudaStream_t st);
 double reduction_decode(unsigned long long slot);

@@ -68,7 +68,9 @@ enum {
   RS_FOOT = 28,  // footprint min x,y,z / max x,y,z of the virgin-local output (reflect.py:1133-1136)
   RS_NGOOD = 34, // number of rays with state > 0 on entry (plain integer count)
   RS_NGOODN = 35, // number of rays with state == 1 after the surface (plain integer count); 36: out-of-table count
-  RS_DERIV = 40   // multiple_reflect, derivative stage: {min t1, max t2, max |dz1|, max |dz2| masked} (base.py:861-871)
+  RS_DERIV = 40,  // multiple_reflect, derivative stage: {min t1, max t2, max |dz1|, max |dz2| masked} (base.py:861-871)
+  RS_DECISION = 44,  // 44..46: the decoded beam-wide decision of the main pass (reflect_decide_kernel)
+  RS_HINT = 48    // 48..63: 32 ints, the last f1/f2 table interval found per element table (f1f2_locate)
 };
 constexpr double kZEps = 1e-12;      // raycing.zEps   (raycing/__init__.py:86)
 constexpr double kDt = 1e-5;         // raycing.dt     (:89)
@@ -420,9 +422,10 @@ __device__ __forceinline__ void local_normal(const xrt_oe_params& p, const SurfD
     const double a = div_by(-x, sd.d0) * ax;
     const double b = div_by(-y, sd.d1);  // -y / R
     const double norm = sqrt(a * a + b * b + 1.0);
-    n[0] = n[3] = a / norm;
-    n[1] = n[4] = b / norm;
-    n[2] = n[5] = 1.0 / norm;
+    const Divisor dn = make_divisor(norm);  // three quotients, one refined reciprocal (same bits as a / norm etc.)
+    n[0] = n[3] = div_by(a, dn);
+    n[1] = n[4] = div_by(b, dn);
+    n[2] = n[5] = div_by(1.0, dn);
     return;
   }
   // EllipticalMirrorParam.local_n (parametric.py:236-249): x = s, y = phi
@@ -453,12 +456,13 @@ __device__ __forceinline__ void bracket(const xrt_oe_params& p, int axis, int ne
   const double xyz = axis == 0 ? r.x : (axis == 1 ? r.y : r.z);
   const double abc = axis == 0 ? r.a : (axis == 1 ? r.b : r.c);
   const double lo = p.brk_lim[axis][0], hi = p.brk_lim[axis][1];
+  const Divisor dabc = make_divisor(abc);  // both quotients share the refined reciprocal (same bits as two divisions)
   if (!neg) {
-    t1 = (lo - xyz) / abc - kDt;
-    t2 = (hi - xyz) / abc + kDt;
+    t1 = div_by(lo - xyz, dabc) - kDt;
+    t2 = div_by(hi - xyz, dabc) + kDt;
   } else {
-    t1 = (hi - xyz) / abc - kDt;
-    t2 = (lo - xyz) / abc + kDt;
+    t1 = div_by(hi - xyz, dabc) - kDt;
+    t2 = div_by(lo - xyz, dabc) + kDt;
   }
   if (t1 < -1e6 * kZEps) t1 = -1e6 * kZEps;
 }
@@ -664,15 +668,17 @@ __device__ __forceinline__ cplx cexp_i(double phi) {  // exp(0 + i phi)
 // np.interp (numpy/core/src/multiarray/compiled_base.c): binary search, slope form -- see f1f2() below
 struct Tables {
   const double *E, *f1, *f2;
+  int* hint;  // interval guesses per element table + a dirty flag (33 ints, block-shared; may be NULL): f1f2_locate
 };
 
-// slope form of np.interp at a located interval [lo, lo + 1]
+// slope form of np.interp at a located interval [lo, lo + 1]; `dx` = make_divisor(xp[lo + 1] - xp[lo]) is shared by
+// the f1 and the f2 interpolation (same quotient bits as the plain division, common.cuh)
 __device__ __forceinline__ double interp_at(const double* __restrict__ xp, const double* __restrict__ fp, int len,
-                                            int lo, double x) {
+                                            int lo, double x, const Divisor& dx) {
   if (lo < 0) return fp[0];
   if (lo >= len - 1) return fp[len - 1];
   if (xp[lo] == x) return fp[lo];
-  const double slope = (fp[lo + 1] - fp[lo]) / (xp[lo + 1] - xp[lo]);
+  const double slope = div_by(fp[lo + 1] - fp[lo], dx);
   double res = slope * (x - xp[lo]) + fp[lo];
   if (isnan(res)) {
     res = slope * (x - xp[lo + 1]) + fp[lo + 1];
@@ -682,14 +688,27 @@ __device__ __forceinline__ double interp_at(const double* __restrict__ xp, const
 }
 
 // Element.get_f1f2 (element.py:252-263): f1 and f2 share the energy grid, so one binary search serves both
-// np.interp calls; the out-of-range ValueError becomes NaN + an error flag
-// the interval of np.interp's binary search: xp[lo] <= E < xp[lo + 1] (lo = len - 1 at the last point), -2: E is
-// outside the table.  Ten dependent loads for a 768-point table -- the kernel issues it before the intersection
-// search, whose FP64 work then hides that latency (XRTB_HOIST_TABLE_SEARCH)
+// np.interp calls; the out-of-range ValueError becomes NaN + an error flag.
+// The interval of np.interp's binary search: xp[lo] <= E < xp[lo + 1] (lo = len - 1 at the last point), -2: E is
+// outside the table.  The search is ten dependent loads for a 768-point table; beams are narrow-band far more often
+// than not, so the last interval found is kept as a guess per element table (`hint`: 32 ints in the block's shared
+// memory, seeded from and -- after a miss -- written back to reduction slots 48..63 once per block) and the search runs
+// only when the energy is not in the guessed interval or one of its two neighbours (four independent loads).  The
+// interval is unique, so the result does not depend on the hint.  hint[32] is the block's "a guess changed" flag.
 __device__ __forceinline__ int f1f2_locate(const Tables& t, int off, int len, double E) {
   const double* __restrict__ xp = t.E + off;
   if (E < xp[0] || E > xp[len - 1]) return -2;
   if (E >= xp[len - 1]) return len - 1;
+  volatile int* hp = t.hint ? t.hint + ((unsigned)off % 31u) : nullptr;  // one word per element table
+  if (hp) {
+    const int h = *hp;
+    if (h >= 1 && h < len - 2) {
+      const double e0 = xp[h - 1], e1 = xp[h], e2 = xp[h + 1], e3 = xp[h + 2];
+      if (e1 <= E && E < e2) return h;
+      if (e0 <= E && E < e1) return h - 1;
+      if (e2 <= E && E < e3) return h + 1;
+    }
+  }
   int lo = 0, hi = len - 1;  // xp[lo] <= E < xp[hi]
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
@@ -697,6 +716,13 @@ __device__ __forceinline__ int f1f2_locate(const Tables& t, int off, int len, do
       lo = mid;
     else
       hi = mid;
+  }
+  if (hp) {
+    // move the guess halfway towards this interval (all the way when it was unset or far off): a band that covers
+    // three intervals then settles on the middle one instead of flipping between the outer two
+    const int h = *hp;
+    *hp = (h >= 1 && h < len - 2 && abs(h - lo) <= 4) ? (h + lo + (lo > h ? 1 : 0)) / 2 : lo;
+    t.hint[32] = 1;
   }
   return lo;
 }
@@ -707,7 +733,9 @@ __device__ __forceinline__ cplx f1f2_at(const Tables& t, int off, int len, int l
     return cplx{nan, nan};
   }
   const double* __restrict__ xp = t.E + off;
-  return cplx{interp_at(xp, t.f1 + off, len, lo, E), interp_at(xp, t.f2 + off, len, lo, E)};
+  Divisor dx{1.0, 1.0};
+  if (lo >= 0 && lo < len - 1) dx = make_divisor(xp[lo + 1] - xp[lo]);
+  return cplx{interp_at(xp, t.f1 + off, len, lo, E, dx), interp_at(xp, t.f2 + off, len, lo, E, dx)};
 }
 __device__ __forceinline__ cplx f1f2(const Tables& t, int off, int len, double E, int* oor) {
   return f1f2_at(t, off, len, f1f2_locate(t, off, len, E), E, oor);
@@ -1215,6 +1243,26 @@ __device__ __forceinline__ Decision decide(const unsigned long long* red) {
 
 __device__ __forceinline__ int sgn(double v) { return (v > 0.0) - (v < 0.0); }
 
+// The decision is decoded ONCE per reflect() by a one-thread kernel between the pre-passes and the main pass and left
+// packed in slots 44..46; every thread of the main pass reads those three words itself (a broadcast load that runs in
+// parallel with its geometry loads) instead of waiting at a block barrier for thread 0 to chase the slots.
+__global__ void reflect_decide_kernel(unsigned long long* red) {
+  const Decision d = decide(red);
+  red[RS_DECISION] = (unsigned long long)d.axis | ((unsigned long long)d.neg << 8) | ((unsigned long long)d.brent << 16);
+  red[RS_DECISION + 1] = (unsigned long long)__double_as_longlong(d.tMin);
+  red[RS_DECISION + 2] = (unsigned long long)__double_as_longlong(d.tMax);
+}
+__device__ __forceinline__ Decision load_decision(const unsigned long long* red) {
+  const unsigned long long w = red[RS_DECISION], a = red[RS_DECISION + 1], b = red[RS_DECISION + 2];
+  Decision d;
+  d.axis = (int)(w & 0xff);
+  d.neg = (int)((w >> 8) & 0xff);
+  d.brent = (int)((w >> 16) & 0xff);
+  d.tMin = __longlong_as_double((long long)a);
+  d.tMax = __longlong_as_double((long long)b);
+  return d;
+}
+
 template <int SURF, bool REFR, int DERIV = 0>
 __device__ __forceinline__ void solve_secant(const xrt_oe_params& p, const SurfDiv& sd, const Ray& r,
                                              const Decision& d, double& t1,
@@ -1414,10 +1462,10 @@ __device__ __forceinline__ void copy_ray(const xrt_beam& dst, const xrt_beam& sr
 }
 
 #ifndef XRTB_REFLECT_MINBLOCKS
-#define XRTB_REFLECT_MINBLOCKS 4
+#define XRTB_REFLECT_MINBLOCKS 2
 #endif
 #ifndef XRTB_REFLECT_THREADS
-#define XRTB_REFLECT_THREADS 256
+#define XRTB_REFLECT_THREADS 512
 #endif
 // r02 structure.  One thread per ray, every global access with unit stride.  The FIELD part of the tile (path, E, Jss,
 // Jpp, Jsp, Es, Ep: 80 B/ray) is fetched by bulk-async copies (cp.async.bulk, the TMA engine; completion on an mbarrier)
@@ -1436,12 +1484,8 @@ struct FieldTile {
 // `src` is the input beam itself
 __device__ __forceinline__ void copy_ray_staged(const xrt_beam& dst, const xrt_beam& src, bool srcIsInput,
                                                 const FieldTile& ft, int tid, bool amp, size_t i, int state) {
-  dst.x[i] = src.x[i];
-  dst.y[i] = src.y[i];
-  dst.z[i] = src.z[i];
-  dst.a[i] = src.a[i];
-  dst.b[i] = src.b[i];
-  dst.c[i] = src.c[i];
+  // (every load before the first store: the arrays are not __restrict__, and a load behind a store would wait for it)
+  const double x = src.x[i], y = src.y[i], z = src.z[i], a = src.a[i], b = src.b[i], c = src.c[i];
   if (srcIsInput) {
     dst.path[i] = ft.path[tid];
     dst.E[i] = ft.E[tid];
@@ -1453,25 +1497,224 @@ __device__ __forceinline__ void copy_ray_staged(const xrt_beam& dst, const xrt_b
       reinterpret_cast<double2*>(dst.Ep)[i] = ft.Ep[tid];
     }
   } else {
-    dst.path[i] = src.path[i];
-    dst.E[i] = src.E[i];
-    dst.Jss[i] = src.Jss[i];
-    dst.Jpp[i] = src.Jpp[i];
-    st_c(dst.Jsp, i, ld_c(src.Jsp, i));
-    if (dst.Es && src.Es) {
-      st_c(dst.Es, i, ld_c(src.Es, i));
-      st_c(dst.Ep, i, ld_c(src.Ep, i));
+    const double path = src.path[i], E = src.E[i], Jss = src.Jss[i], Jpp = src.Jpp[i];
+    const cplx Jsp = ld_c(src.Jsp, i);
+    const bool hasE = dst.Es && src.Es;
+    cplx Es = cplx{0.0, 0.0}, Ep = cplx{0.0, 0.0};
+    if (hasE) {
+      Es = ld_c(src.Es, i);
+      Ep = ld_c(src.Ep, i);
+    }
+    dst.path[i] = path;
+    dst.E[i] = E;
+    dst.Jss[i] = Jss;
+    dst.Jpp[i] = Jpp;
+    st_c(dst.Jsp, i, Jsp);
+    if (hasE) {
+      st_c(dst.Es, i, Es);
+      st_c(dst.Ep, i, Ep);
     }
   }
+  dst.x[i] = x;
+  dst.y[i] = y;
+  dst.z[i] = z;
+  dst.a[i] = a;
+  dst.b[i] = b;
+  dst.c[i] = c;
   dst.state[i] = state;
 }
 
-template <int SURF, int MAT>
+// Eight per-thread keys -> the beam-wide slots: keys 0..2 minima and 3..5 maxima of order-preserving encodings
+// (-> red[RS_FOOT + k]), keys 6 / 7 per-thread 0 / 1 counts (-> red[slot6], red[slot7]; a negative slot is skipped).
+// Warp level on REDUX (two 32-bit passes per 64-bit key instead of five 64-bit shuffle rounds); block level without
+// a barrier: every warp leaves its partial results in shared memory and the LAST warp to arrive combines them, so warps
+// that finish early retire instead of waiting for the slowest one with their registers allocated.
+template <int BT>
+__device__ __forceinline__ void tail_combine(const unsigned long long (&e)[8], unsigned long long (*sh)[8], int* sdone,
+                                             unsigned long long* red, int slot6, int slot7, int lane, int warp) {
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const unsigned hi = (unsigned)(e[k] >> 32), lo = (unsigned)e[k];
+    unsigned long long x;
+    if (k >= 6) {
+      x = __reduce_add_sync(0xffffffffu, lo);
+    } else if (k < 3) {
+      const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+      const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+      x = ((unsigned long long)mh << 32) | ml;
+    } else {
+      const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+      const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+      x = ((unsigned long long)mh << 32) | ml;
+    }
+    if (lane == 0) sh[warp][k] = x;
+  }
+  int last = 0;
+  if (lane == 0) {
+    __threadfence_block();
+    last = (atomicAdd(sdone, 1) == BT / 32 - 1);
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+  __threadfence_block();
+  if (lane < 8) {
+    const int k = lane;
+    unsigned long long x = *(volatile unsigned long long*)&sh[0][k];
+    for (int w = 1; w < BT / 32; ++w) {
+      const unsigned long long y = *(volatile unsigned long long*)&sh[w][k];
+      x = (k >= 6) ? x + y : (k < 3 ? (y < x ? y : x) : (y > x ? y : x));
+    }
+    if (k < 3) {
+      if (x != enc(inf)) atomicMin(&red[RS_FOOT + k], x);
+    } else if (k < 6) {
+      if (x != enc(-inf)) atomicMax(&red[RS_FOOT + k], x);
+    } else if (k == 6) {
+      if (x && slot6 >= 0) atomicAdd(&red[slot6], x);
+    } else {
+      if (x && slot7 >= 0) atomicAdd(&red[slot7], x);
+    }
+  }
+}
+
+// Where the global beam goes.  FUSE = false: into `gb` (OE.reflect as the reference returns it).  FUSE = true: the
+// kernel continues with Screen.expose (screens.py:225-302; the stand-alone kernel is expose_kernel in rays.cu, same
+// operations in the same order) and stores the SCREEN beam instead -- gb never touches HBM (132 B/ray less written,
+// 132 B/ray less read back, one launch less).  The stages arrive in the order the kernel finishes them: geometry,
+// path / E, coherency matrix, amplitudes.
+template <bool FUSE>
+struct GlobalSink {
+  const xrt_beam& gb;
+  const xrt_beam& scr;
+  const xrt_plane_params& sp;
+  double pathS, E;
+  double fx, fz;  // footprint contribution of this ray (x, 0, z on the screen) when cnt == 1
+  unsigned cnt;
+  __device__ __forceinline__ GlobalSink(const xrt_beam& g, const xrt_beam& s, const xrt_plane_params& q)
+      : gb(g), scr(s), sp(q), pathS(0.0), E(0.0), fx(0.0), fz(0.0), cnt(0) {}
+  __device__ __forceinline__ void geometry(size_t i, double x, double y, double z, double a, double b, double c,
+                                           int st) {
+    if (!FUSE) {
+      gb.x[i] = x;
+      gb.y[i] = y;
+      gb.z[i] = z;
+      gb.a[i] = a;
+      gb.b[i] = b;
+      gb.c[i] = c;
+      gb.state[i] = st;
+      return;
+    }
+    // global_to_virgin_local with an explicit basis (beamline.py:251-264): every ray, whatever its state
+    const double x0 = x - sp.center[0], y0 = y - sp.center[1], z0 = z - sp.center[2];
+    double xs = sp.ex[0] * x0 + sp.ex[1] * y0 + sp.ex[2] * z0;
+    const double ys = sp.ey[0] * x0 + sp.ey[1] * y0 + sp.ey[2] * z0;
+    double zs = sp.ez[0] * x0 + sp.ez[1] * y0 + sp.ez[2] * z0;
+    const double as = sp.ex[0] * a + sp.ex[1] * b + sp.ex[2] * c;
+    const double bs = sp.ey[0] * a + sp.ey[1] * b + sp.ey[2] * c;
+    const double cs = sp.ez[0] * a + sp.ez[1] * b + sp.ez[2] * c;
+    double path = -ys / bs;
+    bool bad = isnan(path) || isinf(path);
+    if (sp.only_positive_path) bad = bad || (path < 0.0);
+    if (bad) {
+      path = 0.0;
+      st = sp.lostNum;
+    }
+    xs = xs + as * path;
+    zs = zs + cs * path;
+    if (st == 1 || st == 2) {  // footprint (screens.py:262-268), before compression
+      fx = xs;
+      fz = zs;
+      cnt = 1;
+    }
+    if (sp.has_compressX) xs *= sp.compressX;
+    if (sp.has_compressZ) zs *= sp.compressZ;
+    scr.x[i] = xs;
+    scr.y[i] = 0.0;
+    scr.z[i] = zs;
+    scr.a[i] = as;
+    scr.b[i] = bs;
+    scr.c[i] = cs;
+    scr.state[i] = st;
+    pathS = path;
+  }
+  __device__ __forceinline__ void path_energy(size_t i, double path, double En) {
+    if (!FUSE) {
+      gb.path[i] = path;
+      gb.E[i] = En;
+      return;
+    }
+    scr.path[i] = path + pathS;
+    scr.E[i] = En;
+    E = En;
+  }
+  __device__ __forceinline__ void coherency(size_t i, double Jss, double Jpp, cplx Jsp) {
+    const xrt_beam& o = FUSE ? scr : gb;
+    o.Jss[i] = Jss;
+    o.Jpp[i] = Jpp;
+    st_c(o.Jsp, i, Jsp);
+  }
+  __device__ __forceinline__ bool wants_amplitudes() const { return (FUSE ? scr.Es : gb.Es) != nullptr; }
+  __device__ __forceinline__ void amplitudes(size_t i, cplx Es, cplx Ep) {
+    if (!FUSE) {
+      st_c(gb.Es, i, Es);
+      st_c(gb.Ep, i, Ep);
+      return;
+    }
+    // propPhase = exp(1e7j * (E/CHBAR) * path) (screens.py:257-260)
+    const double CHBAR = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8 / 6.283185307179586476925286766559;
+    const double phi = (1e7 * (E / CHBAR)) * pathS;
+    double sn, cs;
+    sincos_big(phi, sn, cs);
+    const cplx ph = cplx{cs, sn};
+    st_c(scr.Es, i, cmul_np(Es, ph));
+    st_c(scr.Ep, i, cmul_np(Ep, ph));
+  }
+};
+
+// gb of a ray that is passed through (see copy_ray_staged), through the sink
+template <bool FUSE>
+__device__ __forceinline__ void pass_ray(GlobalSink<FUSE>& sink, const xrt_beam& src, bool srcIsInput,
+                                         const FieldTile& ft, int tid, bool amp, size_t i, int state) {
+  const double x = src.x[i], y = src.y[i], z = src.z[i], a = src.a[i], b = src.b[i], c = src.c[i];
+  double path, E, Jss, Jpp;
+  cplx Jsp, Es = cplx{0.0, 0.0}, Ep = cplx{0.0, 0.0};
+  const bool hasE = sink.wants_amplitudes() && (srcIsInput ? amp : src.Es != nullptr);
+  if (srcIsInput) {
+    path = ft.path[tid];
+    E = ft.E[tid];
+    Jss = ft.Jss[tid];
+    Jpp = ft.Jpp[tid];
+    Jsp = cplx{ft.Jsp[tid].x, ft.Jsp[tid].y};
+    if (hasE) {
+      Es = cplx{ft.Es[tid].x, ft.Es[tid].y};
+      Ep = cplx{ft.Ep[tid].x, ft.Ep[tid].y};
+    }
+  } else {
+    path = src.path[i];
+    E = src.E[i];
+    Jss = src.Jss[i];
+    Jpp = src.Jpp[i];
+    Jsp = ld_c(src.Jsp, i);
+    if (hasE) {
+      Es = ld_c(src.Es, i);
+      Ep = ld_c(src.Ep, i);
+    }
+  }
+  sink.geometry(i, x, y, z, a, b, c, state);
+  sink.path_energy(i, path, E);
+  sink.coherency(i, Jss, Jpp, Jsp);
+  if (hasE) sink.amplitudes(i, Es, Ep);
+}
+
+template <int SURF, int MAT, bool FUSE = false>
 __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) reflect_main_kernel(size_t n, xrt_oe_params p, xrt_material_params m,
                                                            xrt_multilayer_params ml, Tables tab, xrt_beam in,
                                                            xrt_beam fb, xrt_beam gb, xrt_beam lb,
-                                                           unsigned long long* red, int bulk_ok) {
+                                                           unsigned long long* red, int bulk_ok, double cosRoll,
+                                                           double sinRoll, xrt_plane_params scrp, xrt_beam scr,
+                                                           unsigned long long* sred) {
   constexpr int BT = XRTB_REFLECT_THREADS;
+  GlobalSink<FUSE> sink(gb, scr, scrp);
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const size_t base = (size_t)blockIdx.x * BT;
@@ -1483,31 +1726,46 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
   const bool hasLb = lb.x != nullptr;
   const bool amp = in.Es != nullptr;
   const bool fbIsInput = fb.x == in.x;
-  __shared__ Decision sdec;  // the beam-wide decision is decoded once per block
-  __shared__ double srollc[2];  // cos, sin of the beam-wide roll (polarisation frame)
   __shared__ __align__(16) FieldTile ft;
   __shared__ __align__(8) uint64_t sbar;
+  __shared__ int shint[34];  // f1/f2 interval guesses per element table, [32] "changed" flag, [33] warps done
   // full tiles of 16-byte aligned arrays go through the bulk-copy engine; the last (ragged) tile and beams that are
   // views at odd offsets are staged with plain loads (each thread only ever reads its own slot)
   const bool bulk = bulk_ok && (base + BT <= n);
-  if (tid == 0) {
-    if (bulk) {
-      mbar_init(&sbar, 1);
-      mbar_fence_init();
-      mbar_expect_tx(&sbar, (uint32_t)(BT * (4 * 8 + (amp ? 3 : 1) * 16)));
-      bulk_g2s(ft.path, in.path + base, BT * 8, &sbar);
-      bulk_g2s(ft.E, in.E + base, BT * 8, &sbar);
-      bulk_g2s(ft.Jss, in.Jss + base, BT * 8, &sbar);
-      bulk_g2s(ft.Jpp, in.Jpp + base, BT * 8, &sbar);
-      bulk_g2s(ft.Jsp, in.Jsp + 2 * base, BT * 16, &sbar);
-      if (amp) {
-        bulk_g2s(ft.Es, in.Es + 2 * base, BT * 16, &sbar);
-        bulk_g2s(ft.Ep, in.Ep + 2 * base, BT * 16, &sbar);
-      }
+  if (tid == 0 && bulk) {
+    mbar_init(&sbar, 1);
+    mbar_fence_init();
+    mbar_expect_tx(&sbar, (uint32_t)(BT * (4 * 8 + (amp ? 3 : 1) * 16)));
+    bulk_g2s(ft.path, in.path + base, BT * 8, &sbar);
+    bulk_g2s(ft.E, in.E + base, BT * 8, &sbar);
+    bulk_g2s(ft.Jss, in.Jss + base, BT * 8, &sbar);
+    bulk_g2s(ft.Jpp, in.Jpp + base, BT * 8, &sbar);
+    bulk_g2s(ft.Jsp, in.Jsp + 2 * base, BT * 16, &sbar);
+    if (amp) {
+      bulk_g2s(ft.Es, in.Es + 2 * base, BT * 16, &sbar);
+      bulk_g2s(ft.Ep, in.Ep + 2 * base, BT * 16, &sbar);
     }
-    sdec = decide(red);
   }
-  if (tid == 32) sincos(p.roll, &srollc[1], &srollc[0]);
+  __shared__ int sdone, sdoneS;  // warps that delivered their tail results (OE slots, fused screen slots)
+  if (tid == 0) sdone = sdoneS = 0;  // (the block barrier below orders this against the tail's atomicAdd)
+  int* const ghint = tab.hint;  // reduction slots 48..63
+  const bool useHint = (MAT != 0 && MAT != 7) && ghint != nullptr;
+  if (useHint) {
+    if (tid >= BT - 32) shint[tid - (BT - 32)] = ghint[tid - (BT - 32)];
+    if (tid < 2) shint[32 + tid] = 0;
+    tab.hint = shint;
+  } else {
+    tab.hint = nullptr;
+  }
+  // state, geometry and the packed decision are requested at once (dead rays included, their values are dropped)
+  int st0 = 0;
+  Ray r;
+  r.x = r.y = r.z = r.a = r.b = r.c = 0.0;
+  if (i < n) {
+    st0 = in.state[i];
+    r = load_ray(in, i);
+  }
+  const Decision d = load_decision(red);
   if (!bulk && i < n) {
     ft.path[tid] = in.path[i];
     ft.E[tid] = in.E[i];
@@ -1519,15 +1777,32 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
       ft.Ep[tid] = reinterpret_cast<const double2*>(in.Ep)[i];
     }
   }
+  const bool alive = i < n && (p.good_mode ? (st0 == 1 || st0 == 2) : (st0 > 0));
+  // the geometric part that every traced ray shares runs BEFORE the block barrier, which then only has to publish
+  // the mbarrier and the hints thread 0 / the last warp set up long ago
+  const SurfDiv sd = make_surf_div<SURF>(p);
+  double t1 = 0.0, t2 = 0.0, x1 = 0.0, y1 = 0.0, z1 = 0.0, x2 = 0.0, y2 = 0.0, z2 = 0.0, dz1 = 1.0, dz2 = -1.0;
+  const bool search = alive && !p.no_intersection
+#ifdef XRTB_USER_INTERSECTION
+                      && SURF != 4
+#endif
+      ;
+  if (alive) to_local(p, r);
+  if (search) {
+    // bracketing (base.py:848-885)
+    bracket(p, d.axis, d.neg, r, t1, t2);
+    if (p.multi_tmin) t1 = p.multi_tmin[i] + kDs;  // multiple_reflect, passes after the first (base.py:1288)
+    dz1 = find_dz<SURF, MAT == 5>(p, sd, t1, r, x1, y1, z1);
+    dz2 = find_dz<SURF, MAT == 5>(p, sd, t2, r, x2, y2, z2);
+  }
   __syncthreads();
 
   if (i < n) {
-    const int st0 = in.state[i];
-    if (!(p.good_mode ? (st0 == 1 || st0 == 2) : (st0 > 0))) {
+    if (!alive) {
       // rays that are not alive pass through untouched (gb = lb = copy of the input, reflect.py:104-109)
       if (bulk) mbar_wait(&sbar, 0);
-      copy_ray_staged(gb, in, true, ft, tid, amp, i, p.dead_state_lost ? p.lostNum : st0);  // Plate: dcm.py:311-312
-      if (p.multi && gb.theta) gb.theta[i] = 0.0;  // lb.theta = zeros_like(lb.x) in every pass (reflect.py:789)
+      pass_ray(sink, in, true, ft, tid, amp, i, p.dead_state_lost ? p.lostNum : st0);  // Plate: dcm.py:311-312
+      if (!FUSE && p.multi && gb.theta) gb.theta[i] = 0.0;  // lb.theta = zeros_like(lb.x) in every pass (reflect.py:789)
       if (hasLb) {
         copy_ray_staged(lb, in, true, ft, tid, amp, i, st0);
         if (p.zero_dead_local) {  // dcm.py:305-310
@@ -1544,12 +1819,7 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
         }
       }
     } else {
-      const Decision d = sdec;
-      Ray r = load_ray(in, i);
       const int lo0 = -3;
-      to_local(p, r);
-      const SurfDiv sd = make_surf_div<SURF>(p);
-      double t1, t2, x1, y1, z1, x2, y2, z2;
       bool ind1 = false;
       if (p.no_intersection) {
         // noIntersectionSearch (reflect.py:676-681): tMax = 0, the point stays where it is
@@ -1564,11 +1834,7 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
         xrtb_user::find_intersection(p.sp, r.x, r.y, r.z, r.a, r.b, r.c, t2, x2, y2, z2);
 #endif
       } else {
-        // bracketing + intersection (base.py:848-885)
-        bracket(p, d.axis, d.neg, r, t1, t2);
-        if (p.multi_tmin) t1 = p.multi_tmin[i] + kDs;  // multiple_reflect, passes after the first (base.py:1288)
-        double dz1 = find_dz<SURF, MAT == 5>(p, sd, t1, r, x1, y1, z1);
-        double dz2 = find_dz<SURF, MAT == 5>(p, sd, t2, r, x2, y2, z2);
+        // intersection (base.py:848-885)
         ind1 = dz1 <= 0.0;             // lost: solution t1
         const bool ind2 = dz2 >= 0.0;  // over: solution t2
         if (ind1 || ind2) dz2 = 0.0;
@@ -1774,7 +2040,7 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
 #ifndef XRTB_POLFRAME_ATAN2
         // cos / sin of rollAngle = roll + atan2(n_x, n_z) by the addition theorem: (n_z, n_x) / hypot(n_x, n_z) IS
         // (cos, sin) of atan2(n_x, n_z), and cos / sin of the beam-wide roll are taken once per block.  Differs from
-        // numpy's sincos(float(rollAngle)) by <= 4e-16 absolute (numpy rounds the angle itself to 2e-16) -- 1e-12 is
+        // numpy's sincos(float(rollAngle)) by <= 4e-16 absolute (cos / sin of the beam-wide roll come from the host) (numpy rounds the angle itself to 2e-16) -- 1e-12 is
         // the parity bar -- and replaces ~170 instructions (atan2 + sincos) by 12.
         {
           const double hx = nrm[3], hz = nrm[5];
@@ -1788,8 +2054,8 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
             cphi = hz * inv;
             sphi = hx * inv;
           }
-          cY = fma(srollc[0], cphi, -(srollc[1] * sphi));
-          sY = fma(srollc[1], cphi, srollc[0] * sphi);
+          cY = fma(cosRoll, cphi, -(sinRoll * sphi));
+          sY = fma(sinRoll, cphi, cosRoll * sphi);
         }
 #else
         const double rollAngle = p.roll + atan2(nrm[3], nrm[5]);
@@ -1829,14 +2095,8 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
         }
         if (goodAfter) {
           if (p.to_global) virgin_to_global(p, v);
-          gb.x[i] = v.x;
-          gb.y[i] = v.y;
-          gb.z[i] = v.z;
-          gb.a[i] = v.a;
-          gb.b[i] = v.b;
-          gb.c[i] = v.c;
-          gb.state[i] = st;
-          if (p.multi && gb.theta) gb.theta[i] = theta;
+          sink.geometry(i, v.x, v.y, v.z, v.a, v.b, v.c, st);
+          if (!FUSE && p.multi && gb.theta) gb.theta[i] = theta;
         }
       }
 
@@ -1852,8 +2112,7 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
           lb.E[i] = E;
         }
         if (goodAfter) {
-          gb.path[i] = path;
-          gb.E[i] = E;
+          sink.path_energy(i, path, E);
         }
       }
       if (st == 1) {  // (then goodAfter holds in every mode)
@@ -1914,10 +2173,9 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
           // ... and back for the virgin-local / global beam (reflect.py:1106-1110)
           const double c = cY, s = sY;
           const double c2 = c * c, s2 = s * s, cs = c * s;
-          gb.Jss[i] = Jss * c2 + Jpp * s2 + 2.0 * Jsp.re * cs;
-          gb.Jpp[i] = Jss * s2 + Jpp * c2 - 2.0 * Jsp.re * cs;
           const double J2r = (Jpp - Jss) * cs + Jsp.re * (c2 - s2);
-          st_c(gb.Jsp, i, cplx{J2r + (Jsp.im * 0.0), 0.0 + Jsp.im});
+          sink.coherency(i, Jss * c2 + Jpp * s2 + 2.0 * Jsp.re * cs, Jss * s2 + Jpp * c2 - 2.0 * Jsp.re * cs,
+                         cplx{J2r + (Jsp.im * 0.0), 0.0 + Jsp.im});
         }
         if (amp) {
           cplx Es = cplx{ft.Es[tid].x, ft.Es[tid].y}, Ep = cplx{ft.Ep[tid].x, ft.Ep[tid].y};
@@ -1955,10 +2213,9 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
             st_c(lb.Es, i, Es);
             st_c(lb.Ep, i, Ep);
           }
-          if (gb.Es) {
-            st_c(gb.Es, i, cplx{cY * Es.re + sY * Ep.re, cY * Es.im + sY * Ep.im});
-            st_c(gb.Ep, i, cplx{-sY * Es.re + cY * Ep.re, -sY * Es.im + cY * Ep.im});
-          }
+          if (sink.wants_amplitudes())
+            sink.amplitudes(i, cplx{cY * Es.re + sY * Ep.re, cY * Es.im + sY * Ep.im},
+                            cplx{-sY * Es.re + cY * Ep.re, -sY * Es.im + cY * Ep.im});
         }
       } else {
         // alive but not good after the surface: the fields stay as they were
@@ -1972,22 +2229,42 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
           }
         }
         if (goodAfter) {
-          gb.Jss[i] = ft.Jss[tid];
-          gb.Jpp[i] = ft.Jpp[tid];
-          reinterpret_cast<double2*>(gb.Jsp)[i] = ft.Jsp[tid];
-          if (amp && gb.Es) {
-            reinterpret_cast<double2*>(gb.Es)[i] = ft.Es[tid];
-            reinterpret_cast<double2*>(gb.Ep)[i] = ft.Ep[tid];
-          }
+          sink.coherency(i, ft.Jss[tid], ft.Jpp[tid], cplx{ft.Jsp[tid].x, ft.Jsp[tid].y});
+          if (amp && sink.wants_amplitudes())
+            sink.amplitudes(i, cplx{ft.Es[tid].x, ft.Es[tid].y}, cplx{ft.Ep[tid].x, ft.Ep[tid].y});
         } else {
           // not intersected rays remain unchanged except their state (reflect.py:131-134)
-          copy_ray_staged(gb, fb, fbIsInput, ft, tid, amp, i, p.dead_state_lost ? p.lostNum : st);  // Plate: dcm.py:331-332
+          pass_ray(sink, fb, fbIsInput, ft, tid, amp, i, p.dead_state_lost ? p.lostNum : st);  // Plate: dcm.py:331-332
         }
       }
     }
   }
 
-  // block-level footprint / counters (skipped when nobody asked for them)
+  // a table-interval guess changed in this block: the last warp to get here hands it to the blocks that follow
+  if (useHint) {
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) last = (atomicAdd(&shint[33], 1) == BT / 32 - 1);
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last && *(volatile int*)&shint[32]) ghint[lane] = *(volatile int*)&shint[lane];
+  }
+  // block-level footprint / counters (skipped when nobody asked for them).  No block barrier: every warp leaves its
+  // eight partial results in shared memory and the LAST warp to arrive combines them -- warps that finish early retire
+  // instead of waiting for the slowest one with their registers allocated.
+  if (FUSE) {
+    // the screen's footprint and good-ray count (Screen.expose, screens.py:262-268) -> the screen's own slots
+    __shared__ unsigned long long shs[BT / 32][8];
+    unsigned long long es[8];
+    es[0] = sink.cnt ? enc(sink.fx) : enc(inf);
+    es[1] = sink.cnt ? enc(0.0) : enc(inf);
+    es[2] = sink.cnt ? enc(sink.fz) : enc(inf);
+    es[3] = sink.cnt ? enc(sink.fx) : enc(-inf);
+    es[4] = sink.cnt ? enc(0.0) : enc(-inf);
+    es[5] = sink.cnt ? enc(sink.fz) : enc(-inf);
+    es[6] = sink.cnt;
+    es[7] = 0;
+    tail_combine<BT>(es, shs, &sdoneS, sred, RS_NGOOD, -1, lane, warp);
+  }
   if (!p.want_footprint) return;
   __shared__ unsigned long long sh[BT / 32][8];
   unsigned long long e[8];
@@ -1998,42 +2275,7 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
   }
   e[6] = ngoodN;
   e[7] = (unsigned long long)oor;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    // warp reduction on REDUX (two 32-bit passes per 64-bit key) instead of five 64-bit shuffle rounds
-    const unsigned hi = (unsigned)(e[k] >> 32), lo = (unsigned)e[k];
-    unsigned long long x;
-    if (k >= 6) {
-      x = __reduce_add_sync(0xffffffffu, lo);  // per-thread counts are 0 / 1
-    } else if (k < 3) {
-      const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
-      const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
-      x = ((unsigned long long)mh << 32) | ml;
-    } else {
-      const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
-      const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
-      x = ((unsigned long long)mh << 32) | ml;
-    }
-    if (lane == 0) sh[warp][k] = x;
-  }
-  __syncthreads();
-  if (threadIdx.x < 8) {
-    const int k = threadIdx.x;
-    unsigned long long x = sh[0][k];
-    for (int w = 1; w < BT / 32; ++w) {
-      const unsigned long long y = sh[w][k];
-      x = (k >= 6) ? x + y : (k < 3 ? (y < x ? y : x) : (y > x ? y : x));
-    }
-    if (k < 3) {
-      if (x != enc(inf)) atomicMin(&red[RS_FOOT + k], x);
-    } else if (k < 6) {
-      if (x != enc(-inf)) atomicMax(&red[RS_FOOT + k], x);
-    } else if (k == 6) {
-      if (x) atomicAdd(&red[RS_NGOODN], x);
-    } else {
-      if (x) atomicAdd(&red[RS_NGOODN + 1], x);  // count of rays whose energy left the f1/f2 tables
-    }
-  }
+  tail_combine<BT>(e, sh, &sdone, red, RS_NGOODN, RS_NGOODN + 1, lane, warp);
 }
 
 // ---------------------------------------------------------------- launchers
@@ -2043,23 +2285,75 @@ static int bulk_copy_ok(const xrt_beam& in) {
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
   return al(in.path) && al(in.E) && al(in.Jss) && al(in.Jpp) && al(in.Jsp) && (in.Es == nullptr || (al(in.Es) && al(in.Ep)));
 }
+// the slot layout Screen.expose leaves (rays.cu, plane_reduction_init_kernel): footprint min / max, counters zero
+__global__ void screen_reduction_init_kernel(unsigned long long* red) {
+  const int i = threadIdx.x;
+  if (i >= XRT_REDUCTION_SLOTS) return;
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  unsigned long long v = 0ull;
+  if (i >= RS_FOOT && i < RS_FOOT + 3) v = enc(inf);
+  if (i >= RS_FOOT + 3 && i < RS_FOOT + 6) v = enc(-inf);
+  red[i] = v;
+}
+
+// everything a main-pass launch needs besides the material switch; scr != NULL: fused Screen.expose (GlobalSink)
+struct MainLaunch {
+  unsigned grid;
+  cudaStream_t st;
+  size_t n;
+  const xrt_oe_params* p;
+  const xrt_material_params* m;
+  const xrt_multilayer_params* ml;
+  Tables t;
+  xrt_beam in, fb, gb, lb;
+  unsigned long long* red;
+  const xrt_plane_params* scrp;  // fused Screen.expose: plane, output beam, the screen's own reduction slots
+  const xrt_beam* scr;
+  unsigned long long* sred;
+};
+
+template <int SURF, int MAT>
+static void launch_one(const MainLaunch& L) {
+  const int bulk_ok = bulk_copy_ok(L.in);
+  const double cR = cos(L.p->roll), sR = sin(L.p->roll);  // polarisation frame: cos / sin(roll + atan2(n_x, n_z))
+  reflect_decide_kernel<<<1, 1, 0, L.st>>>(L.red);
+  xrt_plane_params sp;
+  xrt_beam scr;
+  memset(&sp, 0, sizeof(sp));
+  memset(&scr, 0, sizeof(scr));
+  if (L.scr) {
+    // the fused variant exists for the elements of ray-tracing chains: flat / toroid / elliptic mirrors and crystals
+    if constexpr ((SURF == 0 || SURF == 1 || SURF == 2) && (MAT == 0 || MAT == 1 || MAT == 3)) {
+      sp = *L.scrp;
+      scr = *L.scr;
+      reflect_main_kernel<SURF, MAT, true><<<L.grid, XRTB_REFLECT_THREADS, 0, L.st>>>(
+          L.n, *L.p, *L.m, *L.ml, L.t, L.in, L.fb, L.gb, L.lb, L.red, bulk_ok, cR, sR, sp, scr, L.sred);
+    }
+    return;
+  }
+  reflect_main_kernel<SURF, MAT, false><<<L.grid, XRTB_REFLECT_THREADS, 0, L.st>>>(
+      L.n, *L.p, *L.m, *L.ml, L.t, L.in, L.fb, L.gb, L.lb, L.red, bulk_ok, cR, sR, sp, scr, nullptr);
+}
+
 template <int SURF>
-static int launch_main_mat(int mat, unsigned grid, cudaStream_t st, size_t n, const xrt_oe_params& p,
-                           const xrt_material_params& m, const xrt_multilayer_params& ml, const Tables& t,
-                           const xrt_beam& in, const xrt_beam& fb, const xrt_beam& gb, const xrt_beam& lb,
-                           unsigned long long* red) {
-  const int bulk_ok = bulk_copy_ok(in);
+static int launch_main_mat(int mat, const MainLaunch& L) {
+  if (L.scr && !((SURF == 0 || SURF == 1 || SURF == 2) && (mat == 0 || mat == 1 || mat == 3))) {
+    set_last_error("reflect_expose: the fused reflect + expose kernel is built for flat, toroidal and elliptic "
+                   "surfaces with material kinds 0 (none), 1 (mirror), 3 (crystal); got surface %d, kind %d",
+                   SURF, mat);
+    return 4;
+  }
   switch (mat) {
-    case 0: reflect_main_kernel<SURF, 0><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red, bulk_ok); break;
-    case 1: reflect_main_kernel<SURF, 1><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red, bulk_ok); break;
-    case 2: reflect_main_kernel<SURF, 2><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red, bulk_ok); break;
-    case 3: reflect_main_kernel<SURF, 3><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red, bulk_ok); break;
-    case 4: reflect_main_kernel<SURF, 4><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red, bulk_ok); break;
-    case 6: reflect_main_kernel<SURF, 6><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red, bulk_ok); break;
-    case 7: reflect_main_kernel<SURF, 7><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red, bulk_ok); break;
+    case 0: launch_one<SURF, 0>(L); break;
+    case 1: launch_one<SURF, 1>(L); break;
+    case 2: launch_one<SURF, 2>(L); break;
+    case 3: launch_one<SURF, 3>(L); break;
+    case 4: launch_one<SURF, 4>(L); break;
+    case 6: launch_one<SURF, 6>(L); break;
+    case 7: launch_one<SURF, 7>(L); break;
     case 5:
       if constexpr (SURF == 0 || SURF == 4) {
-        reflect_main_kernel<SURF, 5><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red, bulk_ok);
+        launch_one<SURF, 5>(L);
       } else {
         set_last_error("reflect: refraction is built for flat and parabolic surfaces");
         return 2;
@@ -2086,25 +2380,47 @@ static int check_multilayer(const xrt_material_params& m, xrt_multilayer_params&
 
 // refractive elements: plates (flat) and parabolic lenses, bare or of kind 'plate' / 'lens'
 template <int SURF>
-static int launch_main_refr(int mat, unsigned grid, cudaStream_t st, size_t n, const xrt_oe_params& p,
-                            const xrt_material_params& m, const xrt_multilayer_params& ml, const Tables& t,
-                            const xrt_beam& in, const xrt_beam& fb, const xrt_beam& gb, const xrt_beam& lb,
-                            unsigned long long* red) {
-  const int bulk_ok = bulk_copy_ok(in);
+static int launch_main_refr(int mat, const MainLaunch& L) {
+  if (L.scr) {
+    set_last_error("reflect_expose: no fused variant for parabolic lens surfaces");
+    return 4;
+  }
   switch (mat) {
-    case 0: reflect_main_kernel<SURF, 0><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red, bulk_ok); break;
-    case 5: reflect_main_kernel<SURF, 5><<<grid, XRTB_REFLECT_THREADS, 0, st>>>(n, p, m, ml, t, in, fb, gb, lb, red, bulk_ok); break;
+    case 0: launch_one<SURF, 0>(L); break;
+    case 5: launch_one<SURF, 5>(L); break;
     default: set_last_error("reflect: a parabolic lens takes a material of kind 'lens' / 'plate' or none (got %d)", mat); return 2;
   }
   XRTB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
+int reflect_expose_device(size_t n, const xrt_oe_params* oe, const xrt_material_params* mat, const double* tables,
+                          size_t table_len, const xrt_beam* in, const xrt_beam* fallback, const xrt_beam* gb,
+                          const xrt_beam* lb, unsigned long long* red, const xrt_plane_params* scr_plane,
+                          const xrt_beam* scr, unsigned long long* scr_red, int phase,
+                          unsigned long long index_offset, cudaStream_t st);
+
 int reflect_device(size_t n, const xrt_oe_params* oe, const xrt_material_params* mat, const double* tables,
                    size_t table_len, const xrt_beam* in, const xrt_beam* fallback, const xrt_beam* gb,
                    const xrt_beam* lb, unsigned long long* red, int phase, unsigned long long index_offset,
                    cudaStream_t st) {
-  XRTB_REQUIRE(oe && in && gb && red, "reflect: NULL argument");
+  return reflect_expose_device(n, oe, mat, tables, table_len, in, fallback, gb, lb, red, nullptr, nullptr, nullptr,
+                               phase, index_offset, st);
+}
+
+// OE.reflect, optionally continued by Screen.expose in the same kernel (scr_plane / scr / scr_red given, gb NULL):
+// the global beam never reaches HBM
+int reflect_expose_device(size_t n, const xrt_oe_params* oe, const xrt_material_params* mat, const double* tables,
+                          size_t table_len, const xrt_beam* in, const xrt_beam* fallback, const xrt_beam* gb,
+                          const xrt_beam* lb, unsigned long long* red, const xrt_plane_params* scr_plane,
+                          const xrt_beam* scr, unsigned long long* scr_red, int phase,
+                          unsigned long long index_offset, cudaStream_t st) {
+  XRTB_REQUIRE(oe && in && red, "reflect: NULL argument");
+  XRTB_REQUIRE((gb != nullptr) != (scr != nullptr), "reflect: exactly one of gb (OE.reflect) and scr (fused "
+                                                    "Screen.expose) receives the global beam");
+  XRTB_REQUIRE(scr == nullptr || (scr_plane && scr_red), "reflect_expose: the screen needs its plane parameters and "
+                                                         "reduction slots");
+  XRTB_REQUIRE(scr == nullptr || !oe->multi, "reflect_expose: multiple_reflect passes are not fused");
 #ifdef XRTB_PLUGIN
   XRTB_REQUIRE(oe->surface == XRTB_USER_KIND, "reflect (plug-in): this object serves surface kind %d only (got %d)",
                XRTB_USER_KIND, oe->surface);
@@ -2138,7 +2454,8 @@ int reflect_device(size_t n, const xrt_oe_params* oe, const xrt_material_params*
   if (int rc = check_multilayer(m, ml)) return rc;
   XRTB_REQUIRE(m.kind == 0 || m.kind == 7 || (tables != nullptr && table_len > 0), "reflect: material needs f1/f2 tables");
   XRTB_REQUIRE(m.nelem >= 0 && m.nelem <= XRT_MAX_ELEM, "reflect: at most %d elements per material", XRT_MAX_ELEM);
-  Tables t{tables, tables ? tables + table_len : nullptr, tables ? tables + 2 * table_len : nullptr};
+  Tables t{tables, tables ? tables + table_len : nullptr, tables ? tables + 2 * table_len : nullptr,
+           reinterpret_cast<int*>(red + RS_HINT)};
   xrt_beam lbv;
   memset(&lbv, 0, sizeof(lbv));
   if (lb) lbv = *lb;
@@ -2165,15 +2482,20 @@ int reflect_device(size_t n, const xrt_oe_params* oe, const xrt_material_params*
     XRTB_CUDA_CHECK(cudaGetLastError());
   }
   if ((phase & 2) && n > 0) {
-    const unsigned grid = (unsigned)((n + XRTB_REFLECT_THREADS - 1) / XRTB_REFLECT_THREADS);
+    xrt_beam gbv;
+    memset(&gbv, 0, sizeof(gbv));
+    if (gb) gbv = *gb;
+    MainLaunch L{(unsigned)((n + XRTB_REFLECT_THREADS - 1) / XRTB_REFLECT_THREADS), st, n, oe, &m, &ml, t, *in, fbv,
+                 gbv, lbv, red, scr_plane, scr, scr_red};
+    if (scr) screen_reduction_init_kernel<<<1, XRT_REDUCTION_SLOTS, 0, st>>>(scr_red);
     int rc = 0;
 #ifdef XRTB_PLUGIN
-    rc = launch_main_mat<XRTB_USER_KIND>(m.kind, grid, st, n, *oe, m, ml, t, *in, fbv, *gb, lbv, red);
+    rc = launch_main_mat<XRTB_USER_KIND>(m.kind, L);
 #else
-    if (oe->surface == 0) rc = launch_main_mat<0>(m.kind, grid, st, n, *oe, m, ml, t, *in, fbv, *gb, lbv, red);
-    if (oe->surface == 1) rc = launch_main_mat<1>(m.kind, grid, st, n, *oe, m, ml, t, *in, fbv, *gb, lbv, red);
-    if (oe->surface == 2) rc = launch_main_mat<2>(m.kind, grid, st, n, *oe, m, ml, t, *in, fbv, *gb, lbv, red);
-    if (oe->surface == 3) rc = launch_main_refr<3>(m.kind, grid, st, n, *oe, m, ml, t, *in, fbv, *gb, lbv, red);
+    if (oe->surface == 0) rc = launch_main_mat<0>(m.kind, L);
+    if (oe->surface == 1) rc = launch_main_mat<1>(m.kind, L);
+    if (oe->surface == 2) rc = launch_main_mat<2>(m.kind, L);
+    if (oe->surface == 3) rc = launch_main_refr<3>(m.kind, L);
 #endif
     if (rc) return rc;
   }
@@ -2214,7 +2536,7 @@ int amplitude_device(size_t n, const xrt_material_params* mat, const double* tab
   xrt_multilayer_params ml;
   if (int rc = check_multilayer(*mat, ml)) return rc;
   if (n == 0) return 0;
-  Tables t{tables, tables + table_len, tables + 2 * table_len};
+  Tables t{tables, tables + table_len, tables + 2 * table_len, nullptr};
   amplitude_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, *mat, ml, t, E, bIn, bOut, bH,
                                                                reinterpret_cast<double2*>(rs),
                                                                reinterpret_cast<double2*>(rp), oor_count);

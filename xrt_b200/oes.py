@@ -333,7 +333,10 @@ class OE(object):
             p.g_amp = float(resI)**0.5
 
     # ------------------------------------------------------------------ kernel launch
-    def _launch(self, params, material, beam, gb, lb, fallback=None, index_offset=0, allreduce=None, phases=None):
+    def _launch(self, params, material, beam, gb, lb, fallback=None, index_offset=0, allreduce=None, phases=None,
+                screen=None):
+        """One _reflect_local pass.  *screen* = (plane parameters, screen Beam, the screen's reduction slots): the main
+        pass continues with Screen.expose in the same kernel and writes the screen beam instead of *gb* (None)."""
         lib = _lib.load()
         dev = beam.device
         key = str(dev)
@@ -355,18 +358,42 @@ class OE(object):
             mat_ref, tab_ptr = ctypes.byref(mat), tab.data_ptr()
         else:
             mat_ref, tab_ptr, tlen = None, None, 0
-        cin, cgb = beam.c_struct(), gb.c_struct()
+        cin = beam.c_struct()
+        cgb = gb.c_struct() if gb is not None else None
         clb = lb.c_struct() if lb is not None else None
         cfb = fallback.c_struct() if fallback is not None else None
         args = (len(beam), ctypes.byref(params), mat_ref, tab_ptr, tlen, ctypes.byref(cin),
-                ctypes.byref(cfb) if cfb is not None else None, ctypes.byref(cgb),
+                ctypes.byref(cfb) if cfb is not None else None, ctypes.byref(cgb) if cgb is not None else None,
                 ctypes.byref(clb) if clb is not None else None, red.data_ptr())
         profile = getattr(self, 'profileEvents', None)
         plugin = self._plugin()
-        xrt_reflect_f64 = lib.xrt_reflect_f64 if plugin is None else plugin.reflect
+        if screen is not None:
+            if plugin is not None:
+                raise NotImplementedError('the fused reflect + expose kernel serves the built-in surfaces')
+            sp, sbeam, sred = screen
+            csb = sbeam.c_struct()
+            fused = lib.xrt_reflect_expose_f64
+
+            def xrt_reflect_f64(n, oe, mat, tab, tl, cin_, cfb_, cgb_, clb_, red_, ph, off, st):
+                return fused(n, oe, mat, tab, tl, cin_, cfb_, clb_, red_, ctypes.byref(sp), ctypes.byref(csb),
+                             sred.data_ptr(), ph, off, st)
+        else:
+            xrt_reflect_f64 = lib.xrt_reflect_f64 if plugin is None else plugin.reflect
         if phases is not None:  # multiple_reflect interleaves the derivative stage between the phases
             for ph in phases:
-                _lib.check(xrt_reflect_f64(*args, ph, index_offset, stream), 'xrt_reflect_f64')
+                if allreduce is None:
+                    _lib.check(xrt_reflect_f64(*args, ph, index_offset, stream), 'xrt_reflect_f64')
+                    continue
+                # ray shards: the beam-wide scalars are all-reduced after each pre-pass, also when the caller
+                # interleaves its own stages (pre-pass A = bit 0, B = bit 2, main = bit 1)
+                if ph & 1:
+                    _lib.check(xrt_reflect_f64(*args, 1, index_offset, stream), 'xrt_reflect_f64 (pre-pass A)')
+                    allreduce(red)
+                if ph & 4:
+                    _lib.check(xrt_reflect_f64(*args, 4, index_offset, stream), 'xrt_reflect_f64 (pre-pass B)')
+                    allreduce(red, False)
+                if ph & 2:
+                    _lib.check(xrt_reflect_f64(*args, 2, index_offset, stream), 'xrt_reflect_f64 (main pass)')
         elif allreduce is None and profile is None:
             _lib.check(xrt_reflect_f64(*args, 7, index_offset, stream), 'xrt_reflect_f64')
         else:
@@ -488,25 +515,37 @@ class OE(object):
         return lb
 
     def reflect(self, beam=None, needLocal=True, noIntersectionSearch=False, returnLocalAbsorbed=None,
-                checkTables=True, index_offset=0, allreduce=None, withFootprint=False):
-        """Returns (beamGlobal, beamLocal) like OE.reflect (oes/reflect.py:17-163)."""
+                checkTables=True, index_offset=0, allreduce=None, withFootprint=False, exposeOn=None):
+        """Returns (beamGlobal, beamLocal) like OE.reflect (oes/reflect.py:17-163).
+
+        *exposeOn* = a Screen: the kernel continues with Screen.expose (screens.py:225-302) and the method returns
+        (screenBeam, beamLocal) -- bit for bit what `screen.expose(oe.reflect(beam)[0])` returns, without the global
+        beam ever being written to (and read back from) HBM; for chains that only consume the screen."""
         pitch = self.pitch + (self.bragg if hasattr(self, 'bragg') else 0)
         params = self._make_params(pitch, self.roll + self.positionRoll, self.yaw, self.dx,
                                    createdByDiffract=bool(getattr(beam, 'createdByDiffract', False)))
         params.no_intersection = int(bool(noIntersectionSearch))  # reflect.py:676-681
         # the footprint / counter reductions are only paid for when somebody reads them
         params.want_footprint = int(bool(withFootprint or (checkTables and self.material is not None)))
-        gb = beam.like()
         lb = self._new_local(beam) if needLocal else None
+        if exposeOn is not None:
+            gb, screen = None, exposeOn._fused_target(beam)
+        else:
+            gb, screen = beam.like(), None
         # an element with its own intersection method needs no bracket: pre-pass B is skipped
         phases = (1, 2) if (self.cu_find_intersection and not noIntersectionSearch) else None
         red = self._launch(params, self.material, beam, gb, lb, index_offset=index_offset, allreduce=allreduce,
-                           phases=phases)
+                           phases=phases, screen=screen)
+        if exposeOn is not None:
+            gb = screen[1]
+            gb.parentId = getattr(exposeOn, 'uuid', exposeOn.name)
         if checkTables and self.material is not None:
             self._check_tables(red)
         if withFootprint:
             self.footprint = [self._footprint_from(red)]
-        gb.parentId = lb_parent = getattr(self, 'uuid', self.name)
+        lb_parent = getattr(self, 'uuid', self.name)
+        if exposeOn is None:
+            gb.parentId = lb_parent
         if lb is not None:
             lb.parentId = lb_parent
         return gb, (lb if needLocal else gb)
@@ -848,8 +887,9 @@ class DCM(OE):
         raise AttributeError('use DCM.double_reflect')
 
     def double_reflect(self, beam=None, needLocal=True, fromVacuum1=True, fromVacuum2=True,
-                       returnLocalAbsorbed=None, checkTables=True, index_offset=0, allreduce=None):
-        """Returns (beamGlobal, beamLocal1, beamLocal2) like DCM.double_reflect (oes/dcm.py:247-354)."""
+                       returnLocalAbsorbed=None, checkTables=True, index_offset=0, allreduce=None, exposeOn=None):
+        """Returns (beamGlobal, beamLocal1, beamLocal2) like DCM.double_reflect (oes/dcm.py:247-354).  *exposeOn*: see
+        OE.reflect -- the second crystal's kernel continues with Screen.expose, beamGlobal is the screen beam."""
         p1 = self._make_params(self.pitch + self.bragg, self.roll + self.positionRoll + self.cryst1roll,
                                self.yaw, self.dx, to_global=False)
         p1.from_vacuum = int(bool(fromVacuum1))
@@ -866,10 +906,18 @@ class DCM(OE):
         p2.zero_dead_local = 1
         p2.from_vacuum = int(bool(fromVacuum2))
         p2.dead_state_lost = int(hasattr(self, 't'))  # is instance of Plate (dcm.py:311-312, :331-332)
-        gb2 = beam.like()
         lo2 = self._new_local(beam) if needLocal else None
+        if exposeOn is not None and not hasattr(self, 't'):
+            gb2, screen = None, exposeOn._fused_target(beam)
+        else:
+            gb2, screen = beam.like(), None
         red = self._launch(p2, self.material2, gb, gb2, lo2, fallback=beam, index_offset=index_offset,
-                           allreduce=allreduce)
+                           allreduce=allreduce, screen=screen)
+        if screen is not None:
+            gb2 = screen[1]
+            gb2.parentId = getattr(exposeOn, 'uuid', exposeOn.name)
+        elif exposeOn is not None:
+            gb2 = exposeOn.expose(gb2)
         if checkTables and self.material2 is not None:
             self._check_tables(red)
         if not needLocal:

@@ -99,17 +99,26 @@ class Screen(_Plane):
         self.compressZ = compressZ
         self.footprint = []
 
-    def expose(self, beam=None, onlyPositivePath=False, withHistogram=False, withFootprint=False):
-        """Returns the beam in the local system of the screen (screens.py:225-302)."""
-        if withHistogram:
-            raise NotImplementedError('histogramming is the next row of the scope table (SURVEY.md 8f1)')
-        lib = _lib.load()
+    def _expose_params(self, onlyPositivePath=False):
         p = self._base_params()
         p.only_positive_path = int(bool(onlyPositivePath))
         if self.compressX:
             p.has_compressX, p.compressX = 1, float(self.compressX)
         if self.compressZ:
             p.has_compressZ, p.compressZ = 1, float(self.compressZ)
+        return p
+
+    def _fused_target(self, beam, onlyPositivePath=False):
+        """(plane parameters, output Beam, reduction slots) for an optical element whose kernel continues with this
+        screen's expose (OE.reflect(exposeOn=screen))."""
+        return self._expose_params(onlyPositivePath), beam.like(), self._red(beam.device)
+
+    def expose(self, beam=None, onlyPositivePath=False, withHistogram=False, withFootprint=False):
+        """Returns the beam in the local system of the screen (screens.py:225-302)."""
+        if withHistogram:
+            raise NotImplementedError('histogramming is the next row of the scope table (SURVEY.md 8f1)')
+        lib = _lib.load()
+        p = self._expose_params(onlyPositivePath)
         blo = beam.like()
         red = self._red(beam.device)
         cin, cout = beam.c_struct(), blo.c_struct()
