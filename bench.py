@@ -12,8 +12,9 @@ The Kirchhoff integral of config 4 (N = 1e6 samples -> 1024 x 1024 screen) is ti
 reported under "kirchhoff" with its own roofline.
 
 Multi-GPU (torchrun, one rank per GPU): rays are sharded (weak scaling, `--nrays` per rank); the beam-wide
-scalars of reflect() and Imax are all-reduced (min/max over 64 slots); `--gather beam` adds the all-gather of
-the screen Beam named in the north star.
+scalars of reflect() and Imax are all-reduced (min/max over 64 slots); `gather_beam` reports the same step with
+the all-gather of the screen Beam named in the north star as a second timed line; the Kirchhoff sum shards
+its receiving points AND its samples (packed records all-gathered); `config5` is BASELINE configs[4].
 """
 import argparse
 import json
@@ -85,7 +86,9 @@ class ClockSampler(threading.Thread):
 
 def measured_traffic(kernel_prefix, nrays):
     """dram bytes per launch of a ray kernel, from the committed ncu --set full capture (bytes/ray x rays)."""
-    path = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    path = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
     try:
         with open(path) as f:
             t = json.load(f)
@@ -183,11 +186,52 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def count_own_launches(fn):
+    """How many kernels of libxrt_b200.so one call of fn() launches, MEASURED with the CUPTI-backed torch profiler
+    (every kernel of the process is recorded, torch's own included): kernels whose names carry the library's
+    namespace / kernel names are ours.  Returns (ours, others) or None when the profiler is unavailable."""
+    try:
+        import torch
+        from torch.profiler import profile, ProfilerActivity
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        ours = others = 0
+        for e in prof.events():
+            if getattr(e, 'device_type', None) is None or 'cuda' not in str(e.device_type).lower():
+                continue
+            name = e.name
+            if name.startswith('Memcpy') or name.startswith('Memset'):
+                continue
+            if 'xrtb::' in name or name.startswith('xrtb') or '_kernel' in name and 'at::' not in name:
+                ours += 1
+            else:
+                others += 1
+        return ours, others
+    except Exception:
+        return None
+
+
+def config5_geometry():
+    """BASELINE.json configs[4] (SURVEY 8d 'Config 5'): Undulator tuned to its 7th harmonic -> DCM Si(111) ->
+    vertical + horizontal elliptical-cylinder KB pair (template tests/speed/3_Softi_CXIw2D_speed.py:232-243) -> Screen;
+    the same geometry as tests/test_pipeline.py, where the chain is parity-tested against the numpy oracle."""
+    from xrt_b200.materials import CrystalSi
+    si = CrystalSi(hkl=(1, 1, 1))
+    E0 = 7 * E1
+    Ea = np.array([E0])
+    theta = float(si.get_Bragg_angle(Ea)[0] - si.get_dtheta(Ea)[0])
+    return dict(E0=E0, theta=theta, si=si, dcm_y=20000., vfm_y=30000., hfm_y=30600., scr_y=31800., pitch=3.5e-3,
+                dcm_offset=2 * 10. * np.cos(theta))
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from xrt_b200 import _lib, kernels, synthetic
     from xrt_b200.beamline import BeamLine
+    from xrt_b200.beams import Beam
     from xrt_b200.sources import Undulator
     from xrt_b200.oes import ToroidMirror
     from xrt_b200.materials import Material
@@ -217,11 +261,15 @@ def run_ours(args):
             dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
             dist.barrier()
             torch.cuda.synchronize()
+            # the exchange steps of the ray / wave path go through the library's own C-ABI NCCL entry points
+            comm = parallel.Comm(world, rank, use_capi=not args.torch_collectives)
+            torch.cuda.synchronize()
         finally:
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
-    comm = parallel.Comm(world, rank)
+    else:
+        comm = parallel.Comm(world, rank)
 
     nrays = args.nrays
     bl = BeamLine()
@@ -230,53 +278,42 @@ def run_ours(args):
     screen = Screen(bl, 'scr', center=(0, SCREEN_Y, 25000. * np.tan(2 * 3e-3)))
     src.reset()
     nodes = len(src.tg)
+    ar = comm.allreduce_reductions if world > 1 else None
 
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    stage_names = ('sample', 'undulator', 'fill', 'reflect', 'expose')
-    stage_events = []
+    copy_stream = torch.cuda.Stream()
     host_out = None
     e2e_count = [0]
-    copy_stream = torch.cuda.Stream()
 
-    def step(e2e=False, record=None, fused=not args.unfused_source):
-        marks = [ev() for _ in range(6)] if record is not None else None
+    def step(e2e=False, record=None, fused_chain=True):
+        """One pass of the hot path over a fresh batch: Undulator.shine -> ToroidMirror.reflect -> Screen.expose.
+        fused_chain: the reflect kernel continues with the screen (OE.reflect(exposeOn=)), the global beam between
+        them never reaches HBM; the local beam of the mirror is materialised in both variants."""
+        marks = [ev() for _ in range(4)] if record is not None else None
         off = rank * nrays
-        from xrt_b200.beams import Beam
         beam = Beam(nrays, withAmplitudes=True, uninitialized=True)
-        if fused:
-            # Undulator.shine(): one fused kernel (sample + field integral + Beam assembly)
-            if marks:
-                marks[0].record()
-                marks[1].record()
-            src.shine_uniform_fused(beam, index_offset=off)
+        if marks:
+            marks[0].record()
+        src.shine_uniform_fused(beam, index_offset=off)
+        if marks:
+            marks[1].record()
+        if fused_chain:
+            blo, lb = mirror.reflect(beam, needLocal=True, checkTables=False, index_offset=off, allreduce=ar,
+                                     exposeOn=screen)
             if marks:
                 marks[2].record()
                 marks[3].record()
         else:
-            if marks:
-                marks[0].record()
-            s = src.draw_samples(nrays, index_offset=off)
-            if marks:
-                marks[1].record()
-            I, mJs, mJp = src.build_I_map_device(s['E'], s['theta'], s['psi'])
+            gb, lb = mirror.reflect(beam, needLocal=True, checkTables=False, index_offset=off, allreduce=ar)
             if marks:
                 marks[2].record()
-            src.fill_beam(s, mJs, mJp, beam)
+            blo = screen.expose(gb)
             if marks:
                 marks[3].record()
-        gb, lb = mirror.reflect(beam, needLocal=True, checkTables=False, index_offset=off,
-                                allreduce=comm.allreduce_reductions if world > 1 else None)
         if marks:
-            marks[4].record()
-        blo = screen.expose(gb)
-        if marks:
-            marks[5].record()
             record.append(marks)
-        if args.gather == 'beam' and world > 1:
-            blo = comm.allgather_beam(blo)
         if e2e:
-            # D2H of the result on a copy stream: the copy of step k overlaps the kernels of step k+1; two pinned
-            # host buffers alternate so a consumer owns one result while the next one lands
+            # D2H of the result on a copy stream: the copy of step k overlaps the kernels of step k+1
             buf = host_out[e2e_count[0] % len(host_out)]
             e2e_count[0] += 1
             done = torch.cuda.Event()
@@ -311,63 +348,104 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
+    fused_chain = not args.unfused_chain
     # ---- device-resident throughput
     for _ in range(args.warmup):
-        step()
+        step(fused_chain=fused_chain)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_total = timed(lambda: step(record=stage_events), args.steps)
+    stage_events = []
+    ms_total = timed(lambda: step(record=stage_events, fused_chain=fused_chain), args.steps)
     torch.cuda.synchronize()
     stage_ms = {n: float(np.mean([m[i].elapsed_time(m[i + 1]) for m in stage_events]))
-                for i, n in enumerate(stage_names)}
+                for i, n in enumerate(('shine', 'reflect', 'expose'))}
     ms_step = ms_total / args.steps
     value = world * nrays / (ms_step * 1e-3) / 1e6
+    # the other chain variant, for the comparison the fusion is judged by (few steps, untimed region of the contract)
+    other_steps = max(1, min(args.steps, 3))
+    step(fused_chain=not fused_chain)
+    ms_other = timed(lambda: step(fused_chain=not fused_chain), other_steps) / other_steps
+    launches = count_own_launches(lambda: step(fused_chain=fused_chain)) if rank == 0 else None
 
-    # ---- end to end: result Beam lands in pinned host memory inside the timed region
-    blo = step()
+    # ---- end to end (i): the whole result Beam lands in pinned host memory inside the timed region
+    blo = step(fused_chain=fused_chain)
     bytes_per_ray = blo.bytes_per_ray()
     n_host = len(blo)
     host_out = []
     e2e_note = None
-    for _ in range(2):  # two pinned result buffers (2 x 13.2 GB at 1e8 rays); one if the host cannot pin that much
+    nbuf = 2 if world <= 2 else 1  # 2 x 13.2 GB pinned per rank; one when many ranks share a host (211 GB at 8)
+    for _ in range(nbuf):
         try:
             host_out.append({k: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
                              for k, t in blo.tensors().items()})
         except RuntimeError:
             if not host_out:
-                # not even one pinned Beam: pageable host memory keeps the run alive (slower copies, said in the line)
                 host_out.append({k: torch.empty(t.shape, dtype=t.dtype) for k, t in blo.tensors().items()})
                 e2e_note = 'pinned allocation failed: pageable host buffers'
             break
     del blo
     for _ in range(max(1, args.warmup - 1)):
-        step(e2e=True)
-    ms_e2e = timed(lambda: step(e2e=True), args.steps) / args.steps  # barrier() drains the copy stream
-    if rank == 0:
-        sampler.stop_flag.set()
+        step(e2e=True, fused_chain=fused_chain)
+    ms_e2e = timed(lambda: step(e2e=True, fused_chain=fused_chain), args.steps) / args.steps
     e2e_value = world * nrays / (ms_e2e * 1e-3) / 1e6
     h2d = 6 * nodes * 8 + 8 * 64  # node tables + scalar structs per step
     d2h = n_host * bytes_per_ray
+    # concurrent D2H bandwidth of the box with every rank copying at once: the limiter of (i) named with a number
+    probe = host_out[0]['Es'] if 'Es' in host_out[0] else host_out[0]['x']
+    dprobe = torch.empty(probe.shape, dtype=probe.dtype, device='cuda')
+    pbytes = probe.numel() * probe.element_size()
+
+    def d2h_probe():
+        probe.copy_(dprobe, non_blocking=True)
+    d2h_probe()
+    ms_probe = timed(d2h_probe, 3) / 3
+    d2h_gbs = {'per_gpu_GBs': pbytes / ms_probe / 1e6, 'aggregate_GBs': world * pbytes / ms_probe / 1e6,
+               'bytes_per_copy': pbytes, 'ranks_copying_at_once': world}
+    del dprobe, probe
     host_out = None
 
-    # ---- end to end the way xrt's runner consumes a repeat: only the screen image (get_output + do_hist2d,
+    # ---- end to end (ii): what raycing.get_output reads (x, z, E, Jss, Jpp of the good rays), compacted on the device
+    fields = ('x', 'z', 'E', 'Jss', 'Jpp')
+    pinned = {k: torch.empty(nrays, dtype=torch.float64, pin_memory=True) for k in fields}
+    sel_count = [0]
+
+    def step_compact():
+        b = step(fused_chain=fused_chain)
+        out = b.to_host(fields=fields, good_only=True, rayFlag=(1,), out=pinned)
+        sel_count[0] = len(out['x'])
+    step_compact()
+    ms_comp = timed(step_compact, args.steps) / args.steps
+    e2e_compact = {'value': world * nrays / (ms_comp * 1e-3) / 1e6, 'unit': 'Mrays/s', 'ms_per_step': ms_comp,
+                   'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': sel_count[0] * 8 * len(fields) + 8,
+                   'selected_rays': sel_count[0],
+                   'note': 'Beam.to_host(fields=(x, z, E, Jss, Jpp), good_only=True): xrt_compact_rays_f64 packs the '
+                           'fields raycing.get_output reads (raycing/__init__.py:170-300) of the good rays, in ray '
+                           'order, on the device; only they cross PCIe (blocking call: no overlap with the next step)'}
+    del pinned
+
+    # ---- end to end (iii) the way xrt's runner consumes a repeat: only the screen image (get_output + do_hist2d,
     # xrt/multipro.py:119-171) leaves the GPU -- device histogram, 256 x 256 doubles D2H per step
     from xrt_b200 import histogram
-    blo = step()
+    blo = step(fused_chain=fused_chain)
     gd = blo.state == 1
-    xl = [float(blo.x[gd].min()), float(blo.x[gd].max())]
-    zl = [float(blo.z[gd].min()), float(blo.z[gd].max())]
-    blo_E_min, blo_E_max = blo.E[gd].min(), blo.E[gd].max()
+    lims = torch.stack((blo.x[gd].min(), blo.x[gd].max(), blo.z[gd].min(), blo.z[gd].max(), blo.E[gd].min(),
+                        blo.E[gd].max()))
+    if world > 1:  # common plot limits on every rank
+        lo = lims[0::2].clone()
+        hi = lims[1::2].clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        lims[0::2], lims[1::2] = lo, hi
+    lims = [float(v) for v in lims.tolist()]
     del blo, gd
-    el = [float(blo_E_min), float(blo_E_max)]
-    ph = histogram.PlotHistograms(histogram.Axis('x', xl, 256), histogram.Axis('z', zl, 256),
-                                  histogram.Axis('E', el, 256), fluxKind='total', rayFlag=(1,))
+    ph = histogram.PlotHistograms(histogram.Axis('x', lims[0:2], 256), histogram.Axis('z', lims[2:4], 256),
+                                  histogram.Axis('E', lims[4:6], 256), fluxKind='total', rayFlag=(1,))
     hbytes = sum(t.numel() * t.element_size() for t in (ph._h2, ph._hx, ph._hy, ph._hc, ph._counters))
     host_img = torch.empty(hbytes // 8, dtype=torch.float64, pin_memory=True)
 
     def step_hist():
-        b = step()
+        b = step(fused_chain=fused_chain)
         for t in (ph._h2, ph._hx, ph._hy, ph._hc, ph._counters):
             t.zero_()
         ph.accumulate(b)
@@ -383,32 +461,73 @@ def run_ours(args):
     e2e_hist = {'value': world * nrays / (ms_hist * 1e-3) / 1e6, 'unit': 'Mrays/s', 'ms_per_step': ms_hist,
                 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': hbytes,
                 'note': 'same step + one XYCPlot on the device (xrt_b200.histogram.PlotHistograms: 256 x 256 image and '
-                        'the x, z, E 1-D histograms, each with flux + RGB channels == get_output + do_hist1d/2d); '
-                        'only the histograms cross PCIe, as in xrt where histograms, not rays, are accumulated over '
-                        'repeats (xrt/runner.py:526-530, xrt/multipro.py:296-340)'}
+                        'the x, z, E 1-D histograms, each with flux + RGB channels == get_output + do_hist1d/2d), '
+                        'all-reduced over the ranks; only the histograms cross PCIe, as in xrt where histograms, not '
+                        'rays, are accumulated over repeats (xrt/runner.py:526-530, xrt/multipro.py:296-340)'}
+    if rank == 0:
+        sampler.stop_flag.set()
 
-    # ---- per-kernel times of reflect() (pre-pass A, pre-pass B, main) in a few extra untimed steps
-    mirror.profileEvents = []
-    for _ in range(3):
-        step()
-    torch.cuda.synchronize()
-    refl_ms = [float(np.mean([e[a].elapsed_time(e[b]) for e in mirror.profileEvents]))
-               for a, b in ((0, 1), (4, 2), (5, 3))]
-    mirror.profileEvents = None
+    # ---- the north star's collective: one all-gather of the screen Beam over all ranks (a second timed line)
+    gather_rep = None
+    if world > 1:
+        ng = int(min(nrays, 48e9 / (132 * world)))  # every rank receives world x ng rays: keep the result <= 48 GB
+        ng -= ng % 512
+        src_g = Undulator(BeamLine(), 'ug', eMin=E1 * 0.995, eMax=E1 * 1.005, seed=1234, **undulator_kwargs(ng))
+        src_g.reset()
+
+        def step_gather(gather=True):
+            beam = Beam(ng, withAmplitudes=True, uninitialized=True)
+            src_g.shine_uniform_fused(beam, index_offset=rank * ng)
+            b, _ = mirror.reflect(beam, needLocal=True, checkTables=False, index_offset=rank * ng, allreduce=ar,
+                                  exposeOn=screen)
+            del beam
+            return comm.allgather_beam(b) if gather else b
+        g = step_gather()
+        gathered_rays = len(g)
+        del g
+        gsteps = max(1, min(args.steps, 3))
+        ms_g = timed(step_gather, gsteps) / gsteps
+        step_gather(False)
+        ms_ng = timed(lambda: step_gather(False), gsteps) / gsteps
+        gbytes = 132 * ng * (world - 1)
+        gather_rep = {'workload': 'same step at %d rays per GPU + ONE all-gather of the screen Beam (132 B/ray, 14 arrays '
+                                  'in one NCCL group, %s): every rank ends with all %d rays'
+                                  % (ng, 'xrt_allgather_beam of the C ABI' if not args.torch_collectives
+                                     else 'torch.distributed on one packed buffer', gathered_rays),
+                      'rays_per_gpu': ng, 'ms_per_step': ms_g, 'ms_per_step_without_gather': ms_ng,
+                      'value': world * ng / (ms_g * 1e-3) / 1e6, 'unit': 'Mrays/s',
+                      'value_without_gather': world * ng / (ms_ng * 1e-3) / 1e6,
+                      'allgather_ms': ms_g - ms_ng, 'received_bytes_per_gpu': gbytes,
+                      'allgather_GBs_per_gpu': gbytes / max(ms_g - ms_ng, 1e-6) / 1e6}
+        del src_g
+
+    # ---- per-kernel times of the materialising reflect() (pre-pass A, pre-pass B, main) in a few extra untimed steps
+    def kernel_times(**kw):
+        mirror.profileEvents = []
+        for _ in range(4):
+            beam = Beam(nrays, withAmplitudes=True, uninitialized=True)
+            src.shine_uniform_fused(beam, index_offset=rank * nrays)
+            out = mirror.reflect(beam, needLocal=True, checkTables=False, index_offset=rank * nrays, allreduce=ar, **kw)
+            del out, beam
+        torch.cuda.synchronize()
+        evs = mirror.profileEvents[1:]
+        mirror.profileEvents = None
+        return [float(np.mean([e[a].elapsed_time(e[b]) for e in evs])) for a, b in ((0, 1), (4, 2), (5, 3))]
+    refl_ms = kernel_times()
+    fused_ms = kernel_times(exposeOn=screen)
 
     # ---- rooflines.  Denominators: HBM from MEASURED_PEAKS.json; FP64 has no entry there, so a DFMA stream is
     # measured in this run (xrt_b200_fp64_probe).
     peaks, peak_kind = measured_peaks()
     dfma_tflops, _ = kernels.fp64_probe(0, 8192)
-    und_ms = stage_ms['undulator']
+    und_ms = stage_ms['shine']
     und_tflops = FLOP_PER_SAMPLE_NODE * nrays * nodes / (und_ms * 1e-3) / 1e12
     pair_path = bool(src.gridSymmetric and src.Kx == 0)
     und_instr = 24.5 if pair_path else 57.0  # DFMA-pipe instructions per (sample, node) in SASS
-    roofline_und = {'kernel': ('undulator_kernel<2,1,planar,%s> (Undulator.build_I_map)' if args.unfused_source else
-                               'shine_uniform_kernel<2,planar,%s> (Undulator.shine: sample + field integral + Beam '
-                               'assembly)') % ('pairs' if pair_path else 'nodes'),
+    roofline_und = {'kernel': 'shine_uniform_kernel<2,planar,%s> (Undulator.shine: sample + field integral + Beam '
+                              'assembly)' % ('pairs' if pair_path else 'nodes'),
                     'bound': 'fp64', 'achieved': und_tflops, 'peak': dfma_tflops, 'unit': 'TFLOP/s',
-                    'frac': und_tflops / dfma_tflops, 'traffic': measured_traffic('undulator_kernel' if args.unfused_source else 'shine_uniform_kernel', nrays),
+                    'frac': und_tflops / dfma_tflops, 'traffic': measured_traffic('shine_uniform_kernel', nrays),
                     'issue_slot_frac': 2 * und_instr * nrays * nodes / (und_ms * 1e-3) / 1e12 / dfma_tflops,
                     'note': 'achieved counts the 63 flop per (sample, node) of the reference algorithm (SURVEY 8d); '
                             'the kernel evaluates mirror PAIRS of nodes for a planar undulator on a symmetric grid '
@@ -417,28 +536,33 @@ def run_ours(args):
     main_ms = refl_ms[2]
     main_bytes = 132 + 132 + 140
     main_gbs = main_bytes * nrays / (main_ms * 1e-3) / 1e9
-    roofline_main = {'kernel': 'reflect_main_kernel<toroid, mirror> (OE.reflect)', 'bound': 'hbm',
+    roofline_main = {'kernel': 'reflect_main_kernel<toroid, mirror> (OE.reflect, materialising gb and lb)', 'bound': 'hbm',
                      'achieved': main_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': main_gbs / peaks['hbm_gbs'],
                      'traffic': measured_traffic('reflect_main_kernel', nrays),
                      'peak_source': '%s HBM copy bandwidth (MEASURED_PEAKS.json)' % peak_kind,
-                     'note': '%d algorithmic bytes per ray (132 in, 132 gb, 140 lb); currently limited by the issue rate '
-                             'of the IEEE div/sqrt chains numpy parity requires (~3600 instructions per ray), not by HBM'
+                     'note': '%d algorithmic bytes per ray (132 in, 132 gb, 140 lb); timed in extra steps through '
+                             'OE.reflect() without exposeOn (the step itself runs the fused reflect + expose variant: '
+                             'stages.reflect_expose_fused_main); limited by instruction issue (IEEE div / sqrt chains '
+                             'of numpy parity, 41 %% of the lanes idle behind rays that miss the mirror), not by HBM'
                              % main_bytes,
                      'ms': main_ms, 'share_of_step': main_ms / ms_step}
-    # the dominant kernel of the step goes first
     roofline = roofline_main if main_ms >= und_ms else roofline_und
     roofline_other = roofline_und if main_ms >= und_ms else roofline_main
     hbm = {}
+    fused_bytes = 132 + 132 + 140  # in, screen beam, lb
     stage_list = [('reflect_prepass_dir', 28, refl_ms[0]), ('reflect_prepass_bracket', 52, refl_ms[1]),
-                  ('reflect_main', main_bytes, refl_ms[2]), ('expose', 264, stage_ms['expose'])]
-    if args.unfused_source:
-        stage_list += [('fill', 96 + 132, stage_ms['fill']), ('sample', 64, stage_ms['sample'])]
+                  ('reflect_main', main_bytes, refl_ms[2]), ('reflect_expose_fused_main', fused_bytes, fused_ms[2])]
+    if not fused_chain:
+        stage_list.append(('expose', 264, stage_ms['expose']))
     for name, bpr, ms in stage_list:
         gbs = bpr * nrays / (ms * 1e-3) / 1e9
         hbm[name] = {'ms': ms, 'bytes_per_ray': bpr, 'achieved_gbs': gbs,
                      'frac_of_%s_hbm' % peak_kind: gbs / peaks['hbm_gbs']}
-    hbm['undulator' if args.unfused_source else 'shine_fused (sample + undulator + fill)'] = {'ms': und_ms}
+    hbm['shine_fused (sample + undulator + fill)'] = {'ms': und_ms}
     hbm['reflect_total_in_step'] = {'ms': stage_ms['reflect']}
+    chain = {'fused (OE.reflect(exposeOn=screen): xrt_reflect_expose_f64)': ms_step if fused_chain else ms_other,
+             'unfused (OE.reflect + Screen.expose: the global beam goes through HBM)':
+                 ms_other if fused_chain else ms_step}
 
     # ---- sub-mode 2r: rejection sampling instead of uniformRayDensity, source only
     rej = None
@@ -476,24 +600,27 @@ def run_ours(args):
         dcm = DCM(bl3, 'dcm', center=(0, 2e4, 0), bragg=theta, material=si, material2=si, cryst2perpTransl=10.,
                   limPhysX=[-50, 50], limPhysY=[-100, 100], limPhysX2=[-50, 50], limPhysY2=[-100, 200])
         scr3 = Screen(bl3, 'scr3', center=(0, 3e4, 2 * 10. * np.cos(theta)))
-        ar = comm.allreduce_reductions if world > 1 else None
 
-        def step3():
+        def step3(fused=True):
             b = gs.shine(withAmplitudes=True, index_offset=rank * nrays)
-            gb, lo1, lo2 = dcm.double_reflect(b, needLocal=True, checkTables=False, index_offset=rank * nrays,
-                                              allreduce=ar)
-            return scr3.expose(gb)
+            out = dcm.double_reflect(b, needLocal=True, checkTables=False, index_offset=rank * nrays,
+                                     allreduce=ar, exposeOn=scr3 if fused else None)
+            return out[0] if fused else scr3.expose(out[0])
         out3 = step3()
         good3 = float((out3.state == 1).sum()) / len(out3)
         del out3
-        step3()
-        ms3 = timed(step3, max(1, min(args.steps, 3))) / max(1, min(args.steps, 3))
+        n3 = max(1, min(args.steps, 3))
+        ms3 = timed(step3, n3) / n3
+        step3(False)
+        ms3u = timed(lambda: step3(False), n3) / n3
         dcm_rep = {'workload': 'config3: GeometricSource -> DCM Si(111) (two crystals, thick Bragg amplitudes) -> '
-                               'Screen, %d rays per GPU' % nrays, 'ms_per_step': ms3,
+                               'Screen (fused into the second crystal\'s kernel), %d rays per GPU' % nrays,
+                   'ms_per_step': ms3, 'ms_per_step_unfused': ms3u,
                    'value': world * nrays / (ms3 * 1e-3) / 1e6, 'unit': 'Mrays/s', 'good_fraction': good3}
         del gs, dcm, scr3
 
-    # ---- Kirchhoff sum, config 4
+    # ---- Kirchhoff sum, config 4: the M receiving points are sharded over the ranks; the N samples are sharded too
+    # (every rank owns N / world of them, as if they were its ray shard) and their packed records all-gathered
     kir = None
     if not args.no_kirchhoff:
         N, M = args.kirchhoff_n, args.kirchhoff_m
@@ -501,47 +628,185 @@ def run_ours(args):
         case = synthetic.kirchhoff_case(7, N, M, mesh=(int(round(M ** 0.5)) ** 2 == M))
         sl = slice(rank * Mloc, (rank + 1) * Mloc)
         d = {k: torch.from_numpy(np.ascontiguousarray(case[k][sl])).cuda() for k in ('xM', 'yM', 'zM')}
+        nlo, nhi = comm.shard(N)
         for k in ('nl', 'k', 'Es', 'Ep'):
-            d[k] = torch.from_numpy(np.ascontiguousarray(case[k])).cuda()
-        d['pos'] = torch.from_numpy(np.ascontiguousarray(case['pos'].T)).cuda()
-        d['nrm'] = torch.from_numpy(np.ascontiguousarray(case['nrm'].T)).cuda()
+            d[k] = torch.from_numpy(np.ascontiguousarray(case[k][nlo:nhi])).cuda()
+        d['pos'] = torch.from_numpy(np.ascontiguousarray(case['pos'].T[nlo:nhi])).cuda()
+        d['nrm'] = torch.from_numpy(np.ascontiguousarray(case['nrm'].T[nlo:nhi])).cuda()
+        del case
         out = torch.empty((5, Mloc), dtype=torch.complex128, device='cuda')
+        kev = []
+        # k r <= 4.6e6 /mm x 1e4 mm = 4.6e10 rad here: far below the 2^47 limit of the table-based sin / cos
+        ktab = float(d['k'].abs().max()) * 2e4 < kernels.PHASE_LIMIT_TABLE_SINCOS
 
         def kstep():
-            kernels.kirchhoff(d['xM'], d['yM'], d['zM'], d['nl'], d['Es'], d['Ep'], d['k'], d['pos'], d['nrm'],
-                              out=out, R=args.kirchhoff_r, uniform_normal=True)  # slit: n = (0, 1, 0)
+            m = [ev() for _ in range(3)]
+            m[0].record()
+            rec = kernels.kirchhoff_pack(d['nl'], d['Es'], d['Ep'], d['k'], d['pos'], d['nrm'])
+            rec = comm.allgather_rows(rec)  # world == 1: returns rec
+            m[1].record()
+            kernels.kirchhoff_packed(d['xM'], d['yM'], d['zM'], rec, out=out, R=args.kirchhoff_r,
+                                     uniform_normal=True, table_sincos=ktab)  # slit: n = (0, 1, 0)
+            m[2].record()
+            kev.append(m)
         kstep()
         ksteps = max(1, min(args.steps, 2))
         kms = timed(kstep, ksteps) / ksteps
+        torch.cuda.synchronize()
+        gather_ms = float(np.mean([m[0].elapsed_time(m[1]) for m in kev[1:]]))
+        kernel_ms = float(np.mean([m[1].elapsed_time(m[2]) for m in kev[1:]]))
         pairs = float(N) * M / (kms * 1e-3)
         ktf = FLOP_PER_PAIR * pairs / 1e12
-        kir = {'workload': 'config4: %d samples -> %d receiving points (sharded over %d GPU(s)), fp64, strict '
-                           'numpy rounding' % (N, M, world),
-               'ms': kms, 'pairs_per_s': pairs, 'value': ktf * 1e3, 'unit': 'GFLOP/s (57 flop/pair), all GPUs',
-               'roofline': {'bound': 'fp64', 'achieved': ktf / world, 'peak': dfma_tflops, 'unit': 'TFLOP/s per GPU',
-                            'frac': ktf / world / dfma_tflops, 'traffic': None,
-                            'issue_slot_frac': 65 * 2 * pairs / world / 1e12 / dfma_tflops,
-                            'note': '65 DFMA-pipe instructions per pair in SASS (uniform-normal variant); frac counts '
-                                    'the 57 algorithmic flops, issue_slot_frac the issued ones'}}
+        ktf_kernel = FLOP_PER_PAIR * float(N) * M / (kernel_ms * 1e-3) / 1e12
+        kir = {'workload': 'config4: %d samples -> %d receiving points, fp64, strict numpy rounding; receiving points '
+                           'sharded over %d GPU(s), samples sharded too: packed 128-byte records all-gathered (one '
+                           'collective), then summed on every rank' % (N, M, world),
+               'ms': kms, 'pack_and_allgather_ms': gather_ms, 'kernel_ms': kernel_ms,
+               'allgather_bytes_received_per_gpu': 128 * (N - (nhi - nlo)),
+               'pairs_per_s': pairs, 'value': ktf * 1e3, 'unit': 'GFLOP/s (57 flop/pair), all GPUs',
+               'roofline': {'bound': 'fp64', 'achieved': ktf_kernel / world, 'peak': dfma_tflops,
+                            'unit': 'TFLOP/s per GPU', 'frac': ktf_kernel / world / dfma_tflops, 'traffic': None,
+                            'issue_slot_frac': 63 * 2 * float(N) * M / (kernel_ms * 1e-3) / world / 1e12 / dfma_tflops,
+                            'note': 'kirchhoff_kernel<R=4, strict, uniform normal, table sincos>: 63 DFMA-pipe '
+                                    'instructions per pair in SASS (65 in r01: sin / cos through a 64-entry pi/32 '
+                                    'table); frac counts the 57 algorithmic flops of SURVEY 8d, issue_slot_frac the '
+                                    'issued ones; DMMA shares the FP64 pipe (profiles/r02_kirchhoff_variants.json)'}}
+        del d, out
+
+    # ---- config 5: Undulator (7th harmonic) -> DCM Si(111) -> KB pair -> Screen as rays, then the wave step from the
+    # last KB mirror to a 1024 x 1024 detector with the samples handed over across ranks
+    c5 = None
+    if not args.no_config5:
+        from xrt_b200 import oes, waves
+        g5 = config5_geometry()
+        n5 = int(args.config5_nrays if args.config5_nrays else nrays * 1.25)
+        bl5 = BeamLine()
+        src5 = Undulator(bl5, 'u5', nrays=n5, eE=3., eI=0.5, period=30., n=40, K=1.45, eSigmaX=48.65, eSigmaZ=6.197,
+                         eEpsilonX=0.263, eEpsilonZ=0.008, xPrimeMax=0.03, zPrimeMax=0.03, xPrimeMaxAutoReduce=False,
+                         zPrimeMaxAutoReduce=False, eMin=g5['E0'] - 1., eMax=g5['E0'] + 1., gNodes=64, gIntervals=2,
+                         uniformRayDensity=True, seed=555)
+        src5.reset()
+        au = Material('Au', rho=19.3)
+        P = g5['pitch']
+        dcm5 = oes.DCM(bl5, 'dcm', center=(0, g5['dcm_y'], 0), bragg=g5['theta'], material=g5['si'],
+                       material2=g5['si'], cryst2perpTransl=10., limPhysX=[-20, 20], limPhysY=[-60, 60],
+                       limPhysX2=[-20, 20], limPhysY2=[-60, 120])
+        z1 = g5['dcm_offset']
+        vfm = oes.EllipticalMirrorParam(bl5, 'vfm', center=(0, g5['vfm_y'], z1), pitch=P, p=g5['vfm_y'],
+                                        q=g5['scr_y'] - g5['vfm_y'], isCylindrical=True, material=au,
+                                        limPhysX=[-5, 5], limPhysY=[-150, 150])
+        dyh = g5['hfm_y'] - g5['vfm_y']
+        hfm = oes.EllipticalMirrorParam(bl5, 'hfm', center=(0, g5['vfm_y'] + dyh * np.cos(2 * P),
+                                                          z1 + dyh * np.sin(2 * P)),
+                                        pitch=P, positionRoll=np.pi / 2, p=g5['hfm_y'], q=g5['scr_y'] - g5['hfm_y'],
+                                        isCylindrical=True, material=au, limPhysX=[-5, 5], limPhysY=[-150, 150],
+                                        extraPitch=2 * P)
+        dys = g5['scr_y'] - g5['hfm_y']
+        scr5 = Screen(bl5, 'scr5', center=(0, hfm.center[1] + dys * np.cos(2 * P),
+                                           hfm.center[2] + dys * np.sin(2 * P)))
+        marks5 = []
+
+        def step5(keep_local=False):
+            m = [ev() for _ in range(5)]
+            off5 = rank * n5
+            beam = Beam(n5, withAmplitudes=True, uninitialized=True)
+            m[0].record()
+            src5.shine_uniform_fused(beam, index_offset=off5)
+            m[1].record()
+            d1 = dcm5.double_reflect(beam, needLocal=False, checkTables=False, index_offset=off5, allreduce=ar)[0]
+            del beam
+            m[2].record()
+            d2 = vfm.reflect(d1, needLocal=False, checkTables=False, index_offset=off5, allreduce=ar)[0]
+            del d1
+            m[3].record()
+            d3, lb3 = hfm.reflect(d2, needLocal=keep_local, checkTables=False, index_offset=off5, allreduce=ar,
+                                  exposeOn=scr5)
+            m[4].record()
+            marks5.append(m)
+            return d3, (lb3 if keep_local else None)
+        d3, lb3 = step5(keep_local=True)
+        good5 = float((d3.state == 1).sum()) / len(d3)
+        del d3
+        n5s = max(1, min(args.steps, 3))
+        ms5 = timed(step5, n5s) / n5s
+        torch.cuda.synchronize()
+        st5 = {nm: float(np.mean([m[i].elapsed_time(m[i + 1]) for m in marks5[1:]]))
+               for i, nm in enumerate(('shine (64 nodes)', 'dcm.double_reflect (2 crystals)', 'vfm.reflect',
+                                       'hfm.reflect + screen.expose (fused)'))}
+        # wave step: N5 good rays of the last mirror's local beam (this rank's share) diffract to the detector mesh
+        N5 = args.config5_wave_n
+        side = int(round(args.config5_wave_m ** 0.5))
+        idx = torch.nonzero(lb3.state == 1).flatten()[:N5 // world]
+        lbs = Beam(len(idx), withAmplitudes=True, device=lb3.device, uninitialized=True)
+        for k, t in lb3.tensors().items():
+            if hasattr(lbs, k):
+                setattr(lbs, k, t[idx].contiguous())
+        for k in ('s', 'phi', 'r', 'theta'):
+            if hasattr(lb3, k):
+                setattr(lbs, k, getattr(lb3, k)[idx].contiguous())
+        del lb3
+        zlo, zhi = comm.shard(side)
+        xmesh = np.linspace(-0.05, 0.05, side)
+        zmesh = np.linspace(-0.05, 0.05, side)[zlo:zhi]
+        wev = []
+
+        def wave5():
+            m = [ev(), ev()]
+            wave = scr5.prepare_wave(hfm, xmesh, zmesh)
+            lbs.area = 0
+            m[0].record()
+            waves.diffract(lbs, wave, comm=comm, samplesSharded=world > 1)
+            m[1].record()
+            wev.append(m)
+            return wave
+        w = wave5()
+        Mw = side * side
+        Nw = int(comm.allreduce_sum(torch.tensor([len(lbs)], dtype=torch.int64, device='cuda')).item())
+        del w
+        msw = timed(wave5, 1)
+        pairs5 = float(Nw) * Mw / (msw * 1e-3)
+        c5 = {'workload': 'config5: Undulator(7th harmonic, 64 nodes) -> DCM Si(111) -> vertical + horizontal '
+                          'elliptical KB -> Screen, %d rays per GPU (x %d GPUs); then wave mode: %d good rays of the '
+                          'last mirror (each rank\'s share, records all-gathered) -> Kirchhoff sum to a %d x %d '
+                          'detector sharded by rows' % (n5, world, Nw, side, side),
+              'rays': {'ms_per_step': ms5, 'value': world * n5 / (ms5 * 1e-3) / 1e6, 'unit': 'Mrays/s',
+                       'good_fraction_on_screen': good5, 'stages_ms': st5},
+              'wave': {'ms': msw, 'samples': Nw, 'receiving_points': Mw, 'pairs_per_s': pairs5,
+                       'value': FLOP_PER_PAIR * pairs5 / 1e9, 'unit': 'GFLOP/s (57 flop/pair), all GPUs',
+                       'frac_of_fp64_peak_per_gpu': FLOP_PER_PAIR * pairs5 / 1e12 / world / dfma_tflops,
+                       'note': 'waves.diffract(comm=, samplesSharded=True) through the general-normal kernel (the KB '
+                               'surface normals differ per sample); includes prepare-side packing, the all-gather '
+                               'and the post-processing of diffract'}}
+        del lbs
 
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': 'Mrays/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
                 'config': {'workload': WORKLOAD, 'rays_per_gpu': nrays, 'nodes': nodes, 'with_amplitudes': True,
+                           'chain': 'reflect + expose fused in one kernel (lb materialised)' if fused_chain else
+                                    'three separate calls (gb through HBM)',
                            'l2': 'inputs larger than L2 (>= 13 GB of Beam arrays per step)',
-                           'parallelism': 'rays sharded over %d GPU(s), gather=%s' % (world, args.gather)},
+                           'parallelism': 'rays sharded over %d GPU(s); slot all-reduce %s' % (
+                               world, 'through the C-ABI NCCL entry points' if world > 1 and not args.torch_collectives
+                               else ('torch.distributed' if world > 1 else 'n/a'))},
                 'e2e': {'value': e2e_value, 'unit': 'Mrays/s', 'h2d_bytes_per_step': h2d,
                         'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e,
-                        **({'note': e2e_note} if e2e_note else {})},
-                'e2e_histogram': e2e_hist,
-                'gpu_launches': args.steps * (9 if args.unfused_source else 7),  # source (1 fused or 3), 2 slot inits,
-                # pre-pass A/B, reflect main, expose
+                        'note': 'the WHOLE screen Beam (132 B x every ray) to pinned host memory on a copy stream; '
+                                'PCIe / host-memory bound: see d2h_bandwidth; e2e_compact and e2e_histogram move what a '
+                                'consumer reads' + ('; ' + e2e_note if e2e_note else '')},
+                'd2h_bandwidth': d2h_gbs, 'e2e_compact': e2e_compact, 'e2e_histogram': e2e_hist,
+                'gather_beam': gather_rep,
+                'gpu_launches': (launches[0] * args.steps) if launches else args.steps * (7 if fused_chain else 8),
+                'gpu_launches_source': ('torch profiler (CUPTI) on one step: %d kernels of libxrt_b200.so, %d others'
+                                        % launches) if launches else 'static count of the call path',
                 'clocks': sampler.summary(),
-                'roofline': roofline, 'roofline_second_kernel': roofline_other, 'stages': hbm, 'shine_rejection': rej, 'dcm': dcm_rep, 'kirchhoff': kir,
+                'roofline': roofline, 'roofline_second_kernel': roofline_other, 'stages': hbm, 'chain_ms_per_step': chain,
+                'shine_rejection': rej, 'dcm': dcm_rep, 'kirchhoff': kir, 'config5': c5,
                 'cpu_baseline': cpu_baseline() if world == 1 and not args.no_cpu_baseline else None}
         print(json.dumps(_finite(line)))
     if world > 1:
+        comm.close()
         dist.destroy_process_group()
 
 
@@ -552,13 +817,18 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--nrays', type=int, default=100000000, help='rays per GPU per step')
-    ap.add_argument('--gather', default='none', choices=['none', 'beam'])
+    ap.add_argument('--unfused-chain', action='store_true',
+                    help='time reflect and expose as separate calls (the global beam goes through HBM)')
+    ap.add_argument('--torch-collectives', action='store_true',
+                    help='exchange steps through torch.distributed instead of the C-ABI NCCL entry points')
+    ap.add_argument('--no-config5', action='store_true', help='skip the config-5 (DCM + KB + wave) sub-report')
+    ap.add_argument('--config5-nrays', type=int, default=0, help='rays per GPU in config 5 (default 1.25 x --nrays)')
+    ap.add_argument('--config5-wave-n', type=int, default=1000000)
+    ap.add_argument('--config5-wave-m', type=int, default=1024 * 1024)
     ap.add_argument('--no-kirchhoff', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-rejection', action='store_true')
     ap.add_argument('--no-dcm', action='store_true', help='skip the config-3 (DCM) sub-report')
-    ap.add_argument('--unfused-source', action='store_true',
-                    help='time Undulator.shine as three kernels (sample, field integral, fill) instead of the fused one')
     ap.add_argument('--kirchhoff-n', type=int, default=1000000)
     ap.add_argument('--kirchhoff-m', type=int, default=1024 * 1024)
     ap.add_argument('--kirchhoff-r', type=int, default=4)

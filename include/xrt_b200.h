@@ -41,7 +41,7 @@ int xrt_b200_fp64_probe(int mode, int iters, double* tflops, double* ms);
 
 /* Known-answer access to the device math helpers the kernels are built from (host arrays; tests only):
  * which 0 sincos_big -> (sin, cos); 1 sin_big; 2 rcp_fast; 3 sqrt_rsqrt -> (sqrt, 1/sqrt); 4 (K_1/3, K_2/3);
- * 6 rcp_cubic; 7 sqrt_hrsqrt -> (sqrt, 0.5/sqrt). */
+ * 6 rcp_cubic; 7 sqrt_hrsqrt -> (sqrt, 0.5/sqrt); 8 sincos_tab -> (sin, cos). */
 int xrt_b200_math_probe_host(int which, size_t n, const double* x, double* y0, double* y1);
 
 /* ------------------------------------------------------------------ a17: Fresnel-Kirchhoff sum
@@ -53,12 +53,27 @@ int xrt_b200_math_probe_host(int which, size_t n, const double* x, double* y0, d
  *        bit1 = OpenCL sign/scale convention (default numpy convention, waves.py:844-850)
  *        bits4-6 = register blocking R in {1,2,4} (0 = default 2)
  *        bit9 = all N normals are equal (aperture, flat OE): n.d = n.p - n.q with n.p hoisted per output
+ *        bit11 = sin / cos of the phase through a 64-entry (pi/32) table in shared memory + short polynomials
+ *                instead of the two pi/2-range polynomials (same <= 4e-16 accuracy, 10 % faster).  The caller
+ *                vouches for |k r| < 2^47 rad (1.4e14: 100 keV over 280 m) for every pair; the kernel does not test
  * `workspace` must hold xrt_kirchhoff_workspace_bytes(M, N, flags) bytes of device memory. */
 size_t xrt_kirchhoff_workspace_bytes(size_t M, size_t N, int flags);
 int xrt_kirchhoff_f64(size_t M, size_t N, const double* xM, const double* yM, const double* zM, const double* nl,
                       const double* Es, const double* Ep, const double* k, const double* pos, int pos_stride,
                       const double* nrm, int nrm_stride, double* S, double* P, double* A, double* B, double* C,
                       int flags, void* workspace, void* stream);
+/* The same sum in two steps, for samples that are ray shards of several ranks (shard the M receiving
+ * points, all-gather the N samples): xrt_kirchhoff_pack_f64 turns this rank's samples into 128-byte records
+ * (`records`: N * 128 bytes of device memory), the host all-gathers the records (xrt_allgather_bytes), and
+ * xrt_kirchhoff_packed_f64 sums over all of them.  workspace: xrt_kirchhoff_workspace_bytes(M, N, flags) bytes is
+ * enough (it only holds the split partial sums here).  With bit9 the common normal is the first record's. */
+#define XRT_KIRCHHOFF_RECORD_BYTES 128
+int xrt_kirchhoff_pack_f64(size_t N, const double* nl, const double* Es, const double* Ep, const double* k,
+                           const double* pos, int pos_stride, const double* nrm, int nrm_stride, void* records,
+                           void* stream);
+int xrt_kirchhoff_packed_f64(size_t M, size_t N, const double* xM, const double* yM, const double* zM,
+                             const void* records, double* S, double* P, double* A, double* B, double* C, int flags,
+                             void* workspace, void* stream);
 int xrt_kirchhoff_f64_host(size_t M, size_t N, const double* xM, const double* yM, const double* zM,
                            const double* nl, const double* Es, const double* Ep, const double* k, const double* pos,
                            int pos_stride, const double* nrm, int nrm_stride, double* S, double* P, double* A,
@@ -517,6 +532,40 @@ typedef struct xrt_plot_params {
 } xrt_plot_params;
 
 int xrt_plot_hist_f64(size_t n, const xrt_plot_params* plot, void* stream);
+
+/* ------------------------------------------------------------------ what leaves the GPU: selected rays, selected fields
+ * Dense copies, in ray order, of up to 8 arrays restricted to the rays raycing.get_output would select
+ * (raycing/__init__.py:170-300).  state_mask: bit0 state == 1 (good), bit1 2 (out), bit2 3 (over), bit3 < 0 (lost),
+ * bit4 other positive, bit5 zero -- the mask of xrt_hist2d_f64.  src[k] / dst[k]: DEVICE arrays of words[k] (1 or 2)
+ * 8-byte words per ray (2: complex128); the table of pointers itself is HOST memory.  scratch: device memory of
+ * xrt_compact_scratch_words(n) uint64; afterwards its LAST word holds the number of selected rays (read it with an
+ * 8-byte copy, then copy that many elements of each dst to the host). */
+size_t xrt_compact_scratch_words(size_t n);
+int xrt_compact_rays_f64(size_t n, const int32_t* state, int state_mask, int narr, const double* const* src,
+                         double* const* dst, const int* words, uint64_t* scratch, void* stream);
+
+/* ------------------------------------------------------------------ multi-GPU exchange steps (one process per GPU)
+ * Replace the multi-device slicing of XRT_CL.run_parallel_max (myopencl.py:455-583: sliced arguments are cut into one
+ * chunk per device, results copied back into the host slices) for hosts that shard rays / receiving points over
+ * processes.  NCCL is loaded with dlopen at first use.  `comm` is an ncclComm_t: an existing one, or
+ * one made by xrt_nccl_comm_init from the 128-byte id rank 0 obtains with xrt_nccl_unique_id and passes to the
+ * other ranks over any host channel.  All buffers are DEVICE pointers; calls are asynchronous on `stream`. */
+int xrt_nccl_unique_id(void* id128);
+int xrt_nccl_comm_init(int world, int rank, const void* id128, void** comm);
+int xrt_nccl_comm_destroy(void* comm);
+/* min / max / sum of the 64 reduction slots over all ranks, in place (between the pre-passes and the main pass of
+ * xrt_reflect_f64; base.py:861-871, :1257-1263 take these over the whole beam).  sums = 0 keeps this rank's counter
+ * slots (they were summed by an earlier call).  scratch: world * 64 uint64 of device memory. */
+int xrt_allreduce_slots(void* comm, int world, uint64_t* reductions, int sums, uint64_t* scratch, void* stream);
+/* 0 = max, 1 = min, 2 = sum: how slot `slot` combines (the table xrt_allreduce_slots applies) */
+int xrt_slot_kind(int slot);
+/* The all-gather of the Beam SoA at a Screen: rank r contributes counts[r] rays (shards may be ragged), every rank
+ * receives all of them in rank order in `out` (sum(counts) rays).  One grouped NCCL operation for all arrays. */
+int xrt_allgather_beam(void* comm, int world, int rank, const uint64_t* counts, const xrt_beam* in,
+                       const xrt_beam* out, void* stream);
+/* all-gather-v of raw bytes (the packed input records of the Kirchhoff sum, xrt_kirchhoff_pack_f64): counts in bytes */
+int xrt_allgather_bytes(void* comm, int world, int rank, const uint64_t* counts, const void* in, void* out,
+                        void* stream);
 
 #ifdef __cplusplus
 }

@@ -140,3 +140,91 @@ def test_cuda_linearity_full_size_property(cuda_device):
     for f, p0, p1 in zip(full, parts[0], parts[1]):
         scale = np.abs(f).max()
         assert np.abs(f - (p0 + p1)).max() < 1e-11 * scale * 60
+
+
+def _dev_case(case, rows=None):
+    import torch
+    d = {}
+    for key in ('xM', 'yM', 'zM'):
+        v = case[key] if rows is None else case[key][rows]
+        d[key] = torch.from_numpy(np.ascontiguousarray(v)).cuda()
+    for key in ('nl', 'k', 'Es', 'Ep'):
+        d[key] = torch.from_numpy(np.ascontiguousarray(case[key])).cuda()
+    d['pos'] = torch.from_numpy(np.ascontiguousarray(case['pos'].T)).cuda()
+    d['nrm'] = torch.from_numpy(np.ascontiguousarray(case['nrm'].T)).cuda()
+    return d
+
+
+def _kernel(d, **kw):
+    from xrt_b200 import kernels
+    return kernels.kirchhoff(d['xM'], d['yM'], d['zM'], d['nl'], d['Es'], d['Ep'], d['k'], d['pos'], d['nrm'],
+                             **kw).cpu().numpy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('N,M', [(1, 1), (3, 5), (129, 257), (1000, 300), (5000, 2048), (20000, 64), (40000, 700)])
+@pytest.mark.parametrize('R', [1, 2, 4])
+@pytest.mark.parametrize('table', [False, True])
+def test_cuda_uniform_normal_fast_path_vs_oracle(N, M, R, table, cuda_device):
+    """The variant the bench times (R = 4, uniform_normal, strict, table sincos) and its siblings on the ragged-shape
+    matrix: an aperture (one common normal), every register blocking, both sincos forms, split-N for small M."""
+    case = synthetic.kirchhoff_case(500 + N, N, M, tilt=False)  # n = (0, 1, 0) for every sample
+    d = _dev_case(case)
+    res = _kernel(d, R=R, uniform_normal=True, table_sincos=table)
+    gen = _kernel(d, R=R, uniform_normal=False, table_sincos=table)
+    n = [case['n'][i] for i in range(3)]
+    args = (case['x'], case['y'], case['z'], n, case['nl'], case['Es'], case['Ep'], case['E'], case['xM'], case['yM'],
+            case['zM'])
+    ref = ok.diffraction_integral(*args)
+    sc = ok.term_magnitude_sum(*args)
+    for r, g, o, s in zip(res, gen, ref, sc):
+        assert (np.abs(r - o) / s).max() < TOL
+        assert (np.abs(g - o) / s).max() < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('tilt', [False, True])
+def test_cuda_packed_records_path_equals_one_call(tilt, cuda_device):
+    """xrt_kirchhoff_pack_f64 + xrt_kirchhoff_packed_f64 (what ranks run after all-gathering the records of their ray
+    shards) == xrt_kirchhoff_f64, bit for bit; records concatenated from two 'ranks' included."""
+    import torch
+    from xrt_b200 import kernels
+    case = synthetic.kirchhoff_case(901, 7001, 1500, tilt=tilt)
+    d = _dev_case(case)
+    one = _kernel(d, R=4, uniform_normal=not tilt)
+    h = 3000
+    recs = [kernels.kirchhoff_pack(d['nl'][sl].contiguous(), d['Es'][sl].contiguous(), d['Ep'][sl].contiguous(),
+                                   d['k'][sl].contiguous(), d['pos'][sl].contiguous(), d['nrm'][sl].contiguous())
+            for sl in (slice(0, h), slice(h, None))]
+    rec = torch.cat(recs).contiguous()
+    two = kernels.kirchhoff_packed(d['xM'], d['yM'], d['zM'], rec, R=4, uniform_normal=not tilt).cpu().numpy()
+    assert np.array_equal(one.view(np.float64), two.view(np.float64))
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+def test_cuda_config4_rows_against_oracle_at_full_input_size(cuda_device):
+    """BASELINE.json configs[3] at its real input size: 256 random receiving points of the 1024 x 1024
+    screen against ALL 1e6 slit samples -- 2.6e8 pairs through oracle.kirchhoff in blocks -- with the kernel variant and
+    flags the bench runs (R = 4, uniform normal, strict numpy rounding, table sincos)."""
+    N, M = 1000000, 1024 * 1024
+    case = synthetic.kirchhoff_case(7, N, M, mesh=True)
+    rows = np.sort(np.random.RandomState(4).choice(M, 256, replace=False))
+    d = _dev_case(case, rows)
+    res = _kernel(d, R=4, uniform_normal=True, table_sincos=True)
+    n = [case['n'][i] for i in range(3)]
+    xM, yM, zM = case['xM'][rows], case['yM'][rows], case['zM'][rows]
+    ref = [np.zeros(256, dtype=np.complex128) for _ in range(5)]
+    sc = [np.zeros(256) for _ in range(5)]
+    step = 50000
+    for j0 in range(0, N, step):
+        sl = slice(j0, j0 + step)
+        args = (case['x'][sl], case['y'][sl], case['z'][sl], [v[sl] for v in n], case['nl'][sl], case['Es'][sl],
+                case['Ep'][sl], case['E'][sl], xM, yM, zM)
+        for acc, part in zip(ref, ok.diffraction_integral(*args)):
+            acc += part
+        for acc, part in zip(sc, ok.term_magnitude_sum(*args)):
+            acc += part
+    for r, o, s in zip(res, ref, sc):
+        # the oracle's own blocked float64 accumulation differs from a single pass by ~sqrt(N) eps of the term sum
+        assert (np.abs(r - o) / s).max() < 10 * TOL

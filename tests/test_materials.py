@@ -86,3 +86,51 @@ def test_host_alignment_helpers_match_oracle():
     assert np.array_equal(si.get_Bragg_angle(E), o.get_Bragg_angle(E))
     assert np.array_equal(si.get_dtheta(E), o.get_dtheta(E))
     assert np.array_equal(si.get_dtheta(E, 0.05), o.get_dtheta(E, 0.05))
+
+
+@pytest.mark.gpu
+def test_run_parallel_get_amplitude_kernel_interface(cuda_device):
+    """XRT_CUDA.run_parallel('get_amplitude', ...) with the argument list of the reference kernel
+    (cl/materials.cl:715-748): the silicon cell given atom by atom (8 atoms of the diamond cubic cell, occupancy 1),
+    scattering-factor tables as maxEl x 300 vectors; results against the reference's numpy Crystal.get_amplitude."""
+    from xrt_b200.cuda_backend import XRT_CUDA
+    from xrt_b200.materials import CrystalSi
+    g = golden('amplitude_crystals')
+    fcc = np.array([[0, 0, 0], [0, .5, .5], [.5, 0, .5], [.5, .5, 0]])
+    xyz = np.concatenate([fcc, fcc + 0.25])
+    cl = XRT_CUDA(r'materials.cl')
+    for key in _crystal_keys(g):
+        hkl = tuple(int(c) for c in key[2:5])
+        si = CrystalSi(hkl=hkl)
+        el = si.elements[0]
+        maxEl = len(xyz)
+        nt = len(el.E)
+        elements = np.zeros((maxEl, 8))
+        elements[:, :3] = xyz
+        elements[:, 4] = 1.
+        elements[:, 5] = el.Z
+        elements[:, 7] = nt
+        f0cfs = np.tile(np.asarray(el.f0coeffs, dtype=float), maxEl)
+        vec = lambda a: np.concatenate([np.pad(np.asarray(a, dtype=float), (0, 300 - nt))] * maxEl)  # noqa: E731
+        E = g[key + '_E']
+        n = len(E)
+        rs = np.zeros(n, dtype=np.complex128)
+        rp = np.zeros(n, dtype=np.complex128)
+        out = cl.run_parallel(
+            'get_amplitude', scalarArgs=[np.array(list(hkl) + [0], dtype=np.int32), np.float64(1.), np.float64(0.),
+                                         np.int32(2), np.int32(maxEl)],
+            slicedROArgs=[g[key + '_g0'], g[key + '_gh'], g[key + '_hns0'], E, np.full(n, si.d),
+                          np.full(n, si.chiToF)],
+            nonSlicedROArgs=[elements.ravel(), f0cfs, vec(el.E), vec(el.f1), vec(el.f2)],
+            slicedRWArgs=[rs, rp], dimension=n)
+        assert out[0] is rs and out[1] is rp  # RW arrays are written in place and returned (myopencl.py:550-583)
+        assert np.abs(rs - g[key + '_rs']).max() < ATOL, key
+        assert np.abs(rp - g[key + '_rp']).max() < ATOL, key
+    # a cell of two different elements is refused, not silently approximated
+    elements[1, 5] += 1
+    with pytest.raises(NotImplementedError):
+        cl.run_parallel('get_amplitude', scalarArgs=[np.array([1, 1, 1, 0]), 1., 0., 2, maxEl],
+                        slicedROArgs=[g[key + '_g0'], g[key + '_gh'], g[key + '_hns0'], E, np.full(n, si.d),
+                                      np.full(n, si.chiToF)],
+                        nonSlicedROArgs=[elements.ravel(), f0cfs, vec(el.E), vec(el.f1), vec(el.f2)],
+                        slicedRWArgs=[rs, rp], dimension=n)

@@ -170,3 +170,25 @@ def test_cuda_expose_hemispheric_vs_golden(cuda_device):
     ok = g['out_state'] > 0
     assert np.abs(blo['theta'][ok] - g['out_theta'][ok]).max() <= 1e-12
     assert np.abs(blo['phi'][ok] - g['out_phi'][ok]).max() <= 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('n', [0, 1, 1023, 1024, 1025, 300007])
+def test_beam_to_host_compacts_selected_rays_in_order(n, cuda_device):
+    """Beam.to_host(fields, good_only=True): xrt_compact_rays_f64 == numpy boolean indexing (what raycing.get_output
+    does on the host, raycing/__init__.py:170-300), ray order kept, complex fields included."""
+    import torch
+    from xrt_b200.beams import Beam
+    rng = np.random.RandomState(n + 5)
+    arrs = dict(x=rng.normal(size=n), z=rng.normal(size=n), E=rng.uniform(8e3, 9e3, n), Jss=rng.rand(n), Jpp=rng.rand(n),
+                y=np.zeros(n), a=np.zeros(n), b=np.ones(n), c=np.zeros(n), path=rng.rand(n),
+                Jsp=rng.normal(size=n) + 1j * rng.normal(size=n), Es=rng.normal(size=n) + 1j * rng.normal(size=n),
+                Ep=rng.normal(size=n) * (1 + 0j), state=rng.choice([1, 1, 1, 2, 3, -5, -2001], n).astype(np.int32))
+    b = Beam.from_numpy(arrs)
+    for flags, sel in (((1,), arrs['state'] == 1), ((1, 2), (arrs['state'] == 1) | (arrs['state'] == 2)),
+                       ((4,), arrs['state'] < 0), ((1, 2, 3, 4), np.ones(n, dtype=bool))):
+        got = b.to_host(fields=('x', 'z', 'E', 'Jss', 'Jpp', 'Es', 'Jsp', 'path', 'Ep'), rayFlag=flags)
+        for k, v in got.items():
+            assert np.array_equal(v, arrs[k][sel]), (k, flags)
+    whole = b.to_host(fields=('x', 'Es'), good_only=False)
+    assert np.array_equal(whole['x'], arrs['x']) and np.array_equal(whole['Es'], arrs['Es'])

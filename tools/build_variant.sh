@@ -15,6 +15,6 @@ OBJS=""
 for o in "$ROOT"/build/obj/*.o; do
   if [ "$(basename $o)" != "${SRC%.cu}.o" ]; then OBJS="$OBJS $o"; fi
 done
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o "$ROOT/variants/$TAG/libxrt_b200.so" "$ROOT/variants/$TAG/${SRC%.cu}.o" $OBJS
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o "$ROOT/variants/$TAG/libxrt_b200.so" "$ROOT/variants/$TAG/${SRC%.cu}.o" $OBJS -ldl
 rm -f "$ROOT/variants/$TAG/${SRC%.cu}.o"
 echo "built variants/$TAG/libxrt_b200.so"

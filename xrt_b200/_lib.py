@@ -32,6 +32,8 @@ PROTOTYPES = {
     'xrt_kirchhoff_workspace_bytes': (c_sz, [c_sz, c_sz, c_int]),
     'xrt_kirchhoff_f64': (c_int, [c_sz, c_sz] + [c_dp] * 8 + [c_int, c_dp, c_int] + [c_dp] * 5 +
                           [c_int, c_dp, c_dp]),
+    'xrt_kirchhoff_pack_f64': (c_int, [c_sz] + [c_dp] * 5 + [c_int, c_dp, c_int, c_dp, c_dp]),
+    'xrt_kirchhoff_packed_f64': (c_int, [c_sz, c_sz] + [c_dp] * 9 + [c_int, c_dp, c_dp]),
     'xrt_kirchhoff_f64_host': (c_int, [c_sz, c_sz] + [c_dp] * 8 + [c_int, c_dp, c_int] + [c_dp] * 5 + [c_int]),
     'xrt_undulator_f64': (c_int, [c_sz, c_int, c_dbl, c_dbl, c_dbl] + [c_dp] * 14 + [c_int, c_dp]),
     'xrt_undulator_f64_host': (c_int, [c_sz, c_int, c_dbl, c_dbl, c_dbl] + [c_dp] * 14 + [c_int]),
@@ -68,6 +70,15 @@ PROTOTYPES = {
     'xrt_bm_shine_uniform_f64': (c_int, [c_sz, ctypes.c_uint64, ctypes.c_uint64, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
     'xrt_custom_field_f64': (c_int, [c_sz, c_int, c_dbl, c_dbl] + [c_dp] * 16 + [c_dp]),
     'xrt_custom_field_f64_host': (c_int, [c_sz, c_int, c_dbl, c_dbl] + [c_dp] * 16),
+    'xrt_compact_scratch_words': (c_sz, [c_sz]),
+    'xrt_compact_rays_f64': (c_int, [c_sz, c_dp, c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    'xrt_nccl_unique_id': (c_int, [c_dp]),
+    'xrt_nccl_comm_init': (c_int, [c_int, c_int, c_dp, ctypes.POINTER(ctypes.c_void_p)]),
+    'xrt_nccl_comm_destroy': (c_int, [c_dp]),
+    'xrt_allreduce_slots': (c_int, [c_dp, c_int, c_dp, c_int, c_dp, c_dp]),
+    'xrt_slot_kind': (c_int, [c_int]),
+    'xrt_allgather_beam': (c_int, [c_dp, c_int, c_int, c_dp, c_dp, c_dp, c_dp]),
+    'xrt_allgather_bytes': (c_int, [c_dp, c_int, c_int, c_dp, c_dp, c_dp, c_dp]),
     'xrt_undulator_imap_f64': (c_int, [c_sz, c_int] + [c_dbl] * 7 + [c_int] + [c_dp] * 13 + [c_int, c_dp]),
 }
 

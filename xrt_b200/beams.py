@@ -138,6 +138,71 @@ class Beam(object):
             out[k] = v.cpu().numpy() if isinstance(v, torch.Tensor) else v
         return out
 
+    _STATE_BITS = {1: 1, 2: 2, 3: 4, 'lost': 8, 'other': 16, 0: 32}
+
+    def to_host(self, fields=('x', 'z', 'E', 'Jss', 'Jpp'), good_only=True, rayFlag=(1,), out=None, stream=None):
+        """The fields a consumer of a repeat reads, of the rays it reads them for, as numpy arrays -- and only those
+        cross PCIe.  raycing.get_output (raycing/__init__.py:170-300) takes a few attributes of the rays whose state
+        is in the plot's rayFlag; moving the whole SoA (132 B x every ray) to the host for that is ~5x the bytes.
+
+        *good_only* / *rayFlag*: which states are kept (1 good, 2 out, 3 over, 4 lost = negative states), in ray
+        order; good_only=False keeps every ray (no compaction, plain copies of the chosen fields).
+        *out*: optional dict of pinned host tensors to copy into (a reusable result buffer, each at least as long as
+        the selection); returned views are cut to the selected length.
+        Device side: xrt_compact_rays_f64 (count, scan, scatter), stream-ordered; one 8-byte read tells the host
+        the selected count, then one copy per field."""
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        n = len(self)
+        dev = self.device
+        names = list(fields)
+        tens = [getattr(self, k) for k in names]
+        if not good_only:
+            res = {}
+            for k, t in zip(names, tens):
+                if out is not None and k in out:
+                    out[k][:n].copy_(t, non_blocking=True)
+                    res[k] = out[k][:n]
+                else:
+                    res[k] = t.cpu()
+            torch.cuda.current_stream().synchronize()
+            return {k: v.numpy() for k, v in res.items()}
+        mask = 0
+        for f in rayFlag:
+            mask |= {1: 1, 2: 2, 3: 4, 4: 8}[int(f)]
+        if n == 0:
+            return {k: t.cpu().numpy() for k, t in zip(names, tens)}
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        key = '_compact_scratch'
+        scratch = self.__dict__.get(key)
+        need = lib.xrt_compact_scratch_words(n)
+        if scratch is None or scratch.numel() < need:
+            scratch = torch.empty(need, dtype=torch.int64, device=dev)
+        dst = [torch.empty_like(t) for t in tens]
+        res = {}
+        for c0 in range(0, len(names), 8):
+            grp = list(range(c0, min(c0 + 8, len(names))))
+            m = len(grp)
+            src_p = (ctypes.c_void_p * m)(*[tens[i].data_ptr() for i in grp])
+            dst_p = (ctypes.c_void_p * m)(*[dst[i].data_ptr() for i in grp])
+            words = (ctypes.c_int * m)(*[2 if tens[i].is_complex() else 1 for i in grp])
+            for i in grp:
+                if tens[i].element_size() not in (8, 16) or not tens[i].is_contiguous():
+                    raise ValueError('to_host: {0} is not a contiguous float64 / complex128 array'.format(names[i]))
+            _lib.check(lib.xrt_compact_rays_f64(n, self.state.data_ptr(), mask, m, ctypes.addressof(src_p),
+                                                ctypes.addressof(dst_p), ctypes.addressof(words),
+                                                scratch.data_ptr(), st), 'xrt_compact_rays_f64')
+        cnt = int(scratch[need - 1].item())  # the one host synchronisation: how many rays were selected
+        for k, d in zip(names, dst):
+            if out is not None and k in out:
+                out[k][:cnt].copy_(d[:cnt], non_blocking=True)
+                res[k] = out[k][:cnt]
+            else:
+                res[k] = d[:cnt].cpu()
+        torch.cuda.current_stream().synchronize()
+        return {k: v.numpy() for k, v in res.items()}
+
     def __array__(self):  # pragma: no cover - convenience for interactive use
         raise TypeError('Beam is a container; use beam.to_numpy()')
 

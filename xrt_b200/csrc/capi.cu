@@ -106,6 +106,9 @@ static int fp64_probe(int mode, int iters, double* tflops, double* ms_out) {
 // ---------------------------------------------------------------- device math helpers, exposed for known-answer tests
 __global__ void math_probe_kernel(int which, size_t n, const double* __restrict__ x, double* __restrict__ y0,
                                   double* __restrict__ y1) {
+  __shared__ double2 sctab[64];
+  sincos_tab_fill(sctab, threadIdx.x);
+  __syncthreads();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double v = x[i];
@@ -118,6 +121,7 @@ __global__ void math_probe_kernel(int which, size_t n, const double* __restrict_
     case 4: bessel_k13_k23(v, a, b); break;
     case 6: a = rcp_cubic(v); break;
     case 7: sqrt_hrsqrt(v, a, b); break;
+    case 8: sincos_tab(v, sctab, a, b); break;
     default: break;
   }
   y0[i] = a;
@@ -219,6 +223,21 @@ int xrt_kirchhoff_f64(size_t M, size_t N, const double* xM, const double* yM, co
                           workspace, (cudaStream_t)stream);
 }
 
+int xrt_kirchhoff_pack_f64(size_t N, const double* nl, const double* Es, const double* Ep, const double* k,
+                           const double* pos, int pos_stride, const double* nrm, int nrm_stride, void* records,
+                           void* stream) {
+  XRTB_REQUIRE(pos_stride >= 3 && nrm_stride >= 3, "kirchhoff_pack: pos/nrm strides must be >= 3");
+  XRTB_REQUIRE(N == 0 || (nl && Es && Ep && k && pos && nrm && records), "kirchhoff_pack: NULL argument");
+  return kirchhoff_pack_device(N, nl, Es, Ep, k, pos, pos_stride, nrm, nrm_stride, records, (cudaStream_t)stream);
+}
+
+int xrt_kirchhoff_packed_f64(size_t M, size_t N, const double* xM, const double* yM, const double* zM,
+                             const void* records, double* S, double* P, double* A, double* B, double* C, int flags,
+                             void* workspace, void* stream) {
+  XRTB_REQUIRE(workspace != nullptr && (N == 0 || records != nullptr), "kirchhoff_packed: NULL argument");
+  return kirchhoff_packed_device(M, N, xM, yM, zM, records, S, P, A, B, C, flags, workspace, (cudaStream_t)stream);
+}
+
 int xrt_kirchhoff_f64_host(size_t M, size_t N, const double* xM, const double* yM, const double* zM,
                            const double* nl, const double* Es, const double* Ep, const double* k, const double* pos,
                            int pos_stride, const double* nrm, int nrm_stride, double* S, double* P, double* A,
@@ -249,7 +268,7 @@ int xrt_kirchhoff_f64_host(size_t M, size_t N, const double* xM, const double* y
 
 int xrt_b200_math_probe_host(int which, size_t n, const double* x, double* y0, double* y1) {
   if (n == 0) return 0;
-  XRTB_REQUIRE(which >= 0 && which <= 7 && x && y0 && y1, "math_probe: bad arguments");
+  XRTB_REQUIRE(which >= 0 && which <= 8 && x && y0 && y1, "math_probe: bad arguments");
   cudaStream_t st = 0;
   DevBuf dx, out;
   if (dx.upload(x, n * 8, st) || out.alloc(2 * n * 8)) return 1;
@@ -651,6 +670,14 @@ int xrt_oe_normals_f64(size_t n, const xrt_oe_params* oe, const double* x, const
 
 int xrt_plot_hist_f64(size_t n, const xrt_plot_params* plot, void* stream) {
   return plot_hist_device(n, plot, (cudaStream_t)stream);
+}
+
+size_t xrt_compact_scratch_words(size_t n) { return compact_scratch_words(n); }
+
+int xrt_compact_rays_f64(size_t n, const int32_t* state, int state_mask, int narr, const double* const* src,
+                         double* const* dst, const int* words, uint64_t* scratch, void* stream) {
+  return compact_rays_device(n, state, state_mask, narr, src, dst, words,
+                             reinterpret_cast<unsigned long long*>(scratch), (cudaStream_t)stream);
 }
 
 int xrt_hist2d_f64(size_t n, const double* x, const double* y, const double* w1, const double* w2,

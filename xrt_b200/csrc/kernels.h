@@ -11,6 +11,12 @@ namespace xrtb {
 // kirchhoff.cu
 size_t kirchhoff_workspace_bytes(size_t M, size_t N, int R);
 int kirchhoff_plan_splits(size_t M, size_t N, int R);
+int kirchhoff_pack_device(size_t N, const double* nl, const double* Es, const double* Ep, const double* k,
+                          const double* pos, int pos_stride, const double* nrm, int nrm_stride, void* records,
+                          cudaStream_t st);
+int kirchhoff_packed_device(size_t M, size_t N, const double* xM, const double* yM, const double* zM,
+                            const void* records, double* S, double* P, double* A, double* B, double* C, int flags,
+                            void* part_ws, cudaStream_t st);
 int kirchhoff_device(size_t M, size_t N, const double* xM, const double* yM, const double* zM, const double* nl,
                      const double* Es, const double* Ep, const double* k, const double* pos, int pos_stride,
                      const double* nrm, int nrm_stride, double* S, double* P, double* A, double* B, double* C,
@@ -99,6 +105,9 @@ int geometric_source_device(size_t n, const xrt_geom_params* p, uint64_t seed, u
                             const double* const* deviates, const xrt_beam* out, unsigned long long* flag, int phase,
                             cudaStream_t st);
 
+size_t compact_scratch_words(size_t n);
+int compact_rays_device(size_t n, const int* state, int state_mask, int narr, const double* const* src,
+                        double* const* dst, const int* words, unsigned long long* scratch, cudaStream_t st);
 int plot_hist_device(size_t n, const xrt_plot_params* p, cudaStream_t st);
 int hist2d_device(size_t n, const double* x, const double* y, const double* w1, const double* w2, const int* state,
                   int state_mask, const double* ex, int nx, const double* ey, int ny, double* out, cudaStream_t st);

@@ -68,14 +68,19 @@ __global__ void kirchhoff_pack_kernel(size_t N, const double* __restrict__ nl, c
 #ifndef XRTB_KIRCHHOFF_MINBLOCKS
 #define XRTB_KIRCHHOFF_MINBLOCKS 2
 #endif
-template <int R, int THREADS, int TILE, bool STRICT, bool UNIFORM_N>
+template <int R, int THREADS, int TILE, bool STRICT, bool UNIFORM_N, bool TABSC>
 __global__ void __launch_bounds__(THREADS, XRTB_KIRCHHOFF_MINBLOCKS)
     kirchhoff_kernel(size_t M, size_t N, const double* __restrict__ xM, const double* __restrict__ yM,
                      const double* __restrict__ zM, const KInput* __restrict__ in, size_t n_per_split,
-                     double2* __restrict__ part, double un_x, double un_y, double un_z) {
+                     double2* __restrict__ part, const double* __restrict__ un, double un_scale) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   KInput* tile = reinterpret_cast<KInput*>(smem_raw);                       // [2][TILE]
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + 2 * TILE * sizeof(KInput));  // [2]
+  double2* sctab = reinterpret_cast<double2*>(smem_raw + 2 * TILE * sizeof(KInput) + 16);  // [64] (TABSC)
+  // the common normal of the uniform-normal variant is the first sample's, read here from device memory (r01 fetched
+  // it to the host with a blocking copy inside an entry point that promises to be asynchronous)
+  const double un_x = UNIFORM_N ? un[0] * un_scale : 0.0, un_y = UNIFORM_N ? un[1] * un_scale : 0.0,
+               un_z = UNIFORM_N ? un[2] * un_scale : 0.0;
 
   const int tid = threadIdx.x;
   const size_t base = (size_t)blockIdx.x * (THREADS * R);
@@ -104,6 +109,7 @@ __global__ void __launch_bounds__(THREADS, XRTB_KIRCHHOFF_MINBLOCKS)
     mbar_init(&full[1], 1);
     mbar_fence_init();
   }
+  if (TABSC) sincos_tab_fill(sctab, tid);
   __syncthreads();
 
   auto issue = [&](int t) {
@@ -154,7 +160,12 @@ __global__ void __launch_bounds__(THREADS, XRTB_KIRCHHOFF_MINBLOCKS)
         const double kip = a3.z * hinv;  // k / r
         const double cr = kip * tcos;
         double sn, cs;
-        sincos_big(phase, sn, cs);
+        // (sincos_tab reduces with 32/pi: exact below 2^47 rad = 1.4e14 -- 100 keV over 280 m.  The CALLER vouches for
+        // that range with flag bit 11: a per-pair test in this loop costs 40 % of the kernel)
+        if (TABSC)
+          sincos_tab(phase, sctab, sn, cs);
+        else
+          sincos_big(phase, sn, cs);
         const double gre = cr * cs;
         const double gim = cr * sn;
         // S += g * Es ; P += g * Ep
@@ -233,26 +244,42 @@ __global__ void kirchhoff_finalize_kernel(size_t M, int nsplit, const double2* _
 }
 
 // ---------------------------------------------------------------- host-side launcher
-template <int R, int THREADS, int TILE, bool STRICT, bool UNI>
-static int launch_one(dim3 grid, size_t smem, cudaStream_t st, size_t M, size_t N, const double* xM, const double* yM,
-                      const double* zM, const KInput* in, size_t nps, double2* part, const double* un) {
-  XRTB_CUDA_CHECK(cudaFuncSetAttribute(kirchhoff_kernel<R, THREADS, TILE, STRICT, UNI>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kirchhoff_kernel<R, THREADS, TILE, STRICT, UNI><<<grid, THREADS, smem, st>>>(M, N, xM, yM, zM, in, nps, part, un[0],
-                                                                              un[1], un[2]);
+struct KLaunch {
+  dim3 grid;
+  size_t smem;
+  cudaStream_t st;
+  size_t M, N;
+  const double *xM, *yM, *zM;
+  const KInput* in;
+  size_t nps;
+  double2* part;
+  const double* un;
+  double un_scale;  // 1: un is a normal; 0.5: un points at the doubled normal of a packed record
+};
+
+template <int R, int THREADS, int TILE, bool STRICT, bool UNI, bool TABSC>
+static int launch_one(const KLaunch& L) {
+  XRTB_CUDA_CHECK(cudaFuncSetAttribute(kirchhoff_kernel<R, THREADS, TILE, STRICT, UNI, TABSC>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+  kirchhoff_kernel<R, THREADS, TILE, STRICT, UNI, TABSC><<<L.grid, THREADS, L.smem, L.st>>>(
+      L.M, L.N, L.xM, L.yM, L.zM, L.in, L.nps, L.part, L.un, L.un_scale);
   XRTB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
 template <int R, int THREADS, int TILE>
-static int launch_main(bool strict, bool uni, dim3 grid, size_t smem, cudaStream_t st, size_t M, size_t N,
-                       const double* xM, const double* yM, const double* zM, const KInput* in, size_t nps,
-                       double2* part, const double* un) {
-  if (strict)
-    return uni ? launch_one<R, THREADS, TILE, true, true>(grid, smem, st, M, N, xM, yM, zM, in, nps, part, un)
-               : launch_one<R, THREADS, TILE, true, false>(grid, smem, st, M, N, xM, yM, zM, in, nps, part, un);
-  return uni ? launch_one<R, THREADS, TILE, false, true>(grid, smem, st, M, N, xM, yM, zM, in, nps, part, un)
-             : launch_one<R, THREADS, TILE, false, false>(grid, smem, st, M, N, xM, yM, zM, in, nps, part, un);
+static int launch_main(bool strict, bool uni, bool tabsc, const KLaunch& L) {
+  const int v = (strict ? 4 : 0) | (uni ? 2 : 0) | (tabsc ? 1 : 0);
+  switch (v) {
+    case 0: return launch_one<R, THREADS, TILE, false, false, false>(L);
+    case 1: return launch_one<R, THREADS, TILE, false, false, true>(L);
+    case 2: return launch_one<R, THREADS, TILE, false, true, false>(L);
+    case 3: return launch_one<R, THREADS, TILE, false, true, true>(L);
+    case 4: return launch_one<R, THREADS, TILE, true, false, false>(L);
+    case 5: return launch_one<R, THREADS, TILE, true, false, true>(L);
+    case 6: return launch_one<R, THREADS, TILE, true, true, false>(L);
+    default: return launch_one<R, THREADS, TILE, true, true, true>(L);
+  }
 }
 
 #ifndef XRTB_KIRCHHOFF_THREADS
@@ -263,23 +290,91 @@ constexpr int K_TILE = 128;
 
 size_t kirchhoff_packed_bytes(size_t N) { return N * sizeof(KInput); }
 
-// number of N-splits used for a given problem (also sizes the workspace)
+// number of N-splits used for a given problem (also sizes the workspace).  The grid is (M blocks) x (N splits) of
+// equal CTAs that the hardware scheduler hands to 2 x 148 resident slots as they free up: the last wave is only
+// partly full, so the loss is ~0.5 / waves.  r01 aimed at 4 CTAs per SM (2 - 3 waves): 768 CTAs = 2.59 waves for a
+// 131072-point shard of config 4, i.e. the 0.87 strong-scaling efficiency of SCALE_r01.  Now the split is chosen so
+// that there are >= 32 waves whenever every split still gets >= 16 tiles (2048 samples, ~1 ms of work per CTA), and
+// among the next few candidates the one whose last wave is fullest.  The partial sums are reduced in a fixed order by
+// kirchhoff_finalize_kernel, so the result does not depend on the split.
 int kirchhoff_plan_splits(size_t M, size_t N, int R) {
   const size_t per_cta = (size_t)K_THREADS * R;
-  size_t mblocks = (M + per_cta - 1) / per_cta;
-  size_t target = (size_t)num_sms() * 4;  // >= 4 CTAs per SM keeps every SMSP busy and bounds the tail
-  if (mblocks >= target) return 1;
-  size_t ns = (target + mblocks - 1) / mblocks;
-  size_t max_ns = (N + K_TILE * 4 - 1) / (K_TILE * 4);  // at least 4 tiles per split
+  const size_t mblocks = (M + per_cta - 1) / per_cta;
+  const size_t slots = (size_t)num_sms() * XRTB_KIRCHHOFF_MINBLOCKS;
+  const size_t target = slots * 32;
+  size_t max_ns = N / (K_TILE * 16);
   if (max_ns < 1) max_ns = 1;
-  if (ns > max_ns) ns = max_ns;
-  if (ns > 4096) ns = 4096;
-  return (int)ns;
+  if (max_ns > 4096) max_ns = 4096;
+  if (mblocks == 0) return 1;
+  size_t ns0 = (target + mblocks - 1) / mblocks;
+  if (ns0 < 1) ns0 = 1;
+  if (ns0 >= max_ns) return (int)max_ns;
+  size_t best = ns0;
+  double best_eff = 0.0;
+  for (size_t ns = ns0; ns <= max_ns && ns < ns0 + 8; ++ns) {
+    const double waves = (double)(mblocks * ns) / (double)slots;
+    const double eff = waves / (double)(size_t)(waves + 0.999999);
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best = ns;
+    }
+  }
+  return (int)best;
 }
 
 size_t kirchhoff_workspace_bytes(size_t M, size_t N, int R) {
   int ns = kirchhoff_plan_splits(M, N, R);
   return kirchhoff_packed_bytes(N) + (size_t)ns * 5 * M * sizeof(double2);
+}
+
+int kirchhoff_pack_device(size_t N, const double* nl, const double* Es, const double* Ep, const double* k,
+                          const double* pos, int pos_stride, const double* nrm, int nrm_stride, void* records,
+                          cudaStream_t st) {
+  if (N == 0) return 0;
+  kirchhoff_pack_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(
+      N, nl, reinterpret_cast<const double2*>(Es), reinterpret_cast<const double2*>(Ep), k, pos, pos_stride, nrm,
+      nrm_stride, reinterpret_cast<KInput*>(records));
+  XRTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// the sum from packed records (xrt_kirchhoff_pack_f64; all-gathered over ranks when the samples are ray shards);
+// `part` holds kirchhoff_plan_splits(M, N, R) * 5 * M complex partial sums
+int kirchhoff_packed_device(size_t M, size_t N, const double* xM, const double* yM, const double* zM,
+                            const void* records, double* S, double* P, double* A, double* B, double* C, int flags,
+                            void* part_ws, cudaStream_t st) {
+  if (M == 0) return 0;
+  const bool strict = !(flags & 1);
+  const int convention = (flags >> 1) & 1;
+  const bool uni = (flags >> 9) & 1;  // caller guarantees that all N normals are equal
+  const bool tabsc = (flags >> 11) & 1;  // sincos through the 64-entry table (sincos_tab)
+  int R = (flags >> 4) & 7;
+  if (R == 0) R = 2;
+  XRTB_REQUIRE(R == 1 || R == 2 || R == 4, "kirchhoff: register blocking R must be 1, 2 or 4 (got %d)", R);
+  const KInput* packed = reinterpret_cast<const KInput*>(records);
+  double2* part = reinterpret_cast<double2*>(part_ws);
+  const int nsplit = kirchhoff_plan_splits(M, N, R);
+  const size_t per_cta = (size_t)K_THREADS * R;
+  dim3 grid((unsigned)((M + per_cta - 1) / per_cta), (unsigned)nsplit);
+  size_t nps = (N + nsplit - 1) / nsplit;
+  nps = (nps + K_TILE - 1) / K_TILE * K_TILE;
+  if (nps == 0) nps = K_TILE;
+  const size_t smem = 2 * K_TILE * sizeof(KInput) + 2 * sizeof(uint64_t) + 64 * sizeof(double2);
+  int rc = 0;
+  // the common normal of the uniform-normal variant = the first record's (stored doubled), read by the kernel itself
+  const KLaunch L{grid, smem, st, M, N, xM, yM, zM, packed, nps, part, N ? &packed[0].nx2 : nullptr, 0.5};
+  if (R == 1)
+    rc = launch_main<1, K_THREADS, K_TILE>(strict, uni && N > 0, tabsc, L);
+  else if (R == 2)
+    rc = launch_main<2, K_THREADS, K_TILE>(strict, uni && N > 0, tabsc, L);
+  else
+    rc = launch_main<4, K_THREADS, K_TILE>(strict, uni && N > 0, tabsc, L);
+  if (rc) return rc;
+  kirchhoff_finalize_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(
+      M, nsplit, part, convention, reinterpret_cast<double2*>(S), reinterpret_cast<double2*>(P),
+      reinterpret_cast<double2*>(A), reinterpret_cast<double2*>(B), reinterpret_cast<double2*>(C));
+  XRTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
 }
 
 // device pointers only; `ws` must hold kirchhoff_workspace_bytes(M, N, R) bytes.
@@ -288,45 +383,10 @@ int kirchhoff_device(size_t M, size_t N, const double* xM, const double* yM, con
                      const double* nrm, int nrm_stride, double* S, double* P, double* A, double* B, double* C,
                      int flags, void* ws, cudaStream_t st) {
   if (M == 0) return 0;
-  const bool strict = !(flags & 1);
-  const int convention = (flags >> 1) & 1;
-  const bool uni = (flags >> 9) & 1;  // caller guarantees that all N normals are equal
-  int R = (flags >> 4) & 7;
-  if (R == 0) R = 2;
-  XRTB_REQUIRE(R == 1 || R == 2 || R == 4, "kirchhoff: register blocking R must be 1, 2 or 4 (got %d)", R);
-  KInput* packed = reinterpret_cast<KInput*>(ws);
-  double2* part = reinterpret_cast<double2*>(reinterpret_cast<unsigned char*>(ws) + kirchhoff_packed_bytes(N));
-  const int nsplit = kirchhoff_plan_splits(M, N, R);
-  if (N > 0) {
-    kirchhoff_pack_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(
-        N, nl, reinterpret_cast<const double2*>(Es), reinterpret_cast<const double2*>(Ep), k, pos, pos_stride, nrm,
-        nrm_stride, packed);
-    XRTB_CUDA_CHECK(cudaGetLastError());
-  }
-  const size_t per_cta = (size_t)K_THREADS * R;
-  dim3 grid((unsigned)((M + per_cta - 1) / per_cta), (unsigned)nsplit);
-  size_t nps = (N + nsplit - 1) / nsplit;
-  nps = (nps + K_TILE - 1) / K_TILE * K_TILE;
-  if (nps == 0) nps = K_TILE;
-  const size_t smem = 2 * K_TILE * sizeof(KInput) + 2 * sizeof(uint64_t);
-  int rc = 0;
-  double un[3] = {0.0, 0.0, 0.0};
-  if (uni && N > 0) {  // the common normal = the first sample's (3 doubles, device -> host)
-    XRTB_CUDA_CHECK(cudaMemcpyAsync(un, nrm, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    XRTB_CUDA_CHECK(cudaStreamSynchronize(st));
-  }
-  if (R == 1)
-    rc = launch_main<1, K_THREADS, K_TILE>(strict, uni, grid, smem, st, M, N, xM, yM, zM, packed, nps, part, un);
-  else if (R == 2)
-    rc = launch_main<2, K_THREADS, K_TILE>(strict, uni, grid, smem, st, M, N, xM, yM, zM, packed, nps, part, un);
-  else
-    rc = launch_main<4, K_THREADS, K_TILE>(strict, uni, grid, smem, st, M, N, xM, yM, zM, packed, nps, part, un);
+  int rc = kirchhoff_pack_device(N, nl, Es, Ep, k, pos, pos_stride, nrm, nrm_stride, ws, st);
   if (rc) return rc;
-  kirchhoff_finalize_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(
-      M, nsplit, part, convention, reinterpret_cast<double2*>(S), reinterpret_cast<double2*>(P),
-      reinterpret_cast<double2*>(A), reinterpret_cast<double2*>(B), reinterpret_cast<double2*>(C));
-  XRTB_CUDA_CHECK(cudaGetLastError());
-  return 0;
+  return kirchhoff_packed_device(M, N, xM, yM, zM, ws, S, P, A, B, C, flags,
+                                 reinterpret_cast<unsigned char*>(ws) + kirchhoff_packed_bytes(N), st);
 }
 
 }  // namespace xrtb

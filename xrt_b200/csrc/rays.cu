@@ -319,6 +319,104 @@ int propagate_rect_device(size_t n, const xrt_plane_params* p, const xrt_beam* i
   return 0;
 }
 
+// ---------------------------------------------------------------- compaction of selected rays and fields
+// What a consumer of a repeat reads from a Beam is a handful of fields of the rays raycing.get_output selects
+// (raycing/__init__.py:170-300: `good = (state == 1) | ...`; x, z, E, Jss + Jpp -- 40 B of the 132 B/ray, and 59 % of
+// the rays in BASELINE config 2).  Three small kernels pack those fields of the selected rays densely, in ray order,
+// so that only they cross PCIe: per-block counts, an exclusive scan of the counts (one block), scatter with an
+// in-block ballot scan.  Up to 8 arrays of 8-byte words per call (a complex128 field is two words per ray).
+constexpr int kCompactBlock = 1024;
+__device__ __forceinline__ bool ray_selected(int st, int state_mask) {
+  const int bit = st == 1 ? 1 : (st == 2 ? 2 : (st == 3 ? 4 : (st < 0 ? 8 : (st > 0 ? 16 : 32))));
+  return (bit & state_mask) != 0;
+}
+__global__ void __launch_bounds__(kCompactBlock) compact_count_kernel(size_t n, const int* __restrict__ state,
+                                                                       int state_mask,
+                                                                       unsigned long long* __restrict__ counts) {
+  const size_t i = (size_t)blockIdx.x * kCompactBlock + threadIdx.x;
+  const bool sel = i < n && ray_selected(state[i], state_mask);
+  const int c = __syncthreads_count(sel);
+  if (threadIdx.x == 0) counts[blockIdx.x] = (unsigned long long)c;
+}
+// counts[0 .. nb) -> exclusive prefix sums in place, counts[nb] = total
+__global__ void __launch_bounds__(1024) compact_scan_kernel(size_t nb, unsigned long long* __restrict__ counts) {
+  __shared__ unsigned long long sh[1024];
+  __shared__ unsigned long long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (size_t base = 0; base < nb; base += 1024) {
+    const size_t k = base + threadIdx.x;
+    const unsigned long long v = k < nb ? counts[k] : 0ull;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
+      const unsigned long long t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0ull;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (k < nb) counts[k] = carry + sh[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += sh[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) counts[nb] = carry;
+}
+struct CompactArrays {
+  const double* src[8];
+  double* dst[8];
+  int words[8];
+  int narr;
+};
+__global__ void __launch_bounds__(kCompactBlock) compact_scatter_kernel(size_t n, const int* __restrict__ state,
+                                                                         int state_mask,
+                                                                         const unsigned long long* __restrict__ offs,
+                                                                         CompactArrays a) {
+  __shared__ int wcount[kCompactBlock / 32];
+  const size_t i = (size_t)blockIdx.x * kCompactBlock + threadIdx.x;
+  const bool sel = i < n && ray_selected(state[i], state_mask);
+  const unsigned b = __ballot_sync(0xffffffffu, sel);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) wcount[warp] = __popc(b);
+  __syncthreads();
+  if (!sel) return;
+  int before = 0;
+  for (int w = 0; w < warp; ++w) before += wcount[w];
+  const size_t pos = (size_t)offs[blockIdx.x] + before + __popc(b & ((1u << lane) - 1u));
+  for (int k = 0; k < a.narr; ++k) {
+    if (a.words[k] == 2)
+      reinterpret_cast<double2*>(a.dst[k])[pos] = reinterpret_cast<const double2*>(a.src[k])[i];
+    else
+      a.dst[k][pos] = a.src[k][i];
+  }
+}
+
+size_t compact_scratch_words(size_t n) { return (n + kCompactBlock - 1) / kCompactBlock + 1; }
+
+int compact_rays_device(size_t n, const int* state, int state_mask, int narr, const double* const* src,
+                        double* const* dst, const int* words, unsigned long long* scratch, cudaStream_t st) {
+  XRTB_REQUIRE(state && src && dst && words && scratch, "compact_rays: NULL argument");
+  XRTB_REQUIRE(narr >= 1 && narr <= 8, "compact_rays: 1..8 arrays per call (got %d)", narr);
+  CompactArrays a;
+  a.narr = narr;
+  for (int k = 0; k < narr; ++k) {
+    XRTB_REQUIRE(src[k] && dst[k] && (words[k] == 1 || words[k] == 2), "compact_rays: array %d", k);
+    a.src[k] = src[k];
+    a.dst[k] = dst[k];
+    a.words[k] = words[k];
+  }
+  const size_t nb = (n + kCompactBlock - 1) / kCompactBlock;
+  if (nb == 0) {
+    XRTB_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(unsigned long long), st));
+    return 0;
+  }
+  compact_count_kernel<<<(unsigned)nb, kCompactBlock, 0, st>>>(n, state, state_mask, scratch);
+  compact_scan_kernel<<<1, 1024, 0, st>>>(nb, scratch);
+  compact_scatter_kernel<<<(unsigned)nb, kCompactBlock, 0, st>>>(n, state, state_mask, scratch, a);
+  XRTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 // ---------------------------------------------------------------- f1: weighted 2-D histogram on the device
 // np.histogram2d(y, x, bins=[ny, nx], range=..., weights=w) as xrt's do_hist2d calls it (xrt/multipro.py:119-171)
 // on the rays raycing.get_output selects (state filter) with intensity = Jss + Jpp.  Bin edges come from the host

@@ -954,8 +954,11 @@ __device__ __forceinline__ void crystal_amplitude(const xrt_material_params& m, 
     Fhkl = cmul_np(cmul_np(cplx{4.0, 0.0}, cplx{f0 + anom.re, anom.im}), cplx{m.factDW, 0.0});
     Fhkl_ = Fhkl;
   }
-  if (m.f0scale != 1.0) {
-    F0 = cmul_np(F0, cplx{2.0, 0.0});
+  // diamond: F0 * 2, Fhkl * diamondToFcc (crystals_basic.py:76-80); in general, for a cell of like atoms at r_i with
+  // occupancies o_i: f0scale = sum(o_i) / 4 and d2f = sum(o_i exp(2 pi i hkl.r_i)) / 4 (kernel `get_amplitude`,
+  // cl/materials.cl:203-221, through XRT_CUDA.run_parallel('get_amplitude'))
+  if (m.f0scale != 1.0 || m.d2f_re != 1.0 || m.d2f_im != 0.0) {
+    F0 = cmul_np(F0, cplx{m.f0scale, 0.0});
     Fhkl = cmul_np(Fhkl, cplx{m.d2f_re, m.d2f_im});
     Fhkl_ = cmul_np(Fhkl_, cplx{m.d2f_re, -m.d2f_im});
   }

@@ -102,7 +102,42 @@ class XRT_CUDA(object):
         return fn(scalarArgs or [], slicedROArgs or [], nonSlicedROArgs or [], slicedRWArgs or [],
                   nonSlicedRWArgs or [], int(dimension))
 
-    run_parallel_max = run_parallel
+    #: a xrt_b200.parallel.Comm: run_parallel_max then shards over the ranks (one process per GPU)
+    comm = None
+
+    def run_parallel_max(self, kernelName='', scalarArgs=None, slicedROArgs=None, nonSlicedROArgs=None,
+                         slicedRWArgs=None, nonSlicedRWArgs=None, dimension=0, complexity=0, signal=None):
+        """XRT_CL.run_parallel_max (myopencl.py:455-583) over ranks instead of over the OpenCL devices of one
+        process: every rank calls it with the SAME whole host arrays (SPMD); the sliced arguments are cut into
+        contiguous chunks of `dimension` (x secondDim, :501-503) -- this rank computes its chunk --, the non-sliced
+        ones are replicated (:508-512), and the sliced RW results of all ranks are gathered back into the caller's
+        whole arrays (:552-569), which are also returned.  Without a communicator it is run_parallel."""
+        comm = self.comm
+        if comm is None or comm.world == 1:
+            return self.run_parallel(kernelName, scalarArgs, slicedROArgs, nonSlicedROArgs, slicedRWArgs,
+                                     nonSlicedRWArgs, dimension, complexity, signal)
+        if nonSlicedRWArgs:
+            raise NotImplementedError('run_parallel_max: non-sliced RW arguments cannot be sharded')
+        dimension = int(dimension)
+        start, stop = comm.shard(dimension)
+
+        def cut(a):
+            a = np.asarray(a)
+            second = len(a) // dimension if dimension else 1  # secondDim (myopencl.py:501-503)
+            return a[start * second:stop * second], second
+        ro = [cut(a)[0] for a in (slicedROArgs or [])]
+        rw_full = list(slicedRWArgs or [])
+        rw = []
+        for a in rw_full:
+            part, _ = cut(a)
+            rw.append(np.ascontiguousarray(part).copy())
+        self.run_parallel(kernelName, scalarArgs, ro, nonSlicedROArgs, rw, None, stop - start, complexity, signal)
+        for full, part in zip(rw_full, rw):
+            second = len(full) // dimension if dimension else 1
+            g = comm.allgather_host(part.reshape(stop - start, second) if second > 1 else part,
+                                    device=getattr(self, '_gather_device', None))
+            full[...] = g.reshape(full.shape)
+        return tuple(rw_full)
 
     # ------------------------------------------------------------------ kernels
     def _k_integrate_kirchhoff(self, scalarArgs, slicedRO, nonSlicedRO, slicedRW, nonSlicedRW, dimension):
@@ -127,6 +162,14 @@ class XRT_CUDA(object):
                 raise ValueError('integrate_kirchhoff: slicedRWArgs must be 5 contiguous complex128[dimension]')
             outs.append(a)
         flags = (1 if self.kirchhoffRelaxed else 0) | (_KIRCHHOFF_CONVENTIONS[self.kirchhoffConvention] << 1)
+        if N > 0 and M > 0:
+            # sin / cos through the 64-entry table (same accuracy, 10 % faster) when every phase k r stays below 2^47:
+            # bound it with the bounding boxes of the samples and of the receiving points
+            pv = pos[:3, :] if pos.shape[1] == N and pos.shape[0] in (3, 4) and pos.flags['F_CONTIGUOUS'] else pos[:, :3].T
+            span = np.maximum(np.abs(np.array([xM.max(), yM.max(), zM.max()]) - pv.min(axis=1)),
+                              np.abs(pv.max(axis=1) - np.array([xM.min(), yM.min(), zM.min()])))
+            if np.abs(k).max() * np.linalg.norm(span) < 2.**47:
+                flags |= 1 << 11
         nview = nrm[:3, :] if nrm.shape[1] == N and nrm.shape[0] in (3, 4) and nrm.flags['F_CONTIGUOUS'] else nrm[:, :3].T
         if N > 0 and np.all(nview == nview[:, :1]):
             flags |= 1 << 9  # all normals equal (aperture / flat OE): the kernel hoists n.p out of the pair loop
@@ -219,6 +262,82 @@ class XRT_CUDA(object):
                                            _lib.hptr(Is), _lib.hptr(Ip))
         _lib.check(rc, 'xrt_custom_field_f64_host')
         return Is, Ip
+
+    def _k_get_amplitude(self, scalarArgs, slicedRO, nonSlicedRO, slicedRW, nonSlicedRW, dimension):
+        """Argument list of kernel `get_amplitude` (cl/materials.cl:715-748): scalars [hkl (int4), factDW, thickness
+        (mm), geom_b, maxEl]; sliced RO [BeamInDotNormal, BeamOutDotNormal, BeamInDotHNormal, Energy, IPDistance (d,
+        Angstrom), ChiToF]; non-sliced RO [elements (maxEl x 8: x, y, z, -, occupancy, Z, -, table length), f0cfs
+        (maxEl x 11), E_vector, f1_vector, f2_vector (maxEl x 300)]; sliced RW [refl_s, refl_p].
+        geom_b as the kernel decodes it (:734-736): Bragg when > 1, transmitted when odd; thickness 0 or > 0.5 mm with
+        'Bragg reflected' is the thick-crystal branch (:268).  Numerics are those of the numpy path
+        (Crystal.get_amplitude, crystal.py:492-645 -- SURVEY 8a: numpy is the oracle).  The cell may hold any number of
+        atoms of ONE element (fcc, diamond, ... : their geometric structure factor is taken on the host); cells with
+        different elements are outside the hot path."""
+        import ctypes
+        from .materials import xrt_material_params
+        lib = _lib.load()
+        hkl, factDW, thickness, geom_b, maxEl = scalarArgs[:5]
+        hkl = np.asarray(hkl, dtype=np.float64).ravel()[:3]
+        maxEl = int(maxEl)
+        geom_b = int(geom_b)
+        thickness = float(thickness)
+        bIn, bOut, bH, E, dArr, chiArr = (_lib.as_f64(a) for a in slicedRO)
+        n = dimension if dimension else len(E)
+        if any(len(a) != n for a in (bIn, bOut, bH, E, dArr, chiArr)):
+            raise ValueError('get_amplitude: expected 6 sliced inputs of length dimension')
+        el, f0cfs, Ev, f1v, f2v = (np.asarray(a, dtype=np.float64).ravel() for a in nonSlicedRO)
+        if maxEl < 1 or len(el) < 8 * maxEl or len(f0cfs) < 11 * maxEl or min(len(Ev), len(f1v), len(f2v)) < 300 * maxEl:
+            raise ValueError('get_amplitude: elements / f0cfs / E, f1, f2 vectors are shorter than maxEl needs')
+        el = el[:8 * maxEl].reshape(maxEl, 8)
+        nt = int(round(el[0, 7]))
+        same = all(el[i, 5] == el[0, 5] and int(round(el[i, 7])) == nt and
+                   np.array_equal(f0cfs[11*i:11*i + 11], f0cfs[:11]) and
+                   np.array_equal(Ev[300*i:300*i + nt], Ev[:nt]) and np.array_equal(f1v[300*i:300*i + nt], f1v[:nt])
+                   and np.array_equal(f2v[300*i:300*i + nt], f2v[:nt]) for i in range(maxEl))
+        if not same:
+            raise NotImplementedError('get_amplitude: cells with different elements are outside the hot path '
+                                      '(one-element structures: fcc, diamond, ...)')
+        rs, rp = slicedRW
+        for a in (rs, rp):
+            if not (isinstance(a, np.ndarray) and a.dtype == np.complex128 and a.flags['C_CONTIGUOUS'] and
+                    len(a) == n):
+                raise ValueError('get_amplitude: slicedRWArgs must be 2 contiguous complex128[dimension]')
+        occ = el[:, 4]
+        S = np.sum(occ * np.exp(2j * np.pi * (el[:, :3] @ hkl)))  # sum o_i exp(2 pi i hkl.r_i) (materials.cl:213-216)
+        tables = np.ascontiguousarray(np.concatenate([Ev[:nt], f1v[:nt], f2v[:nt]]))
+        bragg, transmitted = geom_b > 1, (geom_b % 2) == 1
+        thick = bragg and not transmitted and (thickness == 0 or thickness > 0.5)
+        # d and chiToF arrive per ray; the rays of one crystal share them: one launch per distinct pair
+        pairs = np.stack([dArr, chiArr], axis=1)
+        uniq, inv = np.unique(pairs, axis=0, return_inverse=True)
+        inv = inv.ravel()
+        for iu, (d, chiToF) in enumerate(uniq):
+            sel = slice(None) if len(uniq) == 1 else np.nonzero(inv == iu)[0]
+            m = xrt_material_params()
+            m.kind = 3
+            m.nelem = 1
+            m.Z[0] = float(el[0, 5])
+            m.quantity[0] = 1.
+            m.tab_off[0], m.tab_len[0] = 0, nt
+            m.d, m.chiToF, m.factDW = float(d), float(chiToF), float(factDW)
+            m.t = 0. if thick else thickness
+            m.geom = (0 if bragg else 1) | (2 if transmitted else 0)
+            q = 0.5 / float(d)
+            m.f0c[0] = float(f0cfs[5] + np.sum(f0cfs[:5] * np.exp(-f0cfs[6:11] * q * q)))  # get_f0 (materials.cl:46-54)
+            m.hkl_allowed = 1
+            m.f0scale = float(occ.sum()) / 4.
+            m.d2f_re, m.d2f_im = float(S.real) / 4., float(S.imag) / 4.
+            args = [np.ascontiguousarray(a[sel]) for a in (E, bIn, bOut, bH)]
+            o_s = np.empty(len(args[0]), dtype=np.complex128)
+            o_p = np.empty(len(args[0]), dtype=np.complex128)
+            rc = lib.xrt_get_amplitude_f64_host(len(args[0]), ctypes.byref(m), _lib.hptr(tables), nt,
+                                                *[_lib.hptr(a) for a in args], _lib.hptr(o_s), _lib.hptr(o_p))
+            if rc == 3:
+                raise ValueError('E is out of the f1/f2 data table range')
+            _lib.check(rc, 'xrt_get_amplitude_f64_host')
+            rs[sel] = o_s
+            rp[sel] = o_p
+        return rs, rp
 
     def _k_get_amplitude_graded_multilayer(self, scalarArgs, slicedRO, nonSlicedRO, slicedRW, nonSlicedRW,
                                            dimension):

@@ -34,16 +34,48 @@ def fp64_probe(mode=0, iters=4096):
     return tf.value, ms.value
 
 
+_workspaces = {}  # device -> uint8 tensor, grown on demand and kept (packed records + split partial sums)
+
+
+def kirchhoff_workspace(device, nbytes):
+    """One workspace per device, reused by every call on that device's current stream (calls on one stream are
+    ordered, so the next launch can overwrite it) -- r01 allocated 128 MB + 80 * M * splits bytes per call."""
+    key = str(device)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        _workspaces[key] = ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+    return ws
+
+
+PHASE_LIMIT_TABLE_SINCOS = 2.**47  # sincos_tab (common.cuh) reduces with 32/pi: exact below this phase
+
+
+def phase_bound(xM, yM, zM, pos, k):
+    """A bound on |k r| over all pairs from the bounding boxes of the receiving points and of the samples (device
+    reductions + one small host read): what decides whether the table-based sin / cos of the Kirchhoff kernel applies."""
+    if xM.numel() == 0 or k.numel() == 0:
+        return 0.
+    lo = torch.stack((xM.min(), yM.min(), zM.min()))
+    hi = torch.stack((xM.max(), yM.max(), zM.max()))
+    p = pos[:, :3]
+    plo, phi = p.min(dim=0).values, p.max(dim=0).values
+    span = torch.maximum((hi - plo).abs(), (phi - lo).abs())
+    return float((k.abs().max() * span.norm()).item())
+
+
 def kirchhoff(xM, yM, zM, nl, Es, Ep, k, pos, nrm, out=None, convention='numpy', relaxed=False, R=0,
-              workspace=None, uniform_normal=False):
-    """a17 on device tensors.  pos, nrm: (N, 3|4) float64 row-major.  Returns (S, P, A, B, C) complex128[M]."""
+              workspace=None, uniform_normal=False, table_sincos='auto'):
+    """a17 on device tensors.  pos, nrm: (N, 3|4) float64 row-major.  Returns (S, P, A, B, C) complex128[M].
+    table_sincos: 'auto' takes the faster table-based sin / cos when phase_bound() allows it."""
     lib = _lib.load()
     M, N = xM.numel(), nl.numel()
+    if table_sincos == 'auto':
+        table_sincos = phase_bound(xM, yM, zM, pos, k) < PHASE_LIMIT_TABLE_SINCOS
     flags = (1 if relaxed else 0) | ((1 if convention == 'opencl' else 0) << 1) | (int(R) << 4) | \
-        ((1 if uniform_normal else 0) << 9)
+        ((1 if uniform_normal else 0) << 9) | ((1 if table_sincos else 0) << 11)
     need = lib.xrt_kirchhoff_workspace_bytes(M, N, flags)
     if workspace is None or workspace.numel() < need:
-        workspace = torch.empty(max(need, 16), dtype=torch.uint8, device=xM.device)
+        workspace = kirchhoff_workspace(xM.device, need)
     if out is None:
         out = torch.empty((5, M), dtype=C128, device=xM.device)
     ps, ns = pos.shape[1], nrm.shape[1]
@@ -53,6 +85,40 @@ def kirchhoff(xM, yM, zM, nl, Es, Ep, k, pos, nrm, out=None, convention='numpy',
         _chk(nrm, F64, N * ns, 'nrm'), ns, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
         out[3].data_ptr(), out[4].data_ptr(), flags, workspace.data_ptr(), _stream())
     _lib.check(rc, 'xrt_kirchhoff_f64')
+    return out
+
+
+def kirchhoff_pack(nl, Es, Ep, k, pos, nrm):
+    """This rank's samples as 128-byte records (uint8 (N, 128)): what ranks all-gather when the samples are ray
+    shards (waves.diffract(comm=...))."""
+    lib = _lib.load()
+    N = nl.numel()
+    rec = torch.empty((N, 128), dtype=torch.uint8, device=nl.device)
+    ps, ns = pos.shape[1], nrm.shape[1]
+    rc = lib.xrt_kirchhoff_pack_f64(N, _chk(nl, F64, N, 'nl'), _chk(Es, C128, N, 'Es'), _chk(Ep, C128, N, 'Ep'),
+                                    _chk(k, F64, N, 'k'), _chk(pos, F64, N * ps, 'pos'), ps,
+                                    _chk(nrm, F64, N * ns, 'nrm'), ns, rec.data_ptr(), _stream())
+    _lib.check(rc, 'xrt_kirchhoff_pack_f64')
+    return rec
+
+
+def kirchhoff_packed(xM, yM, zM, records, out=None, convention='numpy', relaxed=False, R=0, uniform_normal=False,
+                     table_sincos=False):
+    """a17 from packed records (kirchhoff_pack, possibly all-gathered over ranks).  table_sincos=True: the caller
+    vouches for |k r| < PHASE_LIMIT_TABLE_SINCOS (phase_bound on its own samples and receiving points)."""
+    lib = _lib.load()
+    M, N = xM.numel(), records.shape[0]
+    flags = (1 if relaxed else 0) | ((1 if convention == 'opencl' else 0) << 1) | (int(R) << 4) | \
+        ((1 if uniform_normal else 0) << 9) | ((1 if table_sincos else 0) << 11)
+    ws = kirchhoff_workspace(xM.device, lib.xrt_kirchhoff_workspace_bytes(M, N, flags))
+    if out is None:
+        out = torch.empty((5, M), dtype=C128, device=xM.device)
+    if not (records.is_cuda and records.is_contiguous() and records.dtype == torch.uint8):
+        raise ValueError('records: contiguous CUDA uint8 (N, 128)')
+    rc = lib.xrt_kirchhoff_packed_f64(M, N, _chk(xM, F64, M, 'xM'), _chk(yM, F64, M, 'yM'), _chk(zM, F64, M, 'zM'),
+                                      records.data_ptr(), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                      out[3].data_ptr(), out[4].data_ptr(), flags, ws.data_ptr(), _stream())
+    _lib.check(rc, 'xrt_kirchhoff_packed_f64')
     return out
 
 

@@ -469,6 +469,8 @@ class OE(object):
     def local_to_global(self, lb):
         """OE.local_to_global (oes/base.py:1165-1229) for a device Beam, in place: back-rotation, coherency matrix
         and amplitudes turned by roll + atan2(n_x, n_z), then virgin local -> global."""
+        from .waves import _refuse_two_surface
+        _refuse_two_surface(self, 'local_to_global')
         if self.dx:
             lb.x = lb.x + self.dx
         rots = []

@@ -188,8 +188,12 @@ Screen.prepare_wave = _screen_prepare_wave
 class RectangularAperture(_Plane):
     """Rectangular aperture / slit (apertures.py:52-413)."""
 
+    #: the reference's default blades (apertures.py:64-65): a script that gives neither kind / opening nor blades gets
+    #: a +-10 mm opening, not an open plane
+    DEFAULT_BLADES = {'left': -10, 'right': 10, 'bottom': -10, 'top': 10}
+
     def __init__(self, bl=None, name='', center=[0, 0, 0], kind=None, opening=None, x='auto', z='auto',
-                 alarmLevel=None, blades=None, **kwargs):
+                 alarmLevel=None, blades=DEFAULT_BLADES, **kwargs):
         self.bl = bl
         self.name = name
         if bl is not None:
@@ -208,14 +212,16 @@ class RectangularAperture(_Plane):
         self.isBeamStop = kwargs.get('isBeamStop', False)
         self.spotLimits = [0, 0, 0, 0]
         self.alarmLevel = alarmLevel
-        if blades is not None:
-            self.blades = dict(blades)
-        else:
+        if kind is not None or opening is not None:  # kind / opening take precedence over blades (apertures.py:162-174)
             if kind is None and opening is not None:
                 kind = list(_BLADE_ORDER[:len(opening)]) if hasattr(opening, '__len__') else [_BLADE_ORDER[0]]
             if isinstance(kind, str):
                 kind, opening = (kind,), [opening]
             self.blades = {k: v for k, v in zip(kind or [], opening or []) if v is not None}
+        elif blades is not None:
+            self.blades = {k: v for k, v in dict(blades).items() if v is not None}
+        else:
+            self.blades = {}
         self.set_optical_limits()
 
     def set_optical_limits(self):

@@ -30,6 +30,15 @@ def _rotate_z(x, y, cosangle, sinangle):
     return cosangle*x - sinangle*y, sinangle*x + cosangle*y
 
 
+def _refuse_two_surface(oe, what):
+    """A DCM / Plate / lens as the diffracting or the previous element needs the second-surface frame of the
+    reference (is2ndXtal: yaw = -pi, dt = -t, pitch + bragg, cryst2* angles; waves.py:545-566, oes/base.py:1169-1186),
+    which is outside the hot path: refuse it instead of using the single-surface frame silently."""
+    if hasattr(oe, 'cryst2pitch') or hasattr(oe, 'bragg') and hasattr(oe, 'cryst2perpTransl'):
+        raise NotImplementedError('{0}: two-surface elements (DCM, Plate, lenses) as the diffracting / previous element '
+                                  'are outside the hot path (second-surface frame of waves.py:545-566)'.format(what))
+
+
 def prepare_wave(fromOE, wave, xglo, yglo, zglo):
     """waves.prepare_wave (waves.py:505-584): receiving points -> fromOE-local coordinates, accumulators."""
     n = len(wave)
@@ -48,6 +57,7 @@ def prepare_wave(fromOE, wave, xglo, yglo, zglo):
     x, y = _rotate_z(x, y, b0, a0)
     if hasattr(fromOE, 'rotationSequence'):  # OE
         from .oes import _rotation_list
+        _refuse_two_surface(fromOE, 'prepare_wave')
         rots = _rotation_list(fromOE.rotationSequence, -fromOE.pitch, -(fromOE.roll+fromOE.positionRoll),
                               -fromOE.yaw)
         if fromOE.extraPitch or fromOE.extraRoll or fromOE.extraYaw:
@@ -145,17 +155,46 @@ def _hull_area(x, y):
     return 0.5 * abs(sum(x1*y2-x2*y1 for x1, y1, x2, y2 in lines))
 
 
-def diffract(oeLocal, wave, targetOpenCL='CUDA', precisionOpenCL='float64'):
-    """waves.diffract (waves.py:606-831): fills *wave* with the diffracted field and returns the global beam."""
+def _hull_vertices(x, y):
+    from scipy.spatial import ConvexHull
+    pts = np.vstack((x, y)).T
+    if len(pts) < 3:
+        return pts
+    return pts[ConvexHull(pts).vertices, :]
+
+
+def diffract(oeLocal, wave, targetOpenCL='CUDA', precisionOpenCL='float64', comm=None, samplesSharded=False):
+    """waves.diffract (waves.py:606-831): fills *wave* with the diffracted field and returns the global beam.
+
+    *comm* (xrt_b200.parallel.Comm, one process per GPU): *wave* holds THIS rank's shard of the receiving points --
+    outputs are independent, every rank sums over all samples (the reference's run_parallel_max slices the
+    receiving points the same way, myopencl.py:478-491, waves.py:864-894).  *samplesSharded* = True: *oeLocal* is this
+    rank's ray shard of the diffracting samples too; their packed 128-byte records are all-gathered (one collective),
+    the beam sums of waves.py:692-696 all-reduced and the footprint area taken as the hull of the ranks' hulls."""
     oe = wave.fromOE
+    sharded = comm is not None and comm.world > 1 and samplesSharded
+    dev = oeLocal.device
     good = oeLocal.state == 1
     goodlen = int(good.sum())
-    if goodlen < 1e2 or len(wave.xDiffr) == 0:
+    goodlenAll = goodlen
+    if sharded:
+        goodlenAll = int(comm.allreduce_sum(torch.tensor([goodlen], dtype=torch.int64, device=dev)).item())
+    if goodlenAll < 1e2 or len(wave.xDiffr) == 0:
         return Beam(goodlen, device=oeLocal.device)
     isOE = hasattr(oe, 'rotationSequence')
     if getattr(oeLocal, 'area', None) is None or oeLocal.area <= 0:
         second = oeLocal.y if isOE else oeLocal.z
-        oeLocal.area = _hull_area(oeLocal.x[good].cpu().numpy(), second[good].cpu().numpy())
+        hx, hy = oeLocal.x[good].cpu().numpy(), second[good].cpu().numpy()
+        if sharded:
+            # the hull of the union is the hull of the ranks' hull vertices (a few hundred points per rank)
+            import torch.distributed as dist
+            mine = _hull_vertices(hx, hy)
+            parts = [None] * comm.world
+            dist.all_gather_object(parts, mine)
+            allv = np.concatenate([p for p in parts if len(p)])
+            oeLocal.area = _hull_area(allv[:, 0], allv[:, 1])
+        else:
+            oeLocal.area = _hull_area(hx, hy)
         if hasattr(oeLocal, 'areaFraction'):
             oeLocal.area *= oeLocal.areaFraction
     idx = torch.nonzero(good).flatten()
@@ -176,10 +215,13 @@ def diffract(oeLocal, wave, targetOpenCL='CUDA', precisionOpenCL='float64'):
         nvec = (0., 1., 0.)
         nl = a*nvec[0] + b*nvec[1] + c*nvec[2]
     Jtot = sel(oeLocal.Jss) + sel(oeLocal.Jpp)
+    sums = torch.stack((Jtot.sum(), (Jtot * nl).sum()))
+    if sharded:
+        comm.allreduce_sum(sums)  # waves.py:692-696 over the whole beam
     wave.diffract_repeats += 1
-    wave.beamReflRays += goodlen
-    wave.beamReflSumJ += float(Jtot.sum())
-    wave.beamReflSumJnl += abs(float((Jtot * nl).sum()))
+    wave.beamReflRays += goodlenAll
+    wave.beamReflSumJ += float(sums[0])
+    wave.beamReflSumJnl += abs(float(sums[1]))
 
     E = sel(oeLocal.E)
     # waves.py:842.  torch divides a tensor by a Python scalar as a multiplication by its reciprocal, which is
@@ -190,9 +232,23 @@ def diffract(oeLocal, wave, targetOpenCL='CUDA', precisionOpenCL='float64'):
         nrm = torch.tensor(nvec + (0.,), dtype=F64, device=x.device).repeat(goodlen, 1).contiguous()
     else:
         nrm = torch.stack((nX, nY, nZ, torch.zeros_like(nX)), dim=1).contiguous()
-    out = kernels.kirchhoff(wave.xDiffr.contiguous(), wave.yDiffr.contiguous(), wave.zDiffr.contiguous(), nl,
-                            sel(oeLocal.Es), sel(oeLocal.Ep), k, pos, nrm, convention='numpy',
-                            uniform_normal=nvec is not None)
+    if sharded:
+        # every rank's own bound on |k r| (its samples x its receiving points), the largest decides for all
+        pb = torch.tensor([kernels.phase_bound(wave.xDiffr, wave.yDiffr, wave.zDiffr, pos, k)], dtype=F64, device=dev)
+        far = torch.stack((pos[:, :3].abs().max() if goodlen else torch.zeros((), dtype=F64, device=dev),
+                           torch.stack((wave.xDiffr.abs().max(), wave.yDiffr.abs().max(), wave.zDiffr.abs().max())).max(),
+                           k.abs().max() if goodlen else torch.zeros((), dtype=F64, device=dev)))
+        comm.allreduce_max(far)  # samples of other ranks may lie farther: bound with the global extents
+        pb = max(float(pb[0]), float(far[2] * (far[0] + far[1]) * 3**0.5))
+        rec = kernels.kirchhoff_pack(nl, sel(oeLocal.Es), sel(oeLocal.Ep), k, pos, nrm)
+        rec = comm.allgather_rows(rec)  # the single collective of the sharded Kirchhoff step: 128 B per sample
+        out = kernels.kirchhoff_packed(wave.xDiffr.contiguous(), wave.yDiffr.contiguous(), wave.zDiffr.contiguous(),
+                                       rec, convention='numpy', uniform_normal=nvec is not None,
+                                       table_sincos=pb < kernels.PHASE_LIMIT_TABLE_SINCOS)
+    else:
+        out = kernels.kirchhoff(wave.xDiffr.contiguous(), wave.yDiffr.contiguous(), wave.zDiffr.contiguous(), nl,
+                                sel(oeLocal.Es), sel(oeLocal.Ep), k, pos, nrm, convention='numpy',
+                                uniform_normal=nvec is not None)
     Es, Ep, aE, bE, cE = out[0], out[1], out[2], out[3], out[4]
 
     wave.EsAcc += Es
@@ -200,14 +256,22 @@ def diffract(oeLocal, wave, targetOpenCL='CUDA', precisionOpenCL='float64'):
     wave.aEacc += aE
     wave.bEacc += bE
     wave.cEacc += cE
-    wave.E = torch.full_like(wave.E, float(oeLocal.E[0]))
+    E0 = oeLocal.E[:1].clone() if len(oeLocal) else torch.zeros(1, dtype=F64, device=dev)
+    if sharded:
+        comm.broadcast(E0, 0)  # the first ray of the whole beam
+    wave.E = torch.full_like(wave.E, float(E0[0]))
     wave.Es = wave.EsAcc.clone()
     wave.Ep = wave.EpAcc.clone()
     wave.Jss = (wave.Es * torch.conj(wave.Es)).real.clone()
     wave.Jpp = (wave.Ep * torch.conj(wave.Ep)).real.clone()
     wave.Jsp = wave.Es * torch.conj(wave.Ep)
     if isOE:
-        toRealComp = wave.cEacc if abs(complex(wave.cEacc[0])) > abs(complex(wave.bEacc[0])) else wave.bEacc
+        # decided on the FIRST receiving point of the whole wave (waves.py:719-722): rank 0's when they are sharded
+        useC = torch.tensor([1 if abs(complex(wave.cEacc[0])) > abs(complex(wave.bEacc[0])) else 0],
+                            dtype=torch.int64, device=dev)
+        if comm is not None and comm.world > 1:
+            comm.broadcast(useC, 0)
+        toRealComp = wave.cEacc if int(useC[0]) else wave.bEacc
     else:
         toRealComp = wave.bEacc
     toReal = torch.exp(-1j * torch.angle(toRealComp))
@@ -230,7 +294,13 @@ def diffract(oeLocal, wave, targetOpenCL='CUDA', precisionOpenCL='float64'):
         wave.accepted = oeLocal.accepted
         wave.acceptedE = oeLocal.acceptedE
         wave.seeded = oeLocal.seeded
-        wave.seededI = oeLocal.seededI * len(wave) / len(oeLocal)
+        lens = torch.tensor([len(wave), len(oeLocal)], dtype=torch.int64, device=dev)
+        if comm is not None and comm.world > 1:
+            own = lens.clone()
+            comm.allreduce_sum(lens)
+            if not sharded:
+                lens[1] = own[1]
+        wave.seededI = oeLocal.seededI * int(lens[0]) / int(lens[1])
 
     glo = Beam(copyFrom=wave)
     glo.parentId = getattr(oe, 'uuid', getattr(oe, 'name', None))
