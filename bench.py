@@ -258,7 +258,9 @@ def run_ours(args):
         saved_stdout = os.dup(1)
         os.dup2(2, 1)
         try:
-            dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+            import datetime
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank),
+                                    timeout=datetime.timedelta(seconds=300))  # a hang fails fast instead of after 10 min
             dist.barrier()
             torch.cuda.synchronize()
             # the exchange steps of the ray / wave path go through the library's own C-ABI NCCL entry points
@@ -366,7 +368,8 @@ def run_ours(args):
     other_steps = max(1, min(args.steps, 3))
     step(fused_chain=not fused_chain)
     ms_other = timed(lambda: step(fused_chain=not fused_chain), other_steps) / other_steps
-    launches = count_own_launches(lambda: step(fused_chain=fused_chain)) if rank == 0 else None
+    # (every rank runs the profiled step: it contains the slot all-reduces)
+    launches = count_own_launches(lambda: step(fused_chain=fused_chain))
 
     # ---- end to end (i): the whole result Beam lands in pinned host memory inside the timed region
     blo = step(fused_chain=fused_chain)

@@ -191,13 +191,14 @@ def test_cuda_packed_records_path_equals_one_call(tilt, cuda_device):
     from xrt_b200 import kernels
     case = synthetic.kirchhoff_case(901, 7001, 1500, tilt=tilt)
     d = _dev_case(case)
-    one = _kernel(d, R=4, uniform_normal=not tilt)
+    one = _kernel(d, R=4, uniform_normal=not tilt, table_sincos=True)
     h = 3000
     recs = [kernels.kirchhoff_pack(d['nl'][sl].contiguous(), d['Es'][sl].contiguous(), d['Ep'][sl].contiguous(),
                                    d['k'][sl].contiguous(), d['pos'][sl].contiguous(), d['nrm'][sl].contiguous())
             for sl in (slice(0, h), slice(h, None))]
     rec = torch.cat(recs).contiguous()
-    two = kernels.kirchhoff_packed(d['xM'], d['yM'], d['zM'], rec, R=4, uniform_normal=not tilt).cpu().numpy()
+    two = kernels.kirchhoff_packed(d['xM'], d['yM'], d['zM'], rec, R=4, uniform_normal=not tilt,
+                                   table_sincos=True).cpu().numpy()
     assert np.array_equal(one.view(np.float64), two.view(np.float64))
 
 

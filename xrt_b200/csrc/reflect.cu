@@ -68,6 +68,7 @@ enum {
   RS_FOOT = 28,  // footprint min x,y,z / max x,y,z of the virgin-local output (reflect.py:1133-1136)
   RS_NGOOD = 34, // number of rays with state > 0 on entry (plain integer count)
   RS_NGOODN = 35, // number of rays with state == 1 after the surface (plain integer count); 36: out-of-table count
+  RS_SIDE_NEG = 37,  // 37, 38: good rays that met an asymmetric crystal's planes with n_B.k < 0 / >= 0 (sgbdn check)
   RS_DERIV = 40,  // multiple_reflect, derivative stage: {min t1, max t2, max |dz1|, max |dz2| masked} (base.py:861-871)
   RS_DECISION = 44,  // 44..46: the decoded beam-wide decision of the main pass (reflect_decide_kernel)
   RS_HINT = 48    // 48..63: 32 ints, the last f1/f2 table interval found per element table (f1f2_locate)
@@ -1726,6 +1727,7 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
   double fmin3[3] = {inf, inf, inf}, fmax3[3] = {-inf, -inf, -inf};
   unsigned long long ngoodN = 0;
   int oor = 0;
+  int sideFlags = 0;  // asymmetric crystal: bit0 the ray met the planes with n_B.k < 0, bit1 with n_B.k >= 0
   const bool hasLb = lb.x != nullptr;
   const bool amp = in.Es != nullptr;
   const bool fbIsInput = fb.x == in.x;
@@ -1749,8 +1751,8 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
       bulk_g2s(ft.Ep, in.Ep + 2 * base, BT * 16, &sbar);
     }
   }
-  __shared__ int sdone, sdoneS;  // warps that delivered their tail results (OE slots, fused screen slots)
-  if (tid == 0) sdone = sdoneS = 0;  // (the block barrier below orders this against the tail's atomicAdd)
+  __shared__ int sdone, sdoneS, sdoneB;  // warps that delivered their tail results (OE slots, fused screen slots, sides)
+  if (tid == 0) sdone = sdoneS = sdoneB = 0;  // (the block barrier below orders this against the tail's atomicAdd)
   int* const ghint = tab.hint;  // reduction slots 48..63
   const bool useHint = (MAT != 0 && MAT != 7) && ghint != nullptr;
   if (useHint) {
@@ -1964,6 +1966,7 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
           // good rays hit the same side of the crystal in the supported geometries (documented in DESIGN.md)
           const double ndsn = nrm[0] * nrm[3] + nrm[1] * nrm[4] + nrm[2] * nrm[5];
           const double sgbdn = (bdn < 0.0) ? 1.0 : -1.0;
+          if (p.asymmetric) sideFlags = (bdn < 0.0) ? 1 : 2;  // which side of the planes this ray met (tail: slots 37 / 38)
           const double wHd = (1.0 + 0.0) / ((MAT == 4 ? ml.d : m.d) * 1e-7);
           const double g0 = (nrm[0] - ndsn * nrm[3]) * wHd * sgbdn;
           const double g1 = (nrm[1] - ndsn * nrm[4]) * wHd * sgbdn;
@@ -2269,6 +2272,21 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
     tail_combine<BT>(es, shs, &sdoneS, sred, RS_NGOOD, -1, lane, warp);
   }
   if (!p.want_footprint) return;
+  if ((MAT == 3 || MAT == 4) && p.asymmetric) {
+    // The reference takes the sign sgbdn of the asymmetric-cut deflection from the MEAN of n_B.k over the beam
+    // (reflect.py:575-576), the kernel per ray: the same thing unless rays meet the planes from both sides.  Count the
+    // two sides (slots 37, 38) so that the host can refuse that case instead of deviating silently.
+    __shared__ unsigned long long shb[BT / 32][8];
+    unsigned long long eb[8];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      eb[k] = enc(inf);
+      eb[3 + k] = enc(-inf);
+    }
+    eb[6] = (sideFlags & 1) ? 1ull : 0ull;
+    eb[7] = (sideFlags & 2) ? 1ull : 0ull;
+    tail_combine<BT>(eb, shb, &sdoneB, red, RS_SIDE_NEG, RS_SIDE_NEG + 1, lane, warp);
+  }
   __shared__ unsigned long long sh[BT / 32][8];
   unsigned long long e[8];
 #pragma unroll

@@ -427,8 +427,16 @@ class OE(object):
 
     def _check_tables(self, red):
         """Element.get_f1f2 raises ValueError when an energy is outside the table (element.py:254-260)."""
-        if int(red[RS_OOR].item()) > 0:
+        vals = red[RS_OOR:RS_OOR + 3].tolist()  # out-of-table count, rays on either side of an asymmetric crystal
+        if int(vals[0]) > 0:
             raise ValueError('E is out of the f1/f2 data table range')
+        if int(vals[1]) > 0 and int(vals[2]) > 0:
+            # reflect.py:575-576 takes ONE sign (of the mean n_B.k over the beam) for the deflection by the asymmetric
+            # cut; the kernel takes it per ray, which is the same unless the beam meets the planes from both sides
+            raise NotImplementedError(
+                'rays meet the asymmetric crystal from both sides of its Bragg planes ({0} / {1} rays): the reference '
+                'deflects all of them with the sign of the beam mean; this case is outside the hot path'.format(
+                    int(vals[1]), int(vals[2])))
 
     def _footprint_from(self, red):
         lib = _lib.load()
