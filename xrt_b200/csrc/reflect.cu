@@ -1800,7 +1800,74 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
     dz1 = find_dz<SURF, MAT == 5>(p, sd, t1, r, x1, y1, z1);
     dz2 = find_dz<SURF, MAT == 5>(p, sd, t2, r, x2, y2, z2);
   }
+#ifdef XRTB_SOLVER_COMPACTION
+  // (-DXRTB_SOLVER_COMPACTION: measured and NOT the default -- 13.2 ms instead of 10.9 ms per 1e8 rays in config 2, the
+  // two extra block barriers, the idle warps behind them and 230 B/thread more spills cost more than the dense loop
+  // saves; profiles/r02_reflect_variants.json.)
+  // Root search on DENSE warps.  Only the rays whose bracket ends straddle the surface are searched (59 % in BASELINE
+  // config 2: the others miss the mirror), and in thread <-> ray order the secant loop ran at 17 of 32 lanes.  The
+  // search is a pure function of ten doubles (local ray, bracket, dz at its ends) that returns four (t, point): those
+  // rays are ranked (ballot + warp counts), their records go to shared memory in rank order, thread k searches the
+  // k-th record, and the owner picks the result up -- the loads and stores of the Beam stay in thread <-> ray order
+  // (coalesced, whole sectors; a full class sort of the rays was measured and rejected for what it does to the stores).
+  const bool needSolve = search && !(dz1 <= 0.0 || dz2 >= 0.0) && fabs(dz2) > kZEps;
+  const unsigned solveBallot = __ballot_sync(0xffffffffu, needSolve);
+  __shared__ unsigned short swc[BT / 32];
+  if (lane == 0) swc[warp] = (unsigned short)__popc(solveBallot);
+#endif
   __syncthreads();
+#ifdef XRTB_SOLVER_COMPACTION
+  {
+    extern __shared__ __align__(16) double sdyn[];
+    double(*sx)[BT] = reinterpret_cast<double(*)[BT]>(sdyn);  // [10][BT]
+    int before = 0, n0 = 0;
+#pragma unroll
+    for (int w = 0; w < BT / 32; ++w) {
+      const int c = swc[w];
+      if (w < warp) before += c;
+      n0 += c;
+    }
+    const int pos = before + __popc(solveBallot & ((1u << lane) - 1u));
+    if (needSolve) {
+      sx[0][pos] = r.x;
+      sx[1][pos] = r.y;
+      sx[2][pos] = r.z;
+      sx[3][pos] = r.a;
+      sx[4][pos] = r.b;
+      sx[5][pos] = r.c;
+      sx[6][pos] = t1;
+      sx[7][pos] = t2;
+      sx[8][pos] = dz1;
+      sx[9][pos] = dz2;
+    }
+    __syncthreads();
+    if (tid < n0) {
+      Ray q;
+      q.x = sx[0][tid];
+      q.y = sx[1][tid];
+      q.z = sx[2][tid];
+      q.a = sx[3][tid];
+      q.b = sx[4][tid];
+      q.c = sx[5][tid];
+      double a1 = sx[6][tid], a2 = sx[7][tid], f1 = sx[8][tid], f2 = sx[9][tid], px = 0.0, py = 0.0, pz = 0.0;
+      if (d.brent)
+        solve_brent<SURF, MAT == 5>(p, sd, q, a1, a2, f1, f2, px, py, pz);
+      else
+        solve_secant<SURF, MAT == 5>(p, sd, q, d, a1, a2, f1, f2, px, py, pz);
+      sx[6][tid] = a2;  // (each thread only touches its own record)
+      sx[0][tid] = px;
+      sx[1][tid] = py;
+      sx[2][tid] = pz;
+    }
+    __syncthreads();
+    if (needSolve) {
+      t2 = sx[6][pos];
+      x2 = sx[0][pos];
+      y2 = sx[1][pos];
+      z2 = sx[2][pos];
+    }
+  }
+#endif
 
   if (i < n) {
     if (!alive) {
@@ -1849,12 +1916,14 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
           y2 = y1;
           z2 = z1;
         }
+#ifndef XRTB_SOLVER_COMPACTION
         if (!(ind1 || ind2)) {
           if (d.brent)
             solve_brent<SURF, MAT == 5>(p, sd, r, t1, t2, dz1, dz2, x2, y2, z2);
           else
             solve_secant<SURF, MAT == 5>(p, sd, r, d, t1, t2, dz1, dz2, x2, y2, z2);
         }
+#endif
       }
       if (bulk) mbar_wait(&sbar, 0);  // the field tile landed long ago
       const double tMax = t2;
@@ -2317,6 +2386,13 @@ __global__ void screen_reduction_init_kernel(unsigned long long* red) {
   red[i] = v;
 }
 
+// dynamic shared memory of the main pass: the ten-double records of the rays whose root is searched on dense warps
+#ifdef XRTB_SOLVER_COMPACTION
+constexpr size_t kSolverSmem = 10 * sizeof(double) * XRTB_REFLECT_THREADS;
+#else
+constexpr size_t kSolverSmem = 0;
+#endif
+
 // everything a main-pass launch needs besides the material switch; scr != NULL: fused Screen.expose (GlobalSink)
 struct MainLaunch {
   unsigned grid;
@@ -2347,12 +2423,16 @@ static void launch_one(const MainLaunch& L) {
     if constexpr ((SURF == 0 || SURF == 1 || SURF == 2) && (MAT == 0 || MAT == 1 || MAT == 3)) {
       sp = *L.scrp;
       scr = *L.scr;
-      reflect_main_kernel<SURF, MAT, true><<<L.grid, XRTB_REFLECT_THREADS, 0, L.st>>>(
+      cudaFuncSetAttribute(reflect_main_kernel<SURF, MAT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)kSolverSmem);
+      reflect_main_kernel<SURF, MAT, true><<<L.grid, XRTB_REFLECT_THREADS, kSolverSmem, L.st>>>(
           L.n, *L.p, *L.m, *L.ml, L.t, L.in, L.fb, L.gb, L.lb, L.red, bulk_ok, cR, sR, sp, scr, L.sred);
     }
     return;
   }
-  reflect_main_kernel<SURF, MAT, false><<<L.grid, XRTB_REFLECT_THREADS, 0, L.st>>>(
+  cudaFuncSetAttribute(reflect_main_kernel<SURF, MAT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)kSolverSmem);
+  reflect_main_kernel<SURF, MAT, false><<<L.grid, XRTB_REFLECT_THREADS, kSolverSmem, L.st>>>(
       L.n, *L.p, *L.m, *L.ml, L.t, L.in, L.fb, L.gb, L.lb, L.red, bulk_ok, cR, sR, sp, scr, nullptr);
 }
 
