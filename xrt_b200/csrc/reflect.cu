@@ -1482,6 +1482,12 @@ __device__ __forceinline__ void copy_ray(const xrt_beam& dst, const xrt_beam& sr
 struct FieldTile {
   double path[XRTB_REFLECT_THREADS], E[XRTB_REFLECT_THREADS], Jss[XRTB_REFLECT_THREADS], Jpp[XRTB_REFLECT_THREADS];
   double2 Jsp[XRTB_REFLECT_THREADS], Es[XRTB_REFLECT_THREADS], Ep[XRTB_REFLECT_THREADS];
+  // ... and the geometry (its own mbarrier: needed at once): rays that are passed through (lost, dead) take their
+  // position and direction from here instead of reading them from HBM a second time (20 B/ray of DRAM reads in
+  // BASELINE config 2, where 41 % of the rays miss the mirror)
+  double x[XRTB_REFLECT_THREADS], y[XRTB_REFLECT_THREADS], z[XRTB_REFLECT_THREADS], a[XRTB_REFLECT_THREADS],
+      b[XRTB_REFLECT_THREADS], c[XRTB_REFLECT_THREADS];
+  int state[XRTB_REFLECT_THREADS];
 };
 
 // gb (or lb) of a ray that is passed through: geometry from `src` in global memory, fields from the staged tile when
@@ -1489,7 +1495,9 @@ struct FieldTile {
 __device__ __forceinline__ void copy_ray_staged(const xrt_beam& dst, const xrt_beam& src, bool srcIsInput,
                                                 const FieldTile& ft, int tid, bool amp, size_t i, int state) {
   // (every load before the first store: the arrays are not __restrict__, and a load behind a store would wait for it)
-  const double x = src.x[i], y = src.y[i], z = src.z[i], a = src.a[i], b = src.b[i], c = src.c[i];
+  const double x = srcIsInput ? ft.x[tid] : src.x[i], y = srcIsInput ? ft.y[tid] : src.y[i],
+               z = srcIsInput ? ft.z[tid] : src.z[i], a = srcIsInput ? ft.a[tid] : src.a[i],
+               b = srcIsInput ? ft.b[tid] : src.b[i], c = srcIsInput ? ft.c[tid] : src.c[i];
   if (srcIsInput) {
     dst.path[i] = ft.path[tid];
     dst.E[i] = ft.E[tid];
@@ -1679,7 +1687,9 @@ struct GlobalSink {
 template <bool FUSE>
 __device__ __forceinline__ void pass_ray(GlobalSink<FUSE>& sink, const xrt_beam& src, bool srcIsInput,
                                          const FieldTile& ft, int tid, bool amp, size_t i, int state) {
-  const double x = src.x[i], y = src.y[i], z = src.z[i], a = src.a[i], b = src.b[i], c = src.c[i];
+  const double x = srcIsInput ? ft.x[tid] : src.x[i], y = srcIsInput ? ft.y[tid] : src.y[i],
+               z = srcIsInput ? ft.z[tid] : src.z[i], a = srcIsInput ? ft.a[tid] : src.a[i],
+               b = srcIsInput ? ft.b[tid] : src.b[i], c = srcIsInput ? ft.c[tid] : src.c[i];
   double path, E, Jss, Jpp;
   cplx Jsp, Es = cplx{0.0, 0.0}, Ep = cplx{0.0, 0.0};
   const bool hasE = sink.wants_amplitudes() && (srcIsInput ? amp : src.Es != nullptr);
@@ -1731,15 +1741,25 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
   const bool hasLb = lb.x != nullptr;
   const bool amp = in.Es != nullptr;
   const bool fbIsInput = fb.x == in.x;
-  __shared__ __align__(16) FieldTile ft;
-  __shared__ __align__(8) uint64_t sbar;
+  extern __shared__ __align__(16) unsigned char sdyn_raw[];
+  FieldTile& ft = *reinterpret_cast<FieldTile*>(sdyn_raw);
+  __shared__ __align__(8) uint64_t sbar, sbarG;
   __shared__ int shint[34];  // f1/f2 interval guesses per element table, [32] "changed" flag, [33] warps done
   // full tiles of 16-byte aligned arrays go through the bulk-copy engine; the last (ragged) tile and beams that are
   // views at odd offsets are staged with plain loads (each thread only ever reads its own slot)
   const bool bulk = bulk_ok && (base + BT <= n);
   if (tid == 0 && bulk) {
     mbar_init(&sbar, 1);
+    mbar_init(&sbarG, 1);
     mbar_fence_init();
+    mbar_expect_tx(&sbarG, (uint32_t)(BT * (6 * 8 + 4)));
+    bulk_g2s(ft.state, in.state + base, BT * 4, &sbarG);
+    bulk_g2s(ft.x, in.x + base, BT * 8, &sbarG);
+    bulk_g2s(ft.y, in.y + base, BT * 8, &sbarG);
+    bulk_g2s(ft.z, in.z + base, BT * 8, &sbarG);
+    bulk_g2s(ft.a, in.a + base, BT * 8, &sbarG);
+    bulk_g2s(ft.b, in.b + base, BT * 8, &sbarG);
+    bulk_g2s(ft.c, in.c + base, BT * 8, &sbarG);
     mbar_expect_tx(&sbar, (uint32_t)(BT * (4 * 8 + (amp ? 3 : 1) * 16)));
     bulk_g2s(ft.path, in.path + base, BT * 8, &sbar);
     bulk_g2s(ft.E, in.E + base, BT * 8, &sbar);
@@ -1762,16 +1782,15 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
   } else {
     tab.hint = nullptr;
   }
-  // state, geometry and the packed decision are requested at once (dead rays included, their values are dropped)
-  int st0 = 0;
-  Ray r;
-  r.x = r.y = r.z = r.a = r.b = r.c = 0.0;
-  if (i < n) {
-    st0 = in.state[i];
-    r = load_ray(in, i);
-  }
   const Decision d = load_decision(red);
   if (!bulk && i < n) {
+    ft.state[tid] = in.state[i];
+    ft.x[tid] = in.x[i];
+    ft.y[tid] = in.y[i];
+    ft.z[tid] = in.z[i];
+    ft.a[tid] = in.a[i];
+    ft.b[tid] = in.b[i];
+    ft.c[tid] = in.c[i];
     ft.path[tid] = in.path[i];
     ft.E[tid] = in.E[i];
     ft.Jss[tid] = in.Jss[i];
@@ -1781,6 +1800,22 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
       ft.Es[tid] = reinterpret_cast<const double2*>(in.Es)[i];
       ft.Ep[tid] = reinterpret_cast<const double2*>(in.Ep)[i];
     }
+  }
+  // state and geometry come from the staged tile (the bulk copies were issued by thread 0 above; the barrier makes
+  // the mbarrier initialisation visible before anybody waits on it)
+  __syncthreads();
+  if (bulk) mbar_wait(&sbarG, 0);
+  int st0 = 0;
+  Ray r;
+  r.x = r.y = r.z = r.a = r.b = r.c = 0.0;
+  if (i < n) {
+    st0 = ft.state[tid];
+    r.x = ft.x[tid];
+    r.y = ft.y[tid];
+    r.z = ft.z[tid];
+    r.a = ft.a[tid];
+    r.b = ft.b[tid];
+    r.c = ft.c[tid];
   }
   const bool alive = i < n && (p.good_mode ? (st0 == 1 || st0 == 2) : (st0 > 0));
   // the geometric part that every traced ray shares runs BEFORE the block barrier, which then only has to publish
@@ -1814,12 +1849,9 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
   const unsigned solveBallot = __ballot_sync(0xffffffffu, needSolve);
   __shared__ unsigned short swc[BT / 32];
   if (lane == 0) swc[warp] = (unsigned short)__popc(solveBallot);
-#endif
   __syncthreads();
-#ifdef XRTB_SOLVER_COMPACTION
   {
-    extern __shared__ __align__(16) double sdyn[];
-    double(*sx)[BT] = reinterpret_cast<double(*)[BT]>(sdyn);  // [10][BT]
+    double(*sx)[BT] = reinterpret_cast<double(*)[BT]>(sdyn_raw + sizeof(FieldTile));  // [10][BT]
     int before = 0, n0 = 0;
 #pragma unroll
     for (int w = 0; w < BT / 32; ++w) {
@@ -2157,7 +2189,7 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
         fmax3[1] = v.y;
         fmax3[2] = v.z;
         if (p.multi && st == 3) {  // tmpX, tmpY, tmpZ: the entry point in virgin-local coordinates (after the footprint)
-          double wx = in.x[i], wy = in.y[i], wz = in.z[i];
+          double wx = ft.x[tid], wy = ft.y[tid], wz = ft.z[tid];
           if (p.from_global) {
             wx -= p.center[0];
             wy -= p.center[1];
@@ -2386,11 +2418,11 @@ __global__ void screen_reduction_init_kernel(unsigned long long* red) {
   red[i] = v;
 }
 
-// dynamic shared memory of the main pass: the ten-double records of the rays whose root is searched on dense warps
+// dynamic shared memory of the main pass: the staged tile (+ the records of the optional solver compaction)
 #ifdef XRTB_SOLVER_COMPACTION
-constexpr size_t kSolverSmem = 10 * sizeof(double) * XRTB_REFLECT_THREADS;
+constexpr size_t kSolverSmem = sizeof(FieldTile) + 10 * sizeof(double) * XRTB_REFLECT_THREADS;
 #else
-constexpr size_t kSolverSmem = 0;
+constexpr size_t kSolverSmem = sizeof(FieldTile);  // the staged tile of the block (fields + geometry: 130 B/ray)
 #endif
 
 // everything a main-pass launch needs besides the material switch; scr != NULL: fused Screen.expose (GlobalSink)
