@@ -922,7 +922,9 @@ __device__ __forceinline__ cplx bragg_one_pol(double polFactor, cplx alpha, cplx
   if (ad.re == 0.0 && ad.im == 0.0) ad = cplx{1e-100, 0.0};
   const cplx rb = cdiv(num, ad);
   if (isnan(ra.re) || isnan(ra.im)) ra = rb;
-  if (cabs(rb) < cabs(ra)) ra = rb;
+  // abs(rb) < abs(ra) (crystal.py:592-596) decided on the squared magnitudes: the two roots differ by the absorption
+  // (percents), the values are far from over- / underflow, and two hypot calls per polarisation are ~100 instructions
+  if (cabs2(rb) < cabs2(ra)) ra = rb;
   return cdiv_re(ra, sqrt(fabs(b)));
 }
 
@@ -972,14 +974,16 @@ __device__ __forceinline__ void crystal_amplitude(const xrt_material_params& m, 
   double sa = 1.0 * CH / (2.0 * m.d * E);
   if (sa > 1.0) sa = 1.0 - 1e-16;
   if (sa < -1.0) sa = -1.0 + 1e-16;
-  const double thetaB = asin(sa);
+  // polarisation factor of the p branch: cos(2 thetaB) with thetaB = arcsin(sa) is 1 - 2 sa^2 (agrees with
+  // cos(2.0 * asin(sa)) to 2 ulp; it multiplies chi_h, no cancellation follows) -- asin + cos are ~130 instructions
+  const double cos2ThetaB = fma(-2.0 * sa, sa, 1.0);
   // alpha = (H2/2 - k0H) / k02 + chi0/2 * (1/b - 1)
   const double a1 = (H2 / 2.0 - k0H) / k02;
   const cplx half_chi0 = cdiv_re(chi0, 2.0);
   const cplx a2 = cmul_np(half_chi0, cplx{1.0 / b - 1.0, 0.0});
   const cplx alpha = cplx{a1 + a2.re, 0.0 + a2.im};
   rs = bragg_one_pol(1.0, alpha, chih, chih_, b, m.t, m.geom, chi0, k02, kHs, k0s);
-  rp = bragg_one_pol(cos(2.0 * thetaB), alpha, chih, chih_, b, m.t, m.geom, chi0, k02, kHs, k0s);
+  rp = bragg_one_pol(cos2ThetaB, alpha, chih, chih_, b, m.t, m.geom, chi0, k02, kHs, k0s);
 }
 
 // ---------------------------------------------------------------- f2: multilayer (materials/multilayer.py)
@@ -2400,6 +2404,588 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
   tail_combine<BT>(e, sh, &sdone, red, RS_NGOODN, RS_NGOODN + 1, lane, warp);
 }
 
+#ifndef XRTB_PLUGIN
+// ================================================================ r02 "tile" structure of the main pass
+// The same per-ray arithmetic as reflect_main_kernel (every expression below is taken from there, in the same order),
+// with the work laid out differently:
+//  * the block's 512 rays live in shared memory for the whole kernel: the input tile arrives by bulk-async copies (TMA),
+//    is overwritten IN PLACE with the global beam, the local beam's own values sit next to it, and both beams leave by
+//    bulk-async stores (cp.async.bulk shared -> global): whole 4-KB runs per array, no per-thread store, no address
+//    arithmetic;
+//  * phase 1 (thread <-> ray): frame change, bracket, find_dz at both ends -> class of the ray (searched / not
+//    searched / dead);
+//  * the rays are ranked by class (ballots + one 16-entry prefix), and in phase 2 thread k takes the k-th ray of that
+//    order: the warps that run the root search, the surface normal and the Fresnel / Bragg amplitudes are DENSE (in
+//    BASELINE config 2, where 41 % of the rays miss the mirror, reflect_main_kernel ran them at 19 of 32 lanes), and
+//    because results go to the ray's own slot of the tile the stores to HBM stay whole sectors -- the block-level sort
+//    measured in profiles/r02_reflect_variants.json lost exactly there;
+//  * phase 3 (thread <-> ray): the global beam's coherency matrix and amplitudes are turned back from the local
+//    polarisation frame (the tile keeps the local-frame values, which are the local beam's) and stored, or, fused with
+//    Screen.expose, the whole global ray goes through GlobalSink<true>.
+// Serves flat / toroidal / elliptic surfaces with material kinds 0, 1, 3, single-pass reflect; everything else stays on
+// reflect_main_kernel.  XRTB_REFLECT_TILE=0 in the environment forces the old kernel (tests compare the two bit for bit).
+constexpr int kTileRays = 512;
+struct RayTile {
+  // the global beam, in place of the input
+  double x[kTileRays], y[kTileRays], z[kTileRays], a[kTileRays], b[kTileRays], c[kTileRays];
+  double path[kTileRays], E[kTileRays], Jss[kTileRays], Jpp[kTileRays];  // J, Es, Ep: LOCAL polarisation frame after phase 2
+  double2 Jsp[kTileRays], Es[kTileRays], Ep[kTileRays];
+  // the local beam's own values; la, lb, lc, theta carry (t1, t2, dz1, dz2) from phase 1 to phase 2
+  double lx[kTileRays], ly[kTileRays], lz[kTileRays], la[kTileRays], lb[kTileRays], lc[kTileRays], theta[kTileRays];
+  double2 cs[kTileRays];  // (cosY, sinY) of the polarisation frame; x = 2: fields as they are, x = 3: global ray from fb
+  int state[kTileRays], lstate[kTileRays];
+  unsigned short idx[kTileRays];  // ray slots in class order
+};
+
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// the point find_dz evaluates the surface at (base.py:831-839)
+template <int SURF>
+__device__ __forceinline__ void ray_point(const xrt_oe_params& p, const Ray& r, double t, double& x, double& y,
+                                          double& z) {
+  x = r.x + r.a * t;
+  y = r.y + r.b * t;
+  z = r.z + r.c * t;
+  xyz_to_param<SURF>(p, x, y, z);
+}
+
+template <int SURF, int MAT, bool FUSE>
+__global__ void __launch_bounds__(kTileRays, 2)
+    reflect_tile_kernel(size_t n, xrt_oe_params p, xrt_material_params m, Tables tab, xrt_beam in, xrt_beam fb,
+                        xrt_beam gb, xrt_beam lb, unsigned long long* red, int bulk_ok, double cosRoll, double sinRoll,
+                        xrt_plane_params scrp, xrt_beam scr, unsigned long long* sred) {
+  constexpr int BT = kTileRays;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const size_t base = (size_t)blockIdx.x * BT;
+  const size_t i = base + tid;
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  extern __shared__ __align__(128) unsigned char sdyn_raw[];
+  RayTile& T = *reinterpret_cast<RayTile*>(sdyn_raw);
+  __shared__ __align__(8) uint64_t sbar, sbarG;
+  __shared__ int shint[34];
+  __shared__ unsigned swc[BT / 32];
+  __shared__ int sdone, sdoneS, sdoneB;
+  const bool hasLb = lb.x != nullptr;
+  const bool amp = in.Es != nullptr;
+  const bool fbIsInput = fb.x == in.x;
+  const bool bulk = bulk_ok && (base + BT <= n);
+  if (tid == 0 && bulk) {
+    mbar_init(&sbar, 1);
+    mbar_init(&sbarG, 1);
+    mbar_fence_init();
+    mbar_expect_tx(&sbarG, (uint32_t)(BT * (6 * 8 + 4)));
+    bulk_g2s(T.state, in.state + base, BT * 4, &sbarG);
+    bulk_g2s(T.x, in.x + base, BT * 8, &sbarG);
+    bulk_g2s(T.y, in.y + base, BT * 8, &sbarG);
+    bulk_g2s(T.z, in.z + base, BT * 8, &sbarG);
+    bulk_g2s(T.a, in.a + base, BT * 8, &sbarG);
+    bulk_g2s(T.b, in.b + base, BT * 8, &sbarG);
+    bulk_g2s(T.c, in.c + base, BT * 8, &sbarG);
+    mbar_expect_tx(&sbar, (uint32_t)(BT * (4 * 8 + (amp ? 3 : 1) * 16)));
+    bulk_g2s(T.path, in.path + base, BT * 8, &sbar);
+    bulk_g2s(T.E, in.E + base, BT * 8, &sbar);
+    bulk_g2s(T.Jss, in.Jss + base, BT * 8, &sbar);
+    bulk_g2s(T.Jpp, in.Jpp + base, BT * 8, &sbar);
+    bulk_g2s(T.Jsp, in.Jsp + 2 * base, BT * 16, &sbar);
+    if (amp) {
+      bulk_g2s(T.Es, in.Es + 2 * base, BT * 16, &sbar);
+      bulk_g2s(T.Ep, in.Ep + 2 * base, BT * 16, &sbar);
+    }
+  }
+  if (tid == 0) sdone = sdoneS = sdoneB = 0;
+  int* const ghint = tab.hint;
+  const bool useHint = (MAT != 0) && ghint != nullptr;
+  if (useHint) {
+    if (tid >= BT - 32) shint[tid - (BT - 32)] = ghint[tid - (BT - 32)];
+    if (tid < 2) shint[32 + tid] = 0;
+    tab.hint = shint;
+  } else {
+    tab.hint = nullptr;
+  }
+  const Decision d = load_decision(red);
+  if (!bulk && i < n) {
+    T.state[tid] = in.state[i];
+    T.x[tid] = in.x[i];
+    T.y[tid] = in.y[i];
+    T.z[tid] = in.z[i];
+    T.a[tid] = in.a[i];
+    T.b[tid] = in.b[i];
+    T.c[tid] = in.c[i];
+    T.path[tid] = in.path[i];
+    T.E[tid] = in.E[i];
+    T.Jss[tid] = in.Jss[i];
+    T.Jpp[tid] = in.Jpp[i];
+    T.Jsp[tid] = reinterpret_cast<const double2*>(in.Jsp)[i];
+    if (amp) {
+      T.Es[tid] = reinterpret_cast<const double2*>(in.Es)[i];
+      T.Ep[tid] = reinterpret_cast<const double2*>(in.Ep)[i];
+    }
+  }
+  __syncthreads();
+  if (bulk) mbar_wait(&sbarG, 0);
+  const SurfDiv sd = make_surf_div<SURF>(p);
+
+  // ---- phase 1, thread <-> ray: class of the ray
+  int cls = 0;  // 0 nothing to trace, 1 root search, 2 traced without a search
+  T.cs[tid] = make_double2(2.0, 0.0);
+  if (i < n) {
+    const int st0 = T.state[tid];
+    Ray r{T.x[tid], T.y[tid], T.z[tid], T.a[tid], T.b[tid], T.c[tid]};
+    const bool alive = p.good_mode ? (st0 == 1 || st0 == 2) : (st0 > 0);
+    if (alive) {
+      to_local(p, r);
+      double t1, t2, xx, yy, zz;
+      bracket(p, d.axis, d.neg, r, t1, t2);  // base.py:848-885
+      const double dz1 = find_dz<SURF, false>(p, sd, t1, r, xx, yy, zz);
+      const double dz2 = find_dz<SURF, false>(p, sd, t2, r, xx, yy, zz);
+      cls = (dz1 <= 0.0 || dz2 >= 0.0) ? 2 : 1;
+      T.la[tid] = t1;
+      T.lb[tid] = t2;
+      T.lc[tid] = dz1;
+      T.theta[tid] = dz2;
+    } else {
+      // rays that are not alive pass through untouched (gb = lb = copy of the input, reflect.py:104-109)
+      T.state[tid] = p.dead_state_lost ? p.lostNum : st0;  // Plate: dcm.py:311-312
+      const bool zero = p.zero_dead_local != 0;            // dcm.py:305-310
+      T.lstate[tid] = zero ? 0 : st0;
+      T.lx[tid] = zero ? 0.0 : r.x;
+      T.ly[tid] = zero ? 0.0 : r.y;
+      T.lz[tid] = zero ? 0.0 : r.z;
+      T.la[tid] = r.a;
+      T.lb[tid] = r.b;
+      T.lc[tid] = r.c;
+      T.theta[tid] = 0.0;
+      if (hasLb && lb.s) {
+        lb.s[i] = T.lx[tid];
+        lb.phi[i] = T.ly[tid];
+        lb.r[i] = T.lz[tid];
+      }
+    }
+  }
+  // rank within the class: searched rays first, then the other traced rays
+  const unsigned bh = __ballot_sync(0xffffffffu, cls == 1), bc = __ballot_sync(0xffffffffu, cls == 2);
+  if (lane == 0) swc[warp] = (unsigned)__popc(bh) | ((unsigned)__popc(bc) << 16);
+  __syncthreads();
+  int nH = 0, nC = 0;
+  {
+    int beforeH = 0, beforeC = 0;
+#pragma unroll
+    for (int w = 0; w < BT / 32; ++w) {
+      const unsigned v = swc[w];
+      const int h = (int)(v & 0xffffu), c = (int)(v >> 16);
+      if (w < warp) {
+        beforeH += h;
+        beforeC += c;
+      }
+      nH += h;
+      nC += c;
+    }
+    const unsigned lt = (1u << lane) - 1u;
+    if (cls == 1) T.idx[beforeH + __popc(bh & lt)] = (unsigned short)tid;
+    if (cls == 2) T.idx[nH + beforeC + __popc(bc & lt)] = (unsigned short)tid;
+  }
+  __syncthreads();
+  if (bulk) mbar_wait(&sbar, 0);  // the field part of the tile landed long ago
+
+  // ---- phase 2, thread k <-> k-th traced ray
+  double fmin3[3] = {inf, inf, inf}, fmax3[3] = {-inf, -inf, -inf};
+  unsigned long long ngoodN = 0;
+  int oor = 0;
+  int sideFlags = 0;
+  if (tid < nH + nC) {
+    const int j = T.idx[tid];
+    const size_t ij = base + j;
+    Ray r{T.x[j], T.y[j], T.z[j], T.a[j], T.b[j], T.c[j]};
+    to_local(p, r);
+    double t1 = T.la[j], t2 = T.lb[j], dz1 = T.lc[j], dz2 = T.theta[j];
+    // intersection (base.py:848-885)
+    const bool ind1 = dz1 <= 0.0;  // lost: solution t1
+    const bool ind2 = dz2 >= 0.0;  // over: solution t2
+    if (ind1) t2 = t1;
+    double x2, y2, z2;
+    ray_point<SURF>(p, r, t2, x2, y2, z2);  // what find_dz left for that end of the bracket
+    if (!(ind1 || ind2)) {
+      if (d.brent)
+        solve_brent<SURF, false>(p, sd, r, t1, t2, dz1, dz2, x2, y2, z2);
+      else
+        solve_secant<SURF, false>(p, sd, r, d, t1, t2, dz1, dz2, x2, y2, z2);
+    }
+    const double tMax = t2;
+    const int lo0 = -3;
+    const double lx = x2, ly = y2, lz = z2;
+    double cx = lx, cy = ly, cz = lz;  // Cartesian copy for rays_good
+    param_to_xyz<SURF>(p, cx, cy, cz);
+    // rays_good (base.py:1115-1156)
+    int st = 1;
+    if (p.shape_round) {
+      const double ex = (cx - p.shape_r[0]) / p.shape_r[1], ey = (cy - p.shape_r[2]) / p.shape_r[3];
+      if (ex * ex + ey * ey > 1.0) st = p.lostNum;
+    } else {
+      if (p.has_optX && (((p.physX[0] <= cx) && (cx < p.optX[0])) || ((p.optX[1] <= cx) && (cx < p.physX[1])))) st = 2;
+      if (p.has_optY && (((p.physY[0] <= cy) && (cy < p.optY[0])) || ((p.optY[1] <= cy) && (cy < p.physY[1])))) st = 2;
+      const bool outside = (cx < p.physX[0]) || (cx > p.physX[1]) || (cy < p.physY[0]) || (cy > p.physY[1]);
+      bool over = false;
+      if (p.over_mask & 1) over = over || (cx < p.physX[0]);
+      if (p.over_mask & 2) over = over || (cx > p.physX[1]);
+      if (p.over_mask & 4) over = over || (cy < p.physY[0]);
+      if (p.over_mask & 8) over = over || (cy > p.physY[1]);
+      if (outside) st = p.lostNum;
+      if (over) st = 3;
+    }
+    if (ind1) st = p.lostNum;  // reflect.py:706-707
+    if (hasLb && lb.s) {
+      lb.s[ij] = lx;
+      lb.phi[ij] = ly;
+      lb.r[ij] = lz;
+    }
+    T.lx[j] = cx;
+    T.ly[j] = cy;
+    T.lz[j] = cz;
+    T.lstate[j] = st;
+
+    double la = r.a, lbb = r.b, lc = r.c;
+    double theta = 0.0;
+    double bdn = 0.0, bds = 0.0, bos = 0.0, cY = 1.0, sY = 0.0;
+    if (st == 1) {
+      ++ngoodN;
+      double nrm[6];
+      local_normal<SURF>(p, sd, lx, ly, nrm);
+      bdn = la * nrm[0] + lbb * nrm[1] + lc * nrm[2];
+      if (bdn < -1.0) bdn = -1.0;
+      if (bdn > 1.0) bdn = 1.0;
+      if (hasLb && lb.theta) theta = acos(bdn) - kPi / 2;  // the local beam's theta
+      bds = p.asymmetric ? (la * nrm[3] + lbb * nrm[4] + lc * nrm[5]) : bdn;
+      double ao, bo, co;
+      const bool transmitted = (MAT == 3) && (m.geom & 2);  // toWhere = 2 (reflect.py:749-757, :862-878)
+      if (MAT == 3 && !transmitted) {
+        // crystal as a grating (reflect.py:568-612, :451-469); sgbdn per ray, see reflect_main_kernel
+        const double ndsn = nrm[0] * nrm[3] + nrm[1] * nrm[4] + nrm[2] * nrm[5];
+        const double sgbdn = (bdn < 0.0) ? 1.0 : -1.0;
+        if (p.asymmetric) sideFlags = (bdn < 0.0) ? 1 : 2;
+        const double wHd = (1.0 + 0.0) / (m.d * 1e-7);
+        const double g0 = (nrm[0] - ndsn * nrm[3]) * wHd * sgbdn;
+        const double g1 = (nrm[1] - ndsn * nrm[4]) * wHd * sgbdn;
+        const double g2 = (nrm[2] - ndsn * nrm[5]) * wHd * sgbdn;
+        const double CH = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8;
+        const double bdg = la * g0 + lbb * g1 + lc * g2;
+        const double G2 = g0 * g0 + g1 * g1 + g2 * g2;
+        const double ol = 1.0 * CH / T.E[j] * 1e-7;
+        const double u = bds * bds - 2.0 * bdg * ol - G2 * (ol * ol);
+        const double sg = (m.geom & 1) ? 1.0 : -1.0;  // reflect.py:608: +1 for Laue
+        const double dn = bds + sg * sqrt(fabs(u));
+        ao = la - nrm[3] * dn + g0 * ol;
+        bo = lbb - nrm[4] * dn + g1 * ol;
+        co = lc - nrm[5] * dn + g2 * ol;
+        const double nn = sqrt(ao * ao + bo * bo + co * co);
+        ao = ao / nn;
+        bo = bo / nn;
+        co = co / nn;
+        bos = ao * nrm[3] + bo * nrm[4] + co * nrm[5];
+      } else {
+        ao = la - nrm[0] * 2.0 * bdn;
+        bo = lbb - nrm[1] * 2.0 * bdn;
+        co = lc - nrm[2] * 2.0 * bdn;
+        if (MAT == 3) bos = ao * nrm[3] + bo * nrm[4] + co * nrm[5];
+      }
+      if (!transmitted) {
+        la = ao;
+        lbb = bo;
+        lc = co;
+      }
+      // polarisation frame (reflect.py:948-953; beams.py:448-479), see reflect_main_kernel
+#ifndef XRTB_POLFRAME_ATAN2
+      {
+        const double hx = nrm[3], hz = nrm[5];
+        const double h2 = hx * hx + hz * hz;
+        double cphi = 1.0, sphi = 0.0;  // atan2(0, 0) = 0
+        if (h2 > 0.0) {
+          double y0;
+          asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(h2));
+          const double e = fma(-h2 * y0, y0, 1.0);
+          const double inv = fma(y0, e * fma(0.375, e, 0.5), y0);
+          cphi = hz * inv;
+          sphi = hx * inv;
+        }
+        cY = fma(cosRoll, cphi, -(sinRoll * sphi));
+        sY = fma(sinRoll, cphi, cosRoll * sphi);
+      }
+#else
+      const double rollAngle = p.roll + atan2(nrm[3], nrm[5]);
+      sincos(rollAngle, &sY, &cY);
+#endif
+    }
+    T.la[j] = la;
+    T.lb[j] = lbb;
+    T.lc[j] = lc;
+    T.theta[j] = theta;
+    // virgin-local beam -> global (reflect.py:1112-1136, :125-135)
+    const bool goodAfter = p.created_by_diffract ? (st == 1) : (st == 1 || st == 2);
+    {
+      Ray v{cx, cy, cz, la, lbb, lc};
+      to_virgin(p, v);
+      fmin3[0] = v.x;
+      fmin3[1] = v.y;
+      fmin3[2] = v.z;
+      fmax3[0] = v.x;
+      fmax3[1] = v.y;
+      fmax3[2] = v.z;
+      if (goodAfter) {
+        if (p.to_global) virgin_to_global(p, v);
+        T.x[j] = v.x;
+        T.y[j] = v.y;
+        T.z[j] = v.z;
+        T.a[j] = v.a;
+        T.b[j] = v.b;
+        T.c[j] = v.c;
+        T.state[j] = st;
+      } else {
+        // not intersected rays remain unchanged except their state (reflect.py:131-134): the ray of fb
+        T.state[j] = p.dead_state_lost ? p.lostNum : st;  // Plate: dcm.py:331-332
+        if (!fbIsInput) {
+          T.x[j] = fb.x[ij];
+          T.y[j] = fb.y[ij];
+          T.z[j] = fb.z[ij];
+          T.a[j] = fb.a[ij];
+          T.b[j] = fb.b[ij];
+          T.c[j] = fb.c[ij];
+          T.cs[j] = make_double2(3.0, 0.0);
+        }
+      }
+    }
+    const double E = T.E[j];
+    if (st == 1) {
+      T.path[j] = T.path[j] + tMax;
+      // amplitudes
+      cplx ras = cplx{1.0, 0.0}, rap = cplx{1.0, 0.0};
+      if (MAT == 1) mirror_amplitude(m, tab, E, bdn, ras, rap, &oor, lo0);
+      if (MAT == 3) crystal_amplitude(m, tab, E, bds, bos, bdn, ras, rap, &oor);
+      if (MAT != 0) {
+        if (isnan(ras.re) || isnan(ras.im)) ras = cplx{0.0, 0.0};
+        if (isnan(rap.re) || isnan(rap.im)) rap = cplx{0.0, 0.0};
+      }
+      {
+        // coherency matrix into the local polarisation frame (reflect.py:948-953; beams.py:448-479)
+        double Jss = T.Jss[j], Jpp = T.Jpp[j];
+        cplx Jsp = cplx{T.Jsp[j].x, T.Jsp[j].y};
+        {
+          const double c = cY, s = -sY;
+          const double c2 = c * c, s2 = s * s, cs = c * s;
+          const double J0 = Jss * c2 + Jpp * s2 + 2.0 * Jsp.re * cs;
+          const double J1 = Jss * s2 + Jpp * c2 - 2.0 * Jsp.re * cs;
+          const double J2r = (Jpp - Jss) * cs + Jsp.re * (c2 - s2);
+          Jss = J0;
+          Jpp = J1;
+          Jsp = cplx{J2r + (Jsp.im * 0.0), 0.0 + Jsp.im};
+        }
+        if (MAT != 0) {
+          // reflect.py:1038-1040
+          const cplx js = cmul_np(cmul_np(cplx{Jss, 0.0}, ras), cconj(ras));
+          const cplx jp = cmul_np(cmul_np(cplx{Jpp, 0.0}, rap), cconj(rap));
+          Jsp = cmul_np(cmul_np(Jsp, ras), cconj(rap));
+          Jss = js.re;
+          Jpp = jp.re;
+        }
+        T.Jss[j] = Jss;
+        T.Jpp[j] = Jpp;
+        T.Jsp[j] = make_double2(Jsp.re, Jsp.im);
+      }
+      if (amp) {
+        cplx Es = cplx{T.Es[j].x, T.Es[j].y}, Ep = cplx{T.Ep[j].x, T.Ep[j].y};
+        {
+          // rotate_y(Es, Ep, cosY, -sinY): (c*x + s*z, -s*x + c*z) with s = -sinY
+          const double s = -sY;
+          const cplx e1 = cplx{cY * Es.re + s * Ep.re, cY * Es.im + s * Ep.im};
+          const cplx e2 = cplx{-s * Es.re + cY * Ep.re, -s * Es.im + cY * Ep.im};
+          Es = e1;
+          Ep = e2;
+        }
+        if (MAT != 0) {
+          Es = cmul_np(Es, ras);
+          Ep = cmul_np(Ep, rap);
+        }
+        {
+          // mPh = exp(1e7j * E/CHBAR * tMax) (reflect.py:1061-1064): im = ((1e7*E) * (1/CHBAR)) * tMax
+          const double CHBAR = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8 / 6.283185307179586476925286766559;
+          const double phi = ((1e7 * E) * (1.0 / CHBAR)) * tMax;
+          const cplx mPh = cexp_i(phi);
+          Es = cmul_np(Es, mPh);
+          Ep = cmul_np(Ep, mPh);
+        }
+        T.Es[j] = make_double2(Es.re, Es.im);
+        T.Ep[j] = make_double2(Ep.re, Ep.im);
+      }
+      T.cs[j] = make_double2(cY, sY);
+    }
+  }
+  // the tile is complete: make the generic-proxy writes visible to the bulk-copy engine, then everybody may read it
+  fence_proxy_async_smem();
+  __syncthreads();
+
+  // ---- phase 3, thread <-> ray: what the bulk stores cannot do
+  GlobalSink<FUSE> sink(gb, scr, scrp);
+  if (i < n) {
+    const double2 cs = T.cs[tid];
+    const bool fromFb = cs.x > 2.5;
+    double Jss = T.Jss[tid], Jpp = T.Jpp[tid];
+    cplx Jsp = cplx{T.Jsp[tid].x, T.Jsp[tid].y};
+    const bool hasE = sink.wants_amplitudes() && (fromFb ? fb.Es != nullptr : amp);
+    cplx Es = cplx{0.0, 0.0}, Ep = cplx{0.0, 0.0};
+    if (hasE && !fromFb) {
+      Es = cplx{T.Es[tid].x, T.Es[tid].y};
+      Ep = cplx{T.Ep[tid].x, T.Ep[tid].y};
+    }
+    double path = T.path[tid], E = T.E[tid];
+    if (fromFb) {
+      path = fb.path[i];
+      E = fb.E[i];
+      Jss = fb.Jss[i];
+      Jpp = fb.Jpp[i];
+      Jsp = ld_c(fb.Jsp, i);
+      if (hasE) {
+        Es = ld_c(fb.Es, i);
+        Ep = ld_c(fb.Ep, i);
+      }
+    } else if (cs.x < 1.5) {
+      // ... and back for the virgin-local / global beam (reflect.py:1106-1110)
+      const double c = cs.x, s = cs.y;
+      const double c2 = c * c, s2 = s * s, csn = c * s;
+      const double J2r = (Jpp - Jss) * csn + Jsp.re * (c2 - s2);
+      const double J0 = Jss * c2 + Jpp * s2 + 2.0 * Jsp.re * csn, J1 = Jss * s2 + Jpp * c2 - 2.0 * Jsp.re * csn;
+      Jss = J0;
+      Jpp = J1;
+      Jsp = cplx{J2r + (Jsp.im * 0.0), 0.0 + Jsp.im};
+      if (hasE) {
+        const cplx e1 = cplx{c * Es.re + s * Ep.re, c * Es.im + s * Ep.im};
+        const cplx e2 = cplx{-s * Es.re + c * Ep.re, -s * Es.im + c * Ep.im};
+        Es = e1;
+        Ep = e2;
+      }
+    }
+    if (FUSE) {
+      sink.geometry(i, T.x[tid], T.y[tid], T.z[tid], T.a[tid], T.b[tid], T.c[tid], T.state[tid]);
+      sink.path_energy(i, path, E);
+      sink.coherency(i, Jss, Jpp, Jsp);
+      if (hasE) sink.amplitudes(i, Es, Ep);
+    } else {
+      sink.coherency(i, Jss, Jpp, Jsp);
+      if (hasE) sink.amplitudes(i, Es, Ep);
+      if (!bulk || !fbIsInput) sink.path_energy(i, path, E);
+      if (!bulk) sink.geometry(i, T.x[tid], T.y[tid], T.z[tid], T.a[tid], T.b[tid], T.c[tid], T.state[tid]);
+    }
+    if (hasLb && !bulk) {
+      lb.x[i] = T.lx[tid];
+      lb.y[i] = T.ly[tid];
+      lb.z[i] = T.lz[tid];
+      lb.a[i] = T.la[tid];
+      lb.b[i] = T.lb[tid];
+      lb.c[i] = T.lc[tid];
+      lb.state[i] = T.lstate[tid];
+      if (lb.theta) lb.theta[i] = T.theta[tid];
+      lb.path[i] = T.path[tid];
+      lb.E[i] = T.E[tid];
+      lb.Jss[i] = T.Jss[tid];
+      lb.Jpp[i] = T.Jpp[tid];
+      reinterpret_cast<double2*>(lb.Jsp)[i] = T.Jsp[tid];
+      if (amp && lb.Es) {
+        reinterpret_cast<double2*>(lb.Es)[i] = T.Es[tid];
+        reinterpret_cast<double2*>(lb.Ep)[i] = T.Ep[tid];
+      }
+    }
+  }
+  if (bulk && tid == 0) {
+    if (!FUSE) {
+      bulk_s2g(gb.x + base, T.x, BT * 8);
+      bulk_s2g(gb.y + base, T.y, BT * 8);
+      bulk_s2g(gb.z + base, T.z, BT * 8);
+      bulk_s2g(gb.a + base, T.a, BT * 8);
+      bulk_s2g(gb.b + base, T.b, BT * 8);
+      bulk_s2g(gb.c + base, T.c, BT * 8);
+      bulk_s2g(gb.state + base, T.state, BT * 4);
+      if (fbIsInput) {
+        bulk_s2g(gb.path + base, T.path, BT * 8);
+        bulk_s2g(gb.E + base, T.E, BT * 8);
+      }
+    }
+    if (hasLb) {
+      bulk_s2g(lb.x + base, T.lx, BT * 8);
+      bulk_s2g(lb.y + base, T.ly, BT * 8);
+      bulk_s2g(lb.z + base, T.lz, BT * 8);
+      bulk_s2g(lb.a + base, T.la, BT * 8);
+      bulk_s2g(lb.b + base, T.lb, BT * 8);
+      bulk_s2g(lb.c + base, T.lc, BT * 8);
+      bulk_s2g(lb.state + base, T.lstate, BT * 4);
+      if (lb.theta) bulk_s2g(lb.theta + base, T.theta, BT * 8);
+      bulk_s2g(lb.path + base, T.path, BT * 8);
+      bulk_s2g(lb.E + base, T.E, BT * 8);
+      bulk_s2g(lb.Jss + base, T.Jss, BT * 8);
+      bulk_s2g(lb.Jpp + base, T.Jpp, BT * 8);
+      bulk_s2g(lb.Jsp + 2 * base, T.Jsp, BT * 16);
+      if (amp && lb.Es) {
+        bulk_s2g(lb.Es + 2 * base, T.Es, BT * 16);
+        bulk_s2g(lb.Ep + 2 * base, T.Ep, BT * 16);
+      }
+    }
+    bulk_commit();
+  }
+
+  // a table-interval guess changed in this block: the last warp to get here hands it to the blocks that follow
+  if (useHint) {
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) last = (atomicAdd(&shint[33], 1) == BT / 32 - 1);
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last && *(volatile int*)&shint[32]) ghint[lane] = *(volatile int*)&shint[lane];
+  }
+  if (FUSE) {
+    __shared__ unsigned long long shs[BT / 32][8];
+    unsigned long long es[8];
+    es[0] = sink.cnt ? enc(sink.fx) : enc(inf);
+    es[1] = sink.cnt ? enc(0.0) : enc(inf);
+    es[2] = sink.cnt ? enc(sink.fz) : enc(inf);
+    es[3] = sink.cnt ? enc(sink.fx) : enc(-inf);
+    es[4] = sink.cnt ? enc(0.0) : enc(-inf);
+    es[5] = sink.cnt ? enc(sink.fz) : enc(-inf);
+    es[6] = sink.cnt;
+    es[7] = 0;
+    tail_combine<BT>(es, shs, &sdoneS, sred, RS_NGOOD, -1, lane, warp);
+  }
+  if (p.want_footprint) {
+    if (MAT == 3 && p.asymmetric) {
+      __shared__ unsigned long long shb[BT / 32][8];
+      unsigned long long eb[8];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        eb[k] = enc(inf);
+        eb[3 + k] = enc(-inf);
+      }
+      eb[6] = (sideFlags & 1) ? 1ull : 0ull;
+      eb[7] = (sideFlags & 2) ? 1ull : 0ull;
+      tail_combine<BT>(eb, shb, &sdoneB, red, RS_SIDE_NEG, RS_SIDE_NEG + 1, lane, warp);
+    }
+    __shared__ unsigned long long sh[BT / 32][8];
+    unsigned long long e[8];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      e[k] = enc(fmin3[k]);
+      e[3 + k] = enc(fmax3[k]);
+    }
+    e[6] = ngoodN;
+    e[7] = (unsigned long long)oor;
+    tail_combine<BT>(e, sh, &sdone, red, RS_NGOODN, RS_NGOODN + 1, lane, warp);
+  }
+  // the tile must stay until the bulk stores have read it
+  if (bulk && tid == 0) bulk_wait_read_all();
+}
+#endif  // !XRTB_PLUGIN
+
 // ---------------------------------------------------------------- launchers
 // cp.async.bulk needs 16-byte aligned global addresses: true for whole torch / cudaMalloc allocations, not for a view
 // that starts at an odd element
@@ -2441,11 +3027,62 @@ struct MainLaunch {
   unsigned long long* sred;
 };
 
+#ifndef XRTB_PLUGIN
+// every array the tile kernel loads or stores by bulk copies starts on a 16-byte boundary
+static int tile_bulk_ok(const xrt_beam& b, bool withState) {
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  return al(b.x) && al(b.y) && al(b.z) && al(b.a) && al(b.b) && al(b.c) && al(b.path) && al(b.E) && al(b.Jss) &&
+         al(b.Jpp) && al(b.Jsp) && al(b.Es) && al(b.Ep) && al(b.theta) && (!withState || al(b.state));
+}
+static bool tile_enabled() {
+  const char* e = getenv("XRTB_REFLECT_TILE");
+  return !(e && e[0] == '0');
+}
+
+// the tile structure of the main pass where it is built (see reflect_tile_kernel); false: not served, use the old kernel
+template <int SURF, int MAT>
+static bool launch_tile(const MainLaunch& L, double cR, double sR) {
+  if constexpr ((SURF == 0 || SURF == 1 || SURF == 2) && (MAT == 0 || MAT == 1 || MAT == 3)) {
+    const xrt_oe_params& p = *L.p;
+    if (p.multi || p.multi_tmin || p.no_intersection || p.grating || p.fe_c || !tile_enabled()) return false;
+    int bulk_ok = tile_bulk_ok(L.in, true);
+    if (L.scr == nullptr) bulk_ok = bulk_ok && tile_bulk_ok(L.gb, true);
+    if (L.lb.x) bulk_ok = bulk_ok && tile_bulk_ok(L.lb, true);
+    const unsigned grid = (unsigned)((L.n + kTileRays - 1) / kTileRays);
+    xrt_plane_params sp;
+    xrt_beam scr;
+    memset(&sp, 0, sizeof(sp));
+    memset(&scr, 0, sizeof(scr));
+    if (L.scr) {
+      sp = *L.scrp;
+      scr = *L.scr;
+      auto k = reflect_tile_kernel<SURF, MAT, true>;
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RayTile));
+      cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      k<<<grid, kTileRays, sizeof(RayTile), L.st>>>(L.n, p, *L.m, L.t, L.in, L.fb, L.gb, L.lb, L.red, bulk_ok, cR, sR, sp,
+                                                   scr, L.sred);
+    } else {
+      auto k = reflect_tile_kernel<SURF, MAT, false>;
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RayTile));
+      cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      k<<<grid, kTileRays, sizeof(RayTile), L.st>>>(L.n, p, *L.m, L.t, L.in, L.fb, L.gb, L.lb, L.red, bulk_ok, cR, sR, sp,
+                                                   scr, nullptr);
+    }
+    return true;
+  } else {
+    return false;
+  }
+}
+#endif
+
 template <int SURF, int MAT>
 static void launch_one(const MainLaunch& L) {
   const int bulk_ok = bulk_copy_ok(L.in);
   const double cR = cos(L.p->roll), sR = sin(L.p->roll);  // polarisation frame: cos / sin(roll + atan2(n_x, n_z))
   reflect_decide_kernel<<<1, 1, 0, L.st>>>(L.red);
+#ifndef XRTB_PLUGIN
+  if (launch_tile<SURF, MAT>(L, cR, sR)) return;
+#endif
   xrt_plane_params sp;
   xrt_beam scr;
   memset(&sp, 0, sizeof(sp));
