@@ -1,0 +1,6 @@
+mkdir -p gpurun_out
+XRT_B200_LIB=variants/checked/libxrt_b200.so timeout 400 python tools/gpu_tile_check.py --hash-only gpurun_out/c5_hash_checked.json > gpurun_out/c5_hash_checked.log 2>&1
+timeout 400 python tools/gpu_tile_check.py --hash-only gpurun_out/c5_hash_nr.json > gpurun_out/c5_hash_nr.log 2>&1
+XRT_B200_LIB=variants/checked/libxrt_b200.so timeout 300 python tools/gpu_reflect_time.py --tag checked > gpurun_out/c5_time_checked.log 2>&1
+timeout 300 python tools/gpu_reflect_time.py --tag nr > gpurun_out/c5_time_nr.log 2>&1
+XRTB_REFLECT_TILE=0 timeout 300 python tools/gpu_reflect_time.py --tag nr_old > gpurun_out/c5_time_nr_old.log 2>&1

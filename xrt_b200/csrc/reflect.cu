@@ -154,7 +154,12 @@ __device__ __forceinline__ void virgin_to_global(const xrt_oe_params& p, Ray& r)
 // ---------------------------------------------------------------- surfaces
 // x**(-0.5) as glibc pow returns it (< 1 ulp): 1/sqrt with one residual correction
 __device__ __forceinline__ double pow_m05(double x) {
+#ifdef XRTB_SURF_DIV_CHECKED
   const double y0 = 1.0 / sqrt(x);
+#else
+  // 0 < x <= 1 here (toroid: 1 - (x/r)^2); x == 0 keeps the reference's 1 / 0
+  const double y0 = (x == 0.0) ? 1.0 / x : div_nr(1.0, sqrt_nr(x));
+#endif
   const double e = fma(-x * y0, y0, 1.0);
   return fma(0.5 * y0, e, y0);
 }
@@ -248,6 +253,33 @@ __device__ __forceinline__ double fe_eval(const xrt_oe_params& p, double x, doub
 #endif
 
 // the surface's loop-invariant divisors with their reciprocals refined once per thread (common.cuh, Divisor)
+// quotients of a ray coordinate by a surface radius (toroid): operands are always in the range where the unchecked
+// sequence is the IEEE quotient (common.cuh, div_by_nr); -DXRTB_SURF_DIV_CHECKED restores the range test
+#ifdef XRTB_SURF_DIV_CHECKED
+#define XRTB_SURF_DIV(a, d) div_by(a, d)
+#define XRTB_SURF_SQRT(a) sqrt(a)
+#define XRTB_SECANT_DIV(a, b) ((a) / (b))
+#else
+#define XRTB_SURF_DIV(a, d) div_by_nr(a, d)
+#define XRTB_SURF_SQRT(a) sqrt_nr(a)  // 0 <= a <= 1
+// the secant step (t2 - t1) * dz1 / (dz2 - dz1): inside the loop dz1 and dz2 are non-zero with opposite signs (the pair
+// brackets the root: solve_secant keeps that invariant), so |dz2 - dz1| >= max(|dz1|, |dz2|) > zEps, and the numerator is
+// zero or >= ulp(t) * zEps -- the operands of the unchecked sequence
+#define XRTB_SECANT_DIV(a, b) div_nr(a, b)
+#endif
+// Fresnel / Bragg amplitudes: quotients and roots of finite, non-zero optical quantities (refractive indices,
+// susceptibilities, direction cosines) -- the unchecked primitives give the same correctly rounded values
+#ifdef XRTB_SURF_DIV_CHECKED
+#define XRTB_AMP_DIV(a, b) ((a) / (b))
+#define XRTB_AMP_SQRT(a) sqrt(a)
+#define XRTB_AMP_CDIV(a, b) cdiv(a, b)
+#define XRTB_AMP_CSQRT(a) csqrt_(a)
+#else
+#define XRTB_AMP_DIV(a, b) div_nr(a, b)
+#define XRTB_AMP_SQRT(a) sqrt_nr(a)
+#define XRTB_AMP_CDIV(a, b) cdiv_nr(a, b)
+#define XRTB_AMP_CSQRT(a) csqrt_nr(a)
+#endif
 struct SurfDiv {
   Divisor d0, d1;  // toroid: r, R; ellipse: A*A
 };
@@ -285,10 +317,10 @@ __device__ __forceinline__ double local_surface(const xrt_oe_params& p, const Su
   if (SURF == 1) {
     // ToroidMirror.local_z (oes/__init__.py:398-401)
     const double r = p.sp[1];
-    const double q = div_by(x, sd.d0);  // x / r
+    const double q = XRTB_SURF_DIV(x, sd.d0);  // x / r
     double rx = 1.0 - q * q;
     if (rx < 0.0) rx = 0.0;
-    return div_by(y * y / 2.0, sd.d1) + r * (1.0 - sqrt(rx));  // y**2 / 2.0 / R
+    return XRTB_SURF_DIV(y * y / 2.0, sd.d1) + r * (1.0 - XRTB_SURF_SQRT(rx));  // y**2 / 2.0 / R
   }
   // EllipticalMirrorParam.local_r (parametric.py:228-234): x = s, y = phi
   const double B = p.sp[1];
@@ -417,16 +449,16 @@ __device__ __forceinline__ void local_normal(const xrt_oe_params& p, const SurfD
   }
   if (SURF == 1) {
     // ToroidMirror.local_n (oes/__init__.py:403-411)
-    const double q = div_by(x, sd.d0);  // x / r
+    const double q = XRTB_SURF_DIV(x, sd.d0);  // x / r
     const double rx = 1.0 - q * q;
     const double ax = (rx < 0.0) ? 0.0 : pow_m05(rx);
-    const double a = div_by(-x, sd.d0) * ax;
-    const double b = div_by(-y, sd.d1);  // -y / R
-    const double norm = sqrt(a * a + b * b + 1.0);
+    const double a = XRTB_SURF_DIV(-x, sd.d0) * ax;
+    const double b = XRTB_SURF_DIV(-y, sd.d1);  // -y / R
+    const double norm = XRTB_SURF_SQRT(a * a + b * b + 1.0);
     const Divisor dn = make_divisor(norm);  // three quotients, one refined reciprocal (same bits as a / norm etc.)
-    n[0] = n[3] = div_by(a, dn);
-    n[1] = n[4] = div_by(b, dn);
-    n[2] = n[5] = div_by(1.0, dn);
+    n[0] = n[3] = XRTB_SURF_DIV(a, dn);
+    n[1] = n[4] = XRTB_SURF_DIV(b, dn);
+    n[2] = n[5] = XRTB_SURF_DIV(1.0, dn);
     return;
   }
   // EllipticalMirrorParam.local_n (parametric.py:236-249): x = s, y = phi
@@ -660,6 +692,10 @@ __device__ __forceinline__ cplx cdiv_re(cplx a, double b) {
   const double scl = 1.0 / b;
   return cplx{a.re * scl, a.im * scl};
 }
+__device__ __forceinline__ cplx cdiv_re_amp(cplx a, double b) {  // b finite, non-zero (XRTB_AMP_DIV)
+  const double scl = XRTB_AMP_DIV(1.0, b);
+  return cplx{a.re * scl, a.im * scl};
+}
 __device__ __forceinline__ cplx cexp_i(double phi) {  // exp(0 + i phi)
   double s, c;
   sincos_big(phi, s, c);
@@ -679,7 +715,7 @@ __device__ __forceinline__ double interp_at(const double* __restrict__ xp, const
   if (lo < 0) return fp[0];
   if (lo >= len - 1) return fp[len - 1];
   if (xp[lo] == x) return fp[lo];
-  const double slope = div_by(fp[lo + 1] - fp[lo], dx);
+  const double slope = XRTB_SURF_DIV(fp[lo + 1] - fp[lo], dx);  // table differences over a table step
   double res = slope * (x - xp[lo]) + fp[lo];
   if (isnan(res)) {
     res = slope * (x - xp[lo + 1]) + fp[lo + 1];
@@ -756,10 +792,10 @@ __device__ __forceinline__ cplx refractive_index(const xrt_material_params& m, c
   }
   const double c0 = 1e-24 * 6.02214199e23 * 2.817940285e-5 / 6.283185307179586476925286766559;
   const double CH = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8;
-  const double w = CH / E;
+  const double w = XRTB_AMP_DIV(CH, E);
   const double fac = c0 * (w * w) * m.rho;
   const cplx num = cmul_np(cplx{fac, 0.0}, xf);
-  const cplx q = cdiv_re(num, m.mass);
+  const cplx q = cdiv_re_amp(num, m.mass);
   return cplx{1.0 - q.re, 0.0 - q.im};
 }
 
@@ -771,15 +807,15 @@ __device__ __forceinline__ void mirror_amplitude(const xrt_material_params& m, c
   double sinAlpha2 = 1.0 - bdn * bdn;
   if (sinAlpha2 < 0.0) sinAlpha2 = 0.0;
   const double n1cosAlpha = 1.0 * cosAlpha;
-  const cplx n1n2 = cdiv(cplx{1.0, 0.0}, n2);
+  const cplx n1n2 = XRTB_AMP_CDIV((cplx{1.0, 0.0}), n2);
   const cplx sq = cmul_np(csquare_np(n1n2), cplx{sinAlpha2, 0.0});
-  const cplx cosBeta = csqrt_(cplx{1.0 - sq.re, 0.0 - sq.im});
+  const cplx cosBeta = XRTB_AMP_CSQRT((cplx{1.0 - sq.re, 0.0 - sq.im}));
   const cplx n2cosBeta = cmul_np(n2, cosBeta);
-  rs = cdiv(cplx{n1cosAlpha - n2cosBeta.re, 0.0 - n2cosBeta.im},
-            cplx{n1cosAlpha + n2cosBeta.re, 0.0 + n2cosBeta.im});
+  rs = XRTB_AMP_CDIV((cplx{n1cosAlpha - n2cosBeta.re, 0.0 - n2cosBeta.im}),
+                     (cplx{n1cosAlpha + n2cosBeta.re, 0.0 + n2cosBeta.im}));
   const cplx n2ca = cmul_np(n2, cplx{cosAlpha, 0.0});
   const cplx n1cb = cmul_np(cplx{1.0, 0.0}, cosBeta);
-  rp = cdiv(csub(n2ca, n1cb), cadd(n2ca, n1cb));
+  rp = XRTB_AMP_CDIV(csub(n2ca, n1cb), cadd(n2ca, n1cb));
   if (m.kind == 2) {
     // thin mirror: p2 = exp(2j * E / CHBAR * n2cosBeta * t * 1e7) (material.py:479-482)
     const double CHBAR = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8 / 6.283185307179586476925286766559;
@@ -880,8 +916,8 @@ __device__ __forceinline__ cplx bragg_one_pol(double polFactor, cplx alpha, cplx
   // delta = sqrt(alpha**2 + polFactor**2 * chih * chih_ / b)
   cplx t = cmul_np(cplx{polFactor * polFactor, 0.0}, chih);
   t = cmul_np(t, chih_);
-  t = cdiv_re(t, b);
-  const cplx delta = csqrt_(cadd(csquare_np(alpha), t));
+  t = cdiv_re_amp(t, b);
+  const cplx delta = XRTB_AMP_CSQRT(cadd(csquare_np(alpha), t));
   const cplx num = cmul_np(chih, cplx{polFactor, 0.0});
   if (tmm > 0.0) {
     const double tA = tmm * 1e7;
@@ -917,15 +953,15 @@ __device__ __forceinline__ cplx bragg_one_pol(double polFactor, cplx alpha, cplx
     if (!(geom & 2)) ra = cdiv_re(ra, sqrt(fabs(b)));
     return ra;
   }
-  cplx ra = cdiv(num, cadd(alpha, delta));
+  cplx ra = XRTB_AMP_CDIV(num, cadd(alpha, delta));  // alpha + delta == 0: NaN either way, caught below
   cplx ad = csub(alpha, delta);
   if (ad.re == 0.0 && ad.im == 0.0) ad = cplx{1e-100, 0.0};
-  const cplx rb = cdiv(num, ad);
+  const cplx rb = XRTB_AMP_CDIV(num, ad);
   if (isnan(ra.re) || isnan(ra.im)) ra = rb;
   // abs(rb) < abs(ra) (crystal.py:592-596) decided on the squared magnitudes: the two roots differ by the absorption
   // (percents), the values are far from over- / underflow, and two hypot calls per polarisation are ~100 instructions
   if (cabs2(rb) < cabs2(ra)) ra = rb;
-  return cdiv_re(ra, sqrt(fabs(b)));
+  return cdiv_re_amp(ra, XRTB_AMP_SQRT(fabs(b)));
 }
 
 __device__ __forceinline__ void crystal_amplitude(const xrt_material_params& m, const Tables& t, double E,
@@ -933,8 +969,8 @@ __device__ __forceinline__ void crystal_amplitude(const xrt_material_params& m, 
                                                   int* oor) {
   const double CH = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8;
   const double PI2 = 6.283185307179586476925286766559;
-  const double waveLength = CH / E;
-  const double k = PI2 / waveLength;
+  const double waveLength = XRTB_AMP_DIV(CH, E);
+  const double k = XRTB_AMP_DIV(PI2, waveLength);
   const double k0s = -bInDotN * k;
   double kHs = -bOutDotN * k;
   const double HH = PI2 / m.d;
@@ -943,7 +979,7 @@ __device__ __forceinline__ void crystal_amplitude(const xrt_material_params& m, 
   const double H2 = HH * HH;
   const bool kHs0 = (kHs == 0.0);
   if (kHs0) kHs = 1.0;
-  double b = k0s / kHs;
+  double b = XRTB_AMP_DIV(k0s, kHs);
   if (kHs0) b = -1.0;
   // structure factors (crystals_basic.py:22-31, :76-80)
   const cplx anom = f1f2(t, m.tab_off[0], m.tab_len[0], E, oor);
@@ -971,16 +1007,16 @@ __device__ __forceinline__ void crystal_amplitude(const xrt_material_params& m, 
   const cplx chih = cmul_np(cconj(Fhkl), cplx{c2f, 0.0});
   const cplx chih_ = cmul_np(cconj(Fhkl_), cplx{c2f, 0.0});
   // thetaB (crystal.py:1105-1120)
-  double sa = 1.0 * CH / (2.0 * m.d * E);
+  double sa = XRTB_AMP_DIV(1.0 * CH, 2.0 * m.d * E);
   if (sa > 1.0) sa = 1.0 - 1e-16;
   if (sa < -1.0) sa = -1.0 + 1e-16;
   // polarisation factor of the p branch: cos(2 thetaB) with thetaB = arcsin(sa) is 1 - 2 sa^2 (agrees with
   // cos(2.0 * asin(sa)) to 2 ulp; it multiplies chi_h, no cancellation follows) -- asin + cos are ~130 instructions
   const double cos2ThetaB = fma(-2.0 * sa, sa, 1.0);
   // alpha = (H2/2 - k0H) / k02 + chi0/2 * (1/b - 1)
-  const double a1 = (H2 / 2.0 - k0H) / k02;
-  const cplx half_chi0 = cdiv_re(chi0, 2.0);
-  const cplx a2 = cmul_np(half_chi0, cplx{1.0 / b - 1.0, 0.0});
+  const double a1 = XRTB_AMP_DIV(H2 / 2.0 - k0H, k02);
+  const cplx half_chi0 = cplx{chi0.re * 0.5, chi0.im * 0.5};  // cdiv_re(chi0, 2.0): scl = 1 / 2 exactly
+  const cplx a2 = cmul_np(half_chi0, cplx{XRTB_AMP_DIV(1.0, b) - 1.0, 0.0});
   const cplx alpha = cplx{a1 + a2.re, 0.0 + a2.im};
   rs = bragg_one_pol(1.0, alpha, chih, chih_, b, m.t, m.geom, chi0, k02, kHs, k0s);
   rp = bragg_one_pol(cos2ThetaB, alpha, chih, chih_, b, m.t, m.geom, chi0, k02, kHs, k0s);
@@ -1282,7 +1318,7 @@ __device__ __forceinline__ void solve_secant(const xrt_oe_params& p, const SurfD
   // values in the same operations, with two predicated moves per iteration instead of eight.
   int numit = 2;
   while (fabs(dz2) > kZEps && numit < kMaxIteration) {
-    double t3 = t1 - (t2 - t1) * dz1 / (dz2 - dz1);
+    double t3 = t1 - XRTB_SECANT_DIV((t2 - t1) * dz1, dz2 - dz1);
     if (t3 < d.tMin) t3 = d.tMin;
     if (t3 > d.tMax) t3 = d.tMax;
     const double dz3 = find_dz<SURF, REFR, DERIV>(p, sd, t3, r, x2, y2, z2);
@@ -2424,7 +2460,13 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
 //    Screen.expose, the whole global ray goes through GlobalSink<true>.
 // Serves flat / toroidal / elliptic surfaces with material kinds 0, 1, 3, single-pass reflect; everything else stays on
 // reflect_main_kernel.  XRTB_REFLECT_TILE=0 in the environment forces the old kernel (tests compare the two bit for bit).
-constexpr int kTileRays = 512;
+#ifndef XRTB_TILE_RAYS
+#define XRTB_TILE_RAYS 512
+#endif
+#ifndef XRTB_TILE_MINBLOCKS
+#define XRTB_TILE_MINBLOCKS (1024 / XRTB_TILE_RAYS)
+#endif
+constexpr int kTileRays = XRTB_TILE_RAYS;
 struct RayTile {
   // the global beam, in place of the input
   double x[kTileRays], y[kTileRays], z[kTileRays], a[kTileRays], b[kTileRays], c[kTileRays];
@@ -2457,7 +2499,7 @@ __device__ __forceinline__ void ray_point(const xrt_oe_params& p, const Ray& r, 
 }
 
 template <int SURF, int MAT, bool FUSE>
-__global__ void __launch_bounds__(kTileRays, 2)
+__global__ void __launch_bounds__(kTileRays, XRTB_TILE_MINBLOCKS)
     reflect_tile_kernel(size_t n, xrt_oe_params p, xrt_material_params m, Tables tab, xrt_beam in, xrt_beam fb,
                         xrt_beam gb, xrt_beam lb, unsigned long long* red, int bulk_ok, double cosRoll, double sinRoll,
                         xrt_plane_params scrp, xrt_beam scr, unsigned long long* sred) {
@@ -2467,7 +2509,7 @@ __global__ void __launch_bounds__(kTileRays, 2)
   const size_t base = (size_t)blockIdx.x * BT;
   const size_t i = base + tid;
   const double inf = __longlong_as_double(0x7ff0000000000000ll);
-  extern __shared__ __align__(128) unsigned char sdyn_raw[];
+  extern __shared__ __align__(16) unsigned char sdyn_raw[];
   RayTile& T = *reinterpret_cast<RayTile*>(sdyn_raw);
   __shared__ __align__(8) uint64_t sbar, sbarG;
   __shared__ int shint[34];
@@ -2576,18 +2618,14 @@ __global__ void __launch_bounds__(kTileRays, 2)
   __syncthreads();
   int nH = 0, nC = 0;
   {
-    int beforeH = 0, beforeC = 0;
-#pragma unroll
-    for (int w = 0; w < BT / 32; ++w) {
-      const unsigned v = swc[w];
-      const int h = (int)(v & 0xffffu), c = (int)(v >> 16);
-      if (w < warp) {
-        beforeH += h;
-        beforeC += c;
-      }
-      nH += h;
-      nC += c;
-    }
+    // prefix over the (at most 32) warp counts: lane w holds warp w's packed pair, two warp-wide integer sums (REDUX)
+    static_assert(BT / 32 <= 32, "one lane per warp count");
+    const unsigned v = (lane < BT / 32) ? swc[lane] : 0u;
+    const unsigned tot = __reduce_add_sync(0xffffffffu, v);
+    const unsigned bef = __reduce_add_sync(0xffffffffu, lane < warp ? v : 0u);
+    nH = (int)(tot & 0xffffu);
+    nC = (int)(tot >> 16);
+    const int beforeH = (int)(bef & 0xffffu), beforeC = (int)(bef >> 16);
     const unsigned lt = (1u << lane) - 1u;
     if (cls == 1) T.idx[beforeH + __popc(bh & lt)] = (unsigned short)tid;
     if (cls == 2) T.idx[nH + beforeC + __popc(bc & lt)] = (unsigned short)tid;
