@@ -633,8 +633,13 @@ __global__ void __launch_bounds__(256) reflect_prepass_kernel(size_t n, xrt_oe_p
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const int st = in.state[i];
+#ifndef XRTB_PREPASS_DEPENDENT_LOADS
+    Ray r = load_ray(in, i);  // requested together with the state (dead rays: fetched and dropped), one latency not two
+    if (!(p.good_mode ? (st == 1 || st == 2) : (st > 0))) continue;
+#else
     if (!(p.good_mode ? (st == 1 || st == 2) : (st > 0))) continue;
     Ray r = load_ray(in, i);
+#endif
     to_local(p, r);
     double t1, t2, x, y, z;
     bracket(p, axis, neg, r, t1, t2);
@@ -2641,6 +2646,8 @@ __global__ void __launch_bounds__(kTileRays, XRTB_TILE_MINBLOCKS)
   if (tid < nH + nC) {
     const int j = T.idx[tid];
     const size_t ij = base + j;
+    // (the frame change is repeated here: handing the local ray over through the tile -- six more values per ray --
+    // measured 9.4 instead of 9.0 ms per 1e8 rays)
     Ray r{T.x[j], T.y[j], T.z[j], T.a[j], T.b[j], T.c[j]};
     to_local(p, r);
     double t1 = T.la[j], t2 = T.lb[j], dz1 = T.lc[j], dz2 = T.theta[j];
@@ -3072,9 +3079,14 @@ static int tile_bulk_ok(const xrt_beam& b, bool withState) {
   return al(b.x) && al(b.y) && al(b.z) && al(b.a) && al(b.b) && al(b.c) && al(b.path) && al(b.E) && al(b.Jss) &&
          al(b.Jpp) && al(b.Jsp) && al(b.Es) && al(b.Ep) && al(b.theta) && (!withState || al(b.state));
 }
-static bool tile_enabled() {
+// XRTB_REFLECT_TILE: 0 = reflect_main_kernel always, 1 = the tile kernel wherever it is built, unset = by measurement
+// (profiles/r02_reflect_variants.json): mirrors go through the tile kernel (rays that miss the surface leave idle lanes
+// in thread <-> ray order), crystals through reflect_main_kernel (a DCM meets every ray: nothing to compact, and the
+// second evaluation of the bracket in phase 1 costs more than the bulk stores save -- 25.4 vs 23.8 ms per 1e8 rays)
+static int tile_mode() {
   const char* e = getenv("XRTB_REFLECT_TILE");
-  return !(e && e[0] == '0');
+  if (!e || !e[0]) return -1;
+  return e[0] == '0' ? 0 : 1;
 }
 
 // the tile structure of the main pass where it is built (see reflect_tile_kernel); false: not served, use the old kernel
@@ -3082,7 +3094,9 @@ template <int SURF, int MAT>
 static bool launch_tile(const MainLaunch& L, double cR, double sR) {
   if constexpr ((SURF == 0 || SURF == 1 || SURF == 2) && (MAT == 0 || MAT == 1 || MAT == 3)) {
     const xrt_oe_params& p = *L.p;
-    if (p.multi || p.multi_tmin || p.no_intersection || p.grating || p.fe_c || !tile_enabled()) return false;
+    const int mode = tile_mode();
+    if (p.multi || p.multi_tmin || p.no_intersection || p.grating || p.fe_c || mode == 0) return false;
+    if (mode < 0 && MAT == 3) return false;
     int bulk_ok = tile_bulk_ok(L.in, true);
     if (L.scr == nullptr) bulk_ok = bulk_ok && tile_bulk_ok(L.gb, true);
     if (L.lb.x) bulk_ok = bulk_ok && tile_bulk_ok(L.lb, true);

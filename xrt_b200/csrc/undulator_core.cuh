@@ -112,6 +112,12 @@ __device__ __forceinline__ void node_pair_step(const USample& s, const double4 n
   bp_im = fma(eim, tp, bp_im);
 }
 
+// node-loop unrolling: 1 = one node (pair) per iteration for the R samples of the thread (measured best)
+#ifndef XRTB_NODE_UNROLL
+#define XRTB_NODE_UNROLL 1
+#endif
+constexpr int kNodeUnroll = XRTB_NODE_UNROLL;
+
 struct UTables {
   const double *tg, *ag, *sintg, *costg, *sintgph, *costgph;
 };
@@ -184,7 +190,7 @@ __device__ __forceinline__ void node_loop(const UParams& p, const UTables& tab, 
     __syncthreads();
     load_node_tile(tile, tab, j0, cnt, p.Kx, p.Ky);
     __syncthreads();
-#pragma unroll 1
+#pragma unroll kNodeUnroll
     for (int j = 0; j < cnt; ++j) {
       const double4* q = reinterpret_cast<const double4*>(tile + j);
       const double4 n0 = q[0];
