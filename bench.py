@@ -539,15 +539,21 @@ def run_ours(args):
     main_ms = refl_ms[2]
     main_bytes = 132 + 132 + 140
     main_gbs = main_bytes * nrays / (main_ms * 1e-3) / 1e9
-    roofline_main = {'kernel': 'reflect_main_kernel<toroid, mirror> (OE.reflect, materialising gb and lb)', 'bound': 'hbm',
+    tile = os.environ.get('XRTB_REFLECT_TILE', '') != '0'
+    main_name = 'reflect_tile_kernel' if tile else 'reflect_main_kernel'
+    roofline_main = {'kernel': '%s<toroid, mirror> (OE.reflect, materialising gb and lb)' % main_name, 'bound': 'hbm',
                      'achieved': main_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': main_gbs / peaks['hbm_gbs'],
-                     'traffic': measured_traffic('reflect_main_kernel', nrays),
+                     'traffic': measured_traffic(main_name + '<toroid, mirror> (gb + lb)', nrays),
                      'peak_source': '%s HBM copy bandwidth (MEASURED_PEAKS.json)' % peak_kind,
                      'note': '%d algorithmic bytes per ray (132 in, 132 gb, 140 lb); timed in extra steps through '
                              'OE.reflect() without exposeOn (the step itself runs the fused reflect + expose variant: '
-                             'stages.reflect_expose_fused_main); limited by instruction issue (IEEE div / sqrt chains '
-                             'of numpy parity, 41 %% of the lanes idle behind rays that miss the mirror), not by HBM'
-                             % main_bytes,
+                             'stages.reflect_expose_fused_main).  r02 tile structure: the 512 rays of a block live in '
+                             'shared memory (bulk-async loads, results in place, bulk-async stores), rays are ranked '
+                             'by class so that the root search and the Fresnel amplitudes run on dense warps (41 %% of '
+                             'the rays miss the mirror), divisions / roots without the range test of the IEEE '
+                             'sequences.  Bound by the dependent FP64 chain of one ray (secant search, complex Fresnel '
+                             'arithmetic in numpy rounding order) at 1024 rays in flight per SM (shared memory: 210 B '
+                             'per ray), not by HBM' % main_bytes,
                      'ms': main_ms, 'share_of_step': main_ms / ms_step}
     roofline = roofline_main if main_ms >= und_ms else roofline_und
     roofline_other = roofline_und if main_ms >= und_ms else roofline_main
@@ -639,7 +645,7 @@ def run_ours(args):
         del case
         out = torch.empty((5, Mloc), dtype=torch.complex128, device='cuda')
         kev = []
-        # k r <= 4.6e6 /mm x 1e4 mm = 4.6e10 rad here: far below the 2^47 limit of the table-based sin / cos
+        # k r <= 4.6e6 /mm x 1e4 mm = 4.6e10 rad here: far below the 3.4e12 limit of the table-based sin / cos
         ktab = float(d['k'].abs().max()) * 2e4 < kernels.PHASE_LIMIT_TABLE_SINCOS
 
         def kstep():

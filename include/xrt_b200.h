@@ -53,9 +53,10 @@ int xrt_b200_math_probe_host(int which, size_t n, const double* x, double* y0, d
  *        bit1 = OpenCL sign/scale convention (default numpy convention, waves.py:844-850)
  *        bits4-6 = register blocking R in {1,2,4} (0 = default 2)
  *        bit9 = all N normals are equal (aperture, flat OE): n.d = n.p - n.q with n.p hoisted per output
- *        bit11 = sin / cos of the phase through a 64-entry (pi/32) table in shared memory + short polynomials
- *                instead of the two pi/2-range polynomials (same <= 4e-16 accuracy, 10 % faster).  The caller
- *                vouches for |k r| < 2^47 rad (1.4e14: 100 keV over 280 m) for every pair; the kernel does not test
+ *        bit11 = sin / cos of the phase through a 4096-entry (pi/2048) table in shared memory + two-term polynomials
+ *                instead of the two pi/2-range polynomials (same <= 4e-16 accuracy, 16 % faster).  The caller
+ *                vouches for |k r| < 2^40 pi rad (3.4e12: 100 keV over 6.8 m, 9 keV over 75 m) for every pair; the
+ *                kernel does not test
  * `workspace` must hold xrt_kirchhoff_workspace_bytes(M, N, flags) bytes of device memory. */
 size_t xrt_kirchhoff_workspace_bytes(size_t M, size_t N, int flags);
 int xrt_kirchhoff_f64(size_t M, size_t N, const double* xM, const double* yM, const double* zM, const double* nl,

@@ -45,8 +45,10 @@ def test_sincos_helpers_on_huge_phases(cuda_device):
     assert np.abs(s - s_ref).max() < 4e-16 and np.abs(c - c_ref).max() < 4e-16
     s1, _ = _probe(1, x)  # sin_big (mod pi, one odd polynomial)
     assert np.abs(s1 - s_ref).max() < 4e-16
-    # sincos_tab (mod pi/32, 64-entry table + short polynomials), the Kirchhoff kernel's: valid below 2^47 rad
-    m = np.abs(x) < 2.**47
+    # sincos_tab (mod pi/2048, 4096-entry table + two-term polynomials), the Kirchhoff kernel's: valid below 2^40 pi rad
+    from xrt_b200 import kernels
+    m = np.abs(x) < kernels.PHASE_LIMIT_TABLE_SINCOS
+    assert m.sum() > 5000  # the 1e12-rad phases are inside the range
     s2, c2 = _probe(8, x[m])
     assert np.abs(s2 - s_ref[m]).max() < 5e-16 and np.abs(c2 - c_ref[m]).max() < 5e-16
 

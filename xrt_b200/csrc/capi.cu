@@ -106,8 +106,9 @@ static int fp64_probe(int mode, int iters, double* tflops, double* ms_out) {
 // ---------------------------------------------------------------- device math helpers, exposed for known-answer tests
 __global__ void math_probe_kernel(int which, size_t n, const double* __restrict__ x, double* __restrict__ y0,
                                   double* __restrict__ y1) {
-  __shared__ double2 sctab[64];
-  sincos_tab_fill(sctab, threadIdx.x);
+  extern __shared__ __align__(16) unsigned char probe_smem[];
+  double2* sctab = reinterpret_cast<double2*>(probe_smem);  // [kScTabEntries], filled for the table sincos only
+  if (which == 8) sincos_tab_fill(sctab, threadIdx.x, blockDim.x);
   __syncthreads();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -273,7 +274,10 @@ int xrt_b200_math_probe_host(int which, size_t n, const double* x, double* y0, d
   DevBuf dx, out;
   if (dx.upload(x, n * 8, st) || out.alloc(2 * n * 8)) return 1;
   double* o = out.as<double>();
-  math_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(which, n, dx.as<double>(), o, o + n);
+  const size_t psmem = (which == 8) ? kScTabEntries * sizeof(double2) : 0;
+  if (psmem > 48 * 1024)
+    XRTB_CUDA_CHECK(cudaFuncSetAttribute(math_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+  math_probe_kernel<<<(unsigned)((n + 255) / 256), 256, psmem, st>>>(which, n, dx.as<double>(), o, o + n);
   XRTB_CUDA_CHECK(cudaGetLastError());
   XRTB_CUDA_CHECK(cudaMemcpyAsync(y0, o, n * 8, cudaMemcpyDeviceToHost, st));
   XRTB_CUDA_CHECK(cudaMemcpyAsync(y1, o + n, n * 8, cudaMemcpyDeviceToHost, st));

@@ -23,6 +23,7 @@ int kirchhoff_device(size_t M, size_t N, const double* xM, const double* yM, con
                      int flags, void* ws, cudaStream_t st);
 
 // undulator.cu
+const double2* sin_table_device(cudaStream_t st);  // (cos, sin)(k pi/512) for sin_tab (common.cuh); NULL on failure
 int undulator_raw_device(size_t n, int jend, double Kx, double Ky, const double* gamma, const double* wu,
                          const double* w, const double* ww1, const double* ddphi, const double* ddpsi,
                          const double* tg, const double* ag, const double* sintg, const double* costg,

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(THREADS, XRTB_KIRCHHOFF_MINBLOCKS)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   KInput* tile = reinterpret_cast<KInput*>(smem_raw);                       // [2][TILE]
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + 2 * TILE * sizeof(KInput));  // [2]
-  double2* sctab = reinterpret_cast<double2*>(smem_raw + 2 * TILE * sizeof(KInput) + 16);  // [64] (TABSC)
+  double2* sctab = reinterpret_cast<double2*>(smem_raw + 2 * TILE * sizeof(KInput) + 16);  // [kScTabEntries] (TABSC)
   // the common normal of the uniform-normal variant is the first sample's, read here from device memory (r01 fetched
   // it to the host with a blocking copy inside an entry point that promises to be asynchronous)
   const double un_x = UNIFORM_N ? un[0] * un_scale : 0.0, un_y = UNIFORM_N ? un[1] * un_scale : 0.0,
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(THREADS, XRTB_KIRCHHOFF_MINBLOCKS)
     mbar_init(&full[1], 1);
     mbar_fence_init();
   }
-  if (TABSC) sincos_tab_fill(sctab, tid);
+  if (TABSC) sincos_tab_fill(sctab, tid, THREADS);
   __syncthreads();
 
   auto issue = [&](int t) {
@@ -160,8 +160,8 @@ __global__ void __launch_bounds__(THREADS, XRTB_KIRCHHOFF_MINBLOCKS)
         const double kip = a3.z * hinv;  // k / r
         const double cr = kip * tcos;
         double sn, cs;
-        // (sincos_tab reduces with 32/pi: exact below 2^47 rad = 1.4e14 -- 100 keV over 280 m.  The CALLER vouches for
-        // that range with flag bit 11: a per-pair test in this loop costs 40 % of the kernel)
+        // (sincos_tab reduces with 2^11/pi: exact below 2^40 pi rad = 3.4e12 -- 100 keV over 6.8 m, 9 keV over 75 m.  The
+        // CALLER vouches for that range with flag bit 11: a per-pair test in this loop costs 40 % of the kernel)
         if (TABSC)
           sincos_tab(phase, sctab, sn, cs);
         else
@@ -347,7 +347,7 @@ int kirchhoff_packed_device(size_t M, size_t N, const double* xM, const double* 
   const bool strict = !(flags & 1);
   const int convention = (flags >> 1) & 1;
   const bool uni = (flags >> 9) & 1;  // caller guarantees that all N normals are equal
-  const bool tabsc = (flags >> 11) & 1;  // sincos through the 64-entry table (sincos_tab)
+  const bool tabsc = (flags >> 11) & 1;  // sincos through the shared-memory table (sincos_tab)
   int R = (flags >> 4) & 7;
   if (R == 0) R = 2;
   XRTB_REQUIRE(R == 1 || R == 2 || R == 4, "kirchhoff: register blocking R must be 1, 2 or 4 (got %d)", R);
@@ -359,7 +359,7 @@ int kirchhoff_packed_device(size_t M, size_t N, const double* xM, const double* 
   size_t nps = (N + nsplit - 1) / nsplit;
   nps = (nps + K_TILE - 1) / K_TILE * K_TILE;
   if (nps == 0) nps = K_TILE;
-  const size_t smem = 2 * K_TILE * sizeof(KInput) + 2 * sizeof(uint64_t) + 64 * sizeof(double2);
+  const size_t smem = 2 * K_TILE * sizeof(KInput) + 2 * sizeof(uint64_t) + kScTabEntries * sizeof(double2);
   int rc = 0;
   // the common normal of the uniform-normal variant = the first record's (stored doubled), read by the kernel itself
   const KLaunch L{grid, smem, st, M, N, xM, yM, zM, packed, nps, part, N ? &packed[0].nx2 : nullptr, 0.5};

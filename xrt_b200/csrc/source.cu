@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(U_THREADS)
                          double Tmax, double Pmin, double Pmax, UParams up, UTables tab, xrt_source_params sp,
                          xrt_beam out, unsigned long long* imax_slot) {
   __shared__ UNode tile[U_TILE];
+  __shared__ double2 sctab[kSinTabEntries];
   const size_t base = (size_t)blockIdx.x * (U_THREADS * R);
   Draw d[R];
   USample s[R];
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(U_THREADS)
     fin[r] = wui * (1.0 / g);
     acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0;
   }
-  node_loop<R, PLANAR, SYM>(up, tab, tile, s, acc);
+  node_loop<R, PLANAR, SYM>(up, tab, tile, sctab, s, acc);
   double imax = 0.0;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -778,8 +779,12 @@ int shine_uniform_device(size_t n, uint64_t seed, uint64_t index_offset, const d
   p.dstep = dstep;
   p.jend = jend;
   p.bw_mode = bw_mode;
-  UTables t{tg, ag, sintg, costg, sintgph, costgph};
-  constexpr int R = 2;
+  UTables t{tg, ag, sintg, costg, sintgph, costgph, sin_table_device(st)};
+  XRTB_REQUIRE(t.sintab != nullptr, "undulator: the sin table could not be set up");
+#ifndef XRTB_SHINE_R
+#define XRTB_SHINE_R 2  // samples per thread (3 and 4 measured: profiles/r02_shine_variants.json)
+#endif
+  constexpr int R = XRTB_SHINE_R;
   const unsigned grid = (unsigned)((n + U_THREADS * R - 1) / (U_THREADS * R));
   const bool planar = (Kx == 0.0);
 #define XRTB_S_LAUNCH(PL, SY)                                                                                    \

@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(U_THREADS)
                      const double* __restrict__ psi, double2* __restrict__ Is, double2* __restrict__ Ip,
                      double* __restrict__ Iout) {
   __shared__ UNode tile[U_TILE];
+  __shared__ double2 sctab[kSinTabEntries];
   const size_t base = (size_t)blockIdx.x * (U_THREADS * R);
   USample s[R];
   double acc[R][4];
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(U_THREADS)
     acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0;
   }
 
-  node_loop<R, PLANAR, SYM>(p, tab, tile, s, acc);
+  node_loop<R, PLANAR, SYM>(p, tab, tile, sctab, s, acc);
 
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -72,6 +73,31 @@ __global__ void __launch_bounds__(U_THREADS)
       Ip[i] = ep;
     }
   }
+}
+
+// (cos, sin)(k pi/512), k < 1024, correctly rounded (sincospi), once per device; the node loops stage it into shared memory
+__global__ void sin_table_kernel(double2* tab) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= kSinTabEntries) return;
+  double sn, cs;
+  sincospi((double)k * (2.0 / (double)kSinTabEntries), &sn, &cs);
+  tab[k] = make_double2(cs, sn);
+}
+const double2* sin_table_device(cudaStream_t st) {
+  static double2* tabs[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!tabs[dev]) {
+    double2* t = nullptr;
+    if (cudaMalloc(&t, kSinTabEntries * sizeof(double2)) != cudaSuccess) return nullptr;
+    sin_table_kernel<<<(kSinTabEntries + 255) / 256, 256, 0, st>>>(t);
+    if (cudaStreamSynchronize(st) != cudaSuccess) {  // once per device: other streams may use the table next
+      cudaFree(t);
+      return nullptr;
+    }
+    tabs[dev] = t;
+  }
+  return tabs[dev];
 }
 
 static int launch(int mode, int R, bool symmetric, size_t n, const UParams& p, const UTables& t, const double* gamma,
@@ -119,7 +145,8 @@ int undulator_raw_device(size_t n, int jend, double Kx, double Ky, const double*
   p.Kx = Kx;
   p.Ky = Ky;
   p.jend = jend;
-  UTables t{tg, ag, sintg, costg, sintgph, costgph};
+  UTables t{tg, ag, sintg, costg, sintgph, costgph, sin_table_device(st)};
+  XRTB_REQUIRE(t.sintab != nullptr, "undulator: the sin table could not be set up");
   return launch(0, R, symmetric != 0, n, p, t, gamma, wu, w, ww1, ddphi, ddpsi, Is, Ip, nullptr, st);
 }
 
@@ -138,7 +165,8 @@ int undulator_imap_device(size_t n, int jend, double Kx, double Ky, double L0, d
   p.dstep = dstep;
   p.jend = jend;
   p.bw_mode = bw_mode;
-  UTables t{tg, ag, sintg, costg, sintgph, costgph};
+  UTables t{tg, ag, sintg, costg, sintgph, costgph, sin_table_device(st)};
+  XRTB_REQUIRE(t.sintab != nullptr, "undulator: the sin table could not be set up");
   return launch(1, R, symmetric != 0, n, p, t, gamma, nullptr, w, nullptr, theta, psi, Es, Ep, I, st);
 }
 

@@ -349,7 +349,7 @@ int undulator_ext_device(int variant, int mode, size_t n, int jend, int nmax, do
   p.dstep = dstep;
   p.jend = jend;
   p.bw_mode = bw_mode;
-  UTables t{tg, ag, sintg, costg, sintgph, costgph};
+  UTables t{tg, ag, sintg, costg, sintgph, costgph, nullptr};
   const unsigned grid = (unsigned)((n + E_THREADS - 1) / E_THREADS);
   double2* is2 = reinterpret_cast<double2*>(Is);
   double2* ip2 = reinterpret_cast<double2*>(Ip);

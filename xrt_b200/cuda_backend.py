@@ -19,7 +19,7 @@ myopencl.py:455-583) is replaced by one process per GPU (see xrt_b200/parallel.p
 """
 import numpy as np
 
-from . import _lib
+from . import _lib, kernels
 
 isOpenCL = False  # there is no OpenCL here; kept so `mcl.isOpenCL or mcl.isZMQ` style tests read the same
 isZMQ = False
@@ -163,12 +163,13 @@ class XRT_CUDA(object):
             outs.append(a)
         flags = (1 if self.kirchhoffRelaxed else 0) | (_KIRCHHOFF_CONVENTIONS[self.kirchhoffConvention] << 1)
         if N > 0 and M > 0:
-            # sin / cos through the 64-entry table (same accuracy, 10 % faster) when every phase k r stays below 2^47:
+            # sin / cos through the shared-memory table (same accuracy, faster) when every phase k r stays below
+            # kernels.PHASE_LIMIT_TABLE_SINCOS:
             # bound it with the bounding boxes of the samples and of the receiving points
             pv = pos[:3, :] if pos.shape[1] == N and pos.shape[0] in (3, 4) and pos.flags['F_CONTIGUOUS'] else pos[:, :3].T
             span = np.maximum(np.abs(np.array([xM.max(), yM.max(), zM.max()]) - pv.min(axis=1)),
                               np.abs(pv.max(axis=1) - np.array([xM.min(), yM.min(), zM.min()])))
-            if np.abs(k).max() * np.linalg.norm(span) < 2.**47:
+            if np.abs(k).max() * np.linalg.norm(span) < kernels.PHASE_LIMIT_TABLE_SINCOS:
                 flags |= 1 << 11
         nview = nrm[:3, :] if nrm.shape[1] == N and nrm.shape[0] in (3, 4) and nrm.flags['F_CONTIGUOUS'] else nrm[:, :3].T
         if N > 0 and np.all(nview == nview[:, :1]):

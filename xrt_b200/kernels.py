@@ -47,7 +47,7 @@ def kirchhoff_workspace(device, nbytes):
     return ws
 
 
-PHASE_LIMIT_TABLE_SINCOS = 2.**47  # sincos_tab (common.cuh) reduces with 32/pi: exact below this phase
+PHASE_LIMIT_TABLE_SINCOS = 2.**40 * 3.141592653589793  # sincos_tab (common.cuh) reduces with 2^11/pi: exact below this phase
 
 
 def phase_bound(xM, yM, zM, pos, k):
