@@ -526,7 +526,7 @@ def run_ours(args):
     und_ms = stage_ms['shine']
     und_tflops = FLOP_PER_SAMPLE_NODE * nrays * nodes / (und_ms * 1e-3) / 1e12
     pair_path = bool(src.gridSymmetric and src.Kx == 0)
-    und_instr = 24.5 if pair_path else 57.0  # DFMA-pipe instructions per (sample, node) in SASS
+    und_instr = 22.0 if pair_path else 57.0  # DFMA-pipe instructions per (sample, node) in SASS (44 per node pair)
     roofline_und = {'kernel': 'shine_uniform_kernel<2,planar,%s> (Undulator.shine: sample + field integral + Beam '
                               'assembly)' % ('pairs' if pair_path else 'nodes'),
                     'bound': 'fp64', 'achieved': und_tflops, 'peak': dfma_tflops, 'unit': 'TFLOP/s',
@@ -534,7 +534,8 @@ def run_ours(args):
                     'issue_slot_frac': 2 * und_instr * nrays * nodes / (und_ms * 1e-3) / 1e12 / dfma_tflops,
                     'note': 'achieved counts the 63 flop per (sample, node) of the reference algorithm (SURVEY 8d); '
                             'the kernel evaluates mirror PAIRS of nodes for a planar undulator on a symmetric grid '
-                            '(49 DFMA-pipe instructions per pair), so issue_slot_frac is the pipe utilisation',
+                            '(44 DFMA-pipe instructions per pair; 49 before the sin of the pair phase went through a '
+                            '1024-entry shared-memory table), so issue_slot_frac is the pipe utilisation',
                     'ms': und_ms, 'share_of_step': und_ms / ms_step}
     main_ms = refl_ms[2]
     main_bytes = 132 + 132 + 140
@@ -675,10 +676,10 @@ def run_ours(args):
                'pairs_per_s': pairs, 'value': ktf * 1e3, 'unit': 'GFLOP/s (57 flop/pair), all GPUs',
                'roofline': {'bound': 'fp64', 'achieved': ktf_kernel / world, 'peak': dfma_tflops,
                             'unit': 'TFLOP/s per GPU', 'frac': ktf_kernel / world / dfma_tflops, 'traffic': None,
-                            'issue_slot_frac': 63 * 2 * float(N) * M / (kernel_ms * 1e-3) / world / 1e12 / dfma_tflops,
-                            'note': 'kirchhoff_kernel<R=4, strict, uniform normal, table sincos>: 63 DFMA-pipe '
-                                    'instructions per pair in SASS (65 in r01: sin / cos through a 64-entry pi/32 '
-                                    'table); frac counts the 57 algorithmic flops of SURVEY 8d, issue_slot_frac the '
+                            'issue_slot_frac': 58 * 2 * float(N) * M / (kernel_ms * 1e-3) / world / 1e12 / dfma_tflops,
+                            'note': 'kirchhoff_kernel<R=4, strict, uniform normal, table sincos>: 58 DFMA-pipe '
+                                    'instructions per pair in SASS (65 in r01, 63 with a 64-entry table: sin / cos through '
+                                    'a 4096-entry pi/2048 table in shared memory and two-term polynomials); frac counts the 57 algorithmic flops of SURVEY 8d, issue_slot_frac the '
                                     'issued ones; DMMA shares the FP64 pipe (profiles/r02_kirchhoff_variants.json)'}}
         del d, out
 

@@ -249,43 +249,53 @@ __global__ void __launch_bounds__(256) fill_kernel(size_t n, xrt_source_params p
 // (I, mJs, mJp) never travel through HBM (saves 64 + 64 + 40 + 40 B/ray and two launches); the Philox /
 // Box-Muller integer work and the 132 B/ray of stores hide under the FP64-bound node loop.  Same device
 // functions as the three separate kernels, so the beams are bit-identical (tests/test_shine.py).
+// batches of rays per block (the node tile and the sin table staged once): 4 and 8 measured 15.0 ms instead of 14.1 ms per
+// 1e8 rays -- the loop-carried state costs more than the 16 KB of table staging per 256 rays
+#ifndef XRTB_SHINE_BATCHES
+#define XRTB_SHINE_BATCHES 1
+#endif
 template <int R, bool PLANAR, bool SYM>
-__global__ void __launch_bounds__(U_THREADS)
+__global__ void __launch_bounds__(U_THREADS, (R <= 2) ? 4 : 1)
     shine_uniform_kernel(size_t n, uint64_t seed, uint64_t index_offset, double Emin, double Emax, double Tmin,
                          double Tmax, double Pmin, double Pmax, UParams up, UTables tab, xrt_source_params sp,
                          xrt_beam out, unsigned long long* imax_slot) {
   __shared__ UNode tile[U_TILE];
   __shared__ double2 sctab[kSinTabEntries];
-  const size_t base = (size_t)blockIdx.x * (U_THREADS * R);
-  Draw d[R];
-  USample s[R];
-  double acc[R][4];
-  double abv[R], fin[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const size_t i = base + (size_t)r * U_THREADS + threadIdx.x;
-    d[r] = draw_ray(index_offset + i, seed, Emin, Emax, Tmin, Tmax, Pmin, Pmax, true, sp.eEspread > 0.0);
-    // gamma += gamma * eEspread * normal (synchr.py:2053-2059)
-    const double g = (sp.eEspread > 0.0) ? up.gamma0 + up.gamma0 * sp.eEspread * d[r].n5 : up.gamma0;
-    double wui, ww1i;
-    sample_prefactors(up, g, d[r].E, d[r].theta, d[r].psi, wui, ww1i, abv[r]);
-    s[r] = make_sample(up.Kx, up.Ky, g, wui, d[r].E, ww1i, d[r].theta, d[r].psi);
-    fin[r] = wui * (1.0 / g);
-    acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0;
-  }
-  node_loop<R, PLANAR, SYM>(up, tab, tile, sctab, s, acc);
   double imax = 0.0;
+  // XRTB_SHINE_BATCHES batches of U_THREADS * R rays per block: the node tile and the sin table are staged once
+#pragma unroll 1
+  for (int bt = 0; bt < XRTB_SHINE_BATCHES; ++bt) {
+    const size_t base = ((size_t)blockIdx.x * XRTB_SHINE_BATCHES + bt) * (U_THREADS * R);
+    if (base >= n) break;  // (the same for every thread of the block)
+    Draw d[R];
+    USample s[R];
+    double acc[R][4];
+    double abv[R], fin[R];
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const size_t i = base + (size_t)r * U_THREADS + threadIdx.x;
-    if (i >= n) continue;
-    const double f = fin[r];
-    double I;
-    double2 es, ep;
-    imap_outputs(up, d[r].E, abv[r], f * acc[r][0], f * acc[r][1], f * acc[r][2], f * acc[r][3], I, es, ep);
-    imax = fmax(imax, I);
-    fill_ray(sp, d[r].E, d[r].theta, d[r].psi, cplx{es.x, es.y}, cplx{ep.x, ep.y}, d[r].n1, d[r].n2, d[r].n3,
-             d[r].n4, out, i);
+    for (int r = 0; r < R; ++r) {
+      const size_t i = base + (size_t)r * U_THREADS + threadIdx.x;
+      d[r] = draw_ray(index_offset + i, seed, Emin, Emax, Tmin, Tmax, Pmin, Pmax, true, sp.eEspread > 0.0);
+      // gamma += gamma * eEspread * normal (synchr.py:2053-2059)
+      const double g = (sp.eEspread > 0.0) ? up.gamma0 + up.gamma0 * sp.eEspread * d[r].n5 : up.gamma0;
+      double wui, ww1i;
+      sample_prefactors(up, g, d[r].E, d[r].theta, d[r].psi, wui, ww1i, abv[r]);
+      s[r] = make_sample(up.Kx, up.Ky, g, wui, d[r].E, ww1i, d[r].theta, d[r].psi);
+      fin[r] = wui * (1.0 / g);
+      acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0;
+    }
+    node_loop<R, PLANAR, SYM>(up, tab, tile, sctab, s, acc, bt == 0);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const size_t i = base + (size_t)r * U_THREADS + threadIdx.x;
+      if (i >= n) continue;
+      const double f = fin[r];
+      double I;
+      double2 es, ep;
+      imap_outputs(up, d[r].E, abv[r], f * acc[r][0], f * acc[r][1], f * acc[r][2], f * acc[r][3], I, es, ep);
+      imax = fmax(imax, I);
+      fill_ray(sp, d[r].E, d[r].theta, d[r].psi, cplx{es.x, es.y}, cplx{ep.x, ep.y}, d[r].n1, d[r].n2, d[r].n3,
+               d[r].n4, out, i);
+    }
   }
   // beam-wide max intensity (Imax bookkeeping, sybase.py:1627-1631): non-negative doubles order like integers
   imax = warp_reduce(imax, OpMax());
@@ -785,7 +795,8 @@ int shine_uniform_device(size_t n, uint64_t seed, uint64_t index_offset, const d
 #define XRTB_SHINE_R 2  // samples per thread (3 and 4 measured: profiles/r02_shine_variants.json)
 #endif
   constexpr int R = XRTB_SHINE_R;
-  const unsigned grid = (unsigned)((n + U_THREADS * R - 1) / (U_THREADS * R));
+  const size_t per_block = (size_t)U_THREADS * R * XRTB_SHINE_BATCHES;
+  const unsigned grid = (unsigned)((n + per_block - 1) / per_block);
   const bool planar = (Kx == 0.0);
 #define XRTB_S_LAUNCH(PL, SY)                                                                                    \
   shine_uniform_kernel<R, PL, SY><<<grid, U_THREADS, 0, st>>>(n, seed, index_offset, window[0], window[1], window[2], \

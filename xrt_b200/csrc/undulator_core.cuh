@@ -186,18 +186,23 @@ __device__ __forceinline__ void imap_outputs(const UParams& p, double w, double 
 // Must be called by every thread of the block (it synchronises on the shared node tile).
 template <int R, bool PLANAR, bool SYM>
 __device__ __forceinline__ void node_loop(const UParams& p, const UTables& tab, UNode* tile, double2* sctab,
-                                          const USample* s, double (*acc)[4]) {
+                                          const USample* s, double (*acc)[4], bool first = true) {
+  // first = false: a further batch of samples in the same block -- the sin table is staged already, and so is the
+  // node tile when the grid fits one tile (the usual case: 64 nodes)
   // SYM: only the first half of the nodes is visited (pairs); an odd middle node goes through the general step
   const int jpair = SYM ? p.jend / 2 : 0;
   const int jlast = SYM ? jpair + (p.jend & 1) : p.jend;
-  if (SYM) {  // the sin table of the pair step: 16 KB from L2 into shared memory (published by the barrier below)
+  if (SYM && first) {  // the sin table of the pair step: 16 KB from L2 into shared memory (published by the barrier below)
     for (int k = threadIdx.x; k < kSinTabEntries; k += blockDim.x) sctab[k] = tab.sintab[k];
   }
+  const bool reload = first || jlast > U_TILE;
   for (int j0 = 0; j0 < jlast; j0 += U_TILE) {
     const int cnt = min(U_TILE, jlast - j0);
-    __syncthreads();
-    load_node_tile(tile, tab, j0, cnt, p.Kx, p.Ky);
-    __syncthreads();
+    if (reload) {
+      __syncthreads();
+      load_node_tile(tile, tab, j0, cnt, p.Kx, p.Ky);
+      __syncthreads();
+    }
 #pragma unroll kNodeUnroll
     for (int j = 0; j < cnt; ++j) {
       const double4* q = reinterpret_cast<const double4*>(tile + j);
