@@ -41,7 +41,8 @@ int xrt_b200_fp64_probe(int mode, int iters, double* tflops, double* ms);
 
 /* Known-answer access to the device math helpers the kernels are built from (host arrays; tests only):
  * which 0 sincos_big -> (sin, cos); 1 sin_big; 2 rcp_fast; 3 sqrt_rsqrt -> (sqrt, 1/sqrt); 4 (K_1/3, K_2/3);
- * 6 rcp_cubic; 7 sqrt_hrsqrt -> (sqrt, 0.5/sqrt); 8 sincos_tab -> (sin, cos). */
+ * 6 rcp_cubic; 7 sqrt_hrsqrt -> (sqrt, 0.5/sqrt); 8 sincos_tab -> (sin, cos); 9 sin_tab; 10 the unchecked IEEE
+ * sequences div_nr / sqrt_nr -> (1/x, sqrt|x|); 11 div_nr(x[i], x[i^1]) (n even). */
 int xrt_b200_math_probe_host(int which, size_t n, const double* x, double* y0, double* y1);
 
 /* ------------------------------------------------------------------ a17: Fresnel-Kirchhoff sum

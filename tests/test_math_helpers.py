@@ -81,3 +81,40 @@ def test_bessel_k_fractional_orders(cuda_device):
     assert np.all(k13[~ok] < 1e-299)
     k13, k23 = _probe(4, np.array([0., 900., np.inf]))
     assert np.isinf(k13[0]) and k13[1] == 0 and k13[2] == 0 and k23[2] == 0
+
+
+@pytest.mark.gpu
+def test_sin_table_of_the_undulator_pair_loop(cuda_device):
+    """sin_tab (1024-entry table + r - r^3/6 + r^5/120): the node-pair step's sin, phases O(100) rad."""
+    rng = np.random.RandomState(5)
+    x = np.concatenate([rng.uniform(-300, 300, 6000), rng.uniform(-1e6, 1e6, 2000),
+                        np.array([0., np.pi / 512, np.pi / 1024, -np.pi, 1e-300, 100.0])])
+    s_ref, _ = _exact_sincos(x)
+    s, _ = _probe(9, x)
+    assert np.abs(s - s_ref).max() < 4e-16
+
+
+@pytest.mark.gpu
+def test_unchecked_division_and_sqrt_are_correctly_rounded(cuda_device):
+    """div_nr / sqrt_nr (common.cuh): nvcc's fast path of a / b and sqrt(a) without the range test and the slow-path
+    call -- for ordinary operands the results must be the IEEE ones, bit for bit (reflect.cu relies on it: the toroid
+    surface, the secant step, the Fresnel and Bragg amplitudes)."""
+    rng = np.random.RandomState(6)
+    x = np.concatenate([rng.uniform(-2, 2, 200000), 10.**rng.uniform(-200, 200, 200000) * rng.choice([-1, 1], 200000),
+                        rng.uniform(0.999999, 1.000001, 100000), np.array([1.0, -1.0, 3.0, 1e-290, 1e290, 0.1])])
+    x = x[x != 0]
+    inv, rt = _probe(10, x)
+    assert np.array_equal(inv, 1.0 / x)
+    assert np.array_equal(rt, np.sqrt(np.abs(x)))
+    a = rng.uniform(-1e3, 1e3, 400000) * 10.**rng.uniform(-30, 30, 400000)
+    b = rng.uniform(-1e3, 1e3, 400000) * 10.**rng.uniform(-30, 30, 400000)
+    b[b == 0] = 1.0
+    a[::1000] = 0.0  # zero dividends
+    pairs = np.empty(2 * len(a))
+    pairs[0::2] = a
+    pairs[1::2] = b
+    q, _ = _probe(11, pairs)
+    with np.errstate(all='ignore'):
+        assert np.array_equal(q[0::2], a / b)
+        sel = a != 0
+        assert np.array_equal(q[1::2][sel], (b / a)[sel])

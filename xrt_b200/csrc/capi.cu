@@ -105,7 +105,7 @@ static int fp64_probe(int mode, int iters, double* tflops, double* ms_out) {
 
 // ---------------------------------------------------------------- device math helpers, exposed for known-answer tests
 __global__ void math_probe_kernel(int which, size_t n, const double* __restrict__ x, double* __restrict__ y0,
-                                  double* __restrict__ y1) {
+                                  double* __restrict__ y1, const double2* __restrict__ sintab) {
   extern __shared__ __align__(16) unsigned char probe_smem[];
   double2* sctab = reinterpret_cast<double2*>(probe_smem);  // [kScTabEntries], filled for the table sincos only
   if (which == 8) sincos_tab_fill(sctab, threadIdx.x, blockDim.x);
@@ -123,6 +123,12 @@ __global__ void math_probe_kernel(int which, size_t n, const double* __restrict_
     case 6: a = rcp_cubic(v); break;
     case 7: sqrt_hrsqrt(v, a, b); break;
     case 8: sincos_tab(v, sctab, a, b); break;
+    case 9: a = sin_tab(v, sintab); break;
+    case 10:  // the unchecked IEEE sequences: x -> (1 / x, sqrt(|x|)); pairs (x[2i], x[2i+1]) -> quotient in y1 of the even slot
+      a = div_nr(1.0, v);
+      b = sqrt_nr(fabs(v));
+      break;
+    case 11: a = div_nr(v, x[i ^ 1]); break;  // x[i] / x[i ^ 1]
     default: break;
   }
   y0[i] = a;
@@ -269,7 +275,8 @@ int xrt_kirchhoff_f64_host(size_t M, size_t N, const double* xM, const double* y
 
 int xrt_b200_math_probe_host(int which, size_t n, const double* x, double* y0, double* y1) {
   if (n == 0) return 0;
-  XRTB_REQUIRE(which >= 0 && which <= 8 && x && y0 && y1, "math_probe: bad arguments");
+  XRTB_REQUIRE(which >= 0 && which <= 11 && x && y0 && y1, "math_probe: bad arguments");
+  XRTB_REQUIRE(which != 11 || n % 2 == 0, "math_probe: which = 11 takes pairs");
   cudaStream_t st = 0;
   DevBuf dx, out;
   if (dx.upload(x, n * 8, st) || out.alloc(2 * n * 8)) return 1;
@@ -277,7 +284,9 @@ int xrt_b200_math_probe_host(int which, size_t n, const double* x, double* y0, d
   const size_t psmem = (which == 8) ? kScTabEntries * sizeof(double2) : 0;
   if (psmem > 48 * 1024)
     XRTB_CUDA_CHECK(cudaFuncSetAttribute(math_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-  math_probe_kernel<<<(unsigned)((n + 255) / 256), 256, psmem, st>>>(which, n, dx.as<double>(), o, o + n);
+  const double2* sintab = (which == 9) ? sin_table_device(st) : nullptr;
+  XRTB_REQUIRE(which != 9 || sintab, "math_probe: no sin table");
+  math_probe_kernel<<<(unsigned)((n + 255) / 256), 256, psmem, st>>>(which, n, dx.as<double>(), o, o + n, sintab);
   XRTB_CUDA_CHECK(cudaGetLastError());
   XRTB_CUDA_CHECK(cudaMemcpyAsync(y0, o, n * 8, cudaMemcpyDeviceToHost, st));
   XRTB_CUDA_CHECK(cudaMemcpyAsync(y1, o + n, n * 8, cudaMemcpyDeviceToHost, st));

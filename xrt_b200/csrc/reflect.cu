@@ -261,7 +261,7 @@ __device__ __forceinline__ double fe_eval(const xrt_oe_params& p, double x, doub
 #define XRTB_SECANT_DIV(a, b) ((a) / (b))
 #else
 #define XRTB_SURF_DIV(a, d) div_by_nr(a, d)
-#define XRTB_SURF_SQRT(a) sqrt_nr(a)  // 0 <= a <= 1
+#define XRTB_SURF_SQRT(a) sqrt_nr(a)  // zero or positive normal arguments (squares of coordinates, 1 - q^2)
 // the secant step (t2 - t1) * dz1 / (dz2 - dz1): inside the loop dz1 and dz2 are non-zero with opposite signs (the pair
 // brackets the root: solve_secant keeps that invariant), so |dz2 - dz1| >= max(|dz1|, |dz2|) > zEps, and the numerator is
 // zero or >= ulp(t) * zEps -- the operands of the unchecked sequence
@@ -324,7 +324,7 @@ __device__ __forceinline__ double local_surface(const xrt_oe_params& p, const Su
   }
   // EllipticalMirrorParam.local_r (parametric.py:228-234): x = s, y = phi
   const double B = p.sp[1];
-  double rr = B * sqrt(fabs(1.0 - div_by(x * x, sd.d0)));  // s**2 / A**2
+  double rr = B * XRTB_SURF_SQRT(fabs(1.0 - XRTB_SURF_DIV(x * x, sd.d0)));  // s**2 / A**2
   if (p.sp[6] != 0.0) rr /= fabs(cos(y));
   return (fabs(y) > kPi / 2) ? rr : 1e20;
 }
@@ -345,7 +345,7 @@ __device__ __forceinline__ void xyz_to_param(const xrt_oe_params& p, double& x, 
   const double xx = x;
   x = yN;
   y = atan2(xx, zN);
-  z = sqrt(xx * xx + zN * zN);
+  z = XRTB_SURF_SQRT(xx * xx + zN * zN);
 }
 
 template <int SURF>
@@ -465,16 +465,18 @@ __device__ __forceinline__ void local_normal(const xrt_oe_params& p, const SurfD
   const double A = p.sp[0], B = p.sp[1];
   double A2s2 = A * A - x * x;
   if (A2s2 <= 0.0) A2s2 = 1e22;
-  const double nr = -B / A * x / sqrt(A2s2);
-  const double norm = sqrt(nr * nr + 1.0);
-  const double b = nr / norm;
+  // (A2s2 > 0 and norm >= 1: the unchecked sequences give the IEEE quotients and roots, see XRTB_SURF_DIV)
+  const double nr = XRTB_SURF_DIV(-B / A * x, make_divisor(XRTB_SURF_SQRT(A2s2)));
+  const double norm = XRTB_SURF_SQRT(nr * nr + 1.0);
+  const Divisor dn = make_divisor(norm);
+  const double b = XRTB_SURF_DIV(nr, dn);
   double a, c;
   if (p.sp[6] != 0.0) {
     a = 0.0;
-    c = 1.0 / norm;
+    c = XRTB_SURF_DIV(1.0, dn);
   } else {
-    a = -sin(y) / norm;
-    c = -cos(y) / norm;
+    a = XRTB_SURF_DIV(-sin(y), dn);
+    c = XRTB_SURF_DIV(-cos(y), dn);
   }
   const double cg = p.sp[4], sg = -(-p.sp[5]);  // rotate_x(b, c, cosGamma, -sinGamma): -sinangle*z = +sinGamma*z
   n[0] = n[3] = a;
