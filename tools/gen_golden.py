@@ -1314,6 +1314,8 @@ def gen_blazed():
     find_intersection (first facet hit, shadowing respected) and facet normals; material kind 'mirror'."""
     bl = raycing.BeamLine()
     Au = rm.Material('Au', rho=19.3, kind='mirror')
+    # (a variable line density cannot be generated: BlazedGrating(gratingDensity=[...]) recurses without end in the
+    # reference as it stands -- reset() assigns self.rho0, whose setter calls reset(), gratings.py:377-380 / :416-420)
     for name, kw in (('blazed', dict(blaze=np.radians(1.2), rho=300.)),
                      ('blazed_anti', dict(blaze=np.radians(0.8), antiblaze=np.radians(30.), rho=600.))):
         beam = _source_beam(bl, 2500, 251, dx=0.3, dz=0.02, dxprime=1e-4, dzprime=3e-5, energies=(395., 405.))

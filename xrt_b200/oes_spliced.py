@@ -426,6 +426,8 @@ class BlazedGrating(OE):
         self.antiblaze = kwargs.pop('antiblaze', np.pi*0.4999)
         self.rho0 = kwargs.pop('rho', 1)
         if kwargs.get('gratingDensity') is not None:
+            # (the reference cannot construct this case either: reset() assigns self.rho0 whose setter calls reset()
+            # again, oes/gratings.py:377-380 / :416-420 -- RecursionError; there is nothing to pin a port on)
             raise NotImplementedError('a variable line density (ticks search) is outside the hot path')
         if self.blaze == np.pi/2 or self.antiblaze == np.pi/2:
             raise NotImplementedError('vertical facets (angle == pi/2) are outside the hot path')
