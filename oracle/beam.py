@@ -55,7 +55,7 @@ def concatenate(self, beam):
     (nRefl, s, phi, r, theta, order, Es, Ep) are stacked."""
     for k in ('state', 'x', 'y', 'z', 'a', 'b', 'c', 'path', 'E', 'Jss', 'Jpp', 'Jsp'):
         setattr(self, k, np.concatenate((getattr(self, k), getattr(beam, k))))
-    for k in ('nRefl', 's', 'phi', 'r', 'theta', 'order', 'Es', 'Ep'):
+    for k in ('nRefl', 'elevationD', 'elevationX', 'elevationY', 'elevationZ', 's', 'phi', 'r', 'theta', 'order', 'Es', 'Ep'):
         if hasattr(self, k) and hasattr(beam, k):
             setattr(self, k, np.concatenate((getattr(self, k), getattr(beam, k))))
 

@@ -342,7 +342,7 @@ def _set_t(xyz, abc, surfPhys=None, defSize=maxHalfSizeOfOE):
 
 
 def _bracketing(oe, x, y, z, a, b, c, surfPhysX, surfPhysY, mainPart, info=None, isMulti=False, local_n=None,
-                invertNormal=1):
+                invertNormal=1, needElevationMap=False):
     try:
         maxa = np.max(abs(a[mainPart]))
         maxb = np.max(abs(b[mainPart]))
@@ -370,8 +370,19 @@ def _bracketing(oe, x, y, z, a, b, c, surfPhysX, surfPhysY, mainPart, info=None,
                                              derivOrder=1)
         if info is not None:
             info['deriv'] = infoD
+        if needElevationMap:  # base.py:1285-1287: (dz, x, y, z) at the derivative root = the highest point
+            info_e = find_dz(oe, None, tMax, x, y, z, a, b, c, invertNormal)
+            if info is not None:
+                info['elevation'] = info_e
+            elevation = info_e
+        else:
+            elevation = None
         tMin = tMax + ds
         tMax = tMaxTmp
+        if needElevationMap:
+            return tMin, tMax, elevation
+    if needElevationMap:
+        return tMin, tMax, None
     return tMin, tMax
 
 
@@ -428,7 +439,7 @@ def _grating_deflection(goodN, lb, g, oeNormal, beamInDotNormal, order=1, sig=No
 
 def reflect_local(oe, good, lb, vlb, pitch, roll, yaw, dx=None, dy=None, dz=None, local_n=None, material=None,
                   is2ndXtal=False, surfPhysX=None, surfPhysY=None, surfOptX=None, surfOptY=None, info=None,
-                  noIntersectionSearch=False, fromVacuum=True, isMulti=False):
+                  noIntersectionSearch=False, fromVacuum=True, isMulti=False, needElevationMap=False):
     if local_n is None:
         local_n = oe.local_n
     if surfPhysX is None:
@@ -451,9 +462,24 @@ def reflect_local(oe, good, lb, vlb, pitch, roll, yaw, dx=None, dy=None, dz=None
     mainPartForBracketing = lb.state[good] == 1
     tMin = np.zeros_like(lb.x)
     tMax = np.zeros_like(lb.x)
-    tMin[good], tMax[good] = _bracketing(
-        oe, lb.x[good], lb.y[good], lb.z[good], lb.a[good], lb.b[good], lb.c[good], surfPhysX, surfPhysY,
-        mainPartForBracketing, info, isMulti=isMulti, local_n=local_n, invertNormal=invertNormal)
+    if needElevationMap:  # reflect.py:647-659
+        tMin[good], tMax[good], elev = _bracketing(
+            oe, lb.x[good], lb.y[good], lb.z[good], lb.a[good], lb.b[good], lb.c[good], surfPhysX, surfPhysY,
+            mainPartForBracketing, info, isMulti=isMulti, local_n=local_n, invertNormal=invertNormal,
+            needElevationMap=True)
+        if elev:
+            lb.elevationD[good] = elev[0]
+            if oe.isParametric:
+                tX, tY, tZ = oe.param_to_xyz(elev[1], elev[2], elev[3])
+            else:
+                tX, tY, tZ = elev[1], elev[2], elev[3]
+            lb.elevationX[good] = tX
+            lb.elevationY[good] = tY
+            lb.elevationZ[good] = tZ
+    else:
+        tMin[good], tMax[good] = _bracketing(
+            oe, lb.x[good], lb.y[good], lb.z[good], lb.a[good], lb.b[good], lb.c[good], surfPhysX, surfPhysY,
+            mainPartForBracketing, info, isMulti=isMulti, local_n=local_n, invertNormal=invertNormal)
     if noIntersectionSearch:  # reflect.py:676-681
         tMax[good] = 0.
         if oe.isParametric:
@@ -656,9 +682,10 @@ def reflect(oe, beam, needLocal=True, createdByDiffract=False, info=None, noInte
     return gb, lb
 
 
-def multiple_reflect(oe, beam, maxReflections=1000, infos=None):
-    """OE.multiple_reflect (reflect.py:165-264) without the elevation map.  gb and lb are ONE object there, so every
-    pass works in place on the virgin-local beam; lbN stacks the passes with Beam.concatenate (beams.py:230-295)."""
+def multiple_reflect(oe, beam, maxReflections=1000, infos=None, needElevationMap=False):
+    """OE.multiple_reflect (reflect.py:165-264).  gb and lb are ONE object there, so every pass works in place on the
+    virgin-local beam; lbN stacks the passes with Beam.concatenate (beams.py:230-295).  needElevationMap: elevationD /
+    X / Y / Z of the passes after the first (reflect.py:212-216, :651-659)."""
     gb = ob.Beam(copyFrom=beam)
     lb = gb
     good = beam.state > 0
@@ -670,8 +697,13 @@ def multiple_reflect(oe, beam, maxReflections=1000, infos=None):
     while iRefl < maxReflections:
         tmpX, tmpY, tmpZ = np.copy(lb.x[good]), np.copy(lb.y[good]), np.copy(lb.z[good])
         info = {} if infos is not None else None
+        if iRefl == 0 and needElevationMap:
+            lb.elevationD = -np.ones_like(lb.x)
+            lb.elevationX = -np.ones_like(lb.x)*maxHalfSizeOfOE
+            lb.elevationY = -np.ones_like(lb.x)*maxHalfSizeOfOE
+            lb.elevationZ = -np.ones_like(lb.x)*maxHalfSizeOfOE
         reflect_local(oe, good, lb, gb, oe.pitch, oe.roll, oe.yaw, oe.dx, material=oe.material, info=info,
-                      isMulti=isMulti)
+                      isMulti=isMulti, needElevationMap=needElevationMap)
         if infos is not None:
             infos.append(info)
         if iRefl == 0:

@@ -35,6 +35,25 @@ def test_oracle_multiple_reflect_bit_exact(name):
     assert gb.nRefl.max() == 8 and (gb.nRefl == 3).sum() > 20
 
 
+ELEV = ('elevationD', 'elevationX', 'elevationY', 'elevationZ')
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_oracle_elevation_map_bit_exact(name):
+    """needElevationMap=True (reflect.py:212-216, :651-659; base.py:1285-1287): the highest point of every ray above the
+    surface between two impacts (root of direction . normal) and its distance, per pass."""
+    g = golden('multi_reflect_' + name)
+    e = golden('multi_reflect_' + name + '_elevation')
+    gb, lbN = orf.multiple_reflect(_oracle_spec(name, g), oracle_beam(g, 'in_'), maxReflections=8,
+                                   needElevationMap=True)
+    assert np.array_equal(gb.x, g['gb_x']) and np.array_equal(lbN.x, g['lbN_x'])  # the map does not change the rays
+    for pre, b in (('gb_', gb), ('lbN_', lbN)):
+        for f in ELEV:
+            assert np.array_equal(getattr(b, f), e[pre + f]), pre + f
+    n = len(gb.x)
+    assert (lbN.elevationD[:n] == -1).all() and (lbN.elevationD[n:] > 0).sum() > 1000
+
+
 def _product_oe(name, g):
     from xrt_b200 import oes, materials
     kw = product_oe_kwargs(g)

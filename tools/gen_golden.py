@@ -1077,6 +1077,25 @@ def gen_multi():
         print(name, 'passes', len(oe.footprint), 'nRefl', dict(zip(*np.unique(gb.nRefl, return_counts=True))),
               'state', dict(zip(*np.unique(gb.state, return_counts=True))))
         save('multi_reflect_' + name, rho=19.3, R=float(oe.R), r=float(getattr(oe, 'r', 0.)), **d)
+    # the same passes with needElevationMap=True (reflect.py:212-216, :651-659; base.py:1279-1289): the highest point of
+    # a ray above the surface between two impacts and its distance, per pass.  A second beam line with the same two
+    # elements in the same order (lostNum is the element's ordinal), so that the files above stay byte-identical.
+    bl = raycing.BeamLine()
+    for name, cls, kw in (('bentflat', roe.BentFlatMirror, dict(R=2000.)),
+                          ('toroid', roe.ToroidMirror, dict(R=2000., r=60.))):
+        beam = _source_beam(bl, 600, 301, dx=0.05, dz=0.02, dxprime=1e-4, dzprime=5e-4, energies=(8000, 9000))
+        oe = cls(bl, 'wg', center=(0, 1000, 4.9 if name == 'bentflat' else 2.4), pitch=0.05, material=Au,
+                 limPhysX=[-5, 5], limPhysY=[-100, 100], **kw)
+        gbe, lbNe = oe.multiple_reflect(beam, maxReflections=8, needElevationMap=True)
+        ref = np.load(os.path.join(GOLD, 'multi_reflect_' + name + '.npz'))
+        assert np.array_equal(gbe.x, ref['gb_x']) and np.array_equal(lbNe.x, ref['lbN_x'])
+        assert np.array_equal(gbe.state, ref['gb_state'])
+        e = {}
+        for pre, b in (('gb_', gbe), ('lbN_', lbNe)):
+            for f in ('elevationD', 'elevationX', 'elevationY', 'elevationZ'):
+                e[pre + f] = getattr(b, f)
+        print(name, 'elevation D max', float(lbNe.elevationD.max()), 'rays with a map', int((lbNe.elevationD > -1).sum()))
+        save('multi_reflect_' + name + '_elevation', **e)
 
 
 def gen_shine_wave():
