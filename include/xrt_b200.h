@@ -300,6 +300,14 @@ int xrt_reflect_f64(size_t n, const xrt_oe_params* oe, const xrt_material_params
  * Then xrt_reflect_f64 phases 4 | 2 with xrt_oe_params.multi_tmin = tD search the next intersection. */
 int xrt_reflect_multi_deriv_f64(size_t n, const xrt_oe_params* oe, const xrt_beam* in, uint64_t* reductions,
                                 double* tD, int phase, void* stream);
+/* f4: OE.multiple_reflect(needElevationMap=True) (oes/reflect.py:212-216, :651-659; oes/base.py:1285-1287): after
+ * phase 2 of xrt_reflect_multi_deriv_f64, find_dz(None, tMax = tD, ...) of every traced ray -- elevationD[n] the height
+ * of the ray above the surface where it is farthest from it, elevationX/Y/Z[n] that point in local Cartesian
+ * coordinates.  Rays that are not traced keep their entries (the reference initialises them to -1 and
+ * -maxHalfSizeOfOE). */
+int xrt_reflect_multi_elevation_f64(size_t n, const xrt_oe_params* oe, const xrt_beam* in, const double* tD,
+                                    double* elevationD, double* elevationX, double* elevationY, double* elevationZ,
+                                    void* stream);
 /* decode one reduction slot to double (host helper; slots are order-preserving integer encodings) */
 double xrt_reduction_decode(uint64_t slot);
 

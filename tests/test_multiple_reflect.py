@@ -87,6 +87,33 @@ def test_cuda_multiple_reflect_vs_reference_golden(name, cuda_device):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('name', CASES)
+def test_cuda_elevation_map_vs_reference_golden(name, cuda_device):
+    """multiple_reflect(needElevationMap=True): xrt_reflect_multi_elevation_f64 after the derivative stage of every pass
+    (the built-in toroid and the spliced BentFlatMirror plug-in).  The map must not change the rays; the highest points
+    follow the derivative roots (same iterates as the reference: 1e-9 mm), their heights are second order in them."""
+    g = golden('multi_reflect_' + name)
+    e = golden('multi_reflect_' + name + '_elevation')
+    oe = _product_oe(name, g)
+    beam = device_beam(oracle_beam(g, 'in_'))
+    gb0, lbN0 = oe.multiple_reflect(beam, maxReflections=8)
+    gb, lbN = oe.multiple_reflect(beam, maxReflections=8, needElevationMap=True)
+    d0, d1 = lbN0.to_numpy(), lbN.to_numpy()
+    for f in BEAM_FIELDS:
+        assert np.array_equal(d0[f], d1[f], equal_nan=True), f
+    for pre, b in (('gb_', gb), ('lbN_', lbN)):
+        for f in ELEV:
+            got = getattr(b, f).cpu().numpy()
+            ref = e[pre + f]
+            assert got.shape == ref.shape
+            unset = ref == (-1. if f == 'elevationD' else -1000.)
+            assert np.array_equal(got[unset], ref[unset]), pre + f  # rays without a map keep the initial values
+            tol = 1e-12 if f == 'elevationD' else 1e-9
+            assert np.abs(got - ref).max() <= tol, (pre + f, float(np.abs(got - ref).max()))
+    assert (e['lbN_elevationD'] > 0).sum() > 1000
+
+
+@pytest.mark.gpu
 def test_cuda_multiple_reflect_single_pass_equals_reflect(cuda_device):
     """maxReflections = 1 is one reflect: the global beam of the good rays is OE.reflect's."""
     g = golden('multi_reflect_toroid')

@@ -42,6 +42,7 @@ PROTOTYPES = {
     'xrt_reflect_expose_f64': (c_int, [c_sz, c_dp, c_dp, c_dp, c_sz, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_int,
                                        ctypes.c_uint64, c_dp]),
     'xrt_reflect_multi_deriv_f64': (c_int, [c_sz, c_dp, c_dp, c_dp, c_dp, c_int, c_dp]),
+    'xrt_reflect_multi_elevation_f64': (c_int, [c_sz, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
     'xrt_reduction_decode': (c_dbl, [ctypes.c_uint64]),
     'xrt_expose_f64': (c_int, [c_sz, c_dp, c_dp, c_dp, c_dp, c_dp]),
     'xrt_propagate_rect_f64': (c_int, [c_sz, c_dp, c_dp, c_dp, c_dp, c_dp]),

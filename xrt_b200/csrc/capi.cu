@@ -465,6 +465,13 @@ int xrt_reflect_multi_deriv_f64(size_t n, const xrt_oe_params* oe, const xrt_bea
                                     (cudaStream_t)stream);
 }
 
+int xrt_reflect_multi_elevation_f64(size_t n, const xrt_oe_params* oe, const xrt_beam* in, const double* tD,
+                                    double* elevationD, double* elevationX, double* elevationY, double* elevationZ,
+                                    void* stream) {
+  return reflect_multi_elevation_device(n, oe, in, tD, elevationD, elevationX, elevationY, elevationZ,
+                                        (cudaStream_t)stream);
+}
+
 double xrt_reduction_decode(uint64_t slot) { return reduction_decode(slot); }
 
 // ------------------------------------------------------------------ plane elements

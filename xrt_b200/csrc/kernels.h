@@ -55,6 +55,8 @@ int reflect_expose_device(size_t n, const xrt_oe_params* oe, const xrt_material_
                           unsigned long long index_offset, cudaStream_t st);
 int reflect_multi_deriv_device(size_t n, const xrt_oe_params* oe, const xrt_beam* in, unsigned long long* red,
                                double* tD, int phase, cudaStream_t st);
+int reflect_multi_elevation_device(size_t n, const xrt_oe_params* oe, const xrt_beam* in, const double* tD, double* eD,
+                                   double* eX, double* eY, double* eZ, cudaStream_t st);
 double reduction_decode(unsigned long long slot);
 int surface_device(size_t n, const xrt_oe_params* oe, const double* x, const double* y, double* z, cudaStream_t st);
 int normals_device(size_t n, const xrt_oe_params* oe, const double* x, const double* y, const double* z, double* nx,

@@ -1484,6 +1484,30 @@ __global__ void __launch_bounds__(256) multi_deriv_kernel(size_t n, xrt_oe_param
   }
 }
 
+// needElevationMap (reflect.py:651-659; base.py:1285-1287): find_dz(None, tMax, ...) at the derivative root tD = the
+// height of the ray above the surface where it is farthest from it, and that point (Cartesian for parametric surfaces)
+template <int SURF>
+__global__ void __launch_bounds__(256) multi_elevation_kernel(size_t n, xrt_oe_params p, xrt_beam in,
+                                                              const double* __restrict__ tD, double* __restrict__ eD,
+                                                              double* __restrict__ eX, double* __restrict__ eY,
+                                                              double* __restrict__ eZ) {
+  const SurfDiv sd = make_surf_div<SURF>(p);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int st = in.state[i];
+    if (!(p.good_mode ? (st == 1 || st == 2) : (st > 0))) continue;
+    Ray r = load_ray(in, i);
+    to_local(p, r);
+    double x, y, z;
+    const double dz = find_dz<SURF, true, 0>(p, sd, tD[i], r, x, y, z);
+    param_to_xyz<SURF>(p, x, y, z);
+    eD[i] = dz;
+    eX[i] = x;
+    eY[i] = y;
+    eZ[i] = z;
+  }
+}
+
 __device__ __forceinline__ cplx ld_c(const double* p, size_t i) {
   const double2 v = reinterpret_cast<const double2*>(p)[i];
   return cplx{v.x, v.y};
@@ -3472,6 +3496,29 @@ int reflect_multi_deriv_device(size_t n, const xrt_oe_params* oe, const xrt_beam
   return 0;
 }
 
+// multiple_reflect(needElevationMap=True): elevation distance and point of every traced ray at its derivative root tD
+int reflect_multi_elevation_device(size_t n, const xrt_oe_params* oe, const xrt_beam* in, const double* tD, double* eD,
+                                   double* eX, double* eY, double* eZ, cudaStream_t st) {
+  XRTB_REQUIRE(oe && in && tD && eD && eX && eY && eZ, "reflect_multi_elevation: NULL argument");
+  if (n == 0) return 0;
+  unsigned grid = (unsigned)num_sms() * 8;
+  const size_t need = (n + 255) / 256;
+  if (need < grid) grid = (unsigned)need;
+#ifdef XRTB_PLUGIN
+  XRTB_REQUIRE(oe->surface == XRTB_USER_KIND, "reflect_multi_elevation (plug-in): surface kind %d expected",
+               XRTB_USER_KIND);
+  multi_elevation_kernel<XRTB_USER_KIND><<<grid, 256, 0, st>>>(n, *oe, *in, tD, eD, eX, eY, eZ);
+#else
+  XRTB_REQUIRE(oe->surface >= 0 && oe->surface <= 2, "reflect_multi_elevation: surface kind %d has no multiple_reflect",
+               oe->surface);
+  if (oe->surface == 0) multi_elevation_kernel<0><<<grid, 256, 0, st>>>(n, *oe, *in, tD, eD, eX, eY, eZ);
+  if (oe->surface == 1) multi_elevation_kernel<1><<<grid, 256, 0, st>>>(n, *oe, *in, tD, eD, eX, eY, eZ);
+  if (oe->surface == 2) multi_elevation_kernel<2><<<grid, 256, 0, st>>>(n, *oe, *in, tD, eD, eX, eY, eZ);
+#endif
+  XRTB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 double reduction_decode(unsigned long long slot) { return dec(slot); }
 
 }  // namespace xrtb
@@ -3501,6 +3548,11 @@ XRTB_EXPORT int xrt_plugin_reflect_multi_deriv_f64(size_t n, const xrt_oe_params
                                                    uint64_t* reductions, double* tD, int phase, void* stream) {
   return xrtb::reflect_multi_deriv_device(n, oe, in, reinterpret_cast<unsigned long long*>(reductions), tD, phase,
                                           (cudaStream_t)stream);
+}
+XRTB_EXPORT int xrt_plugin_reflect_multi_elevation_f64(size_t n, const xrt_oe_params* oe, const xrt_beam* in,
+                                                       const double* tD, double* eD, double* eX, double* eY,
+                                                       double* eZ, void* stream) {
+  return xrtb::reflect_multi_elevation_device(n, oe, in, tD, eD, eX, eY, eZ, (cudaStream_t)stream);
 }
 XRTB_EXPORT size_t xrt_plugin_sizeof_oe_params(void) { return sizeof(xrt_oe_params); }
 XRTB_EXPORT int xrt_plugin_surface_kind(void) { return XRTB_USER_KIND; }

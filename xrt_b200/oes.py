@@ -568,8 +568,6 @@ class OE(object):
         included.  Every pass is the fused reflect kernel in its `multi` mode; passes after the first are preceded by
         the derivative stage (xrt_reflect_multi_deriv_f64: the ray leaves the surface before the next intersection is
         searched).  One host synchronisation per pass (the count of rays still alive ends the loop)."""
-        if needElevationMap:
-            raise NotImplementedError('needElevationMap is outside the hot path')
         if self.figureError is not None:
             raise NotImplementedError('multiple_reflect with a figure error is outside the hot path')
         if self.material is not None and getattr(self.material, 'kind', 'mirror') not in ('auto', 'mirror', 'thin mirror'):
@@ -577,6 +575,7 @@ class OE(object):
         lib = _lib.load()
         plugin = self._plugin()
         deriv = lib.xrt_reflect_multi_deriv_f64 if plugin is None else plugin.reflect_multi_deriv
+        elevate = lib.xrt_reflect_multi_elevation_f64 if plugin is None else plugin.reflect_multi_elevation
         self.footprint = []
         n = len(beam)
         dev = beam.device
@@ -585,6 +584,11 @@ class OE(object):
         tD = torch.empty(n, dtype=torch.float64, device=dev)
         cur = beam
         passes = []
+        elev = None
+        if needElevationMap:
+            # elevationD = -1, elevationX / Y / Z = -maxHalfSizeOfOE until a ray has travelled between two impacts
+            # (reflect.py:212-216); the derivative stage of every later pass renews the entries of its traced rays
+            elev = [torch.full((n,), v, dtype=torch.float64, device=dev) for v in (-1., -1000., -1000., -1000.)]
         if int((beam.state > 0).sum()) == 0:  # reflect.py:200-201
             gb = Beam(copyFrom=beam)
             return gb, gb
@@ -604,6 +608,9 @@ class OE(object):
                 for ph in (1, 2):
                     _lib.check(deriv(n, ctypes.byref(params), ctypes.byref(cin), red.data_ptr(), tD.data_ptr(), ph,
                                      stream), 'xrt_reflect_multi_deriv_f64')
+                if elev is not None:  # find_dz at the derivative root (base.py:1285-1287; reflect.py:651-659)
+                    _lib.check(elevate(n, ctypes.byref(params), ctypes.byref(cin), tD.data_ptr(),
+                                       *[e.data_ptr() for e in elev], stream), 'xrt_reflect_multi_elevation_f64')
                 params.multi_tmin = tD.data_ptr()
                 red = self._launch(params, self.material, cur, out, None, phases=(6,))
             self._check_tables(red)
@@ -611,6 +618,9 @@ class OE(object):
             good = (out.state == 1) | (out.state == 2)
             nRefl = nRefl + good.to(torch.int32)
             out.nRefl = nRefl.clone()
+            if elev is not None:
+                for k, e in zip(('elevationD', 'elevationX', 'elevationY', 'elevationZ'), elev):
+                    setattr(out, k, e.clone())
             ngood, ngoodN = torch.stack((good.sum(), (out.state == 1).sum())).tolist()
             if ngoodN == 0 and passes:
                 out.theta = passes[-1].theta.clone()  # lb.theta is only renewed when a ray reflects (reflect.py:789)
