@@ -198,8 +198,15 @@ def find_dz(oe, local_f, t, x0, y0, z0, a, b, c, invertNormal, derivOrder=0):
         x, y, z = oe.xyz_to_param(x, y, z)
     surf = local_f(x, y)
     fe = getattr(oe, 'figureError', None)
-    if fe is not None and not oe.isParametric and derivOrder == 0:  # base.py:825-829
-        surf = surf + fe.local_z_distorted(x, y)
+    if fe is not None and derivOrder == 0:  # base.py:825-829
+        if oe.isParametric:  # local_r_distorted (base.py:790-797): the map acts along z at the Cartesian image of (s, phi)
+            r0 = oe.local_r(x, y)
+            X, Y, Z = oe.param_to_xyz(x, y, r0)
+            Z += fe.local_z_distorted(X, Y)
+            _, _, r1 = oe.xyz_to_param(X, Y, Z)
+            surf = surf + (r1 - r0)
+        else:
+            surf = surf + fe.local_z_distorted(x, y)
     if derivOrder == 0:
         ind = np.isnan(surf)
         if ind.sum() > 0:
@@ -515,7 +522,12 @@ def reflect_local(oe, good, lb, vlb, pitch, roll, yaw, dx=None, dy=None, dz=None
         fe = getattr(oe, 'figureError', None)
         if fe is not None:  # reflect.py:767-776: d_pitch, d_roll rotations of the surface normal
             oeNormal = [np.asarray(v) * np.ones(int(goodNsum)) for v in oeNormal]
-            n_distorted = fe.local_n_distorted(lb.x[goodN], lb.y[goodN])
+            if oe.isParametric:  # base.py:765-768: the slopes are taken at the Cartesian image of (s, phi)
+                rr = oe.local_r(lb.x[goodN], lb.y[goodN])
+                xx, yy, _ = oe.param_to_xyz(lb.x[goodN], lb.y[goodN], rr)
+                n_distorted = fe.local_n_distorted(xx, yy)
+            else:
+                n_distorted = fe.local_n_distorted(lb.x[goodN], lb.y[goodN])
             cosX, sinX = np.cos(n_distorted[0]), np.sin(n_distorted[0])
             oeNormal[-2], oeNormal[-1] = ob.rotate_x(oeNormal[-2], oeNormal[-1], cosX, sinX)
             cosY, sinY = np.cos(n_distorted[1]), np.sin(n_distorted[1])

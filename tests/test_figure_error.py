@@ -32,6 +32,31 @@ def test_oracle_figure_error_bit_exact(name, surface):
     assert np.array_equal(info['footprint'], g['footprint'])
 
 
+PARAM_CASES = ['ellipse_cyl_bump', 'ellipsoid_bump']
+ELLIPSE_KEYS = ('ellipseA', 'ellipseB', 'y0', 'z0', 'cosGamma', 'sinGamma')
+
+
+@pytest.mark.parametrize('name', PARAM_CASES)
+def test_oracle_figure_error_on_parametric_surface_bit_exact(name):
+    """local_r_distorted / local_n_distorted of a parametric element (oes/base.py:790-797, :765-768): the height map is
+    added along z at the Cartesian image of (s, phi, r) and taken back to r; the slopes are read at that (x, y)."""
+    g = golden('reflect_figerr_' + name)
+    fe = osf.FigureErrorSpline(g['fe_x1d'], g['fe_y1d'], g['fe_z'], float(g['fe_xShift']), float(g['fe_yShift']))
+    assert np.array_equal(fe.local_z_spline.get_coeffs(), g['fe_c'])
+    kw = dict(isParametric=True,
+              surfParams=dict(isCylindrical=bool(g['isCylindrical']), **{k: float(g[k]) for k in ELLIPSE_KEYS}))
+    mat = om.Material('Au', rho=float(g['rho']))
+    gb, lb = orf.reflect(oracle_spec(g, 'ellipse_param', mat, figureError=fe, **kw), oracle_beam(g, 'in_'))
+    for pre, b in (('gb_', gb), ('lb_', lb)):
+        for f in OUT_FIELDS + ('s', 'phi', 'r'):
+            if pre + f in g.files:
+                assert np.array_equal(getattr(b, f), g[pre + f]), pre + f
+    # ... and the bump matters: without it the directions differ
+    gb0, _ = orf.reflect(oracle_spec(g, 'ellipse_param', mat, **kw), oracle_beam(g, 'in_'))
+    good = (gb.state == 1) & (gb0.state == 1)
+    assert 1e-10 < np.abs(gb.c[good] - gb0.c[good]).max() < 1e-5
+
+
 def _product_oe(name, surface, g, fe):
     from xrt_b200 import oes, materials
     kw = product_oe_kwargs(g)

@@ -1211,6 +1211,35 @@ def gen_figure_error():
              fe_x1d=fe.x1d, fe_y1d=fe.y1d, fe_z=fe.generate_profile(), **d)
 
 
+def gen_figure_error_param():
+    """A figure error on a PARAMETRIC element (oes/base.py:790-797 local_r_distorted: the height map is added along z at
+    the Cartesian image of (s, phi, r) and taken back to r; :744-770 local_n_distorted at that (x, y)): Gaussian bump on
+    the cylindrical and on the ellipsoidal EllipticalMirrorParam."""
+    import xrt.backends.raycing.figure_error as rfe
+    bl = raycing.BeamLine()
+    Au = rm.Material('Au', rho=19.3)
+    for name, kw in (('ellipse_cyl_bump', dict(pitch=4e-3, p=30000., q=2000., isCylindrical=True)),
+                     ('ellipsoid_bump', dict(pitch=5e-3, p=20000., q=5000., isCylindrical=False))):
+        beam = _source_beam(bl, 2500, 411, dx=0.05, dz=0.03, dxprime=8e-6, dzprime=6e-6, energies=(8000, 10000))
+        lx, ly = [-3, 3], [-90, 80]
+        fe = rfe.GaussianBump(bumpHeight=25., cX=0.2, cY=-10., sigmaX=1.0, sigmaY=30., limPhysX=lx, limPhysY=ly,
+                              gridStep=2.)
+        oe = roe.EllipticalMirrorParam(bl, name, center=(0, kw['p'], 0), material=Au, limPhysX=lx, limPhysY=ly,
+                                       figureError=fe, **kw)
+        d = _capture_reflect(oe, beam)
+        d.update(_oe_params(oe))
+        for k in ('ellipseA', 'ellipseB', 'y0', 'z0', 'cosGamma', 'sinGamma', 'p', 'q'):
+            d[k] = float(getattr(oe, k))
+        d['isCylindrical'] = bool(oe.isCylindrical)
+        spl = fe.local_z_spline
+        ty, tx = spl.get_knots()
+        st = d['gb_state']
+        print(name, {int(x): int((st == x).sum()) for x in np.unique(st)}, 'knots', len(ty), len(tx), 'rms nm',
+              float(fe.get_rms()))
+        save('reflect_figerr_' + name, rho=19.3, fe_ty=ty, fe_tx=tx, fe_c=spl.get_coeffs(), fe_xShift=fe.xShift,
+             fe_yShift=fe.yShift, fe_x1d=fe.x1d, fe_y1d=fe.y1d, fe_z=fe.generate_profile(), **d)
+
+
 def gen_coated():
     """Coated (materials/multilayer.py:528-584): one reflective layer on a substrate, with surface and substrate
     roughness, kind 'mirror' -- amplitudes on a grid and a toroid mirror in a beam line."""
@@ -1364,7 +1393,7 @@ def gen_roughness():
     save('figure_error_roughness', **out)
 
 
-SECTIONS = {'roughness': gen_roughness, 'blazed': gen_blazed, 'hemispheric': gen_hemispheric, 'multilayer_tran': gen_multilayer_tran, 'fzp': gen_fzp, 'laue': gen_laue, 'coated': gen_coated, 'figure_error': gen_figure_error, 'round': gen_round, 'shine_wave': gen_shine_wave, 'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+SECTIONS = {'figure_error_param': gen_figure_error_param, 'roughness': gen_roughness, 'blazed': gen_blazed, 'hemispheric': gen_hemispheric, 'multilayer_tran': gen_multilayer_tran, 'fzp': gen_fzp, 'laue': gen_laue, 'coated': gen_coated, 'figure_error': gen_figure_error, 'round': gen_round, 'shine_wave': gen_shine_wave, 'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)
