@@ -117,6 +117,53 @@ def test_cuda_figure_error_vs_reference_golden(name, surface, cuda_device):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('name', PARAM_CASES)
+def test_cuda_figure_error_on_parametric_surface_vs_reference_golden(name, cuda_device):
+    """EllipticalMirrorParam(figureError=...): the figure-error plug-in variant of the elliptic surface (kind 2) --
+    local_r_distorted in find_dz, the slopes at the Cartesian image of (s, phi).  Tolerances as for the parametric
+    surface without a figure error (tests/test_reflect.py) and for figure errors on z(x, y) surfaces (above)."""
+    from xrt_b200 import figure_error as pfe, oes, materials
+    from xrt_b200.physconsts import CHBAR
+    g = golden('reflect_figerr_' + name)
+    fe = pfe.FigureErrorMap(g['fe_x1d'], g['fe_y1d'], g['fe_z'])
+    kw = product_oe_kwargs(g)
+    oe = oes.EllipticalMirrorParam(product_beamline(g), name, p=float(g['p']), q=float(g['q']),
+                                   isCylindrical=bool(g['isCylindrical']),
+                                   material=materials.Material('Au', rho=float(g['rho'])), figureError=fe, **kw)
+    for k in ELLIPSE_KEYS:
+        assert abs(getattr(oe, k) - float(g[k])) <= 1e-13 * max(1., abs(float(g[k]))), k
+        setattr(oe, k, float(g[k]))
+    oe.lostNum = int(g['lostNum'])
+    assert oe._plugin().figure_error and oe._plugin().kind == 2
+    gb, lb = oe.reflect(device_beam(oracle_beam(g, 'in_')), withFootprint=True)
+    assert np.array_equal(gb.to_numpy()['state'], g['gb_state'])
+    bad = []
+    good = g['lb_state'] == 1
+    for pre, b in (('gb_', gb), ('lb_', lb)):
+        ref = {f: g[pre + f] for f in OUT_FIELDS if pre + f in g.files}
+        dev = b.to_numpy()
+        dpath = dev['path'] - ref['path']
+        assert np.abs(dpath[good]).max() <= 4e-12
+        comp = np.exp(-1e7j * ref['E'] / CHBAR * dpath)
+        dev = dict(dev, Es=dev['Es'] * comp, Ep=dev['Ep'] * comp)
+        phase_ulp = np.spacing((1e7 * ref['E'] / CHBAR * ref['path']).max())
+        bad += compare_beams(dev, ref, ('Es', 'Ep'), 2 * phase_ulp, pre)
+        bad += compare_beams(dev, ref, [f for f in OUT_FIELDS if f not in ('Es', 'Ep')], 1e-12, pre)
+    assert not bad, bad
+    np.testing.assert_allclose(oe.footprint[0], g['footprint'], rtol=1e-12, atol=1e-12)
+    # the bump is seen: the same element without it sends the rays elsewhere
+    oe0 = oes.EllipticalMirrorParam(product_beamline(g), name + '0', p=float(g['p']), q=float(g['q']),
+                                    isCylindrical=bool(g['isCylindrical']),
+                                    material=materials.Material('Au', rho=float(g['rho'])), **kw)
+    for k in ELLIPSE_KEYS:
+        setattr(oe0, k, float(g[k]))
+    oe0.lostNum = int(g['lostNum'])
+    c0 = oe0.reflect(device_beam(oracle_beam(g, 'in_')))[0].to_numpy()
+    both = (c0['state'] == 1) & (g['gb_state'] == 1)
+    assert 1e-10 < np.abs(c0['c'][both] - g['gb_c'][both]).max() < 1e-5
+
+
+@pytest.mark.gpu
 def test_cuda_figure_error_changes_the_beam_and_library_refuses_it(cuda_device):
     """Sanity: the bump really deflects rays (the slopes are ~1e-7 rad), and the plain library object refuses a
     figure-error parameter block instead of ignoring it."""

@@ -53,7 +53,7 @@
 #endif
 // Figure errors (OE(figureError=...): oes/base.py:681-686, :744-770, find_dz :825-829, reflect.py:767-776,
 // figure_error.py:207-265) are a plug-in variant as well: -DXRTB_FIGURE_ERROR compiles the bicubic-spline height map
-// into find_dz and the normal of ONE surface kind (-DXRTB_PLUGIN_KIND=<0|1> or a spliced kind 4), so the kernels of
+// into find_dz and the normal of ONE surface kind (-DXRTB_PLUGIN_KIND=<0|1|2> or a spliced kind 4 / 5), so the kernels of
 // libxrt_b200.so keep their register budget.
 
 namespace xrtb {
@@ -389,7 +389,19 @@ __device__ __forceinline__ double find_dz(const xrt_oe_params& p, const SurfDiv&
   }
   double surf = local_surface<SURF>(p, sd, x, y);
 #ifdef XRTB_FIGURE_ERROR
-  if (p.fe_c) surf = surf + fe_eval(p, x, y, 0) * 1e-6;  // surf += z_distorted, nm -> mm (base.py:825-829)
+  if (p.fe_c) {
+    if (SURF == 2 || SURF == 5) {
+      // parametric element: local_r_distorted (base.py:790-797) -- the height map acts along z at the Cartesian image
+      // of (s, phi, r) and the new point is taken back to r: surf += r1 - r
+      double fx = x, fy = y, fz = surf;
+      param_to_xyz<SURF>(p, fx, fy, fz);
+      fz += fe_eval(p, fx, fy, 0) * 1e-6;
+      xyz_to_param<SURF>(p, fx, fy, fz);
+      surf = surf + (fz - surf);
+    } else {
+      surf = surf + fe_eval(p, x, y, 0) * 1e-6;  // surf += z_distorted, nm -> mm (base.py:825-829)
+    }
+  }
 #endif
   if (isnan(surf)) surf = 0.0;
   double d = z - surf;
@@ -2110,7 +2122,12 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
         if (p.fe_c) {
           // local_n_distorted -> (d_pitch, d_roll) = (atan(dz/dy), -atan(dz/dx)); the surface normal is turned by
           // rotate_x, then rotate_y (reflect.py:767-776); with one normal it is also the normal of the planes
-          const double aa = fe_eval(p, lx, ly, 2) * 1e-6, bb = fe_eval(p, lx, ly, 1) * 1e-6;
+          double fx = lx, fy = ly;
+          if (SURF == 2 || SURF == 5) {  // slopes at the Cartesian image of (s, phi, local_r(s, phi)) (base.py:765-768)
+            double fz = local_surface<SURF>(p, sd, lx, ly);
+            param_to_xyz<SURF>(p, fx, fy, fz);
+          }
+          const double aa = fe_eval(p, fx, fy, 2) * 1e-6, bb = fe_eval(p, fx, fy, 1) * 1e-6;
           double sX, cX, sYY, cYY;
           sincos(atan(bb), &sX, &cX);
           sincos(-atan(aa), &sYY, &cYY);

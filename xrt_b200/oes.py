@@ -173,8 +173,8 @@ class OE(object):
         if self.cu_local_z is None:
             if not fe:
                 return None
-            if self.surfaceKind not in (0, 1) or hasattr(self, 'bragg'):
-                raise NotImplementedError('figure errors are on the hot path for flat, toroidal and spliced z(x, y) '
+            if self.surfaceKind not in (0, 1, 2) or hasattr(self, 'bragg'):
+                raise NotImplementedError('figure errors are on the hot path for flat, toroidal, elliptic and spliced '
                                           'single-surface elements')
             from . import custom
             return custom.plugin_for(builtin_kind=self.surfaceKind, figure_error=True)
