@@ -51,6 +51,17 @@ __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
   return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
 }
 
+// Quotients and roots of ordinary positive numbers in the per-ray set-up of the undulator source (photon energies,
+// gamma, beam sizes, the direction norm >= 1): the compiler's IEEE sequences without their range test (common.cuh,
+// div_nr / sqrt_nr: same bits).  -DXRTB_SOURCE_DIV_CHECKED restores the plain operators.
+#ifdef XRTB_SOURCE_DIV_CHECKED
+#define XRTB_SRC_DIV(a, b) ((a) / (b))
+#define XRTB_SRC_SQRT(a) sqrt(a)
+#else
+#define XRTB_SRC_DIV(a, b) div_nr(a, b)
+#define XRTB_SRC_SQRT(a) sqrt_nr(a)
+#endif
+
 struct Draw {
   double E, theta, psi, u, n1, n2, n3, n4, n5;
 };
@@ -74,7 +85,7 @@ __device__ __forceinline__ Draw draw_ray(uint64_t ctr, uint64_t seed, double Emi
     const double a0 = 1.0 - u53(w[0], w[1]), a1 = u53(w[2], w[3]);
     philox4x32_10(ctr, 3u, seed, w);
     const double b0 = 1.0 - u53(w[0], w[1]), b1 = u53(w[2], w[3]);
-    const double ra = sqrt(-2.0 * log(a0)), rb = sqrt(-2.0 * log(b0));
+    const double ra = XRTB_SRC_SQRT(-2.0 * log(a0)), rb = XRTB_SRC_SQRT(-2.0 * log(b0));  // arguments >= +0
     double sn, cs;
     sincospi(2.0 * a1, &sn, &cs);
     d.n1 = ra * cs;
@@ -129,7 +140,7 @@ __device__ __forceinline__ void fill_ray(const xrt_source_params& p, double E, d
   // get_SIGMA (synchr.py:2240-2249) with get_sigma_r2 = get_sigma_r02 (eEspread = 0): 2*CHeVcm/E*10*L0*Np/PI2**2
   const double CHeVcm = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12;
   const double PI2 = 6.283185307179586476925286766559;
-  double sr2 = 2.0 * CHeVcm / E * 10.0 * p.L0 * p.Np / (PI2 * PI2);
+  double sr2 = XRTB_SRC_DIV(2.0 * CHeVcm, E) * 10.0 * p.L0 * p.Np / (PI2 * PI2);
   if (p.eEspread > 0.0) {
     // get_sigma_r2 with energy spread (synchr.py:2210-2223, onlyOddHarmonics=False as shine passes it) and
     // tanaka_kitamura_Qa2 (sybase.py:664-674)
@@ -144,7 +155,7 @@ __device__ __forceinline__ void fill_ray(const xrt_source_params& p, double E, d
     }
     sr2 = sr2 * pow(Qa2, 2.0 / 3.0);
   }
-  const double SX = sqrt(p.dx * p.dx + sr2), SZ = sqrt(p.dz * p.dz + sr2);
+  const double SX = XRTB_SRC_SQRT(p.dx * p.dx + sr2), SZ = XRTB_SRC_SQRT(p.dz * p.dz + sr2);
   double x = 0.0 + SX * g1;  // np.random.normal(0, SIGMA, n) = loc + scale * gauss
   double y = 0.0;
   double z = 0.0 + SZ * g2;
@@ -177,10 +188,19 @@ __device__ __forceinline__ void fill_ray(const xrt_source_params& p, double E, d
     Ep = cdiv(jp, cplx{sqrt(mJp2), 0.0});
   }
   // normalise (sybase.py:1769-1772)
-  const double norm = sqrt(a * a + b * b + c * c);
+  const double norm = XRTB_SRC_SQRT(a * a + b * b + c * c);  // b = 1: norm >= 1
+#ifdef XRTB_SOURCE_DIV_CHECKED
   a /= norm;
   b /= norm;
   c /= norm;
+#else
+  {
+    const Divisor dn = make_divisor(norm);  // three quotients, one refined reciprocal (same bits as a / norm etc.)
+    a = div_by_nr(a, dn);
+    b = div_by_nr(b, dn);
+    c = div_by_nr(c, dn);
+  }
+#endif
   // pitch / yaw of the source (sybase.py:1785-1786): rotate_beam default sequence z then x
   if (p.has_yaw) {
     const double x1 = p.cosYaw * x - p.sinYaw * y, y1 = p.sinYaw * x + p.cosYaw * y;
@@ -280,7 +300,7 @@ __global__ void __launch_bounds__(U_THREADS, (R <= 2) ? 4 : 1)
       double wui, ww1i;
       sample_prefactors(up, g, d[r].E, d[r].theta, d[r].psi, wui, ww1i, abv[r]);
       s[r] = make_sample(up.Kx, up.Ky, g, wui, d[r].E, ww1i, d[r].theta, d[r].psi);
-      fin[r] = wui * (1.0 / g);
+      fin[r] = wui * XRTB_SRC_DIV(1.0, g);
       acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0;
     }
     node_loop<R, PLANAR, SYM>(up, tab, tile, sctab, s, acc, bt == 0);

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(U_THREADS)
       sample_prefactors(p, g, wi, ph, ps, wui, ww1i, abv[r]);
     }
     s[r] = make_sample(p.Kx, p.Ky, g, wui, wi, ww1i, ph, ps);
-    fin[r] = wui * (1.0 / g);  // wuS*revgamma (synchr.py:2033)
+    fin[r] = wui * XRTB_U_DIV(1.0, g);  // wuS*revgamma (synchr.py:2033)
     acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0;
   }
 

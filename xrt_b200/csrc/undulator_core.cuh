@@ -20,12 +20,22 @@ struct USample {
   double dirx, diry, dirz;
 };
 
+// per-sample prefactors: quotients / roots of ordinary positive numbers (gamma, photon energy, wu): the compiler's IEEE
+// sequences without their range test (common.cuh: same bits); -DXRTB_SOURCE_DIV_CHECKED restores the plain operators
+#ifdef XRTB_SOURCE_DIV_CHECKED
+#define XRTB_U_DIV(a, b) ((a) / (b))
+#define XRTB_U_SQRT(a) sqrt(a)
+#else
+#define XRTB_U_DIV(a, b) div_nr(a, b)
+#define XRTB_U_SQRT(a) sqrt_nr(a)
+#endif
+
 __device__ __forceinline__ USample make_sample(double Kx, double Ky, double gamma, double wu, double w, double ww1,
                                                double phi, double psi) {
   USample s;
-  const double revg = 1.0 / gamma;  // synchr.py:1936
+  const double revg = XRTB_U_DIV(1.0, gamma);  // synchr.py:1936
   s.revg2 = __dmul_rn(revg, revg);
-  const double wwu = w / wu;
+  const double wwu = XRTB_U_DIV(w, wu);
   const double wr = wwu * revg;
   s.ww1 = ww1;
   s.b1 = wr * phi;
@@ -161,22 +171,23 @@ __device__ __forceinline__ void sample_prefactors(const UParams& p, double g, do
   const double PI_ = 3.1415926535897932384626433832795;
   const double g2 = g * g;
   const double kx2h = 0.5 * (p.Kx * p.Kx), ky2h = 0.5 * (p.Ky * p.Ky);
-  wui = PI_ / p.L0 / g2 * (2.0 * g2 - 1.0 - kx2h - ky2h) / 5067.7309392068091;
-  ww1i = wi * ((1.0 + kx2h + ky2h) + g2 * (ph * ph + ps * ps)) / (2.0 * g2 * wui);
-  ab = 1.0 / 6.283185307179586476925286766559 / wui * sin(PI_ * p.Np * ww1i) / sin(PI_ * ww1i);
+  wui = XRTB_U_DIV(XRTB_U_DIV(XRTB_U_DIV(PI_, p.L0), g2) * (2.0 * g2 - 1.0 - kx2h - ky2h), 5067.7309392068091);
+  ww1i = XRTB_U_DIV(wi * ((1.0 + kx2h + ky2h) + g2 * (ph * ph + ps * ps)), 2.0 * g2 * wui);
+  // (the last quotient keeps the IEEE operator: sin(pi ww1) is zero at the harmonics -> inf / nan like numpy)
+  ab = XRTB_U_DIV(1.0 / 6.283185307179586476925286766559, wui) * sin(PI_ * p.Np * ww1i) / sin(PI_ * ww1i);
 }
 
 // I, Es, Ep of synchr.py:2092-2108 from the raw node sums (already multiplied by wu/gamma)
 __device__ __forceinline__ void imap_outputs(const UParams& p, double w, double ab, double is_re, double is_im,
                                              double ip_re, double ip_im, double& I, double2& Es, double2& Ep) {
-  const double bw = p.bw_mode ? 0.001 : 1.0 / w;
+  const double bw = p.bw_mode ? 0.001 : XRTB_U_DIV(1.0, w);
   const double amp2flux = p.amp_const * bw;  // FINE_STR * bwFact * eI / SIE0
   // np.abs of a purely imaginary sum (the node-pair path of a planar undulator) is |im| exactly
   const double as = (is_re == 0.0) ? fabs(is_im) : hypot(is_re, is_im);
   const double ap = (ip_re == 0.0) ? fabs(ip_im) : hypot(ip_re, ip_im);
   const double field = as * as + ap * ap;
   I = amp2flux * (ab * ab) * 0.25 * (p.dstep * p.dstep) * field;
-  const double sc = sqrt(amp2flux) * ab;
+  const double sc = XRTB_U_SQRT(amp2flux) * ab;
   const double hd = 0.5 * p.dstep;
   Es = make_double2(sc * is_re * hd, sc * is_im * hd);
   Ep = make_double2(sc * ip_re * hd, sc * ip_im * hd);
