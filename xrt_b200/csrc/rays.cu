@@ -99,7 +99,9 @@ __global__ void __launch_bounds__(256) expose_kernel(size_t n, xrt_plane_params 
     const double a = p.ex[0] * a0 + p.ex[1] * b0 + p.ex[2] * c0;
     const double b = p.ey[0] * a0 + p.ey[1] * b0 + p.ey[2] * c0;
     const double c = p.ez[0] * a0 + p.ez[1] * b0 + p.ez[2] * c0;
-    double path = -y / b;
+    // (the unchecked IEEE sequence, common.cuh: the same quotient for ordinary operands; b == 0 or an overflowing
+    // quotient gives NaN / inf either way and the ray is lost below -- GlobalSink in reflect.cu does the same)
+    double path = div_nr(-y, b);
     int st = in.state[i];
     bool bad = isnan(path) || isinf(path);
     if (p.only_positive_path) bad = bad || (path < 0.0);
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(256) expose_kernel(size_t n, xrt_plane_params 
     if (in.Es && out.Es) {
       // propPhase = exp(1e7j * (E/CHBAR) * path) (screens.py:257-260)
       const double CHBAR = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8 / 6.283185307179586476925286766559;
-      const double phi = (1e7 * (E / CHBAR)) * path;
+      const double phi = (1e7 * div_nr(E, CHBAR)) * path;
       double s, cs;
       sincos_big(phi, s, cs);
       const cplx ph = cplx{cs, s};

@@ -1707,7 +1707,7 @@ struct GlobalSink {
     const double as = sp.ex[0] * a + sp.ex[1] * b + sp.ex[2] * c;
     const double bs = sp.ey[0] * a + sp.ey[1] * b + sp.ey[2] * c;
     const double cs = sp.ez[0] * a + sp.ez[1] * b + sp.ez[2] * c;
-    double path = -ys / bs;
+    double path = div_nr(-ys, bs);  // as expose_kernel (rays.cu)
     bool bad = isnan(path) || isinf(path);
     if (sp.only_positive_path) bad = bad || (path < 0.0);
     if (bad) {
@@ -1757,7 +1757,7 @@ struct GlobalSink {
     }
     // propPhase = exp(1e7j * (E/CHBAR) * path) (screens.py:257-260)
     const double CHBAR = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8 / 6.283185307179586476925286766559;
-    const double phi = (1e7 * (E / CHBAR)) * pathS;
+    const double phi = (1e7 * div_nr(E, CHBAR)) * pathS;
     double sn, cs;
     sincos_big(phi, sn, cs);
     const cplx ph = cplx{cs, sn};
