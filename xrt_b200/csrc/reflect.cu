@@ -2163,17 +2163,17 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
           const double CH = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8;
           const double bdg = la * g0 + lbb * g1 + lc * g2;
           const double G2 = g0 * g0 + g1 * g1 + g2 * g2;
-          const double ol = 1.0 * CH / ft.E[tid] * 1e-7;
+          const double ol = XRTB_AMP_DIV(1.0 * CH, ft.E[tid]) * 1e-7;
           const double u = bds * bds - 2.0 * bdg * ol - G2 * (ol * ol);
           const double sg = (MAT == 3 && (m.geom & 1)) ? 1.0 : -1.0;  // reflect.py:608: +1 for Laue
-          const double dn = bds + sg * sqrt(fabs(u));
+          const double dn = bds + sg * XRTB_AMP_SQRT(fabs(u));
           ao = la - nrm[3] * dn + g0 * ol;
           bo = lbb - nrm[4] * dn + g1 * ol;
           co = lc - nrm[5] * dn + g2 * ol;
-          const double nn = sqrt(ao * ao + bo * bo + co * co);
-          ao = ao / nn;
-          bo = bo / nn;
-          co = co / nn;
+          const double nn = XRTB_AMP_SQRT(ao * ao + bo * bo + co * co);  // a direction: nn > 0
+          ao = XRTB_AMP_DIV(ao, nn);
+          bo = XRTB_AMP_DIV(bo, nn);
+          co = XRTB_AMP_DIV(co, nn);
           bos = ao * nrm[3] + bo * nrm[4] + co * nrm[5];
         } else if (MAT == 5) {
           // toWhere = 1, refraction (reflect.py:894-919); the transmittivity is evaluated here once (same n)
@@ -2765,17 +2765,17 @@ __global__ void __launch_bounds__(kTileRays, XRTB_TILE_MINBLOCKS)
         const double CH = 6.626069573e-27 * 2.99792458e10 / 1.602176565e-12 * 1e8;
         const double bdg = la * g0 + lbb * g1 + lc * g2;
         const double G2 = g0 * g0 + g1 * g1 + g2 * g2;
-        const double ol = 1.0 * CH / T.E[j] * 1e-7;
+        const double ol = XRTB_AMP_DIV(1.0 * CH, T.E[j]) * 1e-7;
         const double u = bds * bds - 2.0 * bdg * ol - G2 * (ol * ol);
         const double sg = (m.geom & 1) ? 1.0 : -1.0;  // reflect.py:608: +1 for Laue
-        const double dn = bds + sg * sqrt(fabs(u));
+        const double dn = bds + sg * XRTB_AMP_SQRT(fabs(u));
         ao = la - nrm[3] * dn + g0 * ol;
         bo = lbb - nrm[4] * dn + g1 * ol;
         co = lc - nrm[5] * dn + g2 * ol;
-        const double nn = sqrt(ao * ao + bo * bo + co * co);
-        ao = ao / nn;
-        bo = bo / nn;
-        co = co / nn;
+        const double nn = XRTB_AMP_SQRT(ao * ao + bo * bo + co * co);
+        ao = XRTB_AMP_DIV(ao, nn);
+        bo = XRTB_AMP_DIV(bo, nn);
+        co = XRTB_AMP_DIV(co, nn);
         bos = ao * nrm[3] + bo * nrm[4] + co * nrm[5];
       } else {
         ao = la - nrm[0] * 2.0 * bdn;
