@@ -676,10 +676,11 @@ def run_ours(args):
                'pairs_per_s': pairs, 'value': ktf * 1e3, 'unit': 'GFLOP/s (57 flop/pair), all GPUs',
                'roofline': {'bound': 'fp64', 'achieved': ktf_kernel / world, 'peak': dfma_tflops,
                             'unit': 'TFLOP/s per GPU', 'frac': ktf_kernel / world / dfma_tflops, 'traffic': None,
-                            'issue_slot_frac': 58 * 2 * float(N) * M / (kernel_ms * 1e-3) / world / 1e12 / dfma_tflops,
-                            'note': 'kirchhoff_kernel<R=4, strict, uniform normal, table sincos>: 58 DFMA-pipe '
+                            'issue_slot_frac': 57 * 2 * float(N) * M / (kernel_ms * 1e-3) / world / 1e12 / dfma_tflops,
+                            'note': 'kirchhoff_kernel<R=4, strict, uniform normal, table sincos>: 57 DFMA-pipe '
                                     'instructions per pair in SASS (65 in r01, 63 with a 64-entry table: sin / cos through '
-                                    'a 4096-entry pi/2048 table in shared memory and two-term polynomials); frac counts the 57 algorithmic flops of SURVEY 8d, issue_slot_frac the '
+                                    'a 4096-entry pi/2048 table in shared memory and two-term polynomials, k folded into '
+                                    'the packed Es + Ep); frac counts the 57 algorithmic flops of SURVEY 8d, issue_slot_frac the '
                                     'issued ones; DMMA shares the FP64 pipe (profiles/r02_kirchhoff_variants.json)'}}
         del d, out
 

@@ -28,7 +28,7 @@ struct __align__(16) KInput {
   double qx, qy, qz, nl;
   double nx2, ny2, nz2, k;  // 2 n (the kernel works with 0.5/r, see sqrt_hrsqrt), k
   double es_re, es_im, ep_re, ep_im;
-  double w_re, w_im, k2x, nq2;  // Es + Ep, 2 k, 2 n.q (uniform-normal fast path)
+  double w_re, w_im, k2x, nq2;  // k (Es + Ep), 2 k, 2 n.q (uniform-normal fast path)
 };
 static_assert(sizeof(KInput) == 128, "KInput must be 128 bytes");
 
@@ -55,8 +55,10 @@ __global__ void kirchhoff_pack_kernel(size_t N, const double* __restrict__ nl, c
   r.es_im = es.y;
   r.ep_re = ep.x;
   r.ep_im = ep.y;
-  r.w_re = es.x + ep.x;  // numpy forms (Es + Ep) first as well (waves.py:847)
-  r.w_im = es.y + ep.y;
+  // numpy forms (Es + Ep) first as well (waves.py:847); the factor k of k^2 / r is folded in here, once per sample,
+  // instead of once per pair (one FP64 instruction less in the pair loop; A, B, C carry no bit-exactness requirement)
+  r.w_re = kj * (es.x + ep.x);
+  r.w_im = kj * (es.y + ep.y);
   r.k2x = 2.0 * kj;
   r.nq2 = 2.0 * (nx * r.qx + ny * r.qy + nz * r.qz);
   out[j] = r;
@@ -177,12 +179,11 @@ __global__ void __launch_bounds__(THREADS, XRTB_KIRCHHOFF_MINBLOCKS)
         acc[r][2] = fma(-gim, a2.w, acc[r][2]);
         acc[r][3] = fma(gre, a2.w, acc[r][3]);
         acc[r][3] = fma(gim, a2.z, acc[r][3]);
-        // h = (k^2 / r) * g * (Es + Ep)
-        const double kk = kip * a1.w;  // k^2 / r
+        // h = (k / r) * g * (k (Es + Ep)) = (k^2 / r) * g * (Es + Ep)
         const double wre = fma(gre, a3.x, -gim * a3.y);
         const double wim = fma(gre, a3.y, gim * a3.x);
-        const double hre = kk * wre;
-        const double him = kk * wim;
+        const double hre = kip * wre;
+        const double him = kip * wim;
         acc[r][4] = fma(hre, dx, acc[r][4]);
         acc[r][5] = fma(him, dx, acc[r][5]);
         acc[r][6] = fma(hre, dy, acc[r][6]);

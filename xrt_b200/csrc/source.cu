@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(256) fill_kernel(size_t n, xrt_source_params p
 #ifndef XRTB_SHINE_BATCHES
 #define XRTB_SHINE_BATCHES 1
 #endif
-template <int R, bool PLANAR, bool SYM>
+template <int R, bool PLANAR, bool SYM, bool GC = false>
 __global__ void __launch_bounds__(U_THREADS, (R <= 2) ? 4 : 1)
     shine_uniform_kernel(size_t n, uint64_t seed, uint64_t index_offset, double Emin, double Emax, double Tmin,
                          double Tmax, double Pmin, double Pmax, UParams up, UTables tab, xrt_source_params sp,
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(U_THREADS, (R <= 2) ? 4 : 1)
       fin[r] = wui * XRTB_SRC_DIV(1.0, g);
       acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0;
     }
-    node_loop<R, PLANAR, SYM>(up, tab, tile, sctab, s, acc, bt == 0);
+    node_loop<R, PLANAR, SYM, GC>(up, tab, tile, sctab, s, acc, bt == 0);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const size_t i = base + (size_t)r * U_THREADS + threadIdx.x;
@@ -821,7 +821,17 @@ int shine_uniform_device(size_t n, uint64_t seed, uint64_t index_offset, const d
 #define XRTB_S_LAUNCH(PL, SY)                                                                                    \
   shine_uniform_kernel<R, PL, SY><<<grid, U_THREADS, 0, st>>>(n, seed, index_offset, window[0], window[1], window[2], \
                                                              window[3], window[4], window[5], p, t, *sp, *out, imax_slot)
-  if (planar && symmetric)
+#ifdef XRTB_SHINE_NO_GC  // (build switch for A / B comparisons: the per-sample evaluation everywhere)
+  const bool gconst = false;
+#else
+  const bool gconst = !(sp->eEspread > 0.0);
+#endif
+  if (planar && symmetric && gconst)
+    // one gamma for every sample: the gamma-dependent node quantities come from the node tile (GC)
+    shine_uniform_kernel<R, true, true, true><<<grid, U_THREADS, 0, st>>>(n, seed, index_offset, window[0], window[1],
+                                                                          window[2], window[3], window[4], window[5],
+                                                                          p, t, *sp, *out, imax_slot);
+  else if (planar && symmetric)
     XRTB_S_LAUNCH(true, true);
   else if (planar)
     XRTB_S_LAUNCH(true, false);

@@ -9,10 +9,14 @@ namespace xrtb {
 struct __align__(16) UNode {
   double tg, ag, c1, c2;   // node, weight, cos(tg), cos(tg+phase)
   double p1, p2, qn, pad;  // -Ky sin(tg), Kx sin(tg+phase), Ky^2 sin(2tg) + Kx^2 sin(2(tg+phase))
+  // r02: what the pair step derives from the node and gamma ALONE, when every sample has the same gamma (no energy
+  // spread): beta_x, beta_z, beta'_z (synchr.py:2006-2016) -- computed once per node with the per-sample operations
+  // (same bits), 6 of the 44 FP64 instructions of a (sample, node pair)
+  double bx, bz, bpz, pad2;
 };
 
 constexpr int U_THREADS = 128;
-constexpr int U_TILE = 256;  // nodes per shared-memory tile (16 KB)
+constexpr int U_TILE = 256;  // nodes per shared-memory tile (24 KB)
 
 struct USample {
   double ww1, b1, b2, a3;      // phase coefficients
@@ -97,8 +101,9 @@ __device__ __forceinline__ void node_step(const USample& s, const double4 n0, co
 // One sin (no cos), one velocity/denominator evaluation per PAIR of nodes; the sums are purely imaginary.
 // The tables are symmetric to a few ulps only (np.sin/np.cos of mirrored arguments), which moves u by ~1e-15
 // rad: orders below the parity tolerance.  The factor 2 is applied once at the end.
-__device__ __forceinline__ void node_pair_step(const USample& s, const double4 n0, const double4 n1, double& bs_im,
-                                               double& bp_im, const double2* __restrict__ sctab) {
+template <bool GC = false>
+__device__ __forceinline__ void node_pair_step(const USample& s, const double4 n0, const double4 n1, const double4 n2,
+                                               double& bs_im, double& bp_im, const double2* __restrict__ sctab) {
   double ucos = s.ww1 * n0.x;
   ucos = fma(s.b1, n1.x, ucos);
   ucos = fma(s.a3, n1.z, ucos);
@@ -107,10 +112,17 @@ __device__ __forceinline__ void node_pair_step(const USample& s, const double4 n
 #else
   const double sn = sin_tab(ucos, sctab);  // 13 instead of 17 FP64-pipe instructions (common.cuh)
 #endif
-  const double bx = __dmul_rn(s.kyr, n0.z);
-  const double t4 = __dadd_rn(s.revg2, __dmul_rn(bx, bx));
-  const double bz = __dadd_rn(1.0, -0.5 * t4);
-  const double bpz = __dmul_rn(s.hrevg, n1.z);
+  double bx, bz, bpz;
+  if (GC) {  // the same gamma for every sample: taken from the node tile (load_node_tile)
+    bx = n2.x;
+    bz = n2.y;
+    bpz = n2.z;
+  } else {
+    bx = __dmul_rn(s.kyr, n0.z);
+    const double t4 = __dadd_rn(s.revg2, __dmul_rn(bx, bx));
+    bz = __dadd_rn(1.0, -0.5 * t4);
+    bpz = __dmul_rn(s.hrevg, n1.z);
+  }
   double den = __dadd_rn(1.0, -__dmul_rn(s.dirx, bx));
   den = __dadd_rn(den, -__dmul_rn(s.dirz, bz));
   const double rk = rcp_cubic(den);
@@ -137,8 +149,13 @@ struct UTables {
   const double2* sintab;  // (cos, sin)(k pi/512), k < 1024, in device memory (sin_table_device): staged per block
 };
 
-__device__ __forceinline__ void load_node_tile(UNode* tile, const UTables& t, int j0, int cnt, double Kx, double Ky) {
+// gamma0 > 0: every sample has this gamma -- the gamma-dependent node quantities of the pair step are filled in too
+__device__ __forceinline__ void load_node_tile(UNode* tile, const UTables& t, int j0, int cnt, double Kx, double Ky,
+                                               double gamma0 = 0.0) {
   const double Ky2 = Ky * Ky, Kx2 = Kx * Kx;
+  // make_sample's operations on gamma (revg, revg2, kyr, hrevg), then node_pair_step's on the node
+  const double revg = gamma0 > 0.0 ? XRTB_U_DIV(1.0, gamma0) : 0.0;
+  const double revg2 = __dmul_rn(revg, revg), kyr = __dmul_rn(Ky, revg), hrevg = 0.5 * revg;
   for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
     const int g = j0 + j;
     const double st = t.sintg[g], ct = t.costg[g], sp = t.sintgph[g], cp = t.costgph[g];
@@ -153,6 +170,10 @@ __device__ __forceinline__ void load_node_tile(UNode* tile, const UTables& t, in
     const double sin2xph = __dmul_rn(__dmul_rn(2.0, sp), cp);  // synchr.py:1935
     n.qn = __dadd_rn(__dmul_rn(Ky2, sin2x), __dmul_rn(Kx2, sin2xph));
     n.pad = 0.0;
+    n.bx = __dmul_rn(kyr, n.c1);
+    n.bz = __dadd_rn(1.0, -0.5 * __dadd_rn(revg2, __dmul_rn(n.bx, n.bx)));
+    n.bpz = __dmul_rn(hrevg, n.qn);
+    n.pad2 = 0.0;
     tile[j] = n;
   }
 }
@@ -195,7 +216,7 @@ __device__ __forceinline__ void imap_outputs(const UParams& p, double w, double 
 
 // The node loop for R samples of one thread: fills acc[r][0..3] = (Bs.re, Bs.im, Bp.re, Bp.im).
 // Must be called by every thread of the block (it synchronises on the shared node tile).
-template <int R, bool PLANAR, bool SYM>
+template <int R, bool PLANAR, bool SYM, bool GC = false>
 __device__ __forceinline__ void node_loop(const UParams& p, const UTables& tab, UNode* tile, double2* sctab,
                                           const USample* s, double (*acc)[4], bool first = true) {
   // first = false: a further batch of samples in the same block -- the sin table is staged already, and so is the
@@ -211,7 +232,7 @@ __device__ __forceinline__ void node_loop(const UParams& p, const UTables& tab, 
     const int cnt = min(U_TILE, jlast - j0);
     if (reload) {
       __syncthreads();
-      load_node_tile(tile, tab, j0, cnt, p.Kx, p.Ky);
+      load_node_tile(tile, tab, j0, cnt, p.Kx, p.Ky, GC ? p.gamma0 : 0.0);
       __syncthreads();
     }
 #pragma unroll kNodeUnroll
@@ -220,8 +241,9 @@ __device__ __forceinline__ void node_loop(const UParams& p, const UTables& tab, 
       const double4 n0 = q[0];
       const double4 n1 = q[1];
       if (SYM && (j0 + j) < jpair) {
+        const double4 n2 = GC ? q[2] : make_double4(0.0, 0.0, 0.0, 0.0);
 #pragma unroll
-        for (int r = 0; r < R; ++r) node_pair_step(s[r], n0, n1, acc[r][1], acc[r][3], sctab);
+        for (int r = 0; r < R; ++r) node_pair_step<GC>(s[r], n0, n1, n2, acc[r][1], acc[r][3], sctab);
       } else if (SYM) {
         // middle node of an odd grid (tg = 0): counts once, i.e. half of the factor 2 applied below
 #pragma unroll
