@@ -526,7 +526,9 @@ def run_ours(args):
     und_ms = stage_ms['shine']
     und_tflops = FLOP_PER_SAMPLE_NODE * nrays * nodes / (und_ms * 1e-3) / 1e12
     pair_path = bool(src.gridSymmetric and src.Kx == 0)
-    und_instr = 22.0 if pair_path else 57.0  # DFMA-pipe instructions per (sample, node) in SASS (44 per node pair)
+    # DFMA-pipe instructions per (sample, node) in SASS: 38 per node pair when every sample has the same gamma (the
+    # gamma-only node quantities come from the node tile), 44 with an electron energy spread
+    und_instr = (19.0 if not (getattr(src, 'eEspread', 0) or 0) > 0 else 22.0) if pair_path else 57.0
     roofline_und = {'kernel': 'shine_uniform_kernel<2,planar,%s> (Undulator.shine: sample + field integral + Beam '
                               'assembly)' % ('pairs' if pair_path else 'nodes'),
                     'bound': 'fp64', 'achieved': und_tflops, 'peak': dfma_tflops, 'unit': 'TFLOP/s',
@@ -534,8 +536,9 @@ def run_ours(args):
                     'issue_slot_frac': 2 * und_instr * nrays * nodes / (und_ms * 1e-3) / 1e12 / dfma_tflops,
                     'note': 'achieved counts the 63 flop per (sample, node) of the reference algorithm (SURVEY 8d); '
                             'the kernel evaluates mirror PAIRS of nodes for a planar undulator on a symmetric grid '
-                            '(44 DFMA-pipe instructions per pair; 49 before the sin of the pair phase went through a '
-                            '1024-entry shared-memory table), so issue_slot_frac is the pipe utilisation',
+                            '(38 DFMA-pipe instructions per pair: 49 in r01; the sin of the pair phase through a '
+                            '1024-entry shared-memory table: 44; beta_x, beta_z, beta\'_z of a node from the node tile '
+                            'when gamma is the same for every sample: 38), so issue_slot_frac is the pipe utilisation',
                     'ms': und_ms, 'share_of_step': und_ms / ms_step}
     main_ms = refl_ms[2]
     main_bytes = 132 + 132 + 140

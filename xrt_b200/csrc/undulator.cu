@@ -22,7 +22,7 @@ namespace xrtb {
 
 // MODE 0: the reference kernel interface (gamma, wu, w, ww1, ddphi, ddpsi per sample) -> raw (Is, Ip) of _sp_sum
 // MODE 1: fused _build_I_map_conv: (w, theta, psi[, gamma]) -> (I, Es, Ep)
-template <int R, int MODE, bool PLANAR, bool SYM>
+template <int R, int MODE, bool PLANAR, bool SYM, bool GC = false>
 __global__ void __launch_bounds__(U_THREADS)
     undulator_kernel(size_t n, UParams p, UTables tab, const double* __restrict__ gamma, const double* __restrict__ wu,
                      const double* __restrict__ w, const double* __restrict__ ww1, const double* __restrict__ phi,
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(U_THREADS)
     acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0;
   }
 
-  node_loop<R, PLANAR, SYM>(p, tab, tile, sctab, s, acc);
+  node_loop<R, PLANAR, SYM, GC>(p, tab, tile, sctab, s, acc);
 
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -113,9 +113,13 @@ static int launch(int mode, int R, bool symmetric, size_t n, const UParams& p, c
   double2* ip2 = reinterpret_cast<double2*>(Ip);
   const bool planar = (p.Kx == 0.0);
   const bool sym = planar && symmetric;
+  // fused I-map with one gamma for every sample (no per-sample gamma array): gamma-only node quantities from the tile
+  const bool gconst = sym && mode == 1 && gamma == nullptr;
 #define XRTB_U_LAUNCH(RR, MM)                                                                                         \
   do {                                                                                                                \
-    if (sym)                                                                                                          \
+    if (gconst && MM == 1)                                                                                            \
+      undulator_kernel<RR, 1, true, true, true><<<grid, U_THREADS, 0, st>>>(n, p, t, gamma, wu, w, ww1, phi, psi, is2, ip2, I); \
+    else if (sym)                                                                                                     \
       undulator_kernel<RR, MM, true, true><<<grid, U_THREADS, 0, st>>>(n, p, t, gamma, wu, w, ww1, phi, psi, is2, ip2, I); \
     else if (planar)                                                                                                  \
       undulator_kernel<RR, MM, true, false><<<grid, U_THREADS, 0, st>>>(n, p, t, gamma, wu, w, ww1, phi, psi, is2, ip2, I); \
