@@ -1,3 +1,5 @@
+# Run under gpurun at the end of a round: full GPU test suite, smoke(), both bench arms, ncu launch lists + full-set captures
+# (tools/gpu_profile.sh); the results are copied from gpurun_out/ into profiles/rNN_* (see DESIGN.md section 5).
 set -x
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_r02_final.log 2>&1
