@@ -2518,7 +2518,7 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
 //    arithmetic;
 //  * phase 1 (thread <-> ray): frame change, bracket, find_dz at both ends -> class of the ray (searched / not
 //    searched / dead);
-//  * the rays are ranked by class (ballots + one 16-entry prefix), and in phase 2 thread k takes the k-th ray of that
+//  * the rays are ranked by class (ballots, warp counts, two REDUX sums), and in phase 2 thread k takes the k-th ray of that
 //    order: the warps that run the root search, the surface normal and the Fresnel / Bragg amplitudes are DENSE (in
 //    BASELINE config 2, where 41 % of the rays miss the mirror, reflect_main_kernel ran them at 19 of 32 lanes), and
 //    because results go to the ray's own slot of the tile the stores to HBM stay whole sectors -- the block-level sort
@@ -2526,8 +2526,13 @@ __global__ void __launch_bounds__(XRTB_REFLECT_THREADS, XRTB_REFLECT_MINBLOCKS) 
 //  * phase 3 (thread <-> ray): the global beam's coherency matrix and amplitudes are turned back from the local
 //    polarisation frame (the tile keeps the local-frame values, which are the local beam's) and stored, or, fused with
 //    Screen.expose, the whole global ray goes through GlobalSink<true>.
-// Serves flat / toroidal / elliptic surfaces with material kinds 0, 1, 3, single-pass reflect; everything else stays on
-// reflect_main_kernel.  XRTB_REFLECT_TILE=0 in the environment forces the old kernel (tests compare the two bit for bit).
+// Built for flat / toroidal / elliptic surfaces with material kinds 0, 1, 3, single-pass reflect; everything else stays on
+// reflect_main_kernel.  Which of the two runs is decided per element (launch_tile: mirrors here, crystals there -- a DCM
+// traces every ray, there is nothing to compact); XRTB_REFLECT_TILE=0 / 1 in the environment forces one of them (tests
+// compare the two bit for bit).  What the measurements say about this structure -- same time as reflect_main_kernel
+// until the dependent chain of a ray was shortened as well -- is in DESIGN.md section 4 and
+// profiles/r02_reflect_variants.json.  The header of reflect_main_kernel's tile notes ("a block-level class sort was
+// measured and rejected") refers to the variant that scattered its stores to HBM; this one does not.
 #ifndef XRTB_TILE_RAYS
 #define XRTB_TILE_RAYS 512
 #endif
