@@ -192,3 +192,14 @@ def test_beam_to_host_compacts_selected_rays_in_order(n, cuda_device):
             assert np.array_equal(v, arrs[k][sel]), (k, flags)
     whole = b.to_host(fields=('x', 'Es'), good_only=False)
     assert np.array_equal(whole['x'], arrs['x']) and np.array_equal(whole['Es'], arrs['Es'])
+    # the asynchronous pair (to_host_begin / finish: compaction on the compute stream, fields on a copy stream), with
+    # two handles in flight and with caller-supplied pinned buffers
+    h1 = b.to_host_begin(fields=('x', 'Es', 'Jpp'), rayFlag=(1, 2))
+    pinned = {k: torch.empty(max(n, 1), dtype=torch.float64, pin_memory=True) for k in ('z', 'E')}
+    h2 = b.to_host_begin(fields=('z', 'E'), rayFlag=(4,), out=pinned)
+    got2, got1 = h2.finish(), h1.finish()
+    sel12 = (arrs['state'] == 1) | (arrs['state'] == 2)
+    for k, v in got1.items():
+        assert np.array_equal(v, arrs[k][sel12]), k
+    for k, v in got2.items():
+        assert np.array_equal(v, arrs[k][arrs['state'] < 0]), k

@@ -41,6 +41,38 @@ def _device(device=None):
     return torch.device(device)
 
 
+class _HostTransfer(object):
+    """Handle of Beam.to_host_begin: the compacted device arrays, the pinned count and the event that says both are
+    final."""
+    _copy_streams = {}
+
+    def __init__(self, names, dst, cnt_host, ready, out, scratch):
+        self.names, self.dst, self.cnt_host, self.ready, self.out, self._scratch = names, dst, cnt_host, ready, out, scratch
+
+    def finish(self):
+        """Waits for the selected count, copies the fields on the copy stream and returns {field: numpy array}."""
+        self.ready.synchronize()
+        cnt = int(self.cnt_host[0])
+        dev = self.dst[0].device if self.dst else torch.device('cuda', torch.cuda.current_device())
+        cs = _HostTransfer._copy_streams.get(str(dev))
+        if cs is None:
+            cs = _HostTransfer._copy_streams[str(dev)] = torch.cuda.Stream(device=dev)
+        res = {}
+        with torch.cuda.stream(cs):
+            for k, d in zip(self.names, self.dst):
+                if self.out is not None and k in self.out:
+                    self.out[k][:cnt].copy_(d[:cnt], non_blocking=True)
+                    res[k] = self.out[k][:cnt]
+                else:
+                    h = torch.empty(cnt, dtype=d.dtype, pin_memory=True)
+                    h.copy_(d[:cnt], non_blocking=True)
+                    res[k] = h
+                d.record_stream(cs)
+        cs.synchronize()
+        self.dst = self._scratch = None
+        return {k: v.numpy() for k, v in res.items()}
+
+
 class Beam(object):
     def __init__(self, nrays=0, copyFrom=None, withAmplitudes=False, device=None, uninitialized=False):
         if copyFrom is not None:  # only the reference's listOfAttrs travel (beams.py:96-117): no area, toOE, ...
@@ -202,6 +234,45 @@ class Beam(object):
                 res[k] = d[:cnt].cpu()
         torch.cuda.current_stream().synchronize()
         return {k: v.numpy() for k, v in res.items()}
+
+    def to_host_begin(self, fields=('x', 'z', 'E', 'Jss', 'Jpp'), rayFlag=(1,), out=None):
+        """First half of an ASYNCHRONOUS to_host(good_only=True): launches the compaction on the current stream and an
+        8-byte copy of the selected count into pinned memory, then returns a handle at once.  `handle.finish()` -- called
+        after the NEXT step's kernels have been launched -- waits for the count, moves the compacted fields on a copy
+        stream of its own (PCIe runs while the GPU computes the next step) and returns the numpy views.  *out*: dict of
+        pinned host tensors, one per field (alternate between two sets when handles overlap)."""
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        n = len(self)
+        names = list(fields)
+        tens = [getattr(self, k) for k in names]
+        mask = 0
+        for f in rayFlag:
+            mask |= {1: 1, 2: 2, 3: 4, 4: 8}[int(f)]
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        need = lib.xrt_compact_scratch_words(max(n, 1))
+        scratch = torch.empty(need, dtype=torch.int64, device=self.device)
+        dst = [torch.empty_like(t) for t in tens]
+        for c0 in range(0, len(names), 8):
+            grp = list(range(c0, min(c0 + 8, len(names))))
+            m = len(grp)
+            for i in grp:
+                if tens[i].element_size() not in (8, 16) or not tens[i].is_contiguous():
+                    raise ValueError('to_host: {0} is not a contiguous float64 / complex128 array'.format(names[i]))
+            src_p = (ctypes.c_void_p * m)(*[tens[i].data_ptr() for i in grp])
+            dst_p = (ctypes.c_void_p * m)(*[dst[i].data_ptr() for i in grp])
+            words = (ctypes.c_int * m)(*[2 if tens[i].is_complex() else 1 for i in grp])
+            if n:
+                _lib.check(lib.xrt_compact_rays_f64(n, self.state.data_ptr(), mask, m, ctypes.addressof(src_p),
+                                                    ctypes.addressof(dst_p), ctypes.addressof(words),
+                                                    scratch.data_ptr(), st), 'xrt_compact_rays_f64')
+        cnt_host = torch.zeros(1, dtype=torch.int64, pin_memory=True)
+        if n:
+            cnt_host.copy_(scratch[need - 1:need], non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record()
+        return _HostTransfer(names, dst, cnt_host, ready, out, scratch)
 
     def __array__(self):  # pragma: no cover - convenience for interactive use
         raise TypeError('Beam is a container; use beam.to_numpy()')
