@@ -205,3 +205,68 @@ def test_product_random_roughness_equals_reference(name, kw):
     assert np.abs(fe.local_z_spline.get_coeffs() - g[name + '_c']).max() <= 1e-12 * scale
     if name == 'height':
         assert abs(fe.get_rms() - 2.5) < 1e-12
+
+
+# ---------------------------------------------------------------- two-surface element: DCM(figureError=...)
+DCM_CASES = ['waviness', 'bump']
+DCM_KEYS = ('bragg', 'cryst1roll', 'cryst2roll', 'cryst2pitch', 'cryst2finePitch', 'cryst2perpTransl',
+            'cryst2longTransl')
+
+
+@pytest.mark.parametrize('name', DCM_CASES)
+def test_oracle_figure_error_on_dcm_bit_exact(name):
+    """DCM.double_reflect with a figure error (oes/dcm.py:247-354): find_dz adds the height map to local_z1 and to
+    local_z2, each in its own crystal's frame (base.py:825-829); both crystals' normals are turned (reflect.py:767-776).
+    The reference supports it for symmetric cuts only -- with alpha its own np.asarray(oeNormal) fails (scalars of the
+    planes' normal beside the arrays of the turned surface normal, reflect.py:790)."""
+    g = golden('dcm_figerr_' + name)
+    fe = osf.FigureErrorSpline(g['fe_x1d'], g['fe_y1d'], g['fe_z'], float(g['fe_xShift']), float(g['fe_yShift']))
+    assert np.array_equal(fe.local_z_spline.get_coeffs(), g['fe_c'])
+    si = om.CrystalDiamond((1, 1, 1), float(g['d']), 'Si')
+    kw = dict(material2=si, surfPhysX2=list(g['surfPhysX2']), surfPhysY2=list(g['surfPhysY2']), surfOptX2=None,
+              surfOptY2=None, **{k: float(g[k]) for k in DCM_KEYS})
+    gb, lo1, lo2 = orf.double_reflect(oracle_spec(g, 'flat', si, figureError=fe, **kw), oracle_beam(g, 'in_'))
+    for pre, b in (('gb_', gb), ('lo1_', lo1), ('lo2_', lo2)):
+        for f in OUT_FIELDS:
+            if pre + f in g.files:
+                assert np.array_equal(getattr(b, f), g[pre + f]), pre + f
+    gb0, _, _ = orf.double_reflect(oracle_spec(g, 'flat', si, **kw), oracle_beam(g, 'in_'))  # ... and it matters
+    good = (gb.state == 1) & (gb0.state == 1)
+    assert good.sum() > 2000 and 1e-7 < np.abs(gb.c[good] - gb0.c[good]).max() < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', DCM_CASES)
+def test_cuda_figure_error_on_dcm_vs_reference_golden(name, cuda_device):
+    """DCM(figureError=...) through the figure-error plug-in variant of the flat surface, both crystals.  Tolerances:
+    geometry 1e-12 (|dt| <= 4e-12 mm per crystal as for the single-surface figure errors), amplitudes 1e-11 of the
+    group scale after removing exp(i k dt) (the Bragg peak amplifies ulp-level differences, tests/test_dcm.py)."""
+    from xrt_b200 import figure_error as pfe, oes, materials
+    from xrt_b200.physconsts import CHBAR
+    g = golden('dcm_figerr_' + name)
+    fe = pfe.FigureErrorMap(g['fe_x1d'], g['fe_y1d'], g['fe_z'])
+    si = materials.CrystalSi(hkl=(1, 1, 1), tK=float(g['tK']))
+    kw = product_oe_kwargs(g)
+    kw.update({k: float(g[k]) for k in DCM_KEYS})
+    dcm = oes.DCM(product_beamline(g), 'dcm', material=si, material2=si, figureError=fe,
+                  limPhysX2=list(g['surfPhysX2']), limPhysY2=list(g['surfPhysY2']), **kw)
+    dcm.lostNum = int(g['lostNum'])
+    assert dcm._plugin().figure_error and dcm._plugin().kind == 0
+    gb, lo1, lo2 = dcm.double_reflect(device_beam(oracle_beam(g, 'in_')))
+    assert np.array_equal(gb.to_numpy()['state'], g['gb_state'])
+    bad = []
+    for pre, b in (('gb_', gb), ('lo1_', lo1), ('lo2_', lo2)):
+        ref = {f: g[pre + f] for f in OUT_FIELDS if pre + f in g.files}
+        dev = b.to_numpy()
+        good = ref['state'] == 1
+        dpath = np.where(good, dev['path'] - ref['path'], 0.)
+        assert np.abs(dpath).max() <= 8e-12, (pre, float(np.abs(dpath).max()))
+        comp = np.exp(-1e7j * ref['E'] / CHBAR * dpath)
+        dev = dict(dev, Es=dev['Es'] * comp, Ep=dev['Ep'] * comp)
+        bad += compare_beams(dev, ref, ('x', 'y', 'z', 'a', 'b', 'c', 'path', 'E', 'state', 'theta'), 1e-12, pre)
+        bad += compare_beams(dev, ref, ('Jss', 'Jpp', 'Jsp', 'Es', 'Ep'), 1e-11, pre)
+    assert not bad, bad
+    # an asymmetric cut with a figure error has no reference behaviour to match (above): refused
+    dcm.alpha = np.radians(5.)
+    with pytest.raises(NotImplementedError):
+        dcm._plugin()

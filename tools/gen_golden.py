@@ -1240,6 +1240,47 @@ def gen_figure_error_param():
              fe_yShift=fe.yShift, fe_x1d=fe.x1d, fe_y1d=fe.y1d, fe_z=fe.generate_profile(), **d)
 
 
+def gen_figure_error_dcm():
+    """A figure error on a TWO-SURFACE element: DCM(figureError=...) -- find_dz adds the height map to local_z1 AND
+    local_z2 (oes/base.py:825-829, each in its own crystal's local frame), _reflect_local turns the SURFACE normal of both
+    crystals (reflect.py:767-776; with an asymmetric cut the normal of the planes stays)."""
+    import xrt.backends.raycing.figure_error as rfe
+    bl = raycing.BeamLine()
+    si = rm.CrystalSi(hkl=(1, 1, 1))
+    E0 = 9000.
+    lx, ly = [-5, 5], [-60, 60]
+    cases = (('waviness', None, lambda: rfe.Waviness(amplitude=8., xWaveLength=4., yWaveLength=25., limPhysX=lx,
+                                                     limPhysY=ly, gridStep=2.)),
+             # (with an asymmetric cut the reference itself fails: the normal of the planes is a tuple of scalars, the
+             # turned surface normal one of arrays -> np.asarray raises at reflect.py:790)
+             ('bump', None, lambda: rfe.GaussianBump(bumpHeight=20., cX=0.3, cY=5., sigmaX=2., sigmaY=15., limPhysX=lx,
+                                                     limPhysY=ly, gridStep=2.)))
+    for name, alpha, mkfe in cases:
+        beam = _source_beam(bl, 3000, 431, dx=0.2, dz=0.02, dxprime=5e-5, dzprime=2e-5, energies=(8995, 9005))
+        theta = si.get_Bragg_angle(E0) - si.get_dtheta(E0, alpha)
+        fe = mkfe()
+        dcm = roe.DCM(bl, 'dcm', center=(0, 2e4, 0), bragg=float(theta), material=si, material2=si, alpha=alpha,
+                      cryst2perpTransl=10., cryst2finePitch=2e-6, cryst1roll=1e-4, figureError=fe,
+                      limPhysX=lx, limPhysY=ly, limPhysX2=lx, limPhysY2=[-40, 80])
+        gb, lo1, lo2 = dcm.double_reflect(beam)
+        d = _dcm_params(dcm)
+        d.update(beam_dict(beam, 'in_'))
+        d.update(beam_dict(gb, 'gb_'))
+        d.update(beam_dict(lo1, 'lo1_'))
+        d.update(beam_dict(lo2, 'lo2_'))
+        dcm0 = roe.DCM(bl, 'dcm0', center=(0, 2e4, 0), bragg=float(theta), material=si, material2=si, alpha=alpha,
+                       cryst2perpTransl=10., cryst2finePitch=2e-6, cryst1roll=1e-4,
+                       limPhysX=lx, limPhysY=ly, limPhysX2=lx, limPhysY2=[-40, 80])
+        gb0, _, _ = dcm0.double_reflect(beam)
+        both = (gb.state == 1) & (gb0.state == 1)
+        print('dcm_figerr_' + name, {int(s): int((gb.state == s).sum()) for s in np.unique(gb.state)},
+              'max |dc| vs perfect', float(np.abs(gb.c - gb0.c)[both].max()),
+              'intensity ratio', float((gb.Jss + gb.Jpp)[both].sum() / (gb0.Jss + gb0.Jpp)[both].sum()),
+              'rms nm', float(fe.get_rms()))
+        save('dcm_figerr_' + name, d=si.d, tK=si.tK, E0=E0, fe_x1d=fe.x1d, fe_y1d=fe.y1d, fe_z=fe.generate_profile(),
+             fe_c=fe.local_z_spline.get_coeffs(), fe_xShift=fe.xShift, fe_yShift=fe.yShift, **d)
+
+
 def gen_coated():
     """Coated (materials/multilayer.py:528-584): one reflective layer on a substrate, with surface and substrate
     roughness, kind 'mirror' -- amplitudes on a grid and a toroid mirror in a beam line."""
@@ -1393,7 +1434,7 @@ def gen_roughness():
     save('figure_error_roughness', **out)
 
 
-SECTIONS = {'figure_error_param': gen_figure_error_param, 'roughness': gen_roughness, 'blazed': gen_blazed, 'hemispheric': gen_hemispheric, 'multilayer_tran': gen_multilayer_tran, 'fzp': gen_fzp, 'laue': gen_laue, 'coated': gen_coated, 'figure_error': gen_figure_error, 'round': gen_round, 'shine_wave': gen_shine_wave, 'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+SECTIONS = {'figure_error_dcm': gen_figure_error_dcm, 'figure_error_param': gen_figure_error_param, 'roughness': gen_roughness, 'blazed': gen_blazed, 'hemispheric': gen_hemispheric, 'multilayer_tran': gen_multilayer_tran, 'fzp': gen_fzp, 'laue': gen_laue, 'coated': gen_coated, 'figure_error': gen_figure_error, 'round': gen_round, 'shine_wave': gen_shine_wave, 'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)

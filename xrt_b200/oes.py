@@ -173,9 +173,14 @@ class OE(object):
         if self.cu_local_z is None:
             if not fe:
                 return None
-            if self.surfaceKind not in (0, 1, 2) or hasattr(self, 'bragg'):
+            if self.surfaceKind not in (0, 1, 2) or hasattr(self, 't'):
                 raise NotImplementedError('figure errors are on the hot path for flat, toroidal, elliptic and spliced '
-                                          'single-surface elements')
+                                          'single-surface elements and for the DCM (not for plates and lenses)')
+            if self.alpha:
+                # the reference has no behaviour to match: np.asarray(oeNormal) fails on the scalar normal of the
+                # planes beside the turned per-ray surface normal (reflect.py:767-790)
+                raise NotImplementedError('a figure error on an asymmetrically cut crystal fails in the reference '
+                                          '(reflect.py:790); outside the hot path')
             from . import custom
             return custom.plugin_for(builtin_kind=self.surfaceKind, figure_error=True)
         if self.cu_local_n is None:
@@ -927,7 +932,7 @@ class DCM(OE):
         p2.from_vacuum = int(bool(fromVacuum2))
         p2.dead_state_lost = int(hasattr(self, 't'))  # is instance of Plate (dcm.py:311-312, :331-332)
         lo2 = self._new_local(beam) if needLocal else None
-        if exposeOn is not None and not hasattr(self, 't'):
+        if exposeOn is not None and not hasattr(self, 't') and self._plugin() is None:
             gb2, screen = None, exposeOn._fused_target(beam)
         else:
             gb2, screen = beam.like(), None
