@@ -270,3 +270,60 @@ def test_cuda_figure_error_on_dcm_vs_reference_golden(name, cuda_device):
     dcm.alpha = np.radians(5.)
     with pytest.raises(NotImplementedError):
         dcm._plugin()
+
+
+# ---------------------------------------------------------------- Plate(figureError=...): both refracting surfaces
+def _plate_oracle(g, fe):
+    mat = om.Material('C', rho=float(g['rho']), kind='plate')
+    kw = dict(bragg=0., cryst1roll=0., cryst2roll=0., cryst2pitch=float(g['wedgeAngle']), cryst2finePitch=0.,
+              cryst2perpTransl=-float(g['t']), cryst2longTransl=0., material2=mat, t=float(g['t']),
+              surfPhysX2=list(g['surfPhysX2']), surfPhysY2=list(g['surfPhysY2']), surfOptX2=None, surfOptY2=None)
+    if fe is not None:
+        kw['figureError'] = fe
+    return orf.double_refract(oracle_spec(g, 'flat', mat, **kw), oracle_beam(g, 'in_'))
+
+
+def test_oracle_figure_error_on_plate_bit_exact():
+    """Plate.double_refract with a figure error (oes/refractive.py:170-234): the height map displaces the entrance and
+    the exit surface, Snell's law uses the turned normals (reflect.py:767-776, :894-919)."""
+    g = golden('refract_plate_figerr')
+    fe = osf.FigureErrorSpline(g['fe_x1d'], g['fe_y1d'], g['fe_z'], float(g['fe_xShift']), float(g['fe_yShift']))
+    assert np.array_equal(fe.local_z_spline.get_coeffs(), g['fe_c'])
+    gb, lo1, lo2 = _plate_oracle(g, fe)
+    for pre, b in (('gb_', gb), ('lo1_', lo1), ('lo2_', lo2)):
+        for f in OUT_FIELDS:
+            if pre + f in g.files:
+                assert np.array_equal(getattr(b, f), g[pre + f]), pre + f
+    gb0 = _plate_oracle(g, None)[0]
+    good = (gb.state == 1) & (gb0.state == 1)
+    assert good.sum() > 2000 and 1e-8 < np.abs(gb.c[good] - gb0.c[good]).max() < 1e-5
+
+
+@pytest.mark.gpu
+def test_cuda_figure_error_on_plate_vs_reference_golden(cuda_device):
+    """Plate(figureError=...) through the figure-error plug-in variant of the flat surface, both surfaces; tolerances of
+    the single-surface figure-error tests (|dt| <= 4e-12 mm per surface, exp(i k dt) removed, the rest 1e-12)."""
+    from xrt_b200 import figure_error as pfe, oes, materials
+    from xrt_b200.physconsts import CHBAR
+    g = golden('refract_plate_figerr')
+    fe = pfe.FigureErrorMap(g['fe_x1d'], g['fe_y1d'], g['fe_z'])
+    kw = product_oe_kwargs(g)
+    kw['material'] = materials.Material('C', rho=float(g['rho']), kind='plate')
+    oe = oes.Plate(product_beamline(g), 'W', wedgeAngle=float(g['wedgeAngle']), t=float(g['t']), figureError=fe, **kw)
+    oe.lostNum = int(g['lostNum'])
+    assert oe._plugin().figure_error and oe._plugin().kind == 0
+    gb, lo1, lo2 = oe.double_refract(device_beam(oracle_beam(g, 'in_')))
+    assert np.array_equal(gb.to_numpy()['state'], g['gb_state'])
+    bad = []
+    for pre, b in (('gb_', gb), ('lo1_', lo1), ('lo2_', lo2)):
+        ref = {f: g[pre + f] for f in OUT_FIELDS if pre + f in g.files}
+        dev = b.to_numpy()
+        good = ref['state'] == 1
+        dpath = np.where(good, dev['path'] - ref['path'], 0.)
+        assert np.abs(dpath).max() <= 8e-12, (pre, float(np.abs(dpath).max()))
+        comp = np.exp(-1e7j * ref['E'] / CHBAR * dpath)
+        dev = dict(dev, Es=dev['Es'] * comp, Ep=dev['Ep'] * comp)
+        phase_ulp = np.spacing((1e7 * ref['E'] / CHBAR * ref['path']).max())
+        bad += compare_beams(dev, ref, ('Es', 'Ep'), 2 * phase_ulp, pre)
+        bad += compare_beams(dev, ref, [f for f in OUT_FIELDS if f not in ('Es', 'Ep')], 1e-12, pre)
+    assert not bad, bad

@@ -1281,6 +1281,30 @@ def gen_figure_error_dcm():
              fe_c=fe.local_z_spline.get_coeffs(), fe_xShift=fe.xShift, fe_yShift=fe.yShift, **d)
 
 
+def gen_figure_error_plate():
+    """A figure error on a Plate (oes/refractive.py:12-234 derives from DCM): the same height map on the entrance and the
+    exit surface (find_dz, base.py:825-829) and both refraction normals turned (reflect.py:767-776, toWhere = 1)."""
+    import xrt.backends.raycing.figure_error as rfe
+    bl = raycing.BeamLine(azimuth=0.1)
+    ctr = (1e4*np.sin(0.1), 1e4*np.cos(0.1), 0)
+    beam = _source_beam(bl, 2500, 441, dx=0.4, dz=0.3, dxprime=2e-5, dzprime=2e-5, energies=(7000, 11000))
+    C = rm.Material('C', rho=3.52, kind='plate')
+    lx, ly = [-0.9, 1.1], [-1.2, 1.0]
+    fe = rfe.Waviness(amplitude=2000., xWaveLength=0.5, yWaveLength=0.7, limPhysX=lx, limPhysY=ly, gridStep=0.05)
+    pl = roe.Plate(bl, 'W', center=ctr, pitch=np.radians(50.), t=0.3, wedgeAngle=2e-3, material=C, limPhysX=lx,
+                   limPhysY=ly, figureError=fe)
+    d = _capture_refract(pl, beam)
+    pl0 = roe.Plate(bl, 'W0', center=ctr, pitch=np.radians(50.), t=0.3, wedgeAngle=2e-3, material=C, limPhysX=lx,
+                    limPhysY=ly)
+    gb0 = pl0.double_refract(beam)[0]
+    both = (d['gb_state'] == 1) & (gb0.state == 1)
+    st = d['gb_state']
+    print('refract_plate_figerr', {int(x): int((st == x).sum()) for x in np.unique(st)}, 'max |dc| vs perfect',
+          float(np.abs(d['gb_c'] - gb0.c)[both].max()), 'rms nm', float(fe.get_rms()))
+    save('refract_plate_figerr', fe_x1d=fe.x1d, fe_y1d=fe.y1d, fe_z=fe.generate_profile(),
+         fe_c=fe.local_z_spline.get_coeffs(), fe_xShift=fe.xShift, fe_yShift=fe.yShift, **d)
+
+
 def gen_coated():
     """Coated (materials/multilayer.py:528-584): one reflective layer on a substrate, with surface and substrate
     roughness, kind 'mirror' -- amplitudes on a grid and a toroid mirror in a beam line."""
@@ -1434,7 +1458,7 @@ def gen_roughness():
     save('figure_error_roughness', **out)
 
 
-SECTIONS = {'figure_error_dcm': gen_figure_error_dcm, 'figure_error_param': gen_figure_error_param, 'roughness': gen_roughness, 'blazed': gen_blazed, 'hemispheric': gen_hemispheric, 'multilayer_tran': gen_multilayer_tran, 'fzp': gen_fzp, 'laue': gen_laue, 'coated': gen_coated, 'figure_error': gen_figure_error, 'round': gen_round, 'shine_wave': gen_shine_wave, 'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+SECTIONS = {'figure_error_plate': gen_figure_error_plate, 'figure_error_dcm': gen_figure_error_dcm, 'figure_error_param': gen_figure_error_param, 'roughness': gen_roughness, 'blazed': gen_blazed, 'hemispheric': gen_hemispheric, 'multilayer_tran': gen_multilayer_tran, 'fzp': gen_fzp, 'laue': gen_laue, 'coated': gen_coated, 'figure_error': gen_figure_error, 'round': gen_round, 'shine_wave': gen_shine_wave, 'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)

@@ -173,9 +173,9 @@ class OE(object):
         if self.cu_local_z is None:
             if not fe:
                 return None
-            if self.surfaceKind not in (0, 1, 2) or hasattr(self, 't'):
+            if self.surfaceKind not in (0, 1, 2):
                 raise NotImplementedError('figure errors are on the hot path for flat, toroidal, elliptic and spliced '
-                                          'single-surface elements and for the DCM (not for plates and lenses)')
+                                          'single-surface elements, for the DCM and the Plate (not for lenses)')
             if self.alpha:
                 # the reference has no behaviour to match: np.asarray(oeNormal) fails on the scalar normal of the
                 # planes beside the turned per-ray surface normal (reflect.py:767-790)
