@@ -327,3 +327,64 @@ def test_cuda_figure_error_on_plate_vs_reference_golden(cuda_device):
         bad += compare_beams(dev, ref, ('Es', 'Ep'), 2 * phase_ulp, pre)
         bad += compare_beams(dev, ref, [f for f in OUT_FIELDS if f not in ('Es', 'Ep')], 1e-12, pre)
     assert not bad, bad
+
+
+# ---------------------------------------------------------------- DoubleParaboloidLens(figureError=...), nCRL = 3
+def _crl_oracle(g, fe):
+    mat = om.Material('Be', rho=float(g['rho']), kind='lens')
+    kw = dict(bragg=0., cryst1roll=0., cryst2roll=0., cryst2pitch=float(g['wedgeAngle']), cryst2finePitch=0.,
+              cryst2perpTransl=-float(g['t']), cryst2longTransl=0., material2=mat, t=float(g['t']),
+              surfPhysX2=list(g['surfPhysX2']), surfPhysY2=list(g['surfPhysY2']), surfOptX2=None, surfOptY2=None,
+              surfParams=dict(focus=float(g['focus']), zmax=float(g['zmax']), isCylinder=False), nCRL=int(g['nCRL']),
+              zmax=float(g['zmax']), isDouble=True)
+    if fe is not None:
+        kw['figureError'] = fe
+    return orf.multiple_refract(oracle_spec(g, 'paraboloid', mat, **kw), oracle_beam(g, 'in_'))
+
+
+def test_oracle_figure_error_on_lens_stack_bit_exact():
+    """multiple_refract with a figure error (oes/refractive.py:457-549): the same height map on both surfaces of every
+    lens of the stack."""
+    g = golden('refract_crl_figerr')
+    fe = osf.FigureErrorSpline(g['fe_x1d'], g['fe_y1d'], g['fe_z'], float(g['fe_xShift']), float(g['fe_yShift']))
+    assert np.array_equal(fe.local_z_spline.get_coeffs(), g['fe_c'])
+    gb, lo1, lo2 = _crl_oracle(g, fe)
+    for pre, b in (('gb_', gb), ('lo1_', lo1), ('lo2_', lo2)):
+        for f in OUT_FIELDS:
+            if pre + f in g.files:
+                assert np.array_equal(getattr(b, f), g[pre + f]), pre + f
+    gb0 = _crl_oracle(g, None)[0]
+    good = (gb.state == 1) & (gb0.state == 1)
+    assert good.sum() > 2000 and 1e-7 < np.abs(gb.c[good] - gb0.c[good]).max() < 1e-4
+
+
+@pytest.mark.gpu
+def test_cuda_figure_error_on_lens_stack_vs_reference_golden(cuda_device):
+    """DoubleParaboloidLens(figureError=..., nCRL=3).multiple_refract through the figure-error plug-in variant of the
+    parabolic surface (kind 3): six refractions, each with the height map in the intersection search and the turned
+    normal.  |dt| <= 4e-12 mm per surface, exp(i k dt) removed, the rest 1e-12 of the group scale."""
+    from xrt_b200 import figure_error as pfe, oes, materials
+    from xrt_b200.physconsts import CHBAR
+    g = golden('refract_crl_figerr')
+    fe = pfe.FigureErrorMap(g['fe_x1d'], g['fe_y1d'], g['fe_z'])
+    kw = product_oe_kwargs(g)
+    kw['material'] = materials.Material('Be', rho=float(g['rho']), kind='lens')
+    oe = oes.DoubleParaboloidLens(product_beamline(g), 'CRL', t=float(g['t']), focus=float(g['focus']),
+                                  zmax=float(g['zmax']), nCRL=int(g['nCRL']), figureError=fe, **kw)
+    oe.lostNum = int(g['lostNum'])
+    assert oe._plugin().figure_error and oe._plugin().kind == 3
+    gb, lo1, lo2 = oe.multiple_refract(device_beam(oracle_beam(g, 'in_')))
+    assert np.array_equal(gb.to_numpy()['state'], g['gb_state'])
+    bad = []
+    for pre, b, nsurf in (('gb_', gb, 6), ('lo1_', lo1, 1), ('lo2_', lo2, 2)):
+        ref = {f: g[pre + f] for f in OUT_FIELDS if pre + f in g.files}
+        dev = b.to_numpy()
+        good = ref['state'] == 1
+        dpath = np.where(good, dev['path'] - ref['path'], 0.)
+        assert np.abs(dpath).max() <= 4e-12 * nsurf, (pre, float(np.abs(dpath).max()))
+        comp = np.exp(-1e7j * ref['E'] / CHBAR * dpath)
+        dev = dict(dev, Es=dev['Es'] * comp, Ep=dev['Ep'] * comp)
+        phase_ulp = np.spacing((1e7 * ref['E'] / CHBAR * ref['path']).max())
+        bad += compare_beams(dev, ref, ('Es', 'Ep'), 2 * nsurf * phase_ulp, pre)
+        bad += compare_beams(dev, ref, [f for f in OUT_FIELDS if f not in ('Es', 'Ep')], 1e-12, pre)
+    assert not bad, bad

@@ -90,16 +90,16 @@ def test_plugin_objects_build_and_export_without_gpu():
     from xrt_b200 import custom, oes_spliced
     from xrt_b200.oes import xrt_oe_params
     paths = oes_spliced.prebuild()
-    assert len(set(paths)) == len({(c.cu_local_z, c.cu_local_n) for c in oes_spliced.LIBRARY}) + 4  # + 4 figure-error variants
+    assert len(set(paths)) == len({(c.cu_local_z, c.cu_local_n) for c in oes_spliced.LIBRARY}) + 5  # + 5 figure-error variants
     assert sum(custom.SurfacePlugin(p).own_intersection for p in paths) == 1  # BlazedGrating
     plugs = [custom.SurfacePlugin(p) for p in paths]
     assert sorted(q.kind for q in plugs).count(5) == 1  # ParabolicalMirrorParam
     assert sorted((q.kind, q.figure_error) for q in plugs if q.figure_error) == [(0, True), (1, True), (2, True),
-                                                                                 (4, True)]
+                                                                                 (3, True), (4, True)]
     for p in paths:
         assert os.path.dirname(p) == custom.PLUGIN_DIR and os.path.exists(p)
         plug = custom.SurfacePlugin(p)
-        assert plug.kind in (0, 1, 2, 4, 5)
+        assert plug.kind in (0, 1, 2, 3, 4, 5)
         assert plug.lib.xrt_plugin_sizeof_oe_params() == ctypes.sizeof(xrt_oe_params)
 
 

@@ -1305,6 +1305,28 @@ def gen_figure_error_plate():
          fe_c=fe.local_z_spline.get_coeffs(), fe_xShift=fe.xShift, fe_yShift=fe.yShift, **d)
 
 
+def gen_figure_error_lens():
+    """A figure error on a parabolic lens stack (oes/refractive.py:237-549, multiple_refract :457-549): every lens of the
+    CRL carries the same height map on both of its surfaces."""
+    import xrt.backends.raycing.figure_error as rfe
+    bl = raycing.BeamLine()
+    Be = rm.Material('Be', rho=1.848, kind='lens')
+    lx, ly = [-0.6, 0.6], [-0.6, 0.6]
+    beam = _source_beam(bl, 2500, 451, dx=0.2, dz=0.2, dxprime=1e-5, dzprime=1e-5, energies=(8500, 9500))
+    fe = rfe.Waviness(amplitude=1500., xWaveLength=0.35, yWaveLength=0.5, limPhysX=lx, limPhysY=ly, gridStep=0.03)
+    kw = dict(center=(0, 10000, 0), pitch=np.pi/2, t=0.03, material=Be, focus=0.1, zmax=0.5, nCRL=3, limPhysX=lx,
+              limPhysY=ly)
+    ln = roe.DoubleParaboloidLens(bl, 'CRL', figureError=fe, **kw)
+    d = _capture_refract(ln, beam, True)
+    gb0 = roe.DoubleParaboloidLens(bl, 'CRL0', **kw).multiple_refract(beam)[0]
+    st = d['gb_state']
+    both = (st == 1) & (gb0.state == 1)
+    print('refract_crl_figerr', {int(x): int((st == x).sum()) for x in np.unique(st)}, 'max |dc| vs perfect',
+          float(np.abs(d['gb_c'] - gb0.c)[both].max()), 'rms nm', float(fe.get_rms()))
+    save('refract_crl_figerr', focus=0.1, zmax=0.5, nCRL=np.int64(3), fe_x1d=fe.x1d, fe_y1d=fe.y1d,
+         fe_z=fe.generate_profile(), fe_c=fe.local_z_spline.get_coeffs(), fe_xShift=fe.xShift, fe_yShift=fe.yShift, **d)
+
+
 def gen_coated():
     """Coated (materials/multilayer.py:528-584): one reflective layer on a substrate, with surface and substrate
     roughness, kind 'mirror' -- amplitudes on a grid and a toroid mirror in a beam line."""
@@ -1458,7 +1480,7 @@ def gen_roughness():
     save('figure_error_roughness', **out)
 
 
-SECTIONS = {'figure_error_plate': gen_figure_error_plate, 'figure_error_dcm': gen_figure_error_dcm, 'figure_error_param': gen_figure_error_param, 'roughness': gen_roughness, 'blazed': gen_blazed, 'hemispheric': gen_hemispheric, 'multilayer_tran': gen_multilayer_tran, 'fzp': gen_fzp, 'laue': gen_laue, 'coated': gen_coated, 'figure_error': gen_figure_error, 'round': gen_round, 'shine_wave': gen_shine_wave, 'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
+SECTIONS = {'figure_error_lens': gen_figure_error_lens, 'figure_error_plate': gen_figure_error_plate, 'figure_error_dcm': gen_figure_error_dcm, 'figure_error_param': gen_figure_error_param, 'roughness': gen_roughness, 'blazed': gen_blazed, 'hemispheric': gen_hemispheric, 'multilayer_tran': gen_multilayer_tran, 'fzp': gen_fzp, 'laue': gen_laue, 'coated': gen_coated, 'figure_error': gen_figure_error, 'round': gen_round, 'shine_wave': gen_shine_wave, 'multi': gen_multi, 'spliced': gen_spliced, 'field_source': gen_field_source, 'config1': gen_config1, 'mesh': gen_mesh, 'geometric': gen_geometric, 'refractive': gen_refractive, 'bm': gen_bm, 'gratings': gen_gratings, 'undulator_ext': gen_undulator_ext, 'thin': gen_thin_crystals, 'multilayer': gen_multilayer, 'hist': gen_hist, 'wave_oe': gen_wave_oe, 'diffract_oe': gen_diffract_oe, 'brent': gen_brent, 'diffract': gen_diffract, 'kb': gen_kb, 'shine': gen_shine, 'dcm': gen_dcm, 'amplitudes': gen_amplitudes, 'planes': gen_planes, 'reflect': gen_reflect, 'constants': gen_constants, 'kirchhoff': gen_kirchhoff, 'undulator': gen_undulator}
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(SECTIONS)

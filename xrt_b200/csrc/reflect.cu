@@ -3392,7 +3392,11 @@ int reflect_expose_device(size_t n, const xrt_oe_params* oe, const xrt_material_
     if (scr) screen_reduction_init_kernel<<<1, XRT_REDUCTION_SLOTS, 0, st>>>(scr_red);
     int rc = 0;
 #ifdef XRTB_PLUGIN
-    rc = launch_main_mat<XRTB_USER_KIND>(m.kind, L);
+    if constexpr (XRTB_USER_KIND == 3) {
+      rc = launch_main_refr<XRTB_USER_KIND>(m.kind, L);  // the figure-error variant of the parabolic lens surface
+    } else {
+      rc = launch_main_mat<XRTB_USER_KIND>(m.kind, L);
+    }
 #else
     if (oe->surface == 0) rc = launch_main_mat<0>(m.kind, L);
     if (oe->surface == 1) rc = launch_main_mat<1>(m.kind, L);

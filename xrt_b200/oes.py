@@ -173,9 +173,9 @@ class OE(object):
         if self.cu_local_z is None:
             if not fe:
                 return None
-            if self.surfaceKind not in (0, 1, 2):
-                raise NotImplementedError('figure errors are on the hot path for flat, toroidal, elliptic and spliced '
-                                          'single-surface elements, for the DCM and the Plate (not for lenses)')
+            if self.surfaceKind not in (0, 1, 2, 3):
+                raise NotImplementedError('figure errors are on the hot path for flat, toroidal, elliptic, parabolic '
+                                          '(lenses) and spliced surfaces')
             if self.alpha:
                 # the reference has no behaviour to match: np.asarray(oeNormal) fails on the scalar normal of the
                 # planes beside the turned per-ray surface normal (reflect.py:767-790)

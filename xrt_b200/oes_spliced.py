@@ -465,7 +465,7 @@ def prebuild(verbose=False):
                  cu_find_intersection=c.cu_find_intersection) for c in LIBRARY]
     # figure-error variants of the built-in flat and toroidal surfaces (xrt_b200/figure_error.py)
     jobs += [dict(builtin_kind=0, figure_error=True), dict(builtin_kind=1, figure_error=True),
-             dict(builtin_kind=2, figure_error=True),
+             dict(builtin_kind=2, figure_error=True), dict(builtin_kind=3, figure_error=True),
              dict(cu_local_z=BentFlatMirror.cu_local_z, cu_local_n=BentFlatMirror.cu_local_n, figure_error=True)]
     with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
         return list(ex.map(lambda j: custom.build_plugin(verbose=verbose, **j), jobs))
