@@ -574,6 +574,8 @@ class OE(object):
         the derivative stage (xrt_reflect_multi_deriv_f64: the ray leaves the surface before the next intersection is
         searched).  One host synchronisation per pass (the count of rays still alive ends the loop)."""
         if self.figureError is not None:
+            # no reference behaviour to match: in the derivative stage find_dz does `surf += z_distorted` on the
+            # NORMAL returned by local_n (base.py:823-830, :845) -- a tuple fails, a list is extended by the heights
             raise NotImplementedError('multiple_reflect with a figure error is outside the hot path')
         if self.material is not None and getattr(self.material, 'kind', 'mirror') not in ('auto', 'mirror', 'thin mirror'):
             raise NotImplementedError('multiple_reflect is on the hot path for mirrors (and bare surfaces)')
