@@ -388,3 +388,30 @@ def test_cuda_figure_error_on_lens_stack_vs_reference_golden(cuda_device):
         bad += compare_beams(dev, ref, ('Es', 'Ep'), 2 * nsurf * phase_ulp, pre)
         bad += compare_beams(dev, ref, [f for f in OUT_FIELDS if f not in ('Es', 'Ep')], 1e-12, pre)
     assert not bad, bad
+
+
+def test_host_figure_error_plugin_selection_and_refusals():
+    """Host side (no GPU): which plug-in object serves an element with a figure error, and what is refused -- an
+    asymmetric cut (the reference fails at reflect.py:790), multiple_reflect (find_dz adds the heights to the NORMAL in
+    the derivative stage, base.py:823-845)."""
+    from xrt_b200 import figure_error as pfe, oes, materials
+    from xrt_b200.beamline import BeamLine
+    fe = pfe.Waviness(amplitude=5., xWaveLength=1., yWaveLength=2., limPhysX=[-1, 1], limPhysY=[-2, 2], gridStep=0.25)
+    si = materials.CrystalSi(hkl=(1, 1, 1))
+    bl = BeamLine()
+    lim = dict(limPhysX=[-1, 1], limPhysY=[-2, 2])
+    dcm = oes.DCM(bl, 'dcm', center=(0, 1e4, 0), bragg=0.2, material=si, figureError=fe, **lim)
+    assert dcm._plugin().kind == 0 and dcm._plugin().figure_error
+    pl = oes.Plate(bl, 'w', center=(0, 1e4, 0), pitch=1., t=0.1, figureError=fe,
+                   material=materials.Material('C', rho=3.52, kind='plate'), **lim)
+    assert pl._plugin() is dcm._plugin()  # one object per (surface kind, figure error)
+    ln = oes.ParaboloidFlatLens(bl, 'l', center=(0, 1e4, 0), t=0.05, focus=0.2, zmax=0.5, figureError=fe,
+                                material=materials.Material('Be', rho=1.848, kind='lens'), **lim)
+    assert ln._plugin().kind == 3 and ln._plugin().figure_error
+    asym = oes.DCM(bl, 'dcm', center=(0, 1e4, 0), bragg=0.2, material=si, alpha=0.05, figureError=fe, **lim)
+    with pytest.raises(NotImplementedError):
+        asym._plugin()
+    m = oes.OE(bl, 'm', center=(0, 1e4, 0), pitch=3e-3, figureError=fe, **lim)
+    with pytest.raises(NotImplementedError):
+        m.multiple_reflect(None)
+    assert oes.OE(bl, 'm0', center=(0, 1e4, 0), pitch=3e-3, **lim)._plugin() is None
